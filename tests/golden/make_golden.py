@@ -1,0 +1,98 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz by running the REAL reference (/root/reference) through
+oracle/refrun.py.  Run in the build container only:
+
+    python tests/golden/make_golden.py [scenario ...]
+
+Each fixture holds the mesh, parameters, loop-entry state and the reference's own outputs
+after N timesteps of Simulator._run_sim_core_loop (betse/science/sim.py:1132-1390) for the
+INIT phase (from the uniform initial state: vm == 0, vgj == 0 exactly — the degenerate
+edge case) and the SIM phase (from the relaxed state after the full INIT run).
+Seed: np.random.seed(12345) before `seed`.  Versions are recorded in each file.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import refrun  # noqa: E402
+
+NO_NET = {"general network": {"implement network": False},
+          "cutting event": {"event happens": False}}
+
+
+def _m(*ds):
+    out = {}
+
+    def merge(d, m):
+        for k, v in m.items():
+            if isinstance(v, dict):
+                merge(d.setdefault(k, {}), v)
+            else:
+                d[k] = v
+    for d in ds:
+        merge(out, d)
+    return out
+
+
+SMALL = {"world options": {"world size": 100e-6}, "general options": {"comp grid size": 20},
+         "init time settings": {"total time": 1.0, "sampling rate": 0.1}}
+
+SCENARIOS = {
+    # the shipped `betse try` world (C=228, M=1309, 24x25 grid), ion path only
+    "basic_ecm": dict(mods=_m(NO_NET), snaps={"init": [1, 2, 5, 20], "sim": [1, 2, 5, 20]}),
+    "mammal_ecm": dict(mods=_m(NO_NET, SMALL, {"general options": {"ion profile": "mammal"}}),
+                       snaps={"init": [1, 2, 5], "sim": [1, 2, 5, 20]}),
+    # BASELINE configs[0]: Na/K/Cl/Ca/P(+M), no ECM
+    "mammal_noecm": dict(mods=_m(NO_NET, SMALL, {"general options": {
+        "ion profile": "mammal", "simulate extracellular spaces": False}}),
+        snaps={"init": [1, 2, 5], "sim": [1, 2, 5, 20]}),
+    "basic_noecm": dict(mods=_m(NO_NET, SMALL, {"general options": {
+        "simulate extracellular spaces": False}}),
+        snaps={"init": [1, 2], "sim": [1, 5]}),
+    # non-default numerics switches: env smoothing, fast ecm exchange, static GJ, K noise
+    "mammal_ecm_opts": dict(mods=_m(NO_NET, SMALL, {
+        "general options": {"ion profile": "mammal"},
+        "internal parameters": {"sharpness env": 0.9, "fast update ecm": True},
+        "variable settings": {"gap junctions": {"voltage sensitive gj": False},
+                              "noise": {"static noise level": 0.5},
+                              "tight junction scaling": 0.5, "adherens junction scaling": 0.8}}),
+        snaps={"init": [1, 2], "sim": [1, 5]}),
+    "mammal_ecm_polar": dict(mods=_m(NO_NET, SMALL, {
+        "general options": {"ion profile": "mammal"},
+        "internal parameters": {"cell polarizability": 1.0e-4}}),
+        snaps={"init": [1, 2], "sim": [1, 5]}),
+}
+
+
+def main(argv):
+    import scipy
+    names = argv or list(SCENARIOS)
+    for name in names:
+        sc = SCENARIOS[name]
+        cap = refrun.run_reference(sc["mods"], seed=12345, snap_steps=sc["snaps"],
+                                   max_steps={"sim": max(max(sc["snaps"]["sim"]), 12)},
+                                   extra=sc.get("extra"), tweak_p=sc.get("tweak_p"))
+        cap["meta.numpy"] = np.array(np.__version__)
+        cap["meta.scipy"] = np.array(scipy.__version__)
+        cap["meta.seed"] = np.array(12345)
+        cap["meta.scenario"] = np.array(name)
+        # trim: diagnostics only at the last snapshot of each phase
+        for kind in ("init", "sim"):
+            ks = sc["snaps"][kind]
+            for K in ks[:-1]:
+                for f in refrun.DIAG_FIELDS + ["smooth_weight_mem", "smooth_weight_o", "rho_factor",
+                                               "Dm_cells", "D_gj", "D_env", "TJ_modulator"]:
+                    cap.pop("%s.k%d.%s" % (kind, K, f), None)
+        fn = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(fn, **cap)
+        print("wrote", fn, os.path.getsize(fn) // 1024, "KiB",
+              "C=%d M=%d E=%d" % (len(cap["cells.cell_vol"]), len(cap["cells.mem_sa"]),
+                                  len(cap["cells.xypts"])))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])

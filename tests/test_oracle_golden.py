@@ -1,0 +1,39 @@
+"""Pins oracle/betse_oracle.py to the REAL reference: tests/golden/*.npz were produced by
+running the unmodified reference (tests/golden/make_golden.py); the oracle must reproduce
+every recorded field after every recorded number of timesteps."""
+import numpy as np
+import pytest
+
+from oracle.betse_oracle import OracleSim
+from tests import util
+
+
+@pytest.mark.parametrize("name", util.GOLDEN)
+@pytest.mark.parametrize("kind", ["init", "sim"])
+def test_oracle_reproduces_reference(name, kind):
+    cap = util.load_golden(name)
+    o = OracleSim(util.group(cap, "cells."), util.group(cap, kind + ".p."),
+                  util.group(cap, kind + ".s0."))
+    n = 0
+    checked = 0
+    for K in util.snap_steps(cap, kind):
+        while n < K:
+            util.apply_schedule(o, cap, kind, n + 1)
+            o.step()
+            n += 1
+        ref = util.group(cap, "%s.k%d." % (kind, K))
+        polar = float(cap[kind + ".p.cell_polarizability"]) != 0.0
+        for f in util.STATE + util.ENV_STATE + util.DIAG:
+            if f not in ref or not hasattr(o, f):
+                continue
+            if not int(cap[kind + ".p.is_ecm"]) and f in util.ENV_STATE:
+                continue
+            tol = 1e-12
+            if polar and f in ("E_cell_x", "E_cell_y", "Emc"):
+                tol = 1e-6  # Σ(vm - vm_ave)·n̂·sa: catastrophic cancellation (see util.scale_of)
+            if f == "B_field":
+                tol = 1e-9
+            err = util.rel_err(getattr(o, f), ref[f], util.scale_of(f, ref))
+            assert err < tol, (name, kind, K, f, err)
+            checked += 1
+    assert checked > 20
