@@ -1,0 +1,154 @@
+"""ctypes binding of include/betse_b200.h (the C-ABI of libbetse_b200.so).
+
+The structures mirror the header field for field; tests/test_capi.py checks that the
+library exports every symbol the header declares.  There is no CPU fallback: if the
+library is missing or no CUDA device is usable, calls raise ``BetseB200Error``.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libbetse_b200.so")
+
+MAX_IONS = 8
+ABI_VERSION = 1
+NKERNELS = 8
+
+STATUS_NAN_VM = 1
+STATUS_NAN_CONC = 2
+STATUS_NEG_CLAMP = 4
+STEP_DIAG = 1
+
+BUF_CC_MID, BUF_VM_CELL, BUF_FLUX, BUF_CC_ENV, BUF_V_RAW, BUF_CC_ENV_CUR = range(6)
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_bp = C.POINTER(C.c_uint8)
+_d8 = C.c_double * MAX_IONS
+
+
+class BetseB200Error(RuntimeError):
+    pass
+
+
+class Mesh(C.Structure):
+    _fields_ = [
+        ("n_cells", C.c_int32), ("n_mems", C.c_int32), ("ny", C.c_int32), ("nx", C.c_int32),
+        ("mem_to_cells", _ip), ("cell_mem_ptr", _ip), ("nn_i", _ip), ("map_mem2ecm", _ip),
+        ("bflags_mems", _bp),
+        ("mem_sa", _dp), ("mem_nx", _dp), ("mem_ny", _dp), ("R_rads", _dp),
+        ("cell_vol", _dp), ("cell_sa", _dp), ("diviterm", _dp), ("num_mems", _dp),
+        ("memSa_per_envSquare", _dp), ("gj_default_weights", _dp),
+        ("delta", C.c_double), ("gj_len", C.c_double), ("ecm_vol", C.c_double),
+        ("memsa_mean", C.c_double),
+        ("n_cells_owned", C.c_int32), ("n_mems_owned", C.c_int32), ("n_flux_slots", C.c_int32),
+        ("y0", C.c_int32), ("ny_global", C.c_int32), ("y_own0", C.c_int32), ("y_own1", C.c_int32),
+        ("ecm_slot_ptr", _ip), ("ecm_slot_idx", _ip),
+    ]
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("n_ions", C.c_int32),
+        ("iNa", C.c_int32), ("iK", C.c_int32), ("iCa", C.c_int32), ("iP", C.c_int32),
+        ("z", _d8), ("D_free", _d8), ("D_gj", _d8), ("c_env_bound", _d8), ("cenv_uniform", _d8),
+        ("F", C.c_double), ("R", C.c_double), ("q", C.c_double), ("kb", C.c_double),
+        ("eo", C.c_double), ("er", C.c_double), ("cm", C.c_double), ("tm", C.c_double),
+        ("NAv", C.c_double), ("mu", C.c_double),
+        ("T_sim", C.c_double), ("T_p", C.c_double), ("dt", C.c_double),
+        ("alpha_NaK", C.c_double), ("alpha_Ca", C.c_double), ("KmNK_Na", C.c_double),
+        ("KmNK_K", C.c_double), ("KmNK_ATP", C.c_double), ("KmCa_Ca", C.c_double),
+        ("KmCa_ATP", C.c_double),
+        ("cATP", C.c_double), ("cADP", C.c_double), ("cPi", C.c_double), ("deltaGATP", C.c_double),
+        ("gj_surface", C.c_double), ("gj_vthresh", C.c_double), ("gj_min", C.c_double),
+        ("rho_pump", C.c_double), ("rho_channel", C.c_double),
+        ("cell_height", C.c_double), ("vol_env", C.c_double), ("cell_radius", C.c_double),
+        ("true_cell_size", C.c_double),
+        ("ko_env", C.c_double), ("sharpness", C.c_double), ("cell_polarizability", C.c_double),
+        ("smooth_cells", C.c_double),
+        ("bound_V", C.c_double * 4), ("gauss_w", C.c_double * 5),
+        ("NaKATP_block_scalar", C.c_double), ("gj_block_scalar", C.c_double),
+        ("is_ecm", C.c_int32), ("v_sensitive_gj", C.c_int32), ("cluster_open", C.c_int32),
+        ("fast_update_ecm", C.c_int32),
+        ("reserved", C.c_int32 * 4),
+    ]
+
+
+STATE_FIELDS = [
+    "cc_cells", "cc_at_mem_cell", "cc_env", "vm", "gjopen", "Dm_cells", "D_env_eff", "E_env_x",
+    "E_env_y", "v_env", "rho_env", "rho_cells", "vm_ave", "Phi_b", "extra_rho_cells",
+    "extra_rho_env", "extra_J_mem", "NaKATP_block", "gj_block",
+    "fluxes_mem", "fluxes_gj", "fluxes_env_x", "fluxes_env_y", "rate_NaKATP",
+    "Jmem", "Jgj", "Jn", "I_mem", "Jc", "Emc", "dvm",
+    "J_cell_x", "J_cell_y", "E_cell_x", "E_cell_y", "sigma_cell", "cenv_uniform",
+]
+
+
+class StateHost(C.Structure):
+    _fields_ = [(f, _dp) for f in STATE_FIELDS]
+
+
+# Every symbol include/betse_b200.h declares (checked against the header in the tests).
+SYMBOLS = [
+    "betse_abi_version", "betse_device_count", "betse_create", "betse_destroy", "betse_last_error",
+    "betse_create_error", "betse_upload_state", "betse_set_schedule", "betse_step",
+    "betse_step_profile", "betse_kernel_name", "betse_download_sample", "betse_device_buffer",
+    "betse_step_phase", "betse_stream", "betse_sync",
+]
+
+_lib = None
+
+
+def load(build_if_missing=True):
+    """Load libbetse_b200.so (building it in-tree with nvcc if absent)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if not build_if_missing:
+            raise BetseB200Error("libbetse_b200.so not built; run `python -m betse_b200.build`")
+        from . import build as _build
+        _build.build()
+    lib = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    lib.betse_abi_version.restype = C.c_int
+    lib.betse_device_count.restype = C.c_int
+    lib.betse_create.argtypes = [C.POINTER(vp), C.POINTER(Mesh), C.POINTER(Params), C.c_int]
+    lib.betse_destroy.argtypes = [vp]
+    lib.betse_destroy.restype = None
+    lib.betse_last_error.argtypes = [vp, C.c_char_p, C.c_size_t]
+    lib.betse_create_error.argtypes = [C.c_char_p, C.c_size_t]
+    lib.betse_upload_state.argtypes = [vp, C.POINTER(StateHost)]
+    lib.betse_set_schedule.argtypes = [vp, C.POINTER(Params)]
+    lib.betse_step.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_uint32)]
+    lib.betse_step_profile.argtypes = [vp, C.c_int, C.POINTER(C.c_float),
+                                       C.POINTER(C.c_float * NKERNELS), C.POINTER(C.c_int * NKERNELS)]
+    lib.betse_kernel_name.argtypes = [C.c_int]
+    lib.betse_kernel_name.restype = C.c_char_p
+    lib.betse_download_sample.argtypes = [vp, C.POINTER(StateHost)]
+    lib.betse_device_buffer.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    lib.betse_step_phase.argtypes = [vp, C.c_int, C.c_int]
+    lib.betse_stream.argtypes = [vp, C.POINTER(vp)]
+    lib.betse_sync.argtypes = [vp, C.POINTER(C.c_uint32)]
+    if lib.betse_abi_version() != ABI_VERSION:
+        raise BetseB200Error("libbetse_b200.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def as_f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def as_i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def ptr_f64(a):
+    return a.ctypes.data_as(_dp)
+
+
+def ptr_i32(a):
+    return a.ctypes.data_as(_ip)

@@ -1,0 +1,688 @@
+// C-ABI of the B200 BETSE engine (include/betse_b200.h): context, device SoA, CTA packing,
+// env CSR, state upload/download, step scheduling (direct launches or CUDA graphs), profiling.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/betse_b200.h"
+#include "kparams.cuh"
+
+// launchers (kernels.cu)
+void launch_mem(int ni, const KParams* dP, const KArrays& A, int n_ctas, int cur, int diag, cudaStream_t st);
+void launch_ion(int ni, const KParams* dP, const KArrays& A, int ny, int nx, int cur, int diag, cudaStream_t st);
+void launch_ion_smooth(int ni, const KParams* dP, const KArrays& A, int ny, int nx, int nxt, cudaStream_t st);
+void launch_envacc(int ni, const KParams* dP, const KArrays& A, int E, int nxt, cudaStream_t st);
+void launch_field(const KParams* dP, const KArrays& A, int ny, int nx, cudaStream_t st);
+void launch_envmix(int ni, const KParams* dP, const KArrays& A, int cur, cudaStream_t st);
+void launch_diag(int ni, const KParams* dP, const KArrays& A, int n_ctas, int newb, cudaStream_t st);
+void launch_expand_vm(const KParams* dP, const KArrays& A, int M, int cur, cudaStream_t st);
+
+enum { K_ION = 0, K_MEM, K_ENVACC, K_FIELD, K_ENVMIX, K_SMOOTH, K_DIAG, K_EXPAND };
+static const char* kKernelNames[BETSE_NKERNELS] = {
+    "k_ion", "k_mem", "k_envacc", "k_field", "k_envmix", "k_ion_smooth", "k_diag", "k_expand_vm"};
+
+struct betse_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    KParams P;
+    KArrays A;
+    KParams* dP = nullptr;
+    betse_params hp;          // last host params
+    int cur = 0;
+    int C = 0, Co = 0, M = 0, Mo = 0, E = 0, ny = 0, nx = 0, I = 0, n_ctas = 0, n_slots = 0;
+    bool diag_valid = false;
+    std::string err;
+    std::vector<void*> allocs;
+    // CUDA graphs of one plain step, for cur = 0 and cur = 1
+    cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+    bool graphs_built = false;
+    bool use_graphs = true;
+    // profiling
+    cudaEvent_t ev[16];
+    bool ev_init = false;
+};
+
+#define CK(call)                                                                        \
+    do {                                                                                \
+        cudaError_t e_ = (call);                                                        \
+        if (e_ != cudaSuccess) {                                                        \
+            char b_[512];                                                               \
+            snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                     __FILE__, __LINE__);                                               \
+            ctx->err = b_;                                                              \
+            return 1;                                                                   \
+        }                                                                               \
+    } while (0)
+
+static int fail(betse_ctx* ctx, const std::string& msg)
+{
+    ctx->err = msg;
+    return 2;
+}
+
+template <typename T>
+static int dev_alloc(betse_ctx* ctx, T** p, size_t n, bool zero = true)
+{
+    if (n == 0) n = 1;
+    CK(cudaMalloc((void**)p, n * sizeof(T)));
+    ctx->allocs.push_back((void*)*p);
+    if (zero) CK(cudaMemsetAsync(*p, 0, n * sizeof(T), ctx->stream));
+    return 0;
+}
+
+template <typename T>
+static int dev_upload(betse_ctx* ctx, T** p, const T* host, size_t n)
+{
+    int r = dev_alloc(ctx, p, n, host == nullptr);
+    if (r) return r;
+    if (host) CK(cudaMemcpyAsync(*p, host, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+static void fill_kparams(betse_ctx* ctx, const betse_params* hp)
+{
+    KParams& P = ctx->P;
+    P.n_ions = hp->n_ions;
+    P.iNa = hp->iNa; P.iK = hp->iK; P.iCa = hp->iCa;
+    for (int i = 0; i < BT_MAX_IONS; ++i) {
+        const double z = hp->z[i];
+        P.z[i] = z;
+        P.zi[i] = (z == 1.0) ? 1 : (z == -1.0) ? -1 : (z == 2.0) ? 2 : (z == -2.0) ? -2 : 0;
+        P.zF[i] = z * hp->F;                       // sim.zs * p.F
+        P.Dgj_surf[i] = hp->D_gj[i] * hp->gj_surface;
+        P.cbound[i] = hp->c_env_bound[i];
+        P.sig_k[i] = (z * z) * (hp->F * hp->F);
+        P.D_free[i] = hp->D_free[i];
+    }
+    P.F = hp->F;
+    P.RT_sim = hp->R * hp->T_sim;
+    P.RT_p = hp->R * hp->T_p;
+    P.R_T_p = hp->R * hp->T_p;
+    P.kbT_sim = hp->kb * hp->T_sim;
+    P.q = hp->q;
+    P.cm = hp->cm;
+    P.inv_cm = 1.0 / hp->cm;
+    P.tm = hp->tm;
+    P.dt = hp->dt;
+    P.alpha_NaK = hp->alpha_NaK; P.alpha_Ca = hp->alpha_Ca;
+    P.KmNK_Na = hp->KmNK_Na; P.KmNK_K = hp->KmNK_K; P.KmNK_ATP = hp->KmNK_ATP;
+    P.KmCa_Ca = hp->KmCa_Ca; P.KmCa_ATP = hp->KmCa_ATP;
+    P.cATP = hp->cATP; P.cADP = hp->cADP; P.cPi = hp->cPi;
+    P.K0 = exp(-(hp->deltaGATP / (hp->R * hp->T_sim)));
+    P.gj_vthresh = hp->gj_vthresh; P.gj_min = hp->gj_min;
+    P.rho_pump = hp->rho_pump; P.rho_channel = hp->rho_channel;
+    P.NaK_block = hp->NaKATP_block_scalar; P.gj_block = hp->gj_block_scalar;
+    P.env_vol_div = hp->cell_height * (P.delta * P.delta);   // p.cell_height*cells.delta**2
+    P.ko_eo_er = (hp->ko_env * hp->eo) * hp->er;
+    P.screen = (2.0 / (hp->ko_env * P.delta)) * (hp->cell_radius / hp->true_cell_size);
+    P.vol_env = hp->vol_env;
+    P.sharpness = hp->sharpness;
+    P.smooth_cells = hp->smooth_cells;
+    P.is_ecm = hp->is_ecm; P.v_sensitive_gj = hp->v_sensitive_gj;
+    P.cluster_open = hp->cluster_open; P.fast_update_ecm = hp->fast_update_ecm;
+    // scipy.ndimage._gaussian_kernel1d(sigma=1, radius=4) taps, formed by the host in NumPy
+    for (int k = 0; k <= 4; ++k) P.gw[k] = hp->gauss_w[k];
+    ctx->hp = *hp;
+}
+
+extern "C" int betse_abi_version(void) { return BETSE_ABI_VERSION; }
+
+extern "C" int betse_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+extern "C" const char* betse_kernel_name(int k)
+{
+    return (k >= 0 && k < BETSE_NKERNELS) ? kKernelNames[k] : "";
+}
+
+extern "C" int betse_last_error(betse_ctx* ctx, char* buf, size_t n)
+{
+    if (!ctx || !buf || n == 0) return 1;
+    snprintf(buf, n, "%s", ctx->err.c_str());
+    return 0;
+}
+
+static std::string g_create_error;
+
+extern "C" int betse_create_error(char* buf, size_t n)
+{
+    if (!buf || n == 0) return 1;
+    snprintf(buf, n, "%s", g_create_error.c_str());
+    return 0;
+}
+
+static void destroy_graphs(betse_ctx* ctx)
+{
+    for (int i = 0; i < 2; ++i)
+        if (ctx->gexec[i]) { cudaGraphExecDestroy(ctx->gexec[i]); ctx->gexec[i] = nullptr; }
+    ctx->graphs_built = false;
+}
+
+extern "C" void betse_destroy(betse_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    destroy_graphs(ctx);
+    if (ctx->ev_init) for (auto& e : ctx->ev) cudaEventDestroy(e);
+    for (void* p : ctx->allocs) cudaFree(p);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_params* hp)
+{
+    if (hp->abi_version != BETSE_ABI_VERSION) return fail(ctx, "betse_params.abi_version mismatch");
+    if (hp->n_ions < 4 || hp->n_ions > BETSE_MAX_IONS) return fail(ctx, "n_ions must be in [4,8]");
+    if (hp->cell_polarizability != 0.0)
+        return fail(ctx, "cell_polarizability != 0 (sim.py:2048-2080) is not supported by this build");
+    if (hp->iNa < 0 || hp->iK < 0) return fail(ctx, "Na and K must be enabled");
+    if (mesh->n_cells <= 0 || mesh->n_mems <= 0) return fail(ctx, "empty mesh");
+    ctx->C = mesh->n_cells;
+    ctx->Co = mesh->n_cells_owned > 0 ? mesh->n_cells_owned : mesh->n_cells;
+    ctx->M = mesh->n_mems;
+    ctx->Mo = mesh->n_mems_owned > 0 ? mesh->n_mems_owned : mesh->n_mems;
+    ctx->ny = mesh->ny; ctx->nx = mesh->nx; ctx->E = mesh->ny * mesh->nx;
+    ctx->I = hp->n_ions;
+    const int C = ctx->C, Co = ctx->Co, Mo = ctx->Mo, E = ctx->E, I = ctx->I;
+    if (ctx->M != Mo) return fail(ctx, "ghost membranes are not supported: pass owned membranes only");
+    if (mesh->cell_mem_ptr[Co] != Mo) return fail(ctx, "cell_mem_ptr[n_cells_owned] != n_mems_owned");
+
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    memset(&ctx->A, 0, sizeof(KArrays));
+    memset(&ctx->P, 0, sizeof(KParams));
+    KArrays& A = ctx->A;
+    KParams& P = ctx->P;
+    P.delta = mesh->delta;
+    P.gj_len = mesh->gj_len;
+    P.ecm_vol = mesh->ecm_vol;
+    P.memsa_mean = mesh->memsa_mean;
+    P.ny = mesh->ny; P.nx = mesh->nx;
+    P.y0 = mesh->y0;
+    P.ny_global = mesh->ny_global > 0 ? mesh->ny_global : mesh->ny;
+    P.y_own0 = mesh->y_own0;
+    P.y_own1 = mesh->y_own1 > 0 ? mesh->y_own1 : mesh->ny;
+    P.n_cells = C; P.n_cells_owned = Co; P.n_mems_owned = Mo;
+    fill_kparams(ctx, hp);
+
+    // ---- index arrays
+    int r;
+    if ((r = dev_upload(ctx, (int**)&A.mem_to_cells, mesh->mem_to_cells, Mo))) return r;
+    if ((r = dev_upload(ctx, (int**)&A.cell_mem_ptr, mesh->cell_mem_ptr, Co + 1))) return r;
+    if ((r = dev_upload(ctx, (int**)&A.nn_i, mesh->nn_i, Mo))) return r;
+    if ((r = dev_upload(ctx, (int**)&A.map_mem2ecm, mesh->map_mem2ecm, Mo))) return r;
+    std::vector<int> nnc(Mo);
+    for (int m = 0; m < Mo; ++m) {
+        int nn = mesh->nn_i[m];
+        int cn;
+        if (nn >= 0 && nn < Mo) cn = mesh->mem_to_cells[nn];
+        else if (nn <= -2) cn = -(nn + 2);      // multi-GPU: partner lives on a ghost cell: nn = -(ghost_cell+2)
+        else return fail(ctx, "nn_i out of range");
+        if (cn < 0 || cn >= C) return fail(ctx, "partner cell out of range");
+        if (mesh->map_mem2ecm[m] < 0 || mesh->map_mem2ecm[m] >= E) return fail(ctx, "map_mem2ecm out of range");
+        if (mesh->mem_to_cells[m] < 0 || mesh->mem_to_cells[m] >= Co) return fail(ctx, "mem_to_cells out of range");
+        nnc[m] = cn | (mesh->bflags_mems[m] ? (int)0x80000000 : 0);
+    }
+    if ((r = dev_upload(ctx, (int**)&A.nn_cell_flag, nnc.data(), Mo))) return r;
+
+    // ---- CTA packing: contiguous runs of whole cells with <= BT_TPB membranes
+    std::vector<int> cta_start;
+    cta_start.push_back(0);
+    {
+        int c = 0;
+        while (c < Co) {
+            int mstart = mesh->cell_mem_ptr[c];
+            int cc = c;
+            while (cc < Co && (mesh->cell_mem_ptr[cc + 1] - mstart) <= BT_TPB && (cc - c) < BT_MAX_CTA_CELLS) ++cc;
+            if (cc == c) return fail(ctx, "a cell has more than 256 membranes");
+            cta_start.push_back(cc);
+            c = cc;
+        }
+    }
+    ctx->n_ctas = (int)cta_start.size() - 1;
+    P.n_ctas = ctx->n_ctas;
+    if ((r = dev_upload(ctx, (int**)&A.cta_cell_start, cta_start.data(), cta_start.size()))) return r;
+
+    // ---- env point -> flux slot CSR (map_ecm2mem, cells.py:1793-1796), slots in membrane order
+    ctx->n_slots = mesh->n_flux_slots > Mo ? mesh->n_flux_slots : Mo;
+    if (mesh->ecm_slot_ptr && mesh->ecm_slot_idx) {
+        if ((r = dev_upload(ctx, (int**)&A.slot_ptr, mesh->ecm_slot_ptr, E + 1))) return r;
+        if ((r = dev_upload(ctx, (int**)&A.slot_idx, mesh->ecm_slot_idx, mesh->ecm_slot_ptr[E]))) return r;
+    } else {
+        std::vector<int> ptr(E + 1, 0), idx(Mo);
+        for (int m = 0; m < Mo; ++m) ptr[mesh->map_mem2ecm[m] + 1]++;
+        for (int k = 0; k < E; ++k) ptr[k + 1] += ptr[k];
+        std::vector<int> fillp(ptr.begin(), ptr.end() - 1);
+        for (int m = 0; m < Mo; ++m) idx[fillp[mesh->map_mem2ecm[m]]++] = m;
+        if ((r = dev_upload(ctx, (int**)&A.slot_ptr, ptr.data(), E + 1))) return r;
+        if ((r = dev_upload(ctx, (int**)&A.slot_idx, idx.data(), Mo))) return r;
+    }
+
+    // ---- geometry
+    if ((r = dev_upload(ctx, (double**)&A.mem_sa, mesh->mem_sa, Mo))) return r;
+    if ((r = dev_upload(ctx, (double**)&A.mem_nx, mesh->mem_nx, Mo))) return r;
+    if ((r = dev_upload(ctx, (double**)&A.mem_ny, mesh->mem_ny, Mo))) return r;
+    if ((r = dev_upload(ctx, (double**)&A.cell_vol, mesh->cell_vol, Co))) return r;
+    if ((r = dev_upload(ctx, (double**)&A.cell_sa, mesh->cell_sa, Co))) return r;
+    if ((r = dev_upload(ctx, (double**)&A.diviterm, mesh->diviterm, Co))) return r;
+    if ((r = dev_upload(ctx, (double**)&A.num_mems, mesh->num_mems, Co))) return r;
+    if (mesh->memSa_per_envSquare) { if ((r = dev_upload(ctx, (double**)&A.memsa_env, mesh->memSa_per_envSquare, E))) return r; }
+    else if (hp->fast_update_ecm) return fail(ctx, "fast_update_ecm needs memSa_per_envSquare");
+    if (mesh->gj_default_weights) { if ((r = dev_upload(ctx, (double**)&A.gj_w, mesh->gj_default_weights, Mo))) return r; }
+    else if (!hp->v_sensitive_gj) return fail(ctx, "static gap junctions need gj_default_weights");
+
+    // ---- state
+    const size_t IC = (size_t)I * C, IE = (size_t)I * E, IM = (size_t)I * Mo;
+    if ((r = dev_alloc(ctx, &A.cc_cells, IC))) return r;
+    for (int b = 0; b < 2; ++b) {
+        if ((r = dev_alloc(ctx, &A.cc_mid[b], IC))) return r;
+        if ((r = dev_alloc(ctx, &A.vm_cell[b], C))) return r;
+        if ((r = dev_alloc(ctx, &A.cc_env[b], hp->is_ecm ? IE : 1))) return r;
+    }
+    if ((r = dev_alloc(ctx, &A.gjopen, Mo))) return r;
+    if ((r = dev_alloc(ctx, (double**)&A.Dm, IM))) return r;
+    if ((r = dev_alloc(ctx, (double**)&A.Denv, hp->is_ecm ? IE : 1))) return r;
+    if ((r = dev_alloc(ctx, &A.E_x, E))) return r;
+    if ((r = dev_alloc(ctx, &A.E_y, E))) return r;
+    if ((r = dev_alloc(ctx, &A.v_env, E))) return r;
+    if ((r = dev_alloc(ctx, &A.v_raw, E))) return r;
+    if ((r = dev_alloc(ctx, &A.rho_env, E))) return r;
+    if ((r = dev_alloc(ctx, &A.rho_cells, C))) return r;
+    if ((r = dev_alloc(ctx, &A.flux_slots, hp->is_ecm ? (size_t)ctx->n_slots * I : 1))) return r;
+    if ((r = dev_alloc(ctx, &A.cenv_u, 16))) return r;
+    if ((r = dev_alloc(ctx, &A.cenv_part, (size_t)ctx->n_ctas * 8))) return r;
+    if ((r = dev_alloc(ctx, &A.status, 1))) return r;
+    if ((r = dev_alloc(ctx, &A.vm_mem, Mo))) return r;
+    if (hp->is_ecm && hp->sharpness < 1.0) { if ((r = dev_alloc(ctx, &A.scratch_env, IE))) return r; }
+    if (!hp->is_ecm) {
+        double cu[16];
+        for (int i = 0; i < 8; ++i) cu[i] = cu[8 + i] = hp->cenv_uniform[i];
+        CK(cudaMemcpyAsync(A.cenv_u, cu, sizeof cu, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if ((r = dev_alloc(ctx, &ctx->dP, 1, false))) return r;
+    CK(cudaMemcpyAsync(ctx->dP, &ctx->P, sizeof(KParams), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int betse_create(betse_ctx** out, const betse_mesh* mesh, const betse_params* params, int device)
+{
+    if (!out || !mesh || !params) { g_create_error = "null argument"; return 2; }
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        g_create_error = "no CUDA device available (this library has no CPU fallback)";
+        return 3;
+    }
+    if (device < 0 || device >= n) { g_create_error = "device index out of range"; return 2; }
+    betse_ctx* ctx = new betse_ctx();
+    ctx->device = device;
+    int r = create_impl(ctx, mesh, params);
+    if (r) {
+        g_create_error = ctx->err;
+        betse_destroy(ctx);
+        return r;
+    }
+    *out = ctx;
+    return 0;
+}
+
+static int ensure_diag_buffers(betse_ctx* ctx)
+{
+    KArrays& A = ctx->A;
+    if (A.fl_mem) return 0;
+    const size_t IM = (size_t)ctx->I * ctx->Mo, IE = (size_t)ctx->I * ctx->E;
+    int r;
+    if ((r = dev_alloc(ctx, &A.fl_mem, IM))) return r;
+    if ((r = dev_alloc(ctx, &A.fl_gj, IM))) return r;
+    if ((r = dev_alloc(ctx, &A.fl_env_x, ctx->hp.is_ecm ? IE : 1))) return r;
+    if ((r = dev_alloc(ctx, &A.fl_env_y, ctx->hp.is_ecm ? IE : 1))) return r;
+    if ((r = dev_alloc(ctx, &A.rate_NaK, ctx->Mo))) return r;
+    double** mem_arrays[] = {&A.Jmem, &A.Jgj, &A.Jn, &A.I_mem, &A.Jc, &A.Emc, &A.dvm};
+    for (auto p : mem_arrays) if ((r = dev_alloc(ctx, p, ctx->Mo))) return r;
+    double** cell_arrays[] = {&A.J_cell_x, &A.J_cell_y, &A.E_cell_x, &A.E_cell_y, &A.sigma_cell, &A.vm_ave};
+    for (auto p : cell_arrays) if ((r = dev_alloc(ctx, p, ctx->C))) return r;
+    destroy_graphs(ctx);   // KArrays changed
+    return 0;
+}
+
+template <typename T>
+static int opt_array(betse_ctx* ctx, const T** slot, const T* host, size_t n)
+{
+    // optional device array: allocate on first use, then overwrite
+    if (!host) return 0;
+    if (!*slot) {
+        T* p;
+        int r = dev_alloc(ctx, &p, n, false);
+        if (r) return r;
+        *slot = p;
+        destroy_graphs(ctx);
+    }
+    CK(cudaMemcpyAsync((void*)*slot, host, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+extern "C" int betse_upload_state(betse_ctx* ctx, const betse_state_host* s)
+{
+    if (!ctx || !s) return 2;
+    CK(cudaSetDevice(ctx->device));
+    KArrays& A = ctx->A;
+    const int C = ctx->C, Mo = ctx->Mo, E = ctx->E, I = ctx->I;
+    const size_t IC = (size_t)I * C, IE = (size_t)I * E, IM = (size_t)I * Mo;
+    const int cur = ctx->cur;
+    cudaStream_t st = ctx->stream;
+#define UP(dst, src, n) if (src) CK(cudaMemcpyAsync((void*)(dst), (src), (n) * sizeof(double), cudaMemcpyHostToDevice, st))
+    UP(A.cc_cells, s->cc_cells, IC);
+    UP(A.cc_mid[cur], s->cc_at_mem_cell, IC);
+    if (ctx->hp.is_ecm) {
+        UP(A.cc_env[cur], s->cc_env, IE);
+        UP(A.Denv, s->D_env_eff, IE);
+        UP(A.E_x, s->E_env_x, E);
+        UP(A.E_y, s->E_env_y, E);
+    }
+    UP(A.gjopen, s->gjopen, Mo);
+    UP(A.Dm, s->Dm_cells, IM);
+    if (s->vm) {
+        // default mode: vm = vm_cell[cell] - Phi_b[map_mem2ecm] (sim.py:2029) -> keep the per-cell part
+        std::vector<double> vc(C, 0.0);
+        std::vector<int> ptr(ctx->Co + 1), m2e;
+        CK(cudaMemcpy(ptr.data(), A.cell_mem_ptr, (ctx->Co + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+        const double* phi = s->Phi_b;
+        if (phi) { m2e.resize(Mo); CK(cudaMemcpy(m2e.data(), A.map_mem2ecm, Mo * sizeof(int), cudaMemcpyDeviceToHost)); }
+        for (int c = 0; c < ctx->Co; ++c) {
+            const int m = ptr[c];
+            vc[c] = s->vm[m] + (phi ? phi[m2e[m]] : 0.0);
+        }
+        // ghost cells (multi-GPU) are filled by the first exchange
+        CK(cudaMemcpyAsync(A.vm_cell[cur], vc.data(), (size_t)ctx->Co * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    int r;
+    if (s->Phi_b) {
+        bool nz = false;
+        for (int k = 0; k < E; ++k) if (s->Phi_b[k] != 0.0) { nz = true; break; }
+        if (nz || A.phi_b) {
+            if ((r = opt_array(ctx, &A.phi_b, (const double*)s->Phi_b, E))) return r;
+            ctx->P.has_phi = nz ? 1 : 0;
+            CK(cudaMemcpyAsync(ctx->dP, &ctx->P, sizeof(KParams), cudaMemcpyHostToDevice, st));
+        }
+    }
+    if ((r = opt_array(ctx, &A.extra_rho_cells, (const double*)s->extra_rho_cells, C))) return r;
+    if ((r = opt_array(ctx, &A.extra_rho_env, (const double*)s->extra_rho_env, E))) return r;
+    if ((r = opt_array(ctx, &A.extra_J_mem, (const double*)s->extra_J_mem, Mo))) return r;
+    if ((r = opt_array(ctx, &A.NaK_block, (const double*)s->NaKATP_block, Mo))) return r;
+    if ((r = opt_array(ctx, &A.gj_block, (const double*)s->gj_block, Mo))) return r;
+    if (s->cenv_uniform && !ctx->hp.is_ecm) {
+        double cu[16];
+        for (int i = 0; i < 8; ++i) cu[i] = cu[8 + i] = (i < I) ? s->cenv_uniform[i] : 0.0;
+        CK(cudaMemcpyAsync(A.cenv_u, cu, sizeof cu, cudaMemcpyHostToDevice, st));
+    }
+#undef UP
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int betse_set_schedule(betse_ctx* ctx, const betse_params* hp)
+{
+    if (!ctx || !hp) return 2;
+    CK(cudaSetDevice(ctx->device));
+    if (hp->n_ions != ctx->I || hp->is_ecm != ctx->hp.is_ecm) return fail(ctx, "set_schedule cannot change n_ions/is_ecm");
+    if (hp->cell_polarizability != 0.0) return fail(ctx, "cell_polarizability != 0 unsupported");
+    const int has_phi = ctx->P.has_phi;
+    fill_kparams(ctx, hp);
+    ctx->P.has_phi = has_phi;
+    CK(cudaMemcpyAsync(ctx->dP, &ctx->P, sizeof(KParams), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+// One timestep.  Order: env transport of every ion (reads last step's E field and
+// cc_env[cur], writes cc_env[nxt]) -> membranes+cells (reads cc_env[cur] for GHK/NaK, cc_env[nxt]
+// for the Ca pump) -> env accumulation + charge -> env field for the next step.
+static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
+{
+    const int I = ctx->I, cur = ctx->cur, nxt = cur ^ 1;
+    cudaStream_t st = ctx->stream;
+    const KArrays& A = ctx->A;
+    const bool ecm = ctx->hp.is_ecm != 0;
+    if (phase == 0) {
+        if (ecm) {
+            launch_ion(I, ctx->dP, A, ctx->ny, ctx->nx, cur, diag, st);
+            if (evs) cudaEventRecord(evs[1], st);
+            if (ctx->hp.sharpness < 1.0) {
+                launch_ion_smooth(I, ctx->dP, A, ctx->ny, ctx->nx, nxt, st);
+                cudaMemcpyAsync(A.cc_env[nxt], A.scratch_env, (size_t)I * ctx->E * sizeof(double),
+                                cudaMemcpyDeviceToDevice, st);
+            }
+        } else if (evs) cudaEventRecord(evs[1], st);
+        if (evs) cudaEventRecord(evs[2], st);
+        launch_mem(I, ctx->dP, A, ctx->n_ctas, cur, diag, st);
+        if (evs) cudaEventRecord(evs[3], st);
+    } else if (phase == 1) {
+        if (ecm) launch_envacc(I, ctx->dP, A, ctx->E, nxt, st);
+        else launch_envmix(I, ctx->dP, A, cur, st);
+        if (evs) cudaEventRecord(evs[4], st);
+    } else {
+        if (ecm) launch_field(ctx->dP, A, ctx->ny, ctx->nx, st);
+        if (evs) cudaEventRecord(evs[5], st);
+        if (diag) launch_diag(I, ctx->dP, A, ctx->n_ctas, nxt, st);
+        if (evs) cudaEventRecord(evs[6], st);
+        ctx->cur = nxt;
+    }
+}
+
+static void enqueue_step(betse_ctx* ctx, int diag, cudaEvent_t* evs)
+{
+    if (evs) cudaEventRecord(evs[0], ctx->stream);
+    enqueue_phase(ctx, 0, diag, evs);
+    enqueue_phase(ctx, 1, diag, evs);
+    enqueue_phase(ctx, 2, diag, evs);
+}
+
+static int build_graphs(betse_ctx* ctx)
+{
+    const int saved = ctx->cur;
+    for (int b = 0; b < 2; ++b) {
+        ctx->cur = b;
+        cudaGraph_t g;
+        CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        enqueue_step(ctx, 0, nullptr);
+        CK(cudaStreamEndCapture(ctx->stream, &g));
+        CK(cudaGraphInstantiate(&ctx->gexec[b], g, 0));
+        CK(cudaGraphDestroy(g));
+    }
+    ctx->cur = saved;
+    ctx->graphs_built = true;
+    return 0;
+}
+
+static int read_status(betse_ctx* ctx, uint32_t* status_out)
+{
+    unsigned int st = 0;
+    CK(cudaMemcpyAsync(&st, ctx->A.status, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (st) CK(cudaMemsetAsync(ctx->A.status, 0, sizeof st, ctx->stream));
+    if (status_out) *status_out = st;
+    return 0;
+}
+
+extern "C" int betse_step(betse_ctx* ctx, int nsteps, int flags, uint32_t* status_out)
+{
+    if (!ctx || nsteps < 0) return 2;
+    CK(cudaSetDevice(ctx->device));
+    const bool want_diag = (flags & BETSE_STEP_DIAG) != 0;
+    if (want_diag) { int r = ensure_diag_buffers(ctx); if (r) return r; }
+    // warm the launch path once without capture (cudaFuncSetAttribute is not capturable)
+    if (ctx->use_graphs && !ctx->graphs_built && nsteps > 2) {
+        enqueue_step(ctx, 0, nullptr);
+        --nsteps;
+        int r = build_graphs(ctx);
+        if (r) return r;
+    }
+    for (int n = 0; n < nsteps; ++n) {
+        const bool last = (n == nsteps - 1);
+        if (last && want_diag) enqueue_step(ctx, 1, nullptr);
+        else if (ctx->graphs_built) { CK(cudaGraphLaunch(ctx->gexec[ctx->cur], ctx->stream)); ctx->cur ^= 1; }
+        else enqueue_step(ctx, 0, nullptr);
+    }
+    CK(cudaGetLastError());
+    if (want_diag && nsteps > 0) ctx->diag_valid = true;
+    else if (nsteps > 0) ctx->diag_valid = false;
+    return read_status(ctx, status_out);
+}
+
+extern "C" int betse_step_phase(betse_ctx* ctx, int phase, int flags)
+{
+    if (!ctx || phase < 0 || phase > 2) return 2;
+    CK(cudaSetDevice(ctx->device));
+    const int diag = (flags & BETSE_STEP_DIAG) ? 1 : 0;
+    if (diag) { int r = ensure_diag_buffers(ctx); if (r) return r; }
+    enqueue_phase(ctx, phase, diag, nullptr);
+    CK(cudaGetLastError());
+    if (phase == 2) ctx->diag_valid = diag != 0;
+    return 0;
+}
+
+extern "C" int betse_sync(betse_ctx* ctx, uint32_t* status_out)
+{
+    if (!ctx) return 2;
+    CK(cudaSetDevice(ctx->device));
+    return read_status(ctx, status_out);
+}
+
+extern "C" int betse_stream(betse_ctx* ctx, void** cuda_stream)
+{
+    if (!ctx || !cuda_stream) return 2;
+    *cuda_stream = (void*)ctx->stream;
+    return 0;
+}
+
+extern "C" int betse_step_profile(betse_ctx* ctx, int nsteps, float* total_ms,
+                                  float kernel_ms[BETSE_NKERNELS], int kernel_launches[BETSE_NKERNELS])
+{
+    if (!ctx || nsteps <= 0) return 2;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->ev_init) {
+        for (auto& e : ctx->ev) CK(cudaEventCreate(&e));
+        ctx->ev_init = true;
+    }
+    double acc[BETSE_NKERNELS] = {0};
+    int cnt[BETSE_NKERNELS] = {0};
+    const bool ecm = ctx->hp.is_ecm != 0;
+    cudaEvent_t t0 = ctx->ev[14], t1 = ctx->ev[15];
+    // (a) whole-run time, back-to-back launches exactly as betse_step issues them
+    if (ctx->use_graphs && !ctx->graphs_built) { enqueue_step(ctx, 0, nullptr); int r = build_graphs(ctx); if (r) return r; }
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventRecord(t0, ctx->stream));
+    for (int n = 0; n < nsteps; ++n) {
+        if (ctx->graphs_built) { CK(cudaGraphLaunch(ctx->gexec[ctx->cur], ctx->stream)); ctx->cur ^= 1; }
+        else enqueue_step(ctx, 0, nullptr);
+    }
+    CK(cudaEventRecord(t1, ctx->stream));
+    CK(cudaEventSynchronize(t1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, t0, t1));
+    if (total_ms) *total_ms = ms;
+    // (b) per-kernel durations: same steps again with an event after every kernel
+    if (kernel_ms) {
+        const int reps = nsteps < 20 ? nsteps : 20;
+        for (int n = 0; n < reps; ++n) {
+            enqueue_step(ctx, 0, ctx->ev);
+            CK(cudaEventSynchronize(ctx->ev[6]));
+            float d;
+            if (ecm) {
+                CK(cudaEventElapsedTime(&d, ctx->ev[0], ctx->ev[1])); acc[K_ION] += d; cnt[K_ION]++;
+                if (ctx->hp.sharpness < 1.0) { CK(cudaEventElapsedTime(&d, ctx->ev[1], ctx->ev[2])); acc[K_SMOOTH] += d; cnt[K_SMOOTH]++; }
+            }
+            CK(cudaEventElapsedTime(&d, ctx->ev[2], ctx->ev[3])); acc[K_MEM] += d; cnt[K_MEM]++;
+            CK(cudaEventElapsedTime(&d, ctx->ev[3], ctx->ev[4]));
+            if (ecm) { acc[K_ENVACC] += d; cnt[K_ENVACC]++; } else { acc[K_ENVMIX] += d; cnt[K_ENVMIX]++; }
+            if (ecm) { CK(cudaEventElapsedTime(&d, ctx->ev[4], ctx->ev[5])); acc[K_FIELD] += d; cnt[K_FIELD]++; }
+        }
+        for (int k = 0; k < BETSE_NKERNELS; ++k) {
+            kernel_ms[k] = cnt[k] ? (float)(acc[k] / cnt[k]) : 0.f;
+            if (kernel_launches) kernel_launches[k] = cnt[k] ? 1 : 0;   // launches per step
+        }
+    }
+    ctx->diag_valid = false;
+    uint32_t st;
+    return read_status(ctx, &st);
+}
+
+extern "C" int betse_download_sample(betse_ctx* ctx, betse_state_host* s)
+{
+    if (!ctx || !s) return 2;
+    CK(cudaSetDevice(ctx->device));
+    KArrays& A = ctx->A;
+    const int C = ctx->C, Mo = ctx->Mo, E = ctx->E, I = ctx->I;
+    const size_t IC = (size_t)I * C, IE = (size_t)I * E, IM = (size_t)I * Mo;
+    const int cur = ctx->cur;
+    cudaStream_t st = ctx->stream;
+#define DN(dst, src, n) if (dst) { if (!(src)) return fail(ctx, "download of " #dst ": not available"); \
+        CK(cudaMemcpyAsync((dst), (src), (n) * sizeof(double), cudaMemcpyDeviceToHost, st)); }
+    DN(s->cc_cells, A.cc_cells, IC);
+    DN(s->cc_at_mem_cell, A.cc_mid[cur], IC);
+    if (ctx->hp.is_ecm) {
+        DN(s->cc_env, A.cc_env[cur], IE);
+        DN(s->D_env_eff, A.Denv, IE);
+        DN(s->E_env_x, A.E_x, E);
+        DN(s->E_env_y, A.E_y, E);
+        DN(s->v_env, A.v_env, E);
+        DN(s->rho_env, A.rho_env, E);
+    }
+    if (s->vm) {
+        launch_expand_vm(ctx->dP, A, Mo, cur, st);
+        DN(s->vm, A.vm_mem, Mo);
+    }
+    DN(s->gjopen, A.gjopen, Mo);
+    DN(s->Dm_cells, A.Dm, IM);
+    DN(s->rho_cells, A.rho_cells, C);
+    if (s->cenv_uniform) CK(cudaMemcpyAsync(s->cenv_uniform, A.cenv_u + cur * 8, I * sizeof(double), cudaMemcpyDeviceToHost, st));
+    const bool any_diag = s->fluxes_mem || s->fluxes_gj || s->fluxes_env_x || s->fluxes_env_y || s->rate_NaKATP ||
+                          s->Jmem || s->Jgj || s->Jn || s->I_mem || s->Jc || s->Emc || s->dvm || s->J_cell_x ||
+                          s->J_cell_y || s->E_cell_x || s->E_cell_y || s->sigma_cell || s->vm_ave;
+    if (any_diag) {
+        if (!ctx->diag_valid) return fail(ctx, "diagnostics requested but the last step was not run with BETSE_STEP_DIAG");
+        DN(s->fluxes_mem, A.fl_mem, IM);
+        DN(s->fluxes_gj, A.fl_gj, IM);
+        if (ctx->hp.is_ecm) { DN(s->fluxes_env_x, A.fl_env_x, IE); DN(s->fluxes_env_y, A.fl_env_y, IE); }
+        DN(s->rate_NaKATP, A.rate_NaK, Mo);
+        DN(s->Jmem, A.Jmem, Mo); DN(s->Jgj, A.Jgj, Mo); DN(s->Jn, A.Jn, Mo); DN(s->I_mem, A.I_mem, Mo);
+        DN(s->Jc, A.Jc, Mo); DN(s->Emc, A.Emc, Mo); DN(s->dvm, A.dvm, Mo);
+        DN(s->J_cell_x, A.J_cell_x, C); DN(s->J_cell_y, A.J_cell_y, C);
+        DN(s->E_cell_x, A.E_cell_x, C); DN(s->E_cell_y, A.E_cell_y, C);
+        DN(s->sigma_cell, A.sigma_cell, C); DN(s->vm_ave, A.vm_ave, C);
+    }
+#undef DN
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int betse_device_buffer(betse_ctx* ctx, int which, void** dev_ptr, size_t* bytes)
+{
+    if (!ctx || !dev_ptr) return 2;
+    const KArrays& A = ctx->A;
+    const int nxt = ctx->cur ^ 1;
+    size_t b = 0; void* p = nullptr;
+    switch (which) {
+        case BETSE_BUF_CC_MID: p = A.cc_mid[nxt]; b = (size_t)ctx->I * ctx->C * 8; break;
+        case BETSE_BUF_VM_CELL: p = A.vm_cell[nxt]; b = (size_t)ctx->C * 8; break;
+        case BETSE_BUF_FLUX: p = A.flux_slots; b = (size_t)ctx->n_slots * ctx->I * 8; break;
+        case BETSE_BUF_CC_ENV: p = A.cc_env[nxt]; b = (size_t)ctx->I * ctx->E * 8; break;
+        case BETSE_BUF_V_RAW: p = A.v_raw; b = (size_t)ctx->E * 8; break;
+        case BETSE_BUF_CC_ENV_CUR: p = A.cc_env[ctx->cur]; b = (size_t)ctx->I * ctx->E * 8; break;
+        default: return fail(ctx, "unknown buffer id");
+    }
+    *dev_ptr = p;
+    if (bytes) *bytes = b;
+    return 0;
+}

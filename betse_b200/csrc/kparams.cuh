@@ -1,0 +1,68 @@
+// Device-side parameter block and array table shared by all kernels of the tissue step.
+#pragma once
+#include <stdint.h>
+
+#define BT_MAX_IONS 8
+#define BT_TPB 256          // threads per CTA of the membrane kernel == max membranes per CTA
+#define BT_MAX_CTA_CELLS 96 // max cells packed into one membrane-kernel CTA
+
+// Scalars (kernel argument, lives in the constant bank).  Derived products are formed on
+// the host in the same operand order as the reference's NumPy expressions.
+struct KParams {
+    int n_ions, iNa, iK, iCa;
+    int zi[BT_MAX_IONS];          // integer valence class (+-1, +-2) or 0 = generic path
+    double z[BT_MAX_IONS];
+    double zF[BT_MAX_IONS];       // sim.zs * p.F
+    double Dgj_surf[BT_MAX_IONS]; // sim.D_gj[i] * p.gj_surface
+    double cbound[BT_MAX_IONS];   // sim.c_env_bound
+    double sig_k[BT_MAX_IONS];    // z^2 * F^2 (sigma_cell, diagnostics)
+    double D_free[BT_MAX_IONS];
+    double F, RT_sim, RT_p, kbT_sim, q, cm, inv_cm, tm, dt;
+    double alpha_NaK, alpha_Ca, KmNK_Na, KmNK_K, KmNK_ATP, KmCa_Ca, KmCa_ATP;
+    double cATP, cADP, cPi, K0;             // K0 = exp(-deltaGATP/(R*T_sim))
+    double gj_vthresh, gj_min, gj_len;
+    double rho_pump, rho_channel;
+    double NaK_block, gj_block;             // scalar blocks (used when the arrays are null)
+    double delta, env_vol_div;              // env_vol_div = cell_height*delta^2
+    double ecm_vol, memsa_mean, ko_eo_er;   // ko_env*eo*er
+    double screen;                          // (2/(ko_env*delta))*(cell_radius/true_cell_size)
+    double vol_env;                         // no-ECM bath volume
+    double sharpness;
+    double gw[5];                           // gaussian sigma=1 taps w0..w4 (normalised)
+    double smooth_cells, R_T_p;             // R*T_p
+    int is_ecm, v_sensitive_gj, cluster_open, fast_update_ecm;
+    int has_phi;                            // Phi_b != 0 somewhere
+    // local grid geometry (domain decomposition: rows [y0, y0+ny) of a ny_global-row grid)
+    int ny, nx, y0, ny_global, y_own0, y_own1;
+    int n_cells, n_cells_owned, n_mems_owned, n_ctas;
+};
+
+// Device array table (kernel argument).
+struct KArrays {
+    // mesh
+    const int *mem_to_cells, *cell_mem_ptr, *nn_cell_flag, *nn_i, *map_mem2ecm;
+    const int *cta_cell_start;
+    const int *slot_ptr, *slot_idx;
+    const double *mem_sa, *mem_nx, *mem_ny, *cell_vol, *cell_sa, *diviterm, *num_mems;
+    const double *memsa_env, *gj_w;
+    // state
+    double *cc_cells;        // [I,C]
+    double *cc_mid[2];       // [I,C] x2
+    double *cc_env[2];       // [I,E] x2
+    double *vm_cell[2];      // [C]   x2
+    double *gjopen;          // [M]
+    const double *Dm;        // [I,M]
+    const double *Denv;      // [I,E]
+    double *E_x, *E_y, *v_env, *v_raw, *rho_env, *rho_cells;
+    const double *phi_b, *extra_rho_cells, *extra_rho_env, *extra_J_mem;
+    const double *NaK_block, *gj_block;
+    double *flux_slots;      // [slots, I]
+    double *cenv_u;          // [2][8] no-ECM bath concentrations (device-resident, double buffered)
+    double *cenv_part;       // [n_ctas, 8] per-CTA partial sums
+    unsigned int *status;
+    // diagnostics
+    double *fl_mem, *fl_gj, *fl_env_x, *fl_env_y, *rate_NaK;
+    double *Jmem, *Jgj, *Jn, *I_mem, *Jc, *Emc, *dvm, *vm_mem, *vm_ave;
+    double *J_cell_x, *J_cell_y, *E_cell_x, *E_cell_y, *sigma_cell;
+    double *scratch_env;     // [I,E] temp for the sharpness<1 smoothing pass
+};

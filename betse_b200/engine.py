@@ -1,0 +1,371 @@
+"""TissueEngine — Python owner of one ``betse_ctx`` (one GPU, one simulation).
+
+It speaks the reference's vocabulary: the mesh is the set of ``Cells`` attributes the loop
+consumes, parameters are the ``Parameters`` scalars, state arrays carry the names of the
+``Simulator`` attributes (``cc_cells``, ``cc_at_mem``, ``cc_env``, ``vm``, ``gjopen``,
+``Dm_cells``, ``D_env``, ``TJ_modulator``, ``E_env_x`` ...).  All compute happens in
+libbetse_b200.so; nothing here falls back to NumPy.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import BetseB200Error
+
+# Simulator attribute -> (StateHost member, shape key)
+_DOWN_SHAPES = {
+    "cc_cells": "IC", "cc_env": "IE", "vm": "M", "gjopen": "M", "Dm_cells": "IM",
+    "E_env_x": "E", "E_env_y": "E", "v_env": "E", "rho_env": "E", "rho_cells": "C", "vm_ave": "C",
+    "fluxes_mem": "IM", "fluxes_gj": "IM", "fluxes_env_x": "IE", "fluxes_env_y": "IE",
+    "rate_NaKATP": "M", "Jmem": "M", "Jgj": "M", "Jn": "M", "I_mem": "M", "Jc": "M", "Emc": "M",
+    "dvm": "M", "J_cell_x": "C", "J_cell_y": "C", "E_cell_x": "C", "E_cell_y": "C",
+    "sigma_cell": "C",
+}
+DIAG_FIELDS = ("fluxes_mem", "fluxes_gj", "fluxes_env_x", "fluxes_env_y", "rate_NaKATP", "Jmem",
+               "Jgj", "Jn", "I_mem", "Jc", "Emc", "dvm", "J_cell_x", "J_cell_y", "E_cell_x",
+               "E_cell_y", "sigma_cell", "vm_ave")
+
+
+def gaussian_taps():
+    """Taps of scipy.ndimage.gaussian_filter(sigma=1) (truncate=4 -> radius 4), formed exactly
+    like scipy's _gaussian_kernel1d so that v_env matches ion_current.py:104."""
+    x = np.arange(-4, 5)
+    phi = np.exp(-0.5 / 1.0 * x ** 2)
+    phi = phi / phi.sum()
+    return phi[4:].copy()
+
+
+def _scalar(v):
+    return float(np.asarray(v).reshape(-1)[0]) if np.ndim(v) else float(v)
+
+
+class TissueEngine:
+    def __init__(self, mesh, params, state=None, device=0, partition=None):
+        """``mesh``: dict of Cells arrays (keys as in oracle/refrun.py CELLS_FIELDS);
+        ``params``: dict of Parameters scalars + ``ions``; ``state``: dict of Simulator
+        attributes at loop entry (optional, may be uploaded later)."""
+        self.lib = capi.load()
+        if self.lib.betse_device_count() <= 0:
+            raise BetseB200Error("no CUDA device: betse_b200 has no CPU fallback")
+        self._keep = []
+        self.mesh = mesh
+        self.p = {k: (np.asarray(v).item() if np.asarray(v).ndim == 0 and np.asarray(v).dtype.kind != "U"
+                      else np.asarray(v)) for k, v in params.items()}
+        self.is_ecm = bool(self.p["is_ecm"])
+        self.mem_to_cells = capi.as_i32(mesh["mem_to_cells"])
+        self.cell_mem_ptr = capi.as_i32(mesh["cell_mem_ptr"])
+        self.C = len(self.cell_mem_ptr) - 1
+        self.M = len(self.mem_to_cells)
+        gs = np.asarray(mesh["grid_shape"]).astype(int)
+        self.ny, self.nx = int(gs[0]), int(gs[1])
+        self.E = self.ny * self.nx
+        ions = [str(x) for x in self.p["ions"]]
+        self.ions = ions
+        self.I = len(ions)
+        self._sched = {}
+        st = state or {}
+        self._hp = self._make_params(st)
+        m = self._make_mesh(partition)
+        ctx = C.c_void_p()
+        rc = self.lib.betse_create(C.byref(ctx), C.byref(m), C.byref(self._hp), int(device))
+        if rc != 0:
+            buf = C.create_string_buffer(1024)
+            self.lib.betse_create_error(buf, 1024)
+            raise BetseB200Error("betse_create failed (%d): %s" % (rc, buf.value.decode()))
+        self.ctx = ctx
+        self.steps_done = 0
+        if state:
+            self.upload(**state)
+
+    # ------------------------------------------------------------------ construction helpers
+    def _make_mesh(self, partition):
+        mesh, p = self.mesh, self.p
+        m = capi.Mesh()
+        k = self._keep
+
+        def f64(name, required=True):
+            if name not in mesh:
+                if required:
+                    raise KeyError("mesh is missing %r" % name)
+                return None
+            a = capi.as_f64(mesh[name])
+            k.append(a)
+            return capi.ptr_f64(a)
+
+        def i32(a):
+            a = capi.as_i32(a)
+            k.append(a)
+            return capi.ptr_i32(a)
+        m.n_cells, m.n_mems, m.ny, m.nx = self.C, self.M, self.ny, self.nx
+        m.mem_to_cells = i32(self.mem_to_cells)
+        m.cell_mem_ptr = i32(self.cell_mem_ptr)
+        m.nn_i = i32(mesh["nn_i"])
+        m.map_mem2ecm = i32(mesh["map_mem2ecm"])
+        bf = np.zeros(self.M, dtype=np.uint8)
+        bfl = np.asarray(mesh["bflags_mems"])
+        if bfl.dtype == np.bool_ and bfl.size == self.M:
+            bf[:] = bfl
+        else:
+            bf[bfl.astype(np.int64)] = 1       # the reference stores a list of membrane indices
+        k.append(bf)
+        m.bflags_mems = bf.ctypes.data_as(C.POINTER(C.c_uint8))
+        m.mem_sa, m.mem_nx, m.mem_ny = f64("mem_sa"), f64("mem_nx"), f64("mem_ny")
+        m.R_rads = f64("R_rads", required=False)
+        m.cell_vol, m.cell_sa, m.diviterm = f64("cell_vol"), f64("cell_sa"), f64("diviterm")
+        nm = capi.as_f64(np.asarray(mesh["num_mems"], dtype=np.float64))
+        k.append(nm)
+        m.num_mems = capi.ptr_f64(nm)
+        m.memSa_per_envSquare = f64("memSa_per_envSquare", required=False)
+        m.gj_default_weights = f64("gj_default_weights", required=False)
+        m.delta = float(mesh["delta"])
+        m.gj_len = float(mesh["gj_len"])
+        m.ecm_vol = float(mesh["ecm_vol"]) if "ecm_vol" in mesh else float(p["cell_height"]) * m.delta ** 2
+        if "memSa_per_envSquare" in mesh:
+            msa = np.asarray(mesh["memSa_per_envSquare"], dtype=np.float64)
+            m.memsa_mean = float(msa[np.asarray(mesh["map_mem2ecm"]).astype(np.int64)].mean())
+        else:
+            m.memsa_mean = 1.0
+        part = partition or {}
+        m.n_cells_owned = int(part.get("n_cells_owned", self.C))
+        m.n_mems_owned = int(part.get("n_mems_owned", self.M))
+        m.n_flux_slots = int(part.get("n_flux_slots", self.M))
+        m.y0 = int(part.get("y0", 0))
+        m.ny_global = int(part.get("ny_global", self.ny))
+        m.y_own0 = int(part.get("y_own0", 0))
+        m.y_own1 = int(part.get("y_own1", self.ny))
+        if "ecm_slot_ptr" in part:
+            m.ecm_slot_ptr = i32(part["ecm_slot_ptr"])
+            m.ecm_slot_idx = i32(part["ecm_slot_idx"])
+        return m
+
+    def _make_params(self, st):
+        p = self.p
+        hp = capi.Params()
+        hp.abi_version = capi.ABI_VERSION
+        hp.n_ions = self.I
+        idx = {n: i for i, n in enumerate(self.ions)}
+        hp.iNa, hp.iK = idx.get("Na", -1), idx.get("K", -1)
+        hp.iCa, hp.iP = idx.get("Ca", -1), idx.get("P", -1)
+        S = self._sched
+        if "zs" in st:
+            S["zs"] = np.asarray(st["zs"], dtype=float)
+            S["D_free"] = np.asarray(st["D_free"], dtype=float)
+            dgj = np.asarray(st["D_gj"], dtype=float)
+            if dgj.ndim == 2:
+                if not np.all(dgj == dgj[:, :1]):
+                    raise BetseB200Error("non-uniform sim.D_gj is not supported")
+                dgj = dgj[:, 0]
+            S["D_gj"] = dgj
+        for key, default in (("c_env_bound", np.zeros(self.I)), ("T", p.get("T", 310.0)),
+                             ("ko_env", 1.0), ("rho_pump", 1.0), ("rho_channel", 1.0),
+                             ("bound_V", np.zeros(4))):
+            if key in st:
+                S[key] = np.asarray(st[key], dtype=float)
+            S.setdefault(key, np.asarray(default, dtype=float))
+        for key in ("NaKATP_block", "gj_block"):
+            if key in st and np.ndim(st[key]) == 0:
+                S[key] = float(st[key])
+            S.setdefault(key, 1.0)
+        if "zs" not in S:
+            raise BetseB200Error("state must provide zs, D_free and D_gj at construction")
+        for i in range(self.I):
+            hp.z[i] = S["zs"][i]
+            hp.D_free[i] = S["D_free"][i]
+            hp.D_gj[i] = S["D_gj"][i]
+            hp.c_env_bound[i] = np.asarray(S["c_env_bound"]).reshape(-1)[i]
+        if not self.is_ecm and "cc_env" in st:
+            ce = np.asarray(st["cc_env"], dtype=float)
+            for i in range(self.I):
+                hp.cenv_uniform[i] = ce[i].reshape(-1)[0]
+        for f in ("F", "R", "q", "kb", "eo", "er", "cm", "tm", "NAv", "mu", "dt", "alpha_NaK",
+                  "alpha_Ca", "KmNK_Na", "KmNK_K", "KmNK_ATP", "KmCa_Ca", "KmCa_ATP", "cATP", "cADP",
+                  "cPi", "deltaGATP", "gj_surface", "gj_vthresh", "gj_min", "cell_height", "vol_env",
+                  "cell_radius", "true_cell_size", "sharpness", "cell_polarizability", "smooth_cells"):
+            setattr(hp, f, float(p[f]))
+        hp.T_sim = _scalar(S["T"])
+        hp.T_p = float(p["T"])
+        hp.rho_pump, hp.rho_channel = _scalar(S["rho_pump"]), _scalar(S["rho_channel"])
+        hp.ko_env = _scalar(S["ko_env"])
+        bv = np.asarray(S["bound_V"], dtype=float).reshape(-1)
+        for i in range(4):
+            hp.bound_V[i] = bv[i]
+        gw = gaussian_taps()
+        for i in range(5):
+            hp.gauss_w[i] = gw[i]
+        hp.NaKATP_block_scalar = float(S["NaKATP_block"])
+        hp.gj_block_scalar = float(S["gj_block"])
+        hp.is_ecm = int(bool(p["is_ecm"]))
+        hp.v_sensitive_gj = int(bool(p["v_sensitive_gj"]))
+        hp.cluster_open = int(bool(p.get("cluster_open", 1)))
+        hp.fast_update_ecm = int(bool(p.get("fast_update_ecm", 0)))
+        return hp
+
+    def _check(self, rc, what):
+        if rc != 0:
+            buf = C.create_string_buffer(1024)
+            self.lib.betse_last_error(self.ctx, buf, 1024)
+            raise BetseB200Error("%s failed (%d): %s" % (what, rc, buf.value.decode()))
+
+    # ------------------------------------------------------------------ state movement
+    def upload(self, **state):
+        """Upload Simulator attributes (any subset).  Unknown names are ignored so that a whole
+        capture group can be passed."""
+        sh = capi.StateHost()
+        keep = []
+
+        def put(member, arr, n):
+            a = capi.as_f64(arr).reshape(-1)
+            if a.size != n:
+                raise BetseB200Error("%s: expected %d values, got %d" % (member, n, a.size))
+            keep.append(a)
+            setattr(sh, member, capi.ptr_f64(a))
+        I, Cn, M, E = self.I, self.C, self.M, self.E
+        starts = self.cell_mem_ptr[:-1]
+        if "cc_cells" in state:
+            put("cc_cells", state["cc_cells"], I * Cn)
+        if "cc_at_mem" in state:
+            cam = np.asarray(state["cc_at_mem"], dtype=float)
+            put("cc_at_mem_cell", cam[:, starts] if cam.shape[1] == M else cam, I * Cn)
+        if self.is_ecm:
+            if "cc_env" in state:
+                put("cc_env", state["cc_env"], I * E)
+            if "D_env" in state:
+                d = np.asarray(state["D_env"], dtype=float).reshape(I, E)
+                tj = np.asarray(state.get("TJ_modulator", getattr(self, "_tj", 1.0)), dtype=float)
+                self._denv = d
+                self._tj = tj
+                put("D_env_eff", d * tj.reshape(d.shape) if np.ndim(tj) else d * tj, I * E)
+            elif "TJ_modulator" in state:
+                self._tj = np.asarray(state["TJ_modulator"], dtype=float)
+                put("D_env_eff", self._denv * self._tj.reshape(self._denv.shape), I * E)
+            if "E_env_x" in state:
+                put("E_env_x", state["E_env_x"], E)
+                put("E_env_y", state["E_env_y"], E)
+        elif "cc_env" in state:
+            ce = np.asarray(state["cc_env"], dtype=float)
+            put("cenv_uniform", ce.reshape(I, -1)[:, 0], I)
+        if "Phi_b" in state:
+            put("Phi_b", state["Phi_b"], E)
+        if "vm" in state:
+            put("vm", state["vm"], M)
+        if "gjopen" in state:
+            put("gjopen", state["gjopen"], M)
+        if "Dm_cells" in state:
+            put("Dm_cells", state["Dm_cells"], I * M)
+        for name, n in (("extra_rho_cells", Cn), ("extra_rho_env", E), ("extra_J_mem", M)):
+            if name in state and np.any(np.asarray(state[name]) != 0):
+                put(name, state[name], n)
+        resched = False
+        for name in ("NaKATP_block", "gj_block"):
+            if name in state:
+                if np.ndim(state[name]) == 0 or np.size(state[name]) == 1:
+                    v = _scalar(state[name])
+                    if v != self._sched.get(name):
+                        self._sched[name] = v
+                        resched = True
+                else:
+                    put(name, state[name], M)
+        for name in ("c_env_bound", "T", "bound_V", "D_gj"):
+            if name in state:
+                resched |= self._set_sched_value(name, state[name])
+        self._check(self.lib.betse_upload_state(self.ctx, C.byref(sh)), "betse_upload_state")
+        if resched:
+            self._push_schedule()
+
+    def _set_sched_value(self, name, value):
+        v = np.asarray(value, dtype=float)
+        if name == "D_gj" and v.ndim == 2:
+            if not np.all(v == v[:, :1]):
+                raise BetseB200Error("non-uniform sim.D_gj is not supported")
+            v = v[:, 0]
+        old = self._sched.get(name)
+        if old is not None and np.shape(old) == v.shape and np.array_equal(old, v):
+            return False
+        self._sched[name] = v.copy()
+        return True
+
+    def _push_schedule(self):
+        self._hp = self._make_params({})
+        self._check(self.lib.betse_set_schedule(self.ctx, C.byref(self._hp)), "betse_set_schedule")
+
+    def set_field(self, name, value):
+        """Apply one of the quantities TissueHandler.fire_events rewrites."""
+        if name in ("c_env_bound", "T", "bound_V", "D_gj"):
+            if self._set_sched_value(name, value):
+                self._push_schedule()
+        else:
+            self.upload(**{name: value})
+
+    def set_bound_V(self, v):
+        self.set_field("bound_V", v)
+
+    # ------------------------------------------------------------------ stepping
+    def step(self, n=1, diag=False):
+        st = C.c_uint32(0)
+        self._check(self.lib.betse_step(self.ctx, int(n), capi.STEP_DIAG if diag else 0, C.byref(st)),
+                    "betse_step")
+        self.steps_done += n
+        return int(st.value)
+
+    def profile(self, n):
+        """Run ``n`` steps timed on the device.  Returns (total_ms, {kernel: ms_per_launch})."""
+        tot = C.c_float(0)
+        kms = (C.c_float * capi.NKERNELS)()
+        kl = (C.c_int * capi.NKERNELS)()
+        self._check(self.lib.betse_step_profile(self.ctx, int(n), C.byref(tot), C.byref(kms), C.byref(kl)),
+                    "betse_step_profile")
+        self.steps_done += n + min(n, 20)
+        names = [self.lib.betse_kernel_name(k).decode() for k in range(capi.NKERNELS)]
+        return float(tot.value), {names[k]: float(kms[k]) for k in range(capi.NKERNELS) if kl[k]}
+
+    def download(self, fields=("cc_cells", "cc_at_mem", "cc_env", "vm", "gjopen", "rho_cells",
+                               "E_env_x", "E_env_y", "v_env", "rho_env")):
+        """Fetch Simulator attributes by name -> dict of NumPy arrays in the reference's shapes."""
+        sh = capi.StateHost()
+        out = {}
+        I, Cn, M, E = self.I, self.C, self.M, self.E
+        shapes = {"IC": (I, Cn), "IE": (I, E), "IM": (I, M), "M": (M,), "C": (Cn,), "E": (E,)}
+        want_cam = False
+        cenv = None
+        for f in fields:
+            if f == "cc_at_mem":
+                want_cam = True
+                buf = np.empty((I, Cn))
+                sh.cc_at_mem_cell = capi.ptr_f64(buf)
+                out["_cam"] = buf
+                continue
+            if f in ("cc_env",) and not self.is_ecm:
+                cenv = np.empty(I)
+                sh.cenv_uniform = capi.ptr_f64(cenv)
+                continue
+            if not self.is_ecm and _DOWN_SHAPES.get(f, "").endswith("E"):
+                continue
+            if f not in _DOWN_SHAPES:
+                raise KeyError(f)
+            buf = np.empty(shapes[_DOWN_SHAPES[f]])
+            setattr(sh, f, capi.ptr_f64(buf))
+            out[f] = buf
+        self._check(self.lib.betse_download_sample(self.ctx, C.byref(sh)), "betse_download_sample")
+        if want_cam:
+            out["cc_at_mem"] = out.pop("_cam")[:, self.mem_to_cells]
+        if cenv is not None:
+            out["cc_env"] = np.repeat(cenv[:, None], M, axis=1)   # the reference keeps [I,M] (sim.py:487-490)
+        return out
+
+    def device_buffer(self, which):
+        p = C.c_void_p()
+        n = C.c_size_t()
+        self._check(self.lib.betse_device_buffer(self.ctx, which, C.byref(p), C.byref(n)), "betse_device_buffer")
+        return p.value, n.value
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.betse_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,198 @@
+/* betse_b200.h — C ABI of the B200-native BETSE tissue-update engine.
+ *
+ * Drop-in boundary: the reference has no FFI; its seam is the bound-method
+ * dispatch `solver_method = self._run_sim_core_loop` in Simulator.run_sim_core
+ * (betse/science/sim.py:1064-1075).  A Python shim (betse_b200/simloop.py) replaces that
+ * method and drives this library through ctypes.  Every entry point below states the
+ * reference code it stands in for.
+ *
+ * Conventions: plain pointers + sizes, no torch types.  Host arrays are borrowed for the
+ * duration of the call only.  All floating point is IEEE fp64, all indices int32.
+ * Return value 0 = OK, non-zero = argument/CUDA error (text via betse_last_error).
+ * Numerical instability is NOT an error code: it is reported in the status word
+ * (BETSE_STATUS_*), which the shim turns into BetseSimUnstableException
+ * (betse/exceptions.py:625; raised by stb.check_v / stb.no_negs, sim_toolbox.py:332-344,475-503).
+ * One ctx per GPU and simulation; calls on one ctx must come from one host thread at a time.
+ * There is no CPU fallback: every entry point fails if no CUDA device is usable.
+ */
+#ifndef BETSE_B200_H
+#define BETSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BETSE_MAX_IONS 8
+#define BETSE_ABI_VERSION 1
+
+typedef struct betse_ctx betse_ctx;
+
+/* Mesh / index arrays the loop consumes — the `Cells` attributes of SURVEY §2 ★(data),
+ * built by Cells.make_world (betse/science/cells.py:414-526).  All [M] arrays are in the
+ * reference's membrane order (membranes of a cell contiguous, cells.py:1095-1146). */
+typedef struct betse_mesh {
+    int32_t n_cells;              /* C  = len(cells.cell_i)                                  */
+    int32_t n_mems;               /* M  = len(cells.mem_i)                                   */
+    int32_t ny, nx;               /* cells.X.shape; E = ny*nx env points (row-major k=y*nx+x) */
+    const int32_t *mem_to_cells;  /* [M]   cells.mem_to_cells            cells.py:1126       */
+    const int32_t *cell_mem_ptr;  /* [C+1] CSR form of cells.cell_to_mems cells.py:1129-1146 */
+    const int32_t *nn_i;          /* [M]   GJ partner membrane            cells.py:1498-1533 */
+    const int32_t *map_mem2ecm;   /* [M]   nearest env point              cells.py:1758      */
+    const uint8_t *bflags_mems;   /* [M]   1 on cluster-boundary membranes cells.py:1402-1457 */
+    const double *mem_sa;         /* [M]   cells.mem_sa                   cells.py:1110      */
+    const double *mem_nx;         /* [M]   cells.mem_vects_flat[:,2]                         */
+    const double *mem_ny;         /* [M]   cells.mem_vects_flat[:,3]                         */
+    const double *R_rads;         /* [M]   cells.R_rads                   cells.py:1173      */
+    const double *cell_vol;       /* [C]   cells.cell_vol                 cells.py:1385      */
+    const double *cell_sa;        /* [C]   cells.cell_sa                                     */
+    const double *diviterm;       /* [C]   cells.diviterm                 cells.py:1390      */
+    const double *num_mems;       /* [C]   cells.num_mems (as fp64)       cells.py:1309      */
+    const double *memSa_per_envSquare; /* [E] cells.py:1801-1816 (fast_update_ecm only)      */
+    const double *gj_default_weights;  /* [M] cells.py:1995-2008 (static-GJ mode only)       */
+    double delta;                 /* cells.delta: env grid spacing                           */
+    double gj_len;                /* cells.gj_len                                            */
+    double ecm_vol;               /* cells.ecm_vol = cell_height*delta^2                     */
+    double memsa_mean;            /* cells.memSa_per_envSquare[cells.map_mem2ecm].mean()
+                                     (ion_current.py:94-95) – computed by the host in NumPy   */
+    /* Domain decomposition.  Single GPU: own everything, y0 = 0, ny_global = ny. */
+    int32_t n_cells_owned;        /* cells [0,n_cells_owned) are stepped; the rest are ghosts */
+    int32_t n_mems_owned;         /* membranes of owned cells                                 */
+    int32_t n_flux_slots;         /* >= n_mems_owned: env-exchange slots incl. remote membranes */
+    int32_t y0, ny_global;        /* first local grid row in the global grid; global rows      */
+    int32_t y_own0, y_own1;       /* local rows [y_own0,y_own1) are owned (others are halo)     */
+    const int32_t *ecm_slot_ptr;  /* [E+1] env point -> flux slots CSR (NULL: build from map_mem2ecm) */
+    const int32_t *ecm_slot_idx;  /* [..]                                                      */
+} betse_mesh;
+
+/* Scalars the loop reads: physical constants (betse/science/parameters.py:1105-1122), pump
+ * constants (:1064-1081), feature flags, and the per-step schedule that
+ * TissueHandler.fire_events (tissue/tishandler.py:709-917) rewrites: T, c_env_bound,
+ * bound_V.  Re-sent whole through betse_set_schedule whenever any of it changes. */
+typedef struct betse_params {
+    int32_t abi_version;
+    int32_t n_ions;                    /* I                                              */
+    int32_t iNa, iK, iCa, iP;          /* ion indices, -1 if the ion is disabled          */
+    double z[BETSE_MAX_IONS];          /* sim.zs                                         */
+    double D_free[BETSE_MAX_IONS];     /* sim.D_free                                     */
+    double D_gj[BETSE_MAX_IONS];       /* sim.D_gj[i] (uniform over membranes)           */
+    double c_env_bound[BETSE_MAX_IONS];/* sim.c_env_bound                                */
+    double cenv_uniform[BETSE_MAX_IONS];/* no-ECM only: the well-mixed bath value        */
+    double F, R, q, kb, eo, er, cm, tm, NAv, mu;
+    double T_sim;                      /* sim.T  (membrane GHK, pumps, env Nernst-Planck) */
+    double T_p;                        /* p.T    (gap-junction GHK, sigma_cell)           */
+    double dt;
+    double alpha_NaK, alpha_Ca, KmNK_Na, KmNK_K, KmNK_ATP, KmCa_Ca, KmCa_ATP;
+    double cATP, cADP, cPi, deltaGATP;
+    double gj_surface, gj_vthresh, gj_min;
+    double rho_pump, rho_channel;      /* hard-wired 1 in the reference (sim.py:964-965)  */
+    double cell_height, vol_env, cell_radius, true_cell_size;
+    double ko_env;                     /* frozen at init_dynamics (sim.py:974)            */
+    double sharpness;                  /* p.sharpness (<1: fd.integrator smoothing)       */
+    double cell_polarizability;        /* must be 0 in this version                       */
+    double smooth_cells;               /* p.smooth_cells (Jn smoothing weights)           */
+    double bound_V[4];                 /* T, B, L, R (sim.bound_V)                        */
+    double gauss_w[5];                 /* taps w0..w4 of scipy's gaussian_filter(sigma=1) kernel
+                                          (ion_current.py:104), formed by the host in NumPy   */
+    double NaKATP_block_scalar;        /* used when no per-membrane block array is set    */
+    double gj_block_scalar;
+    int32_t is_ecm, v_sensitive_gj, cluster_open, fast_update_ecm;
+    int32_t reserved[4];
+} betse_params;
+
+/* Host-side view of the Simulator state.  NULL members are skipped.  Shapes in brackets;
+ * [I,·] arrays are C-contiguous with the ion index slowest, as np.asarray(sim.cc_cells). */
+typedef struct betse_state_host {
+    double *cc_cells;        /* [I,C] sim.cc_cells                                         */
+    double *cc_at_mem_cell;  /* [I,C] per-cell content of sim.cc_at_mem (it is a gather of a
+                                       per-cell quantity: sim_toolbox.py:1182, sim.py:2310)   */
+    double *cc_env;          /* [I,E] sim.cc_env (ECM); ignored without ECM               */
+    double *vm;              /* [M]   sim.vm                                              */
+    double *gjopen;          /* [M]   sim.gjopen                                          */
+    double *Dm_cells;        /* [I,M] sim.Dm_cells                                        */
+    double *D_env_eff;       /* [I,E] sim.D_env * sim.TJ_modulator (sim.py:2231-2233)     */
+    double *E_env_x;         /* [E]   sim.E_env_x                                         */
+    double *E_env_y;         /* [E]   sim.E_env_y                                         */
+    double *v_env;           /* [E]   sim.v_env      (download only)                      */
+    double *rho_env;         /* [E]   sim.rho_env    (download only)                      */
+    double *rho_cells;       /* [C]   sim.rho_cells  (download only)                      */
+    double *vm_ave;          /* [C]   sim.vm_ave     (download only)                      */
+    double *Phi_b;           /* [E]   sim.Phi_b (boundary-voltage potential; NULL = 0)    */
+    double *extra_rho_cells; /* [C]   sim.extra_rho_cells (NULL = 0)                      */
+    double *extra_rho_env;   /* [E]   sim.extra_rho_env   (NULL = 0)                      */
+    double *extra_J_mem;     /* [M]   sim.extra_J_mem     (NULL = 0)                      */
+    double *NaKATP_block;    /* [M]   sim.NaKATP_block when it is an array                */
+    double *gj_block;        /* [M]   sim.gj_block when it is an array                    */
+    /* diagnostics of the last step run with BETSE_STEP_DIAG (download only) */
+    double *fluxes_mem;      /* [I,M] */
+    double *fluxes_gj;       /* [I,M] */
+    double *fluxes_env_x;    /* [I,E] */
+    double *fluxes_env_y;    /* [I,E] */
+    double *rate_NaKATP;     /* [M]   */
+    double *Jmem, *Jgj, *Jn, *I_mem, *Jc, *Emc, *dvm;   /* [M] */
+    double *J_cell_x, *J_cell_y, *E_cell_x, *E_cell_y, *sigma_cell;  /* [C] */
+    double *cenv_uniform;    /* [I]   no-ECM bath concentrations (download only)          */
+} betse_state_host;
+
+#define BETSE_STATUS_NAN_VM     1u  /* stb.check_v would raise          */
+#define BETSE_STATUS_NAN_CONC   2u  /* stb.no_negs would raise          */
+#define BETSE_STATUS_NEG_CLAMP  4u  /* informational: a negative concentration was clamped */
+
+#define BETSE_STEP_DIAG   1  /* last step of the call also produces the sampled-step diagnostics */
+
+/* Number of distinct kernels a step may launch (for betse_step_profile). */
+#define BETSE_NKERNELS 8
+
+/* Library / device probing (no ctx needed). */
+int  betse_abi_version(void);
+int  betse_device_count(void);
+
+/* Replaces: state set-up at the top of _run_sim_core_loop — takes the mesh and constants the
+ * loop closes over (cells.*, p.*), builds device-side SoA + the cell/CTA packing + env CSR. */
+int  betse_create(betse_ctx **out, const betse_mesh *mesh, const betse_params *params, int device);
+void betse_destroy(betse_ctx *ctx);
+int  betse_last_error(betse_ctx *ctx, char *buf, size_t n);
+int  betse_create_error(char *buf, size_t n);   /* message of the last failed betse_create */
+
+/* Replaces: nothing in the reference (its state already lives in host NumPy); moves the
+ * Simulator attributes created by init_core/init_dynamics (sim.py:452-1012) into HBM. */
+int  betse_upload_state(betse_ctx *ctx, const betse_state_host *state);
+
+/* Replaces: the array/scalar side effects of TissueHandler.fire_events + makeAllChanges
+ * (tishandler.py:709-917,1321-1332): new T / c_env_bound / bound_V / blocks. */
+int  betse_set_schedule(betse_ctx *ctx, const betse_params *params);
+
+/* Replaces: `nsteps` iterations of the loop body, sim.py:1169-1365 (steps 0-11 of SURVEY §3.2).
+ * status_out (nullable) receives the OR of BETSE_STATUS_* over all steps of this call. */
+int  betse_step(betse_ctx *ctx, int nsteps, int flags, uint32_t *status_out);
+
+/* Same as betse_step but timed with CUDA events on the ctx's stream; per-kernel mean
+ * durations (ms per launch) and launch counts are returned for the roofline in bench.py. */
+int  betse_step_profile(betse_ctx *ctx, int nsteps, float *total_ms,
+                        float kernel_ms[BETSE_NKERNELS], int kernel_launches[BETSE_NKERNELS]);
+const char *betse_kernel_name(int k);
+
+/* Replaces: the attribute reads of Simulator.write2storage (sim.py:1789-1884). */
+int  betse_download_sample(betse_ctx *ctx, betse_state_host *state);
+
+/* Multi-GPU plumbing: raw device pointers of the exchange buffers so that the
+ * host side can hand them to NCCL / map them for peer access.  which: see BETSE_BUF_*. */
+#define BETSE_BUF_CC_MID   0  /* [I,C_local] next-step cc_mid (ghost cells are written by the exchange) */
+#define BETSE_BUF_VM_CELL  1  /* [C_local]                                                              */
+#define BETSE_BUF_FLUX     2  /* [n_flux_slots,I] membrane->env exchange slots                          */
+#define BETSE_BUF_CC_ENV   3  /* [I,E_local] next-step cc_env                                           */
+#define BETSE_BUF_V_RAW    4  /* [E_local]                                                              */
+#define BETSE_BUF_CC_ENV_CUR 5
+int  betse_device_buffer(betse_ctx *ctx, int which, void **dev_ptr, size_t *bytes);
+/* A step split at the exchange points: phase 0 = env transport + membrane/cell update,
+ * phase 1 = env accumulation, phase 2 = env field.  betse_step == phases 0,1,2. */
+int  betse_step_phase(betse_ctx *ctx, int phase, int flags);
+int  betse_stream(betse_ctx *ctx, void **cuda_stream);
+int  betse_sync(betse_ctx *ctx, uint32_t *status_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BETSE_B200_H */

@@ -1,0 +1,59 @@
+"""GPU parity against the REAL reference's recorded outputs (tests/golden/*.npz), through the
+C-ABI.  Tolerance: BASELINE.json — per-step ion concentrations and Vmem within 1e-10 relative
+(max-norm over the array), diagnostics against the scale of their summands."""
+import numpy as np
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+TOL_STATE = 1e-10
+
+
+def _engine(cap, kind):
+    from betse_b200.engine import TissueEngine
+    return TissueEngine(util.group(cap, "cells."), util.group(cap, kind + ".p."),
+                        util.group(cap, kind + ".s0."))
+
+
+@pytest.mark.parametrize("name", [n for n in util.GOLDEN if "polar" not in n])
+@pytest.mark.parametrize("kind", ["init", "sim"])
+def test_gpu_matches_reference(name, kind):
+    cap = util.load_golden(name)
+    eng = _engine(cap, kind)
+    ecm = bool(int(cap[kind + ".p.is_ecm"]))
+    snaps = util.snap_steps(cap, kind)
+    n = 0
+    worst = {}
+    for K in snaps:
+        last = K == snaps[-1]
+        while n < K:
+            util.apply_schedule(eng, cap, kind, n + 1)
+            st = eng.step(1, diag=(last and n + 1 == K))
+            assert not (st & 3), "instability flagged"
+            n += 1
+        ref = util.group(cap, "%s.k%d." % (kind, K))
+        fields = list(util.STATE) + (util.ENV_STATE if ecm else [])
+        if last:
+            fields += [f for f in util.DIAG if f in ref and f not in (
+                "J_env_x", "J_env_y", "Jtx", "Jty", "B_field", "rho_env_surf", "Eme")]
+            if not ecm:
+                fields = [f for f in fields if not f.startswith("fluxes_env")]
+        got = eng.download([f for f in fields if f in ref])
+        for f, a in got.items():
+            err = util.rel_err(a, ref[f], util.scale_of(f, ref))
+            worst[f] = max(worst.get(f, 0.0), err)
+            tol = TOL_STATE if f in util.STATE + util.ENV_STATE else 1e-9
+            assert err < tol, (name, kind, K, f, err)
+    print(name, kind, {k: float("%.1e" % v) for k, v in worst.items()})
+    eng.close()
+
+
+def test_polarizability_fails_loudly():
+    """cell_polarizability != 0 (sim.py:2048-2080) is not implemented: creation must refuse, not
+    silently compute something else."""
+    from betse_b200 import BetseB200Error
+    cap = util.load_golden("mammal_ecm_polar")
+    with pytest.raises(BetseB200Error):
+        _engine(cap, "init")
