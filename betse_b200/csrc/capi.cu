@@ -20,7 +20,7 @@ void launch_envacc(int ni, const KParams* dP, const KArrays& A, int E, int nxt, 
 void launch_field(const KParams* dP, const KArrays& A, int ny, int nx, cudaStream_t st);
 void launch_envmix(int ni, const KParams* dP, const KArrays& A, int cur, cudaStream_t st);
 void launch_diag(int ni, const KParams* dP, const KArrays& A, int n_ctas, int newb, cudaStream_t st);
-void launch_expand_vm(const KParams* dP, const KArrays& A, int M, int cur, cudaStream_t st);
+void launch_expand_vm(const KParams* dP, const KArrays& A, int M, int C, int cur, cudaStream_t st);
 
 enum { K_ION = 0, K_MEM, K_ENVACC, K_FIELD, K_ENVMIX, K_SMOOTH, K_DIAG, K_EXPAND };
 static const char* kKernelNames[BETSE_NKERNELS] = {
@@ -303,6 +303,7 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
     if ((r = dev_alloc(ctx, &A.cenv_part, (size_t)ctx->n_ctas * 8))) return r;
     if ((r = dev_alloc(ctx, &A.status, 1))) return r;
     if ((r = dev_alloc(ctx, &A.vm_mem, Mo))) return r;
+    if ((r = dev_alloc(ctx, &A.vm_ave, C))) return r;
     if (hp->is_ecm && hp->sharpness < 1.0) { if ((r = dev_alloc(ctx, &A.scratch_env, IE))) return r; }
     if (!hp->is_ecm) {
         double cu[16];
@@ -350,7 +351,7 @@ static int ensure_diag_buffers(betse_ctx* ctx)
     if ((r = dev_alloc(ctx, &A.rate_NaK, ctx->Mo))) return r;
     double** mem_arrays[] = {&A.Jmem, &A.Jgj, &A.Jn, &A.I_mem, &A.Jc, &A.Emc, &A.dvm};
     for (auto p : mem_arrays) if ((r = dev_alloc(ctx, p, ctx->Mo))) return r;
-    double** cell_arrays[] = {&A.J_cell_x, &A.J_cell_y, &A.E_cell_x, &A.E_cell_y, &A.sigma_cell, &A.vm_ave};
+    double** cell_arrays[] = {&A.J_cell_x, &A.J_cell_y, &A.E_cell_x, &A.E_cell_y, &A.sigma_cell};
     for (auto p : cell_arrays) if ((r = dev_alloc(ctx, p, ctx->C))) return r;
     destroy_graphs(ctx);   // KArrays changed
     return 0;
@@ -639,9 +640,10 @@ extern "C" int betse_download_sample(betse_ctx* ctx, betse_state_host* s)
         DN(s->v_env, A.v_env, E);
         DN(s->rho_env, A.rho_env, E);
     }
-    if (s->vm) {
-        launch_expand_vm(ctx->dP, A, Mo, cur, st);
+    if (s->vm || s->vm_ave) {
+        launch_expand_vm(ctx->dP, A, Mo, ctx->Co, cur, st);
         DN(s->vm, A.vm_mem, Mo);
+        DN(s->vm_ave, A.vm_ave, C);
     }
     DN(s->gjopen, A.gjopen, Mo);
     DN(s->Dm_cells, A.Dm, IM);
@@ -649,7 +651,7 @@ extern "C" int betse_download_sample(betse_ctx* ctx, betse_state_host* s)
     if (s->cenv_uniform) CK(cudaMemcpyAsync(s->cenv_uniform, A.cenv_u + cur * 8, I * sizeof(double), cudaMemcpyDeviceToHost, st));
     const bool any_diag = s->fluxes_mem || s->fluxes_gj || s->fluxes_env_x || s->fluxes_env_y || s->rate_NaKATP ||
                           s->Jmem || s->Jgj || s->Jn || s->I_mem || s->Jc || s->Emc || s->dvm || s->J_cell_x ||
-                          s->J_cell_y || s->E_cell_x || s->E_cell_y || s->sigma_cell || s->vm_ave;
+                          s->J_cell_y || s->E_cell_x || s->E_cell_y || s->sigma_cell;
     if (any_diag) {
         if (!ctx->diag_valid) return fail(ctx, "diagnostics requested but the last step was not run with BETSE_STEP_DIAG");
         DN(s->fluxes_mem, A.fl_mem, IM);
@@ -660,7 +662,7 @@ extern "C" int betse_download_sample(betse_ctx* ctx, betse_state_host* s)
         DN(s->Jc, A.Jc, Mo); DN(s->Emc, A.Emc, Mo); DN(s->dvm, A.dvm, Mo);
         DN(s->J_cell_x, A.J_cell_x, C); DN(s->J_cell_y, A.J_cell_y, C);
         DN(s->E_cell_x, A.E_cell_x, C); DN(s->E_cell_y, A.E_cell_y, C);
-        DN(s->sigma_cell, A.sigma_cell, C); DN(s->vm_ave, A.vm_ave, C);
+        DN(s->sigma_cell, A.sigma_cell, C);
     }
 #undef DN
     CK(cudaStreamSynchronize(st));

@@ -581,6 +581,17 @@ __global__ void k_expand_vm(const KParams* __restrict__ Pp, const KArrays A, con
     A.vm_mem[m] = A.vm_cell[cur][A.mem_to_cells[m]] - phi;
 }
 
+// vm_ave = np.dot(M_sum_mems, vm)/num_mems (sim.py:2038) for download
+__global__ void k_vm_ave(const KParams* __restrict__ Pp, const KArrays A)
+{
+    const KParams& P = *Pp;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.n_cells_owned) return;
+    double s = 0.0;
+    for (int m = A.cell_mem_ptr[c]; m < A.cell_mem_ptr[c + 1]; ++m) s += A.vm_mem[m];
+    A.vm_ave[c] = s / A.num_mems[c];
+}
+
 // ---------------------------------------------------------------------------- launchers
 template <int NI>
 static void launch_mem_t(const KParams* dP, const KArrays& A, int n_ctas, int cur, int diag, cudaStream_t st)
@@ -653,7 +664,8 @@ void launch_diag(int ni, const KParams* dP, const KArrays& A, int n_ctas, int ne
     }
 }
 
-void launch_expand_vm(const KParams* dP, const KArrays& A, int M, int cur, cudaStream_t st)
+void launch_expand_vm(const KParams* dP, const KArrays& A, int M, int C, int cur, cudaStream_t st)
 {
     k_expand_vm<<<(M + 255) / 256, 256, 0, st>>>(dP, A, cur);
+    k_vm_ave<<<(C + 255) / 256, 256, 0, st>>>(dP, A);
 }
