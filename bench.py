@@ -1,0 +1,275 @@
+#!/usr/bin/env python3
+"""bench.py — timesteps/s and membrane-updates/s of the tissue-update loop on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--cells C] [--impl ours|reference]
+
+One "step" = one timestep of Simulator._run_sim_core_loop (betse/science/sim.py:1169-1365) over
+the whole synthetic tissue.  Workload at N=1: BASELINE.json configs[4] on one GPU — a 1 M-cell
+(6 M-membrane) mammal-profile tissue with extracellular spaces on a ~1000x1000 grid.
+Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for what each key means.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "membrane_updates_per_sec"
+UNIT = "membrane-updates/s"
+
+
+def algorithmic_bytes(I, C, M, E, ecm=True):
+    """every persistent array any implementation must read/write once per step.
+    Returns (whole step, membrane/cell kernel share, env kernels share)."""
+    mem = I * (32 * C + 8 * M) + 48 * M + 48 * C
+    env = (I * 24 * E + 72 * E) if ecm else 0
+    return mem + env, mem, env
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        reasons = []
+        for j, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if any(s[3 + j].lower().startswith("active") for s in self.samples):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]),
+                "power_w_max": max(float(s[2]) for s in self.samples), "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def measured_peak_hbm():
+    fn = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(fn):
+        try:
+            return float(json.load(open(fn))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class NS:
+    """Duck-typed stand-in for the reference's Simulator / Cells / Parameters objects."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def namespaces(mesh, p, state):
+    cells = NS(**{k: v for k, v in mesh.items()})
+    cells.mem_nx, cells.mem_ny = mesh["mem_nx"], mesh["mem_ny"]
+    cells.grid_shape = tuple(int(x) for x in mesh["grid_shape"])
+    cells.X = None
+    pp = NS(**{k: v for k, v in p.items()})
+    sim = NS(**{k: (np.array(v, copy=True) if isinstance(v, np.ndarray) else v) for k, v in state.items()})
+    sim.bound_V = {"T": 0, "B": 0, "L": 0, "R": 0}
+    sim.sampled = 0
+    sim.write2storage = lambda t, cells, p: setattr(sim, "sampled", sim.sampled + 1)
+    phase = NS(p=pp, cells=cells, sim=sim, kind=NS(name="INIT"), callbacks=NS(progressed_next=lambda: None))
+    return sim, phase
+
+
+def cpu_reference_run(mesh, p, state, budget_s, max_steps):
+    """Times the oracle (the CPU restatement of the reference loop) on the same workload."""
+    from oracle.betse_oracle import OracleSim
+    o = OracleSim(mesh, p, state)
+    o.diagnostics = False
+    o.update_V()
+    t0 = time.perf_counter()
+    o.step()
+    first = time.perf_counter() - t0
+    n = int(max(1, min(max_steps, budget_s / max(first, 1e-9))))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        o.step()
+    dt = (time.perf_counter() - t0) / n
+    try:
+        from threadpoolctl import threadpool_info
+        thr = max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
+    except Exception:
+        thr = 1
+    return dt, n, thr
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--cells", type=int, default=1_000_000)
+    ap.add_argument("--profile", default="mammal")
+    ap.add_argument("--no-ecm", action="store_true")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    ecm = not args.no_ecm
+
+    from betse_b200 import synth
+    mesh, p, state = synth.make_tissue(args.cells, profile=args.profile, ecm=ecm, dt=1.0e-4)
+    I = len(p["ions"])
+    C, M = len(mesh["cell_vol"]), len(mesh["mem_sa"])
+    gny, gnx = (int(x) for x in mesh["grid_shape"])
+    E = gny * gnx
+    workload = "%s-cell synthetic tissue (%d cells, %d membranes), %s ion profile (I=%d), %s" % (
+        "1M" if abs(C - 1e6) < 2e4 else str(C), C, M, args.profile, I,
+        "extracellular grid %dx%d" % (gny, gnx) if ecm else "no extracellular spaces")
+    config = {"workload": workload, "baseline_config": "configs[4] on one GPU" if abs(C - 1e6) < 2e4 else "custom",
+              "cells": C, "membranes": M, "env_points": E if ecm else 0, "ions": I, "dt": 1.0e-4,
+              "l2_policy": "state per step (~%.2f GB) is larger than the 126 MB L2" %
+                           (algorithmic_bytes(I, C, M, E, ecm)[0] / 1e9),
+              "sampling": "none inside `value`; every 10 steps inside `e2e`"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        per_step, n, thr = cpu_reference_run(mesh, p, state, budget_s=60.0, max_steps=max(1, args.steps))
+        val = M / per_step
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
+                "timesteps_per_sec": 1.0 / per_step, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": thr, "kind": "port",
+                                 "sample": "%d timesteps of the same workload with the NumPy oracle "
+                                           "(sparse restatement of the reference loop; the reference's dense "
+                                           "operators need 48*C^2 bytes and cannot hold this tissue)" % n},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    import torch
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from betse_b200.engine import TissueEngine
+    from betse_b200 import simloop
+
+    eng = TissueEngine(mesh, p, state, device=local_rank)
+    eng.update_V()
+    eng.step(args.warmup)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    total_ms, kms = eng.profile(args.steps)
+    torch.cuda.synchronize()
+    if dist:
+        t = torch.tensor([total_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        dist.barrier()
+    sampler.stop_flag = True
+    status = eng.step(0)
+    check = eng.download(["vm", "cc_cells"])
+    finite = bool(np.isfinite(check["vm"]).all() and np.isfinite(check["cc_cells"]).all())
+    eng.close()
+
+    ms_per_step = total_ms / args.steps
+    steps_per_s = 1e3 / ms_per_step
+    # replicas: each rank advances its own tissue (small/medium tissues: one sim per GPU)
+    value = M * steps_per_s * world
+
+    # ---- end-to-end through the drop-in loop with host buffers
+    e2e = None
+    if not args.no_e2e:
+        sim, phase = namespaces(mesh, p, state)
+        n_e2e = min(args.steps, 100)
+        ts = np.linspace(0, n_e2e * p["dt"], n_e2e)
+        sampled = set(ts[10::10].tolist())
+        stats = {}
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        simloop.run_sim_core_loop(sim, phase, ts, sampled, None, device=local_rank, stats=stats)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        if dist:
+            t = torch.tensor([wall], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            wall = float(t.item())
+        e2e = {"value": M * n_e2e / wall * world, "unit": UNIT,
+               "h2d_bytes_per_step": stats["h2d_bytes"] / n_e2e, "d2h_bytes_per_step": stats["d2h_bytes"] / n_e2e,
+               "timesteps": n_e2e, "sampled_steps": sim.sampled,
+               "what": "run_sim_core_loop() (the Simulator._run_sim_core_loop drop-in) from host NumPy state: "
+                       "engine creation + full state upload + timesteps + download of every write2storage "
+                       "attribute at each sampled step and at the end"}
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak_hbm()
+    b_step, b_mem, b_env = algorithmic_bytes(I, C, M, E, ecm)
+    dom = max(kms, key=lambda k: kms[k])
+    share = {"k_mem": b_mem, "k_ion": I * 24 * E, "k_envacc": 0, "k_field": 72 * E, "k_envmix": 0}
+    ach = share.get(dom, b_mem) / (kms[dom] * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": share.get(dom, b_mem),
+            "kernel_ms": kms, "step": {"algorithmic_bytes": b_step,
+                                       "achieved": b_step / (ms_per_step * 1e-3) / 1e9,
+                                       "frac": b_step / (ms_per_step * 1e-3) / 1e9 / peak}}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "timesteps_per_sec": steps_per_s,
+            "higher_is_better": True, "scaling": "weak" if world > 1 else "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config, "clocks": sampler.summary(),
+            "gpu_launches": int(len(kms) * args.steps), "status_word": status, "finite": finite,
+            "roofline": roof}
+    if e2e:
+        line["e2e"] = e2e
+    if not args.no_cpu_baseline:
+        per_step, n, thr = cpu_reference_run(mesh, p, state, budget_s=args.cpu_budget, max_steps=20)
+        line["cpu_baseline"] = {"value": M / per_step, "unit": UNIT, "cores": thr, "kind": "port",
+                                "ms_per_step": per_step * 1e3,
+                                "sample": "%d timesteps of the same %d-cell workload with the NumPy oracle" % (n, C)}
+    print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -95,7 +95,7 @@ SYMBOLS = [
     "betse_abi_version", "betse_device_count", "betse_create", "betse_destroy", "betse_last_error",
     "betse_create_error", "betse_upload_state", "betse_set_schedule", "betse_step",
     "betse_step_profile", "betse_kernel_name", "betse_download_sample", "betse_device_buffer",
-    "betse_step_phase", "betse_stream", "betse_sync",
+    "betse_step_phase", "betse_stream", "betse_sync", "betse_update_v",
 ]
 
 _lib = None
@@ -132,6 +132,7 @@ def load(build_if_missing=True):
     lib.betse_step_phase.argtypes = [vp, C.c_int, C.c_int]
     lib.betse_stream.argtypes = [vp, C.POINTER(vp)]
     lib.betse_sync.argtypes = [vp, C.POINTER(C.c_uint32)]
+    lib.betse_update_v.argtypes = [vp]
     if lib.betse_abi_version() != ABI_VERSION:
         raise BetseB200Error("libbetse_b200.so ABI version mismatch; rebuild")
     _lib = lib

@@ -16,7 +16,8 @@
 void launch_mem(int ni, const KParams* dP, const KArrays& A, int n_ctas, int cur, int diag, cudaStream_t st);
 void launch_ion(int ni, const KParams* dP, const KArrays& A, int ny, int nx, int cur, int diag, cudaStream_t st);
 void launch_ion_smooth(int ni, const KParams* dP, const KArrays& A, int ny, int nx, int nxt, cudaStream_t st);
-void launch_envacc(int ni, const KParams* dP, const KArrays& A, int E, int nxt, cudaStream_t st);
+void launch_envacc(int ni, const KParams* dP, const KArrays& A, int E, int nxt, int apply, cudaStream_t st);
+void launch_cell_charge(const KParams* dP, const KArrays& A, int C, int cur, cudaStream_t st);
 void launch_field(const KParams* dP, const KArrays& A, int ny, int nx, cudaStream_t st);
 void launch_envmix(int ni, const KParams* dP, const KArrays& A, int cur, cudaStream_t st);
 void launch_diag(int ni, const KParams* dP, const KArrays& A, int n_ctas, int newb, cudaStream_t st);
@@ -469,7 +470,7 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
         launch_mem(I, ctx->dP, A, ctx->n_ctas, cur, diag, st);
         if (evs) cudaEventRecord(evs[3], st);
     } else if (phase == 1) {
-        if (ecm) launch_envacc(I, ctx->dP, A, ctx->E, nxt, st);
+        if (ecm) launch_envacc(I, ctx->dP, A, ctx->E, nxt, 1, st);
         else launch_envmix(I, ctx->dP, A, cur, st);
         if (evs) cudaEventRecord(evs[4], st);
     } else {
@@ -539,6 +540,20 @@ extern "C" int betse_step(betse_ctx* ctx, int nsteps, int flags, uint32_t* statu
     if (want_diag && nsteps > 0) ctx->diag_valid = true;
     else if (nsteps > 0) ctx->diag_valid = false;
     return read_status(ctx, status_out);
+}
+
+extern "C" int betse_update_v(betse_ctx* ctx)
+{
+    if (!ctx) return 2;
+    CK(cudaSetDevice(ctx->device));
+    launch_cell_charge(ctx->dP, ctx->A, ctx->Co, ctx->cur, ctx->stream);
+    if (ctx->hp.is_ecm) {
+        launch_envacc(ctx->I, ctx->dP, ctx->A, ctx->E, ctx->cur, 0, ctx->stream);
+        launch_field(ctx->dP, ctx->A, ctx->ny, ctx->nx, ctx->stream);
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
 }
 
 extern "C" int betse_step_phase(betse_ctx* ctx, int phase, int flags)

@@ -365,7 +365,7 @@ __global__ void k_ion_smooth(const KParams* __restrict__ Pp, const KArrays A, co
 // membrane -> env exchange (update_Co env branch + div_env), env charge, raw env voltage.
 template <int NI>
 __global__ void __launch_bounds__(256)
-k_envacc(const KParams* __restrict__ Pp, const KArrays A, const int nxt)
+k_envacc(const KParams* __restrict__ Pp, const KArrays A, const int nxt, const int apply_flux)
 {
     const KParams& P = *Pp;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -375,7 +375,9 @@ k_envacc(const KParams* __restrict__ Pp, const KArrays A, const int nxt)
     double acc[NI];
 #pragma unroll
     for (int i = 0; i < NI; ++i) acc[i] = 0.0;
-    if (P.fast_update_ecm) {
+    if (!apply_flux) {
+        // charge / raw voltage only (the update_V call that precedes the loop, sim.py:1041)
+    } else if (P.fast_update_ecm) {
         if (s1 > s0) {                       // flux_env[map_mem2ecm] = flux: the last writer wins
             const int s = ldgi(A.slot_idx + s1 - 1);
 #pragma unroll
@@ -396,8 +398,10 @@ k_envacc(const KParams* __restrict__ Pp, const KArrays A, const int nxt)
         double delta_env;
         if (P.fast_update_ecm) delta_env = ((-acc[i]) * msa) / P.ecm_vol;        // sim_toolbox.py:1222-1225
         else delta_env = (-acc[i]) / P.env_vol_div;                             // sim_toolbox.py:1229
-        c = c + delta_env * P.dt;
-        A.cc_env[nxt][(size_t)i * E + k] = c;
+        if (apply_flux) {
+            c = c + delta_env * P.dt;
+            A.cc_env[nxt][(size_t)i * E + k] = c;
+        }
         rho = fma(P.zF[i], c, rho);
     }
     if (A.extra_rho_env) rho += ldg(A.extra_rho_env + k);
@@ -630,16 +634,34 @@ void launch_ion_smooth(int ni, const KParams* dP, const KArrays& A, int ny, int 
     k_ion_smooth<<<g, b, 0, st>>>(dP, A, nxt, ni);
 }
 
-void launch_envacc(int ni, const KParams* dP, const KArrays& A, int E, int nxt, cudaStream_t st)
+void launch_envacc(int ni, const KParams* dP, const KArrays& A, int E, int nxt, int apply, cudaStream_t st)
 {
     const int g = (E + 255) / 256;
     switch (ni) {
-        case 4: k_envacc<4><<<g, 256, 0, st>>>(dP, A, nxt); break;
-        case 5: k_envacc<5><<<g, 256, 0, st>>>(dP, A, nxt); break;
-        case 6: k_envacc<6><<<g, 256, 0, st>>>(dP, A, nxt); break;
-        case 7: k_envacc<7><<<g, 256, 0, st>>>(dP, A, nxt); break;
-        default: k_envacc<8><<<g, 256, 0, st>>>(dP, A, nxt); break;
+        case 4: k_envacc<4><<<g, 256, 0, st>>>(dP, A, nxt, apply); break;
+        case 5: k_envacc<5><<<g, 256, 0, st>>>(dP, A, nxt, apply); break;
+        case 6: k_envacc<6><<<g, 256, 0, st>>>(dP, A, nxt, apply); break;
+        case 7: k_envacc<7><<<g, 256, 0, st>>>(dP, A, nxt, apply); break;
+        default: k_envacc<8><<<g, 256, 0, st>>>(dP, A, nxt, apply); break;
     }
+}
+
+// rho_cells and Vmem from the current concentrations (ion_current.py:19; sim.py:2027-2029)
+__global__ void k_cell_charge(const KParams* __restrict__ Pp, const KArrays A, const int cur)
+{
+    const KParams& P = *Pp;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.n_cells_owned) return;
+    double rho = 0.0;
+    for (int i = 0; i < P.n_ions; ++i) rho = fma(P.zF[i], A.cc_cells[(size_t)i * P.n_cells + c], rho);
+    if (A.extra_rho_cells) rho += A.extra_rho_cells[c];
+    A.rho_cells[c] = rho;
+    A.vm_cell[cur][c] = P.inv_cm * (rho * A.diviterm[c]);
+}
+
+void launch_cell_charge(const KParams* dP, const KArrays& A, int C, int cur, cudaStream_t st)
+{
+    k_cell_charge<<<(C + 255) / 256, 256, 0, st>>>(dP, A, cur);
 }
 
 void launch_field(const KParams* dP, const KArrays& A, int ny, int nx, cudaStream_t st)

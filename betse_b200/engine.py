@@ -75,6 +75,8 @@ class TissueEngine:
             raise BetseB200Error("betse_create failed (%d): %s" % (rc, buf.value.decode()))
         self.ctx = ctx
         self.steps_done = 0
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
         if state:
             self.upload(**state)
 
@@ -219,6 +221,7 @@ class TissueEngine:
             if a.size != n:
                 raise BetseB200Error("%s: expected %d values, got %d" % (member, n, a.size))
             keep.append(a)
+            self.h2d_bytes += a.nbytes
             setattr(sh, member, capi.ptr_f64(a))
         I, Cn, M, E = self.I, self.C, self.M, self.E
         starts = self.cell_mem_ptr[:-1]
@@ -308,6 +311,11 @@ class TissueEngine:
         self.steps_done += n
         return int(st.value)
 
+    def update_V(self):
+        """Simulator.update_V before the loop (sim.py:1041): charge, Vmem, env field from the
+        uploaded concentrations."""
+        self._check(self.lib.betse_update_v(self.ctx), "betse_update_v")
+
     def profile(self, n):
         """Run ``n`` steps timed on the device.  Returns (total_ms, {kernel: ms_per_launch})."""
         tot = C.c_float(0)
@@ -347,6 +355,7 @@ class TissueEngine:
             setattr(sh, f, capi.ptr_f64(buf))
             out[f] = buf
         self._check(self.lib.betse_download_sample(self.ctx, C.byref(sh)), "betse_download_sample")
+        self.d2h_bytes += sum(a.nbytes for a in out.values()) + (cenv.nbytes if cenv is not None else 0)
         if want_cam:
             out["cc_at_mem"] = out.pop("_cam")[:, self.mem_to_cells]
         if cenv is not None:

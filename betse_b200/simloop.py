@@ -1,0 +1,242 @@
+"""Drop-in replacement for ``Simulator._run_sim_core_loop`` (betse/science/sim.py:1132-1390).
+
+The reference picks its time loop through a bound-method dispatch
+(``solver_method = self._run_sim_core_loop``, sim.py:1064-1075).  ``install()`` rebinds that
+method to :func:`run_sim_core_loop`, which keeps the reference's contract —
+
+* on entry ``init_dynamics``, ``clear_storage`` and ``update_V`` have run (sim.py:1034-1041), so
+  every ``Simulator`` array exists as host NumPy;
+* SIM phase: ``phase.dyna.fire_events(phase, t)`` is called every step (sim.py:1187-1188) — it is
+  host-side scalar scheduling and stays the reference's own code; whatever it rewrote is pushed
+  to the device before the step;
+* at every sampled step the attributes ``write2storage`` reads (sim.py:1796-1877) hold that step's
+  values as host NumPy, ``phase.callbacks.progressed_next()`` is called exactly once, then
+  ``write2storage`` and the optional animation frame (sim.py:1368-1381);
+* NaN in Vmem / a concentration raises ``BetseSimUnstableException`` (sim.py:1363,
+  sim_toolbox.py:332-344, 475-503) after the partial state has been copied back, so that
+  ``run_sim_core`` can still pickle it (sim.py:1104-1128)
+
+— while the per-timestep arithmetic runs in libbetse_b200.so with the state resident in HBM.
+The function is duck-typed on ``sim`` / ``phase.cells`` / ``phase.p`` (no reference import),
+so the same code path is exercised on the GPU box from recorded reference states.
+"""
+import time
+
+import numpy as np
+
+from . import capi
+from .capi import BetseB200Error
+from .engine import TissueEngine
+
+_P_FIELDS = [
+    "F", "R", "T", "q", "kb", "eo", "er", "cm", "tm", "dt", "NAv", "mu", "alpha_NaK", "alpha_Ca",
+    "KmNK_Na", "KmNK_K", "KmNK_ATP", "KmCa_Ca", "KmCa_ATP", "cATP", "cADP", "cPi", "deltaGATP",
+    "gj_surface", "gj_vthresh", "gj_min", "v_sensitive_gj", "cluster_open", "is_ecm", "vol_env",
+    "cell_height", "cell_space", "fast_update_ecm", "sharpness", "cell_radius", "true_cell_size",
+    "smooth_cells", "cell_polarizability",
+]
+_STATE_FIELDS = [
+    "cc_cells", "cc_at_mem", "cc_env", "vm", "gjopen", "Dm_cells", "D_gj", "D_free", "zs",
+    "c_env_bound", "T", "extra_rho_cells", "extra_rho_env", "extra_J_mem", "ko_env",
+    "NaKATP_block", "gj_block", "rho_pump", "rho_channel", "D_env", "TJ_modulator", "E_env_x",
+    "E_env_y", "Phi_b",
+]
+# what fire_events / makeAllChanges may rewrite between steps (tishandler.py:728-917, 1321-1332)
+_SCHEDULED = ["Dm_cells", "D_env", "TJ_modulator", "gj_block", "NaKATP_block", "c_env_bound", "T"]
+
+# attributes refreshed at sampled steps (read by write2storage and the exporters)
+_SAMPLED_STATE = ["cc_cells", "cc_at_mem", "cc_env", "vm", "vm_ave", "gjopen", "rho_cells"]
+_SAMPLED_ENV = ["E_env_x", "E_env_y", "v_env", "rho_env"]
+_SAMPLED_DIAG = ["fluxes_mem", "fluxes_gj", "rate_NaKATP", "Jmem", "Jgj", "Jn", "I_mem", "Jc", "Emc",
+                 "dvm", "J_cell_x", "J_cell_y", "E_cell_x", "E_cell_y", "sigma_cell"]
+_SAMPLED_DIAG_ENV = ["fluxes_env_x", "fluxes_env_y"]
+
+
+class SimUnstable(Exception):
+    """Raised when the reference's BetseSimUnstableException is not importable."""
+
+
+def _unstable_exception():
+    try:
+        from betse.exceptions import BetseSimUnstableException
+        return BetseSimUnstableException
+    except Exception:
+        return SimUnstable
+
+
+def mesh_from_cells(cells):
+    """The ``Cells`` attributes the loop consumes -> mesh dict (cells.py, SURVEY §2 ★data)."""
+    m2c = np.asarray(cells.mem_to_cells)
+    ptr = getattr(cells, "cell_mem_ptr", None)
+    if ptr is None:
+        C = len(cells.cell_vol)
+        counts = np.bincount(m2c, minlength=C)
+        ptr = np.concatenate(([0], np.cumsum(counts)))
+        if not np.array_equal(np.repeat(np.arange(C), counts), m2c):
+            raise BetseB200Error("membranes of a cell are not contiguous (cells.py:1095-1146 violated)")
+    mesh = {"mem_to_cells": m2c, "cell_mem_ptr": np.asarray(ptr)}
+    for f in ("nn_i", "bflags_mems", "map_mem2ecm", "mem_sa", "R_rads", "cell_vol", "cell_sa", "diviterm",
+              "num_mems", "memSa_per_envSquare", "gj_default_weights"):
+        mesh[f] = np.asarray(getattr(cells, f))
+    mv = getattr(cells, "mem_vects_flat", None)
+    if mv is not None:
+        mesh["mem_nx"], mesh["mem_ny"] = np.asarray(mv[:, 2]), np.asarray(mv[:, 3])
+    else:
+        mesh["mem_nx"], mesh["mem_ny"] = np.asarray(cells.mem_nx), np.asarray(cells.mem_ny)
+    mesh["delta"] = np.asarray(float(cells.delta))
+    mesh["gj_len"] = np.asarray(float(cells.gj_len))
+    mesh["ecm_vol"] = np.asarray(float(cells.ecm_vol))
+    X = getattr(cells, "X", None)
+    mesh["grid_shape"] = np.asarray(X.shape if X is not None else cells.grid_shape)
+    return mesh
+
+
+def params_from_p(p):
+    out = {f: getattr(p, f) for f in _P_FIELDS}
+    ions = getattr(p, "ions", None)
+    if ions is None:
+        ions = [k for k, v in p.ions_dict.items() if v == 1]
+    out["ions"] = np.array([str(x) for x in ions])
+    return out
+
+
+def state_from_sim(sim):
+    out = {}
+    for f in _STATE_FIELDS:
+        if hasattr(sim, f):
+            v = getattr(sim, f)
+            if v is not None and not isinstance(v, dict):
+                out[f] = np.asarray(v)
+    bv = getattr(sim, "bound_V", None)
+    if isinstance(bv, dict):
+        out["bound_V"] = np.array([bv["T"], bv["B"], bv["L"], bv["R"]], dtype=float)
+    elif bv is not None:
+        out["bound_V"] = np.asarray(bv, dtype=float)
+    return out
+
+
+def check_supported(sim, p):
+    """Refuse loudly instead of silently computing a different model."""
+    bad = []
+    for flag, what in (("molecules_enabled", "general network (networks.py run_loop*)"),
+                       ("grn_enabled", "gene regulatory network"),
+                       ("deformation", "deformation"), ("deform_osmo", "osmotic pressure"),
+                       ("fluid_flow", "fluid flow"), ("Ca_dyn", "ER calcium dynamics")):
+        if bool(getattr(p, flag, False)):
+            bad.append(what)
+    if bool(getattr(p, "dynamic_noise", False)) and "P" in [str(x) for x in params_from_p(p)["ions"]]:
+        bad.append("dynamic noise")
+    if float(getattr(p, "cell_polarizability", 0.0)) != 0.0:
+        bad.append("cell_polarizability != 0")
+    if bad:
+        raise BetseB200Error("betse_b200 does not implement: " + ", ".join(bad) +
+                             " — run this configuration with the reference solver")
+
+
+def engine_from_sim(sim, cells, p, device=0):
+    check_supported(sim, p)
+    return TissueEngine(mesh_from_cells(cells), params_from_p(p), state_from_sim(sim), device=device)
+
+
+def _copy_back(sim, eng, diag):
+    fields = list(_SAMPLED_STATE)
+    if eng.is_ecm:
+        fields += _SAMPLED_ENV
+    if diag:
+        fields += _SAMPLED_DIAG + (_SAMPLED_DIAG_ENV if eng.is_ecm else [])
+    got = eng.download(fields)
+    shp = (eng.ny, eng.nx)
+    for f, a in got.items():
+        if f in ("E_env_x", "E_env_y"):
+            a = a.reshape(shp)                     # the reference keeps these 2-D (sim.py:572-573)
+        setattr(sim, f, a)
+    return 0
+
+
+def run_sim_core_loop(sim, phase, time_steps, time_steps_sampled, anim_cells=None, *,
+                      engine=None, device=0, stats=None):
+    """Same signature and contract as Simulator._run_sim_core_loop (sim.py:1132-1138)."""
+    p, cells = phase.p, phase.cells
+    own_engine = engine is None
+    eng = engine or engine_from_sim(sim, cells, p, device=device)
+    kind = getattr(getattr(phase, "kind", None), "name", str(getattr(phase, "kind", "")))
+    is_sim = kind.upper() == "SIM"
+    fire = getattr(getattr(phase, "dyna", None), "fire_events", None) if is_sim else None
+    sampled = set(time_steps_sampled)
+    Unstable = _unstable_exception()
+    h2d = d2h = 0
+    h2d0, d2h0 = eng.h2d_bytes, eng.d2h_bytes
+    cache = {f: np.array(getattr(sim, f), copy=True) for f in _SCHEDULED if hasattr(sim, f)
+             and getattr(sim, f) is not None} if fire else {}
+    bv_cache = dict(getattr(sim, "bound_V", {})) if fire else {}
+    t0 = time.time()
+    n_total = len(time_steps)
+    n = 0
+    try:
+        while n < n_total:
+            if fire is not None:
+                # scheduled interventions are host-side scalar logic: keep the reference's own code
+                fire(phase=phase, t=time_steps[n])
+                for f in list(cache):
+                    new = np.asarray(getattr(sim, f))
+                    if new.shape != cache[f].shape or not np.array_equal(new, cache[f]):
+                        eng.set_field(f, new)
+                        cache[f] = np.array(new, copy=True)
+                bv = getattr(sim, "bound_V", None)
+                if isinstance(bv, dict) and bv != bv_cache:
+                    raise BetseB200Error("the external-voltage event (tisevevolt.py) is not implemented")
+                run = 1
+            else:
+                # no events: run up to and including the next sampled step in one call
+                run = 1
+                while n + run < n_total and time_steps[n + run - 1] not in sampled:
+                    run += 1
+            last_t = time_steps[n + run - 1]
+            is_sampled = last_t in sampled
+            status = eng.step(run, diag=is_sampled)
+            n += run
+            if status & (capi.STATUS_NAN_VM | capi.STATUS_NAN_CONC):
+                d2h += _copy_back(sim, eng, diag=False)
+                raise Unstable(
+                    "Your simulation has become unstable. Please try a smaller time step,"
+                    "reduce gap junction radius, and/or reduce pump rate coefficients.")
+            if is_sampled:
+                d2h += _copy_back(sim, eng, diag=True)
+                phase.callbacks.progressed_next()
+                sim.write2storage(last_t, cells, p)
+                if anim_cells is not None:
+                    anim_cells.plot_frame(time_step=-1)
+        # leave the Simulator holding the final state, like the reference does
+        if n_total and time_steps[n_total - 1] not in sampled:
+            d2h += _copy_back(sim, eng, diag=False)
+    finally:
+        if stats is not None:
+            h2d = eng.h2d_bytes - (0 if own_engine else h2d0)
+            d2h = eng.d2h_bytes - (0 if own_engine else d2h0)
+            stats.update({"h2d_bytes": h2d, "d2h_bytes": d2h, "wall_s": time.time() - t0,
+                          "steps": n})
+        if own_engine:
+            eng.close()
+
+
+_installed = None
+
+
+def install(device=0):
+    """Rebind the reference's full solver to the B200 loop (sim.py:1064-1075 seam)."""
+    global _installed
+    from betse.science.sim import Simulator
+    if _installed is None:
+        _installed = Simulator._run_sim_core_loop
+
+    def _loop(self, phase, time_steps, time_steps_sampled, anim_cells):
+        return run_sim_core_loop(self, phase, time_steps, time_steps_sampled, anim_cells, device=device)
+    Simulator._run_sim_core_loop = _loop
+
+
+def uninstall():
+    global _installed
+    if _installed is not None:
+        from betse.science.sim import Simulator
+        Simulator._run_sim_core_loop = _installed
+        _installed = None

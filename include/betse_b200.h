@@ -160,6 +160,11 @@ int  betse_create_error(char *buf, size_t n);   /* message of the last failed be
  * Simulator attributes created by init_core/init_dynamics (sim.py:452-1012) into HBM. */
 int  betse_upload_state(betse_ctx *ctx, const betse_state_host *state);
 
+/* Replaces: the Simulator.update_V call that precedes the loop (sim.py:1041 -> 2007-2083 ->
+ * get_current, ion_current.py:13-114): charge, Vmem and the environmental field from the
+ * uploaded concentrations.  Needed only when the caller did not run the reference's update_V. */
+int  betse_update_v(betse_ctx *ctx);
+
 /* Replaces: the array/scalar side effects of TissueHandler.fire_events + makeAllChanges
  * (tishandler.py:709-917,1321-1332): new T / c_env_bound / bound_V / blocks. */
 int  betse_set_schedule(betse_ctx *ctx, const betse_params *params);

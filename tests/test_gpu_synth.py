@@ -1,0 +1,103 @@
+"""GPU vs oracle on synthetic tissues at BASELINE.json sizes (the oracle itself is pinned to the
+real reference by tests/test_oracle_golden.py), plus size-independent properties at 1 M cells."""
+import numpy as np
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(n_cells, profile="mammal", ecm=True, **over):
+    from betse_b200 import synth
+    from betse_b200.engine import TissueEngine
+    from oracle.betse_oracle import OracleSim
+    mesh, p, st = synth.make_tissue(n_cells, profile=profile, ecm=ecm, overrides=over or None)
+    eng = TissueEngine(mesh, p, st)
+    eng.update_V()
+    ora = OracleSim(mesh, p, st)
+    ora.diagnostics = False
+    ora.update_V()
+    return mesh, p, eng, ora
+
+
+def _compare(eng, ora, mesh, p, ecm, tag):
+    fields = ["cc_cells", "cc_at_mem", "gjopen", "vm", "rho_cells", "cc_env"]
+    if ecm:
+        fields += ["E_env_x", "E_env_y", "v_env", "rho_env"]
+    got = eng.download(fields)
+    ref = {f: np.asarray(getattr(ora, f)) for f in fields}
+    cap = {"x.p." + k: np.asarray(v) for k, v in p.items()}
+    cap.update({"cells." + k: np.asarray(v) for k, v in mesh.items()})
+    cap["x.s0.zs"] = ora.zs
+    cap["x.s0.D_gj"] = ora.D_gj
+    tol = util.gpu_tolerances(cap, "x", ref)
+    for f in fields:
+        err = float(np.max(np.abs(got[f].reshape(ref[f].shape) - ref[f])))
+        assert err <= tol[f], (tag, f, err, tol[f])
+
+
+@pytest.mark.parametrize("n_cells,profile,ecm,steps", [
+    (10_000, "mammal", True, 20),      # BASELINE configs[1]
+    (10_000, "basic", True, 5),
+    (10_000, "mammal", False, 10),
+    (100_000, "mammal", True, 3),      # BASELINE configs[2] size (ion path)
+])
+def test_gpu_vs_oracle(n_cells, profile, ecm, steps):
+    mesh, p, eng, ora = _pair(n_cells, profile, ecm)
+    _compare(eng, ora, mesh, p, ecm, "entry")
+    for n in range(steps):
+        st = eng.step(1)
+        ora.step()
+        assert not (st & 3)
+    _compare(eng, ora, mesh, p, ecm, "step%d" % steps)
+    eng.close()
+
+
+def test_batched_steps_equal_single_steps():
+    """betse_step(n) (CUDA-graph replay) == n x betse_step(1): bit-identical state."""
+    from betse_b200 import synth
+    from betse_b200.engine import TissueEngine
+    mesh, p, st = synth.make_tissue(20_000)
+    out = []
+    for batched in (False, True):
+        eng = TissueEngine(mesh, p, st)
+        eng.update_V()
+        if batched:
+            eng.step(12)
+        else:
+            for _ in range(12):
+                eng.step(1)
+        out.append(eng.download(["cc_cells", "cc_env", "vm", "gjopen", "E_env_x"]))
+        eng.close()
+    for f in out[0]:
+        assert np.array_equal(out[0][f], out[1][f]), f
+
+
+def test_full_size_one_step_and_properties():
+    """BASELINE configs[4] size (1 M cells, 6 M membranes, ~1000^2 grid): one step against the
+    oracle, then size-independent properties over more steps: run-to-run determinism and
+    gap-junction mass conservation (every GJ flux has an equal and opposite partner)."""
+    mesh, p, eng, ora = _pair(1_000_000)
+    st = eng.step(1)
+    ora.step()
+    assert not (st & 3)
+    _compare(eng, ora, mesh, p, True, "1M step1")
+    eng.step(9, diag=True)
+    a = eng.download(["cc_cells", "vm", "fluxes_gj"])
+    eng.close()
+    from betse_b200.engine import TissueEngine
+    from betse_b200 import synth
+    mesh2, p2, st2 = synth.make_tissue(1_000_000)
+    eng2 = TissueEngine(mesh2, p2, st2)
+    eng2.update_V()
+    eng2.step(10, diag=True)
+    b = eng2.download(["cc_cells", "vm", "fluxes_gj"])
+    eng2.close()
+    assert np.array_equal(a["cc_cells"], b["cc_cells"]) and np.array_equal(a["vm"], b["vm"])
+    # antisymmetry of junctional flux: f_gj[m]*sa[m] == -f_gj[nn[m]]*sa[nn[m]]
+    nn = np.asarray(mesh["nn_i"])
+    sa = np.asarray(mesh["mem_sa"])
+    fg = a["fluxes_gj"] * sa
+    resid = np.max(np.abs(fg + fg[:, nn]))
+    assert resid <= 1e-9 * np.max(np.abs(fg)) + 1e-300, resid
