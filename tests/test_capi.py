@@ -1,0 +1,83 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol
+include/betse_b200.h declares, the ctypes mirrors agree with the header's structs, and the
+product path fails loudly without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "betse_b200.h")
+
+
+def _header_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(betse_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from betse_b200 import capi
+    lib = capi.load()
+    syms = _header_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(lib, s), "libbetse_b200.so does not export %s" % s
+    assert sorted(capi.SYMBOLS) == syms, (sorted(capi.SYMBOLS), syms)
+    assert lib.betse_abi_version() == capi.ABI_VERSION
+
+
+def test_ctypes_structs_match_header_layout():
+    """Compile a tiny C program against the header and compare sizeof/offsetof with ctypes."""
+    from betse_b200 import capi
+    probes = [("betse_mesh", "memsa_mean", capi.Mesh), ("betse_mesh", "ecm_slot_idx", capi.Mesh),
+              ("betse_params", "T_sim", capi.Params), ("betse_params", "gauss_w", capi.Params),
+              ("betse_state_host", "cenv_uniform", capi.StateHost)]
+    body = "".join('printf("%%zu %%zu\\n", sizeof(%s), offsetof(%s, %s));\n' % (s, s, f) for s, f, _ in probes)
+    prog = '#include <stdio.h>\n#include <stddef.h>\n#include "betse_b200.h"\nint main(){%s return 0;}\n' % body
+    with tempfile.TemporaryDirectory() as td:
+        src = os.path.join(td, "p.c")
+        open(src, "w").write(prog)
+        exe = os.path.join(td, "p")
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
+        out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split("\n")
+    for (s, f, cls), line in zip(probes, out):
+        size, off = (int(x) for x in line.split())
+        assert C.sizeof(cls) == size, (s, C.sizeof(cls), size)
+        assert getattr(cls, f).offset == off, (s, f, getattr(cls, f).offset, off)
+
+
+def test_header_compiles_as_plain_c():
+    with tempfile.TemporaryDirectory() as td:
+        src = os.path.join(td, "h.c")
+        open(src, "w").write('#include "betse_b200.h"\nint main(void){return BETSE_ABI_VERSION==0;}\n')
+        subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        "-c", src, "-o", os.path.join(td, "h.o")], check=True)
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the engine must refuse to construct (it never computes on the host)."""
+    from betse_b200 import capi, BetseB200Error
+    lib = capi.load()
+    if lib.betse_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    from betse_b200 import synth
+    from betse_b200.engine import TissueEngine
+    mesh, p, st = synth.make_tissue(200)
+    with pytest.raises(BetseB200Error):
+        TissueEngine(mesh, p, st)
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under betse_b200/ may import it."""
+    pkg = os.path.join(ROOT, "betse_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), fn
