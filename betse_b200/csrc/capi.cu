@@ -13,15 +13,16 @@
 #include "kparams.cuh"
 
 // launchers (kernels.cu)
-void launch_mem(int ni, const KParams* dP, const KArrays& A, int n_ctas, int cur, int diag, cudaStream_t st);
-void launch_ion(int ni, const KParams* dP, const KArrays& A, int ny, int nx, int cur, int diag, cudaStream_t st);
-void launch_ion_smooth(int ni, const KParams* dP, const KArrays& A, int ny, int nx, int nxt, cudaStream_t st);
-void launch_envacc(int ni, const KParams* dP, const KArrays& A, int E, int nxt, int apply, cudaStream_t st);
-void launch_cell_charge(const KParams* dP, const KArrays& A, int C, int cur, cudaStream_t st);
-void launch_field(const KParams* dP, const KArrays& A, int ny, int nx, cudaStream_t st);
-void launch_envmix(int ni, const KParams* dP, const KArrays& A, int cur, cudaStream_t st);
-void launch_diag(int ni, const KParams* dP, const KArrays& A, int n_ctas, int newb, cudaStream_t st);
-void launch_expand_vm(const KParams* dP, const KArrays& A, int M, int C, int cur, cudaStream_t st);
+void launch_mem(int ni, const KParams& P, const KArrays& A, int n_ctas, int cur, int diag, cudaStream_t st);
+void launch_ion(int ni, const KParams& P, const KArrays& A, int ny, int nx, int cur, int diag, cudaStream_t st);
+void launch_ion_smooth(int ni, const KParams& P, const KArrays& A, int ny, int nx, int nxt, cudaStream_t st);
+void launch_envacc(int ni, const KParams& P, const KArrays& A, int E, int nxt, int apply, cudaStream_t st);
+void launch_cell_charge(const KParams& P, const KArrays& A, int C, int cur, cudaStream_t st);
+void launch_field(const KParams& P, const KArrays& A, int ny, int nx, cudaStream_t st);
+void launch_envmix(int ni, const KParams& P, const KArrays& A, int cur, cudaStream_t st);
+void launch_diag(int ni, const KParams& P, const KArrays& A, int n_ctas, int newb, cudaStream_t st);
+void launch_expand_vm(const KParams& P, const KArrays& A, int M, int C, int cur, cudaStream_t st);
+cudaError_t prepare_kernels(int ni);
 
 enum { K_ION = 0, K_MEM, K_ENVACC, K_FIELD, K_ENVMIX, K_SMOOTH, K_DIAG, K_EXPAND };
 static const char* kKernelNames[BETSE_NKERNELS] = {
@@ -32,10 +33,9 @@ struct betse_ctx {
     cudaStream_t stream = nullptr;
     KParams P;
     KArrays A;
-    KParams* dP = nullptr;
     betse_params hp;          // last host params
     int cur = 0;
-    int C = 0, Co = 0, M = 0, Mo = 0, E = 0, ny = 0, nx = 0, I = 0, n_ctas = 0, n_slots = 0;
+    int C = 0, Co = 0, M = 0, Mo = 0, E = 0, ny = 0, nx = 0, I = 0, n_ctas = 0, n_tiles = 0, n_slots = 0;
     bool diag_valid = false;
     std::string err;
     std::vector<void*> allocs;
@@ -94,6 +94,9 @@ static void fill_kparams(betse_ctx* ctx, const betse_params* hp)
         const double z = hp->z[i];
         P.z[i] = z;
         P.zi[i] = (z == 1.0) ? 1 : (z == -1.0) ? -1 : (z == 2.0) ? 2 : (z == -2.0) ? -2 : 0;
+        // A(+1)=slot0, B(+1)=1, A(+2)=2, B(+2)=3; a negative valence swaps A and B (kernels.cu GhkAB)
+        P.ia[i] = (z == 1.0) ? 0 : (z == -1.0) ? 1 : (z == 2.0) ? 2 : 3;
+        P.ib[i] = (z == 1.0) ? 1 : (z == -1.0) ? 0 : (z == 2.0) ? 3 : 2;
         P.zF[i] = z * hp->F;                       // sim.zs * p.F
         P.Dgj_surf[i] = hp->D_gj[i] * hp->gj_surface;
         P.cbound[i] = hp->c_env_bound[i];
@@ -128,6 +131,15 @@ static void fill_kparams(betse_ctx* ctx, const betse_params* hp)
     P.cluster_open = hp->cluster_open; P.fast_update_ecm = hp->fast_update_ecm;
     // scipy.ndimage._gaussian_kernel1d(sigma=1, radius=4) taps, formed by the host in NumPy
     for (int k = 0; k <= 4; ++k) P.gw[k] = hp->gauss_w[k];
+    P.inv_RT_sim = 1.0 / P.RT_sim; P.inv_RT_p = 1.0 / P.RT_p;
+    P.inv_tm = 1.0 / hp->tm; P.inv_gjl = 1.0 / P.gj_len;
+    P.inv_kbT_sim = 1.0 / P.kbT_sim;
+    P.inv_delta = 1.0 / P.delta; P.inv_2delta = 1.0 / (2.0 * P.delta);
+    P.inv_KmNK_Na = 1.0 / hp->KmNK_Na; P.inv_KmNK_K = 1.0 / hp->KmNK_K; P.inv_KmCa_Ca = 1.0 / hp->KmCa_Ca;
+    P.tNK = hp->cATP / hp->KmNK_ATP; P.tCa = hp->cATP / hp->KmCa_ATP;
+    P.QnNK0 = (hp->cADP * 1e-3) * (hp->cPi * 1e-3); P.QdNK0 = hp->cATP * 1e-3; P.QnCa0 = hp->cADP * hp->cPi;
+    P.dtm = hp->dt * 1.0e3;
+    P.inv_K0 = 1.0 / P.K0;
     ctx->hp = *hp;
 }
 
@@ -214,6 +226,10 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
     P.y_own0 = mesh->y_own0;
     P.y_own1 = mesh->y_own1 > 0 ? mesh->y_own1 : mesh->ny;
     P.n_cells = C; P.n_cells_owned = Co; P.n_mems_owned = Mo;
+    P.yi0 = P.ya0 = P.yf0 = 0;
+    P.yi1 = P.ya1 = P.yf1 = mesh->ny;
+    if ((long long)hp->n_ions * std::max(std::max(C, ctx->M), ctx->E) >= (1LL << 31) - 1)
+        return fail(ctx, "I*max(C,M,E) must stay below 2^31 (32-bit device indices)");
     fill_kparams(ctx, hp);
 
     // ---- index arrays
@@ -253,6 +269,29 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
     ctx->n_ctas = (int)cta_start.size() - 1;
     P.n_ctas = ctx->n_ctas;
     if ((r = dev_upload(ctx, (int**)&A.cta_cell_start, cta_start.data(), cta_start.size()))) return r;
+    // ---- warp packing (k_mem): contiguous runs of whole cells with <= 32 membranes, <= 10 cells
+    std::vector<int> tile_start;
+    tile_start.push_back(0);
+    {
+        int c = 0;
+        while (c < Co) {
+            int mstart = mesh->cell_mem_ptr[c];
+            int cc = c;
+            while (cc < Co && (mesh->cell_mem_ptr[cc + 1] - mstart) <= 32 && (cc - c) < 10) ++cc;
+            if (cc == c) return fail(ctx, "a cell has more than 32 membranes (unsupported by the warp-tile kernel)");
+            tile_start.push_back(cc);
+            c = cc;
+        }
+    }
+    ctx->n_tiles = (int)tile_start.size() - 1;
+    P.n_tiles = ctx->n_tiles;
+    std::vector<int> tdesc((size_t)ctx->n_tiles * 4);
+    for (int t = 0; t < ctx->n_tiles; ++t) {
+        const int a = tile_start[t], b = tile_start[t + 1];
+        tdesc[4 * t] = a; tdesc[4 * t + 1] = b - a;
+        tdesc[4 * t + 2] = mesh->cell_mem_ptr[a]; tdesc[4 * t + 3] = mesh->cell_mem_ptr[b] - mesh->cell_mem_ptr[a];
+    }
+    if ((r = dev_upload(ctx, (int**)&A.tile_desc, tdesc.data(), tdesc.size()))) return r;
 
     // ---- env point -> flux slot CSR (map_ecm2mem, cells.py:1793-1796), slots in membrane order
     ctx->n_slots = mesh->n_flux_slots > Mo ? mesh->n_flux_slots : Mo;
@@ -301,7 +340,7 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
     if ((r = dev_alloc(ctx, &A.rho_cells, C))) return r;
     if ((r = dev_alloc(ctx, &A.flux_slots, hp->is_ecm ? (size_t)ctx->n_slots * I : 1))) return r;
     if ((r = dev_alloc(ctx, &A.cenv_u, 16))) return r;
-    if ((r = dev_alloc(ctx, &A.cenv_part, (size_t)ctx->n_ctas * 8))) return r;
+    if ((r = dev_alloc(ctx, &A.cenv_part, (size_t)ctx->n_tiles * 8))) return r;
     if ((r = dev_alloc(ctx, &A.status, 1))) return r;
     if ((r = dev_alloc(ctx, &A.vm_mem, Mo))) return r;
     if ((r = dev_alloc(ctx, &A.vm_ave, C))) return r;
@@ -311,8 +350,7 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
         for (int i = 0; i < 8; ++i) cu[i] = cu[8 + i] = hp->cenv_uniform[i];
         CK(cudaMemcpyAsync(A.cenv_u, cu, sizeof cu, cudaMemcpyHostToDevice, ctx->stream));
     }
-    if ((r = dev_alloc(ctx, &ctx->dP, 1, false))) return r;
-    CK(cudaMemcpyAsync(ctx->dP, &ctx->P, sizeof(KParams), cudaMemcpyHostToDevice, ctx->stream));
+    CK(prepare_kernels(I));
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
@@ -416,7 +454,7 @@ extern "C" int betse_upload_state(betse_ctx* ctx, const betse_state_host* s)
         if (nz || A.phi_b) {
             if ((r = opt_array(ctx, &A.phi_b, (const double*)s->Phi_b, E))) return r;
             ctx->P.has_phi = nz ? 1 : 0;
-            CK(cudaMemcpyAsync(ctx->dP, &ctx->P, sizeof(KParams), cudaMemcpyHostToDevice, st));
+            destroy_graphs(ctx);      // KParams is baked into the captured launches
         }
     }
     if ((r = opt_array(ctx, &A.extra_rho_cells, (const double*)s->extra_rho_cells, C))) return r;
@@ -443,7 +481,7 @@ extern "C" int betse_set_schedule(betse_ctx* ctx, const betse_params* hp)
     const int has_phi = ctx->P.has_phi;
     fill_kparams(ctx, hp);
     ctx->P.has_phi = has_phi;
-    CK(cudaMemcpyAsync(ctx->dP, &ctx->P, sizeof(KParams), cudaMemcpyHostToDevice, ctx->stream));
+    destroy_graphs(ctx);              // KParams is baked into the captured launches
     return 0;
 }
 
@@ -458,25 +496,25 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
     const bool ecm = ctx->hp.is_ecm != 0;
     if (phase == 0) {
         if (ecm) {
-            launch_ion(I, ctx->dP, A, ctx->ny, ctx->nx, cur, diag, st);
+            launch_ion(I, ctx->P, A, ctx->ny, ctx->nx, cur, diag, st);
             if (evs) cudaEventRecord(evs[1], st);
             if (ctx->hp.sharpness < 1.0) {
-                launch_ion_smooth(I, ctx->dP, A, ctx->ny, ctx->nx, nxt, st);
+                launch_ion_smooth(I, ctx->P, A, ctx->ny, ctx->nx, nxt, st);
                 cudaMemcpyAsync(A.cc_env[nxt], A.scratch_env, (size_t)I * ctx->E * sizeof(double),
                                 cudaMemcpyDeviceToDevice, st);
             }
         } else if (evs) cudaEventRecord(evs[1], st);
         if (evs) cudaEventRecord(evs[2], st);
-        launch_mem(I, ctx->dP, A, ctx->n_ctas, cur, diag, st);
+        launch_mem(I, ctx->P, A, ctx->n_ctas, cur, diag, st);
         if (evs) cudaEventRecord(evs[3], st);
     } else if (phase == 1) {
-        if (ecm) launch_envacc(I, ctx->dP, A, ctx->E, nxt, 1, st);
-        else launch_envmix(I, ctx->dP, A, cur, st);
+        if (ecm) launch_envacc(I, ctx->P, A, ctx->E, nxt, 1, st);
+        else launch_envmix(I, ctx->P, A, cur, st);
         if (evs) cudaEventRecord(evs[4], st);
     } else {
-        if (ecm) launch_field(ctx->dP, A, ctx->ny, ctx->nx, st);
+        if (ecm) launch_field(ctx->P, A, ctx->ny, ctx->nx, st);
         if (evs) cudaEventRecord(evs[5], st);
-        if (diag) launch_diag(I, ctx->dP, A, ctx->n_ctas, nxt, st);
+        if (diag) launch_diag(I, ctx->P, A, ctx->n_ctas, nxt, st);
         if (evs) cudaEventRecord(evs[6], st);
         ctx->cur = nxt;
     }
@@ -546,10 +584,10 @@ extern "C" int betse_update_v(betse_ctx* ctx)
 {
     if (!ctx) return 2;
     CK(cudaSetDevice(ctx->device));
-    launch_cell_charge(ctx->dP, ctx->A, ctx->Co, ctx->cur, ctx->stream);
+    launch_cell_charge(ctx->P, ctx->A, ctx->Co, ctx->cur, ctx->stream);
     if (ctx->hp.is_ecm) {
-        launch_envacc(ctx->I, ctx->dP, ctx->A, ctx->E, ctx->cur, 0, ctx->stream);
-        launch_field(ctx->dP, ctx->A, ctx->ny, ctx->nx, ctx->stream);
+        launch_envacc(ctx->I, ctx->P, ctx->A, ctx->E, ctx->cur, 0, ctx->stream);
+        launch_field(ctx->P, ctx->A, ctx->ny, ctx->nx, ctx->stream);
     }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
@@ -656,7 +694,7 @@ extern "C" int betse_download_sample(betse_ctx* ctx, betse_state_host* s)
         DN(s->rho_env, A.rho_env, E);
     }
     if (s->vm || s->vm_ave) {
-        launch_expand_vm(ctx->dP, A, Mo, ctx->Co, cur, st);
+        launch_expand_vm(ctx->P, A, Mo, ctx->Co, cur, st);
         DN(s->vm, A.vm_mem, Mo);
         DN(s->vm_ave, A.vm_ave, C);
     }

@@ -14,6 +14,7 @@
 //
 // Layouts are SoA: [ion][cell], [ion][membrane], [ion][env point]; the membranes of a cell
 // are contiguous, so a CTA owns a contiguous run of cells and of membranes.
+#include <stdlib.h>
 #include "kparams.cuh"
 
 #define FLOAT_NONCE 1.0e-25   // sim_toolbox.py:52
@@ -25,59 +26,116 @@
 __device__ __forceinline__ double ldg(const double* p) { return __ldg(p); }
 __device__ __forceinline__ int ldgi(const int* p) { return __ldg(p); }
 
-// exp(-alpha_i) and 1/(-expm1(-alpha_i)) for the valence classes, derived from ONE exp/expm1
-// pair evaluated at -alpha_1 (alpha_i = z_i*alpha_1 exactly for z = +-1, +-2).
-struct GhkBase {
-    double e1, inv_e1, em1, rden_p1, inv_e1p1;
-    __device__ __forceinline__ void init(double a1) {
-        const double x = -a1;
-        e1 = exp(x);
-        em1 = expm1(x);
-        inv_e1 = 1.0 / e1;
-        rden_p1 = 1.0 / (-em1);
-        inv_e1p1 = 1.0 / (e1 + 1.0);
-    }
-    // ex = exp(-z a1); rden = 1/(-expm1(-z a1))
-    __device__ __forceinline__ void get(int zi, double z, double a1, double& alpha, double& ex, double& rden) const {
-        if (zi == 1) { alpha = a1; ex = e1; rden = rden_p1; }
-        else if (zi == -1) { alpha = -a1; ex = inv_e1; rden = -e1 * rden_p1; }
-        else if (zi == 2) { alpha = 2.0 * a1; ex = e1 * e1; rden = rden_p1 * inv_e1p1; }
-        else if (zi == -2) { alpha = -2.0 * a1; ex = inv_e1 * inv_e1; rden = -(e1 * e1) * rden_p1 * inv_e1p1; }
-        else {  // generic valence (incl. 0: the reference adds 1e-25 to z, sim_toolbox.py:56)
-            alpha = (z + FLOAT_NONCE) * a1;
-            ex = exp(-alpha);
-            rden = 1.0 / (-expm1(-alpha));
-        }
+// 1/x for finite, normal, non-zero x: MUFU.RCP64H seed (~20 bits) + two Newton steps; <= 1 ulp,
+// branch-free (the compiler's IEEE division carries a slow-path call per use).
+__device__ __forceinline__ double fast_rcp(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+// a/b with one residual correction (<= 1 ulp)
+__device__ __forceinline__ double fast_div(double a, double b)
+{
+    const double r = fast_rcp(b);
+    const double q = a * r;
+    return fma(fma(-b, q, a), r, q);
+}
+
+// GHK flux in "A/B form".  With alpha = z*a1, ex = exp(-alpha), rden = 1/(-expm1(-alpha)) the
+// reference's  -((D*alpha)/d)*((cB - cA*ex)*rden)  (sim_toolbox.py:58-65) equals
+// -(D/d)*(cB*A - cA*B) with A = alpha*rden, B = A*ex.  For the valences that occur (+-1, +-2)
+// everything follows from ONE expm1 at -a1:  A(+1) = a1/(-em1), B(+1) = A(+1)*e1,
+// A(+2) = 2*a1/((-em1)*(e1+1)), B(+2) = A(+2)*e1^2, and A(-z) = B(+z), B(-z) = A(+z).
+struct GhkAB {
+    double A1, B1, A2, B2;
+    __device__ __forceinline__ void init(double a1, double e1, double em1) {
+        const double e1p1 = e1 + 1.0;
+        const double R = fast_rcp((-em1) * e1p1);     // 1/((-em1)(e1+1))
+        A2 = (2.0 * a1) * R;
+        A1 = (a1 * R) * e1p1;
+        B1 = A1 * e1;
+        B2 = A2 * (e1 * e1);
     }
 };
 
-template <int NI>
-__global__ void __launch_bounds__(BT_TPB, 2)
-k_mem(const KParams* __restrict__ Pp, const KArrays A, const int cur, const int diag)
+// generic valence (incl. 0: the reference adds 1e-25 to z, sim_toolbox.py:56); rare, kept out of line
+__device__ __noinline__ double2 ghk_generic(double z, double a1)
 {
-    extern __shared__ double sm[];
-    double* s_mem = sm;                       // [NI][TPB]   f_mem*sa per membrane
-    double* s_gj = sm + NI * BT_TPB;          // [NI][TPB]   f_gj*sa per membrane
-    double* s_cc = sm + 2 * NI * BT_TPB;      // [NI][MAX_CTA_CELLS] updated cell concentrations
-    double* s_sum = s_cc + NI * BT_MAX_CTA_CELLS;  // [NI][MAX_CTA_CELLS] per-cell sum of f_mem*sa (no-ECM bath)
+    const double al = (z + FLOAT_NONCE) * a1;
+    const double a = al / (-expm1(-al));
+    return make_double2(a, a * exp(-al));
+}
 
-    const KParams& P = *Pp;
-    const int tid = threadIdx.x;
+// Shared-memory plan of k_mem, per warp (doubles): staged flux*sa [32][NI] for the membrane and
+// the gap-junction flux (AoS: the warp's slice of flux_slots is a straight copy), and a scratch
+// of 256 doubles (generic build: the GHK A/B tables of the two sides, [8][32]; then the updated
+// concentrations of the tile's cells).
+#define KM_WARP_DOUBLES(NI) (64 * (NI) + 256)
+#define KM_SMEM_DOUBLES(NI) (8 * KM_WARP_DOUBLES(NI))
+
+// The reference's ion order is fixed (Na, K, Cl, Ca, H, P, M; parameters.py:1296), so the shipped
+// ion profiles give three valence signatures.  PROF = 1 builds bake the signature of the NI-ion
+// profile plus the default feature switches (extracellular spaces, voltage-sensitive gap
+// junctions, open cluster boundary, no per-membrane block arrays, no diagnostics) into the
+// kernel; PROF = 0 reads everything from KParams at run time.
+template <int NI> struct StdProf;
+template <> struct StdProf<4> { static constexpr int iNa = 0, iK = 1, iCa = -1; __host__ __device__ static constexpr int z(int i) { constexpr int t[4] = {1, 1, -1, -1}; return t[i]; } };       // basic: Na K P M
+template <> struct StdProf<5> { static constexpr int iNa = 0, iK = 1, iCa = 2; __host__ __device__ static constexpr int z(int i) { constexpr int t[5] = {1, 1, 2, -1, -1}; return t[i]; } };     // basic_Ca: Na K Ca P M
+template <> struct StdProf<6> { static constexpr int iNa = 0, iK = 1, iCa = 3; __host__ __device__ static constexpr int z(int i) { constexpr int t[6] = {1, 1, -1, 2, -1, -1}; return t[i]; } };  // mammal/amphibian/custom: Na K Cl Ca P M
+template <> struct StdProf<7> { static constexpr int iNa = 0, iK = 1, iCa = 3; __host__ __device__ static constexpr int z(int i) { constexpr int t[7] = {1, 1, -1, 2, 1, -1, -1}; return t[i]; } }; // + H
+template <> struct StdProf<8> { static constexpr int iNa = 0, iK = 1, iCa = 3; __host__ __device__ static constexpr int z(int i) { return 0; } };
+
+__device__ __forceinline__ void ghk_pick(const GhkAB& t, int zi, double& A, double& B)
+{
+    const bool two = (zi == 2) || (zi == -2);
+    const double X = two ? t.A2 : t.A1, Y = two ? t.B2 : t.B1;
+    A = (zi < 0) ? Y : X;
+    B = (zi < 0) ? X : Y;
+}
+
+// One WARP per tile of whole cells with <= 32 membranes (host-built packing, tile_desc):
+// lanes are membranes while the fluxes are formed, then (cell, ion) pairs for the membrane->cell
+// sums (fixed summation order => bit-reproducible), then cells for charge and Vmem.  Warps never
+// meet at a block barrier, so a warp stalled on a gather does not hold up its neighbours.
+template <int NI, bool PHI, int MINB, int PROF>
+__global__ void __launch_bounds__(BT_TPB, MINB)
+k_mem(const __grid_constant__ KParams P, const KArrays A, const int cur, const int diag_in)
+{
+    constexpr bool S = (PROF != 0);
+    extern __shared__ double sm[];
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * (BT_TPB / 32) + (threadIdx.x >> 5);
+    if (tile >= P.n_tiles) return;
+    double* s_m = sm + (threadIdx.x >> 5) * KM_WARP_DOUBLES(NI);   // [32][NI] f_mem*sa
+    double* s_g = s_m + 32 * NI;                                    // [32][NI] f_gj*sa
+    double* s_t = s_g + 32 * NI;                                    // 256 doubles of scratch
+
+    const bool is_ecm = S ? true : (P.is_ecm != 0);
+    const bool vsens = S ? true : (P.v_sensitive_gj != 0);
+    const bool cl_open = S ? true : (P.cluster_open != 0);
+    const bool fast_ecm = S ? false : (P.fast_update_ecm != 0);
+    const bool diag = S ? false : (diag_in != 0);
+    const int iNa = S ? StdProf<NI>::iNa : P.iNa, iK = S ? StdProf<NI>::iK : P.iK, iCa = S ? StdProf<NI>::iCa : P.iCa;
+
     const int nxt = cur ^ 1;
-    const int c0 = ldgi(A.cta_cell_start + blockIdx.x);
-    const int c1 = ldgi(A.cta_cell_start + blockIdx.x + 1);
-    const int m0 = ldgi(A.cell_mem_ptr + c0);
-    const int m1 = ldgi(A.cell_mem_ptr + c1);
-    const int nm = m1 - m0, nc = c1 - c0;
+    const int4 td = __ldg(reinterpret_cast<const int4*>(A.tile_desc) + tile);   // {c0, nc, m0, nm}
+    const int c0 = td.x, nc = td.y, m0 = td.z, nm = td.w;
     const int C = P.n_cells;
     const int E = P.ny * P.nx;
     const int Mo = P.n_mems_owned;
     const double* __restrict__ cmid = A.cc_mid[cur];
     const double* __restrict__ vmc = A.vm_cell[cur];
+    const double* __restrict__ cenv = A.cc_env[cur];
     unsigned int flags = 0;
 
-    if (tid < nm) {
-        const int m = m0 + tid;
+    // ---- lanes = membranes
+    if (lane < nm) {
+        const int m = m0 + lane;
         const int c = ldgi(A.mem_to_cells + m);
         const int nnp = ldgi(A.nn_cell_flag + m);
         const int cn = nnp & 0x7fffffff;
@@ -85,56 +143,88 @@ k_mem(const KParams* __restrict__ Pp, const KArrays A, const int cur, const int 
         const int e = ldgi(A.map_mem2ecm + m);
         const double sa = ldg(A.mem_sa + m);
         double g = A.gjopen[m];
+        double Dm[NI], co[NI], cnb[NI], cin[NI];
+#pragma unroll
+        for (int i = 0; i < NI; ++i) Dm[i] = ldg(A.Dm + i * Mo + m);
+#pragma unroll
+        for (int i = 0; i < NI; ++i) cin[i] = cmid[i * C + c];
+#pragma unroll
+        for (int i = 0; i < NI; ++i) co[i] = is_ecm ? cenv[i * E + e] : A.cenv_u[cur * 8 + i];
+#pragma unroll
+        for (int i = 0; i < NI; ++i) cnb[i] = cmid[i * C + cn];
         double vm_own = vmc[c];
         double vm_nb = vmc[cn];
-        if (P.has_phi) {
+        double cCai = 0.0, cCao = 0.0;
+        if (iCa >= 0) {                               // Ca-ATPase inputs: fresh cell value, env after transport
+            cCai = A.cc_cells[iCa * C + c];
+            if (is_ecm) cCao = A.cc_env[nxt][iCa * E + e];
+        }
+        if (PHI) {
             vm_own -= ldg(A.phi_b + e);
             vm_nb -= ldg(A.phi_b + ldgi(A.map_mem2ecm + ldgi(A.nn_i + m)));
         }
-        // ---- shared transcendental bases
-        const double v = vm_own + FLOAT_NONCE;          // electroflux: vBA += 1e-25
-        const double a1 = (v * P.F) / P.RT_sim;         // alpha for z = +1
-        GhkBase gm; gm.init(a1);
-        const double vgj0 = vm_nb - vm_own;             // sim.py:2166
-        const double vg = vgj0 + FLOAT_NONCE;
-        const double ag1 = (vg * P.F) / P.RT_p;         // GJ flux uses p.T (sim.py:2197)
-        GhkBase gg; gg.init(ag1);
-        double gnum = 0.0, rgden = 1.0;
-        if (P.v_sensitive_gj) {                         // gap_junction.py:56-72
-            const double V1 = 1.0e3 * fabs(vgj0);
-            const double al = 0.0013 * exp(-0.077 * (V1 - P.gj_vthresh));
-            double be = 0.0013 * exp(0.14 * (V1 - P.gj_vthresh));
-            be = be / (1.0 + 50.0 * be);
-            const double dtm = P.dt * 1.0e3;
-            gnum = dtm * (al + be * P.gj_min);
-            rgden = 1.0 / (1.0 + al * dtm + be * dtm);
+        // membrane side: electroflux adds 1e-25 to vBA (sim_toolbox.py:54); alpha for z = +1
+        const double a1 = ((vm_own + FLOAT_NONCE) * P.F) * P.inv_RT_sim;
+        GhkAB tm;
+        double keq;                                   // K0/e1 = exp(-dG/RT + F vm/RT): pump Keq
+        {
+            const double e1 = exp(-a1);
+            tm.init(a1, e1, expm1(-a1));
+            keq = P.K0 * fast_rcp(e1);
         }
-        const double gjb = A.gj_block ? ldg(A.gj_block + m) : P.gj_block;
-        const double gjw = P.v_sensitive_gj ? 1.0 : ldg(A.gj_w + m);
-        const double inv_tm = 1.0 / P.tm;
-        const double inv_gjl = 1.0 / P.gj_len;
-        const bool closed_bnd = (!P.cluster_open) && bnd;
+        // gap junction: vgj and its GHK table with p.T (sim.py:2166, 2197).  alpha is small here:
+        // exp(x) = 1 + expm1(x) to <= 1.5 ulp for x >= -1, plain exp below that
+        const double vgj0 = vm_nb - vm_own;
+        const double ag1 = ((vgj0 + FLOAT_NONCE) * P.F) * P.inv_RT_p;
+        GhkAB tg;
+        {
+            const double em1 = expm1(-ag1);
+            const double e1 = (ag1 > 1.0) ? exp(-ag1) : 1.0 + em1;
+            tg.init(ag1, e1, em1);
+        }
+        if (!S) {
+            s_t[0 * 32 + lane] = tm.A1; s_t[1 * 32 + lane] = tm.B1; s_t[2 * 32 + lane] = tm.A2; s_t[3 * 32 + lane] = tm.B2;
+            s_t[4 * 32 + lane] = tg.A1; s_t[5 * 32 + lane] = tg.B1; s_t[6 * 32 + lane] = tg.A2; s_t[7 * 32 + lane] = tg.B2;
+        }
+        // gating (gap_junction.py:56-72) as g' = gjb*((g + dtm*al)*D1 + dtm*be0*gmin) / (D1*(1 + dtm*al) + dtm*be0),
+        // D1 = 1 + 50*be0: the two divisions of the reference folded into one reciprocal
+        double gA = 0.0, gB = 0.0, gD1 = 1.0, gr = 1.0;
+        if (vsens) {
+            const double xg = 1.0e3 * fabs(vgj0) - P.gj_vthresh;
+            const double al = 0.0013 * exp(-0.077 * xg);
+            const double be0 = 0.0013 * exp(0.14 * xg);
+            gD1 = fma(50.0, be0, 1.0);
+            gA = P.dtm * al;
+            gB = (P.dtm * be0) * P.gj_min;
+            gr = fast_rcp(fma(gD1, 1.0 + gA, P.dtm * be0));
+        }
+        const double gjb = (!S && A.gj_block) ? ldg(A.gj_block + m) : P.gj_block;
+        const double gjw = vsens ? 1.0 : ldg(A.gj_w + m);
+        const bool closed_bnd = (!cl_open) && bnd;
 
         // ---- Na/K-ATPase (sim_toolbox.py:71-122); Keq = exp(-dG/RT + F vm/RT) = K0/e1
+        //   f_Na = -3*blk*alpha*fwd*(1 - Q/Keq), fwd = u3*w2*t/((1+u3)(1+w2)(1+t)), Q = Qn/Qd
+        //        = -3*blk*alpha*(u3*w2*t)*(Qd*Keq - Qn) / ((1+u3)(1+w2)(1+t)*Qd*Keq)
         double fNa = 0.0, fK = 0.0;
-        const double K0 = P.K0;                         // exp(-deltaGATP/(R*T_sim))
         if (P.alpha_NaK > 0.0) {
-            const double cNai = cmid[P.iNa * C + c], cKi = cmid[P.iK * C + c];
-            double cNao, cKo;
-            if (P.is_ecm) { cNao = A.cc_env[cur][P.iNa * E + e]; cKo = A.cc_env[cur][P.iK * E + e]; }
-            else { cNao = A.cenv_u[cur * 8 + P.iNa]; cKo = A.cenv_u[cur * 8 + P.iK]; }
+            double cNai = 0.0, cKi = 0.0, cNao = 0.0, cKo = 0.0;
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+                if (i == iNa) { cNao = co[i]; cNai = cin[i]; }
+                if (i == iK) { cKo = co[i]; cKi = cin[i]; }
+            }
             const double a = cNao * 1e-3, b = cKi * 1e-3;
-            const double Qn = (((P.cADP * 1e-3) * (P.cPi * 1e-3)) * (a * a * a)) * (b * b);
+            const double Qn = (P.QnNK0 * (a * a * a)) * (b * b);
             const double a2 = cNai * 1e-3, b2 = cKo * 1e-3;
-            double Qd = ((P.cATP * 1e-3) * (a2 * a2 * a2)) * (b2 * b2);
+            double Qd = (P.QdNK0 * (a2 * a2 * a2)) * (b2 * b2);
             if (Qd == 0.0) Qd = 1.0e-15;
-            const double Q = Qn / Qd;
-            const double Keq = K0 * gm.inv_e1;
-            const double u = cNai / P.KmNK_Na, w = cKo / P.KmNK_K, t = P.cATP / P.KmNK_ATP;
+            const double QdK = Qd * keq;
+            const double u = cNai * P.inv_KmNK_Na, w = cKo * P.inv_KmNK_K, t = P.tNK;
             const double u3 = u * u * u, w2 = w * w;
-            const double fwd = ((u3 * w2) * t) / (((1.0 + u3) * (1.0 + w2)) * (1.0 + t));
-            const double blk = A.NaK_block ? ldg(A.NaK_block + m) : P.NaK_block;
-            fNa = (((-3.0 * blk) * P.alpha_NaK) * fwd) * (1.0 - (Q / Keq));
+            const double num = ((u3 * w2) * t) * (QdK - Qn);
+            const double den = (((1.0 + u3) * (1.0 + w2)) * (1.0 + t)) * QdK;
+            const double blk = (!S && A.NaK_block) ? ldg(A.NaK_block + m) : P.NaK_block;
+            fNa = ((-3.0 * blk) * P.alpha_NaK) * fast_div(num, den);
             fK = -(2.0 / 3.0) * fNa;
             if (diag) A.rate_NaK[m] = -fNa;
             fNa = P.rho_pump * fNa;
@@ -142,105 +232,120 @@ k_mem(const KParams* __restrict__ Pp, const KArrays A, const int cur, const int 
             if (closed_bnd) { fNa = 0.0; fK = 0.0; }
         } else if (diag) A.rate_NaK[m] = 0.0;
 
-        // ---- Ca-ATPase (sim.py:2126-2155, sim_toolbox.py:124-182): fresh cell value, env after transport
+        // ---- Ca-ATPase (sim.py:2126-2155, sim_toolbox.py:124-182)
+        //   f = -alpha*(x*t/((1+x)(1+t)))*(1 - Qn/(Qd*Keq)), Keq = K0/e1^2
         double fCa = 0.0;
-        if (P.iCa >= 0 && P.alpha_Ca > 0.0) {
-            double cCai = A.cc_cells[P.iCa * C + c];
-            double cCao = P.is_ecm ? A.cc_env[nxt][P.iCa * E + e] : A.cenv_u[cur * 8 + P.iCa];
+        if (iCa >= 0 && P.alpha_Ca > 0.0) {
+            if (!is_ecm) {
+#pragma unroll
+                for (int i = 0; i < NI; ++i) if (i == iCa) cCao = co[i];
+            }
             if (cCai != cCai || cCao != cCao) flags |= ST_NAN_CONC;
             if (cCai < 0.0) cCai = 0.0;
             if (cCao < 0.0) cCao = 0.0;
-            const double Qn = (P.cADP * P.cPi) * cCao;
+            const double Qn = P.QnCa0 * cCao;
             double Qd = P.cATP * cCai;
             if (Qd == 0.0) Qd = 1.0e-16;
-            const double Q = Qn / Qd;
-            const double Keq = (K0 * gm.inv_e1) * gm.inv_e1;
-            const double numo = (cCai / P.KmCa_Ca) * (P.cATP / P.KmCa_ATP);
-            const double deno = (1.0 + (cCai / P.KmCa_Ca)) * (1.0 + (P.cATP / P.KmCa_ATP));
-            fCa = (-P.alpha_Ca * (numo / deno)) * (1.0 - (Q / Keq));
+            const double QdK = Qd * ((keq * keq) * P.inv_K0);
+            const double x = cCai * P.inv_KmCa_Ca, t = P.tCa;
+            const double num = (x * t) * (QdK - Qn);
+            const double den = ((1.0 + x) * (1.0 + t)) * QdK;
+            fCa = -P.alpha_Ca * fast_div(num, den);
             fCa = P.rho_pump * fCa;
             if (closed_bnd) fCa = 0.0;
-            fCa = P.rho_pump * fCa;
+            fCa = P.rho_pump * fCa;                         // applied twice in the reference (sim.py:2141, 2155)
         }
 
+        const double Dtm = -(P.inv_tm * P.rho_channel);
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
-            const double cin = cmid[i * C + c];
-            const double cout = P.is_ecm ? A.cc_env[cur][i * E + e] : A.cenv_u[cur * 8 + i];
-            const double Dm = ldg(A.Dm + (size_t)i * Mo + m);
-            double alpha, ex, rden;
-            gm.get(P.zi[i], P.z[i], a1, alpha, ex, rden);
-            // electroflux (sim_toolbox.py:58-65): -((Dc*alpha)/d)*((cB - cA*exp(-alpha))/deno)*rho
-            double f = -((Dm * alpha) * inv_tm) * ((cin - cout * ex) * rden) * P.rho_channel;
+            double Am, Bm, Ag, Bg;
+            if (S) {
+                ghk_pick(tm, StdProf<NI>::z(i), Am, Bm);
+                ghk_pick(tg, StdProf<NI>::z(i), Ag, Bg);
+            } else if (P.zi[i] != 0) {     // table slot of (A, B) for this valence: host-built ia/ib
+                Am = s_t[P.ia[i] * 32 + lane]; Bm = s_t[P.ib[i] * 32 + lane];
+                Ag = s_t[(4 + P.ia[i]) * 32 + lane]; Bg = s_t[(4 + P.ib[i]) * 32 + lane];
+            } else {
+                const double2 xm = ghk_generic(P.z[i], a1), xg = ghk_generic(P.z[i], ag1);
+                Am = xm.x; Bm = xm.y; Ag = xg.x; Bg = xg.y;
+            }
+            // electroflux (sim_toolbox.py:58-65), cA = env, cB = cell
+            double f = (Dm[i] * Dtm) * (cin[i] * Am - co[i] * Bm);
             if (closed_bnd) f = 0.0;
-            if (i == P.iNa) f += fNa;
-            if (i == P.iK) f += fK;
-            if (i == P.iCa) f += fCa;
+            if (i == iNa) f += fNa;
+            if (i == iK) f += fK;
+            if (i == iCa) f += fCa;
             // gap junction: gating advances once per ion (sim.py:1272 -> 2180-2183)
-            if (P.v_sensitive_gj) g = gjb * ((g + gnum) * rgden);
+            if (vsens) g = gjb * ((fma(g + gA, gD1, gB)) * gr);
             else g = gjb * gjw;
-            const double cnb = cmid[i * C + cn];
-            gg.get(P.zi[i], P.z[i], ag1, alpha, ex, rden);
-            double fg = -(((P.Dgj_surf[i] * g) * alpha) * inv_gjl) * ((cnb - cin * ex) * rden);
+            // cA = this cell, cB = partner cell (sim.py:2191-2197)
+            double fg = -((P.Dgj_surf[i] * g) * P.inv_gjl) * (cnb[i] * Ag - cin[i] * Bg);
             if (bnd) fg = 0.0;
-            const double pm = f * sa;
-            s_mem[i * BT_TPB + tid] = pm;
-            s_gj[i * BT_TPB + tid] = fg * sa;
-            if (P.is_ecm) A.flux_slots[(size_t)m * NI + i] = P.fast_update_ecm ? f : pm;
-            if (diag) { A.fl_mem[(size_t)i * Mo + m] = f; A.fl_gj[(size_t)i * Mo + m] = fg; }
+            s_m[lane * NI + i] = f * sa;
+            s_g[lane * NI + i] = fg * sa;
+            if (is_ecm && fast_ecm) A.flux_slots[m * NI + i] = f;
+            if (diag) { A.fl_mem[i * Mo + m] = f; A.fl_gj[i * Mo + m] = fg; }
         }
         A.gjopen[m] = g;
     }
-    __syncthreads();
+    __syncwarp();
 
-    // ---- membranes -> cells (update_Co + update_all_concs), one thread per (ion, cell)
-    for (int p = tid; p < NI * nc; p += BT_TPB) {
-        const int i = p / nc, lc = p - i * nc;
+    // ---- the warp's slice of the membrane->env exchange slots: a straight, coalesced copy
+    if (is_ecm && !fast_ecm) {
+        double* __restrict__ dst = A.flux_slots + m0 * NI;
+        for (int p = lane; p < nm * NI; p += 32) dst[p] = s_m[p];
+    }
+
+    // ---- lanes = (cell, ion) pairs: membranes -> cells (update_Co + update_all_concs)
+    double* s_cc = s_t;      // [nc][NI] updated concentrations (nc*NI <= 10*8 = 80)
+    double* s_sm = s_t + 96; // [nc][NI] per-cell sum of f_mem*sa (no-ECM bath)
+    for (int q = lane; q < nc * NI; q += 32) {
+        const int lc = q / NI, i = q - lc * NI;
         const int c = c0 + lc;
         const int jb = ldgi(A.cell_mem_ptr + c) - m0, je = ldgi(A.cell_mem_ptr + c + 1) - m0;
         double Sm = 0.0, Sg = 0.0;
-        for (int j = jb; j < je; ++j) { Sm += s_mem[i * BT_TPB + j]; Sg += s_gj[i * BT_TPB + j]; }
-        const double vol = ldg(A.cell_vol + c);
+        for (int j = jb; j < je; ++j) { Sm += s_m[j * NI + i]; Sg += s_g[j * NI + i]; }
+        const double rvol = fast_rcp(ldg(A.cell_vol + c));
         const double cc = A.cc_cells[i * C + c];
-        const double cm_new = cc + (Sm / vol) * P.dt;             // sim_toolbox.py:1177-1181
-        double cn_new = cm_new + P.dt * ((-Sg) / vol);            // sim.py:2105-2108
+        const double cm_new = cc + (Sm * rvol) * P.dt;            // sim_toolbox.py:1177-1181
+        double cn_new = cm_new + P.dt * ((-Sg) * rvol);           // sim.py:2105-2108
         if (cn_new != cn_new) flags |= ST_NAN_CONC;
         if (cn_new < 0.0) { cn_new = 0.0; flags |= ST_NEG; }      // no_negs, sim.py:2111
         A.cc_cells[i * C + c] = cn_new;
         A.cc_mid[nxt][i * C + c] = cm_new;                        // the stale cc_at_mem (quirk list)
-        s_cc[i * BT_MAX_CTA_CELLS + lc] = cn_new;
-        s_sum[i * BT_MAX_CTA_CELLS + lc] = Sm;
+        s_cc[q] = cn_new;
+        if (!is_ecm) s_sm[q] = Sm;
     }
-    __syncthreads();
+    __syncwarp();
 
-    // ---- charge and Vmem (ion_current.py:19; sim.py:2027-2029)
-    if (tid < nc) {
-        const int c = c0 + tid;
+    // ---- lanes = cells: charge and Vmem (ion_current.py:19; sim.py:2027-2029)
+    if (lane < nc) {
+        const int c = c0 + lane;
         double rho = 0.0;
 #pragma unroll
-        for (int i = 0; i < NI; ++i) rho = fma(P.zF[i], s_cc[i * BT_MAX_CTA_CELLS + tid], rho);
+        for (int i = 0; i < NI; ++i) rho = fma(P.zF[i], s_cc[lane * NI + i], rho);
         if (A.extra_rho_cells) rho += ldg(A.extra_rho_cells + c);
         A.rho_cells[c] = rho;
         const double vmn = P.inv_cm * (rho * ldg(A.diviterm + c));
         if (vmn != vmn) flags |= ST_NAN_VM;
         A.vm_cell[nxt][c] = vmn;
     }
-    if (!P.is_ecm && tid < NI) {      // per-CTA partial of sum_m f*sa for the bath (no-ECM)
+    if (!is_ecm && lane < NI) {      // per-tile partial of sum_m f*sa for the bath (no-ECM)
         double s = 0.0;
-        for (int lc = 0; lc < nc; ++lc) s += s_sum[tid * BT_MAX_CTA_CELLS + lc];
-        A.cenv_part[(size_t)blockIdx.x * 8 + tid] = s;
+        for (int lc = 0; lc < nc; ++lc) s += s_sm[lc * NI + lane];
+        A.cenv_part[tile * 8 + lane] = s;
     }
     if (flags) atomicOr(A.status, flags);
 }
 
 // no-ECM: cX_env = mean(cX_env + (-flux*(mem_sa/vol_env))*dt)  (sim_toolbox.py:1200-1205)
-__global__ void k_envmix(const KParams* __restrict__ Pp, const KArrays A, const int cur)
+__global__ void k_envmix(const __grid_constant__ KParams P, const KArrays A, const int cur)
 {
-    const KParams& P = *Pp;
     __shared__ double red[256];
     const int i = blockIdx.x;
     double s = 0.0;
-    for (int b = threadIdx.x; b < P.n_ctas; b += blockDim.x) s += A.cenv_part[(size_t)b * 8 + i];
+    for (int b = threadIdx.x; b < P.n_tiles; b += blockDim.x) s += A.cenv_part[(size_t)b * 8 + i];
     red[threadIdx.x] = s;
     __syncthreads();
     for (int o = blockDim.x / 2; o > 0; o >>= 1) {
@@ -255,89 +360,106 @@ __global__ void k_envmix(const KParams* __restrict__ Pp, const KArrays A, const 
 }
 
 // ---------------------------------------------------------------------------- env grid
-// One thread per env point, all ions: Dirichlet edge fill, central gradient (one-sided at the
-// world edge), Nernst-Planck flux with last step's E field, divergence with finitediff.diff's
-// edge convention, forward Euler.  Rows are local rows of a strip [y0, y0+ny) of the world.
+// Env-grid electrodiffusion of every ion (Simulator.update_ecm, sim.py:2209-2254), tiled through
+// shared memory: a CTA owns IT_Y x IT_X outputs; per ion it stages the concentration tile with a
+// 2-point halo (Dirichlet edge fill applied on load), forms the Nernst-Planck flux once per point
+// of tile + 1-point halo (central gradient, one-sided at the world edge; last step's E field,
+// staged once for all ions), then takes fd.divergence with fd.diff's edge convention and steps
+// forward Euler.  Rows are local rows of a strip [y0, y0+ny) of the world; only rows
+// [yi0, yi1) are produced.
+#define IT_X 32
+#define IT_Y 16
 template <int NI>
 __global__ void __launch_bounds__(256)
-k_ion(const KParams* __restrict__ Pp, const KArrays A, const int cur, const int diag)
+k_ion(const __grid_constant__ KParams P, const KArrays A, const int cur, const int diag)
 {
-    const KParams& P = *Pp;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    __shared__ double sC[IT_Y + 4][IT_X + 4];
+    __shared__ double sFx[IT_Y + 2][IT_X + 3], sFy[IT_Y + 2][IT_X + 3];
+    __shared__ double sEx[IT_Y + 2][IT_X + 3], sEy[IT_Y + 2][IT_X + 3];
     const int nx = P.nx, ny = P.ny;
-    if (x >= nx || y >= ny) return;
     const int E = nx * ny;
-    const int gy = y + P.y0, gny = P.ny_global;
-    const bool top = (gy == gny - 1), bot = (gy == 0), lef = (x == 0), rig = (x == nx - 1);
-    // neighbours needed: (y, x+-1), (y+-1, x), (y, x+-2), (y+-2, x); clamp inside the strip –
-    // points whose stencil leaves the strip are halo points, recomputed by their owner.
-    const int k = y * nx + x;
-    const double d = P.delta, inv_d = 1.0 / d, inv_2d = 1.0 / (2.0 * d);
-    const double inv_kbT = 1.0 / P.kbT_sim;
-    const double* __restrict__ Ex = A.E_x;
-    const double* __restrict__ Ey = A.E_y;
+    const int tx0 = blockIdx.x * IT_X, ty0 = P.yi0 + blockIdx.y * IT_Y;
+    const int tid = threadIdx.x;
+    const int gny = P.ny_global;
+    const double inv_d = P.inv_delta, inv_2d = P.inv_2delta;
 
-    auto edge = [&](int yy, int xx) -> bool {
-        const int g = yy + P.y0;
-        return g == 0 || g == gny - 1 || xx == 0 || xx == nx - 1;
-    };
-#pragma unroll
+    // E field on tile + 1 halo (same for every ion)
+    for (int t = tid; t < (IT_Y + 2) * (IT_X + 2); t += 256) {
+        const int ly = t / (IT_X + 2), lx = t - ly * (IT_X + 2);
+        const int y = ty0 + ly - 1, x = tx0 + lx - 1;
+        double ex = 0.0, ey = 0.0;
+        if (x >= 0 && x < nx && y >= 0 && y < ny) { ex = A.E_x[y * nx + x]; ey = A.E_y[y * nx + x]; }
+        sEx[ly][lx] = ex; sEy[ly][lx] = ey;
+    }
+#pragma unroll 1
     for (int i = 0; i < NI; ++i) {
-        const double* __restrict__ c = A.cc_env[cur] + (size_t)i * E;
-        const double* __restrict__ D = A.Denv + (size_t)i * E;
+        const double* __restrict__ c = A.cc_env[cur] + i * E;
+        const double* __restrict__ D = A.Denv + i * E;
         const double cb = P.cbound[i];
-        const double z = P.z[i];
-        auto C = [&](int yy, int xx) -> double {           // concentration with the Dirichlet fill
-            yy = min(max(yy, 0), ny - 1); xx = min(max(xx, 0), nx - 1);
-            return edge(yy, xx) ? cb : c[yy * nx + xx];
-        };
-        auto gcx = [&](int yy, int xx) -> double {         // fd.gradient, finitediff.py:1236-1266
-            if (xx == 0) return (C(yy, 1) - C(yy, 0)) * inv_d;
-            if (xx == nx - 1) return (C(yy, nx - 1) - C(yy, nx - 2)) * inv_d;
-            return -(C(yy, xx - 1) - C(yy, xx + 1)) * inv_2d;
-        };
-        auto gcy = [&](int yy, int xx) -> double {
-            const int g = yy + P.y0;
-            if (g == 0) return (C(yy + 1, xx) - C(yy, xx)) * inv_d;
-            if (g == gny - 1) return (C(yy, xx) - C(yy - 1, xx)) * inv_d;
-            return -(C(yy - 1, xx) - C(yy + 1, xx)) * inv_2d;
-        };
-        auto FX = [&](int yy, int xx) -> double {          // nernst_planck_flux, sim_toolbox.py:409-411
-            yy = min(max(yy, 0), ny - 1); xx = min(max(xx, 0), nx - 1);
-            const int kk = yy * nx + xx;
-            const double Dk = D[kk];
-            const double al = ((Dk * z) * P.q) * inv_kbT;
-            return -Dk * gcx(yy, xx) - (al * (-Ex[kk])) * C(yy, xx);
-        };
-        auto FY = [&](int yy, int xx) -> double {
-            yy = min(max(yy, 0), ny - 1); xx = min(max(xx, 0), nx - 1);
-            const int kk = yy * nx + xx;
-            const double Dk = D[kk];
-            const double al = ((Dk * z) * P.q) * inv_kbT;
-            return -Dk * gcy(yy, xx) - (al * (-Ey[kk])) * C(yy, xx);
-        };
+        const double zq = P.z[i] * P.q;
+        __syncthreads();                       // previous ion's readers of sC / sF are done
+        for (int t = tid; t < (IT_Y + 4) * (IT_X + 4); t += 256) {
+            const int ly = t / (IT_X + 4), lx = t - ly * (IT_X + 4);
+            const int y = ty0 + ly - 2, x = tx0 + lx - 2;
+            double v = 0.0;
+            if (x >= 0 && x < nx && y >= 0 && y < ny) {
+                const int g = y + P.y0;
+                const bool edge = (g == 0 || g == gny - 1 || x == 0 || x == nx - 1);
+                v = edge ? cb : c[y * nx + x];          // Dirichlet fill, sim.py:2211-2217
+            }
+            sC[ly][lx] = v;
+        }
+        __syncthreads();
+        for (int t = tid; t < (IT_Y + 2) * (IT_X + 2); t += 256) {
+            const int ly = t / (IT_X + 2), lx = t - ly * (IT_X + 2);
+            const int y = ty0 + ly - 1, x = tx0 + lx - 1;
+            double fx = 0.0, fy = 0.0;
+            if (x >= 0 && x < nx && y >= 0 && y < ny) {
+                const int g = y + P.y0;
+                const double cc = sC[ly + 1][lx + 1];
+                double gcx, gcy;                                   // fd.gradient, finitediff.py:1236-1266
+                if (x == 0) gcx = (sC[ly + 1][lx + 2] - cc) * inv_d;
+                else if (x == nx - 1) gcx = (cc - sC[ly + 1][lx]) * inv_d;
+                else gcx = -(sC[ly + 1][lx] - sC[ly + 1][lx + 2]) * inv_2d;
+                if (g == 0) gcy = (sC[ly + 2][lx + 1] - cc) * inv_d;
+                else if (g == gny - 1) gcy = (cc - sC[ly][lx + 1]) * inv_d;
+                else gcy = -(sC[ly][lx + 1] - sC[ly + 2][lx + 1]) * inv_2d;
+                const double Dk = D[y * nx + x];
+                const double al = (Dk * zq) * P.inv_kbT_sim;       // nernst_planck_flux, sim_toolbox.py:409-411
+                fx = -Dk * gcx - (al * (-sEx[ly][lx])) * cc;
+                fy = -Dk * gcy - (al * (-sEy[ly][lx])) * cc;
+                if (diag && ly >= 1 && ly <= IT_Y && lx >= 1 && lx <= IT_X && y < P.yi1) {
+                    A.fl_env_x[i * E + y * nx + x] = fx;
+                    A.fl_env_y[i * E + y * nx + x] = fy;
+                }
+            }
+            sFx[ly][lx] = fx; sFy[ly][lx] = fy;
+        }
+        __syncthreads();
         // fd.divergence(-fx, -fy) with fd.diff's edge rows (finitediff.py:1268-1311)
-        double dx, dy;
-        if (lef) dx = ((-FX(y, 0)) - (-FX(y, 1))) * inv_d;
-        else if (rig) dx = ((-FX(y, nx - 2)) - (-FX(y, nx - 1))) * inv_d;
-        else dx = -((-FX(y, x - 1)) - (-FX(y, x + 1))) * inv_2d;
-        if (bot) dy = -((-FY(y + 1, x)) - (-FY(y, x))) * inv_d;
-        else if (top) dy = -((-FY(y, x)) - (-FY(y - 1, x))) * inv_d;
-        else dy = -((-FY(y - 1, x)) - (-FY(y + 1, x))) * inv_2d;
-        const double c0 = edge(y, x) ? cb : c[k];
-        A.cc_env[cur ^ 1][(size_t)i * E + k] = c0 + (dx + dy) * P.dt;
-        if (diag) {
-            A.fl_env_x[(size_t)i * E + k] = FX(y, x);
-            A.fl_env_y[(size_t)i * E + k] = FY(y, x);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int oy = (tid >> 5) + 8 * h, ox = tid & 31;
+            const int y = ty0 + oy, x = tx0 + ox;
+            if (x < nx && y < P.yi1) {
+                const int g = y + P.y0;
+                const int ly = oy + 1, lx = ox + 1;
+                double dx, dy;
+                if (x == 0) dx = ((-sFx[ly][lx]) - (-sFx[ly][lx + 1])) * inv_d;
+                else if (x == nx - 1) dx = ((-sFx[ly][lx - 1]) - (-sFx[ly][lx])) * inv_d;
+                else dx = -((-sFx[ly][lx - 1]) - (-sFx[ly][lx + 1])) * inv_2d;
+                if (g == 0) dy = -((-sFy[ly + 1][lx]) - (-sFy[ly][lx])) * inv_d;
+                else if (g == gny - 1) dy = -((-sFy[ly][lx]) - (-sFy[ly - 1][lx])) * inv_d;
+                else dy = -((-sFy[ly - 1][lx]) - (-sFy[ly + 1][lx])) * inv_2d;
+                A.cc_env[cur ^ 1][i * E + y * nx + x] = sC[oy + 2][ox + 2] + (dx + dy) * P.dt;
+            }
         }
     }
 }
 
 // fd.integrator (finitediff.py:1479-1512) applied to the transported field (sim.py:2249-2252).
-__global__ void k_ion_smooth(const KParams* __restrict__ Pp, const KArrays A, const int nxt, const int n_ions)
+__global__ void k_ion_smooth(const __grid_constant__ KParams P, const KArrays A, const int nxt, const int n_ions)
 {
-    const KParams& P = *Pp;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     const int nx = P.nx, ny = P.ny;
@@ -358,19 +480,18 @@ __global__ void k_ion_smooth(const KParams* __restrict__ Pp, const KArrays A, co
             f += sides * c[k - 1];
             v = f;
         }
-        A.scratch_env[(size_t)i * E + k] = v;
+        A.scratch_env[i * E + k] = v;
     }
 }
 
 // membrane -> env exchange (update_Co env branch + div_env), env charge, raw env voltage.
 template <int NI>
 __global__ void __launch_bounds__(256)
-k_envacc(const KParams* __restrict__ Pp, const KArrays A, const int nxt, const int apply_flux)
+k_envacc(const __grid_constant__ KParams P, const KArrays A, const int nxt, const int apply_flux)
 {
-    const KParams& P = *Pp;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = P.ya0 * P.nx + blockIdx.x * blockDim.x + threadIdx.x;
     const int E = P.nx * P.ny;
-    if (k >= E) return;
+    if (k >= P.ya1 * P.nx) return;
     const int s0 = ldgi(A.slot_ptr + k), s1 = ldgi(A.slot_ptr + k + 1);
     double acc[NI];
 #pragma unroll
@@ -381,26 +502,26 @@ k_envacc(const KParams* __restrict__ Pp, const KArrays A, const int nxt, const i
         if (s1 > s0) {                       // flux_env[map_mem2ecm] = flux: the last writer wins
             const int s = ldgi(A.slot_idx + s1 - 1);
 #pragma unroll
-            for (int i = 0; i < NI; ++i) acc[i] = A.flux_slots[(size_t)s * NI + i];
+            for (int i = 0; i < NI; ++i) acc[i] = A.flux_slots[s * NI + i];
         }
     } else {
         for (int j = s0; j < s1; ++j) {
             const int s = ldgi(A.slot_idx + j);
 #pragma unroll
-            for (int i = 0; i < NI; ++i) acc[i] += A.flux_slots[(size_t)s * NI + i];
+            for (int i = 0; i < NI; ++i) acc[i] += A.flux_slots[s * NI + i];
         }
     }
     double rho = 0.0;
     const double msa = P.fast_update_ecm ? ldg(A.memsa_env + k) : 0.0;
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
-        double c = A.cc_env[nxt][(size_t)i * E + k];
+        double c = A.cc_env[nxt][i * E + k];
         double delta_env;
         if (P.fast_update_ecm) delta_env = ((-acc[i]) * msa) / P.ecm_vol;        // sim_toolbox.py:1222-1225
         else delta_env = (-acc[i]) / P.env_vol_div;                             // sim_toolbox.py:1229
         if (apply_flux) {
             c = c + delta_env * P.dt;
-            A.cc_env[nxt][(size_t)i * E + k] = c;
+            A.cc_env[nxt][i * E + k] = c;
         }
         rho = fma(P.zF[i], c, rho);
     }
@@ -416,14 +537,13 @@ k_envacc(const KParams* __restrict__ Pp, const KArrays A, const int nxt, const i
 #define FT 32
 #define FH 5
 __global__ void __launch_bounds__(256)
-k_field(const KParams* __restrict__ Pp, const KArrays A)
+k_field(const __grid_constant__ KParams P, const KArrays A)
 {
-    const KParams& P = *Pp;
     __shared__ double sA[FT + 2 * FH][FT + 2 * FH + 1];   // raw
     __shared__ double sB[FT + 2][FT + 2 * FH + 1];        // after the axis-0 (y) pass
     __shared__ double sC[FT + 2][FT + 2 + 1];             // screen * v_env
     const int nx = P.nx, ny = P.ny;
-    const int x0 = blockIdx.x * FT, y0 = blockIdx.y * FT;
+    const int x0 = blockIdx.x * FT, y0 = P.yf0 + blockIdx.y * FT;
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     const int gny = P.ny_global;
     for (int t = tid; t < (FT + 2 * FH) * (FT + 2 * FH); t += 256) {
@@ -463,7 +583,7 @@ k_field(const KParams* __restrict__ Pp, const KArrays A)
         if (x >= 0 && x < nx && y >= 0 && y < ny) {
             v = s;
             if (P.has_phi) v += A.phi_b[y * nx + x];
-            if (ly >= 1 && ly <= FT && lx >= 1 && lx <= FT) A.v_env[y * nx + x] = v;
+            if (ly >= 1 && ly <= FT && lx >= 1 && lx <= FT && y < P.yf1) A.v_env[y * nx + x] = v;
         }
         sC[ly][lx] = P.screen * v;
     }
@@ -472,7 +592,7 @@ k_field(const KParams* __restrict__ Pp, const KArrays A)
     for (int t = tid; t < FT * FT; t += 256) {
         const int ly = t / FT + 1, lx = t % FT + 1;
         const int y = y0 + ly - 1, x = x0 + lx - 1;
-        if (x >= nx || y >= ny) continue;
+        if (x >= nx || y >= P.yf1) continue;
         const int gy = y + P.y0;
         double gx, gyv;
         if (x == 0) gx = (sC[ly][lx + 1] - sC[ly][lx]) / d;
@@ -492,11 +612,10 @@ k_field(const KParams* __restrict__ Pp, const KArrays A)
 // per-membrane vm, vm_ave, dvm.  Same CTA packing as k_mem.
 template <int NI>
 __global__ void __launch_bounds__(BT_TPB)
-k_diag(const KParams* __restrict__ Pp, const KArrays A, const int newb)
+k_diag(const __grid_constant__ KParams P, const KArrays A, const int newb)
 {
     __shared__ double s_a[BT_TPB], s_b[BT_TPB];
     __shared__ double s_c[BT_MAX_CTA_CELLS], s_d[BT_MAX_CTA_CELLS];
-    const KParams& P = *Pp;
     const int tid = threadIdx.x;
     const int c0 = ldgi(A.cta_cell_start + blockIdx.x), c1 = ldgi(A.cta_cell_start + blockIdx.x + 1);
     const int m0 = ldgi(A.cell_mem_ptr + c0), m1 = ldgi(A.cell_mem_ptr + c1);
@@ -575,9 +694,8 @@ k_diag(const KParams* __restrict__ Pp, const KArrays A, const int newb)
 }
 
 // per-membrane Vmem for download: vm = vm_cell[cell] - Phi_b[map_mem2ecm]
-__global__ void k_expand_vm(const KParams* __restrict__ Pp, const KArrays A, const int cur)
+__global__ void k_expand_vm(const __grid_constant__ KParams P, const KArrays A, const int cur)
 {
-    const KParams& P = *Pp;
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= P.n_mems_owned) return;
     double phi = 0.0;
@@ -586,9 +704,8 @@ __global__ void k_expand_vm(const KParams* __restrict__ Pp, const KArrays A, con
 }
 
 // vm_ave = np.dot(M_sum_mems, vm)/num_mems (sim.py:2038) for download
-__global__ void k_vm_ave(const KParams* __restrict__ Pp, const KArrays A)
+__global__ void k_vm_ave(const __grid_constant__ KParams P, const KArrays A)
 {
-    const KParams& P = *Pp;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= P.n_cells_owned) return;
     double s = 0.0;
@@ -597,59 +714,118 @@ __global__ void k_vm_ave(const KParams* __restrict__ Pp, const KArrays A)
 }
 
 // ---------------------------------------------------------------------------- launchers
+// tuning/testing switches: BETSE_KMEM_GENERIC=1 forces the run-time-configured build
+static bool kmem_generic()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("BETSE_KMEM_GENERIC"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
+// register budget of k_mem: 3 CTAs/SM (80 registers) unless BETSE_KMEM_MINB=2 (128 registers)
+static int kmem_minb()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("BETSE_KMEM_MINB"); v = (e && e[0] == '2') ? 2 : 3; }
+    return v;
+}
+
 template <int NI>
-static void launch_mem_t(const KParams* dP, const KArrays& A, int n_ctas, int cur, int diag, cudaStream_t st)
+static void launch_mem_t(const KParams& P, const KArrays& A, int n_ctas, int cur, int diag, cudaStream_t st)
 {
-    const size_t smem = (size_t)(2 * NI * BT_TPB + 2 * NI * BT_MAX_CTA_CELLS) * sizeof(double);
-    static_assert((2 * 8 * BT_TPB + 2 * 8 * BT_MAX_CTA_CELLS) * sizeof(double) <= 48 * 1024, "fits default smem");
-    k_mem<NI><<<n_ctas, BT_TPB, smem, st>>>(dP, A, cur, diag);
+    const size_t smem = (size_t)KM_SMEM_DOUBLES(NI) * sizeof(double);
+    const int grid = (P.n_tiles + (BT_TPB / 32) - 1) / (BT_TPB / 32);
+    const bool minb2 = kmem_minb() == 2;
+    // the specialised build applies to the shipped ion profiles with the default feature switches
+    bool std_prof = NI <= 7 && P.is_ecm && P.v_sensitive_gj && P.cluster_open && !P.fast_update_ecm && !diag &&
+                    !A.gj_block && !A.NaK_block && P.iNa == StdProf<NI>::iNa && P.iK == StdProf<NI>::iK &&
+                    P.iCa == StdProf<NI>::iCa && !kmem_generic();
+    for (int i = 0; i < NI && std_prof; ++i) std_prof = (P.zi[i] == StdProf<NI>::z(i)) && P.zi[i] != 0;
+    if (P.has_phi) k_mem<NI, true, 2, 0><<<grid, BT_TPB, smem, st>>>(P, A, cur, diag);
+    else if (std_prof && minb2) k_mem<NI, false, 2, 1><<<grid, BT_TPB, smem, st>>>(P, A, cur, diag);
+    else if (std_prof) k_mem<NI, false, 3, 1><<<grid, BT_TPB, smem, st>>>(P, A, cur, diag);
+    else k_mem<NI, false, 2, 0><<<grid, BT_TPB, smem, st>>>(P, A, cur, diag);
 }
 
-void launch_mem(int ni, const KParams* dP, const KArrays& A, int n_ctas, int cur, int diag, cudaStream_t st)
+template <typename K>
+static cudaError_t prep_one(K kern, int smem)
+{
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e) return e;
+    return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+}
+
+template <int NI>
+static cudaError_t prepare_mem_t()
+{
+    const int smem = (int)(KM_SMEM_DOUBLES(NI) * sizeof(double));
+    cudaError_t e;
+    if ((e = prep_one(k_mem<NI, true, 2, 0>, smem))) return e;
+    if ((e = prep_one(k_mem<NI, false, 2, 0>, smem))) return e;
+    if ((e = prep_one(k_mem<NI, false, 2, 1>, smem))) return e;
+    return prep_one(k_mem<NI, false, 3, 1>, smem);
+}
+
+// not capturable: called once per context before the first launch
+cudaError_t prepare_kernels(int ni)
 {
     switch (ni) {
-        case 4: launch_mem_t<4>(dP, A, n_ctas, cur, diag, st); break;
-        case 5: launch_mem_t<5>(dP, A, n_ctas, cur, diag, st); break;
-        case 6: launch_mem_t<6>(dP, A, n_ctas, cur, diag, st); break;
-        case 7: launch_mem_t<7>(dP, A, n_ctas, cur, diag, st); break;
-        default: launch_mem_t<8>(dP, A, n_ctas, cur, diag, st); break;
+        case 4: return prepare_mem_t<4>();
+        case 5: return prepare_mem_t<5>();
+        case 6: return prepare_mem_t<6>();
+        case 7: return prepare_mem_t<7>();
+        default: return prepare_mem_t<8>();
     }
 }
 
-void launch_ion(int ni, const KParams* dP, const KArrays& A, int ny, int nx, int cur, int diag, cudaStream_t st)
+void launch_mem(int ni, const KParams& P, const KArrays& A, int n_ctas, int cur, int diag, cudaStream_t st)
 {
-    dim3 b(32, 8), g((nx + 31) / 32, (ny + 7) / 8);
     switch (ni) {
-        case 4: k_ion<4><<<g, b, 0, st>>>(dP, A, cur, diag); break;
-        case 5: k_ion<5><<<g, b, 0, st>>>(dP, A, cur, diag); break;
-        case 6: k_ion<6><<<g, b, 0, st>>>(dP, A, cur, diag); break;
-        case 7: k_ion<7><<<g, b, 0, st>>>(dP, A, cur, diag); break;
-        default: k_ion<8><<<g, b, 0, st>>>(dP, A, cur, diag); break;
+        case 4: launch_mem_t<4>(P, A, n_ctas, cur, diag, st); break;
+        case 5: launch_mem_t<5>(P, A, n_ctas, cur, diag, st); break;
+        case 6: launch_mem_t<6>(P, A, n_ctas, cur, diag, st); break;
+        case 7: launch_mem_t<7>(P, A, n_ctas, cur, diag, st); break;
+        default: launch_mem_t<8>(P, A, n_ctas, cur, diag, st); break;
     }
 }
 
-void launch_ion_smooth(int ni, const KParams* dP, const KArrays& A, int ny, int nx, int nxt, cudaStream_t st)
+void launch_ion(int ni, const KParams& P, const KArrays& A, int ny, int nx, int cur, int diag, cudaStream_t st)
 {
-    dim3 b(32, 8), g((nx + 31) / 32, (ny + 7) / 8);
-    k_ion_smooth<<<g, b, 0, st>>>(dP, A, nxt, ni);
+    const int rows = P.yi1 - P.yi0;
+    if (rows <= 0) return;
+    dim3 b(256), g((nx + IT_X - 1) / IT_X, (rows + IT_Y - 1) / IT_Y);
+    switch (ni) {
+        case 4: k_ion<4><<<g, b, 0, st>>>(P, A, cur, diag); break;
+        case 5: k_ion<5><<<g, b, 0, st>>>(P, A, cur, diag); break;
+        case 6: k_ion<6><<<g, b, 0, st>>>(P, A, cur, diag); break;
+        case 7: k_ion<7><<<g, b, 0, st>>>(P, A, cur, diag); break;
+        default: k_ion<8><<<g, b, 0, st>>>(P, A, cur, diag); break;
+    }
 }
 
-void launch_envacc(int ni, const KParams* dP, const KArrays& A, int E, int nxt, int apply, cudaStream_t st)
+void launch_ion_smooth(int ni, const KParams& P, const KArrays& A, int ny, int nx, int nxt, cudaStream_t st)
 {
-    const int g = (E + 255) / 256;
+    dim3 b(32, 8), g((nx + 31) / 32, (ny + 7) / 8);
+    k_ion_smooth<<<g, b, 0, st>>>(P, A, nxt, ni);
+}
+
+void launch_envacc(int ni, const KParams& P, const KArrays& A, int E, int nxt, int apply, cudaStream_t st)
+{
+    const int n = (P.ya1 - P.ya0) * P.nx;
+    if (n <= 0) return;
+    const int g = (n + 255) / 256;
     switch (ni) {
-        case 4: k_envacc<4><<<g, 256, 0, st>>>(dP, A, nxt, apply); break;
-        case 5: k_envacc<5><<<g, 256, 0, st>>>(dP, A, nxt, apply); break;
-        case 6: k_envacc<6><<<g, 256, 0, st>>>(dP, A, nxt, apply); break;
-        case 7: k_envacc<7><<<g, 256, 0, st>>>(dP, A, nxt, apply); break;
-        default: k_envacc<8><<<g, 256, 0, st>>>(dP, A, nxt, apply); break;
+        case 4: k_envacc<4><<<g, 256, 0, st>>>(P, A, nxt, apply); break;
+        case 5: k_envacc<5><<<g, 256, 0, st>>>(P, A, nxt, apply); break;
+        case 6: k_envacc<6><<<g, 256, 0, st>>>(P, A, nxt, apply); break;
+        case 7: k_envacc<7><<<g, 256, 0, st>>>(P, A, nxt, apply); break;
+        default: k_envacc<8><<<g, 256, 0, st>>>(P, A, nxt, apply); break;
     }
 }
 
 // rho_cells and Vmem from the current concentrations (ion_current.py:19; sim.py:2027-2029)
-__global__ void k_cell_charge(const KParams* __restrict__ Pp, const KArrays A, const int cur)
+__global__ void k_cell_charge(const __grid_constant__ KParams P, const KArrays A, const int cur)
 {
-    const KParams& P = *Pp;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= P.n_cells_owned) return;
     double rho = 0.0;
@@ -659,35 +835,37 @@ __global__ void k_cell_charge(const KParams* __restrict__ Pp, const KArrays A, c
     A.vm_cell[cur][c] = P.inv_cm * (rho * A.diviterm[c]);
 }
 
-void launch_cell_charge(const KParams* dP, const KArrays& A, int C, int cur, cudaStream_t st)
+void launch_cell_charge(const KParams& P, const KArrays& A, int C, int cur, cudaStream_t st)
 {
-    k_cell_charge<<<(C + 255) / 256, 256, 0, st>>>(dP, A, cur);
+    k_cell_charge<<<(C + 255) / 256, 256, 0, st>>>(P, A, cur);
 }
 
-void launch_field(const KParams* dP, const KArrays& A, int ny, int nx, cudaStream_t st)
+void launch_field(const KParams& P, const KArrays& A, int ny, int nx, cudaStream_t st)
 {
-    dim3 b(32, 8), g((nx + FT - 1) / FT, (ny + FT - 1) / FT);
-    k_field<<<g, b, 0, st>>>(dP, A);
+    const int rows = P.yf1 - P.yf0;
+    if (rows <= 0) return;
+    dim3 b(32, 8), g((nx + FT - 1) / FT, (rows + FT - 1) / FT);
+    k_field<<<g, b, 0, st>>>(P, A);
 }
 
-void launch_envmix(int ni, const KParams* dP, const KArrays& A, int cur, cudaStream_t st)
+void launch_envmix(int ni, const KParams& P, const KArrays& A, int cur, cudaStream_t st)
 {
-    k_envmix<<<ni, 256, 0, st>>>(dP, A, cur);
+    k_envmix<<<ni, 256, 0, st>>>(P, A, cur);
 }
 
-void launch_diag(int ni, const KParams* dP, const KArrays& A, int n_ctas, int newb, cudaStream_t st)
+void launch_diag(int ni, const KParams& P, const KArrays& A, int n_ctas, int newb, cudaStream_t st)
 {
     switch (ni) {
-        case 4: k_diag<4><<<n_ctas, BT_TPB, 0, st>>>(dP, A, newb); break;
-        case 5: k_diag<5><<<n_ctas, BT_TPB, 0, st>>>(dP, A, newb); break;
-        case 6: k_diag<6><<<n_ctas, BT_TPB, 0, st>>>(dP, A, newb); break;
-        case 7: k_diag<7><<<n_ctas, BT_TPB, 0, st>>>(dP, A, newb); break;
-        default: k_diag<8><<<n_ctas, BT_TPB, 0, st>>>(dP, A, newb); break;
+        case 4: k_diag<4><<<n_ctas, BT_TPB, 0, st>>>(P, A, newb); break;
+        case 5: k_diag<5><<<n_ctas, BT_TPB, 0, st>>>(P, A, newb); break;
+        case 6: k_diag<6><<<n_ctas, BT_TPB, 0, st>>>(P, A, newb); break;
+        case 7: k_diag<7><<<n_ctas, BT_TPB, 0, st>>>(P, A, newb); break;
+        default: k_diag<8><<<n_ctas, BT_TPB, 0, st>>>(P, A, newb); break;
     }
 }
 
-void launch_expand_vm(const KParams* dP, const KArrays& A, int M, int C, int cur, cudaStream_t st)
+void launch_expand_vm(const KParams& P, const KArrays& A, int M, int C, int cur, cudaStream_t st)
 {
-    k_expand_vm<<<(M + 255) / 256, 256, 0, st>>>(dP, A, cur);
-    k_vm_ave<<<(C + 255) / 256, 256, 0, st>>>(dP, A);
+    k_expand_vm<<<(M + 255) / 256, 256, 0, st>>>(P, A, cur);
+    k_vm_ave<<<(C + 255) / 256, 256, 0, st>>>(P, A);
 }

@@ -6,11 +6,12 @@
 #define BT_TPB 256          // threads per CTA of the membrane kernel == max membranes per CTA
 #define BT_MAX_CTA_CELLS 96 // max cells packed into one membrane-kernel CTA
 
-// Scalars (kernel argument, lives in the constant bank).  Derived products are formed on
+// Scalars (passed BY VALUE as a __grid_constant__ kernel argument: lives in the constant bank).  Derived products are formed on
 // the host in the same operand order as the reference's NumPy expressions.
 struct KParams {
     int n_ions, iNa, iK, iCa;
     int zi[BT_MAX_IONS];          // integer valence class (+-1, +-2) or 0 = generic path
+    int ia[BT_MAX_IONS], ib[BT_MAX_IONS];  // slots of (A, B) in the GHK table {A1,B1,A2,B2} for this valence
     double z[BT_MAX_IONS];
     double zF[BT_MAX_IONS];       // sim.zs * p.F
     double Dgj_surf[BT_MAX_IONS]; // sim.D_gj[i] * p.gj_surface
@@ -34,14 +35,24 @@ struct KParams {
     int has_phi;                            // Phi_b != 0 somewhere
     // local grid geometry (domain decomposition: rows [y0, y0+ny) of a ny_global-row grid)
     int ny, nx, y0, ny_global, y_own0, y_own1;
-    int n_cells, n_cells_owned, n_mems_owned, n_ctas;
+    int n_cells, n_cells_owned, n_mems_owned, n_ctas, n_tiles;
+    // kernel row ranges in local rows (single GPU: all [0, ny)): ion transport, membrane->env
+    // accumulation, env field (E rows; v_env is written on the accumulation rows)
+    int yi0, yi1, ya0, ya1, yf0, yf1;
+    // reciprocals of constants (formed once on the host; x*inv differs from x/c by <= 1 ulp)
+    double inv_RT_sim, inv_RT_p, inv_tm, inv_gjl, inv_kbT_sim, inv_delta, inv_2delta;
+    double inv_KmNK_Na, inv_KmNK_K, inv_KmCa_Ca, tNK, tCa;   // tNK = cATP/KmNK_ATP, tCa = cATP/KmCa_ATP
+    double QnNK0, QdNK0, QnCa0;    // (cADP*1e-3)*(cPi*1e-3), cATP*1e-3, cADP*cPi
+    double dtm;                    // dt*1e3 (gap_junction.py:68)
+    double inv_K0;
 };
 
 // Device array table (kernel argument).
 struct KArrays {
     // mesh
     const int *mem_to_cells, *cell_mem_ptr, *nn_cell_flag, *nn_i, *map_mem2ecm;
-    const int *cta_cell_start;
+    const int *cta_cell_start;   // CTA packing (k_diag): whole cells, <= BT_TPB membranes
+    const int *tile_desc;        // warp packing (k_mem): int4 {c0, nc, m0, nm} per tile of whole cells, <= 32 membranes
     const int *slot_ptr, *slot_idx;
     const double *mem_sa, *mem_nx, *mem_ny, *cell_vol, *cell_sa, *diviterm, *num_mems;
     const double *memsa_env, *gj_w;
@@ -58,7 +69,7 @@ struct KArrays {
     const double *NaK_block, *gj_block;
     double *flux_slots;      // [slots, I]
     double *cenv_u;          // [2][8] no-ECM bath concentrations (device-resident, double buffered)
-    double *cenv_part;       // [n_ctas, 8] per-CTA partial sums
+    double *cenv_part;       // [n_tiles, 8] per-tile partial sums
     unsigned int *status;
     // diagnostics
     double *fl_mem, *fl_gj, *fl_env_x, *fl_env_y, *rate_NaK;
