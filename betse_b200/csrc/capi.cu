@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <string>
@@ -285,6 +286,7 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
     }
     ctx->n_tiles = (int)tile_start.size() - 1;
     P.n_tiles = ctx->n_tiles;
+    { const char* e = getenv("BETSE_PF_TILES"); P.pf_tiles = e ? atoi(e) : 4096; }
     std::vector<int> tdesc((size_t)ctx->n_tiles * 4);
     for (int t = 0; t < ctx->n_tiles; ++t) {
         const int a = tile_start[t], b = tile_start[t + 1];

@@ -26,6 +26,8 @@
 __device__ __forceinline__ double ldg(const double* p) { return __ldg(p); }
 __device__ __forceinline__ int ldgi(const int* p) { return __ldg(p); }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // 1/x for finite, normal, non-zero x: MUFU.RCP64H seed (~20 bits) + two Newton steps; <= 1 ulp,
 // branch-free (the compiler's IEEE division carries a slow-path call per use).
 __device__ __forceinline__ double fast_rcp(double x)
@@ -124,6 +126,9 @@ k_mem(const __grid_constant__ KParams P, const KArrays A, const int cur, const i
 
     const int nxt = cur ^ 1;
     const int4 td = __ldg(reinterpret_cast<const int4*>(A.tile_desc) + tile);   // {c0, nc, m0, nm}
+    // the tile some rounds ahead: its streamed inputs are pulled into L2 at the end of this warp's work
+    int4 tf = make_int4(0, 0, 0, 0);
+    if (P.pf_tiles > 0 && tile + P.pf_tiles < P.n_tiles) tf = __ldg(reinterpret_cast<const int4*>(A.tile_desc) + tile + P.pf_tiles);
     const int c0 = td.x, nc = td.y, m0 = td.z, nm = td.w;
     const int C = P.n_cells;
     const int E = P.ny * P.nx;
@@ -132,6 +137,19 @@ k_mem(const __grid_constant__ KParams P, const KArrays A, const int cur, const i
     const double* __restrict__ vmc = A.vm_cell[cur];
     const double* __restrict__ cenv = A.cc_env[cur];
     unsigned int flags = 0;
+
+    // inputs of the later phases, requested now so that they are in flight during the flux math:
+    // lane q = (cell, ion) pair (first round), lane = cell
+    const int q0lc = lane / NI, q0i = lane - q0lc * NI;
+    const bool q0ok = lane < nc * NI;
+    int q0jb = 0, q0je = 0;
+    double q0vol = 1.0, q0cc = 0.0, dvt = 0.0;
+    if (q0ok) {
+        q0jb = ldgi(A.cell_mem_ptr + c0 + q0lc) - m0; q0je = ldgi(A.cell_mem_ptr + c0 + q0lc + 1) - m0;
+        q0vol = ldg(A.cell_vol + c0 + q0lc);
+        q0cc = A.cc_cells[q0i * C + c0 + q0lc];
+    }
+    if (lane < nc) dvt = ldg(A.diviterm + c0 + lane);
 
     // ---- lanes = membranes
     if (lane < nm) {
@@ -303,11 +321,16 @@ k_mem(const __grid_constant__ KParams P, const KArrays A, const int cur, const i
     for (int q = lane; q < nc * NI; q += 32) {
         const int lc = q / NI, i = q - lc * NI;
         const int c = c0 + lc;
-        const int jb = ldgi(A.cell_mem_ptr + c) - m0, je = ldgi(A.cell_mem_ptr + c + 1) - m0;
+        int jb = q0jb, je = q0je;
+        double vol = q0vol, cc = q0cc;
+        if (q != lane) {
+            jb = ldgi(A.cell_mem_ptr + c) - m0; je = ldgi(A.cell_mem_ptr + c + 1) - m0;
+            vol = ldg(A.cell_vol + c);
+            cc = A.cc_cells[i * C + c];
+        }
         double Sm = 0.0, Sg = 0.0;
         for (int j = jb; j < je; ++j) { Sm += s_m[j * NI + i]; Sg += s_g[j * NI + i]; }
-        const double rvol = fast_rcp(ldg(A.cell_vol + c));
-        const double cc = A.cc_cells[i * C + c];
+        const double rvol = fast_rcp(vol);
         const double cm_new = cc + (Sm * rvol) * P.dt;            // sim_toolbox.py:1177-1181
         double cn_new = cm_new + P.dt * ((-Sg) * rvol);           // sim.py:2105-2108
         if (cn_new != cn_new) flags |= ST_NAN_CONC;
@@ -327,7 +350,7 @@ k_mem(const __grid_constant__ KParams P, const KArrays A, const int cur, const i
         for (int i = 0; i < NI; ++i) rho = fma(P.zF[i], s_cc[lane * NI + i], rho);
         if (A.extra_rho_cells) rho += ldg(A.extra_rho_cells + c);
         A.rho_cells[c] = rho;
-        const double vmn = P.inv_cm * (rho * ldg(A.diviterm + c));
+        const double vmn = P.inv_cm * (rho * dvt);
         if (vmn != vmn) flags |= ST_NAN_VM;
         A.vm_cell[nxt][c] = vmn;
     }
@@ -337,6 +360,23 @@ k_mem(const __grid_constant__ KParams P, const KArrays A, const int cur, const i
         A.cenv_part[tile * 8 + lane] = s;
     }
     if (flags) atomicOr(A.status, flags);
+
+    // ---- L2 prefetch of a later tile's streamed membrane arrays (<= 32 membranes: <= 3 lines of
+    // doubles, <= 2 of int32 per array; lane = line)
+    if (tf.w > 0 && lane < 3) {
+        const int mf = tf.z;
+        const size_t o8 = ((size_t)mf * 8 & ~(size_t)127) + (size_t)lane * 128;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) prefetch_l2((const char*)(A.Dm + i * Mo) + o8);
+        prefetch_l2((const char*)A.mem_sa + o8);
+        prefetch_l2((const char*)A.gjopen + o8);
+        if (lane < 2) {
+            const size_t o4 = ((size_t)mf * 4 & ~(size_t)127) + (size_t)lane * 128;
+            prefetch_l2((const char*)A.mem_to_cells + o4);
+            prefetch_l2((const char*)A.nn_cell_flag + o4);
+            prefetch_l2((const char*)A.map_mem2ecm + o4);
+        }
+    }
 }
 
 // no-ECM: cX_env = mean(cX_env + (-flux*(mem_sa/vol_env))*dt)  (sim_toolbox.py:1200-1205)
@@ -722,11 +762,12 @@ static bool kmem_generic()
     return v == 1;
 }
 
-// register budget of k_mem: 3 CTAs/SM (80 registers) unless BETSE_KMEM_MINB=2 (128 registers)
+// register budget of k_mem: measured best at 2 CTAs/SM (128 registers, no spills: 0.46 ms at 1 M cells)
+// against 3 (80 registers, 0.52 ms) and 4 (64 registers, 0.77 ms); BETSE_KMEM_MINB=3|4 selects the others
 static int kmem_minb()
 {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("BETSE_KMEM_MINB"); v = (e && e[0] == '2') ? 2 : 3; }
+    if (v < 0) { const char* e = getenv("BETSE_KMEM_MINB"); v = (e && e[0] == '3') ? 3 : (e && e[0] == '4') ? 4 : 2; }
     return v;
 }
 
@@ -743,6 +784,7 @@ static void launch_mem_t(const KParams& P, const KArrays& A, int n_ctas, int cur
     for (int i = 0; i < NI && std_prof; ++i) std_prof = (P.zi[i] == StdProf<NI>::z(i)) && P.zi[i] != 0;
     if (P.has_phi) k_mem<NI, true, 2, 0><<<grid, BT_TPB, smem, st>>>(P, A, cur, diag);
     else if (std_prof && minb2) k_mem<NI, false, 2, 1><<<grid, BT_TPB, smem, st>>>(P, A, cur, diag);
+    else if (std_prof && kmem_minb() == 4) k_mem<NI, false, 4, 1><<<grid, BT_TPB, smem, st>>>(P, A, cur, diag);
     else if (std_prof) k_mem<NI, false, 3, 1><<<grid, BT_TPB, smem, st>>>(P, A, cur, diag);
     else k_mem<NI, false, 2, 0><<<grid, BT_TPB, smem, st>>>(P, A, cur, diag);
 }
@@ -763,6 +805,7 @@ static cudaError_t prepare_mem_t()
     if ((e = prep_one(k_mem<NI, true, 2, 0>, smem))) return e;
     if ((e = prep_one(k_mem<NI, false, 2, 0>, smem))) return e;
     if ((e = prep_one(k_mem<NI, false, 2, 1>, smem))) return e;
+    if ((e = prep_one(k_mem<NI, false, 4, 1>, smem))) return e;
     return prep_one(k_mem<NI, false, 3, 1>, smem);
 }
 

@@ -36,6 +36,7 @@ struct KParams {
     // local grid geometry (domain decomposition: rows [y0, y0+ny) of a ny_global-row grid)
     int ny, nx, y0, ny_global, y_own0, y_own1;
     int n_cells, n_cells_owned, n_mems_owned, n_ctas, n_tiles;
+    int pf_tiles;                           // k_mem: L2 prefetch distance in tiles (0 = off)
     // kernel row ranges in local rows (single GPU: all [0, ny)): ion transport, membrane->env
     // accumulation, env field (E rows; v_env is written on the accumulation rows)
     int yi0, yi1, ya0, ya1, yf0, yf1;
