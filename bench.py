@@ -23,6 +23,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "membrane_updates_per_sec"
 UNIT = "membrane-updates/s"
+KNAMES = ["k_ion", "k_mem", "k_envacc", "k_field", "k_envmix", "k_ion_smooth", "k_diag", "k_xchg"]
 
 
 def algorithmic_bytes(I, C, M, E, ecm=True):
@@ -152,7 +153,8 @@ def main():
     workload = "%s-cell synthetic tissue (%d cells, %d membranes), %s ion profile (I=%d), %s" % (
         "1M" if abs(C - 1e6) < 2e4 else str(C), C, M, args.profile, I,
         "extracellular grid %dx%d" % (gny, gnx) if ecm else "no extracellular spaces")
-    config = {"workload": workload, "baseline_config": "configs[4] on one GPU" if abs(C - 1e6) < 2e4 else "custom",
+    config = {"decomposition": ("%d strips of env-grid rows, halo exchange by NVLink peer stores" % world)
+              if world > 1 else "single domain", "workload": workload, "baseline_config": "configs[4] on one GPU" if abs(C - 1e6) < 2e4 else "custom",
               "cells": C, "membranes": M, "env_points": E if ecm else 0, "ions": I, "dt": 1.0e-4,
               "l2_policy": "state per step (~%.2f GB) is larger than the 126 MB L2" %
                            (algorithmic_bytes(I, C, M, E, ecm)[0] / 1e9),
@@ -186,9 +188,19 @@ def main():
     from betse_b200.engine import TissueEngine
     from betse_b200 import simloop
 
-    eng = TissueEngine(mesh, p, state, device=local_rank)
-    eng.update_V()
-    eng.step(args.warmup)
+    if world > 1:
+        # one tissue cut into `world` strips (strong scaling): halo exchange over NVLink peer stores
+        from betse_b200.strips import DistributedStrips
+        t_part = time.perf_counter()
+        ds = DistributedStrips(mesh, p, state, local_rank, dist)
+        t_part = time.perf_counter() - t_part
+        eng = ds.engine
+        ds.update_V()
+        ds.step(args.warmup)
+    else:
+        eng = TissueEngine(mesh, p, state, device=local_rank)
+        eng.update_V()
+        eng.step(args.warmup)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -206,16 +218,55 @@ def main():
     status = eng.step(0)
     check = eng.download(["vm", "cc_cells"])
     finite = bool(np.isfinite(check["vm"]).all() and np.isfinite(check["cc_cells"]).all())
-    eng.close()
+    if dist:
+        t = torch.tensor([0.0 if finite else 1.0, float(status)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        finite, status = bool(t[0].item() == 0.0), int(t[1].item())
+        kt = torch.tensor([kms.get(k, 0.0) for k in KNAMES], device="cuda")
+        dist.all_reduce(kt, op=dist.ReduceOp.MAX)
+        kms = {k: float(v) for k, v in zip(KNAMES, kt.tolist()) if v > 0}
+        ds.close()
+    else:
+        eng.close()
 
     ms_per_step = total_ms / args.steps
     steps_per_s = 1e3 / ms_per_step
-    # replicas: each rank advances its own tissue (small/medium tissues: one sim per GPU)
-    value = M * steps_per_s * world
+    # N > 1: ONE tissue over N GPUs, so membranes/s = global membranes x steps/s
+    value = M * steps_per_s
 
     # ---- end-to-end through the drop-in loop with host buffers
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and world > 1:
+        # end to end over N strips: host state -> strips (partition on the host, upload), timesteps,
+        # download of each rank's owned Vmem / concentrations every 10 steps
+        from betse_b200.strips import DistributedStrips
+        n_e2e = min(args.steps, 100)
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ds2 = DistributedStrips(mesh, p, state, local_rank, dist)
+        ds2.update_V()
+        done = 0
+        d2h = 0
+        while done < n_e2e:
+            k = min(10, n_e2e - done)
+            ds2.step(k)
+            done += k
+            out = ds2.download_local(["vm", "cc_cells", "cc_env", "gjopen"])
+            d2h += sum(a.nbytes for a in out.values())
+        torch.cuda.synchronize()
+        dist.barrier()
+        wall = time.perf_counter() - t0
+        tt = torch.tensor([wall, float(ds2.engine.h2d_bytes), float(d2h)], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ds2.close()
+        e2e = {"value": M * n_e2e / float(tt[0].item()), "unit": UNIT,
+               "h2d_bytes_per_step": float(tt[1].item()) / n_e2e, "d2h_bytes_per_step": float(tt[2].item()) / n_e2e,
+               "timesteps": n_e2e, "sampled_steps": n_e2e // 10,
+               "what": "DistributedStrips from host NumPy state on every rank: partition + engine creation + "
+                       "strip upload + timesteps + download of the rank's owned vm/cc_cells/cc_env/gjopen every "
+                       "10 steps (bytes are per rank, max over ranks)"}
+    elif not args.no_e2e:
         sim, phase = namespaces(mesh, p, state)
         n_e2e = min(args.steps, 100)
         ts = np.linspace(0, n_e2e * p["dt"], n_e2e)
@@ -230,7 +281,7 @@ def main():
             t = torch.tensor([wall], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             wall = float(t.item())
-        e2e = {"value": M * n_e2e / wall * world, "unit": UNIT,
+        e2e = {"value": M * n_e2e / wall, "unit": UNIT,
                "h2d_bytes_per_step": stats["h2d_bytes"] / n_e2e, "d2h_bytes_per_step": stats["d2h_bytes"] / n_e2e,
                "timesteps": n_e2e, "sampled_steps": sim.sampled,
                "what": "run_sim_core_loop() (the Simulator._run_sim_core_loop drop-in) from host NumPy state: "
@@ -244,24 +295,26 @@ def main():
 
     peak, peak_src = measured_peak_hbm()
     b_step, b_mem, b_env = algorithmic_bytes(I, C, M, E, ecm)
-    dom = max(kms, key=lambda k: kms[k])
-    share = {"k_mem": b_mem, "k_ion": I * 24 * E, "k_envacc": 0, "k_field": 72 * E, "k_envmix": 0}
-    ach = share.get(dom, b_mem) / (kms[dom] * 1e-3) / 1e9
+    dom = max((k for k in kms if k != "k_xchg"), key=lambda k: kms[k])
+    # per-launch algorithmic bytes of one rank's kernel (a rank holds 1/world of the tissue)
+    share = {"k_mem": b_mem / world, "k_ion": I * 24 * E / world, "k_envacc": 0, "k_field": 72 * E / world, "k_envmix": 0}
+    ach = share.get(dom, b_mem / world) / (kms[dom] * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
             "traffic": None, "peak_source": peak_src,
-            "algorithmic_bytes_per_launch": share.get(dom, b_mem),
-            "kernel_ms": kms, "step": {"algorithmic_bytes": b_step,
+            "algorithmic_bytes_per_launch": share.get(dom, b_mem / world),
+            "kernel_ms": kms, "step": {"algorithmic_bytes": b_step, "n_gpus": world,
                                        "achieved": b_step / (ms_per_step * 1e-3) / 1e9,
-                                       "frac": b_step / (ms_per_step * 1e-3) / 1e9 / peak}}
+                                       "frac": b_step / (ms_per_step * 1e-3) / 1e9 / (peak * world)}}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "timesteps_per_sec": steps_per_s,
-            "higher_is_better": True, "scaling": "weak" if world > 1 else "strong", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config, "clocks": sampler.summary(),
-            "gpu_launches": int(len(kms) * args.steps), "status_word": status, "finite": finite,
+            "gpu_launches": int((len(kms) + (1 if "k_xchg" in kms else 0)) * args.steps * world),
+            "status_word": status, "finite": finite,
             "roofline": roof}
     if e2e:
         line["e2e"] = e2e
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         per_step, n, thr = cpu_reference_run(mesh, p, state, budget_s=args.cpu_budget, max_steps=20)
         line["cpu_baseline"] = {"value": M / per_step, "unit": UNIT, "cores": thr, "kind": "port",
                                 "ms_per_step": per_step * 1e3,

@@ -19,9 +19,10 @@ NKERNELS = 8
 STATUS_NAN_VM = 1
 STATUS_NAN_CONC = 2
 STATUS_NEG_CLAMP = 4
+STATUS_XCHG_TIMEOUT = 8
 STEP_DIAG = 1
-
-BUF_CC_MID, BUF_VM_CELL, BUF_FLUX, BUF_CC_ENV, BUF_V_RAW, BUF_CC_ENV_CUR = range(6)
+XCHG_X1, XCHG_X2 = 0, 1
+XCHG_PUSH, XCHG_WAIT = 1, 2
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -82,7 +83,7 @@ STATE_FIELDS = [
     "extra_rho_env", "extra_J_mem", "NaKATP_block", "gj_block",
     "fluxes_mem", "fluxes_gj", "fluxes_env_x", "fluxes_env_y", "rate_NaKATP",
     "Jmem", "Jgj", "Jn", "I_mem", "Jc", "Emc", "dvm",
-    "J_cell_x", "J_cell_y", "E_cell_x", "E_cell_y", "sigma_cell", "cenv_uniform",
+    "J_cell_x", "J_cell_y", "E_cell_x", "E_cell_y", "sigma_cell", "cenv_uniform", "vm_cell",
 ]
 
 
@@ -90,12 +91,32 @@ class StateHost(C.Structure):
     _fields_ = [(f, _dp) for f in STATE_FIELDS]
 
 
+class WindowInfo(C.Structure):
+    _fields_ = [
+        ("base", C.c_void_p), ("bytes", C.c_uint64), ("ipc_handle", C.c_uint8 * 64),
+        ("off_cc_mid", C.c_uint64 * 2), ("off_vm_cell", C.c_uint64 * 2), ("off_flux", C.c_uint64),
+        ("off_cc_env", C.c_uint64 * 2), ("off_v_raw", C.c_uint64), ("off_flags", C.c_uint64),
+        ("n_cells", C.c_int32), ("n_env", C.c_int32), ("nx", C.c_int32), ("n_ions", C.c_int32),
+    ]
+
+
+class Neighbor(C.Structure):
+    _fields_ = [
+        ("side", C.c_int32), ("same_process", C.c_int32), ("info", WindowInfo),
+        ("n_send_cells", C.c_int32), ("send_cells", _ip), ("recv_cell0", C.c_int32),
+        ("n_send_flux", C.c_int32), ("send_flux", _ip), ("recv_slot0", C.c_int32),
+        ("cc_rows", C.c_int32), ("cc_src_row0", C.c_int32), ("cc_dst_row0", C.c_int32),
+        ("v_rows", C.c_int32), ("v_src_row0", C.c_int32), ("v_dst_row0", C.c_int32),
+    ]
+
+
 # Every symbol include/betse_b200.h declares (checked against the header in the tests).
 SYMBOLS = [
     "betse_abi_version", "betse_device_count", "betse_create", "betse_destroy", "betse_last_error",
     "betse_create_error", "betse_upload_state", "betse_set_schedule", "betse_step",
-    "betse_step_profile", "betse_kernel_name", "betse_download_sample", "betse_device_buffer",
-    "betse_step_phase", "betse_stream", "betse_sync", "betse_update_v",
+    "betse_step_profile", "betse_kernel_name", "betse_download_sample",
+    "betse_step_phase", "betse_stream", "betse_sync", "betse_update_v", "betse_update_v_phase",
+    "betse_set_row_ranges", "betse_window", "betse_attach_neighbor", "betse_exchange",
 ]
 
 _lib = None
@@ -128,7 +149,11 @@ def load(build_if_missing=True):
     lib.betse_kernel_name.argtypes = [C.c_int]
     lib.betse_kernel_name.restype = C.c_char_p
     lib.betse_download_sample.argtypes = [vp, C.POINTER(StateHost)]
-    lib.betse_device_buffer.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    lib.betse_update_v_phase.argtypes = [vp, C.c_int]
+    lib.betse_set_row_ranges.argtypes = [vp] + [C.c_int] * 6
+    lib.betse_window.argtypes = [vp, C.POINTER(WindowInfo)]
+    lib.betse_attach_neighbor.argtypes = [vp, C.POINTER(Neighbor)]
+    lib.betse_exchange.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     lib.betse_step_phase.argtypes = [vp, C.c_int, C.c_int]
     lib.betse_stream.argtypes = [vp, C.POINTER(vp)]
     lib.betse_sync.argtypes = [vp, C.POINTER(C.c_uint32)]

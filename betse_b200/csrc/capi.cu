@@ -12,6 +12,7 @@
 
 #include "../../include/betse_b200.h"
 #include "kparams.cuh"
+#include "xchg.cuh"
 
 // launchers (kernels.cu)
 void launch_mem(int ni, const KParams& P, const KArrays& A, int n_ctas, int cur, int diag, cudaStream_t st);
@@ -24,10 +25,11 @@ void launch_envmix(int ni, const KParams& P, const KArrays& A, int cur, cudaStre
 void launch_diag(int ni, const KParams& P, const KArrays& A, int n_ctas, int newb, cudaStream_t st);
 void launch_expand_vm(const KParams& P, const KArrays& A, int M, int C, int cur, cudaStream_t st);
 cudaError_t prepare_kernels(int ni);
+void launch_xchg(const KParams& P, const KArrays& A, const XPlan& X, int which, int buf, int mode, cudaStream_t st);
 
-enum { K_ION = 0, K_MEM, K_ENVACC, K_FIELD, K_ENVMIX, K_SMOOTH, K_DIAG, K_EXPAND };
+enum { K_ION = 0, K_MEM, K_ENVACC, K_FIELD, K_ENVMIX, K_SMOOTH, K_DIAG, K_XCHG };
 static const char* kKernelNames[BETSE_NKERNELS] = {
-    "k_ion", "k_mem", "k_envacc", "k_field", "k_envmix", "k_ion_smooth", "k_diag", "k_expand_vm"};
+    "k_ion", "k_mem", "k_envacc", "k_field", "k_envmix", "k_ion_smooth", "k_diag", "k_xchg"};
 
 struct betse_ctx {
     int device = 0;
@@ -38,6 +40,11 @@ struct betse_ctx {
     int cur = 0;
     int C = 0, Co = 0, M = 0, Mo = 0, E = 0, ny = 0, nx = 0, I = 0, n_ctas = 0, n_tiles = 0, n_slots = 0;
     bool diag_valid = false;
+    // exchange window (every buffer a neighbouring rank writes) and the halo-exchange plan
+    char* win = nullptr;
+    betse_window_info winfo;
+    XPlan X;
+    std::vector<void*> ipc_opened;
     std::string err;
     std::vector<void*> allocs;
     // CUDA graphs of one plain step, for cur = 0 and cur = 1
@@ -188,6 +195,7 @@ extern "C" void betse_destroy(betse_ctx* ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     destroy_graphs(ctx);
     if (ctx->ev_init) for (auto& e : ctx->ev) cudaEventDestroy(e);
+    for (void* p : ctx->ipc_opened) cudaIpcCloseMemHandle(p);
     for (void* p : ctx->allocs) cudaFree(p);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -326,10 +334,35 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
     // ---- state
     const size_t IC = (size_t)I * C, IE = (size_t)I * E, IM = (size_t)I * Mo;
     if ((r = dev_alloc(ctx, &A.cc_cells, IC))) return r;
-    for (int b = 0; b < 2; ++b) {
-        if ((r = dev_alloc(ctx, &A.cc_mid[b], IC))) return r;
-        if ((r = dev_alloc(ctx, &A.vm_cell[b], C))) return r;
-        if ((r = dev_alloc(ctx, &A.cc_env[b], hp->is_ecm ? IE : 1))) return r;
+    {
+        // the exchange window: one allocation (>= 4 MiB so that it is never sub-allocated and its
+        // IPC handle maps exactly this block), carved at 256-byte boundaries
+        betse_window_info& W = ctx->winfo;
+        memset(&W, 0, sizeof W);
+        size_t off = 0;
+        auto carve = [&](size_t n_doubles) { size_t o = off; off += ((n_doubles * 8 + 255) / 256) * 256; return o; };
+        const size_t nIE = hp->is_ecm ? IE : 1, nSl = hp->is_ecm ? (size_t)ctx->n_slots * I : 1;
+        for (int b = 0; b < 2; ++b) { W.off_cc_mid[b] = carve(IC); W.off_vm_cell[b] = carve(C); W.off_cc_env[b] = carve(nIE); }
+        W.off_flux = carve(nSl);
+        W.off_v_raw = carve(E);
+        W.off_flags = carve(16);
+        if (off < ((size_t)4 << 20)) off = (size_t)4 << 20;
+        W.bytes = off;
+        if ((r = dev_alloc(ctx, &ctx->win, off))) return r;
+        W.base = ctx->win;
+        W.n_cells = C; W.n_env = E; W.nx = ctx->nx; W.n_ions = I;
+        for (int b = 0; b < 2; ++b) {
+            A.cc_mid[b] = (double*)(ctx->win + W.off_cc_mid[b]);
+            A.vm_cell[b] = (double*)(ctx->win + W.off_vm_cell[b]);
+            A.cc_env[b] = (double*)(ctx->win + W.off_cc_env[b]);
+        }
+        A.flux_slots = (double*)(ctx->win + W.off_flux);
+        A.v_raw = (double*)(ctx->win + W.off_v_raw);
+        memset(&ctx->X, 0, sizeof(XPlan));
+        ctx->X.my_flags = (unsigned long long*)(ctx->win + W.off_flags);
+        ctx->X.epoch = ctx->X.my_flags + 4;
+        ctx->X.done_ctr = (unsigned int*)(ctx->X.my_flags + 6);
+        { const char* e = getenv("BETSE_XCHG_TIMEOUT_MS"); ctx->X.timeout_ns = (unsigned long long)(e ? atoll(e) : 10000) * 1000000ull; }
     }
     if ((r = dev_alloc(ctx, &A.gjopen, Mo))) return r;
     if ((r = dev_alloc(ctx, (double**)&A.Dm, IM))) return r;
@@ -337,10 +370,8 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
     if ((r = dev_alloc(ctx, &A.E_x, E))) return r;
     if ((r = dev_alloc(ctx, &A.E_y, E))) return r;
     if ((r = dev_alloc(ctx, &A.v_env, E))) return r;
-    if ((r = dev_alloc(ctx, &A.v_raw, E))) return r;
     if ((r = dev_alloc(ctx, &A.rho_env, E))) return r;
     if ((r = dev_alloc(ctx, &A.rho_cells, C))) return r;
-    if ((r = dev_alloc(ctx, &A.flux_slots, hp->is_ecm ? (size_t)ctx->n_slots * I : 1))) return r;
     if ((r = dev_alloc(ctx, &A.cenv_u, 16))) return r;
     if ((r = dev_alloc(ctx, &A.cenv_part, (size_t)ctx->n_tiles * 8))) return r;
     if ((r = dev_alloc(ctx, &A.status, 1))) return r;
@@ -434,7 +465,9 @@ extern "C" int betse_upload_state(betse_ctx* ctx, const betse_state_host* s)
     }
     UP(A.gjopen, s->gjopen, Mo);
     UP(A.Dm, s->Dm_cells, IM);
-    if (s->vm) {
+    if (s->vm_cell) {
+        CK(cudaMemcpyAsync(A.vm_cell[cur], s->vm_cell, (size_t)C * sizeof(double), cudaMemcpyHostToDevice, st));
+    } else if (s->vm) {
         // default mode: vm = vm_cell[cell] - Phi_b[map_mem2ecm] (sim.py:2029) -> keep the per-cell part
         std::vector<double> vc(C, 0.0);
         std::vector<int> ptr(ctx->Co + 1), m2e;
@@ -525,8 +558,14 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
 static void enqueue_step(betse_ctx* ctx, int diag, cudaEvent_t* evs)
 {
     if (evs) cudaEventRecord(evs[0], ctx->stream);
+    const bool nbr = ctx->X.n_nbr > 0;
+    const int nxt = ctx->cur ^ 1;
     enqueue_phase(ctx, 0, diag, evs);
+    if (nbr) launch_xchg(ctx->P, ctx->A, ctx->X, BETSE_XCHG_X1, nxt, BETSE_XCHG_PUSH | BETSE_XCHG_WAIT, ctx->stream);
+    if (evs) cudaEventRecord(evs[7], ctx->stream);
     enqueue_phase(ctx, 1, diag, evs);
+    if (nbr) launch_xchg(ctx->P, ctx->A, ctx->X, BETSE_XCHG_X2, nxt, BETSE_XCHG_PUSH | BETSE_XCHG_WAIT, ctx->stream);
+    if (evs) cudaEventRecord(evs[8], ctx->stream);
     enqueue_phase(ctx, 2, diag, evs);
 }
 
@@ -582,16 +621,29 @@ extern "C" int betse_step(betse_ctx* ctx, int nsteps, int flags, uint32_t* statu
     return read_status(ctx, status_out);
 }
 
+extern "C" int betse_update_v_phase(betse_ctx* ctx, int phase)
+{
+    if (!ctx || phase < 0 || phase > 1) return 2;
+    CK(cudaSetDevice(ctx->device));
+    if (phase == 0) {
+        launch_cell_charge(ctx->P, ctx->A, ctx->Co, ctx->cur, ctx->stream);
+        if (ctx->hp.is_ecm) launch_envacc(ctx->I, ctx->P, ctx->A, ctx->E, ctx->cur, 0, ctx->stream);
+    } else if (ctx->hp.is_ecm) launch_field(ctx->P, ctx->A, ctx->ny, ctx->nx, ctx->stream);
+    CK(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int betse_update_v(betse_ctx* ctx)
 {
     if (!ctx) return 2;
-    CK(cudaSetDevice(ctx->device));
-    launch_cell_charge(ctx->P, ctx->A, ctx->Co, ctx->cur, ctx->stream);
-    if (ctx->hp.is_ecm) {
-        launch_envacc(ctx->I, ctx->P, ctx->A, ctx->E, ctx->cur, 0, ctx->stream);
-        launch_field(ctx->P, ctx->A, ctx->ny, ctx->nx, ctx->stream);
+    int r;
+    if ((r = betse_update_v_phase(ctx, 0))) return r;
+    if (ctx->X.n_nbr > 0) {
+        // ghost-cell Vmem / concentrations and the env halo rows of the CURRENT buffers
+        launch_xchg(ctx->P, ctx->A, ctx->X, BETSE_XCHG_X1, ctx->cur, BETSE_XCHG_PUSH | BETSE_XCHG_WAIT, ctx->stream);
+        launch_xchg(ctx->P, ctx->A, ctx->X, BETSE_XCHG_X2, ctx->cur, BETSE_XCHG_PUSH | BETSE_XCHG_WAIT, ctx->stream);
     }
-    CK(cudaGetLastError());
+    if ((r = betse_update_v_phase(ctx, 1))) return r;
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
@@ -660,13 +712,17 @@ extern "C" int betse_step_profile(betse_ctx* ctx, int nsteps, float* total_ms,
                 if (ctx->hp.sharpness < 1.0) { CK(cudaEventElapsedTime(&d, ctx->ev[1], ctx->ev[2])); acc[K_SMOOTH] += d; cnt[K_SMOOTH]++; }
             }
             CK(cudaEventElapsedTime(&d, ctx->ev[2], ctx->ev[3])); acc[K_MEM] += d; cnt[K_MEM]++;
-            CK(cudaEventElapsedTime(&d, ctx->ev[3], ctx->ev[4]));
+            if (ctx->X.n_nbr > 0) {      // both exchange kernels (push + wait for the neighbours)
+                CK(cudaEventElapsedTime(&d, ctx->ev[3], ctx->ev[7])); acc[K_XCHG] += d;
+                CK(cudaEventElapsedTime(&d, ctx->ev[4], ctx->ev[8])); acc[K_XCHG] += d; cnt[K_XCHG]++;
+            }
+            CK(cudaEventElapsedTime(&d, ctx->ev[7], ctx->ev[4]));
             if (ecm) { acc[K_ENVACC] += d; cnt[K_ENVACC]++; } else { acc[K_ENVMIX] += d; cnt[K_ENVMIX]++; }
-            if (ecm) { CK(cudaEventElapsedTime(&d, ctx->ev[4], ctx->ev[5])); acc[K_FIELD] += d; cnt[K_FIELD]++; }
+            if (ecm) { CK(cudaEventElapsedTime(&d, ctx->ev[8], ctx->ev[5])); acc[K_FIELD] += d; cnt[K_FIELD]++; }
         }
         for (int k = 0; k < BETSE_NKERNELS; ++k) {
             kernel_ms[k] = cnt[k] ? (float)(acc[k] / cnt[k]) : 0.f;
-            if (kernel_launches) kernel_launches[k] = cnt[k] ? 1 : 0;   // launches per step
+            if (kernel_launches) kernel_launches[k] = cnt[k] ? (k == K_XCHG ? 2 : 1) : 0;   // launches per step
         }
     }
     ctx->diag_valid = false;
@@ -724,22 +780,88 @@ extern "C" int betse_download_sample(betse_ctx* ctx, betse_state_host* s)
     return 0;
 }
 
-extern "C" int betse_device_buffer(betse_ctx* ctx, int which, void** dev_ptr, size_t* bytes)
+extern "C" int betse_set_row_ranges(betse_ctx* ctx, int yi0, int yi1, int ya0, int ya1, int yf0, int yf1)
 {
-    if (!ctx || !dev_ptr) return 2;
-    const KArrays& A = ctx->A;
-    const int nxt = ctx->cur ^ 1;
-    size_t b = 0; void* p = nullptr;
-    switch (which) {
-        case BETSE_BUF_CC_MID: p = A.cc_mid[nxt]; b = (size_t)ctx->I * ctx->C * 8; break;
-        case BETSE_BUF_VM_CELL: p = A.vm_cell[nxt]; b = (size_t)ctx->C * 8; break;
-        case BETSE_BUF_FLUX: p = A.flux_slots; b = (size_t)ctx->n_slots * ctx->I * 8; break;
-        case BETSE_BUF_CC_ENV: p = A.cc_env[nxt]; b = (size_t)ctx->I * ctx->E * 8; break;
-        case BETSE_BUF_V_RAW: p = A.v_raw; b = (size_t)ctx->E * 8; break;
-        case BETSE_BUF_CC_ENV_CUR: p = A.cc_env[ctx->cur]; b = (size_t)ctx->I * ctx->E * 8; break;
-        default: return fail(ctx, "unknown buffer id");
+    if (!ctx) return 2;
+    const int ny = ctx->ny;
+    if (yi0 < 0 || yi1 > ny || ya0 < 0 || ya1 > ny || yf0 < 0 || yf1 > ny || yi0 > yi1 || ya0 > ya1 || yf0 > yf1)
+        return fail(ctx, "row range outside the local grid");
+    KParams& P = ctx->P;
+    P.yi0 = yi0; P.yi1 = yi1; P.ya0 = ya0; P.ya1 = ya1; P.yf0 = yf0; P.yf1 = yf1;
+    destroy_graphs(ctx);
+    return 0;
+}
+
+extern "C" int betse_window(betse_ctx* ctx, betse_window_info* out)
+{
+    if (!ctx || !out) return 2;
+    CK(cudaSetDevice(ctx->device));
+    *out = ctx->winfo;
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, ctx->win);
+    if (e == cudaSuccess) memcpy(out->ipc_handle, &h, sizeof h);
+    else { cudaGetLastError(); memset(out->ipc_handle, 0, sizeof out->ipc_handle); }   // same-process use still works
+    return 0;
+}
+
+extern "C" int betse_attach_neighbor(betse_ctx* ctx, const betse_neighbor* nb)
+{
+    if (!ctx || !nb) return 2;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->X.n_nbr >= 2) return fail(ctx, "a strip has at most two neighbours");
+    if (nb->side != 0 && nb->side != 1) return fail(ctx, "neighbor.side must be 0 or 1");
+    if (!ctx->hp.is_ecm) return fail(ctx, "domain decomposition needs extracellular spaces (no-ECM tissues run as replicas)");
+    if (ctx->P.has_phi) return fail(ctx, "domain decomposition does not support a boundary-voltage potential (Phi_b)");
+    const betse_window_info& W = nb->info;
+    if (W.n_ions != ctx->I || W.nx != ctx->nx) return fail(ctx, "neighbour window has different n_ions / nx");
+    char* base = (char*)W.base;
+    if (!nb->same_process) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, W.ipc_handle, sizeof h);
+        void* p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->ipc_opened.push_back(p);
+        base = (char*)p;
     }
-    *dev_ptr = p;
-    if (bytes) *bytes = b;
+    if (!base) return fail(ctx, "neighbour window pointer is null");
+    if (nb->recv_cell0 < 0 || nb->recv_cell0 + nb->n_send_cells > W.n_cells) return fail(ctx, "ghost-cell range outside the neighbour");
+    if (nb->cc_rows < 0 || nb->v_rows < 0 || (nb->cc_dst_row0 + nb->cc_rows) * W.nx > W.n_env ||
+        (nb->v_dst_row0 + nb->v_rows) * W.nx > W.n_env || (nb->cc_src_row0 + nb->cc_rows) > ctx->ny ||
+        (nb->v_src_row0 + nb->v_rows) > ctx->ny) return fail(ctx, "row block outside the grid");
+    for (int j = 0; j < nb->n_send_cells; ++j)
+        if (nb->send_cells[j] < 0 || nb->send_cells[j] >= ctx->Co) return fail(ctx, "send_cells entry is not an owned cell");
+    for (int j = 0; j < nb->n_send_flux; ++j)
+        if (nb->send_flux[j] < 0 || nb->send_flux[j] >= ctx->Mo) return fail(ctx, "send_flux entry is not an owned membrane");
+    XNbr& x = ctx->X.nb[ctx->X.n_nbr];
+    memset(&x, 0, sizeof x);
+    for (int b = 0; b < 2; ++b) {
+        x.cc_mid[b] = (double*)(base + W.off_cc_mid[b]);
+        x.vm_cell[b] = (double*)(base + W.off_vm_cell[b]);
+        x.cc_env[b] = (double*)(base + W.off_cc_env[b]);
+    }
+    x.flux = (double*)(base + W.off_flux);
+    x.v_raw = (double*)(base + W.off_v_raw);
+    x.flags = (unsigned long long*)(base + W.off_flags);
+    x.Cn = W.n_cells; x.En = W.n_env; x.side = nb->side;
+    x.n_send_cells = nb->n_send_cells; x.recv_cell0 = nb->recv_cell0;
+    x.n_send_flux = nb->n_send_flux; x.recv_slot0 = nb->recv_slot0;
+    x.cc_rows = nb->cc_rows; x.cc_src_row0 = nb->cc_src_row0; x.cc_dst_row0 = nb->cc_dst_row0;
+    x.v_rows = nb->v_rows; x.v_src_row0 = nb->v_src_row0; x.v_dst_row0 = nb->v_dst_row0;
+    int r;
+    if ((r = dev_upload(ctx, (int**)&x.send_cells, nb->send_cells, nb->n_send_cells))) return r;
+    if ((r = dev_upload(ctx, (int**)&x.send_flux, nb->send_flux, nb->n_send_flux))) return r;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->X.n_nbr++;
+    destroy_graphs(ctx);
+    return 0;
+}
+
+extern "C" int betse_exchange(betse_ctx* ctx, int which, int buf_next, int mode)
+{
+    if (!ctx || (which != BETSE_XCHG_X1 && which != BETSE_XCHG_X2) || !(mode & 3)) return 2;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->X.n_nbr == 0) return 0;
+    launch_xchg(ctx->P, ctx->A, ctx->X, which, buf_next ? (ctx->cur ^ 1) : ctx->cur, mode, ctx->stream);
+    CK(cudaGetLastError());
     return 0;
 }

@@ -55,7 +55,8 @@ class TissueEngine:
         self.is_ecm = bool(self.p["is_ecm"])
         self.mem_to_cells = capi.as_i32(mesh["mem_to_cells"])
         self.cell_mem_ptr = capi.as_i32(mesh["cell_mem_ptr"])
-        self.C = len(self.cell_mem_ptr) - 1
+        self.Co = len(self.cell_mem_ptr) - 1                      # owned cells
+        self.C = int((partition or {}).get("n_cells", self.Co))   # + ghost cells (domain decomposition)
         self.M = len(self.mem_to_cells)
         gs = np.asarray(mesh["grid_shape"]).astype(int)
         self.ny, self.nx = int(gs[0]), int(gs[1])
@@ -123,7 +124,9 @@ class TissueEngine:
         m.delta = float(mesh["delta"])
         m.gj_len = float(mesh["gj_len"])
         m.ecm_vol = float(mesh["ecm_vol"]) if "ecm_vol" in mesh else float(p["cell_height"]) * m.delta ** 2
-        if "memSa_per_envSquare" in mesh:
+        if "memsa_mean" in mesh:          # a strip of a decomposed tissue carries the global mean
+            m.memsa_mean = float(mesh["memsa_mean"])
+        elif "memSa_per_envSquare" in mesh:
             msa = np.asarray(mesh["memSa_per_envSquare"], dtype=np.float64)
             m.memsa_mean = float(msa[np.asarray(mesh["map_mem2ecm"]).astype(np.int64)].mean())
         else:
@@ -227,7 +230,9 @@ class TissueEngine:
         starts = self.cell_mem_ptr[:-1]
         if "cc_cells" in state:
             put("cc_cells", state["cc_cells"], I * Cn)
-        if "cc_at_mem" in state:
+        if "cc_mid" in state:           # per-cell form (incl. ghost cells), partition.py
+            put("cc_at_mem_cell", state["cc_mid"], I * Cn)
+        elif "cc_at_mem" in state:
             cam = np.asarray(state["cc_at_mem"], dtype=float)
             put("cc_at_mem_cell", cam[:, starts] if cam.shape[1] == M else cam, I * Cn)
         if self.is_ecm:
@@ -250,7 +255,9 @@ class TissueEngine:
             put("cenv_uniform", ce.reshape(I, -1)[:, 0], I)
         if "Phi_b" in state:
             put("Phi_b", state["Phi_b"], E)
-        if "vm" in state:
+        if "vm_cell" in state:
+            put("vm_cell", state["vm_cell"], Cn)
+        elif "vm" in state:
             put("vm", state["vm"], M)
         if "gjopen" in state:
             put("gjopen", state["gjopen"], M)
@@ -362,11 +369,41 @@ class TissueEngine:
             out["cc_env"] = np.repeat(cenv[:, None], M, axis=1)   # the reference keeps [I,M] (sim.py:487-490)
         return out
 
-    def device_buffer(self, which):
-        p = C.c_void_p()
-        n = C.c_size_t()
-        self._check(self.lib.betse_device_buffer(self.ctx, which, C.byref(p), C.byref(n)), "betse_device_buffer")
-        return p.value, n.value
+    # ------------------------------------------------------------------ domain decomposition
+    def window(self):
+        """This rank's exchange window (include/betse_b200.h: betse_window_info)."""
+        w = capi.WindowInfo()
+        self._check(self.lib.betse_window(self.ctx, C.byref(w)), "betse_window")
+        return w
+
+    def set_row_ranges(self, yi, ya, yf):
+        self._check(self.lib.betse_set_row_ranges(self.ctx, int(yi[0]), int(yi[1]), int(ya[0]), int(ya[1]),
+                                                  int(yf[0]), int(yf[1])), "betse_set_row_ranges")
+
+    def attach_neighbor(self, side, info, plan, same_process):
+        """``plan``: dict of the send lists / row blocks towards that neighbour (partition.py)."""
+        nb = capi.Neighbor()
+        nb.side, nb.same_process, nb.info = int(side), int(bool(same_process)), info
+        sc, sf = capi.as_i32(plan["send_cells"]), capi.as_i32(plan["send_flux"])
+        nb.n_send_cells, nb.send_cells, nb.recv_cell0 = len(sc), capi.ptr_i32(sc), int(plan["recv_cell0"])
+        nb.n_send_flux, nb.send_flux, nb.recv_slot0 = len(sf), capi.ptr_i32(sf), int(plan["recv_slot0"])
+        nb.cc_rows, nb.cc_src_row0, nb.cc_dst_row0 = (int(x) for x in plan["cc_rows"])
+        nb.v_rows, nb.v_src_row0, nb.v_dst_row0 = (int(x) for x in plan["v_rows"])
+        self._check(self.lib.betse_attach_neighbor(self.ctx, C.byref(nb)), "betse_attach_neighbor")
+
+    def exchange(self, which, buf_next, mode):
+        self._check(self.lib.betse_exchange(self.ctx, int(which), int(bool(buf_next)), int(mode)), "betse_exchange")
+
+    def step_phase(self, phase, diag=False):
+        self._check(self.lib.betse_step_phase(self.ctx, int(phase), capi.STEP_DIAG if diag else 0), "betse_step_phase")
+
+    def update_V_phase(self, phase):
+        self._check(self.lib.betse_update_v_phase(self.ctx, int(phase)), "betse_update_v_phase")
+
+    def sync(self):
+        st = C.c_uint32(0)
+        self._check(self.lib.betse_sync(self.ctx, C.byref(st)), "betse_sync")
+        return int(st.value)
 
     def close(self):
         if getattr(self, "ctx", None):

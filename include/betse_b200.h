@@ -134,6 +134,7 @@ typedef struct betse_state_host {
     double *Jmem, *Jgj, *Jn, *I_mem, *Jc, *Emc, *dvm;   /* [M] */
     double *J_cell_x, *J_cell_y, *E_cell_x, *E_cell_y, *sigma_cell;  /* [C] */
     double *cenv_uniform;    /* [I]   no-ECM bath concentrations (download only)          */
+    double *vm_cell;         /* [C]   per-cell Vmem incl. ghost cells (upload only; overrides vm)  */
 } betse_state_host;
 
 #define BETSE_STATUS_NAN_VM     1u  /* stb.check_v would raise          */
@@ -182,18 +183,69 @@ const char *betse_kernel_name(int k);
 /* Replaces: the attribute reads of Simulator.write2storage (sim.py:1789-1884). */
 int  betse_download_sample(betse_ctx *ctx, betse_state_host *state);
 
-/* Multi-GPU plumbing: raw device pointers of the exchange buffers so that the
- * host side can hand them to NCCL / map them for peer access.  which: see BETSE_BUF_*. */
-#define BETSE_BUF_CC_MID   0  /* [I,C_local] next-step cc_mid (ghost cells are written by the exchange) */
-#define BETSE_BUF_VM_CELL  1  /* [C_local]                                                              */
-#define BETSE_BUF_FLUX     2  /* [n_flux_slots,I] membrane->env exchange slots                          */
-#define BETSE_BUF_CC_ENV   3  /* [I,E_local] next-step cc_env                                           */
-#define BETSE_BUF_V_RAW    4  /* [E_local]                                                              */
-#define BETSE_BUF_CC_ENV_CUR 5
-int  betse_device_buffer(betse_ctx *ctx, int which, void **dev_ptr, size_t *bytes);
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU: the tissue is cut into strips of env-grid rows; each rank owns the
+ * cells whose centre lies in its rows.  The reference has no counterpart (one process, one
+ * thread); what crosses a strip edge every timestep is exactly what the reference's index arrays
+ * couple: gap-junction partners (cells.nn_i, cells.py:1498-1533), membrane->env-square exchange
+ * (cells.map_mem2ecm, cells.py:1758) and the env-grid stencils (update_ecm, sim.py:2209-2254;
+ * gaussian_filter + gradient, ion_current.py:101-109).
+ *
+ * Every buffer a neighbour writes lives in ONE device allocation per ctx, the "window"; ranks
+ * exchange its CUDA-IPC handle (or the raw pointer when they share a process) and then PUSH their
+ * boundary values straight into the neighbour's window with ordinary stores over NVLink, followed
+ * by a release-store of an epoch flag; the consumer spins on its own flag (bounded; a timeout sets
+ * BETSE_STATUS_XCHG_TIMEOUT).  No host round trip and no NCCL call on the data path.
+ * Exchange points of one step:  X1 after the membrane/cell kernel (ghost-cell concentrations and
+ * Vmem + membrane fluxes into squares the neighbour owns), X2 after the env accumulation (env
+ * concentration rows + raw env voltage rows). */
+#define BETSE_STATUS_XCHG_TIMEOUT 8u   /* a neighbour's flag did not arrive (multi-GPU only) */
+
+#define BETSE_XCHG_X1 0
+#define BETSE_XCHG_X2 1
+#define BETSE_XCHG_PUSH 1   /* mode bits of betse_exchange */
+#define BETSE_XCHG_WAIT 2
+
+typedef struct betse_window_info {
+    void    *base;             /* device pointer of the window in THIS process                  */
+    uint64_t bytes;
+    uint8_t  ipc_handle[64];   /* cudaIpcMemHandle_t of the window                               */
+    uint64_t off_cc_mid[2];    /* [I,C] x2  byte offsets inside the window                       */
+    uint64_t off_vm_cell[2];   /* [C]   x2                                                       */
+    uint64_t off_flux;         /* [n_flux_slots, I]                                              */
+    uint64_t off_cc_env[2];    /* [I,E] x2                                                       */
+    uint64_t off_v_raw;        /* [E]                                                            */
+    uint64_t off_flags;        /* uint64 [2 exchange points][2 sides]                            */
+    int32_t  n_cells, n_env, nx, n_ions;   /* leading dimensions of the arrays above             */
+} betse_window_info;
+
+/* One neighbouring strip.  side 0 = the strip below (smaller y), 1 = above. */
+typedef struct betse_neighbor {
+    int32_t side;
+    int32_t same_process;          /* 1: info.base is directly usable; 0: open info.ipc_handle   */
+    betse_window_info info;        /* the NEIGHBOUR's window                                     */
+    /* X1: my owned cells that are ghosts there, and my membranes whose env square it owns */
+    int32_t n_send_cells;  const int32_t *send_cells;  int32_t recv_cell0;   /* first ghost index there */
+    int32_t n_send_flux;   const int32_t *send_flux;   int32_t recv_slot0;   /* first remote slot there */
+    /* X2: contiguous row blocks (local row numbers on each side) */
+    int32_t cc_rows, cc_src_row0, cc_dst_row0;     /* cc_env rows                                */
+    int32_t v_rows,  v_src_row0,  v_dst_row0;      /* raw env voltage rows                       */
+} betse_neighbor;
+
+/* Kernel row ranges of a strip (local rows): ion transport [yi0,yi1), env accumulation
+ * [ya0,ya1), field E rows [yf0,yf1).  Single GPU: all [0,ny). */
+int  betse_set_row_ranges(betse_ctx *ctx, int yi0, int yi1, int ya0, int ya1, int yf0, int yf1);
+int  betse_window(betse_ctx *ctx, betse_window_info *out);
+int  betse_attach_neighbor(betse_ctx *ctx, const betse_neighbor *nb);
+/* Enqueue one exchange point on the ctx's stream.  buf_next = 1: the double-buffered arrays are
+ * the ones the running step is producing (cur^1); 0: the current ones (initial exchange). */
+int  betse_exchange(betse_ctx *ctx, int which, int buf_next, int mode);
 /* A step split at the exchange points: phase 0 = env transport + membrane/cell update,
- * phase 1 = env accumulation, phase 2 = env field.  betse_step == phases 0,1,2. */
+ * phase 1 = env accumulation, phase 2 = env field (+ buffer flip).  betse_step on a ctx with
+ * neighbours == phase 0, X1, phase 1, X2, phase 2 (captured in one CUDA graph). */
 int  betse_step_phase(betse_ctx *ctx, int phase, int flags);
+/* update_V split the same way: phase 0 = cell charge + env charge, phase 1 = env field. */
+int  betse_update_v_phase(betse_ctx *ctx, int phase);
 int  betse_stream(betse_ctx *ctx, void **cuda_stream);
 int  betse_sync(betse_ctx *ctx, uint32_t *status_out);
 
