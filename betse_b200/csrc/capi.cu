@@ -16,7 +16,7 @@
 
 // launchers (kernels.cu)
 void launch_mem(int ni, const KParams& P, const KArrays& A, int n_ctas, int cur, int diag, cudaStream_t st);
-void launch_ion(int ni, const KParams& P, const KArrays& A, int ny, int nx, int cur, int diag, cudaStream_t st);
+void launch_ion(const KParams& P, const KArrays& A, int nx, int cur, int diag, int ion0, int n, cudaStream_t st);
 void launch_ion_smooth(int ni, const KParams& P, const KArrays& A, int ny, int nx, int nxt, cudaStream_t st);
 void launch_envacc(int ni, const KParams& P, const KArrays& A, int E, int nxt, int apply, cudaStream_t st);
 void launch_cell_charge(const KParams& P, const KArrays& A, int C, int cur, cudaStream_t st);
@@ -34,6 +34,9 @@ static const char* kKernelNames[BETSE_NKERNELS] = {
 struct betse_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;          // env transport of the non-Ca ions, next to k_mem
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool overlap = true;
     KParams P;
     KArrays A;
     betse_params hp;          // last host params
@@ -195,6 +198,9 @@ extern "C" void betse_destroy(betse_ctx* ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     destroy_graphs(ctx);
     if (ctx->ev_init) for (auto& e : ctx->ev) cudaEventDestroy(e);
+    if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     for (void* p : ctx->ipc_opened) cudaIpcCloseMemHandle(p);
     for (void* p : ctx->allocs) cudaFree(p);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -221,6 +227,10 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
 
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    { const char* e = getenv("BETSE_OVERLAP"); ctx->overlap = !(e && e[0] == '0'); }
     memset(&ctx->A, 0, sizeof(KArrays));
     memset(&ctx->P, 0, sizeof(KParams));
     KArrays& A = ctx->A;
@@ -530,8 +540,22 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
     const KArrays& A = ctx->A;
     const bool ecm = ctx->hp.is_ecm != 0;
     if (phase == 0) {
-        if (ecm) {
-            launch_ion(I, ctx->P, A, ctx->ny, ctx->nx, cur, diag, st);
+        // The membrane kernel reads cc_env[nxt] of Ca only (the Ca-ATPase sees the transported value,
+        // sim.py:1282 after 2254): the Ca row is transported first, the other ions run on a second
+        // stream NEXT TO the membrane kernel (which is latency-bound and leaves issue slots free).
+        const bool overlap = ecm && ctx->overlap && !evs && ctx->hp.sharpness >= 1.0;
+        if (ecm && overlap) {
+            const int iCa = ctx->hp.iCa;
+            if (iCa >= 0) launch_ion(ctx->P, A, ctx->nx, cur, diag, iCa, 1, st);
+            cudaEventRecord(ctx->ev_fork, st);
+            cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0);
+            if (iCa >= 0) {
+                launch_ion(ctx->P, A, ctx->nx, cur, diag, 0, iCa, ctx->stream2);
+                launch_ion(ctx->P, A, ctx->nx, cur, diag, iCa + 1, I - iCa - 1, ctx->stream2);
+            } else launch_ion(ctx->P, A, ctx->nx, cur, diag, 0, I, ctx->stream2);
+            cudaEventRecord(ctx->ev_join, ctx->stream2);
+        } else if (ecm) {
+            launch_ion(ctx->P, A, ctx->nx, cur, diag, 0, I, st);
             if (evs) cudaEventRecord(evs[1], st);
             if (ctx->hp.sharpness < 1.0) {
                 launch_ion_smooth(I, ctx->P, A, ctx->ny, ctx->nx, nxt, st);
@@ -541,6 +565,7 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
         } else if (evs) cudaEventRecord(evs[1], st);
         if (evs) cudaEventRecord(evs[2], st);
         launch_mem(I, ctx->P, A, ctx->n_ctas, cur, diag, st);
+        if (overlap) cudaStreamWaitEvent(st, ctx->ev_join, 0);
         if (evs) cudaEventRecord(evs[3], st);
     } else if (phase == 1) {
         if (ecm) launch_envacc(I, ctx->P, A, ctx->E, nxt, 1, st);

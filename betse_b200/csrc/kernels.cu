@@ -409,90 +409,80 @@ __global__ void k_envmix(const __grid_constant__ KParams P, const KArrays A, con
 // [yi0, yi1) are produced.
 #define IT_X 32
 #define IT_Y 16
-template <int NI>
+// blockIdx.z selects the ion: ions [ion0 + z] (a CTA per ion and tile keeps small strips busy and
+// lets the Ca row, which the Ca-ATPase reads after transport, run ahead of the others).
 __global__ void __launch_bounds__(256)
-k_ion(const __grid_constant__ KParams P, const KArrays A, const int cur, const int diag)
+k_ion(const __grid_constant__ KParams P, const KArrays A, const int cur, const int diag, const int ion0)
 {
     __shared__ double sC[IT_Y + 4][IT_X + 4];
     __shared__ double sFx[IT_Y + 2][IT_X + 3], sFy[IT_Y + 2][IT_X + 3];
-    __shared__ double sEx[IT_Y + 2][IT_X + 3], sEy[IT_Y + 2][IT_X + 3];
     const int nx = P.nx, ny = P.ny;
     const int E = nx * ny;
     const int tx0 = blockIdx.x * IT_X, ty0 = P.yi0 + blockIdx.y * IT_Y;
     const int tid = threadIdx.x;
     const int gny = P.ny_global;
     const double inv_d = P.inv_delta, inv_2d = P.inv_2delta;
+    const int i = ion0 + blockIdx.z;
+    const double* __restrict__ c = A.cc_env[cur] + i * E;
+    const double* __restrict__ D = A.Denv + i * E;
+    const double cb = P.cbound[i];
+    const double zq = P.z[i] * P.q;
 
-    // E field on tile + 1 halo (same for every ion)
+    for (int t = tid; t < (IT_Y + 4) * (IT_X + 4); t += 256) {
+        const int ly = t / (IT_X + 4), lx = t - ly * (IT_X + 4);
+        const int y = ty0 + ly - 2, x = tx0 + lx - 2;
+        double v = 0.0;
+        if (x >= 0 && x < nx && y >= 0 && y < ny) {
+            const int g = y + P.y0;
+            const bool edge = (g == 0 || g == gny - 1 || x == 0 || x == nx - 1);
+            v = edge ? cb : c[y * nx + x];          // Dirichlet fill, sim.py:2211-2217
+        }
+        sC[ly][lx] = v;
+    }
+    __syncthreads();
     for (int t = tid; t < (IT_Y + 2) * (IT_X + 2); t += 256) {
         const int ly = t / (IT_X + 2), lx = t - ly * (IT_X + 2);
         const int y = ty0 + ly - 1, x = tx0 + lx - 1;
-        double ex = 0.0, ey = 0.0;
-        if (x >= 0 && x < nx && y >= 0 && y < ny) { ex = A.E_x[y * nx + x]; ey = A.E_y[y * nx + x]; }
-        sEx[ly][lx] = ex; sEy[ly][lx] = ey;
+        double fx = 0.0, fy = 0.0;
+        if (x >= 0 && x < nx && y >= 0 && y < ny) {
+            const int g = y + P.y0;
+            const int k = y * nx + x;
+            const double cc = sC[ly + 1][lx + 1];
+            double gcx, gcy;                                   // fd.gradient, finitediff.py:1236-1266
+            if (x == 0) gcx = (sC[ly + 1][lx + 2] - cc) * inv_d;
+            else if (x == nx - 1) gcx = (cc - sC[ly + 1][lx]) * inv_d;
+            else gcx = -(sC[ly + 1][lx] - sC[ly + 1][lx + 2]) * inv_2d;
+            if (g == 0) gcy = (sC[ly + 2][lx + 1] - cc) * inv_d;
+            else if (g == gny - 1) gcy = (cc - sC[ly][lx + 1]) * inv_d;
+            else gcy = -(sC[ly][lx + 1] - sC[ly + 2][lx + 1]) * inv_2d;
+            const double Dk = D[k];
+            const double al = (Dk * zq) * P.inv_kbT_sim;       // nernst_planck_flux, sim_toolbox.py:409-411
+            fx = -Dk * gcx - (al * (-A.E_x[k])) * cc;
+            fy = -Dk * gcy - (al * (-A.E_y[k])) * cc;
+            if (diag && ly >= 1 && ly <= IT_Y && lx >= 1 && lx <= IT_X && y < P.yi1) {
+                A.fl_env_x[i * E + k] = fx;
+                A.fl_env_y[i * E + k] = fy;
+            }
+        }
+        sFx[ly][lx] = fx; sFy[ly][lx] = fy;
     }
-#pragma unroll 1
-    for (int i = 0; i < NI; ++i) {
-        const double* __restrict__ c = A.cc_env[cur] + i * E;
-        const double* __restrict__ D = A.Denv + i * E;
-        const double cb = P.cbound[i];
-        const double zq = P.z[i] * P.q;
-        __syncthreads();                       // previous ion's readers of sC / sF are done
-        for (int t = tid; t < (IT_Y + 4) * (IT_X + 4); t += 256) {
-            const int ly = t / (IT_X + 4), lx = t - ly * (IT_X + 4);
-            const int y = ty0 + ly - 2, x = tx0 + lx - 2;
-            double v = 0.0;
-            if (x >= 0 && x < nx && y >= 0 && y < ny) {
-                const int g = y + P.y0;
-                const bool edge = (g == 0 || g == gny - 1 || x == 0 || x == nx - 1);
-                v = edge ? cb : c[y * nx + x];          // Dirichlet fill, sim.py:2211-2217
-            }
-            sC[ly][lx] = v;
-        }
-        __syncthreads();
-        for (int t = tid; t < (IT_Y + 2) * (IT_X + 2); t += 256) {
-            const int ly = t / (IT_X + 2), lx = t - ly * (IT_X + 2);
-            const int y = ty0 + ly - 1, x = tx0 + lx - 1;
-            double fx = 0.0, fy = 0.0;
-            if (x >= 0 && x < nx && y >= 0 && y < ny) {
-                const int g = y + P.y0;
-                const double cc = sC[ly + 1][lx + 1];
-                double gcx, gcy;                                   // fd.gradient, finitediff.py:1236-1266
-                if (x == 0) gcx = (sC[ly + 1][lx + 2] - cc) * inv_d;
-                else if (x == nx - 1) gcx = (cc - sC[ly + 1][lx]) * inv_d;
-                else gcx = -(sC[ly + 1][lx] - sC[ly + 1][lx + 2]) * inv_2d;
-                if (g == 0) gcy = (sC[ly + 2][lx + 1] - cc) * inv_d;
-                else if (g == gny - 1) gcy = (cc - sC[ly][lx + 1]) * inv_d;
-                else gcy = -(sC[ly][lx + 1] - sC[ly + 2][lx + 1]) * inv_2d;
-                const double Dk = D[y * nx + x];
-                const double al = (Dk * zq) * P.inv_kbT_sim;       // nernst_planck_flux, sim_toolbox.py:409-411
-                fx = -Dk * gcx - (al * (-sEx[ly][lx])) * cc;
-                fy = -Dk * gcy - (al * (-sEy[ly][lx])) * cc;
-                if (diag && ly >= 1 && ly <= IT_Y && lx >= 1 && lx <= IT_X && y < P.yi1) {
-                    A.fl_env_x[i * E + y * nx + x] = fx;
-                    A.fl_env_y[i * E + y * nx + x] = fy;
-                }
-            }
-            sFx[ly][lx] = fx; sFy[ly][lx] = fy;
-        }
-        __syncthreads();
-        // fd.divergence(-fx, -fy) with fd.diff's edge rows (finitediff.py:1268-1311)
+    __syncthreads();
+    // fd.divergence(-fx, -fy) with fd.diff's edge rows (finitediff.py:1268-1311)
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int oy = (tid >> 5) + 8 * h, ox = tid & 31;
-            const int y = ty0 + oy, x = tx0 + ox;
-            if (x < nx && y < P.yi1) {
-                const int g = y + P.y0;
-                const int ly = oy + 1, lx = ox + 1;
-                double dx, dy;
-                if (x == 0) dx = ((-sFx[ly][lx]) - (-sFx[ly][lx + 1])) * inv_d;
-                else if (x == nx - 1) dx = ((-sFx[ly][lx - 1]) - (-sFx[ly][lx])) * inv_d;
-                else dx = -((-sFx[ly][lx - 1]) - (-sFx[ly][lx + 1])) * inv_2d;
-                if (g == 0) dy = -((-sFy[ly + 1][lx]) - (-sFy[ly][lx])) * inv_d;
-                else if (g == gny - 1) dy = -((-sFy[ly][lx]) - (-sFy[ly - 1][lx])) * inv_d;
-                else dy = -((-sFy[ly - 1][lx]) - (-sFy[ly + 1][lx])) * inv_2d;
-                A.cc_env[cur ^ 1][i * E + y * nx + x] = sC[oy + 2][ox + 2] + (dx + dy) * P.dt;
-            }
+    for (int h = 0; h < 2; ++h) {
+        const int oy = (tid >> 5) + 8 * h, ox = tid & 31;
+        const int y = ty0 + oy, x = tx0 + ox;
+        if (x < nx && y < P.yi1) {
+            const int g = y + P.y0;
+            const int ly = oy + 1, lx = ox + 1;
+            double dx, dy;
+            if (x == 0) dx = ((-sFx[ly][lx]) - (-sFx[ly][lx + 1])) * inv_d;
+            else if (x == nx - 1) dx = ((-sFx[ly][lx - 1]) - (-sFx[ly][lx])) * inv_d;
+            else dx = -((-sFx[ly][lx - 1]) - (-sFx[ly][lx + 1])) * inv_2d;
+            if (g == 0) dy = -((-sFy[ly + 1][lx]) - (-sFy[ly][lx])) * inv_d;
+            else if (g == gny - 1) dy = -((-sFy[ly][lx]) - (-sFy[ly - 1][lx])) * inv_d;
+            else dy = -((-sFy[ly - 1][lx]) - (-sFy[ly + 1][lx])) * inv_2d;
+            A.cc_env[cur ^ 1][i * E + y * nx + x] = sC[oy + 2][ox + 2] + (dx + dy) * P.dt;
         }
     }
 }
@@ -832,18 +822,13 @@ void launch_mem(int ni, const KParams& P, const KArrays& A, int n_ctas, int cur,
     }
 }
 
-void launch_ion(int ni, const KParams& P, const KArrays& A, int ny, int nx, int cur, int diag, cudaStream_t st)
+// ions [ion0, ion0 + n)
+void launch_ion(const KParams& P, const KArrays& A, int nx, int cur, int diag, int ion0, int n, cudaStream_t st)
 {
     const int rows = P.yi1 - P.yi0;
-    if (rows <= 0) return;
-    dim3 b(256), g((nx + IT_X - 1) / IT_X, (rows + IT_Y - 1) / IT_Y);
-    switch (ni) {
-        case 4: k_ion<4><<<g, b, 0, st>>>(P, A, cur, diag); break;
-        case 5: k_ion<5><<<g, b, 0, st>>>(P, A, cur, diag); break;
-        case 6: k_ion<6><<<g, b, 0, st>>>(P, A, cur, diag); break;
-        case 7: k_ion<7><<<g, b, 0, st>>>(P, A, cur, diag); break;
-        default: k_ion<8><<<g, b, 0, st>>>(P, A, cur, diag); break;
-    }
+    if (rows <= 0 || n <= 0) return;
+    dim3 b(256), g((nx + IT_X - 1) / IT_X, (rows + IT_Y - 1) / IT_Y, n);
+    k_ion<<<g, b, 0, st>>>(P, A, cur, diag, ion0);
 }
 
 void launch_ion_smooth(int ni, const KParams& P, const KArrays& A, int ny, int nx, int nxt, cudaStream_t st)

@@ -73,10 +73,11 @@ k_xchg(const __grid_constant__ KParams P, const KArrays A, const __grid_constant
                 for (int t = gtid; t < nv; t += gsz) nb.v_raw[nb.v_dst_row0 * nx + t] = A.v_raw[nb.v_src_row0 * nx + t];
             }
         }
-        // publish: every CTA's stores are fenced to system scope before the last CTA raises the flags
-        __threadfence_system();
+        // publish: the CTA's stores are ordered before thread 0's system-scope fence by the barrier
+        // (fences are cumulative), and the last CTA to arrive raises the flags
         __syncthreads();
         if (threadIdx.x == 0) {
+            __threadfence_system();
             const unsigned int prev = atomicAdd(X.done_ctr + which, 1u);
             s_last = (prev == gridDim.x - 1) ? 1 : 0;
         }
@@ -99,7 +100,6 @@ k_xchg(const __grid_constant__ KParams P, const KArrays A, const __grid_constant
             const unsigned long long* f = X.my_flags + which * 2 + X.nb[k].side;
             while (ld_acquire_sys(f) < e) {
                 if (globaltimer_ns() - t0 > X.timeout_ns) { atomicOr(A.status, ST_XCHG_TIMEOUT); break; }
-                __nanosleep(64);
             }
         }
     }
@@ -117,9 +117,9 @@ void launch_xchg(const KParams& P, const KArrays& A, const XPlan& X, int which, 
             if (w > work) work = w;
         }
     }
-    int grid = (int)((work + 1023) / 1024);
+    int grid = (int)((work + 2047) / 2048);     // 8 stores per thread: the blocks are a few hundred KB
     if (grid < 1) grid = 1;
-    if (grid > 64) grid = 64;
+    if (grid > 48) grid = 48;
     if (!(mode & XCHG_PUSH)) grid = 1;
     k_xchg<<<grid, 256, 0, st>>>(P, A, X, which, buf, mode);
 }

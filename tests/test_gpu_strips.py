@@ -59,3 +59,22 @@ def test_strips_on_reference_mesh_match_golden():
     for f, a in got.items():
         err = float(np.max(np.abs(a.reshape(np.shape(ref[f])) - ref[f])))
         assert err <= tol[f], (f, err, tol[f])
+
+
+def test_multiprocess_strips_over_ipc():
+    """One process per GPU, CUDA-IPC windows over NVLink (tools/check_multigpu.py); needs >= 2 GPUs."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    world = min(n, 4)
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                          "--master-addr", "127.0.0.1", "--master-port", "29533",
+                          os.path.join(root, "tools", "check_multigpu.py"), "--cells", "60000", "--steps", "12"],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert '"ok": true' in res.stdout
