@@ -91,6 +91,19 @@ class StateHost(C.Structure):
     _fields_ = [(f, _dp) for f in STATE_FIELDS]
 
 
+class GateTerm(C.Structure):
+    _fields_ = [("type", C.c_int32), ("pad", C.c_int32), ("p", C.c_double * 4)]
+
+
+class Channel(C.Structure):
+    _fields_ = [
+        ("ion", C.c_int32), ("mpower", C.c_int32), ("hpower", C.c_int32), ("kind", C.c_int32 * 4),
+        ("reserved", C.c_int32), ("a", GateTerm * 4), ("b", GateTerm * 4),
+        ("time_unit", C.c_double), ("max_Dm", C.c_double), ("rel_perm", C.c_double), ("v_shift", C.c_double),
+        ("target_mask", _bp), ("m0", _dp), ("h0", _dp),
+    ]
+
+
 class WindowInfo(C.Structure):
     _fields_ = [
         ("base", C.c_void_p), ("bytes", C.c_uint64), ("ipc_handle", C.c_uint8 * 64),
@@ -117,6 +130,7 @@ SYMBOLS = [
     "betse_step_profile", "betse_kernel_name", "betse_download_sample",
     "betse_step_phase", "betse_stream", "betse_sync", "betse_update_v", "betse_update_v_phase",
     "betse_set_row_ranges", "betse_window", "betse_attach_neighbor", "betse_exchange",
+    "betse_set_channels", "betse_channel_state",
 ]
 
 _lib = None
@@ -154,6 +168,8 @@ def load(build_if_missing=True):
     lib.betse_window.argtypes = [vp, C.POINTER(WindowInfo)]
     lib.betse_attach_neighbor.argtypes = [vp, C.POINTER(Neighbor)]
     lib.betse_exchange.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    lib.betse_set_channels.argtypes = [vp, C.c_int, C.POINTER(Channel), C.c_int]
+    lib.betse_channel_state.argtypes = [vp, C.c_int, _dp, _dp, _dp, _dp]
     lib.betse_step_phase.argtypes = [vp, C.c_int, C.c_int]
     lib.betse_stream.argtypes = [vp, C.POINTER(vp)]
     lib.betse_sync.argtypes = [vp, C.POINTER(C.c_uint32)]

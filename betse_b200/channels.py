@@ -1,0 +1,209 @@
+"""Voltage-gated channel library as DATA: every Hodgkin-Huxley style model of the
+reference's ``betse/science/channels/{vg_na,vg_k,vg_ca,vg_cl}.py`` restated as a small table of
+gating terms, so that ONE device kernel (csrc/channels.cu: k_chan) evaluates any of them.
+
+A model gives, as functions of ``U = 1000*vm + shift`` [mV], the four quantities of
+``ChannelsABC.update_mh`` (channels/channelsabc.py:40-60): mInf, mTau, hInf, hTau.  Each quantity is
+
+* ``("T", a)``       the term a,
+* ``("R", a, b)``    a/(a+b)     (steady state from opening/closing rates),
+* ``("S", a, b)``    1/(a+b)     (time constant from the rates),
+
+and a term is ``(type, p0, p1, p2, p3)``:
+
+====  =======================================  ==============================================
+type  value                                    reference form
+====  =======================================  ==============================================
+0     p0                                       constants (leak channels: 1)
+1     p0 + p1/(1 + exp((U - p2)/p3))           Boltzmann steady states and bell-less taus
+2     p0*U + p1                                linear taus (vg_k.py Kv1p3, Kv1p5)
+3     p0 + p1*exp((p2 - U)/p3)                 exponential taus / rates
+4     p0 + p1*exp(-((U + p2)/p3)**2)           Gaussian taus (vg_k.py K_Fast)
+5     p0*(U - p1)/(1 - exp(-(U - p1)/p2))      "linoid" opening rate
+6     p0*(W - p1)/(1 - exp(-(W - p1)/p2)),     "linoid" closing rate written in -V
+      W = -U
+====  =======================================  ==============================================
+
+``tests/test_channels_table.py`` holds every entry to the reference's own class over a voltage
+sweep (build container only: needs /root/reference).  The NumPy evaluator below is set-up / test
+code (initial gate values of synthetic tissues); the per-timestep evaluation is the CUDA kernel.
+"""
+import numpy as np
+
+CONST, SIG, LIN, EXP, GAUSS, LINOID, LINOID_NEG = range(7)
+KIND = {"T": 0, "R": 1, "S": 2}
+
+
+def _c(v):
+    return (CONST, float(v), 0.0, 0.0, 0.0)
+
+
+def _sig(v0, s, A=1.0, c0=0.0):
+    return (SIG, float(c0), float(A), float(v0), float(s))
+
+
+def _lin(a, b):
+    return (LIN, float(a), float(b), 0.0, 0.0)
+
+
+def _exp(A, v0, s, c0=0.0):
+    """c0 + A*exp((v0 - U)/s)"""
+    return (EXP, float(c0), float(A), float(v0), float(s))
+
+
+def _gauss(c0, A, v0, s):
+    return (GAUSS, float(c0), float(A), float(v0), float(s))
+
+
+def _linoid(a, v0, s):
+    return (LINOID, float(a), float(v0), float(s), 0.0)
+
+
+def _linoid_neg(a, v0, s):
+    return (LINOID_NEG, float(a), float(v0), float(s), 0.0)
+
+
+def _T(a):
+    return ("T", a)
+
+
+def _leak(ion):
+    one = _T(_c(1.0))
+    return dict(ion=ion, time_unit=1.0, mpow=0, hpow=0, shift=0.0, q=[one, one, one, one])
+
+
+def _hh(ion, mpow, hpow, mInf, mTau, hInf, hTau, shift=0.0, time_unit=1.0e3):
+    return dict(ion=ion, time_unit=time_unit, mpow=mpow, hpow=hpow, shift=shift, q=[mInf, mTau, hInf, hTau])
+
+
+def _na_m(v0):          # the Hammil-type activation shared by Nav1p2/1p3/Rat1/Rat3 (vg_na.py:169-186 ...)
+    a, b = _linoid(0.182, v0, 9.0), _linoid_neg(0.124, -v0, 9.0)
+    return ("R", a, b), ("S", a, b)
+
+
+_one = _T(_c(1.0))
+_m12, _t12 = _na_m(-35.0)
+_m13, _t13 = _na_m(-26.0)
+_hT_rat = ("S", _linoid(0.024, -50.0, 5.0), _linoid_neg(0.0091, 75.000123, 5.0))
+_r2ma, _r2mb = _linoid(0.091, -38.0, 5.0), _linoid_neg(0.062, 38.0, 5.0)
+_r2ha, _r2hb = _exp(0.016, -55.0, 15.0), _sig(17.0, -21.0, A=2.07)
+_c21a, _c21b = _sig(8.0, -12.5, A=8.5), _sig(-74.0, 14.5, A=35.0)
+_c23ma, _c23mb = _sig(-7.0, -8.0, A=2.6), _sig(-26.0, 4.0, A=0.18)
+_c23ha, _c23hb = _sig(-32.0, 8.0, A=0.0025), _sig(-42.0, -10.0, A=0.19)
+_c22ma, _c22mb = _linoid(0.1, 20.0, 10.0), _exp(0.4, -25.0, 18.0)
+_c22ha, _c22hb = _exp(0.01, -50.0, 10.0), _sig(-17.0, -17.0, A=0.1)
+_cgma, _cgmb = _linoid(0.055, -27.0, 3.8), _exp(0.94, -75.0, 17.0)
+_cgha, _cghb = _exp(0.000457, -13.0, 50.0), _sig(-15.0, -28.0, A=0.0065)
+
+MODELS = {
+    # ---- vg_na.py
+    "Nav1p2": _hh("Na", 3, 1, _m12, _t12, _T(_sig(-65.0, 6.2)), _hT_rat, shift=-10.0),        # :131-186
+    "Nav1p3": _hh("Na", 3, 1, _m13, _t13, _T(_sig(-65.0, 8.1)), _T(_exp(0.265, 0.0, 9.47, c0=0.40))),  # :188-240
+    "NavRat2": _hh("Na", 3, 1, ("R", _r2ma, _r2mb), ("S", _r2ma, _r2mb), ("R", _r2ha, _r2hb), ("S", _r2ha, _r2hb)),  # :242-286
+    "NavRat1": _hh("Na", 3, 1, _m12, _t12, _T(_sig(-65.0, 6.2)), _hT_rat),                   # :288-328
+    "NavRat3": _hh("Na", 3, 1, _m12, _t12, _T(_sig(-65.0, 6.2)), _hT_rat),                   # :330-370
+    "NaLeak": _leak("Na"),                                                                    # :372-413
+    "Nav1p6": _hh("Na", 1, 0, _T(_sig(-17.0, -1.0 / (0.03937 * 4.2))), _one, _one, _one),     # :415-452
+    # ---- vg_k.py
+    "Kv1p1": _hh("K", 1, 2, _T(_sig(-30.5, -11.3943)), _T(_sig(-76.56, 26.1479, A=30.0)),
+                 _T(_sig(-30.0, 27.3943)), _T(_sig(-160.56, -100.0, A=15000.0))),             # :133-178
+    "Kv1p2": _hh("K", 1, 1, _T(_sig(-21.0, -11.3943)), _T(_sig(-67.56, 34.1479, A=150.0)),
+                 _T(_sig(-22.0, 11.3943)), _T(_sig(-46.56, -44.1479, A=15000.0))),            # :180-229
+    "Kv1p3": _hh("K", 1, 1, _T(_sig(-14.1, -10.3)), _T(_lin(-0.2840, 19.16)),
+                 _T(_sig(-33.0, 3.7)), _T(_lin(-13.76, 1162.4))),                             # :231-278
+    "Kv1p4": _hh("K", 1, 1, _T(_sig(-21.7, -16.9)), _T(_c(3.0)), _T(_sig(-73.6, 12.8)), _T(_c(119.0))),  # :280-323
+    "Kv1p5": _hh("K", 1, 1, _T(_sig(-6.0, -6.4)), _T(_lin(-0.1163, 8.33)),
+                 _T(_sig(-25.3, 3.5)), _T(_lin(-15.5, 1620.0))),                              # :325-374
+    "Kv1p6": _hh("K", 1, 1, _T(_sig(-20.8, -8.1)), _T(_sig(-46.56, 44.14, A=30.0)),
+                 _T(_sig(-22.0, 11.39)), _T(_sig(-46.56, -44.14, A=5000.0))),                 # :376-419
+    "Kv2p1": _hh("K", 1, 1, _T(_sig(-9.2, -6.6)), _T(_sig(-46.56, 44.14, A=100.0)),
+                 _T(_sig(-19.0, 5.0)), _T(_sig(-46.56, -44.14, A=10000.0))),                  # :421-454
+    "Kv2p2": _hh("K", 1, 1, _T(_sig(5.0, -12.0)), _T(_sig(-46.56, -44.14, A=130.0)),
+                 _T(_sig(-16.3, 4.8)), _T(_sig(-46.56, -44.14, A=10000.0))),                  # :456-487
+    "Kv3p1": _hh("K", 1, 0, _T(_sig(18.7, -9.7)), _T(_sig(-46.56, -44.14, A=20.0)), _one, _one),  # :489-519
+    "Kv3p2": _hh("K", 2, 0, _T(_sig(-0.373267, -8.568187)),
+                 _T(_sig(19.220623, 4.451533, A=19.106496, c0=3.241643)), _one, _one),        # :521-551
+    "Kv3p3": _hh("K", 2, 1, _T(_sig(35.0, -7.3)), _T(_sig(22.414149, 9.704638, A=27.913114, c0=0.676808)),
+                 _T(_sig(-28.293856, 29.385636, A=0.75, c0=0.25)),
+                 _T(_exp(2776.119438, 0.0, 7.309565, c0=199.786728))),                        # :553-594
+    "Kv3p4": _hh("K", 1, 1, _T(_sig(-3.4, -8.4)), _T(_sig(4.44, 38.14, A=10.0)),
+                 _T(_sig(-53.32, 7.4)), _T(_sig(-46.56, -44.14, A=20000.0))),                 # :596-639
+    "K_Fast": _hh("K", 1, 1, _T(_sig(-47.0, -29.0)), _T(_gauss(0.34, 0.92, 71.0, 59.0)),
+                  _T(_sig(-56.0, 10.0)), _T(_gauss(8.0, 49.0, 73.0, 23.0))),                  # :641-682
+    "KLeak": _leak("K"),                                                                      # :684-728
+    "Kir2p1": _hh("K", 1, 2, _T(_sig(-96.48, 23.26)), _T(_sig(-32.9, 27.93, A=-3.37, c0=3.7)),
+                  _T(_sig(-168.28, -44.13)), _T(_sig(-118.29, -27.23, A=306.3, c0=0.85))),    # :730-775
+    # ---- vg_ca.py
+    "Cav3p3": _hh("Ca", 1, 1, _T(_sig(-45.454426, -5.073015)),
+                  _T(_sig(-40.040397, 4.110392, A=54.187616, c0=3.394938)),
+                  _T(_sig(-74.031965, 8.416382)), _T(_exp(0.003816, 0.0, 4.781719, c0=109.701136))),  # :132-179
+    "Cav2p1": _hh("Ca", 1, 0, ("R", _c21a, _c21b), ("S", _c21a, _c21b), _one, _one),          # :181-240
+    "Cav1p3": _hh("Ca", 2, 1, _T(_sig(-30.0, -6.0)), _T(_sig(-25.0, 5.0, A=20.0, c0=5.0)),
+                  _T(_sig(-80.0, 6.4)), _T(_sig(-40.0, 7.0, A=50.0, c0=20.0))),               # :242-290
+    "Cav1p2": _hh("Ca", 2, 1, _T(_sig(-30.0, -6.0)), _T(_sig(-25.0, 5.0, A=20.0, c0=5.0)),
+                  _T(_sig(-80.0, 6.4)), _T(_sig(-40.0, 7.0, A=50.0, c0=20.0)), shift=-10.0),  # :292-340
+    "Cav2p3": _hh("Ca", 1, 1, ("R", _c23ma, _c23mb), ("S", _c23ma, _c23mb),
+                  ("R", _c23ha, _c23hb), ("S", _c23ha, _c23hb)),                              # :342-400
+    "Cav2p2": _hh("Ca", 2, 1, ("R", _c22ma, _c22mb), ("S", _c22ma, _c22mb),
+                  ("R", _c22ha, _c22hb), ("S", _c22ha, _c22hb)),                              # :402-466
+    "Ca_L2": _hh("Ca", 2, 1, _T(_sig(-30.0, -6.0)), _T(_c(10.0)), _T(_sig(-80.0, 6.4)), _T(_c(59.0))),  # :522-573
+    "Ca_L3": _hh("Ca", 2, 1, _T(_sig(-30.0, -6.0)), _T(_c(10.0)), _T(_sig(-80.0, 6.4)), _T(_c(59.0)),
+                 shift=-15.0),                                                                # :575-635
+    "Cav_G": _hh("Ca", 2, 1, ("R", _cgma, _cgmb), ("S", _cgma, _cgmb), ("R", _cgha, _cghb), ("S", _cgha, _cghb)),  # :637-697
+    "CaLeak": _leak("Ca"),                                                                    # :699-745
+    # ---- vg_cl.py
+    "ClLeak": _leak("Cl"),                                                                    # :132-175
+}
+# Not tabulated (refused at set-up): vg_ca.Cav3p1 (piecewise tau), vg_funny, cation, Morris-Lecar, wound.
+
+CLASS_OF_ION = {"Na": "vg_na", "K": "vg_k", "Ca": "vg_ca", "Cl": "vg_cl"}
+
+
+def term(t, U):
+    ty, p0, p1, p2, p3 = t
+    if ty == CONST:
+        return np.full_like(U, p0)
+    if ty == SIG:
+        return p0 + p1 / (1 + np.exp((U - p2) / p3))
+    if ty == LIN:
+        return p0 * U + p1
+    if ty == EXP:
+        return p0 + p1 * np.exp((p2 - U) / p3)
+    if ty == GAUSS:
+        return p0 + p1 * np.exp(-((U + p2) / p3) ** 2)
+    if ty == LINOID:
+        return p0 * (U - p1) / (1 - np.exp(-(U - p1) / p2))
+    if ty == LINOID_NEG:
+        W = -U
+        return p0 * (W - p1) / (1 - np.exp(-(W - p1) / p2))
+    raise ValueError(ty)
+
+
+def quantity(q, U):
+    if q[0] == "T":
+        return term(q[1], U)
+    a, b = term(q[1], U), term(q[2], U)
+    return a / (a + b) if q[0] == "R" else 1 / (a + b)
+
+
+def gates(model, vm):
+    """(mInf, mTau, hInf, hTau) of ``model`` at membrane voltages ``vm`` [V] (NumPy; set-up/tests)."""
+    M = MODELS[model]
+    U = np.asarray(vm, dtype=float) * 1000 + M["shift"]
+    return tuple(quantity(q, U) for q in M["q"])
+
+
+def initial_state(model, vm):
+    """m, h at the first time step (every tabulated model starts at its steady state:
+    e.g. vg_na.py:210-228)."""
+    mInf, _, hInf, _ = gates(model, vm)
+    return mInf, hInf
+
+
+def make_channel(name, model, max_Dm, targets=None, init_active=True, rel_perm=1.0, m=None, h=None):
+    """A channel spec as TissueEngine.set_channels expects it."""
+    if model not in MODELS:
+        raise KeyError("channel type %r is not tabulated (betse_b200/channels.py)" % model)
+    return {"name": name, "model": model, "ion": MODELS[model]["ion"], "maxDm": float(max_Dm),
+            "targets": None if targets is None else np.asarray(targets, dtype=np.int64),
+            "init_active": bool(init_active), "rel_perm": float(rel_perm), "m": m, "h": h}

@@ -13,6 +13,7 @@
 #include "../../include/betse_b200.h"
 #include "kparams.cuh"
 #include "xchg.cuh"
+#include "channels.cuh"
 
 // launchers (kernels.cu)
 void launch_mem(int ni, const KParams& P, const KArrays& A, int n_ctas, int cur, int diag, cudaStream_t st);
@@ -25,6 +26,8 @@ void launch_envmix(int ni, const KParams& P, const KArrays& A, int cur, cudaStre
 void launch_diag(int ni, const KParams& P, const KArrays& A, int n_ctas, int newb, cudaStream_t st);
 void launch_expand_vm(const KParams& P, const KArrays& A, int M, int C, int cur, cudaStream_t st);
 cudaError_t prepare_kernels(int ni);
+void launch_chan(const KParams& P, const KArrays& A, const KChan& ch, int cur, cudaStream_t st);
+void launch_cell_update(const KParams& P, const KArrays& A, int cur, cudaStream_t st);
 void launch_xchg(const KParams& P, const KArrays& A, const XPlan& X, int which, int buf, int mode, cudaStream_t st);
 
 enum { K_ION = 0, K_MEM, K_ENVACC, K_FIELD, K_ENVMIX, K_SMOOTH, K_DIAG, K_XCHG };
@@ -48,6 +51,7 @@ struct betse_ctx {
     betse_window_info winfo;
     XPlan X;
     std::vector<void*> ipc_opened;
+    std::vector<KChan> chans;                // voltage-gated channels, applied in order
     std::string err;
     std::vector<void*> allocs;
     // CUDA graphs of one plain step, for cur = 0 and cur = 1
@@ -543,7 +547,8 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
         // The membrane kernel reads cc_env[nxt] of Ca only (the Ca-ATPase sees the transported value,
         // sim.py:1282 after 2254): the Ca row is transported first, the other ions run on a second
         // stream NEXT TO the membrane kernel (which is latency-bound and leaves issue slots free).
-        const bool overlap = ecm && ctx->overlap && !evs && ctx->hp.sharpness >= 1.0;
+        const bool chans = !ctx->chans.empty();
+        const bool overlap = ecm && ctx->overlap && !evs && ctx->hp.sharpness >= 1.0 && !chans;
         if (ecm && overlap) {
             const int iCa = ctx->hp.iCa;
             if (iCa >= 0) launch_ion(ctx->P, A, ctx->nx, cur, diag, iCa, 1, st);
@@ -566,6 +571,12 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
         if (evs) cudaEventRecord(evs[2], st);
         launch_mem(I, ctx->P, A, ctx->n_ctas, cur, diag, st);
         if (overlap) cudaStreamWaitEvent(st, ctx->ev_join, 0);
+        if (chans) {
+            // run_loop_channels (networks.py:3115-3213): between the ion loop's fluxes and update_all_concs
+            if (A.chanJ) cudaMemsetAsync(A.chanJ, 0, (size_t)ctx->Mo * sizeof(double), st);
+            for (const KChan& ch : ctx->chans) launch_chan(ctx->P, A, ch, cur, st);
+            launch_cell_update(ctx->P, A, cur, st);
+        }
         if (evs) cudaEventRecord(evs[3], st);
     } else if (phase == 1) {
         if (ecm) launch_envacc(I, ctx->P, A, ctx->E, nxt, 1, st);
@@ -805,6 +816,70 @@ extern "C" int betse_download_sample(betse_ctx* ctx, betse_state_host* s)
     return 0;
 }
 
+extern "C" int betse_set_channels(betse_ctx* ctx, int n, const betse_channel* chs, int affect_charge)
+{
+    if (!ctx || n < 0 || (n > 0 && !chs)) return 2;
+    CK(cudaSetDevice(ctx->device));
+    if (n > 0 && !ctx->hp.is_ecm) return fail(ctx, "channels without extracellular spaces are not implemented");
+    if (n > 0 && ctx->hp.fast_update_ecm) return fail(ctx, "channels with fast_update_ecm are not implemented");
+    if (n > 0 && ctx->X.n_nbr > 0) return fail(ctx, "channels on a domain-decomposed tissue are not implemented");
+    KArrays& A = ctx->A;
+    const int Mo = ctx->Mo;
+    int r;
+    ctx->chans.clear();
+    destroy_graphs(ctx);
+    ctx->P.defer = n > 0 ? 1 : 0;
+    ctx->P.chan_charge = (n > 0 && affect_charge) ? 1 : 0;
+    if (n == 0) return 0;
+    if (!A.dsum_m) {
+        if ((r = dev_alloc(ctx, &A.dsum_m, (size_t)ctx->I * ctx->C))) return r;
+        if ((r = dev_alloc(ctx, &A.dsum_g, (size_t)ctx->I * ctx->C))) return r;
+        if ((r = dev_alloc(ctx, &A.chan_slots, (size_t)ctx->n_slots))) return r;
+        if ((r = dev_alloc(ctx, &A.chanJ, (size_t)Mo))) return r;
+    }
+    for (int k = 0; k < n; ++k) {
+        const betse_channel& c = chs[k];
+        if (c.ion < 0 || c.ion >= ctx->I) return fail(ctx, "channel ion index out of range");
+        if (c.mpower < 0 || c.mpower > 8 || c.hpower < 0 || c.hpower > 8) return fail(ctx, "channel gate powers must be in [0,8]");
+        if (!c.m0 || !c.h0) return fail(ctx, "channel needs initial gate states m0/h0");
+        KChan d;
+        memset(&d, 0, sizeof d);
+        d.ion = c.ion; d.mpow = c.mpower; d.hpow = c.hpower;
+        for (int q = 0; q < 4; ++q) {
+            if (c.kind[q] < 0 || c.kind[q] > 2) return fail(ctx, "channel quantity kind must be 0, 1 or 2");
+            d.kind[q] = c.kind[q];
+            if (c.a[q].type < 0 || c.a[q].type > 6 || c.b[q].type < 0 || c.b[q].type > 6) return fail(ctx, "unknown gate term type");
+            d.a[q].type = c.a[q].type; d.b[q].type = c.b[q].type;
+            for (int j = 0; j < 4; ++j) { d.a[q].p[j] = c.a[q].p[j]; d.b[q].p[j] = c.b[q].p[j]; }
+        }
+        d.dt_tu = ctx->hp.dt * c.time_unit;
+        d.maxDm = c.max_Dm; d.rel_perm = c.rel_perm; d.shift = c.v_shift;
+        if (c.target_mask) { if ((r = dev_upload(ctx, (unsigned char**)&d.mask, c.target_mask, Mo))) return r; }
+        if ((r = dev_upload(ctx, &d.m, c.m0, Mo))) return r;
+        if ((r = dev_upload(ctx, &d.h, c.h0, Mo))) return r;
+        if ((r = dev_alloc(ctx, &d.P, Mo))) return r;
+        if ((r = dev_alloc(ctx, &d.flux, Mo))) return r;
+        ctx->chans.push_back(d);
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int betse_channel_state(betse_ctx* ctx, int k, double* m, double* h, double* P, double* flux)
+{
+    if (!ctx) return 2;
+    CK(cudaSetDevice(ctx->device));
+    if (k < 0 || k >= (int)ctx->chans.size()) return fail(ctx, "channel index out of range");
+    const KChan& d = ctx->chans[k];
+    const size_t nb = (size_t)ctx->Mo * sizeof(double);
+    if (m) CK(cudaMemcpyAsync(m, d.m, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (h) CK(cudaMemcpyAsync(h, d.h, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (P) CK(cudaMemcpyAsync(P, d.P, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (flux) CK(cudaMemcpyAsync(flux, d.flux, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 extern "C" int betse_set_row_ranges(betse_ctx* ctx, int yi0, int yi1, int ya0, int ya1, int yf0, int yf1)
 {
     if (!ctx) return 2;
@@ -837,6 +912,7 @@ extern "C" int betse_attach_neighbor(betse_ctx* ctx, const betse_neighbor* nb)
     if (nb->side != 0 && nb->side != 1) return fail(ctx, "neighbor.side must be 0 or 1");
     if (!ctx->hp.is_ecm) return fail(ctx, "domain decomposition needs extracellular spaces (no-ECM tissues run as replicas)");
     if (ctx->P.has_phi) return fail(ctx, "domain decomposition does not support a boundary-voltage potential (Phi_b)");
+    if (!ctx->chans.empty()) return fail(ctx, "channels on a domain-decomposed tissue are not implemented");
     const betse_window_info& W = nb->info;
     if (W.n_ions != ctx->I || W.nx != ctx->nx) return fail(ctx, "neighbour window has different n_ions / nx");
     char* base = (char*)W.base;

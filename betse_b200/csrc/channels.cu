@@ -1,0 +1,179 @@
+// Voltage-gated channels of the general network:
+//   MasterOfNetworks.run_loop_channels        betse/science/chemistry/networks.py:3115-3213
+//   VgNaABC/VgKABC/VgCaABC/VgClABC.run        betse/science/channels/vg_na.py:75-112 (and siblings)
+//   ChannelsABC.update_mh                     betse/science/channels/channelsabc.py:40-60
+// The ~35 Hodgkin-Huxley models are DATA (betse_b200/channels.py: a table of gating terms held to
+// the reference classes by tests/test_channels_table.py); k_chan evaluates any of them.
+//
+// Semantics that matter: a channel's GHK flux is applied IMMEDIATELY (update_Co inside the loop
+// over channels), so the next channel sees the updated cell and env concentrations, and all of it
+// happens between the flux computation of the ion loop and update_all_concs (sim.py:1290-1357).
+// Hence, with channels, k_mem only DEFERS its membrane->cell sums (KParams.defer), the channels
+// run one after the other (k_chan: gates, flux, cell update; k_chan_env: env update), and
+// k_cell_update then applies the deferred sums exactly as k_mem's tail would have.
+#include "kparams.cuh"
+#include "channels.cuh"
+
+#define FLOAT_NONCE 1.0e-25
+#define ST_NAN_VM 1u
+#define ST_NAN_CONC 2u
+#define ST_NEG 4u
+
+// same reciprocal as k_mem's tail (kernels.cu: fast_rcp) so that the deferred update is bit-identical to the fused one
+__device__ __forceinline__ double fast_rcp(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
+__device__ __forceinline__ double gate_term(const KTerm& t, double U)
+{
+    switch (t.type) {
+        case 0: return t.p[0];
+        case 1: return t.p[0] + t.p[1] / (1.0 + exp((U - t.p[2]) / t.p[3]));
+        case 2: return t.p[0] * U + t.p[1];
+        case 3: return t.p[0] + t.p[1] * exp((t.p[2] - U) / t.p[3]);
+        case 4: { const double x = (U + t.p[2]) / t.p[3]; return t.p[0] + t.p[1] * exp(-(x * x)); }
+        case 5: { const double x = U - t.p[1]; return t.p[0] * x / (1.0 - exp(-x / t.p[2])); }
+        default: { const double x = -U - t.p[1]; return t.p[0] * x / (1.0 - exp(-x / t.p[2])); }
+    }
+}
+
+__device__ __forceinline__ double gate_quantity(const KChan& ch, int q, double U)
+{
+    const double a = gate_term(ch.a[q], U);
+    if (ch.kind[q] == 0) return a;
+    const double b = gate_term(ch.b[q], U);
+    return ch.kind[q] == 1 ? a / (a + b) : 1.0 / (a + b);
+}
+
+__device__ __forceinline__ double ipow(double x, int n)
+{
+    double r = 1.0;
+    for (int k = 0; k < n; ++k) r *= x;
+    return r;
+}
+
+// One warp per tile of whole cells (the packing of k_mem): lanes = membranes for gates and flux,
+// then lanes = cells for the immediate concentration update of the conducted ion.
+__global__ void __launch_bounds__(BT_TPB)
+k_chan(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ KChan ch, const int cur)
+{
+    __shared__ double s_all[(BT_TPB / 32) * 32];
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * (BT_TPB / 32) + (threadIdx.x >> 5);
+    if (tile >= P.n_tiles) return;
+    double* s_f = s_all + (threadIdx.x >> 5) * 32;
+    const int4 td = __ldg(reinterpret_cast<const int4*>(A.tile_desc) + tile);
+    const int c0 = td.x, nc = td.y, m0 = td.z, nm = td.w;
+    const int C = P.n_cells, E = P.ny * P.nx;
+    const int ion = ch.ion;
+    double* __restrict__ ccell = A.cc_cells + ion * C;
+    const double* __restrict__ cenv = A.cc_env[cur ^ 1] + ion * E;   // after this step's transport (+ earlier channels)
+
+    double fsa = 0.0;
+    if (lane < nm) {
+        const int m = m0 + lane;
+        const int c = __ldg(A.mem_to_cells + m);
+        const int e = __ldg(A.map_mem2ecm + m);
+        double vm = A.vm_cell[cur][c];
+        if (P.has_phi) vm -= __ldg(A.phi_b + e);
+        double Pm = 0.0;
+        if (!ch.mask || ch.mask[m]) {
+            const double U = vm * 1000.0 + ch.shift;              // V = vm[targets]*1000 + v_corr (vg_na.py:91)
+            const double mInf = gate_quantity(ch, 0, U), mTau = gate_quantity(ch, 1, U);
+            const double hInf = gate_quantity(ch, 2, U), hTau = gate_quantity(ch, 3, U);
+            const double dt = ch.dt_tu;                            // p.dt*time_unit (channelsabc.py:56)
+            const double mm = (mTau * ch.m[m] + dt * mInf) / (mTau + dt);
+            const double hh = (hTau * ch.h[m] + dt * hInf) / (hTau + dt);
+            ch.m[m] = mm; ch.h[m] = hh;
+            Pm = ipow(mm, ch.mpow) * ipow(hh, ch.hpow);            // vg_na.py:104
+        }
+        ch.P[m] = Pm;
+        const double DChan = ((Pm * ch.rel_perm) * ch.maxDm) * 1.0;   // moddy == 1 (no modulators), networks.py:3164
+        // stb.electroflux(cenv[map_mem2ecm], cmem, DChan, tm, z, vm, sim.T, rho=rho_channel), sim_toolbox.py:18-69
+        const double alpha = ((P.z[ion] + FLOAT_NONCE) * (vm + FLOAT_NONCE) * P.F) / P.RT_sim;
+        const double ex = exp(-alpha), deno = -expm1(-alpha);
+        const double cB = ccell[c], cA = P.is_ecm ? cenv[e] : A.cenv_u[cur * 8 + ion];
+        const double f = -((DChan * alpha) / P.tm) * ((cB - cA * ex) / deno) * P.rho_channel;
+        fsa = f * __ldg(A.mem_sa + m);
+        if (P.is_ecm) A.chan_slots[m] = fsa;
+        if (ch.flux) ch.flux[m] = f;
+        if (A.chanJ) A.chanJ[m] += (-f * P.F) * P.z[ion];         // extra_J_mem += -f_ED*p.F*zzz, networks.py:3199
+    }
+    s_f[lane] = fsa;
+    __syncwarp();
+    if (lane < nc) {                                              // update_Co cell branch, sim_toolbox.py:1177-1181
+        const int c = c0 + lane;
+        const int jb = __ldg(A.cell_mem_ptr + c) - m0, je = __ldg(A.cell_mem_ptr + c + 1) - m0;
+        double S = 0.0;
+        for (int j = jb; j < je; ++j) S += s_f[j];
+        const double cn = ccell[c] + (S / __ldg(A.cell_vol + c)) * P.dt;
+        ccell[c] = cn;
+    }
+}
+
+// update_Co env branch for one channel: cc_env[ion] += div_env(-f)*dt (sim_toolbox.py:1189-1195, 1209-1234)
+__global__ void __launch_bounds__(256)
+k_chan_env(const __grid_constant__ KParams P, const KArrays A, const int ion, const int nxt)
+{
+    const int k = P.ya0 * P.nx + blockIdx.x * blockDim.x + threadIdx.x;
+    const int E = P.nx * P.ny;
+    if (k >= P.ya1 * P.nx) return;
+    const int s0 = __ldg(A.slot_ptr + k), s1 = __ldg(A.slot_ptr + k + 1);
+    if (s1 == s0) return;
+    double acc = 0.0;
+    for (int j = s0; j < s1; ++j) acc += A.chan_slots[__ldg(A.slot_idx + j)];
+    double* c = A.cc_env[nxt] + ion * E + k;
+    *c = *c + ((-acc) / P.env_vol_div) * P.dt;
+}
+
+// The deferred tail of k_mem (update_all_concs, sim.py:2086-2111; charge and Vmem, ion_current.py:19,
+// sim.py:2027-2029), applied to the concentrations the channels left behind.
+__global__ void __launch_bounds__(256)
+k_cell_update(const __grid_constant__ KParams P, const KArrays A, const int cur)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.n_cells_owned) return;
+    const int C = P.n_cells, nxt = cur ^ 1;
+    unsigned int flags = 0;
+    const double rvol = fast_rcp(__ldg(A.cell_vol + c));
+    double rho = 0.0;
+    for (int i = 0; i < P.n_ions; ++i) {
+        const double cc = A.cc_cells[i * C + c];
+        const double Sm = A.dsum_m[i * C + c], Sg = A.dsum_g[i * C + c];
+        const double cm_new = cc + (Sm * rvol) * P.dt;
+        double cn_new = cm_new + P.dt * ((-Sg) * rvol);
+        if (cn_new != cn_new) flags |= ST_NAN_CONC;
+        if (cn_new < 0.0) { cn_new = 0.0; flags |= ST_NEG; }
+        A.cc_cells[i * C + c] = cn_new;
+        A.cc_mid[nxt][i * C + c] = cm_new;
+        rho = fma(P.zF[i], cn_new, rho);
+    }
+    if (A.extra_rho_cells) rho += __ldg(A.extra_rho_cells + c);
+    A.rho_cells[c] = rho;
+    const double vmn = P.inv_cm * (rho * __ldg(A.diviterm + c));
+    if (vmn != vmn) flags |= ST_NAN_VM;
+    A.vm_cell[nxt][c] = vmn;
+    if (flags) atomicOr(A.status, flags);
+}
+
+void launch_chan(const KParams& P, const KArrays& A, const KChan& ch, int cur, cudaStream_t st)
+{
+    const int grid = (P.n_tiles + (BT_TPB / 32) - 1) / (BT_TPB / 32);
+    k_chan<<<grid, BT_TPB, 0, st>>>(P, A, ch, cur);
+    if (P.is_ecm) {
+        const int n = (P.ya1 - P.ya0) * P.nx;
+        if (n > 0) k_chan_env<<<(n + 255) / 256, 256, 0, st>>>(P, A, ch.ion, cur ^ 1);
+    }
+}
+
+void launch_cell_update(const KParams& P, const KArrays& A, int cur, cudaStream_t st)
+{
+    k_cell_update<<<(P.n_cells_owned + 255) / 256, 256, 0, st>>>(P, A, cur);
+}

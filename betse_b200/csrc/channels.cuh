@@ -1,0 +1,14 @@
+// Device-side description of one voltage-gated channel (csrc/channels.cu, betse_b200/channels.py).
+#pragma once
+
+struct KTerm { int type; double p[4]; };
+
+struct KChan {
+    int ion, mpow, hpow;
+    int kind[4];                 // mInf, mTau, hInf, hTau: 0 = term a, 1 = a/(a+b), 2 = 1/(a+b)
+    KTerm a[4], b[4];
+    double dt_tu;                // p.dt * time_unit
+    double maxDm, rel_perm, shift;
+    const unsigned char* mask;   // [M] targets (null = every membrane)
+    double *m, *h, *P, *flux;    // [M] gate states, open probability, last flux
+};

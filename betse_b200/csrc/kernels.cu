@@ -330,6 +330,10 @@ k_mem(const __grid_constant__ KParams P, const KArrays A, const int cur, const i
         }
         double Sm = 0.0, Sg = 0.0;
         for (int j = jb; j < je; ++j) { Sm += s_m[j * NI + i]; Sg += s_g[j * NI + i]; }
+        if (!S && P.defer) {              // channels act before update_all_concs: k_cell_update applies these
+            A.dsum_m[i * C + c] = Sm; A.dsum_g[i * C + c] = Sg;
+            continue;
+        }
         const double rvol = fast_rcp(vol);
         const double cm_new = cc + (Sm * rvol) * P.dt;            // sim_toolbox.py:1177-1181
         double cn_new = cm_new + P.dt * ((-Sg) * rvol);           // sim.py:2105-2108
@@ -343,7 +347,7 @@ k_mem(const __grid_constant__ KParams P, const KArrays A, const int cur, const i
     __syncwarp();
 
     // ---- lanes = cells: charge and Vmem (ion_current.py:19; sim.py:2027-2029)
-    if (lane < nc) {
+    if (lane < nc && (S || !P.defer)) {
         const int c = c0 + lane;
         double rho = 0.0;
 #pragma unroll
@@ -663,7 +667,8 @@ k_diag(const __grid_constant__ KParams P, const KArrays A, const int newb)
             dm = fma(P.zF[i], A.fl_mem[(size_t)i * Mo + m], dm);
             dg = fma(P.zF[i], A.fl_gj[(size_t)i * Mo + m], dg);
         }
-        const double Jmem = -dm + (A.extra_J_mem ? ldg(A.extra_J_mem + m) : 0.0);
+        // sim.extra_J_mem: uploaded, or (channels + substances_affect_charge) this step's channel currents
+        const double Jmem = -dm + ((P.chan_charge && A.chanJ) ? A.chanJ[m] : (A.extra_J_mem ? ldg(A.extra_J_mem + m) : 0.0));
         A.Jmem[m] = Jmem; A.Jgj[m] = dg;
         Jn0 = Jmem + dg;
         double phi = 0.0;
@@ -770,7 +775,7 @@ static void launch_mem_t(const KParams& P, const KArrays& A, int n_ctas, int cur
     // the specialised build applies to the shipped ion profiles with the default feature switches
     bool std_prof = NI <= 7 && P.is_ecm && P.v_sensitive_gj && P.cluster_open && !P.fast_update_ecm && !diag &&
                     !A.gj_block && !A.NaK_block && P.iNa == StdProf<NI>::iNa && P.iK == StdProf<NI>::iK &&
-                    P.iCa == StdProf<NI>::iCa && !kmem_generic();
+                    P.iCa == StdProf<NI>::iCa && !kmem_generic() && !P.defer;
     for (int i = 0; i < NI && std_prof; ++i) std_prof = (P.zi[i] == StdProf<NI>::z(i)) && P.zi[i] != 0;
     if (P.has_phi) k_mem<NI, true, 2, 0><<<grid, BT_TPB, smem, st>>>(P, A, cur, diag);
     else if (std_prof && minb2) k_mem<NI, false, 2, 1><<<grid, BT_TPB, smem, st>>>(P, A, cur, diag);

@@ -37,6 +37,8 @@ struct KParams {
     int ny, nx, y0, ny_global, y_own0, y_own1;
     int n_cells, n_cells_owned, n_mems_owned, n_ctas, n_tiles;
     int pf_tiles;                           // k_mem: L2 prefetch distance in tiles (0 = off)
+    int defer;                              // k_mem stores its membrane->cell sums instead of applying them (channels)
+    int chan_charge;                        // p.substances_affect_charge: Jmem takes the channels' extra_J_mem
     // kernel row ranges in local rows (single GPU: all [0, ny)): ion transport, membrane->env
     // accumulation, env field (E rows; v_env is written on the accumulation rows)
     int yi0, yi1, ya0, ya1, yf0, yf1;
@@ -77,4 +79,8 @@ struct KArrays {
     double *Jmem, *Jgj, *Jn, *I_mem, *Jc, *Emc, *dvm, *vm_mem, *vm_ave;
     double *J_cell_x, *J_cell_y, *E_cell_x, *E_cell_y, *sigma_cell;
     double *scratch_env;     // [I,E] temp for the sharpness<1 smoothing pass
+    // voltage-gated channels (channels.cu)
+    double *dsum_m, *dsum_g; // [I,C] deferred sums of f_mem*sa and f_gj*sa per cell
+    double *chan_slots;      // [M]   f*sa of the channel being applied (membrane -> env exchange)
+    double *chanJ;           // [M]   extra_J_mem accumulated over the channels of this step
 };

@@ -369,6 +369,66 @@ class TissueEngine:
             out["cc_env"] = np.repeat(cenv[:, None], M, axis=1)   # the reference keeps [I,M] (sim.py:487-490)
         return out
 
+    # ------------------------------------------------------------------ voltage-gated channels
+    def set_channels(self, specs, phase_init=False, affect_charge=None):
+        """``specs``: channel dicts (betse_b200.channels.make_channel / the reference's
+        ``MasterOfNetworks.channels`` via simloop.channels_from_sim), applied in order.  In the
+        INIT phase channels with ``init_active`` False are skipped (networks.py:3140-3141)."""
+        from . import channels as chlib
+        specs = [c for c in specs if not (phase_init and not c["init_active"])]
+        self.channel_names = [c.get("name", "chan%d" % k) for k, c in enumerate(specs)]
+        arr = (capi.Channel * max(1, len(specs)))()
+        keep = []
+        idx = {n: i for i, n in enumerate(self.ions)}
+        for k, c in enumerate(specs):
+            if c["model"] not in chlib.MODELS:
+                raise BetseB200Error("channel type %r is not tabulated (betse_b200/channels.py)" % c["model"])
+            mdl = chlib.MODELS[c["model"]]
+            if mdl["ion"] not in idx:
+                raise BetseB200Error("channel %r conducts %s, which this ion profile does not simulate"
+                                     % (c.get("name"), mdl["ion"]))
+            d = arr[k]
+            d.ion, d.mpower, d.hpower = idx[mdl["ion"]], int(mdl["mpow"]), int(mdl["hpow"])
+            for q, spec in enumerate(mdl["q"]):
+                d.kind[q] = chlib.KIND[spec[0]]
+                terms = [spec[1], spec[2] if len(spec) > 2 else (0, 0.0, 0.0, 0.0, 0.0)]
+                for dst, t in zip((d.a[q], d.b[q]), terms):
+                    dst.type = int(t[0])
+                    for j in range(4):
+                        dst.p[j] = float(t[1 + j])
+            d.time_unit, d.max_Dm = float(mdl["time_unit"]), float(c["maxDm"])
+            d.rel_perm, d.v_shift = float(c.get("rel_perm", 1.0)), float(mdl["shift"])
+            m0, h0 = np.ones(self.M), np.ones(self.M)
+            tg = c.get("targets")
+            if tg is None:
+                tg = np.arange(self.M)
+            else:
+                tg = np.asarray(tg).astype(np.int64)
+                mask = np.zeros(self.M, dtype=np.uint8)
+                mask[tg] = 1
+                keep.append(mask)
+                d.target_mask = mask.ctypes.data_as(C.POINTER(C.c_uint8))
+            if c.get("m") is None:      # fresh channel: steady state at the current Vmem (vg_na.py:210-228)
+                vm = self.download(["vm"])["vm"][tg]
+                cm, chh = chlib.initial_state(c["model"], vm)
+            else:
+                cm, chh = c["m"], c["h"]
+            m0[tg] = np.asarray(cm, dtype=float) * np.ones(len(tg))
+            h0[tg] = np.asarray(chh, dtype=float) * np.ones(len(tg))
+            keep += [m0, h0]
+            d.m0, d.h0 = capi.ptr_f64(m0), capi.ptr_f64(h0)
+        if affect_charge is None:
+            affect_charge = bool(self.p.get("substances_affect_charge", 0))
+        self._check(self.lib.betse_set_channels(self.ctx, len(specs), arr, int(bool(affect_charge))), "betse_set_channels")
+        self.n_channels = len(specs)
+
+    def channel_state(self, k):
+        """{'m','h','P','flux'} of channel ``k`` ([M] each)."""
+        out = {f: np.empty(self.M) for f in ("m", "h", "P", "flux")}
+        self._check(self.lib.betse_channel_state(self.ctx, int(k), *(capi.ptr_f64(out[f]) for f in ("m", "h", "P", "flux"))),
+                    "betse_channel_state")
+        return out
+
     # ------------------------------------------------------------------ domain decomposition
     def window(self):
         """This rank's exchange window (include/betse_b200.h: betse_window_info)."""

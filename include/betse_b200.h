@@ -184,6 +184,37 @@ const char *betse_kernel_name(int k);
 int  betse_download_sample(betse_ctx *ctx, betse_state_host *state);
 
 /* ---------------------------------------------------------------------------------------------
+ * Voltage-gated channels of the general network:
+ * MasterOfNetworks.run_loop_channels (betse/science/chemistry/networks.py:3115-3213) driving the
+ * Hodgkin-Huxley classes of betse/science/channels/vg_{na,k,ca,cl}.py through
+ * ChannelsABC.update_mh (channels/channelsabc.py:40-60).  A model is DATA: the four quantities
+ * mInf, mTau, hInf, hTau as terms of U = 1000*vm + v_shift [mV] (betse_b200/channels.py documents
+ * the term types and is held to the reference classes by tests/test_channels_table.py). */
+typedef struct betse_gate_term { int32_t type; int32_t pad; double p[4]; } betse_gate_term;
+
+typedef struct betse_channel {
+    int32_t ion;                  /* index of the conducted ion (channel_core.ions[0])            */
+    int32_t mpower, hpower;       /* P = m^mpower * h^hpower (vg_na.py:104)                        */
+    int32_t kind[4];              /* mInf, mTau, hInf, hTau: 0 = a, 1 = a/(a+b), 2 = 1/(a+b)       */
+    int32_t reserved;
+    betse_gate_term a[4], b[4];
+    double time_unit;             /* channel_core.time_unit (1e3 for models in ms)                 */
+    double max_Dm;                /* Channel.maxDm (networks.py:6559)                              */
+    double rel_perm;              /* channel_core.rel_perm[0]                                      */
+    double v_shift;               /* mV added to V inside the model (e.g. vg_ca.py:315: V - 10)    */
+    const uint8_t *target_mask;   /* [M] 1 on channel_core.targets; NULL = every membrane          */
+    const double *m0, *h0;        /* [M] gate states at loop entry (read on targets only)          */
+} betse_channel;
+
+/* Replaces: the channel objects the loop closes over (Channel.init_channel, networks.py:6550-6629).
+ * Channels are applied in list order, each with an immediate concentration update, between the
+ * flux computation of the ion loop and update_all_concs (sim.py:1290-1357).  n = 0 removes them.
+ * affect_charge = p.substances_affect_charge (Jmem takes the channels' currents, networks.py:2971). */
+int  betse_set_channels(betse_ctx *ctx, int n, const betse_channel *channels, int affect_charge);
+/* Gate states / open probability / last flux of channel k, [M] each (NULL members are skipped). */
+int  betse_channel_state(betse_ctx *ctx, int k, double *m, double *h, double *P, double *flux);
+
+/* ---------------------------------------------------------------------------------------------
  * Multi-GPU: the tissue is cut into strips of env-grid rows; each rank owns the
  * cells whose centre lies in its rows.  The reference has no counterpart (one process, one
  * thread); what crosses a strip edge every timestep is exactly what the reference's index arrays

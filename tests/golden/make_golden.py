@@ -68,6 +68,45 @@ SCENARIOS = {
 }
 
 
+def chan_extra(sim, phase):
+    """Channel library state (networks.py:6550-6629; channels/*.py): model, targets, gates."""
+    out = {}
+    core = getattr(getattr(sim, "molecules", None), "core", None)
+    if core is None or not getattr(core, "channels", None):
+        return out
+    names = list(core.channels)
+    out["chan.names"] = np.array(names)
+    for k, n in enumerate(names):
+        c = core.channels[n]
+        cc = c.channel_core
+        out["chan%d.model" % k] = np.array(type(cc).__name__)
+        out["chan%d.ion" % k] = np.array(cc.ions[0])
+        out["chan%d.rel_perm" % k] = np.asarray(float(cc.rel_perm[0]))
+        out["chan%d.maxDm" % k] = np.asarray(float(c.maxDm))
+        out["chan%d.init_active" % k] = np.asarray(int(bool(c.init_active)))
+        out["chan%d.targets" % k] = np.asarray(cc.targets, dtype=np.int64)
+        out["chan%d.m" % k] = np.asarray(cc.m, dtype=float) * np.ones(len(cc.targets))
+        out["chan%d.h" % k] = np.asarray(cc.h, dtype=float) * np.ones(len(cc.targets))
+        if hasattr(cc, "P"):
+            out["chan%d.P" % k] = np.asarray(cc.P, dtype=float)
+        if getattr(cc, "chan_flux", None) is not None:
+            out["chan%d.flux" % k] = np.asarray(cc.chan_flux, dtype=float)
+    return out
+
+
+CHANNELS = [
+    {"name": "Nav", "channel class": "Na", "channel type": "Nav1p3", "max Dm": 2.0e-14, "apply to": "all", "init active": False},
+    {"name": "Kv", "channel class": "K", "channel type": "Kv1p5", "max Dm": 1.0e-15, "apply to": "all", "init active": False},
+    {"name": "K_Leak", "channel class": "K", "channel type": "KLeak", "max Dm": 0.6e-17, "apply to": "all", "init active": True},
+    {"name": "Cav", "channel class": "Ca", "channel type": "Cav1p2", "max Dm": 1.0e-15, "apply to": "all", "init active": False},
+]
+# BASELINE configs[2] in small: voltage-gated Na/K/Ca channels + pumps, full ion profile, ECM
+SCENARIOS["mammal_ecm_chan"] = dict(
+    mods=_m(SMALL, {"cutting event": {"event happens": False}, "general options": {"ion profile": "mammal"},
+                    "general network": {"implement network": True, "biomolecules": [], "channels": CHANNELS}}),
+    snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=chan_extra)
+
+
 def main(argv):
     import scipy
     names = argv or list(SCENARIOS)

@@ -1,0 +1,84 @@
+"""Voltage-gated channels on the GPU (BASELINE configs[2]) through the C ABI:
+against the REAL reference's recorded run of a general network with Nav1p3 / Kv1p5 / KLeak /
+Cav1p2 (tests/golden/mammal_ecm_chan.npz), and against the oracle on a synthetic tissue."""
+import numpy as np
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("kind", ["init", "sim"])
+def test_channels_match_reference(kind):
+    from betse_b200.engine import TissueEngine
+    cap = util.load_golden("mammal_ecm_chan")
+    eng = TissueEngine(util.group(cap, "cells."), util.group(cap, kind + ".p."), util.group(cap, kind + ".s0."))
+    specs = util.channels_of(cap, kind)
+    eng.set_channels(specs, phase_init=(kind == "init"))
+    active = [c for c in specs if not (kind == "init" and not c["init_active"])]
+    n = 0
+    snaps = util.snap_steps(cap, kind)
+    for K in snaps:
+        last = K == snaps[-1]
+        while n < K:
+            assert not util.group(cap, "%s.sched.k%d." % (kind, n + 1))
+            st = eng.step(1, diag=(last and n + 1 == K))
+            assert not (st & 3)
+            n += 1
+        ref = util.group(cap, "%s.k%d." % (kind, K))
+        fields = list(util.STATE) + util.ENV_STATE + (["Jmem", "fluxes_mem"] if last else [])
+        got = eng.download([f for f in fields if f in ref])
+        tols = util.gpu_tolerances(cap, kind, ref)
+        for f, a in got.items():
+            err = float(np.max(np.abs(np.asarray(a).reshape(np.shape(ref[f])) - ref[f])))
+            assert err <= tols[f], (kind, K, f, err, tols[f])
+        for k, c in enumerate(active):
+            j = [s["name"] for s in specs].index(c["name"])
+            stt = eng.channel_state(k)
+            tg = c["targets"]
+            for f in ("m", "h"):
+                r = ref["chan%d.%s" % (j, f)]
+                assert np.max(np.abs(stt[f][tg] - r)) <= 1e-10 * max(np.max(np.abs(r)), 1e-300), (kind, K, c["name"], f)
+            r = ref["chan%d.P" % j]
+            assert np.max(np.abs(stt["P"] - r)) <= 1e-10 * max(np.max(np.abs(r)), 1e-300), (kind, K, c["name"], "P")
+    eng.close()
+
+
+def test_channels_vs_oracle_synthetic():
+    """10 k-cell synthetic tissue with the four channels of BASELINE configs[2], 15 steps."""
+    from betse_b200 import channels as chlib
+    from betse_b200 import synth
+    from betse_b200.engine import TissueEngine
+    from oracle.betse_oracle import OracleSim
+    mesh, p, st = synth.make_tissue(10_000)
+    p["substances_affect_charge"] = 1
+    eng = TissueEngine(mesh, p, st)
+    eng.update_V()
+    ora0 = OracleSim(mesh, p, st)
+    ora0.diagnostics = False
+    ora0.update_V()
+    specs = []
+    for name, model, dm in (("Nav", "Nav1p3", 2.0e-14), ("Kv", "Kv1p5", 1.0e-15), ("K_Leak", "KLeak", 0.6e-17),
+                            ("Cav", "Cav1p2", 1.0e-15)):
+        m0, h0 = chlib.initial_state(model, ora0.vm)
+        specs.append(chlib.make_channel(name, model, dm, m=m0, h=h0))
+    ora = OracleSim(mesh, p, st, channels=specs)
+    ora.diagnostics = False
+    ora.update_V()
+    eng.set_channels(specs)
+    for n in range(15):
+        s = eng.step(1)
+        ora.step()
+        assert not (s & 3)
+    got = eng.download(["cc_cells", "cc_env", "vm", "gjopen"])
+    for f, a in got.items():
+        r = np.asarray(getattr(ora, f))
+        scale = max(float(np.max(np.abs(r))), 1e-300)
+        tol = 1e-10 * scale if f != "vm" else max(1e-10 * scale, 4e-12)
+        assert float(np.max(np.abs(a.reshape(r.shape) - r))) <= tol, f
+    for k, c in enumerate(ora.channels):
+        stt = eng.channel_state(k)
+        for f in ("m", "h", "P"):
+            assert np.max(np.abs(stt[f] - c[f])) <= 1e-10 * max(np.max(np.abs(c[f])), 1e-300), (c["name"], f)
+    eng.close()

@@ -13,7 +13,7 @@ from tests import util
 def test_oracle_reproduces_reference(name, kind):
     cap = util.load_golden(name)
     o = OracleSim(util.group(cap, "cells."), util.group(cap, kind + ".p."),
-                  util.group(cap, kind + ".s0."))
+                  util.group(cap, kind + ".s0."), channels=util.channels_of(cap, kind), phase_init=(kind == "init"))
     n = 0
     checked = 0
     for K in util.snap_steps(cap, kind):
@@ -36,4 +36,10 @@ def test_oracle_reproduces_reference(name, kind):
             err = util.rel_err(getattr(o, f), ref[f], util.scale_of(f, ref))
             assert err < tol, (name, kind, K, f, err)
             checked += 1
+        for k, c in enumerate(o.channels):          # gate states of the channel library
+            for f in ("m", "h", "P"):
+                key = "chan%d.%s" % (k, f)
+                if key in ref and not (kind == "init" and not c["init_active"]):
+                    assert util.rel_err(c[f], ref[key]) < 1e-12, (name, kind, K, key)
+                    checked += 1
     assert checked > 20

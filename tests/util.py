@@ -125,3 +125,18 @@ def gpu_tolerances(cap, kind, ref):
         for f in ("E_cell_x", "E_cell_y", "Emc"):
             tol[f] = tol["Jn"] / smin
     return tol
+
+
+def channels_of(cap, kind, where="s0"):
+    """Channel specs recorded by tests/golden/make_golden.py:chan_extra."""
+    g = group(cap, "%s.%s." % (kind, where))
+    if "chan.names" not in g:
+        return []
+    out = []
+    for k, n in enumerate(g["chan.names"]):
+        pre = "chan%d." % k
+        out.append({"name": str(n), "model": str(g[pre + "model"]), "ion": str(g[pre + "ion"]),
+                    "maxDm": float(g[pre + "maxDm"]), "rel_perm": float(g[pre + "rel_perm"]),
+                    "init_active": bool(int(g[pre + "init_active"])), "targets": g[pre + "targets"],
+                    "m": g[pre + "m"], "h": g[pre + "h"]})
+    return out
