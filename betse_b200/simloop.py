@@ -33,7 +33,7 @@ _P_FIELDS = [
     "KmNK_Na", "KmNK_K", "KmNK_ATP", "KmCa_Ca", "KmCa_ATP", "cATP", "cADP", "cPi", "deltaGATP",
     "gj_surface", "gj_vthresh", "gj_min", "v_sensitive_gj", "cluster_open", "is_ecm", "vol_env",
     "cell_height", "cell_space", "fast_update_ecm", "sharpness", "cell_radius", "true_cell_size",
-    "smooth_cells", "cell_polarizability",
+    "smooth_cells", "cell_polarizability", "substances_affect_charge",
 ]
 _STATE_FIELDS = [
     "cc_cells", "cc_at_mem", "cc_env", "vm", "gjopen", "Dm_cells", "D_gj", "D_free", "zs",
@@ -115,11 +115,46 @@ def state_from_sim(sim):
     return out
 
 
+def channels_from_sim(sim):
+    """Channel specs of the general network (``sim.molecules.core.channels``, built by
+    ``Channel.init_channel``, networks.py:6550-6629) with their current gate states."""
+    core = getattr(getattr(sim, "molecules", None), "core", None)
+    out = []
+    for name, chan in (getattr(core, "channels", None) or {}).items():
+        cc = chan.channel_core
+        if len(cc.ions) != 1:
+            raise BetseB200Error("channel %r conducts %d ions; only single-ion channels are implemented" % (name, len(cc.ions)))
+        out.append({"name": name, "model": type(cc).__name__, "ion": cc.ions[0], "maxDm": float(chan.maxDm),
+                    "rel_perm": float(cc.rel_perm[0]), "init_active": bool(chan.init_active),
+                    "targets": None if cc.targets is None else np.asarray(cc.targets),
+                    "m": np.asarray(cc.m, dtype=float), "h": np.asarray(cc.h, dtype=float), "_obj": chan})
+    return out
+
+
+def _network_is_channels_only(sim):
+    core = getattr(getattr(sim, "molecules", None), "core", None)
+    if core is None:
+        return False
+    if len(getattr(core, "molecules", {}) or {}) or len(getattr(core, "reactions", {}) or {}) or \
+            len(getattr(core, "reactions_env", {}) or {}) or len(getattr(core, "transporters", {}) or {}) or \
+            len(getattr(core, "modulators", {}) or {}):
+        return False
+    for chan in (getattr(core, "channels", None) or {}).values():
+        # activators / inhibitors make `moddy` != 1 (networks.py:3147): not implemented
+        for f in ("channel_activators_list", "channel_inhibitors_list"):
+            v = getattr(chan, f, None)
+            if v not in (None, "None", []):
+                return False
+    return True
+
+
 def check_supported(sim, p):
     """Refuse loudly instead of silently computing a different model."""
     bad = []
-    for flag, what in (("molecules_enabled", "general network (networks.py run_loop*)"),
-                       ("grn_enabled", "gene regulatory network"),
+    if bool(getattr(p, "molecules_enabled", False)) and not _network_is_channels_only(sim):
+        bad.append("general network with substances / reactions / transporters / modulated channels "
+                   "(networks.py run_loop*; plain voltage-gated channels are supported)")
+    for flag, what in (("grn_enabled", "gene regulatory network"),
                        ("deformation", "deformation"), ("deform_osmo", "osmotic pressure"),
                        ("fluid_flow", "fluid flow"), ("Ca_dyn", "ER calcium dynamics")):
         if bool(getattr(p, flag, False)):
@@ -133,9 +168,15 @@ def check_supported(sim, p):
                              " — run this configuration with the reference solver")
 
 
-def engine_from_sim(sim, cells, p, device=0):
+def engine_from_sim(sim, cells, p, device=0, phase_init=False):
     check_supported(sim, p)
-    return TissueEngine(mesh_from_cells(cells), params_from_p(p), state_from_sim(sim), device=device)
+    eng = TissueEngine(mesh_from_cells(cells), params_from_p(p), state_from_sim(sim), device=device)
+    eng.chan_specs = []
+    if bool(getattr(p, "molecules_enabled", False)):
+        specs = channels_from_sim(sim)
+        eng.set_channels(specs, phase_init=phase_init, affect_charge=bool(getattr(p, "substances_affect_charge", False)))
+        eng.chan_specs = [c for c in specs if not (phase_init and not c["init_active"])]
+    return eng
 
 
 def _copy_back(sim, eng, diag):
@@ -150,6 +191,13 @@ def _copy_back(sim, eng, diag):
         if f in ("E_env_x", "E_env_y"):
             a = a.reshape(shp)                     # the reference keeps these 2-D (sim.py:572-573)
         setattr(sim, f, a)
+    # channel objects keep their gate state / open probability / flux (read by the exporters and by
+    # the next phase through the pickled Simulator)
+    for k, c in enumerate(getattr(eng, "chan_specs", [])):
+        cc = c["_obj"].channel_core
+        stt = eng.channel_state(k)
+        tg = slice(None) if cc.targets is None else np.asarray(cc.targets)
+        cc.m, cc.h, cc.P, cc.chan_flux = stt["m"][tg], stt["h"][tg], stt["P"], stt["flux"]
     return 0
 
 
@@ -158,9 +206,9 @@ def run_sim_core_loop(sim, phase, time_steps, time_steps_sampled, anim_cells=Non
     """Same signature and contract as Simulator._run_sim_core_loop (sim.py:1132-1138)."""
     p, cells = phase.p, phase.cells
     own_engine = engine is None
-    eng = engine or engine_from_sim(sim, cells, p, device=device)
     kind = getattr(getattr(phase, "kind", None), "name", str(getattr(phase, "kind", "")))
     is_sim = kind.upper() == "SIM"
+    eng = engine or engine_from_sim(sim, cells, p, device=device, phase_init=not is_sim)
     fire = getattr(getattr(phase, "dyna", None), "fire_events", None) if is_sim else None
     sampled = set(time_steps_sampled)
     Unstable = _unstable_exception()
