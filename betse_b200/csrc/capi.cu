@@ -85,7 +85,7 @@ template <typename T>
 static int dev_alloc(betse_ctx* ctx, T** p, size_t n, bool zero = true)
 {
     if (n == 0) n = 1;
-    CK(cudaMalloc((void**)p, n * sizeof(T)));
+    CK(cudaMalloc((void**)p, n * sizeof(T) + 16));   // 16 bytes of slack: k_mem_pipe fetches 16-byte aligned supersets of rows
     ctx->allocs.push_back((void*)*p);
     if (zero) CK(cudaMemsetAsync(*p, 0, n * sizeof(T), ctx->stream));
     return 0;

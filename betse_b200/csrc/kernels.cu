@@ -17,61 +17,7 @@
 #include <stdlib.h>
 #include "kparams.cuh"
 
-#define FLOAT_NONCE 1.0e-25   // sim_toolbox.py:52
-
-#define ST_NAN_VM 1u
-#define ST_NAN_CONC 2u
-#define ST_NEG 4u
-
-__device__ __forceinline__ double ldg(const double* p) { return __ldg(p); }
-__device__ __forceinline__ int ldgi(const int* p) { return __ldg(p); }
-
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-// 1/x for finite, normal, non-zero x: MUFU.RCP64H seed (~20 bits) + two Newton steps; <= 1 ulp,
-// branch-free (the compiler's IEEE division carries a slow-path call per use).
-__device__ __forceinline__ double fast_rcp(double x)
-{
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    return r;
-}
-// a/b with one residual correction (<= 1 ulp)
-__device__ __forceinline__ double fast_div(double a, double b)
-{
-    const double r = fast_rcp(b);
-    const double q = a * r;
-    return fma(fma(-b, q, a), r, q);
-}
-
-// GHK flux in "A/B form".  With alpha = z*a1, ex = exp(-alpha), rden = 1/(-expm1(-alpha)) the
-// reference's  -((D*alpha)/d)*((cB - cA*ex)*rden)  (sim_toolbox.py:58-65) equals
-// -(D/d)*(cB*A - cA*B) with A = alpha*rden, B = A*ex.  For the valences that occur (+-1, +-2)
-// everything follows from ONE expm1 at -a1:  A(+1) = a1/(-em1), B(+1) = A(+1)*e1,
-// A(+2) = 2*a1/((-em1)*(e1+1)), B(+2) = A(+2)*e1^2, and A(-z) = B(+z), B(-z) = A(+z).
-struct GhkAB {
-    double A1, B1, A2, B2;
-    __device__ __forceinline__ void init(double a1, double e1, double em1) {
-        const double e1p1 = e1 + 1.0;
-        const double R = fast_rcp((-em1) * e1p1);     // 1/((-em1)(e1+1))
-        A2 = (2.0 * a1) * R;
-        A1 = (a1 * R) * e1p1;
-        B1 = A1 * e1;
-        B2 = A2 * (e1 * e1);
-    }
-};
-
-// generic valence (incl. 0: the reference adds 1e-25 to z, sim_toolbox.py:56); rare, kept out of line
-__device__ __noinline__ double2 ghk_generic(double z, double a1)
-{
-    const double al = (z + FLOAT_NONCE) * a1;
-    const double a = al / (-expm1(-al));
-    return make_double2(a, a * exp(-al));
-}
+#include "kmath.cuh"
 
 // Shared-memory plan of k_mem, per warp (doubles): staged flux*sa [32][NI] for the membrane and
 // the gap-junction flux (AoS: the warp's slice of flux_slots is a straight copy), and a scratch
@@ -79,26 +25,6 @@ __device__ __noinline__ double2 ghk_generic(double z, double a1)
 // concentrations of the tile's cells).
 #define KM_WARP_DOUBLES(NI) (64 * (NI) + 256)
 #define KM_SMEM_DOUBLES(NI) (8 * KM_WARP_DOUBLES(NI))
-
-// The reference's ion order is fixed (Na, K, Cl, Ca, H, P, M; parameters.py:1296), so the shipped
-// ion profiles give three valence signatures.  PROF = 1 builds bake the signature of the NI-ion
-// profile plus the default feature switches (extracellular spaces, voltage-sensitive gap
-// junctions, open cluster boundary, no per-membrane block arrays, no diagnostics) into the
-// kernel; PROF = 0 reads everything from KParams at run time.
-template <int NI> struct StdProf;
-template <> struct StdProf<4> { static constexpr int iNa = 0, iK = 1, iCa = -1; __host__ __device__ static constexpr int z(int i) { constexpr int t[4] = {1, 1, -1, -1}; return t[i]; } };       // basic: Na K P M
-template <> struct StdProf<5> { static constexpr int iNa = 0, iK = 1, iCa = 2; __host__ __device__ static constexpr int z(int i) { constexpr int t[5] = {1, 1, 2, -1, -1}; return t[i]; } };     // basic_Ca: Na K Ca P M
-template <> struct StdProf<6> { static constexpr int iNa = 0, iK = 1, iCa = 3; __host__ __device__ static constexpr int z(int i) { constexpr int t[6] = {1, 1, -1, 2, -1, -1}; return t[i]; } };  // mammal/amphibian/custom: Na K Cl Ca P M
-template <> struct StdProf<7> { static constexpr int iNa = 0, iK = 1, iCa = 3; __host__ __device__ static constexpr int z(int i) { constexpr int t[7] = {1, 1, -1, 2, 1, -1, -1}; return t[i]; } }; // + H
-template <> struct StdProf<8> { static constexpr int iNa = 0, iK = 1, iCa = 3; __host__ __device__ static constexpr int z(int i) { return 0; } };
-
-__device__ __forceinline__ void ghk_pick(const GhkAB& t, int zi, double& A, double& B)
-{
-    const bool two = (zi == 2) || (zi == -2);
-    const double X = two ? t.A2 : t.A1, Y = two ? t.B2 : t.B1;
-    A = (zi < 0) ? Y : X;
-    B = (zi < 0) ? X : Y;
-}
 
 // One WARP per tile of whole cells with <= 32 membranes (host-built packing, tile_desc):
 // lanes are membranes while the fluxes are formed, then (cell, ion) pairs for the membrane->cell
@@ -184,40 +110,21 @@ k_mem(const __grid_constant__ KParams P, const KArrays A, const int cur, const i
         // membrane side: electroflux adds 1e-25 to vBA (sim_toolbox.py:54); alpha for z = +1
         const double a1 = ((vm_own + FLOAT_NONCE) * P.F) * P.inv_RT_sim;
         GhkAB tm;
-        double keq;                                   // K0/e1 = exp(-dG/RT + F vm/RT): pump Keq
-        {
-            const double e1 = exp(-a1);
-            tm.init(a1, e1, expm1(-a1));
-            keq = P.K0 * fast_rcp(e1);
-        }
-        // gap junction: vgj and its GHK table with p.T (sim.py:2166, 2197).  alpha is small here:
-        // exp(x) = 1 + expm1(x) to <= 1.5 ulp for x >= -1, plain exp below that
+        const double keq = P.K0 * fast_rcp(ghk_table(a1, tm));   // K0/e1 = exp(-dG/RT + F vm/RT): pump Keq
+        // gap junction: vgj and its GHK table with p.T (sim.py:2166, 2197)
         const double vgj0 = vm_nb - vm_own;
         const double ag1 = ((vgj0 + FLOAT_NONCE) * P.F) * P.inv_RT_p;
         GhkAB tg;
-        {
-            const double em1 = expm1(-ag1);
-            const double e1 = (ag1 > 1.0) ? exp(-ag1) : 1.0 + em1;
-            tg.init(ag1, e1, em1);
-        }
+        ghk_table(ag1, tg);
         if (!S) {
             s_t[0 * 32 + lane] = tm.A1; s_t[1 * 32 + lane] = tm.B1; s_t[2 * 32 + lane] = tm.A2; s_t[3 * 32 + lane] = tm.B2;
             s_t[4 * 32 + lane] = tg.A1; s_t[5 * 32 + lane] = tg.B1; s_t[6 * 32 + lane] = tg.A2; s_t[7 * 32 + lane] = tg.B2;
         }
-        // gating (gap_junction.py:56-72) as g' = gjb*((g + dtm*al)*D1 + dtm*be0*gmin) / (D1*(1 + dtm*al) + dtm*be0),
-        // D1 = 1 + 50*be0: the two divisions of the reference folded into one reciprocal
-        double gA = 0.0, gB = 0.0, gD1 = 1.0, gr = 1.0;
-        if (vsens) {
-            const double xg = 1.0e3 * fabs(vgj0) - P.gj_vthresh;
-            const double al = 0.0013 * exp(-0.077 * xg);
-            const double be0 = 0.0013 * exp(0.14 * xg);
-            gD1 = fma(50.0, be0, 1.0);
-            gA = P.dtm * al;
-            gB = (P.dtm * be0) * P.gj_min;
-            gr = fast_rcp(fma(gD1, 1.0 + gA, P.dtm * be0));
-        }
+        // gating (gap_junction.py:56-72): one implicit-Euler sub-step is the affine map g' = g*gc1 + gc2
         const double gjb = (!S && A.gj_block) ? ldg(A.gj_block + m) : P.gj_block;
-        const double gjw = vsens ? 1.0 : ldg(A.gj_w + m);
+        double gc1 = 0.0, gc2;
+        if (vsens) gj_gate_map(vgj0, P, gjb, gc1, gc2);
+        else gc2 = gjb * ldg(A.gj_w + m);             // static gap junctions, sim.py:2186
         const bool closed_bnd = (!cl_open) && bnd;
 
         // ---- Na/K-ATPase (sim_toolbox.py:71-122); Keq = exp(-dG/RT + F vm/RT) = K0/e1
@@ -295,8 +202,7 @@ k_mem(const __grid_constant__ KParams P, const KArrays A, const int cur, const i
             if (i == iK) f += fK;
             if (i == iCa) f += fCa;
             // gap junction: gating advances once per ion (sim.py:1272 -> 2180-2183)
-            if (vsens) g = gjb * ((fma(g + gA, gD1, gB)) * gr);
-            else g = gjb * gjw;
+            g = fma(g, gc1, gc2);
             // cA = this cell, cB = partner cell (sim.py:2191-2197)
             double fg = -((P.Dgj_surf[i] * g) * P.inv_gjl) * (cnb[i] * Ag - cin[i] * Bg);
             if (bnd) fg = 0.0;
@@ -766,6 +672,12 @@ static int kmem_minb()
     return v;
 }
 
+// kmem_pipe.cu: the persistent, software-pipelined build of the specialised kernel
+bool kmem_pipe_enabled();
+cudaError_t prepare_mem_pipe(int ni);
+void launch_mem_pipe(int ni, const KParams& P, const KArrays& A, int n_sms, int cur, cudaStream_t st);
+static int g_n_sms = 148;
+
 template <int NI>
 static void launch_mem_t(const KParams& P, const KArrays& A, int n_ctas, int cur, int diag, cudaStream_t st)
 {
@@ -778,6 +690,7 @@ static void launch_mem_t(const KParams& P, const KArrays& A, int n_ctas, int cur
                     P.iCa == StdProf<NI>::iCa && !kmem_generic() && !P.defer;
     for (int i = 0; i < NI && std_prof; ++i) std_prof = (P.zi[i] == StdProf<NI>::z(i)) && P.zi[i] != 0;
     if (P.has_phi) k_mem<NI, true, 2, 0><<<grid, BT_TPB, smem, st>>>(P, A, cur, diag);
+    else if (std_prof && kmem_pipe_enabled()) launch_mem_pipe(NI, P, A, g_n_sms, cur, st);
     else if (std_prof && minb2) k_mem<NI, false, 2, 1><<<grid, BT_TPB, smem, st>>>(P, A, cur, diag);
     else if (std_prof && kmem_minb() == 4) k_mem<NI, false, 4, 1><<<grid, BT_TPB, smem, st>>>(P, A, cur, diag);
     else if (std_prof) k_mem<NI, false, 3, 1><<<grid, BT_TPB, smem, st>>>(P, A, cur, diag);
@@ -807,6 +720,11 @@ static cudaError_t prepare_mem_t()
 // not capturable: called once per context before the first launch
 cudaError_t prepare_kernels(int ni)
 {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) g_n_sms = sms;
+    cudaError_t ep = prepare_mem_pipe(ni);
+    if (ep) return ep;
     switch (ni) {
         case 4: return prepare_mem_t<4>();
         case 5: return prepare_mem_t<5>();

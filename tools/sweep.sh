@@ -1,6 +1,6 @@
 #!/bin/bash
-# usage (on the GPU box): tools/sweep.sh  -> prints ms/step and kernel times for env-var variants
-for ov in 1 0; do
-  BETSE_OVERLAP=$ov python bench.py --steps 100 --warmup 10 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('overlap=$ov', round(d['ms_per_step'],4), {k:round(v,4) for k,v in d['roofline']['kernel_ms'].items()})"
+# usage (on the GPU box): tools/sweep.sh "VAR=val VAR2=val" "VAR=val2" ...  -> ms/step and kernel times per env-var variant
+for v in "$@"; do
+  env $v python bench.py --steps 100 --warmup 10 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('$v', round(d['ms_per_step'],4), {k:round(x,4) for k,x in d['roofline']['kernel_ms'].items()}, 'finite', d.get('finite'), 'status', d.get('status_word'))"
 done
