@@ -26,6 +26,11 @@ void launch_envmix(int ni, const KParams& P, const KArrays& A, int cur, cudaStre
 void launch_diag(int ni, const KParams& P, const KArrays& A, int n_ctas, int newb, cudaStream_t st);
 void launch_expand_vm(const KParams& P, const KArrays& A, int M, int C, int cur, cudaStream_t st);
 cudaError_t prepare_kernels(int ni);
+// kmem_pipe.cu: the per-tile constant blocks of the pipelined membrane kernel
+unsigned tile_pack_size(int ni, int nm, int nc);
+void tile_pack_fill(char* blk, int ni, int nm, int nc, const double* mem_sa, const double* cell_vol, const double* diviterm,
+                    const int* mem_to_cells, const int* nn_cell_flag, const int* map_mem2ecm, const int* cell_mem_ptr);
+void launch_pack_dm(const KParams& P, const KArrays& A, cudaStream_t st);
 void launch_chan(const KParams& P, const KArrays& A, const KChan& ch, int cur, cudaStream_t st);
 void launch_cell_update(const KParams& P, const KArrays& A, int cur, cudaStream_t st);
 void launch_xchg(const KParams& P, const KArrays& A, const XPlan& X, int which, int buf, int mode, cudaStream_t st);
@@ -316,6 +321,27 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
         tdesc[4 * t + 2] = mesh->cell_mem_ptr[a]; tdesc[4 * t + 3] = mesh->cell_mem_ptr[b] - mesh->cell_mem_ptr[a];
     }
     if ((r = dev_upload(ctx, (int**)&A.tile_desc, tdesc.data(), tdesc.size()))) return r;
+    // ---- tile pack (k_mem_pipe): every tile's constant inputs as one contiguous, 16-byte aligned block; the Dm rows
+    //      are (re)filled on the device whenever Dm_cells is uploaded (launch_pack_dm)
+    if (hp->n_ions <= 7) {
+        std::vector<int> toff(ctx->n_tiles);
+        size_t total = 0;
+        for (int t = 0; t < ctx->n_tiles; ++t) {
+            toff[t] = (int)(total / 16);
+            total += tile_pack_size(hp->n_ions, tdesc[4 * t + 3], tdesc[4 * t + 1]);
+        }
+        if (total / 16 >= ((size_t)1 << 31)) return fail(ctx, "tile pack exceeds 32 GB");
+        std::vector<char> pack(total, 0);
+        for (int t = 0; t < ctx->n_tiles; ++t) {
+            const int c0 = tdesc[4 * t], nc = tdesc[4 * t + 1], m0 = tdesc[4 * t + 2], nm = tdesc[4 * t + 3];
+            tile_pack_fill(pack.data() + (size_t)toff[t] * 16, hp->n_ions, nm, nc, mesh->mem_sa + m0, mesh->cell_vol + c0,
+                           mesh->diviterm + c0, mesh->mem_to_cells + m0, nnc.data() + m0, mesh->map_mem2ecm + m0,
+                           mesh->cell_mem_ptr + c0);
+        }
+        if ((r = dev_upload(ctx, (char**)&A.tile_pack, pack.data(), total))) return r;
+        if ((r = dev_upload(ctx, (int**)&A.tile_off, toff.data(), toff.size()))) return r;
+        CK(cudaStreamSynchronize(ctx->stream));     // the host vectors go out of scope
+    }
 
     // ---- env point -> flux slot CSR (map_ecm2mem, cells.py:1793-1796), slots in membrane order
     ctx->n_slots = mesh->n_flux_slots > Mo ? mesh->n_flux_slots : Mo;
@@ -479,6 +505,7 @@ extern "C" int betse_upload_state(betse_ctx* ctx, const betse_state_host* s)
     }
     UP(A.gjopen, s->gjopen, Mo);
     UP(A.Dm, s->Dm_cells, IM);
+    if (s->Dm_cells) launch_pack_dm(ctx->P, A, st);
     if (s->vm_cell) {
         CK(cudaMemcpyAsync(A.vm_cell[cur], s->vm_cell, (size_t)C * sizeof(double), cudaMemcpyHostToDevice, st));
     } else if (s->vm) {

@@ -1,29 +1,26 @@
 // k_mem_pipe — the membranes->cells kernel of the tissue step as a persistent, software-pipelined
 // warp kernel (same arithmetic as kernels.cu:k_mem; shared helpers in kmath.cuh).
 //
-// Why: k_mem is latency- and LSU-bound, not bandwidth-bound (ncu, profiles/r01d, r01e: 38 % issue
-// utilisation, long-scoreboard stalls; a first cp.async-only pipeline moved the stall to the LSU:
-// 50 LDGSTS per tile at ~8 cycles each).  A tile's inputs arrive in three dependent round trips
-// (tile descriptor -> membrane index arrays -> gathers through those indices).  Here every warp
-// walks a strided sequence of tiles and keeps the NEXT tiles' inputs in flight while it does the
-// arithmetic of the current one:
+// Why: k_mem is latency- and LSU-bound, not bandwidth-bound (ncu summaries profiles/r01d, r01e:
+// 38 % issue utilisation with long-scoreboard stalls; a cp.async-only pipeline moved the stall to
+// the LSU — 50 LDGSTS per tile at ~8 cycles each; one TMA bulk copy per row costs ~12 issue slots
+// per copy because UBLKCP takes uniform operands and per-lane copies are serialised).  A tile's
+// inputs arrive in three dependent round trips (tile descriptor -> membrane index arrays ->
+// gathers through those indices).  Here every warp walks a strided sequence of tiles and keeps
+// the NEXT tiles' inputs in flight while it does the arithmetic of the current one:
 //
-//   S = per-membrane streams of a tile (Dm[I], mem_sa, gjopen, mem_to_cells, nn_cell_flag,
-//       map_mem2ecm): contiguous rows -> ONE TMA bulk copy per row (cp.async.bulk, issued by one
-//       lane per row, completion on an mbarrier), two tiles ahead;
-//   C = per-cell block (cell_vol, diviterm, Vmem, cc_cells[I], cc_mid[I], cell_mem_ptr): rows
-//       again, one tile ahead, same mbarrier;
-//   G = gathers through the landed indices of S (env concentrations at the membrane's env square,
-//       partner-cell concentrations and Vmem, transported Ca): cp.async (LDGSTS), one tile ahead.
+//   K = the tile's constant block ("tile pack", built once by the host + k_pack_dm): Dm[I][nm],
+//       mem_sa[nm], cell_vol[nc], diviterm[nc], mem_to_cells[nm], nn_cell_flag[nm],
+//       map_mem2ecm[nm], cell_mem_ptr[nc+1] contiguous and 16-byte aligned -> ONE TMA bulk copy
+//       (cp.async.bulk by lane 0, completion on an mbarrier), two tiles ahead;
+//   G = state and gathers, cp.async (LDGSTS), one tile ahead: gjopen; Vmem, cc_cells, cc_mid of
+//       the tile's cells; through the landed indices of K: env concentrations at the membrane's
+//       env square, partner-cell concentrations and Vmem, transported Ca.
 //
-//   iteration t:  wait (mbarrier of t-1, cp.async group)   -> S(t+1), C(t), G(t) have landed
-//                 S(t), G(t) -> registers
-//                 issue S(t+2) into S(t)'s buffer, C(t+1), G(t+1)
-//                 arithmetic of tile t (staging of f*sa aliases the consumed G(t) buffer)
-//
-// Bulk copies need 16-byte aligned addresses and sizes: a row is fetched as the aligned superset of
-// [start, start+n) and read back at the offset (start*esize mod 16)/esize.  Array bases are 16-byte
-// aligned (cudaMalloc / 256-byte carved window) and allocations carry 16 bytes of slack (capi.cu).
+//   iteration t:  wait (mbarrier of t-1, cp.async group)   -> K(t+1), G(t) have landed
+//                 K(t), G(t) -> registers
+//                 issue K(t+2) into K(t)'s buffer, G(t+1)
+//                 arithmetic of tile t (staging of f*sa aliases the consumed gather rows)
 //
 // Reference lines as in k_mem: sim.py:1193-1283, 2086-2111, 2162-2206; sim_toolbox.py:18-182,
 // 1155-1207; channels/gap_junction.py:53-77; ion_current.py:19; sim.py:2027-2029.
@@ -32,16 +29,13 @@
 #include "kmath.cuh"
 
 #define KP_MAXC 10                                   // cells per tile (host packing, capi.cu)
-#define KP_ROW8 34                                   // doubles per membrane row (32 + alignment slack; 272 B)
-#define KP_ROW4 36                                   // ints per membrane index row (144 B)
-#define KP_CROW8 12                                  // doubles per cell row (10 + slack; 96 B)
-#define KP_CROW4 16                                  // ints of the cell_mem_ptr row (11 + slack; 64 B)
 #define KP_SST 33                                    // staging stride (doubles): conflict-free f*sa [ion][membrane]
 // per-warp shared memory, in doubles
-#define KP_S(NI) (((NI) + 2) * KP_ROW8 + 3 * KP_ROW4 / 2)
-#define KP_G(NI) ((2 * (NI) + 2) * 32)               // co[NI][32], cnb[NI][32], vnb[32], cao[32]; then staging 2*NI*33
-#define KP_C(NI) ((3 + 2 * (NI)) * KP_CROW8 + KP_CROW4 / 2)
-#define KP_WARP(NI) (2 + 2 * KP_S(NI) + 2 * KP_G(NI) + 2 * KP_C(NI) + (NI) * KP_MAXC)
+#define KP_K(NI) ((((NI) + 1) * 32 + 2 * KP_MAXC) + ((3 * 32 + KP_MAXC + 1 + 3) / 4) * 2)   // tile pack, max size, 16 B multiple
+#define KP_G(NI) ((2 * (NI) + 3) * 32)               // co[NI][32], cnb[NI][32], vnb[32], cao[32], gj[32]; then staging 2*NI*33
+#define KP_C(NI) (KP_MAXC + 2 * (NI) * KP_MAXC)      // vmo[c], cc[c][NI], cmid[c][NI]
+#define KP_AUX 16                                    // cell_mem_ptr[11] (6 doubles) + cell_vol[10] of the current tile (tiles with > 32/NI cells)
+#define KP_WARP(NI) (2 + 2 * KP_K(NI) + 2 * KP_G(NI) + 2 * KP_C(NI) + (NI) * KP_MAXC + KP_AUX)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp8(uint32_t s, const void* g)
@@ -56,6 +50,10 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, unsigned count)
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, unsigned bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, unsigned parity)
 {
@@ -75,67 +73,36 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, unsigned
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-// One lane = one row of the S or C block (set up once per kernel).
-struct KRow {
-    const char* src;   // row base in global memory (null: this lane has no row)
-    int sh;            // log2(element size)
-    int kind;          // 0: membrane row (S), 1: cell row (C), 2: cell_mem_ptr row (C, nc+1 elements)
-    int dst;           // byte offset inside the S / C buffer
-};
-
-template <int NI>
-__device__ __forceinline__ KRow make_row(const KArrays& A, const int lane, const int C, const int Mo, const int cur)
+// bytes of a tile's constant block (the layout in the header), rounded up to 16
+__host__ __device__ __forceinline__ unsigned tile_pack_bytes(int ni, int nm, int nc)
 {
-    KRow r;
-    r.src = nullptr; r.sh = 3; r.kind = 0; r.dst = 0;
-    if (lane < NI) { r.src = (const char*)(A.Dm + (size_t)lane * Mo); r.dst = lane * (KP_ROW8 * 8); }
-    else if (lane == NI) { r.src = (const char*)A.mem_sa; r.dst = NI * (KP_ROW8 * 8); }
-    else if (lane == NI + 1) { r.src = (const char*)A.gjopen; r.dst = (NI + 1) * (KP_ROW8 * 8); }
-    else if (lane < NI + 5) {
-        const int j = lane - (NI + 2);
-        r.src = (const char*)(j == 0 ? A.mem_to_cells : j == 1 ? A.nn_cell_flag : A.map_mem2ecm);
-        r.sh = 2; r.dst = (NI + 2) * (KP_ROW8 * 8) + j * (KP_ROW4 * 4);
-    } else if (lane < 3 * NI + 9) {
-        const int j = lane - (NI + 5);
-        r.kind = 1; r.dst = j * (KP_CROW8 * 8);
-        if (j == 0) r.src = (const char*)A.cell_vol;
-        else if (j == 1) r.src = (const char*)A.diviterm;
-        else if (j == 2) r.src = (const char*)A.vm_cell[cur];
-        else if (j < 3 + NI) r.src = (const char*)(A.cc_cells + (size_t)(j - 3) * C);
-        else if (j < 3 + 2 * NI) r.src = (const char*)(A.cc_mid[cur] + (size_t)(j - 3 - NI) * C);
-        else { r.src = (const char*)A.cell_mem_ptr; r.sh = 2; r.kind = 2; }
-    }
-    return r;
+    return (8u * ((ni + 1) * nm + 2 * nc) + 4u * (3 * nm + nc + 1) + 15u) & ~15u;
 }
 
-// rows of S(tdS) -> Sdst and of C(tdC) -> Cdst, completion on `bar`
-__device__ __forceinline__ void issue_rows(const KRow& r, const int4 tdS, const int4 tdC, const uint32_t Sdst,
-                                           const uint32_t Cdst, const uint32_t bar, const int lane)
+// the constant block of tile td (offset off16*16 in the pack) -> Kdst; always completes one phase of `bar`
+template <int NI>
+__device__ __forceinline__ void issue_K(const KArrays& A, const int4 td, const int off16, const uint32_t Kdst,
+                                        const uint32_t bar, const int lane)
 {
-    int start, n;
-    uint32_t dstb;
-    if (r.kind == 0) { start = tdS.z; n = tdS.w; dstb = Sdst; }
-    else { start = tdC.x; n = tdC.y ? tdC.y + (r.kind == 2 ? 1 : 0) : 0; dstb = Cdst; }
-    if (r.src == nullptr) n = 0;
-    const uintptr_t a = (uintptr_t)r.src + ((size_t)start << r.sh);
-    const unsigned head = (unsigned)(a & 15);
-    const unsigned bytes = n ? ((head + ((unsigned)n << r.sh) + 15u) & ~15u) : 0u;
-    const unsigned total = __reduce_add_sync(0xffffffffu, bytes);
-    if (total) {
-        if (lane == 0) mbar_expect_tx(bar, total);
-        if (bytes) bulk_g2s(dstb + r.dst, (const void*)(a - head), bytes, bar);
+    if (lane == 0) {
+        if (td.w > 0) {
+            const unsigned bytes = tile_pack_bytes(NI, td.w, td.y);
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(Kdst, A.tile_pack + (size_t)off16 * 16, bytes, bar);
+        } else mbar_arrive(bar);
     }
 }
 
-// gathers of tile td through the indices in its (landed) S buffer
+// state + gathers of tile td through the indices in its (landed) constant block K
 template <int NI>
-__device__ __forceinline__ void issue_G(const KArrays& A, const int4 td, const double* S, double* G, const int lane,
-                                        const int C, const int E, const int cur)
+__device__ __forceinline__ void issue_G(const KArrays& A, const int4 td, const double* K, double* G, double* Cs,
+                                        const int lane, const int C, const int E, const int cur)
 {
-    if (lane < td.w) {
-        const int* Si = reinterpret_cast<const int*>(S + (NI + 2) * KP_ROW8) + (td.z & 3) + lane;
-        const int cn = Si[KP_ROW4] & 0x7fffffff;
-        const int e = Si[2 * KP_ROW4];
+    const int c0 = td.x, nc = td.y, m0 = td.z, nm = td.w;
+    if (lane < nm) {
+        const int* Ki = reinterpret_cast<const int*>(K + (NI + 1) * nm + 2 * nc);
+        const int cn = Ki[nm + lane] & 0x7fffffff;
+        const int e = Ki[2 * nm + lane];
         const double* __restrict__ cenv = A.cc_env[cur] + e;
         const double* __restrict__ cmid = A.cc_mid[cur] + cn;
         const uint32_t g = smem_u32(G + lane);
@@ -145,6 +112,14 @@ __device__ __forceinline__ void issue_G(const KArrays& A, const int4 td, const d
         for (int i = 0; i < NI; ++i) cp8(g + (NI + i) * 256, cmid + (size_t)i * C);
         cp8(g + (2 * NI) * 256, A.vm_cell[cur] + cn);
         if (StdProf<NI>::iCa >= 0) cp8(g + (2 * NI + 1) * 256, A.cc_env[cur ^ 1] + (size_t)StdProf<NI>::iCa * E + e);
+        cp8(g + (2 * NI + 2) * 256, A.gjopen + m0 + lane);
+    }
+    if (lane < nc) cp8(smem_u32(Cs + lane), A.vm_cell[cur] + c0 + lane);
+    for (int q = lane; q < nc * NI; q += 32) {
+        const int lc = q / NI, i = q - lc * NI;
+        const size_t o = (size_t)i * C + c0 + lc;
+        cp8(smem_u32(Cs + KP_MAXC + q), A.cc_cells + o);
+        cp8(smem_u32(Cs + KP_MAXC + NI * KP_MAXC + q), A.cc_mid[cur] + o);
     }
 }
 
@@ -160,19 +135,21 @@ k_mem_pipe(const __grid_constant__ KParams P, const KArrays A, const int cur)
     const int nt = P.n_tiles;
     double* base = sm + (size_t)wib * KP_WARP(NI);
     // rings (buffer b = 0/1) by plain arithmetic: an indexed pointer array would live in local memory
-    double* const S0 = base + 2;
-    double* const G0 = S0 + 2 * KP_S(NI);
+    double* const K0 = base + 2;
+    double* const G0 = K0 + 2 * KP_K(NI);
     double* const C0 = G0 + 2 * KP_G(NI);
     double* const s_cc = C0 + 2 * KP_C(NI);
-#define SB(b) (S0 + (b) * KP_S(NI))
+    double* const s_aux = s_cc + NI * KP_MAXC;
+#define KB(b) (K0 + (b) * KP_K(NI))
 #define GB(b) (G0 + (b) * KP_G(NI))
 #define CB(b) (C0 + (b) * KP_C(NI))
     const uint32_t bar0 = smem_u32(base);             // two mbarriers (one per iteration parity)
 
     constexpr int iNa = StdProf<NI>::iNa, iK = StdProf<NI>::iK, iCa = StdProf<NI>::iCa;
     const int nxt = cur ^ 1;
-    const int C = P.n_cells, E = P.ny * P.nx, Mo = P.n_mems_owned;
+    const int C = P.n_cells, E = P.ny * P.nx;
     const int4* __restrict__ TD = reinterpret_cast<const int4*>(A.tile_desc);
+    const int* __restrict__ TO = A.tile_off;
     const int4 zero4 = make_int4(0, 0, 0, 0);
     unsigned int flags = 0;
 
@@ -183,71 +160,74 @@ k_mem_pipe(const __grid_constant__ KParams P, const KArrays A, const int cur)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncwarp();
-    const KRow row = make_row<NI>(A, lane, C, Mo, cur);
     // tile-independent lane roles of the later phases: lane = (cell, ion) pair; slot-copy element p = lane + 32k
     const int q0c = lane / NI, q0i = lane - q0c * NI;
     int cpy[NI];                                       // staging index of element p = lane + 32 k of the [membrane][ion] slot block
 #pragma unroll
     for (int k = 0; k < NI; ++k) { const int p = lane + 32 * k; const int m = p / NI; cpy[k] = (p - m * NI) * KP_SST + m; }
 
-    // ---- prologue = pseudo-iterations -2 (barrier 0: S(t)) and -1 (barrier 1: S(t+1), C(t));
-    //      then G(t) through the landed indices of S(t)
+    // ---- prologue = pseudo-iterations -2 (barrier 0: K(t)) and -1 (barrier 1: K(t+1)); then G(t)
     int4 td0 = (tile < nt) ? __ldg(TD + tile) : zero4;
     int4 td1 = (tile + W < nt) ? __ldg(TD + tile + W) : zero4;
     int4 td2 = (tile + 2 * W < nt) ? __ldg(TD + tile + 2 * W) : zero4;
+    int to2 = (tile + 2 * W < nt) ? __ldg(TO + tile + 2 * W) : 0;
     if (td0.w == 0) return;
-    issue_rows(row, td0, zero4, smem_u32(SB(0)), smem_u32(CB(0)), bar0, lane);
-    issue_rows(row, td1, td0, smem_u32(SB(1)), smem_u32(CB(0)), bar0 + 8, lane);
+    issue_K<NI>(A, td0, __ldg(TO + tile), smem_u32(KB(0)), bar0, lane);
+    issue_K<NI>(A, td1, (tile + W < nt) ? __ldg(TO + tile + W) : 0, smem_u32(KB(1)), bar0 + 8, lane);
     mbar_wait(bar0, 0);
-    issue_G<NI>(A, td0, SB(0), GB(0), lane, C, E, cur);
+    issue_G<NI>(A, td0, KB(0), GB(0), CB(0), lane, C, E, cur);
 
     int it = 0;
     for (; tile < nt; tile += W, ++it) {
         const int pb = it & 1;                         // buffer parity of the current tile
-        // everything issued during iteration it-1 (barrier (it+1)&1, its use number ((it+1)>>1)) and the gathers
+        // the constant block issued during iteration it-1 (barrier (it+1)&1, its use number (it+1)>>1) and the cp.asyncs
         mbar_wait(bar0 + 8 * (pb ^ 1), ((it + 1) >> 1) & 1);
         cp_wait_all();
         __syncwarp();
         const int c0 = td0.x, nc = td0.y, m0 = td0.z, nm = td0.w;
-        double* S = SB(pb);
+        const double* K = KB(pb);
         double* G = GB(pb);
-        const double* Cc = CB(pb);
-        // offsets of the aligned supersets (see the header)
-        const int oS0 = m0 & 1, oS1 = (m0 + Mo) & 1, oC0 = c0 & 1, oC1 = (c0 + C) & 1;
-        const int* c_ptr = reinterpret_cast<const int*>(Cc + (3 + 2 * NI) * KP_CROW8) + (c0 & 3);
-        const double* c_vol = Cc + oC0;
-        const double* c_dvt = Cc + KP_CROW8 + oC0;
-        const double* c_vmo = Cc + 2 * KP_CROW8 + oC0;
-        const double* c_cc = Cc + 3 * KP_CROW8;        // row i at i*KP_CROW8 + (i odd ? oC1 : oC0)
-        const double* c_cmi = Cc + (3 + NI) * KP_CROW8;
+        const double* Cs = CB(pb);
+        const double* c_cc = Cs + KP_MAXC;             // [cell][ion]
+        const double* c_cmi = c_cc + NI * KP_MAXC;
 
-        // ---- this tile's streams and gathers -> registers
+        // ---- this tile's constants, state and gathers -> registers
         int lc = 0, nnp = 0;
         double sa = 0.0, g = 0.0, vm_nb = 0.0, cCao = 0.0;
         double Dm[NI], co[NI], cnb[NI];
         const bool act = lane < nm;
+        // per-cell constants (lanes = (cell, ion) pairs / cells) are read now: the block is overwritten below
+        const int* Ki = reinterpret_cast<const int*>(K + (NI + 1) * nm + 2 * nc);
+        int jb0 = 0, je0 = 0;
+        double vol0 = 1.0, dvt = 0.0;
+        if (lane < nc * NI) { jb0 = Ki[3 * nm + q0c] - m0; je0 = Ki[3 * nm + q0c + 1] - m0; vol0 = K[(NI + 1) * nm + q0c]; }
+        if (lane < nc) dvt = K[(NI + 1) * nm + nc + lane];
         if (act) {
-            const int* Si = reinterpret_cast<const int*>(S + (NI + 2) * KP_ROW8) + (m0 & 3) + lane;
-            lc = Si[0] - c0;
-            nnp = Si[KP_ROW4];
+            lc = Ki[lane] - c0;
+            nnp = Ki[nm + lane];
 #pragma unroll
-            for (int i = 0; i < NI; ++i) Dm[i] = S[i * KP_ROW8 + ((i & 1) ? oS1 : oS0) + lane];
-            sa = S[NI * KP_ROW8 + oS0 + lane];
-            g = S[(NI + 1) * KP_ROW8 + oS0 + lane];
+            for (int i = 0; i < NI; ++i) Dm[i] = K[i * nm + lane];
+            sa = K[NI * nm + lane];
 #pragma unroll
             for (int i = 0; i < NI; ++i) co[i] = G[i * 32 + lane];
 #pragma unroll
             for (int i = 0; i < NI; ++i) cnb[i] = G[(NI + i) * 32 + lane];
             vm_nb = G[(2 * NI) * 32 + lane];
             if (iCa >= 0) cCao = G[(2 * NI + 1) * 32 + lane];
+            g = G[(2 * NI + 2) * 32 + lane];
+        }
+        if (nc * NI > 32) {                            // later rounds of the (cell, ion) phase: keep ptr/vol of all cells
+            if (lane <= nc) reinterpret_cast<int*>(s_aux)[lane] = Ki[3 * nm + lane];
+            if (lane < nc) s_aux[6 + lane] = K[(NI + 1) * nm + lane];
         }
         __syncwarp();
-        // ---- keep the pipeline full: S(t+2) into the buffer just drained, C(t+1), G(t+1)
+        // ---- keep the pipeline full: K(t+2) into the buffer just drained, G(t+1)
         const int4 td3 = (tile + 3 * W < nt) ? __ldg(TD + tile + 3 * W) : zero4;
-        issue_rows(row, td2, td1, smem_u32(S), smem_u32(CB(pb ^ 1)), bar0 + 8 * pb, lane);
-        issue_G<NI>(A, td1, SB(pb ^ 1), GB(pb ^ 1), lane, C, E, cur);
+        const int to3 = (tile + 3 * W < nt) ? __ldg(TO + tile + 3 * W) : 0;
+        issue_K<NI>(A, td2, to2, smem_u32(K), bar0 + 8 * pb, lane);
+        issue_G<NI>(A, td1, KB(pb ^ 1), GB(pb ^ 1), CB(pb ^ 1), lane, C, E, cur);
 
-        double* s_m = G;                               // [NI][33] f_mem*sa   (the consumed gather buffer)
+        double* s_m = G;                               // [NI][33] f_mem*sa   (the consumed gather rows)
         double* s_g = G + NI * KP_SST;                 // [NI][33] f_gj*sa
 
         // ---- lanes = membranes
@@ -256,10 +236,10 @@ k_mem_pipe(const __grid_constant__ KParams P, const KArrays A, const int cur)
             const bool bnd = nnp < 0;
             double cin[NI];
 #pragma unroll
-            for (int i = 0; i < NI; ++i) cin[i] = c_cmi[i * KP_CROW8 + ((i & 1) ? oC1 : oC0) + lc];
-            const double vm_own = c_vmo[lc];
+            for (int i = 0; i < NI; ++i) cin[i] = c_cmi[lc * NI + i];
+            const double vm_own = Cs[lc];
             double cCai = 0.0;
-            if (iCa >= 0) cCai = c_cc[iCa * KP_CROW8 + ((iCa & 1) ? oC1 : oC0) + lc];
+            if (iCa >= 0) cCai = c_cc[lc * NI + iCa];
             // membrane side: electroflux adds 1e-25 to vBA (sim_toolbox.py:54); alpha for z = +1
             const double a1 = ((vm_own + FLOAT_NONCE) * P.F) * P.inv_RT_sim;
             GhkAB tm;
@@ -342,28 +322,28 @@ k_mem_pipe(const __grid_constant__ KParams P, const KArrays A, const int cur)
 
         // ---- lanes = (cell, ion) pairs: membranes -> cells (update_Co + update_all_concs)
         for (int q = lane; q < nc * NI; q += 32) {
-            int qc = q0c, i = q0i;
-            if (q != lane) { qc = q / NI; i = q - qc * NI; }
+            int qc = q0c, i = q0i, jb = jb0, je = je0;
+            double vol = vol0;
+            if (q != lane) {
+                qc = q / NI; i = q - qc * NI;
+                jb = reinterpret_cast<const int*>(s_aux)[qc] - m0; je = reinterpret_cast<const int*>(s_aux)[qc + 1] - m0;
+                vol = s_aux[6 + qc];
+            }
             const int c = c0 + qc;
-            const int jb = c_ptr[qc] - m0, je = c_ptr[qc + 1] - m0;
             const double* pm = s_m + i * KP_SST + jb;
             const double* pg = s_g + i * KP_SST + jb;
             const int n = je - jb;
-            double vm_[8], vg_[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) { vm_[k] = (k < n) ? pm[k] : 0.0; vg_[k] = (k < n) ? pg[k] : 0.0; }
             double Sm = 0.0, Sg = 0.0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { if (k < n) { Sm += vm_[k]; Sg += vg_[k]; } }
+            for (int k = 0; k < 8; ++k) { if (k < n) { Sm += pm[k]; Sg += pg[k]; } }
             for (int k = 8; k < n; ++k) { Sm += pm[k]; Sg += pg[k]; }
-            const int oc = (i & 1) ? oC1 : oC0;
-            const double rvol = fast_rcp(c_vol[qc]);
-            const double cm_new = c_cc[i * KP_CROW8 + oc + qc] + (Sm * rvol) * P.dt;   // sim_toolbox.py:1177-1181
-            double cn_new = cm_new + P.dt * ((-Sg) * rvol);                            // sim.py:2105-2108
+            const double rvol = fast_rcp(vol);
+            const double cm_new = c_cc[q] + (Sm * rvol) * P.dt;          // sim_toolbox.py:1177-1181
+            double cn_new = cm_new + P.dt * ((-Sg) * rvol);              // sim.py:2105-2108
             if (cn_new != cn_new) flags |= ST_NAN_CONC;
-            if (cn_new < 0.0) { cn_new = 0.0; flags |= ST_NEG; }                       // no_negs, sim.py:2111
+            if (cn_new < 0.0) { cn_new = 0.0; flags |= ST_NEG; }         // no_negs, sim.py:2111
             A.cc_cells[(size_t)i * C + c] = cn_new;
-            A.cc_mid[nxt][(size_t)i * C + c] = cm_new;                                 // the stale cc_at_mem (quirk list)
+            A.cc_mid[nxt][(size_t)i * C + c] = cm_new;                   // the stale cc_at_mem (quirk list)
             s_cc[q] = cn_new;
         }
         __syncwarp();
@@ -376,17 +356,51 @@ k_mem_pipe(const __grid_constant__ KParams P, const KArrays A, const int cur)
             for (int i = 0; i < NI; ++i) rho = fma(P.zF[i], s_cc[lane * NI + i], rho);
             if (A.extra_rho_cells) rho += ldg(A.extra_rho_cells + c);
             A.rho_cells[c] = rho;
-            const double vmn = P.inv_cm * (rho * c_dvt[lane]);
+            const double vmn = P.inv_cm * (rho * dvt);
             if (vmn != vmn) flags |= ST_NAN_VM;
             A.vm_cell[nxt][c] = vmn;
         }
-        td0 = td1; td1 = td2; td2 = td3;
+        td0 = td1; td1 = td2; td2 = td3; to2 = to3;
     }
     cp_wait_all();
     if (flags) atomicOr(A.status, flags);
-#undef SB
+#undef KB
 #undef GB
 #undef CB
+}
+
+// ---------------------------------------------------------------------------- tile pack
+// Refresh the Dm rows of every tile's constant block from the canonical [ion][membrane] array
+// (after an upload of Dm_cells: init state, scheduled interventions).  One warp per tile.
+__global__ void k_pack_dm(const __grid_constant__ KParams P, const KArrays A)
+{
+    const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (tile >= P.n_tiles) return;
+    const int4 td = __ldg(reinterpret_cast<const int4*>(A.tile_desc) + tile);
+    double* K = reinterpret_cast<double*>(const_cast<char*>(A.tile_pack) + (size_t)__ldg(A.tile_off + tile) * 16);
+    if (lane < td.w)
+        for (int i = 0; i < P.n_ions; ++i) K[i * td.w + lane] = A.Dm[(size_t)i * P.n_mems_owned + td.z + lane];
+}
+
+void launch_pack_dm(const KParams& P, const KArrays& A, cudaStream_t st)
+{
+    if (!A.tile_pack || P.n_tiles <= 0) return;
+    k_pack_dm<<<(P.n_tiles + 7) / 8, 256, 0, st>>>(P, A);
+}
+
+// Host side of the pack (capi.cu:create_impl): byte size of tile t's block and the constant part of its contents.
+unsigned tile_pack_size(int ni, int nm, int nc) { return tile_pack_bytes(ni, nm, nc); }
+
+void tile_pack_fill(char* blk, int ni, int nm, int nc, const double* mem_sa, const double* cell_vol, const double* diviterm,
+                    const int* mem_to_cells, const int* nn_cell_flag, const int* map_mem2ecm, const int* cell_mem_ptr)
+{
+    double* K = reinterpret_cast<double*>(blk);
+    for (int j = 0; j < nm; ++j) K[ni * nm + j] = mem_sa[j];
+    for (int j = 0; j < nc; ++j) { K[(ni + 1) * nm + j] = cell_vol[j]; K[(ni + 1) * nm + nc + j] = diviterm[j]; }
+    int* Ki = reinterpret_cast<int*>(K + (ni + 1) * nm + 2 * nc);
+    for (int j = 0; j < nm; ++j) { Ki[j] = mem_to_cells[j]; Ki[nm + j] = nn_cell_flag[j]; Ki[2 * nm + j] = map_mem2ecm[j]; }
+    for (int j = 0; j <= nc; ++j) Ki[3 * nm + j] = cell_mem_ptr[j];
 }
 
 // ---------------------------------------------------------------------------- launch

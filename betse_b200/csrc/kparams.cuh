@@ -56,6 +56,8 @@ struct KArrays {
     const int *mem_to_cells, *cell_mem_ptr, *nn_cell_flag, *nn_i, *map_mem2ecm;
     const int *cta_cell_start;   // CTA packing (k_diag): whole cells, <= BT_TPB membranes
     const int *tile_desc;        // warp packing (k_mem): int4 {c0, nc, m0, nm} per tile of whole cells, <= 32 membranes
+    const char *tile_pack;       // k_mem_pipe: per-tile constant block (layout: kmem_pipe.cu header), 16-byte aligned blocks
+    const int *tile_off;         // offset of tile t's block in tile_pack, in units of 16 bytes
     const int *slot_ptr, *slot_idx;
     const double *mem_sa, *mem_nx, *mem_ny, *cell_vol, *cell_sa, *diviterm, *num_mems;
     const double *memsa_env, *gj_w;
