@@ -27,7 +27,7 @@ void launch_diag(int ni, const KParams& P, const KArrays& A, int n_ctas, int new
 void launch_expand_vm(const KParams& P, const KArrays& A, int M, int C, int cur, cudaStream_t st);
 cudaError_t prepare_kernels(int ni);
 // kmem_pipe.cu: the per-tile constant blocks of the pipelined membrane kernel
-unsigned tile_pack_size(int ni, int nm, int nc);
+unsigned tile_pack_size(int ni);
 void tile_pack_fill(char* blk, int ni, int nm, int nc, const double* mem_sa, const double* cell_vol, const double* diviterm,
                     const int* mem_to_cells, const int* nn_cell_flag, const int* map_mem2ecm, const int* cell_mem_ptr);
 void launch_pack_dm(const KParams& P, const KArrays& A, cudaStream_t st);
@@ -153,6 +153,7 @@ static void fill_kparams(betse_ctx* ctx, const betse_params* hp)
     for (int k = 0; k <= 4; ++k) P.gw[k] = hp->gauss_w[k];
     P.inv_RT_sim = 1.0 / P.RT_sim; P.inv_RT_p = 1.0 / P.RT_p;
     P.inv_tm = 1.0 / hp->tm; P.inv_gjl = 1.0 / P.gj_len;
+    for (int i = 0; i < BT_MAX_IONS; ++i) P.Dgj_len[i] = P.Dgj_surf[i] * P.inv_gjl;
     P.inv_kbT_sim = 1.0 / P.kbT_sim;
     P.inv_delta = 1.0 / P.delta; P.inv_2delta = 1.0 / (2.0 * P.delta);
     P.inv_KmNK_Na = 1.0 / hp->KmNK_Na; P.inv_KmNK_K = 1.0 / hp->KmNK_K; P.inv_KmCa_Ca = 1.0 / hp->KmCa_Ca;
@@ -297,7 +298,7 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
     ctx->n_ctas = (int)cta_start.size() - 1;
     P.n_ctas = ctx->n_ctas;
     if ((r = dev_upload(ctx, (int**)&A.cta_cell_start, cta_start.data(), cta_start.size()))) return r;
-    // ---- warp packing (k_mem): contiguous runs of whole cells with <= 32 membranes, <= 10 cells
+    // ---- warp packing (k_mem): contiguous runs of whole cells with <= 32 membranes, <= BT_TILE_MAXC cells
     std::vector<int> tile_start;
     tile_start.push_back(0);
     {
@@ -305,7 +306,7 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
         while (c < Co) {
             int mstart = mesh->cell_mem_ptr[c];
             int cc = c;
-            while (cc < Co && (mesh->cell_mem_ptr[cc + 1] - mstart) <= 32 && (cc - c) < 10) ++cc;
+            while (cc < Co && (mesh->cell_mem_ptr[cc + 1] - mstart) <= 32 && (cc - c) < BT_TILE_MAXC) ++cc;
             if (cc == c) return fail(ctx, "a cell has more than 32 membranes (unsupported by the warp-tile kernel)");
             tile_start.push_back(cc);
             c = cc;
@@ -321,26 +322,19 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
         tdesc[4 * t + 2] = mesh->cell_mem_ptr[a]; tdesc[4 * t + 3] = mesh->cell_mem_ptr[b] - mesh->cell_mem_ptr[a];
     }
     if ((r = dev_upload(ctx, (int**)&A.tile_desc, tdesc.data(), tdesc.size()))) return r;
-    // ---- tile pack (k_mem_pipe): every tile's constant inputs as one contiguous, 16-byte aligned block; the Dm rows
-    //      are (re)filled on the device whenever Dm_cells is uploaded (launch_pack_dm)
+    // ---- tile pack (k_mem_pipe): every tile's constant inputs as one fixed-size block; the DmS rows are (re)built
+    //      on the device whenever Dm_cells or the schedule scalars are uploaded (launch_pack_dm)
     if (hp->n_ions <= 7) {
-        std::vector<int> toff(ctx->n_tiles);
-        size_t total = 0;
-        for (int t = 0; t < ctx->n_tiles; ++t) {
-            toff[t] = (int)(total / 16);
-            total += tile_pack_size(hp->n_ions, tdesc[4 * t + 3], tdesc[4 * t + 1]);
-        }
-        if (total / 16 >= ((size_t)1 << 31)) return fail(ctx, "tile pack exceeds 32 GB");
-        std::vector<char> pack(total, 0);
+        const size_t blk = tile_pack_size(hp->n_ions);
+        std::vector<char> pack((size_t)ctx->n_tiles * blk, 0);
         for (int t = 0; t < ctx->n_tiles; ++t) {
             const int c0 = tdesc[4 * t], nc = tdesc[4 * t + 1], m0 = tdesc[4 * t + 2], nm = tdesc[4 * t + 3];
-            tile_pack_fill(pack.data() + (size_t)toff[t] * 16, hp->n_ions, nm, nc, mesh->mem_sa + m0, mesh->cell_vol + c0,
+            tile_pack_fill(pack.data() + (size_t)t * blk, hp->n_ions, nm, nc, mesh->mem_sa + m0, mesh->cell_vol + c0,
                            mesh->diviterm + c0, mesh->mem_to_cells + m0, nnc.data() + m0, mesh->map_mem2ecm + m0,
                            mesh->cell_mem_ptr + c0);
         }
-        if ((r = dev_upload(ctx, (char**)&A.tile_pack, pack.data(), total))) return r;
-        if ((r = dev_upload(ctx, (int**)&A.tile_off, toff.data(), toff.size()))) return r;
-        CK(cudaStreamSynchronize(ctx->stream));     // the host vectors go out of scope
+        if ((r = dev_upload(ctx, (char**)&A.tile_pack, pack.data(), pack.size()))) return r;
+        CK(cudaStreamSynchronize(ctx->stream));     // the host vector goes out of scope
     }
 
     // ---- env point -> flux slot CSR (map_ecm2mem, cells.py:1793-1796), slots in membrane order
@@ -558,6 +552,7 @@ extern "C" int betse_set_schedule(betse_ctx* ctx, const betse_params* hp)
     fill_kparams(ctx, hp);
     ctx->P.has_phi = has_phi;
     destroy_graphs(ctx);              // KParams is baked into the captured launches
+    launch_pack_dm(ctx->P, ctx->A, ctx->stream);   // DmS carries rho_channel/tm
     return 0;
 }
 

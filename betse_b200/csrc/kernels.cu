@@ -182,6 +182,7 @@ k_mem(const __grid_constant__ KParams P, const KArrays A, const int cur, const i
         }
 
         const double Dtm = -(P.inv_tm * P.rho_channel);
+        const double sa_g = bnd ? 0.0 : sa;
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
             double Am, Bm, Ag, Bg;
@@ -195,21 +196,27 @@ k_mem(const __grid_constant__ KParams P, const KArrays A, const int cur, const i
                 const double2 xm = ghk_generic(P.z[i], a1), xg = ghk_generic(P.z[i], ag1);
                 Am = xm.x; Bm = xm.y; Ag = xg.x; Bg = xg.y;
             }
-            // electroflux (sim_toolbox.py:58-65), cA = env, cB = cell
-            double f = (Dm[i] * Dtm) * (cin[i] * Am - co[i] * Bm);
-            if (closed_bnd) f = 0.0;
-            if (i == iNa) f += fNa;
-            if (i == iK) f += fK;
-            if (i == iCa) f += fCa;
+            // electroflux (sim_toolbox.py:58-65), cA = env, cB = cell; the flux is formed already times the
+            // membrane area ((Dm*Dtm)*sa is what the tile pack of k_mem_pipe stores: same operand order)
+            const double pm_ = cin[i] * Am - co[i] * Bm;
+            double fsa = closed_bnd ? 0.0 : (((Dm[i] * Dtm) * sa) * pm_);
+            if (i == iNa) fsa = fma(fNa, sa, fsa);
+            if (i == iK) fsa = fma(fK, sa, fsa);
+            if (i == iCa) fsa = fma(fCa, sa, fsa);
             // gap junction: gating advances once per ion (sim.py:1272 -> 2180-2183)
             g = fma(g, gc1, gc2);
-            // cA = this cell, cB = partner cell (sim.py:2191-2197)
-            double fg = -((P.Dgj_surf[i] * g) * P.inv_gjl) * (cnb[i] * Ag - cin[i] * Bg);
-            if (bnd) fg = 0.0;
-            s_m[lane * NI + i] = f * sa;
-            s_g[lane * NI + i] = fg * sa;
-            if (is_ecm && fast_ecm) A.flux_slots[m * NI + i] = f;
-            if (diag) { A.fl_mem[i * Mo + m] = f; A.fl_gj[i * Mo + m] = fg; }
+            // cA = this cell, cB = partner cell (sim.py:2191-2197); zero at boundary membranes through sa_g
+            const double pg_ = cnb[i] * Ag - cin[i] * Bg;
+            s_m[lane * NI + i] = fsa;
+            s_g[lane * NI + i] = -(P.Dgj_len[i] * (g * sa_g)) * pg_;
+            if ((is_ecm && fast_ecm) || diag) {     // per-area fluxes (fast ECM update, sampled-step diagnostics)
+                double f = closed_bnd ? 0.0 : ((Dm[i] * Dtm) * pm_);
+                if (i == iNa) f += fNa;
+                if (i == iK) f += fK;
+                if (i == iCa) f += fCa;
+                if (is_ecm && fast_ecm) A.flux_slots[m * NI + i] = f;
+                if (diag) { A.fl_mem[i * Mo + m] = f; A.fl_gj[i * Mo + m] = bnd ? 0.0 : (-(P.Dgj_len[i] * g) * pg_); }
+            }
         }
         A.gjopen[m] = g;
     }

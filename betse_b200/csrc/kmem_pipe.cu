@@ -9,10 +9,11 @@
 // gathers through those indices).  Here every warp walks a strided sequence of tiles and keeps
 // the NEXT tiles' inputs in flight while it does the arithmetic of the current one:
 //
-//   K = the tile's constant block ("tile pack", built once by the host + k_pack_dm): Dm[I][nm],
-//       mem_sa[nm], cell_vol[nc], diviterm[nc], mem_to_cells[nm], nn_cell_flag[nm],
-//       map_mem2ecm[nm], cell_mem_ptr[nc+1] contiguous and 16-byte aligned -> ONE TMA bulk copy
-//       (cp.async.bulk by lane 0, completion on an mbarrier), two tiles ahead;
+//   K = the tile's constant block ("tile pack", fixed size, built by the host + k_pack_dm):
+//       DmS[I][32] = (Dm*(-rho_channel/tm))*mem_sa, mem_sa[32], cell_vol[8], diviterm[8],
+//       mem_to_cells[32], nn_cell_flag[32], map_mem2ecm[32], cell_mem_ptr[9(+3)] -> ONE TMA bulk
+//       copy (cp.async.bulk by lane 0, completion on an mbarrier), two tiles ahead; every offset
+//       inside the block is a compile-time constant;
 //   G = state and gathers, cp.async (LDGSTS), one tile ahead: gjopen; Vmem, cc_cells, cc_mid of
 //       the tile's cells; through the landed indices of K: env concentrations at the membrane's
 //       env square, partner-cell concentrations and Vmem, transported Ca.
@@ -28,14 +29,16 @@
 #include <stdint.h>
 #include "kmath.cuh"
 
-#define KP_MAXC 10                                   // cells per tile (host packing, capi.cu)
+#define KP_MAXC BT_TILE_MAXC                         // cells per tile (host packing, capi.cu)
 #define KP_SST 33                                    // staging stride (doubles): conflict-free f*sa [ion][membrane]
+// tile pack block, in doubles: DmS[NI][32], sa[32], vol[MAXC], dvt[MAXC] | ints: m2c[32], nnp[32], e[32], ptr[MAXC+4]
+#define KP_KD(NI) (((NI) + 1) * 32 + 2 * KP_MAXC)    // doubles before the int section
+#define KP_K(NI) (KP_KD(NI) + (96 + KP_MAXC + 4) / 2)
 // per-warp shared memory, in doubles
-#define KP_K(NI) ((((NI) + 1) * 32 + 2 * KP_MAXC) + ((3 * 32 + KP_MAXC + 1 + 3) / 4) * 2)   // tile pack, max size, 16 B multiple
 #define KP_G(NI) ((2 * (NI) + 3) * 32)               // co[NI][32], cnb[NI][32], vnb[32], cao[32], gj[32]; then staging 2*NI*33
-#define KP_C(NI) (KP_MAXC + 2 * (NI) * KP_MAXC)      // vmo[c], cc[c][NI], cmid[c][NI]
-#define KP_AUX 16                                    // cell_mem_ptr[11] (6 doubles) + cell_vol[10] of the current tile (tiles with > 32/NI cells)
-#define KP_WARP(NI) (2 + 2 * KP_K(NI) + 2 * KP_G(NI) + 2 * KP_C(NI) + (NI) * KP_MAXC + KP_AUX)
+#define KP_C(NI) (KP_MAXC + 2 * (NI) * KP_MAXC)      // vmo[c], cc[c][NI] (then the updated values), cmid[c][NI]
+#define KP_AUX (KP_MAXC + 8)                         // cell_mem_ptr[MAXC+1] (6 doubles) + cell_vol[MAXC]: tiles with > 32/NI cells
+#define KP_WARP(NI) (2 + 2 * KP_K(NI) + 2 * KP_G(NI) + 2 * KP_C(NI) + KP_AUX)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp8(uint32_t s, const void* g)
@@ -73,22 +76,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, unsigned
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-// bytes of a tile's constant block (the layout in the header), rounded up to 16
-__host__ __device__ __forceinline__ unsigned tile_pack_bytes(int ni, int nm, int nc)
-{
-    return (8u * ((ni + 1) * nm + 2 * nc) + 4u * (3 * nm + nc + 1) + 15u) & ~15u;
-}
-
-// the constant block of tile td (offset off16*16 in the pack) -> Kdst; always completes one phase of `bar`
+// the constant block of tile `tile` -> Kdst; always completes one phase of `bar`
 template <int NI>
-__device__ __forceinline__ void issue_K(const KArrays& A, const int4 td, const int off16, const uint32_t Kdst,
+__device__ __forceinline__ void issue_K(const KArrays& A, const int tile, const bool valid, const uint32_t Kdst,
                                         const uint32_t bar, const int lane)
 {
     if (lane == 0) {
-        if (td.w > 0) {
-            const unsigned bytes = tile_pack_bytes(NI, td.w, td.y);
-            mbar_expect_tx(bar, bytes);
-            bulk_g2s(Kdst, A.tile_pack + (size_t)off16 * 16, bytes, bar);
+        if (valid) {
+            mbar_expect_tx(bar, KP_K(NI) * 8);
+            bulk_g2s(Kdst, A.tile_pack + (size_t)tile * (KP_K(NI) * 8), KP_K(NI) * 8, bar);
         } else mbar_arrive(bar);
     }
 }
@@ -96,13 +92,13 @@ __device__ __forceinline__ void issue_K(const KArrays& A, const int4 td, const i
 // state + gathers of tile td through the indices in its (landed) constant block K
 template <int NI>
 __device__ __forceinline__ void issue_G(const KArrays& A, const int4 td, const double* K, double* G, double* Cs,
-                                        const int lane, const int C, const int E, const int cur)
+                                        const int lane, const int o0, const int C, const int E, const int cur)
 {
     const int c0 = td.x, nc = td.y, m0 = td.z, nm = td.w;
     if (lane < nm) {
-        const int* Ki = reinterpret_cast<const int*>(K + (NI + 1) * nm + 2 * nc);
-        const int cn = Ki[nm + lane] & 0x7fffffff;
-        const int e = Ki[2 * nm + lane];
+        const int* Ki = reinterpret_cast<const int*>(K + KP_KD(NI));
+        const int cn = Ki[32 + lane] & 0x7fffffff;
+        const int e = Ki[64 + lane];
         const double* __restrict__ cenv = A.cc_env[cur] + e;
         const double* __restrict__ cmid = A.cc_mid[cur] + cn;
         const uint32_t g = smem_u32(G + lane);
@@ -114,12 +110,17 @@ __device__ __forceinline__ void issue_G(const KArrays& A, const int4 td, const d
         if (StdProf<NI>::iCa >= 0) cp8(g + (2 * NI + 1) * 256, A.cc_env[cur ^ 1] + (size_t)StdProf<NI>::iCa * E + e);
         cp8(g + (2 * NI + 2) * 256, A.gjopen + m0 + lane);
     }
-    if (lane < nc) cp8(smem_u32(Cs + lane), A.vm_cell[cur] + c0 + lane);
-    for (int q = lane; q < nc * NI; q += 32) {
+    const uint32_t cs = smem_u32(Cs);
+    if (lane < nc) cp8(cs + lane * 8, A.vm_cell[cur] + c0 + lane);
+    if (lane < nc * NI) {                              // first round of (cell, ion) pairs: o0 = ion*C + cell-in-tile
+        cp8(cs + (KP_MAXC + lane) * 8, A.cc_cells + o0 + c0);
+        cp8(cs + (KP_MAXC + NI * KP_MAXC + lane) * 8, A.cc_mid[cur] + o0 + c0);
+    }
+    for (int q = lane + 32; q < nc * NI; q += 32) {
         const int lc = q / NI, i = q - lc * NI;
         const size_t o = (size_t)i * C + c0 + lc;
-        cp8(smem_u32(Cs + KP_MAXC + q), A.cc_cells + o);
-        cp8(smem_u32(Cs + KP_MAXC + NI * KP_MAXC + q), A.cc_mid[cur] + o);
+        cp8(cs + (KP_MAXC + q) * 8, A.cc_cells + o);
+        cp8(cs + (KP_MAXC + NI * KP_MAXC + q) * 8, A.cc_mid[cur] + o);
     }
 }
 
@@ -138,8 +139,7 @@ k_mem_pipe(const __grid_constant__ KParams P, const KArrays A, const int cur)
     double* const K0 = base + 2;
     double* const G0 = K0 + 2 * KP_K(NI);
     double* const C0 = G0 + 2 * KP_G(NI);
-    double* const s_cc = C0 + 2 * KP_C(NI);
-    double* const s_aux = s_cc + NI * KP_MAXC;
+    double* const s_aux = C0 + 2 * KP_C(NI);
 #define KB(b) (K0 + (b) * KP_K(NI))
 #define GB(b) (G0 + (b) * KP_G(NI))
 #define CB(b) (C0 + (b) * KP_C(NI))
@@ -149,7 +149,6 @@ k_mem_pipe(const __grid_constant__ KParams P, const KArrays A, const int cur)
     const int nxt = cur ^ 1;
     const int C = P.n_cells, E = P.ny * P.nx;
     const int4* __restrict__ TD = reinterpret_cast<const int4*>(A.tile_desc);
-    const int* __restrict__ TO = A.tile_off;
     const int4 zero4 = make_int4(0, 0, 0, 0);
     unsigned int flags = 0;
 
@@ -162,6 +161,7 @@ k_mem_pipe(const __grid_constant__ KParams P, const KArrays A, const int cur)
     __syncwarp();
     // tile-independent lane roles of the later phases: lane = (cell, ion) pair; slot-copy element p = lane + 32k
     const int q0c = lane / NI, q0i = lane - q0c * NI;
+    const int o0 = q0i * C + q0c;
     int cpy[NI];                                       // staging index of element p = lane + 32 k of the [membrane][ion] slot block
 #pragma unroll
     for (int k = 0; k < NI; ++k) { const int p = lane + 32 * k; const int m = p / NI; cpy[k] = (p - m * NI) * KP_SST + m; }
@@ -169,13 +169,11 @@ k_mem_pipe(const __grid_constant__ KParams P, const KArrays A, const int cur)
     // ---- prologue = pseudo-iterations -2 (barrier 0: K(t)) and -1 (barrier 1: K(t+1)); then G(t)
     int4 td0 = (tile < nt) ? __ldg(TD + tile) : zero4;
     int4 td1 = (tile + W < nt) ? __ldg(TD + tile + W) : zero4;
-    int4 td2 = (tile + 2 * W < nt) ? __ldg(TD + tile + 2 * W) : zero4;
-    int to2 = (tile + 2 * W < nt) ? __ldg(TO + tile + 2 * W) : 0;
     if (td0.w == 0) return;
-    issue_K<NI>(A, td0, __ldg(TO + tile), smem_u32(KB(0)), bar0, lane);
-    issue_K<NI>(A, td1, (tile + W < nt) ? __ldg(TO + tile + W) : 0, smem_u32(KB(1)), bar0 + 8, lane);
+    issue_K<NI>(A, tile, true, smem_u32(KB(0)), bar0, lane);
+    issue_K<NI>(A, tile + W, tile + W < nt, smem_u32(KB(1)), bar0 + 8, lane);
     mbar_wait(bar0, 0);
-    issue_G<NI>(A, td0, KB(0), GB(0), CB(0), lane, C, E, cur);
+    issue_G<NI>(A, td0, KB(0), GB(0), CB(0), lane, o0, C, E, cur);
 
     int it = 0;
     for (; tile < nt; tile += W, ++it) {
@@ -187,27 +185,24 @@ k_mem_pipe(const __grid_constant__ KParams P, const KArrays A, const int cur)
         const int c0 = td0.x, nc = td0.y, m0 = td0.z, nm = td0.w;
         const double* K = KB(pb);
         double* G = GB(pb);
-        const double* Cs = CB(pb);
-        const double* c_cc = Cs + KP_MAXC;             // [cell][ion]
+        double* Cs = CB(pb);
+        double* c_cc = Cs + KP_MAXC;                   // [cell][ion]; overwritten in place by the updated values
         const double* c_cmi = c_cc + NI * KP_MAXC;
+        const int* Ki = reinterpret_cast<const int*>(K + KP_KD(NI));
 
-        // ---- this tile's constants, state and gathers -> registers
-        int lc = 0, nnp = 0;
-        double sa = 0.0, g = 0.0, vm_nb = 0.0, cCao = 0.0;
-        double Dm[NI], co[NI], cnb[NI];
+        // ---- this tile's constants, state and gathers -> registers (the K block is overwritten below)
+        int lc = 0, nnp = 0, jb0 = 0, je0 = 0;
+        double sa = 0.0, g = 0.0, vm_nb = 0.0, cCao = 0.0, vol0 = 1.0, dvt = 0.0;
+        double DmS[NI], co[NI], cnb[NI];
         const bool act = lane < nm;
-        // per-cell constants (lanes = (cell, ion) pairs / cells) are read now: the block is overwritten below
-        const int* Ki = reinterpret_cast<const int*>(K + (NI + 1) * nm + 2 * nc);
-        int jb0 = 0, je0 = 0;
-        double vol0 = 1.0, dvt = 0.0;
-        if (lane < nc * NI) { jb0 = Ki[3 * nm + q0c] - m0; je0 = Ki[3 * nm + q0c + 1] - m0; vol0 = K[(NI + 1) * nm + q0c]; }
-        if (lane < nc) dvt = K[(NI + 1) * nm + nc + lane];
+        if (lane < nc * NI) { jb0 = Ki[96 + q0c] - m0; je0 = Ki[96 + q0c + 1] - m0; vol0 = K[(NI + 1) * 32 + q0c]; }
+        if (lane < nc) dvt = K[(NI + 1) * 32 + KP_MAXC + lane];
         if (act) {
             lc = Ki[lane] - c0;
-            nnp = Ki[nm + lane];
+            nnp = Ki[32 + lane];
 #pragma unroll
-            for (int i = 0; i < NI; ++i) Dm[i] = K[i * nm + lane];
-            sa = K[NI * nm + lane];
+            for (int i = 0; i < NI; ++i) DmS[i] = K[i * 32 + lane];
+            sa = K[NI * 32 + lane];
 #pragma unroll
             for (int i = 0; i < NI; ++i) co[i] = G[i * 32 + lane];
 #pragma unroll
@@ -217,15 +212,14 @@ k_mem_pipe(const __grid_constant__ KParams P, const KArrays A, const int cur)
             g = G[(2 * NI + 2) * 32 + lane];
         }
         if (nc * NI > 32) {                            // later rounds of the (cell, ion) phase: keep ptr/vol of all cells
-            if (lane <= nc) reinterpret_cast<int*>(s_aux)[lane] = Ki[3 * nm + lane];
-            if (lane < nc) s_aux[6 + lane] = K[(NI + 1) * nm + lane];
+            if (lane <= nc) reinterpret_cast<int*>(s_aux)[lane] = Ki[96 + lane];
+            if (lane < nc) s_aux[6 + lane] = K[(NI + 1) * 32 + lane];
         }
         __syncwarp();
         // ---- keep the pipeline full: K(t+2) into the buffer just drained, G(t+1)
-        const int4 td3 = (tile + 3 * W < nt) ? __ldg(TD + tile + 3 * W) : zero4;
-        const int to3 = (tile + 3 * W < nt) ? __ldg(TO + tile + 3 * W) : 0;
-        issue_K<NI>(A, td2, to2, smem_u32(K), bar0 + 8 * pb, lane);
-        issue_G<NI>(A, td1, KB(pb ^ 1), GB(pb ^ 1), CB(pb ^ 1), lane, C, E, cur);
+        const int4 td2 = (tile + 2 * W < nt) ? __ldg(TD + tile + 2 * W) : zero4;
+        issue_K<NI>(A, tile + 2 * W, tile + 2 * W < nt, smem_u32(K), bar0 + 8 * pb, lane);
+        issue_G<NI>(A, td1, KB(pb ^ 1), GB(pb ^ 1), CB(pb ^ 1), lane, o0, C, E, cur);
 
         double* s_m = G;                               // [NI][33] f_mem*sa   (the consumed gather rows)
         double* s_g = G + NI * KP_SST;                 // [NI][33] f_gj*sa
@@ -233,7 +227,6 @@ k_mem_pipe(const __grid_constant__ KParams P, const KArrays A, const int cur)
         // ---- lanes = membranes
         if (act) {
             const int m = m0 + lane;
-            const bool bnd = nnp < 0;
             double cin[NI];
 #pragma unroll
             for (int i = 0; i < NI; ++i) cin[i] = c_cmi[lc * NI + i];
@@ -251,6 +244,7 @@ k_mem_pipe(const __grid_constant__ KParams P, const KArrays A, const int cur)
             ghk_table(ag1, tg);
             double gc1, gc2;                           // gating sub-step g' = g*gc1 + gc2 (gap_junction.py:56-72)
             gj_gate_map(vgj0, P, P.gj_block, gc1, gc2);
+            const double sa_g = (nnp < 0) ? 0.0 : sa;   // no gap-junction flux at boundary membranes (sim.py:2199-2201)
 
             // ---- Na/K-ATPase (sim_toolbox.py:71-122)
             double fNa = 0.0, fK = 0.0;
@@ -289,21 +283,18 @@ k_mem_pipe(const __grid_constant__ KParams P, const KArrays A, const int cur)
                 fCa = P.rho_pump * fCa;                 // applied twice in the reference (sim.py:2141, 2155)
             }
 
-            const double Dtm = -(P.inv_tm * P.rho_channel);
 #pragma unroll
             for (int i = 0; i < NI; ++i) {
                 double Am, Bm, Ag, Bg;
                 ghk_pick(tm, StdProf<NI>::z(i), Am, Bm);
                 ghk_pick(tg, StdProf<NI>::z(i), Ag, Bg);
-                double f = (Dm[i] * Dtm) * (cin[i] * Am - co[i] * Bm);     // sim_toolbox.py:58-65
-                if (i == iNa) f += fNa;
-                if (i == iK) f += fK;
-                if (i == iCa) f += fCa;
+                double fsa = DmS[i] * (cin[i] * Am - co[i] * Bm);          // sim_toolbox.py:58-65, times mem_sa
+                if (i == iNa) fsa = fma(fNa, sa, fsa);
+                if (i == iK) fsa = fma(fK, sa, fsa);
+                if (i == iCa) fsa = fma(fCa, sa, fsa);
                 g = fma(g, gc1, gc2);                                      // once per ion (sim.py:1272 -> 2180-2183)
-                double fg = -((P.Dgj_surf[i] * g) * P.inv_gjl) * (cnb[i] * Ag - cin[i] * Bg);   // sim.py:2191-2197
-                if (bnd) fg = 0.0;
-                s_m[i * KP_SST + lane] = f * sa;
-                s_g[i * KP_SST + lane] = fg * sa;
+                s_m[i * KP_SST + lane] = fsa;
+                s_g[i * KP_SST + lane] = -(P.Dgj_len[i] * (g * sa_g)) * (cnb[i] * Ag - cin[i] * Bg);   // sim.py:2191-2197
             }
             A.gjopen[m] = g;
         }
@@ -322,14 +313,16 @@ k_mem_pipe(const __grid_constant__ KParams P, const KArrays A, const int cur)
 
         // ---- lanes = (cell, ion) pairs: membranes -> cells (update_Co + update_all_concs)
         for (int q = lane; q < nc * NI; q += 32) {
-            int qc = q0c, i = q0i, jb = jb0, je = je0;
+            int i = q0i, jb = jb0, je = je0;
+            size_t oc = (size_t)(o0 + c0);
             double vol = vol0;
             if (q != lane) {
-                qc = q / NI; i = q - qc * NI;
+                const int qc = q / NI;
+                i = q - qc * NI;
                 jb = reinterpret_cast<const int*>(s_aux)[qc] - m0; je = reinterpret_cast<const int*>(s_aux)[qc + 1] - m0;
                 vol = s_aux[6 + qc];
+                oc = (size_t)i * C + c0 + qc;
             }
-            const int c = c0 + qc;
             const double* pm = s_m + i * KP_SST + jb;
             const double* pg = s_g + i * KP_SST + jb;
             const int n = je - jb;
@@ -342,9 +335,9 @@ k_mem_pipe(const __grid_constant__ KParams P, const KArrays A, const int cur)
             double cn_new = cm_new + P.dt * ((-Sg) * rvol);              // sim.py:2105-2108
             if (cn_new != cn_new) flags |= ST_NAN_CONC;
             if (cn_new < 0.0) { cn_new = 0.0; flags |= ST_NEG; }         // no_negs, sim.py:2111
-            A.cc_cells[(size_t)i * C + c] = cn_new;
-            A.cc_mid[nxt][(size_t)i * C + c] = cm_new;                   // the stale cc_at_mem (quirk list)
-            s_cc[q] = cn_new;
+            A.cc_cells[oc] = cn_new;
+            A.cc_mid[nxt][oc] = cm_new;                                  // the stale cc_at_mem (quirk list)
+            c_cc[q] = cn_new;
         }
         __syncwarp();
 
@@ -353,14 +346,14 @@ k_mem_pipe(const __grid_constant__ KParams P, const KArrays A, const int cur)
             const int c = c0 + lane;
             double rho = 0.0;
 #pragma unroll
-            for (int i = 0; i < NI; ++i) rho = fma(P.zF[i], s_cc[lane * NI + i], rho);
+            for (int i = 0; i < NI; ++i) rho = fma(P.zF[i], c_cc[lane * NI + i], rho);
             if (A.extra_rho_cells) rho += ldg(A.extra_rho_cells + c);
             A.rho_cells[c] = rho;
             const double vmn = P.inv_cm * (rho * dvt);
             if (vmn != vmn) flags |= ST_NAN_VM;
             A.vm_cell[nxt][c] = vmn;
         }
-        td0 = td1; td1 = td2; td2 = td3; to2 = to3;
+        td0 = td1; td1 = td2;
     }
     cp_wait_all();
     if (flags) atomicOr(A.status, flags);
@@ -370,17 +363,22 @@ k_mem_pipe(const __grid_constant__ KParams P, const KArrays A, const int cur)
 }
 
 // ---------------------------------------------------------------------------- tile pack
-// Refresh the Dm rows of every tile's constant block from the canonical [ion][membrane] array
-// (after an upload of Dm_cells: init state, scheduled interventions).  One warp per tile.
+// (Re)build the DmS rows of every tile's constant block from the canonical [ion][membrane] array:
+// DmS = (Dm * -(rho_channel/tm)) * mem_sa, the operand order of kernels.cu:k_mem.  Runs after an
+// upload of Dm_cells (init state, scheduled interventions) and after betse_set_schedule.
 __global__ void k_pack_dm(const __grid_constant__ KParams P, const KArrays A)
 {
     const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (tile >= P.n_tiles) return;
     const int4 td = __ldg(reinterpret_cast<const int4*>(A.tile_desc) + tile);
-    double* K = reinterpret_cast<double*>(const_cast<char*>(A.tile_pack) + (size_t)__ldg(A.tile_off + tile) * 16);
-    if (lane < td.w)
-        for (int i = 0; i < P.n_ions; ++i) K[i * td.w + lane] = A.Dm[(size_t)i * P.n_mems_owned + td.z + lane];
+    const int ni = P.n_ions;
+    double* K = reinterpret_cast<double*>(const_cast<char*>(A.tile_pack)) + (size_t)tile * ((ni + 1) * 32 + 2 * KP_MAXC + (96 + KP_MAXC + 4) / 2);
+    if (lane < td.w) {
+        const double Dtm = -(P.inv_tm * P.rho_channel);
+        const double sa = A.mem_sa[td.z + lane];
+        for (int i = 0; i < ni; ++i) K[i * 32 + lane] = (A.Dm[(size_t)i * P.n_mems_owned + td.z + lane] * Dtm) * sa;
+    }
 }
 
 void launch_pack_dm(const KParams& P, const KArrays& A, cudaStream_t st)
@@ -389,18 +387,18 @@ void launch_pack_dm(const KParams& P, const KArrays& A, cudaStream_t st)
     k_pack_dm<<<(P.n_tiles + 7) / 8, 256, 0, st>>>(P, A);
 }
 
-// Host side of the pack (capi.cu:create_impl): byte size of tile t's block and the constant part of its contents.
-unsigned tile_pack_size(int ni, int nm, int nc) { return tile_pack_bytes(ni, nm, nc); }
+// Host side of the pack (capi.cu:create_impl): block size in bytes and the constant part of a block.
+unsigned tile_pack_size(int ni) { return (unsigned)(((ni + 1) * 32 + 2 * KP_MAXC + (96 + KP_MAXC + 4) / 2) * 8); }
 
 void tile_pack_fill(char* blk, int ni, int nm, int nc, const double* mem_sa, const double* cell_vol, const double* diviterm,
                     const int* mem_to_cells, const int* nn_cell_flag, const int* map_mem2ecm, const int* cell_mem_ptr)
 {
     double* K = reinterpret_cast<double*>(blk);
-    for (int j = 0; j < nm; ++j) K[ni * nm + j] = mem_sa[j];
-    for (int j = 0; j < nc; ++j) { K[(ni + 1) * nm + j] = cell_vol[j]; K[(ni + 1) * nm + nc + j] = diviterm[j]; }
-    int* Ki = reinterpret_cast<int*>(K + (ni + 1) * nm + 2 * nc);
-    for (int j = 0; j < nm; ++j) { Ki[j] = mem_to_cells[j]; Ki[nm + j] = nn_cell_flag[j]; Ki[2 * nm + j] = map_mem2ecm[j]; }
-    for (int j = 0; j <= nc; ++j) Ki[3 * nm + j] = cell_mem_ptr[j];
+    for (int j = 0; j < nm; ++j) K[ni * 32 + j] = mem_sa[j];
+    for (int j = 0; j < nc; ++j) { K[(ni + 1) * 32 + j] = cell_vol[j]; K[(ni + 1) * 32 + KP_MAXC + j] = diviterm[j]; }
+    int* Ki = reinterpret_cast<int*>(K + (ni + 1) * 32 + 2 * KP_MAXC);
+    for (int j = 0; j < nm; ++j) { Ki[j] = mem_to_cells[j]; Ki[32 + j] = nn_cell_flag[j]; Ki[64 + j] = map_mem2ecm[j]; }
+    for (int j = 0; j <= nc; ++j) Ki[96 + j] = cell_mem_ptr[j];
 }
 
 // ---------------------------------------------------------------------------- launch
@@ -419,21 +417,23 @@ bool kmem_pipe_enabled()
     return v == 1;
 }
 
-template <int NI, int MINB>
+template <int NI, int WPC, int MINB>
 static cudaError_t prep_pipe()
 {
-    const int smem = (int)(4 * KP_WARP(NI) * sizeof(double));
-    cudaError_t e = cudaFuncSetAttribute(k_mem_pipe<NI, 4, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int smem = (int)(WPC * KP_WARP(NI) * sizeof(double));
+    cudaError_t e = cudaFuncSetAttribute(k_mem_pipe<NI, WPC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e) return e;
-    return cudaFuncSetAttribute(k_mem_pipe<NI, 4, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    return cudaFuncSetAttribute(k_mem_pipe<NI, WPC, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
 }
 
 template <int NI>
 static cudaError_t prep_pipe_ni()
 {
     cudaError_t e;
-    if ((e = prep_pipe<NI, 2>())) return e;
-    if ((e = prep_pipe<NI, 3>())) return e;
+    if ((e = prep_pipe<NI, 4, 2>())) return e;
+    if ((e = prep_pipe<NI, 4, 3>())) return e;
+    if ((e = prep_pipe<NI, 5, 3>())) return e;
+    if ((e = prep_pipe<NI, 4, 4>())) return e;
     return cudaSuccess;
 }
 
@@ -448,20 +448,30 @@ cudaError_t prepare_mem_pipe(int ni)
     }
 }
 
+template <int NI, int WPC, int MINB>
+static void launch_pipe_cfg(const KParams& P, const KArrays& A, int n_sms, int cur, cudaStream_t st)
+{
+    const size_t smem = WPC * KP_WARP(NI) * sizeof(double);
+    int grid = n_sms * MINB;
+    const int need = (P.n_tiles + WPC - 1) / WPC;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    k_mem_pipe<NI, WPC, MINB><<<grid, WPC * 32, smem, st>>>(P, A, cur);
+}
+
+// resident warps per SM: 16 = 4 CTAs x 4 warps (128 registers), 15 = 3 x 5, 12 = 3 x 4, 8 = 2 x 4; a CTA count that
+// does not fit in shared memory (7-ion profile) falls back to the next smaller one
 template <int NI>
 static void launch_pipe_t(const KParams& P, const KArrays& A, int n_sms, int cur, cudaStream_t st)
 {
-    const size_t smem = 4 * KP_WARP(NI) * sizeof(double);
-    static int ctas_per_sm = -1;
-    if (ctas_per_sm < 0) { ctas_per_sm = env_int("BETSE_KMEM_WARPS", 12) / 4; if (ctas_per_sm < 1) ctas_per_sm = 1; }
-    int cps = ctas_per_sm;
-    while (cps > 1 && (smem + 1024) * cps > 228 * 1024) --cps;   // what fits next to each other on one SM
-    int grid = n_sms * cps;
-    const int need = (P.n_tiles + 3) / 4;
-    if (grid > need) grid = need;
-    if (grid < 1) grid = 1;
-    if (cps >= 3) k_mem_pipe<NI, 4, 3><<<grid, 128, smem, st>>>(P, A, cur);
-    else k_mem_pipe<NI, 4, 2><<<grid, 128, smem, st>>>(P, A, cur);
+    static int warps = -1;
+    if (warps < 0) warps = env_int("BETSE_KMEM_WARPS", 12);
+    const size_t per_warp = KP_WARP(NI) * sizeof(double);
+    const size_t cap = 227 * 1024;
+    if (warps >= 16 && (4 * per_warp + 1024) * 4 <= cap + 4096) launch_pipe_cfg<NI, 4, 4>(P, A, n_sms, cur, st);
+    else if (warps >= 15 && (5 * per_warp + 1024) * 3 <= cap + 3072) launch_pipe_cfg<NI, 5, 3>(P, A, n_sms, cur, st);
+    else if (warps >= 12 && (4 * per_warp + 1024) * 3 <= cap + 3072) launch_pipe_cfg<NI, 4, 3>(P, A, n_sms, cur, st);
+    else launch_pipe_cfg<NI, 4, 2>(P, A, n_sms, cur, st);
 }
 
 void launch_mem_pipe(int ni, const KParams& P, const KArrays& A, int n_sms, int cur, cudaStream_t st)

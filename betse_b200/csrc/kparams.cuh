@@ -5,6 +5,7 @@
 #define BT_MAX_IONS 8
 #define BT_TPB 256          // threads per CTA of the membrane kernel == max membranes per CTA
 #define BT_MAX_CTA_CELLS 96 // max cells packed into one membrane-kernel CTA
+#define BT_TILE_MAXC 8      // max cells of one warp tile (<= 32 membranes)
 
 // Scalars (passed BY VALUE as a __grid_constant__ kernel argument: lives in the constant bank).  Derived products are formed on
 // the host in the same operand order as the reference's NumPy expressions.
@@ -15,6 +16,7 @@ struct KParams {
     double z[BT_MAX_IONS];
     double zF[BT_MAX_IONS];       // sim.zs * p.F
     double Dgj_surf[BT_MAX_IONS]; // sim.D_gj[i] * p.gj_surface
+    double Dgj_len[BT_MAX_IONS];  // Dgj_surf[i] / cells.gj_len
     double cbound[BT_MAX_IONS];   // sim.c_env_bound
     double sig_k[BT_MAX_IONS];    // z^2 * F^2 (sigma_cell, diagnostics)
     double D_free[BT_MAX_IONS];
@@ -56,8 +58,7 @@ struct KArrays {
     const int *mem_to_cells, *cell_mem_ptr, *nn_cell_flag, *nn_i, *map_mem2ecm;
     const int *cta_cell_start;   // CTA packing (k_diag): whole cells, <= BT_TPB membranes
     const int *tile_desc;        // warp packing (k_mem): int4 {c0, nc, m0, nm} per tile of whole cells, <= 32 membranes
-    const char *tile_pack;       // k_mem_pipe: per-tile constant block (layout: kmem_pipe.cu header), 16-byte aligned blocks
-    const int *tile_off;         // offset of tile t's block in tile_pack, in units of 16 bytes
+    const char *tile_pack;       // k_mem_pipe: fixed-size per-tile constant blocks (layout: kmem_pipe.cu header)
     const int *slot_ptr, *slot_idx;
     const double *mem_sa, *mem_nx, *mem_ny, *cell_vol, *cell_sa, *diviterm, *num_mems;
     const double *memsa_env, *gj_w;
