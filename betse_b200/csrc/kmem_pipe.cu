@@ -30,12 +30,13 @@
 #include "kmath.cuh"
 
 #define KP_MAXC BT_TILE_MAXC                         // cells per tile (host packing, capi.cu)
-#define KP_SST 33                                    // staging stride (doubles): conflict-free f*sa [ion][membrane]
+#define KP_SST(NI) ((NI) | 1)                        // staging stride (doubles) of f*sa [membrane][ion]: odd => the membrane-lane stores,
+                                                     // the (cell, ion)-lane sums and the slot copy all stay (nearly) bank-conflict free
 // tile pack block, in doubles: DmS[NI][32], sa[32], vol[MAXC], dvt[MAXC] | ints: m2c[32], nnp[32], e[32], ptr[MAXC+4]
 #define KP_KD(NI) (((NI) + 1) * 32 + 2 * KP_MAXC)    // doubles before the int section
 #define KP_K(NI) (KP_KD(NI) + (96 + KP_MAXC + 4) / 2)
 // per-warp shared memory, in doubles
-#define KP_G(NI) ((2 * (NI) + 3) * 32)               // co[NI][32], cnb[NI][32], vnb[32], cao[32], gj[32]; then staging 2*NI*33
+#define KP_G(NI) ((2 * (NI) + 3) * 32)               // co[NI][32], cnb[NI][32], vnb[32], cao[32], gj[32]; then staging 2*32*KP_SST
 #define KP_C(NI) (KP_MAXC + 2 * (NI) * KP_MAXC)      // vmo[c], cc[c][NI] (then the updated values), cmid[c][NI]
 #define KP_AUX (KP_MAXC + 8)                         // cell_mem_ptr[MAXC+1] (6 doubles) + cell_vol[MAXC]: tiles with > 32/NI cells
 #define KP_WARP(NI) (2 + 2 * KP_K(NI) + 2 * KP_G(NI) + 2 * KP_C(NI) + KP_AUX)
@@ -164,7 +165,7 @@ k_mem_pipe(const __grid_constant__ KParams P, const KArrays A, const int cur)
     const int o0 = q0i * C + q0c;
     int cpy[NI];                                       // staging index of element p = lane + 32 k of the [membrane][ion] slot block
 #pragma unroll
-    for (int k = 0; k < NI; ++k) { const int p = lane + 32 * k; const int m = p / NI; cpy[k] = (p - m * NI) * KP_SST + m; }
+    for (int k = 0; k < NI; ++k) { const int p = lane + 32 * k; const int m = p / NI; cpy[k] = m * KP_SST(NI) + (p - m * NI); }
 
     // ---- prologue = pseudo-iterations -2 (barrier 0: K(t)) and -1 (barrier 1: K(t+1)); then G(t)
     int4 td0 = (tile < nt) ? __ldg(TD + tile) : zero4;
@@ -221,8 +222,8 @@ k_mem_pipe(const __grid_constant__ KParams P, const KArrays A, const int cur)
         issue_K<NI>(A, tile + 2 * W, tile + 2 * W < nt, smem_u32(K), bar0 + 8 * pb, lane);
         issue_G<NI>(A, td1, KB(pb ^ 1), GB(pb ^ 1), CB(pb ^ 1), lane, o0, C, E, cur);
 
-        double* s_m = G;                               // [NI][33] f_mem*sa   (the consumed gather rows)
-        double* s_g = G + NI * KP_SST;                 // [NI][33] f_gj*sa
+        double* s_m = G;                               // [32][KP_SST] f_mem*sa   (the consumed gather rows)
+        double* s_g = G + 32 * KP_SST(NI);             // [32][KP_SST] f_gj*sa
 
         // ---- lanes = membranes
         if (act) {
@@ -293,8 +294,8 @@ k_mem_pipe(const __grid_constant__ KParams P, const KArrays A, const int cur)
                 if (i == iK) fsa = fma(fK, sa, fsa);
                 if (i == iCa) fsa = fma(fCa, sa, fsa);
                 g = fma(g, gc1, gc2);                                      // once per ion (sim.py:1272 -> 2180-2183)
-                s_m[i * KP_SST + lane] = fsa;
-                s_g[i * KP_SST + lane] = -(P.Dgj_len[i] * (g * sa_g)) * (cnb[i] * Ag - cin[i] * Bg);   // sim.py:2191-2197
+                s_m[lane * KP_SST(NI) + i] = fsa;
+                s_g[lane * KP_SST(NI) + i] = -(P.Dgj_len[i] * (g * sa_g)) * (cnb[i] * Ag - cin[i] * Bg);   // sim.py:2191-2197
             }
             A.gjopen[m] = g;
         }
@@ -323,13 +324,13 @@ k_mem_pipe(const __grid_constant__ KParams P, const KArrays A, const int cur)
                 vol = s_aux[6 + qc];
                 oc = (size_t)i * C + c0 + qc;
             }
-            const double* pm = s_m + i * KP_SST + jb;
-            const double* pg = s_g + i * KP_SST + jb;
+            const double* pm = s_m + jb * KP_SST(NI) + i;
+            const double* pg = s_g + jb * KP_SST(NI) + i;
             const int n = je - jb;
             double Sm = 0.0, Sg = 0.0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { if (k < n) { Sm += pm[k]; Sg += pg[k]; } }
-            for (int k = 8; k < n; ++k) { Sm += pm[k]; Sg += pg[k]; }
+            for (int k = 0; k < 8; ++k) { if (k < n) { Sm += pm[k * KP_SST(NI)]; Sg += pg[k * KP_SST(NI)]; } }
+            for (int k = 8; k < n; ++k) { Sm += pm[k * KP_SST(NI)]; Sg += pg[k * KP_SST(NI)]; }
             const double rvol = fast_rcp(vol);
             const double cm_new = c_cc[q] + (Sm * rvol) * P.dt;          // sim_toolbox.py:1177-1181
             double cn_new = cm_new + P.dt * ((-Sg) * rvol);              // sim.py:2105-2108
