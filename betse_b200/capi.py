@@ -13,13 +13,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libbetse_b200.so")
 
 MAX_IONS = 8
-ABI_VERSION = 1
+ABI_VERSION = 2
 NKERNELS = 8
 
 STATUS_NAN_VM = 1
 STATUS_NAN_CONC = 2
 STATUS_NEG_CLAMP = 4
 STATUS_XCHG_TIMEOUT = 8
+STATUS_NEG_NET = 16
 STEP_DIAG = 1
 XCHG_X1, XCHG_X2 = 0, 1
 XCHG_PUSH, XCHG_WAIT = 1, 2
@@ -98,9 +99,20 @@ class GateTerm(C.Structure):
 class Channel(C.Structure):
     _fields_ = [
         ("ion", C.c_int32), ("mpower", C.c_int32), ("hpower", C.c_int32), ("kind", C.c_int32 * 4),
-        ("reserved", C.c_int32), ("a", GateTerm * 4), ("b", GateTerm * 4),
+        ("handler", C.c_int32), ("mod_prog", C.c_int32), ("reserved", C.c_int32),
+        ("a", GateTerm * 4), ("b", GateTerm * 4),
         ("time_unit", C.c_double), ("max_Dm", C.c_double), ("rel_perm", C.c_double), ("v_shift", C.c_double),
         ("target_mask", _bp), ("m0", _dp), ("h0", _dp),
+    ]
+
+
+class Network(C.Structure):
+    _fields_ = [
+        ("n_species", C.c_int32), ("n_rates", C.c_int32), ("n_programs", C.c_int32),
+        ("n_consts", C.c_int32), ("n_cell_arrays", C.c_int32), ("n_mem_arrays", C.c_int32),
+        ("c_cells", _dp), ("code", _ip), ("prog_ptr", _ip), ("consts", _dp), ("cell_arrays", _dp),
+        ("mem_arrays", _dp), ("growth_mask", _bp), ("stoich", _dp), ("Dgj", _dp), ("z", _dp),
+        ("time_factor", _dp),
     ]
 
 
@@ -130,7 +142,7 @@ SYMBOLS = [
     "betse_step_profile", "betse_kernel_name", "betse_download_sample",
     "betse_step_phase", "betse_stream", "betse_sync", "betse_update_v", "betse_update_v_phase",
     "betse_set_row_ranges", "betse_window", "betse_attach_neighbor", "betse_exchange",
-    "betse_set_channels", "betse_channel_state",
+    "betse_set_channels", "betse_channel_state", "betse_set_network", "betse_network_state",
 ]
 
 _lib = None
@@ -169,7 +181,9 @@ def load(build_if_missing=True):
     lib.betse_attach_neighbor.argtypes = [vp, C.POINTER(Neighbor)]
     lib.betse_exchange.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     lib.betse_set_channels.argtypes = [vp, C.c_int, C.POINTER(Channel), C.c_int]
-    lib.betse_channel_state.argtypes = [vp, C.c_int, _dp, _dp, _dp, _dp]
+    lib.betse_channel_state.argtypes = [vp, C.c_int, _dp, _dp, _dp, _dp, _dp]
+    lib.betse_set_network.argtypes = [vp, C.c_int, C.POINTER(Network)]
+    lib.betse_network_state.argtypes = [vp, C.c_int, _dp, _dp]
     lib.betse_step_phase.argtypes = [vp, C.c_int, C.c_int]
     lib.betse_stream.argtypes = [vp, C.POINTER(vp)]
     lib.betse_sync.argtypes = [vp, C.POINTER(C.c_uint32)]

@@ -14,6 +14,7 @@
 #include "kparams.cuh"
 #include "xchg.cuh"
 #include "channels.cuh"
+#include "network.cuh"
 
 // launchers (kernels.cu)
 void launch_mem(int ni, const KParams& P, const KArrays& A, int n_ctas, int cur, int diag, cudaStream_t st);
@@ -31,7 +32,8 @@ unsigned tile_pack_size(int ni);
 void tile_pack_fill(char* blk, int ni, int nm, int nc, const double* mem_sa, const double* cell_vol, const double* diviterm,
                     const int* mem_to_cells, const int* nn_cell_flag, const int* map_mem2ecm, const int* cell_mem_ptr);
 void launch_pack_dm(const KParams& P, const KArrays& A, cudaStream_t st);
-void launch_chan(const KParams& P, const KArrays& A, const KChan& ch, int cur, cudaStream_t st);
+void launch_chan(const KParams& P, const KArrays& A, const KChan& ch, const KNet& N, int cur, cudaStream_t st);
+void launch_net(const KParams& P, const KArrays& A, const KNet& N, const double* h_Dgj, int n_ions, int cur, cudaStream_t st);
 void launch_cell_update(const KParams& P, const KArrays& A, int cur, cudaStream_t st);
 void launch_xchg(const KParams& P, const KArrays& A, const XPlan& X, int which, int buf, int mode, cudaStream_t st);
 
@@ -57,6 +59,10 @@ struct betse_ctx {
     XPlan X;
     std::vector<void*> ipc_opened;
     std::vector<KChan> chans;                // voltage-gated channels, applied in order
+    KNet nets[2];                            // network handlers: 0 general network, 1 gene regulatory network
+    bool net_on[2] = {false, false};
+    int net_nprog[2] = {0, 0};
+    std::vector<double> net_Dgj[2];          // host copy (which substances pass gap junctions)
     std::string err;
     std::vector<void*> allocs;
     // CUDA graphs of one plain step, for cur = 0 and cur = 1
@@ -243,6 +249,7 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
     { const char* e = getenv("BETSE_OVERLAP"); ctx->overlap = !(e && e[0] == '0'); }
     memset(&ctx->A, 0, sizeof(KArrays));
     memset(&ctx->P, 0, sizeof(KParams));
+    memset(ctx->nets, 0, sizeof ctx->nets);
     KArrays& A = ctx->A;
     KParams& P = ctx->P;
     P.delta = mesh->delta;
@@ -569,7 +576,7 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
         // The membrane kernel reads cc_env[nxt] of Ca only (the Ca-ATPase sees the transported value,
         // sim.py:1282 after 2254): the Ca row is transported first, the other ions run on a second
         // stream NEXT TO the membrane kernel (which is latency-bound and leaves issue slots free).
-        const bool chans = !ctx->chans.empty();
+        const bool chans = !ctx->chans.empty() || ctx->net_on[0] || ctx->net_on[1];   // deferred-update mode
         const bool overlap = ecm && ctx->overlap && !evs && ctx->hp.sharpness >= 1.0 && !chans;
         if (ecm && overlap) {
             const int iCa = ctx->hp.iCa;
@@ -594,9 +601,13 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
         launch_mem(I, ctx->P, A, ctx->n_ctas, cur, diag, st);
         if (overlap) cudaStreamWaitEvent(st, ctx->ev_join, 0);
         if (chans) {
-            // run_loop_channels (networks.py:3115-3213): between the ion loop's fluxes and update_all_concs
+            // between the ion loop's fluxes and update_all_concs (sim.py:1290-1357), per handler: run_loop_channels
+            // (networks.py:3115-3213), then run_loop (networks.py:2805-2982)
             if (A.chanJ) cudaMemsetAsync(A.chanJ, 0, (size_t)ctx->Mo * sizeof(double), st);
-            for (const KChan& ch : ctx->chans) launch_chan(ctx->P, A, ch, cur, st);
+            for (int h = 0; h < 2; ++h) {
+                for (const KChan& ch : ctx->chans) if (ch.handler == h) launch_chan(ctx->P, A, ch, ctx->nets[h], cur, st);
+                if (ctx->net_on[h]) launch_net(ctx->P, A, ctx->nets[h], ctx->net_Dgj[h].data(), I, cur, st);
+            }
             launch_cell_update(ctx->P, A, cur, st);
         }
         if (evs) cudaEventRecord(evs[3], st);
@@ -850,9 +861,9 @@ extern "C" int betse_set_channels(betse_ctx* ctx, int n, const betse_channel* ch
     int r;
     ctx->chans.clear();
     destroy_graphs(ctx);
-    ctx->P.defer = n > 0 ? 1 : 0;
+    ctx->P.defer = (n > 0 || ctx->net_on[0] || ctx->net_on[1]) ? 1 : 0;
     ctx->P.chan_charge = (n > 0 && affect_charge) ? 1 : 0;
-    if (n == 0) return 0;
+    if (!ctx->P.defer) return 0;
     if (!A.dsum_m) {
         if ((r = dev_alloc(ctx, &A.dsum_m, (size_t)ctx->I * ctx->C))) return r;
         if ((r = dev_alloc(ctx, &A.dsum_g, (size_t)ctx->I * ctx->C))) return r;
@@ -874,6 +885,11 @@ extern "C" int betse_set_channels(betse_ctx* ctx, int n, const betse_channel* ch
             d.a[q].type = c.a[q].type; d.b[q].type = c.b[q].type;
             for (int j = 0; j < 4; ++j) { d.a[q].p[j] = c.a[q].p[j]; d.b[q].p[j] = c.b[q].p[j]; }
         }
+        d.handler = c.handler; d.mod_prog = c.mod_prog;
+        if (c.handler < 0 || c.handler > 1) return fail(ctx, "channel handler must be 0 or 1");
+        if (c.mod_prog >= 0 && !ctx->net_on[c.handler]) return fail(ctx, "channel modulator without its network: call betse_set_network first");
+        if (c.mod_prog >= 0 && (c.mod_prog < ctx->nets[c.handler].n_rates || c.mod_prog >= ctx->net_nprog[c.handler]))
+            return fail(ctx, "channel mod_prog is not a membrane-zone program of its network");
         d.dt_tu = ctx->hp.dt * c.time_unit;
         d.maxDm = c.max_Dm; d.rel_perm = c.rel_perm; d.shift = c.v_shift;
         if (c.target_mask) { if ((r = dev_upload(ctx, (unsigned char**)&d.mask, c.target_mask, Mo))) return r; }
@@ -881,13 +897,14 @@ extern "C" int betse_set_channels(betse_ctx* ctx, int n, const betse_channel* ch
         if ((r = dev_upload(ctx, &d.h, c.h0, Mo))) return r;
         if ((r = dev_alloc(ctx, &d.P, Mo))) return r;
         if ((r = dev_alloc(ctx, &d.flux, Mo))) return r;
+        if ((r = dev_alloc(ctx, &d.D, Mo))) return r;
         ctx->chans.push_back(d);
     }
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
-extern "C" int betse_channel_state(betse_ctx* ctx, int k, double* m, double* h, double* P, double* flux)
+extern "C" int betse_channel_state(betse_ctx* ctx, int k, double* m, double* h, double* P, double* flux, double* DChan)
 {
     if (!ctx) return 2;
     CK(cudaSetDevice(ctx->device));
@@ -898,6 +915,95 @@ extern "C" int betse_channel_state(betse_ctx* ctx, int k, double* m, double* h, 
     if (h) CK(cudaMemcpyAsync(h, d.h, nb, cudaMemcpyDeviceToHost, ctx->stream));
     if (P) CK(cudaMemcpyAsync(P, d.P, nb, cudaMemcpyDeviceToHost, ctx->stream));
     if (flux) CK(cudaMemcpyAsync(flux, d.flux, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (DChan) CK(cudaMemcpyAsync(DChan, d.D, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+static int ensure_defer_buffers(betse_ctx* ctx)
+{
+    KArrays& A = ctx->A;
+    int r;
+    if (A.dsum_m) return 0;
+    if ((r = dev_alloc(ctx, &A.dsum_m, (size_t)ctx->I * ctx->C))) return r;
+    if ((r = dev_alloc(ctx, &A.dsum_g, (size_t)ctx->I * ctx->C))) return r;
+    if ((r = dev_alloc(ctx, &A.chan_slots, (size_t)ctx->n_slots))) return r;
+    if ((r = dev_alloc(ctx, &A.chanJ, (size_t)ctx->Mo))) return r;
+    return 0;
+}
+
+extern "C" int betse_set_network(betse_ctx* ctx, int handler, const betse_network* net)
+{
+    if (!ctx || handler < 0 || handler > 1) return 2;
+    CK(cudaSetDevice(ctx->device));
+    destroy_graphs(ctx);
+    if (!net) {
+        ctx->net_on[handler] = false;
+        ctx->P.defer = (!ctx->chans.empty() || ctx->net_on[0] || ctx->net_on[1]) ? 1 : 0;
+        return 0;
+    }
+    if (ctx->X.n_nbr > 0) return fail(ctx, "networks on a domain-decomposed tissue are not implemented");
+    if (!ctx->hp.is_ecm || ctx->hp.fast_update_ecm) return fail(ctx, "networks without extracellular spaces / with fast_update_ecm are not implemented");
+    const int K = net->n_species, R = net->n_rates, C = ctx->C, Mo = ctx->Mo;
+    if (K <= 0 || R < K || R > NET_MAX_RATES) return fail(ctx, "network: need 0 < n_species <= n_rates <= 48");
+    if (net->n_programs < R) return fail(ctx, "network: n_programs < n_rates");
+    if (!net->c_cells || !net->code || !net->prog_ptr || !net->stoich || !net->Dgj || !net->z || !net->time_factor)
+        return fail(ctx, "network: null table");
+    // validate the programs: operands in range, stack discipline
+    const int n_pairs = net->prog_ptr[net->n_programs];
+    for (int p = 0; p < net->n_programs; ++p) {
+        int depth = 0;
+        if (net->prog_ptr[p] > net->prog_ptr[p + 1]) return fail(ctx, "network: prog_ptr not monotone");
+        for (int pc = net->prog_ptr[p]; pc < net->prog_ptr[p + 1]; ++pc) {
+            const int op = net->code[2 * pc], arg = net->code[2 * pc + 1];
+            const bool memzone = p >= R;
+            if (op < 0 || op > RL_EXP) return fail(ctx, "network: unknown opcode");
+            if (op == RL_PUSHC && (arg < 0 || arg >= net->n_consts)) return fail(ctx, "network: constant index out of range");
+            if (op == RL_PUSHS && (arg < 0 || arg >= K)) return fail(ctx, "network: substance index out of range");
+            if (op == RL_PUSHA && (arg < 0 || arg >= (memzone ? net->n_mem_arrays : net->n_cell_arrays))) return fail(ctx, "network: array index out of range");
+            if ((op == RL_PUSHI || op == RL_PUSHM) && (arg < 0 || arg >= ctx->I)) return fail(ctx, "network: ion index out of range");
+            if (op == RL_PUSHV && !memzone) return fail(ctx, "network: Vmem in a cell-zone program");
+            if (op <= RL_PUSHV) ++depth;
+            else if (op != RL_NEG && op != RL_EXP) --depth;
+            if (depth < 1 || depth > NET_STACK) return fail(ctx, "network: program violates the stack discipline");
+        }
+        if (depth != 1) return fail(ctx, "network: program does not leave exactly one value");
+    }
+    KNet N;
+    memset(&N, 0, sizeof N);
+    N.K = K; N.n_rates = R;
+    int r;
+    if ((r = dev_upload(ctx, &N.c, net->c_cells, (size_t)K * C))) return r;
+    if ((r = dev_alloc(ctx, &N.rates, (size_t)R * C))) return r;
+    if ((r = dev_alloc(ctx, &N.gj_delta, (size_t)C))) return r;
+    if ((r = dev_upload(ctx, (int**)&N.code, net->code, (size_t)2 * std::max(1, n_pairs)))) return r;
+    if ((r = dev_upload(ctx, (int**)&N.ptr, net->prog_ptr, (size_t)net->n_programs + 1))) return r;
+    if ((r = dev_upload(ctx, (double**)&N.consts, net->consts, (size_t)std::max(1, net->n_consts)))) return r;
+    if (net->n_cell_arrays > 0) { if ((r = dev_upload(ctx, (double**)&N.cell_arrays, net->cell_arrays, (size_t)net->n_cell_arrays * C))) return r; }
+    if (net->n_mem_arrays > 0) { if ((r = dev_upload(ctx, (double**)&N.mem_arrays, net->mem_arrays, (size_t)net->n_mem_arrays * Mo))) return r; }
+    if (net->growth_mask) { if ((r = dev_upload(ctx, (unsigned char**)&N.gmask, net->growth_mask, (size_t)K * C))) return r; }
+    if ((r = dev_upload(ctx, (double**)&N.stoich, net->stoich, (size_t)K * R))) return r;
+    if ((r = dev_upload(ctx, (double**)&N.Dgj, net->Dgj, (size_t)K))) return r;
+    if ((r = dev_upload(ctx, (double**)&N.z, net->z, (size_t)K))) return r;
+    if ((r = dev_upload(ctx, (double**)&N.tdf, net->time_factor, (size_t)K))) return r;
+    if ((r = ensure_defer_buffers(ctx))) return r;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->nets[handler] = N;
+    ctx->net_Dgj[handler].assign(net->Dgj, net->Dgj + K);
+    ctx->net_on[handler] = true;
+    ctx->net_nprog[handler] = net->n_programs;
+    ctx->P.defer = 1;
+    return 0;
+}
+
+extern "C" int betse_network_state(betse_ctx* ctx, int handler, double* c_cells, double* rates)
+{
+    if (!ctx || handler < 0 || handler > 1) return 2;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->net_on[handler]) return fail(ctx, "no network on this handler");
+    const KNet& N = ctx->nets[handler];
+    if (c_cells) CK(cudaMemcpyAsync(c_cells, N.c, (size_t)N.K * ctx->C * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (rates) CK(cudaMemcpyAsync(rates, N.rates, (size_t)N.n_rates * ctx->C * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }

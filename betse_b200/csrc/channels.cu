@@ -13,6 +13,7 @@
 // k_cell_update then applies the deferred sums exactly as k_mem's tail would have.
 #include "kparams.cuh"
 #include "channels.cuh"
+#include "network.cuh"
 
 #define FLOAT_NONCE 1.0e-25
 #define ST_NAN_VM 1u
@@ -62,7 +63,8 @@ __device__ __forceinline__ double ipow(double x, int n)
 // One warp per tile of whole cells (the packing of k_mem): lanes = membranes for gates and flux,
 // then lanes = cells for the immediate concentration update of the conducted ion.
 __global__ void __launch_bounds__(BT_TPB)
-k_chan(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ KChan ch, const int cur)
+k_chan(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ KChan ch, const __grid_constant__ KNet N,
+       const int cur)
 {
     __shared__ double s_all[(BT_TPB / 32) * 32];
     const int lane = threadIdx.x & 31;
@@ -95,7 +97,10 @@ k_chan(const __grid_constant__ KParams P, const KArrays A, const __grid_constant
             Pm = ipow(mm, ch.mpow) * ipow(hh, ch.hpow);            // vg_na.py:104
         }
         ch.P[m] = Pm;
-        const double DChan = ((Pm * ch.rel_perm) * ch.maxDm) * 1.0;   // moddy == 1 (no modulators), networks.py:3164
+        // moddy = eval(chan.alpha_eval_string) in the membrane zone (networks.py:3147; compiled by ratelaw.py)
+        const double moddy = (ch.mod_prog >= 0) ? rl_eval(N, ch.mod_prog, c, m, A, C, P.n_mems_owned, cur, vm) : 1.0;
+        const double DChan = ((Pm * ch.rel_perm) * ch.maxDm) * moddy;   // networks.py:3164
+        if (ch.D) ch.D[m] = DChan;
         // stb.electroflux(cenv[map_mem2ecm], cmem, DChan, tm, z, vm, sim.T, rho=rho_channel), sim_toolbox.py:18-69
         const double alpha = ((P.z[ion] + FLOAT_NONCE) * (vm + FLOAT_NONCE) * P.F) / P.RT_sim;
         const double ex = exp(-alpha), deno = -expm1(-alpha);
@@ -163,10 +168,10 @@ k_cell_update(const __grid_constant__ KParams P, const KArrays A, const int cur)
     if (flags) atomicOr(A.status, flags);
 }
 
-void launch_chan(const KParams& P, const KArrays& A, const KChan& ch, int cur, cudaStream_t st)
+void launch_chan(const KParams& P, const KArrays& A, const KChan& ch, const KNet& N, int cur, cudaStream_t st)
 {
     const int grid = (P.n_tiles + (BT_TPB / 32) - 1) / (BT_TPB / 32);
-    k_chan<<<grid, BT_TPB, 0, st>>>(P, A, ch, cur);
+    k_chan<<<grid, BT_TPB, 0, st>>>(P, A, ch, N, cur);
     if (P.is_ecm) {
         const int n = (P.ya1 - P.ya0) * P.nx;
         if (n > 0) k_chan_env<<<(n + 255) / 256, 256, 0, st>>>(P, A, ch.ion, cur ^ 1);

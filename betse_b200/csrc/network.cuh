@@ -1,0 +1,69 @@
+// Device-side description of one network handler (general network / gene regulatory network):
+// substances, compiled rate-law programs (betse_b200/ratelaw.py) and their tables.
+#pragma once
+#include "kparams.cuh"
+
+#define NET_MAX_RATES 48    // growth/decay rates + cell-zone reactions of one handler
+#define NET_STACK 16        // ratelaw.MAX_STACK
+
+// opcodes of the postfix programs (ratelaw.py)
+enum { RL_PUSHC = 0, RL_PUSHS, RL_PUSHA, RL_PUSHI, RL_PUSHM, RL_PUSHV, RL_ADD, RL_SUB, RL_MUL, RL_DIV, RL_POW, RL_NEG, RL_EXP };
+
+struct KNet {
+    int K;                      // substances
+    int n_rates;                // K growth/decay rates + R reactions (columns of reaction_matrix)
+    double* c;                  // [K][C] concentrations in the cells
+    double* rates;              // [n_rates][C] rates of the last step (reaction_rates / download)
+    double* gj_delta;           // [C] scratch of the gap-junction transport
+    const int* code;            // (op, arg) pairs
+    const int* ptr;             // [n_programs + 1] program ranges (in pairs)
+    const double* consts;
+    const double* cell_arrays;  // [n][C] per-cell constants (growth_mod_function_cells ...)
+    const double* mem_arrays;   // [n][M] per-membrane constants
+    const unsigned char* gmask; // [K][C] growth_targets_cell (null: every cell)
+    const double* stoich;       // [K][n_rates] substance rows of reaction_matrix
+    const double* Dgj;          // [K] gap-junction diffusion constant; < 0: ignoreGJ
+    const double* z;            // [K]
+    const double* tdf;          // [K] modify_time_factor
+};
+
+// One rate law at cell c (membrane m < 0: cell zone).
+__device__ __forceinline__ double rl_eval(const KNet& N, const int prog, const int c, const int m, const KArrays& A,
+                                          const int C, const int M, const int cur, const double vm)
+{
+    double st[NET_STACK];
+    int sp = 0;
+    const int p0 = __ldg(N.ptr + prog), p1 = __ldg(N.ptr + prog + 1);
+    for (int pc = p0; pc < p1; ++pc) {
+        const int2 ins = __ldg(reinterpret_cast<const int2*>(N.code) + pc);
+        const int op = ins.x, arg = ins.y;
+        if (op <= RL_PUSHV) {
+            double v;
+            switch (op) {
+                case RL_PUSHC: v = __ldg(N.consts + arg); break;
+                case RL_PUSHS: v = N.c[(size_t)arg * C + c]; break;
+                case RL_PUSHA: v = (m < 0) ? __ldg(N.cell_arrays + (size_t)arg * C + c) : __ldg(N.mem_arrays + (size_t)arg * M + m); break;
+                case RL_PUSHI: v = A.cc_cells[(size_t)arg * C + c]; break;
+                case RL_PUSHM: v = A.cc_mid[cur][(size_t)arg * C + c]; break;
+                default: v = vm; break;
+            }
+            st[sp++] = v;
+        } else if (op == RL_NEG) st[sp - 1] = -st[sp - 1];
+        else if (op == RL_EXP) st[sp - 1] = exp(st[sp - 1]);
+        else {
+            const double b = st[--sp], a = st[sp - 1];
+            double r;
+            switch (op) {
+                case RL_ADD: r = a + b; break;
+                case RL_SUB: r = a - b; break;
+                case RL_MUL: r = a * b; break;
+                case RL_DIV: r = a / b; break;
+                default:     // NumPy's scalar-exponent fast paths (x**1, x**2, x**0.5, x**-1, x**0), else pow
+                    r = (b == 1.0) ? a : (b == 2.0) ? a * a : (b == 0.5) ? sqrt(a) : (b == -1.0) ? 1.0 / a : (b == 0.0) ? 1.0 : pow(a, b);
+                    break;
+            }
+            st[sp - 1] = r;
+        }
+    }
+    return st[0];
+}

@@ -417,17 +417,69 @@ class TissueEngine:
             h0[tg] = np.asarray(chh, dtype=float) * np.ones(len(tg))
             keep += [m0, h0]
             d.m0, d.h0 = capi.ptr_f64(m0), capi.ptr_f64(h0)
+            # modulation by network substances: program index handed out by set_network
+            d.handler = int(c.get("handler", 0))
+            d.mod_prog = int(c.get("mod_prog", -1))
         if affect_charge is None:
             affect_charge = bool(self.p.get("substances_affect_charge", 0))
         self._check(self.lib.betse_set_channels(self.ctx, len(specs), arr, int(bool(affect_charge))), "betse_set_channels")
         self.n_channels = len(specs)
 
     def channel_state(self, k):
-        """{'m','h','P','flux'} of channel ``k`` ([M] each)."""
-        out = {f: np.empty(self.M) for f in ("m", "h", "P", "flux")}
-        self._check(self.lib.betse_channel_state(self.ctx, int(k), *(capi.ptr_f64(out[f]) for f in ("m", "h", "P", "flux"))),
+        """{'m','h','P','flux','DChan'} of channel ``k`` ([M] each)."""
+        out = {f: np.empty(self.M) for f in ("m", "h", "P", "flux", "DChan")}
+        self._check(self.lib.betse_channel_state(self.ctx, int(k), *(capi.ptr_f64(out[f]) for f in ("m", "h", "P", "flux", "DChan"))),
                     "betse_channel_state")
         return out
+
+    # ------------------------------------------------------------------ general / gene network
+    def set_network(self, net, handler=0):
+        """``net``: a compiled network (betse_b200.network.compile_network): substances, rate
+        programs, tables.  ``handler`` 0 = general network, 1 = gene regulatory network."""
+        from . import ratelaw
+        K = len(net["species"])
+        programs = list(net["rate_programs"]) + list(net["mod_programs"])
+        code, ptr = ratelaw.pack_programs(programs)
+        tabs = net["tables"]
+        n = capi.Network()
+        keep = []
+
+        def f64(a):
+            a = capi.as_f64(a)
+            keep.append(a)
+            return capi.ptr_f64(a)
+        n.n_species, n.n_rates, n.n_programs = K, len(net["rate_programs"]), len(programs)
+        n.n_consts, n.n_cell_arrays, n.n_mem_arrays = len(tabs.consts), len(tabs.cell_arrays), len(tabs.mem_arrays)
+        c0 = np.zeros((K, self.C))
+        c0[:, :self.Co] = np.asarray(net["c_cells"], dtype=float).reshape(K, -1)
+        n.c_cells = f64(c0)
+        keep += [code, ptr]
+        n.code, n.prog_ptr = capi.ptr_i32(code), capi.ptr_i32(ptr)
+        n.consts = f64(np.asarray(tabs.consts if tabs.consts else [0.0]))
+        if tabs.cell_arrays:
+            n.cell_arrays = f64(np.stack(tabs.cell_arrays))
+        if tabs.mem_arrays:
+            n.mem_arrays = f64(np.stack(tabs.mem_arrays))
+        gm = net.get("growth_mask")
+        if gm is not None:
+            gm = np.ascontiguousarray(gm, dtype=np.uint8).reshape(K, self.C)
+            keep.append(gm)
+            n.growth_mask = gm.ctypes.data_as(C.POINTER(C.c_uint8))
+        n.stoich = f64(np.asarray(net["stoich"], dtype=float).reshape(K, n.n_rates))
+        n.Dgj, n.z, n.time_factor = f64(net["Dgj"]), f64(net["z"]), f64(net["time_factor"])
+        self._check(self.lib.betse_set_network(self.ctx, int(handler), C.byref(n)), "betse_set_network")
+        self.networks = getattr(self, "networks", {})
+        self.networks[int(handler)] = {"species": list(net["species"]), "n_rates": n.n_rates}
+
+    def network_state(self, handler=0, rates=False):
+        """Substance concentrations [K][C] (and the last rates [n_rates][C]) of a handler."""
+        info = self.networks[int(handler)]
+        c = np.empty((len(info["species"]), self.C))
+        r = np.empty((info["n_rates"], self.C)) if rates else None
+        self._check(self.lib.betse_network_state(self.ctx, int(handler), capi.ptr_f64(c),
+                                                 capi.ptr_f64(r) if rates else None), "betse_network_state")
+        self.d2h_bytes += c.nbytes + (r.nbytes if rates else 0)
+        return (c[:, :self.Co], r[:, :self.Co]) if rates else c[:, :self.Co]
 
     # ------------------------------------------------------------------ domain decomposition
     def window(self):

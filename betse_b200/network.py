@@ -1,0 +1,157 @@
+"""Host side of the general network / gene regulatory network on the GPU.
+
+``describe_core`` reads a live ``MasterOfNetworks`` (betse/science/chemistry/networks.py) into a
+plain *network description*; ``compile_network`` turns a description into the tables
+``TissueEngine.set_network`` uploads.  A description is also what the golden fixtures record, so the
+GPU tests exercise the same compile path without the reference.
+
+Implemented subset (everything else is refused with the reason, never approximated):
+
+* substances with growth/decay (``write_growth_and_decay``, networks.py:1187-1310) and cell-zone
+  reactions (``write_reactions``, 1312-1572), integrated by ``run_loop`` (2805-2914);
+* gap-junction transport of substances (``Molecule.transport`` -> ``stb.molecule_mover``,
+  sim_toolbox.py:976-1006);
+* modulation of voltage-gated channels by substances (``alpha_eval_string``, networks.py:3147-3164).
+"""
+import numpy as np
+
+from . import ratelaw
+from .capi import BetseB200Error
+
+
+def _is_none(v):
+    return v is None or (isinstance(v, str) and v == "None") or (hasattr(v, "__len__") and len(v) == 0)
+
+
+def unsupported_reasons(core, p):
+    """Why this MasterOfNetworks cannot run on the device (empty list: it can)."""
+    bad = []
+    if getattr(core, "mit_enabled", False):
+        bad.append("mitochondria")
+    for attr, what in (("transporters", "transporters (run_loop_transporters, networks.py:2985-3107)"),
+                       ("modulators", "modulators (run_loop_modulators, networks.py:3282-3325)"),
+                       ("reactions_env", "extracellular reactions"), ("reactions_mit", "mitochondrial reactions")):
+        if len(getattr(core, attr, None) or {}):
+            bad.append(what)
+    for name, m in (getattr(core, "molecules", None) or {}).items():
+        why = []
+        if float(getattr(m, "Dm", 0.0) or 0.0) != 0.0:
+            why.append("membrane-permeable (Dm != 0)")
+        for flag, what in (("update_intra_conc", "update intracellular"), ("active_pumping", "active pumping"),
+                           ("ion_channel_gating", "ligand gating"), ("change_bounds", "boundary change event"),
+                           ("cell_clamp", "cell clamp"), ("transmem", "transmembrane transport")):
+            if bool(getattr(m, flag, False)):
+                why.append(what)
+        if np.any(np.asarray(m.c_env) != 0.0) or float(getattr(m, "c_bound", 0.0) or 0.0) > 1.0e-15:
+            why.append("present in the environment (extracellular transport)")
+        if float(getattr(m, "z", 0.0) or 0.0) != 0.0 and bool(getattr(p, "substances_affect_charge", False)):
+            why.append("charged substance with 'substances affect charge'")
+        if why:
+            bad.append("substance %r: %s" % (name, ", ".join(why)))
+    for name, r in (getattr(core, "reactions", None) or {}).items():
+        if str(getattr(r, "reaction_zone", "cell")) != "cell":
+            bad.append("reaction %r outside the cell zone" % name)
+    return bad
+
+
+def describe_core(core, sim, p, cells, record_static=True):
+    """Live ``MasterOfNetworks`` -> network description (plain dict of strings and arrays)."""
+    species = list(core.molecules)
+    ions = [str(k) for k in sim.ionlabel.values()] if hasattr(sim, "ionlabel") else \
+        [k for k, v in p.ions_dict.items() if v == 1]
+    K, C = len(species), len(cells.cell_vol)
+    names = list(core.cell_concs.keys())
+    rmat = np.asarray(core.reaction_matrix, dtype=float)
+    rows = [names.index(s) for s in species]
+    other = [i for i in range(len(names)) if i not in rows]
+    if rmat.size and np.any(rmat[other] != 0.0):
+        raise BetseB200Error("network reactions that produce or consume simulation ions are not implemented")
+    desc = {
+        "species": species, "ions": ions,
+        "c_cells": np.stack([np.asarray(core.molecules[s].c_cells, dtype=float) for s in species]) if K else np.zeros((0, C)),
+        "gad_strings": [core.molecules[s].gad_eval_string for s in species],
+        "reaction_names": list(core.reactions),
+        "reaction_strings": [core.reactions[r].reaction_eval_string for r in core.reactions],
+        "stoich": rmat[rows] if rmat.size else np.zeros((K, K)),
+        "growth_targets": [np.asarray(core.molecules[s].growth_targets_cell, dtype=np.int64) for s in species],
+        "Dgj": np.array([-1.0 if core.molecules[s].ignoreGJ else float(core.molecules[s].Dgj) for s in species]),
+        "z": np.array([float(core.molecules[s].z) for s in species]),
+        "time_factor": np.array([float(core.molecules[s].modify_time_factor) for s in species]),
+        "chan_names": list(core.channels),
+        "chan_mod_strings": [core.channels[c].alpha_eval_string for c in core.channels],
+        "static": {},
+    }
+    if record_static:
+        # resolve every static leaf once so that the description is self-contained
+        rec = {}
+        compile_network(desc, C, len(cells.mem_sa), ratelaw.live_resolver(core, sim, p, cells, record=rec))
+        desc["static"] = rec
+    return desc
+
+
+def compile_network(desc, n_cells, n_mems, resolver=None):
+    """Description -> {'species','tables','rate_programs','mod_programs','mod_index', ...} for
+    ``TissueEngine.set_network``.  ``resolver`` defaults to the description's recorded static values."""
+    if resolver is None:
+        resolver = ratelaw.table_resolver(desc["static"])
+    species = list(desc["species"])
+    K = len(species)
+    tabs = ratelaw.Tables(species, list(desc["ions"]), n_cells, n_mems)
+    try:
+        rates = [ratelaw.compile_expr(s, tabs, resolver, "cell") for s in desc["gad_strings"]]
+        rates += [ratelaw.compile_expr(s, tabs, resolver, "cell") for s in desc["reaction_strings"]]
+        mods = [ratelaw.compile_expr(s, tabs, resolver, "mem") for s in desc["chan_mod_strings"]]
+    except ratelaw.RateLawError as e:
+        raise BetseB200Error("network rate law not supported on the device: %s" % e)
+    stoich = np.asarray(desc["stoich"], dtype=float).reshape(K, -1)
+    if stoich.shape[1] != len(rates):
+        raise BetseB200Error("reaction_matrix has %d columns for %d rate laws" % (stoich.shape[1], len(rates)))
+    mask = np.zeros((K, n_cells), dtype=np.uint8)
+    for k, tg in enumerate(desc["growth_targets"]):
+        mask[k, np.asarray(tg, dtype=np.int64)] = 1
+    # modulators that fold to the constant 1 need no program (moddy == 1)
+    mod_index, mod_programs = [], []
+    for pr in mods:
+        if len(pr.code) == 1 and pr.code[0][0] == ratelaw.PUSHC and tabs.consts[pr.code[0][1]] == 1.0:
+            mod_index.append(-1)
+        else:
+            mod_index.append(len(rates) + len(mod_programs))
+            mod_programs.append(pr)
+    return {"species": species, "tables": tabs, "rate_programs": rates, "mod_programs": mod_programs,
+            "mod_index": mod_index, "c_cells": np.asarray(desc["c_cells"], dtype=float), "stoich": stoich,
+            "growth_mask": None if mask.all() else mask, "Dgj": np.asarray(desc["Dgj"], dtype=float),
+            "z": np.asarray(desc["z"], dtype=float), "time_factor": np.asarray(desc["time_factor"], dtype=float),
+            "chan_names": list(desc["chan_names"])}
+
+
+# ---- flat (npz-friendly) form of a description, used by the golden fixtures
+def flatten(desc, prefix):
+    out = {prefix + "species": np.array(desc["species"]), prefix + "ions": np.array(desc["ions"]),
+           prefix + "c_cells": np.asarray(desc["c_cells"]), prefix + "gad_strings": np.array(desc["gad_strings"]),
+           prefix + "reaction_names": np.array(desc["reaction_names"], dtype=str),
+           prefix + "reaction_strings": np.array(desc["reaction_strings"], dtype=str),
+           prefix + "stoich": np.asarray(desc["stoich"]), prefix + "Dgj": desc["Dgj"], prefix + "z": desc["z"],
+           prefix + "time_factor": desc["time_factor"], prefix + "chan_names": np.array(desc["chan_names"], dtype=str),
+           prefix + "chan_mod_strings": np.array(desc["chan_mod_strings"], dtype=str),
+           prefix + "static_keys": np.array(list(desc["static"].keys()), dtype=str)}
+    for k, tg in enumerate(desc["growth_targets"]):
+        out["%sgrowth_targets%d" % (prefix, k)] = np.asarray(tg, dtype=np.int64)
+    for j, v in enumerate(desc["static"].values()):
+        out["%sstatic%d" % (prefix, j)] = np.asarray(v, dtype=np.float64)
+    return out
+
+
+def unflatten(cap, prefix):
+    g = lambda k: cap[prefix + k]
+    species = [str(x) for x in g("species")]
+    keys = [str(x) for x in g("static_keys")]
+    return {"species": species, "ions": [str(x) for x in g("ions")], "c_cells": np.asarray(g("c_cells")),
+            "gad_strings": [str(x) for x in g("gad_strings")],
+            "reaction_names": [str(x) for x in g("reaction_names")],
+            "reaction_strings": [str(x) for x in g("reaction_strings")], "stoich": np.asarray(g("stoich")),
+            "growth_targets": [np.asarray(cap["%sgrowth_targets%d" % (prefix, k)]) for k in range(len(species))],
+            "Dgj": np.asarray(g("Dgj")), "z": np.asarray(g("z")), "time_factor": np.asarray(g("time_factor")),
+            "chan_names": [str(x) for x in g("chan_names")],
+            "chan_mod_strings": [str(x) for x in g("chan_mod_strings")],
+            "static": {k: (float(cap["%sstatic%d" % (prefix, j)]) if np.ndim(cap["%sstatic%d" % (prefix, j)]) == 0
+                           else np.asarray(cap["%sstatic%d" % (prefix, j)])) for j, k in enumerate(keys)}}

@@ -115,47 +115,44 @@ def state_from_sim(sim):
     return out
 
 
-def channels_from_sim(sim):
-    """Channel specs of the general network (``sim.molecules.core.channels``, built by
-    ``Channel.init_channel``, networks.py:6550-6629) with their current gate states."""
-    core = getattr(getattr(sim, "molecules", None), "core", None)
+def _handlers(sim, p):
+    """(handler index, MasterOfNetworks) of the enabled network handlers, in the order the loop runs them
+    (sim.py:1290-1318): 0 = general network (sim.molecules.core), 1 = gene regulatory network (sim.grn.core)."""
     out = []
-    for name, chan in (getattr(core, "channels", None) or {}).items():
-        cc = chan.channel_core
-        if len(cc.ions) != 1:
-            raise BetseB200Error("channel %r conducts %d ions; only single-ion channels are implemented" % (name, len(cc.ions)))
-        out.append({"name": name, "model": type(cc).__name__, "ion": cc.ions[0], "maxDm": float(chan.maxDm),
-                    "rel_perm": float(cc.rel_perm[0]), "init_active": bool(chan.init_active),
-                    "targets": None if cc.targets is None else np.asarray(cc.targets),
-                    "m": np.asarray(cc.m, dtype=float), "h": np.asarray(cc.h, dtype=float), "_obj": chan})
+    if bool(getattr(p, "molecules_enabled", False)) and getattr(getattr(sim, "molecules", None), "core", None) is not None:
+        out.append((0, sim.molecules.core))
+    if bool(getattr(p, "grn_enabled", False)) and getattr(getattr(sim, "grn", None), "core", None) is not None:
+        out.append((1, sim.grn.core))
     return out
 
 
-def _network_is_channels_only(sim):
-    core = getattr(getattr(sim, "molecules", None), "core", None)
-    if core is None:
-        return False
-    if len(getattr(core, "molecules", {}) or {}) or len(getattr(core, "reactions", {}) or {}) or \
-            len(getattr(core, "reactions_env", {}) or {}) or len(getattr(core, "transporters", {}) or {}) or \
-            len(getattr(core, "modulators", {}) or {}):
-        return False
-    for chan in (getattr(core, "channels", None) or {}).values():
-        # activators / inhibitors make `moddy` != 1 (networks.py:3147): not implemented
-        for f in ("channel_activators_list", "channel_inhibitors_list"):
-            v = getattr(chan, f, None)
-            if v not in (None, "None", []):
-                return False
-    return True
+def channels_from_sim(sim, p=None):
+    """Channel specs of the network handlers (``core.channels``, built by ``Channel.init_channel``,
+    networks.py:6550-6629) with their current gate states, in application order."""
+    handlers = _handlers(sim, p) if p is not None else \
+        [(0, core) for core in [getattr(getattr(sim, "molecules", None), "core", None)] if core is not None]
+    out = []
+    for h, core in handlers:
+        for name, chan in (getattr(core, "channels", None) or {}).items():
+            cc = chan.channel_core
+            if len(cc.ions) != 1:
+                raise BetseB200Error("channel %r conducts %d ions; only single-ion channels are implemented" % (name, len(cc.ions)))
+            out.append({"name": name, "model": type(cc).__name__, "ion": cc.ions[0], "maxDm": float(chan.maxDm),
+                        "rel_perm": float(cc.rel_perm[0]), "init_active": bool(chan.init_active),
+                        "targets": None if cc.targets is None else np.asarray(cc.targets),
+                        "m": np.asarray(cc.m, dtype=float), "h": np.asarray(cc.h, dtype=float), "_obj": chan,
+                        "handler": h, "mod_prog": -1})
+    return out
 
 
 def check_supported(sim, p):
     """Refuse loudly instead of silently computing a different model."""
+    from . import network as netlib
     bad = []
-    if bool(getattr(p, "molecules_enabled", False)) and not _network_is_channels_only(sim):
-        bad.append("general network with substances / reactions / transporters / modulated channels "
-                   "(networks.py run_loop*; plain voltage-gated channels are supported)")
-    for flag, what in (("grn_enabled", "gene regulatory network"),
-                       ("deformation", "deformation"), ("deform_osmo", "osmotic pressure"),
+    for h, core in _handlers(sim, p):
+        bad += ["%s: %s" % ("general network" if h == 0 else "gene regulatory network", why)
+                for why in netlib.unsupported_reasons(core, p)]
+    for flag, what in (("deformation", "deformation"), ("deform_osmo", "osmotic pressure"),
                        ("fluid_flow", "fluid flow"), ("Ca_dyn", "ER calcium dynamics")):
         if bool(getattr(p, flag, False)):
             bad.append(what)
@@ -164,16 +161,34 @@ def check_supported(sim, p):
     if float(getattr(p, "cell_polarizability", 0.0)) != 0.0:
         bad.append("cell_polarizability != 0")
     if bad:
-        raise BetseB200Error("betse_b200 does not implement: " + ", ".join(bad) +
+        raise BetseB200Error("betse_b200 does not implement: " + "; ".join(bad) +
                              " — run this configuration with the reference solver")
 
 
 def engine_from_sim(sim, cells, p, device=0, phase_init=False):
+    from . import network as netlib
+    from . import ratelaw
     check_supported(sim, p)
     eng = TissueEngine(mesh_from_cells(cells), params_from_p(p), state_from_sim(sim), device=device)
     eng.chan_specs = []
-    if bool(getattr(p, "molecules_enabled", False)):
-        specs = channels_from_sim(sim)
+    eng.net_cores = {}
+    handlers = _handlers(sim, p)
+    if handlers:
+        specs = channels_from_sim(sim, p)
+        for h, core in handlers:
+            if len(getattr(core, "molecules", None) or {}) == 0:
+                continue
+            desc = netlib.describe_core(core, sim, p, cells, record_static=False)
+            comp = netlib.compile_network(desc, eng.Co, eng.M, ratelaw.live_resolver(core, sim, p, cells))
+            eng.set_network(comp, handler=h)
+            eng.net_cores[h] = core
+            for c in specs:
+                if c["handler"] == h:
+                    c["mod_prog"] = comp["mod_index"][comp["chan_names"].index(c["name"])]
+        for c in specs:
+            if c["handler"] not in eng.net_cores and c["_obj"].alpha_eval_string.replace(" ", "") not in (
+                    "((np.ones(sim.mdl))*(np.ones(sim.mdl)))",):
+                raise BetseB200Error("channel %r is modulated but its network has no substances" % c["name"])
         eng.set_channels(specs, phase_init=phase_init, affect_charge=bool(getattr(p, "substances_affect_charge", False)))
         eng.chan_specs = [c for c in specs if not (phase_init and not c["init_active"])]
     return eng
@@ -197,7 +212,17 @@ def _copy_back(sim, eng, diag):
         cc = c["_obj"].channel_core
         stt = eng.channel_state(k)
         tg = slice(None) if cc.targets is None else np.asarray(cc.targets)
-        cc.m, cc.h, cc.P, cc.chan_flux = stt["m"][tg], stt["h"][tg], stt["P"], stt["flux"]
+        cc.m, cc.h, cc.P, cc.chan_flux, cc.DChan = stt["m"][tg], stt["h"][tg], stt["P"], stt["flux"], stt["DChan"]
+    # network substances (read by MasterOfNetworks.write_data, networks.py:4210-4260, and the exporters)
+    m2c = eng.mem_to_cells.astype(np.int64)
+    for h, core in getattr(eng, "net_cores", {}).items():
+        c, rates = eng.network_state(h, rates=True)
+        for k, name in enumerate(eng.networks[h]["species"]):
+            mol = core.molecules[name]
+            mol.c_cells = c[k].copy()
+            mol.cc_at_mem = c[k][m2c]
+        nk = len(eng.networks[h]["species"])
+        core.reaction_rates = rates[nk:].copy()
     return 0
 
 
@@ -243,6 +268,9 @@ def run_sim_core_loop(sim, phase, time_steps, time_steps_sampled, anim_cells=Non
             is_sampled = last_t in sampled
             status = eng.step(run, diag=is_sampled)
             n += run
+            if status & capi.STATUS_NEG_NET:
+                d2h += _copy_back(sim, eng, diag=False)
+                raise Unstable("Network concentration in cells below zero! Your simulation has become unstable.")
             if status & (capi.STATUS_NAN_VM | capi.STATUS_NAN_CONC):
                 d2h += _copy_back(sim, eng, diag=False)
                 raise Unstable(

@@ -26,7 +26,7 @@ extern "C" {
 #endif
 
 #define BETSE_MAX_IONS 8
-#define BETSE_ABI_VERSION 1
+#define BETSE_ABI_VERSION 2
 
 typedef struct betse_ctx betse_ctx;
 
@@ -196,6 +196,9 @@ typedef struct betse_channel {
     int32_t ion;                  /* index of the conducted ion (channel_core.ions[0])            */
     int32_t mpower, hpower;       /* P = m^mpower * h^hpower (vg_na.py:104)                        */
     int32_t kind[4];              /* mInf, mTau, hInf, hTau: 0 = a, 1 = a/(a+b), 2 = 1/(a+b)       */
+    int32_t handler;              /* network handler the channel belongs to: 0 general network, 1 gene network */
+    int32_t mod_prog;             /* program index of chan.alpha_eval_string (networks.py:3147) in that handler's
+                                     betse_network, < 0: no modulation (moddy == 1)                */
     int32_t reserved;
     betse_gate_term a[4], b[4];
     double time_unit;             /* channel_core.time_unit (1e3 for models in ms)                 */
@@ -211,8 +214,46 @@ typedef struct betse_channel {
  * flux computation of the ion loop and update_all_concs (sim.py:1290-1357).  n = 0 removes them.
  * affect_charge = p.substances_affect_charge (Jmem takes the channels' currents, networks.py:2971). */
 int  betse_set_channels(betse_ctx *ctx, int n, const betse_channel *channels, int affect_charge);
-/* Gate states / open probability / last flux of channel k, [M] each (NULL members are skipped). */
-int  betse_channel_state(betse_ctx *ctx, int k, double *m, double *h, double *P, double *flux);
+/* Gate states / open probability / last flux / DChan (networks.py:3164) of channel k, [M] each (NULL members are skipped). */
+int  betse_channel_state(betse_ctx *ctx, int k, double *m, double *h, double *P, double *flux, double *DChan);
+
+/* ---------------------------------------------------------------------------------------------
+ * General network / gene regulatory network (MasterOfNetworks, networks.py).
+ * The reference writes every rate law as a Python expression string and evals it per timestep
+ * (write_growth_and_decay networks.py:1187-1310, write_reactions 1312-1572, channel
+ * alpha_eval_string 1102-1110); the host compiles those strings into postfix programs
+ * (betse_b200/ratelaw.py) that the device interprets per cell / per membrane.
+ *
+ * Implemented: substances with growth/decay and cell-zone reactions (run_loop, networks.py:2805-2914),
+ * gap-junction transport of substances (molecule_mover, sim_toolbox.py:976-1006), channel
+ * modulation by substances.  Refused by the host shim: membrane-permeable substances (Dm != 0),
+ * substances present in the environment, pumps, ligand gating, transporters, modulators,
+ * mitochondria, boundary / clamp events. */
+#define BETSE_STATUS_NEG_NET 16u  /* a network substance went negative (sim_toolbox.py:1124-1150 raises) */
+
+typedef struct betse_network {
+    int32_t n_species;            /* K substances, MasterOfNetworks.molecules order                 */
+    int32_t n_rates;              /* K growth/decay rates + R cell-zone reactions = columns of reaction_matrix */
+    int32_t n_programs;           /* n_rates rate programs followed by channel-modulator programs   */
+    int32_t n_consts, n_cell_arrays, n_mem_arrays;
+    const double  *c_cells;       /* [K][C] concentrations at loop entry                            */
+    const int32_t *code;          /* (opcode, argument) pairs of all programs                       */
+    const int32_t *prog_ptr;      /* [n_programs + 1] program ranges, in pairs                      */
+    const double  *consts;        /* [n_consts]                                                     */
+    const double  *cell_arrays;   /* [n_cell_arrays][C] per-cell constants (growth_mod_function_cells ...) */
+    const double  *mem_arrays;    /* [n_mem_arrays][M]                                              */
+    const uint8_t *growth_mask;   /* [K][C] 1 on growth_targets_cell (networks.py:2844-2846); NULL = all */
+    const double  *stoich;        /* [K][n_rates] substance rows of reaction_matrix (networks.py:2686-2725) */
+    const double  *Dgj;           /* [K] gap-junction diffusion constant; < 0: ignoreGJ             */
+    const double  *z;             /* [K] charge                                                     */
+    const double  *time_factor;   /* [K] modify_time_factor                                         */
+} betse_network;
+
+/* handler 0 = sim.molecules.core, 1 = sim.grn.core (run in that order, sim.py:1290-1318).  net == NULL
+ * removes the handler.  Call before betse_set_channels when channels carry mod_prog >= 0. */
+int  betse_set_network(betse_ctx *ctx, int handler, const betse_network *net);
+/* Substance concentrations [K][C] and the last rates [n_rates][C] (NULL members are skipped). */
+int  betse_network_state(betse_ctx *ctx, int handler, double *c_cells, double *rates);
 
 /* ---------------------------------------------------------------------------------------------
  * Multi-GPU: the tissue is cut into strips of env-grid rows; each rank owns the

@@ -107,6 +107,59 @@ SCENARIOS["mammal_ecm_chan"] = dict(
     snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=chan_extra)
 
 
+def _substance(name, prod, acts=None, inh=None, Dgj=1e-15, gj_imp=True, cell=0.1, z=0, apply_to="all"):
+    gd = {"production rate": prod, "decay rate": 1.0, "apply to": apply_to, "modulator function": "None"}
+    if acts:
+        gd.update({"activators": [a for a, _, _ in acts], "Km activators": [k for _, k, _ in acts],
+                   "n activators": [n for _, _, n in acts]})
+    if inh:
+        gd.update({"inhibitors": [a for a, _, _ in inh], "Km inhibitors": [k for _, k, _ in inh],
+                   "n inhibitors": [n for _, _, n in inh]})
+    return {"name": name, "Dm": 0.0, "Do": 1.0e-10, "Dgj": Dgj, "z": z, "env conc": 0.0, "cell conc": cell,
+            "scale factor": 1.0, "update intracellular": False, "use time dilation": False, "transmem": False,
+            "initial asymmetry": "None", "TJ permeable": False, "GJ impermeable": gj_imp, "TJ factor": 1.0,
+            "growth and decay": gd,
+            "plotting": {"plot 2D": False, "animate": False, "autoscale colorbar": True, "max val": 2.0, "min val": 0.0}}
+
+
+def net_extra(sim, phase):
+    """General network state (MasterOfNetworks, networks.py): the description betse_b200.network
+    compiles (strings, tables, static terms) + substance concentrations, rates and channel DChan."""
+    from betse_b200 import network as netlib
+    out = chan_extra(sim, phase)
+    core = sim.molecules.core
+    desc = netlib.describe_core(core, sim, phase.p, phase.cells)
+    out.update(netlib.flatten(desc, "net0."))
+    if getattr(core, "reaction_rates", None) is not None and len(core.reaction_rates):
+        out["net0.reaction_rates"] = np.asarray(core.reaction_rates, dtype=float)
+    for k, n in enumerate(core.channels):
+        cc = core.channels[n].channel_core
+        if getattr(cc, "DChan", None) is not None:
+            out["chan%d.DChan" % k] = np.asarray(cc.DChan, dtype=float) * np.ones(sim.mdl)
+    return out
+
+
+# BASELINE configs[3] in small: a gene-regulatory style network (Hill activation / inhibition, the shape of
+# extra_configs/grn_basic.yaml) + a gap-junction permeable substance grown in one tissue profile (the shipped
+# default's 'X') + a cell-zone reaction, coupled to Vmem through substance-modulated K channels
+_NET_BIO = [_substance("G1", 2.0, inh=[("G3", 0.01, 1)]), _substance("G2", 2.0, acts=[("G1", 1, 1)]),
+            _substance("G3", 15.0, acts=[("G1", 1, 1), ("G2", 1, 2.5)]),
+            _substance("X", 0.1, Dgj=1e-15, gj_imp=False, cell=0.05, apply_to=["Spot"])]
+_NET_RX = [{"name": "make_X", "reaction zone": "cell", "reactants": ["G2"], "reactant multipliers": [1],
+            "Km reactants": [1.0], "products": ["X"], "product multipliers": [1], "Km products": [0.1],
+            "max rate": 5.0e-3, "standard free energy": "None"}]
+_NET_CH = [dict(c) for c in CHANNELS]
+_NET_CH[2] = dict(_NET_CH[2], **{"channel inhibitors": ["X"], "inhibitor Km": [0.05], "inhibitor n": [2.0],
+                                 "inhibitor zone": ["cell"]})
+_NET_CH[1] = dict(_NET_CH[1], **{"channel activators": ["G3"], "activator Km": [0.5], "activator n": [1.0],
+                                 "activator zone": ["cell"]})
+SCENARIOS["mammal_ecm_net"] = dict(
+    mods=_m(SMALL, {"cutting event": {"event happens": False}, "general options": {"ion profile": "mammal"},
+                    "general network": {"implement network": True, "biomolecules": _NET_BIO, "reactions": _NET_RX,
+                                        "channels": _NET_CH}}),
+    snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=net_extra)
+
+
 def main(argv):
     import scipy
     names = argv or list(SCENARIOS)

@@ -39,6 +39,8 @@ def test_ctypes_structs_match_header_layout():
               ("betse_params", "T_sim", capi.Params), ("betse_params", "gauss_w", capi.Params),
               ("betse_state_host", "cenv_uniform", capi.StateHost),
               ("betse_channel", "time_unit", capi.Channel), ("betse_channel", "h0", capi.Channel),
+              ("betse_channel", "mod_prog", capi.Channel),
+              ("betse_network", "c_cells", capi.Network), ("betse_network", "time_factor", capi.Network),
               ("betse_neighbor", "v_dst_row0", capi.Neighbor), ("betse_window_info", "off_flags", capi.WindowInfo)]
     body = "".join('printf("%%zu %%zu\\n", sizeof(%s), offsetof(%s, %s));\n' % (s, s, f) for s, f, _ in probes)
     prog = '#include <stdio.h>\n#include <stddef.h>\n#include "betse_b200.h"\nint main(){%s return 0;}\n' % body

@@ -1,0 +1,106 @@
+"""General network on the GPU (BASELINE configs[3]) through the C ABI: growth/decay with
+Hill regulation, a cell-zone reaction, gap-junction transport of a substance and substance-modulated K channels,
+against the REAL reference's recorded run (tests/golden/mammal_ecm_net.npz) and against the oracle on a
+synthetic 50 k-cell tissue."""
+import numpy as np
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _attach(eng, desc, specs, phase_init):
+    from betse_b200 import network as netlib
+    comp = netlib.compile_network(desc, eng.Co, eng.M)
+    eng.set_network(comp, handler=0)
+    for c in specs:
+        c["handler"] = 0
+        c["mod_prog"] = comp["mod_index"][comp["chan_names"].index(c["name"])]
+    eng.set_channels(specs, phase_init=phase_init)
+    return comp
+
+
+@pytest.mark.parametrize("kind", ["init", "sim"])
+def test_network_matches_reference(kind):
+    from betse_b200.engine import TissueEngine
+    cap = util.load_golden("mammal_ecm_net")
+    eng = TissueEngine(util.group(cap, "cells."), util.group(cap, kind + ".p."), util.group(cap, kind + ".s0."))
+    specs = util.channels_of(cap, kind)
+    desc = util.networks_of(cap, kind)[0]
+    _attach(eng, desc, specs, kind == "init")
+    active = [c for c in specs if not (kind == "init" and not c["init_active"])]
+    n = 0
+    snaps = util.snap_steps(cap, kind)
+    for K in snaps:
+        last = K == snaps[-1]
+        while n < K:
+            assert not util.group(cap, "%s.sched.k%d." % (kind, n + 1))
+            st = eng.step(1, diag=(last and n + 1 == K))
+            assert not (st & (3 | 16)), st
+            n += 1
+        ref = util.group(cap, "%s.k%d." % (kind, K))
+        got = eng.download([f for f in list(util.STATE) + util.ENV_STATE if f in ref])
+        tols = util.gpu_tolerances(cap, kind, ref)
+        for f, a in got.items():
+            err = float(np.max(np.abs(np.asarray(a).reshape(np.shape(ref[f])) - ref[f])))
+            assert err <= tols[f], (kind, K, f, err, tols[f])
+        c, rates = eng.network_state(0, rates=True)
+        want = ref["net0.c_cells"]
+        for k, nme in enumerate(desc["species"]):
+            assert util.rel_err(c[k], want[k]) <= 1e-10, (kind, K, nme, util.rel_err(c[k], want[k]))
+        rr = ref["net0.reaction_rates"]
+        assert util.rel_err(rates[-rr.shape[0]:], rr) <= 1e-10
+        for k, ch in enumerate(active):
+            j = [s["name"] for s in specs].index(ch["name"])
+            stt = eng.channel_state(k)
+            r = ref["chan%d.DChan" % j]
+            assert np.max(np.abs(stt["DChan"] - r)) <= 1e-10 * max(np.max(np.abs(r)), 1e-300), (kind, K, ch["name"])
+    eng.close()
+
+
+def test_network_vs_oracle_synthetic_50k():
+    """BASELINE configs[3]: 50 k-cell tissue with a per-cell regulatory network coupled to Vmem (the strings and
+    tables of the recorded network, re-targeted to the synthetic tissue), 12 steps."""
+    from betse_b200 import channels as chlib
+    from betse_b200 import synth
+    from betse_b200.engine import TissueEngine
+    from oracle.betse_oracle import OracleSim
+    cap = util.load_golden("mammal_ecm_net")
+    desc = util.networks_of(cap, "sim")[0]
+    mesh, p, st = synth.make_tissue(50_000)
+    C, M = len(mesh["cell_vol"]), len(mesh["mem_sa"])
+    rng = np.random.default_rng(3)
+    desc = dict(desc)
+    desc["c_cells"] = rng.uniform(0.02, 1.5, (len(desc["species"]), C))
+    desc["growth_targets"] = [np.arange(C), np.arange(C), np.arange(C), np.arange(0, C, 7)]
+    desc["static"] = {k: (v if np.ndim(v) == 0 else np.ones(M if "mdl" in k else C)) for k, v in desc["static"].items()}
+    desc["static"]["self.molecules['G1'].growth_mod_function_cells"] = rng.uniform(0.5, 1.5, C)   # a spatial modulator function
+    eng = TissueEngine(mesh, p, st)
+    eng.update_V()
+    ora0 = OracleSim(mesh, p, st)
+    ora0.diagnostics = False
+    ora0.update_V()
+    specs = []
+    for name, model, dm in (("Nav", "Nav1p3", 2.0e-14), ("Kv", "Kv1p5", 1.0e-15), ("K_Leak", "KLeak", 0.6e-17),
+                            ("Cav", "Cav1p2", 1.0e-15)):
+        m0, h0 = chlib.initial_state(model, ora0.vm)
+        specs.append(chlib.make_channel(name, model, dm, m=m0, h=h0))
+    ora = OracleSim(mesh, p, st, channels=[dict(s) for s in specs], networks=[desc])
+    ora.diagnostics = False
+    ora.update_V()
+    _attach(eng, desc, specs, False)
+    for n in range(12):
+        s = eng.step(1)
+        ora.step()
+        assert not (s & (3 | 16))
+    got = eng.download(["cc_cells", "cc_env", "vm", "gjopen"])
+    for f, a in got.items():
+        r = np.asarray(getattr(ora, f))
+        scale = max(float(np.max(np.abs(r))), 1e-300)
+        tol = 1e-10 * scale if f != "vm" else max(1e-10 * scale, 4e-12)
+        assert float(np.max(np.abs(a.reshape(r.shape) - r))) <= tol, f
+    c = eng.network_state(0)
+    for k, nme in enumerate(desc["species"]):
+        assert util.rel_err(c[k], ora.networks[0].c[nme]) <= 1e-10, nme
+    eng.close()

@@ -1,0 +1,78 @@
+"""Host logic of the network path: the rate-law compiler (betse_b200/ratelaw.py)
+against Python ``eval`` of the same reference-generated strings, and the network description round trip."""
+import numpy as np
+import pytest
+
+from betse_b200 import network as netlib
+from betse_b200 import ratelaw
+from oracle.betse_oracle import OracleSim
+from tests import util
+
+
+def _setup(kind="sim"):
+    cap = util.load_golden("mammal_ecm_net")
+    descs = util.networks_of(cap, kind)
+    o = OracleSim(util.group(cap, "cells."), util.group(cap, kind + ".p."), util.group(cap, kind + ".s0."),
+                  channels=util.channels_of(cap, kind), phase_init=(kind == "init"), networks=descs)
+    return cap, descs, o
+
+
+def test_compiled_programs_equal_python_eval():
+    """Every growth/decay, reaction and channel-modulator string: bytecode (run on the host interpreter)
+    == eval of the string, on random concentrations."""
+    cap, descs, o = _setup()
+    d, net = descs[0], o.networks[0]
+    C, M = o.cdl, o.mdl
+    comp = netlib.compile_network(d, C, M)
+    rng = np.random.default_rng(7)
+    for trial in range(3):
+        for n in net.species:
+            net.c[n] = rng.uniform(0.0, 3.0, C)
+        spec = np.stack([net.c[n] for n in net.species])
+        strings = d["gad_strings"] + d["reaction_strings"]
+        for pr, s in zip(comp["rate_programs"], strings):
+            want = net.eval_string(s) * np.ones(C)
+            got = ratelaw.run_numpy(pr, comp["tables"], spec, ions=o.cc_cells)
+            assert np.allclose(got, want, rtol=1e-14, atol=0), s
+        mods = iter(comp["mod_programs"])
+        for s, idx in zip(d["chan_mod_strings"], comp["mod_index"]):
+            want = net.eval_string(s) * np.ones(M)
+            if idx < 0:
+                assert np.all(want == 1.0)
+                continue
+            got = ratelaw.run_numpy(next(mods), comp["tables"], spec, vm=o.vm, mem_to_cells=o.mem_to_cells)
+            assert np.allclose(got, want, rtol=1e-14, atol=0), s
+    assert comp["mod_index"] == [-1, 5, 6, -1]          # Nav and Cav are not modulated
+    assert comp["growth_mask"] is not None and comp["growth_mask"][3].sum() == 4   # X grows in the 'Spot' profile only
+
+
+def test_static_terms_are_folded():
+    cap, descs, o = _setup()
+    comp = netlib.compile_network(descs[0], o.cdl, o.mdl)
+    for pr in comp["rate_programs"]:
+        ops = [op for op, _ in pr.code]
+        assert ratelaw.PUSHA not in ops                   # np.ones(...) and uniform profiles fold to constants
+        assert pr.max_depth() <= ratelaw.MAX_STACK
+
+
+@pytest.mark.parametrize("src,msg", [
+    ("self.env_concs['X'][cells.map_cell2ecm]/2.0", "extracellular"),
+    ("self.cell_concs['Nope']*2", "unknown substance"),
+    ("np.sin(self.cell_concs['X'])", "unsupported construct"),
+    ("self.mem_concs['X']*2", "zone"),
+])
+def test_unsupported_expressions_are_refused(src, msg):
+    tabs = ratelaw.Tables(["X"], ["Na", "K"], 4, 12)
+    with pytest.raises(ratelaw.RateLawError) as e:
+        ratelaw.compile_expr(src, tabs, ratelaw.table_resolver({}), "cell")
+    assert msg in str(e.value)
+
+
+def test_description_roundtrip():
+    cap, descs, _ = _setup()
+    flat = netlib.flatten(descs[0], "x.")
+    back = netlib.unflatten(flat, "x.")
+    assert back["gad_strings"] == descs[0]["gad_strings"] and back["species"] == descs[0]["species"]
+    assert set(back["static"]) == set(descs[0]["static"])
+    for k, v in back["static"].items():
+        assert np.array_equal(np.asarray(v), np.asarray(descs[0]["static"][k]))

@@ -13,7 +13,8 @@ from tests import util
 def test_oracle_reproduces_reference(name, kind):
     cap = util.load_golden(name)
     o = OracleSim(util.group(cap, "cells."), util.group(cap, kind + ".p."),
-                  util.group(cap, kind + ".s0."), channels=util.channels_of(cap, kind), phase_init=(kind == "init"))
+                  util.group(cap, kind + ".s0."), channels=util.channels_of(cap, kind), phase_init=(kind == "init"),
+                  networks=util.networks_of(cap, kind))
     n = 0
     checked = 0
     for K in util.snap_steps(cap, kind):
@@ -41,5 +42,18 @@ def test_oracle_reproduces_reference(name, kind):
                 key = "chan%d.%s" % (k, f)
                 if key in ref and not (kind == "init" and not c["init_active"]):
                     assert util.rel_err(c[f], ref[key]) < 1e-12, (name, kind, K, key)
+                    checked += 1
+        for h, net in enumerate(o.networks):        # network substances, rates, channel DChan (networks.py:2805-2982, 3164)
+            want = ref["net%d.c_cells" % h]
+            for k, nme in enumerate(net.species):
+                assert util.rel_err(net.c[nme], want[k]) < 1e-12, (name, kind, K, nme)
+                checked += 1
+            if "net%d.reaction_rates" % h in ref:
+                nrx = ref["net%d.reaction_rates" % h].shape[0]
+                assert util.rel_err(net.rates[-nrx:], ref["net%d.reaction_rates" % h]) < 1e-12
+            for k, c in enumerate(o.channels):
+                key = "chan%d.DChan" % k
+                if key in ref and "DChan" in c and not (kind == "init" and not c["init_active"]):
+                    assert util.rel_err(c["DChan"], ref[key]) < 1e-12, (name, kind, K, key)
                     checked += 1
     assert checked > 20

@@ -61,3 +61,77 @@ def test_install_and_engine_inputs_from_live_reference(monkeypatch, tmp_path):
     assert [c["model"] for c in seen["specs"]] == ["Nav1p3", "Kv1p5", "KLeak", "Cav1p2"]
     assert [c["init_active"] for c in seen["specs"]] == [False, False, True, False]
     assert all(len(c["m"]) == M for c in seen["specs"])
+
+
+def test_network_inputs_from_live_reference(monkeypatch, tmp_path):
+    """General network with substances: the shim compiles the live MasterOfNetworks (strings evaluated against the
+    real objects) and hands substance-modulated channels their program indices."""
+    from oracle import refrun, refshim
+    refshim.bypass_science_init()
+    from betse.science.parameters import Parameters
+    from betse.science.simrunner import SimRunner
+    from betse.science.phase import phasecallbacks
+    from betse_b200 import simloop
+    from tests.golden import make_golden as mg
+
+    seen = {}
+
+    class FakeEngine:
+        def __init__(self, mesh, params, state, device=0, partition=None):
+            self.ions = [str(x) for x in params["ions"]]
+            self.Co, self.M = len(mesh["cell_vol"]), len(mesh["mem_sa"])
+
+        def set_network(self, comp, handler=0):
+            seen["net"] = (handler, comp)
+
+        def set_channels(self, specs, phase_init=False, affect_charge=None):
+            seen.update(specs=specs)
+            raise _Stop()
+
+    monkeypatch.setattr(simloop, "TissueEngine", FakeEngine)
+    simloop.install()
+    try:
+        fn = refrun.write_config(str(tmp_path), mg.SCENARIOS["mammal_ecm_net"]["mods"])
+        np.random.seed(12345)
+        p = Parameters.make(fn)
+        p.anim.is_while_sim = p.anim.is_after_sim = p.plot.is_after_sim = False
+        runner = SimRunner(p=p, callbacks=phasecallbacks.SimCallbacksNoop())
+        runner.seed()
+        with pytest.raises(_Stop):
+            runner.init()
+    finally:
+        simloop.uninstall()
+    handler, comp = seen["net"]
+    assert handler == 0 and comp["species"] == ["G1", "G2", "G3", "X"]
+    assert len(comp["rate_programs"]) == 5 and comp["mod_index"] == [-1, 5, 6, -1]
+    assert list(comp["Dgj"]) == [-1.0, -1.0, -1.0, 1e-15]
+    assert [c["mod_prog"] for c in seen["specs"]] == [-1, 5, 6, -1]
+    assert comp["growth_mask"][3].sum() == 4 and comp["growth_mask"][:3].all()
+
+
+def test_unsupported_network_is_refused(monkeypatch, tmp_path):
+    """A membrane-permeable substance (Dm != 0) is outside the implemented subset: refused with the reason."""
+    from oracle import refrun, refshim
+    refshim.bypass_science_init()
+    from betse.science.parameters import Parameters
+    from betse.science.simrunner import SimRunner
+    from betse.science.phase import phasecallbacks
+    from betse_b200 import simloop
+    from betse_b200.capi import BetseB200Error
+    from tests.golden import make_golden as mg
+    import copy
+    mods = copy.deepcopy(mg.SCENARIOS["mammal_ecm_net"]["mods"])
+    mods["general network"]["biomolecules"][3]["Dm"] = 1.0e-18
+    simloop.install()
+    try:
+        fn = refrun.write_config(str(tmp_path), mods)
+        np.random.seed(12345)
+        p = Parameters.make(fn)
+        p.anim.is_while_sim = p.anim.is_after_sim = p.plot.is_after_sim = False
+        runner = SimRunner(p=p, callbacks=phasecallbacks.SimCallbacksNoop())
+        runner.seed()
+        with pytest.raises(BetseB200Error) as e:
+            runner.init()
+    finally:
+        simloop.uninstall()
+    assert "membrane-permeable" in str(e.value)

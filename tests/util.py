@@ -140,3 +140,14 @@ def channels_of(cap, kind, where="s0"):
                     "init_active": bool(int(g[pre + "init_active"])), "targets": g[pre + "targets"],
                     "m": g[pre + "m"], "h": g[pre + "h"]})
     return out
+
+
+def networks_of(cap, kind, where="s0"):
+    """Network descriptions recorded by tests/golden/make_golden.py:net_extra (general network first)."""
+    from betse_b200 import network as netlib
+    out = []
+    for h in range(2):
+        pre = "%s.%s.net%d." % (kind, where, h)
+        if pre + "species" in cap:
+            out.append(netlib.unflatten(cap, pre))
+    return out
