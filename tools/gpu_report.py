@@ -9,7 +9,7 @@ out = open("gpurun_out/report.txt", "w")
 def P(*a):
     s = " ".join(str(x) for x in a); print(s); out.write(s + "\n")
 for name in util.GOLDEN:
-    if "polar" in name or "chan" in name: continue
+    if "polar" in name or "chan" in name or "net" in name: continue
     cap = util.load_golden(name)
     for kind in ("init", "sim"):
         eng = TissueEngine(util.group(cap, "cells."), util.group(cap, kind + ".p."), util.group(cap, kind + ".s0."))
