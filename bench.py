@@ -269,7 +269,7 @@ def main():
                        "10 steps (bytes are per rank, max over ranks)"}
     elif not args.no_e2e:
         sim, phase = namespaces(mesh, p, state)
-        n_e2e = min(args.steps, 100)
+        n_e2e = args.steps
         ts = np.linspace(0, n_e2e * p["dt"], n_e2e)
         sampled = set(ts[10::10].tolist())
         stats = {}

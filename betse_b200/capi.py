@@ -84,7 +84,7 @@ STATE_FIELDS = [
     "extra_rho_env", "extra_J_mem", "NaKATP_block", "gj_block",
     "fluxes_mem", "fluxes_gj", "fluxes_env_x", "fluxes_env_y", "rate_NaKATP",
     "Jmem", "Jgj", "Jn", "I_mem", "Jc", "Emc", "dvm",
-    "J_cell_x", "J_cell_y", "E_cell_x", "E_cell_y", "sigma_cell", "cenv_uniform", "vm_cell",
+    "J_cell_x", "J_cell_y", "E_cell_x", "E_cell_y", "sigma_cell", "E_gj_x", "E_gj_y", "cenv_uniform", "vm_cell",
 ]
 
 
@@ -142,7 +142,7 @@ SYMBOLS = [
     "betse_step_profile", "betse_kernel_name", "betse_download_sample",
     "betse_step_phase", "betse_stream", "betse_sync", "betse_update_v", "betse_update_v_phase",
     "betse_set_row_ranges", "betse_window", "betse_attach_neighbor", "betse_exchange",
-    "betse_set_channels", "betse_channel_state", "betse_set_network", "betse_network_state",
+    "betse_set_channels", "betse_channel_state", "betse_set_network", "betse_network_state", "betse_host_alloc", "betse_host_free",
 ]
 
 _lib = None
@@ -185,6 +185,9 @@ def load(build_if_missing=True):
     lib.betse_set_network.argtypes = [vp, C.c_int, C.POINTER(Network)]
     lib.betse_network_state.argtypes = [vp, C.c_int, _dp, _dp]
     lib.betse_step_phase.argtypes = [vp, C.c_int, C.c_int]
+    lib.betse_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    lib.betse_host_free.argtypes = [vp]
+    lib.betse_host_free.restype = None
     lib.betse_stream.argtypes = [vp, C.POINTER(vp)]
     lib.betse_sync.argtypes = [vp, C.POINTER(C.c_uint32)]
     lib.betse_update_v.argtypes = [vp]

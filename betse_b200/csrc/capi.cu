@@ -29,8 +29,7 @@ void launch_expand_vm(const KParams& P, const KArrays& A, int M, int C, int cur,
 cudaError_t prepare_kernels(int ni);
 // kmem_pipe.cu: the per-tile constant blocks of the pipelined membrane kernel
 unsigned tile_pack_size(int ni);
-void tile_pack_fill(char* blk, int ni, int nm, int nc, const double* mem_sa, const double* cell_vol, const double* diviterm,
-                    const int* mem_to_cells, const int* nn_cell_flag, const int* map_mem2ecm, const int* cell_mem_ptr);
+void launch_pack_const(const KParams& P, const KArrays& A, cudaStream_t st);
 void launch_pack_dm(const KParams& P, const KArrays& A, cudaStream_t st);
 void launch_chan(const KParams& P, const KArrays& A, const KChan& ch, const KNet& N, int cur, cudaStream_t st);
 void launch_net(const KParams& P, const KArrays& A, const KNet& N, const double* h_Dgj, int n_ions, int cur, cudaStream_t st);
@@ -329,21 +328,6 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
         tdesc[4 * t + 2] = mesh->cell_mem_ptr[a]; tdesc[4 * t + 3] = mesh->cell_mem_ptr[b] - mesh->cell_mem_ptr[a];
     }
     if ((r = dev_upload(ctx, (int**)&A.tile_desc, tdesc.data(), tdesc.size()))) return r;
-    // ---- tile pack (k_mem_pipe): every tile's constant inputs as one fixed-size block; the DmS rows are (re)built
-    //      on the device whenever Dm_cells or the schedule scalars are uploaded (launch_pack_dm)
-    if (hp->n_ions <= 7) {
-        const size_t blk = tile_pack_size(hp->n_ions);
-        std::vector<char> pack((size_t)ctx->n_tiles * blk, 0);
-        for (int t = 0; t < ctx->n_tiles; ++t) {
-            const int c0 = tdesc[4 * t], nc = tdesc[4 * t + 1], m0 = tdesc[4 * t + 2], nm = tdesc[4 * t + 3];
-            tile_pack_fill(pack.data() + (size_t)t * blk, hp->n_ions, nm, nc, mesh->mem_sa + m0, mesh->cell_vol + c0,
-                           mesh->diviterm + c0, mesh->mem_to_cells + m0, nnc.data() + m0, mesh->map_mem2ecm + m0,
-                           mesh->cell_mem_ptr + c0);
-        }
-        if ((r = dev_upload(ctx, (char**)&A.tile_pack, pack.data(), pack.size()))) return r;
-        CK(cudaStreamSynchronize(ctx->stream));     // the host vector goes out of scope
-    }
-
     // ---- env point -> flux slot CSR (map_ecm2mem, cells.py:1793-1796), slots in membrane order
     ctx->n_slots = mesh->n_flux_slots > Mo ? mesh->n_flux_slots : Mo;
     if (mesh->ecm_slot_ptr && mesh->ecm_slot_idx) {
@@ -371,6 +355,15 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
     else if (hp->fast_update_ecm) return fail(ctx, "fast_update_ecm needs memSa_per_envSquare");
     if (mesh->gj_default_weights) { if ((r = dev_upload(ctx, (double**)&A.gj_w, mesh->gj_default_weights, Mo))) return r; }
     else if (!hp->v_sensitive_gj) return fail(ctx, "static gap junctions need gj_default_weights");
+
+    // ---- tile pack (k_mem_pipe): every tile's constant inputs as one fixed-size block, built on the device; the DmS
+    //      rows are (re)built whenever Dm_cells or the schedule scalars are uploaded (launch_pack_dm)
+    if (hp->n_ions <= 7) {
+        const size_t bytes = (size_t)ctx->n_tiles * tile_pack_size(hp->n_ions);
+        if ((r = dev_alloc(ctx, (char**)&A.tile_pack, bytes))) return r;
+        launch_pack_const(ctx->P, A, ctx->stream);
+        CK(cudaGetLastError());
+    }
 
     // ---- state
     const size_t IC = (size_t)I * C, IE = (size_t)I * E, IM = (size_t)I * Mo;
@@ -462,7 +455,7 @@ static int ensure_diag_buffers(betse_ctx* ctx)
     if ((r = dev_alloc(ctx, &A.fl_env_x, ctx->hp.is_ecm ? IE : 1))) return r;
     if ((r = dev_alloc(ctx, &A.fl_env_y, ctx->hp.is_ecm ? IE : 1))) return r;
     if ((r = dev_alloc(ctx, &A.rate_NaK, ctx->Mo))) return r;
-    double** mem_arrays[] = {&A.Jmem, &A.Jgj, &A.Jn, &A.I_mem, &A.Jc, &A.Emc, &A.dvm};
+    double** mem_arrays[] = {&A.Jmem, &A.Jgj, &A.Jn, &A.I_mem, &A.Jc, &A.Emc, &A.dvm, &A.E_gj_x, &A.E_gj_y};
     for (auto p : mem_arrays) if ((r = dev_alloc(ctx, p, ctx->Mo))) return r;
     double** cell_arrays[] = {&A.J_cell_x, &A.J_cell_y, &A.E_cell_x, &A.E_cell_y, &A.sigma_cell};
     for (auto p : cell_arrays) if ((r = dev_alloc(ctx, p, ctx->C))) return r;
@@ -831,7 +824,7 @@ extern "C" int betse_download_sample(betse_ctx* ctx, betse_state_host* s)
     if (s->cenv_uniform) CK(cudaMemcpyAsync(s->cenv_uniform, A.cenv_u + cur * 8, I * sizeof(double), cudaMemcpyDeviceToHost, st));
     const bool any_diag = s->fluxes_mem || s->fluxes_gj || s->fluxes_env_x || s->fluxes_env_y || s->rate_NaKATP ||
                           s->Jmem || s->Jgj || s->Jn || s->I_mem || s->Jc || s->Emc || s->dvm || s->J_cell_x ||
-                          s->J_cell_y || s->E_cell_x || s->E_cell_y || s->sigma_cell;
+                          s->J_cell_y || s->E_cell_x || s->E_cell_y || s->sigma_cell || s->E_gj_x || s->E_gj_y;
     if (any_diag) {
         if (!ctx->diag_valid) return fail(ctx, "diagnostics requested but the last step was not run with BETSE_STEP_DIAG");
         DN(s->fluxes_mem, A.fl_mem, IM);
@@ -843,6 +836,7 @@ extern "C" int betse_download_sample(betse_ctx* ctx, betse_state_host* s)
         DN(s->J_cell_x, A.J_cell_x, C); DN(s->J_cell_y, A.J_cell_y, C);
         DN(s->E_cell_x, A.E_cell_x, C); DN(s->E_cell_y, A.E_cell_y, C);
         DN(s->sigma_cell, A.sigma_cell, C);
+        DN(s->E_gj_x, A.E_gj_x, Mo); DN(s->E_gj_y, A.E_gj_y, Mo);
     }
 #undef DN
     CK(cudaStreamSynchronize(st));
@@ -1006,6 +1000,18 @@ extern "C" int betse_network_state(betse_ctx* ctx, int handler, double* c_cells,
     if (rates) CK(cudaMemcpyAsync(rates, N.rates, (size_t)N.n_rates * ctx->C * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
+}
+
+extern "C" int betse_host_alloc(size_t bytes, void** out)
+{
+    if (!out) return 2;
+    *out = nullptr;
+    return cudaHostAlloc(out, bytes ? bytes : 8, cudaHostAllocDefault) == cudaSuccess ? 0 : 1;
+}
+
+extern "C" void betse_host_free(void* p)
+{
+    if (p) cudaFreeHost(p);
 }
 
 extern "C" int betse_set_row_ranges(betse_ctx* ctx, int yi0, int yi1, int ya0, int ya1, int yf0, int yf1)

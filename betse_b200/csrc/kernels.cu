@@ -590,6 +590,14 @@ k_diag(const __grid_constant__ KParams P, const KArrays A, const int newb)
         vmo = A.vm_cell[newb ^ 1][c] - phi;
         A.vm_mem[m] = vm;
         A.dvm[m] = (vm - vmo) / P.dt;
+        // gap-junction field of this step (update_gj, sim.py:2166-2172): from the Vmem the step started with
+        {
+            const int nnp = ldgi(A.nn_cell_flag + m);
+            double vnb = A.vm_cell[newb ^ 1][nnp & 0x7fffffff];
+            if (P.has_phi) vnb -= ldg(A.phi_b + ldgi(A.map_mem2ecm + ldgi(A.nn_i + m)));
+            const double Egj = -(vnb - vmo) / P.gj_len;
+            A.E_gj_x[m] = Egj * nxv; A.E_gj_y[m] = Egj * nyv;
+        }
     }
     s_a[tid] = act ? Jn0 * sa : 0.0;
     s_b[tid] = act ? vm : 0.0;

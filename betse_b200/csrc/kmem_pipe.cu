@@ -388,19 +388,39 @@ void launch_pack_dm(const KParams& P, const KArrays& A, cudaStream_t st)
     k_pack_dm<<<(P.n_tiles + 7) / 8, 256, 0, st>>>(P, A);
 }
 
-// Host side of the pack (capi.cu:create_impl): block size in bytes and the constant part of a block.
-unsigned tile_pack_size(int ni) { return (unsigned)(((ni + 1) * 32 + 2 * KP_MAXC + (96 + KP_MAXC + 4) / 2) * 8); }
-
-void tile_pack_fill(char* blk, int ni, int nm, int nc, const double* mem_sa, const double* cell_vol, const double* diviterm,
-                    const int* mem_to_cells, const int* nn_cell_flag, const int* map_mem2ecm, const int* cell_mem_ptr)
+// The constant part of every block (membrane areas, cell volumes, index rows), built on the device from the
+// arrays betse_create uploaded anyway.  One warp per tile; unused slots stay zero (the pack is memset first).
+__global__ void k_pack_const(const __grid_constant__ KParams P, const KArrays A)
 {
-    double* K = reinterpret_cast<double*>(blk);
-    for (int j = 0; j < nm; ++j) K[ni * 32 + j] = mem_sa[j];
-    for (int j = 0; j < nc; ++j) { K[(ni + 1) * 32 + j] = cell_vol[j]; K[(ni + 1) * 32 + KP_MAXC + j] = diviterm[j]; }
-    int* Ki = reinterpret_cast<int*>(K + (ni + 1) * 32 + 2 * KP_MAXC);
-    for (int j = 0; j < nm; ++j) { Ki[j] = mem_to_cells[j]; Ki[32 + j] = nn_cell_flag[j]; Ki[64 + j] = map_mem2ecm[j]; }
-    for (int j = 0; j <= nc; ++j) Ki[96 + j] = cell_mem_ptr[j];
+    const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (tile >= P.n_tiles) return;
+    const int4 td = __ldg(reinterpret_cast<const int4*>(A.tile_desc) + tile);
+    const int c0 = td.x, nc = td.y, m0 = td.z, nm = td.w, ni = P.n_ions;
+    const int kd = (ni + 1) * 32 + 2 * KP_MAXC;
+    double* K = reinterpret_cast<double*>(const_cast<char*>(A.tile_pack)) + (size_t)tile * (kd + (96 + KP_MAXC + 4) / 2);
+    int* Ki = reinterpret_cast<int*>(K + kd);
+    if (lane < nm) {
+        K[ni * 32 + lane] = A.mem_sa[m0 + lane];
+        Ki[lane] = A.mem_to_cells[m0 + lane];
+        Ki[32 + lane] = A.nn_cell_flag[m0 + lane];
+        Ki[64 + lane] = A.map_mem2ecm[m0 + lane];
+    }
+    if (lane < nc) {
+        K[(ni + 1) * 32 + lane] = A.cell_vol[c0 + lane];
+        K[(ni + 1) * 32 + KP_MAXC + lane] = A.diviterm[c0 + lane];
+    }
+    if (lane <= nc) Ki[96 + lane] = A.cell_mem_ptr[c0 + lane];
 }
+
+void launch_pack_const(const KParams& P, const KArrays& A, cudaStream_t st)
+{
+    if (!A.tile_pack || P.n_tiles <= 0) return;
+    k_pack_const<<<(P.n_tiles + 7) / 8, 256, 0, st>>>(P, A);
+}
+
+// byte size of one block (capi.cu:create_impl allocates n_tiles of them)
+unsigned tile_pack_size(int ni) { return (unsigned)(((ni + 1) * 32 + 2 * KP_MAXC + (96 + KP_MAXC + 4) / 2) * 8); }
 
 // ---------------------------------------------------------------------------- launch
 // BETSE_KMEM_PIPE=0 falls back to the one-tile-per-warp kernel; BETSE_KMEM_WARPS = resident warps

@@ -81,6 +81,7 @@ struct KArrays {
     double *fl_mem, *fl_gj, *fl_env_x, *fl_env_y, *rate_NaK;
     double *Jmem, *Jgj, *Jn, *I_mem, *Jc, *Emc, *dvm, *vm_mem, *vm_ave;
     double *J_cell_x, *J_cell_y, *E_cell_x, *E_cell_y, *sigma_cell;
+    double *E_gj_x, *E_gj_y; // [M] gap-junction field (sim.py:2168-2172)
     double *scratch_env;     // [I,E] temp for the sharpness<1 smoothing pass
     // voltage-gated channels (channels.cu)
     double *dsum_m, *dsum_g; // [I,C] deferred sums of f_mem*sa and f_gj*sa per cell

@@ -20,11 +20,11 @@ _DOWN_SHAPES = {
     "fluxes_mem": "IM", "fluxes_gj": "IM", "fluxes_env_x": "IE", "fluxes_env_y": "IE",
     "rate_NaKATP": "M", "Jmem": "M", "Jgj": "M", "Jn": "M", "I_mem": "M", "Jc": "M", "Emc": "M",
     "dvm": "M", "J_cell_x": "C", "J_cell_y": "C", "E_cell_x": "C", "E_cell_y": "C",
-    "sigma_cell": "C",
+    "sigma_cell": "C", "E_gj_x": "M", "E_gj_y": "M",
 }
 DIAG_FIELDS = ("fluxes_mem", "fluxes_gj", "fluxes_env_x", "fluxes_env_y", "rate_NaKATP", "Jmem",
                "Jgj", "Jn", "I_mem", "Jc", "Emc", "dvm", "J_cell_x", "J_cell_y", "E_cell_x",
-               "E_cell_y", "sigma_cell", "vm_ave")
+               "E_cell_y", "sigma_cell", "vm_ave", "E_gj_x", "E_gj_y")
 
 
 def gaussian_taps():
@@ -334,9 +334,25 @@ class TissueEngine:
         names = [self.lib.betse_kernel_name(k).decode() for k in range(capi.NKERNELS)]
         return float(tot.value), {names[k]: float(kms[k]) for k in range(capi.NKERNELS) if kl[k]}
 
+    def _pinned_buffer(self, name, shape):
+        """A reusable page-locked array for ``name`` (betse_host_alloc); freed by close()."""
+        pool = self.__dict__.setdefault("_pinned", {})
+        if name not in pool:
+            n = int(np.prod(shape))
+            ptr = C.c_void_p()
+            if self.lib.betse_host_alloc(C.c_size_t(n * 8), C.byref(ptr)) != 0 or not ptr.value:
+                raise BetseB200Error("betse_host_alloc(%d bytes) failed" % (n * 8))
+            arr = np.ctypeslib.as_array((C.c_double * n).from_address(ptr.value)).reshape(shape)
+            pool[name] = (ptr, arr)
+        return pool[name][1]
+
     def download(self, fields=("cc_cells", "cc_at_mem", "cc_env", "vm", "gjopen", "rho_cells",
-                               "E_env_x", "E_env_y", "v_env", "rho_env")):
-        """Fetch Simulator attributes by name -> dict of NumPy arrays in the reference's shapes."""
+                               "E_env_x", "E_env_y", "v_env", "rho_env"), pinned=False):
+        """Fetch Simulator attributes by name -> dict of NumPy arrays in the reference's shapes.
+
+        ``pinned=True`` returns views of page-locked staging buffers that the NEXT pinned download of the
+        same field overwrites and that die with the engine — for consumers that copy what they keep, like
+        ``Simulator.write2storage`` (sim.py:1789-1884: np.copy / ``*1`` of every array it stores)."""
         sh = capi.StateHost()
         out = {}
         I, Cn, M, E = self.I, self.C, self.M, self.E
@@ -358,7 +374,7 @@ class TissueEngine:
                 continue
             if f not in _DOWN_SHAPES:
                 raise KeyError(f)
-            buf = np.empty(shapes[_DOWN_SHAPES[f]])
+            buf = self._pinned_buffer(f, shapes[_DOWN_SHAPES[f]]) if pinned else np.empty(shapes[_DOWN_SHAPES[f]])
             setattr(sh, f, capi.ptr_f64(buf))
             out[f] = buf
         self._check(self.lib.betse_download_sample(self.ctx, C.byref(sh)), "betse_download_sample")
@@ -518,6 +534,8 @@ class TissueEngine:
         return int(st.value)
 
     def close(self):
+        for ptr, _ in self.__dict__.pop("_pinned", {}).values():
+            self.lib.betse_host_free(ptr)
         if getattr(self, "ctx", None):
             self.lib.betse_destroy(self.ctx)
             self.ctx = None

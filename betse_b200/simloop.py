@@ -50,6 +50,11 @@ _SAMPLED_ENV = ["E_env_x", "E_env_y", "v_env", "rho_env"]
 _SAMPLED_DIAG = ["fluxes_mem", "fluxes_gj", "rate_NaKATP", "Jmem", "Jgj", "Jn", "I_mem", "Jc", "Emc",
                  "dvm", "J_cell_x", "J_cell_y", "E_cell_x", "E_cell_y", "sigma_cell"]
 _SAMPLED_DIAG_ENV = ["fluxes_env_x", "fluxes_env_y"]
+# exactly what Simulator.write2storage reads (sim.py:1796-1877) — the per-sample download; everything else
+# (per-ion flux arrays, J's, E_cell ...) is only read after the phase and comes with the final copy-back
+_W2S_STATE = ["cc_cells", "vm", "vm_ave", "gjopen", "rho_cells"]
+_W2S_ENV = ["cc_env", "E_env_x", "E_env_y", "v_env"]
+_W2S_DIAG = ["I_mem", "J_cell_x", "J_cell_y", "rate_NaKATP", "E_gj_x", "E_gj_y"]
 
 
 class SimUnstable(Exception):
@@ -194,17 +199,27 @@ def engine_from_sim(sim, cells, p, device=0, phase_init=False):
     return eng
 
 
-def _copy_back(sim, eng, diag):
-    fields = list(_SAMPLED_STATE)
-    if eng.is_ecm:
-        fields += _SAMPLED_ENV
-    if diag:
-        fields += _SAMPLED_DIAG + (_SAMPLED_DIAG_ENV if eng.is_ecm else [])
-    got = eng.download(fields)
+def _copy_back(sim, eng, diag, sample_only=False):
+    """Device state -> Simulator attributes.  ``sample_only``: just what write2storage reads, through the
+    engine's page-locked staging (views that the next sample overwrites — write2storage copies what it
+    keeps; vm_ave, which it appends as is (sim.py:1877), gets its own array)."""
+    if sample_only:
+        fields = _W2S_STATE + (_W2S_ENV if eng.is_ecm else ["cc_env"]) + (_W2S_DIAG if diag else [])
+    else:
+        fields = list(_SAMPLED_STATE)
+        if eng.is_ecm:
+            fields += _SAMPLED_ENV
+        if diag:
+            fields += _SAMPLED_DIAG + ["E_gj_x", "E_gj_y"] + (_SAMPLED_DIAG_ENV if eng.is_ecm else [])
+    got = eng.download(fields, pinned=sample_only)
     shp = (eng.ny, eng.nx)
     for f, a in got.items():
         if f in ("E_env_x", "E_env_y"):
             a = a.reshape(shp)                     # the reference keeps these 2-D (sim.py:572-573)
+        if sample_only and f == "vm_ave":
+            a = a.copy()
+        elif sample_only:
+            eng.__dict__.setdefault("_lent", {})[f] = a          # a view of engine-owned staging, see _detach
         setattr(sim, f, a)
     # channel objects keep their gate state / open probability / flux (read by the exporters and by
     # the next phase through the pickled Simulator)
@@ -224,6 +239,14 @@ def _copy_back(sim, eng, diag):
         nk = len(eng.networks[h]["species"])
         core.reaction_rates = rates[nk:].copy()
     return 0
+
+
+def _detach(sim, eng):
+    """Before the engine dies: any Simulator attribute still aliasing its page-locked staging gets its own copy."""
+    for f, a in getattr(eng, "_lent", {}).items():
+        if getattr(sim, f, None) is a:
+            setattr(sim, f, np.array(a, copy=True))
+    eng.__dict__["_lent"] = {}
 
 
 def run_sim_core_loop(sim, phase, time_steps, time_steps_sampled, anim_cells=None, *,
@@ -277,7 +300,9 @@ def run_sim_core_loop(sim, phase, time_steps, time_steps_sampled, anim_cells=Non
                     "Your simulation has become unstable. Please try a smaller time step,"
                     "reduce gap junction radius, and/or reduce pump rate coefficients.")
             if is_sampled:
-                d2h += _copy_back(sim, eng, diag=True)
+                # the last step of the phase leaves complete, engine-independent arrays on the Simulator
+                final = n >= n_total
+                d2h += _copy_back(sim, eng, diag=True, sample_only=(anim_cells is None and not final))
                 phase.callbacks.progressed_next()
                 sim.write2storage(last_t, cells, p)
                 if anim_cells is not None:
@@ -291,6 +316,7 @@ def run_sim_core_loop(sim, phase, time_steps, time_steps_sampled, anim_cells=Non
             d2h = eng.d2h_bytes - (0 if own_engine else d2h0)
             stats.update({"h2d_bytes": h2d, "d2h_bytes": d2h, "wall_s": time.time() - t0,
                           "steps": n})
+        _detach(sim, eng)
         if own_engine:
             eng.close()
 

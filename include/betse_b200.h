@@ -133,6 +133,7 @@ typedef struct betse_state_host {
     double *rate_NaKATP;     /* [M]   */
     double *Jmem, *Jgj, *Jn, *I_mem, *Jc, *Emc, *dvm;   /* [M] */
     double *J_cell_x, *J_cell_y, *E_cell_x, *E_cell_y, *sigma_cell;  /* [C] */
+    double *E_gj_x, *E_gj_y; /* [M]   gap-junction field of the step (sim.py:2168-2172; stored by write2storage) */
     double *cenv_uniform;    /* [I]   no-ECM bath concentrations (download only)          */
     double *vm_cell;         /* [C]   per-cell Vmem incl. ghost cells (upload only; overrides vm)  */
 } betse_state_host;
@@ -216,6 +217,11 @@ typedef struct betse_channel {
 int  betse_set_channels(betse_ctx *ctx, int n, const betse_channel *channels, int affect_charge);
 /* Gate states / open probability / last flux / DChan (networks.py:3164) of channel k, [M] each (NULL members are skipped). */
 int  betse_channel_state(betse_ctx *ctx, int k, double *m, double *h, double *P, double *flux, double *DChan);
+
+/* Page-locked host staging for sampled-step downloads (the buffers write2storage copies from, sim.py:1789-1884):
+ * device->host copies into these run at PCIe speed without the driver's bounce buffer. */
+int  betse_host_alloc(size_t bytes, void **out);
+void betse_host_free(void *p);
 
 /* ---------------------------------------------------------------------------------------------
  * General network / gene regulatory network (MasterOfNetworks, networks.py).

@@ -104,3 +104,49 @@ def test_full_size_one_step_and_properties():
     # ulp of the (cancelling) products, i.e. eps*(D*g/L)*c*sa, not of the tiny net flux
     scale = (np.max(st2["D_gj"]) * p2["gj_surface"] / float(mesh2["gj_len"])) * np.max(a["cc_cells"]) * np.max(sa)
     assert resid <= 1e-9 * np.max(np.abs(fg)) + 64 * util.EPS * scale, (resid, scale)
+
+
+def test_dropin_loop_sampling_contract():
+    """run_sim_core_loop (the Simulator._run_sim_core_loop drop-in, sim.py:1132-1390) on a synthetic tissue:
+    what write2storage sees at every sampled step equals the oracle's state at that step; sampled-step views are
+    engine-owned staging, the arrays left on the Simulator at the end are not."""
+    import bench
+    from betse_b200 import simloop, synth
+    from oracle.betse_oracle import OracleSim
+    mesh, p, state = synth.make_tissue(3000)
+    sim, phase = bench.namespaces(mesh, p, state)
+    n = 25
+    ts = np.linspace(0, n * p["dt"], n)
+    sampled = set(ts[4::5].tolist())
+    ora = OracleSim(mesh, p, state)
+    ora.diagnostics = False
+    ora.update_V()
+    seen = []
+
+    def w2s(t, cells, pp):
+        k = int(np.argmin(np.abs(ts - t))) + 1
+        seen.append((k, {f: np.copy(getattr(sim, f)) for f in
+                         ("cc_cells", "cc_env", "vm", "vm_ave", "gjopen", "rho_cells", "I_mem", "E_gj_x", "v_env",
+                          "E_env_x", "rate_NaKATP", "J_cell_x")}, sim.vm_ave))
+    sim.write2storage = w2s
+    simloop.run_sim_core_loop(sim, phase, ts, sampled, None)
+    assert [k for k, _, _ in seen] == [5, 10, 15, 20, 25]
+    assert len({id(v) for _, _, v in seen}) == len(seen)          # vm_ave is appended uncopied by the reference
+    done = 0
+    for k, got, _ in seen:
+        while done < k:
+            ora.step()
+            done += 1
+        for f in ("cc_cells", "cc_env", "gjopen"):
+            assert util.rel_err(got[f].reshape(np.shape(getattr(ora, f))), getattr(ora, f)) < 1e-10, (k, f)
+        assert np.max(np.abs(got["vm"] - ora.vm)) < 1e-10 * np.max(np.abs(ora.vm)) + 4e-12
+        assert got["E_env_x"].shape == ora.E_env_x.shape
+    # after the loop: complete, engine-independent arrays (diagnostics included)
+    for f in ("cc_cells", "vm", "fluxes_mem", "Jn", "E_gj_x", "cc_at_mem", "I_mem", "E_env_x"):
+        a = getattr(sim, f)
+        while isinstance(a, np.ndarray) and a.base is not None:
+            a = a.base
+        assert isinstance(a, np.ndarray) and a.flags.owndata, f      # not a view of page-locked staging
+    assert util.rel_err(sim.cc_cells, ora.cc_cells) < 1e-10
+    tol = 4 * (1e-10 * np.max(np.abs(ora.vm)) + 4e-12) / ora.gj_len
+    assert np.max(np.abs(sim.E_gj_x - ora.E_gj_x)) <= tol

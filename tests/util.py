@@ -16,7 +16,7 @@ ENV_STATE = ["E_env_x", "E_env_y", "v_env", "rho_env"]
 # compared against the scale of their *summands*, see scale_of().
 DIAG = ["fluxes_mem", "fluxes_gj", "fluxes_env_x", "fluxes_env_y", "rate_NaKATP", "Jmem", "Jgj",
         "Jn", "I_mem", "J_cell_x", "J_cell_y", "Jc", "Eme", "E_cell_x", "E_cell_y", "Emc", "dvm",
-        "J_env_x", "J_env_y", "Jtx", "Jty", "B_field", "sigma_cell", "rho_env_surf"]
+        "J_env_x", "J_env_y", "Jtx", "Jty", "B_field", "sigma_cell", "rho_env_surf", "E_gj_x", "E_gj_y"]
 
 
 def load_golden(name):
@@ -99,6 +99,7 @@ def gpu_tolerances(cap, kind, ref):
     b_vm = b_rho * float(np.max(cells["diviterm"])) / cm
     tol["vm"] = tol["vm_ave"] = max(1e-10 * mx("vm"), b_vm)
     tol["dvm"] = 2 * tol["vm"] / dt
+    tol["E_gj_x"] = tol["E_gj_y"] = 4 * tol["vm"] / float(cells["gj_len"])   # -(vm[nn] - vm[m])/gj_len, sim.py:2166-2172
     if "rho_env" in ref and int(P["is_ecm"]):
         b_re = 16 * EPS * float(np.max(np.dot(zF, np.abs(ref["cc_env"]))))
         tol["rho_env"] = max(1e-10 * mx("rho_env"), b_re)
