@@ -84,7 +84,8 @@ STATE_FIELDS = [
     "extra_rho_env", "extra_J_mem", "NaKATP_block", "gj_block",
     "fluxes_mem", "fluxes_gj", "fluxes_env_x", "fluxes_env_y", "rate_NaKATP",
     "Jmem", "Jgj", "Jn", "I_mem", "Jc", "Emc", "dvm",
-    "J_cell_x", "J_cell_y", "E_cell_x", "E_cell_y", "sigma_cell", "E_gj_x", "E_gj_y", "cenv_uniform", "vm_cell",
+    "J_cell_x", "J_cell_y", "E_cell_x", "E_cell_y", "sigma_cell", "E_gj_x", "E_gj_y",
+    "J_env_x", "J_env_y", "B_field", "Jtx", "Jty", "cenv_uniform", "vm_cell",
 ]
 
 

@@ -15,6 +15,7 @@
 #include "xchg.cuh"
 #include "channels.cuh"
 #include "network.cuh"
+#include "hh.cuh"
 
 // launchers (kernels.cu)
 void launch_mem(int ni, const KParams& P, const KArrays& A, int n_ctas, int cur, int diag, cudaStream_t st);
@@ -29,6 +30,8 @@ void launch_expand_vm(const KParams& P, const KArrays& A, int M, int C, int cur,
 cudaError_t prepare_kernels(int ni);
 // kmem_pipe.cu: the per-tile constant blocks of the pipelined membrane kernel
 unsigned tile_pack_size(int ni);
+void launch_hh_setup(const HHBuf& H, int ny, int nx, cudaStream_t st);
+void launch_hh(const KParams& P, const KArrays& A, const HHBuf& H, cudaStream_t st);
 void launch_pack_const(const KParams& P, const KArrays& A, cudaStream_t st);
 void launch_pack_dm(const KParams& P, const KArrays& A, cudaStream_t st);
 void launch_chan(const KParams& P, const KArrays& A, const KChan& ch, const KNet& N, int cur, cudaStream_t st);
@@ -58,6 +61,8 @@ struct betse_ctx {
     XPlan X;
     std::vector<void*> ipc_opened;
     std::vector<KChan> chans;                // voltage-gated channels, applied in order
+    HHBuf hh;                                // Helmholtz-Hodge diagnostics (sampled steps, undivided ECM tissues)
+    bool hh_on = false;
     KNet nets[2];                            // network handlers: 0 general network, 1 gene regulatory network
     bool net_on[2] = {false, false};
     int net_nprog[2] = {0, 0};
@@ -459,6 +464,23 @@ static int ensure_diag_buffers(betse_ctx* ctx)
     for (auto p : mem_arrays) if ((r = dev_alloc(ctx, p, ctx->Mo))) return r;
     double** cell_arrays[] = {&A.J_cell_x, &A.J_cell_y, &A.E_cell_x, &A.E_cell_y, &A.sigma_cell};
     for (auto p : cell_arrays) if ((r = dev_alloc(ctx, p, ctx->C))) return r;
+    // Helmholtz-Hodge decomposition of the env current (ion_current.py:50-73): undivided ECM tissues only
+    if (ctx->hp.is_ecm && ctx->X.n_nbr == 0 && ctx->ny > 2 && ctx->nx > 2) {
+        HHBuf& H = ctx->hh;
+        memset(&H, 0, sizeof H);
+        const size_t my = ctx->ny - 2, mx = ctx->nx - 2, E = ctx->E;
+        if ((r = dev_alloc(ctx, &H.Sy, my * my))) return r;
+        if ((r = dev_alloc(ctx, &H.Sx, mx * mx))) return r;
+        if ((r = dev_alloc(ctx, &H.ly, my))) return r;
+        if ((r = dev_alloc(ctx, &H.lx, mx))) return r;
+        double** eb[] = {&H.Jx, &H.Jy, &H.bA, &H.bB, &H.uA, &H.uB, &H.J_env_x, &H.J_env_y, &H.B_field, &H.Jtx, &H.Jty};
+        for (auto pp : eb) if ((r = dev_alloc(ctx, pp, E))) return r;
+        if ((r = dev_alloc(ctx, &H.R, my * mx))) return r;
+        if ((r = dev_alloc(ctx, &H.T1, my * mx))) return r;
+        launch_hh_setup(H, ctx->ny, ctx->nx, ctx->stream);
+        CK(cudaGetLastError());
+        ctx->hh_on = true;
+    }
     destroy_graphs(ctx);   // KArrays changed
     return 0;
 }
@@ -612,6 +634,11 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
         if (ecm) launch_field(ctx->P, A, ctx->ny, ctx->nx, st);
         if (evs) cudaEventRecord(evs[5], st);
         if (diag) launch_diag(I, ctx->P, A, ctx->n_ctas, nxt, st);
+        if (diag && ecm && ctx->hh_on && ctx->X.n_nbr == 0) {
+            ctx->hh.mu = ctx->hp.mu;
+            for (int q = 0; q < 4; ++q) ctx->hh.bound[q] = ctx->hp.bound_V[q];
+            launch_hh(ctx->P, A, ctx->hh, st);
+        }
         if (evs) cudaEventRecord(evs[6], st);
         ctx->cur = nxt;
     }
@@ -824,7 +851,7 @@ extern "C" int betse_download_sample(betse_ctx* ctx, betse_state_host* s)
     if (s->cenv_uniform) CK(cudaMemcpyAsync(s->cenv_uniform, A.cenv_u + cur * 8, I * sizeof(double), cudaMemcpyDeviceToHost, st));
     const bool any_diag = s->fluxes_mem || s->fluxes_gj || s->fluxes_env_x || s->fluxes_env_y || s->rate_NaKATP ||
                           s->Jmem || s->Jgj || s->Jn || s->I_mem || s->Jc || s->Emc || s->dvm || s->J_cell_x ||
-                          s->J_cell_y || s->E_cell_x || s->E_cell_y || s->sigma_cell || s->E_gj_x || s->E_gj_y;
+                          s->J_cell_y || s->E_cell_x || s->E_cell_y || s->sigma_cell || s->E_gj_x || s->E_gj_y || s->J_env_x || s->J_env_y || s->B_field || s->Jtx || s->Jty;
     if (any_diag) {
         if (!ctx->diag_valid) return fail(ctx, "diagnostics requested but the last step was not run with BETSE_STEP_DIAG");
         DN(s->fluxes_mem, A.fl_mem, IM);
@@ -837,6 +864,11 @@ extern "C" int betse_download_sample(betse_ctx* ctx, betse_state_host* s)
         DN(s->E_cell_x, A.E_cell_x, C); DN(s->E_cell_y, A.E_cell_y, C);
         DN(s->sigma_cell, A.sigma_cell, C);
         DN(s->E_gj_x, A.E_gj_x, Mo); DN(s->E_gj_y, A.E_gj_y, Mo);
+        if (s->J_env_x || s->J_env_y || s->B_field || s->Jtx || s->Jty) {
+            if (!ctx->hh_on) return fail(ctx, "J_env / B_field / Jtx: the Helmholtz-Hodge diagnostics need an undivided tissue with extracellular spaces");
+            DN(s->J_env_x, ctx->hh.J_env_x, E); DN(s->J_env_y, ctx->hh.J_env_y, E); DN(s->B_field, ctx->hh.B_field, E);
+            DN(s->Jtx, ctx->hh.Jtx, E); DN(s->Jty, ctx->hh.Jty, E);
+        }
     }
 #undef DN
     CK(cudaStreamSynchronize(st));

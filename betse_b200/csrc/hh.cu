@@ -1,0 +1,213 @@
+// Helmholtz-Hodge decomposition of the extracellular current density (sampled steps only):
+//   get_current, env part          betse/science/physics/ion_current.py:50-73
+//   stb.HH_Decomp                  betse/science/sim_toolbox.py:1236-1290
+//   fd.divergence / fd.gradient    betse/science/math/finitediff.py:1236-1311
+//   cells.lapENVinv (Dirichlet)    betse/science/cells.py:503-504, finitediff.py:252-431
+// Outputs J_env_x/y (the divergence-free part: what write2storage stores as I_tot_*), B_field,
+// Jtx/Jty.  They feed nothing back into the timestep, so this runs when a step is sampled.
+//
+// The reference multiplies by a dense (E x E) pseudo-inverse of the Laplacian whose border rows are
+// the identity/d^2 and whose interior rows are the 5-point stencil/d^2.  That matrix is regular, so
+// pinv == inverse and "lapENVinv . b" is the Dirichlet solve with border values u = b*d^2 lifted to
+// the right-hand side (SURVEY §8 notes, checked to 7e-15 against the dense product).  The interior
+// problem is diagonalised by the type-I sine transform in both axes; for a diagnostic evaluated
+// every ~10th step a transform as two dense products with the sine matrices is plenty
+// (u = Sy (Sy R Sx / lambda) Sx / ((my+1)(mx+1)), 4 x ~1e9 FMA at a 1000^2 grid).
+#include <math.h>
+#include "kparams.cuh"
+
+#include "hh.cuh"
+
+__global__ void k_hh_sine(double* S, double* lam, const int n)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (k >= n) return;
+    const long long prod = (long long)(j + 1) * (k + 1) % (2LL * (n + 1));     // exact argument reduction
+    S[(size_t)j * n + k] = sinpi((double)prod / (double)(n + 1));
+    if (j == 0) lam[k] = 2.0 * cospi((double)(k + 1) / (double)(n + 1)) - 2.0;
+}
+
+// Jx = np.dot(p.F*sim.zs, sim.fluxes_env_x) (ion_current.py:52-54)
+__global__ void k_hh_J(const __grid_constant__ KParams P, const KArrays A, HHBuf H)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int E = P.nx * P.ny;
+    if (k >= E) return;
+    double jx = 0.0, jy = 0.0;
+    for (int i = 0; i < P.n_ions; ++i) {
+        jx = fma(P.zF[i], A.fl_env_x[(size_t)i * E + k], jx);
+        jy = fma(P.zF[i], A.fl_env_y[(size_t)i * E + k], jy);
+    }
+    H.Jx[k] = jx; H.Jy[k] = jy;
+}
+
+// fd.diff (finitediff.py:1268-1303): edge rows carry the opposite sign convention to fd.gradient
+__device__ __forceinline__ double diff_x(const double* F, int y, int x, int nx, double d)
+{
+    const double* r = F + (size_t)y * nx;
+    if (x == 0) return (r[0] - r[1]) / d;
+    if (x == nx - 1) return (r[nx - 2] - r[nx - 1]) / d;
+    return -(r[x - 1] - r[x + 1]) / (2.0 * d);
+}
+__device__ __forceinline__ double diff_y(const double* F, int y, int x, int ny, int nx, double d)
+{
+    if (y == 0) return -(F[(size_t)nx + x] - F[x]) / d;
+    if (y == ny - 1) return -(F[(size_t)(ny - 1) * nx + x] - F[(size_t)(ny - 2) * nx + x]) / d;
+    return -(F[(size_t)(y - 1) * nx + x] - F[(size_t)(y + 1) * nx + x]) / (2.0 * d);
+}
+
+// right-hand sides: bA = -div(-Jy, Jx) with a zero border, bB = div(Jx, Jy) with the border set from bound_V
+__global__ void k_hh_rhs(const __grid_constant__ KParams P, HHBuf H)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int nx = P.nx, ny = P.ny;
+    if (x >= nx) return;
+    const double d = P.delta;
+    const size_t k = (size_t)y * nx + x;
+    const bool border = (x == 0 || x == nx - 1 || y == 0 || y == ny - 1);
+    // divJr = diff(-Jy, axis 0 -> x) + diff(Jx, axis 1 -> y)
+    double a = 0.0;
+    if (!border) a = -(-diff_x(H.Jy, y, x, nx, d) + diff_y(H.Jx, y, x, ny, nx, d));
+    H.bA[k] = a;
+    double b;
+    const double id2 = 1.0 / (d * d);
+    if (y == ny - 1) b = -H.bound[0] * id2;          // T  (sim_toolbox.py:1271-1274: rows are assigned last)
+    else if (y == 0) b = -H.bound[1] * id2;          // B
+    else if (x == nx - 1) b = -H.bound[3] * id2;     // R
+    else if (x == 0) b = -H.bound[2] * id2;          // L
+    else b = diff_x(H.Jx, y, x, nx, d) + diff_y(H.Jy, y, x, ny, nx, d);
+    H.bB[k] = b;
+}
+
+// border lift: u = b*d^2 on the border; interior rhs R = b*d^2 - (adjacent border values)
+__global__ void k_hh_lift(const __grid_constant__ KParams P, const double* b, double* u, double* R)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int nx = P.nx, ny = P.ny;
+    if (x >= nx) return;
+    const double d2 = P.delta * P.delta;
+    const size_t k = (size_t)y * nx + x;
+    const bool border = (x == 0 || x == nx - 1 || y == 0 || y == ny - 1);
+    if (border) { u[k] = b[k] * d2; return; }
+    double r = b[k] * d2;
+    if (y == 1) r -= b[x] * d2;
+    if (y == ny - 2) r -= b[(size_t)(ny - 1) * nx + x] * d2;
+    if (x == 1) r -= b[(size_t)y * nx] * d2;
+    if (x == nx - 2) r -= b[(size_t)y * nx + nx - 1] * d2;
+    R[(size_t)(y - 1) * (nx - 2) + (x - 1)] = r;
+}
+
+// C[M][N] = A[M][K] . B[K][N] (row major), 64x64 tile per CTA, 4x4 per thread
+__global__ void __launch_bounds__(256)
+k_hh_gemm(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C, int M, int N, int K)
+{
+    __shared__ double sA[16][64 + 1], sB[16][64 + 1];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+    double acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        for (int t = threadIdx.x; t < 64 * 16; t += 256) {
+            const int rr = t >> 4, kk = t & 15;                       // A tile: rows r0.., cols k0..
+            sA[kk][rr] = (r0 + rr < M && k0 + kk < K) ? A[(size_t)(r0 + rr) * K + k0 + kk] : 0.0;
+            const int kb = t >> 6, cc = t & 63;                       // B tile: rows k0.., cols c0..
+            sB[kb][cc] = (k0 + kb < K && c0 + cc < N) ? B[(size_t)(k0 + kb) * N + c0 + cc] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = sA[kk][ty * 4 + i]; b[i] = sB[kk][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = r0 + ty * 4 + i, c = c0 + tx * 4 + j;
+            if (r < M && c < N) C[(size_t)r * N + c] = acc[i][j];
+        }
+}
+
+// spectral division (the two dstn factors of 2 folded in) / back-transform normalisation + scatter into u
+__global__ void k_hh_scale(double* T, const double* ly, const double* lx, int my, int mx)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+    if (l >= mx) return;
+    T[(size_t)k * mx + l] = (4.0 * T[(size_t)k * mx + l]) / (ly[k] + lx[l]);
+}
+__global__ void k_hh_scatter(const double* T, double* u, int my, int mx)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+    if (l >= mx) return;
+    u[(size_t)(k + 1) * (mx + 2) + l + 1] = T[(size_t)k * mx + l] / ((double)(my + 1) * (double)(mx + 1));   // 4 S uh S / (4 (my+1)(mx+1))
+}
+
+// fd.gradient (finitediff.py:1236-1266)
+__device__ __forceinline__ void grad_at(const double* F, int y, int x, int ny, int nx, double d, double& gx, double& gy)
+{
+    const double* r = F + (size_t)y * nx;
+    if (x == 0) gx = (r[1] - r[0]) / d;
+    else if (x == nx - 1) gx = (r[nx - 1] - r[nx - 2]) / d;
+    else gx = -(r[x - 1] - r[x + 1]) / (2.0 * d);
+    if (y == 0) gy = (F[(size_t)nx + x] - F[x]) / d;
+    else if (y == ny - 1) gy = (F[(size_t)(ny - 1) * nx + x] - F[(size_t)(ny - 2) * nx + x]) / d;
+    else gy = -(F[(size_t)(y - 1) * nx + x] - F[(size_t)(y + 1) * nx + x]) / (2.0 * d);
+}
+
+__global__ void k_hh_out(const __grid_constant__ KParams P, HHBuf H)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int nx = P.nx, ny = P.ny;
+    if (x >= nx) return;
+    const size_t k = (size_t)y * nx + x;
+    double gAx, gAy, gBx, gBy;
+    grad_at(H.uA, y, x, ny, nx, P.delta, gAx, gAy);
+    grad_at(H.uB, y, x, ny, nx, P.delta, gBx, gBy);
+    const double Fx = -gAy, Fy = gAx;                 // the rotational (divergence-free) part
+    H.J_env_x[k] = Fx; H.J_env_y[k] = Fy;
+    H.B_field[k] = H.uA[k] * H.mu;                    // ion_current.py:63
+    H.Jtx[k] = Fx + gBx; H.Jty[k] = Fy + gBy;         // ion_current.py:67-68
+}
+
+static void gemm(const double* A, const double* B, double* C, int M, int N, int K, cudaStream_t st)
+{
+    dim3 g((N + 63) / 64, (M + 63) / 64);
+    k_hh_gemm<<<g, 256, 0, st>>>(A, B, C, M, N, K);
+}
+
+void launch_hh_setup(const HHBuf& H, int ny, int nx, cudaStream_t st)
+{
+    const int my = ny - 2, mx = nx - 2;
+    k_hh_sine<<<dim3((my + 127) / 128, my), 128, 0, st>>>(H.Sy, H.ly, my);
+    k_hh_sine<<<dim3((mx + 127) / 128, mx), 128, 0, st>>>(H.Sx, H.lx, mx);
+}
+
+static void poisson(const KParams& P, const HHBuf& H, const double* b, double* u, cudaStream_t st)
+{
+    const int ny = P.ny, nx = P.nx, my = ny - 2, mx = nx - 2;
+    dim3 gE((nx + 127) / 128, ny), gI((mx + 127) / 128, my);
+    k_hh_lift<<<gE, 128, 0, st>>>(P, b, u, H.R);
+    gemm(H.Sy, H.R, H.T1, my, mx, my, st);           // Sy . R
+    gemm(H.T1, H.Sx, H.R, my, mx, mx, st);           // . Sx
+    k_hh_scale<<<gI, 128, 0, st>>>(H.R, H.ly, H.lx, my, mx);
+    gemm(H.Sy, H.R, H.T1, my, mx, my, st);
+    gemm(H.T1, H.Sx, H.R, my, mx, mx, st);
+    k_hh_scatter<<<gI, 128, 0, st>>>(H.R, u, my, mx);
+}
+
+void launch_hh(const KParams& P, const KArrays& A, const HHBuf& H, cudaStream_t st)
+{
+    const int E = P.nx * P.ny;
+    dim3 gE((P.nx + 127) / 128, P.ny);
+    k_hh_J<<<(E + 255) / 256, 256, 0, st>>>(P, A, H);
+    k_hh_rhs<<<gE, 128, 0, st>>>(P, H);
+    poisson(P, H, H.bA, H.uA, st);
+    poisson(P, H, H.bB, H.uB, st);
+    k_hh_out<<<gE, 128, 0, st>>>(P, H);
+}

@@ -21,10 +21,11 @@ _DOWN_SHAPES = {
     "rate_NaKATP": "M", "Jmem": "M", "Jgj": "M", "Jn": "M", "I_mem": "M", "Jc": "M", "Emc": "M",
     "dvm": "M", "J_cell_x": "C", "J_cell_y": "C", "E_cell_x": "C", "E_cell_y": "C",
     "sigma_cell": "C", "E_gj_x": "M", "E_gj_y": "M",
+    "J_env_x": "E", "J_env_y": "E", "B_field": "E", "Jtx": "E", "Jty": "E",
 }
 DIAG_FIELDS = ("fluxes_mem", "fluxes_gj", "fluxes_env_x", "fluxes_env_y", "rate_NaKATP", "Jmem",
                "Jgj", "Jn", "I_mem", "Jc", "Emc", "dvm", "J_cell_x", "J_cell_y", "E_cell_x",
-               "E_cell_y", "sigma_cell", "vm_ave", "E_gj_x", "E_gj_y")
+               "E_cell_y", "sigma_cell", "vm_ave", "E_gj_x", "E_gj_y", "J_env_x", "J_env_y", "B_field", "Jtx", "Jty")
 
 
 def gaussian_taps():

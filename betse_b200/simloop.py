@@ -49,7 +49,7 @@ _SAMPLED_STATE = ["cc_cells", "cc_at_mem", "cc_env", "vm", "vm_ave", "gjopen", "
 _SAMPLED_ENV = ["E_env_x", "E_env_y", "v_env", "rho_env"]
 _SAMPLED_DIAG = ["fluxes_mem", "fluxes_gj", "rate_NaKATP", "Jmem", "Jgj", "Jn", "I_mem", "Jc", "Emc",
                  "dvm", "J_cell_x", "J_cell_y", "E_cell_x", "E_cell_y", "sigma_cell"]
-_SAMPLED_DIAG_ENV = ["fluxes_env_x", "fluxes_env_y"]
+_SAMPLED_DIAG_ENV = ["fluxes_env_x", "fluxes_env_y", "J_env_x", "J_env_y", "B_field", "Jtx", "Jty"]
 # exactly what Simulator.write2storage reads (sim.py:1796-1877) — the per-sample download; everything else
 # (per-ion flux arrays, J's, E_cell ...) is only read after the phase and comes with the final copy-back
 _W2S_STATE = ["cc_cells", "vm", "vm_ave", "gjopen", "rho_cells"]
@@ -205,6 +205,8 @@ def _copy_back(sim, eng, diag, sample_only=False):
     keeps; vm_ave, which it appends as is (sim.py:1877), gets its own array)."""
     if sample_only:
         fields = _W2S_STATE + (_W2S_ENV if eng.is_ecm else ["cc_env"]) + (_W2S_DIAG if diag else [])
+        if diag and eng.is_ecm:
+            fields += ["J_env_x", "J_env_y"]       # I_tot_x_time / I_tot_y_time (sim.py:1866-1867)
     else:
         fields = list(_SAMPLED_STATE)
         if eng.is_ecm:

@@ -134,6 +134,8 @@ typedef struct betse_state_host {
     double *Jmem, *Jgj, *Jn, *I_mem, *Jc, *Emc, *dvm;   /* [M] */
     double *J_cell_x, *J_cell_y, *E_cell_x, *E_cell_y, *sigma_cell;  /* [C] */
     double *E_gj_x, *E_gj_y; /* [M]   gap-junction field of the step (sim.py:2168-2172; stored by write2storage) */
+    double *J_env_x, *J_env_y, *B_field, *Jtx, *Jty;  /* [E] Helmholtz-Hodge decomposition of the env current
+                                (ion_current.py:50-73, sim_toolbox.py:1236-1290); undivided ECM tissues */
     double *cenv_uniform;    /* [I]   no-ECM bath concentrations (download only)          */
     double *vm_cell;         /* [C]   per-cell Vmem incl. ghost cells (upload only; overrides vm)  */
 } betse_state_host;

@@ -150,3 +150,31 @@ def test_dropin_loop_sampling_contract():
     assert util.rel_err(sim.cc_cells, ora.cc_cells) < 1e-10
     tol = 4 * (1e-10 * np.max(np.abs(ora.vm)) + 4e-12) / ora.gj_len
     assert np.max(np.abs(sim.E_gj_x - ora.E_gj_x)) <= tol
+
+
+def test_helmholtz_hodge_vs_oracle_rectangular_grid():
+    """csrc/hh.cu against the oracle's DST solve on a tissue whose env grid is not square and large enough that the
+    sine-matrix products span several 64x64 tiles (the golden worlds are 20x19)."""
+    from betse_b200 import synth
+    from betse_b200.engine import TissueEngine
+    from oracle.betse_oracle import OracleSim
+    mesh, p, st = synth.make_tissue(20_000)
+    rng = np.random.default_rng(11)        # a rough extracellular field, so that real currents flow in the env grid
+    st = dict(st)
+    st["cc_env"] = np.asarray(st["cc_env"]) * (1.0 + 0.02 * rng.standard_normal(np.shape(st["cc_env"])))
+    eng = TissueEngine(mesh, p, st)
+    eng.update_V()
+    ora = OracleSim(mesh, p, st)
+    ora.diagnostics = False
+    ora.update_V()
+    for n in range(3):
+        s = eng.step(1, diag=(n == 2))
+        ora.diagnostics = (n == 2)
+        ora.step()
+        assert not (s & 3)
+    got = eng.download(["J_env_x", "J_env_y", "Jtx", "Jty", "B_field"])
+    sJ = max(np.max(np.abs(ora.Jtx)), np.max(np.abs(ora.Jty)))
+    for f in ("J_env_x", "J_env_y", "Jtx", "Jty"):
+        assert np.max(np.abs(got[f].ravel() - np.asarray(getattr(ora, f)).ravel())) <= 1e-9 * sJ, f
+    assert np.max(np.abs(got["B_field"] - ora.B_field)) <= 1e-7 * np.max(np.abs(ora.B_field)) + 1e-9 * sJ * p["mu"] * 1e-3
+    eng.close()

@@ -111,6 +111,15 @@ def gpu_tolerances(cap, kind, ref):
             tol["E_env_x"] = tol["E_env_y"] = max(1e-10 * e_scale, 4 * k * e_scale * 8)
         else:
             tol["E_env_x"] = tol["E_env_y"] = 1e-300
+    if "Jtx" in ref and int(P["is_ecm"]):
+        # Helmholtz-Hodge parts of J_env = sum_i z_i F f_env_i (ion_current.py:50-73): the decomposition differentiates
+        # and re-integrates a cancelling sum whose inputs carry 1e-10, so every part is judged against |J total|; the
+        # divergence-free part J_env is 1e-6 of it on these tissues.  B_field = mu*potential: a J error times the domain size.
+        sJt = max(mx("Jtx"), mx("Jty"))
+        for f in ("J_env_x", "J_env_y", "Jtx", "Jty"):
+            tol[f] = 1e-9 * sJt
+        L = float(max(cells["grid_shape"])) * float(cells["delta"])
+        tol["B_field"] = max(1e-8 * mx("B_field"), 1e-9 * sJt * float(P["mu"]) * L)
     if "fluxes_mem" in ref:
         zs = np.asarray(S0["zs"], dtype=float)
         sJ = float(np.max(np.dot(zF, np.abs(ref["fluxes_mem"]))))

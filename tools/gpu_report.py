@@ -23,7 +23,7 @@ for name in util.GOLDEN:
             ref = util.group(cap, "%s.k%d." % (kind, K))
             fields = list(util.STATE) + (util.ENV_STATE if ecm else [])
             if last:
-                fields += [f for f in util.DIAG if f in ref and f not in ("J_env_x","J_env_y","Jtx","Jty","B_field","rho_env_surf","Eme")]
+                fields += [f for f in util.DIAG if f in ref and f not in ("rho_env_surf","Eme") and (ecm or f not in ("J_env_x","J_env_y","Jtx","Jty","B_field"))]
                 if not ecm: fields = [f for f in fields if not f.startswith("fluxes_env")]
             got = eng.download([f for f in fields if f in ref])
             errs = {f: util.rel_err(a, ref[f], util.scale_of(f, ref)) for f, a in got.items()}
