@@ -178,6 +178,7 @@ def engine_from_sim(sim, cells, p, device=0, phase_init=False):
     eng.chan_specs = []
     eng.net_cores = {}
     handlers = _handlers(sim, p)
+    eng.all_cores = [core for _, core in handlers]
     if handlers:
         specs = channels_from_sim(sim, p)
         for h, core in handlers:
@@ -240,6 +241,15 @@ def _copy_back(sim, eng, diag, sample_only=False):
             mol.cc_at_mem = c[k][m2c]
         nk = len(eng.networks[h]["species"])
         core.reaction_rates = rates[nk:].copy()
+    # MasterOfNetworks.energy_charge (networks.py:3996-4012), the tail of run_loop; write_data appends it
+    # (networks.py:4256) whether or not the network has substances
+    for core in getattr(eng, "all_cores", []):
+        mols = getattr(core, "molecules", None) or {}
+        if "AMP" in mols:
+            cc = core.cell_concs
+            core.chi = (cc["ATP"] + 0.5 * cc["ADP"]) / (cc["ATP"] + cc["ADP"] + cc["AMP"])
+        else:
+            core.chi = np.zeros(len(eng.mem_to_cells) and eng.Co)
     return 0
 
 
@@ -258,8 +268,17 @@ def run_sim_core_loop(sim, phase, time_steps, time_steps_sampled, anim_cells=Non
     own_engine = engine is None
     kind = getattr(getattr(phase, "kind", None), "name", str(getattr(phase, "kind", "")))
     is_sim = kind.upper() == "SIM"
-    eng = engine or engine_from_sim(sim, cells, p, device=device, phase_init=not is_sim)
     fire = getattr(getattr(phase, "dyna", None), "fire_events", None) if is_sim else None
+    ev_cut = getattr(getattr(phase, "dyna", None), "event_cut", None)
+    if fire is not None and engine is None and ev_cut is not None and not ev_cut.is_fired and len(time_steps):
+        # The cutting event (tishandler.py:884-913) fires inside the FIRST fire_events call of the phase
+        # (event_cut_time is hard-wired to 0, parameters.py:686-687) and re-indexes the mesh and every state array
+        # on the host (TissueHandler._cut_cells, tishandler.py:921-1285: the reference's own code).  Nothing has run on
+        # the device yet, so let it happen before the engine is built from the (then post-cut) Simulator; the loop's
+        # own call for this step finds the event fired and only re-evaluates the scheduled scalars for the same t.
+        fire(phase=phase, t=time_steps[0])
+        cells = phase.cells
+    eng = engine or engine_from_sim(sim, cells, p, device=device, phase_init=not is_sim)
     sampled = set(time_steps_sampled)
     Unstable = _unstable_exception()
     h2d = d2h = 0

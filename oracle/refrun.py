@@ -154,11 +154,13 @@ class LoopRecorder:
     """Wraps the reference's Simulator._run_sim_core_loop to record entry state and the
     state after chosen step counts, without altering what the reference computes."""
 
-    def __init__(self, snap_steps, max_steps=None, extra=None):
+    def __init__(self, snap_steps, max_steps=None, extra=None, trace=(), precut=False):
         self.snap_steps = {k: sorted(set(v)) for k, v in snap_steps.items()}
         self.max_steps = max_steps or {}
         self.capture = {}
         self.extra = extra  # optional callable(sim, phase) -> dict of extra arrays
+        self.trace = tuple(trace)   # fields recorded at EVERY sampled step: <phase>.trace.<field> [n_sampled, ...]
+        self.precut = precut        # fire a pending cutting event before the entry snapshot (see wrapped)
 
     def install(self):
         from betse.science.sim import Simulator
@@ -169,6 +171,17 @@ class LoopRecorder:
         def wrapped(sim, phase, time_steps, time_steps_sampled, anim_cells):
             kind = phase.kind.name.lower()
             cap = rec.capture
+            dyna = getattr(phase, "dyna", None)
+            ev = getattr(dyna, "event_cut", None)
+            if rec.precut and kind == "sim" and ev is not None and not ev.is_fired and len(time_steps):
+                # The cutting event fires inside the FIRST fire_events call of the phase (tishandler.py:884-913,
+                # event_cut_time == 0, parameters.py:687) and re-indexes every array.  Firing it here, before the
+                # entry snapshot, is the same computation (fire_events is the first statement of the loop body that
+                # touches state, sim.py:1187-1188, and is a pure function of t once the cut has fired); the fixture
+                # then holds the post-cut mesh (sim.cells.*) and state.
+                dyna.fire_events(phase=phase, t=time_steps[0])
+                for k, v in snapshot_cells(phase.cells).items():
+                    cap["sim.cells." + k] = v
             if "cells.mem_sa" not in cap:
                 for k, v in snapshot_cells(phase.cells).items():
                     cap["cells." + k] = v
@@ -189,6 +202,8 @@ class LoopRecorder:
             sched_fields = ("Dm_cells", "D_env", "TJ_modulator", "gj_block", "NaKATP_block",
                             "c_env_bound", "T", "bound_V", "D_gj")
             prev = snapshot(sim, sched_fields)
+            tr = {f: [] for f in rec.trace}
+            tr_steps = []
             for n in range(min(nmax, len(time_steps))):
                 orig(sim, phase=phase, time_steps=time_steps[n:n + 1],
                      time_steps_sampled=time_steps_sampled, anim_cells=anim_cells)
@@ -197,12 +212,21 @@ class LoopRecorder:
                     if f not in prev or prev[f].shape != v.shape or not np.array_equal(prev[f], v):
                         cap["%s.sched.k%d.%s" % (kind, n + 1, f)] = v
                 prev = cur
+                if rec.trace and time_steps[n] in time_steps_sampled:
+                    tr_steps.append(n + 1)
+                    for f in rec.trace:
+                        tr[f].append(np.array(getattr(sim, f), dtype=float, copy=True))
                 if (n + 1) in snaps:
                     for k, v in snapshot(sim, STATE_FIELDS + DIAG_FIELDS).items():
                         cap["%s.k%d.%s" % (kind, n + 1, k)] = v
                     if rec.extra:
                         for k, v in rec.extra(sim, phase).items():
                             cap["%s.k%d.%s" % (kind, n + 1, k)] = v
+
+            if rec.trace:
+                cap[kind + ".trace.steps"] = np.array(tr_steps, dtype=np.int64)
+                for f in rec.trace:
+                    cap["%s.trace.%s" % (kind, f)] = np.array(tr[f])
 
         Simulator._run_sim_core_loop = wrapped
         return self
@@ -213,7 +237,7 @@ class LoopRecorder:
 
 
 def run_reference(mods, seed=12345, snap_steps=None, max_steps=None, phases=("init", "sim"),
-                  extra=None, workdir=None, keep=False, tweak_p=None):
+                  extra=None, workdir=None, keep=False, tweak_p=None, trace=(), precut=False):
     """Run the real reference on the shipped default config + ``mods``.
 
     Returns the capture dict.  ``np.random.seed(seed)`` is set once before ``seed`` (the
@@ -235,7 +259,7 @@ def run_reference(mods, seed=12345, snap_steps=None, max_steps=None, phases=("in
         p.plot.is_after_sim = False
         if tweak_p:
             tweak_p(p)
-        rec = LoopRecorder(snap_steps, max_steps=max_steps, extra=extra).install()
+        rec = LoopRecorder(snap_steps, max_steps=max_steps, extra=extra, trace=trace, precut=precut).install()
         try:
             runner = SimRunner(p=p, callbacks=phasecallbacks.SimCallbacksNoop())
             runner.seed()

@@ -160,6 +160,14 @@ SCENARIOS["mammal_ecm_net"] = dict(
     snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=net_extra)
 
 
+# BASELINE configs[0] as SHIPPED (`betse try`): the unmodified default sim_config.yaml — basic ion profile, ECM on,
+# general network on (substance X grown in the 'Spot' profile, Nav1p3 / Kv1p5 / X-inhibited KLeak channels) and the
+# cutting event, which removes the 'surgery' wedge at the first SIM step.  Full phases (500 + 350 timesteps) with the
+# Vmem / concentration traces at every sampled step: the "final Vmem traces within 1e-6 V" bar of BASELINE.json.
+SCENARIOS["default_try"] = dict(mods={}, snaps={"init": [500], "sim": [350]}, extra=net_extra,
+                                trace=("vm", "cc_cells"), precut=True, full=True)
+
+
 def main(argv):
     import scipy
     names = argv or list(SCENARIOS)
@@ -167,7 +175,8 @@ def main(argv):
         sc = SCENARIOS[name]
         cap = refrun.run_reference(sc["mods"], seed=12345, snap_steps=sc["snaps"],
                                    max_steps={"sim": max(max(sc["snaps"]["sim"]), 12)},
-                                   extra=sc.get("extra"), tweak_p=sc.get("tweak_p"))
+                                   extra=sc.get("extra"), tweak_p=sc.get("tweak_p"),
+                                   trace=sc.get("trace", ()), precut=sc.get("precut", False))
         cap["meta.numpy"] = np.array(np.__version__)
         cap["meta.scipy"] = np.array(scipy.__version__)
         cap["meta.seed"] = np.array(12345)

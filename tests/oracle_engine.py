@@ -1,0 +1,98 @@
+"""TEST INFRASTRUCTURE: a stand-in for betse_b200.engine.TissueEngine backed by the CPU oracle.
+
+The drop-in loop (betse_b200/simloop.py) is host logic around the CUDA engine: event scheduling, the cutting event,
+sampling, copy-back, write2storage.  The build container has the real reference but no GPU, the GPU box has a GPU but
+no reference — so the host logic is held to the reference's own full run HERE, with the device replaced by the
+oracle (tests/test_simloop_reference.py), and the device is held to the oracle / the recorded reference on the GPU
+box (tests/test_gpu_*.py).  Never imported by the product."""
+import numpy as np
+
+from oracle.betse_oracle import OracleNetwork, OracleSim, SimUnstable
+
+
+class OracleEngine:
+    def __init__(self, mesh, params, state, device=0, partition=None):
+        self._args = (mesh, params, state)
+        self.ions = [str(x) for x in params["ions"]]
+        self.Co = self.C = len(mesh["cell_vol"])
+        self.M = len(mesh["mem_sa"])
+        self.is_ecm = bool(params["is_ecm"])
+        self.ny, self.nx = (int(x) for x in mesh["grid_shape"])
+        self.mem_to_cells = np.asarray(mesh["mem_to_cells"])
+        self.h2d_bytes = self.d2h_bytes = 0
+        self.networks = {}
+        self._descs = {}
+        self._specs = []
+        self._phase_init = False
+        self._o = None
+        self.sets = []
+
+    # ---- what simloop.engine_from_sim calls
+    def set_network(self, comp, handler=0):
+        self._descs[int(handler)] = comp["_desc"]          # attached by the test's compile_network wrapper
+        self.networks[int(handler)] = {"species": list(comp["species"])}
+
+    def set_channels(self, specs, phase_init=False, affect_charge=None):
+        self._specs = [{k: v for k, v in c.items() if k != "_obj"} for c in specs]
+        self._phase_init = bool(phase_init)
+
+    def _sim(self):
+        if self._o is None:
+            mesh, params, state = self._args
+            state = dict(state)
+            # sim.py:781-786 (the engine derives these from the mesh too)
+            nm = np.asarray(mesh["num_mems"], dtype=float)[np.asarray(mesh["mem_to_cells"])]
+            nfrac = float(params["smooth_cells"])
+            state.setdefault("smooth_weight_mem", (nfrac * nm - 1) / (nfrac * nm))
+            state.setdefault("smooth_weight_o", 1 / (nfrac * nm))
+            self._o = OracleSim(mesh, params, state, channels=self._specs, phase_init=self._phase_init,
+                                networks=[self._descs[h] for h in sorted(self._descs)])
+            self._active = [c for c in self._o.channels if not (self._phase_init and not c["init_active"])]
+        return self._o
+
+    def set_field(self, name, value):
+        self.sets.append(name)
+        o = self._sim()
+        if name == "bound_V":
+            o.bound_V = dict(zip("TBLR", value))
+        else:
+            setattr(o, name, np.array(value, dtype=float))
+
+    def step(self, n=1, diag=False):
+        o = self._sim()
+        o.diagnostics = True
+        for _ in range(n):
+            try:
+                o.step()
+            except SimUnstable:
+                return 1
+        return 0
+
+    def download(self, fields, pinned=False):
+        o = self._sim()
+        out = {}
+        for f in fields:
+            if not self.is_ecm and f in ("E_env_x", "E_env_y", "v_env", "rho_env"):
+                continue
+            out[f] = np.array(getattr(o, f), dtype=float, copy=True)
+            if f in ("E_env_x", "E_env_y"):
+                out[f] = out[f].ravel()
+        return out
+
+    def channel_state(self, k):
+        c = self._active[k]
+        m, h = np.ones(self.M), np.ones(self.M)
+        m[c["targets"]], h[c["targets"]] = c["m"], c["h"]
+        return {"m": m, "h": h, "P": c["P"], "flux": c.get("flux", np.zeros(self.M)),
+                "DChan": c.get("DChan", np.zeros(self.M))}
+
+    def network_state(self, handler=0, rates=False):
+        net = self._sim().networks[sorted(self._descs).index(int(handler))]
+        c = np.stack([net.c[n] for n in net.species])
+        if rates:
+            r = net.rates if net.rates is not None else np.zeros((len(net.species), self.C))
+            return c, np.asarray(r)
+        return c
+
+    def close(self):
+        pass

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 def test_channels_match_reference(kind):
     from betse_b200.engine import TissueEngine
     cap = util.load_golden("mammal_ecm_chan")
-    eng = TissueEngine(util.group(cap, "cells."), util.group(cap, kind + ".p."), util.group(cap, kind + ".s0."))
+    eng = TissueEngine(util.mesh_of(cap, kind), util.group(cap, kind + ".p."), util.group(cap, kind + ".s0."))
     specs = util.channels_of(cap, kind)
     eng.set_channels(specs, phase_init=(kind == "init"))
     active = [c for c in specs if not (kind == "init" and not c["init_active"])]

@@ -25,7 +25,7 @@ def _attach(eng, desc, specs, phase_init):
 def test_network_matches_reference(kind):
     from betse_b200.engine import TissueEngine
     cap = util.load_golden("mammal_ecm_net")
-    eng = TissueEngine(util.group(cap, "cells."), util.group(cap, kind + ".p."), util.group(cap, kind + ".s0."))
+    eng = TissueEngine(util.mesh_of(cap, kind), util.group(cap, kind + ".p."), util.group(cap, kind + ".s0."))
     specs = util.channels_of(cap, kind)
     desc = util.networks_of(cap, kind)[0]
     _attach(eng, desc, specs, kind == "init")

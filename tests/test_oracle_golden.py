@@ -8,11 +8,11 @@ from oracle.betse_oracle import OracleSim
 from tests import util
 
 
-@pytest.mark.parametrize("name", util.GOLDEN)
+@pytest.mark.parametrize("name", [n for n in util.GOLDEN if n != "default_try"])   # full run: tests/test_full_run.py
 @pytest.mark.parametrize("kind", ["init", "sim"])
 def test_oracle_reproduces_reference(name, kind):
     cap = util.load_golden(name)
-    o = OracleSim(util.group(cap, "cells."), util.group(cap, kind + ".p."),
+    o = OracleSim(util.mesh_of(cap, kind), util.group(cap, kind + ".p."),
                   util.group(cap, kind + ".s0."), channels=util.channels_of(cap, kind), phase_init=(kind == "init"),
                   networks=util.networks_of(cap, kind))
     n = 0

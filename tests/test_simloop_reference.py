@@ -135,3 +135,86 @@ def test_unsupported_network_is_refused(monkeypatch, tmp_path):
     finally:
         simloop.uninstall()
     assert "membrane-permeable" in str(e.value)
+
+
+def _run_try(tmp_path, use_dropin, monkeypatch=None):
+    """`betse try` (seed + init + sim of the SHIPPED default config, cutting event included) -> the Simulator
+    after the SIM phase.  ``use_dropin``: through betse_b200.simloop with the device replaced by the CPU oracle."""
+    from oracle import refrun, refshim
+    refshim.bypass_science_init()
+    from betse.science.parameters import Parameters
+    from betse.science.simrunner import SimRunner
+    from betse.science.phase import phasecallbacks
+    from betse_b200 import network as netlib
+    from betse_b200 import simloop
+    from tests.oracle_engine import OracleEngine
+
+    engines = []
+    if use_dropin:
+        real_compile = netlib.compile_network
+
+        def compile_rec(desc, nc, nm, resolver=None):
+            rec = {}
+
+            def res(text):
+                v = resolver(text)
+                rec[text] = np.asarray(v, dtype=np.float64) if np.ndim(v) else float(v)
+                return v
+            comp = real_compile(desc, nc, nm, res)
+            comp["_desc"] = dict(desc, static=rec)
+            return comp
+
+        class Eng(OracleEngine):
+            def __init__(self, *a, **k):
+                super().__init__(*a, **k)
+                engines.append(self)
+
+        monkeypatch.setattr(netlib, "compile_network", compile_rec)
+        monkeypatch.setattr(simloop, "TissueEngine", Eng)
+        simloop.install()
+    try:
+        fn = refrun.write_config(str(tmp_path), {})
+        np.random.seed(12345)
+        p = Parameters.make(fn)
+        p.anim.is_while_sim = p.anim.is_after_sim = p.plot.is_after_sim = False
+        runner = SimRunner(p=p, callbacks=phasecallbacks.SimCallbacksNoop())
+        runner.seed()
+        runner.init()
+        phase = runner.sim()
+    finally:
+        if use_dropin:
+            simloop.uninstall()
+    return phase.sim, phase.cells, engines
+
+
+def test_betse_try_through_the_dropin_matches_the_reference(monkeypatch, tmp_path):
+    """The whole host side of the drop-in against the reference's own run of its shipped default configuration:
+    INIT (500 steps) and SIM (350 steps, cutting event at the first step, three voltage-gated channels, substance X),
+    sampled-step storage (`vm_time`, `cc_time`, ...) as `write2storage` leaves it.  The engine here is the CPU
+    oracle (tests/oracle_engine.py); the CUDA engine is held to the same recorded run in tests/test_full_run.py."""
+    ref_sim, ref_cells, _ = _run_try(tmp_path / "ref", False)
+    (tmp_path / "new").mkdir()
+    new_sim, new_cells, engines = _run_try(tmp_path / "new", True, monkeypatch)
+    assert len(engines) == 2                                  # one engine per phase
+    assert len(new_cells.mem_i) == len(ref_cells.mem_i) < engines[0].M      # the cut happened, on both paths alike
+    assert engines[1].M == len(ref_cells.mem_i)               # the SIM engine was built from the post-cut mesh
+    assert len(new_sim.time) == len(ref_sim.time) and np.allclose(new_sim.time, ref_sim.time, rtol=0, atol=0)
+    assert len(ref_sim.vm_time) >= 30
+    for a, r in zip(new_sim.vm_time, ref_sim.vm_time):
+        assert np.max(np.abs(a - r)) <= 1e-6                  # BASELINE.json: Vmem traces within 1e-6 V
+        assert np.max(np.abs(a - r)) <= 1e-9 * np.max(np.abs(r))
+    for name in ("cc_time", "cc_env_time", "gjopen_time", "vm_ave_time", "rho_cells_time", "I_mem_time",
+                 "venv_time", "efield_gj_x_time", "rate_NaKATP_time"):
+        got, want = getattr(new_sim, name), getattr(ref_sim, name)
+        assert len(got) == len(want) and len(want) >= 30, name
+        for a, r in zip(got, want):
+            a, r = np.asarray(a, dtype=float), np.asarray(r, dtype=float)
+            assert a.shape == r.shape, name
+            assert np.max(np.abs(a - r)) <= 1e-7 * max(np.max(np.abs(r)), 1e-300), name
+    # final state left on the Simulator
+    for f in ("cc_cells", "cc_env", "vm", "gjopen"):
+        a, r = np.asarray(getattr(new_sim, f)), np.asarray(getattr(ref_sim, f))
+        assert np.max(np.abs(a - r)) <= 1e-9 * np.max(np.abs(r)), f
+    x_new = new_sim.molecules.core.molecules["X"].c_cells
+    x_ref = ref_sim.molecules.core.molecules["X"].c_cells
+    assert np.max(np.abs(x_new - x_ref)) <= 1e-9 * np.max(np.abs(x_ref))

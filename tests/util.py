@@ -28,6 +28,12 @@ def group(cap, prefix):
     return {k[len(prefix):]: v for k, v in cap.items() if k.startswith(prefix)}
 
 
+def mesh_of(cap, kind):
+    """Mesh of a phase: the cutting event re-indexes the SIM-phase mesh (fixture default_try, oracle/refrun.py)."""
+    g = group(cap, kind + ".cells.")
+    return g if g else group(cap, "cells.")
+
+
 def snap_steps(cap, kind):
     return sorted({int(k.split(".")[1][1:]) for k in cap if k.startswith(kind + ".k")})
 
@@ -84,7 +90,7 @@ def gpu_tolerances(cap, kind, ref):
     """
     P = group(cap, kind + ".p.")
     S0 = group(cap, kind + ".s0.")
-    cells = group(cap, "cells.")
+    cells = mesh_of(cap, kind)
     zF = np.abs(np.asarray(S0["zs"], dtype=float)) * float(P["F"])
     cm, dt = float(P["cm"]), float(P["dt"])
 
