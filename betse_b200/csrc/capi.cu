@@ -32,6 +32,7 @@ cudaError_t prepare_kernels(int ni);
 unsigned tile_pack_size(int ni);
 void launch_hh_setup(const HHBuf& H, int ny, int nx, cudaStream_t st);
 void launch_hh(const KParams& P, const KArrays& A, const HHBuf& H, cudaStream_t st);
+void launch_phi_b(const KParams& P, const HHBuf& H, const double bound[4], double* phi, cudaStream_t st);
 void launch_pack_const(const KParams& P, const KArrays& A, cudaStream_t st);
 void launch_pack_dm(const KParams& P, const KArrays& A, cudaStream_t st);
 void launch_chan(const KParams& P, const KArrays& A, const KChan& ch, const KNet& N, int cur, cudaStream_t st);
@@ -63,6 +64,12 @@ struct betse_ctx {
     std::vector<KChan> chans;                // voltage-gated channels, applied in order
     HHBuf hh;                                // Helmholtz-Hodge diagnostics (sampled steps, undivided ECM tissues)
     bool hh_on = false;
+    bool poisson_on = false;                 // sine matrices + work buffers of the Dirichlet Poisson solve (HH, Phi_b)
+    // boundary-voltage potential Phi_b (ion_current.py:84-90): [new, old] while sim.bound_V ramps, see update_phi_b
+    double* phi[2] = {nullptr, nullptr};
+    int phi_new = 0;
+    bool phi_lag = false, phi_nz = false;
+    double bound_prev[4] = {0, 0, 0, 0};
     KNet nets[2];                            // network handlers: 0 general network, 1 gene regulatory network
     bool net_on[2] = {false, false};
     int net_nprog[2] = {0, 0};
@@ -449,6 +456,29 @@ extern "C" int betse_create(betse_ctx** out, const betse_mesh* mesh, const betse
     return 0;
 }
 
+static int ensure_phi(betse_ctx* ctx);
+
+// sine matrices, eigenvalues and work buffers of the Dirichlet Poisson solve on the env grid (csrc/hh.cu)
+static int ensure_poisson(betse_ctx* ctx)
+{
+    if (ctx->poisson_on) return 0;
+    int r;
+    HHBuf& H = ctx->hh;
+    memset(&H, 0, sizeof H);
+    const size_t my = ctx->ny - 2, mx = ctx->nx - 2;
+    if ((r = dev_alloc(ctx, &H.Sy, my * my))) return r;
+    if ((r = dev_alloc(ctx, &H.Sx, mx * mx))) return r;
+    if ((r = dev_alloc(ctx, &H.ly, my))) return r;
+    if ((r = dev_alloc(ctx, &H.lx, mx))) return r;
+    if ((r = dev_alloc(ctx, &H.bB, (size_t)ctx->E))) return r;
+    if ((r = dev_alloc(ctx, &H.R, my * mx))) return r;
+    if ((r = dev_alloc(ctx, &H.T1, my * mx))) return r;
+    launch_hh_setup(H, ctx->ny, ctx->nx, ctx->stream);
+    CK(cudaGetLastError());
+    ctx->poisson_on = true;
+    return 0;
+}
+
 static int ensure_diag_buffers(betse_ctx* ctx)
 {
     KArrays& A = ctx->A;
@@ -466,19 +496,10 @@ static int ensure_diag_buffers(betse_ctx* ctx)
     for (auto p : cell_arrays) if ((r = dev_alloc(ctx, p, ctx->C))) return r;
     // Helmholtz-Hodge decomposition of the env current (ion_current.py:50-73): undivided ECM tissues only
     if (ctx->hp.is_ecm && ctx->X.n_nbr == 0 && ctx->ny > 2 && ctx->nx > 2) {
+        if ((r = ensure_poisson(ctx))) return r;
         HHBuf& H = ctx->hh;
-        memset(&H, 0, sizeof H);
-        const size_t my = ctx->ny - 2, mx = ctx->nx - 2, E = ctx->E;
-        if ((r = dev_alloc(ctx, &H.Sy, my * my))) return r;
-        if ((r = dev_alloc(ctx, &H.Sx, mx * mx))) return r;
-        if ((r = dev_alloc(ctx, &H.ly, my))) return r;
-        if ((r = dev_alloc(ctx, &H.lx, mx))) return r;
-        double** eb[] = {&H.Jx, &H.Jy, &H.bA, &H.bB, &H.uA, &H.uB, &H.J_env_x, &H.J_env_y, &H.B_field, &H.Jtx, &H.Jty};
-        for (auto pp : eb) if ((r = dev_alloc(ctx, pp, E))) return r;
-        if ((r = dev_alloc(ctx, &H.R, my * mx))) return r;
-        if ((r = dev_alloc(ctx, &H.T1, my * mx))) return r;
-        launch_hh_setup(H, ctx->ny, ctx->nx, ctx->stream);
-        CK(cudaGetLastError());
+        double** eb[] = {&H.Jx, &H.Jy, &H.bA, &H.uA, &H.uB, &H.J_env_x, &H.J_env_y, &H.B_field, &H.Jtx, &H.Jty};
+        for (auto pp : eb) if ((r = dev_alloc(ctx, pp, ctx->E))) return r;
         ctx->hh_on = true;
     }
     destroy_graphs(ctx);   // KArrays changed
@@ -543,8 +564,14 @@ extern "C" int betse_upload_state(betse_ctx* ctx, const betse_state_host* s)
     if (s->Phi_b) {
         bool nz = false;
         for (int k = 0; k < E; ++k) if (s->Phi_b[k] != 0.0) { nz = true; break; }
-        if (nz || A.phi_b) {
-            if ((r = opt_array(ctx, &A.phi_b, (const double*)s->Phi_b, E))) return r;
+        for (int q = 0; q < 4; ++q) ctx->bound_prev[q] = ctx->hp.bound_V[q];
+        if (nz || ctx->phi[0]) {
+            // the uploaded potential belongs to the bound_V the Simulator holds now: new == old
+            if ((r = ensure_phi(ctx))) return r;
+            CK(cudaMemcpyAsync(ctx->phi[ctx->phi_new], s->Phi_b, (size_t)E * sizeof(double), cudaMemcpyHostToDevice, st));
+            A.phi_b = A.phi_b_old = ctx->phi[ctx->phi_new];
+            ctx->phi_lag = false;
+            ctx->phi_nz = nz;
             ctx->P.has_phi = nz ? 1 : 0;
             destroy_graphs(ctx);      // KParams is baked into the captured launches
         }
@@ -564,6 +591,51 @@ extern "C" int betse_upload_state(betse_ctx* ctx, const betse_state_host* s)
     return 0;
 }
 
+static int ensure_phi(betse_ctx* ctx)
+{
+    if (ctx->phi[0]) return 0;
+    int r;
+    if ((r = dev_alloc(ctx, &ctx->phi[0], (size_t)ctx->E))) return r;
+    if ((r = dev_alloc(ctx, &ctx->phi[1], (size_t)ctx->E))) return r;
+    ctx->A.phi_b = ctx->A.phi_b_old = ctx->phi[ctx->phi_new];
+    return 0;
+}
+
+// sim.bound_V changed (the external-voltage event, tissue/event/tisevevolt.py:76-88): Phi_b = lapENVinv . (-div_Jb)
+// (ion_current.py:84-90, 160-168) is re-solved on the device.  get_current runs inside update_V at the END of a step,
+// so the step that starts now still reads the Vmem formed with the previous potential (phi_b_old) and closes with
+// the new one (phi_b); betse_step retires the lag after that one step.
+static int update_phi_b(betse_ctx* ctx, const double bound[4])
+{
+    bool nz = false;
+    for (int q = 0; q < 4; ++q) nz = nz || bound[q] != 0.0;
+    for (int q = 0; q < 4; ++q) ctx->bound_prev[q] = bound[q];
+    if (!nz && !ctx->phi[0]) return 0;                 // never had a potential: Phi_b stays identically 0
+    if (ctx->X.n_nbr > 0) return fail(ctx, "domain decomposition does not support a boundary-voltage potential (Phi_b)");
+    if (ctx->ny <= 2 || ctx->nx <= 2) return fail(ctx, "env grid too small for the boundary-voltage solve");
+    int r;
+    if ((r = ensure_phi(ctx))) return r;
+    if ((r = ensure_poisson(ctx))) return r;
+    const int old = ctx->phi_new;
+    if (ctx->phi_lag) {
+        // two schedule changes without a step in between: the step still starts from `old`'s predecessor
+        if (nz) launch_phi_b(ctx->P, ctx->hh, bound, ctx->phi[ctx->phi_new], ctx->stream);
+        else CK(cudaMemsetAsync(ctx->phi[ctx->phi_new], 0, (size_t)ctx->E * sizeof(double), ctx->stream));
+    } else {
+        ctx->phi_new = old ^ 1;
+        if (nz) launch_phi_b(ctx->P, ctx->hh, bound, ctx->phi[ctx->phi_new], ctx->stream);
+        else CK(cudaMemsetAsync(ctx->phi[ctx->phi_new], 0, (size_t)ctx->E * sizeof(double), ctx->stream));
+        ctx->A.phi_b = ctx->phi[ctx->phi_new];
+        ctx->A.phi_b_old = ctx->phi[old];
+        ctx->phi_lag = true;
+    }
+    CK(cudaGetLastError());
+    ctx->phi_nz = nz;
+    ctx->P.has_phi = 1;                                // the old or the new potential may be non-zero
+    destroy_graphs(ctx);
+    return 0;
+}
+
 extern "C" int betse_set_schedule(betse_ctx* ctx, const betse_params* hp)
 {
     if (!ctx || !hp) return 2;
@@ -575,6 +647,9 @@ extern "C" int betse_set_schedule(betse_ctx* ctx, const betse_params* hp)
     ctx->P.has_phi = has_phi;
     destroy_graphs(ctx);              // KParams is baked into the captured launches
     launch_pack_dm(ctx->P, ctx->A, ctx->stream);   // DmS carries rho_channel/tm
+    bool bv = false;
+    for (int q = 0; q < 4; ++q) bv = bv || hp->bound_V[q] != ctx->bound_prev[q];
+    if (bv) { int r = update_phi_b(ctx, hp->bound_V); if (r) return r; }
     return 0;
 }
 
@@ -691,6 +766,16 @@ extern "C" int betse_step(betse_ctx* ctx, int nsteps, int flags, uint32_t* statu
     CK(cudaSetDevice(ctx->device));
     const bool want_diag = (flags & BETSE_STEP_DIAG) != 0;
     if (want_diag) { int r = ensure_diag_buffers(ctx); if (r) return r; }
+    const int asked = nsteps;
+    if (ctx->phi_lag && nsteps > 0) {
+        // first step after a change of sim.bound_V: starts from the old potential, closes with the new one
+        enqueue_step(ctx, (nsteps == 1 && want_diag) ? 1 : 0, nullptr);
+        ctx->A.phi_b_old = ctx->A.phi_b;
+        ctx->phi_lag = false;
+        ctx->P.has_phi = ctx->phi_nz ? 1 : 0;
+        destroy_graphs(ctx);
+        --nsteps;
+    }
     // warm the launch path once without capture (cudaFuncSetAttribute is not capturable)
     if (ctx->use_graphs && !ctx->graphs_built && nsteps > 2) {
         enqueue_step(ctx, 0, nullptr);
@@ -705,8 +790,8 @@ extern "C" int betse_step(betse_ctx* ctx, int nsteps, int flags, uint32_t* statu
         else enqueue_step(ctx, 0, nullptr);
     }
     CK(cudaGetLastError());
-    if (want_diag && nsteps > 0) ctx->diag_valid = true;
-    else if (nsteps > 0) ctx->diag_valid = false;
+    if (want_diag && asked > 0) ctx->diag_valid = true;
+    else if (asked > 0) ctx->diag_valid = false;
     return read_status(ctx, status_out);
 }
 
@@ -844,6 +929,10 @@ extern "C" int betse_download_sample(betse_ctx* ctx, betse_state_host* s)
         launch_expand_vm(ctx->P, A, Mo, ctx->Co, cur, st);
         DN(s->vm, A.vm_mem, Mo);
         DN(s->vm_ave, A.vm_ave, C);
+    }
+    if (s->Phi_b) {                                    // sim.Phi_b of the last update_V (ion_current.py:114, 171)
+        if (A.phi_b) CK(cudaMemcpyAsync(s->Phi_b, A.phi_b, (size_t)E * sizeof(double), cudaMemcpyDeviceToHost, st));
+        else memset(s->Phi_b, 0, (size_t)E * sizeof(double));
     }
     DN(s->gjopen, A.gjopen, Mo);
     DN(s->Dm_cells, A.Dm, IM);

@@ -201,6 +201,31 @@ static void poisson(const KParams& P, const HHBuf& H, const double* b, double* u
     k_hh_scatter<<<gI, 128, 0, st>>>(H.R, u, my, mx);
 }
 
+// -div_Jb of the boundary-voltage problem (ion_current.py:84-90 / 160-168): zero inside, +bound_V/d^2 on the border;
+// assignment order R, L, T, B — the top/bottom rows own the corners
+__global__ void k_phi_rhs(const __grid_constant__ KParams P, double* b, const double vT, const double vB, const double vL, const double vR)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int nx = P.nx, ny = P.ny;
+    if (x >= nx) return;
+    const double d2 = P.delta * P.delta;
+    double v = 0.0;
+    if (y == 0) v = -(-vB / d2);
+    else if (y == ny - 1) v = -(-vT / d2);
+    else if (x == 0) v = -(-vL / d2);
+    else if (x == nx - 1) v = -(-vR / d2);
+    b[(size_t)y * nx + x] = v;
+}
+
+// Phi_b = lapENVinv . (-div_Jb): the potential of an externally applied voltage (tissue/event/tisevevolt.py),
+// solved when sim.bound_V changes.  Uses the sine matrices and work buffers of the HH diagnostics.
+void launch_phi_b(const KParams& P, const HHBuf& H, const double bound[4], double* phi, cudaStream_t st)
+{
+    dim3 gE((P.nx + 127) / 128, P.ny);
+    k_phi_rhs<<<gE, 128, 0, st>>>(P, H.bB, bound[0], bound[1], bound[2], bound[3]);
+    poisson(P, H, H.bB, phi, st);
+}
+
 void launch_hh(const KParams& P, const KArrays& A, const HHBuf& H, cudaStream_t st)
 {
     const int E = P.nx * P.ny;

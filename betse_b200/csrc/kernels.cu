@@ -104,8 +104,8 @@ k_mem(const __grid_constant__ KParams P, const KArrays A, const int cur, const i
             if (is_ecm) cCao = A.cc_env[nxt][iCa * E + e];
         }
         if (PHI) {
-            vm_own -= ldg(A.phi_b + e);
-            vm_nb -= ldg(A.phi_b + ldgi(A.map_mem2ecm + ldgi(A.nn_i + m)));
+            vm_own -= ldg(A.phi_b_old + e);         // sim.vm of the step's start: update_V of the previous step (sim.py:2029)
+            vm_nb -= ldg(A.phi_b_old + ldgi(A.map_mem2ecm + ldgi(A.nn_i + m)));
         }
         // membrane side: electroflux adds 1e-25 to vBA (sim_toolbox.py:54); alpha for z = +1
         const double a1 = ((vm_own + FLOAT_NONCE) * P.F) * P.inv_RT_sim;
@@ -584,17 +584,17 @@ k_diag(const __grid_constant__ KParams P, const KArrays A, const int newb)
         const double Jmem = -dm + ((P.chan_charge && A.chanJ) ? A.chanJ[m] : (A.extra_J_mem ? ldg(A.extra_J_mem + m) : 0.0));
         A.Jmem[m] = Jmem; A.Jgj[m] = dg;
         Jn0 = Jmem + dg;
-        double phi = 0.0;
-        if (P.has_phi) phi = ldg(A.phi_b + ldgi(A.map_mem2ecm + m));
+        double phi = 0.0, phi_o = 0.0;
+        if (P.has_phi) { phi = ldg(A.phi_b + ldgi(A.map_mem2ecm + m)); phi_o = ldg(A.phi_b_old + ldgi(A.map_mem2ecm + m)); }
         vm = A.vm_cell[newb][c] - phi;
-        vmo = A.vm_cell[newb ^ 1][c] - phi;
+        vmo = A.vm_cell[newb ^ 1][c] - phi_o;
         A.vm_mem[m] = vm;
         A.dvm[m] = (vm - vmo) / P.dt;
         // gap-junction field of this step (update_gj, sim.py:2166-2172): from the Vmem the step started with
         {
             const int nnp = ldgi(A.nn_cell_flag + m);
             double vnb = A.vm_cell[newb ^ 1][nnp & 0x7fffffff];
-            if (P.has_phi) vnb -= ldg(A.phi_b + ldgi(A.map_mem2ecm + ldgi(A.nn_i + m)));
+            if (P.has_phi) vnb -= ldg(A.phi_b_old + ldgi(A.map_mem2ecm + ldgi(A.nn_i + m)));
             const double Egj = -(vnb - vmo) / P.gj_len;
             A.E_gj_x[m] = Egj * nxv; A.E_gj_y[m] = Egj * nyv;
         }

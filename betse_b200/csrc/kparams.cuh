@@ -71,6 +71,7 @@ struct KArrays {
     const double *Dm;        // [I,M]
     const double *Denv;      // [I,E]
     double *E_x, *E_y, *v_env, *v_raw, *rho_env, *rho_cells;
+    const double *phi_b_old;     // Phi_b the Vmem of the previous step was formed with (differs from phi_b while bound_V ramps)
     const double *phi_b, *extra_rho_cells, *extra_rho_env, *extra_J_mem;
     const double *NaK_block, *gj_block;
     double *flux_slots;      // [slots, I]

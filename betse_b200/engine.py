@@ -21,7 +21,7 @@ _DOWN_SHAPES = {
     "rate_NaKATP": "M", "Jmem": "M", "Jgj": "M", "Jn": "M", "I_mem": "M", "Jc": "M", "Emc": "M",
     "dvm": "M", "J_cell_x": "C", "J_cell_y": "C", "E_cell_x": "C", "E_cell_y": "C",
     "sigma_cell": "C", "E_gj_x": "M", "E_gj_y": "M",
-    "J_env_x": "E", "J_env_y": "E", "B_field": "E", "Jtx": "E", "Jty": "E",
+    "J_env_x": "E", "J_env_y": "E", "B_field": "E", "Jtx": "E", "Jty": "E", "Phi_b": "E",
 }
 DIAG_FIELDS = ("fluxes_mem", "fluxes_gj", "fluxes_env_x", "fluxes_env_y", "rate_NaKATP", "Jmem",
                "Jgj", "Jn", "I_mem", "Jc", "Emc", "dvm", "J_cell_x", "J_cell_y", "E_cell_x",
@@ -371,7 +371,7 @@ class TissueEngine:
                 cenv = np.empty(I)
                 sh.cenv_uniform = capi.ptr_f64(cenv)
                 continue
-            if not self.is_ecm and _DOWN_SHAPES.get(f, "").endswith("E"):
+            if not self.is_ecm and _DOWN_SHAPES.get(f, "").endswith("E") and f != "Phi_b":
                 continue
             if f not in _DOWN_SHAPES:
                 raise KeyError(f)

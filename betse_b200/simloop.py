@@ -45,7 +45,7 @@ _STATE_FIELDS = [
 _SCHEDULED = ["Dm_cells", "D_env", "TJ_modulator", "gj_block", "NaKATP_block", "c_env_bound", "T"]
 
 # attributes refreshed at sampled steps (read by write2storage and the exporters)
-_SAMPLED_STATE = ["cc_cells", "cc_at_mem", "cc_env", "vm", "vm_ave", "gjopen", "rho_cells"]
+_SAMPLED_STATE = ["cc_cells", "cc_at_mem", "cc_env", "vm", "vm_ave", "gjopen", "rho_cells", "Phi_b"]
 _SAMPLED_ENV = ["E_env_x", "E_env_y", "v_env", "rho_env"]
 _SAMPLED_DIAG = ["fluxes_mem", "fluxes_gj", "rate_NaKATP", "Jmem", "Jgj", "Jn", "I_mem", "Jc", "Emc",
                  "dvm", "J_cell_x", "J_cell_y", "E_cell_x", "E_cell_y", "sigma_cell"]
@@ -301,7 +301,9 @@ def run_sim_core_loop(sim, phase, time_steps, time_steps_sampled, anim_cells=Non
                         cache[f] = np.array(new, copy=True)
                 bv = getattr(sim, "bound_V", None)
                 if isinstance(bv, dict) and bv != bv_cache:
-                    raise BetseB200Error("the external-voltage event (tisevevolt.py) is not implemented")
+                    # the external-voltage event (tissue/event/tisevevolt.py:76-88): Phi_b is re-solved on the device
+                    eng.set_bound_V([bv["T"], bv["B"], bv["L"], bv["R"]])
+                    bv_cache = dict(bv)
                 run = 1
             else:
                 # no events: run up to and including the next sampled step in one call

@@ -160,6 +160,19 @@ SCENARIOS["mammal_ecm_net"] = dict(
     snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=net_extra)
 
 
+# The external-voltage event (tissue/event/tisevevolt.py: bound_V ramps, Phi_b = one Dirichlet Poisson solve per step,
+# ion_current.py:84-90, subtracted from Vmem in update_V, sim.py:2029) — ramp up, plateau and ramp down inside the
+# first 20 SIM steps, left/right electrodes so that it differs from the top/bottom default; ECM and no-ECM
+_VOLT = {"apply external voltage": {"event happens": True, "change start": 2.0e-4, "change finish": 1.4e-3,
+                                    "change rate": 2.0e-4, "peak voltage": 5.0e-3,
+                                    "positive voltage boundary": "left", "negative voltage boundary": "right"}}
+SCENARIOS["mammal_ecm_volt"] = dict(mods=_m(NO_NET, SMALL, _VOLT, {"general options": {"ion profile": "mammal"}}),
+                                    snaps={"init": [1, 2], "sim": [1, 2, 3, 5, 9, 16, 20]})
+SCENARIOS["basic_noecm_volt"] = dict(mods=_m(NO_NET, SMALL, _VOLT, {"apply external voltage": {
+    "positive voltage boundary": "top", "negative voltage boundary": "right"},
+    "general options": {"simulate extracellular spaces": False}}), snaps={"init": [1, 2], "sim": [1, 3, 9, 20]})
+
+
 # BASELINE configs[0] as SHIPPED (`betse try`): the unmodified default sim_config.yaml — basic ion profile, ECM on,
 # general network on (substance X grown in the 'Spot' profile, Nav1p3 / Kv1p5 / X-inhibited KLeak channels) and the
 # cutting event, which removes the 'surgery' wedge at the first SIM step.  Full phases (500 + 350 timesteps) with the

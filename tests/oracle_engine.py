@@ -58,6 +58,9 @@ class OracleEngine:
         else:
             setattr(o, name, np.array(value, dtype=float))
 
+    def set_bound_V(self, v):
+        self.set_field("bound_V", v)
+
     def step(self, n=1, diag=False):
         o = self._sim()
         o.diagnostics = True

@@ -137,7 +137,7 @@ def test_unsupported_network_is_refused(monkeypatch, tmp_path):
     assert "membrane-permeable" in str(e.value)
 
 
-def _run_try(tmp_path, use_dropin, monkeypatch=None):
+def _run_try(tmp_path, use_dropin, monkeypatch=None, mods=None):
     """`betse try` (seed + init + sim of the SHIPPED default config, cutting event included) -> the Simulator
     after the SIM phase.  ``use_dropin``: through betse_b200.simloop with the device replaced by the CPU oracle."""
     from oracle import refrun, refshim
@@ -173,7 +173,7 @@ def _run_try(tmp_path, use_dropin, monkeypatch=None):
         monkeypatch.setattr(simloop, "TissueEngine", Eng)
         simloop.install()
     try:
-        fn = refrun.write_config(str(tmp_path), {})
+        fn = refrun.write_config(str(tmp_path), mods or {})
         np.random.seed(12345)
         p = Parameters.make(fn)
         p.anim.is_while_sim = p.anim.is_after_sim = p.plot.is_after_sim = False
@@ -218,3 +218,20 @@ def test_betse_try_through_the_dropin_matches_the_reference(monkeypatch, tmp_pat
     x_new = new_sim.molecules.core.molecules["X"].c_cells
     x_ref = ref_sim.molecules.core.molecules["X"].c_cells
     assert np.max(np.abs(x_new - x_ref)) <= 1e-9 * np.max(np.abs(x_ref))
+
+
+def test_voltage_event_through_the_dropin_matches_the_reference(monkeypatch, tmp_path):
+    """The external-voltage event (tissue/event/tisevevolt.py): fire_events ramps sim.bound_V on the host, the loop
+    forwards it (TissueEngine.set_bound_V -> Phi_b re-solved by the engine), Vmem follows the reference's."""
+    from tests.golden import make_golden as mg
+    mods = mg.SCENARIOS["mammal_ecm_volt"]["mods"]
+    ref_sim, _, _ = _run_try(tmp_path / "ref", False, mods=mods)
+    (tmp_path / "new").mkdir()
+    new_sim, _, engines = _run_try(tmp_path / "new", True, monkeypatch, mods=mods)
+    assert "bound_V" in engines[1].sets
+    assert len(new_sim.vm_time) == len(ref_sim.vm_time) >= 30
+    for a, r in zip(new_sim.vm_time, ref_sim.vm_time):
+        assert np.max(np.abs(a - r)) <= 1e-9 * np.max(np.abs(r))
+    assert np.max(np.abs(ref_sim.vm_time[0] - ref_sim.vm_time[5])) > 1e-4       # plateau vs after the event: it acted
+    for a, r in zip(new_sim.cc_time, ref_sim.cc_time):
+        assert np.max(np.abs(np.asarray(a) - np.asarray(r))) <= 1e-9 * np.max(np.abs(np.asarray(r)))
