@@ -64,6 +64,7 @@ struct betse_ctx {
     std::vector<KChan> chans;                // voltage-gated channels, applied in order
     HHBuf hh;                                // Helmholtz-Hodge diagnostics (sampled steps, undivided ECM tissues)
     bool hh_on = false;
+    bool want_hh = true;
     bool poisson_on = false;                 // sine matrices + work buffers of the Dirichlet Poisson solve (HH, Phi_b)
     // boundary-voltage potential Phi_b (ion_current.py:84-90): [new, old] while sim.bound_V ramps, see update_phi_b
     double* phi[2] = {nullptr, nullptr};
@@ -161,6 +162,8 @@ static void fill_kparams(betse_ctx* ctx, const betse_params* hp)
     P.env_vol_div = hp->cell_height * (P.delta * P.delta);   // p.cell_height*cells.delta**2
     P.ko_eo_er = (hp->ko_env * hp->eo) * hp->er;
     P.screen = (2.0 / (hp->ko_env * P.delta)) * (hp->cell_radius / hp->true_cell_size);
+    P.true_cell_size = hp->true_cell_size; P.cell_radius = hp->cell_radius;
+    P.polar = hp->cell_polarizability != 0.0 ? 1 : 0;
     P.vol_env = hp->vol_env;
     P.sharpness = hp->sharpness;
     P.smooth_cells = hp->smooth_cells;
@@ -238,8 +241,12 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
 {
     if (hp->abi_version != BETSE_ABI_VERSION) return fail(ctx, "betse_params.abi_version mismatch");
     if (hp->n_ions < 4 || hp->n_ions > BETSE_MAX_IONS) return fail(ctx, "n_ions must be in [4,8]");
-    if (hp->cell_polarizability != 0.0)
-        return fail(ctx, "cell_polarizability != 0 (sim.py:2048-2080) is not supported by this build");
+    if (hp->cell_polarizability != 0.0) {
+        // Vmem becomes per-membrane state advanced from Jn every step (sim.py:2048-2080)
+        if (!mesh->R_rads) return fail(ctx, "cell_polarizability != 0 needs cells.R_rads");
+        if (mesh->n_cells_owned > 0 && mesh->n_cells_owned != mesh->n_cells)
+            return fail(ctx, "cell_polarizability != 0 on a domain-decomposed tissue is not implemented");
+    }
     if (hp->iNa < 0 || hp->iK < 0) return fail(ctx, "Na and K must be enabled");
     if (mesh->n_cells <= 0 || mesh->n_mems <= 0) return fail(ctx, "empty mesh");
     ctx->C = mesh->n_cells;
@@ -423,6 +430,11 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
     if ((r = dev_alloc(ctx, &A.status, 1))) return r;
     if ((r = dev_alloc(ctx, &A.vm_mem, Mo))) return r;
     if ((r = dev_alloc(ctx, &A.vm_ave, C))) return r;
+    if (hp->cell_polarizability != 0.0) {
+        if ((r = dev_alloc(ctx, &A.vm_pol[0], Mo))) return r;
+        if ((r = dev_alloc(ctx, &A.vm_pol[1], Mo))) return r;
+        if ((r = dev_upload(ctx, (double**)&A.R_rads, mesh->R_rads, Mo))) return r;
+    }
     if (hp->is_ecm && hp->sharpness < 1.0) { if ((r = dev_alloc(ctx, &A.scratch_env, IE))) return r; }
     if (!hp->is_ecm) {
         double cu[16];
@@ -543,6 +555,8 @@ extern "C" int betse_upload_state(betse_ctx* ctx, const betse_state_host* s)
     UP(A.gjopen, s->gjopen, Mo);
     UP(A.Dm, s->Dm_cells, IM);
     if (s->Dm_cells) launch_pack_dm(ctx->P, A, st);
+    if (ctx->P.polar && s->vm)
+        CK(cudaMemcpyAsync(A.vm_pol[cur], s->vm, (size_t)Mo * sizeof(double), cudaMemcpyHostToDevice, st));
     if (s->vm_cell) {
         CK(cudaMemcpyAsync(A.vm_cell[cur], s->vm_cell, (size_t)C * sizeof(double), cudaMemcpyHostToDevice, st));
     } else if (s->vm) {
@@ -641,7 +655,7 @@ extern "C" int betse_set_schedule(betse_ctx* ctx, const betse_params* hp)
     if (!ctx || !hp) return 2;
     CK(cudaSetDevice(ctx->device));
     if (hp->n_ions != ctx->I || hp->is_ecm != ctx->hp.is_ecm) return fail(ctx, "set_schedule cannot change n_ions/is_ecm");
-    if (hp->cell_polarizability != 0.0) return fail(ctx, "cell_polarizability != 0 unsupported");
+    if ((hp->cell_polarizability != 0.0) != (ctx->P.polar != 0)) return fail(ctx, "set_schedule cannot switch cell_polarizability on or off");
     const int has_phi = ctx->P.has_phi;
     fill_kparams(ctx, hp);
     ctx->P.has_phi = has_phi;
@@ -709,7 +723,7 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
         if (ecm) launch_field(ctx->P, A, ctx->ny, ctx->nx, st);
         if (evs) cudaEventRecord(evs[5], st);
         if (diag) launch_diag(I, ctx->P, A, ctx->n_ctas, nxt, st);
-        if (diag && ecm && ctx->hh_on && ctx->X.n_nbr == 0) {
+        if (diag && ctx->want_hh && ecm && ctx->hh_on && ctx->X.n_nbr == 0) {
             ctx->hh.mu = ctx->hp.mu;
             for (int q = 0; q < 4; ++q) ctx->hh.bound[q] = ctx->hp.bound_V[q];
             launch_hh(ctx->P, A, ctx->hh, st);
@@ -721,6 +735,10 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
 
 static void enqueue_step(betse_ctx* ctx, int diag, cudaEvent_t* evs)
 {
+    // cell_polarizability != 0: update_V integrates Vmem from Jn (sim.py:2059-2061), so get_current's membrane part
+    // (k_diag) belongs to every step; the Helmholtz-Hodge part stays with the sampled steps
+    ctx->want_hh = diag != 0;
+    if (ctx->P.polar) diag = 1;
     if (evs) cudaEventRecord(evs[0], ctx->stream);
     const bool nbr = ctx->X.n_nbr > 0;
     const int nxt = ctx->cur ^ 1;
@@ -765,7 +783,7 @@ extern "C" int betse_step(betse_ctx* ctx, int nsteps, int flags, uint32_t* statu
     if (!ctx || nsteps < 0) return 2;
     CK(cudaSetDevice(ctx->device));
     const bool want_diag = (flags & BETSE_STEP_DIAG) != 0;
-    if (want_diag) { int r = ensure_diag_buffers(ctx); if (r) return r; }
+    if (want_diag || ctx->P.polar) { int r = ensure_diag_buffers(ctx); if (r) return r; }
     const int asked = nsteps;
     if (ctx->phi_lag && nsteps > 0) {
         // first step after a change of sim.bound_V: starts from the old potential, closes with the new one
@@ -811,6 +829,7 @@ extern "C" int betse_update_v(betse_ctx* ctx)
 {
     if (!ctx) return 2;
     int r;
+    if (ctx->P.polar) return fail(ctx, "betse_update_v with cell_polarizability != 0: upload the Vmem of the loop entry instead (sim.py:1041 has run)");
     if ((r = betse_update_v_phase(ctx, 0))) return r;
     if (ctx->X.n_nbr > 0) {
         // ghost-cell Vmem / concentrations and the env halo rows of the CURRENT buffers
@@ -827,7 +846,7 @@ extern "C" int betse_step_phase(betse_ctx* ctx, int phase, int flags)
     if (!ctx || phase < 0 || phase > 2) return 2;
     CK(cudaSetDevice(ctx->device));
     const int diag = (flags & BETSE_STEP_DIAG) ? 1 : 0;
-    if (diag) { int r = ensure_diag_buffers(ctx); if (r) return r; }
+    if (diag || ctx->P.polar) { int r = ensure_diag_buffers(ctx); if (r) return r; }
     enqueue_phase(ctx, phase, diag, nullptr);
     CK(cudaGetLastError());
     if (phase == 2) ctx->diag_valid = diag != 0;
@@ -853,6 +872,7 @@ extern "C" int betse_step_profile(betse_ctx* ctx, int nsteps, float* total_ms,
 {
     if (!ctx || nsteps <= 0) return 2;
     CK(cudaSetDevice(ctx->device));
+    if (ctx->P.polar) { int r = ensure_diag_buffers(ctx); if (r) return r; }
     if (!ctx->ev_init) {
         for (auto& e : ctx->ev) CK(cudaEventCreate(&e));
         ctx->ev_init = true;
@@ -926,6 +946,7 @@ extern "C" int betse_download_sample(betse_ctx* ctx, betse_state_host* s)
         DN(s->rho_env, A.rho_env, E);
     }
     if (s->vm || s->vm_ave) {
+        if (ctx->P.polar) CK(cudaMemcpyAsync(A.vm_mem, A.vm_pol[cur], (size_t)Mo * sizeof(double), cudaMemcpyDeviceToDevice, st));
         launch_expand_vm(ctx->P, A, Mo, ctx->Co, cur, st);
         DN(s->vm, A.vm_mem, Mo);
         DN(s->vm_ave, A.vm_ave, C);

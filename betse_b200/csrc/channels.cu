@@ -84,7 +84,8 @@ k_chan(const __grid_constant__ KParams P, const KArrays A, const __grid_constant
         const int c = __ldg(A.mem_to_cells + m);
         const int e = __ldg(A.map_mem2ecm + m);
         double vm = A.vm_cell[cur][c];
-        if (P.has_phi) vm -= __ldg(A.phi_b_old + e);
+        if (P.polar) vm = A.vm_pol[cur][m];
+        else if (P.has_phi) vm -= __ldg(A.phi_b_old + e);
         double Pm = 0.0;
         if (!ch.mask || ch.mask[m]) {
             const double U = vm * 1000.0 + ch.shift;              // V = vm[targets]*1000 + v_corr (vg_na.py:91)

@@ -104,8 +104,13 @@ k_mem(const __grid_constant__ KParams P, const KArrays A, const int cur, const i
             if (is_ecm) cCao = A.cc_env[nxt][iCa * E + e];
         }
         if (PHI) {
-            vm_own -= ldg(A.phi_b_old + e);         // sim.vm of the step's start: update_V of the previous step (sim.py:2029)
-            vm_nb -= ldg(A.phi_b_old + ldgi(A.map_mem2ecm + ldgi(A.nn_i + m)));
+            if (P.polar) {                          // Vmem is membrane state (sim.py:2059-2061); vgj = vm[nn_i] - vm (sim.py:2166)
+                vm_own = A.vm_pol[cur][m];
+                vm_nb = A.vm_pol[cur][ldgi(A.nn_i + m)];
+            } else {
+                vm_own -= ldg(A.phi_b_old + e);     // sim.vm of the step's start: update_V of the previous step (sim.py:2029)
+                vm_nb -= ldg(A.phi_b_old + ldgi(A.map_mem2ecm + ldgi(A.nn_i + m)));
+            }
         }
         // membrane side: electroflux adds 1e-25 to vBA (sim_toolbox.py:54); alpha for z = +1
         const double a1 = ((vm_own + FLOAT_NONCE) * P.F) * P.inv_RT_sim;
@@ -563,6 +568,7 @@ k_diag(const __grid_constant__ KParams P, const KArrays A, const int newb)
 {
     __shared__ double s_a[BT_TPB], s_b[BT_TPB];
     __shared__ double s_c[BT_MAX_CTA_CELLS], s_d[BT_MAX_CTA_CELLS];
+    const bool polar = P.polar != 0;
     const int tid = threadIdx.x;
     const int c0 = ldgi(A.cta_cell_start + blockIdx.x), c1 = ldgi(A.cta_cell_start + blockIdx.x + 1);
     const int m0 = ldgi(A.cell_mem_ptr + c0), m1 = ldgi(A.cell_mem_ptr + c1);
@@ -586,15 +592,20 @@ k_diag(const __grid_constant__ KParams P, const KArrays A, const int newb)
         Jn0 = Jmem + dg;
         double phi = 0.0, phi_o = 0.0;
         if (P.has_phi) { phi = ldg(A.phi_b + ldgi(A.map_mem2ecm + m)); phi_o = ldg(A.phi_b_old + ldgi(A.map_mem2ecm + m)); }
-        vm = A.vm_cell[newb][c] - phi;
-        vmo = A.vm_cell[newb ^ 1][c] - phi_o;
-        A.vm_mem[m] = vm;
-        A.dvm[m] = (vm - vmo) / P.dt;
+        if (polar) {
+            vmo = A.vm_pol[newb ^ 1][m];               // Vmem the step started with; the new one needs Jn (below)
+        } else {
+            vm = A.vm_cell[newb][c] - phi;
+            vmo = A.vm_cell[newb ^ 1][c] - phi_o;
+            A.vm_mem[m] = vm;
+            A.dvm[m] = (vm - vmo) / P.dt;
+        }
         // gap-junction field of this step (update_gj, sim.py:2166-2172): from the Vmem the step started with
         {
             const int nnp = ldgi(A.nn_cell_flag + m);
             double vnb = A.vm_cell[newb ^ 1][nnp & 0x7fffffff];
-            if (P.has_phi) vnb -= ldg(A.phi_b_old + ldgi(A.map_mem2ecm + ldgi(A.nn_i + m)));
+            if (polar) vnb = A.vm_pol[newb ^ 1][ldgi(A.nn_i + m)];
+            else if (P.has_phi) vnb -= ldg(A.phi_b_old + ldgi(A.map_mem2ecm + ldgi(A.nn_i + m)));
             const double Egj = -(vnb - vmo) / P.gj_len;
             A.E_gj_x[m] = Egj * nxv; A.E_gj_y[m] = Egj * nyv;
         }
@@ -608,10 +619,16 @@ k_diag(const __grid_constant__ KParams P, const KArrays A, const int newb)
         double s = 0.0, sv = 0.0;
         for (int j = jb; j < je; ++j) { s += s_a[j]; sv += s_b[j]; }
         s_c[tid] = s / ldg(A.cell_sa + cc);
-        A.vm_ave[cc] = sv / ldg(A.num_mems + cc);
+        if (!polar) A.vm_ave[cc] = sv / ldg(A.num_mems + cc);
+        else {                                         // sigma_cell (sim.py:2018-2019) is needed by the Vmem update
+            double sg = 0.0;
+#pragma unroll
+            for (int i = 0; i < NI; ++i) sg += (((P.sig_k[i] * A.cc_cells[i * C + cc]) * P.D_free[i]) * 0.1) / P.R_T_p;
+            s_d[tid] = sg / (double)NI;
+        }
     }
     __syncthreads();
-    double Jn = 0.0;
+    double Jn = 0.0, Rr = 1.0;
     if (act) {
         const double nmem = ldg(A.num_mems + c);
         const double wm = (P.smooth_cells * nmem - 1.0) / (P.smooth_cells * nmem);   // sim.py:782-786
@@ -619,8 +636,50 @@ k_diag(const __grid_constant__ KParams P, const KArrays A, const int newb)
         Jn = wm * Jn0 + s_c[c - c0] * wo;
         A.Jn[m] = Jn;
         A.I_mem[m] = -Jn * sa;
+        if (polar) {
+            // implicit-Euler Vmem towards vm_o = rho_surf/cm through the cytosol conductance (sim.py:2057-2061)
+            Rr = ldg(A.R_rads + m);
+            const double sg = s_d[c - c0];
+            const double vm_o = A.vm_cell[newb][c];
+            const double dtcm = P.dt / P.cm;
+            vm = ((vmo - dtcm * Jn) + ((P.dt * sg) * vm_o) / (P.cm * Rr)) / (1.0 + (P.dt * sg) / (P.cm * Rr));
+            if (vm != vm) atomicOr(A.status, (unsigned)ST_NAN_VM);
+            A.vm_pol[newb][m] = vm;
+            A.vm_mem[m] = vm;
+            A.dvm[m] = (vm - vmo) / P.dt;
+        }
     }
     __syncthreads();
+    if (polar) {
+        // vm_ave, then the cell field from the Vmem spread over each cell (sim.py:2064-2076)
+        s_b[tid] = act ? vm : 0.0;
+        __syncthreads();
+        if (tid < nc) {
+            const int cc = c0 + tid;
+            const int jb = ldgi(A.cell_mem_ptr + cc) - m0, je = ldgi(A.cell_mem_ptr + cc + 1) - m0;
+            double sv = 0.0;
+            for (int j = jb; j < je; ++j) sv += s_b[j];
+            const double va = sv / ldg(A.num_mems + cc);
+            A.vm_ave[cc] = va;
+            s_c[tid] = va;
+        }
+        __syncthreads();
+        double gE = 0.0;
+        if (act) gE = (vm - s_c[c - c0]) / (Rr * (P.true_cell_size / P.cell_radius));
+        __syncthreads();
+        s_a[tid] = act ? ((-gE) * nxv) * sa : 0.0;
+        s_b[tid] = act ? ((-gE) * nyv) * sa : 0.0;
+        __syncthreads();
+        if (tid < nc) {
+            const int cc = c0 + tid;
+            const int jb = ldgi(A.cell_mem_ptr + cc) - m0, je = ldgi(A.cell_mem_ptr + cc + 1) - m0;
+            double sx = 0.0, sy = 0.0;
+            for (int j = jb; j < je; ++j) { sx += s_a[j]; sy += s_b[j]; }
+            const double csa = ldg(A.cell_sa + cc);
+            A.E_cell_x[cc] = sx / csa; A.E_cell_y[cc] = sy / csa;
+        }
+        __syncthreads();
+    }
     s_a[tid] = act ? (Jn * nxv) * sa : 0.0;
     s_b[tid] = act ? (Jn * nyv) * sa : 0.0;
     __syncthreads();
@@ -636,8 +695,7 @@ k_diag(const __grid_constant__ KParams P, const KArrays A, const int newb)
         for (int i = 0; i < NI; ++i) sg += (((P.sig_k[i] * A.cc_cells[i * C + cc]) * P.D_free[i]) * 0.1) / P.R_T_p;
         sg = sg / (double)NI;
         A.J_cell_x[cc] = Jx; A.J_cell_y[cc] = Jy; A.sigma_cell[cc] = sg;
-        const double Ecx = Jx / sg, Ecy = Jy / sg;
-        A.E_cell_x[cc] = Ecx; A.E_cell_y[cc] = Ecy;
+        if (!polar) { A.E_cell_x[cc] = Jx / sg; A.E_cell_y[cc] = Jy / sg; }
         s_c[tid] = Jx; s_d[tid] = Jy;
     }
     __syncthreads();
@@ -645,7 +703,8 @@ k_diag(const __grid_constant__ KParams P, const KArrays A, const int newb)
         const double Jx = s_c[c - c0], Jy = s_d[c - c0];
         A.Jc[m] = Jx * nxv + Jy * nyv;
         const double sg = A.sigma_cell[c];
-        A.Emc[m] = (Jx / sg) * nxv + (Jy / sg) * nyv;
+        if (polar) A.Emc[m] = A.E_cell_x[c] * nxv + A.E_cell_y[c] * nyv;      // sim.py:2079-2080
+        else A.Emc[m] = (Jx / sg) * nxv + (Jy / sg) * nyv;
     }
 }
 
@@ -653,7 +712,7 @@ k_diag(const __grid_constant__ KParams P, const KArrays A, const int newb)
 __global__ void k_expand_vm(const __grid_constant__ KParams P, const KArrays A, const int cur)
 {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= P.n_mems_owned) return;
+    if (m >= P.n_mems_owned || P.polar) return;      // polar: vm_mem already holds the membrane state
     double phi = 0.0;
     if (P.has_phi) phi = A.phi_b[A.map_mem2ecm[m]];
     A.vm_mem[m] = A.vm_cell[cur][A.mem_to_cells[m]] - phi;
@@ -704,7 +763,7 @@ static void launch_mem_t(const KParams& P, const KArrays& A, int n_ctas, int cur
                     !A.gj_block && !A.NaK_block && P.iNa == StdProf<NI>::iNa && P.iK == StdProf<NI>::iK &&
                     P.iCa == StdProf<NI>::iCa && !kmem_generic() && !P.defer;
     for (int i = 0; i < NI && std_prof; ++i) std_prof = (P.zi[i] == StdProf<NI>::z(i)) && P.zi[i] != 0;
-    if (P.has_phi) k_mem<NI, true, 2, 0><<<grid, BT_TPB, smem, st>>>(P, A, cur, diag);
+    if (P.has_phi || P.polar) k_mem<NI, true, 2, 0><<<grid, BT_TPB, smem, st>>>(P, A, cur, diag);
     else if (std_prof && kmem_pipe_enabled()) launch_mem_pipe(NI, P, A, g_n_sms, cur, st);
     else if (std_prof && minb2) k_mem<NI, false, 2, 1><<<grid, BT_TPB, smem, st>>>(P, A, cur, diag);
     else if (std_prof && kmem_minb() == 4) k_mem<NI, false, 4, 1><<<grid, BT_TPB, smem, st>>>(P, A, cur, diag);

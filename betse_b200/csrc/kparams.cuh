@@ -28,12 +28,14 @@ struct KParams {
     double NaK_block, gj_block;             // scalar blocks (used when the arrays are null)
     double delta, env_vol_div;              // env_vol_div = cell_height*delta^2
     double ecm_vol, memsa_mean, ko_eo_er;   // ko_env*eo*er
+    double true_cell_size, cell_radius;     // p.true_cell_size, p.cell_radius (sim.py:2068)
     double screen;                          // (2/(ko_env*delta))*(cell_radius/true_cell_size)
     double vol_env;                         // no-ECM bath volume
     double sharpness;
     double gw[5];                           // gaussian sigma=1 taps w0..w4 (normalised)
     double smooth_cells, R_T_p;             // R*T_p
     int is_ecm, v_sensitive_gj, cluster_open, fast_update_ecm;
+    int polar;                              // cell_polarizability != 0: Vmem is per-membrane state (sim.py:2048-2080)
     int has_phi;                            // Phi_b != 0 somewhere
     // local grid geometry (domain decomposition: rows [y0, y0+ny) of a ny_global-row grid)
     int ny, nx, y0, ny_global, y_own0, y_own1;
@@ -67,6 +69,8 @@ struct KArrays {
     double *cc_mid[2];       // [I,C] x2
     double *cc_env[2];       // [I,E] x2
     double *vm_cell[2];      // [C]   x2
+    double *vm_pol[2];       // [M]   x2: Vmem itself when cell_polarizability != 0 (then vm_cell is vm_o, sim.py:2057)
+    const double *R_rads;    // [M]   cells.R_rads (polarizability branch only)
     double *gjopen;          // [M]
     const double *Dm;        // [I,M]
     const double *Denv;      // [I,E]

@@ -64,7 +64,8 @@ k_net_gj(const __grid_constant__ KParams P, const KArrays A, const __grid_consta
             const double gjb = A.gj_block ? __ldg(A.gj_block + m) : P.gj_block;
             const double D = (__ldg(N.Dgj + k) * gjb) * A.gjopen[m];          // Dgj*sim.gj_block*sim.gjopen
             double va = A.vm_cell[cur][cn], vb = A.vm_cell[cur][c];
-            if (P.has_phi) { va -= __ldg(A.phi_b_old + __ldg(A.map_mem2ecm + __ldg(A.nn_i + m))); vb -= __ldg(A.phi_b_old + __ldg(A.map_mem2ecm + m)); }
+            if (P.polar) { va = A.vm_pol[cur][__ldg(A.nn_i + m)]; vb = A.vm_pol[cur][m]; }
+            else if (P.has_phi) { va -= __ldg(A.phi_b_old + __ldg(A.map_mem2ecm + __ldg(A.nn_i + m))); vb -= __ldg(A.phi_b_old + __ldg(A.map_mem2ecm + m)); }
             double vBA = va - vb;                                          // sim.vgj (sim.py:2166) ...
             for (int q = 0; q < nonces; ++q) vBA += FLOAT_NONCE;           // ... after the in-place `vBA += 1e-25` of every earlier electroflux call
             const double zc = __ldg(N.z + k) + FLOAT_NONCE;

@@ -163,8 +163,6 @@ def check_supported(sim, p):
             bad.append(what)
     if bool(getattr(p, "dynamic_noise", False)) and "P" in [str(x) for x in params_from_p(p)["ions"]]:
         bad.append("dynamic noise")
-    if float(getattr(p, "cell_polarizability", 0.0)) != 0.0:
-        bad.append("cell_polarizability != 0")
     if bad:
         raise BetseB200Error("betse_b200 does not implement: " + "; ".join(bad) +
                              " — run this configuration with the reference solver")

@@ -91,7 +91,7 @@ typedef struct betse_params {
     double cell_height, vol_env, cell_radius, true_cell_size;
     double ko_env;                     /* frozen at init_dynamics (sim.py:974)            */
     double sharpness;                  /* p.sharpness (<1: fd.integrator smoothing)       */
-    double cell_polarizability;        /* must be 0 in this version                       */
+    double cell_polarizability;        /* != 0: Vmem is per-membrane state integrated from Jn (sim.py:2048-2080) */
     double smooth_cells;               /* p.smooth_cells (Jn smoothing weights)           */
     double bound_V[4];                 /* T, B, L, R (sim.bound_V)                        */
     double gauss_w[5];                 /* taps w0..w4 of scipy's gaussian_filter(sigma=1) kernel

@@ -18,7 +18,7 @@ def _engine(cap, kind):
                         util.group(cap, kind + ".s0."))
 
 
-@pytest.mark.parametrize("name", [n for n in util.GOLDEN if "polar" not in n and "chan" not in n and "net" not in n and n != "default_try"])
+@pytest.mark.parametrize("name", [n for n in util.GOLDEN if "chan" not in n and "net" not in n and n != "default_try"])
 @pytest.mark.parametrize("kind", ["init", "sim"])
 def test_gpu_matches_reference(name, kind):
     cap = util.load_golden(name)
@@ -50,12 +50,3 @@ def test_gpu_matches_reference(name, kind):
             assert err <= tols[f], (name, kind, K, f, "abs err %.3e > tol %.3e (rel %.2e)" % (err, tols[f], rel))
     print(name, kind, {k: float("%.1e" % v) for k, v in worst.items()})
     eng.close()
-
-
-def test_polarizability_fails_loudly():
-    """cell_polarizability != 0 (sim.py:2048-2080) is not implemented: creation must refuse, not
-    silently compute something else."""
-    from betse_b200 import BetseB200Error
-    cap = util.load_golden("mammal_ecm_polar")
-    with pytest.raises(BetseB200Error):
-        _engine(cap, "init")

@@ -140,6 +140,14 @@ def gpu_tolerances(cap, kind, ref):
         smin = float(np.min(ref["sigma_cell"])) if "sigma_cell" in ref else 1.0
         for f in ("E_cell_x", "E_cell_y", "Emc"):
             tol[f] = tol["Jn"] / smin
+        if float(P["cell_polarizability"]) != 0.0:
+            # sim.py:2059-2076: Vmem integrates Jn (dt/cm per step), and the cell field is the area-weighted sum of
+            # (vm - vm_ave)/R over a closed polygon — differences of nearly equal Vmem values
+            tol["vm"] = tol["vm_ave"] = max(tol["vm"], tol["Jn"] * dt / cm)
+            tol["dvm"] = 2 * tol["vm"] / dt
+            rmin = float(np.min(cells["R_rads"])) * float(P["true_cell_size"]) / float(P["cell_radius"])
+            for f in ("E_cell_x", "E_cell_y", "Emc"):
+                tol[f] = 4 * tol["vm"] / rmin
     return tol
 
 
