@@ -100,7 +100,7 @@ class GateTerm(C.Structure):
 class Channel(C.Structure):
     _fields_ = [
         ("ion", C.c_int32), ("mpower", C.c_int32), ("hpower", C.c_int32), ("kind", C.c_int32 * 4),
-        ("handler", C.c_int32), ("mod_prog", C.c_int32), ("reserved", C.c_int32),
+        ("handler", C.c_int32), ("mod_prog", C.c_int32), ("same_gates", C.c_int32),
         ("a", GateTerm * 4), ("b", GateTerm * 4),
         ("time_unit", C.c_double), ("max_Dm", C.c_double), ("rel_perm", C.c_double), ("v_shift", C.c_double),
         ("target_mask", _bp), ("m0", _dp), ("h0", _dp),

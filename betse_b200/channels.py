@@ -76,6 +76,20 @@ def _hh(ion, mpow, hpow, mInf, mTau, hInf, hTau, shift=0.0, time_unit=1.0e3):
     return dict(ion=ion, time_unit=time_unit, mpow=mpow, hpow=hpow, shift=shift, q=[mInf, mTau, hInf, hTau])
 
 
+def _multi(model, ions, rel_perm, module, init_shift=None):
+    """A family that conducts several ions through one gate (vg_funny.py:73-74, cation.py:64-65): the ions are
+    applied one after the other with ``DChan = P*rel_perm[j]*maxDm*moddy`` (networks.py:3158-3203)."""
+    model = dict(model, ion=ions[0], ions=list(ions), rel_perm=[float(x) for x in rel_perm], module=module)
+    if init_shift is not None:
+        model["init_shift"] = float(init_shift)     # the class initialises its gates with another offset than it runs with
+    return model
+
+
+def _hcn(v0, s, tau, shift, pm_na=0.2, init_shift=None):
+    m = _hh("Na", 1, 0, _T(_sig(v0, s)), _T(_c(tau)), _T(_c(1.0)), _T(_c(1.0)), shift=shift)
+    return _multi(m, ["Na", "K", "Ca"], [pm_na, 1.0, 0.05], "vg_funny", init_shift)
+
+
 def _na_m(v0):          # the Hammil-type activation shared by Nav1p2/1p3/Rat1/Rat3 (vg_na.py:169-186 ...)
     a, b = _linoid(0.182, v0, 9.0), _linoid_neg(0.124, -v0, 9.0)
     return ("R", a, b), ("S", a, b)
@@ -153,8 +167,18 @@ MODELS = {
     "CaLeak": _leak("Ca"),                                                                    # :699-745
     # ---- vg_cl.py
     "ClLeak": _leak("Cl"),                                                                    # :132-175
+    # ---- vg_funny.py: hyperpolarisation-activated Na/K/Ca channels (ions, rel_perm: :73-74)
+    "HCN2": _hcn(-99.0, 6.2, 184.0, -10.0),                                                   # :134-191
+    "HCN4": _hcn(-100.0, 9.6, 461.0, -10.0),                                                  # :193-251
+    "HCN1": _hcn(-94.0, 8.1, 30.0, 0.0),                                                      # :253-289
+    "HCNLeak": _multi(_leak("Na"), ["Na", "K", "Ca"], [0.33, 1.0, 0.05], "vg_funny"),         # :291-344
+    "HCN2_cAMP": _hcn(-99.0, 6.2, 184.0, -20.0),                                              # :346-404
+    "HCN4_cAMP": _hcn(-100.0, 9.6, 461.0, -24.0, init_shift=-20.0),                           # :406-465 (init V-20, run V-24)
+    # ---- cation.py: non-selective leaks (ions, rel_perm: :64-65)
+    "CatLeak": _multi(_leak("Na"), ["Na", "K", "Ca"], [1.0, 1.0, 0.0], "cation"),             # :113-159
+    "CatLeak2": _multi(_leak("Na"), ["Na", "K", "Ca"], [1.0, 1.0, 1.0], "cation"),            # :162-208
 }
-# Not tabulated (refused at set-up): vg_ca.Cav3p1 (piecewise tau), vg_funny, cation, Morris-Lecar, wound.
+# Not tabulated (refused at set-up): vg_ca.Cav3p1 (piecewise tau), Morris-Lecar (no YAML channel class selects it), wound.
 
 CLASS_OF_ION = {"Na": "vg_na", "K": "vg_k", "Ca": "vg_ca", "Cl": "vg_cl"}
 
@@ -196,14 +220,26 @@ def gates(model, vm):
 def initial_state(model, vm):
     """m, h at the first time step (every tabulated model starts at its steady state:
     e.g. vg_na.py:210-228)."""
+    M = MODELS[model]
+    if "init_shift" in M:
+        U = np.asarray(vm, dtype=float) * 1000 + M["init_shift"]
+        return quantity(M["q"][0], U), quantity(M["q"][2], U)
     mInf, _, hInf, _ = gates(model, vm)
     return mInf, hInf
+
+
+def ions_of(model):
+    """(ions, rel_perm) a model conducts, in the order the reference applies them."""
+    M = MODELS[model]
+    return list(M.get("ions", [M["ion"]])), list(M.get("rel_perm", [1.0]))
 
 
 def make_channel(name, model, max_Dm, targets=None, init_active=True, rel_perm=1.0, m=None, h=None):
     """A channel spec as TissueEngine.set_channels expects it."""
     if model not in MODELS:
         raise KeyError("channel type %r is not tabulated (betse_b200/channels.py)" % model)
-    return {"name": name, "model": model, "ion": MODELS[model]["ion"], "maxDm": float(max_Dm),
+    ions, perms = ions_of(model)
+    return {"name": name, "model": model, "ion": ions[0], "ions": ions, "maxDm": float(max_Dm),
             "targets": None if targets is None else np.asarray(targets, dtype=np.int64),
-            "init_active": bool(init_active), "rel_perm": float(rel_perm), "m": m, "h": h}
+            "init_active": bool(init_active), "rel_perm": float(rel_perm) * perms[0],
+            "rel_perms": [float(rel_perm) * x for x in perms], "m": m, "h": h}

@@ -1010,6 +1010,14 @@ extern "C" int betse_set_channels(betse_ctx* ctx, int n, const betse_channel* ch
         const betse_channel& c = chs[k];
         if (c.ion < 0 || c.ion >= ctx->I) return fail(ctx, "channel ion index out of range");
         if (c.mpower < 0 || c.mpower > 8 || c.hpower < 0 || c.hpower > 8) return fail(ctx, "channel gate powers must be in [0,8]");
+        if (c.same_gates) {
+            // a further ion of the previous entry's channel (channel_core.ions[j], rel_perm[j]; networks.py:3158-3203)
+            if (k == 0) return fail(ctx, "channel entry 0 cannot share the gates of a previous entry");
+            KChan d = ctx->chans.back();
+            d.ion = c.ion; d.rel_perm = c.rel_perm; d.frozen = 1;
+            ctx->chans.push_back(d);
+            continue;
+        }
         if (!c.m0 || !c.h0) return fail(ctx, "channel needs initial gate states m0/h0");
         KChan d;
         memset(&d, 0, sizeof d);

@@ -87,7 +87,8 @@ k_chan(const __grid_constant__ KParams P, const KArrays A, const __grid_constant
         if (P.polar) vm = A.vm_pol[cur][m];
         else if (P.has_phi) vm -= __ldg(A.phi_b_old + e);
         double Pm = 0.0;
-        if (!ch.mask || ch.mask[m]) {
+        if (ch.frozen) Pm = ch.P[m];
+        else if (!ch.mask || ch.mask[m]) {
             const double U = vm * 1000.0 + ch.shift;              // V = vm[targets]*1000 + v_corr (vg_na.py:91)
             const double mInf = gate_quantity(ch, 0, U), mTau = gate_quantity(ch, 1, U);
             const double hInf = gate_quantity(ch, 2, U), hTau = gate_quantity(ch, 3, U);
@@ -97,7 +98,7 @@ k_chan(const __grid_constant__ KParams P, const KArrays A, const __grid_constant
             ch.m[m] = mm; ch.h[m] = hh;
             Pm = ipow(mm, ch.mpow) * ipow(hh, ch.hpow);            // vg_na.py:104
         }
-        ch.P[m] = Pm;
+        if (!ch.frozen) ch.P[m] = Pm;
         // moddy = eval(chan.alpha_eval_string) in the membrane zone (networks.py:3147; compiled by ratelaw.py)
         const double moddy = (ch.mod_prog >= 0) ? rl_eval(N, ch.mod_prog, c, m, A, C, P.n_mems_owned, cur, vm) : 1.0;
         const double DChan = ((Pm * ch.rel_perm) * ch.maxDm) * moddy;   // networks.py:3164

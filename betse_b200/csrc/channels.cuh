@@ -12,6 +12,8 @@ struct KChan {
     const unsigned char* mask;   // [M] targets (null = every membrane)
     double *m, *h, *P, *flux;    // [M] gate states, open probability, last flux
     double *D;                   // [M] DChan = P*rel_perm*maxDm*moddy (networks.py:3164)
+    int frozen;                  // this entry is a further conducted ion of the PREVIOUS entry's channel (multi-ion families:
+                                 // vg_funny, cation): same m/h/P arrays, gates already advanced (networks.py:3156-3158)
     int handler;                 // network handler the channel belongs to (0 general network, 1 gene network)
     int mod_prog;                // program of alpha_eval_string in that handler's table (< 0: moddy == 1)
 };

@@ -394,18 +394,32 @@ class TissueEngine:
         from . import channels as chlib
         specs = [c for c in specs if not (phase_init and not c["init_active"])]
         self.channel_names = [c.get("name", "chan%d" % k) for k, c in enumerate(specs)]
-        arr = (capi.Channel * max(1, len(specs)))()
-        keep = []
         idx = {n: i for i, n in enumerate(self.ions)}
-        for k, c in enumerate(specs):
+        # one C-ABI entry per (channel, conducted ion): multi-ion families (vg_funny, cation) follow their first
+        # entry with `same_gates` entries (networks.py:3158-3203: the gates advance once, each ion gets its flux)
+        entries, self._chan_entry = [], []
+        for c in specs:
             if c["model"] not in chlib.MODELS:
                 raise BetseB200Error("channel type %r is not tabulated (betse_b200/channels.py)" % c["model"])
+            ions, perms = chlib.ions_of(c["model"])
+            perms = list(c.get("rel_perms") or ([float(c.get("rel_perm", 1.0))] if len(ions) == 1 else perms))
+            for ion in ions:
+                if ion not in idx:
+                    raise BetseB200Error("channel %r conducts %s, which this ion profile does not simulate"
+                                         % (c.get("name"), ion))
+            self._chan_entry.append(len(entries))
+            entries += [(c, ion, float(pm), j) for j, (ion, pm) in enumerate(zip(ions, perms))]
+        arr = (capi.Channel * max(1, len(entries)))()
+        keep = []
+        for k, (c, ion_name, rel_perm, j) in enumerate(entries):
             mdl = chlib.MODELS[c["model"]]
-            if mdl["ion"] not in idx:
-                raise BetseB200Error("channel %r conducts %s, which this ion profile does not simulate"
-                                     % (c.get("name"), mdl["ion"]))
             d = arr[k]
-            d.ion, d.mpower, d.hpower = idx[mdl["ion"]], int(mdl["mpow"]), int(mdl["hpow"])
+            d.handler = int(c.get("handler", 0))
+            d.mod_prog = int(c.get("mod_prog", -1))
+            d.ion, d.rel_perm, d.same_gates = idx[ion_name], rel_perm, int(j > 0)
+            if j > 0:
+                continue
+            d.mpower, d.hpower = int(mdl["mpow"]), int(mdl["hpow"])
             for q, spec in enumerate(mdl["q"]):
                 d.kind[q] = chlib.KIND[spec[0]]
                 terms = [spec[1], spec[2] if len(spec) > 2 else (0, 0.0, 0.0, 0.0, 0.0)]
@@ -414,7 +428,7 @@ class TissueEngine:
                     for j in range(4):
                         dst.p[j] = float(t[1 + j])
             d.time_unit, d.max_Dm = float(mdl["time_unit"]), float(c["maxDm"])
-            d.rel_perm, d.v_shift = float(c.get("rel_perm", 1.0)), float(mdl["shift"])
+            d.v_shift = float(mdl["shift"])
             m0, h0 = np.ones(self.M), np.ones(self.M)
             tg = c.get("targets")
             if tg is None:
@@ -434,17 +448,15 @@ class TissueEngine:
             h0[tg] = np.asarray(chh, dtype=float) * np.ones(len(tg))
             keep += [m0, h0]
             d.m0, d.h0 = capi.ptr_f64(m0), capi.ptr_f64(h0)
-            # modulation by network substances: program index handed out by set_network
-            d.handler = int(c.get("handler", 0))
-            d.mod_prog = int(c.get("mod_prog", -1))
         if affect_charge is None:
             affect_charge = bool(self.p.get("substances_affect_charge", 0))
-        self._check(self.lib.betse_set_channels(self.ctx, len(specs), arr, int(bool(affect_charge))), "betse_set_channels")
+        self._check(self.lib.betse_set_channels(self.ctx, len(entries), arr, int(bool(affect_charge))), "betse_set_channels")
         self.n_channels = len(specs)
 
     def channel_state(self, k):
         """{'m','h','P','flux','DChan'} of channel ``k`` ([M] each)."""
         out = {f: np.empty(self.M) for f in ("m", "h", "P", "flux", "DChan")}
+        k = self._chan_entry[int(k)]         # flux / DChan: the last conducted ion's, as the reference leaves them (networks.py:3201-3203)
         self._check(self.lib.betse_channel_state(self.ctx, int(k), *(capi.ptr_f64(out[f]) for f in ("m", "h", "P", "flux", "DChan"))),
                     "betse_channel_state")
         return out

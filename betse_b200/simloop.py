@@ -140,10 +140,9 @@ def channels_from_sim(sim, p=None):
     for h, core in handlers:
         for name, chan in (getattr(core, "channels", None) or {}).items():
             cc = chan.channel_core
-            if len(cc.ions) != 1:
-                raise BetseB200Error("channel %r conducts %d ions; only single-ion channels are implemented" % (name, len(cc.ions)))
-            out.append({"name": name, "model": type(cc).__name__, "ion": cc.ions[0], "maxDm": float(chan.maxDm),
-                        "rel_perm": float(cc.rel_perm[0]), "init_active": bool(chan.init_active),
+            out.append({"name": name, "model": type(cc).__name__, "ion": cc.ions[0], "ions": list(cc.ions),
+                        "maxDm": float(chan.maxDm), "rel_perm": float(cc.rel_perm[0]),
+                        "rel_perms": [float(x) for x in cc.rel_perm], "init_active": bool(chan.init_active),
                         "targets": None if cc.targets is None else np.asarray(cc.targets),
                         "m": np.asarray(cc.m, dtype=float), "h": np.asarray(cc.h, dtype=float), "_obj": chan,
                         "handler": h, "mod_prog": -1})

@@ -202,7 +202,8 @@ typedef struct betse_channel {
     int32_t handler;              /* network handler the channel belongs to: 0 general network, 1 gene network */
     int32_t mod_prog;             /* program index of chan.alpha_eval_string (networks.py:3147) in that handler's
                                      betse_network, < 0: no modulation (moddy == 1)                */
-    int32_t reserved;
+    int32_t same_gates;           /* 1: a further conducted ion (channel_core.ions[j > 0], rel_perm[j]) of the
+                                     PREVIOUS entry's channel — only `ion` and `rel_perm` are read (vg_funny, cation) */
     betse_gate_term a[4], b[4];
     double time_unit;             /* channel_core.time_unit (1e3 for models in ms)                 */
     double max_Dm;                /* Channel.maxDm (networks.py:6559)                              */

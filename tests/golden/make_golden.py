@@ -107,6 +107,19 @@ SCENARIOS["mammal_ecm_chan"] = dict(
     snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=chan_extra)
 
 
+# multi-ion families: a hyperpolarisation-activated HCN2 (vg_funny.py: Na/K/Ca through one gate) on the whole tissue
+# and a non-selective cation leak (cation.py) on one tissue profile, next to a voltage-gated K channel
+CHANNELS_MULTI = [
+    {"name": "Funny", "channel class": "Fun", "channel type": "HCN2", "max Dm": 5.0e-16, "apply to": "all", "init active": True},
+    {"name": "Kv", "channel class": "K", "channel type": "Kv1p5", "max Dm": 1.0e-15, "apply to": "all", "init active": False},
+    {"name": "Leaky", "channel class": "Cat", "channel type": "CatLeak2", "max Dm": 2.0e-18, "apply to": ["Spot"], "init active": True},
+]
+SCENARIOS["mammal_ecm_chan_multi"] = dict(
+    mods=_m(SMALL, {"cutting event": {"event happens": False}, "general options": {"ion profile": "mammal"},
+                    "general network": {"implement network": True, "biomolecules": [], "channels": CHANNELS_MULTI}}),
+    snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=chan_extra)
+
+
 def _substance(name, prod, acts=None, inh=None, Dgj=1e-15, gj_imp=True, cell=0.1, z=0, apply_to="all"):
     gd = {"production rate": prod, "decay rate": 1.0, "apply to": apply_to, "modulator function": "None"}
     if acts:

@@ -14,7 +14,8 @@ def _ref_class(model):
     from oracle import refshim
     refshim.bypass_science_init()
     import importlib
-    mod = importlib.import_module("betse.science.channels." + ch.CLASS_OF_ION[ch.MODELS[model]["ion"]])
+    M = ch.MODELS[model]
+    mod = importlib.import_module("betse.science.channels." + M.get("module", ch.CLASS_OF_ION[M["ion"]]))
     return getattr(mod, model)
 
 
@@ -22,7 +23,8 @@ def _ref_class(model):
 def test_table_matches_reference_class(model):
     vm = np.linspace(-0.120, 0.060, 721) + 1.234e-5      # avoids the removable 0/0 points of the rates
     obj = _ref_class(model)()
-    obj.init(vm.copy(), None, None, targets=None)
+    import types
+    obj.init(vm.copy(), types.SimpleNamespace(mem_i=np.arange(len(vm))), None, targets=None)   # cation.py:47 reads cells.mem_i
     V = vm * 1000 + obj.v_corr
     m0, h0 = np.array(obj.m, dtype=float) * np.ones_like(vm), np.array(obj.h, dtype=float) * np.ones_like(vm)
     obj._calculate_state(V)
@@ -35,4 +37,5 @@ def test_table_matches_reference_class(model):
     assert np.max(np.abs(gm - m0)) < 1e-13 and np.max(np.abs(gh - h0)) < 1e-13
     M = ch.MODELS[model]
     assert float(obj._mpower) == M["mpow"] and float(obj._hpower) == M["hpow"]
-    assert obj.time_unit == M["time_unit"] and list(obj.ions) == [M["ion"]] and list(obj.rel_perm) == [1.0]
+    ions, perms = ch.ions_of(model)
+    assert obj.time_unit == M["time_unit"] and list(obj.ions) == ions and [float(x) for x in obj.rel_perm] == perms

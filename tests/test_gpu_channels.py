@@ -10,9 +10,10 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("kind", ["init", "sim"])
-def test_channels_match_reference(kind):
+@pytest.mark.parametrize("fixture", ["mammal_ecm_chan", "mammal_ecm_chan_multi"])   # _multi: vg_funny HCN2 + cation leak (Na/K/Ca each)
+def test_channels_match_reference(fixture, kind):
     from betse_b200.engine import TissueEngine
-    cap = util.load_golden("mammal_ecm_chan")
+    cap = util.load_golden(fixture)
     eng = TissueEngine(util.mesh_of(cap, kind), util.group(cap, kind + ".p."), util.group(cap, kind + ".s0."))
     specs = util.channels_of(cap, kind)
     eng.set_channels(specs, phase_init=(kind == "init"))
@@ -42,6 +43,8 @@ def test_channels_match_reference(kind):
                 assert np.max(np.abs(stt[f][tg] - r)) <= 1e-10 * max(np.max(np.abs(r)), 1e-300), (kind, K, c["name"], f)
             r = ref["chan%d.P" % j]
             assert np.max(np.abs(stt["P"] - r)) <= 1e-10 * max(np.max(np.abs(r)), 1e-300), (kind, K, c["name"], "P")
+            r = ref["chan%d.flux" % j]                      # chan_flux: the LAST conducted ion's flux (networks.py:3201)
+            assert np.max(np.abs(stt["flux"] - r)) <= max(1e-10 * np.max(np.abs(r)), tols["fluxes_mem"] if "fluxes_mem" in tols else 0.0), (kind, K, c["name"], "flux")
     eng.close()
 
 
