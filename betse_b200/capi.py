@@ -114,6 +114,7 @@ class Network(C.Structure):
         ("c_cells", _dp), ("code", _ip), ("prog_ptr", _ip), ("consts", _dp), ("cell_arrays", _dp),
         ("mem_arrays", _dp), ("growth_mask", _bp), ("stoich", _dp), ("Dgj", _dp), ("z", _dp),
         ("time_factor", _dp),
+        ("env_on", _bp), ("Dm", _dp), ("c_bound", _dp), ("c_env", _dp), ("D_env", _dp),
     ]
 
 
@@ -143,7 +144,8 @@ SYMBOLS = [
     "betse_step_profile", "betse_kernel_name", "betse_download_sample",
     "betse_step_phase", "betse_stream", "betse_sync", "betse_update_v", "betse_update_v_phase",
     "betse_set_row_ranges", "betse_window", "betse_attach_neighbor", "betse_exchange",
-    "betse_set_channels", "betse_channel_state", "betse_set_network", "betse_network_state", "betse_host_alloc", "betse_host_free",
+    "betse_set_channels", "betse_channel_state", "betse_set_network", "betse_network_state",
+    "betse_network_env_state", "betse_host_alloc", "betse_host_free",
 ]
 
 _lib = None
@@ -185,6 +187,7 @@ def load(build_if_missing=True):
     lib.betse_channel_state.argtypes = [vp, C.c_int, _dp, _dp, _dp, _dp, _dp]
     lib.betse_set_network.argtypes = [vp, C.c_int, C.POINTER(Network)]
     lib.betse_network_state.argtypes = [vp, C.c_int, _dp, _dp]
+    lib.betse_network_env_state.argtypes = [vp, C.c_int, _dp]
     lib.betse_step_phase.argtypes = [vp, C.c_int, C.c_int]
     lib.betse_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     lib.betse_host_free.argtypes = [vp]

@@ -36,7 +36,8 @@ void launch_phi_b(const KParams& P, const HHBuf& H, const double bound[4], doubl
 void launch_pack_const(const KParams& P, const KArrays& A, cudaStream_t st);
 void launch_pack_dm(const KParams& P, const KArrays& A, cudaStream_t st);
 void launch_chan(const KParams& P, const KArrays& A, const KChan& ch, const KNet& N, int cur, cudaStream_t st);
-void launch_net(const KParams& P, const KArrays& A, const KNet& N, const double* h_Dgj, int n_ions, int cur, cudaStream_t st);
+void launch_net(const KParams& P, const KArrays& A, const KNet& N, const double* h_Dgj, const double* h_Dm,
+                const unsigned char* h_env_on, int n_ions, int cur, cudaStream_t st);
 void launch_cell_update(const KParams& P, const KArrays& A, int cur, cudaStream_t st);
 void launch_xchg(const KParams& P, const KArrays& A, const XPlan& X, int which, int buf, int mode, cudaStream_t st);
 
@@ -75,6 +76,8 @@ struct betse_ctx {
     bool net_on[2] = {false, false};
     int net_nprog[2] = {0, 0};
     std::vector<double> net_Dgj[2];          // host copy (which substances pass gap junctions)
+    std::vector<double> net_Dm[2];           // host copy (which substances cross the membrane)
+    std::vector<unsigned char> net_env_on[2];
     std::string err;
     std::vector<void*> allocs;
     // CUDA graphs of one plain step, for cur = 0 and cur = 1
@@ -710,7 +713,8 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
             if (A.chanJ) cudaMemsetAsync(A.chanJ, 0, (size_t)ctx->Mo * sizeof(double), st);
             for (int h = 0; h < 2; ++h) {
                 for (const KChan& ch : ctx->chans) if (ch.handler == h) launch_chan(ctx->P, A, ch, ctx->nets[h], cur, st);
-                if (ctx->net_on[h]) launch_net(ctx->P, A, ctx->nets[h], ctx->net_Dgj[h].data(), I, cur, st);
+                if (ctx->net_on[h]) launch_net(ctx->P, A, ctx->nets[h], ctx->net_Dgj[h].data(), ctx->net_Dm[h].data(),
+                                               ctx->net_env_on[h].data(), I, cur, st);
             }
             launch_cell_update(ctx->P, A, cur, st);
         }
@@ -1130,6 +1134,25 @@ extern "C" int betse_set_network(betse_ctx* ctx, int handler, const betse_networ
     if ((r = dev_upload(ctx, (double**)&N.Dgj, net->Dgj, (size_t)K))) return r;
     if ((r = dev_upload(ctx, (double**)&N.z, net->z, (size_t)K))) return r;
     if ((r = dev_upload(ctx, (double**)&N.tdf, net->time_factor, (size_t)K))) return r;
+    ctx->net_Dm[handler].assign((size_t)K, 0.0);
+    ctx->net_env_on[handler].assign((size_t)K, 0);
+    if (net->env_on) {
+        bool any = false;
+        for (int k = 0; k < K; ++k) any = any || net->env_on[k] != 0;
+        if (any) {
+            if (!net->Dm || !net->c_bound || !net->c_env || !net->D_env) return fail(ctx, "network: env_on needs Dm, c_bound, c_env and D_env");
+            if (ctx->hp.sharpness < 1.0) return fail(ctx, "network substances in the environment with sharpness < 1 are not implemented");
+            const size_t E = (size_t)ctx->E;
+            if ((r = dev_upload(ctx, &N.c_env, net->c_env, (size_t)K * E))) return r;
+            if ((r = dev_alloc(ctx, &N.env_tmp, 2 * E))) return r;
+            if ((r = dev_alloc(ctx, &N.mem_delta, (size_t)K * C))) return r;
+            if ((r = dev_upload(ctx, (double**)&N.Dm, net->Dm, (size_t)K))) return r;
+            if ((r = dev_upload(ctx, (double**)&N.c_bound, net->c_bound, (size_t)K))) return r;
+            if ((r = dev_upload(ctx, (double**)&N.D_env, net->D_env, (size_t)K * E))) return r;
+            ctx->net_Dm[handler].assign(net->Dm, net->Dm + K);
+            ctx->net_env_on[handler].assign(net->env_on, net->env_on + K);
+        }
+    }
     if ((r = ensure_defer_buffers(ctx))) return r;
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->nets[handler] = N;
@@ -1149,6 +1172,20 @@ extern "C" int betse_network_state(betse_ctx* ctx, int handler, double* c_cells,
     if (c_cells) CK(cudaMemcpyAsync(c_cells, N.c, (size_t)N.K * ctx->C * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (rates) CK(cudaMemcpyAsync(rates, N.rates, (size_t)N.n_rates * ctx->C * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int betse_network_env_state(betse_ctx* ctx, int handler, double* c_env)
+{
+    if (!ctx || handler < 0 || handler > 1 || !c_env) return 2;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->net_on[handler]) return fail(ctx, "no network on this handler");
+    const KNet& N = ctx->nets[handler];
+    const size_t nb = (size_t)N.K * ctx->E * sizeof(double);
+    if (N.c_env) {
+        CK(cudaMemcpyAsync(c_env, N.c_env, nb, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    } else memset(c_env, 0, nb);
     return 0;
 }
 

@@ -34,6 +34,7 @@ k_net(const __grid_constant__ KParams P, const KArrays A, const __grid_constant_
         double d = 0.0;
         for (int j = 0; j < N.n_rates; ++j) d += __ldg(N.stoich + k * N.n_rates + j) * r[j];   // np.dot(reaction_matrix, all_rates)
         double cn = N.c[(size_t)k * C + c] + d * P.dt;                      // networks.py:2914
+        if (N.mem_delta && __ldg(N.Dm + k) != 0.0) cn = cn + N.mem_delta[(size_t)k * C + c] * P.dt;   // update_Co cell branch, sim_toolbox.py:1177-1181
         if (__ldg(N.Dgj + k) < 0.0 && cn < 0.0) { flags |= ST_NEG_NET; cn = 0.0; }
         N.c[(size_t)k * C + c] = cn;
     }
@@ -97,9 +98,136 @@ k_net_gj_apply(const __grid_constant__ KParams P, const KArrays A, const __grid_
     N.c[(size_t)k * P.n_cells + c] = cn;
 }
 
-void launch_net(const KParams& P, const KArrays& A, const KNet& N, const double* h_Dgj, int n_ions, int cur, cudaStream_t st)
+// ---------------------------------------------------------------------------- membrane + extracellular legs
+// Molecule.transport -> stb.molecule_mover (networks.py:5670-5700, sim_toolbox.py:909-1153) for substances with a
+// membrane permeability and/or a presence in the environment:
+//   k_net_mem       GHK flux between the env square of each membrane and its cell (sim_toolbox.py:943-954) from the
+//                   concentration the step STARTED with (cmems = cc_at_mem, refreshed by update_intra before this
+//                   step's growth/decay, networks.py:2832 + 5722-5724); per-cell sums for k_net, exchange slots for
+//   k_net_env_acc   update_Co env branch: c_env += div_env(-f)*dt (sim_toolbox.py:1189-1195, 1209-1234)
+//   k_sub_flux / k_sub_div   Dirichlet fill with c_bound, Nernst-Planck flux with D = Do*D_env_weight(*TJ factor),
+//                   divergence with fd.diff's edge rows, forward Euler times the time-dilation factor
+//                   (sim_toolbox.py:1061-1112); same stencil conventions as kernels.cu:k_ion.
+__global__ void __launch_bounds__(BT_TPB)
+k_net_mem(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ KNet N, const int k, const int cur)
+{
+    __shared__ double s_all[(BT_TPB / 32) * 32];
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * (BT_TPB / 32) + (threadIdx.x >> 5);
+    if (tile >= P.n_tiles) return;
+    double* s_f = s_all + (threadIdx.x >> 5) * 32;
+    const int4 td = __ldg(reinterpret_cast<const int4*>(A.tile_desc) + tile);
+    const int c0 = td.x, nc = td.y, m0 = td.z, nm = td.w;
+    const int C = P.n_cells, E = P.ny * P.nx;
+    const double Dm = __ldg(N.Dm + k);
+    const double zc = __ldg(N.z + k) + FLOAT_NONCE;
+    double fsa = 0.0;
+    if (lane < nm) {
+        const int m = m0 + lane;
+        const int c = __ldg(A.mem_to_cells + m);
+        const int e = __ldg(A.map_mem2ecm + m);
+        double vm = A.vm_cell[cur][c];
+        if (P.polar) vm = A.vm_pol[cur][m];
+        else if (P.has_phi) vm -= __ldg(A.phi_b_old + e);
+        const double alpha = ((zc * (vm + FLOAT_NONCE)) * P.F) / P.RT_sim;    // sim.T (sim_toolbox.py:947)
+        const double ex = exp(-alpha), deno = -expm1(-alpha);
+        const double cA = N.c_env[(size_t)k * E + e], cB = N.c[(size_t)k * C + c];
+        double f = -((Dm * alpha) / P.tm) * ((cB - cA * ex) / deno) * P.rho_channel;
+        if (!P.cluster_open && __ldg(A.nn_cell_flag + m) < 0) f = 0.0;        // f_X_ED[cells.bflags_mems] = 0
+        fsa = f * __ldg(A.mem_sa + m);
+        A.chan_slots[m] = fsa;
+    }
+    s_f[lane] = fsa;
+    __syncwarp();
+    if (lane < nc) {
+        const int c = c0 + lane;
+        const int jb = __ldg(A.cell_mem_ptr + c) - m0, je = __ldg(A.cell_mem_ptr + c + 1) - m0;
+        double S = 0.0;
+        for (int j = jb; j < je; ++j) S += s_f[j];
+        N.mem_delta[(size_t)k * C + c] = S / __ldg(A.cell_vol + c);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_net_env_acc(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ KNet N, const int k)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int E = P.nx * P.ny;
+    if (q >= E) return;
+    const int s0 = __ldg(A.slot_ptr + q), s1 = __ldg(A.slot_ptr + q + 1);
+    if (s1 == s0) return;
+    double acc = 0.0;
+    for (int j = s0; j < s1; ++j) acc += A.chan_slots[__ldg(A.slot_idx + j)];
+    double* c = N.c_env + (size_t)k * E + q;
+    *c = *c + ((-acc) / P.env_vol_div) * P.dt;
+}
+
+__device__ __forceinline__ double sub_cval(const double* __restrict__ c, const int y, const int x, const int ny, const int nx, const double cb)
+{
+    return (y == 0 || y == ny - 1 || x == 0 || x == nx - 1) ? cb : c[(size_t)y * nx + x];
+}
+
+__global__ void __launch_bounds__(256)
+k_sub_flux(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ KNet N, const int k)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int nx = P.nx, ny = P.ny;
+    if (x >= nx) return;
+    const int E = nx * ny;
+    const size_t q = (size_t)y * nx + x;
+    const double* __restrict__ c = N.c_env + (size_t)k * E;
+    const double cb = __ldg(N.c_bound + k);
+    const double inv_d = P.inv_delta, inv_2d = P.inv_2delta;
+    const double cc = sub_cval(c, y, x, ny, nx, cb);
+    double gcx, gcy;                                       // fd.gradient, finitediff.py:1236-1266
+    if (x == 0) gcx = (sub_cval(c, y, 1, ny, nx, cb) - cc) * inv_d;
+    else if (x == nx - 1) gcx = (cc - sub_cval(c, y, nx - 2, ny, nx, cb)) * inv_d;
+    else gcx = -(sub_cval(c, y, x - 1, ny, nx, cb) - sub_cval(c, y, x + 1, ny, nx, cb)) * inv_2d;
+    if (y == 0) gcy = (sub_cval(c, 1, x, ny, nx, cb) - cc) * inv_d;
+    else if (y == ny - 1) gcy = (cc - sub_cval(c, ny - 2, x, ny, nx, cb)) * inv_d;
+    else gcy = -(sub_cval(c, y - 1, x, ny, nx, cb) - sub_cval(c, y + 1, x, ny, nx, cb)) * inv_2d;
+    const double Dk = __ldg(N.D_env + (size_t)k * E + q);
+    const double al = (Dk * (__ldg(N.z + k) * P.q)) * P.inv_kbT_sim;          // nernst_planck_flux, sim_toolbox.py:409-411
+    N.env_tmp[q] = -Dk * gcx - (al * (-A.E_x[q])) * cc;
+    N.env_tmp[E + q] = -Dk * gcy - (al * (-A.E_y[q])) * cc;
+}
+
+__global__ void __launch_bounds__(256)
+k_sub_div(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ KNet N, const int k)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int nx = P.nx, ny = P.ny;
+    if (x >= nx) return;
+    const int E = nx * ny;
+    const size_t q = (size_t)y * nx + x;
+    const double* __restrict__ Fx = N.env_tmp;
+    const double* __restrict__ Fy = N.env_tmp + E;
+    const double inv_d = P.inv_delta, inv_2d = P.inv_2delta;
+    double dx, dy;                                         // fd.divergence(-fx, -fy) with fd.diff's edge rows (finitediff.py:1268-1311)
+    if (x == 0) dx = ((-Fx[q]) - (-Fx[q + 1])) * inv_d;
+    else if (x == nx - 1) dx = ((-Fx[q - 1]) - (-Fx[q])) * inv_d;
+    else dx = -((-Fx[q - 1]) - (-Fx[q + 1])) * inv_2d;
+    if (y == 0) dy = -((-Fy[q + nx]) - (-Fy[q])) * inv_d;
+    else if (y == ny - 1) dy = -((-Fy[q]) - (-Fy[q - nx])) * inv_d;
+    else dy = -((-Fy[q - nx]) - (-Fy[q + nx])) * inv_2d;
+    double* c = N.c_env + (size_t)k * E;
+    double cn = sub_cval(c, y, x, ny, nx, __ldg(N.c_bound + k)) + ((dx + dy) * P.dt) * __ldg(N.tdf + k);
+    if (cn < 0.0) { atomicOr(A.status, ST_NEG_NET); cn = 0.0; }            // sim_toolbox.py:1140-1150 raises
+    c[q] = cn;
+}
+
+void launch_net(const KParams& P, const KArrays& A, const KNet& N, const double* h_Dgj, const double* h_Dm,
+                const unsigned char* h_env_on, int n_ions, int cur, cudaStream_t st)
 {
     if (N.K <= 0) return;
+    const int tgrid = (P.n_tiles + (BT_TPB / 32) - 1) / (BT_TPB / 32);
+    const int E = P.nx * P.ny;
+    if (N.c_env)
+        for (int k = 0; k < N.K; ++k) {
+            if (!h_env_on[k] || h_Dm[k] == 0.0) continue;
+            k_net_mem<<<tgrid, BT_TPB, 0, st>>>(P, A, N, k, cur);
+            k_net_env_acc<<<(E + 255) / 256, 256, 0, st>>>(P, A, N, k);
+        }
     k_net<<<(P.n_cells_owned + 127) / 128, 128, 0, st>>>(P, A, N, cur);
     const int grid = (P.n_tiles + (BT_TPB / 32) - 1) / (BT_TPB / 32);
     int nonces = n_ions;
@@ -108,5 +236,13 @@ void launch_net(const KParams& P, const KArrays& A, const KNet& N, const double*
         ++nonces;
         k_net_gj<<<grid, BT_TPB, 0, st>>>(P, A, N, k, cur, nonces);
         k_net_gj_apply<<<(P.n_cells_owned + 255) / 256, 256, 0, st>>>(P, A, N, k);
+    }
+    if (N.c_env) {
+        dim3 gE((P.nx + 255) / 256, P.ny);
+        for (int k = 0; k < N.K; ++k) {
+            if (!h_env_on[k]) continue;
+            k_sub_flux<<<gE, 256, 0, st>>>(P, A, N, k);
+            k_sub_div<<<gE, 256, 0, st>>>(P, A, N, k);
+        }
     }
 }

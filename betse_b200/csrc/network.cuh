@@ -25,6 +25,13 @@ struct KNet {
     const double* Dgj;          // [K] gap-junction diffusion constant; < 0: ignoreGJ
     const double* z;            // [K]
     const double* tdf;          // [K] modify_time_factor
+    // membrane / extracellular legs (null when no substance of the handler has them)
+    double* c_env;              // [K][E] env concentrations
+    double* env_tmp;            // [E] scratch of the env transport
+    double* mem_delta;          // [K][C] sum_mems(f_mem*mem_sa)/cell_vol of this step's membrane flux
+    const double* Dm;           // [K]
+    const double* c_bound;      // [K]
+    const double* D_env;        // [K][E]
 };
 
 // One rate law at cell c (membrane m < 0: cell zone).

@@ -496,9 +496,19 @@ class TissueEngine:
             n.growth_mask = gm.ctypes.data_as(C.POINTER(C.c_uint8))
         n.stoich = f64(np.asarray(net["stoich"], dtype=float).reshape(K, n.n_rates))
         n.Dgj, n.z, n.time_factor = f64(net["Dgj"]), f64(net["z"]), f64(net["time_factor"])
+        env_on = np.asarray(net.get("env_on", np.zeros(K)), dtype=np.uint8).reshape(K)
+        if env_on.any():       # membrane / extracellular legs of molecule_mover (sim_toolbox.py:909-1153)
+            if not self.is_ecm:
+                raise BetseB200Error("network substances in the environment need extracellular spaces")
+            eo = np.ascontiguousarray(env_on)
+            keep.append(eo)
+            n.env_on = eo.ctypes.data_as(C.POINTER(C.c_uint8))
+            n.Dm, n.c_bound = f64(np.asarray(net["Dm"], dtype=float).reshape(K)), f64(np.asarray(net["c_bound"], dtype=float).reshape(K))
+            n.c_env = f64(np.asarray(net["c_env"], dtype=float).reshape(K, self.E))
+            n.D_env = f64(np.asarray(net["D_env"], dtype=float).reshape(K, self.E))
         self._check(self.lib.betse_set_network(self.ctx, int(handler), C.byref(n)), "betse_set_network")
         self.networks = getattr(self, "networks", {})
-        self.networks[int(handler)] = {"species": list(net["species"]), "n_rates": n.n_rates}
+        self.networks[int(handler)] = {"species": list(net["species"]), "n_rates": n.n_rates, "env_on": env_on.astype(bool)}
 
     def network_state(self, handler=0, rates=False):
         """Substance concentrations [K][C] (and the last rates [n_rates][C]) of a handler."""
@@ -509,6 +519,14 @@ class TissueEngine:
                                                  capi.ptr_f64(r) if rates else None), "betse_network_state")
         self.d2h_bytes += c.nbytes + (r.nbytes if rates else 0)
         return (c[:, :self.Co], r[:, :self.Co]) if rates else c[:, :self.Co]
+
+    def network_env_state(self, handler=0):
+        """Env concentrations [K][E] of a handler's substances (zeros for substances that live in the cells only)."""
+        info = self.networks[int(handler)]
+        c = np.empty((len(info["species"]), self.E))
+        self._check(self.lib.betse_network_env_state(self.ctx, int(handler), capi.ptr_f64(c)), "betse_network_env_state")
+        self.d2h_bytes += c.nbytes
+        return c
 
     # ------------------------------------------------------------------ domain decomposition
     def window(self):

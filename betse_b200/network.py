@@ -35,15 +35,15 @@ def unsupported_reasons(core, p):
             bad.append(what)
     for name, m in (getattr(core, "molecules", None) or {}).items():
         why = []
-        if float(getattr(m, "Dm", 0.0) or 0.0) != 0.0:
-            why.append("membrane-permeable (Dm != 0)")
         for flag, what in (("update_intra_conc", "update intracellular"), ("active_pumping", "active pumping"),
                            ("ion_channel_gating", "ligand gating"), ("change_bounds", "boundary change event"),
                            ("cell_clamp", "cell clamp"), ("transmem", "transmembrane transport")):
             if bool(getattr(m, flag, False)):
                 why.append(what)
-        if np.any(np.asarray(m.c_env) != 0.0) or float(getattr(m, "c_bound", 0.0) or 0.0) > 1.0e-15:
-            why.append("present in the environment (extracellular transport)")
+        if _in_env(m) and float(getattr(p, "sharpness", 1.0)) < 1.0:
+            why.append("extracellular transport with 'sharpness env' < 1")
+        if _in_env(m) and float(getattr(m, "Mu_mem", 0.0) or 0.0) != 0.0:
+            why.append("electrophoretic membrane mobility (Mu_mem)")
         if float(getattr(m, "z", 0.0) or 0.0) != 0.0 and bool(getattr(p, "substances_affect_charge", False)):
             why.append("charged substance with 'substances affect charge'")
         if why:
@@ -52,6 +52,14 @@ def unsupported_reasons(core, p):
         if str(getattr(r, "reaction_zone", "cell")) != "cell":
             bad.append("reaction %r outside the cell zone" % name)
     return bad
+
+
+def _in_env(m):
+    """Does the substance cross the membrane or exist outside the cells?  (molecule_mover: the membrane flux needs
+    Dm != 0, sim_toolbox.py:943-954; the extracellular transport runs when c_env is not identically 0 or the
+    boundary concentration is, sim_toolbox.py:1064-1066)"""
+    return (float(getattr(m, "Dm", 0.0) or 0.0) != 0.0 or bool(np.any(np.asarray(m.c_env) != 0.0))
+            or float(getattr(m, "c_bound", 0.0) or 0.0) > 1.0e-15)
 
 
 def describe_core(core, sim, p, cells, record_static=True):
@@ -81,6 +89,27 @@ def describe_core(core, sim, p, cells, record_static=True):
         "chan_mod_strings": [core.channels[c].alpha_eval_string for c in core.channels],
         "static": {},
     }
+    # Molecule.transport -> stb.molecule_mover (networks.py:5670-5700, sim_toolbox.py:909-1153): membrane and
+    # extracellular legs of the substances that have them
+    env_on = np.array([_in_env(core.molecules[s]) for s in species], dtype=np.uint8)
+    if env_on.any() and bool(getattr(p, "is_ecm", False)):
+        E = int(np.asarray(sim.D_env_weight).size)
+        D_env = np.zeros((K, E))
+        c_env = np.zeros((K, E))
+        for k, s in enumerate(species):
+            m = core.molecules[s]
+            if not env_on[k]:
+                continue
+            mult = np.ones(E)
+            if not bool(m.ignoreTJ):                    # sim_toolbox.py:1079-1085
+                mult = np.array(sim.D_env_weight, dtype=float).ravel().copy()
+                tj = np.asarray(sim.TJ_targets, dtype=np.int64)
+                mult[tj] = mult[tj] * float(m.TJ_factor)
+            D_env[k] = mult * float(m.Do)
+            c_env[k] = np.asarray(m.c_env, dtype=float)
+        desc.update({"env_on": env_on, "Dm": np.array([float(core.molecules[s].Dm or 0.0) for s in species]),
+                     "c_bound": np.array([float(core.molecules[s].c_bound or 0.0) for s in species]),
+                     "c_env": c_env, "D_env": D_env})
     if record_static:
         # resolve every static leaf once so that the description is self-contained
         rec = {}
@@ -121,7 +150,8 @@ def compile_network(desc, n_cells, n_mems, resolver=None):
             "mod_index": mod_index, "c_cells": np.asarray(desc["c_cells"], dtype=float), "stoich": stoich,
             "growth_mask": None if mask.all() else mask, "Dgj": np.asarray(desc["Dgj"], dtype=float),
             "z": np.asarray(desc["z"], dtype=float), "time_factor": np.asarray(desc["time_factor"], dtype=float),
-            "chan_names": list(desc["chan_names"])}
+            "chan_names": list(desc["chan_names"]),
+            **{k: np.asarray(desc[k]) for k in ("env_on", "Dm", "c_bound", "c_env", "D_env") if k in desc}}
 
 
 # ---- flat (npz-friendly) form of a description, used by the golden fixtures
@@ -134,6 +164,9 @@ def flatten(desc, prefix):
            prefix + "time_factor": desc["time_factor"], prefix + "chan_names": np.array(desc["chan_names"], dtype=str),
            prefix + "chan_mod_strings": np.array(desc["chan_mod_strings"], dtype=str),
            prefix + "static_keys": np.array(list(desc["static"].keys()), dtype=str)}
+    for k in ("env_on", "Dm", "c_bound", "c_env", "D_env"):
+        if k in desc:
+            out[prefix + k] = np.asarray(desc[k])
     for k, tg in enumerate(desc["growth_targets"]):
         out["%sgrowth_targets%d" % (prefix, k)] = np.asarray(tg, dtype=np.int64)
     for j, v in enumerate(desc["static"].values()):
@@ -145,7 +178,8 @@ def unflatten(cap, prefix):
     g = lambda k: cap[prefix + k]
     species = [str(x) for x in g("species")]
     keys = [str(x) for x in g("static_keys")]
-    return {"species": species, "ions": [str(x) for x in g("ions")], "c_cells": np.asarray(g("c_cells")),
+    return {**{k: np.asarray(cap[prefix + k]) for k in ("env_on", "Dm", "c_bound", "c_env", "D_env") if prefix + k in cap},
+            "species": species, "ions": [str(x) for x in g("ions")], "c_cells": np.asarray(g("c_cells")),
             "gad_strings": [str(x) for x in g("gad_strings")],
             "reaction_names": [str(x) for x in g("reaction_names")],
             "reaction_strings": [str(x) for x in g("reaction_strings")], "stoich": np.asarray(g("stoich")),

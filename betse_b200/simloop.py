@@ -232,10 +232,14 @@ def _copy_back(sim, eng, diag, sample_only=False):
     m2c = eng.mem_to_cells.astype(np.int64)
     for h, core in getattr(eng, "net_cores", {}).items():
         c, rates = eng.network_state(h, rates=True)
+        env_on = eng.networks[h].get("env_on")
+        cenv = eng.network_env_state(h) if env_on is not None and np.any(env_on) else None
         for k, name in enumerate(eng.networks[h]["species"]):
             mol = core.molecules[name]
             mol.c_cells = c[k].copy()
             mol.cc_at_mem = c[k][m2c]
+            if cenv is not None and env_on[k]:
+                mol.c_env = cenv[k].copy()
         nk = len(eng.networks[h]["species"])
         core.reaction_rates = rates[nk:].copy()
     # MasterOfNetworks.energy_charge (networks.py:3996-4012), the tail of run_loop; write_data appends it

@@ -256,6 +256,14 @@ typedef struct betse_network {
     const double  *Dgj;           /* [K] gap-junction diffusion constant; < 0: ignoreGJ             */
     const double  *z;             /* [K] charge                                                     */
     const double  *time_factor;   /* [K] modify_time_factor                                         */
+    /* Membrane and extracellular legs of Molecule.transport -> stb.molecule_mover (networks.py:5670-5700,
+     * sim_toolbox.py:909-1153).  env_on == NULL: every substance lives in the cells only. */
+    const uint8_t *env_on;        /* [K] 1: the substance crosses the membrane and/or exists in the environment */
+    const double  *Dm;            /* [K] membrane diffusion constant (0: no trans-membrane flux)    */
+    const double  *c_bound;       /* [K] concentration at the global boundary (Molecule.c_bound)     */
+    const double  *c_env;         /* [K][E] env concentrations at loop entry (rows with env_on == 0 are ignored) */
+    const double  *D_env;         /* [K][E] Do * D_env_weight (* TJ_factor on sim.TJ_targets) or Do where the
+                                     substance passes tight junctions (sim_toolbox.py:1075-1085)     */
 } betse_network;
 
 /* handler 0 = sim.molecules.core, 1 = sim.grn.core (run in that order, sim.py:1290-1318).  net == NULL
@@ -263,6 +271,8 @@ typedef struct betse_network {
 int  betse_set_network(betse_ctx *ctx, int handler, const betse_network *net);
 /* Substance concentrations [K][C] and the last rates [n_rates][C] (NULL members are skipped). */
 int  betse_network_state(betse_ctx *ctx, int handler, double *c_cells, double *rates);
+/* Env concentrations [K][E] of the substances (rows with env_on == 0 come back as zeros). */
+int  betse_network_env_state(betse_ctx *ctx, int handler, double *c_env);
 
 /* ---------------------------------------------------------------------------------------------
  * Multi-GPU: the tissue is cut into strips of env-grid rows; each rank owns the

@@ -173,6 +173,28 @@ SCENARIOS["mammal_ecm_net"] = dict(
     snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=net_extra)
 
 
+# Substances that cross the membrane and diffuse / electro-migrate through the extracellular grid (Molecule.transport ->
+# stb.molecule_mover, sim_toolbox.py:909-1153): S1 neutral, membrane- and gap-junction permeable, held back by tight
+# junctions; S2 extracellular only (bath + boundary), passes tight junctions; S3 a cation with a membrane permeability;
+# G1 regulated by S1 inside the cell.  'substances affect Vmem' off: charged substances then leave Vmem alone.
+def _env_substance(name, Dm, z, env, cell, gj_imp, tj_perm, tj_factor=1.0, prod=0.0, inh=None):
+    s = _substance(name, prod, inh=inh, Dgj=1e-15, gj_imp=gj_imp, cell=cell, z=z)
+    s.update({"Dm": Dm, "env conc": env, "TJ permeable": tj_perm, "TJ factor": tj_factor})
+    return s
+
+
+_ENV_BIO = [_env_substance("S1", 2.0e-17, 0, 0.5, 0.1, False, False, tj_factor=0.5),
+            _env_substance("S2", 0.0, 0, 0.2, 0.0, True, True),
+            _env_substance("S3", 5.0e-18, 1, 0.3, 0.05, True, False),
+            _substance("G1", 2.0, inh=[("S1", 0.2, 2)])]
+SCENARIOS["mammal_ecm_net_env"] = dict(
+    mods=_m(SMALL, {"cutting event": {"event happens": False}, "general options": {"ion profile": "mammal"},
+                    "internal parameters": {"substances affect Vmem": False},
+                    "general network": {"implement network": True, "biomolecules": _ENV_BIO, "reactions": [],
+                                        "channels": [dict(_NET_CH[2], **{"channel inhibitors": ["S1"]})]}}),
+    snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=net_extra)
+
+
 # The external-voltage event (tissue/event/tisevevolt.py: bound_V ramps, Phi_b = one Dirichlet Poisson solve per step,
 # ion_current.py:84-90, subtracted from Vmem in update_V, sim.py:2029) — ramp up, plateau and ramp down inside the
 # first 20 SIM steps, left/right electrodes so that it differs from the top/bottom default; ECM and no-ECM

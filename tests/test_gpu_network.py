@@ -22,9 +22,10 @@ def _attach(eng, desc, specs, phase_init):
 
 
 @pytest.mark.parametrize("kind", ["init", "sim"])
-def test_network_matches_reference(kind):
+@pytest.mark.parametrize("fixture", ["mammal_ecm_net", "mammal_ecm_net_env"])   # _env: membrane + extracellular transport of substances
+def test_network_matches_reference(fixture, kind):
     from betse_b200.engine import TissueEngine
-    cap = util.load_golden("mammal_ecm_net")
+    cap = util.load_golden(fixture)
     eng = TissueEngine(util.mesh_of(cap, kind), util.group(cap, kind + ".p."), util.group(cap, kind + ".s0."))
     specs = util.channels_of(cap, kind)
     desc = util.networks_of(cap, kind)[0]
@@ -49,8 +50,14 @@ def test_network_matches_reference(kind):
         want = ref["net0.c_cells"]
         for k, nme in enumerate(desc["species"]):
             assert util.rel_err(c[k], want[k]) <= 1e-10, (kind, K, nme, util.rel_err(c[k], want[k]))
-        rr = ref["net0.reaction_rates"]
-        assert util.rel_err(rates[-rr.shape[0]:], rr) <= 1e-10
+        if "net0.c_env" in ref:
+            ce = eng.network_env_state(0)
+            for k, nme in enumerate(desc["species"]):
+                if desc["env_on"][k]:
+                    assert util.rel_err(ce[k], ref["net0.c_env"][k]) <= 1e-10, (kind, K, nme, "env", util.rel_err(ce[k], ref["net0.c_env"][k]))
+        if "net0.reaction_rates" in ref:
+            rr = ref["net0.reaction_rates"]
+            assert util.rel_err(rates[-rr.shape[0]:], rr) <= 1e-10
         for k, ch in enumerate(active):
             j = [s["name"] for s in specs].index(ch["name"])
             stt = eng.channel_state(k)

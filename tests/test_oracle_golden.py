@@ -48,6 +48,11 @@ def test_oracle_reproduces_reference(name, kind):
             for k, nme in enumerate(net.species):
                 assert util.rel_err(net.c[nme], want[k]) < 1e-12, (name, kind, K, nme)
                 checked += 1
+            if "net%d.c_env" % h in ref:             # membrane / extracellular legs of molecule_mover (sim_toolbox.py:909-1153)
+                for k, nme in enumerate(net.species):
+                    if net.env_on[k]:
+                        assert util.rel_err(net.c_env[nme], ref["net%d.c_env" % h][k]) < 1e-12, (name, kind, K, nme, "env")
+                        checked += 1
             if "net%d.reaction_rates" % h in ref:
                 nrx = ref["net%d.reaction_rates" % h].shape[0]
                 assert util.rel_err(net.rates[-nrx:], ref["net%d.reaction_rates" % h]) < 1e-12

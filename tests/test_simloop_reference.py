@@ -110,7 +110,7 @@ def test_network_inputs_from_live_reference(monkeypatch, tmp_path):
 
 
 def test_unsupported_network_is_refused(monkeypatch, tmp_path):
-    """A membrane-permeable substance (Dm != 0) is outside the implemented subset: refused with the reason."""
+    """A substance with intracellular transport ('update intracellular') is outside the implemented subset: refused with the reason."""
     from oracle import refrun, refshim
     refshim.bypass_science_init()
     from betse.science.parameters import Parameters
@@ -121,7 +121,7 @@ def test_unsupported_network_is_refused(monkeypatch, tmp_path):
     from tests.golden import make_golden as mg
     import copy
     mods = copy.deepcopy(mg.SCENARIOS["mammal_ecm_net"]["mods"])
-    mods["general network"]["biomolecules"][3]["Dm"] = 1.0e-18
+    mods["general network"]["biomolecules"][3]["update intracellular"] = True
     simloop.install()
     try:
         fn = refrun.write_config(str(tmp_path), mods)
@@ -134,7 +134,7 @@ def test_unsupported_network_is_refused(monkeypatch, tmp_path):
             runner.init()
     finally:
         simloop.uninstall()
-    assert "membrane-permeable" in str(e.value)
+    assert "update intracellular" in str(e.value)
 
 
 def _run_try(tmp_path, use_dropin, monkeypatch=None, mods=None):
@@ -235,3 +235,21 @@ def test_voltage_event_through_the_dropin_matches_the_reference(monkeypatch, tmp
     assert np.max(np.abs(ref_sim.vm_time[0] - ref_sim.vm_time[5])) > 1e-4       # plateau vs after the event: it acted
     for a, r in zip(new_sim.cc_time, ref_sim.cc_time):
         assert np.max(np.abs(np.asarray(a) - np.asarray(r))) <= 1e-9 * np.max(np.abs(np.asarray(r)))
+
+
+def test_env_substances_through_the_dropin_match_the_reference(monkeypatch, tmp_path):
+    """Substances that cross the membrane and move through the extracellular grid (Molecule.transport ->
+    stb.molecule_mover): the shim derives D_env (D_env_weight, TJ factor), c_bound and the env concentrations from
+    the live objects, and copies c_env back for write_data (networks.py:4210-4226)."""
+    from tests.golden import make_golden as mg
+    mods = mg.SCENARIOS["mammal_ecm_net_env"]["mods"]
+    ref_sim, _, _ = _run_try(tmp_path / "ref", False, mods=mods)
+    (tmp_path / "new").mkdir()
+    new_sim, _, engines = _run_try(tmp_path / "new", True, monkeypatch, mods=mods)
+    for name in ("S1", "S2", "S3", "G1"):
+        a, r = new_sim.molecules.core.molecules[name], ref_sim.molecules.core.molecules[name]
+        assert len(a.c_cells_time) == len(r.c_cells_time) >= 30
+        for x, y in zip(a.c_cells_time + a.c_env_time, r.c_cells_time + r.c_env_time):
+            assert np.max(np.abs(np.asarray(x) - np.asarray(y))) <= 1e-9 * max(np.max(np.abs(np.asarray(y))), 1e-300), name
+    for a, r in zip(new_sim.vm_time, ref_sim.vm_time):
+        assert np.max(np.abs(a - r)) <= 1e-9 * np.max(np.abs(r))

@@ -13,6 +13,8 @@ mesh, p, state = synth.make_tissue(a.cells)
 sim, phase = bench.namespaces(mesh, p, state)
 T = {}
 def tic(): return time.perf_counter()
+_m, _p, _s = synth.make_tissue(2000)          # CUDA context + module load outside the measurements
+_e = TissueEngine(_m, _p, _s, device=0); _e.step(3); _e.close()
 t = tic(); m = simloop.mesh_from_cells(phase.cells); pr = simloop.params_from_p(phase.p); st = simloop.state_from_sim(sim); T["shim dicts"] = tic() - t
 t = tic(); eng = TissueEngine(m, pr, st, device=0); T["TissueEngine() incl. upload"] = tic() - t
 t = tic(); eng.step(10, diag=True); T["10 steps (first: graph build)"] = tic() - t
@@ -22,5 +24,13 @@ for grp, fields in (("state", simloop._SAMPLED_STATE), ("env", simloop._SAMPLED_
     nb = sum(x.nbytes for x in got.values())
     T["download %s (%d MB)" % (grp, nb >> 20)] = dt
 t = tic(); simloop._copy_back(sim, eng, diag=True); T["_copy_back(diag=True)"] = tic() - t
-t = tic(); eng.close(); T["close"] = tic() - t
+t = tic(); got = eng.download(list(simloop._W2S_STATE + simloop._W2S_ENV + simloop._W2S_DIAG + ["J_env_x", "J_env_y"]), pinned=True); T["download write2storage set, pinned, first (alloc)"] = tic() - t
+t = tic(); got = eng.download(list(simloop._W2S_STATE + simloop._W2S_ENV + simloop._W2S_DIAG + ["J_env_x", "J_env_y"]), pinned=True); T["download write2storage set, pinned (%d MB)" % (sum(x.nbytes for x in got.values()) >> 20)] = tic() - t
+t = tic(); eng.step(1, diag=True); T["1 step with diagnostics (k_diag + Helmholtz-Hodge)"] = tic() - t
+t = tic(); eng.step(1); T["1 step"] = tic() - t
+t = tic()
+for ptr, _ in eng.__dict__.pop("_pinned", {}).values():
+    eng.lib.betse_host_free(ptr)
+T["close: free pinned staging"] = tic() - t
+t = tic(); eng.close(); T["close: betse_destroy"] = tic() - t
 for k, v in T.items(): print("%-40s %8.1f ms" % (k, v * 1e3))
