@@ -115,6 +115,7 @@ class Network(C.Structure):
         ("mem_arrays", _dp), ("growth_mask", _bp), ("stoich", _dp), ("Dgj", _dp), ("z", _dp),
         ("time_factor", _dp),
         ("env_on", _bp), ("Dm", _dp), ("c_bound", _dp), ("c_env", _dp), ("D_env", _dp),
+        ("scale_factor", _dp), ("affect_charge", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

@@ -78,6 +78,7 @@ struct betse_ctx {
     std::vector<double> net_Dgj[2];          // host copy (which substances pass gap junctions)
     std::vector<double> net_Dm[2];           // host copy (which substances cross the membrane)
     std::vector<unsigned char> net_env_on[2];
+    bool net_affect[2] = {false, false};
     std::string err;
     std::vector<void*> allocs;
     // CUDA graphs of one plain step, for cur = 0 and cur = 1
@@ -711,6 +712,10 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
             // between the ion loop's fluxes and update_all_concs (sim.py:1290-1357), per handler: run_loop_channels
             // (networks.py:3115-3213), then run_loop (networks.py:2805-2982)
             if (A.chanJ) cudaMemsetAsync(A.chanJ, 0, (size_t)ctx->Mo * sizeof(double), st);
+            if (A.extra_Jenv_x) {                                            // clear_run_loop, networks.py:2799-2801
+                cudaMemsetAsync(A.extra_Jenv_x, 0, (size_t)ctx->E * sizeof(double), st);
+                cudaMemsetAsync(A.extra_Jenv_y, 0, (size_t)ctx->E * sizeof(double), st);
+            }
             for (int h = 0; h < 2; ++h) {
                 for (const KChan& ch : ctx->chans) if (ch.handler == h) launch_chan(ctx->P, A, ch, ctx->nets[h], cur, st);
                 if (ctx->net_on[h]) launch_net(ctx->P, A, ctx->nets[h], ctx->net_Dgj[h].data(), ctx->net_Dm[h].data(),
@@ -1002,7 +1007,7 @@ extern "C" int betse_set_channels(betse_ctx* ctx, int n, const betse_channel* ch
     ctx->chans.clear();
     destroy_graphs(ctx);
     ctx->P.defer = (n > 0 || ctx->net_on[0] || ctx->net_on[1]) ? 1 : 0;
-    ctx->P.chan_charge = (n > 0 && affect_charge) ? 1 : 0;
+    ctx->P.chan_charge = ((n > 0 && affect_charge) || ctx->net_affect[0] || ctx->net_affect[1]) ? 1 : 0;
     if (!ctx->P.defer) return 0;
     if (!A.dsum_m) {
         if ((r = dev_alloc(ctx, &A.dsum_m, (size_t)ctx->I * ctx->C))) return r;
@@ -1154,6 +1159,27 @@ extern "C" int betse_set_network(betse_ctx* ctx, int handler, const betse_networ
         }
     }
     if ((r = ensure_defer_buffers(ctx))) return r;
+    ctx->net_affect[handler] = false;
+    if (net->affect_charge) {
+        // sim.extra_rho_cells / extra_rho_env / extra_J_mem / extra_Jenv are the handler's arrays from now on
+        // (networks.py:2971-2977: published every step, whatever the substances' charges)
+        std::vector<double> ones((size_t)K, 1.0);
+        N.affect = 1;
+        if ((r = dev_upload(ctx, (double**)&N.scale, net->scale_factor ? net->scale_factor : ones.data(), (size_t)K))) return r;
+        if ((r = dev_alloc(ctx, &N.fmem_tmp, (size_t)Mo))) return r;
+        if ((r = dev_alloc(ctx, &N.rho_cells, (size_t)C))) return r;
+        ctx->A.extra_rho_cells = N.rho_cells;
+        if (N.c_env) {
+            if ((r = dev_alloc(ctx, &N.rho_env, (size_t)ctx->E))) return r;
+            ctx->A.extra_rho_env = N.rho_env;
+            if (!ctx->A.extra_Jenv_x) {
+                if ((r = dev_alloc(ctx, &ctx->A.extra_Jenv_x, (size_t)ctx->E))) return r;
+                if ((r = dev_alloc(ctx, &ctx->A.extra_Jenv_y, (size_t)ctx->E))) return r;
+            }
+        }
+        ctx->net_affect[handler] = true;
+        ctx->P.chan_charge = 1;
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->nets[handler] = N;
     ctx->net_Dgj[handler].assign(net->Dgj, net->Dgj + K);

@@ -38,6 +38,7 @@ __global__ void k_hh_J(const __grid_constant__ KParams P, const KArrays A, HHBuf
         jx = fma(P.zF[i], A.fl_env_x[(size_t)i * E + k], jx);
         jy = fma(P.zF[i], A.fl_env_y[(size_t)i * E + k], jy);
     }
+    if (A.extra_Jenv_x) { jx += A.extra_Jenv_x[k]; jy += A.extra_Jenv_y[k]; }      // + sim.extra_Jenv_x (ion_current.py:53-54)
     H.Jx[k] = jx; H.Jy[k] = jy;
 }
 

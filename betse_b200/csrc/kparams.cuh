@@ -92,4 +92,5 @@ struct KArrays {
     double *dsum_m, *dsum_g; // [I,C] deferred sums of f_mem*sa and f_gj*sa per cell
     double *chan_slots;      // [M]   f*sa of the channel being applied (membrane -> env exchange)
     double *chanJ;           // [M]   extra_J_mem accumulated over the channels of this step
+    double *extra_Jenv_x, *extra_Jenv_y;   // [E] charged network substances moving through the env grid (networks.py:2953-2954)
 };

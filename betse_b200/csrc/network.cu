@@ -44,7 +44,7 @@ k_net(const __grid_constant__ KParams P, const KArrays A, const __grid_constant_
 // gap-junction transport of substance k: per-cell sum of -f_gj*mem_sa (one warp per tile, the packing of k_mem)
 __global__ void __launch_bounds__(BT_TPB)
 k_net_gj(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ KNet N, const int k, const int cur,
-         const int nonces)
+         const int nonces, const int has_mem)
 {
     __shared__ double s_all[(BT_TPB / 32) * 32];
     const int lane = threadIdx.x & 31;
@@ -61,6 +61,7 @@ k_net_gj(const __grid_constant__ KParams P, const KArrays A, const __grid_consta
         const int c = __ldg(A.mem_to_cells + m);
         const int nnp = __ldg(A.nn_cell_flag + m);
         const int cn = nnp & 0x7fffffff;
+        double fgj = 0.0;
         if (nnp >= 0) {                                                    // fgj_X[cells.bflags_mems] = 0
             const double gjb = A.gj_block ? __ldg(A.gj_block + m) : P.gj_block;
             const double D = (__ldg(N.Dgj + k) * gjb) * A.gjopen[m];          // Dgj*sim.gj_block*sim.gjopen
@@ -75,6 +76,12 @@ k_net_gj(const __grid_constant__ KParams P, const KArrays A, const __grid_consta
             const double cA = cc[c], cB = cc[cn];                          // cX_mems[mem_i], cX_mems[nn_i]
             const double f = -((D * alpha) / P.gj_len) * ((cB - cA * ex) / deno);
             fsa = -f * __ldg(A.mem_sa + m);
+            fgj = f;
+        }
+        if (N.affect) {                                                    // networks.py:2946
+            const double z = __ldg(N.z + k), sc = __ldg(N.scale + k);
+            const double fm = has_mem ? N.fmem_tmp[m] : 0.0;
+            A.chanJ[m] += (((-z) * fm) * P.F) * sc + ((z * fgj) * P.F) * sc;
         }
     }
     s_f[lane] = fsa;
@@ -136,6 +143,13 @@ k_net_mem(const __grid_constant__ KParams P, const KArrays A, const __grid_const
         if (!P.cluster_open && __ldg(A.nn_cell_flag + m) < 0) f = 0.0;        // f_X_ED[cells.bflags_mems] = 0
         fsa = f * __ldg(A.mem_sa + m);
         A.chan_slots[m] = fsa;
+        if (N.affect) {
+            if (__ldg(N.Dgj + k) >= 0.0) N.fmem_tmp[m] = f;                  // joined with f_gj in k_net_gj
+            else {                                                          // networks.py:2946 with f_gj == 0
+                const double z = __ldg(N.z + k), sc = __ldg(N.scale + k);
+                A.chanJ[m] += (((-z) * f) * P.F) * sc + ((z * 0.0) * P.F) * sc;
+            }
+        }
     }
     s_f[lane] = fsa;
     __syncwarp();
@@ -146,6 +160,18 @@ k_net_mem(const __grid_constant__ KParams P, const KArrays A, const __grid_const
         for (int j = jb; j < je; ++j) S += s_f[j];
         N.mem_delta[(size_t)k * C + c] = S / __ldg(A.cell_vol + c);
     }
+}
+
+// extra_rho_cells / extra_rho_env of the handler: F*c*z*scale_factor over its substances (networks.py:2945, 2950)
+__global__ void __launch_bounds__(256)
+k_net_charge(const __grid_constant__ KParams P, const __grid_constant__ KNet N, const int n, const int stride, const int env)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const double* __restrict__ src = env ? N.c_env : N.c;
+    double rho = 0.0;
+    for (int k = 0; k < N.K; ++k) rho += ((P.F * src[(size_t)k * stride + q]) * __ldg(N.z + k)) * __ldg(N.scale + k);
+    (env ? N.rho_env : N.rho_cells)[q] = rho;
 }
 
 __global__ void __launch_bounds__(256)
@@ -188,8 +214,15 @@ k_sub_flux(const __grid_constant__ KParams P, const KArrays A, const __grid_cons
     else gcy = -(sub_cval(c, y - 1, x, ny, nx, cb) - sub_cval(c, y + 1, x, ny, nx, cb)) * inv_2d;
     const double Dk = __ldg(N.D_env + (size_t)k * E + q);
     const double al = (Dk * (__ldg(N.z + k) * P.q)) * P.inv_kbT_sim;          // nernst_planck_flux, sim_toolbox.py:409-411
-    N.env_tmp[q] = -Dk * gcx - (al * (-A.E_x[q])) * cc;
-    N.env_tmp[E + q] = -Dk * gcy - (al * (-A.E_y[q])) * cc;
+    const double fx = -Dk * gcx - (al * (-A.E_x[q])) * cc;
+    const double fy = -Dk * gcy - (al * (-A.E_y[q])) * cc;
+    N.env_tmp[q] = fx;
+    N.env_tmp[E + q] = fy;
+    if (N.affect) {                                                        // networks.py:2953-2954
+        const double z = __ldg(N.z + k), sc = __ldg(N.scale + k);
+        A.extra_Jenv_x[q] += ((fx * z) * P.F) * sc;
+        A.extra_Jenv_y[q] += ((fy * z) * P.F) * sc;
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -234,7 +267,7 @@ void launch_net(const KParams& P, const KArrays& A, const KNet& N, const double*
     for (int k = 0; k < N.K; ++k) {
         if (h_Dgj[k] < 0.0) continue;
         ++nonces;
-        k_net_gj<<<grid, BT_TPB, 0, st>>>(P, A, N, k, cur, nonces);
+        k_net_gj<<<grid, BT_TPB, 0, st>>>(P, A, N, k, cur, nonces, (N.c_env && h_env_on[k] && h_Dm[k] != 0.0) ? 1 : 0);
         k_net_gj_apply<<<(P.n_cells_owned + 255) / 256, 256, 0, st>>>(P, A, N, k);
     }
     if (N.c_env) {
@@ -244,5 +277,9 @@ void launch_net(const KParams& P, const KArrays& A, const KNet& N, const double*
             k_sub_flux<<<gE, 256, 0, st>>>(P, A, N, k);
             k_sub_div<<<gE, 256, 0, st>>>(P, A, N, k);
         }
+    }
+    if (N.affect) {
+        k_net_charge<<<(P.n_cells_owned + 255) / 256, 256, 0, st>>>(P, N, P.n_cells_owned, P.n_cells, 0);
+        if (N.c_env) k_net_charge<<<(E + 255) / 256, 256, 0, st>>>(P, N, E, E, 1);
     }
 }

@@ -32,6 +32,12 @@ struct KNet {
     const double* Dm;           // [K]
     const double* c_bound;      // [K]
     const double* D_env;        // [K][E]
+    // p.substances_affect_charge (networks.py:2942-2977)
+    int affect;
+    const double* scale;        // [K] scale_factor
+    double* fmem_tmp;           // [M] membrane flux of the substance in flight (joined with its gap-junction flux)
+    double* rho_cells;          // [C] extra_rho_cells of this handler
+    double* rho_env;            // [E] extra_rho_env
 };
 
 // One rate law at cell c (membrane m < 0: cell zone).

@@ -506,6 +506,10 @@ class TissueEngine:
             n.Dm, n.c_bound = f64(np.asarray(net["Dm"], dtype=float).reshape(K)), f64(np.asarray(net["c_bound"], dtype=float).reshape(K))
             n.c_env = f64(np.asarray(net["c_env"], dtype=float).reshape(K, self.E))
             n.D_env = f64(np.asarray(net["D_env"], dtype=float).reshape(K, self.E))
+        if net.get("scale_factor") is not None:
+            n.scale_factor = f64(np.asarray(net["scale_factor"], dtype=float).reshape(K))
+        n.affect_charge = int(bool(self.p.get("substances_affect_charge", 0)) if net.get("affect_charge") is None
+                              else bool(net["affect_charge"]))
         self._check(self.lib.betse_set_network(self.ctx, int(handler), C.byref(n)), "betse_set_network")
         self.networks = getattr(self, "networks", {})
         self.networks[int(handler)] = {"species": list(net["species"]), "n_rates": n.n_rates, "env_on": env_on.astype(bool)}

@@ -44,8 +44,6 @@ def unsupported_reasons(core, p):
             why.append("extracellular transport with 'sharpness env' < 1")
         if _in_env(m) and float(getattr(m, "Mu_mem", 0.0) or 0.0) != 0.0:
             why.append("electrophoretic membrane mobility (Mu_mem)")
-        if float(getattr(m, "z", 0.0) or 0.0) != 0.0 and bool(getattr(p, "substances_affect_charge", False)):
-            why.append("charged substance with 'substances affect charge'")
         if why:
             bad.append("substance %r: %s" % (name, ", ".join(why)))
     for name, r in (getattr(core, "reactions", None) or {}).items():
@@ -85,6 +83,7 @@ def describe_core(core, sim, p, cells, record_static=True):
         "Dgj": np.array([-1.0 if core.molecules[s].ignoreGJ else float(core.molecules[s].Dgj) for s in species]),
         "z": np.array([float(core.molecules[s].z) for s in species]),
         "time_factor": np.array([float(core.molecules[s].modify_time_factor) for s in species]),
+        "scale_factor": np.array([float(getattr(core.molecules[s], "scale_factor", 1.0)) for s in species]),
         "chan_names": list(core.channels),
         "chan_mod_strings": [core.channels[c].alpha_eval_string for c in core.channels],
         "static": {},
@@ -151,7 +150,7 @@ def compile_network(desc, n_cells, n_mems, resolver=None):
             "growth_mask": None if mask.all() else mask, "Dgj": np.asarray(desc["Dgj"], dtype=float),
             "z": np.asarray(desc["z"], dtype=float), "time_factor": np.asarray(desc["time_factor"], dtype=float),
             "chan_names": list(desc["chan_names"]),
-            **{k: np.asarray(desc[k]) for k in ("env_on", "Dm", "c_bound", "c_env", "D_env") if k in desc}}
+            **{k: np.asarray(desc[k]) for k in ("env_on", "Dm", "c_bound", "c_env", "D_env", "scale_factor") if k in desc}}
 
 
 # ---- flat (npz-friendly) form of a description, used by the golden fixtures
@@ -164,7 +163,7 @@ def flatten(desc, prefix):
            prefix + "time_factor": desc["time_factor"], prefix + "chan_names": np.array(desc["chan_names"], dtype=str),
            prefix + "chan_mod_strings": np.array(desc["chan_mod_strings"], dtype=str),
            prefix + "static_keys": np.array(list(desc["static"].keys()), dtype=str)}
-    for k in ("env_on", "Dm", "c_bound", "c_env", "D_env"):
+    for k in ("env_on", "Dm", "c_bound", "c_env", "D_env", "scale_factor"):
         if k in desc:
             out[prefix + k] = np.asarray(desc[k])
     for k, tg in enumerate(desc["growth_targets"]):
@@ -178,7 +177,7 @@ def unflatten(cap, prefix):
     g = lambda k: cap[prefix + k]
     species = [str(x) for x in g("species")]
     keys = [str(x) for x in g("static_keys")]
-    return {**{k: np.asarray(cap[prefix + k]) for k in ("env_on", "Dm", "c_bound", "c_env", "D_env") if prefix + k in cap},
+    return {**{k: np.asarray(cap[prefix + k]) for k in ("env_on", "Dm", "c_bound", "c_env", "D_env", "scale_factor") if prefix + k in cap},
             "species": species, "ions": [str(x) for x in g("ions")], "c_cells": np.asarray(g("c_cells")),
             "gad_strings": [str(x) for x in g("gad_strings")],
             "reaction_names": [str(x) for x in g("reaction_names")],

@@ -264,6 +264,11 @@ typedef struct betse_network {
     const double  *c_env;         /* [K][E] env concentrations at loop entry (rows with env_on == 0 are ignored) */
     const double  *D_env;         /* [K][E] Do * D_env_weight (* TJ_factor on sim.TJ_targets) or Do where the
                                      substance passes tight junctions (sim_toolbox.py:1075-1085)     */
+    /* p.substances_affect_charge (networks.py:2942-2977): charged substances add F*c*z*scale to the charge of cells
+     * and env squares, -z*f_mem*F*scale + z*f_gj*F*scale to the membrane current, z*F*scale*f_env to J_env. */
+    const double  *scale_factor;  /* [K] Molecule.scale_factor (NULL: 1)                             */
+    int32_t affect_charge;
+    int32_t reserved;
 } betse_network;
 
 /* handler 0 = sim.molecules.core, 1 = sim.grn.core (run in that order, sim.py:1290-1318).  net == NULL

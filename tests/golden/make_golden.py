@@ -195,6 +195,17 @@ SCENARIOS["mammal_ecm_net_env"] = dict(
     snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=net_extra)
 
 
+# the same with 'substances affect Vmem' on (the shipped default): the cation S3 and an anion S4 (scale factor 0.5) add to
+# the charge of cells and env squares, their membrane / gap-junction fluxes to the membrane current (networks.py:2942-2977)
+_ENVQ_BIO = [dict(b) for b in _ENV_BIO[:3]] + [dict(_env_substance("S4", 1.0e-17, -1, 0.1, 0.4, False, True), **{"scale factor": 0.5}),
+                                               _substance("G1", 2.0, inh=[("S1", 0.2, 2)])]
+SCENARIOS["mammal_ecm_net_envq"] = dict(
+    mods=_m(SMALL, {"cutting event": {"event happens": False}, "general options": {"ion profile": "mammal"},
+                    "general network": {"implement network": True, "biomolecules": _ENVQ_BIO, "reactions": [],
+                                        "channels": [dict(_NET_CH[2], **{"channel inhibitors": ["S1"]})]}}),
+    snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=net_extra)
+
+
 # The external-voltage event (tissue/event/tisevevolt.py: bound_V ramps, Phi_b = one Dirichlet Poisson solve per step,
 # ion_current.py:84-90, subtracted from Vmem in update_V, sim.py:2029) — ramp up, plateau and ramp down inside the
 # first 20 SIM steps, left/right electrodes so that it differs from the top/bottom default; ECM and no-ECM

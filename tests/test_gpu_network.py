@@ -22,7 +22,8 @@ def _attach(eng, desc, specs, phase_init):
 
 
 @pytest.mark.parametrize("kind", ["init", "sim"])
-@pytest.mark.parametrize("fixture", ["mammal_ecm_net", "mammal_ecm_net_env"])   # _env: membrane + extracellular transport of substances
+# _env: membrane + extracellular transport of substances; _envq: charged substances with 'substances affect Vmem' on
+@pytest.mark.parametrize("fixture", ["mammal_ecm_net", "mammal_ecm_net_env", "mammal_ecm_net_envq"])
 def test_network_matches_reference(fixture, kind):
     from betse_b200.engine import TissueEngine
     cap = util.load_golden(fixture)
@@ -41,7 +42,8 @@ def test_network_matches_reference(fixture, kind):
             assert not (st & (3 | 16)), st
             n += 1
         ref = util.group(cap, "%s.k%d." % (kind, K))
-        got = eng.download([f for f in list(util.STATE) + util.ENV_STATE if f in ref])
+        extra = ["Jmem", "Jgj", "Jn", "I_mem", "Jtx", "Jty"] if last else []      # carry extra_J_mem / extra_Jenv (ion_current.py:27, 53-54)
+        got = eng.download([f for f in list(util.STATE) + util.ENV_STATE + extra if f in ref])
         tols = util.gpu_tolerances(cap, kind, ref)
         for f, a in got.items():
             err = float(np.max(np.abs(np.asarray(a).reshape(np.shape(ref[f])) - ref[f])))
