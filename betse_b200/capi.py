@@ -107,6 +107,10 @@ class Channel(C.Structure):
     ]
 
 
+class Modulator(C.Structure):
+    _fields_ = [("target", C.c_int32), ("prog", C.c_int32), ("max_val", C.c_double)]
+
+
 class Network(C.Structure):
     _fields_ = [
         ("n_species", C.c_int32), ("n_rates", C.c_int32), ("n_programs", C.c_int32),
@@ -115,7 +119,8 @@ class Network(C.Structure):
         ("mem_arrays", _dp), ("growth_mask", _bp), ("stoich", _dp), ("Dgj", _dp), ("z", _dp),
         ("time_factor", _dp),
         ("env_on", _bp), ("Dm", _dp), ("c_bound", _dp), ("c_env", _dp), ("D_env", _dp),
-        ("scale_factor", _dp), ("affect_charge", C.c_int32), ("reserved", C.c_int32),
+        ("scale_factor", _dp), ("affect_charge", C.c_int32), ("n_modulators", C.c_int32),
+        ("modulators", C.POINTER(Modulator)),
     ]
 
 

@@ -38,6 +38,7 @@ void launch_pack_dm(const KParams& P, const KArrays& A, cudaStream_t st);
 void launch_chan(const KParams& P, const KArrays& A, const KChan& ch, const KNet& N, int cur, cudaStream_t st);
 void launch_net(const KParams& P, const KArrays& A, const KNet& N, const double* h_Dgj, const double* h_Dm,
                 const unsigned char* h_env_on, int n_ions, int cur, cudaStream_t st);
+void launch_net_mod(const KParams& P, const KArrays& A, const KNet& N, int prog, double max_val, double* dst, int cur, cudaStream_t st);
 void launch_cell_update(const KParams& P, const KArrays& A, int cur, cudaStream_t st);
 void launch_xchg(const KParams& P, const KArrays& A, const XPlan& X, int which, int buf, int mode, cudaStream_t st);
 
@@ -79,6 +80,7 @@ struct betse_ctx {
     std::vector<double> net_Dm[2];           // host copy (which substances cross the membrane)
     std::vector<unsigned char> net_env_on[2];
     bool net_affect[2] = {false, false};
+    std::vector<betse_modulator> net_mods[2];   // sim modulators of each handler (run_loop_modulators)
     std::string err;
     std::vector<void*> allocs;
     // CUDA graphs of one plain step, for cur = 0 and cur = 1
@@ -718,6 +720,10 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
             }
             for (int h = 0; h < 2; ++h) {
                 for (const KChan& ch : ctx->chans) if (ch.handler == h) launch_chan(ctx->P, A, ch, ctx->nets[h], cur, st);
+                if (ctx->net_on[h])
+                    for (const betse_modulator& md : ctx->net_mods[h])
+                        launch_net_mod(ctx->P, A, ctx->nets[h], md.prog, md.max_val,
+                                       const_cast<double*>(md.target == 0 ? A.gj_block : A.NaK_block), cur, st);
                 if (ctx->net_on[h]) launch_net(ctx->P, A, ctx->nets[h], ctx->net_Dgj[h].data(), ctx->net_Dm[h].data(),
                                                ctx->net_env_on[h].data(), I, cur, st);
             }
@@ -1159,6 +1165,22 @@ extern "C" int betse_set_network(betse_ctx* ctx, int handler, const betse_networ
         }
     }
     if ((r = ensure_defer_buffers(ctx))) return r;
+    ctx->net_mods[handler].clear();
+    for (int j = 0; j < net->n_modulators; ++j) {
+        const betse_modulator& md = net->modulators[j];
+        if (md.target < 0 || md.target > 1) return fail(ctx, "network: modulator target must be 0 (gap junctions) or 1 (Na/K-ATPase)");
+        if (md.prog < R || md.prog >= net->n_programs) return fail(ctx, "network: modulator program is not a membrane-zone program");
+        // the block becomes a per-membrane array (it starts from the value in force now)
+        const double** slot = md.target == 0 ? &ctx->A.gj_block : &ctx->A.NaK_block;
+        if (!*slot) {
+            std::vector<double> init((size_t)Mo, md.target == 0 ? ctx->P.gj_block : ctx->P.NaK_block);
+            double* p;
+            if ((r = dev_upload(ctx, &p, (const double*)init.data(), (size_t)Mo))) return r;
+            CK(cudaStreamSynchronize(ctx->stream));
+            *slot = p;
+        }
+        ctx->net_mods[handler].push_back(md);
+    }
     ctx->net_affect[handler] = false;
     if (net->affect_charge) {
         // sim.extra_rho_cells / extra_rho_env / extra_J_mem / extra_Jenv are the handler's arrays from now on

@@ -105,6 +105,26 @@ k_net_gj_apply(const __grid_constant__ KParams P, const KArrays A, const __grid_
     N.c[(size_t)k * P.n_cells + c] = cn;
 }
 
+// run_loop_modulators (networks.py:3282-3325): sim.gj_block / sim.NaKATP_block = max_val * eval(alpha_eval_string),
+// membrane zone; in force from the gap-junction transport of the substances of this step onwards.
+__global__ void __launch_bounds__(256)
+k_net_mod(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ KNet N, const int prog, const double max_val,
+          double* __restrict__ dst, const int cur)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= P.n_mems_owned) return;
+    const int c = __ldg(A.mem_to_cells + m);
+    double vm = A.vm_cell[cur][c];
+    if (P.polar) vm = A.vm_pol[cur][m];
+    else if (P.has_phi) vm -= __ldg(A.phi_b_old + __ldg(A.map_mem2ecm + m));
+    dst[m] = max_val * rl_eval(N, prog, c, m, A, P.n_cells, P.n_mems_owned, cur, vm);
+}
+
+void launch_net_mod(const KParams& P, const KArrays& A, const KNet& N, int prog, double max_val, double* dst, int cur, cudaStream_t st)
+{
+    k_net_mod<<<(P.n_mems_owned + 255) / 256, 256, 0, st>>>(P, A, N, prog, max_val, dst, cur);
+}
+
 // ---------------------------------------------------------------------------- membrane + extracellular legs
 // Molecule.transport -> stb.molecule_mover (networks.py:5670-5700, sim_toolbox.py:909-1153) for substances with a
 // membrane permeability and/or a presence in the environment:

@@ -506,6 +506,13 @@ class TissueEngine:
             n.Dm, n.c_bound = f64(np.asarray(net["Dm"], dtype=float).reshape(K)), f64(np.asarray(net["c_bound"], dtype=float).reshape(K))
             n.c_env = f64(np.asarray(net["c_env"], dtype=float).reshape(K, self.E))
             n.D_env = f64(np.asarray(net["D_env"], dtype=float).reshape(K, self.E))
+        mods = list(net.get("modulators") or [])
+        if mods:
+            marr = (capi.Modulator * len(mods))()
+            for j, (target, prog, mx) in enumerate(mods):
+                marr[j].target, marr[j].prog, marr[j].max_val = int(target), int(prog), float(mx)
+            keep.append(marr)
+            n.n_modulators, n.modulators = len(mods), marr
         if net.get("scale_factor") is not None:
             n.scale_factor = f64(np.asarray(net["scale_factor"], dtype=float).reshape(K))
         n.affect_charge = int(bool(self.p.get("substances_affect_charge", 0)) if net.get("affect_charge") is None

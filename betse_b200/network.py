@@ -23,13 +23,19 @@ def _is_none(v):
     return v is None or (isinstance(v, str) and v == "None") or (hasattr(v, "__len__") and len(v) == 0)
 
 
+# run_loop_modulators targets implemented on the device (networks.py:3296-3299); 'TJ' works in the env zone
+MOD_TARGETS = {"GJ": 0, "Na/K-ATPase": 1}
+
+
 def unsupported_reasons(core, p):
     """Why this MasterOfNetworks cannot run on the device (empty list: it can)."""
     bad = []
     if getattr(core, "mit_enabled", False):
         bad.append("mitochondria")
+    for name, mod in (getattr(core, "modulators", None) or {}).items():
+        if str(mod.target_label) not in MOD_TARGETS:
+            bad.append("modulator %r of %s (extracellular zone)" % (name, mod.target_label))
     for attr, what in (("transporters", "transporters (run_loop_transporters, networks.py:2985-3107)"),
-                       ("modulators", "modulators (run_loop_modulators, networks.py:3282-3325)"),
                        ("reactions_env", "extracellular reactions"), ("reactions_mit", "mitochondrial reactions")):
         if len(getattr(core, attr, None) or {}):
             bad.append(what)
@@ -86,6 +92,11 @@ def describe_core(core, sim, p, cells, record_static=True):
         "scale_factor": np.array([float(getattr(core.molecules[s], "scale_factor", 1.0)) for s in species]),
         "chan_names": list(core.channels),
         "chan_mod_strings": [core.channels[c].alpha_eval_string for c in core.channels],
+        # run_loop_modulators (networks.py:3282-3325): modulator = max_val * eval(alpha_eval_string) -> sim.gj_block / NaKATP_block
+        "modulator_names": list(getattr(core, "modulators", None) or {}),
+        "modulator_strings": [m.alpha_eval_string for m in (getattr(core, "modulators", None) or {}).values()],
+        "modulator_targets": [str(m.target_label) for m in (getattr(core, "modulators", None) or {}).values()],
+        "modulator_max": np.array([float(m.max_val) for m in (getattr(core, "modulators", None) or {}).values()]),
         "static": {},
     }
     # Molecule.transport -> stb.molecule_mover (networks.py:5670-5700, sim_toolbox.py:909-1153): membrane and
@@ -129,6 +140,7 @@ def compile_network(desc, n_cells, n_mems, resolver=None):
         rates = [ratelaw.compile_expr(s, tabs, resolver, "cell") for s in desc["gad_strings"]]
         rates += [ratelaw.compile_expr(s, tabs, resolver, "cell") for s in desc["reaction_strings"]]
         mods = [ratelaw.compile_expr(s, tabs, resolver, "mem") for s in desc["chan_mod_strings"]]
+        modulators = [ratelaw.compile_expr(s, tabs, resolver, "mem") for s in desc.get("modulator_strings", [])]
     except ratelaw.RateLawError as e:
         raise BetseB200Error("network rate law not supported on the device: %s" % e)
     stoich = np.asarray(desc["stoich"], dtype=float).reshape(K, -1)
@@ -145,8 +157,18 @@ def compile_network(desc, n_cells, n_mems, resolver=None):
         else:
             mod_index.append(len(rates) + len(mod_programs))
             mod_programs.append(pr)
+    # sim modulators: always a program (a constant one when nothing regulates them), after the channel programs
+    modulator_index = []
+    for pr in modulators:
+        modulator_index.append(len(rates) + len(mod_programs))
+        mod_programs.append(pr)
+    for t in desc.get("modulator_targets", []):
+        if t not in MOD_TARGETS:
+            raise BetseB200Error("modulator target %r is not implemented" % t)
     return {"species": species, "tables": tabs, "rate_programs": rates, "mod_programs": mod_programs,
-            "mod_index": mod_index, "c_cells": np.asarray(desc["c_cells"], dtype=float), "stoich": stoich,
+            "mod_index": mod_index,
+            "modulators": [(MOD_TARGETS[t], i, float(mx)) for t, i, mx in
+                           zip(desc.get("modulator_targets", []), modulator_index, desc.get("modulator_max", []))], "c_cells": np.asarray(desc["c_cells"], dtype=float), "stoich": stoich,
             "growth_mask": None if mask.all() else mask, "Dgj": np.asarray(desc["Dgj"], dtype=float),
             "z": np.asarray(desc["z"], dtype=float), "time_factor": np.asarray(desc["time_factor"], dtype=float),
             "chan_names": list(desc["chan_names"]),
@@ -163,6 +185,11 @@ def flatten(desc, prefix):
            prefix + "time_factor": desc["time_factor"], prefix + "chan_names": np.array(desc["chan_names"], dtype=str),
            prefix + "chan_mod_strings": np.array(desc["chan_mod_strings"], dtype=str),
            prefix + "static_keys": np.array(list(desc["static"].keys()), dtype=str)}
+    if desc.get("modulator_names"):
+        out.update({prefix + "modulator_names": np.array(desc["modulator_names"], dtype=str),
+                    prefix + "modulator_strings": np.array(desc["modulator_strings"], dtype=str),
+                    prefix + "modulator_targets": np.array(desc["modulator_targets"], dtype=str),
+                    prefix + "modulator_max": np.asarray(desc["modulator_max"], dtype=float)})
     for k in ("env_on", "Dm", "c_bound", "c_env", "D_env", "scale_factor"):
         if k in desc:
             out[prefix + k] = np.asarray(desc[k])
@@ -177,7 +204,11 @@ def unflatten(cap, prefix):
     g = lambda k: cap[prefix + k]
     species = [str(x) for x in g("species")]
     keys = [str(x) for x in g("static_keys")]
-    return {**{k: np.asarray(cap[prefix + k]) for k in ("env_on", "Dm", "c_bound", "c_env", "D_env", "scale_factor") if prefix + k in cap},
+    mods = {}
+    if prefix + "modulator_names" in cap:
+        mods = {"modulator_names": [str(x) for x in g("modulator_names")], "modulator_strings": [str(x) for x in g("modulator_strings")],
+                "modulator_targets": [str(x) for x in g("modulator_targets")], "modulator_max": np.asarray(g("modulator_max"))}
+    return {**mods, **{k: np.asarray(cap[prefix + k]) for k in ("env_on", "Dm", "c_bound", "c_env", "D_env", "scale_factor") if prefix + k in cap},
             "species": species, "ions": [str(x) for x in g("ions")], "c_cells": np.asarray(g("c_cells")),
             "gad_strings": [str(x) for x in g("gad_strings")],
             "reaction_names": [str(x) for x in g("reaction_names")],

@@ -240,6 +240,10 @@ void betse_host_free(void *p);
  * mitochondria, boundary / clamp events. */
 #define BETSE_STATUS_NEG_NET 16u  /* a network substance went negative (sim_toolbox.py:1124-1150 raises) */
 
+/* One sim modulator (Modulator, networks.py:6655-6700; run_loop_modulators, networks.py:3282-3325):
+ * target = max_val * program(membrane), written over sim.gj_block (target 0) or sim.NaKATP_block (target 1). */
+typedef struct betse_modulator { int32_t target; int32_t prog; double max_val; } betse_modulator;
+
 typedef struct betse_network {
     int32_t n_species;            /* K substances, MasterOfNetworks.molecules order                 */
     int32_t n_rates;              /* K growth/decay rates + R cell-zone reactions = columns of reaction_matrix */
@@ -268,7 +272,8 @@ typedef struct betse_network {
      * and env squares, -z*f_mem*F*scale + z*f_gj*F*scale to the membrane current, z*F*scale*f_env to J_env. */
     const double  *scale_factor;  /* [K] Molecule.scale_factor (NULL: 1)                             */
     int32_t affect_charge;
-    int32_t reserved;
+    int32_t n_modulators;
+    const betse_modulator *modulators;   /* programs are membrane-zone programs (index >= n_rates)    */
 } betse_network;
 
 /* handler 0 = sim.molecules.core, 1 = sim.grn.core (run in that order, sim.py:1290-1318).  net == NULL

@@ -206,6 +206,18 @@ SCENARIOS["mammal_ecm_net_envq"] = dict(
     snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=net_extra)
 
 
+# sim modulators (run_loop_modulators, networks.py:3282-3325): G3 closes gap junctions, X drives the Na/K-ATPase
+_MODS = [{"name": "gj_mod", "target": "GJ", "max effect": 1.0, "inhibitors": ["G3"], "inhibitor Km": [2.0], "inhibitor n": [2.0],
+          "inhibitor zone": ["cell"]},
+         {"name": "pump_mod", "target": "Na/K-ATPase", "max effect": 1.5, "activators": ["X"], "activator Km": [0.05],
+          "activator n": [1.0], "activator zone": ["cell"]}]
+SCENARIOS["mammal_ecm_net_mod"] = dict(
+    mods=_m(SMALL, {"cutting event": {"event happens": False}, "general options": {"ion profile": "mammal"},
+                    "general network": {"implement network": True, "biomolecules": _NET_BIO, "reactions": _NET_RX,
+                                        "channels": _NET_CH, "modulators": _MODS}}),
+    snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=net_extra)
+
+
 # The external-voltage event (tissue/event/tisevevolt.py: bound_V ramps, Phi_b = one Dirichlet Poisson solve per step,
 # ion_current.py:84-90, subtracted from Vmem in update_V, sim.py:2029) — ramp up, plateau and ramp down inside the
 # first 20 SIM steps, left/right electrodes so that it differs from the top/bottom default; ECM and no-ECM

@@ -23,7 +23,8 @@ def _attach(eng, desc, specs, phase_init):
 
 @pytest.mark.parametrize("kind", ["init", "sim"])
 # _env: membrane + extracellular transport of substances; _envq: charged substances with 'substances affect Vmem' on
-@pytest.mark.parametrize("fixture", ["mammal_ecm_net", "mammal_ecm_net_env", "mammal_ecm_net_envq"])
+# _mod: sim modulators (gap junctions, Na/K-ATPase)
+@pytest.mark.parametrize("fixture", ["mammal_ecm_net", "mammal_ecm_net_env", "mammal_ecm_net_envq", "mammal_ecm_net_mod"])
 def test_network_matches_reference(fixture, kind):
     from betse_b200.engine import TissueEngine
     cap = util.load_golden(fixture)
@@ -37,7 +38,7 @@ def test_network_matches_reference(fixture, kind):
     for K in snaps:
         last = K == snaps[-1]
         while n < K:
-            assert not util.group(cap, "%s.sched.k%d." % (kind, n + 1))
+            util.apply_schedule(eng, cap, kind, n + 1)
             st = eng.step(1, diag=(last and n + 1 == K))
             assert not (st & (3 | 16)), st
             n += 1

@@ -40,7 +40,13 @@ def snap_steps(cap, kind):
 
 def apply_schedule(obj, cap, kind, n):
     """Apply what fire_events rewrote for (1-based) step n (oracle/refrun.py)."""
+    # sim modulators rewrite these inside the loop (run_loop_modulators, networks.py:3296-3299): not a schedule
+    targets = [str(t) for h in range(2) for t in cap.get("%s.s0.net%d.modulator_targets" % (kind, h), [])]
+    skip = {"GJ": "gj_block", "Na/K-ATPase": "NaKATP_block"}
+    skip = {skip[t] for t in targets if t in skip}
     for f, v in group(cap, "%s.sched.k%d." % (kind, n)).items():
+        if f in skip:
+            continue
         if f == "bound_V":
             obj.set_bound_V(v) if hasattr(obj, "set_bound_V") else setattr(
                 obj, "bound_V", dict(zip("TBLR", v)))
