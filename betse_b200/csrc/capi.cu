@@ -1080,7 +1080,6 @@ extern "C" int betse_set_channels(betse_ctx* ctx, int n, const betse_channel* ch
 {
     if (!ctx || n < 0 || (n > 0 && !chs)) return 2;
     CK(cudaSetDevice(ctx->device));
-    if (n > 0 && !ctx->hp.is_ecm) return fail(ctx, "channels without extracellular spaces are not implemented");
     if (n > 0 && ctx->hp.fast_update_ecm) return fail(ctx, "channels with fast_update_ecm are not implemented");
     if (n > 0 && ctx->X.n_nbr > 0) return fail(ctx, "channels on a domain-decomposed tissue are not implemented");
     KArrays& A = ctx->A;
@@ -1095,6 +1094,7 @@ extern "C" int betse_set_channels(betse_ctx* ctx, int n, const betse_channel* ch
         if ((r = dev_alloc(ctx, &A.dsum_m, (size_t)ctx->I * ctx->C))) return r;
         if ((r = dev_alloc(ctx, &A.dsum_g, (size_t)ctx->I * ctx->C))) return r;
         if ((r = dev_alloc(ctx, &A.chan_slots, (size_t)ctx->n_slots))) return r;
+    if ((r = dev_alloc(ctx, &A.chan_part, (size_t)ctx->n_tiles))) return r;
         if ((r = dev_alloc(ctx, &A.chanJ, (size_t)Mo))) return r;
     }
     for (int k = 0; k < n; ++k) {
@@ -1163,6 +1163,7 @@ static int ensure_defer_buffers(betse_ctx* ctx)
     if ((r = dev_alloc(ctx, &A.dsum_m, (size_t)ctx->I * ctx->C))) return r;
     if ((r = dev_alloc(ctx, &A.dsum_g, (size_t)ctx->I * ctx->C))) return r;
     if ((r = dev_alloc(ctx, &A.chan_slots, (size_t)ctx->n_slots))) return r;
+    if ((r = dev_alloc(ctx, &A.chan_part, (size_t)ctx->n_tiles))) return r;
     if ((r = dev_alloc(ctx, &A.chanJ, (size_t)ctx->Mo))) return r;
     return 0;
 }
@@ -1178,7 +1179,7 @@ extern "C" int betse_set_network(betse_ctx* ctx, int handler, const betse_networ
         return 0;
     }
     if (ctx->X.n_nbr > 0) return fail(ctx, "networks on a domain-decomposed tissue are not implemented");
-    if (!ctx->hp.is_ecm || ctx->hp.fast_update_ecm) return fail(ctx, "networks without extracellular spaces / with fast_update_ecm are not implemented");
+    if (ctx->hp.fast_update_ecm) return fail(ctx, "networks with fast_update_ecm are not implemented");
     const int K = net->n_species, R = net->n_rates, C = ctx->C, Mo = ctx->Mo;
     if (K <= 0 || R < K || R > NET_MAX_RATES) return fail(ctx, "network: need 0 < n_species <= n_rates <= 48");
     if (net->n_programs < R) return fail(ctx, "network: n_programs < n_rates");
@@ -1228,6 +1229,7 @@ extern "C" int betse_set_network(betse_ctx* ctx, int handler, const betse_networ
         for (int k = 0; k < K; ++k) any = any || net->env_on[k] != 0;
         if (any) {
             if (!net->Dm || !net->c_bound || !net->c_env || !net->D_env) return fail(ctx, "network: env_on needs Dm, c_bound, c_env and D_env");
+            if (!ctx->hp.is_ecm) return fail(ctx, "network substances outside the cells need extracellular spaces");
             if (ctx->hp.sharpness < 1.0) return fail(ctx, "network substances in the environment with sharpness < 1 are not implemented");
             const size_t E = (size_t)ctx->E;
             if ((r = dev_upload(ctx, &N.c_env, net->c_env, (size_t)K * E))) return r;

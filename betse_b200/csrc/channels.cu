@@ -115,6 +115,11 @@ k_chan(const __grid_constant__ KParams P, const KArrays A, const __grid_constant
     }
     s_f[lane] = fsa;
     __syncwarp();
+    if (!P.is_ecm && lane == 0) {                                 // no-ECM: the tile's share of sum_m f*sa (k_chan_mix)
+        double S = 0.0;
+        for (int j = 0; j < nm; ++j) S += s_f[j];
+        A.chan_part[tile] = S;
+    }
     if (lane < nc) {                                              // update_Co cell branch, sim_toolbox.py:1177-1181
         const int c = c0 + lane;
         const int jb = __ldg(A.cell_mem_ptr + c) - m0, je = __ldg(A.cell_mem_ptr + c + 1) - m0;
@@ -138,6 +143,26 @@ k_chan_env(const __grid_constant__ KParams P, const KArrays A, const int ion, co
     for (int j = s0; j < s1; ++j) acc += A.chan_slots[__ldg(A.slot_idx + j)];
     double* c = A.cc_env[nxt] + ion * E + k;
     *c = *c + ((-acc) / P.env_vol_div) * P.dt;
+}
+
+// update_Co without extracellular spaces (sim_toolbox.py:1198-1205): cX_env = mean(cX_env + (-f*mem_sa/vol_env)*dt) —
+// the bath is one number per ion; the channel's flux moves it before the next channel reads it.
+__global__ void __launch_bounds__(256)
+k_chan_mix(const __grid_constant__ KParams P, const KArrays A, const int ion, const int cur)
+{
+    __shared__ double red[256];
+    double s = 0.0;
+    for (int b = threadIdx.x; b < P.n_tiles; b += blockDim.x) s += A.chan_part[b];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double c = A.cenv_u[cur * 8 + ion];
+        A.cenv_u[cur * 8 + ion] = c + ((-red[0] / P.vol_env) * P.dt) / (double)P.n_mems_owned;
+    }
 }
 
 // The deferred tail of k_mem (update_all_concs, sim.py:2086-2111; charge and Vmem, ion_current.py:19,
@@ -177,7 +202,7 @@ void launch_chan(const KParams& P, const KArrays& A, const KChan& ch, const KNet
     if (P.is_ecm) {
         const int n = (P.ya1 - P.ya0) * P.nx;
         if (n > 0) k_chan_env<<<(n + 255) / 256, 256, 0, st>>>(P, A, ch.ion, cur ^ 1);
-    }
+    } else k_chan_mix<<<1, 256, 0, st>>>(P, A, ch.ion, cur);
 }
 
 void launch_cell_update(const KParams& P, const KArrays& A, int cur, cudaStream_t st)

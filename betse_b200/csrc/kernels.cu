@@ -250,6 +250,7 @@ k_mem(const __grid_constant__ KParams P, const KArrays A, const int cur, const i
         for (int j = jb; j < je; ++j) { Sm += s_m[j * NI + i]; Sg += s_g[j * NI + i]; }
         if (!S && P.defer) {              // channels act before update_all_concs: k_cell_update applies these
             A.dsum_m[i * C + c] = Sm; A.dsum_g[i * C + c] = Sg;
+            if (!is_ecm) s_sm[q] = Sm;    // the bath still takes this step's membrane fluxes (k_envmix)
             continue;
         }
         const double rvol = fast_rcp(vol);

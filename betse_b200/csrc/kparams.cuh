@@ -91,6 +91,7 @@ struct KArrays {
     // voltage-gated channels (channels.cu)
     double *dsum_m, *dsum_g; // [I,C] deferred sums of f_mem*sa and f_gj*sa per cell
     double *chan_slots;      // [M]   f*sa of the channel being applied (membrane -> env exchange)
+    double *chan_part;       // [n_tiles] per-tile sums of it (no-ECM: the channel's share of the well-mixed bath)
     double *chanJ;           // [M]   extra_J_mem accumulated over the channels of this step
     double *extra_Jenv_x, *extra_Jenv_y;   // [E] charged network substances moving through the env grid (networks.py:2953-2954)
 };

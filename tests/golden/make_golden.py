@@ -239,6 +239,13 @@ SCENARIOS["default_try"] = dict(mods={}, snaps={"init": [500], "sim": [350]}, ex
                                 trace=("vm", "cc_cells"), precut=True, full=True)
 
 
+# BASELINE configs[0] to the letter: the default sample simulation with the Na/K/Cl/Ca/P(+M) profile and WITHOUT
+# extracellular spaces (one well-mixed bath) — network, channels and cutting event as shipped; full phases with traces
+SCENARIOS["default_try_noecm"] = dict(mods={"general options": {"ion profile": "mammal", "simulate extracellular spaces": False}},
+                                      snaps={"init": [500], "sim": [350]}, extra=net_extra,
+                                      trace=("vm", "cc_cells"), precut=True, full=True)
+
+
 def main(argv):
     import scipy
     names = argv or list(SCENARIOS)

@@ -38,10 +38,14 @@ def _check(cap, kind, got, who):
             assert err <= tol, (who, kind, f, "sample %d" % j, err, tol)
 
 
+FIXTURES = ["default_try", "default_try_noecm"]   # shipped default (ECM on); BASELINE configs[0] to the letter (mammal profile, no ECM)
+
+
 @pytest.mark.parametrize("kind", ["init", "sim"])
-def test_oracle_full_run(kind):
+@pytest.mark.parametrize("fixture", FIXTURES)
+def test_oracle_full_run(fixture, kind):
     from oracle.betse_oracle import OracleSim
-    cap = util.load_golden("default_try")
+    cap = util.load_golden(fixture)
     o = OracleSim(util.mesh_of(cap, kind), util.group(cap, kind + ".p."), util.group(cap, kind + ".s0."),
                   channels=util.channels_of(cap, kind), phase_init=(kind == "init"), networks=util.networks_of(cap, kind))
     o.diagnostics = False
@@ -58,10 +62,11 @@ def test_oracle_full_run(kind):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind", ["init", "sim"])
-def test_gpu_full_run(kind):
+@pytest.mark.parametrize("fixture", FIXTURES)
+def test_gpu_full_run(fixture, kind):
     from betse_b200 import network as netlib
     from betse_b200.engine import TissueEngine
-    cap = util.load_golden("default_try")
+    cap = util.load_golden(fixture)
     eng = TissueEngine(util.mesh_of(cap, kind), util.group(cap, kind + ".p."), util.group(cap, kind + ".s0."))
     specs = util.channels_of(cap, kind)
     desc = util.networks_of(cap, kind)[0]
