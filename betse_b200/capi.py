@@ -74,7 +74,7 @@ class Params(C.Structure):
         ("NaKATP_block_scalar", C.c_double), ("gj_block_scalar", C.c_double),
         ("is_ecm", C.c_int32), ("v_sensitive_gj", C.c_int32), ("cluster_open", C.c_int32),
         ("fast_update_ecm", C.c_int32),
-        ("reserved", C.c_int32 * 4),
+        ("sigma_env", C.c_double), ("reserved_d", C.c_double),
     ]
 
 
@@ -86,6 +86,7 @@ STATE_FIELDS = [
     "Jmem", "Jgj", "Jn", "I_mem", "Jc", "Emc", "dvm",
     "J_cell_x", "J_cell_y", "E_cell_x", "E_cell_y", "sigma_cell", "E_gj_x", "E_gj_y",
     "J_env_x", "J_env_y", "B_field", "Jtx", "Jty", "cenv_uniform", "vm_cell",
+    "D_env_weight",
 ]
 
 

@@ -34,6 +34,7 @@ unsigned tile_pack_size(int ni);
 void launch_hh_setup(const HHBuf& H, int ny, int nx, cudaStream_t st);
 void launch_hh(const KParams& P, const KArrays& A, const HHBuf& H, cudaStream_t st);
 void launch_phi_b(const KParams& P, const HHBuf& H, const double bound[4], double* phi, cudaStream_t st);
+void launch_noecm_field(const KParams& P, const KArrays& A, const HHBuf& H, double sigma, const double* D_env_weight, int old, cudaStream_t st);
 void launch_pack_const(const KParams& P, const KArrays& A, cudaStream_t st);
 void launch_pack_dm(const KParams& P, const KArrays& A, cudaStream_t st);
 void launch_chan(const KParams& P, const KArrays& A, const KChan& ch, const KNet& N, int cur, cudaStream_t st);
@@ -68,6 +69,7 @@ struct betse_ctx {
     HHBuf hh;                                // Helmholtz-Hodge diagnostics (sampled steps, undivided ECM tissues)
     bool hh_on = false;
     bool want_hh = true;
+    const double* denv_w = nullptr;          // [E] sim.D_env_weight (no-ECM field diagnostics)
     bool poisson_on = false;                 // sine matrices + work buffers of the Dirichlet Poisson solve (HH, Phi_b)
     // boundary-voltage potential Phi_b (ion_current.py:84-90): [new, old] while sim.bound_V ramps, see update_phi_b
     double* phi[2] = {nullptr, nullptr};
@@ -576,9 +578,11 @@ static int ensure_poisson(betse_ctx* ctx)
 static int ensure_diag_buffers(betse_ctx* ctx)
 {
     KArrays& A = ctx->A;
-    if (A.fl_mem) return 0;
     const size_t IM = (size_t)ctx->I * ctx->Mo, IE = (size_t)ctx->I * ctx->E;
     int r;
+    const bool want_hh = (ctx->hp.is_ecm || ctx->denv_w) && ctx->X.n_nbr == 0 && ctx->ny > 2 && ctx->nx > 2;
+    if (A.fl_mem && (ctx->hh_on || !want_hh)) return 0;
+    if (!A.fl_mem) {
     if ((r = dev_alloc(ctx, &A.fl_mem, IM))) return r;
     if ((r = dev_alloc(ctx, &A.fl_gj, IM))) return r;
     if ((r = dev_alloc(ctx, &A.fl_env_x, ctx->hp.is_ecm ? IE : 1))) return r;
@@ -588,8 +592,10 @@ static int ensure_diag_buffers(betse_ctx* ctx)
     for (auto p : mem_arrays) if ((r = dev_alloc(ctx, p, ctx->Mo))) return r;
     double** cell_arrays[] = {&A.J_cell_x, &A.J_cell_y, &A.E_cell_x, &A.E_cell_y, &A.sigma_cell};
     for (auto p : cell_arrays) if ((r = dev_alloc(ctx, p, ctx->C))) return r;
-    // Helmholtz-Hodge decomposition of the env current (ion_current.py:50-73): undivided ECM tissues only
-    if (ctx->hp.is_ecm && ctx->X.n_nbr == 0 && ctx->ny > 2 && ctx->nx > 2) {
+    }
+    // Helmholtz-Hodge decomposition of the env current (ion_current.py:50-73) / of the bath current of a tissue without
+    // extracellular spaces (ion_current.py:116-158): undivided tissues only
+    if (want_hh && !ctx->hh_on) {
         if ((r = ensure_poisson(ctx))) return r;
         HHBuf& H = ctx->hh;
         double** eb[] = {&H.Jx, &H.Jy, &H.bA, &H.uA, &H.uB, &H.J_env_x, &H.J_env_y, &H.B_field, &H.Jtx, &H.Jty};
@@ -671,6 +677,9 @@ extern "C" int betse_upload_state(betse_ctx* ctx, const betse_state_host* s)
             ctx->P.has_phi = nz ? 1 : 0;
             destroy_graphs(ctx);      // KParams is baked into the captured launches
         }
+    }
+    if (s->D_env_weight && !ctx->hp.is_ecm) {
+        if ((r = opt_array(ctx, &ctx->denv_w, (const double*)s->D_env_weight, E))) return r;
     }
     if ((r = opt_array(ctx, &A.extra_rho_cells, (const double*)s->extra_rho_cells, C))) return r;
     if ((r = opt_array(ctx, &A.extra_rho_env, (const double*)s->extra_rho_env, E))) return r;
@@ -818,6 +827,11 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
             ctx->hh.mu = ctx->hp.mu;
             for (int q = 0; q < 4; ++q) ctx->hh.bound[q] = ctx->hp.bound_V[q];
             launch_hh(ctx->P, A, ctx->hh, st);
+        }
+        if (diag && ctx->want_hh && !ecm && ctx->hh_on && ctx->denv_w) {
+            ctx->hh.mu = ctx->hp.mu;
+            for (int q = 0; q < 4; ++q) ctx->hh.bound[q] = 0.0;          // HH_Decomp(..., bounds=None)
+            launch_noecm_field(ctx->P, A, ctx->hh, ctx->hp.sigma_env, ctx->denv_w, cur, st);
         }
         if (evs) cudaEventRecord(evs[6], st);
         ctx->cur = nxt;
@@ -1035,6 +1049,13 @@ extern "C" int betse_download_sample(betse_ctx* ctx, betse_state_host* s)
         DN(s->E_env_y, A.E_y, E);
         DN(s->v_env, A.v_env, E);
         DN(s->rho_env, A.rho_env, E);
+    } else if (s->E_env_x || s->E_env_y || s->v_env) {
+        // the local field potential and its field: diagnostics of the last sampled step (ion_current.py:116-158)
+        if (!ctx->hh_on || !ctx->denv_w || !ctx->diag_valid)
+            return fail(ctx, "v_env / E_env without extracellular spaces: upload D_env_weight and run the step with BETSE_STEP_DIAG");
+        DN(s->E_env_x, A.E_x, E);
+        DN(s->E_env_y, A.E_y, E);
+        DN(s->v_env, A.v_env, E);
     }
     if (s->vm || s->vm_ave) {
         if (ctx->P.polar) CK(cudaMemcpyAsync(A.vm_mem, A.vm_pol[cur], (size_t)Mo * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -1066,7 +1087,7 @@ extern "C" int betse_download_sample(betse_ctx* ctx, betse_state_host* s)
         DN(s->sigma_cell, A.sigma_cell, C);
         DN(s->E_gj_x, A.E_gj_x, Mo); DN(s->E_gj_y, A.E_gj_y, Mo);
         if (s->J_env_x || s->J_env_y || s->B_field || s->Jtx || s->Jty) {
-            if (!ctx->hh_on) return fail(ctx, "J_env / B_field / Jtx: the Helmholtz-Hodge diagnostics need an undivided tissue with extracellular spaces");
+            if (!ctx->hh_on) return fail(ctx, "J_env / B_field / Jtx: the Helmholtz-Hodge diagnostics need an undivided tissue (and sim.D_env_weight without extracellular spaces)");
             DN(s->J_env_x, ctx->hh.J_env_x, E); DN(s->J_env_y, ctx->hh.J_env_y, E); DN(s->B_field, ctx->hh.B_field, E);
             DN(s->Jtx, ctx->hh.Jtx, E); DN(s->Jty, ctx->hh.Jty, E);
         }

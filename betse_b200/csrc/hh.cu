@@ -227,6 +227,108 @@ void launch_phi_b(const KParams& P, const HHBuf& H, const double bound[4], doubl
     poisson(P, H, H.bB, phi, st);
 }
 
+// ---------------------------------------------------------------------------- no-ECM field diagnostics
+// get_current without extracellular spaces (ion_current.py:116-158): a local field potential from Vmem/2 scattered to
+// the env squares of the membranes, smoothed by gaussian_filter(sigma=1) in scipy's default 'reflect' mode, its gradient
+// smoothed through a Helmholtz-Hodge decomposition and reconstruction (stb.smooth_flux, sim_toolbox.py:1318-1333), the
+// bath current sigma*E*D_env_weight decomposed again.  Nothing of it feeds back into the timestep (update_ecm only runs
+// with ECM); write2storage stores v_env and J_env (sim.py:1826, 1866-1867), so it runs at sampled steps.
+__global__ void k_ne_scatter(const __grid_constant__ KParams P, const KArrays A, double* __restrict__ phi, const int old)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int E = P.nx * P.ny;
+    if (q >= E) return;
+    const int s0 = A.slot_ptr[q], s1 = A.slot_ptr[q + 1];
+    double v = 0.0;
+    if (s1 > s0) {
+        // vce[cells.map_mem2ecm] = vc[cells.mem_to_cells] (ion_current.py:121): fancy assignment, the last membrane of
+        // the square wins; sic — a per-MEMBRANE array indexed by the membrane's CELL index
+        // update_V calls get_current BEFORE it renews Vmem (sim.py:2010-2013): this is the Vmem the step started with
+        const int m = A.slot_idx[s1 - 1];
+        const int mm = A.mem_to_cells[m];                    // used as a MEMBRANE index
+        double vm;
+        if (P.polar) vm = A.vm_pol[old][mm];
+        else {
+            vm = A.vm_cell[old][A.mem_to_cells[mm]];
+            if (P.has_phi) vm -= A.phi_b_old[A.map_mem2ecm[mm]];
+        }
+        v = vm / 2.0;
+    }
+    phi[q] = -v;
+}
+
+__device__ __forceinline__ int refl(int i, const int n)          // scipy 'reflect': d c b a | a b c d | d c b a
+{
+    if (i < 0) i = -i - 1;
+    if (i >= n) i = 2 * n - i - 1;
+    return i < 0 ? 0 : (i >= n ? n - 1 : i);
+}
+
+// one separable pass of gaussian_filter(sigma=1, mode='reflect'); axis 0 = rows (y), then axis 1 (x), like scipy
+__global__ void k_ne_gauss(const __grid_constant__ KParams P, const double* __restrict__ in, double* __restrict__ out, const int axis)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int nx = P.nx, ny = P.ny;
+    if (x >= nx) return;
+    const int n = axis == 0 ? ny : nx, i0 = axis == 0 ? y : x;
+    auto at = [&](int i) { i = refl(i, n); return axis == 0 ? in[(size_t)i * nx + x] : in[(size_t)y * nx + i]; };
+    double s = at(i0) * P.gw[0];                       // scipy correlate1d, symmetric form (as kernels.cu:k_field)
+    s += (at(i0 - 4) + at(i0 + 4)) * P.gw[4];
+    s += (at(i0 - 3) + at(i0 + 3)) * P.gw[3];
+    s += (at(i0 - 2) + at(i0 + 2)) * P.gw[2];
+    s += (at(i0 - 1) + at(i0 + 1)) * P.gw[1];
+    out[(size_t)y * nx + x] = s;
+}
+
+// F = delta*Phi (scaled in place of a copy), then fd.gradient(F, delta) -> (Jx, Jy) = the field HH smooths
+__global__ void k_ne_scale(double* __restrict__ dst, const double* __restrict__ src, const double f, const int n)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n) dst[q] = f * src[q];
+}
+__global__ void k_ne_grad(const __grid_constant__ KParams P, const double* __restrict__ F, double* __restrict__ gx, double* __restrict__ gy)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= P.nx) return;
+    double a, b;
+    grad_at(F, y, x, P.ny, P.nx, P.delta, a, b);
+    gx[(size_t)y * P.nx + x] = a; gy[(size_t)y * P.nx + x] = b;
+}
+// E = -(smoothed gradient); J = sigma*E*D_env_weight (ion_current.py:138-143)
+__global__ void k_ne_EJ(const __grid_constant__ KParams P, const KArrays A, HHBuf H, const double sigma, const double* __restrict__ W)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= P.nx * P.ny) return;
+    const double ex = -H.Jtx[q], ey = -H.Jty[q];
+    A.E_x[q] = ex; A.E_y[q] = ey;
+    H.Jx[q] = (sigma * ex) * W[q];
+    H.Jy[q] = (sigma * ey) * W[q];
+}
+
+static void hh_core(const KParams& P, const HHBuf& H, cudaStream_t st)
+{
+    dim3 gE((P.nx + 127) / 128, P.ny);
+    k_hh_rhs<<<gE, 128, 0, st>>>(P, H);
+    poisson(P, H, H.bA, H.uA, st);
+    poisson(P, H, H.bB, H.uB, st);
+    k_hh_out<<<gE, 128, 0, st>>>(P, H);
+}
+
+// H.bound must be zero (HH_Decomp without bounds, ion_current.py:134, 145); work: H.uA / H.uB double as Gaussian scratch
+void launch_noecm_field(const KParams& P, const KArrays& A, const HHBuf& H, double sigma, const double* D_env_weight, int old, cudaStream_t st)
+{
+    const int E = P.nx * P.ny;
+    dim3 gE((P.nx + 127) / 128, P.ny);
+    k_ne_scatter<<<(E + 255) / 256, 256, 0, st>>>(P, A, H.uA, old);
+    k_ne_gauss<<<gE, 128, 0, st>>>(P, H.uA, H.uB, 0);
+    k_ne_gauss<<<gE, 128, 0, st>>>(P, H.uB, A.v_env, 1);                   // sim.v_env = Phi (ion_current.py:158)
+    k_ne_scale<<<(E + 255) / 256, 256, 0, st>>>(H.uA, A.v_env, P.delta, E);
+    k_ne_grad<<<gE, 128, 0, st>>>(P, H.uA, H.Jx, H.Jy);
+    hh_core(P, H, st);                                                      // stb.smooth_flux: Jtx/Jty = Fr + Fd
+    k_ne_EJ<<<(E + 255) / 256, 256, 0, st>>>(P, A, H, sigma, D_env_weight);
+    hh_core(P, H, st);
+}
+
 void launch_hh(const KParams& P, const KArrays& A, const HHBuf& H, cudaStream_t st)
 {
     const int E = P.nx * P.ny;

@@ -23,6 +23,8 @@ _DOWN_SHAPES = {
     "sigma_cell": "C", "E_gj_x": "M", "E_gj_y": "M",
     "J_env_x": "E", "J_env_y": "E", "B_field": "E", "Jtx": "E", "Jty": "E", "Phi_b": "E",
 }
+# what get_current leaves on the env grid of a tissue WITHOUT extracellular spaces (ion_current.py:116-158)
+_NOECM_FIELD = ("v_env", "E_env_x", "E_env_y", "J_env_x", "J_env_y", "B_field", "Jtx", "Jty")
 DIAG_FIELDS = ("fluxes_mem", "fluxes_gj", "fluxes_env_x", "fluxes_env_y", "rate_NaKATP", "Jmem",
                "Jgj", "Jn", "I_mem", "Jc", "Emc", "dvm", "J_cell_x", "J_cell_y", "E_cell_x",
                "E_cell_y", "sigma_cell", "vm_ave", "E_gj_x", "E_gj_y", "J_env_x", "J_env_y", "B_field", "Jtx", "Jty")
@@ -165,7 +167,7 @@ class TissueEngine:
             S["D_gj"] = dgj
         for key, default in (("c_env_bound", np.zeros(self.I)), ("T", p.get("T", 310.0)),
                              ("ko_env", 1.0), ("rho_pump", 1.0), ("rho_channel", 1.0),
-                             ("bound_V", np.zeros(4))):
+                             ("bound_V", np.zeros(4)), ("sigma", 0.0)):
             if key in st:
                 S[key] = np.asarray(st[key], dtype=float)
             S.setdefault(key, np.asarray(default, dtype=float))
@@ -193,6 +195,7 @@ class TissueEngine:
         hp.T_p = float(p["T"])
         hp.rho_pump, hp.rho_channel = _scalar(S["rho_pump"]), _scalar(S["rho_channel"])
         hp.ko_env = _scalar(S["ko_env"])
+        hp.sigma_env = _scalar(S["sigma"])
         bv = np.asarray(S["bound_V"], dtype=float).reshape(-1)
         for i in range(4):
             hp.bound_V[i] = bv[i]
@@ -256,6 +259,9 @@ class TissueEngine:
             put("cenv_uniform", ce.reshape(I, -1)[:, 0], I)
         if "Phi_b" in state:
             put("Phi_b", state["Phi_b"], E)
+        if "D_env_weight" in state and not self.is_ecm:     # no-ECM field diagnostics (ion_current.py:116-158)
+            put("D_env_weight", state["D_env_weight"], E)
+            self.noecm_field = True
         if "vm_cell" in state:
             put("vm_cell", state["vm_cell"], Cn)
         elif "vm" in state:
@@ -371,7 +377,8 @@ class TissueEngine:
                 cenv = np.empty(I)
                 sh.cenv_uniform = capi.ptr_f64(cenv)
                 continue
-            if not self.is_ecm and _DOWN_SHAPES.get(f, "").endswith("E") and f != "Phi_b":
+            if not self.is_ecm and _DOWN_SHAPES.get(f, "").endswith("E") and f != "Phi_b" and not (
+                    getattr(self, "noecm_field", False) and f in _NOECM_FIELD):
                 continue
             if f not in _DOWN_SHAPES:
                 raise KeyError(f)

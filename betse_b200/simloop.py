@@ -39,7 +39,7 @@ _STATE_FIELDS = [
     "cc_cells", "cc_at_mem", "cc_env", "vm", "gjopen", "Dm_cells", "D_gj", "D_free", "zs",
     "c_env_bound", "T", "extra_rho_cells", "extra_rho_env", "extra_J_mem", "ko_env",
     "NaKATP_block", "gj_block", "rho_pump", "rho_channel", "D_env", "TJ_modulator", "E_env_x",
-    "E_env_y", "Phi_b",
+    "E_env_y", "Phi_b", "D_env_weight", "sigma",
 ]
 # what fire_events / makeAllChanges may rewrite between steps (tishandler.py:728-917, 1321-1332)
 _SCHEDULED = ["Dm_cells", "D_env", "TJ_modulator", "gj_block", "NaKATP_block", "c_env_bound", "T"]
@@ -202,8 +202,11 @@ def _copy_back(sim, eng, diag, sample_only=False):
     engine's page-locked staging (views that the next sample overwrites — write2storage copies what it
     keeps; vm_ave, which it appends as is (sim.py:1877), gets its own array)."""
     if sample_only:
+        noecm_field = diag and not eng.is_ecm and getattr(eng, "noecm_field", False)
         fields = _W2S_STATE + (_W2S_ENV if eng.is_ecm else ["cc_env"]) + (_W2S_DIAG if diag else [])
-        if diag and eng.is_ecm:
+        if noecm_field:
+            fields += ["v_env"]                    # venv_time: the local field potential (ion_current.py:158)
+        if diag and (eng.is_ecm or noecm_field):
             fields += ["J_env_x", "J_env_y"]       # I_tot_x_time / I_tot_y_time (sim.py:1866-1867)
     else:
         fields = list(_SAMPLED_STATE)
@@ -211,11 +214,13 @@ def _copy_back(sim, eng, diag, sample_only=False):
             fields += _SAMPLED_ENV
         if diag:
             fields += _SAMPLED_DIAG + ["E_gj_x", "E_gj_y"] + (_SAMPLED_DIAG_ENV if eng.is_ecm else [])
+            if not eng.is_ecm and getattr(eng, "noecm_field", False):
+                fields += ["v_env", "E_env_x", "E_env_y", "J_env_x", "J_env_y", "B_field", "Jtx", "Jty"]
     got = eng.download(fields, pinned=sample_only)
     shp = (eng.ny, eng.nx)
     for f, a in got.items():
-        if f in ("E_env_x", "E_env_y"):
-            a = a.reshape(shp)                     # the reference keeps these 2-D (sim.py:572-573)
+        if f in ("E_env_x", "E_env_y", "J_env_x", "J_env_y", "Jtx", "Jty"):
+            a = a.reshape(shp)                     # the reference keeps these 2-D (sim.py:572-573; sim_toolbox.py:1266-1290)
         if sample_only and f == "vm_ave":
             a = a.copy()
         elif sample_only:

@@ -99,7 +99,9 @@ typedef struct betse_params {
     double NaKATP_block_scalar;        /* used when no per-membrane block array is set    */
     double gj_block_scalar;
     int32_t is_ecm, v_sensitive_gj, cluster_open, fast_update_ecm;
-    int32_t reserved[4];
+    double sigma_env;                  /* sim.sigma: bath conductivity of the no-ECM field diagnostics (sim.py:986-996,
+                                          ion_current.py:142-143)                            */
+    double reserved_d;
 } betse_params;
 
 /* Host-side view of the Simulator state.  NULL members are skipped.  Shapes in brackets;
@@ -138,6 +140,7 @@ typedef struct betse_state_host {
                                 (ion_current.py:50-73, sim_toolbox.py:1236-1290); undivided ECM tissues */
     double *cenv_uniform;    /* [I]   no-ECM bath concentrations (download only)          */
     double *vm_cell;         /* [C]   per-cell Vmem incl. ghost cells (upload only; overrides vm)  */
+    double *D_env_weight;    /* [E]   sim.D_env_weight (no-ECM field diagnostics, ion_current.py:142-143; upload only) */
 } betse_state_host;
 
 #define BETSE_STATUS_NAN_VM     1u  /* stb.check_v would raise          */

@@ -20,6 +20,7 @@ class OracleEngine:
         self.ny, self.nx = (int(x) for x in mesh["grid_shape"])
         self.mem_to_cells = np.asarray(mesh["mem_to_cells"])
         self.h2d_bytes = self.d2h_bytes = 0
+        self.noecm_field = (not self.is_ecm) and "D_env_weight" in state
         self.networks = {}
         self._descs = {}
         self._specs = []
@@ -46,6 +47,8 @@ class OracleEngine:
             nfrac = float(params["smooth_cells"])
             state.setdefault("smooth_weight_mem", (nfrac * nm - 1) / (nfrac * nm))
             state.setdefault("smooth_weight_o", 1 / (nfrac * nm))
+            # no-ECM field diagnostics (ion_current.py:116-171) are not part of the engine's contract: any weight will do
+            state.setdefault("D_env_weight", np.ones(self.ny * self.nx))
             self._o = OracleSim(mesh, params, state, channels=self._specs, phase_init=self._phase_init,
                                 networks=[self._descs[h] for h in sorted(self._descs)])
             self._active = [c for c in self._o.channels if not (self._phase_init and not c["init_active"])]
@@ -76,11 +79,11 @@ class OracleEngine:
         o = self._sim()
         out = {}
         for f in fields:
-            if not self.is_ecm and f in ("E_env_x", "E_env_y", "v_env", "rho_env"):
+            if not self.is_ecm and (f == "rho_env" or (f in ("E_env_x", "E_env_y", "v_env") and not self.noecm_field)):
                 continue
             out[f] = np.array(getattr(o, f), dtype=float, copy=True)
-            if f in ("E_env_x", "E_env_y"):
-                out[f] = out[f].ravel()
+            if out[f].ndim == 2 and f != "cc_cells" and out[f].shape == (self.ny, self.nx):
+                out[f] = out[f].ravel()          # the engine hands env-grid fields out flat
         return out
 
     def channel_state(self, k):

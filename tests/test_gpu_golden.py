@@ -37,10 +37,9 @@ def test_gpu_matches_reference(name, kind):
         ref = util.group(cap, "%s.k%d." % (kind, K))
         fields = list(util.STATE) + (util.ENV_STATE if ecm else [])
         if last:
-            hh = ("J_env_x", "J_env_y", "Jtx", "Jty", "B_field")     # Helmholtz-Hodge parts: ECM tissues (csrc/hh.cu)
-            fields += [f for f in util.DIAG if f in ref and f not in ("rho_env_surf", "Eme") and (ecm or f not in hh)]
-            if not ecm:
-                fields = [f for f in fields if not f.startswith("fluxes_env")]
+            fields += [f for f in util.DIAG if f in ref and f not in ("rho_env_surf", "Eme")]
+            if not ecm:      # no-ECM field diagnostics (ion_current.py:116-158): local field potential, its field, bath current
+                fields = [f for f in fields if not f.startswith("fluxes_env")] + ["v_env", "E_env_x", "E_env_y"]
         got = eng.download([f for f in fields if f in ref])
         tols = util.gpu_tolerances(cap, kind, ref)
         for f, a in got.items():

@@ -187,14 +187,17 @@ def _run_try(tmp_path, use_dropin, monkeypatch=None, mods=None):
     return phase.sim, phase.cells, engines
 
 
-def test_betse_try_through_the_dropin_matches_the_reference(monkeypatch, tmp_path):
+@pytest.mark.parametrize("variant", ["shipped", "configs0_noecm"])
+def test_betse_try_through_the_dropin_matches_the_reference(variant, monkeypatch, tmp_path):
     """The whole host side of the drop-in against the reference's own run of its shipped default configuration:
     INIT (500 steps) and SIM (350 steps, cutting event at the first step, three voltage-gated channels, substance X),
     sampled-step storage (`vm_time`, `cc_time`, ...) as `write2storage` leaves it.  The engine here is the CPU
     oracle (tests/oracle_engine.py); the CUDA engine is held to the same recorded run in tests/test_full_run.py."""
-    ref_sim, ref_cells, _ = _run_try(tmp_path / "ref", False)
+    # "configs0_noecm": BASELINE configs[0] to the letter (Na/K/Cl/Ca/P(+M) profile, no extracellular spaces)
+    mods = {} if variant == "shipped" else {"general options": {"ion profile": "mammal", "simulate extracellular spaces": False}}
+    ref_sim, ref_cells, _ = _run_try(tmp_path / "ref", False, mods=mods)
     (tmp_path / "new").mkdir()
-    new_sim, new_cells, engines = _run_try(tmp_path / "new", True, monkeypatch)
+    new_sim, new_cells, engines = _run_try(tmp_path / "new", True, monkeypatch, mods=mods)
     assert len(engines) == 2                                  # one engine per phase
     assert len(new_cells.mem_i) == len(ref_cells.mem_i) < engines[0].M      # the cut happened, on both paths alike
     assert engines[1].M == len(ref_cells.mem_i)               # the SIM engine was built from the post-cut mesh
@@ -204,7 +207,8 @@ def test_betse_try_through_the_dropin_matches_the_reference(monkeypatch, tmp_pat
         assert np.max(np.abs(a - r)) <= 1e-6                  # BASELINE.json: Vmem traces within 1e-6 V
         assert np.max(np.abs(a - r)) <= 1e-9 * np.max(np.abs(r))
     for name in ("cc_time", "cc_env_time", "gjopen_time", "vm_ave_time", "rho_cells_time", "I_mem_time",
-                 "venv_time", "efield_gj_x_time", "rate_NaKATP_time"):
+                 "venv_time", "efield_gj_x_time", "rate_NaKATP_time", "I_tot_x_time", "I_tot_y_time",
+                 "I_cell_x_time"):
         got, want = getattr(new_sim, name), getattr(ref_sim, name)
         assert len(got) == len(want) and len(want) >= 30, name
         for a, r in zip(got, want):

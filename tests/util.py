@@ -132,6 +132,17 @@ def gpu_tolerances(cap, kind, ref):
             tol[f] = 1e-9 * sJt
         L = float(max(cells["grid_shape"])) * float(cells["delta"])
         tol["B_field"] = max(1e-8 * mx("B_field"), 1e-9 * sJt * float(P["mu"]) * L)
+    if "Jtx" in ref and not int(P["is_ecm"]):
+        # without extracellular spaces (ion_current.py:116-158): v_env is Vmem/2 scattered and smoothed, E its (Helmholtz-Hodge
+        # smoothed) difference quotient times delta, J = sigma*E*D_env_weight decomposed once more
+        tol["v_env"] = tol["vm"]
+        e_scale = max(mx("E_env_x"), mx("E_env_y"))
+        tol["E_env_x"] = tol["E_env_y"] = max(1e-9 * e_scale, 8 * tol["vm"])
+        sJt = max(mx("Jtx"), mx("Jty"))
+        for f in ("J_env_x", "J_env_y", "Jtx", "Jty"):
+            tol[f] = 1e-9 * sJt
+        L = float(max(cells["grid_shape"])) * float(cells["delta"])
+        tol["B_field"] = max(1e-8 * mx("B_field"), 1e-9 * sJt * float(P["mu"]) * L)
     if "fluxes_mem" in ref:
         zs = np.asarray(S0["zs"], dtype=float)
         sJ = float(np.max(np.dot(zF, np.abs(ref["fluxes_mem"]))))
