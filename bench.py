@@ -300,8 +300,16 @@ def main():
     # per-launch algorithmic bytes of one rank's kernel (a rank holds 1/world of the tissue)
     share = {"k_mem": b_mem / world, "k_ion": I * 24 * E / world, "k_envacc": 0, "k_field": 72 * E / world, "k_envmix": 0}
     ach = share.get(dom, b_mem / world) / (kms[dom] * 1e-3) / 1e9
+    traffic = None     # measured DRAM bytes per launch of the dominant kernel (one `ncu --set full` capture of this workload)
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        w = tr["workload"]
+        if w["cells"] == C and w["ions"] == I and bool(w["ecm"]) == bool(ecm) and world == w["n_gpus"]:
+            traffic = tr["bytes_per_launch"].get(dom)
+    except Exception:
+        pass
     roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "traffic": None, "peak_source": peak_src,
+            "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": share.get(dom, b_mem / world),
             "kernel_ms": kms, "step": {"algorithmic_bytes": b_step, "n_gpus": world,
                                        "achieved": b_step / (ms_per_step * 1e-3) / 1e9,
