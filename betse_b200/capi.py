@@ -112,6 +112,11 @@ class Modulator(C.Structure):
     _fields_ = [("target", C.c_int32), ("prog", C.c_int32), ("max_val", C.c_double)]
 
 
+class LigandGate(C.Structure):
+    _fields_ = [("species", C.c_int32), ("ion", C.c_int32), ("extracell", C.c_int32), ("pad", C.c_int32),
+                ("K", C.c_double), ("n", C.c_double), ("max_val", C.c_double), ("mod", C.c_double)]
+
+
 class Network(C.Structure):
     _fields_ = [
         ("n_species", C.c_int32), ("n_rates", C.c_int32), ("n_programs", C.c_int32),
@@ -122,6 +127,7 @@ class Network(C.Structure):
         ("env_on", _bp), ("Dm", _dp), ("c_bound", _dp), ("c_env", _dp), ("D_env", _dp),
         ("scale_factor", _dp), ("affect_charge", C.c_int32), ("n_modulators", C.c_int32),
         ("modulators", C.POINTER(Modulator)),
+        ("ligand_gates", C.POINTER(LigandGate)), ("n_ligand_gates", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

@@ -40,6 +40,10 @@ void launch_pack_dm(const KParams& P, const KArrays& A, cudaStream_t st);
 void launch_chan(const KParams& P, const KArrays& A, const KChan& ch, const KNet& N, int cur, cudaStream_t st);
 void launch_net(const KParams& P, const KArrays& A, const KNet& N, const double* h_Dgj, const double* h_Dm,
                 const unsigned char* h_env_on, int n_ions, int cur, cudaStream_t st);
+void launch_lig_prep(const KParams& P, const KArrays& A, const KNet& N, int sp, int extracell, double Kn, double n,
+                     double max_val, double* Dm_mod, cudaStream_t st);
+void launch_net_lig(const KParams& P, const KArrays& A, int ion, const double* Dm_mod, double mod, int cur, int diag, cudaStream_t st);
+void launch_chan_env(const KParams& P, const KArrays& A, int ion, int cur, cudaStream_t st);
 void launch_net_mod(const KParams& P, const KArrays& A, const KNet& N, int prog, double max_val, double* dst, int cur, cudaStream_t st);
 void launch_cell_update(const KParams& P, const KArrays& A, int cur, cudaStream_t st);
 void launch_xchg(const KParams& P, const KArrays& A, const XPlan& X, int which, int buf, int mode, cudaStream_t st);
@@ -84,6 +88,8 @@ struct betse_ctx {
     std::vector<unsigned char> net_env_on[2];
     bool net_affect[2] = {false, false};
     std::vector<betse_modulator> net_mods[2];   // sim modulators of each handler (run_loop_modulators)
+    std::vector<betse_ligand_gate> net_gates[2];   // ligand-gated channels (Molecule.gating)
+    double* lig_tmp[2] = {nullptr, nullptr};       // [n_gates][M] openings formed before the substances advance
     std::string err;
     std::vector<void*> allocs;
     // CUDA graphs of one plain step, for cur = 0 and cur = 1
@@ -809,8 +815,18 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
                     for (const betse_modulator& md : ctx->net_mods[h])
                         launch_net_mod(ctx->P, A, ctx->nets[h], md.prog, md.max_val,
                                        const_cast<double*>(md.target == 0 ? A.gj_block : A.NaK_block), cur, st);
-                if (ctx->net_on[h]) launch_net(ctx->P, A, ctx->nets[h], ctx->net_Dgj[h].data(), ctx->net_Dm[h].data(),
-                                               ctx->net_env_on[h].data(), I, cur, st);
+                if (ctx->net_on[h]) {
+                    const std::vector<betse_ligand_gate>& gs = ctx->net_gates[h];
+                    for (size_t j = 0; j < gs.size(); ++j)
+                        launch_lig_prep(ctx->P, A, ctx->nets[h], gs[j].species, gs[j].extracell, pow(gs[j].K, gs[j].n), gs[j].n,
+                                        gs[j].max_val, ctx->lig_tmp[h] + j * (size_t)ctx->Mo, st);
+                    launch_net(ctx->P, A, ctx->nets[h], ctx->net_Dgj[h].data(), ctx->net_Dm[h].data(),
+                               ctx->net_env_on[h].data(), I, cur, st);
+                    for (size_t j = 0; j < gs.size(); ++j) {
+                        launch_net_lig(ctx->P, A, gs[j].ion, ctx->lig_tmp[h] + j * (size_t)ctx->Mo, gs[j].mod, cur, diag, st);
+                        launch_chan_env(ctx->P, A, gs[j].ion, cur, st);
+                    }
+                }
             }
             launch_cell_update(ctx->P, A, cur, st);
         }
@@ -1264,6 +1280,17 @@ extern "C" int betse_set_network(betse_ctx* ctx, int handler, const betse_networ
         }
     }
     if ((r = ensure_defer_buffers(ctx))) return r;
+    ctx->net_gates[handler].clear();
+    for (int j = 0; j < net->n_ligand_gates; ++j) {
+        const betse_ligand_gate& g = net->ligand_gates[j];
+        if (g.species < 0 || g.species >= K || g.ion < 0 || g.ion >= ctx->I) return fail(ctx, "network: ligand gate species / ion out of range");
+        if (g.extracell && !(net->env_on && net->env_on[g.species] && ctx->hp.is_ecm))
+            return fail(ctx, "network: an extracellular ligand needs extracellular spaces and env_on for its substance");
+        ctx->net_gates[handler].push_back(g);
+    }
+    if (net->n_ligand_gates > 0) {
+        if ((r = dev_alloc(ctx, &ctx->lig_tmp[handler], (size_t)net->n_ligand_gates * Mo))) return r;
+    }
     ctx->net_mods[handler].clear();
     for (int j = 0; j < net->n_modulators; ++j) {
         const betse_modulator& md = net->modulators[j];

@@ -205,6 +205,15 @@ void launch_chan(const KParams& P, const KArrays& A, const KChan& ch, const KNet
     } else k_chan_mix<<<1, 256, 0, st>>>(P, A, ch.ion, cur);
 }
 
+// env side of an immediate update_Co for fluxes left in chan_slots / chan_part (ligand-gated channels)
+void launch_chan_env(const KParams& P, const KArrays& A, int ion, int cur, cudaStream_t st)
+{
+    if (P.is_ecm) {
+        const int n = (P.ya1 - P.ya0) * P.nx;
+        if (n > 0) k_chan_env<<<(n + 255) / 256, 256, 0, st>>>(P, A, ion, cur ^ 1);
+    } else k_chan_mix<<<1, 256, 0, st>>>(P, A, ion, cur);
+}
+
 void launch_cell_update(const KParams& P, const KArrays& A, int cur, cudaStream_t st)
 {
     k_cell_update<<<(P.n_cells_owned + 255) / 256, 256, 0, st>>>(P, A, cur);

@@ -125,6 +125,93 @@ void launch_net_mod(const KParams& P, const KArrays& A, const KNet& N, int prog,
     k_net_mod<<<(P.n_mems_owned + 255) / 256, 256, 0, st>>>(P, A, N, prog, max_val, dst, cur);
 }
 
+// Ligand-gated channel (Molecule.gating, networks.py:5847-5916), one warp per tile of whole cells (the packing of
+// k_mem): Hill opening from the ligand at the membrane, GHK flux of the conducted ion, which the reference both ADDS to
+// sim.fluxes_mem (so update_all_concs applies it: deferred cell sums, membrane->env exchange slots, Jmem) and applies
+// IMMEDIATELY through update_Co (cells here; env squares / the bath by k_chan_env / k_chan_mix).
+__device__ __forceinline__ double np_pow(const double a, const double b)      // NumPy's scalar-exponent fast paths, as in rl_eval
+{
+    return (b == 1.0) ? a : (b == 2.0) ? a * a : (b == 0.5) ? sqrt(a) : (b == -1.0) ? 1.0 / a : (b == 0.0) ? 1.0 : pow(a, b);
+}
+
+// The opening of a gate is formed from the ligand as the step FOUND it (cc_at_mem is refreshed by update_intra before
+// the substance's growth/decay, its c_env moves only in its own transport, which follows the gating): k_lig_prep runs
+// before the handler's substances are advanced, k_net_lig — which only touches ions, as nothing of a substance's
+// transport reads them — after it, so the rate laws still see the ions untouched by the gates (networks.py:2826-2853).
+__global__ void __launch_bounds__(256)
+k_lig_prep(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ KNet N, const int sp, const int extracell,
+           const double Kn, const double n, const double max_val, double* __restrict__ Dm_mod)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= P.n_mems_owned) return;
+    const int E = P.ny * P.nx;
+    const double x = extracell ? N.c_env[(size_t)sp * E + __ldg(A.map_mem2ecm + m)] : N.c[(size_t)sp * P.n_cells + __ldg(A.mem_to_cells + m)];
+    const double xn = np_pow(x, n);
+    const double hill = xn / (Kn + xn);                                       // tb.hill, math/toolbox.py:322
+    Dm_mod[m] = extracell ? (max_val * hill) : ((P.rho_channel * max_val) * hill);   // networks.py:5859-5873
+}
+
+__global__ void __launch_bounds__(BT_TPB)
+k_net_lig(const __grid_constant__ KParams P, const KArrays A, const int ion, const double* __restrict__ Dm_mod_arr,
+          const double mod, const int cur, const int diag)
+{
+    __shared__ double s_all[(BT_TPB / 32) * 32];
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * (BT_TPB / 32) + (threadIdx.x >> 5);
+    if (tile >= P.n_tiles) return;
+    double* s_f = s_all + (threadIdx.x >> 5) * 32;
+    const int4 td = __ldg(reinterpret_cast<const int4*>(A.tile_desc) + tile);
+    const int c0 = td.x, nc = td.y, m0 = td.z, nm = td.w;
+    const int C = P.n_cells, E = P.ny * P.nx, NI = P.n_ions, Mo = P.n_mems_owned;
+    double* __restrict__ ccell = A.cc_cells + (size_t)ion * C;
+    double fsa = 0.0;
+    if (lane < nm) {
+        const int m = m0 + lane;
+        const int c = __ldg(A.mem_to_cells + m);
+        const int e = __ldg(A.map_mem2ecm + m);
+        double vm = A.vm_cell[cur][c];
+        if (P.polar) vm = A.vm_pol[cur][m];
+        else if (P.has_phi) vm -= __ldg(A.phi_b_old + e);
+        const double Dchan = (P.rho_channel * Dm_mod_arr[m]) * mod;
+        const double alpha = ((P.z[ion] + FLOAT_NONCE) * (vm + FLOAT_NONCE) * P.F) / P.RT_sim;
+        const double ex = exp(-alpha), deno = -expm1(-alpha);
+        const double cB = ccell[c], cA = P.is_ecm ? A.cc_env[cur ^ 1][(size_t)ion * E + e] : A.cenv_u[cur * 8 + ion];
+        const double f = -((Dchan * alpha) / P.tm) * ((cB - cA * ex) / deno) * P.rho_channel;
+        fsa = f * __ldg(A.mem_sa + m);
+        // sim.fluxes_mem[ion] += chan_flx: this step's update_all_concs moves it a second time
+        if (P.is_ecm) { A.chan_slots[m] = fsa; A.flux_slots[(size_t)m * NI + ion] += fsa; }
+        if (diag) A.fl_mem[(size_t)ion * Mo + m] += f;
+    }
+    s_f[lane] = fsa;
+    __syncwarp();
+    if (!P.is_ecm && lane == 0) {
+        double S = 0.0;
+        for (int j = 0; j < nm; ++j) S += s_f[j];
+        A.chan_part[tile] = S;
+        A.cenv_part[tile * 8 + ion] += S;                                     // deferred share of the bath (k_envmix)
+    }
+    if (lane < nc) {
+        const int c = c0 + lane;
+        const int jb = __ldg(A.cell_mem_ptr + c) - m0, je = __ldg(A.cell_mem_ptr + c + 1) - m0;
+        double S = 0.0;
+        for (int j = jb; j < je; ++j) S += s_f[j];
+        A.dsum_m[(size_t)ion * C + c] += S;                                   // deferred: update_all_concs (k_cell_update)
+        ccell[c] = ccell[c] + (S / __ldg(A.cell_vol + c)) * P.dt;              // immediate: update_Co cell branch
+    }
+}
+
+void launch_lig_prep(const KParams& P, const KArrays& A, const KNet& N, int sp, int extracell, double Kn, double n,
+                     double max_val, double* Dm_mod, cudaStream_t st)
+{
+    k_lig_prep<<<(P.n_mems_owned + 255) / 256, 256, 0, st>>>(P, A, N, sp, extracell, Kn, n, max_val, Dm_mod);
+}
+
+void launch_net_lig(const KParams& P, const KArrays& A, int ion, const double* Dm_mod, double mod, int cur, int diag, cudaStream_t st)
+{
+    const int grid = (P.n_tiles + (BT_TPB / 32) - 1) / (BT_TPB / 32);
+    k_net_lig<<<grid, BT_TPB, 0, st>>>(P, A, ion, Dm_mod, mod, cur, diag);
+}
+
 // ---------------------------------------------------------------------------- membrane + extracellular legs
 // Molecule.transport -> stb.molecule_mover (networks.py:5670-5700, sim_toolbox.py:909-1153) for substances with a
 // membrane permeability and/or a presence in the environment:

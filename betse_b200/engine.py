@@ -520,6 +520,14 @@ class TissueEngine:
                 marr[j].target, marr[j].prog, marr[j].max_val = int(target), int(prog), float(mx)
             keep.append(marr)
             n.n_modulators, n.modulators = len(mods), marr
+        gates = list(net.get("ligand_gates") or [])
+        if gates:
+            garr = (capi.LigandGate * len(gates))()
+            for j, g in enumerate(gates):
+                garr[j].species, garr[j].ion, garr[j].extracell = int(g["species"]), int(g["ion"]), int(bool(g["extracell"]))
+                garr[j].K, garr[j].n, garr[j].max_val, garr[j].mod = float(g["K"]), float(g["n"]), float(g["max"]), float(g["mod"])
+            keep.append(garr)
+            n.n_ligand_gates, n.ligand_gates = len(gates), garr
         if net.get("scale_factor") is not None:
             n.scale_factor = f64(np.asarray(net["scale_factor"], dtype=float).reshape(K))
         n.affect_charge = int(bool(self.p.get("substances_affect_charge", 0)) if net.get("affect_charge") is None

@@ -42,7 +42,7 @@ def unsupported_reasons(core, p):
     for name, m in (getattr(core, "molecules", None) or {}).items():
         why = []
         for flag, what in (("update_intra_conc", "update intracellular"), ("active_pumping", "active pumping"),
-                           ("ion_channel_gating", "ligand gating"), ("change_bounds", "boundary change event"),
+                           ("change_bounds", "boundary change event"),
                            ("cell_clamp", "cell clamp"), ("transmem", "transmembrane transport")):
             if bool(getattr(m, flag, False)):
                 why.append(what)
@@ -101,7 +101,19 @@ def describe_core(core, sim, p, cells, record_static=True):
     }
     # Molecule.transport -> stb.molecule_mover (networks.py:5670-5700, sim_toolbox.py:909-1153): membrane and
     # extracellular legs of the substances that have them
-    env_on = np.array([_in_env(core.molecules[s]) for s in species], dtype=np.uint8)
+    # Molecule.gating (networks.py:5847-5916): ligand-gated channels, one entry per (substance, conducted ion)
+    lig = []
+    for k, s in enumerate(species):
+        m = core.molecules[s]
+        if bool(getattr(m, "ion_channel_gating", False)) and bool(getattr(m, "use_gating_ligand", False)):
+            for ion_tag in m.gating_ion:
+                lig.append({"species": k, "ion": int(ion_tag), "K": float(m.gating_Hill_K), "n": float(m.gating_Hill_n),
+                            "max": float(m.gating_max_val), "extracell": bool(m.gating_extracell),
+                            "mod_string": str(m.gating_mod_eval_string)})
+    if lig:
+        desc["ligand_gates"] = lig
+    env_on = np.array([_in_env(core.molecules[s]) or any(g["species"] == k and g["extracell"] for g in lig)
+                       for k, s in enumerate(species)], dtype=np.uint8)
     if env_on.any() and bool(getattr(p, "is_ecm", False)):
         E = int(np.asarray(sim.D_env_weight).size)
         D_env = np.zeros((K, E))
@@ -165,8 +177,20 @@ def compile_network(desc, n_cells, n_mems, resolver=None):
     for t in desc.get("modulator_targets", []):
         if t not in MOD_TARGETS:
             raise BetseB200Error("modulator target %r is not implemented" % t)
+    # ligand-gated channels: the regulation of the gate itself (gating_mod_eval_string) must fold to a constant — it
+    # is evaluated in the middle of run_loop's per-substance sequence (networks.py:2922-2925), which a device kernel
+    # working from the step's starting concentrations cannot mirror for other substances
+    gates = []
+    for g in desc.get("ligand_gates", []):
+        try:
+            pr = ratelaw.compile_expr(g["mod_string"], tabs, resolver, "mem")
+        except ratelaw.RateLawError as e:
+            raise BetseB200Error("ligand-gated channel: %s" % e)
+        if len(pr.code) != 1 or pr.code[0][0] != ratelaw.PUSHC:
+            raise BetseB200Error("ligand-gated channels regulated by further substances are not implemented")
+        gates.append(dict(g, mod=float(tabs.consts[pr.code[0][1]])))
     return {"species": species, "tables": tabs, "rate_programs": rates, "mod_programs": mod_programs,
-            "mod_index": mod_index,
+            "mod_index": mod_index, "ligand_gates": gates,
             "modulators": [(MOD_TARGETS[t], i, float(mx)) for t, i, mx in
                            zip(desc.get("modulator_targets", []), modulator_index, desc.get("modulator_max", []))], "c_cells": np.asarray(desc["c_cells"], dtype=float), "stoich": stoich,
             "growth_mask": None if mask.all() else mask, "Dgj": np.asarray(desc["Dgj"], dtype=float),
@@ -185,6 +209,9 @@ def flatten(desc, prefix):
            prefix + "time_factor": desc["time_factor"], prefix + "chan_names": np.array(desc["chan_names"], dtype=str),
            prefix + "chan_mod_strings": np.array(desc["chan_mod_strings"], dtype=str),
            prefix + "static_keys": np.array(list(desc["static"].keys()), dtype=str)}
+    for j, g in enumerate(desc.get("ligand_gates", [])):
+        out["%slig%d" % (prefix, j)] = np.array([g["species"], g["ion"], g["K"], g["n"], g["max"], float(g["extracell"])])
+        out["%slig%d.mod_string" % (prefix, j)] = np.array(g["mod_string"])
     if desc.get("modulator_names"):
         out.update({prefix + "modulator_names": np.array(desc["modulator_names"], dtype=str),
                     prefix + "modulator_strings": np.array(desc["modulator_strings"], dtype=str),
@@ -205,6 +232,13 @@ def unflatten(cap, prefix):
     species = [str(x) for x in g("species")]
     keys = [str(x) for x in g("static_keys")]
     mods = {}
+    j = 0
+    while "%slig%d" % (prefix, j) in cap:
+        v = np.asarray(cap["%slig%d" % (prefix, j)], dtype=float)
+        mods.setdefault("ligand_gates", []).append({"species": int(v[0]), "ion": int(v[1]), "K": float(v[2]), "n": float(v[3]),
+                                                    "max": float(v[4]), "extracell": bool(v[5]),
+                                                    "mod_string": str(cap["%slig%d.mod_string" % (prefix, j)])})
+        j += 1
     if prefix + "modulator_names" in cap:
         mods = {"modulator_names": [str(x) for x in g("modulator_names")], "modulator_strings": [str(x) for x in g("modulator_strings")],
                 "modulator_targets": [str(x) for x in g("modulator_targets")], "modulator_max": np.asarray(g("modulator_max"))}

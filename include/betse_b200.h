@@ -247,6 +247,15 @@ void betse_host_free(void *p);
  * target = max_val * program(membrane), written over sim.gj_block (target 0) or sim.NaKATP_block (target 1). */
 typedef struct betse_modulator { int32_t target; int32_t prog; double max_val; } betse_modulator;
 
+/* One ligand-gated channel (Molecule.gating, networks.py:5847-5916): substance `species` opens a channel for ion `ion`,
+ * Dchan = rho_channel * Dm_mod * mod, Dm_mod = rho_channel*max*hill(c at the membrane) (intracellular ligand) or
+ * max*hill(c_env at the membrane's env square) (extracellular); its GHK flux is added to fluxes_mem AND applied
+ * immediately, like the reference does. */
+typedef struct betse_ligand_gate {
+    int32_t species, ion, extracell, pad;
+    double K, n, max_val, mod;            /* hill(x) = x^n / (K^n + x^n); mod = the folded gating_mod_eval_string */
+} betse_ligand_gate;
+
 typedef struct betse_network {
     int32_t n_species;            /* K substances, MasterOfNetworks.molecules order                 */
     int32_t n_rates;              /* K growth/decay rates + R cell-zone reactions = columns of reaction_matrix */
@@ -277,6 +286,9 @@ typedef struct betse_network {
     int32_t affect_charge;
     int32_t n_modulators;
     const betse_modulator *modulators;   /* programs are membrane-zone programs (index >= n_rates)    */
+    const betse_ligand_gate *ligand_gates;
+    int32_t n_ligand_gates;
+    int32_t reserved;
 } betse_network;
 
 /* handler 0 = sim.molecules.core, 1 = sim.grn.core (run in that order, sim.py:1290-1318).  net == NULL

@@ -218,6 +218,23 @@ SCENARIOS["mammal_ecm_net_mod"] = dict(
     snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=net_extra)
 
 
+# ligand-gated channels (Molecule.gating, networks.py:5847-5916): L1 opens a Na/K channel from inside the cell, L2 a Ca
+# channel from the extracellular side (it lives in the bath and crosses the membrane slowly)
+def _ligand(sub, ions, K, peak, extracell):
+    sub["ion channel gating"] = {"channel name": "gate_" + sub["name"], "ion channel target": ions,
+                                 "target Hill coefficient": K, "target Hill exponent": 2.0, "peak channel opening": peak,
+                                 "acts extracellularly": extracell, "activators": "None", "inhibitors": "None"}
+    return sub
+
+
+_LIG_BIO = [_ligand(_substance("L1", 0.5, Dgj=1e-15, gj_imp=False, cell=0.2, apply_to=["Spot"]), ["Na", "K"], 0.3, 5.0e-17, False),
+            _ligand(_env_substance("L2", 1.0e-18, 0, 0.4, 0.0, True, True), ["Ca"], 0.5, 2.0e-17, True)]
+SCENARIOS["mammal_ecm_net_lig"] = dict(
+    mods=_m(SMALL, {"cutting event": {"event happens": False}, "general options": {"ion profile": "mammal"},
+                    "general network": {"implement network": True, "biomolecules": _LIG_BIO, "reactions": [], "channels": []}}),
+    snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=net_extra)
+
+
 # The external-voltage event (tissue/event/tisevevolt.py: bound_V ramps, Phi_b = one Dirichlet Poisson solve per step,
 # ion_current.py:84-90, subtracted from Vmem in update_V, sim.py:2029) — ramp up, plateau and ramp down inside the
 # first 20 SIM steps, left/right electrodes so that it differs from the top/bottom default; ECM and no-ECM
