@@ -117,6 +117,11 @@ class LigandGate(C.Structure):
                 ("K", C.c_double), ("n", C.c_double), ("max_val", C.c_double), ("mod", C.c_double)]
 
 
+class SubstancePump(C.Structure):
+    _fields_ = [("species", C.c_int32), ("into_cell", C.c_int32), ("uses_ATP", C.c_int32), ("pad", C.c_int32),
+                ("max_val", C.c_double), ("Km", C.c_double)]
+
+
 class Network(C.Structure):
     _fields_ = [
         ("n_species", C.c_int32), ("n_rates", C.c_int32), ("n_programs", C.c_int32),
@@ -127,7 +132,8 @@ class Network(C.Structure):
         ("env_on", _bp), ("Dm", _dp), ("c_bound", _dp), ("c_env", _dp), ("D_env", _dp),
         ("scale_factor", _dp), ("affect_charge", C.c_int32), ("n_modulators", C.c_int32),
         ("modulators", C.POINTER(Modulator)),
-        ("ligand_gates", C.POINTER(LigandGate)), ("n_ligand_gates", C.c_int32), ("reserved", C.c_int32),
+        ("ligand_gates", C.POINTER(LigandGate)), ("n_ligand_gates", C.c_int32), ("n_pumps", C.c_int32),
+        ("pumps", C.POINTER(SubstancePump)),
     ]
 
 

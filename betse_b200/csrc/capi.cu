@@ -39,7 +39,8 @@ void launch_pack_const(const KParams& P, const KArrays& A, cudaStream_t st);
 void launch_pack_dm(const KParams& P, const KArrays& A, cudaStream_t st);
 void launch_chan(const KParams& P, const KArrays& A, const KChan& ch, const KNet& N, int cur, cudaStream_t st);
 void launch_net(const KParams& P, const KArrays& A, const KNet& N, const double* h_Dgj, const double* h_Dm,
-                const unsigned char* h_env_on, int n_ions, int cur, cudaStream_t st);
+                const unsigned char* h_env_on, const betse_substance_pump* pumps, int n_pumps, double dG_RT,
+                int n_ions, int cur, cudaStream_t st);
 void launch_lig_prep(const KParams& P, const KArrays& A, const KNet& N, int sp, int extracell, double Kn, double n,
                      double max_val, double* Dm_mod, cudaStream_t st);
 void launch_net_lig(const KParams& P, const KArrays& A, int ion, const double* Dm_mod, double mod, int cur, int diag, cudaStream_t st);
@@ -89,6 +90,7 @@ struct betse_ctx {
     bool net_affect[2] = {false, false};
     std::vector<betse_modulator> net_mods[2];   // sim modulators of each handler (run_loop_modulators)
     std::vector<betse_ligand_gate> net_gates[2];   // ligand-gated channels (Molecule.gating)
+    std::vector<betse_substance_pump> net_pumps[2]; // the substances' own pumps / transporters (Molecule.pump)
     double* lig_tmp[2] = {nullptr, nullptr};       // [n_gates][M] openings formed before the substances advance
     std::string err;
     std::vector<void*> allocs;
@@ -821,7 +823,8 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
                         launch_lig_prep(ctx->P, A, ctx->nets[h], gs[j].species, gs[j].extracell, pow(gs[j].K, gs[j].n), gs[j].n,
                                         gs[j].max_val, ctx->lig_tmp[h] + j * (size_t)ctx->Mo, st);
                     launch_net(ctx->P, A, ctx->nets[h], ctx->net_Dgj[h].data(), ctx->net_Dm[h].data(),
-                               ctx->net_env_on[h].data(), I, cur, st);
+                               ctx->net_env_on[h].data(), ctx->net_pumps[h].data(), (int)ctx->net_pumps[h].size(),
+                               ctx->hp.deltaGATP / (ctx->hp.R * ctx->hp.T_sim), I, cur, st);
                     for (size_t j = 0; j < gs.size(); ++j) {
                         launch_net_lig(ctx->P, A, gs[j].ion, ctx->lig_tmp[h] + j * (size_t)ctx->Mo, gs[j].mod, cur, diag, st);
                         launch_chan_env(ctx->P, A, gs[j].ion, cur, st);
@@ -1280,6 +1283,19 @@ extern "C" int betse_set_network(betse_ctx* ctx, int handler, const betse_networ
         }
     }
     if ((r = ensure_defer_buffers(ctx))) return r;
+    ctx->net_pumps[handler].clear();
+    if (net->n_pumps > 0) {
+        std::vector<unsigned char> pumped((size_t)K, 0);
+        for (int j = 0; j < net->n_pumps; ++j) {
+            const betse_substance_pump& q = net->pumps[j];
+            if (q.species < 0 || q.species >= K || pumped[q.species]) return fail(ctx, "network: pump species out of range or pumped twice");
+            if (!(net->env_on && net->env_on[q.species] && N.c_env)) return fail(ctx, "network: a pumped substance needs env_on and extracellular spaces");
+            pumped[q.species] = 1;
+            ctx->net_pumps[handler].push_back(q);
+        }
+        if ((r = dev_upload(ctx, (unsigned char**)&N.pumped, (const unsigned char*)pumped.data(), (size_t)K))) return r;
+        if ((r = dev_alloc(ctx, &N.c_save, (size_t)net->n_pumps * C))) return r;
+    }
     ctx->net_gates[handler].clear();
     for (int j = 0; j < net->n_ligand_gates; ++j) {
         const betse_ligand_gate& g = net->ligand_gates[j];

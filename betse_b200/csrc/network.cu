@@ -10,6 +10,7 @@
 // k_net_gj    substances that pass gap junctions: GHK flux between the two cells of every membrane from the
 //             updated concentrations, zero at the cluster boundary (sim_toolbox.py:976-1006), summed per cell;
 // k_net_gj_apply  c += dt*delta*time_dilation_factor, negative check.
+#include "../../include/betse_b200.h"
 #include "kparams.cuh"
 #include "network.cuh"
 
@@ -34,7 +35,8 @@ k_net(const __grid_constant__ KParams P, const KArrays A, const __grid_constant_
         double d = 0.0;
         for (int j = 0; j < N.n_rates; ++j) d += __ldg(N.stoich + k * N.n_rates + j) * r[j];   // np.dot(reaction_matrix, all_rates)
         double cn = N.c[(size_t)k * C + c] + d * P.dt;                      // networks.py:2914
-        if (N.mem_delta && __ldg(N.Dm + k) != 0.0) cn = cn + N.mem_delta[(size_t)k * C + c] * P.dt;   // update_Co cell branch, sim_toolbox.py:1177-1181
+        // update_Co cell branch, sim_toolbox.py:1177-1181 (a pumped substance gets its membrane leg after the pump)
+        if (N.mem_delta && __ldg(N.Dm + k) != 0.0 && !(N.pumped && N.pumped[k])) cn = cn + N.mem_delta[(size_t)k * C + c] * P.dt;
         if (__ldg(N.Dgj + k) < 0.0 && cn < 0.0) { flags |= ST_NEG_NET; cn = 0.0; }
         N.c[(size_t)k * C + c] = cn;
     }
@@ -223,7 +225,8 @@ void launch_net_lig(const KParams& P, const KArrays& A, int ion, const double* D
 //                   divergence with fd.diff's edge rows, forward Euler times the time-dilation factor
 //                   (sim_toolbox.py:1061-1112); same stencil conventions as kernels.cu:k_ion.
 __global__ void __launch_bounds__(BT_TPB)
-k_net_mem(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ KNet N, const int k, const int cur)
+k_net_mem(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ KNet N, const int k, const int cur,
+          const double* __restrict__ csrc)
 {
     __shared__ double s_all[(BT_TPB / 32) * 32];
     const int lane = threadIdx.x & 31;
@@ -245,7 +248,7 @@ k_net_mem(const __grid_constant__ KParams P, const KArrays A, const __grid_const
         else if (P.has_phi) vm -= __ldg(A.phi_b_old + e);
         const double alpha = ((zc * (vm + FLOAT_NONCE)) * P.F) / P.RT_sim;    // sim.T (sim_toolbox.py:947)
         const double ex = exp(-alpha), deno = -expm1(-alpha);
-        const double cA = N.c_env[(size_t)k * E + e], cB = N.c[(size_t)k * C + c];
+        const double cA = N.c_env[(size_t)k * E + e], cB = csrc ? csrc[c] : N.c[(size_t)k * C + c];
         double f = -((Dm * alpha) / P.tm) * ((cB - cA * ex) / deno) * P.rho_channel;
         if (!P.cluster_open && __ldg(A.nn_cell_flag + m) < 0) f = 0.0;        // f_X_ED[cells.bflags_mems] = 0
         fsa = f * __ldg(A.mem_sa + m);
@@ -279,6 +282,89 @@ k_net_charge(const __grid_constant__ KParams P, const __grid_constant__ KNet N, 
     double rho = 0.0;
     for (int k = 0; k < N.K; ++k) rho += ((P.F * src[(size_t)k * stride + q]) * __ldg(N.z + k)) * __ldg(N.scale + k);
     (env ? N.rho_env : N.rho_cells)[q] = rho;
+}
+
+// Molecule.pump (networks.py:5809-5844) -> stb.molecule_pump / stb.molecule_transporter (sim_toolbox.py:658-907) with n = 1,
+// Km_ATP = 1 and Keq = 1 as Molecule.pump passes them: flux from the substance AFTER its growth/decay and its env square,
+// immediate update_Co (cells here, env squares by k_net_env_acc).
+__global__ void __launch_bounds__(BT_TPB)
+k_net_pump(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ KNet N, const int k, const int into_cell,
+           const int uses_ATP, const double alpha_max, const double Km, const double dG_RT, const int cur)
+{
+    __shared__ double s_all[(BT_TPB / 32) * 32];
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * (BT_TPB / 32) + (threadIdx.x >> 5);
+    if (tile >= P.n_tiles) return;
+    double* s_f = s_all + (threadIdx.x >> 5) * 32;
+    const int4 td = __ldg(reinterpret_cast<const int4*>(A.tile_desc) + tile);
+    const int c0 = td.x, nc = td.y, m0 = td.z, nm = td.w;
+    const int C = P.n_cells, E = P.ny * P.nx;
+    const double z = __ldg(N.z + k);
+    double* __restrict__ cc = N.c + (size_t)k * C;
+    double fsa = 0.0;
+    if (lane < nm) {
+        const int m = m0 + lane;
+        const int c = __ldg(A.mem_to_cells + m);
+        const int e = __ldg(A.map_mem2ecm + m);
+        double vm = A.vm_cell[cur][c];
+        if (P.polar) vm = A.vm_pol[cur][m];
+        else if (P.has_phi) vm -= __ldg(A.phi_b_old + e);
+        const double xe = N.c_env[(size_t)k * E + e], xc = cc[c];
+        double f;
+        if (uses_ATP) {
+            const double cATP = P.cATP;
+            if (!into_cell) {
+                const double Qn = (P.cADP * P.cPi) * xe;
+                double Qd = cATP * xc;
+                if (Qd == 0.0) Qd = 1.0e-10;
+                const double Keq = exp(-dG_RT + ((((1.0 * z) * P.F) * vm) / P.RT_sim));
+                const double alpha = alpha_max * (1.0 - ((Qn / Qd) / Keq));
+                const double numo = (xc / Km) * (cATP / 1.0), deno = (1.0 + (xc / Km)) * (1.0 + (cATP / 1.0));
+                f = ((-P.rho_pump) * alpha) * (numo / deno);
+            } else {
+                const double Qn = (P.cADP * P.cPi) * xc;
+                double Qd = cATP * xe;
+                if (Qd == 0.0) Qd = 1.0e-10;
+                const double Keq = exp(-dG_RT - (((z * P.F) * vm) / P.RT_sim));
+                const double alpha = alpha_max * (1.0 - ((Qn / Qd) / Keq));
+                const double numo = (xe / Km) * (cATP / 1.0), deno = (1.0 + (xe / Km)) * (1.0 + (cATP / 1.0));
+                f = (P.rho_pump * alpha) * (numo / deno);
+            }
+        } else if (!into_cell) {
+            double Qd = xc;
+            if (Qd == 0.0) Qd = 1.0e-15;
+            const double Keq = 1.0 * exp(((z * P.F) * vm) / P.RT_sim);
+            const double alpha = alpha_max * (1.0 - ((xe / Qd) / Keq));
+            f = ((-P.rho_pump) * alpha) * ((xc / Km) / (1.0 + (xc / Km)));
+        } else {
+            double Qd = xe;
+            if (Qd == 0.0) Qd = 1.0e-15;
+            const double Keq = 1.0 * exp(-((z * P.F) * vm) / P.RT_sim);
+            const double alpha = alpha_max * (1.0 - ((xc / Qd) / Keq));
+            f = (P.rho_pump * alpha) * ((xe / Km) / (1.0 + (xe / Km)));
+        }
+        if (!P.cluster_open && __ldg(A.nn_cell_flag + m) < 0) f = 0.0;
+        fsa = f * __ldg(A.mem_sa + m);
+        A.chan_slots[m] = fsa;
+    }
+    s_f[lane] = fsa;
+    __syncwarp();
+    if (lane < nc) {
+        const int c = c0 + lane;
+        const int jb = __ldg(A.cell_mem_ptr + c) - m0, je = __ldg(A.cell_mem_ptr + c + 1) - m0;
+        double S = 0.0;
+        for (int j = jb; j < je; ++j) S += s_f[j];
+        cc[c] = cc[c] + (S / __ldg(A.cell_vol + c)) * P.dt;                   // update_Co cell branch
+    }
+}
+
+// the deferred membrane leg of a pumped substance: c += sum_mems(f*sa)/vol * dt
+__global__ void __launch_bounds__(256)
+k_net_apply_mem(const __grid_constant__ KParams P, const __grid_constant__ KNet N, const int k)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.n_cells_owned) return;
+    N.c[(size_t)k * P.n_cells + c] = N.c[(size_t)k * P.n_cells + c] + N.mem_delta[(size_t)k * P.n_cells + c] * P.dt;
 }
 
 __global__ void __launch_bounds__(256)
@@ -357,18 +443,37 @@ k_sub_div(const __grid_constant__ KParams P, const KArrays A, const __grid_const
 }
 
 void launch_net(const KParams& P, const KArrays& A, const KNet& N, const double* h_Dgj, const double* h_Dm,
-                const unsigned char* h_env_on, int n_ions, int cur, cudaStream_t st)
+                const unsigned char* h_env_on, const betse_substance_pump* pumps, int n_pumps, double dG_RT,
+                int n_ions, int cur, cudaStream_t st)
 {
     if (N.K <= 0) return;
     const int tgrid = (P.n_tiles + (BT_TPB / 32) - 1) / (BT_TPB / 32);
     const int E = P.nx * P.ny;
+    auto pump_of = [&](int k) { for (int j = 0; j < n_pumps; ++j) if (pumps[j].species == k) return j; return -1; };
     if (N.c_env)
         for (int k = 0; k < N.K; ++k) {
-            if (!h_env_on[k] || h_Dm[k] == 0.0) continue;
-            k_net_mem<<<tgrid, BT_TPB, 0, st>>>(P, A, N, k, cur);
+            if (!h_env_on[k] || h_Dm[k] == 0.0 || pump_of(k) >= 0) continue;
+            k_net_mem<<<tgrid, BT_TPB, 0, st>>>(P, A, N, k, cur, nullptr);
             k_net_env_acc<<<(E + 255) / 256, 256, 0, st>>>(P, A, N, k);
         }
+    // pumped substances: pump (from the concentration after growth/decay), then the membrane leg (from the
+    // concentration before it: cc_at_mem), each with its immediate update_Co (networks.py:2914-2935)
+    for (int j = 0; j < n_pumps; ++j)
+        if (h_Dm[pumps[j].species] != 0.0)
+            cudaMemcpyAsync(N.c_save + (size_t)j * P.n_cells, N.c + (size_t)pumps[j].species * P.n_cells,
+                            (size_t)P.n_cells * sizeof(double), cudaMemcpyDeviceToDevice, st);
     k_net<<<(P.n_cells_owned + 127) / 128, 128, 0, st>>>(P, A, N, cur);
+    for (int j = 0; j < n_pumps; ++j) {
+        const betse_substance_pump& q = pumps[j];
+        const int k = q.species;
+        k_net_pump<<<tgrid, BT_TPB, 0, st>>>(P, A, N, k, q.into_cell, q.uses_ATP, q.max_val, q.Km, dG_RT, cur);
+        k_net_env_acc<<<(E + 255) / 256, 256, 0, st>>>(P, A, N, k);
+        if (h_Dm[k] != 0.0) {
+            k_net_mem<<<tgrid, BT_TPB, 0, st>>>(P, A, N, k, cur, N.c_save + (size_t)j * P.n_cells);
+            k_net_apply_mem<<<(P.n_cells_owned + 255) / 256, 256, 0, st>>>(P, N, k);
+            k_net_env_acc<<<(E + 255) / 256, 256, 0, st>>>(P, A, N, k);
+        }
+    }
     const int grid = (P.n_tiles + (BT_TPB / 32) - 1) / (BT_TPB / 32);
     int nonces = n_ions;
     for (int k = 0; k < N.K; ++k) {

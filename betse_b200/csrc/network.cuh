@@ -32,6 +32,8 @@ struct KNet {
     const double* Dm;           // [K]
     const double* c_bound;      // [K]
     const double* D_env;        // [K][E]
+    const unsigned char* pumped; // [K] 1: the substance has its own pump -> its membrane leg follows the pump (launch_net)
+    double* c_save;             // [n_pumps][C] a pumped substance's concentration before growth/decay (cc_at_mem of its membrane leg)
     // p.substances_affect_charge (networks.py:2942-2977)
     int affect;
     const double* scale;        // [K] scale_factor

@@ -528,6 +528,14 @@ class TissueEngine:
                 garr[j].K, garr[j].n, garr[j].max_val, garr[j].mod = float(g["K"]), float(g["n"]), float(g["max"]), float(g["mod"])
             keep.append(garr)
             n.n_ligand_gates, n.ligand_gates = len(gates), garr
+        pumps = list(net.get("pumps") or [])
+        if pumps:
+            parr = (capi.SubstancePump * len(pumps))()
+            for j, q in enumerate(pumps):
+                parr[j].species, parr[j].into_cell, parr[j].uses_ATP = int(q["species"]), int(bool(q["into_cell"])), int(bool(q["uses_ATP"]))
+                parr[j].max_val, parr[j].Km = float(q["max"]), float(q["Km"])
+            keep.append(parr)
+            n.n_pumps, n.pumps = len(pumps), parr
         if net.get("scale_factor") is not None:
             n.scale_factor = f64(np.asarray(net["scale_factor"], dtype=float).reshape(K))
         n.affect_charge = int(bool(self.p.get("substances_affect_charge", 0)) if net.get("affect_charge") is None

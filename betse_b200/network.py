@@ -41,7 +41,7 @@ def unsupported_reasons(core, p):
             bad.append(what)
     for name, m in (getattr(core, "molecules", None) or {}).items():
         why = []
-        for flag, what in (("update_intra_conc", "update intracellular"), ("active_pumping", "active pumping"),
+        for flag, what in (("update_intra_conc", "update intracellular"),
                            ("change_bounds", "boundary change event"),
                            ("cell_clamp", "cell clamp"), ("transmem", "transmembrane transport")):
             if bool(getattr(m, flag, False)):
@@ -112,8 +112,18 @@ def describe_core(core, sim, p, cells, record_static=True):
                             "mod_string": str(m.gating_mod_eval_string)})
     if lig:
         desc["ligand_gates"] = lig
+    # Molecule.pump (networks.py:5809-5844): active pump (stb.molecule_pump) or facilitated transporter
+    # (stb.molecule_transporter) of the substance itself, applied right after its growth/decay
+    pumps = [{"species": k, "into_cell": bool(core.molecules[s].pump_to_cell), "max": float(core.molecules[s].pump_max_val),
+              "Km": float(core.molecules[s].pump_Km), "uses_ATP": bool(core.molecules[s].pumps_use_ATP)}
+             for k, s in enumerate(species)
+             if bool(getattr(core.molecules[s], "active_pumping", False)) and bool(getattr(core.molecules[s], "use_pumping", False))]
+    if pumps:
+        desc["pumps"] = pumps
+        if any(g["extracell"] and any(q["species"] == g["species"] for q in pumps) for g in lig):
+            raise BetseB200Error("a pumped substance that also gates a channel from outside the cell is not implemented")
     env_on = np.array([_in_env(core.molecules[s]) or any(g["species"] == k and g["extracell"] for g in lig)
-                       for k, s in enumerate(species)], dtype=np.uint8)
+                       or any(q["species"] == k for q in pumps) for k, s in enumerate(species)], dtype=np.uint8)
     if env_on.any() and bool(getattr(p, "is_ecm", False)):
         E = int(np.asarray(sim.D_env_weight).size)
         D_env = np.zeros((K, E))
@@ -190,7 +200,7 @@ def compile_network(desc, n_cells, n_mems, resolver=None):
             raise BetseB200Error("ligand-gated channels regulated by further substances are not implemented")
         gates.append(dict(g, mod=float(tabs.consts[pr.code[0][1]])))
     return {"species": species, "tables": tabs, "rate_programs": rates, "mod_programs": mod_programs,
-            "mod_index": mod_index, "ligand_gates": gates,
+            "mod_index": mod_index, "ligand_gates": gates, "pumps": list(desc.get("pumps", [])),
             "modulators": [(MOD_TARGETS[t], i, float(mx)) for t, i, mx in
                            zip(desc.get("modulator_targets", []), modulator_index, desc.get("modulator_max", []))], "c_cells": np.asarray(desc["c_cells"], dtype=float), "stoich": stoich,
             "growth_mask": None if mask.all() else mask, "Dgj": np.asarray(desc["Dgj"], dtype=float),
@@ -212,6 +222,8 @@ def flatten(desc, prefix):
     for j, g in enumerate(desc.get("ligand_gates", [])):
         out["%slig%d" % (prefix, j)] = np.array([g["species"], g["ion"], g["K"], g["n"], g["max"], float(g["extracell"])])
         out["%slig%d.mod_string" % (prefix, j)] = np.array(g["mod_string"])
+    for j, q in enumerate(desc.get("pumps", [])):
+        out["%spump%d" % (prefix, j)] = np.array([q["species"], float(q["into_cell"]), q["max"], q["Km"], float(q["uses_ATP"])])
     if desc.get("modulator_names"):
         out.update({prefix + "modulator_names": np.array(desc["modulator_names"], dtype=str),
                     prefix + "modulator_strings": np.array(desc["modulator_strings"], dtype=str),
@@ -239,9 +251,15 @@ def unflatten(cap, prefix):
                                                     "max": float(v[4]), "extracell": bool(v[5]),
                                                     "mod_string": str(cap["%slig%d.mod_string" % (prefix, j)])})
         j += 1
+    j = 0
+    while "%spump%d" % (prefix, j) in cap:
+        v = np.asarray(cap["%spump%d" % (prefix, j)], dtype=float)
+        mods.setdefault("pumps", []).append({"species": int(v[0]), "into_cell": bool(v[1]), "max": float(v[2]), "Km": float(v[3]),
+                                             "uses_ATP": bool(v[4])})
+        j += 1
     if prefix + "modulator_names" in cap:
-        mods = {"modulator_names": [str(x) for x in g("modulator_names")], "modulator_strings": [str(x) for x in g("modulator_strings")],
-                "modulator_targets": [str(x) for x in g("modulator_targets")], "modulator_max": np.asarray(g("modulator_max"))}
+        mods = {**mods, **{"modulator_names": [str(x) for x in g("modulator_names")], "modulator_strings": [str(x) for x in g("modulator_strings")],
+                "modulator_targets": [str(x) for x in g("modulator_targets")], "modulator_max": np.asarray(g("modulator_max"))}}
     return {**mods, **{k: np.asarray(cap[prefix + k]) for k in ("env_on", "Dm", "c_bound", "c_env", "D_env", "scale_factor") if prefix + k in cap},
             "species": species, "ions": [str(x) for x in g("ions")], "c_cells": np.asarray(g("c_cells")),
             "gad_strings": [str(x) for x in g("gad_strings")],

@@ -256,6 +256,14 @@ typedef struct betse_ligand_gate {
     double K, n, max_val, mod;            /* hill(x) = x^n / (K^n + x^n); mod = the folded gating_mod_eval_string */
 } betse_ligand_gate;
 
+/* Molecule.pump (networks.py:5809-5844): the substance's own active pump (stb.molecule_pump, sim_toolbox.py:658-775,
+ * with the fixed cATP/cADP/cPi of the parameters) or facilitated transporter (stb.molecule_transporter, :777-907),
+ * applied right after the substance's growth/decay and before its membrane / gap-junction / extracellular transport. */
+typedef struct betse_substance_pump {
+    int32_t species, into_cell, uses_ATP, pad;
+    double max_val, Km;
+} betse_substance_pump;
+
 typedef struct betse_network {
     int32_t n_species;            /* K substances, MasterOfNetworks.molecules order                 */
     int32_t n_rates;              /* K growth/decay rates + R cell-zone reactions = columns of reaction_matrix */
@@ -288,7 +296,8 @@ typedef struct betse_network {
     const betse_modulator *modulators;   /* programs are membrane-zone programs (index >= n_rates)    */
     const betse_ligand_gate *ligand_gates;
     int32_t n_ligand_gates;
-    int32_t reserved;
+    int32_t n_pumps;
+    const betse_substance_pump *pumps;   /* at most one per substance; the substance needs env_on      */
 } betse_network;
 
 /* handler 0 = sim.molecules.core, 1 = sim.grn.core (run in that order, sim.py:1290-1318).  net == NULL

@@ -235,6 +235,21 @@ SCENARIOS["mammal_ecm_net_lig"] = dict(
     snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=net_extra)
 
 
+# active pumping of substances (Molecule.pump, networks.py:5809-5844): Q1 pumped OUT of the cells with ATP (it also leaks
+# back through the membrane), Q2 carried INTO the cells by a facilitated transporter, a cation
+def _pumped(sub, into_cell, rate, Km, atp):
+    sub["active pumping"] = {"turn on": True, "pump to cell": into_cell, "maximum rate": rate, "pump Km": Km, "uses ATP": atp}
+    return sub
+
+
+_PUMP_BIO = [_pumped(_env_substance("Q1", 1.0e-17, 0, 0.05, 0.5, False, True), False, 2.0e-9, 0.2, True),
+             _pumped(_env_substance("Q2", 0.0, 1, 0.4, 0.02, True, False, tj_factor=0.5), True, 1.0e-9, 0.3, False)]
+SCENARIOS["mammal_ecm_net_pump"] = dict(
+    mods=_m(SMALL, {"cutting event": {"event happens": False}, "general options": {"ion profile": "mammal"},
+                    "general network": {"implement network": True, "biomolecules": _PUMP_BIO, "reactions": [], "channels": []}}),
+    snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=net_extra)
+
+
 # The external-voltage event (tissue/event/tisevevolt.py: bound_V ramps, Phi_b = one Dirichlet Poisson solve per step,
 # ion_current.py:84-90, subtracted from Vmem in update_V, sim.py:2029) — ramp up, plateau and ramp down inside the
 # first 20 SIM steps, left/right electrodes so that it differs from the top/bottom default; ECM and no-ECM
