@@ -122,6 +122,18 @@ class SubstancePump(C.Structure):
                 ("max_val", C.c_double), ("Km", C.c_double)]
 
 
+TR_MAX_TERMS = 12
+
+
+class TransporterTerm(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("index", C.c_int32), ("sign", C.c_int32), ("pad", C.c_int32), ("coeff", C.c_double)]
+
+
+class Transporter(C.Structure):
+    _fields_ = [("prog", C.c_int32), ("n_terms", C.c_int32), ("net_z", C.c_double), ("cell_mask", _bp), ("env_mask", _bp),
+                ("mem_mask", _bp), ("terms", TransporterTerm * TR_MAX_TERMS)]
+
+
 class Network(C.Structure):
     _fields_ = [
         ("n_species", C.c_int32), ("n_rates", C.c_int32), ("n_programs", C.c_int32),
@@ -134,6 +146,8 @@ class Network(C.Structure):
         ("modulators", C.POINTER(Modulator)),
         ("ligand_gates", C.POINTER(LigandGate)), ("n_ligand_gates", C.c_int32), ("n_pumps", C.c_int32),
         ("pumps", C.POINTER(SubstancePump)),
+        ("transporters", C.POINTER(Transporter)), ("n_transporters", C.c_int32), ("reserved", C.c_int32),
+        ("mem_sa_over_vol", _dp),
     ]
 
 

@@ -45,6 +45,10 @@ void launch_lig_prep(const KParams& P, const KArrays& A, const KNet& N, int sp, 
                      double max_val, double* Dm_mod, cudaStream_t st);
 void launch_net_lig(const KParams& P, const KArrays& A, int ion, const double* Dm_mod, double mod, int cur, int diag, cudaStream_t st);
 void launch_chan_env(const KParams& P, const KArrays& A, int ion, int cur, cudaStream_t st);
+void launch_transporter(const KParams& P, const KArrays& A, const KNet& N, const betse_transporter& T,
+                        const unsigned char* d_cell_mask, const unsigned char* d_env_mask, const unsigned char* d_mem_mask,
+                        int cur, cudaStream_t st);
+void launch_tw_gather(const KParams& P, const KArrays& A, double* row, const double* src, cudaStream_t st);
 void launch_net_mod(const KParams& P, const KArrays& A, const KNet& N, int prog, double max_val, double* dst, int cur, cudaStream_t st);
 void launch_cell_update(const KParams& P, const KArrays& A, int cur, cudaStream_t st);
 void launch_xchg(const KParams& P, const KArrays& A, const XPlan& X, int which, int buf, int mode, cudaStream_t st);
@@ -91,6 +95,9 @@ struct betse_ctx {
     std::vector<betse_modulator> net_mods[2];   // sim modulators of each handler (run_loop_modulators)
     std::vector<betse_ligand_gate> net_gates[2];   // ligand-gated channels (Molecule.gating)
     std::vector<betse_substance_pump> net_pumps[2]; // the substances' own pumps / transporters (Molecule.pump)
+    std::vector<betse_transporter> net_trans[2];    // transporters (run_loop_transporters); masks below are device copies
+    std::vector<const unsigned char*> net_trans_cm[2], net_trans_em[2], net_trans_mm[2];
+    int net_tw_rows[2] = {0, 0};
     double* lig_tmp[2] = {nullptr, nullptr};       // [n_gates][M] openings formed before the substances advance
     std::string err;
     std::vector<void*> allocs;
@@ -812,7 +819,23 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
                 cudaMemsetAsync(A.extra_Jenv_y, 0, (size_t)ctx->E * sizeof(double), st);
             }
             for (int h = 0; h < 2; ++h) {
-                for (const KChan& ch : ctx->chans) if (ch.handler == h) launch_chan(ctx->P, A, ch, ctx->nets[h], cur, st);
+                if (ctx->net_on[h] && !ctx->net_trans[h].empty()) {
+                    const KNet& Nh = ctx->nets[h];
+                    for (int k = 0; k < Nh.K && Nh.tw; ++k)
+                        if (Nh.tw_s[k] >= 0) launch_tw_gather(ctx->P, A, Nh.tw + (size_t)Nh.tw_s[k] * ctx->Mo, Nh.c + (size_t)k * ctx->C, st);
+                    for (int i = 0; i < I && Nh.tw; ++i)
+                        if (Nh.tw_i[i] >= 0) launch_tw_gather(ctx->P, A, Nh.tw + (size_t)Nh.tw_i[i] * ctx->Mo, A.cc_cells + (size_t)i * ctx->C, st);
+                    for (size_t j = 0; j < ctx->net_trans[h].size(); ++j)
+                        launch_transporter(ctx->P, A, ctx->nets[h], ctx->net_trans[h][j], ctx->net_trans_cm[h][j],
+                                           ctx->net_trans_em[h][j], ctx->net_trans_mm[h][j], cur, st);
+                }
+                for (const KChan& ch : ctx->chans) if (ch.handler == h) {
+                    launch_chan(ctx->P, A, ch, ctx->nets[h], cur, st);
+                    // the channel's update_Co renews sim.cc_at_mem[ion] (sim_toolbox.py:1182): a transporter's nudge of it ends here
+                    if (ctx->net_on[h] && ctx->nets[h].tw && ctx->nets[h].tw_i[ch.ion] >= 0)
+                        launch_tw_gather(ctx->P, A, ctx->nets[h].tw + (size_t)ctx->nets[h].tw_i[ch.ion] * ctx->Mo,
+                                         A.cc_cells + (size_t)ch.ion * ctx->C, st);
+                }
                 if (ctx->net_on[h])
                     for (const betse_modulator& md : ctx->net_mods[h])
                         launch_net_mod(ctx->P, A, ctx->nets[h], md.prog, md.max_val,
@@ -1239,7 +1262,10 @@ extern "C" int betse_set_network(betse_ctx* ctx, int handler, const betse_networ
             if (op == RL_PUSHA && (arg < 0 || arg >= (memzone ? net->n_mem_arrays : net->n_cell_arrays))) return fail(ctx, "network: array index out of range");
             if ((op == RL_PUSHI || op == RL_PUSHM) && (arg < 0 || arg >= ctx->I)) return fail(ctx, "network: ion index out of range");
             if (op == RL_PUSHV && !memzone) return fail(ctx, "network: Vmem in a cell-zone program");
-            if (op <= RL_PUSHV) ++depth;
+            if ((op == RL_PUSHE || op == RL_PUSHJ) && (!memzone || !ctx->hp.is_ecm)) return fail(ctx, "network: env concentration outside a membrane-zone program / without extracellular spaces");
+            if (op == RL_PUSHE && (arg < 0 || arg >= K || !(net->env_on && net->env_on[arg]))) return fail(ctx, "network: env concentration of a substance without env_on");
+            if (op == RL_PUSHJ && (arg < 0 || arg >= ctx->I)) return fail(ctx, "network: ion index out of range");
+            if (op <= RL_LAST_PUSH) ++depth;
             else if (op != RL_NEG && op != RL_EXP) --depth;
             if (depth < 1 || depth > NET_STACK) return fail(ctx, "network: program violates the stack discipline");
         }
@@ -1247,7 +1273,7 @@ extern "C" int betse_set_network(betse_ctx* ctx, int handler, const betse_networ
     }
     KNet N;
     memset(&N, 0, sizeof N);
-    N.K = K; N.n_rates = R;
+    N.K = K; N.n_rates = R; N.E = ctx->E;
     int r;
     if ((r = dev_upload(ctx, &N.c, net->c_cells, (size_t)K * C))) return r;
     if ((r = dev_alloc(ctx, &N.rates, (size_t)R * C))) return r;
@@ -1283,6 +1309,46 @@ extern "C" int betse_set_network(betse_ctx* ctx, int handler, const betse_networ
         }
     }
     if ((r = ensure_defer_buffers(ctx))) return r;
+    ctx->net_trans[handler].clear(); ctx->net_trans_cm[handler].clear(); ctx->net_trans_em[handler].clear();
+    ctx->net_trans_mm[handler].clear();
+    ctx->net_tw_rows[handler] = 0;
+    for (int k = 0; k < NET_MAX_RATES; ++k) N.tw_s[k] = -1;
+    for (int i = 0; i < 8; ++i) N.tw_i[i] = -1;
+    if (net->n_transporters > 0) {
+        if (!net->mem_sa_over_vol) return fail(ctx, "network: transporters need mem_sa_over_vol");
+        int rows = 0;
+        for (int j = 0; j < net->n_transporters; ++j)
+            for (int q = 0; q < net->transporters[j].n_terms && q < BETSE_TR_MAX_TERMS; ++q) {
+                const betse_transporter_term& t = net->transporters[j].terms[q];
+                if (t.kind == 0 && t.index >= 0 && t.index < 8 && N.tw_i[t.index] < 0) N.tw_i[t.index] = (signed char)rows++;
+                if (t.kind == 2 && t.index >= 0 && t.index < NET_MAX_RATES && N.tw_s[t.index] < 0) N.tw_s[t.index] = (signed char)rows++;
+            }
+        ctx->net_tw_rows[handler] = rows;
+        if (rows > 0) { if ((r = dev_alloc(ctx, &N.tw, (size_t)rows * Mo))) return r; }
+        if ((r = dev_alloc(ctx, &N.tr_flux, (size_t)Mo))) return r;
+        if ((r = dev_upload(ctx, (double**)&N.sa_over_vol, net->mem_sa_over_vol, (size_t)Mo))) return r;
+    }
+    for (int j = 0; j < net->n_transporters; ++j) {
+        const betse_transporter& T = net->transporters[j];
+        if (!ctx->hp.is_ecm) return fail(ctx, "network: transporters without extracellular spaces are not implemented");
+        if (T.prog < R || T.prog >= net->n_programs) return fail(ctx, "network: transporter program is not a membrane-zone program");
+        if (T.n_terms < 0 || T.n_terms > BETSE_TR_MAX_TERMS) return fail(ctx, "network: transporter with too many terms");
+        for (int q = 0; q < T.n_terms; ++q) {
+            const betse_transporter_term& t = T.terms[q];
+            const bool ion = t.kind == 0 || t.kind == 1, sub = t.kind == 2 || t.kind == 3;
+            if ((!ion && !sub) || (ion && (t.index < 0 || t.index >= ctx->I)) || (sub && (t.index < 0 || t.index >= K)) ||
+                (t.sign != 1 && t.sign != -1)) return fail(ctx, "network: bad transporter term");
+            if (t.kind == 3 && !(net->env_on && net->env_on[t.index] && N.c_env)) return fail(ctx, "network: a transporter moves a substance outside the cells that has no env_on");
+        }
+        const unsigned char *cm = nullptr, *em = nullptr, *mm = nullptr;
+        if (T.cell_mask) { if ((r = dev_upload(ctx, (unsigned char**)&cm, (const unsigned char*)T.cell_mask, (size_t)C))) return r; }
+        if (T.env_mask) { if ((r = dev_upload(ctx, (unsigned char**)&em, (const unsigned char*)T.env_mask, (size_t)ctx->E))) return r; }
+        if (T.mem_mask) { if ((r = dev_upload(ctx, (unsigned char**)&mm, (const unsigned char*)T.mem_mask, (size_t)Mo))) return r; }
+        ctx->net_trans[handler].push_back(T);
+        ctx->net_trans_cm[handler].push_back(cm);
+        ctx->net_trans_em[handler].push_back(em);
+        ctx->net_trans_mm[handler].push_back(mm);
+    }
     ctx->net_pumps[handler].clear();
     if (net->n_pumps > 0) {
         std::vector<unsigned char> pumped((size_t)K, 0);

@@ -107,6 +107,116 @@ k_net_gj_apply(const __grid_constant__ KParams P, const KArrays A, const __grid_
     N.c[(size_t)k * P.n_cells + c] = cn;
 }
 
+// ---------------------------------------------------------------------------- transporters
+// run_loop_transporters (networks.py:2985-3107), cell zone with extracellular spaces.
+//   k_trans_flux   flux = rho_pump * eval(transporter_eval_string) on every membrane (one warp per tile of whole cells),
+//                  f*mem_sa into the exchange slots, the per-cell sum of it, extra_J_mem += net_z*flux*F
+//   k_trans_cell   X[cell] += coeff * ((sign * sum_mems(flux*mem_sa)) / cell_vol) * dt on the target cells
+//   k_trans_env    X[env]  += coeff * div_env(sign*flux) * dt on the target env squares
+//   k_trans_tweak  the reference also nudges mem_concs[X] at the target membranes by -/+flux*(mem_sa/mem_vol)*dt
+//                  (networks.py:3020-3022, 3070-3072); the value lives until the next update_intra / update_Co and is read
+//                  by LATER membrane-zone rate laws of the same step: kept as rows of membrane values (KNet.tw, gathered
+//                  from the cells by k_tw_gather) that rl_eval reads instead of the cell arrays.
+__global__ void __launch_bounds__(BT_TPB)
+k_trans_flux(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ KNet N, const int prog, const double net_z,
+             const int cur)
+{
+    __shared__ double s_all[(BT_TPB / 32) * 32];
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * (BT_TPB / 32) + (threadIdx.x >> 5);
+    if (tile >= P.n_tiles) return;
+    double* s_f = s_all + (threadIdx.x >> 5) * 32;
+    const int4 td = __ldg(reinterpret_cast<const int4*>(A.tile_desc) + tile);
+    const int c0 = td.x, nc = td.y, m0 = td.z, nm = td.w;
+    double fsa = 0.0;
+    if (lane < nm) {
+        const int m = m0 + lane;
+        const int c = __ldg(A.mem_to_cells + m);
+        double vm = A.vm_cell[cur][c];
+        if (P.polar) vm = A.vm_pol[cur][m];
+        else if (P.has_phi) vm -= __ldg(A.phi_b_old + __ldg(A.map_mem2ecm + m));
+        const double f = P.rho_pump * rl_eval(N, prog, c, m, A, P.n_cells, P.n_mems_owned, cur, vm);
+        fsa = f * __ldg(A.mem_sa + m);
+        A.chan_slots[m] = fsa;
+        N.tr_flux[m] = f;
+        if (N.affect) A.chanJ[m] += (net_z * f) * P.F;                      // networks.py:3004
+    }
+    s_f[lane] = fsa;
+    __syncwarp();
+    if (lane < nc) {
+        const int c = c0 + lane;
+        const int jb = __ldg(A.cell_mem_ptr + c) - m0, je = __ldg(A.cell_mem_ptr + c + 1) - m0;
+        double S = 0.0;
+        for (int j = jb; j < je; ++j) S += s_f[j];
+        N.gj_delta[c] = S;                                                  // scratch [C]: sum_mems(flux*mem_sa)
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_trans_cell(const __grid_constant__ KParams P, const KArrays A, const double* __restrict__ S, double* __restrict__ dst,
+             const double sign, const double coeff, const unsigned char* __restrict__ mask)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.n_cells_owned || (mask && !mask[c])) return;
+    dst[c] = dst[c] + (coeff * ((sign * S[c]) / __ldg(A.cell_vol + c))) * P.dt;
+}
+
+__global__ void __launch_bounds__(256)
+k_trans_env(const __grid_constant__ KParams P, const KArrays A, double* __restrict__ dst, const double sign, const double coeff,
+            const unsigned char* __restrict__ mask)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= P.nx * P.ny || (mask && !mask[q])) return;
+    const int s0 = __ldg(A.slot_ptr + q), s1 = __ldg(A.slot_ptr + q + 1);
+    if (s1 == s0) return;
+    double acc = 0.0;
+    for (int j = s0; j < s1; ++j) acc += sign * A.chan_slots[__ldg(A.slot_idx + j)];
+    dst[q] = dst[q] + (coeff * (acc / P.env_vol_div)) * P.dt;              // stb.div_env, sim_toolbox.py:1229
+}
+
+__global__ void __launch_bounds__(256)
+k_tw_gather(const __grid_constant__ KParams P, const KArrays A, double* __restrict__ row, const double* __restrict__ src)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < P.n_mems_owned) row[m] = src[__ldg(A.mem_to_cells + m)];
+}
+
+void launch_tw_gather(const KParams& P, const KArrays& A, double* row, const double* src, cudaStream_t st)
+{
+    k_tw_gather<<<(P.n_mems_owned + 255) / 256, 256, 0, st>>>(P, A, row, src);
+}
+
+__global__ void __launch_bounds__(256)
+k_trans_tweak(const __grid_constant__ KParams P, const __grid_constant__ KNet N, const int row, const double sign,
+              const unsigned char* __restrict__ mask)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= P.n_mems_owned || (mask && !mask[m])) return;
+    double* t = N.tw + (size_t)row * P.n_mems_owned + m;
+    *t = *t + sign * ((N.tr_flux[m] * __ldg(N.sa_over_vol + m)) * P.dt);
+}
+
+void launch_transporter(const KParams& P, const KArrays& A, const KNet& N, const betse_transporter& T,
+                        const unsigned char* d_cell_mask, const unsigned char* d_env_mask, const unsigned char* d_mem_mask,
+                        int cur, cudaStream_t st)
+{
+    const int tgrid = (P.n_tiles + (BT_TPB / 32) - 1) / (BT_TPB / 32);
+    const int E = P.nx * P.ny, C = P.n_cells;
+    k_trans_flux<<<tgrid, BT_TPB, 0, st>>>(P, A, N, T.prog, T.net_z, cur);
+    for (int q = 0; q < T.n_terms; ++q) {
+        const betse_transporter_term& t = T.terms[q];
+        if (t.kind == 0 || t.kind == 2) {
+            double* dst = t.kind == 0 ? A.cc_cells + (size_t)t.index * C : N.c + (size_t)t.index * C;
+            k_trans_cell<<<(P.n_cells_owned + 255) / 256, 256, 0, st>>>(P, A, N.gj_delta, dst, (double)t.sign, t.coeff, d_cell_mask);
+            const int row = t.kind == 0 ? N.tw_i[t.index] : N.tw_s[t.index];
+            if (N.tw && row >= 0) k_trans_tweak<<<(P.n_mems_owned + 255) / 256, 256, 0, st>>>(P, N, row, (double)t.sign, d_mem_mask);
+        } else {
+            double* dst = t.kind == 1 ? A.cc_env[cur ^ 1] + (size_t)t.index * E : N.c_env + (size_t)t.index * E;
+            k_trans_env<<<(E + 255) / 256, 256, 0, st>>>(P, A, dst, (double)t.sign, t.coeff, d_env_mask);
+        }
+    }
+}
+
 // run_loop_modulators (networks.py:3282-3325): sim.gj_block / sim.NaKATP_block = max_val * eval(alpha_eval_string),
 // membrane zone; in force from the gap-junction transport of the substances of this step onwards.
 __global__ void __launch_bounds__(256)

@@ -7,10 +7,12 @@
 #define NET_STACK 16        // ratelaw.MAX_STACK
 
 // opcodes of the postfix programs (ratelaw.py)
-enum { RL_PUSHC = 0, RL_PUSHS, RL_PUSHA, RL_PUSHI, RL_PUSHM, RL_PUSHV, RL_ADD, RL_SUB, RL_MUL, RL_DIV, RL_POW, RL_NEG, RL_EXP };
+enum { RL_PUSHC = 0, RL_PUSHS, RL_PUSHA, RL_PUSHI, RL_PUSHM, RL_PUSHV, RL_PUSHE, RL_PUSHJ, RL_ADD, RL_SUB, RL_MUL, RL_DIV, RL_POW, RL_NEG, RL_EXP };
+#define RL_LAST_PUSH RL_PUSHJ
 
 struct KNet {
     int K;                      // substances
+    int E;                      // env points (ny*nx)
     int n_rates;                // K growth/decay rates + R reactions (columns of reaction_matrix)
     double* c;                  // [K][C] concentrations in the cells
     double* rates;              // [n_rates][C] rates of the last step (reaction_rates / download)
@@ -32,6 +34,15 @@ struct KNet {
     const double* Dm;           // [K]
     const double* c_bound;      // [K]
     const double* D_env;        // [K][E]
+    // Membrane values (mem_concs[X] = Molecule.cc_at_mem / sim.cc_at_mem[ion]) of everything a transporter moves in the
+    // cells: the reference updates the cell value AND nudges the membrane value (networks.py:3016-3022), two separate
+    // arrays until the next update_intra / update_Co — so later membrane-zone rate laws of the step read these rows
+    // (gathered from the cells when the handler's block starts, re-gathered when a channel's update_Co renews an ion)
+    double* tw;                 // [n_rows][M]
+    double* tr_flux;            // [M] flux of the transporter in flight
+    const double* sa_over_vol;  // [M] mem_sa/mem_vol
+    signed char tw_s[NET_MAX_RATES];   // row of substance k (< 0: none)
+    signed char tw_i[8];               // row of ion i
     const unsigned char* pumped; // [K] 1: the substance has its own pump -> its membrane leg follows the pump (launch_net)
     double* c_save;             // [n_pumps][C] a pumped substance's concentration before growth/decay (cc_at_mem of its membrane leg)
     // p.substances_affect_charge (networks.py:2942-2977)
@@ -52,13 +63,19 @@ __device__ __forceinline__ double rl_eval(const KNet& N, const int prog, const i
     for (int pc = p0; pc < p1; ++pc) {
         const int2 ins = __ldg(reinterpret_cast<const int2*>(N.code) + pc);
         const int op = ins.x, arg = ins.y;
-        if (op <= RL_PUSHV) {
+        if (op <= RL_LAST_PUSH) {
             double v;
             switch (op) {
+                // outside the membrane (membrane zone only): substance / ion at the membrane's env square; the ions' env
+                // field is the one this step's transport left (cc_env[cur ^ 1]), what sim.cc_env holds during the network block
+                case RL_PUSHE: v = N.c_env[(size_t)arg * N.E + __ldg(A.map_mem2ecm + m)]; break;
+                case RL_PUSHJ: v = A.cc_env[cur ^ 1][(size_t)arg * N.E + __ldg(A.map_mem2ecm + m)]; break;
                 case RL_PUSHC: v = __ldg(N.consts + arg); break;
-                case RL_PUSHS: v = N.c[(size_t)arg * C + c]; break;
+                case RL_PUSHS: v = (m >= 0 && N.tw && N.tw_s[arg] >= 0) ? N.tw[(size_t)N.tw_s[arg] * M + m] : N.c[(size_t)arg * C + c];
+                               break;
                 case RL_PUSHA: v = (m < 0) ? __ldg(N.cell_arrays + (size_t)arg * C + c) : __ldg(N.mem_arrays + (size_t)arg * M + m); break;
-                case RL_PUSHI: v = A.cc_cells[(size_t)arg * C + c]; break;
+                case RL_PUSHI: v = (m >= 0 && N.tw && N.tw_i[arg] >= 0) ? N.tw[(size_t)N.tw_i[arg] * M + m] : A.cc_cells[(size_t)arg * C + c];
+                               break;
                 case RL_PUSHM: v = A.cc_mid[cur][(size_t)arg * C + c]; break;
                 default: v = vm; break;
             }

@@ -528,6 +528,29 @@ class TissueEngine:
                 garr[j].K, garr[j].n, garr[j].max_val, garr[j].mod = float(g["K"]), float(g["n"]), float(g["max"]), float(g["mod"])
             keep.append(garr)
             n.n_ligand_gates, n.ligand_gates = len(gates), garr
+        trs = list(net.get("transporters") or [])
+        if trs:
+            tarr = (capi.Transporter * len(trs))()
+            for j, t in enumerate(trs):
+                if len(t["terms"]) > capi.TR_MAX_TERMS:
+                    raise BetseB200Error("a transporter with more than %d reactants + products" % capi.TR_MAX_TERMS)
+                tarr[j].prog, tarr[j].n_terms, tarr[j].net_z = int(t["prog"]), len(t["terms"]), float(t["net_z"])
+                for q, (kind, index, sign, coeff) in enumerate(t["terms"]):
+                    tt = tarr[j].terms[q]
+                    tt.kind, tt.index, tt.sign, tt.coeff = int(kind), int(index), int(sign), float(coeff)
+                for member, n_ in (("cell_mask", self.C), ("env_mask", self.E), ("mem_mask", self.M)):
+                    mk = t.get(member)
+                    if mk is not None:
+                        mk = np.ascontiguousarray(np.asarray(mk, dtype=np.uint8).reshape(-1))
+                        if mk.size < n_:
+                            mk = np.concatenate((mk, np.zeros(n_ - mk.size, dtype=np.uint8)))
+                        keep.append(mk)
+                        setattr(tarr[j], member, mk.ctypes.data_as(C.POINTER(C.c_uint8)))
+            keep.append(tarr)
+            n.n_transporters, n.transporters = len(trs), tarr
+            if "mem_vol" not in self.mesh:
+                raise BetseB200Error("transporters need cells.mem_vol in the mesh")
+            n.mem_sa_over_vol = f64(np.asarray(self.mesh["mem_sa"], dtype=float) / np.asarray(self.mesh["mem_vol"], dtype=float))
         pumps = list(net.get("pumps") or [])
         if pumps:
             parr = (capi.SubstancePump * len(pumps))()

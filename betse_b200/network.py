@@ -35,8 +35,12 @@ def unsupported_reasons(core, p):
     for name, mod in (getattr(core, "modulators", None) or {}).items():
         if str(mod.target_label) not in MOD_TARGETS:
             bad.append("modulator %r of %s (extracellular zone)" % (name, mod.target_label))
-    for attr, what in (("transporters", "transporters (run_loop_transporters, networks.py:2985-3107)"),
-                       ("reactions_env", "extracellular reactions"), ("reactions_mit", "mitochondrial reactions")):
+    for name, t in (getattr(core, "transporters", None) or {}).items():
+        if str(getattr(t, "reaction_zone", "cell")) != "cell":
+            bad.append("transporter %r outside the cell zone" % name)
+        if not bool(getattr(p, "is_ecm", False)):
+            bad.append("transporter %r without extracellular spaces" % name)
+    for attr, what in (("reactions_env", "extracellular reactions"), ("reactions_mit", "mitochondrial reactions")):
         if len(getattr(core, attr, None) or {}):
             bad.append(what)
     for name, m in (getattr(core, "molecules", None) or {}).items():
@@ -69,8 +73,11 @@ def _in_env(m):
 def describe_core(core, sim, p, cells, record_static=True):
     """Live ``MasterOfNetworks`` -> network description (plain dict of strings and arrays)."""
     species = list(core.molecules)
-    ions = [str(k) for k in sim.ionlabel.values()] if hasattr(sim, "ionlabel") else \
-        [k for k, v in p.ions_dict.items() if v == 1]
+    # short ion names ('Na', 'K', ...: the keys of MasterOfNetworks.cell_concs, networks.py:186-206) in the Simulator's index order
+    enabled = [k for k, v in p.ions_dict.items() if v == 1]
+    if hasattr(sim, "get_ion"):
+        enabled = sorted(enabled, key=lambda k: int(sim.get_ion(k)))
+    ions = [str(k) for k in enabled]
     K, C = len(species), len(cells.cell_vol)
     names = list(core.cell_concs.keys())
     rmat = np.asarray(core.reaction_matrix, dtype=float)
@@ -101,6 +108,22 @@ def describe_core(core, sim, p, cells, record_static=True):
     }
     # Molecule.transport -> stb.molecule_mover (networks.py:5670-5700, sim_toolbox.py:909-1153): membrane and
     # extracellular legs of the substances that have them
+    # run_loop_transporters (networks.py:2985-3107): flux = rho_pump * eval(transporter_eval_string) on every membrane;
+    # each reactant / product moves by coeff * (-/+) sum_mems(flux*mem_sa)/cell_vol in the cells ('mem_concs' tag) or
+    # coeff * div_env(-/+flux) outside ('env_concs' tag), on the transporter's target cells / env squares
+    trans = []
+    for name, t in (getattr(core, "transporters", None) or {}).items():
+        terms = [(str(x), float(c), str(tag), -1) for x, c, tag in zip(t.reactants_list, t.reactants_coeff, t.react_transport_tag)]
+        terms += [(str(x), float(c), str(tag), +1) for x, c, tag in zip(t.products_list, t.products_coeff, t.prod_transport_tag)]
+        for x, c, tag, sg in terms:
+            if tag not in ("mem_concs", "env_concs"):
+                raise BetseB200Error("transporter %r: zone %r is not implemented" % (name, tag))
+        trans.append({"name": str(name), "eval_string": str(t.transporter_eval_string), "net_z": float(t.net_z), "terms": terms,
+                      "targets_cell": np.asarray(t.transporter_targets_cell, dtype=np.int64),
+                      "targets_mem": np.asarray(t.transporter_targets_mem, dtype=np.int64),
+                      "targets_env": np.asarray(t.transporter_targets_env, dtype=np.int64)})
+    if trans:
+        desc["transporters"] = trans
     # Molecule.gating (networks.py:5847-5916): ligand-gated channels, one entry per (substance, conducted ion)
     lig = []
     for k, s in enumerate(species):
@@ -123,7 +146,9 @@ def describe_core(core, sim, p, cells, record_static=True):
         if any(g["extracell"] and any(q["species"] == g["species"] for q in pumps) for g in lig):
             raise BetseB200Error("a pumped substance that also gates a channel from outside the cell is not implemented")
     env_on = np.array([_in_env(core.molecules[s]) or any(g["species"] == k and g["extracell"] for g in lig)
-                       or any(q["species"] == k for q in pumps) for k, s in enumerate(species)], dtype=np.uint8)
+                       or any(q["species"] == k for q in pumps)
+                       or any(x == s and tag == "env_concs" for t in trans for x, _, tag, _ in t["terms"])   # moved outside by a transporter
+                       for k, s in enumerate(species)], dtype=np.uint8)
     if env_on.any() and bool(getattr(p, "is_ecm", False)):
         E = int(np.asarray(sim.D_env_weight).size)
         D_env = np.zeros((K, E))
@@ -187,6 +212,39 @@ def compile_network(desc, n_cells, n_mems, resolver=None):
     for t in desc.get("modulator_targets", []):
         if t not in MOD_TARGETS:
             raise BetseB200Error("modulator target %r is not implemented" % t)
+    # transporters: one membrane-zone program each, after the modulators' programs
+    transporters = []
+    ions = list(desc["ions"])
+    for t in desc.get("transporters", []):
+        try:
+            pr = ratelaw.compile_expr(t["eval_string"], tabs, resolver, "mem")
+        except ratelaw.RateLawError as e:
+            raise BetseB200Error("transporter %r not supported on the device: %s" % (t["name"], e))
+        terms = []
+        for x, coeff, tag, sign in t["terms"]:
+            env = tag == "env_concs"
+            if x in species:
+                terms.append((3 if env else 2, species.index(x), int(sign), float(coeff)))
+            elif x in ions:
+                terms.append((1 if env else 0, ions.index(x), int(sign), float(coeff)))
+            else:
+                raise BetseB200Error("transporter %r moves %r, which is neither a substance nor a simulated ion" % (t["name"], x))
+        cm = np.zeros(n_cells, dtype=np.uint8)
+        cm[np.asarray(t["targets_cell"], dtype=np.int64)] = 1
+        em = None
+        if len(t["targets_env"]):
+            n_env = int(np.asarray(desc["c_env"]).shape[1]) if "c_env" in desc else int(np.max(t["targets_env"])) + 1
+            em = np.zeros(n_env, dtype=np.uint8)
+            em[np.asarray(t["targets_env"], dtype=np.int64)] = 1
+        mm = np.zeros(n_mems, dtype=np.uint8)
+        mm[np.asarray(t["targets_mem"], dtype=np.int64)] = 1
+        transporters.append({"prog": len(rates) + len(mod_programs), "net_z": float(t["net_z"]), "terms": terms,
+                             "cell_mask": None if cm.all() else cm, "env_mask": em, "mem_mask": None if mm.all() else mm})
+        mod_programs.append(pr)
+    eo = np.asarray(desc.get("env_on", np.zeros(K)), dtype=bool)
+    for k in sorted(tabs.env_species):
+        if not eo[k]:
+            raise BetseB200Error("a rate law reads %r outside the cells, where it does not exist" % species[k])
     # ligand-gated channels: the regulation of the gate itself (gating_mod_eval_string) must fold to a constant — it
     # is evaluated in the middle of run_loop's per-substance sequence (networks.py:2922-2925), which a device kernel
     # working from the step's starting concentrations cannot mirror for other substances
@@ -200,7 +258,7 @@ def compile_network(desc, n_cells, n_mems, resolver=None):
             raise BetseB200Error("ligand-gated channels regulated by further substances are not implemented")
         gates.append(dict(g, mod=float(tabs.consts[pr.code[0][1]])))
     return {"species": species, "tables": tabs, "rate_programs": rates, "mod_programs": mod_programs,
-            "mod_index": mod_index, "ligand_gates": gates, "pumps": list(desc.get("pumps", [])),
+            "mod_index": mod_index, "ligand_gates": gates, "pumps": list(desc.get("pumps", [])), "transporters": transporters,
             "modulators": [(MOD_TARGETS[t], i, float(mx)) for t, i, mx in
                            zip(desc.get("modulator_targets", []), modulator_index, desc.get("modulator_max", []))], "c_cells": np.asarray(desc["c_cells"], dtype=float), "stoich": stoich,
             "growth_mask": None if mask.all() else mask, "Dgj": np.asarray(desc["Dgj"], dtype=float),
@@ -222,6 +280,16 @@ def flatten(desc, prefix):
     for j, g in enumerate(desc.get("ligand_gates", [])):
         out["%slig%d" % (prefix, j)] = np.array([g["species"], g["ion"], g["K"], g["n"], g["max"], float(g["extracell"])])
         out["%slig%d.mod_string" % (prefix, j)] = np.array(g["mod_string"])
+    for j, t in enumerate(desc.get("transporters", [])):
+        pre = "%strans%d." % (prefix, j)
+        out.update({pre + "name": np.array(t["name"]), pre + "eval_string": np.array(t["eval_string"]), pre + "net_z": np.asarray(t["net_z"]),
+                    pre + "term_names": np.array([x for x, _, _, _ in t["terms"]], dtype=str),
+                    pre + "term_tags": np.array([tag for _, _, tag, _ in t["terms"]], dtype=str),
+                    pre + "term_coeff": np.array([c for _, c, _, _ in t["terms"]], dtype=float),
+                    pre + "term_sign": np.array([sg for _, _, _, sg in t["terms"]], dtype=np.int64),
+                    pre + "targets_cell": np.asarray(t["targets_cell"], dtype=np.int64),
+                    pre + "targets_mem": np.asarray(t["targets_mem"], dtype=np.int64),
+                    pre + "targets_env": np.asarray(t["targets_env"], dtype=np.int64)})
     for j, q in enumerate(desc.get("pumps", [])):
         out["%spump%d" % (prefix, j)] = np.array([q["species"], float(q["into_cell"]), q["max"], q["Km"], float(q["uses_ATP"])])
     if desc.get("modulator_names"):
@@ -250,6 +318,16 @@ def unflatten(cap, prefix):
         mods.setdefault("ligand_gates", []).append({"species": int(v[0]), "ion": int(v[1]), "K": float(v[2]), "n": float(v[3]),
                                                     "max": float(v[4]), "extracell": bool(v[5]),
                                                     "mod_string": str(cap["%slig%d.mod_string" % (prefix, j)])})
+        j += 1
+    j = 0
+    while "%strans%d.name" % (prefix, j) in cap:
+        pre = "%strans%d." % (prefix, j)
+        mods.setdefault("transporters", []).append({
+            "name": str(cap[pre + "name"]), "eval_string": str(cap[pre + "eval_string"]), "net_z": float(cap[pre + "net_z"]),
+            "terms": [(str(x), float(c), str(tag), int(sg)) for x, c, tag, sg in
+                      zip(cap[pre + "term_names"], cap[pre + "term_coeff"], cap[pre + "term_tags"], cap[pre + "term_sign"])],
+            "targets_cell": np.asarray(cap[pre + "targets_cell"]), "targets_mem": np.asarray(cap[pre + "targets_mem"]),
+            "targets_env": np.asarray(cap[pre + "targets_env"])})
         j += 1
     j = 0
     while "%spump%d" % (prefix, j) in cap:

@@ -31,8 +31,9 @@ import operator
 import numpy as np
 
 # opcodes (mirrored in csrc/network.cuh)
-PUSHC, PUSHS, PUSHA, PUSHI, PUSHM, PUSHV, ADD, SUB, MUL, DIV, POW, NEG, EXP = range(13)
-OP_NAMES = ["PUSHC", "PUSHS", "PUSHA", "PUSHI", "PUSHM", "PUSHV", "ADD", "SUB", "MUL", "DIV", "POW", "NEG", "EXP"]
+PUSHC, PUSHS, PUSHA, PUSHI, PUSHM, PUSHV, PUSHE, PUSHJ, ADD, SUB, MUL, DIV, POW, NEG, EXP = range(15)
+OP_NAMES = ["PUSHC", "PUSHS", "PUSHA", "PUSHI", "PUSHM", "PUSHV", "PUSHE", "PUSHJ", "ADD", "SUB", "MUL", "DIV", "POW", "NEG", "EXP"]
+LAST_PUSH = PUSHJ
 MAX_STACK = 16
 
 
@@ -55,7 +56,7 @@ class Program:
     def max_depth(self):
         d = m = 0
         for op, _ in self.code:
-            if op <= PUSHV:
+            if op <= LAST_PUSH:
                 d += 1
             elif op in (NEG, EXP):
                 pass
@@ -73,6 +74,7 @@ class Tables:
         self.consts = []
         self.cell_arrays = []
         self.mem_arrays = []
+        self.env_species = set()      # substances some program reads outside the membrane (need env storage)
 
     def const(self, v):
         v = float(v)
@@ -100,6 +102,20 @@ def _subscript_key(node):
 
 def _dynamic(node, tables, zone):
     """(op, arg) if ``node`` is a device-resident quantity, else None."""
+    # self.env_concs['X'][cells.map_mem2ecm]: X outside the membrane (transporters, networks.py:2346-2430)
+    if isinstance(node, ast.Subscript) and isinstance(node.value, ast.Subscript) \
+            and isinstance(node.value.value, ast.Attribute) and node.value.value.attr == "env_concs" \
+            and isinstance(node.value.value.value, ast.Name) and node.value.value.value.id == "self":
+        key = _subscript_key(node.value)
+        idx = ast.unparse(node.slice)
+        if zone != "mem" or idx != "cells.map_mem2ecm":
+            raise RateLawError("env_concs[%r][%s] in the %s zone is not implemented" % (key, idx, zone))
+        if key in tables.species:
+            tables.env_species.add(tables.species.index(key))
+            return (PUSHE, tables.species.index(key))
+        if key in tables.ions:
+            return (PUSHJ, tables.ions.index(key))
+        raise RateLawError("unknown substance %r" % key)
     # self.cell_concs['X'] / self.mem_concs['X'] / self.env_concs[...]
     if isinstance(node, ast.Subscript) and isinstance(node.value, ast.Attribute) \
             and isinstance(node.value.value, ast.Name) and node.value.value.id == "self":
@@ -110,11 +126,11 @@ def _dynamic(node, tables, zone):
             if key in tables.species:
                 return (PUSHS, tables.species.index(key))
             if key in tables.ions:
-                # cell zone: sim.cc_cells[ion] (networks.py:186-206).  In the membrane zone the dictionary entry
-                # is sim.cc_at_mem[ion], which earlier channels of the same step overwrite (networks.py:3182):
-                # not reproduced yet
-                if zone != "cell":
-                    raise RateLawError("ion %r as a membrane-zone regulator is not implemented" % key)
+                # cell zone: sim.cc_cells[ion] (networks.py:186-206).  Membrane zone: sim.cc_at_mem[ion], which during the
+                # network block of a step IS sim.cc_cells[ion][mem_to_cells] — set so at the end of the ion loop
+                # (update_intra, sim.py:2310) and by every update_Co since (sim_toolbox.py:1182) — so the same read
+                # serves both zones (a transporter's own tweak of mem_concs, networks.py:3020-3022, lives only until
+                # the next update_Co and is not reproduced)
                 return (PUSHI, tables.ions.index(key))
             raise RateLawError("unknown substance %r" % key)
         if dic in ("env_concs", "mit_concs", "bound_concs"):
@@ -252,7 +268,8 @@ def pack_programs(programs):
     return np.asarray(code if code else [0, 0], dtype=np.int32), np.asarray(ptr, dtype=np.int32)
 
 
-def run_numpy(prog, tables, species, ions=None, ions_mid=None, vm=None, mem_to_cells=None):
+def run_numpy(prog, tables, species, ions=None, ions_mid=None, vm=None, mem_to_cells=None, species_env=None, ions_env=None,
+              map_mem2ecm=None):
     """Host interpreter of a program (tests only): ``species`` [K][C]; membrane-zone programs
     gather cell quantities through ``mem_to_cells``."""
     st = []
@@ -270,6 +287,10 @@ def run_numpy(prog, tables, species, ions=None, ions_mid=None, vm=None, mem_to_c
             st.append(g(ions_mid[arg]))
         elif op == PUSHV:
             st.append(vm)
+        elif op == PUSHE:
+            st.append(species_env[arg][map_mem2ecm])
+        elif op == PUSHJ:
+            st.append(ions_env[arg][map_mem2ecm])
         elif op == NEG:
             st.append(-st.pop())
         elif op == EXP:

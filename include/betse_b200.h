@@ -264,6 +264,31 @@ typedef struct betse_substance_pump {
     double max_val, Km;
 } betse_substance_pump;
 
+/* One transporter (run_loop_transporters, networks.py:2985-3107; strings from write_transporters, :2090-2614), cell zone,
+ * with extracellular spaces: flux[m] = rho_pump * program(membrane) on every membrane; every reactant (sign -1) and
+ * product (sign +1) then moves by coeff * sign * sum_mems(flux*mem_sa)/cell_vol in the cells of cell_mask, or by
+ * coeff * div_env(sign*flux) on the env squares of env_mask; extra_J_mem += net_z*flux*F. */
+#define BETSE_TR_MAX_TERMS 12
+typedef struct betse_transporter_term {
+    int32_t kind;                 /* 0 ion in the cells, 1 ion outside, 2 substance in the cells, 3 substance outside */
+    int32_t index;                /* ion / substance index                                           */
+    int32_t sign;                 /* -1 reactant, +1 product                                         */
+    int32_t pad;
+    double coeff;
+} betse_transporter_term;
+typedef struct betse_transporter {
+    int32_t prog;                 /* membrane-zone program of transporter_eval_string                */
+    int32_t n_terms;
+    double net_z;
+    const uint8_t *cell_mask;     /* [C] transporter_targets_cell; NULL = every cell                 */
+    const uint8_t *env_mask;      /* [E] transporter_targets_env;  NULL = every env square           */
+    const uint8_t *mem_mask;      /* [M] transporter_targets_mem;  NULL = every membrane: where the reference also nudges
+                                     mem_concs[X] -/+= flux*(mem_sa/mem_vol)*dt (networks.py:3020-3022, 3070-3072), a value
+                                     that lives until the next update_intra / update_Co and that LATER rate laws of the same
+                                     step (transporters, channel modulation, sim modulators) read                  */
+    betse_transporter_term terms[BETSE_TR_MAX_TERMS];
+} betse_transporter;
+
 typedef struct betse_network {
     int32_t n_species;            /* K substances, MasterOfNetworks.molecules order                 */
     int32_t n_rates;              /* K growth/decay rates + R cell-zone reactions = columns of reaction_matrix */
@@ -298,6 +323,10 @@ typedef struct betse_network {
     int32_t n_ligand_gates;
     int32_t n_pumps;
     const betse_substance_pump *pumps;   /* at most one per substance; the substance needs env_on      */
+    const betse_transporter *transporters;   /* applied in order, before the handler's channels (sim.py:1293-1297) */
+    int32_t n_transporters;
+    int32_t reserved;
+    const double *mem_sa_over_vol;       /* [M] cells.mem_sa / cells.mem_vol (needed with transporters)  */
 } betse_network;
 
 /* handler 0 = sim.molecules.core, 1 = sim.grn.core (run in that order, sim.py:1290-1318).  net == NULL

@@ -250,6 +250,25 @@ SCENARIOS["mammal_ecm_net_pump"] = dict(
     snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=net_extra)
 
 
+# transporters (run_loop_transporters, networks.py:2985-3107): a reversible carrier bringing T1 into the cells from the
+# bath, and an electrogenic exporter on one tissue profile that moves 3 Na+ out per T2 -> G1 turnover, activated by T1
+_TR = [{"name": "carrier", "reaction zone": "cell", "reactants": ["T1"], "reactant multipliers": [1], "Km reactants": [0.5],
+        "products": ["T1"], "product multipliers": [1], "Km products": [0.5], "transfered out of cell": [],
+        "transfered into cell": ["T1"], "max rate": 5.0e-9, "standard free energy": 0, "apply to": "all", "ignore ECM": True,
+        "transporter activators": "None", "transporter inhibitors": "None"},
+       {"name": "exporter", "reaction zone": "cell", "reactants": ["Na", "T2"], "reactant multipliers": [3, 1],
+        "Km reactants": [10.0, 0.1], "products": ["Na", "G1"], "product multipliers": [3, 1], "Km products": [140.0, 1.0],
+        "transfered out of cell": ["Na"], "transfered into cell": [], "max rate": 2.0e-9, "standard free energy": -20e3,
+        "apply to": ["Spot"], "ignore ECM": True, "transporter activators": ["T1"], "activator Km": [0.3], "activator n": [1.0],
+        "activator zone": ["cell"], "transporter inhibitors": "None"}]
+_TR_BIO = [_env_substance("T1", 0.0, 0, 0.5, 0.1, True, True), _substance("T2", 1.0, cell=0.5), _substance("G1", 0.2, cell=0.05)]
+SCENARIOS["mammal_ecm_net_trans"] = dict(
+    mods=_m(SMALL, {"cutting event": {"event happens": False}, "general options": {"ion profile": "mammal"},
+                    "general network": {"implement network": True, "biomolecules": _TR_BIO, "reactions": [], "channels": [],
+                                        "transporters": _TR}}),
+    snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=net_extra)
+
+
 # The external-voltage event (tissue/event/tisevevolt.py: bound_V ramps, Phi_b = one Dirichlet Poisson solve per step,
 # ion_current.py:84-90, subtracted from Vmem in update_V, sim.py:2029) — ramp up, plateau and ramp down inside the
 # first 20 SIM steps, left/right electrodes so that it differs from the top/bottom default; ECM and no-ECM

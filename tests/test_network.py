@@ -28,6 +28,7 @@ def test_compiled_programs_equal_python_eval():
     for trial in range(3):
         for n in net.species:
             net.c[n] = rng.uniform(0.0, 3.0, C)
+            net.cmem[n] = net.c[n][o.mem_to_cells]
         spec = np.stack([net.c[n] for n in net.species])
         strings = d["gad_strings"] + d["reaction_strings"]
         for pr, s in zip(comp["rate_programs"], strings):
@@ -56,7 +57,7 @@ def test_static_terms_are_folded():
 
 
 @pytest.mark.parametrize("src,msg", [
-    ("self.env_concs['X'][cells.map_cell2ecm]/2.0", "extracellular"),
+    ("self.env_concs['X'][cells.map_cell2ecm]/2.0", "cell zone is not implemented"),
     ("self.cell_concs['Nope']*2", "unknown substance"),
     ("np.sin(self.cell_concs['X'])", "unsupported construct"),
     ("self.mem_concs['X']*2", "zone"),
@@ -76,3 +77,36 @@ def test_description_roundtrip():
     assert set(back["static"]) == set(descs[0]["static"])
     for k, v in back["static"].items():
         assert np.array_equal(np.asarray(v), np.asarray(descs[0]["static"][k]))
+
+
+def test_transporter_programs_equal_python_eval():
+    """Transporter rate laws (write_transporters, networks.py:2090-2614): concentrations outside the membrane
+    (env_concs[...][cells.map_mem2ecm]), ions at the membrane, np.exp of the electrochemical term and Vmem."""
+    cap = util.load_golden("mammal_ecm_net_trans")
+    kind = "sim"
+    descs = util.networks_of(cap, kind)
+    o = OracleSim(util.mesh_of(cap, kind), util.group(cap, kind + ".p."), util.group(cap, kind + ".s0."), networks=descs)
+    d, net = descs[0], o.networks[0]
+    comp = netlib.compile_network(d, o.cdl, o.mdl)
+    assert len(comp["transporters"]) == 2 and comp["transporters"][1]["net_z"] == 3.0
+    kinds = sorted((k, sg) for k, _, sg, _ in comp["transporters"][1]["terms"])
+    assert kinds == [(0, -1), (1, 1), (2, -1), (2, 1)]          # Na leaves the cells for the env grid; T2 -> G1 inside
+    rng = np.random.default_rng(11)
+    for n in net.species:
+        net.c[n] = rng.uniform(0.05, 2.0, o.cdl)
+        net.cmem[n] = net.c[n][o.mem_to_cells]
+        if n in net.c_env:
+            net.c_env[n] = rng.uniform(0.05, 2.0, o.n_env)
+    o.vm = rng.uniform(-0.07, 0.01, o.mdl)
+    o.cc_at_mem = o.cc_cells[:, o.mem_to_cells].copy()        # as the ion loop leaves it before the network block (sim.py:2310)
+    spec = np.stack([net.c[n] for n in net.species])
+    spec_env = np.stack([net.c_env.get(n, np.zeros(o.n_env)) for n in net.species])
+    for t, ct in zip(d["transporters"], comp["transporters"]):
+        want = net.eval_string(t["eval_string"]) * np.ones(o.mdl)
+        pr = (comp["rate_programs"] + comp["mod_programs"])[ct["prog"]]
+        got = ratelaw.run_numpy(pr, comp["tables"], spec, ions=o.cc_cells, vm=o.vm, mem_to_cells=o.mem_to_cells,
+                                species_env=spec_env, ions_env=o.cc_env, map_mem2ecm=o.map_mem2ecm)
+        # (1 - Q/Keq) cancels when the transporter is near equilibrium: judge against the size of the uncancelled rate
+        scale = float(np.max(np.abs(want)))
+        print(t["name"], float(np.max(np.abs(got - want))) / scale)
+        assert np.max(np.abs(got - want)) <= 1e-12 * scale, t["name"]
