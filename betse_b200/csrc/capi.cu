@@ -40,7 +40,7 @@ void launch_pack_dm(const KParams& P, const KArrays& A, cudaStream_t st);
 void launch_chan(const KParams& P, const KArrays& A, const KChan& ch, const KNet& N, int cur, cudaStream_t st);
 void launch_net(const KParams& P, const KArrays& A, const KNet& N, const double* h_Dgj, const double* h_Dm,
                 const unsigned char* h_env_on, const betse_substance_pump* pumps, int n_pumps, double dG_RT,
-                int n_ions, int cur, cudaStream_t st);
+                const unsigned char* h_intra, int n_ions, int cur, cudaStream_t st);
 void launch_lig_prep(const KParams& P, const KArrays& A, const KNet& N, int sp, int extracell, double Kn, double n,
                      double max_val, double* Dm_mod, cudaStream_t st);
 void launch_net_lig(const KParams& P, const KArrays& A, int ion, const double* Dm_mod, double mod, int cur, int diag, cudaStream_t st);
@@ -98,6 +98,7 @@ struct betse_ctx {
     std::vector<betse_transporter> net_trans[2];    // transporters (run_loop_transporters); masks below are device copies
     std::vector<const unsigned char*> net_trans_cm[2], net_trans_em[2], net_trans_mm[2];
     int net_tw_rows[2] = {0, 0};
+    std::vector<unsigned char> net_intra[2];        // substances with intracellular transport (membrane values of their own)
     double* lig_tmp[2] = {nullptr, nullptr};       // [n_gates][M] openings formed before the substances advance
     std::string err;
     std::vector<void*> allocs;
@@ -847,7 +848,8 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
                                         gs[j].max_val, ctx->lig_tmp[h] + j * (size_t)ctx->Mo, st);
                     launch_net(ctx->P, A, ctx->nets[h], ctx->net_Dgj[h].data(), ctx->net_Dm[h].data(),
                                ctx->net_env_on[h].data(), ctx->net_pumps[h].data(), (int)ctx->net_pumps[h].size(),
-                               ctx->hp.deltaGATP / (ctx->hp.R * ctx->hp.T_sim), I, cur, st);
+                               ctx->hp.deltaGATP / (ctx->hp.R * ctx->hp.T_sim),
+                               ctx->net_intra[h].empty() ? nullptr : ctx->net_intra[h].data(), I, cur, st);
                     for (size_t j = 0; j < gs.size(); ++j) {
                         launch_net_lig(ctx->P, A, gs[j].ion, ctx->lig_tmp[h] + j * (size_t)ctx->Mo, gs[j].mod, cur, diag, st);
                         launch_chan_env(ctx->P, A, gs[j].ion, cur, st);
@@ -1349,6 +1351,19 @@ extern "C" int betse_set_network(betse_ctx* ctx, int handler, const betse_networ
         ctx->net_trans_em[handler].push_back(em);
         ctx->net_trans_mm[handler].push_back(mm);
     }
+    ctx->net_intra[handler].clear();
+    if (net->intra_on) {
+        bool any = false;
+        for (int k = 0; k < K; ++k) any = any || net->intra_on[k] != 0;
+        if (any) {
+            if (!net->Do || !net->c_mems || !net->R_rads || !net->mem_sa_over_vol) return fail(ctx, "network: intra_on needs Do, c_mems, R_rads and mem_sa_over_vol");
+            if ((r = dev_upload(ctx, &N.cmem, net->c_mems, (size_t)K * Mo))) return r;
+            if ((r = dev_upload(ctx, (double**)&N.Do, net->Do, (size_t)K))) return r;
+            if ((r = dev_upload(ctx, (double**)&N.R_rads, net->R_rads, (size_t)Mo))) return r;
+            if (!N.sa_over_vol) { if ((r = dev_upload(ctx, (double**)&N.sa_over_vol, net->mem_sa_over_vol, (size_t)Mo))) return r; }
+            ctx->net_intra[handler].assign(net->intra_on, net->intra_on + K);
+        }
+    }
     ctx->net_pumps[handler].clear();
     if (net->n_pumps > 0) {
         std::vector<unsigned char> pumped((size_t)K, 0);
@@ -1442,6 +1457,34 @@ extern "C" int betse_network_env_state(betse_ctx* ctx, int handler, double* c_en
         CK(cudaMemcpyAsync(c_env, N.c_env, nb, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     } else memset(c_env, 0, nb);
+    return 0;
+}
+
+static __global__ void k_gather_mems(const double* __restrict__ c, const int* __restrict__ m2c, double* __restrict__ out, int M)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < M) out[m] = c[m2c[m]];
+}
+
+extern "C" int betse_network_mem_state(betse_ctx* ctx, int handler, double* c_mems)
+{
+    if (!ctx || handler < 0 || handler > 1 || !c_mems) return 2;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->net_on[handler]) return fail(ctx, "no network on this handler");
+    const KNet& N = ctx->nets[handler];
+    const int Mo = ctx->Mo;
+    double* tmp = nullptr;
+    CK(cudaMalloc((void**)&tmp, (size_t)Mo * sizeof(double)));
+    for (int k = 0; k < N.K; ++k) {
+        const bool intra = !ctx->net_intra[handler].empty() && ctx->net_intra[handler][k];
+        const double* src = tmp;
+        if (intra) src = N.cmem + (size_t)k * Mo;
+        else k_gather_mems<<<(Mo + 255) / 256, 256, 0, ctx->stream>>>(N.c + (size_t)k * ctx->C, ctx->A.mem_to_cells, tmp, Mo);
+        int xr = xfer(ctx, c_mems + (size_t)k * Mo, src, (size_t)Mo * sizeof(double), cudaMemcpyDeviceToHost);
+        if (xr) { cudaFree(tmp); return xr; }
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    cudaFree(tmp);
     return 0;
 }
 

@@ -552,14 +552,33 @@ k_sub_div(const __grid_constant__ KParams P, const KArrays A, const __grid_const
     c[q] = cn;
 }
 
+// Molecule.update_intra with intracellular transport (networks.py:5727-5795) for a neutral substance (En = uflow = 0):
+// the membrane value relaxes implicitly towards the cell value the step started with
+__global__ void __launch_bounds__(256)
+k_net_intra(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ KNet N, const int k)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= P.n_mems_owned) return;
+    const double g = __ldg(N.sa_over_vol + m) / 0.75;                        // gamma = mem_sa/((3/4)*mem_vol)
+    const double Do = __ldg(N.Do + k), dt = P.dt * __ldg(N.tdf + k), Rr = __ldg(N.R_rads + m);
+    const double cav = N.c[(size_t)k * P.n_cells + __ldg(A.mem_to_cells + m)];
+    double* cm = N.cmem + (size_t)k * P.n_mems_owned + m;
+    const double alpha_tot = 0.0;
+    *cm = (((((g * Do) * dt) * cav) / Rr) + ((((g * alpha_tot) * cav) * dt) / 2.0) + *cm) /
+          ((1.0 + (((g * Do) * dt) / Rr)) - (((g * alpha_tot) * dt) / 2.0));
+}
+
 void launch_net(const KParams& P, const KArrays& A, const KNet& N, const double* h_Dgj, const double* h_Dm,
                 const unsigned char* h_env_on, const betse_substance_pump* pumps, int n_pumps, double dG_RT,
-                int n_ions, int cur, cudaStream_t st)
+                const unsigned char* h_intra, int n_ions, int cur, cudaStream_t st)
 {
     if (N.K <= 0) return;
     const int tgrid = (P.n_tiles + (BT_TPB / 32) - 1) / (BT_TPB / 32);
     const int E = P.nx * P.ny;
     auto pump_of = [&](int k) { for (int j = 0; j < n_pumps; ++j) if (pumps[j].species == k) return j; return -1; };
+    if (N.cmem)
+        for (int k = 0; k < N.K; ++k)
+            if (h_intra && h_intra[k]) k_net_intra<<<(P.n_mems_owned + 255) / 256, 256, 0, st>>>(P, A, N, k);
     if (N.c_env)
         for (int k = 0; k < N.K; ++k) {
             if (!h_env_on[k] || h_Dm[k] == 0.0 || pump_of(k) >= 0) continue;

@@ -43,6 +43,11 @@ struct KNet {
     const double* sa_over_vol;  // [M] mem_sa/mem_vol
     signed char tw_s[NET_MAX_RATES];   // row of substance k (< 0: none)
     signed char tw_i[8];               // row of ion i
+    // 'update intracellular' (diagnostic case): membrane values of their own
+    double* cmem;               // [K][M]
+    const unsigned char* intra; // [K]
+    const double* Do;           // [K]
+    const double* R_rads;       // [M]
     const unsigned char* pumped; // [K] 1: the substance has its own pump -> its membrane leg follows the pump (launch_net)
     double* c_save;             // [n_pumps][C] a pumped substance's concentration before growth/decay (cc_at_mem of its membrane leg)
     // p.substances_affect_charge (networks.py:2942-2977)

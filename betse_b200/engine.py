@@ -30,6 +30,11 @@ DIAG_FIELDS = ("fluxes_mem", "fluxes_gj", "fluxes_env_x", "fluxes_env_y", "rate_
                "E_cell_y", "sigma_cell", "vm_ave", "E_gj_x", "E_gj_y", "J_env_x", "J_env_y", "B_field", "Jtx", "Jty")
 
 
+def trs_needs_vol(net):
+    """Transporters upload mem_sa/mem_vol themselves (set_network)."""
+    return bool(net.get("transporters"))
+
+
 def gaussian_taps():
     """Taps of scipy.ndimage.gaussian_filter(sigma=1) (truncate=4 -> radius 4), formed exactly
     like scipy's _gaussian_kernel1d so that v_env matches ion_current.py:104."""
@@ -528,6 +533,18 @@ class TissueEngine:
                 garr[j].K, garr[j].n, garr[j].max_val, garr[j].mod = float(g["K"]), float(g["n"]), float(g["max"]), float(g["mod"])
             keep.append(garr)
             n.n_ligand_gates, n.ligand_gates = len(gates), garr
+        intra = np.asarray(net.get("intra_on", np.zeros(K)), dtype=np.uint8).reshape(K)
+        if intra.any():
+            if "mem_vol" not in self.mesh or "R_rads" not in self.mesh:
+                raise BetseB200Error("'update intracellular' needs cells.mem_vol and cells.R_rads in the mesh")
+            io = np.ascontiguousarray(intra)
+            keep.append(io)
+            n.intra_on = io.ctypes.data_as(C.POINTER(C.c_uint8))
+            n.Do = f64(np.asarray(net["Do"], dtype=float).reshape(K))
+            n.c_mems = f64(np.asarray(net["c_mems"], dtype=float).reshape(K, self.M))
+            n.R_rads = f64(np.asarray(self.mesh["R_rads"], dtype=float))
+            if not trs_needs_vol(net):
+                n.mem_sa_over_vol = f64(np.asarray(self.mesh["mem_sa"], dtype=float) / np.asarray(self.mesh["mem_vol"], dtype=float))
         trs = list(net.get("transporters") or [])
         if trs:
             tarr = (capi.Transporter * len(trs))()
@@ -565,7 +582,8 @@ class TissueEngine:
                               else bool(net["affect_charge"]))
         self._check(self.lib.betse_set_network(self.ctx, int(handler), C.byref(n)), "betse_set_network")
         self.networks = getattr(self, "networks", {})
-        self.networks[int(handler)] = {"species": list(net["species"]), "n_rates": n.n_rates, "env_on": env_on.astype(bool)}
+        self.networks[int(handler)] = {"species": list(net["species"]), "n_rates": n.n_rates, "env_on": env_on.astype(bool),
+                                       "intra_on": intra.astype(bool)}
 
     def network_state(self, handler=0, rates=False):
         """Substance concentrations [K][C] (and the last rates [n_rates][C]) of a handler."""
@@ -576,6 +594,14 @@ class TissueEngine:
                                                  capi.ptr_f64(r) if rates else None), "betse_network_state")
         self.d2h_bytes += c.nbytes + (r.nbytes if rates else 0)
         return (c[:, :self.Co], r[:, :self.Co]) if rates else c[:, :self.Co]
+
+    def network_mem_state(self, handler=0):
+        """Membrane values [K][M] of a handler's substances (Molecule.cc_at_mem)."""
+        info = self.networks[int(handler)]
+        c = np.empty((len(info["species"]), self.M))
+        self._check(self.lib.betse_network_mem_state(self.ctx, int(handler), capi.ptr_f64(c)), "betse_network_mem_state")
+        self.d2h_bytes += c.nbytes
+        return c
 
     def network_env_state(self, handler=0):
         """Env concentrations [K][E] of a handler's substances (zeros for substances that live in the cells only)."""

@@ -45,8 +45,26 @@ def unsupported_reasons(core, p):
             bad.append(what)
     for name, m in (getattr(core, "molecules", None) or {}).items():
         why = []
-        for flag, what in (("update_intra_conc", "update intracellular"),
-                           ("change_bounds", "boundary change event"),
+        if bool(getattr(m, "update_intra_conc", False)):
+            # Molecule.update_intra with intracellular transport (networks.py:5714-5806): the membrane value becomes state
+            # of its own.  Implemented where it stays a DIAGNOSTIC (nothing reads it back): neutral substances that neither
+            # cross the membrane nor pass gap junctions and are not pumped, gating or moved by a transporter
+            blockers = []
+            if float(getattr(m, "z", 0.0) or 0.0) != 0.0 or float(getattr(m, "Mu_mem", 0.0) or 0.0) != 0.0:
+                blockers.append("charged")
+            if float(getattr(m, "Dm", 0.0) or 0.0) != 0.0:
+                blockers.append("membrane-permeable")
+            if not bool(getattr(m, "ignoreGJ", False)):
+                blockers.append("gap-junction permeable")
+            if bool(getattr(m, "active_pumping", False)) and bool(getattr(m, "use_pumping", False)):
+                blockers.append("pumped")
+            if bool(getattr(m, "ion_channel_gating", False)) and bool(getattr(m, "use_gating_ligand", False)):
+                blockers.append("gating a channel")
+            if any(name in list(t.reactants_list) + list(t.products_list) for t in (getattr(core, "transporters", None) or {}).values()):
+                blockers.append("moved by a transporter")
+            if blockers:
+                why.append("update intracellular of a substance that is " + ", ".join(blockers))
+        for flag, what in (("change_bounds", "boundary change event"),
                            ("cell_clamp", "cell clamp"), ("transmem", "transmembrane transport")):
             if bool(getattr(m, flag, False)):
                 why.append(what)
@@ -108,6 +126,10 @@ def describe_core(core, sim, p, cells, record_static=True):
     }
     # Molecule.transport -> stb.molecule_mover (networks.py:5670-5700, sim_toolbox.py:909-1153): membrane and
     # extracellular legs of the substances that have them
+    intra = np.array([bool(getattr(core.molecules[s], "update_intra_conc", False)) for s in species], dtype=np.uint8)
+    if intra.any():
+        desc.update({"intra_on": intra, "Do": np.array([float(core.molecules[s].Do or 0.0) for s in species]),
+                     "c_mems": np.stack([np.asarray(core.molecules[s].cc_at_mem, dtype=float) * np.ones(len(cells.mem_sa)) for s in species])})
     # run_loop_transporters (networks.py:2985-3107): flux = rho_pump * eval(transporter_eval_string) on every membrane;
     # each reactant / product moves by coeff * (-/+) sum_mems(flux*mem_sa)/cell_vol in the cells ('mem_concs' tag) or
     # coeff * div_env(-/+flux) outside ('env_concs' tag), on the transporter's target cells / env squares
@@ -241,6 +263,12 @@ def compile_network(desc, n_cells, n_mems, resolver=None):
         transporters.append({"prog": len(rates) + len(mod_programs), "net_z": float(t["net_z"]), "terms": terms,
                              "cell_mask": None if cm.all() else cm, "env_mask": em, "mem_mask": None if mm.all() else mm})
         mod_programs.append(pr)
+    io = np.asarray(desc.get("intra_on", np.zeros(K)), dtype=bool)
+    for pr in mods + modulators:
+        for op, arg in pr.code:
+            if op == ratelaw.PUSHS and io[arg]:
+                raise BetseB200Error("a membrane-zone rate law reads %r, whose membrane value is transported inside the cell "
+                                     "('update intracellular'): not implemented" % species[arg])
     eo = np.asarray(desc.get("env_on", np.zeros(K)), dtype=bool)
     for k in sorted(tabs.env_species):
         if not eo[k]:
@@ -264,7 +292,7 @@ def compile_network(desc, n_cells, n_mems, resolver=None):
             "growth_mask": None if mask.all() else mask, "Dgj": np.asarray(desc["Dgj"], dtype=float),
             "z": np.asarray(desc["z"], dtype=float), "time_factor": np.asarray(desc["time_factor"], dtype=float),
             "chan_names": list(desc["chan_names"]),
-            **{k: np.asarray(desc[k]) for k in ("env_on", "Dm", "c_bound", "c_env", "D_env", "scale_factor") if k in desc}}
+            **{k: np.asarray(desc[k]) for k in ("env_on", "Dm", "c_bound", "c_env", "D_env", "scale_factor", "intra_on", "Do", "c_mems") if k in desc}}
 
 
 # ---- flat (npz-friendly) form of a description, used by the golden fixtures
@@ -297,7 +325,7 @@ def flatten(desc, prefix):
                     prefix + "modulator_strings": np.array(desc["modulator_strings"], dtype=str),
                     prefix + "modulator_targets": np.array(desc["modulator_targets"], dtype=str),
                     prefix + "modulator_max": np.asarray(desc["modulator_max"], dtype=float)})
-    for k in ("env_on", "Dm", "c_bound", "c_env", "D_env", "scale_factor"):
+    for k in ("env_on", "Dm", "c_bound", "c_env", "D_env", "scale_factor", "intra_on", "Do", "c_mems"):
         if k in desc:
             out[prefix + k] = np.asarray(desc[k])
     for k, tg in enumerate(desc["growth_targets"]):
@@ -338,7 +366,7 @@ def unflatten(cap, prefix):
     if prefix + "modulator_names" in cap:
         mods = {**mods, **{"modulator_names": [str(x) for x in g("modulator_names")], "modulator_strings": [str(x) for x in g("modulator_strings")],
                 "modulator_targets": [str(x) for x in g("modulator_targets")], "modulator_max": np.asarray(g("modulator_max"))}}
-    return {**mods, **{k: np.asarray(cap[prefix + k]) for k in ("env_on", "Dm", "c_bound", "c_env", "D_env", "scale_factor") if prefix + k in cap},
+    return {**mods, **{k: np.asarray(cap[prefix + k]) for k in ("env_on", "Dm", "c_bound", "c_env", "D_env", "scale_factor", "intra_on", "Do", "c_mems") if prefix + k in cap},
             "species": species, "ions": [str(x) for x in g("ions")], "c_cells": np.asarray(g("c_cells")),
             "gad_strings": [str(x) for x in g("gad_strings")],
             "reaction_names": [str(x) for x in g("reaction_names")],

@@ -241,10 +241,12 @@ def _copy_back(sim, eng, diag, sample_only=False):
         c, rates = eng.network_state(h, rates=True)
         env_on = eng.networks[h].get("env_on")
         cenv = eng.network_env_state(h) if env_on is not None and np.any(env_on) else None
+        intra = eng.networks[h].get("intra_on")
+        cmem = eng.network_mem_state(h) if intra is not None and np.any(intra) else None
         for k, name in enumerate(eng.networks[h]["species"]):
             mol = core.molecules[name]
             mol.c_cells = c[k].copy()
-            mol.cc_at_mem = c[k][m2c]
+            mol.cc_at_mem = cmem[k].copy() if cmem is not None and intra[k] else c[k][m2c]
             if cenv is not None and env_on[k]:
                 mol.c_env = cenv[k].copy()
         nk = len(eng.networks[h]["species"])

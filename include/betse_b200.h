@@ -327,6 +327,13 @@ typedef struct betse_network {
     int32_t n_transporters;
     int32_t reserved;
     const double *mem_sa_over_vol;       /* [M] cells.mem_sa / cells.mem_vol (needed with transporters)  */
+    /* Molecule.update_intra with 'update intracellular' (networks.py:5714-5806) for neutral substances whose membrane
+     * value nothing reads back: cc_at_mem relaxes towards the cell value, (g*Do*dt*c/R + cc)/(1 + g*Do*dt/R),
+     * g = mem_sa/(3/4 mem_vol).  intra_on == NULL: every membrane value is the cell value. */
+    const uint8_t *intra_on;             /* [K]                                                          */
+    const double  *Do;                   /* [K] Molecule.Do                                              */
+    const double  *c_mems;               /* [K][M] cc_at_mem at loop entry (rows with intra_on == 0 ignored) */
+    const double  *R_rads;               /* [M] cells.R_rads                                             */
 } betse_network;
 
 /* handler 0 = sim.molecules.core, 1 = sim.grn.core (run in that order, sim.py:1290-1318).  net == NULL
@@ -336,6 +343,8 @@ int  betse_set_network(betse_ctx *ctx, int handler, const betse_network *net);
 int  betse_network_state(betse_ctx *ctx, int handler, double *c_cells, double *rates);
 /* Env concentrations [K][E] of the substances (rows with env_on == 0 come back as zeros). */
 int  betse_network_env_state(betse_ctx *ctx, int handler, double *c_env);
+/* Membrane values [K][M] (Molecule.cc_at_mem): the cell value gathered, or the transported value with intra_on. */
+int  betse_network_mem_state(betse_ctx *ctx, int handler, double *c_mems);
 
 /* ---------------------------------------------------------------------------------------------
  * Multi-GPU: the tissue is cut into strips of env-grid rows; each rank owns the

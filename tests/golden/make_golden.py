@@ -140,11 +140,19 @@ def net_extra(sim, phase):
     compiles (strings, tables, static terms) + substance concentrations, rates and channel DChan."""
     from betse_b200 import network as netlib
     out = chan_extra(sim, phase)
-    core = sim.molecules.core
-    desc = netlib.describe_core(core, sim, phase.p, phase.cells)
-    out.update(netlib.flatten(desc, "net0."))
-    if getattr(core, "reaction_rates", None) is not None and len(core.reaction_rates):
-        out["net0.reaction_rates"] = np.asarray(core.reaction_rates, dtype=float)
+    p = phase.p
+    for h, holder in ((0, getattr(sim, "molecules", None) if p.molecules_enabled else None),
+                      (1, getattr(sim, "grn", None) if p.grn_enabled else None)):     # sim.py:1290-1319: general network, then GRN
+        core_h = getattr(holder, "core", None)
+        if core_h is None or not len(getattr(core_h, "molecules", None) or {}):
+            continue
+        desc = netlib.describe_core(core_h, sim, p, phase.cells)
+        out.update(netlib.flatten(desc, "net%d." % h))
+        if getattr(core_h, "reaction_rates", None) is not None and len(core_h.reaction_rates):
+            out["net%d.reaction_rates" % h] = np.asarray(core_h.reaction_rates, dtype=float)
+    core = sim.molecules.core if p.molecules_enabled and getattr(sim, "molecules", None) is not None else None
+    if core is None:
+        return out
     for k, n in enumerate(core.channels):
         cc = core.channels[n].channel_core
         if getattr(cc, "DChan", None) is not None:
@@ -266,6 +274,15 @@ SCENARIOS["mammal_ecm_net_trans"] = dict(
     mods=_m(SMALL, {"cutting event": {"event happens": False}, "general options": {"ion profile": "mammal"},
                     "general network": {"implement network": True, "biomolecules": _TR_BIO, "reactions": [], "channels": [],
                                         "transporters": _TR}}),
+    snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=net_extra)
+
+
+# BASELINE configs[3]: the SHIPPED gene regulatory network (extra_configs/grn_basic.yaml: three genes, Hill activation /
+# inhibition) run by the second handler (sim.grn.core, sim.py:1305-1319), general network off
+SCENARIOS["mammal_ecm_grn"] = dict(
+    mods=_m(SMALL, {"cutting event": {"event happens": False}, "general options": {"ion profile": "mammal"},
+                    "general network": {"implement network": False},
+                    "gene regulatory network settings": {"gene regulatory network simulated": True}}),
     snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=net_extra)
 
 

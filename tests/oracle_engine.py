@@ -32,7 +32,8 @@ class OracleEngine:
     def set_network(self, comp, handler=0):
         self._descs[int(handler)] = comp["_desc"]          # attached by the test's compile_network wrapper
         self.networks[int(handler)] = {"species": list(comp["species"]),
-                                       "env_on": np.asarray(comp.get("env_on", np.zeros(len(comp["species"]))), dtype=bool)}
+                                       "env_on": np.asarray(comp.get("env_on", np.zeros(len(comp["species"]))), dtype=bool),
+                                       "intra_on": np.asarray(comp.get("intra_on", np.zeros(len(comp["species"]))), dtype=bool)}
 
     def set_channels(self, specs, phase_init=False, affect_charge=None):
         self._specs = [{k: v for k, v in c.items() if k != "_obj"} for c in specs]
@@ -100,6 +101,10 @@ class OracleEngine:
             r = net.rates if net.rates is not None else np.zeros((len(net.species), self.C))
             return c, np.asarray(r)
         return c
+
+    def network_mem_state(self, handler=0):
+        net = self._sim().networks[sorted(self._descs).index(int(handler))]
+        return np.stack([net.cmem[n] for n in net.species])
 
     def network_env_state(self, handler=0):
         net = self._sim().networks[sorted(self._descs).index(int(handler))]

@@ -116,3 +116,35 @@ def test_network_vs_oracle_synthetic_50k():
     for k, nme in enumerate(desc["species"]):
         assert util.rel_err(c[k], ora.networks[0].c[nme]) <= 1e-10, nme
     eng.close()
+
+
+@pytest.mark.parametrize("kind", ["init", "sim"])
+def test_gene_network_handler_matches_reference(kind):
+    """BASELINE configs[3]: the SHIPPED gene regulatory network (extra_configs/grn_basic.yaml) run by the second handler
+    (sim.grn.core, sim.py:1305-1319) — betse_set_network(handler = 1) — against the real reference's recorded run."""
+    from betse_b200 import network as netlib
+    from betse_b200.engine import TissueEngine
+    cap = util.load_golden("mammal_ecm_grn")
+    assert util.network_handlers(cap, kind) == [1]
+    desc = util.networks_of(cap, kind)[0]
+    eng = TissueEngine(util.mesh_of(cap, kind), util.group(cap, kind + ".p."), util.group(cap, kind + ".s0."))
+    eng.set_network(netlib.compile_network(desc, eng.Co, eng.M), handler=1)
+    eng.set_channels([], phase_init=(kind == "init"))
+    n = 0
+    for K in util.snap_steps(cap, kind):
+        while n < K:
+            util.apply_schedule(eng, cap, kind, n + 1)
+            assert not (eng.step(1) & (3 | 16))
+            n += 1
+        ref = util.group(cap, "%s.k%d." % (kind, K))
+        got = eng.download([f for f in list(util.STATE) + util.ENV_STATE if f in ref])
+        tols = util.gpu_tolerances(cap, kind, ref)
+        for f, a in got.items():
+            err = float(np.max(np.abs(np.asarray(a).reshape(np.shape(ref[f])) - ref[f])))
+            assert err <= tols[f], (kind, K, f, err, tols[f])
+        c = eng.network_state(1)
+        cm = eng.network_mem_state(1)             # grn_basic.yaml leaves 'update intracellular' at its default (on)
+        for k, nme in enumerate(desc["species"]):
+            assert util.rel_err(c[k], ref["net1.c_cells"][k]) <= 1e-10, (kind, K, nme)
+            assert util.rel_err(cm[k], ref["net1.c_mems"][k]) <= 1e-10, (kind, K, nme, "mems")
+    eng.close()

@@ -43,11 +43,15 @@ def test_oracle_reproduces_reference(name, kind):
                 if key in ref and not (kind == "init" and not c["init_active"]):
                     assert util.rel_err(c[f], ref[key]) < 1e-12, (name, kind, K, key)
                     checked += 1
-        for h, net in enumerate(o.networks):        # network substances, rates, channel DChan (networks.py:2805-2982, 3164)
+        for h, net in zip(util.network_handlers(cap, kind), o.networks):        # network substances, rates, channel DChan (networks.py:2805-2982, 3164)
             want = ref["net%d.c_cells" % h]
             for k, nme in enumerate(net.species):
                 assert util.rel_err(net.c[nme], want[k]) < 1e-12, (name, kind, K, nme)
                 checked += 1
+            if "net%d.c_mems" % h in ref:            # membrane values under intracellular transport (networks.py:5727-5795)
+                for k, nme in enumerate(net.species):
+                    assert util.rel_err(net.cmem[nme], ref["net%d.c_mems" % h][k]) < 1e-12, (name, kind, K, nme, "mems")
+                    checked += 1
             if "net%d.c_env" % h in ref:             # membrane / extracellular legs of molecule_mover (sim_toolbox.py:909-1153)
                 for k, nme in enumerate(net.species):
                     if net.env_on[k]:

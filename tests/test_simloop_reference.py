@@ -257,3 +257,21 @@ def test_env_substances_through_the_dropin_match_the_reference(monkeypatch, tmp_
             assert np.max(np.abs(np.asarray(x) - np.asarray(y))) <= 1e-9 * max(np.max(np.abs(np.asarray(y))), 1e-300), name
     for a, r in zip(new_sim.vm_time, ref_sim.vm_time):
         assert np.max(np.abs(a - r)) <= 1e-9 * np.max(np.abs(r))
+
+
+def test_gene_network_through_the_dropin_matches_the_reference(monkeypatch, tmp_path):
+    """BASELINE configs[3]: the shipped gene regulatory network (extra_configs/grn_basic.yaml) is the SECOND handler
+    (sim.grn.core); the shim compiles it from the live MasterOfGenes and writes the genes back for write_data."""
+    from tests.golden import make_golden as mg
+    mods = mg.SCENARIOS["mammal_ecm_grn"]["mods"]
+    ref_sim, _, _ = _run_try(tmp_path / "ref", False, mods=mods)
+    (tmp_path / "new").mkdir()
+    new_sim, _, engines = _run_try(tmp_path / "new", True, monkeypatch, mods=mods)
+    assert list(engines[1].networks) == [1]
+    for name in ("Gene 1", "Gene 2", "Gene 3"):
+        a, r = new_sim.grn.core.molecules[name], ref_sim.grn.core.molecules[name]
+        assert len(a.c_cells_time) == len(r.c_cells_time) >= 30
+        for x, y in zip(a.c_cells_time + a.c_mems_time, r.c_cells_time + r.c_mems_time):   # c_mems: 'update intracellular' is on
+            assert np.max(np.abs(np.asarray(x) - np.asarray(y))) <= 1e-9 * np.max(np.abs(np.asarray(y))), name
+    for a, r in zip(new_sim.vm_time, ref_sim.vm_time):
+        assert np.max(np.abs(a - r)) <= 1e-9 * np.max(np.abs(r))

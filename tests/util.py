@@ -183,6 +183,11 @@ def channels_of(cap, kind, where="s0"):
     return out
 
 
+def network_handlers(cap, kind, where="s0"):
+    """Handler ids of the recorded networks: 0 = general network (sim.molecules.core), 1 = gene regulatory network."""
+    return [h for h in range(2) if "%s.%s.net%d.species" % (kind, where, h) in cap]
+
+
 def networks_of(cap, kind, where="s0"):
     """Network descriptions recorded by tests/golden/make_golden.py:net_extra (general network first)."""
     from betse_b200 import network as netlib
