@@ -569,6 +569,7 @@ extern "C" int betse_create(betse_ctx** out, const betse_mesh* mesh, const betse
 }
 
 static int ensure_phi(betse_ctx* ctx);
+static void publish_affect(betse_ctx* ctx);
 
 // sine matrices, eigenvalues and work buffers of the Dirichlet Poisson solve on the env grid (csrc/hh.cu)
 static int ensure_poisson(betse_ctx* ctx)
@@ -814,12 +815,18 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
         if (chans) {
             // between the ion loop's fluxes and update_all_concs (sim.py:1290-1357), per handler: run_loop_channels
             // (networks.py:3115-3213), then run_loop (networks.py:2805-2982)
-            if (A.chanJ) cudaMemsetAsync(A.chanJ, 0, (size_t)ctx->Mo * sizeof(double), st);
-            if (A.extra_Jenv_x) {                                            // clear_run_loop, networks.py:2799-2801
-                cudaMemsetAsync(A.extra_Jenv_x, 0, (size_t)ctx->E * sizeof(double), st);
-                cudaMemsetAsync(A.extra_Jenv_y, 0, (size_t)ctx->E * sizeof(double), st);
-            }
             for (int h = 0; h < 2; ++h) {
+                // every MasterOfNetworks keeps its OWN extra_J_mem / extra_Jenv (clear_run_loop, networks.py:2790-2801) and
+                // publishes them at the end of its run_loop (networks.py:2971-2977): with both handlers enabled the LAST one
+                // wins, so the accumulators start from zero at every enabled handler's block
+                bool enabled = ctx->net_on[h];
+                for (const KChan& ch : ctx->chans) enabled = enabled || ch.handler == h;
+                if (!enabled) continue;
+                if (A.chanJ) cudaMemsetAsync(A.chanJ, 0, (size_t)ctx->Mo * sizeof(double), st);
+                if (A.extra_Jenv_x) {
+                    cudaMemsetAsync(A.extra_Jenv_x, 0, (size_t)ctx->E * sizeof(double), st);
+                    cudaMemsetAsync(A.extra_Jenv_y, 0, (size_t)ctx->E * sizeof(double), st);
+                }
                 if (ctx->net_on[h] && !ctx->net_trans[h].empty()) {
                     const KNet& Nh = ctx->nets[h];
                     for (int k = 0; k < Nh.K && Nh.tw; ++k)
@@ -1201,6 +1208,7 @@ extern "C" int betse_set_channels(betse_ctx* ctx, int n, const betse_channel* ch
         ctx->chans.push_back(d);
     }
     CK(cudaStreamSynchronize(ctx->stream));
+    publish_affect(ctx);
     return 0;
 }
 
@@ -1218,6 +1226,26 @@ extern "C" int betse_channel_state(betse_ctx* ctx, int k, double* m, double* h, 
     if (DChan) { int xr = xfer(ctx, DChan, d.D, nb, cudaMemcpyDeviceToHost); if (xr) return xr; }
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
+}
+
+// sim.extra_rho_cells / sim.extra_rho_env are the arrays of the LAST enabled handler once its run_loop has published them
+// (networks.py:2971-2977): zeros when that handler has no (charged) substances
+static void publish_affect(betse_ctx* ctx)
+{
+    int hl = -1;
+    for (int h = 0; h < 2; ++h) {
+        bool enabled = ctx->net_on[h];
+        for (const KChan& ch : ctx->chans) enabled = enabled || ch.handler == h;
+        if (enabled) hl = h;
+    }
+    if (hl < 0 || !ctx->P.chan_charge) return;
+    if (ctx->net_on[hl] && ctx->net_affect[hl]) {
+        ctx->A.extra_rho_cells = ctx->nets[hl].rho_cells;
+        ctx->A.extra_rho_env = ctx->nets[hl].rho_env;        // null: the handler has nothing outside the cells
+    } else {
+        ctx->A.extra_rho_cells = nullptr;
+        ctx->A.extra_rho_env = nullptr;
+    }
 }
 
 static int ensure_defer_buffers(betse_ctx* ctx)
@@ -1413,10 +1441,8 @@ extern "C" int betse_set_network(betse_ctx* ctx, int handler, const betse_networ
         if ((r = dev_upload(ctx, (double**)&N.scale, net->scale_factor ? net->scale_factor : ones.data(), (size_t)K))) return r;
         if ((r = dev_alloc(ctx, &N.fmem_tmp, (size_t)Mo))) return r;
         if ((r = dev_alloc(ctx, &N.rho_cells, (size_t)C))) return r;
-        ctx->A.extra_rho_cells = N.rho_cells;
         if (N.c_env) {
             if ((r = dev_alloc(ctx, &N.rho_env, (size_t)ctx->E))) return r;
-            ctx->A.extra_rho_env = N.rho_env;
             if (!ctx->A.extra_Jenv_x) {
                 if ((r = dev_alloc(ctx, &ctx->A.extra_Jenv_x, (size_t)ctx->E))) return r;
                 if ((r = dev_alloc(ctx, &ctx->A.extra_Jenv_y, (size_t)ctx->E))) return r;
@@ -1431,6 +1457,7 @@ extern "C" int betse_set_network(betse_ctx* ctx, int handler, const betse_networ
     ctx->net_on[handler] = true;
     ctx->net_nprog[handler] = net->n_programs;
     ctx->P.defer = 1;
+    publish_affect(ctx);
     return 0;
 }
 

@@ -286,6 +286,14 @@ SCENARIOS["mammal_ecm_grn"] = dict(
     snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=net_extra)
 
 
+# both handlers at once (the reference's own `enable_networks` test scenario, betse_test/_fixture/simconf/simconfwrapper.py:252-259):
+# the shipped general network (substance X, Nav1p3 / Kv1p5 / X-inhibited KLeak) AND the shipped gene regulatory network
+SCENARIOS["mammal_ecm_net2"] = dict(
+    mods=_m(SMALL, {"cutting event": {"event happens": False}, "general options": {"ion profile": "mammal"},
+                    "gene regulatory network settings": {"gene regulatory network simulated": True}}),
+    snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=net_extra)
+
+
 # The external-voltage event (tissue/event/tisevevolt.py: bound_V ramps, Phi_b = one Dirichlet Poisson solve per step,
 # ion_current.py:84-90, subtracted from Vmem in update_V, sim.py:2029) — ramp up, plateau and ramp down inside the
 # first 20 SIM steps, left/right electrodes so that it differs from the top/bottom default; ECM and no-ECM

@@ -51,7 +51,7 @@ class OracleEngine:
             # no-ECM field diagnostics (ion_current.py:116-171) are not part of the engine's contract: any weight will do
             state.setdefault("D_env_weight", np.ones(self.ny * self.nx))
             self._o = OracleSim(mesh, params, state, channels=self._specs, phase_init=self._phase_init,
-                                networks=[self._descs[h] for h in sorted(self._descs)])
+                                networks=[self._descs[h] for h in sorted(self._descs)], net_handlers=sorted(self._descs))
             self._active = [c for c in self._o.channels if not (self._phase_init and not c["init_active"])]
         return self._o
 

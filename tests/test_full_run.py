@@ -47,7 +47,8 @@ def test_oracle_full_run(fixture, kind):
     from oracle.betse_oracle import OracleSim
     cap = util.load_golden(fixture)
     o = OracleSim(util.mesh_of(cap, kind), util.group(cap, kind + ".p."), util.group(cap, kind + ".s0."),
-                  channels=util.channels_of(cap, kind), phase_init=(kind == "init"), networks=util.networks_of(cap, kind))
+                  channels=util.channels_of(cap, kind), phase_init=(kind == "init"), networks=util.networks_of(cap, kind),
+                  net_handlers=util.network_handlers(cap, kind))
     o.diagnostics = False
     got = _run_traces(o, cap, kind, lambda x: x.step(), getattr)
     _check(cap, kind, got, "oracle")

@@ -148,3 +148,46 @@ def test_gene_network_handler_matches_reference(kind):
             assert util.rel_err(c[k], ref["net1.c_cells"][k]) <= 1e-10, (kind, K, nme)
             assert util.rel_err(cm[k], ref["net1.c_mems"][k]) <= 1e-10, (kind, K, nme, "mems")
     eng.close()
+
+
+@pytest.mark.parametrize("kind", ["init", "sim"])
+def test_both_handlers_match_reference(kind):
+    """The reference's `enable_networks` scenario: the shipped general network (handler 0: substance X, three channels, one
+    of them inhibited by X) and the shipped gene regulatory network (handler 1) in the same step (sim.py:1290-1319)."""
+    from betse_b200 import network as netlib
+    from betse_b200.engine import TissueEngine
+    cap = util.load_golden("mammal_ecm_net2")
+    assert util.network_handlers(cap, kind) == [0, 1]
+    descs = util.networks_of(cap, kind)
+    eng = TissueEngine(util.mesh_of(cap, kind), util.group(cap, kind + ".p."), util.group(cap, kind + ".s0."))
+    specs = util.channels_of(cap, kind)
+    for h, desc in enumerate(descs):
+        comp = netlib.compile_network(desc, eng.Co, eng.M)
+        eng.set_network(comp, handler=h)
+        if h == 0:
+            for c in specs:
+                c["handler"] = 0
+                c["mod_prog"] = comp["mod_index"][comp["chan_names"].index(c["name"])]
+    eng.set_channels(specs, phase_init=(kind == "init"))
+    n = 0
+    snaps = util.snap_steps(cap, kind)
+    for K in snaps:
+        last = K == snaps[-1]
+        while n < K:
+            util.apply_schedule(eng, cap, kind, n + 1)
+            assert not (eng.step(1, diag=(last and n + 1 == K)) & (3 | 16))
+            n += 1
+        ref = util.group(cap, "%s.k%d." % (kind, K))
+        # Jmem / Jn: each MasterOfNetworks publishes its OWN extra_J_mem, the gene network's (no channels: zero) last — the
+        # channels' currents of the general network are not in sim.extra_J_mem (networks.py:2971-2977)
+        extra = ["Jmem", "Jn", "I_mem"] if last else []
+        got = eng.download([f for f in list(util.STATE) + util.ENV_STATE + extra if f in ref])
+        tols = util.gpu_tolerances(cap, kind, ref)
+        for f, a in got.items():
+            err = float(np.max(np.abs(np.asarray(a).reshape(np.shape(ref[f])) - ref[f])))
+            assert err <= tols[f], (kind, K, f, err, tols[f])
+        for h, desc in enumerate(descs):
+            c = eng.network_state(h)
+            for k, nme in enumerate(desc["species"]):
+                assert util.rel_err(c[k], ref["net%d.c_cells" % h][k]) <= 1e-10, (kind, K, h, nme)
+    eng.close()

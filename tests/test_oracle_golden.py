@@ -14,7 +14,7 @@ def test_oracle_reproduces_reference(name, kind):
     cap = util.load_golden(name)
     o = OracleSim(util.mesh_of(cap, kind), util.group(cap, kind + ".p."),
                   util.group(cap, kind + ".s0."), channels=util.channels_of(cap, kind), phase_init=(kind == "init"),
-                  networks=util.networks_of(cap, kind))
+                  networks=util.networks_of(cap, kind), net_handlers=util.network_handlers(cap, kind))
     n = 0
     checked = 0
     for K in util.snap_steps(cap, kind):
