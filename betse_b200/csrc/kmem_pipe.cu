@@ -14,9 +14,11 @@
 //       mem_to_cells[32], nn_cell_flag[32], map_mem2ecm[32], cell_mem_ptr[9(+3)] -> ONE TMA bulk
 //       copy (cp.async.bulk by lane 0, completion on an mbarrier), two tiles ahead; every offset
 //       inside the block is a compile-time constant;
-//   G = state and gathers, cp.async (LDGSTS), one tile ahead: gjopen; Vmem, cc_cells, cc_mid of
-//       the tile's cells; through the landed indices of K: env concentrations at the membrane's
-//       env square, partner-cell concentrations and Vmem, transported Ca.
+//   G = state and gathers, one tile ahead: Vmem, cc_cells, cc_mid of the tile's cells by cp.async (LDGSTS); the
+//       per-membrane gathers through the landed indices of K — env concentrations at the membrane's env square,
+//       partner-cell concentrations and Vmem, transported Ca, gjopen — by cp.async into shared memory
+//       (BETSE_KMEM_GREG=0) or, default, by plain loads into REGISTERS issued after the flux phase of the current tile
+//       (168 registers, no spills at 3 CTAs x 4 warps; 113 of 268 shared-memory wavefronts per tile less)
 //
 //   iteration t:  wait (mbarrier of t-1, cp.async group)   -> K(t+1), G(t) have landed
 //                 K(t), G(t) -> registers
@@ -91,12 +93,12 @@ __device__ __forceinline__ void issue_K(const KArrays& A, const int tile, const 
 }
 
 // state + gathers of tile td through the indices in its (landed) constant block K
-template <int NI>
+template <int NI, bool GREG = false>
 __device__ __forceinline__ void issue_G(const KArrays& A, const int4 td, const double* K, double* G, double* Cs,
                                         const int lane, const int o0, const int C, const int E, const int cur)
 {
     const int c0 = td.x, nc = td.y, m0 = td.z, nm = td.w;
-    if (lane < nm) {
+    if (!GREG && lane < nm) {
         const int* Ki = reinterpret_cast<const int*>(K + KP_KD(NI));
         const int cn = Ki[32 + lane] & 0x7fffffff;
         const int e = Ki[64 + lane];
@@ -125,7 +127,34 @@ __device__ __forceinline__ void issue_G(const KArrays& A, const int4 td, const d
     }
 }
 
-template <int NI, int WPC, int MINB>
+// GREG variant: the per-membrane gathers of the NEXT tile go straight into registers (plain loads issued after the flux
+// phase of the current tile, when most registers are free again) instead of through cp.async + shared memory: fewer
+// shared-memory wavefronts, the pipe the kernel is bound by
+template <int NI>
+struct GReg { double co[NI], cnb[NI], vm_nb, cao, g; };
+
+template <int NI>
+__device__ __forceinline__ void load_G(const KArrays& A, const int4 td, const double* K, GReg<NI>& R,
+                                       const int lane, const int C, const int E, const int cur)
+{
+    const int m0 = td.z, nm = td.w;
+    if (lane < nm) {
+        const int* Ki = reinterpret_cast<const int*>(K + KP_KD(NI));
+        const int cn = Ki[32 + lane] & 0x7fffffff;
+        const int e = Ki[64 + lane];
+        const double* __restrict__ cenv = A.cc_env[cur] + e;
+        const double* __restrict__ cmid = A.cc_mid[cur] + cn;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) R.co[i] = cenv[(size_t)i * E];
+#pragma unroll
+        for (int i = 0; i < NI; ++i) R.cnb[i] = cmid[(size_t)i * C];
+        R.vm_nb = A.vm_cell[cur][cn];
+        R.cao = (StdProf<NI>::iCa >= 0) ? A.cc_env[cur ^ 1][(size_t)StdProf<NI>::iCa * E + e] : 0.0;
+        R.g = A.gjopen[m0 + lane];
+    }
+}
+
+template <int NI, int WPC, int MINB, bool GREG>
 __global__ void __launch_bounds__(WPC * 32, MINB)
 k_mem_pipe(const __grid_constant__ KParams P, const KArrays A, const int cur)
 {
@@ -174,7 +203,9 @@ k_mem_pipe(const __grid_constant__ KParams P, const KArrays A, const int cur)
     issue_K<NI>(A, tile, true, smem_u32(KB(0)), bar0, lane);
     issue_K<NI>(A, tile + W, tile + W < nt, smem_u32(KB(1)), bar0 + 8, lane);
     mbar_wait(bar0, 0);
-    issue_G<NI>(A, td0, KB(0), GB(0), CB(0), lane, o0, C, E, cur);
+    issue_G<NI, GREG>(A, td0, KB(0), GB(0), CB(0), lane, o0, C, E, cur);
+    GReg<NI> R;
+    if (GREG) load_G<NI>(A, td0, KB(0), R, lane, C, E, cur);
 
     int it = 0;
     for (; tile < nt; tile += W, ++it) {
@@ -204,13 +235,19 @@ k_mem_pipe(const __grid_constant__ KParams P, const KArrays A, const int cur)
 #pragma unroll
             for (int i = 0; i < NI; ++i) DmS[i] = K[i * 32 + lane];
             sa = K[NI * 32 + lane];
+            if (GREG) {
 #pragma unroll
-            for (int i = 0; i < NI; ++i) co[i] = G[i * 32 + lane];
+                for (int i = 0; i < NI; ++i) { co[i] = R.co[i]; cnb[i] = R.cnb[i]; }
+                vm_nb = R.vm_nb; cCao = R.cao; g = R.g;
+            } else {
 #pragma unroll
-            for (int i = 0; i < NI; ++i) cnb[i] = G[(NI + i) * 32 + lane];
-            vm_nb = G[(2 * NI) * 32 + lane];
-            if (iCa >= 0) cCao = G[(2 * NI + 1) * 32 + lane];
-            g = G[(2 * NI + 2) * 32 + lane];
+                for (int i = 0; i < NI; ++i) co[i] = G[i * 32 + lane];
+#pragma unroll
+                for (int i = 0; i < NI; ++i) cnb[i] = G[(NI + i) * 32 + lane];
+                vm_nb = G[(2 * NI) * 32 + lane];
+                if (iCa >= 0) cCao = G[(2 * NI + 1) * 32 + lane];
+                g = G[(2 * NI + 2) * 32 + lane];
+            }
         }
         if (nc * NI > 32) {                            // later rounds of the (cell, ion) phase: keep ptr/vol of all cells
             if (lane <= nc) reinterpret_cast<int*>(s_aux)[lane] = Ki[96 + lane];
@@ -220,7 +257,7 @@ k_mem_pipe(const __grid_constant__ KParams P, const KArrays A, const int cur)
         // ---- keep the pipeline full: K(t+2) into the buffer just drained, G(t+1)
         const int4 td2 = (tile + 2 * W < nt) ? __ldg(TD + tile + 2 * W) : zero4;
         issue_K<NI>(A, tile + 2 * W, tile + 2 * W < nt, smem_u32(K), bar0 + 8 * pb, lane);
-        issue_G<NI>(A, td1, KB(pb ^ 1), GB(pb ^ 1), CB(pb ^ 1), lane, o0, C, E, cur);
+        issue_G<NI, GREG>(A, td1, KB(pb ^ 1), GB(pb ^ 1), CB(pb ^ 1), lane, o0, C, E, cur);
 
         double* s_m = G;                               // [32][KP_SST] f_mem*sa   (the consumed gather rows)
         double* s_g = G + 32 * KP_SST(NI);             // [32][KP_SST] f_gj*sa
@@ -300,6 +337,8 @@ k_mem_pipe(const __grid_constant__ KParams P, const KArrays A, const int cur)
             A.gjopen[m] = g;
         }
         __syncwarp();
+        // the next tile's per-membrane gathers, into registers (its constant block K(t+1) landed before this iteration)
+        if (GREG && td1.w > 0) load_G<NI>(A, td1, KB(pb ^ 1), R, lane, C, E, cur);
 
         // ---- the warp's slice of the membrane->env exchange slots ([membrane][ion], contiguous)
         {
@@ -442,9 +481,11 @@ template <int NI, int WPC, int MINB>
 static cudaError_t prep_pipe()
 {
     const int smem = (int)(WPC * KP_WARP(NI) * sizeof(double));
-    cudaError_t e = cudaFuncSetAttribute(k_mem_pipe<NI, WPC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(k_mem_pipe<NI, WPC, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e) return e;
-    return cudaFuncSetAttribute(k_mem_pipe<NI, WPC, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if ((e = cudaFuncSetAttribute(k_mem_pipe<NI, WPC, MINB, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100))) return e;
+    if ((e = cudaFuncSetAttribute(k_mem_pipe<NI, WPC, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
+    return cudaFuncSetAttribute(k_mem_pipe<NI, WPC, MINB, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
 }
 
 template <int NI>
@@ -477,7 +518,10 @@ static void launch_pipe_cfg(const KParams& P, const KArrays& A, int n_sms, int c
     const int need = (P.n_tiles + WPC - 1) / WPC;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    k_mem_pipe<NI, WPC, MINB><<<grid, WPC * 32, smem, st>>>(P, A, cur);
+    static int greg = -1;
+    if (greg < 0) greg = env_int("BETSE_KMEM_GREG", 1) ? 1 : 0;     // measured: k_mem 0.344 -> 0.335 ms at 1M cells (profiles/r01_sweeps.txt)
+    if (greg) k_mem_pipe<NI, WPC, MINB, true><<<grid, WPC * 32, smem, st>>>(P, A, cur);
+    else k_mem_pipe<NI, WPC, MINB, false><<<grid, WPC * 32, smem, st>>>(P, A, cur);
 }
 
 // resident warps per SM: 16 = 4 CTAs x 4 warps (128 registers), 15 = 3 x 5, 12 = 3 x 4, 8 = 2 x 4; a CTA count that
