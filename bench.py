@@ -241,7 +241,7 @@ def main():
         # end to end over N strips: host state -> strips (partition on the host, upload), timesteps,
         # download of each rank's owned Vmem / concentrations every 10 steps
         from betse_b200.strips import DistributedStrips
-        n_e2e = min(args.steps, 100)
+        n_e2e = args.steps
         dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()

@@ -55,9 +55,12 @@ class RankPart:
         self.__dict__.update(kw)
 
 
-def partition(mesh, params, state, R, bounds=None):
+def partition(mesh, params, state, R, bounds=None, only=None):
+    """-> list of R ``RankPart``.  ``only=r``: build rank r alone (what a rank of a multi-process run needs: its own part
+    and, for the exchange plans, the sizes of its two neighbours); the other entries of the list are None / size stubs."""
     if R < 1:
         raise ValueError("R must be >= 1")
+    need = list(range(R)) if only is None else [r for r in (only - 1, only, only + 1) if 0 <= r < R]
     ny, nx = (int(x) for x in mesh["grid_shape"])
     ptr = np.asarray(mesh["cell_mem_ptr"]).astype(np.int64)
     m2c = np.asarray(mesh["mem_to_cells"]).astype(np.int64)
@@ -96,32 +99,36 @@ def partition(mesh, params, state, R, bounds=None):
     memsa_mean = float(msa_env[m2e].mean()) if msa_env is not None else 1.0
 
     # ---- pass 1: ownership lists of every rank
-    own_cells, own_mems, ghosts, remote_in = [], [], [], []
-    for r in range(R):
+    own_cells, own_mems, ghosts, remote_in = {}, {}, {}, {}
+    for r in need:
         oc = np.nonzero(owner_c == r)[0]
         cnt = counts[oc]
         lp = np.concatenate(([0], np.cumsum(cnt)))
         om = np.repeat(ptr[oc] - lp[:-1], cnt) + np.arange(lp[-1])
-        own_cells.append(oc)
-        own_mems.append(om)
+        own_cells[r] = oc
+        own_mems[r] = om
         rc = pc[om]
         rem = owner_c[rc] != r
         gl = np.unique(rc[rem])
         go = owner_c[gl]
         if np.any(np.abs(go - r) > 1):
             raise BetseB200Error("a gap-junction partner lives two strips away: strips are too thin")
-        ghosts.append((gl[go == r - 1], gl[go == r + 1]))
+        ghosts[r] = (gl[go == r - 1], gl[go == r + 1])
         # membranes of the neighbours whose env square this rank owns (ascending global index)
         inc = np.nonzero((env_m == r) & (owner_m != r))[0]
-        remote_in.append((inc[owner_m[inc] == r - 1], inc[owner_m[inc] == r + 1]))
+        remote_in[r] = (inc[owner_m[inc] == r - 1], inc[owner_m[inc] == r + 1])
 
-    parts = []
-    for r in range(R):
+    parts = [None] * R
+    for r in need:
         a, b = int(bounds[r]), int(bounds[r + 1])
         lo, hi = max(0, a - H), min(ny, b + H)
         oc, om = own_cells[r], own_mems[r]
         Co, Mo = len(oc), len(om)
         g_lo, g_hi = ghosts[r]
+        if only is not None and r != only:       # a neighbour: only what the exchange plan of `only` reads
+            parts[r] = RankPart(rank=r, R=R, Co=Co, Mo=Mo, row_lo=lo, row_hi=hi, a=a, b=b, nx=nx, ny=ny, plans={},
+                                n_ghost=(len(g_lo), len(g_hi)), n_remote=(len(remote_in[r][0]), len(remote_in[r][1])))
+            continue
         cells_l = np.concatenate((oc, g_lo, g_hi))
         Cl = len(cells_l)
         g2l_c = np.full(C, -1, dtype=np.int64)
@@ -202,13 +209,13 @@ def partition(mesh, params, state, R, bounds=None):
         for f in ("zs", "D_free", "D_gj", "c_env_bound", "T", "ko_env", "rho_pump", "rho_channel", "bound_V"):
             if f in S:
                 st[f] = S[f]
-        parts.append(RankPart(rank=r, R=R, mesh=mesh_l, state=st, part=part, rows=krows, plans={},
+        parts[r] = (RankPart(rank=r, R=R, mesh=mesh_l, state=st, part=part, rows=krows, plans={},
                               own_cells=oc, own_mems=om, cells_local=cells_l, row_lo=lo, row_hi=hi,
                               a=a, b=b, G=G, H=H, nx=nx, ny=ny, Co=Co, Mo=Mo, g2l_c=g2l_c, g2l_m=g2l_m,
                               n_ghost=(len(g_lo), len(g_hi)), n_remote=(len(r_lo), len(r_hi))))
 
     # ---- pass 2: exchange plans (what rank r pushes into neighbour s)
-    for r in range(R):
+    for r in (range(R) if only is None else [only]):
         P = parts[r]
         for side, s in ((0, r - 1), (1, r + 1)):
             if s < 0 or s >= R:

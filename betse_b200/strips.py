@@ -100,10 +100,7 @@ class DistributedStrips:
     def __init__(self, mesh, params, state, device, dist, bounds=None):
         self.dist = dist
         self.rank, self.R = dist.get_rank(), dist.get_world_size()
-        parts = partition(mesh, params, state, self.R, bounds=bounds)
-        self.part = parts[self.rank]
-        self.sizes = [(p.Co, p.Mo, (p.b - p.a) * p.nx) for p in parts]
-        del parts
+        self.part = partition(mesh, params, state, self.R, bounds=bounds, only=self.rank)[self.rank]
         self.engine = _rank_engine(self.part, params, device)
         mine = _info_to_bytes(self.engine.window())
         allinfo = [None] * self.R
