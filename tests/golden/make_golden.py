@@ -294,6 +294,17 @@ SCENARIOS["mammal_ecm_net2"] = dict(
     snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=net_extra)
 
 
+# cell polarizability != 0 TOGETHER with the networks: per-membrane Vmem feeds the channels' gates, the channel
+# modulation, the substances' gap-junction and membrane legs and the transporters (vm = sim.vm[m] everywhere)
+SCENARIOS["mammal_ecm_polar_net"] = dict(
+    mods=_m(SMALL, {"cutting event": {"event happens": False}, "general options": {"ion profile": "mammal"},
+                    "internal parameters": {"cell polarizability": 1.0e-4},
+                    "general network": {"implement network": True, "biomolecules": _NET_BIO[3:] + _ENV_BIO[:1] + _TR_BIO[1:],
+                                        "reactions": [], "channels": [dict(c) for c in CHANNELS[:2]] + [_NET_CH[2]],
+                                        "transporters": [dict(_TR[1], **{"transporter activators": ["S1"]})]}}),
+    snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=net_extra)
+
+
 # The external-voltage event (tissue/event/tisevevolt.py: bound_V ramps, Phi_b = one Dirichlet Poisson solve per step,
 # ion_current.py:84-90, subtracted from Vmem in update_V, sim.py:2029) — ramp up, plateau and ramp down inside the
 # first 20 SIM steps, left/right electrodes so that it differs from the top/bottom default; ECM and no-ECM
