@@ -192,3 +192,67 @@ def test_both_handlers_match_reference(kind):
             for k, nme in enumerate(desc["species"]):
                 assert util.rel_err(c[k], ref["net%d.c_cells" % h][k]) <= 1e-10, (kind, K, h, nme)
     eng.close()
+
+
+def _retarget(desc, C, M, E, rng, targets_every=7):
+    """A recorded network description (95-cell fixture) re-targeted to a synthetic tissue: same strings and constants,
+    per-cell / per-membrane / per-env-square tables re-drawn at the new sizes."""
+    d = dict(desc)
+    K = len(d["species"])
+    d["c_cells"] = rng.uniform(0.05, 1.0, (K, C))
+    d["growth_targets"] = [np.arange(C) for _ in range(K)]
+    d["static"] = {k: (v if np.ndim(v) == 0 else np.ones(M if "mdl" in k else C)) for k, v in d["static"].items()}
+    # charged substances add F*c*z to the charge (networks.py:2945): keep them dilute, the reference balances that charge at
+    # set-up (networks.py:3905-3946) and a random field would not
+    dilute = np.where(np.asarray(d["z"]) != 0.0, 1.0e-3, 1.0)[:, None]
+    d["c_cells"] = d["c_cells"] * dilute
+    if "env_on" in d:
+        d["c_env"] = np.where(np.asarray(d["env_on"], dtype=bool)[:, None], rng.uniform(0.05, 0.6, (K, E)), 0.0) * dilute
+        d["c_bound"] = np.asarray(d["c_bound"]) * dilute[:, 0]
+        Do = np.where(np.asarray(d["D_env"]).max(axis=1) > 0, np.asarray(d["D_env"]).max(axis=1), 0.0)
+        d["D_env"] = Do[:, None] * rng.uniform(0.2, 1.0, (K, E))
+    if "c_mems" in d:
+        d["c_mems"] = rng.uniform(0.05, 1.0, (K, M))
+    if "transporters" in d:
+        d["transporters"] = [dict(t, targets_cell=np.arange(0, C, targets_every if j else 1), targets_mem=np.arange(M),
+                                  targets_env=np.arange(E)) for j, t in enumerate(d["transporters"])]
+    return d
+
+
+@pytest.mark.parametrize("fixture", ["mammal_ecm_net_trans", "mammal_ecm_net_pump", "mammal_ecm_net_lig", "mammal_ecm_net_envq"])
+def test_network_features_vs_oracle_synthetic_30k(fixture):
+    """The membrane / extracellular / transporter / pump / ligand-gate kernels at a size and grid shape the fixtures do
+    not have (30 k cells, 174 x 174 grid): the recorded rate laws re-targeted to a synthetic tissue, 8 steps vs the oracle."""
+    from betse_b200 import network as netlib
+    from betse_b200 import synth
+    from betse_b200.engine import TissueEngine
+    from oracle.betse_oracle import OracleSim
+    cap = util.load_golden(fixture)
+    mesh, p, st = synth.make_tissue(30_000)
+    p["substances_affect_charge"] = int(cap["sim.p.substances_affect_charge"])
+    C, M = len(mesh["cell_vol"]), len(mesh["mem_sa"])
+    E = int(np.prod(mesh["grid_shape"]))
+    desc = _retarget(util.networks_of(cap, "sim")[0], C, M, E, np.random.default_rng(5))
+    eng = TissueEngine(mesh, p, st)
+    eng.update_V()
+    ora = OracleSim(mesh, p, st, networks=[desc])
+    ora.diagnostics = False
+    ora.update_V()
+    eng.set_network(netlib.compile_network(desc, eng.Co, eng.M), handler=0)
+    eng.set_channels([])
+    for n in range(8):
+        assert not (eng.step(1) & (3 | 16))
+        ora.step()
+    got = eng.download(["cc_cells", "cc_env", "vm", "gjopen"])
+    for f, a in got.items():
+        r = np.asarray(getattr(ora, f))
+        scale = max(float(np.max(np.abs(r))), 1e-300)
+        tol = 1e-10 * scale if f != "vm" else max(1e-10 * scale, 4e-12)
+        assert float(np.max(np.abs(a.reshape(r.shape) - r))) <= tol, (f, float(np.max(np.abs(a.reshape(r.shape) - r))), tol)
+    c, ce = eng.network_state(0), eng.network_env_state(0)
+    net = ora.networks[0]
+    for k, nme in enumerate(desc["species"]):
+        assert util.rel_err(c[k], net.c[nme]) <= 1e-10, nme
+        if nme in net.c_env:
+            assert util.rel_err(ce[k], net.c_env[nme]) <= 1e-10, (nme, "env")
+    eng.close()
