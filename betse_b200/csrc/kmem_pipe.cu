@@ -142,12 +142,14 @@ __device__ __forceinline__ void load_G(const KArrays& A, const int4 td, const do
         const int* Ki = reinterpret_cast<const int*>(K + KP_KD(NI));
         const int cn = Ki[32 + lane] & 0x7fffffff;
         const int e = Ki[64 + lane];
-        const double* __restrict__ cenv = A.cc_env[cur] + e;
-        const double* __restrict__ cmid = A.cc_mid[cur] + cn;
+        // uniform row bases + a 32-bit lane index: one address instruction per load
+        const double* __restrict__ cenv = A.cc_env[cur];
+        const double* __restrict__ cmid = A.cc_mid[cur];
+        const unsigned ue = (unsigned)e, ucn = (unsigned)cn;
 #pragma unroll
-        for (int i = 0; i < NI; ++i) R.co[i] = cenv[(size_t)i * E];
+        for (int i = 0; i < NI; ++i) R.co[i] = (cenv + (size_t)i * E)[ue];
 #pragma unroll
-        for (int i = 0; i < NI; ++i) R.cnb[i] = cmid[(size_t)i * C];
+        for (int i = 0; i < NI; ++i) R.cnb[i] = (cmid + (size_t)i * C)[ucn];
         R.vm_nb = A.vm_cell[cur][cn];
         R.cao = (StdProf<NI>::iCa >= 0) ? A.cc_env[cur ^ 1][(size_t)StdProf<NI>::iCa * E + e] : 0.0;
         R.g = A.gjopen[m0 + lane];
