@@ -178,3 +178,32 @@ def test_helmholtz_hodge_vs_oracle_rectangular_grid():
         assert np.max(np.abs(got[f].ravel() - np.asarray(getattr(ora, f)).ravel())) <= 1e-9 * sJ, f
     assert np.max(np.abs(got["B_field"] - ora.B_field)) <= 1e-7 * np.max(np.abs(ora.B_field)) + 1e-9 * sJ * p["mu"] * 1e-3
     eng.close()
+
+
+def test_dropin_loop_raises_on_instability():
+    """Error convention of the seam (SURVEY §8b): NaN in Vmem / a concentration is not an error code but a status word;
+    the drop-in copies the partial state back and raises the reference's BetseSimUnstableException (a stand-in class
+    where the reference is not importable), like stb.check_v / stb.no_negs would (sim_toolbox.py:332-344, 475-503), so
+    that run_sim_core can still pickle what there is (sim.py:1104-1128)."""
+    import bench
+    from betse_b200 import capi, simloop, synth
+    from betse_b200.engine import TissueEngine
+    mesh, p, state = synth.make_tissue(2000)
+    # the status word itself: a NaN concentration surfaces within one step
+    bad = dict(state)
+    cc = np.array(state["cc_cells"], dtype=float, copy=True)
+    cc[1, 17] = np.nan
+    bad["cc_cells"] = cc
+    eng = TissueEngine(mesh, p, bad)
+    st = eng.step(1)
+    assert st & (capi.STATUS_NAN_VM | capi.STATUS_NAN_CONC), st
+    eng.close()
+    # through the drop-in: exception after the copy-back, not a silent continue
+    sim, phase = bench.namespaces(mesh, p, bad)
+    n = 12
+    ts = np.linspace(0, n * p["dt"], n)
+    Unstable = simloop._unstable_exception()
+    with pytest.raises(Unstable):
+        simloop.run_sim_core_loop(sim, phase, ts, set(ts[3::4].tolist()), None)
+    assert np.isnan(np.asarray(sim.cc_cells)).any() or np.isnan(np.asarray(sim.vm)).any()   # the partial state came back
+    assert sim.sampled == 0                                                                   # nothing was stored after it

@@ -275,3 +275,42 @@ def test_gene_network_through_the_dropin_matches_the_reference(monkeypatch, tmp_
             assert np.max(np.abs(np.asarray(x) - np.asarray(y))) <= 1e-9 * np.max(np.abs(np.asarray(y))), name
     for a, r in zip(new_sim.vm_time, ref_sim.vm_time):
         assert np.max(np.abs(a - r)) <= 1e-9 * np.max(np.abs(r))
+
+
+def test_instability_raises_the_reference_exception(monkeypatch, tmp_path):
+    """NaN reported by the engine's status word -> BetseSimUnstableException out of the drop-in, caught by the
+    reference's own run_sim_core, which pickles the partial phase and re-raises (sim.py:1104-1128)."""
+    import os
+    from oracle import refrun, refshim
+    refshim.bypass_science_init()
+    from betse.exceptions import BetseSimUnstableException
+    from betse.science.parameters import Parameters
+    from betse.science.simrunner import SimRunner
+    from betse.science.phase import phasecallbacks
+    from betse_b200 import capi, network as netlib, simloop
+    from tests.golden.make_golden import NO_NET, SMALL, _m
+    from tests.oracle_engine import OracleEngine
+
+    class Eng(OracleEngine):
+        def step(self, n=1, diag=False):
+            st = super().step(n, diag)
+            self._steps = getattr(self, "_steps", 0) + n
+            if self._steps >= 35:                               # after a few sampled steps of the INIT phase (100 steps, every 10th)
+                self._sim().vm[3] = np.nan
+                return capi.STATUS_NAN_VM
+            return st
+
+    monkeypatch.setattr(simloop, "TissueEngine", Eng)
+    simloop.install()
+    try:
+        fn = refrun.write_config(str(tmp_path), _m(NO_NET, SMALL))
+        np.random.seed(12345)
+        p = Parameters.make(fn)
+        p.anim.is_while_sim = p.anim.is_after_sim = p.plot.is_after_sim = False
+        runner = SimRunner(p=p, callbacks=phasecallbacks.SimCallbacksNoop())
+        runner.seed()
+        with pytest.raises(BetseSimUnstableException):
+            runner.init()
+    finally:
+        simloop.uninstall()
+    assert os.path.exists(p.init_pickle_filename)             # the partial phase was saved before the re-raise
