@@ -42,6 +42,9 @@ def _compare(eng, ora, mesh, p, ecm, tag):
     (10_000, "basic", True, 5),
     (10_000, "mammal", False, 10),
     (100_000, "mammal", True, 3),      # BASELINE configs[2] size (ion path)
+    (1, "mammal", True, 10),           # edge: the smallest tissue (4 cells, one partial warp tile, 7x7 grid: every env tile is an edge tile)
+    (1, "basic", False, 10),
+    (30, "mammal", True, 10),          # edge: fewer cells than one CTA's worth, most membranes on the cluster boundary
 ])
 def test_gpu_vs_oracle(n_cells, profile, ecm, steps):
     mesh, p, eng, ora = _pair(n_cells, profile, ecm)
