@@ -1292,7 +1292,8 @@ extern "C" int betse_set_network(betse_ctx* ctx, int handler, const betse_networ
             if (op == RL_PUSHA && (arg < 0 || arg >= (memzone ? net->n_mem_arrays : net->n_cell_arrays))) return fail(ctx, "network: array index out of range");
             if ((op == RL_PUSHI || op == RL_PUSHM) && (arg < 0 || arg >= ctx->I)) return fail(ctx, "network: ion index out of range");
             if (op == RL_PUSHV && !memzone) return fail(ctx, "network: Vmem in a cell-zone program");
-            if ((op == RL_PUSHE || op == RL_PUSHJ) && (!memzone || !ctx->hp.is_ecm)) return fail(ctx, "network: env concentration outside a membrane-zone program / without extracellular spaces");
+            if ((op == RL_PUSHE || op == RL_PUSHJ) && !ctx->hp.is_ecm) return fail(ctx, "network: env concentration in a rate law without extracellular spaces");
+            if ((op == RL_PUSHE || op == RL_PUSHJ) && !memzone && !net->map_cell2ecm) return fail(ctx, "network: a cell-zone rate law reads an env concentration: map_cell2ecm needed");
             if (op == RL_PUSHE && (arg < 0 || arg >= K || !(net->env_on && net->env_on[arg]))) return fail(ctx, "network: env concentration of a substance without env_on");
             if (op == RL_PUSHJ && (arg < 0 || arg >= ctx->I)) return fail(ctx, "network: ion index out of range");
             if (op <= RL_LAST_PUSH) ++depth;
@@ -1304,6 +1305,12 @@ extern "C" int betse_set_network(betse_ctx* ctx, int handler, const betse_networ
     KNet N;
     memset(&N, 0, sizeof N);
     N.K = K; N.n_rates = R; N.E = ctx->E;
+    if (net->map_cell2ecm) {
+        for (int c = 0; c < ctx->Co; ++c)
+            if (net->map_cell2ecm[c] < 0 || net->map_cell2ecm[c] >= ctx->E) return fail(ctx, "network: map_cell2ecm out of range");
+        int rr = dev_upload(ctx, (int**)&N.cell2ecm, net->map_cell2ecm, (size_t)C);
+        if (rr) return rr;
+    }
     int r;
     if ((r = dev_upload(ctx, &N.c, net->c_cells, (size_t)K * C))) return r;
     if ((r = dev_alloc(ctx, &N.rates, (size_t)R * C))) return r;

@@ -13,6 +13,7 @@ enum { RL_PUSHC = 0, RL_PUSHS, RL_PUSHA, RL_PUSHI, RL_PUSHM, RL_PUSHV, RL_PUSHE,
 struct KNet {
     int K;                      // substances
     int E;                      // env points (ny*nx)
+    const int* cell2ecm;        // [C] cells.map_cell2ecm (cell-zone rate laws that read concentrations outside the cells)
     int n_rates;                // K growth/decay rates + R reactions (columns of reaction_matrix)
     double* c;                  // [K][C] concentrations in the cells
     double* rates;              // [n_rates][C] rates of the last step (reaction_rates / download)
@@ -71,10 +72,11 @@ __device__ __forceinline__ double rl_eval(const KNet& N, const int prog, const i
         if (op <= RL_LAST_PUSH) {
             double v;
             switch (op) {
-                // outside the membrane (membrane zone only): substance / ion at the membrane's env square; the ions' env
+                // outside the cells: substance / ion at the membrane's env square (membrane zone) or at the env square of
+                // the cell centre (cell zone, cells.map_cell2ecm); the ions' env
                 // field is the one this step's transport left (cc_env[cur ^ 1]), what sim.cc_env holds during the network block
-                case RL_PUSHE: v = N.c_env[(size_t)arg * N.E + __ldg(A.map_mem2ecm + m)]; break;
-                case RL_PUSHJ: v = A.cc_env[cur ^ 1][(size_t)arg * N.E + __ldg(A.map_mem2ecm + m)]; break;
+                case RL_PUSHE: v = N.c_env[(size_t)arg * N.E + (m >= 0 ? __ldg(A.map_mem2ecm + m) : __ldg(N.cell2ecm + c))]; break;
+                case RL_PUSHJ: v = A.cc_env[cur ^ 1][(size_t)arg * N.E + (m >= 0 ? __ldg(A.map_mem2ecm + m) : __ldg(N.cell2ecm + c))]; break;
                 case RL_PUSHC: v = __ldg(N.consts + arg); break;
                 case RL_PUSHS: v = (m >= 0 && N.tw && N.tw_s[arg] >= 0) ? N.tw[(size_t)N.tw_s[arg] * M + m] : N.c[(size_t)arg * C + c];
                                break;

@@ -545,6 +545,11 @@ class TissueEngine:
             n.R_rads = f64(np.asarray(self.mesh["R_rads"], dtype=float))
             if not trs_needs_vol(net):
                 n.mem_sa_over_vol = f64(np.asarray(self.mesh["mem_sa"], dtype=float) / np.asarray(self.mesh["mem_vol"], dtype=float))
+        if "map_cell2ecm" in self.mesh and self.is_ecm:
+            mc = np.zeros(self.C, dtype=np.int32)
+            mc[:self.Co] = np.asarray(self.mesh["map_cell2ecm"]).astype(np.int32)[:self.Co]
+            keep.append(mc)
+            n.map_cell2ecm = capi.ptr_i32(mc)
         trs = list(net.get("transporters") or [])
         if trs:
             tarr = (capi.Transporter * len(trs))()

@@ -108,7 +108,9 @@ def _dynamic(node, tables, zone):
             and isinstance(node.value.value.value, ast.Name) and node.value.value.value.id == "self":
         key = _subscript_key(node.value)
         idx = ast.unparse(node.slice)
-        if zone != "mem" or idx != "cells.map_mem2ecm":
+        # membrane zone: the env square of the membrane; cell zone: the env square of the cell centre (get_influencers,
+        # networks.py:5242-5265)
+        if (zone, idx) not in (("mem", "cells.map_mem2ecm"), ("cell", "cells.map_cell2ecm")):
             raise RateLawError("env_concs[%r][%s] in the %s zone is not implemented" % (key, idx, zone))
         if key in tables.species:
             tables.env_species.add(tables.species.index(key))
@@ -269,7 +271,7 @@ def pack_programs(programs):
 
 
 def run_numpy(prog, tables, species, ions=None, ions_mid=None, vm=None, mem_to_cells=None, species_env=None, ions_env=None,
-              map_mem2ecm=None):
+              map_mem2ecm=None, map_cell2ecm=None):
     """Host interpreter of a program (tests only): ``species`` [K][C]; membrane-zone programs
     gather cell quantities through ``mem_to_cells``."""
     st = []
@@ -288,9 +290,9 @@ def run_numpy(prog, tables, species, ions=None, ions_mid=None, vm=None, mem_to_c
         elif op == PUSHV:
             st.append(vm)
         elif op == PUSHE:
-            st.append(species_env[arg][map_mem2ecm])
+            st.append(species_env[arg][map_mem2ecm if prog.zone == "mem" else map_cell2ecm])
         elif op == PUSHJ:
-            st.append(ions_env[arg][map_mem2ecm])
+            st.append(ions_env[arg][map_mem2ecm if prog.zone == "mem" else map_cell2ecm])
         elif op == NEG:
             st.append(-st.pop())
         elif op == EXP:

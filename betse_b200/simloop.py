@@ -83,6 +83,8 @@ def mesh_from_cells(cells):
     for f in ("nn_i", "bflags_mems", "map_mem2ecm", "mem_sa", "R_rads", "cell_vol", "cell_sa", "diviterm",
               "num_mems", "memSa_per_envSquare", "gj_default_weights"):
         mesh[f] = np.asarray(getattr(cells, f))
+    if getattr(cells, "map_cell2ecm", None) is not None:
+        mesh["map_cell2ecm"] = np.asarray(cells.map_cell2ecm)    # cell-zone rate laws reading env concentrations
     if getattr(cells, "mem_vol", None) is not None:
         mesh["mem_vol"] = np.asarray(cells.mem_vol)          # transporters' membrane-value nudge (networks.py:3020-3022)
     mv = getattr(cells, "mem_vects_flat", None)

@@ -334,6 +334,7 @@ typedef struct betse_network {
     const double  *Do;                   /* [K] Molecule.Do                                              */
     const double  *c_mems;               /* [K][M] cc_at_mem at loop entry (rows with intra_on == 0 ignored) */
     const double  *R_rads;               /* [M] cells.R_rads                                             */
+    const int32_t *map_cell2ecm;         /* [C] cells.map_cell2ecm: cell-zone rate laws reading env concentrations (NULL: none do) */
 } betse_network;
 
 /* handler 0 = sim.molecules.core, 1 = sim.grn.core (run in that order, sim.py:1290-1318).  net == NULL

@@ -305,6 +305,22 @@ SCENARIOS["mammal_ecm_polar_net"] = dict(
     snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=net_extra)
 
 
+# regulators OUTSIDE the cells in cell-zone rate laws (get_influencers with zone 'env', networks.py:5242-5265): the gene G1
+# is repressed by the bath substance S2 and activated by extracellular K+ at the env square of the cell centre
+def _zoned(sub, **zones):
+    sub["growth and decay"].update(zones)
+    return sub
+
+
+_ENVZ_BIO = [_env_substance("S2", 0.0, 0, 0.2, 0.0, True, True),
+             _zoned(_substance("G1", 2.0, acts=[("K", 5.0, 1)], inh=[("S2", 0.2, 2)]),
+                    **{"zone activators": ["env"], "zone inhibitors": ["env"]})]
+SCENARIOS["mammal_ecm_net_envzone"] = dict(
+    mods=_m(SMALL, {"cutting event": {"event happens": False}, "general options": {"ion profile": "mammal"},
+                    "general network": {"implement network": True, "biomolecules": _ENVZ_BIO, "reactions": [], "channels": []}}),
+    snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=net_extra)
+
+
 # The external-voltage event (tissue/event/tisevevolt.py: bound_V ramps, Phi_b = one Dirichlet Poisson solve per step,
 # ion_current.py:84-90, subtracted from Vmem in update_V, sim.py:2029) — ramp up, plateau and ramp down inside the
 # first 20 SIM steps, left/right electrodes so that it differs from the top/bottom default; ECM and no-ECM

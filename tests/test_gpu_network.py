@@ -27,7 +27,8 @@ def _attach(eng, desc, specs, phase_init):
 @pytest.mark.parametrize("fixture", ["mammal_ecm_net", "mammal_ecm_net_env", "mammal_ecm_net_envq", "mammal_ecm_net_mod",
                                      "mammal_ecm_net_lig", "mammal_ecm_net_pump",    # _pump: Molecule.pump (ATP pump out, carrier in)
                                      "mammal_ecm_net_trans",                         # _trans: transporters (carrier; electrogenic exporter)
-                                     "mammal_ecm_polar_net"])                        # per-membrane Vmem (polarizability) under all of it
+                                     "mammal_ecm_polar_net",                         # per-membrane Vmem (polarizability) under all of it
+                                     "mammal_ecm_net_envzone"])                      # cell-zone rate laws regulated from outside the cells
 def test_network_matches_reference(fixture, kind):
     from betse_b200.engine import TissueEngine
     cap = util.load_golden(fixture)

@@ -57,7 +57,8 @@ def test_static_terms_are_folded():
 
 
 @pytest.mark.parametrize("src,msg", [
-    ("self.env_concs['X'][cells.map_cell2ecm]/2.0", "cell zone is not implemented"),
+    ("self.env_concs['X'][cells.map_mem2ecm]/2.0", "cell zone is not implemented"),      # the membrane map in a cell-zone law
+    ("self.env_concs['X']/2.0", "extracellular"),                                       # a whole env field (env-zone reactions)
     ("self.cell_concs['Nope']*2", "unknown substance"),
     ("np.sin(self.cell_concs['X'])", "unsupported construct"),
     ("self.mem_concs['X']*2", "zone"),
