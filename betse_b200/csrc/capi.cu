@@ -569,6 +569,7 @@ extern "C" int betse_create(betse_ctx** out, const betse_mesh* mesh, const betse
 }
 
 static int ensure_phi(betse_ctx* ctx);
+static double nan_value() { return nan(""); }
 static void publish_affect(betse_ctx* ctx);
 
 // sine matrices, eigenvalues and work buffers of the Dirichlet Poisson solve on the env grid (csrc/hh.cu)
@@ -1346,6 +1347,10 @@ extern "C" int betse_set_network(betse_ctx* ctx, int handler, const betse_networ
         }
     }
     if ((r = ensure_defer_buffers(ctx))) return r;
+    {
+        std::vector<double> nan((size_t)K, nan_value());
+        if ((r = dev_upload(ctx, &N.clamp, (const double*)nan.data(), (size_t)K))) return r;
+    }
     ctx->net_trans[handler].clear(); ctx->net_trans_cm[handler].clear(); ctx->net_trans_em[handler].clear();
     ctx->net_trans_mm[handler].clear();
     ctx->net_tw_rows[handler] = 0;
@@ -1519,6 +1524,19 @@ extern "C" int betse_network_mem_state(betse_ctx* ctx, int handler, double* c_me
         CK(cudaStreamSynchronize(ctx->stream));
     }
     cudaFree(tmp);
+    return 0;
+}
+
+extern "C" int betse_network_set_events(betse_ctx* ctx, int handler, const double* c_bound, const double* clamp)
+{
+    if (!ctx || handler < 0 || handler > 1) return 2;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->net_on[handler]) return fail(ctx, "no network on this handler");
+    const KNet& N = ctx->nets[handler];
+    // device arrays, not kernel parameters: the captured step graphs stay valid
+    if (c_bound && N.c_bound) CK(cudaMemcpyAsync((void*)N.c_bound, c_bound, (size_t)N.K * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (clamp && N.clamp) CK(cudaMemcpyAsync(N.clamp, clamp, (size_t)N.K * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 

@@ -35,6 +35,7 @@ k_net(const __grid_constant__ KParams P, const KArrays A, const __grid_constant_
         double d = 0.0;
         for (int j = 0; j < N.n_rates; ++j) d += __ldg(N.stoich + k * N.n_rates + j) * r[j];   // np.dot(reaction_matrix, all_rates)
         double cn = N.c[(size_t)k * C + c] + d * P.dt;                      // networks.py:2914
+        if (N.clamp) { const double cl = N.clamp[k]; if (cl == cl) cn = cl; }   // cell_clamp_method: before the transport (networks.py:2932-2936)
         // update_Co cell branch, sim_toolbox.py:1177-1181 (a pumped substance gets its membrane leg after the pump)
         if (N.mem_delta && __ldg(N.Dm + k) != 0.0 && !(N.pumped && N.pumped[k])) cn = cn + N.mem_delta[(size_t)k * C + c] * P.dt;
         if (__ldg(N.Dgj + k) < 0.0 && cn < 0.0) { flags |= ST_NEG_NET; cn = 0.0; }

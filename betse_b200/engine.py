@@ -600,6 +600,12 @@ class TissueEngine:
         self.d2h_bytes += c.nbytes + (r.nbytes if rates else 0)
         return (c[:, :self.Co], r[:, :self.Co]) if rates else c[:, :self.Co]
 
+    def set_network_events(self, handler, c_bound=None, clamp=None):
+        """Scheduled values of the substances' own events for the step about to run (network.event_values)."""
+        keep = [None if a is None else capi.as_f64(np.asarray(a, dtype=float)) for a in (c_bound, clamp)]
+        self._check(self.lib.betse_network_set_events(self.ctx, int(handler), *(None if a is None else capi.ptr_f64(a) for a in keep)),
+                    "betse_network_set_events")
+
     def network_mem_state(self, handler=0):
         """Membrane values [K][M] of a handler's substances (Molecule.cc_at_mem)."""
         info = self.networks[int(handler)]

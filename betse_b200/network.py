@@ -64,10 +64,13 @@ def unsupported_reasons(core, p):
                 blockers.append("moved by a transporter")
             if blockers:
                 why.append("update intracellular of a substance that is " + ", ".join(blockers))
-        for flag, what in (("change_bounds", "boundary change event"),
-                           ("cell_clamp", "cell clamp"), ("transmem", "transmembrane transport")):
-            if bool(getattr(m, flag, False)):
-                why.append(what)
+        if bool(getattr(m, "transmem", False)):
+            why.append("transmembrane transport")
+        if bool(getattr(m, "change_bounds", False)) and bool(getattr(m, "change_at_bounds", False)) and not bool(getattr(p, "is_ecm", False)):
+            why.append("boundary change event without extracellular spaces")
+        if bool(getattr(m, "cell_clamp", False)) and bool(getattr(m, "cell_clamp_event", False)) and \
+                bool(getattr(m, "active_pumping", False)) and bool(getattr(m, "use_pumping", False)):
+            why.append("cell clamp of a pumped substance")
         if _in_env(m) and float(getattr(p, "sharpness", 1.0)) < 1.0:
             why.append("extracellular transport with 'sharpness env' < 1")
         if _in_env(m) and float(getattr(m, "Mu_mem", 0.0) or 0.0) != 0.0:
@@ -86,6 +89,36 @@ def _in_env(m):
     boundary concentration is, sim_toolbox.py:1064-1066)"""
     return (float(getattr(m, "Dm", 0.0) or 0.0) != 0.0 or bool(np.any(np.asarray(m.c_env) != 0.0))
             or float(getattr(m, "c_bound", 0.0) or 0.0) > 1.0e-15)
+
+
+def pulse(t, t_on, t_off, t_change):
+    """tb.pulse (betse/science/math/toolbox.py:353-382): difference of two logistic steps."""
+    g = (1 / t_change) * 10
+    with np.errstate(over="ignore"):                  # exp -> inf far from the ramps, as in the reference: 1/(1+inf) = 0
+        y1 = 1 / (1 + (np.exp(-g * (t - t_on))))
+        y2 = 1 / (1 + (np.exp(-g * (t - t_off))))
+    return y1 - y2
+
+
+def event_values(desc, t):
+    """Scheduled values of the substances' own events at time ``t`` (host-side scalar logic, like fire_events):
+    (c_bound [K], clamp [K] with NaN where no clamp is in force).
+    Molecule.update_boundary (networks.py:6043-6066), Molecule.cell_clamp_method (networks.py:6069-6088)."""
+    K = len(desc["species"])
+    c_bound = np.array(desc.get("c_bound", np.zeros(K)), dtype=float, copy=True)
+    clamp = np.full(K, np.nan)
+    for ev in desc.get("events", []):
+        k = ev["species"]
+        if ev.get("bounds") is not None:
+            target, start, end, rate, c_envo = ev["bounds"]
+            eff = pulse(t, start, end, rate)
+            c_bound[k] = target * eff + c_envo * (1 - eff)
+        if ev.get("clamp") is not None:
+            target, start, end, rate, c_cello = ev["clamp"]
+            if start <= t <= end:
+                eff = pulse(t, start, end, rate)
+                clamp[k] = target * eff + c_cello * (1 - eff)
+    return c_bound, clamp
 
 
 def describe_core(core, sim, p, cells, record_static=True):
@@ -126,6 +159,20 @@ def describe_core(core, sim, p, cells, record_static=True):
     }
     # Molecule.transport -> stb.molecule_mover (networks.py:5670-5700, sim_toolbox.py:909-1153): membrane and
     # extracellular legs of the substances that have them
+    events = []
+    for k, s in enumerate(species):
+        m = core.molecules[s]
+        ev = {"species": k, "bounds": None, "clamp": None}
+        if bool(getattr(m, "change_bounds", False)) and bool(getattr(m, "change_at_bounds", False)):
+            ev["bounds"] = (float(m.change_bounds_target), float(m.change_bounds_start), float(m.change_bounds_end),
+                            float(m.change_bounds_rate), float(m.c_envo))
+        if bool(getattr(m, "cell_clamp", False)) and bool(getattr(m, "cell_clamp_event", False)):
+            ev["clamp"] = (float(m.cell_clamp_target), float(m.cell_clamp_start), float(m.cell_clamp_end),
+                           float(m.cell_clamp_rate), float(m.c_cello))
+        if ev["bounds"] is not None or ev["clamp"] is not None:
+            events.append(ev)
+    if events:
+        desc["events"] = events
     intra = np.array([bool(getattr(core.molecules[s], "update_intra_conc", False)) for s in species], dtype=np.uint8)
     if intra.any():
         desc.update({"intra_on": intra, "Do": np.array([float(core.molecules[s].Do or 0.0) for s in species]),
@@ -168,6 +215,7 @@ def describe_core(core, sim, p, cells, record_static=True):
         if any(g["extracell"] and any(q["species"] == g["species"] for q in pumps) for g in lig):
             raise BetseB200Error("a pumped substance that also gates a channel from outside the cell is not implemented")
     env_on = np.array([_in_env(core.molecules[s]) or any(g["species"] == k and g["extracell"] for g in lig)
+                       or any(ev["species"] == k and ev["bounds"] is not None for ev in events)
                        or any(q["species"] == k for q in pumps)
                        or any(x == s and tag == "env_concs" for t in trans for x, _, tag, _ in t["terms"])   # moved outside by a transporter
                        for k, s in enumerate(species)], dtype=np.uint8)
@@ -287,6 +335,7 @@ def compile_network(desc, n_cells, n_mems, resolver=None):
         gates.append(dict(g, mod=float(tabs.consts[pr.code[0][1]])))
     return {"species": species, "tables": tabs, "rate_programs": rates, "mod_programs": mod_programs,
             "mod_index": mod_index, "ligand_gates": gates, "pumps": list(desc.get("pumps", [])), "transporters": transporters,
+            "events": list(desc.get("events", [])),
             "modulators": [(MOD_TARGETS[t], i, float(mx)) for t, i, mx in
                            zip(desc.get("modulator_targets", []), modulator_index, desc.get("modulator_max", []))], "c_cells": np.asarray(desc["c_cells"], dtype=float), "stoich": stoich,
             "growth_mask": None if mask.all() else mask, "Dgj": np.asarray(desc["Dgj"], dtype=float),
@@ -318,6 +367,9 @@ def flatten(desc, prefix):
                     pre + "targets_cell": np.asarray(t["targets_cell"], dtype=np.int64),
                     pre + "targets_mem": np.asarray(t["targets_mem"], dtype=np.int64),
                     pre + "targets_env": np.asarray(t["targets_env"], dtype=np.int64)})
+    for j, ev in enumerate(desc.get("events", [])):
+        nan5 = (np.nan,) * 5
+        out["%sevent%d" % (prefix, j)] = np.array((ev["species"],) + tuple(ev["bounds"] or nan5) + tuple(ev["clamp"] or nan5), dtype=float)
     for j, q in enumerate(desc.get("pumps", [])):
         out["%spump%d" % (prefix, j)] = np.array([q["species"], float(q["into_cell"]), q["max"], q["Km"], float(q["uses_ATP"])])
     if desc.get("modulator_names"):
@@ -356,6 +408,12 @@ def unflatten(cap, prefix):
                       zip(cap[pre + "term_names"], cap[pre + "term_coeff"], cap[pre + "term_tags"], cap[pre + "term_sign"])],
             "targets_cell": np.asarray(cap[pre + "targets_cell"]), "targets_mem": np.asarray(cap[pre + "targets_mem"]),
             "targets_env": np.asarray(cap[pre + "targets_env"])})
+        j += 1
+    j = 0
+    while "%sevent%d" % (prefix, j) in cap:
+        v = np.asarray(cap["%sevent%d" % (prefix, j)], dtype=float)
+        mods.setdefault("events", []).append({"species": int(v[0]), "bounds": None if np.isnan(v[1]) else tuple(float(x) for x in v[1:6]),
+                                              "clamp": None if np.isnan(v[6]) else tuple(float(x) for x in v[6:11])})
         j += 1
     j = 0
     while "%spump%d" % (prefix, j) in cap:

@@ -27,6 +27,7 @@ import numpy as np
 from . import capi
 from .capi import BetseB200Error
 from .engine import TissueEngine
+from .network import event_values as netlib_event_values
 
 _P_FIELDS = [
     "F", "R", "T", "q", "kb", "eo", "er", "cm", "tm", "dt", "NAv", "mu", "alpha_NaK", "alpha_Ca",
@@ -189,6 +190,9 @@ def engine_from_sim(sim, cells, p, device=0, phase_init=False):
             comp = netlib.compile_network(desc, eng.Co, eng.M, ratelaw.live_resolver(core, sim, p, cells))
             eng.set_network(comp, handler=h)
             eng.net_cores[h] = core
+            if comp.get("events"):
+                eng.net_events = getattr(eng, "net_events", {})
+                eng.net_events[h] = (desc, [None, None])        # description + the values last pushed
             for c in specs:
                 if c["handler"] == h:
                     c["mod_prog"] = comp["mod_index"][comp["chan_names"].index(c["name"])]
@@ -251,6 +255,11 @@ def _copy_back(sim, eng, diag, sample_only=False):
             mol.cc_at_mem = cmem[k].copy() if cmem is not None and intra[k] else c[k][m2c]
             if cenv is not None and env_on[k]:
                 mol.c_env = cenv[k].copy()
+        for desc_h, last in ([getattr(eng, "net_events", {}).get(h)] if h in getattr(eng, "net_events", {}) else []):
+            if last[0] is not None:         # Molecule.update_boundary leaves the ramped boundary value on the object
+                for ev in desc_h.get("events", []):
+                    if ev["bounds"] is not None:
+                        core.molecules[desc_h["species"][ev["species"]]].c_bound = float(last[0][ev["species"]])
         nk = len(eng.networks[h]["species"])
         core.reaction_rates = rates[nk:].copy()
     # MasterOfNetworks.energy_charge (networks.py:3996-4012), the tail of run_loop; write_data appends it
@@ -317,11 +326,19 @@ def run_sim_core_loop(sim, phase, time_steps, time_steps_sampled, anim_cells=Non
                     eng.set_bound_V([bv["T"], bv["B"], bv["L"], bv["R"]])
                     bv_cache = dict(bv)
                 run = 1
+            elif getattr(eng, "net_events", None):
+                run = 1                     # substances with timed events: the schedule is evaluated for every step
             else:
                 # no events: run up to and including the next sampled step in one call
                 run = 1
                 while n + run < n_total and time_steps[n + run - 1] not in sampled:
                     run += 1
+            # Molecule.update_boundary / cell_clamp_method (networks.py:2929-2933): host-side scalar schedules of the step's time
+            for h, (desc_h, last) in getattr(eng, "net_events", {}).items():
+                cb, cl = netlib_event_values(desc_h, float(time_steps[n]))
+                if last[0] is None or not np.array_equal(cb, last[0]) or not np.array_equal(cl, last[1], equal_nan=True):
+                    eng.set_network_events(h, cb, cl)
+                    last[0], last[1] = cb, cl
             last_t = time_steps[n + run - 1]
             is_sampled = last_t in sampled
             status = eng.step(run, diag=is_sampled)

@@ -346,6 +346,11 @@ int  betse_network_state(betse_ctx *ctx, int handler, double *c_cells, double *r
 int  betse_network_env_state(betse_ctx *ctx, int handler, double *c_env);
 /* Membrane values [K][M] (Molecule.cc_at_mem): the cell value gathered, or the transported value with intra_on. */
 int  betse_network_mem_state(betse_ctx *ctx, int handler, double *c_mems);
+/* The substances' own timed events, evaluated by the host for the step about to run (scalar schedule logic like
+ * fire_events): c_bound [K] (Molecule.update_boundary, networks.py:6043-6066; NULL: unchanged) and clamp [K] — the value
+ * every cell takes right after growth/decay, NaN where no clamp is in force (Molecule.cell_clamp_method,
+ * networks.py:6069-6088; NULL: none). */
+int  betse_network_set_events(betse_ctx *ctx, int handler, const double *c_bound, const double *clamp);
 
 /* ---------------------------------------------------------------------------------------------
  * Multi-GPU: the tissue is cut into strips of env-grid rows; each rank owns the

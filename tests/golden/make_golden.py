@@ -321,6 +321,21 @@ SCENARIOS["mammal_ecm_net_envzone"] = dict(
     snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=net_extra)
 
 
+# the substances' own timed events (networks.py:2929-2933): the bath concentration of B1 is ramped at the global boundary
+# (Molecule.update_boundary), C1 is clamped inside the cells for a while (Molecule.cell_clamp_method); both act in the
+# first 20 steps of either phase (INIT dt = 1e-2 s, SIM dt = 1e-4 s: two events each)
+_EVT_BIO = [dict(_env_substance("B1", 1.0e-17, 0, 0.2, 0.1, True, True),
+                 **{"change at bounds": {"event happens": True, "change start": 5.0e-4, "change finish": 0.12,
+                                         "change rate": 3.0e-4, "concentration": 1.5}}),
+            dict(_substance("C1", 0.5, Dgj=1e-15, gj_imp=False, cell=0.3),
+                 **{"clamp cell conc": {"event happens": True, "change start": 3.0e-4, "change finish": 0.05,
+                                        "change rate": 2.0e-4, "concentration": 0.9}})]
+SCENARIOS["mammal_ecm_net_events"] = dict(
+    mods=_m(SMALL, {"cutting event": {"event happens": False}, "general options": {"ion profile": "mammal"},
+                    "general network": {"implement network": True, "biomolecules": _EVT_BIO, "reactions": [], "channels": []}}),
+    snaps={"init": [1, 2, 5, 13], "sim": [1, 2, 4, 6, 9, 20]}, extra=net_extra)
+
+
 # The external-voltage event (tissue/event/tisevevolt.py: bound_V ramps, Phi_b = one Dirichlet Poisson solve per step,
 # ion_current.py:84-90, subtracted from Vmem in update_V, sim.py:2029) — ramp up, plateau and ramp down inside the
 # first 20 SIM steps, left/right electrodes so that it differs from the top/bottom default; ECM and no-ECM

@@ -102,6 +102,11 @@ class OracleEngine:
             return c, np.asarray(r)
         return c
 
+    def set_network_events(self, handler, c_bound=None, clamp=None):
+        self.sets.append("net_events")
+        net = self._sim().networks[sorted(self._descs).index(int(handler))]
+        net.forced_events = (np.array(c_bound, dtype=float), np.array(clamp, dtype=float))
+
     def network_mem_state(self, handler=0):
         net = self._sim().networks[sorted(self._descs).index(int(handler))]
         return np.stack([net.cmem[n] for n in net.species])

@@ -5,6 +5,7 @@ synthetic 50 k-cell tissue."""
 import numpy as np
 import pytest
 
+from betse_b200.network import event_values as netlib_events
 from tests import util
 
 pytestmark = pytest.mark.gpu
@@ -28,7 +29,8 @@ def _attach(eng, desc, specs, phase_init):
                                      "mammal_ecm_net_lig", "mammal_ecm_net_pump",    # _pump: Molecule.pump (ATP pump out, carrier in)
                                      "mammal_ecm_net_trans",                         # _trans: transporters (carrier; electrogenic exporter)
                                      "mammal_ecm_polar_net",                         # per-membrane Vmem (polarizability) under all of it
-                                     "mammal_ecm_net_envzone"])                      # cell-zone rate laws regulated from outside the cells
+                                     "mammal_ecm_net_envzone",                       # cell-zone rate laws regulated from outside the cells
+                                     "mammal_ecm_net_events"])                       # boundary ramp and cell clamp of substances
 def test_network_matches_reference(fixture, kind):
     from betse_b200.engine import TissueEngine
     cap = util.load_golden(fixture)
@@ -43,6 +45,8 @@ def test_network_matches_reference(fixture, kind):
         last = K == snaps[-1]
         while n < K:
             util.apply_schedule(eng, cap, kind, n + 1)
+            if desc.get("events"):          # the substances' own timed events: the host evaluates the schedule of the step's time
+                eng.set_network_events(0, *netlib_events(desc, float(cap[kind + ".time_steps"][n])))
             st = eng.step(1, diag=(last and n + 1 == K))
             assert not (st & (3 | 16)), st
             n += 1

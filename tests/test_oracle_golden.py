@@ -20,6 +20,7 @@ def test_oracle_reproduces_reference(name, kind):
     for K in util.snap_steps(cap, kind):
         while n < K:
             util.apply_schedule(o, cap, kind, n + 1)
+            util.set_time(o, cap, kind, n + 1)
             o.step()
             n += 1
         ref = util.group(cap, "%s.k%d." % (kind, K))

@@ -314,3 +314,20 @@ def test_instability_raises_the_reference_exception(monkeypatch, tmp_path):
     finally:
         simloop.uninstall()
     assert os.path.exists(p.init_pickle_filename)             # the partial phase was saved before the re-raise
+
+
+def test_substance_events_through_the_dropin_match_the_reference(monkeypatch, tmp_path):
+    """Molecule.update_boundary / cell_clamp_method (networks.py:2929-2933): the loop evaluates the schedules of every
+    step's time on the host and hands the values to the engine; both phases."""
+    from tests.golden import make_golden as mg
+    mods = mg.SCENARIOS["mammal_ecm_net_events"]["mods"]
+    ref_sim, _, _ = _run_try(tmp_path / "ref", False, mods=mods)
+    (tmp_path / "new").mkdir()
+    new_sim, _, engines = _run_try(tmp_path / "new", True, monkeypatch, mods=mods)
+    assert "net_events" in engines[0].sets and "net_events" in engines[1].sets
+    for name in ("B1", "C1"):
+        a, r = new_sim.molecules.core.molecules[name], ref_sim.molecules.core.molecules[name]
+        assert len(a.c_cells_time) == len(r.c_cells_time) >= 30
+        for x, y in zip(a.c_cells_time + a.c_env_time, r.c_cells_time + r.c_env_time):
+            assert np.max(np.abs(np.asarray(x) - np.asarray(y))) <= 1e-9 * max(np.max(np.abs(np.asarray(y))), 1e-300), name
+    assert abs(new_sim.molecules.core.molecules["B1"].c_bound - ref_sim.molecules.core.molecules["B1"].c_bound) <= 1e-12

@@ -55,6 +55,12 @@ def apply_schedule(obj, cap, kind, n):
                 obj, f, np.array(v, dtype=float))
 
 
+def set_time(obj, cap, kind, n):
+    """Hand the time of (1-based) step n to an oracle / engine wrapper whose networks carry timed substance events."""
+    if hasattr(obj, "t"):
+        obj.t = float(cap[kind + ".time_steps"][n - 1])
+
+
 def scale_of(field, ref):
     """Magnitude against which the error of ``field`` is judged."""
     def mx(f):
