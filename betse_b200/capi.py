@@ -179,7 +179,8 @@ SYMBOLS = [
     "betse_step_phase", "betse_stream", "betse_sync", "betse_update_v", "betse_update_v_phase",
     "betse_set_row_ranges", "betse_window", "betse_attach_neighbor", "betse_exchange",
     "betse_set_channels", "betse_channel_state", "betse_set_network", "betse_network_state",
-    "betse_network_env_state", "betse_network_mem_state", "betse_network_set_events", "betse_host_alloc", "betse_host_free",
+    "betse_network_env_state", "betse_network_mem_state", "betse_network_set_events", "betse_set_noise_flux",
+    "betse_host_alloc", "betse_host_free",
 ]
 
 _lib = None
@@ -224,6 +225,7 @@ def load(build_if_missing=True):
     lib.betse_network_env_state.argtypes = [vp, C.c_int, _dp]
     lib.betse_network_mem_state.argtypes = [vp, C.c_int, _dp]
     lib.betse_network_set_events.argtypes = [vp, C.c_int, _dp, _dp]
+    lib.betse_set_noise_flux.argtypes = [vp, C.c_int, _dp]
     lib.betse_step_phase.argtypes = [vp, C.c_int, C.c_int]
     lib.betse_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     lib.betse_host_free.argtypes = [vp]

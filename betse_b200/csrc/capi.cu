@@ -45,6 +45,7 @@ void launch_lig_prep(const KParams& P, const KArrays& A, const KNet& N, int sp, 
                      double max_val, double* Dm_mod, cudaStream_t st);
 void launch_net_lig(const KParams& P, const KArrays& A, int ion, const double* Dm_mod, double mod, int cur, int diag, cudaStream_t st);
 void launch_chan_env(const KParams& P, const KArrays& A, int ion, int cur, cudaStream_t st);
+void launch_flux_apply(const KParams& P, const KArrays& A, int ion, const double* flux, cudaStream_t st);
 void launch_transporter(const KParams& P, const KArrays& A, const KNet& N, const betse_transporter& T,
                         const unsigned char* d_cell_mask, const unsigned char* d_env_mask, const unsigned char* d_mem_mask,
                         int cur, cudaStream_t st);
@@ -98,6 +99,10 @@ struct betse_ctx {
     std::vector<betse_transporter> net_trans[2];    // transporters (run_loop_transporters); masks below are device copies
     std::vector<const unsigned char*> net_trans_cm[2], net_trans_em[2], net_trans_mm[2];
     int net_tw_rows[2] = {0, 0};
+    // dynamic noise (sim.py:1322-1339): the host's draw for the NEXT step
+    double* noise_flux = nullptr;
+    int noise_ion = -1;
+    bool noise_on = false, noise_pending = false;
     std::vector<unsigned char> net_intra[2];        // substances with intracellular transport (membrane values of their own)
     double* lig_tmp[2] = {nullptr, nullptr};       // [n_gates][M] openings formed before the substances advance
     std::string err;
@@ -789,7 +794,7 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
         // The membrane kernel reads cc_env[nxt] of Ca only (the Ca-ATPase sees the transported value,
         // sim.py:1282 after 2254): the Ca row is transported first, the other ions run on a second
         // stream NEXT TO the membrane kernel (which is latency-bound and leaves issue slots free).
-        const bool chans = !ctx->chans.empty() || ctx->net_on[0] || ctx->net_on[1];   // deferred-update mode
+        const bool chans = !ctx->chans.empty() || ctx->net_on[0] || ctx->net_on[1] || ctx->noise_on;   // deferred-update mode
         const bool overlap = ecm && ctx->overlap && !evs && ctx->hp.sharpness >= 1.0 && !chans;
         if (ecm && overlap) {
             const int iCa = ctx->hp.iCa;
@@ -863,6 +868,12 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
                         launch_chan_env(ctx->P, A, gs[j].ion, cur, st);
                     }
                 }
+            }
+            if (ctx->noise_pending) {
+                // after the networks, before update_all_concs (sim.py:1322-1339)
+                launch_flux_apply(ctx->P, A, ctx->noise_ion, ctx->noise_flux, st);
+                launch_chan_env(ctx->P, A, ctx->noise_ion, cur, st);
+                ctx->noise_pending = false;
             }
             launch_cell_update(ctx->P, A, cur, st);
         }
@@ -1537,6 +1548,28 @@ extern "C" int betse_network_set_events(betse_ctx* ctx, int handler, const doubl
     if (c_bound && N.c_bound) CK(cudaMemcpyAsync((void*)N.c_bound, c_bound, (size_t)N.K * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     if (clamp && N.clamp) CK(cudaMemcpyAsync(N.clamp, clamp, (size_t)N.K * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int betse_set_noise_flux(betse_ctx* ctx, int ion, const double* flux)
+{
+    if (!ctx || !flux) return 2;
+    CK(cudaSetDevice(ctx->device));
+    if (ion < 0 || ion >= ctx->I) return fail(ctx, "noise flux: ion index out of range");
+    if (ctx->X.n_nbr > 0) return fail(ctx, "dynamic noise on a domain-decomposed tissue is not implemented");
+    if (ctx->hp.fast_update_ecm) return fail(ctx, "dynamic noise with fast_update_ecm is not implemented");
+    int r;
+    if (!ctx->noise_on) {
+        if ((r = ensure_defer_buffers(ctx))) return r;
+        if ((r = dev_alloc(ctx, &ctx->noise_flux, (size_t)ctx->Mo))) return r;
+        ctx->noise_on = true;
+        ctx->P.defer = 1;
+        ctx->use_graphs = false;         // the extra launch exists only in steps that carry a draw
+        destroy_graphs(ctx);
+    }
+    if ((r = xfer(ctx, ctx->noise_flux, flux, (size_t)ctx->Mo * sizeof(double), cudaMemcpyHostToDevice))) return r;
+    ctx->noise_ion = ion;
+    ctx->noise_pending = true;
     return 0;
 }
 

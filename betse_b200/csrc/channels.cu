@@ -205,6 +205,46 @@ void launch_chan(const KParams& P, const KArrays& A, const KChan& ch, const KNet
     } else k_chan_mix<<<1, 256, 0, st>>>(P, A, ch.ion, cur);
 }
 
+// update_Co of one ion for a membrane flux handed in by the host: the dynamic-noise random walk on the protein
+// concentration (sim.py:1322-1339; the draw itself is np.random.random(mdl) on the host, the reference's own stream)
+__global__ void __launch_bounds__(BT_TPB)
+k_flux_apply(const __grid_constant__ KParams P, const KArrays A, const int ion, const double* __restrict__ flux)
+{
+    __shared__ double s_all[(BT_TPB / 32) * 32];
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * (BT_TPB / 32) + (threadIdx.x >> 5);
+    if (tile >= P.n_tiles) return;
+    double* s_f = s_all + (threadIdx.x >> 5) * 32;
+    const int4 td = __ldg(reinterpret_cast<const int4*>(A.tile_desc) + tile);
+    const int c0 = td.x, nc = td.y, m0 = td.z, nm = td.w;
+    double* __restrict__ ccell = A.cc_cells + (size_t)ion * P.n_cells;
+    double fsa = 0.0;
+    if (lane < nm) {
+        fsa = flux[m0 + lane] * __ldg(A.mem_sa + m0 + lane);
+        if (P.is_ecm) A.chan_slots[m0 + lane] = fsa;
+    }
+    s_f[lane] = fsa;
+    __syncwarp();
+    if (!P.is_ecm && lane == 0) {
+        double S = 0.0;
+        for (int j = 0; j < nm; ++j) S += s_f[j];
+        A.chan_part[tile] = S;
+    }
+    if (lane < nc) {
+        const int c = c0 + lane;
+        const int jb = __ldg(A.cell_mem_ptr + c) - m0, je = __ldg(A.cell_mem_ptr + c + 1) - m0;
+        double S = 0.0;
+        for (int j = jb; j < je; ++j) S += s_f[j];
+        ccell[c] = ccell[c] + (S / __ldg(A.cell_vol + c)) * P.dt;
+    }
+}
+
+void launch_flux_apply(const KParams& P, const KArrays& A, int ion, const double* flux, cudaStream_t st)
+{
+    const int grid = (P.n_tiles + (BT_TPB / 32) - 1) / (BT_TPB / 32);
+    k_flux_apply<<<grid, BT_TPB, 0, st>>>(P, A, ion, flux);
+}
+
 // env side of an immediate update_Co for fluxes left in chan_slots / chan_part (ligand-gated channels)
 void launch_chan_env(const KParams& P, const KArrays& A, int ion, int cur, cudaStream_t st)
 {

@@ -606,6 +606,14 @@ class TissueEngine:
         self._check(self.lib.betse_network_set_events(self.ctx, int(handler), *(None if a is None else capi.ptr_f64(a) for a in keep)),
                     "betse_network_set_events")
 
+    def set_noise_flux(self, flux, ion="P"):
+        """Dynamic noise: the host's draw of sim.protein_noise_flux for the next timestep (sim.py:1322-1339)."""
+        if ion not in self.ions:
+            raise BetseB200Error("dynamic noise needs the %s ion" % ion)
+        a = capi.as_f64(np.asarray(flux, dtype=float).reshape(self.M))
+        self.h2d_bytes += a.nbytes
+        self._check(self.lib.betse_set_noise_flux(self.ctx, self.ions.index(ion), capi.ptr_f64(a)), "betse_set_noise_flux")
+
     def network_mem_state(self, handler=0):
         """Membrane values [K][M] of a handler's substances (Molecule.cc_at_mem)."""
         info = self.networks[int(handler)]

@@ -165,8 +165,6 @@ def check_supported(sim, p):
                        ("fluid_flow", "fluid flow"), ("Ca_dyn", "ER calcium dynamics")):
         if bool(getattr(p, flag, False)):
             bad.append(what)
-    if bool(getattr(p, "dynamic_noise", False)) and "P" in [str(x) for x in params_from_p(p)["ions"]]:
-        bad.append("dynamic noise")
     if bad:
         raise BetseB200Error("betse_b200 does not implement: " + "; ".join(bad) +
                              " — run this configuration with the reference solver")
@@ -301,6 +299,7 @@ def run_sim_core_loop(sim, phase, time_steps, time_steps_sampled, anim_cells=Non
         cells = phase.cells
     eng = engine or engine_from_sim(sim, cells, p, device=device, phase_init=not is_sim)
     sampled = set(time_steps_sampled)
+    noisy = is_sim and getattr(p, "dynamic_noise", False) == 1 and "P" in eng.ions
     Unstable = _unstable_exception()
     h2d = d2h = 0
     h2d0, d2h0 = eng.h2d_bytes, eng.d2h_bytes
@@ -326,8 +325,8 @@ def run_sim_core_loop(sim, phase, time_steps, time_steps_sampled, anim_cells=Non
                     eng.set_bound_V([bv["T"], bv["B"], bv["L"], bv["R"]])
                     bv_cache = dict(bv)
                 run = 1
-            elif getattr(eng, "net_events", None):
-                run = 1                     # substances with timed events: the schedule is evaluated for every step
+            elif getattr(eng, "net_events", None) or noisy:
+                run = 1                     # substances with timed events / dynamic noise: host input for every step
             else:
                 # no events: run up to and including the next sampled step in one call
                 run = 1
@@ -339,6 +338,11 @@ def run_sim_core_loop(sim, phase, time_steps, time_steps_sampled, anim_cells=Non
                 if last[0] is None or not np.array_equal(cb, last[0]) or not np.array_equal(cl, last[1], equal_nan=True):
                     eng.set_network_events(h, cb, cl)
                     last[0], last[1] = cb, cl
+            if noisy:
+                # dynamic noise (sim.py:1322-1339): the draw comes from NumPy's global stream, like the reference's — nothing
+                # else in the loop draws from it, so the sequence is the one the reference would have used
+                sim.protein_noise_flux = p.dynamic_noise_level * (np.random.random(eng.M) - 0.5)
+                eng.set_noise_flux(sim.protein_noise_flux)
             last_t = time_steps[n + run - 1]
             is_sampled = last_t in sampled
             status = eng.step(run, diag=is_sampled)

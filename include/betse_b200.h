@@ -224,6 +224,11 @@ int  betse_set_channels(betse_ctx *ctx, int n, const betse_channel *channels, in
 /* Gate states / open probability / last flux / DChan (networks.py:3164) of channel k, [M] each (NULL members are skipped). */
 int  betse_channel_state(betse_ctx *ctx, int k, double *m, double *h, double *P, double *flux, double *DChan);
 
+/* Dynamic noise (sim.py:1322-1339): protein_noise_flux [M] = p.dynamic_noise_level*(np.random.random(mdl) - 0.5), drawn by
+ * the host from the reference's own random stream, applied to ion `ion` (P) by the NEXT timestep only — update_Co after
+ * the networks and before update_all_concs. */
+int  betse_set_noise_flux(betse_ctx *ctx, int ion, const double *flux);
+
 /* Page-locked host staging for sampled-step downloads (the buffers write2storage copies from, sim.py:1789-1884):
  * device->host copies into these run at PCIe speed without the driver's bounce buffer. */
 int  betse_host_alloc(size_t bytes, void **out);

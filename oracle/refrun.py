@@ -207,6 +207,9 @@ class LoopRecorder:
             for n in range(min(nmax, len(time_steps))):
                 orig(sim, phase=phase, time_steps=time_steps[n:n + 1],
                      time_steps_sampled=time_steps_sampled, anim_cells=anim_cells)
+                if kind == "sim" and getattr(phase.p, "dynamic_noise", False) and hasattr(sim, "protein_noise_flux"):
+                    # the random walk on the protein concentration of THIS step (sim.py:1322-1339): the replay needs the draw
+                    cap["sim.noise.k%d" % (n + 1)] = np.array(sim.protein_noise_flux, dtype=float, copy=True)
                 cur = snapshot(sim, sched_fields)
                 for f, v in cur.items():
                     if f not in prev or prev[f].shape != v.shape or not np.array_equal(prev[f], v):

@@ -336,6 +336,13 @@ SCENARIOS["mammal_ecm_net_events"] = dict(
     snaps={"init": [1, 2, 5, 13], "sim": [1, 2, 4, 6, 9, 20]}, extra=net_extra)
 
 
+# dynamic noise (sim.py:1322-1339): a random walk on the protein concentration, one np.random.random(mdl) draw per SIM step
+SCENARIOS["mammal_ecm_dynnoise"] = dict(
+    mods=_m(NO_NET, SMALL, {"general options": {"ion profile": "mammal"},
+                            "variable settings": {"noise": {"dynamic noise": True, "dynamic noise level": 1.0e-6}}}),
+    snaps={"init": [1, 2], "sim": [1, 2, 5, 20]})
+
+
 # The external-voltage event (tissue/event/tisevevolt.py: bound_V ramps, Phi_b = one Dirichlet Poisson solve per step,
 # ion_current.py:84-90, subtracted from Vmem in update_V, sim.py:2029) — ramp up, plateau and ramp down inside the
 # first 20 SIM steps, left/right electrodes so that it differs from the top/bottom default; ECM and no-ECM

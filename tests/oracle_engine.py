@@ -102,6 +102,10 @@ class OracleEngine:
             return c, np.asarray(r)
         return c
 
+    def set_noise_flux(self, flux, ion="P"):
+        self.sets.append("noise")
+        self._sim().noise_flux = np.array(flux, dtype=float)
+
     def set_network_events(self, handler, c_bound=None, clamp=None):
         self.sets.append("net_events")
         net = self._sim().networks[sorted(self._descs).index(int(handler))]

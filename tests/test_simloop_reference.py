@@ -331,3 +331,24 @@ def test_substance_events_through_the_dropin_match_the_reference(monkeypatch, tm
         for x, y in zip(a.c_cells_time + a.c_env_time, r.c_cells_time + r.c_env_time):
             assert np.max(np.abs(np.asarray(x) - np.asarray(y))) <= 1e-9 * max(np.max(np.abs(np.asarray(y))), 1e-300), name
     assert abs(new_sim.molecules.core.molecules["B1"].c_bound - ref_sim.molecules.core.molecules["B1"].c_bound) <= 1e-12
+
+
+def test_dynamic_noise_through_the_dropin_matches_the_reference(monkeypatch, tmp_path):
+    """Dynamic noise (sim.py:1322-1339): the loop draws protein_noise_flux from NumPy's global stream every SIM step, as
+    the reference does, and hands it to the engine (TissueEngine.set_noise_flux); with the same seed both runs walk the
+    protein concentration alike."""
+    from tests.golden import make_golden as mg
+    mods = mg.SCENARIOS["mammal_ecm_dynnoise"]["mods"]
+    ref_sim, _, _ = _run_try(tmp_path / "ref", False, mods=mods)
+    (tmp_path / "new").mkdir()
+    new_sim, _, engines = _run_try(tmp_path / "new", True, monkeypatch, mods=mods)
+    assert engines[1].sets.count("noise") >= 100               # one draw per SIM step
+    assert "noise" not in engines[0].sets                      # INIT draws nothing
+    iP = ref_sim.iP
+    assert np.ptp(ref_sim.cc_time[-1][iP]) > 0                 # the walk happened
+    assert np.array_equal(new_sim.protein_noise_flux, ref_sim.protein_noise_flux)
+    for a, r in zip(new_sim.cc_time, ref_sim.cc_time):
+        a, r = np.asarray(a), np.asarray(r)
+        assert np.max(np.abs(a[iP] - r[iP])) <= 1e-10 * np.max(np.abs(r[iP]))
+    for a, r in zip(new_sim.vm_time, ref_sim.vm_time):
+        assert np.max(np.abs(a - r)) <= 1e-9 * np.max(np.abs(r))

@@ -44,6 +44,9 @@ def apply_schedule(obj, cap, kind, n):
     targets = [str(t) for h in range(2) for t in cap.get("%s.s0.net%d.modulator_targets" % (kind, h), [])]
     skip = {"GJ": "gj_block", "Na/K-ATPase": "NaKATP_block"}
     skip = {skip[t] for t in targets if t in skip}
+    key = "%s.noise.k%d" % (kind, n)
+    if key in cap:          # dynamic noise: the reference's own draw of this step (oracle/refrun.py)
+        obj.set_noise_flux(cap[key]) if hasattr(obj, "set_noise_flux") else setattr(obj, "noise_flux", np.array(cap[key], dtype=float))
     for f, v in group(cap, "%s.sched.k%d." % (kind, n)).items():
         if f in skip:
             continue
