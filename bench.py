@@ -284,7 +284,7 @@ def main():
             wall = float(t.item())
         e2e = {"value": M * n_e2e / wall, "unit": UNIT,
                "h2d_bytes_per_step": stats["h2d_bytes"] / n_e2e, "d2h_bytes_per_step": stats["d2h_bytes"] / n_e2e,
-               "timesteps": n_e2e, "sampled_steps": sim.sampled,
+               "timesteps": n_e2e, "sampled_steps": sim.sampled, "seconds": stats.get("seconds"),
                "what": "run_sim_core_loop() (the Simulator._run_sim_core_loop drop-in) from host NumPy state: "
                        "engine creation + full state upload + timesteps + download of every write2storage "
                        "attribute at each sampled step and at the end"}

@@ -164,9 +164,14 @@ static bool host_is_pinned(const void* p)
 // copy, so the chunk is split over a few threads
 static void par_memcpy(char* dst, const char* src, size_t n)
 {
-    const int T = 4;
+    static const int T = [] {
+        const unsigned hw = std::thread::hardware_concurrency();
+        const char* e = getenv("BETSE_COPY_THREADS");
+        const int n = e ? atoi(e) : 0;
+        return n >= 1 ? (n > 8 ? 8 : n) : (int)(hw >= 16 ? 8 : hw >= 8 ? 4 : 2);
+    }();
     if (n < ((size_t)2 << 20)) { memcpy(dst, src, n); return; }
-    std::thread th[T - 1];
+    std::thread th[8];
     const size_t per = ((n / T) + 4095) & ~(size_t)4095;
     for (int t = 1; t < T; ++t) {
         const size_t off = (size_t)t * per;
@@ -1578,6 +1583,19 @@ extern "C" int betse_host_alloc(size_t bytes, void** out)
     if (!out) return 2;
     *out = nullptr;
     return cudaHostAlloc(out, bytes ? bytes : 8, cudaHostAllocDefault) == cudaSuccess ? 0 : 1;
+}
+
+extern "C" int betse_host_alloc_on(int device, size_t bytes, void** out)
+{
+    if (!out) return 2;
+    *out = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess) return 1;
+    return cudaHostAlloc(out, bytes ? bytes : 8, cudaHostAllocDefault) == cudaSuccess ? 0 : 1;
+}
+
+extern "C" void betse_host_copy(void* dst, const void* src, size_t bytes)
+{
+    par_memcpy(static_cast<char*>(dst), static_cast<const char*>(src), bytes);
 }
 
 extern "C" void betse_host_free(void* p)

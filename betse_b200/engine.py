@@ -48,6 +48,43 @@ def _scalar(v):
     return float(np.asarray(v).reshape(-1)[0]) if np.ndim(v) else float(v)
 
 
+def _pinned_array(lib, ptr, n, shape):
+    """NumPy view of page-locked memory that frees it (betse_host_free) when the last view dies — an array lent to the
+    Simulator at the end of a phase simply outlives the engine, no copy."""
+    import weakref
+    raw = (C.c_double * n).from_address(ptr.value)
+    weakref.finalize(raw, lib.betse_host_free, C.c_void_p(ptr.value))
+    return np.ctypeslib.as_array(raw).reshape(shape)
+
+
+class PinnedPrefetch:
+    """Page-locked staging for the sampled-step downloads, allocated on a helper thread: pinning a few hundred MB costs
+    as much as uploading the tissue, so the loop starts it before it builds the engine (TissueEngine.adopt_pinned)."""
+
+    def __init__(self, device, shapes):
+        import threading
+        self.lib = capi.load()
+        self.device, self.shapes, self.got = int(device), dict(shapes), {}
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        for name, shape in self.shapes.items():
+            n = int(np.prod(shape))
+            ptr = C.c_void_p()
+            if self.lib.betse_host_alloc_on(self.device, C.c_size_t(n * 8), C.byref(ptr)) != 0 or not ptr.value:
+                return                  # the engine allocates what is missing (and reports the failure) itself
+            self.got[name] = _pinned_array(self.lib, ptr, n, shape)
+
+    def join(self):
+        self.thread.join()
+        got, self.got = self.got, {}
+        return got
+
+    def release(self):
+        self.join().clear()
+
+
 class TissueEngine:
     def __init__(self, mesh, params, state=None, device=0, partition=None):
         """``mesh``: dict of Cells arrays (keys as in oracle/refrun.py CELLS_FIELDS);
@@ -346,17 +383,26 @@ class TissueEngine:
         names = [self.lib.betse_kernel_name(k).decode() for k in range(capi.NKERNELS)]
         return float(tot.value), {names[k]: float(kms[k]) for k in range(capi.NKERNELS) if kl[k]}
 
+    def adopt_pinned(self, prefetch):
+        """Take over staging that a PinnedPrefetch allocated while this engine was being built."""
+        self.__dict__["_prefetch"] = prefetch
+
     def _pinned_buffer(self, name, shape):
         """A reusable page-locked array for ``name`` (betse_host_alloc); freed by close()."""
         pool = self.__dict__.setdefault("_pinned", {})
+        pf = self.__dict__.pop("_prefetch", None)
+        if pf is not None:
+            for k, arr in pf.join().items():
+                pool.setdefault(k, arr)
+        if name in pool and pool[name].shape != tuple(shape):
+            del pool[name]
         if name not in pool:
             n = int(np.prod(shape))
             ptr = C.c_void_p()
             if self.lib.betse_host_alloc(C.c_size_t(n * 8), C.byref(ptr)) != 0 or not ptr.value:
                 raise BetseB200Error("betse_host_alloc(%d bytes) failed" % (n * 8))
-            arr = np.ctypeslib.as_array((C.c_double * n).from_address(ptr.value)).reshape(shape)
-            pool[name] = (ptr, arr)
-        return pool[name][1]
+            pool[name] = _pinned_array(self.lib, ptr, n, shape)
+        return pool[name]
 
     def download(self, fields=("cc_cells", "cc_at_mem", "cc_env", "vm", "gjopen", "rho_cells",
                                "E_env_x", "E_env_y", "v_env", "rho_env"), pinned=False):
@@ -667,8 +713,10 @@ class TissueEngine:
         return int(st.value)
 
     def close(self):
-        for ptr, _ in self.__dict__.pop("_pinned", {}).values():
-            self.lib.betse_host_free(ptr)
+        pf = self.__dict__.pop("_prefetch", None)
+        if pf is not None:
+            pf.release()
+        self.__dict__.pop("_pinned", {}).clear()        # staging not lent to anyone is freed here (see _pinned_array)
         if getattr(self, "ctx", None):
             self.lib.betse_destroy(self.ctx)
             self.ctx = None

@@ -20,13 +20,14 @@ method to :func:`run_sim_core_loop`, which keeps the reference's contract —
 The function is duck-typed on ``sim`` / ``phase.cells`` / ``phase.p`` (no reference import),
 so the same code path is exercised on the GPU box from recorded reference states.
 """
+import os
 import time
 
 import numpy as np
 
 from . import capi
 from .capi import BetseB200Error
-from .engine import TissueEngine
+from .engine import PinnedPrefetch, TissueEngine, _DOWN_SHAPES
 from .network import event_values as netlib_event_values
 
 _P_FIELDS = [
@@ -203,17 +204,39 @@ def engine_from_sim(sim, cells, p, device=0, phase_init=False):
     return eng
 
 
+def _sample_fields(is_ecm, diag, noecm_field=False):
+    """The per-sample download: what write2storage reads."""
+    noecm_field = diag and not is_ecm and noecm_field
+    fields = _W2S_STATE + (_W2S_ENV if is_ecm else ["cc_env"]) + (_W2S_DIAG if diag else [])
+    if noecm_field:
+        fields += ["v_env"]                    # venv_time: the local field potential (ion_current.py:158)
+    if diag and (is_ecm or noecm_field):
+        fields += ["J_env_x", "J_env_y"]       # I_tot_x_time / I_tot_y_time (sim.py:1866-1867)
+    return fields
+
+
+def _prefetch_staging(cells, p, device):
+    """Start pinning the sampled-step staging while the engine is being built (ECM tissues; anything unexpected:
+    no prefetch, the engine allocates on first use)."""
+    try:
+        if not bool(p.is_ecm):
+            return None
+        I = len(params_from_p(p)["ions"])
+        X = getattr(cells, "X", None)
+        E = int(np.prod(X.shape if X is not None else cells.grid_shape))
+        dims = {"I": I, "C": len(cells.cell_vol), "M": len(cells.mem_sa), "E": E}
+        shapes = {f: tuple(dims[k] for k in _DOWN_SHAPES[f]) for f in _sample_fields(True, True)}
+        return PinnedPrefetch(device, shapes)
+    except Exception:
+        return None
+
+
 def _copy_back(sim, eng, diag, sample_only=False):
     """Device state -> Simulator attributes.  ``sample_only``: just what write2storage reads, through the
     engine's page-locked staging (views that the next sample overwrites — write2storage copies what it
     keeps; vm_ave, which it appends as is (sim.py:1877), gets its own array)."""
     if sample_only:
-        noecm_field = diag and not eng.is_ecm and getattr(eng, "noecm_field", False)
-        fields = _W2S_STATE + (_W2S_ENV if eng.is_ecm else ["cc_env"]) + (_W2S_DIAG if diag else [])
-        if noecm_field:
-            fields += ["v_env"]                    # venv_time: the local field potential (ion_current.py:158)
-        if diag and (eng.is_ecm or noecm_field):
-            fields += ["J_env_x", "J_env_y"]       # I_tot_x_time / I_tot_y_time (sim.py:1866-1867)
+        fields = _sample_fields(eng.is_ecm, diag, getattr(eng, "noecm_field", False))
     else:
         fields = list(_SAMPLED_STATE)
         if eng.is_ecm:
@@ -240,8 +263,8 @@ def _copy_back(sim, eng, diag, sample_only=False):
         tg = slice(None) if cc.targets is None else np.asarray(cc.targets)
         cc.m, cc.h, cc.P, cc.chan_flux, cc.DChan = stt["m"][tg], stt["h"][tg], stt["P"], stt["flux"], stt["DChan"]
     # network substances (read by MasterOfNetworks.write_data, networks.py:4210-4260, and the exporters)
-    m2c = eng.mem_to_cells.astype(np.int64)
     for h, core in getattr(eng, "net_cores", {}).items():
+        m2c = eng.mem_to_cells.astype(np.int64)
         c, rates = eng.network_state(h, rates=True)
         env_on = eng.networks[h].get("env_on")
         cenv = eng.network_env_state(h) if env_on is not None and np.any(env_on) else None
@@ -272,11 +295,19 @@ def _copy_back(sim, eng, diag, sample_only=False):
     return 0
 
 
-def _detach(sim, eng):
-    """Before the engine dies: any Simulator attribute still aliasing its page-locked staging gets its own copy."""
-    for f, a in getattr(eng, "_lent", {}).items():
+def _detach(sim, eng, own_engine=False):
+    """Simulator attributes still aliasing the engine's page-locked staging: an engine that dies now leaves them the
+    memory (engine._pinned_array frees it with the last view); one that lives on will overwrite its staging, so they get
+    their own copy."""
+    for f, a in ({} if own_engine else getattr(eng, "_lent", {})).items():
         if getattr(sim, f, None) is a:
-            setattr(sim, f, np.array(a, copy=True))
+            lib = getattr(eng, "lib", None)
+            if lib is not None and a.flags.c_contiguous:
+                own = np.empty_like(a)
+                lib.betse_host_copy(own.ctypes.data, a.ctypes.data, a.nbytes)
+            else:
+                own = np.array(a, copy=True)
+            setattr(sim, f, own)
     eng.__dict__["_lent"] = {}
 
 
@@ -297,8 +328,24 @@ def run_sim_core_loop(sim, phase, time_steps, time_steps_sampled, anim_cells=Non
         # own call for this step finds the event fired and only re-evaluates the scheduled scalars for the same t.
         fire(phase=phase, t=time_steps[0])
         cells = phase.cells
-    eng = engine or engine_from_sim(sim, cells, p, device=device, phase_init=not is_sim)
+    t0 = time.time()
+    tm = {"engine": 0.0, "steps": 0.0, "samples": 0.0, "final": 0.0, "close": 0.0}
     sampled = set(time_steps_sampled)
+    if engine is None:
+        pf = _prefetch_staging(cells, p, device) if (
+            anim_cells is None and len(sampled) > 1 and hasattr(TissueEngine, "adopt_pinned")
+            and os.environ.get("BETSE_PIN_PREFETCH", "1") != "0") else None
+        try:
+            eng = engine_from_sim(sim, cells, p, device=device, phase_init=not is_sim)
+        except BaseException:
+            if pf is not None:
+                pf.release()
+            raise
+        if pf is not None:
+            eng.adopt_pinned(pf)
+    else:
+        eng = engine
+    tm["engine"] = time.time() - t0
     noisy = is_sim and getattr(p, "dynamic_noise", False) == 1 and "P" in eng.ions
     Unstable = _unstable_exception()
     h2d = d2h = 0
@@ -306,7 +353,6 @@ def run_sim_core_loop(sim, phase, time_steps, time_steps_sampled, anim_cells=Non
     cache = {f: np.array(getattr(sim, f), copy=True) for f in _SCHEDULED if hasattr(sim, f)
              and getattr(sim, f) is not None} if fire else {}
     bv_cache = dict(getattr(sim, "bound_V", {})) if fire else {}
-    t0 = time.time()
     n_total = len(time_steps)
     n = 0
     try:
@@ -345,7 +391,9 @@ def run_sim_core_loop(sim, phase, time_steps, time_steps_sampled, anim_cells=Non
                 eng.set_noise_flux(sim.protein_noise_flux)
             last_t = time_steps[n + run - 1]
             is_sampled = last_t in sampled
+            t1 = time.time()
             status = eng.step(run, diag=is_sampled)
+            tm["steps"] += time.time() - t1
             n += run
             if status & capi.STATUS_NEG_NET:
                 d2h += _copy_back(sim, eng, diag=False)
@@ -358,23 +406,29 @@ def run_sim_core_loop(sim, phase, time_steps, time_steps_sampled, anim_cells=Non
             if is_sampled:
                 # the last step of the phase leaves complete, engine-independent arrays on the Simulator
                 final = n >= n_total
+                t1 = time.time()
                 d2h += _copy_back(sim, eng, diag=True, sample_only=(anim_cells is None and not final))
+                tm["final" if final else "samples"] += time.time() - t1
                 phase.callbacks.progressed_next()
                 sim.write2storage(last_t, cells, p)
                 if anim_cells is not None:
                     anim_cells.plot_frame(time_step=-1)
         # leave the Simulator holding the final state, like the reference does
         if n_total and time_steps[n_total - 1] not in sampled:
+            t1 = time.time()
             d2h += _copy_back(sim, eng, diag=False)
+            tm["final"] += time.time() - t1
     finally:
-        if stats is not None:
-            h2d = eng.h2d_bytes - (0 if own_engine else h2d0)
-            d2h = eng.d2h_bytes - (0 if own_engine else d2h0)
-            stats.update({"h2d_bytes": h2d, "d2h_bytes": d2h, "wall_s": time.time() - t0,
-                          "steps": n})
-        _detach(sim, eng)
+        h2d = eng.h2d_bytes - (0 if own_engine else h2d0)
+        d2h = eng.d2h_bytes - (0 if own_engine else d2h0)
+        t1 = time.time()
+        _detach(sim, eng, own_engine)
         if own_engine:
             eng.close()
+        tm["close"] = time.time() - t1
+        if stats is not None:
+            stats.update({"h2d_bytes": h2d, "d2h_bytes": d2h, "wall_s": time.time() - t0, "steps": n,
+                          "seconds": {k: round(v, 4) for k, v in tm.items()}})
 
 
 _installed = None

@@ -232,6 +232,10 @@ int  betse_set_noise_flux(betse_ctx *ctx, int ion, const double *flux);
 /* Page-locked host staging for sampled-step downloads (the buffers write2storage copies from, sim.py:1789-1884):
  * device->host copies into these run at PCIe speed without the driver's bounce buffer. */
 int  betse_host_alloc(size_t bytes, void **out);
+/* the same from a helper thread (binds `device` first): staging can be pinned while the engine is being built */
+int  betse_host_alloc_on(int device, size_t bytes, void **out);
+/* dst[0..bytes) = src[0..bytes) split over a few threads: a fresh NumPy destination is first-touch page faults */
+void betse_host_copy(void *dst, const void *src, size_t bytes);
 void betse_host_free(void *p);
 
 /* ---------------------------------------------------------------------------------------------

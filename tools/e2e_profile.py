@@ -29,8 +29,7 @@ t = tic(); got = eng.download(list(simloop._W2S_STATE + simloop._W2S_ENV + simlo
 t = tic(); eng.step(1, diag=True); T["1 step with diagnostics (k_diag + Helmholtz-Hodge)"] = tic() - t
 t = tic(); eng.step(1); T["1 step"] = tic() - t
 t = tic()
-for ptr, _ in eng.__dict__.pop("_pinned", {}).values():
-    eng.lib.betse_host_free(ptr)
+eng.__dict__.pop("_pinned", {}).clear()
 T["close: free pinned staging"] = tic() - t
 t = tic(); eng.close(); T["close: betse_destroy"] = tic() - t
 for k, v in T.items(): print("%-40s %8.1f ms" % (k, v * 1e3))
