@@ -149,6 +149,7 @@ class Network(C.Structure):
         ("transporters", C.POINTER(Transporter)), ("n_transporters", C.c_int32), ("reserved", C.c_int32),
         ("mem_sa_over_vol", _dp),
         ("intra_on", _bp), ("Do", _dp), ("c_mems", _dp), ("R_rads", _dp), ("map_cell2ecm", _ip),
+        ("mu_mem", _dp), ("Emc", _dp),
     ]
 
 

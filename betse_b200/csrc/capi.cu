@@ -103,6 +103,7 @@ struct betse_ctx {
     double* noise_flux = nullptr;
     int noise_ion = -1;
     bool noise_on = false, noise_pending = false;
+    bool need_emc = false;          // a network substance reads sim.Emc every step (update_intra of charged substances)
     std::vector<unsigned char> net_intra[2];        // substances with intracellular transport (membrane values of their own)
     double* lig_tmp[2] = {nullptr, nullptr};       // [n_gates][M] openings formed before the substances advance
     std::string err;
@@ -911,7 +912,7 @@ static void enqueue_step(betse_ctx* ctx, int diag, cudaEvent_t* evs)
     // cell_polarizability != 0: update_V integrates Vmem from Jn (sim.py:2059-2061), so get_current's membrane part
     // (k_diag) belongs to every step; the Helmholtz-Hodge part stays with the sampled steps
     ctx->want_hh = diag != 0;
-    if (ctx->P.polar) diag = 1;
+    if (ctx->P.polar || ctx->need_emc) diag = 1;
     if (evs) cudaEventRecord(evs[0], ctx->stream);
     const bool nbr = ctx->X.n_nbr > 0;
     const int nxt = ctx->cur ^ 1;
@@ -1134,6 +1135,20 @@ extern "C" int betse_download_sample(betse_ctx* ctx, betse_state_host* s)
     if (s->Phi_b) {                                    // sim.Phi_b of the last update_V (ion_current.py:114, 171)
         if (A.phi_b) CK(cudaMemcpyAsync(s->Phi_b, A.phi_b, (size_t)E * sizeof(double), cudaMemcpyDeviceToHost, st));
         else memset(s->Phi_b, 0, (size_t)E * sizeof(double));
+    }
+    // what the network handlers published last (networks.py:2971-2977): the host's update_V of the NEXT phase reads them
+    if (s->extra_rho_cells) {
+        if (A.extra_rho_cells) CK(cudaMemcpyAsync(s->extra_rho_cells, A.extra_rho_cells, (size_t)C * sizeof(double), cudaMemcpyDeviceToHost, st));
+        else memset(s->extra_rho_cells, 0, (size_t)C * sizeof(double));
+    }
+    if (s->extra_rho_env) {
+        if (A.extra_rho_env) CK(cudaMemcpyAsync(s->extra_rho_env, A.extra_rho_env, (size_t)E * sizeof(double), cudaMemcpyDeviceToHost, st));
+        else memset(s->extra_rho_env, 0, (size_t)E * sizeof(double));
+    }
+    if (s->extra_J_mem) {
+        const double* src = (ctx->P.chan_charge && A.chanJ) ? A.chanJ : A.extra_J_mem;
+        if (src) CK(cudaMemcpyAsync(s->extra_J_mem, src, (size_t)Mo * sizeof(double), cudaMemcpyDeviceToHost, st));
+        else memset(s->extra_J_mem, 0, (size_t)Mo * sizeof(double));
     }
     DN(s->gjopen, A.gjopen, Mo);
     DN(s->Dm_cells, A.Dm, IM);
@@ -1418,6 +1433,17 @@ extern "C" int betse_set_network(betse_ctx* ctx, int handler, const betse_networ
             if ((r = dev_upload(ctx, (double**)&N.R_rads, net->R_rads, (size_t)Mo))) return r;
             if (!N.sa_over_vol) { if ((r = dev_upload(ctx, (double**)&N.sa_over_vol, net->mem_sa_over_vol, (size_t)Mo))) return r; }
             ctx->net_intra[handler].assign(net->intra_on, net->intra_on + K);
+            if ((r = dev_alloc(ctx, &N.gjf, (size_t)Mo))) return r;
+            if (net->mu_mem) { if ((r = dev_upload(ctx, (double**)&N.mu_mem, net->mu_mem, (size_t)K))) return r; }
+            // charged substances drift in the cell's field: sim.Emc (k_diag) is then part of every step
+            for (int k = 0; k < K; ++k)
+                if (net->intra_on[k] && (net->z[k] != 0.0 || (net->mu_mem && net->mu_mem[k] != 0.0))) ctx->need_emc = true;
+            if (ctx->need_emc) {
+                if (ctx->X.n_nbr > 0) return fail(ctx, "network: 'update intracellular' of a charged substance on a domain-decomposed tissue is not implemented");
+                if ((r = ensure_diag_buffers(ctx))) return r;
+                if (net->Emc) { if ((r = xfer(ctx, ctx->A.Emc, net->Emc, (size_t)Mo * sizeof(double), cudaMemcpyHostToDevice))) return r; }
+                destroy_graphs(ctx);
+            }
         }
     }
     ctx->net_pumps[handler].clear();

@@ -47,7 +47,7 @@ k_net(const __grid_constant__ KParams P, const KArrays A, const __grid_constant_
 // gap-junction transport of substance k: per-cell sum of -f_gj*mem_sa (one warp per tile, the packing of k_mem)
 __global__ void __launch_bounds__(BT_TPB)
 k_net_gj(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ KNet N, const int k, const int cur,
-         const int nonces, const int has_mem)
+         const int nonces, const int has_mem, const int use_cmem)
 {
     __shared__ double s_all[(BT_TPB / 32) * 32];
     const int lane = threadIdx.x & 31;
@@ -76,11 +76,16 @@ k_net_gj(const __grid_constant__ KParams P, const KArrays A, const __grid_consta
             const double zc = __ldg(N.z + k) + FLOAT_NONCE;
             const double alpha = ((zc * vBA) * P.F) / P.RT_p;              // p.T (sim_toolbox.py:986)
             const double ex = exp(-alpha), deno = -expm1(-alpha);
-            const double cA = cc[c], cB = cc[cn];                          // cX_mems[mem_i], cX_mems[nn_i]
+            double cA = cc[c], cB = cc[cn];                                // cX_mems[mem_i], cX_mems[nn_i]
+            if (use_cmem) {                                                // 'update intracellular': the transported membrane values
+                const double* __restrict__ cmv = N.cmem + (size_t)k * P.n_mems_owned;
+                cA = cmv[m]; cB = cmv[__ldg(A.nn_i + m)];
+            }
             const double f = -((D * alpha) / P.gj_len) * ((cB - cA * ex) / deno);
             fsa = -f * __ldg(A.mem_sa + m);
             fgj = f;
         }
+        if (use_cmem) N.gjf[m] = fgj;
         if (N.affect) {                                                    // networks.py:2946
             const double z = __ldg(N.z + k), sc = __ldg(N.scale + k);
             const double fm = has_mem ? N.fmem_tmp[m] : 0.0;
@@ -337,7 +342,7 @@ void launch_net_lig(const KParams& P, const KArrays& A, int ion, const double* D
 //                   (sim_toolbox.py:1061-1112); same stencil conventions as kernels.cu:k_ion.
 __global__ void __launch_bounds__(BT_TPB)
 k_net_mem(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ KNet N, const int k, const int cur,
-          const double* __restrict__ csrc)
+          const double* __restrict__ csrc, const int use_cmem)
 {
     __shared__ double s_all[(BT_TPB / 32) * 32];
     const int lane = threadIdx.x & 31;
@@ -359,9 +364,11 @@ k_net_mem(const __grid_constant__ KParams P, const KArrays A, const __grid_const
         else if (P.has_phi) vm -= __ldg(A.phi_b_old + e);
         const double alpha = ((zc * (vm + FLOAT_NONCE)) * P.F) / P.RT_sim;    // sim.T (sim_toolbox.py:947)
         const double ex = exp(-alpha), deno = -expm1(-alpha);
-        const double cA = N.c_env[(size_t)k * E + e], cB = csrc ? csrc[c] : N.c[(size_t)k * C + c];
+        double* cmv = use_cmem ? N.cmem + (size_t)k * P.n_mems_owned + m : nullptr;
+        const double cA = N.c_env[(size_t)k * E + e], cB = cmv ? *cmv : csrc ? csrc[c] : N.c[(size_t)k * C + c];
         double f = -((Dm * alpha) / P.tm) * ((cB - cA * ex) / deno) * P.rho_channel;
         if (!P.cluster_open && __ldg(A.nn_cell_flag + m) < 0) f = 0.0;        // f_X_ED[cells.bflags_mems] = 0
+        if (cmv) *cmv = cB + (f * (__ldg(N.sa_over_vol + m) / 0.75)) * P.dt;  // update_Co(update_at_mems=True), sim_toolbox.py:1183-1185
         fsa = f * __ldg(A.mem_sa + m);
         A.chan_slots[m] = fsa;
         if (N.affect) {
@@ -553,8 +560,9 @@ k_sub_div(const __grid_constant__ KParams P, const KArrays A, const __grid_const
     c[q] = cn;
 }
 
-// Molecule.update_intra with intracellular transport (networks.py:5727-5795) for a neutral substance (En = uflow = 0):
-// the membrane value relaxes implicitly towards the cell value the step started with
+// Molecule.update_intra with intracellular transport (networks.py:5727-5795; transmem False, no motor transport): the
+// membrane value relaxes implicitly towards the cell value the step started with; charged substances also drift in the
+// cell's field normal to the membrane (sim.Emc of the previous step's update_V)
 __global__ void __launch_bounds__(256)
 k_net_intra(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ KNet N, const int k)
 {
@@ -564,9 +572,30 @@ k_net_intra(const __grid_constant__ KParams P, const KArrays A, const __grid_con
     const double Do = __ldg(N.Do + k), dt = P.dt * __ldg(N.tdf + k), Rr = __ldg(N.R_rads + m);
     const double cav = N.c[(size_t)k * P.n_cells + __ldg(A.mem_to_cells + m)];
     double* cm = N.cmem + (size_t)k * P.n_mems_owned + m;
-    const double alpha_tot = 0.0;
-    *cm = (((((g * Do) * dt) * cav) / Rr) + ((((g * alpha_tot) * cav) * dt) / 2.0) + *cm) /
-          ((1.0 + (((g * Do) * dt) / Rr)) - (((g * alpha_tot) * dt) / 2.0));
+    const double z = __ldg(N.z + k), mu = N.mu_mem ? __ldg(N.mu_mem + k) : 0.0;
+    double alpha_tot = 0.0;
+    if (z != 0.0 || mu != 0.0) {
+        const double En = A.Emc[m];
+        alpha_tot = ((0.0 + (((Do * P.q) * z) / P.kbT_sim) * En) + mu * En) + 0.0;
+    }
+    const double v = (((((g * Do) * dt) * cav) / Rr) + ((((g * alpha_tot) * cav) * dt) / 2.0) + *cm) /
+                     ((1.0 + (((g * Do) * dt) / Rr)) - (((g * alpha_tot) * dt) / 2.0));
+    if (v < 0.0) atomicOr(A.status, ST_NEG_NET);                             // networks.py:5798-5804
+    *cm = v;
+}
+
+// the membrane values of an 'update intracellular' substance after its gap-junction flux (sim_toolbox.py:1001-1005),
+// and molecule_mover's closing check of them (sim_toolbox.py:1139-1142)
+__global__ void __launch_bounds__(256)
+k_net_cmem_gj(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ KNet N, const int k)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= P.n_mems_owned) return;
+    const double g = __ldg(N.sa_over_vol + m) / 0.75;
+    double* cm = N.cmem + (size_t)k * P.n_mems_owned + m;
+    const double v = *cm + (((-N.gjf[m]) * g) * __ldg(N.tdf + k)) * P.dt;
+    if (v < 0.0) atomicOr(A.status, ST_NEG_NET);
+    *cm = v;
 }
 
 void launch_net(const KParams& P, const KArrays& A, const KNet& N, const double* h_Dgj, const double* h_Dm,
@@ -583,7 +612,7 @@ void launch_net(const KParams& P, const KArrays& A, const KNet& N, const double*
     if (N.c_env)
         for (int k = 0; k < N.K; ++k) {
             if (!h_env_on[k] || h_Dm[k] == 0.0 || pump_of(k) >= 0) continue;
-            k_net_mem<<<tgrid, BT_TPB, 0, st>>>(P, A, N, k, cur, nullptr);
+            k_net_mem<<<tgrid, BT_TPB, 0, st>>>(P, A, N, k, cur, nullptr, (N.cmem && h_intra && h_intra[k]) ? 1 : 0);
             k_net_env_acc<<<(E + 255) / 256, 256, 0, st>>>(P, A, N, k);
         }
     // pumped substances: pump (from the concentration after growth/decay), then the membrane leg (from the
@@ -599,7 +628,7 @@ void launch_net(const KParams& P, const KArrays& A, const KNet& N, const double*
         k_net_pump<<<tgrid, BT_TPB, 0, st>>>(P, A, N, k, q.into_cell, q.uses_ATP, q.max_val, q.Km, dG_RT, cur);
         k_net_env_acc<<<(E + 255) / 256, 256, 0, st>>>(P, A, N, k);
         if (h_Dm[k] != 0.0) {
-            k_net_mem<<<tgrid, BT_TPB, 0, st>>>(P, A, N, k, cur, N.c_save + (size_t)j * P.n_cells);
+            k_net_mem<<<tgrid, BT_TPB, 0, st>>>(P, A, N, k, cur, N.c_save + (size_t)j * P.n_cells, 0);
             k_net_apply_mem<<<(P.n_cells_owned + 255) / 256, 256, 0, st>>>(P, N, k);
             k_net_env_acc<<<(E + 255) / 256, 256, 0, st>>>(P, A, N, k);
         }
@@ -609,8 +638,10 @@ void launch_net(const KParams& P, const KArrays& A, const KNet& N, const double*
     for (int k = 0; k < N.K; ++k) {
         if (h_Dgj[k] < 0.0) continue;
         ++nonces;
-        k_net_gj<<<grid, BT_TPB, 0, st>>>(P, A, N, k, cur, nonces, (N.c_env && h_env_on[k] && h_Dm[k] != 0.0) ? 1 : 0);
+        const int use_cmem = (N.cmem && h_intra && h_intra[k]) ? 1 : 0;
+        k_net_gj<<<grid, BT_TPB, 0, st>>>(P, A, N, k, cur, nonces, (N.c_env && h_env_on[k] && h_Dm[k] != 0.0) ? 1 : 0, use_cmem);
         k_net_gj_apply<<<(P.n_cells_owned + 255) / 256, 256, 0, st>>>(P, A, N, k);
+        if (use_cmem) k_net_cmem_gj<<<(P.n_mems_owned + 255) / 256, 256, 0, st>>>(P, A, N, k);
     }
     if (N.c_env) {
         dim3 gE((P.nx + 255) / 256, P.ny);

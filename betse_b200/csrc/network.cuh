@@ -49,6 +49,8 @@ struct KNet {
     const unsigned char* intra; // [K]
     const double* Do;           // [K]
     const double* R_rads;       // [M]
+    const double* mu_mem;       // [K] Molecule.Mu_mem
+    double* gjf;                // [M] gap-junction flux of the substance in flight (membrane values move after all are read)
     double* clamp;              // [K] cell clamp in force this step (NaN: none), Molecule.cell_clamp_method
     const unsigned char* pumped; // [K] 1: the substance has its own pump -> its membrane leg follows the pump (launch_net)
     double* c_save;             // [n_pumps][C] a pumped substance's concentration before growth/decay (cc_at_mem of its membrane leg)

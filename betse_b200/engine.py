@@ -22,6 +22,7 @@ _DOWN_SHAPES = {
     "dvm": "M", "J_cell_x": "C", "J_cell_y": "C", "E_cell_x": "C", "E_cell_y": "C",
     "sigma_cell": "C", "E_gj_x": "M", "E_gj_y": "M",
     "J_env_x": "E", "J_env_y": "E", "B_field": "E", "Jtx": "E", "Jty": "E", "Phi_b": "E",
+    "extra_rho_cells": "C", "extra_rho_env": "E", "extra_J_mem": "M",
 }
 # what get_current leaves on the env grid of a tissue WITHOUT extracellular spaces (ion_current.py:116-158)
 _NOECM_FIELD = ("v_env", "E_env_x", "E_env_y", "J_env_x", "J_env_y", "B_field", "Jtx", "Jty")
@@ -299,6 +300,13 @@ class TissueEngine:
         elif "cc_env" in state:
             ce = np.asarray(state["cc_env"], dtype=float)
             put("cenv_uniform", ce.reshape(I, -1)[:, 0], I)
+        if "E_cell_x" in state and "E_cell_y" in state and "mem_nx" in self.mesh:
+            # sim.Emc as update_V left it (sim.py:2079-2080): what update_intra of a charged substance reads in the
+            # first step (set_network hands it on)
+            ex, ey = np.asarray(state["E_cell_x"], dtype=float), np.asarray(state["E_cell_y"], dtype=float)
+            if ex.shape == (self.Co,) and ey.shape == (self.Co,):
+                m2c = self.mem_to_cells.astype(np.int64)
+                self._Emc0 = ex[m2c] * np.asarray(self.mesh["mem_nx"], dtype=float) + ey[m2c] * np.asarray(self.mesh["mem_ny"], dtype=float)
         if "Phi_b" in state:
             put("Phi_b", state["Phi_b"], E)
         if "D_env_weight" in state and not self.is_ecm:     # no-ECM field diagnostics (ion_current.py:116-158)
@@ -589,6 +597,10 @@ class TissueEngine:
             n.Do = f64(np.asarray(net["Do"], dtype=float).reshape(K))
             n.c_mems = f64(np.asarray(net["c_mems"], dtype=float).reshape(K, self.M))
             n.R_rads = f64(np.asarray(self.mesh["R_rads"], dtype=float))
+            if "mu_mem" in net:
+                n.mu_mem = f64(np.asarray(net["mu_mem"], dtype=float).reshape(K))
+            if getattr(self, "_Emc0", None) is not None:
+                n.Emc = f64(self._Emc0)
             if not trs_needs_vol(net):
                 n.mem_sa_over_vol = f64(np.asarray(self.mesh["mem_sa"], dtype=float) / np.asarray(self.mesh["mem_vol"], dtype=float))
         if "map_cell2ecm" in self.mesh and self.is_ecm:

@@ -47,21 +47,26 @@ def unsupported_reasons(core, p):
         why = []
         if bool(getattr(m, "update_intra_conc", False)):
             # Molecule.update_intra with intracellular transport (networks.py:5714-5806): the membrane value becomes state
-            # of its own.  Implemented where it stays a DIAGNOSTIC (nothing reads it back): neutral substances that neither
-            # cross the membrane nor pass gap junctions and are not pumped, gating or moved by a transporter
+            # of its own: it relaxes towards the cell value (electrophoresis in the cell's field included), and the
+            # membrane and gap-junction legs of molecule_mover read and move IT.  Not implemented where further consumers
+            # read it: pumps, ligand gates, transporters (and membrane-zone rate laws, compile_network)
             blockers = []
-            if float(getattr(m, "z", 0.0) or 0.0) != 0.0 or float(getattr(m, "Mu_mem", 0.0) or 0.0) != 0.0:
-                blockers.append("charged")
-            if float(getattr(m, "Dm", 0.0) or 0.0) != 0.0:
-                blockers.append("membrane-permeable")
-            if not bool(getattr(m, "ignoreGJ", False)):
-                blockers.append("gap-junction permeable")
+            if not bool(getattr(p, "is_ecm", False)) and float(getattr(m, "Dm", 0.0) or 0.0) != 0.0:
+                blockers.append("membrane-permeable in a tissue without extracellular spaces")
             if bool(getattr(m, "active_pumping", False)) and bool(getattr(m, "use_pumping", False)):
                 blockers.append("pumped")
             if bool(getattr(m, "ion_channel_gating", False)) and bool(getattr(m, "use_gating_ligand", False)):
                 blockers.append("gating a channel")
             if any(name in list(t.reactants_list) + list(t.products_list) for t in (getattr(core, "transporters", None) or {}).values()):
                 blockers.append("moved by a transporter")
+            regs = []
+            for holder, attrs in (("channels", ("channel_activators_list", "channel_inhibitors_list")),
+                                  ("modulators", ("modulator_activators_list", "modulator_inhibitors_list"))):
+                for obj in (getattr(core, holder, None) or {}).values():
+                    for a in attrs:
+                        regs += [str(x) for x in (getattr(obj, a, None) or [])]
+            if name in regs:
+                blockers.append("regulating a channel or modulator (membrane-zone rate law)")
             if blockers:
                 why.append("update intracellular of a substance that is " + ", ".join(blockers))
         if bool(getattr(m, "transmem", False)):
@@ -176,6 +181,7 @@ def describe_core(core, sim, p, cells, record_static=True):
     intra = np.array([bool(getattr(core.molecules[s], "update_intra_conc", False)) for s in species], dtype=np.uint8)
     if intra.any():
         desc.update({"intra_on": intra, "Do": np.array([float(core.molecules[s].Do or 0.0) for s in species]),
+                     "mu_mem": np.array([float(getattr(core.molecules[s], "Mu_mem", 0.0) or 0.0) for s in species]),
                      "c_mems": np.stack([np.asarray(core.molecules[s].cc_at_mem, dtype=float) * np.ones(len(cells.mem_sa)) for s in species])})
     # run_loop_transporters (networks.py:2985-3107): flux = rho_pump * eval(transporter_eval_string) on every membrane;
     # each reactant / product moves by coeff * (-/+) sum_mems(flux*mem_sa)/cell_vol in the cells ('mem_concs' tag) or
@@ -341,7 +347,7 @@ def compile_network(desc, n_cells, n_mems, resolver=None):
             "growth_mask": None if mask.all() else mask, "Dgj": np.asarray(desc["Dgj"], dtype=float),
             "z": np.asarray(desc["z"], dtype=float), "time_factor": np.asarray(desc["time_factor"], dtype=float),
             "chan_names": list(desc["chan_names"]),
-            **{k: np.asarray(desc[k]) for k in ("env_on", "Dm", "c_bound", "c_env", "D_env", "scale_factor", "intra_on", "Do", "c_mems") if k in desc}}
+            **{k: np.asarray(desc[k]) for k in ("env_on", "Dm", "c_bound", "c_env", "D_env", "scale_factor", "intra_on", "Do", "mu_mem", "c_mems") if k in desc}}
 
 
 # ---- flat (npz-friendly) form of a description, used by the golden fixtures
@@ -377,7 +383,7 @@ def flatten(desc, prefix):
                     prefix + "modulator_strings": np.array(desc["modulator_strings"], dtype=str),
                     prefix + "modulator_targets": np.array(desc["modulator_targets"], dtype=str),
                     prefix + "modulator_max": np.asarray(desc["modulator_max"], dtype=float)})
-    for k in ("env_on", "Dm", "c_bound", "c_env", "D_env", "scale_factor", "intra_on", "Do", "c_mems"):
+    for k in ("env_on", "Dm", "c_bound", "c_env", "D_env", "scale_factor", "intra_on", "Do", "mu_mem", "c_mems"):
         if k in desc:
             out[prefix + k] = np.asarray(desc[k])
     for k, tg in enumerate(desc["growth_targets"]):
@@ -424,7 +430,7 @@ def unflatten(cap, prefix):
     if prefix + "modulator_names" in cap:
         mods = {**mods, **{"modulator_names": [str(x) for x in g("modulator_names")], "modulator_strings": [str(x) for x in g("modulator_strings")],
                 "modulator_targets": [str(x) for x in g("modulator_targets")], "modulator_max": np.asarray(g("modulator_max"))}}
-    return {**mods, **{k: np.asarray(cap[prefix + k]) for k in ("env_on", "Dm", "c_bound", "c_env", "D_env", "scale_factor", "intra_on", "Do", "c_mems") if prefix + k in cap},
+    return {**mods, **{k: np.asarray(cap[prefix + k]) for k in ("env_on", "Dm", "c_bound", "c_env", "D_env", "scale_factor", "intra_on", "Do", "mu_mem", "c_mems") if prefix + k in cap},
             "species": species, "ions": [str(x) for x in g("ions")], "c_cells": np.asarray(g("c_cells")),
             "gad_strings": [str(x) for x in g("gad_strings")],
             "reaction_names": [str(x) for x in g("reaction_names")],

@@ -41,7 +41,7 @@ _STATE_FIELDS = [
     "cc_cells", "cc_at_mem", "cc_env", "vm", "gjopen", "Dm_cells", "D_gj", "D_free", "zs",
     "c_env_bound", "T", "extra_rho_cells", "extra_rho_env", "extra_J_mem", "ko_env",
     "NaKATP_block", "gj_block", "rho_pump", "rho_channel", "D_env", "TJ_modulator", "E_env_x",
-    "E_env_y", "Phi_b", "D_env_weight", "sigma",
+    "E_env_y", "Phi_b", "D_env_weight", "sigma", "E_cell_x", "E_cell_y",
 ]
 # what fire_events / makeAllChanges may rewrite between steps (tishandler.py:728-917, 1321-1332)
 _SCHEDULED = ["Dm_cells", "D_env", "TJ_modulator", "gj_block", "NaKATP_block", "c_env_bound", "T"]
@@ -239,6 +239,9 @@ def _copy_back(sim, eng, diag, sample_only=False):
         fields = _sample_fields(eng.is_ecm, diag, getattr(eng, "noecm_field", False))
     else:
         fields = list(_SAMPLED_STATE)
+        if getattr(eng, "net_cores", None) or getattr(eng, "chan_specs", None):
+            # what the handlers published last (networks.py:2971-2977): the NEXT phase's update_V reads them on the host
+            fields += ["extra_rho_cells", "extra_J_mem"] + (["extra_rho_env"] if eng.is_ecm else [])
         if eng.is_ecm:
             fields += _SAMPLED_ENV
         if diag:

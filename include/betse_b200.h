@@ -344,6 +344,12 @@ typedef struct betse_network {
     const double  *c_mems;               /* [K][M] cc_at_mem at loop entry (rows with intra_on == 0 ignored) */
     const double  *R_rads;               /* [M] cells.R_rads                                             */
     const int32_t *map_cell2ecm;         /* [C] cells.map_cell2ecm: cell-zone rate laws reading env concentrations (NULL: none do) */
+    /* intra_on substances that are charged / membrane-permeable / gap-junction permeable: the membrane value is state that
+     * feeds back — update_intra adds electrophoresis in the cell's field ((Do*q*z/(kb*T) + Mu_mem)*Emc, Emc as the previous
+     * step's update_V left it; at loop entry from betse_state_host.Emc), and molecule_mover's membrane and gap-junction legs
+     * read and move the membrane values (sim_toolbox.py:962-1005, 1183-1185). */
+    const double  *mu_mem;               /* [K] Molecule.Mu_mem (NULL: zeros)                            */
+    const double  *Emc;                  /* [M] sim.Emc at loop entry (NULL: zeros)                      */
 } betse_network;
 
 /* handler 0 = sim.molecules.core, 1 = sim.grn.core (run in that order, sim.py:1290-1318).  net == NULL

@@ -36,6 +36,7 @@ STATE_FIELDS = [
     "NaKATP_block", "gj_block", "CaATP_block", "rho_pump", "rho_channel",
     "D_env", "TJ_modulator", "E_env_x", "E_env_y", "v_env", "rho_env", "Phi_b", "D_env_weight",
     "rho_cells", "vm_ave", "Jn", "envV",
+    "E_cell_x", "E_cell_y",        # read by Molecule.update_intra of charged substances in the first step
 ]
 # Additional per-step outputs (diagnostics recomputed from scratch every step).
 DIAG_FIELDS = [

@@ -286,6 +286,27 @@ SCENARIOS["mammal_ecm_grn"] = dict(
     snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=net_extra)
 
 
+# 'update intracellular' ON (the default when a config omits the key; the shipped grn_basic.yaml and metabo_basic.yaml do) for
+# substances whose membrane value feeds back: Molecule.update_intra relaxes cc_at_mem towards the cell value, with
+# electrophoresis in the cell's field for charged ones (networks.py:5714-5806); molecule_mover's membrane and gap-junction
+# legs read and move the membrane values (update_at_mems / update_intra branches, sim_toolbox.py:962-1005, 1183-1185).
+# (The shipped metabo_basic.yaml itself cannot serve: the reference halts on it in the first step — "ATP in environment
+# below zero" — with the default world.)
+_INTRA_BIO = [dict(_substance("A", 0.5, Dgj=1e-15, gj_imp=False, cell=0.5, z=-1), **{"Dm": 1.0e-17, "env conc": 0.2,
+                                                                                       "update intracellular": True}),
+              dict(_substance("B", 0.2, Dgj=1e-14, gj_imp=False, cell=0.05, apply_to=["Spot"]), **{"update intracellular": True}),
+              dict(_substance("Cp", 1.0, cell=0.3, z=1), **{"update intracellular": True}),
+              _substance("D", 0.3, acts=[("B", 0.1, 1)])]
+_INTRA_RX = [{"name": "A_to_B", "reaction zone": "cell", "reactants": ["A"], "reactant multipliers": [1],
+              "Km reactants": [0.5], "products": ["B"], "product multipliers": [1], "Km products": [0.1],
+              "max rate": 2.0e-2, "standard free energy": "None"}]
+SCENARIOS["mammal_ecm_net_intra"] = dict(
+    mods=_m(SMALL, {"cutting event": {"event happens": False}, "general options": {"ion profile": "mammal"},
+                    "general network": {"implement network": True, "biomolecules": _INTRA_BIO, "reactions": _INTRA_RX,
+                                        "channels": []}}),
+    snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=net_extra)
+
+
 # both handlers at once (the reference's own `enable_networks` test scenario, betse_test/_fixture/simconf/simconfwrapper.py:252-259):
 # the shipped general network (substance X, Nav1p3 / Kv1p5 / X-inhibited KLeak) AND the shipped gene regulatory network
 SCENARIOS["mammal_ecm_net2"] = dict(

@@ -30,7 +30,8 @@ def _attach(eng, desc, specs, phase_init):
                                      "mammal_ecm_net_trans",                         # _trans: transporters (carrier; electrogenic exporter)
                                      "mammal_ecm_polar_net",                         # per-membrane Vmem (polarizability) under all of it
                                      "mammal_ecm_net_envzone",                       # cell-zone rate laws regulated from outside the cells
-                                     "mammal_ecm_net_events"])                       # boundary ramp and cell clamp of substances
+                                     "mammal_ecm_net_events",                        # boundary ramp and cell clamp of substances
+                                     "mammal_ecm_net_intra"])                        # 'update intracellular': transported membrane values
 def test_network_matches_reference(fixture, kind):
     from betse_b200.engine import TissueEngine
     cap = util.load_golden(fixture)
@@ -69,6 +70,10 @@ def test_network_matches_reference(fixture, kind):
         if "net0.reaction_rates" in ref:
             rr = ref["net0.reaction_rates"]
             assert util.rel_err(rates[-rr.shape[0]:], rr) <= 1e-10
+        if "net0.c_mems" in ref and np.any(desc.get("intra_on", 0)):
+            cm = eng.network_mem_state(0)
+            for k, nme in enumerate(desc["species"]):
+                assert util.rel_err(cm[k], ref["net0.c_mems"][k]) <= 1e-10, (kind, K, nme, "mems", util.rel_err(cm[k], ref["net0.c_mems"][k]))
         for k, ch in enumerate(active):
             j = [s["name"] for s in specs].index(ch["name"])
             stt = eng.channel_state(k)

@@ -352,3 +352,21 @@ def test_dynamic_noise_through_the_dropin_matches_the_reference(monkeypatch, tmp
         assert np.max(np.abs(a[iP] - r[iP])) <= 1e-10 * np.max(np.abs(r[iP]))
     for a, r in zip(new_sim.vm_time, ref_sim.vm_time):
         assert np.max(np.abs(a - r)) <= 1e-9 * np.max(np.abs(r))
+
+
+def test_intracellular_transport_through_the_dropin_matches_the_reference(monkeypatch, tmp_path):
+    """'update intracellular' on for charged, membrane- and gap-junction permeable substances: the membrane values
+    (Molecule.cc_at_mem -> c_mems_time) are transported state that the shim uploads, the engine advances and write_data
+    stores (networks.py:5714-5806; sim_toolbox.py:962-1005, 1183-1185)."""
+    from tests.golden import make_golden as mg
+    mods = mg.SCENARIOS["mammal_ecm_net_intra"]["mods"]
+    ref_sim, _, _ = _run_try(tmp_path / "ref", False, mods=mods)
+    (tmp_path / "new").mkdir()
+    new_sim, _, engines = _run_try(tmp_path / "new", True, monkeypatch, mods=mods)
+    for name in ("A", "B", "Cp", "D"):
+        a, r = new_sim.molecules.core.molecules[name], ref_sim.molecules.core.molecules[name]
+        assert len(a.c_cells_time) == len(r.c_cells_time) >= 30
+        for x, y in zip(a.c_cells_time + a.c_mems_time, r.c_cells_time + r.c_mems_time):
+            assert np.max(np.abs(np.asarray(x) - np.asarray(y))) <= 1e-9 * max(np.max(np.abs(np.asarray(y))), 1e-300), name
+    for a, r in zip(new_sim.vm_time, ref_sim.vm_time):
+        assert np.max(np.abs(a - r)) <= 1e-9 * np.max(np.abs(r))
