@@ -22,6 +22,8 @@ type  value                                    reference form
 5     p0*(U - p1)/(1 - exp(-(U - p1)/p2))      "linoid" opening rate
 6     p0*(W - p1)/(1 - exp(-(W - p1)/p2)),     "linoid" closing rate written in -V
       W = -U
+7     1 where U >= p2, else                    exponential tau overwritten with 1 above a voltage
+      p0 + p1*exp(-U/p3)                       (vg_ca.py Cav3p1: ``_mTau[V >= -10e-3] = 1.0``)
 ====  =======================================  ==============================================
 
 ``tests/test_channels_table.py`` holds every entry to the reference's own class over a voltage
@@ -30,7 +32,7 @@ code (initial gate values of synthetic tissues); the per-timestep evaluation is 
 """
 import numpy as np
 
-CONST, SIG, LIN, EXP, GAUSS, LINOID, LINOID_NEG = range(7)
+CONST, SIG, LIN, EXP, GAUSS, LINOID, LINOID_NEG, EXP_CUT = range(8)
 KIND = {"T": 0, "R": 1, "S": 2}
 
 
@@ -151,6 +153,9 @@ MODELS = {
     "Cav3p3": _hh("Ca", 1, 1, _T(_sig(-45.454426, -5.073015)),
                   _T(_sig(-40.040397, 4.110392, A=54.187616, c0=3.394938)),
                   _T(_sig(-74.031965, 8.416382)), _T(_exp(0.003816, 0.0, 4.781719, c0=109.701136))),  # :132-179
+    "Cav3p1": _hh("Ca", 1, 1, _T(_sig(-42.921064, -5.163208)),
+                  _T((EXP_CUT, -0.855809, 1.493527, -10e-3, 27.414182)),       # the cut is at -10e-3 *mV*, as written
+                  _T(_sig(-72.907420, 4.575763)), _T(_exp(0.002883, 0.0, 5.598574, c0=9.987873))),  # :468-520
     "Cav2p1": _hh("Ca", 1, 0, ("R", _c21a, _c21b), ("S", _c21a, _c21b), _one, _one),          # :181-240
     "Cav1p3": _hh("Ca", 2, 1, _T(_sig(-30.0, -6.0)), _T(_sig(-25.0, 5.0, A=20.0, c0=5.0)),
                   _T(_sig(-80.0, 6.4)), _T(_sig(-40.0, 7.0, A=50.0, c0=20.0))),               # :242-290
@@ -178,7 +183,7 @@ MODELS = {
     "CatLeak": _multi(_leak("Na"), ["Na", "K", "Ca"], [1.0, 1.0, 0.0], "cation"),             # :113-159
     "CatLeak2": _multi(_leak("Na"), ["Na", "K", "Ca"], [1.0, 1.0, 1.0], "cation"),            # :162-208
 }
-# Not tabulated (refused at set-up): vg_ca.Cav3p1 (piecewise tau), Morris-Lecar (no YAML channel class selects it), wound.
+# Not tabulated (refused at set-up): Morris-Lecar (no YAML channel class selects it), wound.
 
 CLASS_OF_ION = {"Na": "vg_na", "K": "vg_k", "Ca": "vg_ca", "Cl": "vg_cl"}
 
@@ -200,6 +205,8 @@ def term(t, U):
     if ty == LINOID_NEG:
         W = -U
         return p0 * (W - p1) / (1 - np.exp(-(W - p1) / p2))
+    if ty == EXP_CUT:
+        return np.where(U >= p2, 1.0, p0 + p1 * np.exp(-U / p3))
     raise ValueError(ty)
 
 

@@ -85,3 +85,55 @@ def test_channels_vs_oracle_synthetic():
         for f in ("m", "h", "P"):
             assert np.max(np.abs(stt[f] - c[f])) <= 1e-10 * max(np.max(np.abs(c[f])), 1e-300), (c["name"], f)
     eng.close()
+
+
+def test_every_tabulated_model_on_the_device():
+    """Each model of the gating table (betse_b200/channels.py, pinned to the reference's classes by
+    tests/test_channels_table.py) through k_chan, 3 steps on a 2 k-cell tissue, against the table's NumPy evaluation in the
+    oracle.  The synthetic tissue rests near 0 V, so every model also runs as copies shifted by -70.3, -24.7 and +15.4 mV
+    (both sides of Cav3p1's tau cut-off, vg_ca.py:515-519)."""
+    import copy
+    from betse_b200 import channels as chlib
+    from betse_b200 import synth
+    from betse_b200.engine import TissueEngine
+    from oracle.betse_oracle import OracleSim
+    mesh, p, st = synth.make_tissue(2_000)
+    ora0 = OracleSim(mesh, p, st)
+    ora0.diagnostics = False
+    ora0.update_V()
+    base = sorted(chlib.MODELS)
+    added = []
+    try:
+        for model in base:
+            for dv in (-70.3, -24.7, 15.4):        # off the round voltages where the rates have removable 0/0 points
+                name = "%s@%+.1f" % (model, dv)
+                chlib.MODELS[name] = dict(copy.deepcopy(chlib.MODELS[model]), shift=chlib.MODELS[model]["shift"] + dv)
+                added.append(name)
+        n_run, bad = 0, []
+        for model in base + added:
+            ions, _ = chlib.ions_of(model)
+            if any(i not in p["ions"] for i in ions):
+                continue
+            m0, h0 = chlib.initial_state(model, ora0.vm)
+            spec = chlib.make_channel("c", model, 1.0e-16, m=m0, h=h0)
+            ora = OracleSim(mesh, p, st, channels=[dict(spec)])
+            ora.diagnostics = False
+            ora.update_V()
+            eng = TissueEngine(mesh, p, st)
+            eng.update_V()
+            eng.set_channels([spec])
+            for n in range(3):
+                assert not (eng.step(1) & 3), model
+                ora.step()
+            stt, c = eng.channel_state(0), ora.channels[0]
+            for f in ("m", "h", "P"):
+                err = np.max(np.abs(stt[f] - c[f])) / max(np.max(np.abs(c[f])), 1e-300)
+                if err > 1e-10:
+                    bad.append((model, f, float(err)))
+            eng.close()
+            n_run += 1
+        assert not bad, bad
+        assert n_run >= 4 * 40
+    finally:
+        for name in added:
+            del chlib.MODELS[name]
