@@ -187,8 +187,10 @@ static int xfer(betse_ctx* ctx, void* dst, const void* src, size_t bytes, cudaMe
 {
     cudaStream_t st = ctx->stream;
     const bool down = kind == cudaMemcpyDeviceToHost;
-    // uploads: the driver's own pageable path measured faster than a host-side bounce (source pages are resident)
-    if (!down || bytes < ((size_t)1 << 20) || host_is_pinned(dst)) {
+    // uploads: the driver's own pageable path measured faster than a single-threaded host-side bounce (source pages are
+    // resident); BETSE_H2D_BOUNCE=1 stages them through the page-locked pair with the multi-threaded copy
+    static const bool h2d_bounce = [] { const char* e = getenv("BETSE_H2D_BOUNCE"); return e && atoi(e) != 0; }();
+    if ((!down && !h2d_bounce) || bytes < ((size_t)1 << 20) || host_is_pinned(down ? dst : src)) {
         CK(cudaMemcpyAsync(dst, src, bytes, kind, st));
         return 0;
     }
@@ -216,7 +218,7 @@ static int xfer(betse_ctx* ctx, void* dst, const void* src, size_t bytes, cudaMe
         for (size_t i = 0; i < nch; ++i) {
             const size_t off = i * XCHUNK, n = bytes - off < XCHUNK ? bytes - off : XCHUNK;
             CK(cudaEventSynchronize(ctx->xev[i & 1]));              // the buffer's previous DMA (if any) has drained
-            memcpy(ctx->xbuf[i & 1], (const char*)src + off, n);
+            par_memcpy(ctx->xbuf[i & 1], (const char*)src + off, n);
             CK(cudaMemcpyAsync((char*)dst + off, ctx->xbuf[i & 1], n, kind, st));
             CK(cudaEventRecord(ctx->xev[i & 1], st));
         }
