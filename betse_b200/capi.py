@@ -181,7 +181,7 @@ SYMBOLS = [
     "betse_set_row_ranges", "betse_window", "betse_attach_neighbor", "betse_exchange",
     "betse_set_channels", "betse_channel_state", "betse_set_network", "betse_network_state",
     "betse_network_env_state", "betse_network_mem_state", "betse_network_set_events", "betse_set_noise_flux",
-    "betse_host_alloc", "betse_host_alloc_on", "betse_host_copy", "betse_host_free",
+    "betse_host_alloc", "betse_host_alloc_on", "betse_host_copy", "betse_host_expand", "betse_host_free",
 ]
 
 _lib = None
@@ -232,6 +232,8 @@ def load(build_if_missing=True):
     lib.betse_host_alloc_on.argtypes = [C.c_int, C.c_size_t, C.POINTER(vp)]
     lib.betse_host_copy.argtypes = [vp, vp, C.c_size_t]
     lib.betse_host_copy.restype = None
+    lib.betse_host_expand.argtypes = [_dp, _dp, _ip, C.c_int, C.c_size_t, C.c_size_t]
+    lib.betse_host_expand.restype = None
     lib.betse_host_free.argtypes = [vp]
     lib.betse_host_free.restype = None
     lib.betse_stream.argtypes = [vp, C.POINTER(vp)]

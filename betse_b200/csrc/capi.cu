@@ -1626,6 +1626,27 @@ extern "C" void betse_host_copy(void* dst, const void* src, size_t bytes)
     par_memcpy(static_cast<char*>(dst), static_cast<const char*>(src), bytes);
 }
 
+extern "C" void betse_host_expand(double* dst, const double* src, const int32_t* idx, int n_rows, size_t n_src, size_t n_dst)
+{
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int T = n_dst < ((size_t)1 << 16) ? 1 : (hw >= 16 ? 8 : hw >= 8 ? 4 : 2);
+    auto work = [=](size_t m0, size_t m1) {
+        for (int i = 0; i < n_rows; ++i) {
+            const double* s = src + (size_t)i * n_src;
+            double* d = dst + (size_t)i * n_dst;
+            for (size_t m = m0; m < m1; ++m) d[m] = s[idx[m]];
+        }
+    };
+    std::thread th[8];
+    const size_t per = (n_dst + T - 1) / T;
+    for (int t = 1; t < T; ++t) {
+        const size_t a = (size_t)t * per, b = a + per < n_dst ? a + per : n_dst;
+        th[t - 1] = std::thread([=] { if (a < b) work(a, b); });
+    }
+    work(0, per < n_dst ? per : n_dst);
+    for (int t = 1; t < T; ++t) th[t - 1].join();
+}
+
 extern "C" void betse_host_free(void* p)
 {
     if (p) cudaFreeHost(p);

@@ -447,7 +447,10 @@ class TissueEngine:
         self._check(self.lib.betse_download_sample(self.ctx, C.byref(sh)), "betse_download_sample")
         self.d2h_bytes += sum(a.nbytes for a in out.values()) + (cenv.nbytes if cenv is not None else 0)
         if want_cam:
-            out["cc_at_mem"] = out.pop("_cam")[:, self.mem_to_cells]
+            cam = out.pop("_cam")
+            out["cc_at_mem"] = np.empty((I, M))
+            self.lib.betse_host_expand(capi.ptr_f64(out["cc_at_mem"]), capi.ptr_f64(cam), capi.ptr_i32(self.mem_to_cells),
+                                       I, Cn, M)
         if cenv is not None:
             out["cc_env"] = np.repeat(cenv[:, None], M, axis=1)   # the reference keeps [I,M] (sim.py:487-490)
         return out

@@ -236,6 +236,9 @@ int  betse_host_alloc(size_t bytes, void **out);
 int  betse_host_alloc_on(int device, size_t bytes, void **out);
 /* dst[0..bytes) = src[0..bytes) split over a few threads: a fresh NumPy destination is first-touch page faults */
 void betse_host_copy(void *dst, const void *src, size_t bytes);
+/* dst[i][m] = src[i][idx[m]] (rows of n_src -> rows of n_dst doubles) over a few threads: sim.cc_at_mem [I][M] from the
+ * per-cell array the device keeps (cc_at_mem is a gather of a per-cell quantity, sim_toolbox.py:1181-1182) */
+void betse_host_expand(double *dst, const double *src, const int32_t *idx, int n_rows, size_t n_src, size_t n_dst);
 void betse_host_free(void *p);
 
 /* ---------------------------------------------------------------------------------------------
