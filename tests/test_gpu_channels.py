@@ -48,13 +48,14 @@ def test_channels_match_reference(fixture, kind):
     eng.close()
 
 
-def test_channels_vs_oracle_synthetic():
-    """10 k-cell synthetic tissue with the four channels of BASELINE configs[2], 15 steps."""
+@pytest.mark.parametrize("n_cells,steps", [(10_000, 15), (100_000, 6)])        # 100 k cells: BASELINE configs[2] to the letter
+def test_channels_vs_oracle_synthetic(n_cells, steps):
+    """Synthetic tissue with the four channels of BASELINE configs[2] (mammal profile, vg Na / K / Ca + leak, Na/K pump)."""
     from betse_b200 import channels as chlib
     from betse_b200 import synth
     from betse_b200.engine import TissueEngine
     from oracle.betse_oracle import OracleSim
-    mesh, p, st = synth.make_tissue(10_000)
+    mesh, p, st = synth.make_tissue(n_cells)
     p["substances_affect_charge"] = 1
     eng = TissueEngine(mesh, p, st)
     eng.update_V()
@@ -70,7 +71,7 @@ def test_channels_vs_oracle_synthetic():
     ora.diagnostics = False
     ora.update_V()
     eng.set_channels(specs)
-    for n in range(15):
+    for n in range(steps):
         s = eng.step(1)
         ora.step()
         assert not (s & 3)

@@ -222,14 +222,15 @@ def _retarget(desc, C, M, E, rng, targets_every=7):
         Do = np.where(np.asarray(d["D_env"]).max(axis=1) > 0, np.asarray(d["D_env"]).max(axis=1), 0.0)
         d["D_env"] = Do[:, None] * rng.uniform(0.2, 1.0, (K, E))
     if "c_mems" in d:
-        d["c_mems"] = rng.uniform(0.05, 1.0, (K, M))
+        d["c_mems"] = rng.uniform(0.05, 1.0, (K, M)) * dilute
     if "transporters" in d:
         d["transporters"] = [dict(t, targets_cell=np.arange(0, C, targets_every if j else 1), targets_mem=np.arange(M),
                                   targets_env=np.arange(E)) for j, t in enumerate(d["transporters"])]
     return d
 
 
-@pytest.mark.parametrize("fixture", ["mammal_ecm_net_trans", "mammal_ecm_net_pump", "mammal_ecm_net_lig", "mammal_ecm_net_envq"])
+@pytest.mark.parametrize("fixture", ["mammal_ecm_net_trans", "mammal_ecm_net_pump", "mammal_ecm_net_lig", "mammal_ecm_net_envq",
+                                     "mammal_ecm_net_intra"])
 def test_network_features_vs_oracle_synthetic_30k(fixture):
     """The membrane / extracellular / transporter / pump / ligand-gate kernels at a size and grid shape the fixtures do
     not have (30 k cells, 174 x 174 grid): the recorded rate laws re-targeted to a synthetic tissue, 8 steps vs the oracle."""
@@ -265,4 +266,8 @@ def test_network_features_vs_oracle_synthetic_30k(fixture):
         assert util.rel_err(c[k], net.c[nme]) <= 1e-10, nme
         if nme in net.c_env:
             assert util.rel_err(ce[k], net.c_env[nme]) <= 1e-10, (nme, "env")
+    if np.any(desc.get("intra_on", 0)):
+        cm = eng.network_mem_state(0)
+        for k, nme in enumerate(desc["species"]):
+            assert util.rel_err(cm[k], net.cmem[nme]) <= 1e-10, (nme, "mems")
     eng.close()
