@@ -121,8 +121,10 @@ class DistributedStrips:
     def profile(self, n):
         return self.engine.profile(n)
 
-    def download_local(self, fields):
-        return self.engine.download(fields)
+    def download_local(self, fields, pinned=False):
+        """This rank's strip of the named fields.  ``pinned``: views of the engine's page-locked staging, overwritten by
+        the next pinned download (for consumers that copy what they keep, like write2storage)."""
+        return self.engine.download(fields, pinned=pinned)
 
     def close(self):
         self.dist.barrier()
