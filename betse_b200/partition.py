@@ -124,6 +124,10 @@ def partition(mesh, params, state, R, bounds=None, only=None):
         lo, hi = max(0, a - H), min(ny, b + H)
         oc, om = own_cells[r], own_mems[r]
         Co, Mo = len(oc), len(om)
+        # cells numbered along the rows (lattice-seeded meshes, the synthetic tissues) give every strip ONE range of
+        # cells and membranes: plain slices then, instead of gathers over millions of indices
+        om_ix = slice(int(om[0]), int(om[-1]) + 1) if Mo and int(om[-1]) - int(om[0]) + 1 == Mo else om
+        oc_ix = slice(int(oc[0]), int(oc[-1]) + 1) if Co and int(oc[-1]) - int(oc[0]) + 1 == Co else oc
         g_lo, g_hi = ghosts[r]
         if only is not None and r != only:       # a neighbour: only what the exchange plan of `only` reads
             parts[r] = RankPart(rank=r, R=R, Co=Co, Mo=Mo, row_lo=lo, row_hi=hi, a=a, b=b, nx=nx, ny=ny, plans={},
@@ -134,20 +138,20 @@ def partition(mesh, params, state, R, bounds=None, only=None):
         g2l_c = np.full(C, -1, dtype=np.int64)
         g2l_c[cells_l] = np.arange(Cl)
         g2l_m = np.full(M, -1, dtype=np.int64)
-        g2l_m[om] = np.arange(Mo)
-        rc = pc[om]
+        g2l_m[om_ix] = np.arange(Mo)
+        rc = pc[om_ix]
         rem = owner_c[rc] != r
-        nn_l = np.where(rem, -(g2l_c[rc] + 2), g2l_m[nn[om]])
-        cnt = counts[oc]
+        nn_l = np.where(rem, -(g2l_c[rc] + 2), g2l_m[nn[om_ix]])
+        cnt = counts[oc_ix]
         ptr_l = np.concatenate(([0], np.cumsum(cnt)))
         rows = slice(lo * nx, hi * nx)
         El = (hi - lo) * nx
-        m2e_l = m2e[om] - lo * nx
+        m2e_l = m2e[om_ix] - lo * nx
         if np.any(m2e_l < 0) or np.any(m2e_l >= El):
             raise BetseB200Error("internal: membrane env square outside the local window")
         # ---- env square -> flux slot CSR over the owned squares, ordered by global membrane index
         r_lo, r_hi = remote_in[r]
-        mine = np.nonzero(env_m[om] == r)[0]
+        mine = np.nonzero(env_m[om_ix] == r)[0]
         sq = np.concatenate((m2e_l[mine], m2e[r_lo] - lo * nx, m2e[r_hi] - lo * nx))
         gid = np.concatenate((om[mine], r_lo, r_hi))
         slot = np.concatenate((mine, Mo + np.arange(len(r_lo) + len(r_hi))))
@@ -156,12 +160,12 @@ def partition(mesh, params, state, R, bounds=None, only=None):
         slot_ptr = np.concatenate(([0], np.cumsum(np.bincount(sq, minlength=El))))
 
         def cellf(name):
-            return np.asarray(mesh[name])[oc]
+            return np.asarray(mesh[name])[oc_ix]
 
         def memf(name):
-            return np.asarray(mesh[name])[om]
+            return np.asarray(mesh[name])[om_ix]
         mesh_l = {
-            "mem_to_cells": g2l_c[m2c[om]], "cell_mem_ptr": ptr_l, "nn_i": nn_l, "bflags_mems": bfl[om],
+            "mem_to_cells": g2l_c[m2c[om_ix]], "cell_mem_ptr": ptr_l, "nn_i": nn_l, "bflags_mems": bfl[om_ix],
             "map_mem2ecm": m2e_l, "mem_sa": memf("mem_sa"), "mem_nx": memf("mem_nx"), "mem_ny": memf("mem_ny"),
             "cell_vol": cellf("cell_vol"), "cell_sa": cellf("cell_sa"), "diviterm": cellf("diviterm"),
             "num_mems": cellf("num_mems"), "delta": mesh["delta"], "gj_len": mesh["gj_len"],
@@ -190,8 +194,8 @@ def partition(mesh, params, state, R, bounds=None, only=None):
         st["cc_mid"] = cam[:, ptr[cells_l]] if cam.shape[1] == M else cam[:, cells_l]
         st["cc_env"] = np.asarray(S["cc_env"], dtype=float).reshape(I, -1)[:, rows]
         st["vm_cell"] = np.asarray(S["vm"], dtype=float)[ptr[cells_l]]
-        st["gjopen"] = np.asarray(S["gjopen"], dtype=float)[om]
-        st["Dm_cells"] = np.asarray(S["Dm_cells"], dtype=float)[:, om]
+        st["gjopen"] = np.asarray(S["gjopen"], dtype=float)[om_ix]
+        st["Dm_cells"] = np.asarray(S["Dm_cells"], dtype=float)[:, om_ix]
         st["D_env"] = np.asarray(S["D_env"], dtype=float).reshape(I, -1)[:, rows]
         tj = np.asarray(S.get("TJ_modulator", 1.0), dtype=float)
         st["TJ_modulator"] = tj.reshape(I, -1)[:, rows] if tj.ndim else tj
@@ -205,7 +209,7 @@ def partition(mesh, params, state, R, bounds=None, only=None):
         for f in ("NaKATP_block", "gj_block"):
             if f in S:
                 v = np.asarray(S[f], dtype=float)
-                st[f] = v[om] if v.ndim and v.size == M else v
+                st[f] = v[om_ix] if v.ndim and v.size == M else v
         for f in ("zs", "D_free", "D_gj", "c_env_bound", "T", "ko_env", "rho_pump", "rho_channel", "bound_V"):
             if f in S:
                 st[f] = S[f]
