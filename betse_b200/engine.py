@@ -54,7 +54,8 @@ def _pinned_array(lib, ptr, n, shape):
     Simulator at the end of a phase simply outlives the engine, no copy."""
     import weakref
     raw = (C.c_double * n).from_address(ptr.value)
-    weakref.finalize(raw, lib.betse_host_free, C.c_void_p(ptr.value))
+    fin = weakref.finalize(raw, lib.betse_host_free, C.c_void_p(ptr.value))
+    fin.atexit = False              # at interpreter exit the OS reclaims it; the CUDA runtime may already be gone
     return np.ctypeslib.as_array(raw).reshape(shape)
 
 
