@@ -85,3 +85,23 @@ def test_product_does_not_import_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), fn
+
+
+def test_host_helpers_without_a_gpu():
+    """betse_host_copy / betse_host_expand are plain host code (threaded memcpy / row gather used by the copy-back of
+    Simulator arrays): exact against NumPy, odd sizes and sizes below and above the threading thresholds."""
+    from betse_b200 import capi
+    lib = capi.load()
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 1000, (1 << 18) + 3, (3 << 20) + 17):
+        src = rng.random(n)
+        dst = np.full(n, -1.0)
+        lib.betse_host_copy(dst.ctypes.data, src.ctypes.data, C.c_size_t(src.nbytes))
+        assert np.array_equal(dst, src)
+    for n_src, rows in ((5, 1), (1000, 4), (70_000, 6)):
+        counts = rng.integers(3, 8, n_src)
+        idx = np.repeat(np.arange(n_src), counts).astype(np.int32)
+        src = rng.random((rows, n_src))
+        dst = np.empty((rows, len(idx)))
+        lib.betse_host_expand(capi.ptr_f64(dst), capi.ptr_f64(src), capi.ptr_i32(idx), rows, n_src, len(idx))
+        assert np.array_equal(dst, src[:, idx])
