@@ -36,7 +36,7 @@ def _bflags_bool(mesh, M):
 def strip_bounds(mesh, R):
     """Row boundaries [a_0=0, a_1, ..., a_R=ny] balancing membranes (+ a grid term) per strip."""
     ny, nx = (int(x) for x in mesh["grid_shape"])
-    mrow = np.asarray(mesh["map_mem2ecm"]).astype(np.int64) // nx
+    mrow = np.asarray(mesh["map_mem2ecm"], dtype=np.int64) // nx
     w = np.bincount(mrow, minlength=ny).astype(float) + 0.3 * nx
     cw = np.concatenate(([0.0], np.cumsum(w)))
     b = [0]
@@ -62,10 +62,10 @@ def partition(mesh, params, state, R, bounds=None, only=None):
         raise ValueError("R must be >= 1")
     need = list(range(R)) if only is None else [r for r in (only - 1, only, only + 1) if 0 <= r < R]
     ny, nx = (int(x) for x in mesh["grid_shape"])
-    ptr = np.asarray(mesh["cell_mem_ptr"]).astype(np.int64)
-    m2c = np.asarray(mesh["mem_to_cells"]).astype(np.int64)
-    nn = np.asarray(mesh["nn_i"]).astype(np.int64)
-    m2e = np.asarray(mesh["map_mem2ecm"]).astype(np.int64)
+    ptr = np.asarray(mesh["cell_mem_ptr"], dtype=np.int64)
+    m2c = np.asarray(mesh["mem_to_cells"], dtype=np.int64)
+    nn = np.asarray(mesh["nn_i"], dtype=np.int64)
+    m2e = np.asarray(mesh["map_mem2ecm"], dtype=np.int64)
     C, M = len(ptr) - 1, len(m2c)
     if not bool(np.asarray(params["is_ecm"]).item() if np.ndim(params["is_ecm"]) == 0 else params["is_ecm"]):
         raise BetseB200Error("domain decomposition needs extracellular spaces; no-ECM tissues run as replicas")
