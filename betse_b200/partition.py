@@ -84,10 +84,12 @@ def partition(mesh, params, state, R, bounds=None, only=None):
     owner_c = np.searchsorted(bounds[1:], crow, side="right")
     owner_m = owner_c[m2c]                       # rank that steps the membrane
     env_m = np.searchsorted(bounds[1:], mrow, side="right")   # rank that owns its env square
-    if np.any(np.abs(owner_m - env_m) > 1):
+    out_m = np.nonzero(env_m != owner_m)[0]     # membranes whose env square lies in a neighbour's strip: the strip edges only
+    if np.any(np.abs(owner_m[out_m] - env_m[out_m]) > 1):
         raise BetseB200Error("a membrane maps to an env square two strips away: strips are too thin")
-    a_m, b_m = bounds[owner_m], bounds[owner_m + 1]
-    G = int(max(0, np.max(np.maximum(a_m - mrow, mrow - (b_m - 1)))))   # reach of membranes outside their strip
+    a_m, b_m = bounds[owner_m[out_m]], bounds[owner_m[out_m] + 1]
+    # reach of membranes outside their strip (zero for every membrane inside it)
+    G = int(max(0, np.max(np.maximum(a_m - mrow[out_m], mrow[out_m] - (b_m - 1))))) if len(out_m) else 0
     H = G + V_HALO
     if R > 1 and np.min(np.diff(bounds)) < H:
         raise BetseB200Error("strips of %d rows are thinner than the %d-row halo; use fewer ranks"
