@@ -117,7 +117,7 @@ def partition(mesh, params, state, R, bounds=None, only=None):
             raise BetseB200Error("a gap-junction partner lives two strips away: strips are too thin")
         ghosts[r] = (gl[go == r - 1], gl[go == r + 1])
         # membranes of the neighbours whose env square this rank owns (ascending global index)
-        inc = np.nonzero((env_m == r) & (owner_m != r))[0]
+        inc = out_m[env_m[out_m] == r]           # == nonzero((env_m == r) & (owner_m != r)), from the edge membranes
         remote_in[r] = (inc[owner_m[inc] == r - 1], inc[owner_m[inc] == r + 1])
 
     parts = [None] * R
