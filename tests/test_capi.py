@@ -105,3 +105,26 @@ def test_host_helpers_without_a_gpu():
         dst = np.empty((rows, len(idx)))
         lib.betse_host_expand(capi.ptr_f64(dst), capi.ptr_f64(src), capi.ptr_i32(idx), rows, n_src, len(idx))
         assert np.array_equal(dst, src[:, idx])
+
+
+def test_staging_prefetch_degrades_without_a_gpu():
+    """The drop-in loop pins its sample staging on a helper thread (simloop._prefetch_staging -> engine.PinnedPrefetch):
+    the field list and shapes are those of the per-sample download, and without a CUDA device the thread simply hands
+    back nothing (the engine then allocates — and reports — on first use)."""
+    import types
+    from betse_b200 import simloop, synth
+    mesh, p, state = synth.make_tissue(500)
+    cells = types.SimpleNamespace(cell_vol=mesh["cell_vol"], mem_sa=mesh["mem_sa"], X=None,
+                                  grid_shape=tuple(int(x) for x in mesh["grid_shape"]))
+    pp = types.SimpleNamespace(**p)
+    pf = simloop._prefetch_staging(cells, pp, 0)
+    assert pf is not None
+    I, Cn, M, E = len(p["ions"]), len(mesh["cell_vol"]), len(mesh["mem_sa"]), int(np.prod(mesh["grid_shape"]))
+    assert set(pf.shapes) == set(simloop._sample_fields(True, True))
+    assert pf.shapes["cc_cells"] == (I, Cn) and pf.shapes["vm"] == (M,) and pf.shapes["cc_env"] == (I, E)
+    assert pf.shapes["J_env_x"] == (E,) and pf.shapes["I_mem"] == (M,)
+    got = pf.join()
+    assert got == {} or set(got) <= set(pf.shapes)           # {} here; on a GPU box the arrays
+    pf.release()
+    pp.is_ecm = False
+    assert simloop._prefetch_staging(cells, pp, 0) is None     # tissues without extracellular spaces: allocated on first use
