@@ -19,7 +19,7 @@
 #include "hh.cuh"
 
 // launchers (kernels.cu)
-void launch_mem(int ni, const KParams& P, const KArrays& A, int n_ctas, int cur, int diag, cudaStream_t st);
+int launch_mem(int ni, const KParams& P, const KArrays& A, int n_ctas, int cur, int diag, cudaStream_t st);   // returns 1 when the fluxes went to flux_ell
 void launch_ion(const KParams& P, const KArrays& A, int nx, int cur, int diag, int ion0, int n, cudaStream_t st);
 void launch_ion_smooth(int ni, const KParams& P, const KArrays& A, int ny, int nx, int nxt, cudaStream_t st);
 void launch_envacc(int ni, const KParams& P, const KArrays& A, int E, int nxt, int apply, cudaStream_t st);
@@ -37,6 +37,13 @@ void launch_phi_b(const KParams& P, const HHBuf& H, const double bound[4], doubl
 void launch_noecm_field(const KParams& P, const KArrays& A, const HHBuf& H, double sigma, const double* D_env_weight, int old, cudaStream_t st);
 void launch_pack_const(const KParams& P, const KArrays& A, cudaStream_t st);
 void launch_pack_dm(const KParams& P, const KArrays& A, cudaStream_t st);
+// kcell.cu: the lane-per-cell membrane kernel, its cell pack and the env accumulation that reads its fluxes
+bool kcell_enabled();
+void launch_pack_cell_const(const KParams& P, const KArrays& A, int* mem_ell, cudaStream_t st);
+void launch_pack_cell_dm(const KParams& P, const KArrays& A, cudaStream_t st);
+void launch_slot_off(const int* slot_idx, const int* mem_ell, int* slot_off, int n, int Mo, int ni, cudaStream_t st);
+void launch_gather_int(int* dst, const int* src, const int* idx, int n, cudaStream_t st);
+void launch_envacc_ell(int ni, const KParams& P, const KArrays& A, int nxt, cudaStream_t st);
 void launch_chan(const KParams& P, const KArrays& A, const KChan& ch, const KNet& N, int cur, cudaStream_t st);
 void launch_net(const KParams& P, const KArrays& A, const KNet& N, const double* h_Dgj, const double* h_Dm,
                 const unsigned char* h_env_on, const betse_substance_pump* pumps, int n_pumps, double dG_RT,
@@ -52,7 +59,7 @@ void launch_transporter(const KParams& P, const KArrays& A, const KNet& N, const
 void launch_tw_gather(const KParams& P, const KArrays& A, double* row, const double* src, cudaStream_t st);
 void launch_net_mod(const KParams& P, const KArrays& A, const KNet& N, int prog, double max_val, double* dst, int cur, cudaStream_t st);
 void launch_cell_update(const KParams& P, const KArrays& A, int cur, cudaStream_t st);
-void launch_xchg(const KParams& P, const KArrays& A, const XPlan& X, int which, int buf, int mode, cudaStream_t st);
+void launch_xchg(const KParams& P, const KArrays& A, const XPlan& X, int which, int buf, int mode, int flux_ell, cudaStream_t st);
 
 enum { K_ION = 0, K_MEM, K_ENVACC, K_FIELD, K_ENVMIX, K_SMOOTH, K_DIAG, K_XCHG };
 static const char* kKernelNames[BETSE_NKERNELS] = {
@@ -70,6 +77,8 @@ struct betse_ctx {
     int cur = 0;
     int C = 0, Co = 0, M = 0, Mo = 0, E = 0, ny = 0, nx = 0, I = 0, n_ctas = 0, n_tiles = 0, n_slots = 0;
     bool diag_valid = false;
+    int* mem_ell = nullptr;                  // [Mo] position of every membrane's fluxes in flux_ell (cell pack of k_cell)
+    int flux_is_ell = 0;                     // layout the last membrane kernel wrote its membrane -> env fluxes in
     // exchange window (every buffer a neighbouring rank writes) and the halo-exchange plan
     char* win = nullptr;
     betse_window_info winfo;
@@ -497,6 +506,34 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
         CK(cudaGetLastError());
     }
 
+    // ---- cell pack (k_cell): SELL-32 rows of the per-membrane constants, built on the device like the tile pack
+    if (hp->n_ions <= 7 && hp->is_ecm) {
+        const int nb = (Co + 31) / 32;
+        std::vector<int> row0(nb + 1, 0);
+        for (int b = 0; b < nb; ++b) {
+            int kb = 0;
+            const int c1 = std::min(Co, (b + 1) * 32);
+            for (int c = b * 32; c < c1; ++c) kb = std::max(kb, mesh->cell_mem_ptr[c + 1] - mesh->cell_mem_ptr[c]);
+            row0[b + 1] = row0[b] + kb;
+        }
+        const long long R32 = (long long)row0[nb] * 32;
+        if (R32 * hp->n_ions < (1LL << 31) - 64) {       // 32-bit flux positions; otherwise k_mem stays in charge
+            P.n_blocks = nb; P.ell_R32 = (int)R32;
+            if ((r = dev_upload(ctx, (int**)&A.blk_row0, row0.data(), row0.size()))) return r;
+            if ((r = dev_alloc(ctx, (double**)&A.ell_DmS, (size_t)R32 * I))) return r;
+            if ((r = dev_alloc(ctx, (double**)&A.ell_sa, (size_t)R32))) return r;
+            if ((r = dev_alloc(ctx, (int**)&A.ell_nnp, (size_t)R32))) return r;
+            if ((r = dev_alloc(ctx, (int**)&A.ell_esq, (size_t)R32))) return r;
+            if ((r = dev_alloc(ctx, &A.flux_ell, (size_t)R32 * I))) return r;
+            if ((r = dev_alloc(ctx, &ctx->mem_ell, (size_t)Mo))) return r;
+            const int n_sl = mesh->ecm_slot_ptr ? mesh->ecm_slot_ptr[E] : Mo;
+            if ((r = dev_alloc(ctx, (int**)&A.slot_off, (size_t)n_sl))) return r;
+            launch_pack_cell_const(ctx->P, A, ctx->mem_ell, ctx->stream);
+            launch_slot_off(A.slot_idx, ctx->mem_ell, const_cast<int*>(A.slot_off), n_sl, Mo, I, ctx->stream);
+            CK(cudaGetLastError());
+        }
+    }
+
     // ---- state
     const size_t IC = (size_t)I * C, IE = (size_t)I * E, IM = (size_t)I * Mo;
     if ((r = dev_alloc(ctx, &A.cc_cells, IC))) return r;
@@ -673,7 +710,7 @@ extern "C" int betse_upload_state(betse_ctx* ctx, const betse_state_host* s)
     }
     UP(A.gjopen, s->gjopen, Mo);
     UP(A.Dm, s->Dm_cells, IM);
-    if (s->Dm_cells) launch_pack_dm(ctx->P, A, st);
+    if (s->Dm_cells) { launch_pack_dm(ctx->P, A, st); launch_pack_cell_dm(ctx->P, A, st); }
     if (ctx->P.polar && s->vm)
         CK(cudaMemcpyAsync(A.vm_pol[cur], s->vm, (size_t)Mo * sizeof(double), cudaMemcpyHostToDevice, st));
     if (s->vm_cell) {
@@ -718,9 +755,20 @@ extern "C" int betse_upload_state(betse_ctx* ctx, const betse_state_host* s)
     if ((r = opt_array(ctx, &A.NaK_block, (const double*)s->NaKATP_block, Mo))) return r;
     if ((r = opt_array(ctx, &A.gj_block, (const double*)s->gj_block, Mo))) return r;
     if (s->cenv_uniform && !ctx->hp.is_ecm) {
+        // NaN = keep what the device holds for that ion (a scheduled change of one ion's bath, tishandler.py:759-777)
         double cu[16];
-        for (int i = 0; i < 8; ++i) cu[i] = cu[8 + i] = (i < I) ? s->cenv_uniform[i] : 0.0;
-        CK(cudaMemcpyAsync(A.cenv_u, cu, sizeof cu, cudaMemcpyHostToDevice, st));
+        bool all = true;
+        for (int i = 0; i < I; ++i) all = all && s->cenv_uniform[i] == s->cenv_uniform[i];
+        if (all) {
+            for (int i = 0; i < 8; ++i) cu[i] = cu[8 + i] = (i < I) ? s->cenv_uniform[i] : 0.0;
+            CK(cudaMemcpy(A.cenv_u, cu, sizeof cu, cudaMemcpyHostToDevice));
+        } else {
+            for (int i = 0; i < I; ++i) {
+                if (s->cenv_uniform[i] != s->cenv_uniform[i]) continue;
+                CK(cudaMemcpy(A.cenv_u + i, s->cenv_uniform + i, sizeof(double), cudaMemcpyHostToDevice));
+                CK(cudaMemcpy(A.cenv_u + 8 + i, s->cenv_uniform + i, sizeof(double), cudaMemcpyHostToDevice));
+            }
+        }
     }
 #undef UP
     CK(cudaStreamSynchronize(st));
@@ -783,6 +831,7 @@ extern "C" int betse_set_schedule(betse_ctx* ctx, const betse_params* hp)
     ctx->P.has_phi = has_phi;
     destroy_graphs(ctx);              // KParams is baked into the captured launches
     launch_pack_dm(ctx->P, ctx->A, ctx->stream);   // DmS carries rho_channel/tm
+    launch_pack_cell_dm(ctx->P, ctx->A, ctx->stream);
     bool bv = false;
     for (int q = 0; q < 4; ++q) bv = bv || hp->bound_V[q] != ctx->bound_prev[q];
     if (bv) { int r = update_phi_b(ctx, hp->bound_V); if (r) return r; }
@@ -824,7 +873,7 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
             }
         } else if (evs) cudaEventRecord(evs[1], st);
         if (evs) cudaEventRecord(evs[2], st);
-        launch_mem(I, ctx->P, A, ctx->n_ctas, cur, diag, st);
+        ctx->flux_is_ell = launch_mem(I, ctx->P, A, ctx->n_ctas, cur, diag, st);
         if (overlap) cudaStreamWaitEvent(st, ctx->ev_join, 0);
         if (chans) {
             // between the ion loop's fluxes and update_all_concs (sim.py:1290-1357), per handler: run_loop_channels
@@ -887,7 +936,8 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
         }
         if (evs) cudaEventRecord(evs[3], st);
     } else if (phase == 1) {
-        if (ecm) launch_envacc(I, ctx->P, A, ctx->E, nxt, 1, st);
+        if (ecm && ctx->flux_is_ell) launch_envacc_ell(I, ctx->P, A, nxt, st);
+        else if (ecm) launch_envacc(I, ctx->P, A, ctx->E, nxt, 1, st);
         else launch_envmix(I, ctx->P, A, cur, st);
         if (evs) cudaEventRecord(evs[4], st);
     } else {
@@ -919,10 +969,10 @@ static void enqueue_step(betse_ctx* ctx, int diag, cudaEvent_t* evs)
     const bool nbr = ctx->X.n_nbr > 0;
     const int nxt = ctx->cur ^ 1;
     enqueue_phase(ctx, 0, diag, evs);
-    if (nbr) launch_xchg(ctx->P, ctx->A, ctx->X, BETSE_XCHG_X1, nxt, BETSE_XCHG_PUSH | BETSE_XCHG_WAIT, ctx->stream);
+    if (nbr) launch_xchg(ctx->P, ctx->A, ctx->X, BETSE_XCHG_X1, nxt, BETSE_XCHG_PUSH | BETSE_XCHG_WAIT, ctx->flux_is_ell, ctx->stream);
     if (evs) cudaEventRecord(evs[7], ctx->stream);
     enqueue_phase(ctx, 1, diag, evs);
-    if (nbr) launch_xchg(ctx->P, ctx->A, ctx->X, BETSE_XCHG_X2, nxt, BETSE_XCHG_PUSH | BETSE_XCHG_WAIT, ctx->stream);
+    if (nbr) launch_xchg(ctx->P, ctx->A, ctx->X, BETSE_XCHG_X2, nxt, BETSE_XCHG_PUSH | BETSE_XCHG_WAIT, ctx->flux_is_ell, ctx->stream);
     if (evs) cudaEventRecord(evs[8], ctx->stream);
     enqueue_phase(ctx, 2, diag, evs);
 }
@@ -1009,8 +1059,8 @@ extern "C" int betse_update_v(betse_ctx* ctx)
     if ((r = betse_update_v_phase(ctx, 0))) return r;
     if (ctx->X.n_nbr > 0) {
         // ghost-cell Vmem / concentrations and the env halo rows of the CURRENT buffers
-        launch_xchg(ctx->P, ctx->A, ctx->X, BETSE_XCHG_X1, ctx->cur, BETSE_XCHG_PUSH | BETSE_XCHG_WAIT, ctx->stream);
-        launch_xchg(ctx->P, ctx->A, ctx->X, BETSE_XCHG_X2, ctx->cur, BETSE_XCHG_PUSH | BETSE_XCHG_WAIT, ctx->stream);
+        launch_xchg(ctx->P, ctx->A, ctx->X, BETSE_XCHG_X1, ctx->cur, BETSE_XCHG_PUSH | BETSE_XCHG_WAIT, ctx->flux_is_ell, ctx->stream);
+        launch_xchg(ctx->P, ctx->A, ctx->X, BETSE_XCHG_X2, ctx->cur, BETSE_XCHG_PUSH | BETSE_XCHG_WAIT, ctx->flux_is_ell, ctx->stream);
     }
     if ((r = betse_update_v_phase(ctx, 1))) return r;
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1723,6 +1773,10 @@ extern "C" int betse_attach_neighbor(betse_ctx* ctx, const betse_neighbor* nb)
     int r;
     if ((r = dev_upload(ctx, (int**)&x.send_cells, nb->send_cells, nb->n_send_cells))) return r;
     if ((r = dev_upload(ctx, (int**)&x.send_flux, nb->send_flux, nb->n_send_flux))) return r;
+    if (ctx->mem_ell) {          // where k_cell leaves the same fluxes
+        if ((r = dev_alloc(ctx, (int**)&x.send_flux_ell, (size_t)nb->n_send_flux, false))) return r;
+        launch_gather_int(const_cast<int*>(x.send_flux_ell), ctx->mem_ell, x.send_flux, nb->n_send_flux, ctx->stream);
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->X.n_nbr++;
     destroy_graphs(ctx);
@@ -1734,7 +1788,7 @@ extern "C" int betse_exchange(betse_ctx* ctx, int which, int buf_next, int mode)
     if (!ctx || (which != BETSE_XCHG_X1 && which != BETSE_XCHG_X2) || !(mode & 3)) return 2;
     CK(cudaSetDevice(ctx->device));
     if (ctx->X.n_nbr == 0) return 0;
-    launch_xchg(ctx->P, ctx->A, ctx->X, which, buf_next ? (ctx->cur ^ 1) : ctx->cur, mode, ctx->stream);
+    launch_xchg(ctx->P, ctx->A, ctx->X, which, buf_next ? (ctx->cur ^ 1) : ctx->cur, mode, ctx->flux_is_ell, ctx->stream);
     CK(cudaGetLastError());
     return 0;
 }

@@ -112,10 +112,11 @@ k_mem(const __grid_constant__ KParams P, const KArrays A, const int cur, const i
                 vm_nb -= ldg(A.phi_b_old + ldgi(A.map_mem2ecm + ldgi(A.nn_i + m)));
             }
         }
-        // membrane side: electroflux adds 1e-25 to vBA (sim_toolbox.py:54); alpha for z = +1
-        const double a1 = ((vm_own + FLOAT_NONCE) * P.F) * P.inv_RT_sim;
-        GhkAB tm;
-        const double keq = P.K0 * fast_rcp(ghk_table(a1, tm));   // K0/e1 = exp(-dG/RT + F vm/RT): pump Keq
+        // membrane side: electroflux adds 1e-25 to vBA (sim_toolbox.py:54); alpha for z = +1; pump Keq = K0/e1
+        MemSide ms;
+        const double a1 = mem_side(vm_own, P, ms);
+        const GhkAB& tm = ms.t;
+        const double keq = ms.keq;
         // gap junction: vgj and its GHK table with p.T (sim.py:2166, 2197)
         const double vgj0 = vm_nb - vm_own;
         const double ag1 = ((vgj0 + FLOAT_NONCE) * P.F) * P.inv_RT_p;
@@ -132,9 +133,7 @@ k_mem(const __grid_constant__ KParams P, const KArrays A, const int cur, const i
         else gc2 = gjb * ldg(A.gj_w + m);             // static gap junctions, sim.py:2186
         const bool closed_bnd = (!cl_open) && bnd;
 
-        // ---- Na/K-ATPase (sim_toolbox.py:71-122); Keq = exp(-dG/RT + F vm/RT) = K0/e1
-        //   f_Na = -3*blk*alpha*fwd*(1 - Q/Keq), fwd = u3*w2*t/((1+u3)(1+w2)(1+t)), Q = Qn/Qd
-        //        = -3*blk*alpha*(u3*w2*t)*(Qd*Keq - Qn) / ((1+u3)(1+w2)(1+t)*Qd*Keq)
+        // ---- Na/K-ATPase (sim_toolbox.py:71-122), kmath.cuh: nak_cell / nak_flux
         double fNa = 0.0, fK = 0.0;
         if (P.alpha_NaK > 0.0) {
             double cNai = 0.0, cKi = 0.0, cNao = 0.0, cKo = 0.0;
@@ -143,18 +142,10 @@ k_mem(const __grid_constant__ KParams P, const KArrays A, const int cur, const i
                 if (i == iNa) { cNao = co[i]; cNai = cin[i]; }
                 if (i == iK) { cKo = co[i]; cKi = cin[i]; }
             }
-            const double a = cNao * 1e-3, b = cKi * 1e-3;
-            const double Qn = (P.QnNK0 * (a * a * a)) * (b * b);
-            const double a2 = cNai * 1e-3, b2 = cKo * 1e-3;
-            double Qd = (P.QdNK0 * (a2 * a2 * a2)) * (b2 * b2);
-            if (Qd == 0.0) Qd = 1.0e-15;
-            const double QdK = Qd * keq;
-            const double u = cNai * P.inv_KmNK_Na, w = cKo * P.inv_KmNK_K, t = P.tNK;
-            const double u3 = u * u * u, w2 = w * w;
-            const double num = ((u3 * w2) * t) * (QdK - Qn);
-            const double den = (((1.0 + u3) * (1.0 + w2)) * (1.0 + t)) * QdK;
+            NaKCell nc_;
+            nak_cell(cNai, cKi, P, nc_);
             const double blk = (!S && A.NaK_block) ? ldg(A.NaK_block + m) : P.NaK_block;
-            fNa = ((-3.0 * blk) * P.alpha_NaK) * fast_div(num, den);
+            fNa = nak_flux(nc_, keq, cNao, cKo, blk, P);
             fK = -(2.0 / 3.0) * fNa;
             if (diag) A.rate_NaK[m] = -fNa;
             fNa = P.rho_pump * fNa;
@@ -162,8 +153,7 @@ k_mem(const __grid_constant__ KParams P, const KArrays A, const int cur, const i
             if (closed_bnd) { fNa = 0.0; fK = 0.0; }
         } else if (diag) A.rate_NaK[m] = 0.0;
 
-        // ---- Ca-ATPase (sim.py:2126-2155, sim_toolbox.py:124-182)
-        //   f = -alpha*(x*t/((1+x)(1+t)))*(1 - Qn/(Qd*Keq)), Keq = K0/e1^2
+        // ---- Ca-ATPase (sim.py:2126-2155, sim_toolbox.py:124-182), kmath.cuh: ca_cell / ca_flux
         double fCa = 0.0;
         if (iCa >= 0 && P.alpha_Ca > 0.0) {
             if (!is_ecm) {
@@ -173,14 +163,9 @@ k_mem(const __grid_constant__ KParams P, const KArrays A, const int cur, const i
             if (cCai != cCai || cCao != cCao) flags |= ST_NAN_CONC;
             if (cCai < 0.0) cCai = 0.0;
             if (cCao < 0.0) cCao = 0.0;
-            const double Qn = P.QnCa0 * cCao;
-            double Qd = P.cATP * cCai;
-            if (Qd == 0.0) Qd = 1.0e-16;
-            const double QdK = Qd * ((keq * keq) * P.inv_K0);
-            const double x = cCai * P.inv_KmCa_Ca, t = P.tCa;
-            const double num = (x * t) * (QdK - Qn);
-            const double den = ((1.0 + x) * (1.0 + t)) * QdK;
-            fCa = -P.alpha_Ca * fast_div(num, den);
+            CaCell cac;
+            ca_cell(cCai, keq, P, cac);
+            fCa = ca_flux(cac, cCao, P);
             fCa = P.rho_pump * fCa;
             if (closed_bnd) fCa = 0.0;
             fCa = P.rho_pump * fCa;                         // applied twice in the reference (sim.py:2141, 2155)
@@ -202,25 +187,26 @@ k_mem(const __grid_constant__ KParams P, const KArrays A, const int cur, const i
                 Am = xm.x; Bm = xm.y; Ag = xg.x; Bg = xg.y;
             }
             // electroflux (sim_toolbox.py:58-65), cA = env, cB = cell; the flux is formed already times the
-            // membrane area ((Dm*Dtm)*sa is what the tile pack of k_mem_pipe stores: same operand order)
-            const double pm_ = cin[i] * Am - co[i] * Bm;
-            double fsa = closed_bnd ? 0.0 : (((Dm[i] * Dtm) * sa) * pm_);
+            // membrane area ((Dm*Dtm)*sa is what the cell pack of k_cell stores: same operand order)
+            const double cinAm = __dmul_rn(cin[i], Am);
+            const double DmS = __dmul_rn(__dmul_rn(Dm[i], Dtm), sa);
+            double fsa = closed_bnd ? 0.0 : ghk_mem_flux(DmS, cinAm, co[i], Bm);
             if (i == iNa) fsa = fma(fNa, sa, fsa);
             if (i == iK) fsa = fma(fK, sa, fsa);
             if (i == iCa) fsa = fma(fCa, sa, fsa);
             // gap junction: gating advances once per ion (sim.py:1272 -> 2180-2183)
             g = fma(g, gc1, gc2);
             // cA = this cell, cB = partner cell (sim.py:2191-2197); zero at boundary membranes through sa_g
-            const double pg_ = cnb[i] * Ag - cin[i] * Bg;
             s_m[lane * NI + i] = fsa;
-            s_g[lane * NI + i] = -(P.Dgj_len[i] * (g * sa_g)) * pg_;
+            s_g[lane * NI + i] = ghk_gj_flux(P.Dgj_len[i], __dmul_rn(g, sa_g), cnb[i], Ag, cin[i], Bg);
             if ((is_ecm && fast_ecm) || diag) {     // per-area fluxes (fast ECM update, sampled-step diagnostics)
+                const double pm_ = fma(-co[i], Bm, cinAm);
                 double f = closed_bnd ? 0.0 : ((Dm[i] * Dtm) * pm_);
                 if (i == iNa) f += fNa;
                 if (i == iK) f += fK;
                 if (i == iCa) f += fCa;
                 if (is_ecm && fast_ecm) A.flux_slots[m * NI + i] = f;
-                if (diag) { A.fl_mem[i * Mo + m] = f; A.fl_gj[i * Mo + m] = bnd ? 0.0 : (-(P.Dgj_len[i] * g) * pg_); }
+                if (diag) { A.fl_mem[i * Mo + m] = f; A.fl_gj[i * Mo + m] = bnd ? 0.0 : ghk_gj_flux(P.Dgj_len[i], g, cnb[i], Ag, cin[i], Bg); }
             }
         }
         A.gjopen[m] = g;
@@ -254,8 +240,8 @@ k_mem(const __grid_constant__ KParams P, const KArrays A, const int cur, const i
             continue;
         }
         const double rvol = fast_rcp(vol);
-        const double cm_new = cc + (Sm * rvol) * P.dt;            // sim_toolbox.py:1177-1181
-        double cn_new = cm_new + P.dt * ((-Sg) * rvol);           // sim.py:2105-2108
+        double cm_new, cn_new;
+        cell_conc_update(cc, Sm, Sg, rvol, P.dt, cm_new, cn_new);
         if (cn_new != cn_new) flags |= ST_NAN_CONC;
         if (cn_new < 0.0) { cn_new = 0.0; flags |= ST_NEG; }      // no_negs, sim.py:2111
         A.cc_cells[i * C + c] = cn_new;
@@ -753,8 +739,12 @@ cudaError_t prepare_mem_pipe(int ni);
 void launch_mem_pipe(int ni, const KParams& P, const KArrays& A, int n_sms, int cur, cudaStream_t st);
 static int g_n_sms = 148;
 
+// kcell.cu: the lane-per-cell build of the specialised kernel (fluxes in flux_ell)
+bool kcell_enabled();
+void launch_cell(int ni, const KParams& P, const KArrays& A, int cur, cudaStream_t st);
+
 template <int NI>
-static void launch_mem_t(const KParams& P, const KArrays& A, int n_ctas, int cur, int diag, cudaStream_t st)
+static int launch_mem_t(const KParams& P, const KArrays& A, int n_ctas, int cur, int diag, cudaStream_t st)
 {
     const size_t smem = (size_t)KM_SMEM_DOUBLES(NI) * sizeof(double);
     const int grid = (P.n_tiles + (BT_TPB / 32) - 1) / (BT_TPB / 32);
@@ -765,11 +755,13 @@ static void launch_mem_t(const KParams& P, const KArrays& A, int n_ctas, int cur
                     P.iCa == StdProf<NI>::iCa && !kmem_generic() && !P.defer;
     for (int i = 0; i < NI && std_prof; ++i) std_prof = (P.zi[i] == StdProf<NI>::z(i)) && P.zi[i] != 0;
     if (P.has_phi || P.polar) k_mem<NI, true, 2, 0><<<grid, BT_TPB, smem, st>>>(P, A, cur, diag);
+    else if (std_prof && NI <= 7 && kcell_enabled() && A.ell_DmS) { launch_cell(NI, P, A, cur, st); return 1; }
     else if (std_prof && kmem_pipe_enabled()) launch_mem_pipe(NI, P, A, g_n_sms, cur, st);
     else if (std_prof && minb2) k_mem<NI, false, 2, 1><<<grid, BT_TPB, smem, st>>>(P, A, cur, diag);
     else if (std_prof && kmem_minb() == 4) k_mem<NI, false, 4, 1><<<grid, BT_TPB, smem, st>>>(P, A, cur, diag);
     else if (std_prof) k_mem<NI, false, 3, 1><<<grid, BT_TPB, smem, st>>>(P, A, cur, diag);
     else k_mem<NI, false, 2, 0><<<grid, BT_TPB, smem, st>>>(P, A, cur, diag);
+    return 0;
 }
 
 template <typename K>
@@ -809,14 +801,14 @@ cudaError_t prepare_kernels(int ni)
     }
 }
 
-void launch_mem(int ni, const KParams& P, const KArrays& A, int n_ctas, int cur, int diag, cudaStream_t st)
+int launch_mem(int ni, const KParams& P, const KArrays& A, int n_ctas, int cur, int diag, cudaStream_t st)
 {
     switch (ni) {
-        case 4: launch_mem_t<4>(P, A, n_ctas, cur, diag, st); break;
-        case 5: launch_mem_t<5>(P, A, n_ctas, cur, diag, st); break;
-        case 6: launch_mem_t<6>(P, A, n_ctas, cur, diag, st); break;
-        case 7: launch_mem_t<7>(P, A, n_ctas, cur, diag, st); break;
-        default: launch_mem_t<8>(P, A, n_ctas, cur, diag, st); break;
+        case 4: return launch_mem_t<4>(P, A, n_ctas, cur, diag, st);
+        case 5: return launch_mem_t<5>(P, A, n_ctas, cur, diag, st);
+        case 6: return launch_mem_t<6>(P, A, n_ctas, cur, diag, st);
+        case 7: return launch_mem_t<7>(P, A, n_ctas, cur, diag, st);
+        default: return launch_mem_t<8>(P, A, n_ctas, cur, diag, st);
     }
 }
 

@@ -148,3 +148,89 @@ __device__ __forceinline__ void ghk_pick(const GhkAB& t, int zi, double& A, doub
     B = (zi < 0) ? X : Y;
 }
 
+// ---------------------------------------------------------------------------- shared membrane math
+// Every membrane kernel (kernels.cu:k_mem, kmem_pipe.cu:k_mem_pipe, kcell.cu:k_cell) forms its fluxes through the
+// functions below, split into the part that depends on the CELL only (its Vmem and concentrations: computed once per
+// membrane by the lane-per-membrane kernels, once per cell by k_cell) and the part that depends on the membrane (env
+// square, gap-junction partner).  Same functions, same operand order => bit-identical results across the kernels;
+// products that cross the cell/membrane boundary are rounded explicitly (__dmul_rn) so that the compiler's FMA
+// contraction cannot differ between a value used once (per membrane) and six times (per cell).
+
+// membrane side of a cell: GHK table at alpha(z=+1) of the cell's Vmem and the pumps' equilibrium constant
+// Keq = exp(-dG/RT + F vm/RT) = K0/e1 (sim_toolbox.py:54-65, 96-100)
+struct MemSide { GhkAB t; double keq; };
+__device__ __forceinline__ double mem_side(double vm_own, const KParams& P, MemSide& s)
+{
+    const double a1 = ((vm_own + FLOAT_NONCE) * P.F) * P.inv_RT_sim;
+    s.keq = P.K0 * fast_rcp(ghk_table(a1, s.t));
+    return a1;
+}
+
+// Na/K-ATPase (sim_toolbox.py:71-122):  f_Na = -3 blk alpha fwd (1 - Q/Keq),
+//   fwd = u3 w2 t / ((1+u3)(1+w2)(1+t)),  Q = Qn/Qd  =>  f_Na = -3 blk alpha (u3 t w2)(Qd Keq - Qn) / ((1+u3)(1+t)(1+w2) Qd Keq)
+// cell part: everything of cNai, cKi;  membrane part: cNao, cKo (the membrane's env square)
+struct NaKCell { double bb, Qd3, u3t, dct; };
+__device__ __forceinline__ void nak_cell(double cNai, double cKi, const KParams& P, NaKCell& c)
+{
+    const double b = cKi * 1e-3;
+    c.bb = __dmul_rn(b, b);
+    const double a2 = cNai * 1e-3;
+    c.Qd3 = __dmul_rn(P.QdNK0, __dmul_rn(__dmul_rn(a2, a2), a2));
+    const double u = cNai * P.inv_KmNK_Na;
+    const double u3 = __dmul_rn(__dmul_rn(u, u), u);
+    c.u3t = __dmul_rn(u3, P.tNK);
+    c.dct = __dmul_rn(1.0 + u3, 1.0 + P.tNK);
+}
+// returns f_Na before rho_pump (its negative is sim.rate_NaKATP)
+__device__ __forceinline__ double nak_flux(const NaKCell& c, double keq, double cNao, double cKo, double blk, const KParams& P)
+{
+    const double a = cNao * 1e-3;
+    const double Qn = __dmul_rn(__dmul_rn(P.QnNK0, __dmul_rn(__dmul_rn(a, a), a)), c.bb);
+    const double b2 = cKo * 1e-3;
+    double Qd = __dmul_rn(c.Qd3, __dmul_rn(b2, b2));
+    if (Qd == 0.0) Qd = 1.0e-15;
+    const double QdK = __dmul_rn(Qd, keq);
+    const double w = cKo * P.inv_KmNK_K;
+    const double w2 = __dmul_rn(w, w);
+    const double num = __dmul_rn(__dmul_rn(c.u3t, w2), __dsub_rn(QdK, Qn));
+    const double den = __dmul_rn(__dmul_rn(c.dct, 1.0 + w2), QdK);
+    return ((-3.0 * blk) * P.alpha_NaK) * fast_div(num, den);
+}
+
+// Ca-ATPase (sim.py:2126-2155, sim_toolbox.py:124-182):  f = -alpha (x t/((1+x)(1+t))) (1 - Qn/(Qd Keq)),
+// Keq = K0/e1^2; only Qn = cADP cPi cCao depends on the membrane.  cCai is the fresh cell value (after no_negs).
+struct CaCell { double g1, g2; };                   // -alpha x t/((1+x)(1+t)),  1/(Qd Keq)
+__device__ __forceinline__ void ca_cell(double cCai, double keq, const KParams& P, CaCell& c)
+{
+    double Qd = P.cATP * cCai;
+    if (Qd == 0.0) Qd = 1.0e-16;
+    const double QdK = Qd * ((keq * keq) * P.inv_K0);
+    c.g2 = fast_rcp(QdK);
+    const double x = cCai * P.inv_KmCa_Ca;
+    c.g1 = -P.alpha_Ca * fast_div(x * P.tCa, (1.0 + x) * (1.0 + P.tCa));
+}
+__device__ __forceinline__ double ca_flux(const CaCell& c, double cCao, const KParams& P)
+{
+    const double Qn = __dmul_rn(P.QnCa0, cCao);
+    return __dmul_rn(c.g1, fma(-Qn, c.g2, 1.0));
+}
+
+// one ion through one membrane, already times the membrane area: DmS = (Dm*(-rho_channel/tm))*mem_sa,
+// cinAm = cin*A (cell part), co*B (membrane part)  (sim_toolbox.py:58-65 in A/B form)
+__device__ __forceinline__ double ghk_mem_flux(double DmS, double cinAm, double co, double Bm)
+{
+    return __dmul_rn(DmS, fma(-co, Bm, cinAm));
+}
+// gap-junction flux times area; gsa = g*sa (0 at boundary membranes), cA = this cell, cB = partner (sim.py:2191-2197)
+__device__ __forceinline__ double ghk_gj_flux(double Dgj_len, double gsa, double cnb, double Ag, double cin, double Bg)
+{
+    return __dmul_rn(-__dmul_rn(Dgj_len, gsa), fma(cnb, Ag, -__dmul_rn(cin, Bg)));
+}
+
+// update_Co + update_all_concs of one (cell, ion) (sim_toolbox.py:1177-1181, sim.py:2105-2108): cm = the stale
+// cc_at_mem (after the membrane fluxes), cn = the new cell concentration (after the gap-junction fluxes, before no_negs)
+__device__ __forceinline__ void cell_conc_update(double cc, double Sm, double Sg, double rvol, double dt, double& cm_new, double& cn_new)
+{
+    cm_new = fma(__dmul_rn(Sm, rvol), dt, cc);
+    cn_new = fma(dt, __dmul_rn(-Sg, rvol), cm_new);
+}

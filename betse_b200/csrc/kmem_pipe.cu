@@ -273,11 +273,11 @@ k_mem_pipe(const __grid_constant__ KParams P, const KArrays A, const int cur)
             const double vm_own = Cs[lc];
             double cCai = 0.0;
             if (iCa >= 0) cCai = c_cc[lc * NI + iCa];
-            // membrane side: electroflux adds 1e-25 to vBA (sim_toolbox.py:54); alpha for z = +1
-            const double a1 = ((vm_own + FLOAT_NONCE) * P.F) * P.inv_RT_sim;
-            GhkAB tm;
-            const double keq = P.K0 * fast_rcp(ghk_table(a1, tm));   // K0/e1 = exp(-dG/RT + F vm/RT): pump Keq
-            // gap junction: vgj and its GHK table with p.T (sim.py:2166, 2197)
+            // membrane side (per-cell quantities, recomputed by every membrane lane here) and gap-junction side
+            MemSide ms;
+            mem_side(vm_own, P, ms);
+            const GhkAB& tm = ms.t;
+            const double keq = ms.keq;
             const double vgj0 = vm_nb - vm_own;
             const double ag1 = ((vgj0 + FLOAT_NONCE) * P.F) * P.inv_RT_p;
             GhkAB tg;
@@ -286,39 +286,23 @@ k_mem_pipe(const __grid_constant__ KParams P, const KArrays A, const int cur)
             gj_gate_map(vgj0, P, P.gj_block, gc1, gc2);
             const double sa_g = (nnp < 0) ? 0.0 : sa;   // no gap-junction flux at boundary membranes (sim.py:2199-2201)
 
-            // ---- Na/K-ATPase (sim_toolbox.py:71-122)
             double fNa = 0.0, fK = 0.0;
             if (P.alpha_NaK > 0.0) {
-                const double cNao = co[iNa], cNai = cin[iNa], cKo = co[iK], cKi = cin[iK];
-                const double a = cNao * 1e-3, b = cKi * 1e-3;
-                const double Qn = (P.QnNK0 * (a * a * a)) * (b * b);
-                const double a2 = cNai * 1e-3, b2 = cKo * 1e-3;
-                double Qd = (P.QdNK0 * (a2 * a2 * a2)) * (b2 * b2);
-                if (Qd == 0.0) Qd = 1.0e-15;
-                const double QdK = Qd * keq;
-                const double u = cNai * P.inv_KmNK_Na, w = cKo * P.inv_KmNK_K, t = P.tNK;
-                const double u3 = u * u * u, w2 = w * w;
-                const double num = ((u3 * w2) * t) * (QdK - Qn);
-                const double den = (((1.0 + u3) * (1.0 + w2)) * (1.0 + t)) * QdK;
-                fNa = ((-3.0 * P.NaK_block) * P.alpha_NaK) * fast_div(num, den);
+                NaKCell nc_;
+                nak_cell(cin[iNa], cin[iK], P, nc_);
+                fNa = nak_flux(nc_, keq, co[iNa], co[iK], P.NaK_block, P);
                 fK = -(2.0 / 3.0) * fNa;
                 fNa = P.rho_pump * fNa;
                 fK = P.rho_pump * fK;
             }
-            // ---- Ca-ATPase (sim.py:2126-2155, sim_toolbox.py:124-182)
             double fCa = 0.0;
             if (iCa >= 0 && P.alpha_Ca > 0.0) {
                 if (cCai != cCai || cCao != cCao) flags |= ST_NAN_CONC;
                 if (cCai < 0.0) cCai = 0.0;
                 if (cCao < 0.0) cCao = 0.0;
-                const double Qn = P.QnCa0 * cCao;
-                double Qd = P.cATP * cCai;
-                if (Qd == 0.0) Qd = 1.0e-16;
-                const double QdK = Qd * ((keq * keq) * P.inv_K0);
-                const double x = cCai * P.inv_KmCa_Ca, t = P.tCa;
-                const double num = (x * t) * (QdK - Qn);
-                const double den = ((1.0 + x) * (1.0 + t)) * QdK;
-                fCa = -P.alpha_Ca * fast_div(num, den);
+                CaCell cac;
+                ca_cell(cCai, keq, P, cac);
+                fCa = ca_flux(cac, cCao, P);
                 fCa = P.rho_pump * fCa;
                 fCa = P.rho_pump * fCa;                 // applied twice in the reference (sim.py:2141, 2155)
             }
@@ -328,13 +312,13 @@ k_mem_pipe(const __grid_constant__ KParams P, const KArrays A, const int cur)
                 double Am, Bm, Ag, Bg;
                 ghk_pick(tm, StdProf<NI>::z(i), Am, Bm);
                 ghk_pick(tg, StdProf<NI>::z(i), Ag, Bg);
-                double fsa = DmS[i] * (cin[i] * Am - co[i] * Bm);          // sim_toolbox.py:58-65, times mem_sa
+                double fsa = ghk_mem_flux(DmS[i], __dmul_rn(cin[i], Am), co[i], Bm);
                 if (i == iNa) fsa = fma(fNa, sa, fsa);
                 if (i == iK) fsa = fma(fK, sa, fsa);
                 if (i == iCa) fsa = fma(fCa, sa, fsa);
                 g = fma(g, gc1, gc2);                                      // once per ion (sim.py:1272 -> 2180-2183)
                 s_m[lane * KP_SST(NI) + i] = fsa;
-                s_g[lane * KP_SST(NI) + i] = -(P.Dgj_len[i] * (g * sa_g)) * (cnb[i] * Ag - cin[i] * Bg);   // sim.py:2191-2197
+                s_g[lane * KP_SST(NI) + i] = ghk_gj_flux(P.Dgj_len[i], __dmul_rn(g, sa_g), cnb[i], Ag, cin[i], Bg);
             }
             A.gjopen[m] = g;
         }
@@ -373,8 +357,8 @@ k_mem_pipe(const __grid_constant__ KParams P, const KArrays A, const int cur)
             for (int k = 0; k < 8; ++k) { if (k < n) { Sm += pm[k * KP_SST(NI)]; Sg += pg[k * KP_SST(NI)]; } }
             for (int k = 8; k < n; ++k) { Sm += pm[k * KP_SST(NI)]; Sg += pg[k * KP_SST(NI)]; }
             const double rvol = fast_rcp(vol);
-            const double cm_new = c_cc[q] + (Sm * rvol) * P.dt;          // sim_toolbox.py:1177-1181
-            double cn_new = cm_new + P.dt * ((-Sg) * rvol);              // sim.py:2105-2108
+            double cm_new, cn_new;
+            cell_conc_update(c_cc[q], Sm, Sg, rvol, P.dt, cm_new, cn_new);
             if (cn_new != cn_new) flags |= ST_NAN_CONC;
             if (cn_new < 0.0) { cn_new = 0.0; flags |= ST_NEG; }         // no_negs, sim.py:2111
             A.cc_cells[oc] = cn_new;

@@ -41,6 +41,7 @@ struct KParams {
     int ny, nx, y0, ny_global, y_own0, y_own1;
     int n_cells, n_cells_owned, n_mems_owned, n_ctas, n_tiles;
     int pf_tiles;                           // k_mem: L2 prefetch distance in tiles (0 = off)
+    int n_blocks, ell_R32;                  // k_cell: blocks of 32 cells, elements per row array of the cell pack (rows * 32)
     int defer;                              // k_mem stores its membrane->cell sums instead of applying them (channels)
     int chan_charge;                        // p.substances_affect_charge: Jmem takes the channels' extra_J_mem
     // kernel row ranges in local rows (single GPU: all [0, ny)): ion transport, membrane->env
@@ -62,6 +63,13 @@ struct KArrays {
     const int *tile_desc;        // warp packing (k_mem): int4 {c0, nc, m0, nm} per tile of whole cells, <= 32 membranes
     const char *tile_pack;       // k_mem_pipe: fixed-size per-tile constant blocks (layout: kmem_pipe.cu header)
     const int *slot_ptr, *slot_idx;
+    // cell pack of k_cell (SELL-32: block b = cells 32b..32b+31; row blk_row0[b] + k holds membrane k of each cell)
+    const int *blk_row0;         // [n_blocks + 1] first row of every block
+    const double *ell_DmS;       // [I][rows*32] (Dm*(-rho_channel/tm))*mem_sa
+    const double *ell_sa;        // [rows*32]
+    const int *ell_nnp, *ell_esq; // [rows*32] partner cell | boundary bit, env square
+    double *flux_ell;            // [rows][I][32] membrane -> env exchange, written by k_cell
+    const int *slot_off;         // [slots] position of every env-square slot in flux_ell (>= 0) or in flux_slots (-(s*I)-1)
     const double *mem_sa, *mem_nx, *mem_ny, *cell_vol, *cell_sa, *diviterm, *num_mems;
     const double *memsa_env, *gj_w;
     // state

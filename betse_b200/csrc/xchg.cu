@@ -34,7 +34,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
 
 __global__ void __launch_bounds__(256)
 k_xchg(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ XPlan X,
-       const int which, const int buf, const int mode)
+       const int which, const int buf, const int mode, const int flux_ell)
 {
     const int NI = P.n_ions;
     const int C = P.n_cells, E = P.ny * P.nx, nx = P.nx;
@@ -60,8 +60,11 @@ k_xchg(const __grid_constant__ KParams P, const KArrays A, const __grid_constant
                 const int nf = nb.n_send_flux;
                 for (int t = gtid; t < nf * NI; t += gsz) {
                     const int j = t / NI, i = t - j * NI;
-                    const int m = __ldg(nb.send_flux + j);
-                    nb.flux[(nb.recv_slot0 + j) * NI + i] = A.flux_slots[m * NI + i];
+                    // the receiver's remote slots are [slot][ion] whichever kernel produced the fluxes here
+                    double v;
+                    if (flux_ell) v = A.flux_ell[(size_t)__ldg(nb.send_flux_ell + j) + i * 32];
+                    else v = A.flux_slots[__ldg(nb.send_flux + j) * NI + i];
+                    nb.flux[(nb.recv_slot0 + j) * NI + i] = v;
                 }
             } else {
                 const int ncc = nb.cc_rows * nx;
@@ -105,7 +108,7 @@ k_xchg(const __grid_constant__ KParams P, const KArrays A, const __grid_constant
     }
 }
 
-void launch_xchg(const KParams& P, const KArrays& A, const XPlan& X, int which, int buf, int mode, cudaStream_t st)
+void launch_xchg(const KParams& P, const KArrays& A, const XPlan& X, int which, int buf, int mode, int flux_ell, cudaStream_t st)
 {
     // enough CTAs to cover the largest block copy; the wait-only form needs one
     long long work = 1;
@@ -121,5 +124,5 @@ void launch_xchg(const KParams& P, const KArrays& A, const XPlan& X, int which, 
     if (grid < 1) grid = 1;
     if (grid > 48) grid = 48;
     if (!(mode & XCHG_PUSH)) grid = 1;
-    k_xchg<<<grid, 256, 0, st>>>(P, A, X, which, buf, mode);
+    k_xchg<<<grid, 256, 0, st>>>(P, A, X, which, buf, mode, flux_ell);
 }

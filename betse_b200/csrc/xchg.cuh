@@ -12,6 +12,7 @@ struct XNbr {
     int n_send_cells, recv_cell0;
     int n_send_flux, recv_slot0;
     const int *send_cells, *send_flux;
+    const int *send_flux_ell;       // position of the same membranes' fluxes in flux_ell (k_cell), or null
     int cc_rows, cc_src_row0, cc_dst_row0;
     int v_rows, v_src_row0, v_dst_row0;
 };

@@ -325,15 +325,22 @@ class TissueEngine:
             if name in state and np.any(np.asarray(state[name]) != 0):
                 put(name, state[name], n)
         resched = False
+        blk_arrays = self.__dict__.setdefault("_block_arrays", set())
         for name in ("NaKATP_block", "gj_block"):
             if name in state:
                 if np.ndim(state[name]) == 0 or np.size(state[name]) == 1:
                     v = _scalar(state[name])
-                    if v != self._sched.get(name):
+                    if name in blk_arrays:
+                        # the device holds a per-membrane array for this block (sim.NaKATP_block starts as np.ones(mdl),
+                        # sim.py:848-849) and the kernels read the array once it exists: a scalar rebinding of the
+                        # Simulator attribute (tishandler.py:790) replaces it as a whole
+                        put(name, np.full(M, v), M)
+                    elif v != self._sched.get(name):
                         self._sched[name] = v
                         resched = True
                 else:
                     put(name, state[name], M)
+                    blk_arrays.add(name)
         for name in ("c_env_bound", "T", "bound_V", "D_gj"):
             if name in state:
                 resched |= self._set_sched_value(name, state[name])
@@ -367,6 +374,20 @@ class TissueEngine:
 
     def set_bound_V(self, v):
         self.set_field("bound_V", v)
+
+    def set_bath(self, values):
+        """Tissue WITHOUT extracellular spaces: overwrite the well-mixed bath concentration of some ions
+        (``{ion index: value}``) — the global K_env / Cl_env / Na_env events write ``sim.cc_env[ion][:]`` on every step
+        (tishandler.py:759-777); the other ions keep the value the device has advanced."""
+        if self.is_ecm:
+            raise BetseB200Error("set_bath applies to tissues without extracellular spaces")
+        ce = np.full(self.I, np.nan)
+        for i, v in values.items():
+            ce[int(i)] = float(v)
+        sh = capi.StateHost()
+        sh.cenv_uniform = capi.ptr_f64(ce)
+        self.h2d_bytes += 8 * len(values)
+        self._check(self.lib.betse_upload_state(self.ctx, C.byref(sh)), "betse_upload_state")
 
     # ------------------------------------------------------------------ stepping
     def step(self, n=1, diag=False):

@@ -155,6 +155,20 @@ def channels_from_sim(sim, p=None):
     return out
 
 
+def _bath_event_ions(sim, p):
+    """Ion indices whose bath concentration a global event rewrites every step when the tissue has no extracellular
+    spaces (tishandler.py:745-777: ``sim.cc_env[ion][:] = ...`` under K_env / Cl_env / Na_env)."""
+    go = getattr(p, "global_options", None) or {}
+    out = []
+    if go.get("K_env", 0) != 0:
+        out.append(int(sim.iK))
+    if go.get("Cl_env", 0) != 0 and getattr(p, "ions_dict", {}).get("Cl", 0) == 1:
+        out.append(int(sim.iCl))
+    if go.get("Na_env", 0) != 0:
+        out.append(int(sim.iNa))
+    return out
+
+
 def check_supported(sim, p):
     """Refuse loudly instead of silently computing a different model."""
     from . import network as netlib
@@ -382,6 +396,7 @@ def run_sim_core_loop(sim, phase, time_steps, time_steps_sampled, anim_cells=Non
     cache = {f: np.array(getattr(sim, f), copy=True) for f in _SCHEDULED if hasattr(sim, f)
              and getattr(sim, f) is not None} if fire else {}
     bv_cache = dict(getattr(sim, "bound_V", {})) if fire else {}
+    bath_events = _bath_event_ions(sim, p) if (fire and not eng.is_ecm) else []
     n_total = len(time_steps)
     n = 0
     try:
@@ -394,6 +409,10 @@ def run_sim_core_loop(sim, phase, time_steps, time_steps_sampled, anim_cells=Non
                     if new.shape != cache[f].shape or not np.array_equal(new, cache[f]):
                         eng.set_field(f, new)
                         cache[f] = np.array(new, copy=True)
+                if bath_events:
+                    # without extracellular spaces the global K_env / Cl_env / Na_env events overwrite the bath
+                    # concentration itself on every step (tishandler.py:759-777), whatever the step before made of it
+                    eng.set_bath({i: float(np.asarray(sim.cc_env[i]).reshape(-1)[0]) for i in bath_events})
                 bv = getattr(sim, "bound_V", None)
                 if isinstance(bv, dict) and bv != bv_cache:
                     # the external-voltage event (tissue/event/tisevevolt.py:76-88): Phi_b is re-solved on the device

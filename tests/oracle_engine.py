@@ -66,6 +66,12 @@ class OracleEngine:
     def set_bound_V(self, v):
         self.set_field("bound_V", v)
 
+    def set_bath(self, values):
+        self.sets.append("bath")
+        o = self._sim()
+        for i, v in values.items():
+            o.cc_env[int(i)][:] = float(v)
+
     def step(self, n=1, diag=False):
         o = self._sim()
         o.diagnostics = True

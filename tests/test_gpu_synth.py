@@ -210,3 +210,69 @@ def test_dropin_loop_raises_on_instability():
         simloop.run_sim_core_loop(sim, phase, ts, set(ts[3::4].tolist()), None)
     assert np.isnan(np.asarray(sim.cc_cells)).any() or np.isnan(np.asarray(sim.vm)).any()   # the partial state came back
     assert sim.sampled == 0                                                                   # nothing was stored after it
+
+
+def test_block_array_then_scalar_reaches_the_device():
+    """'block NaKATP pump' (tishandler.py:789-790): sim.NaKATP_block is np.ones(mdl) at loop entry (sim.py:848-849) and
+    is REBOUND to a scalar by fire_events; the device must follow the scalar, not keep the stale array of ones.  Same
+    for sim.gj_block (array -> array subset rewritten in place)."""
+    from betse_b200 import synth
+    from betse_b200.engine import TissueEngine
+    from oracle.betse_oracle import OracleSim
+    mesh, p, st = synth.make_tissue(3000)
+    M = len(mesh["mem_sa"])
+    st = dict(st, NaKATP_block=np.ones(M), gj_block=np.ones(M))
+    eng = TissueEngine(mesh, p, st)
+    eng.update_V()
+    ora = OracleSim(mesh, p, st)
+    ora.diagnostics = False
+    ora.update_V()
+    gjb = np.ones(M)
+    gjb[::3] = 0.25
+    for n, (blk, gj) in enumerate([(1.0, None), (0.4, gjb), (0.0, gjb), (0.7, np.ones(M))]):
+        eng.set_field("NaKATP_block", blk)                # scalar, like the reference's rebinding
+        ora.NaKATP_block = np.asarray(blk, dtype=float)
+        if gj is not None:
+            eng.set_field("gj_block", gj)
+            ora.gj_block = np.array(gj)
+        for _ in range(3):
+            assert not (eng.step(1) & 3)
+            ora.step()
+        _compare(eng, ora, mesh, p, True, "block phase %d" % n)
+    eng.close()
+
+
+def test_cell_kernel_equals_generic_kernel_bitwise(monkeypatch):
+    """k_cell (lane per cell, cell pack) and the run-time-configured k_mem share their arithmetic (csrc/kmath.cuh):
+    the states they produce must be bit-identical, on a uniform sheet and on a ragged reference mesh (3-7 membranes per
+    cell: padded rows of the cell pack)."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+from tests import util
+from betse_b200 import synth
+from betse_b200.engine import TissueEngine
+out = {}
+mesh, p, st = synth.make_tissue(5000)
+eng = TissueEngine(mesh, p, st); eng.update_V(); eng.step(7)
+out["synth"] = eng.download(["cc_cells", "cc_at_mem", "cc_env", "vm", "gjopen", "E_env_x"]); eng.close()
+cap = util.load_golden("mammal_ecm")
+mesh, p, s0 = util.group(cap, "cells."), util.group(cap, "sim.p."), util.group(cap, "sim.s0.")
+eng = TissueEngine(mesh, p, s0); eng.step(7)
+out["golden"] = eng.download(["cc_cells", "cc_at_mem", "cc_env", "vm", "gjopen", "E_env_x"]); eng.close()
+np.savez(sys.argv[1], **{k + "." + f: a for k, d in out.items() for f, a in d.items()})
+''' % util.ROOT
+    import os
+    import tempfile
+    res = {}
+    with tempfile.TemporaryDirectory() as d:
+        for tag, env in (("cell", {"BETSE_KCELL": "1"}), ("generic", {"BETSE_KCELL": "0", "BETSE_KMEM_GENERIC": "1"})):
+            fn = os.path.join(d, tag + ".npz")
+            subprocess.run([sys.executable, "-c", code, fn], check=True, env=dict(os.environ, **env))
+            with np.load(fn) as z:
+                res[tag] = {k: z[k] for k in z.files}
+    assert res["cell"].keys() == res["generic"].keys() and len(res["cell"]) == 12
+    for k in res["cell"]:
+        assert np.array_equal(res["cell"][k], res["generic"][k]), k

@@ -4,6 +4,7 @@ import os
 
 import numpy as np
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GOLDEN = sorted(os.path.splitext(os.path.basename(f))[0]
                 for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
