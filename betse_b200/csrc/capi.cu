@@ -14,12 +14,14 @@
 #include "../../include/betse_b200.h"
 #include "kparams.cuh"
 #include "xchg.cuh"
+#include <climits>
 #include "channels.cuh"
 #include "network.cuh"
 #include "hh.cuh"
 
 // launchers (kernels.cu)
-int launch_mem(int ni, const KParams& P, const KArrays& A, int n_ctas, int cur, int diag, cudaStream_t st);   // returns 1 when the fluxes went to flux_ell
+int launch_mem(int ni, const KParams& P, const KArrays& A, int n_ctas, int cur, int diag, int fuse, cudaStream_t st);   // bit 0: fluxes in flux_ell, bit 1: env accumulation fused
+int mem_kernel_kind(int ni, const KParams& P, const KArrays& A, int diag);
 void launch_ion(const KParams& P, const KArrays& A, int nx, int cur, int diag, int ion0, int n, cudaStream_t st);
 void launch_ion_smooth(int ni, const KParams& P, const KArrays& A, int ny, int nx, int nxt, cudaStream_t st);
 void launch_envacc(int ni, const KParams& P, const KArrays& A, int E, int nxt, int apply, cudaStream_t st);
@@ -78,7 +80,10 @@ struct betse_ctx {
     int C = 0, Co = 0, M = 0, Mo = 0, E = 0, ny = 0, nx = 0, I = 0, n_ctas = 0, n_tiles = 0, n_slots = 0;
     bool diag_valid = false;
     int* mem_ell = nullptr;                  // [Mo] position of every membrane's fluxes in flux_ell (cell pack of k_cell)
+    int* kc_sync = nullptr;                  // k_cell: ticket + group counters, zeroed before every launch
+    int kc_sync_n = 0;
     int flux_is_ell = 0;                     // layout the last membrane kernel wrote its membrane -> env fluxes in
+    int env_fused = 0;                       // the last membrane kernel ran the env accumulation itself (fused schedule)
     // exchange window (every buffer a neighbouring rank writes) and the halo-exchange plan
     char* win = nullptr;
     betse_window_info winfo;
@@ -509,16 +514,19 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
     // ---- cell pack (k_cell): SELL-32 rows of the per-membrane constants, built on the device like the tile pack
     if (hp->n_ions <= 7 && hp->is_ecm) {
         const int nb = (Co + 31) / 32;
-        std::vector<int> row0(nb + 1, 0);
+        std::vector<int> row0(2 * (nb + 1), 0);          // int2 {first row, first membrane} per block
         for (int b = 0; b < nb; ++b) {
             int kb = 0;
             const int c1 = std::min(Co, (b + 1) * 32);
             for (int c = b * 32; c < c1; ++c) kb = std::max(kb, mesh->cell_mem_ptr[c + 1] - mesh->cell_mem_ptr[c]);
-            row0[b + 1] = row0[b] + kb;
+            row0[2 * (b + 1)] = row0[2 * b] + kb;
+            row0[2 * b + 1] = mesh->cell_mem_ptr[b * 32];
         }
-        const long long R32 = (long long)row0[nb] * 32;
+        row0[2 * nb + 1] = Mo;
+        const long long R32 = (long long)row0[2 * nb] * 32;
         if (R32 * hp->n_ions < (1LL << 31) - 64) {       // 32-bit flux positions; otherwise k_mem stays in charge
             P.n_blocks = nb; P.ell_R32 = (int)R32;
+            { const char* e = getenv("BETSE_KCELL_PF"); P.pf_dist = e ? atoi(e) : 1024; }
             if ((r = dev_upload(ctx, (int**)&A.blk_row0, row0.data(), row0.size()))) return r;
             if ((r = dev_alloc(ctx, (double**)&A.ell_DmS, (size_t)R32 * I))) return r;
             if ((r = dev_alloc(ctx, (double**)&A.ell_sa, (size_t)R32))) return r;
@@ -528,9 +536,49 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
             if ((r = dev_alloc(ctx, &ctx->mem_ell, (size_t)Mo))) return r;
             const int n_sl = mesh->ecm_slot_ptr ? mesh->ecm_slot_ptr[E] : Mo;
             if ((r = dev_alloc(ctx, (int**)&A.slot_off, (size_t)n_sl))) return r;
+            const int n_grp = (nb + KC_GRP - 1) / KC_GRP;
+            if ((r = dev_alloc(ctx, &ctx->kc_sync, (size_t)n_grp + 1))) return r;     // [ticket | group counters]
+            A.ticket = ctx->kc_sync; A.cell_done = ctx->kc_sync + 1;
+            ctx->kc_sync_n = n_grp + 1;
             launch_pack_cell_const(ctx->P, A, ctx->mem_ell, ctx->stream);
             launch_slot_off(A.slot_idx, ctx->mem_ell, const_cast<int*>(A.slot_off), n_sl, Mo, I, ctx->stream);
             CK(cudaGetLastError());
+            // ---- fused schedule (undivided tissues): env task v = squares [v*CHUNK, (v+1)*CHUNK) runs once the cell
+            //      blocks that feed it are done; it is released `lag` blocks behind the last of them, so that it
+            //      hardly ever waits and the fluxes it reads are still in L2
+            const bool whole = ctx->Co == ctx->C && !mesh->ecm_slot_ptr;
+            const char* fe = getenv("BETSE_FUSE");
+            if (whole && !(fe && fe[0] == '0')) {
+                const int nv = (E + KC_ENV_CHUNK - 1) / KC_ENV_CHUNK;
+                std::vector<int> lo(nv, INT_MAX), hi(nv, -1);
+                for (int m = 0; m < Mo; ++m) {
+                    const int v = mesh->map_mem2ecm[m] / KC_ENV_CHUNK, u = mesh->mem_to_cells[m] / 32;
+                    lo[v] = std::min(lo[v], u); hi[v] = std::max(hi[v], u);
+                }
+                int lag = 2 * 148 * 8;
+                { const char* e = getenv("BETSE_FUSE_LAG"); if (e) lag = atoi(e); }
+                std::vector<int> dep(2 * (size_t)nv), sched;
+                sched.reserve((size_t)nb + nv);
+                std::vector<long long> rel(nv);
+                long long run = -1;
+                for (int v = 0; v < nv; ++v) {
+                    if (hi[v] >= 0) {
+                        dep[2 * v] = lo[v] / KC_GRP; dep[2 * v + 1] = hi[v] / KC_GRP;
+                        // the whole last group must hold smaller tickets than the env task
+                        run = std::max(run, (long long)std::min(nb - 1, (hi[v] / KC_GRP + 1) * KC_GRP - 1) + lag);
+                    } else { dep[2 * v] = 1; dep[2 * v + 1] = 0; }      // nothing to wait for
+                    rel[v] = run;
+                }
+                int v = 0;
+                for (int u = 0; u < nb; ++u) {
+                    sched.push_back(u);
+                    while (v < nv && rel[v] <= u) sched.push_back((int)(0x80000000u | (unsigned)v++));
+                }
+                while (v < nv) sched.push_back((int)(0x80000000u | (unsigned)v++));
+                P.n_sched = (int)sched.size();
+                if ((r = dev_upload(ctx, (int**)&A.sched, sched.data(), sched.size()))) return r;
+                if ((r = dev_upload(ctx, (int**)&A.env_dep, dep.data(), dep.size()))) return r;
+            }
         }
     }
 
@@ -852,7 +900,11 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
         // sim.py:1282 after 2254): the Ca row is transported first, the other ions run on a second
         // stream NEXT TO the membrane kernel (which is latency-bound and leaves issue slots free).
         const bool chans = !ctx->chans.empty() || ctx->net_on[0] || ctx->net_on[1] || ctx->noise_on;   // deferred-update mode
-        const bool overlap = ecm && ctx->overlap && !evs && ctx->hp.sharpness >= 1.0 && !chans;
+        // fused schedule (k_cell runs the env accumulation itself, undivided tissues): every ion's transport must have
+        // finished before the kernel starts, so nothing is left to run next to it
+        const bool fuse = ecm && ctx->P.n_sched > 0 && ctx->X.n_nbr == 0 && !chans && ctx->hp.sharpness >= 1.0 &&
+                          mem_kernel_kind(I, ctx->P, A, diag) == 2;
+        const bool overlap = ecm && ctx->overlap && !evs && ctx->hp.sharpness >= 1.0 && !chans && !fuse;
         if (ecm && overlap) {
             const int iCa = ctx->hp.iCa;
             if (iCa >= 0) launch_ion(ctx->P, A, ctx->nx, cur, diag, iCa, 1, st);
@@ -873,7 +925,12 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
             }
         } else if (evs) cudaEventRecord(evs[1], st);
         if (evs) cudaEventRecord(evs[2], st);
-        ctx->flux_is_ell = launch_mem(I, ctx->P, A, ctx->n_ctas, cur, diag, st);
+        if (ctx->kc_sync) cudaMemsetAsync(ctx->kc_sync, 0, (size_t)ctx->kc_sync_n * sizeof(int), st);
+        {
+            const int mk = launch_mem(I, ctx->P, A, ctx->n_ctas, cur, diag, fuse ? 1 : 0, st);
+            ctx->flux_is_ell = mk & 1;
+            ctx->env_fused = (mk >> 1) & 1;
+        }
         if (overlap) cudaStreamWaitEvent(st, ctx->ev_join, 0);
         if (chans) {
             // between the ion loop's fluxes and update_all_concs (sim.py:1290-1357), per handler: run_loop_channels
@@ -936,7 +993,8 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
         }
         if (evs) cudaEventRecord(evs[3], st);
     } else if (phase == 1) {
-        if (ecm && ctx->flux_is_ell) launch_envacc_ell(I, ctx->P, A, nxt, st);
+        if (ecm && ctx->env_fused) { /* done inside k_cell */ }
+        else if (ecm && ctx->flux_is_ell) launch_envacc_ell(I, ctx->P, A, nxt, st);
         else if (ecm) launch_envacc(I, ctx->P, A, ctx->E, nxt, 1, st);
         else launch_envmix(I, ctx->P, A, cur, st);
         if (evs) cudaEventRecord(evs[4], st);

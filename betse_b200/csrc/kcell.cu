@@ -25,19 +25,36 @@ template <int NI>
 struct MemIn { double DmS[NI], co[NI], cnb[NI], vnb, cao, g, sa; int nnp; };
 struct MemIdx { int nnp, esq; };
 
-template <int NI, int MINB>
-__global__ void __launch_bounds__(KC_WARPS * 32, MINB)
-k_cell(const __grid_constant__ KParams P, const KArrays A, const int cur)
+// hint: pull [p, p + bytes) into L2 (one bulk prefetch, no registers held): the streams of a task some hundred tasks
+// ahead, so that the loads that later need them pay L2, not DRAM, latency
+__device__ __forceinline__ void l2_prefetch(const void* p, unsigned bytes)
 {
-    const int lane = threadIdx.x & 31;
-    const int task = blockIdx.x * KC_WARPS + (threadIdx.x >> 5);
-    if (task >= P.n_blocks) return;
+    if (bytes == 0) return;
+    const unsigned long long a = (unsigned long long)p;
+    const unsigned long long a0 = a & ~15ull;
+    const unsigned n = (unsigned)(((a + bytes + 15ull) & ~15ull) - a0);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"(n) : "memory");
+}
+
+// ---- one block of 32 cells: lane = cell
+template <int NI, bool FUSE>
+__device__ __forceinline__ void cell_task(const KParams& P, const KArrays& A, const int cur, const int task, const int lane,
+                                          unsigned int& flags)
+{
     constexpr int iNa = StdProf<NI>::iNa, iK = StdProf<NI>::iK, iCa = StdProf<NI>::iCa;
     const int nxt = cur ^ 1;
     const int C = P.n_cells, E = P.ny * P.nx;
     const size_t R32 = (size_t)P.ell_R32;
-    const int row0 = ldgi(A.blk_row0 + task);
-    const int Kb = ldgi(A.blk_row0 + task + 1) - row0;
+    const int2 h0 = __ldg(reinterpret_cast<const int2*>(A.blk_row0) + task);          // {first row, first membrane}
+    const int2 h1 = __ldg(reinterpret_cast<const int2*>(A.blk_row0) + task + 1);
+    const int row0 = h0.x, Kb = h1.x - h0.x;
+    // header of the block whose streams this task pulls into L2 (issued after the first membrane, below)
+    const int up = task + P.pf_dist;
+    int2 u0 = make_int2(0, 0), u1 = make_int2(0, 0);
+    if (P.pf_dist > 0 && up < P.n_blocks) {
+        u0 = __ldg(reinterpret_cast<const int2*>(A.blk_row0) + up);
+        u1 = __ldg(reinterpret_cast<const int2*>(A.blk_row0) + up + 1);
+    }
     const int c = task * 32 + lane;
     const bool valid = c < P.n_cells_owned;
     int m_beg = 0, nm = 0;
@@ -47,7 +64,6 @@ k_cell(const __grid_constant__ KParams P, const KArrays A, const int cur)
     const double* __restrict__ vmc = A.vm_cell[cur];
     const double* __restrict__ cenv = A.cc_env[cur];
     const double* __restrict__ cenvCa = A.cc_env[nxt] + (size_t)(iCa >= 0 ? iCa : 0) * E;   // Ca after transport (sim.py:1282 after 2254)
-    unsigned int flags = 0;
 
     auto idx_load = [&](MemIdx& x, const int k) {
         if (k < nm) {
@@ -170,6 +186,24 @@ k_cell(const __grid_constant__ KParams P, const KArrays A, const int cur)
         gather(b, ib, k + 1);
         idx_load(ia, k + 2);
         compute(a, k);
+        if (k == 0 && u1.x > u0.x) {
+            // streams of block `up`, one bulk prefetch per array and lane: cell-pack rows, gjopen, the cells' own state
+            const unsigned rb = (unsigned)(u1.x - u0.x) * 256u;                 // bytes of the block's rows (doubles)
+            const size_t r0 = (size_t)u0.x * 32;
+            const int cu = up * 32;
+            const int ncu = min(32, P.n_cells_owned - cu);
+            if (lane < NI) l2_prefetch(A.ell_DmS + lane * R32 + r0, rb);
+            else if (lane == NI) l2_prefetch(A.ell_sa + r0, rb);
+            else if (lane == NI + 1) l2_prefetch(A.ell_nnp + r0, rb / 2);
+            else if (lane == NI + 2) l2_prefetch(A.ell_esq + r0, rb / 2);
+            else if (lane == NI + 3) l2_prefetch(A.gjopen + u0.y, (unsigned)(u1.y - u0.y) * 8u);
+            else if (lane < 2 * NI + 4) l2_prefetch(A.cc_cells + (size_t)(lane - NI - 4) * C + cu, ncu * 8u);
+            else if (lane < 3 * NI + 4) l2_prefetch(cmid + (size_t)(lane - 2 * NI - 4) * C + cu, ncu * 8u);
+            else if (lane == 3 * NI + 4) l2_prefetch(vmc + cu, ncu * 8u);
+            else if (lane == 3 * NI + 5) l2_prefetch(A.cell_vol + cu, ncu * 8u);
+            else if (lane == 3 * NI + 6) l2_prefetch(A.diviterm + cu, ncu * 8u);
+            else if (lane == 3 * NI + 7) l2_prefetch(A.cell_mem_ptr + cu, (ncu + 1) * 4u);
+        }
         if (k + 1 < Kb) {
             gather(a, ia, k + 2);
             idx_load(ib, k + 3);
@@ -198,6 +232,88 @@ k_cell(const __grid_constant__ KParams P, const KArrays A, const int cur)
         if (vmn != vmn) flags |= ST_NAN_VM;
         A.vm_cell[nxt][c] = vmn;
     }
+    if (FUSE) {
+        // publish: the fluxes of this block are visible before its group's counter moves
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(A.cell_done + task / KC_GRP, 1);
+    }
+}
+
+// ---- fused env task: membrane -> env exchange of KC_ENV_CHUNK squares (the body of k_envacc_ell), run inside the
+//      membrane kernel once every cell block that feeds these squares has published its fluxes: the fluxes are then
+//      read from L2, they need not wait for the whole tissue and a kernel boundary
+template <int NI>
+__device__ __forceinline__ void env_task(const KParams& P, const KArrays& A, const int nxt, const int v, const int lane)
+{
+    const int2 dep = __ldg(reinterpret_cast<const int2*>(A.env_dep) + v);       // groups [x, y] of cell tasks that feed the chunk
+    if (lane == 0) {
+        for (int g = dep.x; g <= dep.y; ++g) {
+            const int want = min(KC_GRP, P.n_blocks - g * KC_GRP);
+            const volatile int* ctr = A.cell_done + g;
+            while (*ctr < want) __nanosleep(64);
+        }
+        __threadfence();
+    }
+    __syncwarp();
+    const int E = P.nx * P.ny;
+    const int base = v * KC_ENV_CHUNK;
+#pragma unroll 1
+    for (int j = 0; j < KC_ENV_CHUNK / 32; ++j) {
+        const int k = base + j * 32 + lane;
+        if (k >= E) break;
+        const int s0 = ldgi(A.slot_ptr + k), s1 = ldgi(A.slot_ptr + k + 1);
+        double acc[NI];
+#pragma unroll
+        for (int i = 0; i < NI; ++i) acc[i] = 0.0;
+        for (int jj = s0; jj < s1; ++jj) {
+            const int off = ldgi(A.slot_off + jj);
+            // L2 loads: the producer's stores went to L2, this SM's L1 may hold nothing newer
+            if (off >= 0) {
+#pragma unroll
+                for (int i = 0; i < NI; ++i) acc[i] += __ldcg(A.flux_ell + (size_t)off + i * 32);
+            } else {
+                const double* __restrict__ f = A.flux_slots + (size_t)(-(off + 1));
+#pragma unroll
+                for (int i = 0; i < NI; ++i) acc[i] += __ldcg(f + i);
+            }
+        }
+        double rho = 0.0;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            double c = A.cc_env[nxt][(size_t)i * E + k];
+            const double delta_env = (-acc[i]) / P.env_vol_div;                     // sim_toolbox.py:1229
+            c = c + delta_env * P.dt;
+            A.cc_env[nxt][(size_t)i * E + k] = c;
+            rho = fma(P.zF[i], c, rho);
+        }
+        if (A.extra_rho_env) rho += ldg(A.extra_rho_env + k);
+        A.rho_env[k] = rho;
+        A.v_raw[k] = (s1 > s0) ? ((rho * P.env_vol_div) / P.memsa_mean) / P.ko_eo_er : 0.0;   // ion_current.py:93-97
+    }
+}
+
+// Persistent: every warp draws tickets; ticket t is block t of the cell pack, or (FUSE) entry t of the host-built
+// schedule, which interleaves the env tasks a fixed lag behind the cell blocks that feed them.  A waiting env task only
+// ever waits for cell tasks with SMALLER tickets, i.e. tasks that running warps already hold: no deadlock.
+template <int NI, int MINB, bool FUSE>
+__global__ void __launch_bounds__(KC_WARPS * 32, MINB)
+k_cell(const __grid_constant__ KParams P, const KArrays A, const int cur)
+{
+    const int lane = threadIdx.x & 31;
+    unsigned int flags = 0;
+    const int n_tickets = FUSE ? P.n_sched : P.n_blocks;
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(A.ticket, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= n_tickets) break;
+        if (FUSE) {
+            const int code = ldgi(A.sched + t);
+            if (code < 0) env_task<NI>(P, A, cur ^ 1, code & 0x7fffffff, lane);
+            else cell_task<NI, true>(P, A, cur, code, lane, flags);
+        } else cell_task<NI, false>(P, A, cur, t, lane, flags);
+    }
     if (flags) atomicOr(A.status, flags);
 }
 
@@ -208,7 +324,7 @@ __global__ void k_pack_cell_const(const __grid_constant__ KParams P, const KArra
     const int task = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (task >= P.n_blocks) return;
-    const int row0 = A.blk_row0[task], Kb = A.blk_row0[task + 1] - row0;
+    const int row0 = A.blk_row0[2 * task], Kb = A.blk_row0[2 * task + 2] - row0;
     const int c = task * 32 + lane;
     int m_beg = 0, nm = 0;
     if (c < P.n_cells_owned) { m_beg = A.cell_mem_ptr[c]; nm = A.cell_mem_ptr[c + 1] - m_beg; }
@@ -235,7 +351,7 @@ __global__ void k_pack_cell_dm(const __grid_constant__ KParams P, const KArrays 
     const int task = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (task >= P.n_blocks) return;
-    const int row0 = A.blk_row0[task], Kb = A.blk_row0[task + 1] - row0;
+    const int row0 = A.blk_row0[2 * task], Kb = A.blk_row0[2 * task + 2] - row0;
     const int c = task * 32 + lane;
     int m_beg = 0, nm = 0;
     if (c < P.n_cells_owned) { m_beg = A.cell_mem_ptr[c]; nm = A.cell_mem_ptr[c + 1] - m_beg; }
@@ -361,23 +477,37 @@ bool kcell_enabled()
     return v == 1;
 }
 
-template <int NI>
-static void launch_cell_t(const KParams& P, const KArrays& A, int cur, cudaStream_t st)
+static int g_kc_sms = 148;
+
+void kcell_set_sms(int n) { if (n > 0) g_kc_sms = n; }
+
+template <int NI, bool FUSE>
+static void launch_cell_f(const KParams& P, const KArrays& A, int cur, cudaStream_t st)
 {
     static int minb = -1;
-    if (minb < 0) minb = kc_env_int("BETSE_KCELL_MINB", 3);      // resident CTAs (of 4 warps) per SM: 2 = 255 registers, 3 = 168, 4 = 128
-    const int grid = (P.n_blocks + KC_WARPS - 1) / KC_WARPS;
-    if (minb <= 2) k_cell<NI, 2><<<grid, KC_WARPS * 32, 0, st>>>(P, A, cur);
-    else if (minb == 3) k_cell<NI, 3><<<grid, KC_WARPS * 32, 0, st>>>(P, A, cur);
-    else k_cell<NI, 4><<<grid, KC_WARPS * 32, 0, st>>>(P, A, cur);
+    if (minb < 0) minb = kc_env_int("BETSE_KCELL_MINB", 2);      // resident CTAs (of 4 warps) per SM: 2 = 255 registers, 3 = 168, 4 = 128
+    const int need = ((FUSE ? P.n_sched : P.n_blocks) + KC_WARPS - 1) / KC_WARPS;
+    const int mb = minb <= 2 ? 2 : (minb == 3 ? 3 : 4);
+    const int grid = need < g_kc_sms * mb ? need : g_kc_sms * mb;
+    if (mb == 2) k_cell<NI, 2, FUSE><<<grid, KC_WARPS * 32, 0, st>>>(P, A, cur);
+    else if (mb == 3) k_cell<NI, 3, FUSE><<<grid, KC_WARPS * 32, 0, st>>>(P, A, cur);
+    else k_cell<NI, 4, FUSE><<<grid, KC_WARPS * 32, 0, st>>>(P, A, cur);
 }
 
-void launch_cell(int ni, const KParams& P, const KArrays& A, int cur, cudaStream_t st)
+template <int NI>
+static void launch_cell_t(const KParams& P, const KArrays& A, int cur, int fuse, cudaStream_t st)
+{
+    if (fuse) launch_cell_f<NI, true>(P, A, cur, st);
+    else launch_cell_f<NI, false>(P, A, cur, st);
+}
+
+// the caller zeroes A.ticket (and, fused, A.cell_done) on the same stream before every launch
+void launch_cell(int ni, const KParams& P, const KArrays& A, int cur, int fuse, cudaStream_t st)
 {
     switch (ni) {
-        case 4: launch_cell_t<4>(P, A, cur, st); break;
-        case 5: launch_cell_t<5>(P, A, cur, st); break;
-        case 6: launch_cell_t<6>(P, A, cur, st); break;
-        default: launch_cell_t<7>(P, A, cur, st); break;
+        case 4: launch_cell_t<4>(P, A, cur, fuse, st); break;
+        case 5: launch_cell_t<5>(P, A, cur, fuse, st); break;
+        case 6: launch_cell_t<6>(P, A, cur, fuse, st); break;
+        default: launch_cell_t<7>(P, A, cur, fuse, st); break;
     }
 }

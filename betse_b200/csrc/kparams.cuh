@@ -6,6 +6,8 @@
 #define BT_TPB 256          // threads per CTA of the membrane kernel == max membranes per CTA
 #define BT_MAX_CTA_CELLS 96 // max cells packed into one membrane-kernel CTA
 #define BT_TILE_MAXC 8      // max cells of one warp tile (<= 32 membranes)
+#define KC_GRP 16           // k_cell: cell blocks per completion counter (fused env tasks wait on whole groups)
+#define KC_ENV_CHUNK 128    // k_cell: env squares per fused env task (4 per lane)
 
 // Scalars (passed BY VALUE as a __grid_constant__ kernel argument: lives in the constant bank).  Derived products are formed on
 // the host in the same operand order as the reference's NumPy expressions.
@@ -42,6 +44,8 @@ struct KParams {
     int n_cells, n_cells_owned, n_mems_owned, n_ctas, n_tiles;
     int pf_tiles;                           // k_mem: L2 prefetch distance in tiles (0 = off)
     int n_blocks, ell_R32;                  // k_cell: blocks of 32 cells, elements per row array of the cell pack (rows * 32)
+    int pf_dist;                            // k_cell: a block pulls the streams of block + pf_dist into L2 (0 = off)
+    int n_sched;                            // k_cell, fused: tickets of the schedule (cell blocks + env tasks)
     int defer;                              // k_mem stores its membrane->cell sums instead of applying them (channels)
     int chan_charge;                        // p.substances_affect_charge: Jmem takes the channels' extra_J_mem
     // kernel row ranges in local rows (single GPU: all [0, ny)): ion transport, membrane->env
@@ -64,7 +68,11 @@ struct KArrays {
     const char *tile_pack;       // k_mem_pipe: fixed-size per-tile constant blocks (layout: kmem_pipe.cu header)
     const int *slot_ptr, *slot_idx;
     // cell pack of k_cell (SELL-32: block b = cells 32b..32b+31; row blk_row0[b] + k holds membrane k of each cell)
-    const int *blk_row0;         // [n_blocks + 1] first row of every block
+    const int *blk_row0;         // [n_blocks + 1] int2 {first row, first membrane} of every block
+    int *ticket;                 // k_cell: next ticket (zeroed before every launch)
+    int *cell_done;              // k_cell, fused: finished cell blocks per group of KC_GRP (zeroed before every launch)
+    const int *sched;            // k_cell, fused: ticket -> cell block (>= 0) or env task | 0x80000000
+    const int *env_dep;          // k_cell, fused: int2 {first, last} group of cell blocks that feed each env task
     const double *ell_DmS;       // [I][rows*32] (Dm*(-rho_channel/tm))*mem_sa
     const double *ell_sa;        // [rows*32]
     const int *ell_nnp, *ell_esq; // [rows*32] partner cell | boundary bit, env square
