@@ -43,6 +43,8 @@ void launch_pack_dm(const KParams& P, const KArrays& A, cudaStream_t st);
 bool kcell_enabled();
 void launch_pack_cell_const(const KParams& P, const KArrays& A, int* mem_ell, cudaStream_t st);
 void launch_pack_cell_dm(const KParams& P, const KArrays& A, cudaStream_t st);
+size_t cell_pack_row_bytes(int ni);
+cudaError_t prepare_cell(int ni, int kb_max);
 void launch_slot_off(const int* slot_idx, const int* mem_ell, int* slot_off, int n, int Mo, int ni, cudaStream_t st);
 void launch_gather_int(int* dst, const int* src, const int* idx, int n, cudaStream_t st);
 void launch_envacc_ell(int ni, const KParams& P, const KArrays& A, int nxt, cudaStream_t st);
@@ -524,14 +526,13 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
         }
         row0[2 * nb + 1] = Mo;
         const long long R32 = (long long)row0[2 * nb] * 32;
+        int kb_max = 0;
+        for (int b = 0; b < nb; ++b) kb_max = std::max(kb_max, row0[2 * (b + 1)] - row0[2 * b]);
         if (R32 * hp->n_ions < (1LL << 31) - 64) {       // 32-bit flux positions; otherwise k_mem stays in charge
-            P.n_blocks = nb; P.ell_R32 = (int)R32;
+            P.n_blocks = nb; P.ell_rows = row0[2 * nb]; P.kb_max = kb_max;
             { const char* e = getenv("BETSE_KCELL_PF"); P.pf_dist = e ? atoi(e) : 1024; }
             if ((r = dev_upload(ctx, (int**)&A.blk_row0, row0.data(), row0.size()))) return r;
-            if ((r = dev_alloc(ctx, (double**)&A.ell_DmS, (size_t)R32 * I))) return r;
-            if ((r = dev_alloc(ctx, (double**)&A.ell_sa, (size_t)R32))) return r;
-            if ((r = dev_alloc(ctx, (int**)&A.ell_nnp, (size_t)R32))) return r;
-            if ((r = dev_alloc(ctx, (int**)&A.ell_esq, (size_t)R32))) return r;
+            if ((r = dev_alloc(ctx, (char**)&A.cpack, (size_t)row0[2 * nb] * cell_pack_row_bytes(I)))) return r;
             if ((r = dev_alloc(ctx, &A.flux_ell, (size_t)R32 * I))) return r;
             if ((r = dev_alloc(ctx, &ctx->mem_ell, (size_t)Mo))) return r;
             const int n_sl = mesh->ecm_slot_ptr ? mesh->ecm_slot_ptr[E] : Mo;
@@ -640,6 +641,7 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
         CK(cudaMemcpyAsync(A.cenv_u, cu, sizeof cu, cudaMemcpyHostToDevice, ctx->stream));
     }
     CK(prepare_kernels(I));
+    CK(prepare_cell(I, ctx->P.kb_max));
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }

@@ -320,130 +320,97 @@ __global__ void k_envmix(const __grid_constant__ KParams P, const KArrays A, con
 // [yi0, yi1) are produced.
 #define IT_X 32
 #define IT_Y 16
-// One CTA per 32x16 tile walks the ions [ion0, ion0 + n): the E field of the tile is staged once for all of them, rows
-// are dealt to warps and columns to lanes (no index divisions), and the tile's position against the world edge is
-// decided once per point and kept in registers across the ions.
-// (Round 1 ran one CTA per (ion, tile) with flat index loops: 300 thread-instructions per point-ion, issue-bound at
-// 1.7 TB/s — profiles/r01h_ncu_full_step_kernels_summary.csv.)
-__global__ void __launch_bounds__(256, 4)
-k_ion(const __grid_constant__ KParams P, const KArrays A, const int cur, const int diag, const int ion0, const int n_ion)
+// blockIdx.z selects the ion: ions [ion0 + z] (a CTA per ion and tile keeps small strips busy and lets the Ca row,
+// which the Ca-ATPase reads after transport, run ahead of the others).  INTERIOR tiles — tile + 2-point halo strictly
+// inside the world and off its Dirichlet ring, all output rows wanted — take a build without any bounds / edge logic
+// (round 1 spent ~300 thread-instructions per point-ion, most of them on those tests: 1.7 TB/s).
+template <bool INTERIOR>
+__device__ __forceinline__ void ion_tile(const KParams& P, const KArrays& A, const int cur, const int diag, const int i,
+                                         double (*sC)[IT_X + 4], double (*sFx)[IT_X + 3], double (*sFy)[IT_X + 3])
 {
-    __shared__ double sC[IT_Y + 4][IT_X + 4];
-    __shared__ double sFx[IT_Y + 2][IT_X + 3], sFy[IT_Y + 2][IT_X + 3];
-    __shared__ double sEx[IT_Y + 2][IT_X + 2], sEy[IT_Y + 2][IT_X + 2];
     const int nx = P.nx, ny = P.ny;
     const int E = nx * ny;
     const int tx0 = blockIdx.x * IT_X, ty0 = P.yi0 + blockIdx.y * IT_Y;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int tid = threadIdx.x;
     const int gny = P.ny_global;
     const double inv_d = P.inv_delta, inv_2d = P.inv_2delta;
+    const double* __restrict__ c = A.cc_env[cur] + (size_t)i * E;
+    const double* __restrict__ D = A.Denv + (size_t)i * E;
+    const double cb = P.cbound[i];
+    const double zq = P.z[i] * P.q;
 
-    // E field of tile + 1-point halo (last step's field), once for all ions
-#pragma unroll
-    for (int rr = 0; rr < 3; ++rr) {
-        const int ly = w + 8 * rr;
-        if (ly < IT_Y + 2) {
-            const int y = ty0 + ly - 1;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int lx = lane + 32 * h;
-                if (lx < IT_X + 2) {
-                    const int x = tx0 + lx - 1;
-                    double ex = 0.0, ey = 0.0;
-                    if (x >= 0 && x < nx && y >= 0 && y < ny) { ex = A.E_x[y * nx + x]; ey = A.E_y[y * nx + x]; }
-                    sEx[ly][lx] = ex; sEy[ly][lx] = ey;
-                }
+    for (int t = tid; t < (IT_Y + 4) * (IT_X + 4); t += 256) {
+        const int ly = t / (IT_X + 4), lx = t - ly * (IT_X + 4);
+        const int y = ty0 + ly - 2, x = tx0 + lx - 2;
+        double v = 0.0;
+        if (INTERIOR) v = c[y * nx + x];
+        else if (x >= 0 && x < nx && y >= 0 && y < ny) {
+            const int g = y + P.y0;
+            const bool edge = (g == 0 || g == gny - 1 || x == 0 || x == nx - 1);
+            v = edge ? cb : c[y * nx + x];          // Dirichlet fill, sim.py:2211-2217
+        }
+        sC[ly][lx] = v;
+    }
+    __syncthreads();
+    for (int t = tid; t < (IT_Y + 2) * (IT_X + 2); t += 256) {
+        const int ly = t / (IT_X + 2), lx = t - ly * (IT_X + 2);
+        const int y = ty0 + ly - 1, x = tx0 + lx - 1;
+        double fx = 0.0, fy = 0.0;
+        if (INTERIOR || (x >= 0 && x < nx && y >= 0 && y < ny)) {
+            const int g = y + P.y0;
+            const int k = y * nx + x;
+            const double cc = sC[ly + 1][lx + 1];
+            double gcx, gcy;                                   // fd.gradient, finitediff.py:1236-1266
+            if (!INTERIOR && x == 0) gcx = (sC[ly + 1][lx + 2] - cc) * inv_d;
+            else if (!INTERIOR && x == nx - 1) gcx = (cc - sC[ly + 1][lx]) * inv_d;
+            else gcx = -(sC[ly + 1][lx] - sC[ly + 1][lx + 2]) * inv_2d;
+            if (!INTERIOR && g == 0) gcy = (sC[ly + 2][lx + 1] - cc) * inv_d;
+            else if (!INTERIOR && g == gny - 1) gcy = (cc - sC[ly][lx + 1]) * inv_d;
+            else gcy = -(sC[ly][lx + 1] - sC[ly + 2][lx + 1]) * inv_2d;
+            const double Dk = D[k];
+            const double al = (Dk * zq) * P.inv_kbT_sim;       // nernst_planck_flux, sim_toolbox.py:409-411
+            fx = -Dk * gcx - (al * (-A.E_x[k])) * cc;
+            fy = -Dk * gcy - (al * (-A.E_y[k])) * cc;
+            if (diag && ly >= 1 && ly <= IT_Y && lx >= 1 && lx <= IT_X && y < P.yi1) {
+                A.fl_env_x[(size_t)i * E + k] = fx;
+                A.fl_env_y[(size_t)i * E + k] = fy;
             }
+        }
+        sFx[ly][lx] = fx; sFy[ly][lx] = fy;
+    }
+    __syncthreads();
+    // fd.divergence(-fx, -fy) with fd.diff's edge rows (finitediff.py:1268-1311)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int oy = (tid >> 5) + 8 * h, ox = tid & 31;
+        const int y = ty0 + oy, x = tx0 + ox;
+        if (INTERIOR || (x < nx && y < P.yi1)) {
+            const int g = y + P.y0;
+            const int ly = oy + 1, lx = ox + 1;
+            double dx, dy;
+            if (!INTERIOR && x == 0) dx = ((-sFx[ly][lx]) - (-sFx[ly][lx + 1])) * inv_d;
+            else if (!INTERIOR && x == nx - 1) dx = ((-sFx[ly][lx - 1]) - (-sFx[ly][lx])) * inv_d;
+            else dx = -((-sFx[ly][lx - 1]) - (-sFx[ly][lx + 1])) * inv_2d;
+            if (!INTERIOR && g == 0) dy = -((-sFy[ly + 1][lx]) - (-sFy[ly][lx])) * inv_d;
+            else if (!INTERIOR && g == gny - 1) dy = -((-sFy[ly][lx]) - (-sFy[ly - 1][lx])) * inv_d;
+            else dy = -((-sFy[ly - 1][lx]) - (-sFy[ly + 1][lx])) * inv_2d;
+            A.cc_env[cur ^ 1][(size_t)i * E + y * nx + x] = sC[oy + 2][ox + 2] + (dx + dy) * P.dt;
         }
     }
-    // small grids (strips of a decomposed tissue): gridDim.z CTAs share a tile's ions
-    for (int ii = blockIdx.z; ii < n_ion; ii += gridDim.z) {
-        const int i = ion0 + ii;
-        const double* __restrict__ c = A.cc_env[cur] + (size_t)i * E;
-        const double* __restrict__ D = A.Denv + (size_t)i * E;
-        const double cb = P.cbound[i];
-        const double zq = P.z[i] * P.q;
-        __syncthreads();                                  // the previous ion's flux tile has been consumed (and sE is complete)
-        // concentration tile + 2-point halo, Dirichlet fill on load (sim.py:2211-2217)
-#pragma unroll
-        for (int rr = 0; rr < 3; ++rr) {
-            const int ly = w + 8 * rr;
-            if (ly < IT_Y + 4) {
-                const int y = ty0 + ly - 2;
-                const int g = y + P.y0;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int lx = lane + 32 * h;
-                    if (lx < IT_X + 4) {
-                        const int x = tx0 + lx - 2;
-                        double v = 0.0;
-                        if (x >= 0 && x < nx && y >= 0 && y < ny) {
-                            const bool edge = (g == 0 || g == gny - 1 || x == 0 || x == nx - 1);
-                            v = edge ? cb : c[y * nx + x];
-                        }
-                        sC[ly][lx] = v;
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        // Nernst-Planck flux on tile + 1-point halo: fd.gradient (finitediff.py:1236-1266), sim_toolbox.py:409-411
-#pragma unroll
-        for (int rr = 0; rr < 3; ++rr) {
-            const int ly = w + 8 * rr;
-            if (ly < IT_Y + 2) {
-                const int y = ty0 + ly - 1;
-                const int g = y + P.y0;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int lx = lane + 32 * h;
-                    if (lx < IT_X + 2) {
-                        const int x = tx0 + lx - 1;
-                        double fx = 0.0, fy = 0.0;
-                        if (x >= 0 && x < nx && y >= 0 && y < ny) {
-                            const int k = y * nx + x;
-                            const double cc = sC[ly + 1][lx + 1];
-                            double gcx, gcy;
-                            if (x == 0) gcx = (sC[ly + 1][lx + 2] - cc) * inv_d;
-                            else if (x == nx - 1) gcx = (cc - sC[ly + 1][lx]) * inv_d;
-                            else gcx = -(sC[ly + 1][lx] - sC[ly + 1][lx + 2]) * inv_2d;
-                            if (g == 0) gcy = (sC[ly + 2][lx + 1] - cc) * inv_d;
-                            else if (g == gny - 1) gcy = (cc - sC[ly][lx + 1]) * inv_d;
-                            else gcy = -(sC[ly][lx + 1] - sC[ly + 2][lx + 1]) * inv_2d;
-                            const double Dk = D[k];
-                            const double al = (Dk * zq) * P.inv_kbT_sim;
-                            fx = -Dk * gcx - (al * (-sEx[ly][lx])) * cc;
-                            fy = -Dk * gcy - (al * (-sEy[ly][lx])) * cc;
-                            if (diag && ly >= 1 && ly <= IT_Y && lx >= 1 && lx <= IT_X && y < P.yi1) {
-                                A.fl_env_x[(size_t)i * E + k] = fx;
-                                A.fl_env_y[(size_t)i * E + k] = fy;
-                            }
-                        }
-                        sFx[ly][lx] = fx; sFy[ly][lx] = fy;
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        // fd.divergence(-fx, -fy) with fd.diff's edge rows (finitediff.py:1268-1311), forward Euler
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int oy = w + 8 * h, ox = lane;
-            const int y = ty0 + oy, x = tx0 + ox;
-            if (x < nx && y < P.yi1) {
-                const int g = y + P.y0;
-                const int ly = oy + 1, lx = ox + 1;
-                double dx, dy;
-                if (x == 0) dx = ((-sFx[ly][lx]) - (-sFx[ly][lx + 1])) * inv_d;
-                else if (x == nx - 1) dx = ((-sFx[ly][lx - 1]) - (-sFx[ly][lx])) * inv_d;
-                else dx = -((-sFx[ly][lx - 1]) - (-sFx[ly][lx + 1])) * inv_2d;
-                if (g == 0) dy = -((-sFy[ly + 1][lx]) - (-sFy[ly][lx])) * inv_d;
-                else if (g == gny - 1) dy = -((-sFy[ly][lx]) - (-sFy[ly - 1][lx])) * inv_d;
-                else dy = -((-sFy[ly - 1][lx]) - (-sFy[ly + 1][lx])) * inv_2d;
-                A.cc_env[cur ^ 1][(size_t)i * E + y * nx + x] = sC[oy + 2][ox + 2] + (dx + dy) * P.dt;
-            }
-        }
-    }
+}
+
+__global__ void __launch_bounds__(256)
+k_ion(const __grid_constant__ KParams P, const KArrays A, const int cur, const int diag, const int ion0)
+{
+    __shared__ double sC[IT_Y + 4][IT_X + 4];
+    __shared__ double sFx[IT_Y + 2][IT_X + 3], sFy[IT_Y + 2][IT_X + 3];
+    const int tx0 = blockIdx.x * IT_X, ty0 = P.yi0 + blockIdx.y * IT_Y;
+    const int g0 = ty0 + P.y0;
+    // tile + halo 2 inside the local rows and strictly inside the world's Dirichlet ring; every output row wanted
+    const bool interior = tx0 - 2 >= 1 && tx0 + IT_X + 1 <= P.nx - 2 && g0 - 2 >= 1 && g0 + IT_Y + 1 <= P.ny_global - 2 &&
+                          ty0 - 2 >= 0 && ty0 + IT_Y + 1 <= P.ny - 1 && ty0 + IT_Y <= P.yi1;
+    if (interior) ion_tile<true>(P, A, cur, diag, ion0 + blockIdx.z, sC, sFx, sFy);
+    else ion_tile<false>(P, A, cur, diag, ion0 + blockIdx.z, sC, sFx, sFy);
 }
 
 // fd.integrator (finitediff.py:1479-1512) applied to the transported field (sim.py:2249-2252).
@@ -816,7 +783,7 @@ int mem_kernel_kind(int ni, const KParams& P, const KArrays& A, int diag)
         default: sp = false;
     }
     if (!sp) return 0;
-    if (kcell_enabled() && A.ell_DmS) return 2;
+    if (kcell_enabled() && A.cpack) return 2;
     return kmem_pipe_enabled() ? 1 : 0;
 }
 
@@ -892,11 +859,8 @@ void launch_ion(const KParams& P, const KArrays& A, int nx, int cur, int diag, i
 {
     const int rows = P.yi1 - P.yi0;
     if (rows <= 0 || n <= 0) return;
-    dim3 b(256), g((nx + IT_X - 1) / IT_X, (rows + IT_Y - 1) / IT_Y, 1);
-    const int tiles = (int)(g.x * g.y);
-    int nz = (4 * g_n_sms + tiles - 1) / tiles;
-    g.z = nz < 1 ? 1 : (nz > n ? n : nz);
-    k_ion<<<g, b, 0, st>>>(P, A, cur, diag, ion0, n);
+    dim3 b(256), g((nx + IT_X - 1) / IT_X, (rows + IT_Y - 1) / IT_Y, n);
+    k_ion<<<g, b, 0, st>>>(P, A, cur, diag, ion0);
 }
 
 void launch_ion_smooth(int ni, const KParams& P, const KArrays& A, int ny, int nx, int nxt, cudaStream_t st)

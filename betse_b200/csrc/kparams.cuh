@@ -43,7 +43,7 @@ struct KParams {
     int ny, nx, y0, ny_global, y_own0, y_own1;
     int n_cells, n_cells_owned, n_mems_owned, n_ctas, n_tiles;
     int pf_tiles;                           // k_mem: L2 prefetch distance in tiles (0 = off)
-    int n_blocks, ell_R32;                  // k_cell: blocks of 32 cells, elements per row array of the cell pack (rows * 32)
+    int n_blocks, ell_rows, kb_max;         // k_cell: blocks of 32 cells, rows of the cell pack, rows of its widest block
     int pf_dist;                            // k_cell: a block pulls the streams of block + pf_dist into L2 (0 = off)
     int n_sched;                            // k_cell, fused: tickets of the schedule (cell blocks + env tasks)
     int defer;                              // k_mem stores its membrane->cell sums instead of applying them (channels)
@@ -73,9 +73,8 @@ struct KArrays {
     int *cell_done;              // k_cell, fused: finished cell blocks per group of KC_GRP (zeroed before every launch)
     const int *sched;            // k_cell, fused: ticket -> cell block (>= 0) or env task | 0x80000000
     const int *env_dep;          // k_cell, fused: int2 {first, last} group of cell blocks that feed each env task
-    const double *ell_DmS;       // [I][rows*32] (Dm*(-rho_channel/tm))*mem_sa
-    const double *ell_sa;        // [rows*32]
-    const int *ell_nnp, *ell_esq; // [rows*32] partner cell | boundary bit, env square
+    const char *cpack;           // [rows] x {DmS[I][32] doubles = (Dm*(-rho_channel/tm))*mem_sa, mem_sa[32] doubles,
+                                 //            partner cell | boundary bit [32] ints, env square [32] ints}
     double *flux_ell;            // [rows][I][32] membrane -> env exchange, written by k_cell
     const int *slot_off;         // [slots] position of every env-square slot in flux_ell (>= 0) or in flux_slots (-(s*I)-1)
     const double *mem_sa, *mem_nx, *mem_ny, *cell_vol, *cell_sa, *diviterm, *num_mems;
