@@ -531,6 +531,7 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
         if (R32 * hp->n_ions < (1LL << 31) - 64) {       // 32-bit flux positions; otherwise k_mem stays in charge
             P.n_blocks = nb; P.ell_rows = row0[2 * nb]; P.kb_max = kb_max;
             { const char* e = getenv("BETSE_KCELL_PF"); P.pf_dist = e ? atoi(e) : 1024; }
+            { const char* e = getenv("BETSE_KCELL_PERSIST"); P.kc_persist = e ? atoi(e) : 1; }
             if ((r = dev_upload(ctx, (int**)&A.blk_row0, row0.data(), row0.size()))) return r;
             if ((r = dev_alloc(ctx, (char**)&A.cpack, (size_t)row0[2 * nb] * cell_pack_row_bytes(I)))) return r;
             if ((r = dev_alloc(ctx, &A.flux_ell, (size_t)R32 * I))) return r;
@@ -548,8 +549,10 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
             //      blocks that feed it are done; it is released `lag` blocks behind the last of them, so that it
             //      hardly ever waits and the fluxes it reads are still in L2
             const bool whole = ctx->Co == ctx->C && !mesh->ecm_slot_ptr;
+            // (measured, profiles/r02b_*, r02c_*: NOT a win — a block's fluxes are consumed tens of microseconds after they
+            //  were written, by when 100+ MB of streams have passed through the L2; off unless BETSE_FUSE=1)
             const char* fe = getenv("BETSE_FUSE");
-            if (whole && !(fe && fe[0] == '0')) {
+            if (whole && fe && fe[0] == '1' && P.kc_persist) {
                 const int nv = (E + KC_ENV_CHUNK - 1) / KC_ENV_CHUNK;
                 std::vector<int> lo(nv, INT_MAX), hi(nv, -1);
                 for (int m = 0; m < Mo; ++m) {

@@ -100,11 +100,21 @@ __device__ __forceinline__ void cell_task(const KParams& P, const KArrays& A, co
         u1 = __ldg(reinterpret_cast<const int2*>(A.blk_row0) + up + 1);
     }
 
-    auto gather = [&](MemIn<NI>& x, const int k) {
+    // register build: the index pair of membrane k is loaded two membranes ahead (ia / ib), so that the gathers through
+    // them do not wait for a second round trip; staged build: they are in shared memory
+    int2 ia = make_int2(0, 0), ib = make_int2(0, 0);
+    auto idx_load = [&](int2& x, const int k) {
+        if (!STAGED && k < nm) {
+            const char* r = rows + (size_t)k * ROWB;
+            x.x = __ldcs(reinterpret_cast<const int*>(r + (NI + 1) * 256) + lane);
+            x.y = __ldcs(reinterpret_cast<const int*>(r + (NI + 1) * 256 + 128) + lane);
+        }
+    };
+    auto gather = [&](MemIn<NI>& x, const int2& ix, const int k) {
         if (k < nm) {
             const char* r = rows + (size_t)k * ROWB;
-            const int nnp = reinterpret_cast<const int*>(r + (NI + 1) * 256)[lane];
-            const unsigned q = (unsigned)reinterpret_cast<const int*>(r + (NI + 1) * 256 + 128)[lane];
+            const int nnp = STAGED ? reinterpret_cast<const int*>(r + (NI + 1) * 256)[lane] : ix.x;
+            const unsigned q = (unsigned)(STAGED ? reinterpret_cast<const int*>(r + (NI + 1) * 256 + 128)[lane] : ix.y);
             const unsigned cn = (unsigned)(nnp & 0x7fffffff);
 #pragma unroll
             for (int i = 0; i < NI; ++i) x.co[i] = (cenv + (size_t)i * E)[q];
@@ -121,7 +131,9 @@ __device__ __forceinline__ void cell_task(const KParams& P, const KArrays& A, co
 #pragma unroll
     for (int i = 0; i < NI; ++i) { cc[i] = 0.0; cin[i] = 0.0; }
     MemIn<NI> a, b;
-    gather(a, 0);
+    idx_load(ia, 0);
+    idx_load(ib, 1);
+    gather(a, ia, 0);
     if (valid) {
         vm_own = vmc[c];
 #pragma unroll
@@ -211,7 +223,8 @@ __device__ __forceinline__ void cell_task(const KParams& P, const KArrays& A, co
     // ---- the cell's membranes, two register buffers: membrane k is computed while the gathers of k+1 load
 #pragma unroll 1
     for (int k = 0; k < Kb; k += 2) {
-        gather(b, k + 1);
+        gather(b, ib, k + 1);
+        idx_load(ia, k + 2);
         compute(a, k);
         if (!STAGED && k == 0 && u1.x > u0.x) {
             // streams of block `up`, one bulk prefetch per array and lane: its rows, gjopen, the cells' own state
@@ -227,7 +240,8 @@ __device__ __forceinline__ void cell_task(const KParams& P, const KArrays& A, co
             else if (lane == 2 * NI + 5) l2_prefetch(A.cell_mem_ptr + cu, (ncu + 1) * 4u);
         }
         if (k + 1 < Kb) {
-            gather(a, k + 2);
+            gather(a, ia, k + 2);
+            idx_load(ib, k + 3);
             compute(b, k + 1);
         }
     }
@@ -345,13 +359,14 @@ k_cell(const __grid_constant__ KParams P, const KArrays A, const int cur)
     };
     if (!STAGED) {
         for (;;) {
-            const int t = claim();
+            const int t = P.kc_persist ? claim() : (int)(blockIdx.x * KC_WARPS + (threadIdx.x >> 5));
             if (t >= n_tickets) break;
             if (FUSE) {
                 const int code = ldgi(A.sched + t);
                 if (code < 0) env_task<NI>(P, A, cur ^ 1, code & 0x7fffffff, lane);
                 else cell_task<NI, false, FUSE>(P, A, cur, code, lane, nullptr, flags);
             } else cell_task<NI, false, false>(P, A, cur, t, lane, nullptr, flags);
+            if (!P.kc_persist) break;
         }
     } else {
         // per warp: two mbarriers, two stages of [kb_max rows | gap-junction states of the block]
@@ -630,7 +645,7 @@ static void launch_cell_f(const KParams& P, const KArrays& A, int cur, cudaStrea
         return;
     }
     const int mb = minb <= 2 ? 2 : 3;
-    const int grid = need < g_kc_sms * mb ? need : g_kc_sms * mb;
+    const int grid = (!P.kc_persist || need < g_kc_sms * mb) ? need : g_kc_sms * mb;
     if (mb == 2) k_cell<NI, 2, false, FUSE><<<grid, KC_WARPS * 32, 0, st>>>(P, A, cur);
     else k_cell<NI, 3, false, FUSE><<<grid, KC_WARPS * 32, 0, st>>>(P, A, cur);
 }

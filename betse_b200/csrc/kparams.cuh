@@ -46,6 +46,7 @@ struct KParams {
     int n_blocks, ell_rows, kb_max;         // k_cell: blocks of 32 cells, rows of the cell pack, rows of its widest block
     int pf_dist;                            // k_cell: a block pulls the streams of block + pf_dist into L2 (0 = off)
     int n_sched;                            // k_cell, fused: tickets of the schedule (cell blocks + env tasks)
+    int kc_persist;                         // k_cell, register build: persistent warps drawing tickets (1) or one block per warp (0)
     int defer;                              // k_mem stores its membrane->cell sums instead of applying them (channels)
     int chan_charge;                        // p.substances_affect_charge: Jmem takes the channels' extra_J_mem
     // kernel row ranges in local rows (single GPU: all [0, ny)): ion transport, membrane->env

@@ -211,3 +211,45 @@ def make_tissue(n_cells, profile="mammal", ecm=True, dt=1.0e-4, seed=20241017, d
     # p.vol_env (no-ECM bath volume) follows the world size in the reference; keep the default
     state = make_state(mesh, p, prof)
     return mesh, p, state
+
+
+# ---------------------------------------------------------------------------- BASELINE workloads beyond the ion path
+BASELINE_CHANNELS = (("Nav", "Nav1p3", 2.0e-14), ("Kv", "Kv1p5", 1.0e-15), ("K_Leak", "KLeak", 0.6e-17),
+                     ("Cav", "Cav1p2", 1.0e-15))
+
+
+def baseline_channels(vm):
+    """BASELINE configs[2]: the default general network's Nav1p3 / Kv1p5 / KLeak (sim_config.yaml) plus one voltage-gated
+    Ca channel (Cav1p2, vg_ca.py:292-340), each at its steady state for the Vmem given (vg_na.py:210-228)."""
+    from . import channels as chlib
+    specs = []
+    for name, model, dm in BASELINE_CHANNELS:
+        m0, h0 = chlib.initial_state(model, vm)
+        specs.append(chlib.make_channel(name, model, dm, m=m0, h=h0))
+    return specs
+
+
+def retarget_network(desc, C, M, E, rng, targets_every=7):
+    """A recorded network description (strings, constants and tables of a reference run on a small mesh,
+    betse_b200.network.unflatten) re-targeted to a synthetic tissue: same rate laws, per-cell / per-membrane /
+    per-env-square tables re-drawn at the new sizes."""
+    d = dict(desc)
+    K = len(d["species"])
+    d["c_cells"] = rng.uniform(0.05, 1.0, (K, C))
+    d["growth_targets"] = [np.arange(C) for _ in range(K)]
+    d["static"] = {k: (v if np.ndim(v) == 0 else np.ones(M if "mdl" in k else C)) for k, v in d["static"].items()}
+    # charged substances add F*c*z to the charge (networks.py:2945): keep them dilute, the reference balances that charge at
+    # set-up (networks.py:3905-3946) and a random field would not
+    dilute = np.where(np.asarray(d["z"]) != 0.0, 1.0e-3, 1.0)[:, None]
+    d["c_cells"] = d["c_cells"] * dilute
+    if "env_on" in d:
+        d["c_env"] = np.where(np.asarray(d["env_on"], dtype=bool)[:, None], rng.uniform(0.05, 0.6, (K, E)), 0.0) * dilute
+        d["c_bound"] = np.asarray(d["c_bound"]) * dilute[:, 0]
+        Do = np.where(np.asarray(d["D_env"]).max(axis=1) > 0, np.asarray(d["D_env"]).max(axis=1), 0.0)
+        d["D_env"] = Do[:, None] * rng.uniform(0.2, 1.0, (K, E))
+    if "c_mems" in d:
+        d["c_mems"] = rng.uniform(0.05, 1.0, (K, M)) * dilute
+    if "transporters" in d:
+        d["transporters"] = [dict(t, targets_cell=np.arange(0, C, targets_every if j else 1), targets_mem=np.arange(M),
+                                  targets_env=np.arange(E)) for j, t in enumerate(d["transporters"])]
+    return d

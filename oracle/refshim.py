@@ -15,7 +15,20 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("BETSE_REFERENCE", "/root/reference")
+def _find_reference():
+    """$BETSE_REFERENCE, else the read-only checkout of the build container, else the copy that
+    tools/install_reference.py leaves under baseline/_ref (git-ignored; it travels to the GPU box)."""
+    env = os.environ.get("BETSE_REFERENCE")
+    if env:
+        return env
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for cand in ("/root/reference", os.path.join(here, "baseline", "_ref")):
+        if os.path.isdir(os.path.join(cand, "betse", "science")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _find_reference()
 
 _STUB_ROOTS = ("matplotlib", "ruamel", "pydot", "mpl_toolkits")
 

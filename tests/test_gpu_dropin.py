@@ -1,0 +1,70 @@
+"""The REAL drop-in on a GPU: `simloop.install()` rebinds Simulator._run_sim_core_loop (betse/science/sim.py:1064-1075) of
+the unmodified reference, `SimRunner.seed/init/sim` (simrunner.py:93-296) runs the shipped default configuration
+(`betse try`: 228 cells, basic ion profile, extracellular spaces, general network with substance X and three channels,
+cutting event) once with the reference's own NumPy loop and once through the CUDA engine, and the stored time series are
+compared.  Needs the reference tree: /root/reference (build container) or baseline/_ref (tools/install_reference.py
+puts it there; it travels to the GPU box with gpurun) — skipped, visibly, when neither exists."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _have_reference():
+    from oracle import refshim
+    return refshim.reference_available()
+
+
+def _run(tmp_path, use_dropin, mods=None):
+    from oracle import refrun, refshim
+    refshim.bypass_science_init()
+    from betse.science.parameters import Parameters
+    from betse.science.simrunner import SimRunner
+    from betse.science.phase import phasecallbacks
+    from betse_b200 import simloop
+    if use_dropin:
+        simloop.install()
+    try:
+        fn = refrun.write_config(str(tmp_path), mods or {})
+        np.random.seed(12345)
+        p = Parameters.make(fn)
+        p.anim.is_while_sim = p.anim.is_after_sim = p.plot.is_after_sim = False
+        runner = SimRunner(p=p, callbacks=phasecallbacks.SimCallbacksNoop())
+        runner.seed()
+        runner.init()
+        phase = runner.sim()
+    finally:
+        if use_dropin:
+            simloop.uninstall()
+    return phase.sim, phase.cells
+
+
+@pytest.mark.parametrize("variant", ["shipped", "mammal_ion_path"])
+def test_betse_try_reference_loop_vs_cuda_dropin(variant, tmp_path):
+    if not _have_reference():
+        pytest.skip("reference tree absent: neither /root/reference nor baseline/_ref (run tools/install_reference.py)")
+    from tests.golden.make_golden import NO_NET, SMALL, _m
+    mods = {} if variant == "shipped" else _m(NO_NET, SMALL, {"general options": {"ion profile": "mammal"}})
+    (tmp_path / "ref").mkdir()
+    (tmp_path / "new").mkdir()
+    ref_sim, ref_cells = _run(tmp_path / "ref", False, mods)
+    new_sim, new_cells = _run(tmp_path / "new", True, mods)
+    assert len(new_cells.mem_i) == len(ref_cells.mem_i)
+    assert len(new_sim.time) == len(ref_sim.time) and len(ref_sim.vm_time) >= 30
+    for a, r in zip(new_sim.vm_time, ref_sim.vm_time):
+        assert np.max(np.abs(a - r)) <= 1e-6                       # BASELINE.json: final Vmem traces within 1e-6 V
+        assert np.max(np.abs(a - r)) <= 1e-8 * np.max(np.abs(r))
+    for name in ("cc_time", "cc_env_time", "gjopen_time", "vm_ave_time", "rho_cells_time", "I_mem_time", "venv_time"):
+        got, want = getattr(new_sim, name), getattr(ref_sim, name)
+        assert len(got) == len(want) >= 30, name
+        for a, r in zip(got, want):
+            a, r = np.asarray(a, dtype=float), np.asarray(r, dtype=float)
+            assert a.shape == r.shape, name
+            assert np.max(np.abs(a - r)) <= 1e-8 * max(np.max(np.abs(r)), 1e-300), name
+    for f in ("cc_cells", "cc_env", "vm", "gjopen"):
+        a, r = np.asarray(getattr(new_sim, f)), np.asarray(getattr(ref_sim, f))
+        assert np.max(np.abs(a - r)) <= 1e-8 * np.max(np.abs(r)), f
+    if variant == "shipped":
+        x_new = new_sim.molecules.core.molecules["X"].c_cells
+        x_ref = ref_sim.molecules.core.molecules["X"].c_cells
+        assert np.max(np.abs(x_new - x_ref)) <= 1e-8 * np.max(np.abs(x_ref))

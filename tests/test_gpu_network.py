@@ -205,28 +205,8 @@ def test_both_handlers_match_reference(kind):
 
 
 def _retarget(desc, C, M, E, rng, targets_every=7):
-    """A recorded network description (95-cell fixture) re-targeted to a synthetic tissue: same strings and constants,
-    per-cell / per-membrane / per-env-square tables re-drawn at the new sizes."""
-    d = dict(desc)
-    K = len(d["species"])
-    d["c_cells"] = rng.uniform(0.05, 1.0, (K, C))
-    d["growth_targets"] = [np.arange(C) for _ in range(K)]
-    d["static"] = {k: (v if np.ndim(v) == 0 else np.ones(M if "mdl" in k else C)) for k, v in d["static"].items()}
-    # charged substances add F*c*z to the charge (networks.py:2945): keep them dilute, the reference balances that charge at
-    # set-up (networks.py:3905-3946) and a random field would not
-    dilute = np.where(np.asarray(d["z"]) != 0.0, 1.0e-3, 1.0)[:, None]
-    d["c_cells"] = d["c_cells"] * dilute
-    if "env_on" in d:
-        d["c_env"] = np.where(np.asarray(d["env_on"], dtype=bool)[:, None], rng.uniform(0.05, 0.6, (K, E)), 0.0) * dilute
-        d["c_bound"] = np.asarray(d["c_bound"]) * dilute[:, 0]
-        Do = np.where(np.asarray(d["D_env"]).max(axis=1) > 0, np.asarray(d["D_env"]).max(axis=1), 0.0)
-        d["D_env"] = Do[:, None] * rng.uniform(0.2, 1.0, (K, E))
-    if "c_mems" in d:
-        d["c_mems"] = rng.uniform(0.05, 1.0, (K, M)) * dilute
-    if "transporters" in d:
-        d["transporters"] = [dict(t, targets_cell=np.arange(0, C, targets_every if j else 1), targets_mem=np.arange(M),
-                                  targets_env=np.arange(E)) for j, t in enumerate(d["transporters"])]
-    return d
+    from betse_b200 import synth
+    return synth.retarget_network(desc, C, M, E, rng, targets_every)
 
 
 @pytest.mark.parametrize("fixture", ["mammal_ecm_net_trans", "mammal_ecm_net_pump", "mammal_ecm_net_lig", "mammal_ecm_net_envq",
