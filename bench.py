@@ -269,7 +269,7 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))      # plumbing only: handles, barriers, max-reduce of times
-    from betse_b200.engine import TissueEngine
+    from betse_b200.engine import EnsembleEngine, TissueEngine
     from betse_b200 import simloop
 
     strips = world > 1 and cfg == "c5"
@@ -283,7 +283,7 @@ def main():
         ds.step(args.warmup)
     else:
         # N > 1 with a small tissue: one independent replica per GPU, no communication
-        eng = TissueEngine(mesh, p, state, device=local_rank, replicas=B) if B > 1 else TissueEngine(mesh, p, state, device=local_rank)
+        eng = EnsembleEngine(mesh, p, state, device=local_rank, replicas=B) if B > 1 else TissueEngine(mesh, p, state, device=local_rank)
         eng.update_V()
         attach(eng, w)
         eng.step(args.warmup)
@@ -317,6 +317,11 @@ def main():
         kt = torch.tensor([kms.get(k, 0.0) for k in KNAMES], device="cuda")
         dist.all_reduce(kt, op=dist.ReduceOp.MAX)
         kms = {k: float(v) for k, v in zip(KNAMES, kt.tolist()) if v > 0}
+    solo_ms = None
+    if B > 1:
+        # kernel shares and the step time of ONE member stepped alone (after the timed region; the ensemble is done)
+        solo_total, kms = eng.members[0].profile(args.steps)
+        solo_ms = solo_total / args.steps
     if ds is not None:
         ds.close()
     else:
@@ -369,7 +374,7 @@ def main():
         n_e2e = args.steps
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        eng2 = TissueEngine(mesh, p, state, device=local_rank, replicas=B) if B > 1 else TissueEngine(mesh, p, state, device=local_rank)
+        eng2 = EnsembleEngine(mesh, p, state, device=local_rank, replicas=B) if B > 1 else TissueEngine(mesh, p, state, device=local_rank)
         eng2.update_V()
         attach(eng2, w)
         done = 0
@@ -427,7 +432,7 @@ def main():
     peak, peak_src = measured_peak_hbm()
     dom = max((k for k in kms if k != "k_xchg"), key=lambda k: kms[k])
     # per-launch algorithmic bytes of one rank's kernel (a rank holds 1/world of a decomposed tissue)
-    div = world if strips else 1
+    div = world if strips else (B if B > 1 else 1)      # ensembles: kernel_ms are of ONE member
     share = {"k_mem": b_mem / div, "k_ion": I * 24 * E * B / div, "k_envacc": 0, "k_field": 72 * E * B / div, "k_envmix": 0}
     ach = share.get(dom, b_mem / div) / (kms[dom] * 1e-3) / 1e9
     traffic = None     # measured DRAM bytes per launch of the dominant kernel (one `ncu --set full` capture of this workload)
@@ -449,8 +454,11 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "timesteps_per_sec": steps_per_s,
             "higher_is_better": True, "scaling": "strong" if strips else ("weak" if world > 1 else "strong"), "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config, "clocks": sampler.summary(),
-            "gpu_launches": int((len(kms) + (1 if "k_xchg" in kms else 0)) * args.steps * world),
+            "gpu_launches": int((len(kms) + (1 if "k_xchg" in kms else 0)) * args.steps * world * B),
             "status_word": status, "finite": finite,
+            **({"ensemble": {"members": B, "solo_ms_per_step": solo_ms, "speedup_vs_solo_per_gpu": B * solo_ms / ms_per_step,
+                             "what": "B independent tissues, one CUDA graph of B streams x 10 timesteps per launch (betse_ensemble_step); "
+                                     "kernel_ms are of one member stepped alone"}} if B > 1 else {}),
             "roofline": roof}
     if e2e:
         line["e2e"] = e2e

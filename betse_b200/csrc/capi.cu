@@ -128,6 +128,11 @@ struct betse_ctx {
     cudaGraphExec_t gexec[2] = {nullptr, nullptr};
     bool graphs_built = false;
     bool use_graphs = true;
+    unsigned long long graph_epoch = 0;      // bumped whenever captured launches of this ctx went stale (destroy_graphs)
+    // ensemble graphs led by this ctx (betse_ensemble_step): members, steps per launch, buffer parity, epochs at capture
+    struct EnsGraph { std::vector<betse_ctx*> members; int nsteps; int cur; unsigned long long epochs; cudaGraphExec_t exec; };
+    std::vector<EnsGraph> ens;
+    cudaEvent_t ens_ev[2] = {nullptr, nullptr};
     // profiling
     cudaEvent_t ev[16];
     bool ev_init = false;
@@ -347,6 +352,9 @@ static void destroy_graphs(betse_ctx* ctx)
     for (int i = 0; i < 2; ++i)
         if (ctx->gexec[i]) { cudaGraphExecDestroy(ctx->gexec[i]); ctx->gexec[i] = nullptr; }
     ctx->graphs_built = false;
+    ctx->graph_epoch++;
+    for (auto& g : ctx->ens) if (g.exec) cudaGraphExecDestroy(g.exec);
+    ctx->ens.clear();
 }
 
 extern "C" void betse_destroy(betse_ctx* ctx)
@@ -359,6 +367,7 @@ extern "C" void betse_destroy(betse_ctx* ctx)
     if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    for (auto& e : ctx->ens_ev) if (e) cudaEventDestroy(e);
     for (void* p : ctx->ipc_opened) cudaIpcCloseMemHandle(p);
     for (void* p : ctx->allocs) cudaFree(p);
     for (int b = 0; b < 2; ++b) { if (ctx->xbuf[b]) cudaFreeHost(ctx->xbuf[b]); if (ctx->xev[b]) cudaEventDestroy(ctx->xev[b]); }
@@ -1100,6 +1109,94 @@ extern "C" int betse_step(betse_ctx* ctx, int nsteps, int flags, uint32_t* statu
     if (want_diag && asked > 0) ctx->diag_valid = true;
     else if (asked > 0) ctx->diag_valid = false;
     return read_status(ctx, status_out);
+}
+
+// Ensemble of small tissues (last bullet: 228-10 k cell tissues are launch-latency bound and run as parameter
+// ensembles): n independent contexts of ONE device advance nsteps timesteps each inside ONE CUDA graph — every member's
+// kernels on the member's own stream, forked from and joined to the leader's (ctxs[0]) stream, so the members' small
+// kernels share the GPU and the host pays one launch for n x nsteps timesteps.  Each member runs exactly the kernels
+// betse_step would launch for it: results are bit-identical to stepping it alone.
+extern "C" int betse_ensemble_step(betse_ctx** ctxs, int n, int nsteps, int launches, uint32_t* status_out, float* device_ms)
+{
+    if (!ctxs || n <= 0 || !ctxs[0] || nsteps <= 0 || launches < 0) return 2;
+    betse_ctx* ctx = ctxs[0];                     // leader: owns the graph, its stream carries the fork and the join
+    CK(cudaSetDevice(ctx->device));
+    unsigned long long epochs = 0;
+    for (int j = 0; j < n; ++j) {
+        betse_ctx* c = ctxs[j];
+        if (!c) return fail(ctx, "betse_ensemble_step: null member");
+        if (c->device != ctx->device) return fail(ctx, "betse_ensemble_step: members must live on one device");
+        if (c->cur != ctx->cur) return fail(ctx, "betse_ensemble_step: members are not in lockstep (step them only through the ensemble)");
+        if (c->X.n_nbr > 0) return fail(ctx, "betse_ensemble_step: a member is part of a decomposed tissue");
+        if (c->phi_lag || c->noise_on || c->P.polar || c->need_emc)
+            return fail(ctx, "betse_ensemble_step: boundary-voltage ramps, dynamic noise and per-step diagnostics are stepped through betse_step");
+        epochs += c->graph_epoch;
+    }
+    if (!ctx->ens_ev[0]) { CK(cudaEventCreate(&ctx->ens_ev[0])); CK(cudaEventCreate(&ctx->ens_ev[1])); }
+    betse_ctx::EnsGraph* g = nullptr;
+    for (auto& e : ctx->ens)
+        if (e.nsteps == nsteps && e.cur == ctx->cur && e.epochs == epochs && (int)e.members.size() == n &&
+            std::equal(e.members.begin(), e.members.end(), ctxs)) g = &e;
+    if (!g) {
+        // (the caller has stepped every member once through betse_step before the first capture: kernels are loaded)
+        static thread_local std::vector<cudaEvent_t> evs;
+        for (int j = 0; j < n; ++j) CK(cudaStreamSynchronize(ctxs[j]->stream));
+        std::vector<int> saved(n);
+        for (int j = 0; j < n; ++j) saved[j] = ctxs[j]->cur;
+        while ((int)evs.size() < n) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); evs.push_back(e); }
+        cudaGraph_t graph;
+        CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        CK(cudaEventRecord(evs[0], ctx->stream));
+        for (int j = 1; j < n; ++j) CK(cudaStreamWaitEvent(ctxs[j]->stream, evs[0], 0));
+        for (int j = 0; j < n; ++j)
+            for (int s = 0; s < nsteps; ++s) enqueue_step(ctxs[j], 0, nullptr);
+        for (int j = 1; j < n; ++j) {
+            CK(cudaEventRecord(evs[j], ctxs[j]->stream));
+            CK(cudaStreamWaitEvent(ctx->stream, evs[j], 0));
+        }
+        CK(cudaStreamEndCapture(ctx->stream, &graph));
+        for (int j = 0; j < n; ++j) ctxs[j]->cur = saved[j];
+        betse_ctx::EnsGraph e;
+        e.members.assign(ctxs, ctxs + n); e.nsteps = nsteps; e.cur = ctx->cur; e.epochs = epochs; e.exec = nullptr;
+        CK(cudaGraphInstantiate(&e.exec, graph, 0));
+        CK(cudaGraphDestroy(graph));
+        ctx->ens.push_back(e);
+        g = &ctx->ens.back();
+    }
+    CK(cudaEventRecord(ctx->ens_ev[0], ctx->stream));
+    for (int l = 0; l < launches; ++l) {
+        if (l > 0 && (nsteps & 1)) {
+            // odd steps per launch flip the buffer parity: the other parity's graph
+            for (int j = 0; j < n; ++j) ctxs[j]->cur ^= 1;
+            int r = betse_ensemble_step(ctxs, n, nsteps, 0, nullptr, nullptr);
+            for (int j = 0; j < n; ++j) ctxs[j]->cur ^= 1;
+            if (r) return r;
+        }
+        const int want = ctx->cur ^ ((l & 1) && (nsteps & 1) ? 1 : 0);
+        betse_ctx::EnsGraph* gl = nullptr;
+        for (auto& e : ctx->ens)
+            if (e.nsteps == nsteps && e.cur == want && e.epochs == epochs && (int)e.members.size() == n &&
+                std::equal(e.members.begin(), e.members.end(), ctxs)) gl = &e;
+        if (!gl) return fail(ctx, "betse_ensemble_step: graph of the other buffer parity is missing");
+        CK(cudaGraphLaunch(gl->exec, ctx->stream));
+    }
+    CK(cudaEventRecord(ctx->ens_ev[1], ctx->stream));
+    if ((launches * nsteps) & 1) for (int j = 0; j < n; ++j) ctxs[j]->cur ^= 1;
+    for (int j = 0; j < n; ++j) if (launches > 0) ctxs[j]->diag_valid = false;
+    CK(cudaGetLastError());
+    if (launches == 0) return 0;
+    CK(cudaEventSynchronize(ctx->ens_ev[1]));
+    if (device_ms) CK(cudaEventElapsedTime(device_ms, ctx->ens_ev[0], ctx->ens_ev[1]));
+    uint32_t all = 0;
+    for (int j = 0; j < n; ++j) {
+        uint32_t st = 0;
+        betse_ctx* c = ctxs[j];
+        { betse_ctx* ctx = c; int r = read_status(ctx, &st); if (r) return r; }
+        if (status_out) status_out[j] = st;
+        all |= st;
+    }
+    (void)all;
+    return 0;
 }
 
 extern "C" int betse_update_v_phase(betse_ctx* ctx, int phase)

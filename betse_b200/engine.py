@@ -763,3 +763,95 @@ class TissueEngine:
             self.close()
         except Exception:
             pass
+
+
+class EnsembleEngine:
+    """B independent small tissues on ONE GPU, advanced together (last bullet: tissues of 228-10 k cells are
+    launch-latency bound, the reference runs one process per parameter set, simrunner.py:93-296).  Every member is a full
+    TissueEngine of its own — its own state, parameters, schedule, channels — so a member computes exactly what it would
+    compute alone (bit-identical, tests/test_gpu_ensemble.py); `step` hands all members to betse_ensemble_step, which
+    runs n x k timesteps as one CUDA graph with one stream per member.
+
+    ``members``: list of (mesh, params, state) triples, or ``replicas=B`` copies of one triple (a parameter ensemble
+    starts from copies and then calls ``members[j].set_field`` / ``upload`` per member)."""
+
+    STEPS_PER_LAUNCH = 10
+
+    def __init__(self, mesh=None, params=None, state=None, device=0, replicas=1, members=None):
+        if members is None:
+            members = [(mesh, params, state)] * int(replicas)
+        self.members = [TissueEngine(m, p, s, device=device) for (m, p, s) in members]
+        self.lib = self.members[0].lib
+        self.B = len(self.members)
+        self._ctxs = (C.c_void_p * self.B)(*[e.ctx for e in self.members])
+        self._warm = False
+        self.device_ms = 0.0
+        m0 = self.members[0]
+        self.Co, self.M, self.E, self.I = m0.Co, m0.M, m0.E, m0.I
+
+    @property
+    def h2d_bytes(self):
+        return sum(e.h2d_bytes for e in self.members)
+
+    @property
+    def d2h_bytes(self):
+        return sum(e.d2h_bytes for e in self.members)
+
+    def update_V(self):
+        for e in self.members:
+            e.update_V()
+
+    def set_channels(self, specs, **kw):
+        for e in self.members:
+            e.set_channels([dict(s) for s in specs], **kw)
+
+    def _run(self, k, launches):
+        st = (C.c_uint32 * self.B)()
+        ms = C.c_float(0)
+        rc = self.lib.betse_ensemble_step(self._ctxs, self.B, int(k), int(launches), st, C.byref(ms))
+        self.members[0]._check(rc, "betse_ensemble_step")
+        for e in self.members:
+            e.steps_done += k * launches
+        self.device_ms += float(ms.value)
+        return [int(x) for x in st], float(ms.value)
+
+    def step(self, n=1):
+        """n timesteps of every member; returns the OR of the members' status words (``self.status`` holds them all)."""
+        status = [0] * self.B
+        n = int(n)
+        if n > 0 and not self._warm:
+            status = [e.step(1) for e in self.members]          # loads every kernel outside a capture
+            self._warm = True
+            n -= 1
+        k = self.STEPS_PER_LAUNCH
+        for chunk, count in ((k, n // k), (n % k, 1 if n % k else 0)):
+            if count:
+                st, _ = self._run(chunk, count)
+                status = [a | b for a, b in zip(status, st)]
+        self.status = status
+        out = 0
+        for s in status:
+            out |= s
+        return out
+
+    def profile(self, n):
+        """n timesteps of every member, device-timed; -> (total ms, {})."""
+        if not self._warm:
+            self.step(1)
+        k = min(self.STEPS_PER_LAUNCH, n)
+        self._run(k, 2)                                        # capture + instantiate (both parities) outside the timed launches
+        _, ms = self._run(k, n // k)
+        if n % k:
+            self._run(n % k, 1)
+            ms += self._run(n % k, 1)[1]
+            ms -= 0.0
+        return ms, {}
+
+    def download(self, fields, pinned=False):
+        """Fields of every member stacked on a leading member axis."""
+        got = [e.download(fields, pinned=pinned) for e in self.members]
+        return {f: np.stack([g[f] for g in got]) for f in got[0]}
+
+    def close(self):
+        for e in self.members:
+            e.close()

@@ -180,6 +180,14 @@ int  betse_set_schedule(betse_ctx *ctx, const betse_params *params);
  * status_out (nullable) receives the OR of BETSE_STATUS_* over all steps of this call. */
 int  betse_step(betse_ctx *ctx, int nsteps, int flags, uint32_t *status_out);
 
+/* Ensembles of small tissues (last bullet; BASELINE configs[0]-[1] are launch-latency bound): the reference
+ * runs one Simulator per process and parameter set (simrunner.py:93-296 per configuration file); here `n` independent
+ * contexts of ONE device advance `nsteps` timesteps each per graph launch, `launches` launches back to back — each member's
+ * kernels on its own stream inside ONE CUDA graph.  Every member must have been stepped at least once through betse_step
+ * (kernels loaded) and all members must be in lockstep.  Bit-identical to stepping each member alone.  status_out
+ * (nullable) receives one status word per member, device_ms (nullable) the device time of the launches. */
+int  betse_ensemble_step(betse_ctx **ctxs, int n, int nsteps, int launches, uint32_t *status_out, float *device_ms);
+
 /* Same as betse_step but timed with CUDA events on the ctx's stream; per-kernel mean
  * durations (ms per launch) and launch counts are returned for the roofline in bench.py. */
 int  betse_step_profile(betse_ctx *ctx, int nsteps, float *total_ms,
