@@ -20,7 +20,7 @@
 #include "hh.cuh"
 
 // launchers (kernels.cu)
-int launch_mem(int ni, const KParams& P, const KArrays& A, int n_ctas, int cur, int diag, int fuse, cudaStream_t st);   // bit 0: fluxes in flux_ell, bit 1: env accumulation fused
+int launch_mem(int ni, const KParams& P, const KArrays& A, int n_ctas, int cur, int diag, cudaStream_t st);   // 1: the membrane -> env fluxes went to flux_ell (k_cell)
 int mem_kernel_kind(int ni, const KParams& P, const KArrays& A, int diag);
 void launch_ion(const KParams& P, const KArrays& A, int nx, int cur, int diag, int ion0, int n, cudaStream_t st);
 void launch_ion_smooth(int ni, const KParams& P, const KArrays& A, int ny, int nx, int nxt, cudaStream_t st);
@@ -44,10 +44,11 @@ bool kcell_enabled();
 void launch_pack_cell_const(const KParams& P, const KArrays& A, int* mem_ell, cudaStream_t st);
 void launch_pack_cell_dm(const KParams& P, const KArrays& A, cudaStream_t st);
 size_t cell_pack_row_bytes(int ni);
-cudaError_t prepare_cell(int ni, int kb_max);
+cudaError_t prepare_cell(int ni, int kb_min);
+bool kcell_pipe_fits(int ni, int kb_min);
 void launch_slot_off(const int* slot_idx, const int* mem_ell, int* slot_off, int n, int Mo, int ni, cudaStream_t st);
 void launch_gather_int(int* dst, const int* src, const int* idx, int n, cudaStream_t st);
-void launch_envacc_ell(int ni, const KParams& P, const KArrays& A, int nxt, cudaStream_t st);
+void launch_envacc_ell(int ni, const KParams& P, const KArrays& A, int nxt, int deps, cudaStream_t st);
 void launch_chan(const KParams& P, const KArrays& A, const KChan& ch, const KNet& N, int cur, cudaStream_t st);
 void launch_net(const KParams& P, const KArrays& A, const KNet& N, const double* h_Dgj, const double* h_Dm,
                 const unsigned char* h_env_on, const betse_substance_pump* pumps, int n_pumps, double dG_RT,
@@ -82,10 +83,11 @@ struct betse_ctx {
     int C = 0, Co = 0, M = 0, Mo = 0, E = 0, ny = 0, nx = 0, I = 0, n_ctas = 0, n_tiles = 0, n_slots = 0;
     bool diag_valid = false;
     int* mem_ell = nullptr;                  // [Mo] position of every membrane's fluxes in flux_ell (cell pack of k_cell)
-    int* kc_sync = nullptr;                  // k_cell: ticket + group counters, zeroed before every launch
+    int* kc_sync = nullptr;                  // k_cell, register build: [ticket | completion counters per group of blocks], zeroed before every launch
     int kc_sync_n = 0;
+    bool env_deps = false;                   // env_dep is built: k_envacc_ell may run next to k_cell (undivided tissues)
+    int env_by_consumer = 0;                 // this step's env accumulation was launched next to k_cell (phase 1 skips it)
     int flux_is_ell = 0;                     // layout the last membrane kernel wrote its membrane -> env fluxes in
-    int env_fused = 0;                       // the last membrane kernel ran the env accumulation itself (fused schedule)
     // exchange window (every buffer a neighbouring rank writes) and the halo-exchange plan
     char* win = nullptr;
     betse_window_info winfo;
@@ -535,10 +537,14 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
         }
         row0[2 * nb + 1] = Mo;
         const long long R32 = (long long)row0[2 * nb] * 32;
-        int kb_max = 0;
-        for (int b = 0; b < nb; ++b) kb_max = std::max(kb_max, row0[2 * (b + 1)] - row0[2 * b]);
-        if (R32 * hp->n_ions < (1LL << 31) - 64) {       // 32-bit flux positions; otherwise k_mem stays in charge
-            P.n_blocks = nb; P.ell_rows = row0[2 * nb]; P.kb_max = kb_max;
+        int kb_max = 0, kb_min = INT_MAX;
+        for (int b = 0; b < nb; ++b) {
+            kb_max = std::max(kb_max, row0[2 * (b + 1)] - row0[2 * b]);
+            kb_min = std::min(kb_min, row0[2 * (b + 1)] - row0[2 * b]);
+        }
+        // 32-bit flux positions and 29-bit env squares (the rows' flag bits); otherwise k_mem stays in charge
+        if (R32 * hp->n_ions < (1LL << 31) - 64 && E < (1 << 29) && nb > 0) {
+            P.n_blocks = nb; P.ell_rows = row0[2 * nb]; P.kb_max = kb_max; P.kb_min = kb_min;
             { const char* e = getenv("BETSE_KCELL_PF"); P.pf_dist = e ? atoi(e) : 1024; }
             { const char* e = getenv("BETSE_KCELL_PERSIST"); P.kc_persist = e ? atoi(e) : 1; }
             if ((r = dev_upload(ctx, (int**)&A.blk_row0, row0.data(), row0.size()))) return r;
@@ -547,51 +553,34 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
             if ((r = dev_alloc(ctx, &ctx->mem_ell, (size_t)Mo))) return r;
             const int n_sl = mesh->ecm_slot_ptr ? mesh->ecm_slot_ptr[E] : Mo;
             if ((r = dev_alloc(ctx, (int**)&A.slot_off, (size_t)n_sl))) return r;
-            const int n_grp = (nb + KC_GRP - 1) / KC_GRP;
-            if ((r = dev_alloc(ctx, &ctx->kc_sync, (size_t)n_grp + 1))) return r;     // [ticket | group counters]
-            A.ticket = ctx->kc_sync; A.cell_done = ctx->kc_sync + 1;
-            ctx->kc_sync_n = n_grp + 1;
+            if (!kcell_pipe_fits(I, kb_min)) {
+                const int n_grp = (nb + KC_GRP - 1) / KC_GRP;
+                if ((r = dev_alloc(ctx, &ctx->kc_sync, (size_t)n_grp + 1))) return r;
+                A.ticket = ctx->kc_sync;
+                ctx->kc_sync_n = 1;
+                // env accumulation next to k_cell (undivided tissues): CTA v of k_envacc_ell = squares [256 v, 256 v + 256)
+                // waits for the groups of cell blocks [first, last] that feed them
+                const char* ed = getenv("BETSE_ENVDEPS");
+                // (measured, profiles/r02f_sweep.txt: 0.49 ms/step against 0.42 — with one 256-thread CTA per SM next to k_cell
+                //  the accumulation is latency-bound and becomes the critical path; opt-in with BETSE_ENVDEPS=1)
+                if (ctx->Co == ctx->C && !mesh->ecm_slot_ptr && ed && ed[0] == '1') {
+                    const int nv = (E + 255) / 256;
+                    std::vector<int> dep(2 * (size_t)nv);
+                    for (int v = 0; v < nv; ++v) { dep[2 * v] = INT_MAX; dep[2 * v + 1] = -1; }
+                    for (int m = 0; m < Mo; ++m) {
+                        const int v = mesh->map_mem2ecm[m] / 256, g = mesh->mem_to_cells[m] / 32 / KC_GRP;
+                        dep[2 * v] = std::min(dep[2 * v], g); dep[2 * v + 1] = std::max(dep[2 * v + 1], g);
+                    }
+                    for (int v = 0; v < nv; ++v) if (dep[2 * v + 1] < 0) { dep[2 * v] = 1; dep[2 * v + 1] = 0; }   // nothing to wait for
+                    if ((r = dev_upload(ctx, (int**)&A.env_dep, dep.data(), dep.size()))) return r;
+                    A.cell_done = ctx->kc_sync + 1;
+                    ctx->kc_sync_n = n_grp + 1;
+                    ctx->env_deps = true;
+                }
+            }
             launch_pack_cell_const(ctx->P, A, ctx->mem_ell, ctx->stream);
             launch_slot_off(A.slot_idx, ctx->mem_ell, const_cast<int*>(A.slot_off), n_sl, Mo, I, ctx->stream);
             CK(cudaGetLastError());
-            // ---- fused schedule (undivided tissues): env task v = squares [v*CHUNK, (v+1)*CHUNK) runs once the cell
-            //      blocks that feed it are done; it is released `lag` blocks behind the last of them, so that it
-            //      hardly ever waits and the fluxes it reads are still in L2
-            const bool whole = ctx->Co == ctx->C && !mesh->ecm_slot_ptr;
-            // (measured, profiles/r02b_*, r02c_*: NOT a win — a block's fluxes are consumed tens of microseconds after they
-            //  were written, by when 100+ MB of streams have passed through the L2; off unless BETSE_FUSE=1)
-            const char* fe = getenv("BETSE_FUSE");
-            if (whole && fe && fe[0] == '1' && P.kc_persist) {
-                const int nv = (E + KC_ENV_CHUNK - 1) / KC_ENV_CHUNK;
-                std::vector<int> lo(nv, INT_MAX), hi(nv, -1);
-                for (int m = 0; m < Mo; ++m) {
-                    const int v = mesh->map_mem2ecm[m] / KC_ENV_CHUNK, u = mesh->mem_to_cells[m] / 32;
-                    lo[v] = std::min(lo[v], u); hi[v] = std::max(hi[v], u);
-                }
-                int lag = 2 * 148 * 8;
-                { const char* e = getenv("BETSE_FUSE_LAG"); if (e) lag = atoi(e); }
-                std::vector<int> dep(2 * (size_t)nv), sched;
-                sched.reserve((size_t)nb + nv);
-                std::vector<long long> rel(nv);
-                long long run = -1;
-                for (int v = 0; v < nv; ++v) {
-                    if (hi[v] >= 0) {
-                        dep[2 * v] = lo[v] / KC_GRP; dep[2 * v + 1] = hi[v] / KC_GRP;
-                        // the whole last group must hold smaller tickets than the env task
-                        run = std::max(run, (long long)std::min(nb - 1, (hi[v] / KC_GRP + 1) * KC_GRP - 1) + lag);
-                    } else { dep[2 * v] = 1; dep[2 * v + 1] = 0; }      // nothing to wait for
-                    rel[v] = run;
-                }
-                int v = 0;
-                for (int u = 0; u < nb; ++u) {
-                    sched.push_back(u);
-                    while (v < nv && rel[v] <= u) sched.push_back((int)(0x80000000u | (unsigned)v++));
-                }
-                while (v < nv) sched.push_back((int)(0x80000000u | (unsigned)v++));
-                P.n_sched = (int)sched.size();
-                if ((r = dev_upload(ctx, (int**)&A.sched, sched.data(), sched.size()))) return r;
-                if ((r = dev_upload(ctx, (int**)&A.env_dep, dep.data(), dep.size()))) return r;
-            }
         }
     }
 
@@ -653,7 +642,7 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
         CK(cudaMemcpyAsync(A.cenv_u, cu, sizeof cu, cudaMemcpyHostToDevice, ctx->stream));
     }
     CK(prepare_kernels(I));
-    CK(prepare_cell(I, ctx->P.kb_max));
+    CK(prepare_cell(I, ctx->P.kb_min));
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
@@ -914,11 +903,12 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
         // sim.py:1282 after 2254): the Ca row is transported first, the other ions run on a second
         // stream NEXT TO the membrane kernel (which is latency-bound and leaves issue slots free).
         const bool chans = !ctx->chans.empty() || ctx->net_on[0] || ctx->net_on[1] || ctx->noise_on;   // deferred-update mode
-        // fused schedule (k_cell runs the env accumulation itself, undivided tissues): every ion's transport must have
-        // finished before the kernel starts, so nothing is left to run next to it
-        const bool fuse = ecm && ctx->P.n_sched > 0 && ctx->X.n_nbr == 0 && !chans && ctx->hp.sharpness >= 1.0 &&
-                          mem_kernel_kind(I, ctx->P, A, diag) == 2;
-        const bool overlap = ecm && ctx->overlap && !evs && ctx->hp.sharpness >= 1.0 && !chans && !fuse;
+        const bool overlap = ecm && ctx->overlap && !evs && ctx->hp.sharpness >= 1.0 && !chans;
+        // the env accumulation runs NEXT TO k_cell (second stream, behind the other ions' transport) and consumes the fluxes
+        // of a cell block as soon as its neighbours have finished too
+        const bool consumer = overlap && ctx->env_deps && ctx->X.n_nbr == 0 && mem_kernel_kind(I, ctx->P, A, diag) == 2;
+        ctx->env_by_consumer = consumer ? 1 : 0;
+        if (ctx->kc_sync && mem_kernel_kind(I, ctx->P, A, diag) == 2) cudaMemsetAsync(ctx->kc_sync, 0, (size_t)ctx->kc_sync_n * sizeof(int), st);
         if (ecm && overlap) {
             const int iCa = ctx->hp.iCa;
             if (iCa >= 0) launch_ion(ctx->P, A, ctx->nx, cur, diag, iCa, 1, st);
@@ -939,11 +929,10 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
             }
         } else if (evs) cudaEventRecord(evs[1], st);
         if (evs) cudaEventRecord(evs[2], st);
-        if (ctx->kc_sync) cudaMemsetAsync(ctx->kc_sync, 0, (size_t)ctx->kc_sync_n * sizeof(int), st);
-        {
-            const int mk = launch_mem(I, ctx->P, A, ctx->n_ctas, cur, diag, fuse ? 1 : 0, st);
-            ctx->flux_is_ell = mk & 1;
-            ctx->env_fused = (mk >> 1) & 1;
+        ctx->flux_is_ell = launch_mem(I, ctx->P, A, ctx->n_ctas, cur, diag, st);
+        if (consumer) {
+            launch_envacc_ell(I, ctx->P, A, nxt, 1, ctx->stream2);
+            cudaEventRecord(ctx->ev_join, ctx->stream2);
         }
         if (overlap) cudaStreamWaitEvent(st, ctx->ev_join, 0);
         if (chans) {
@@ -1007,8 +996,8 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
         }
         if (evs) cudaEventRecord(evs[3], st);
     } else if (phase == 1) {
-        if (ecm && ctx->env_fused) { /* done inside k_cell */ }
-        else if (ecm && ctx->flux_is_ell) launch_envacc_ell(I, ctx->P, A, nxt, st);
+        if (ecm && ctx->env_by_consumer) { /* launched next to k_cell */ }
+        else if (ecm && ctx->flux_is_ell) launch_envacc_ell(I, ctx->P, A, nxt, 0, st);
         else if (ecm) launch_envacc(I, ctx->P, A, ctx->E, nxt, 1, st);
         else launch_envmix(I, ctx->P, A, cur, st);
         if (evs) cudaEventRecord(evs[4], st);

@@ -10,14 +10,20 @@
 //   * per-membrane constants live in a sliced-ELL "cell pack" (SELL-32: block b = cells 32b..32b+31, row k of the
 //     block holds membrane k of each of its cells; a row is DmS[I][32], mem_sa[32], partner[32], env square[32]), so
 //     lane = cell reads them coalesced, and because neighbouring cells have neighbouring partners and env squares,
-//     the gathers of one row touch two or three lines instead of 32;
-//   * persistent warps draw tickets (blocks in order).  STAGED build: the whole block of the NEXT ticket — its rows are
-//     contiguous — arrives by ONE TMA bulk copy (cp.async.bulk + mbarrier) in shared memory while the current block is
-//     computed (12 KB per warp in flight all the time: the first build, which kept one membrane's loads in registers,
-//     stalled at 59 % of the copy bandwidth for lack of bytes in flight, profiles/r02a_*); the gathers of membrane k+1
-//     load into a second register buffer while membrane k is computed.  Register build (ragged meshes whose widest
-//     block does not fit the stage): rows are loaded one membrane ahead, blocks further ahead are pulled into L2 by
-//     bulk prefetches.
+//     the gathers of one row touch two or three lines instead of 32.
+//
+// Two builds:
+//   * k_cell_pipe (default): the rows of the pack are ONE stream; every warp owns a contiguous range of blocks, i.e. a
+//     contiguous range of rows, and runs a three-stage software pipeline over it with cp.async (LDGSTS) into per-warp
+//     shared-memory rings — the row's index pair four rows ahead, everything addressed through it (env concentrations
+//     at the membrane's square, the partner cell's concentrations and Vmem, the transported Ca) together with the
+//     row's DmS / area / gap-junction state two rows ahead, the next block's per-cell state with its first row.  Every
+//     lane copies only what it consumes itself, so cp.async.wait_group is the only synchronisation.  (The register
+//     build below spent 46 % of its stall samples on the first use of a gathered value and on the dependent loads of a
+//     block's prologue, with two warps per scheduler to hide them: profiles/r02a_*.)  Block boundaries travel with the
+//     data: bits 29/30 of a row's env-square word mark the last / first row of a block, bit 31 a lane without membrane.
+//   * k_cell (register build; meshes with a one-membrane block, ion profiles whose rings do not fit): persistent warps
+//     draw blocks in order, the gathers of membrane k+1 load into a second register buffer while membrane k is computed.
 //
 // Reference lines as in k_mem: sim.py:1193-1283, 2086-2111, 2162-2206; sim_toolbox.py:18-182, 1155-1207;
 // channels/gap_junction.py:53-77; ion_current.py:19; sim.py:2027-2029.
@@ -27,36 +33,27 @@
 
 #define KC_WARPS 4
 #define KC_ROWB(NI) (((NI) + 2) * 256)          // bytes of one row of the cell pack
+#define KC_INV   0x80000000u                     // env-square word: the lane has no membrane in this row
+#define KC_FIRST 0x40000000u                     //                  first row of its block
+#define KC_LAST  0x20000000u                     //                  last row of its block
+#define KC_QMASK 0x1fffffffu
+#define KC_DEPS_SMEM (116 * 1024)
 
 template <int NI>
 struct MemIn { double co[NI], cnb[NI], vnb, cao; int nnp; };
 
 __device__ __forceinline__ uint32_t kc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void kc_mbar_init(uint32_t bar, unsigned count)
+__device__ __forceinline__ void kc_cp8(uint32_t dst, const void* src)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void kc_mbar_expect_tx(uint32_t bar, unsigned bytes)
+__device__ __forceinline__ void kc_cp4(uint32_t dst, const void* src)
 {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void kc_mbar_wait(uint32_t bar, unsigned parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "KC_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra KC_DONE;\n"
-        "bra KC_WAIT;\n"
-        "KC_DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void kc_bulk_g2s(uint32_t dst, const void* src, unsigned bytes, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
+__device__ __forceinline__ void kc_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void kc_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 // hint: pull [p, p + bytes) into L2 (one bulk prefetch, no registers held)
 __device__ __forceinline__ void l2_prefetch(const void* p, unsigned bytes)
 {
@@ -67,12 +64,122 @@ __device__ __forceinline__ void l2_prefetch(const void* p, unsigned bytes)
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"(n) : "memory");
 }
 
-// ---- one block of 32 cells: lane = cell.  STAGED: `stage` holds the block's rows and its gap-junction states.
-template <int NI, bool STAGED, bool FUSE>
-__device__ __forceinline__ void cell_task(const KParams& P, const KArrays& A, const int cur, const int task, const int lane,
-                                          const char* __restrict__ stage, unsigned int& flags)
+// ---- the flux math of one membrane (lane = cell), shared by both builds.  Inputs: the cell-side terms, the membrane's
+//      gathered values; adds to the cell's sums, stores the membrane -> env fluxes and the new gap-junction state.
+template <int NI>
+struct CellSide {
+    double cin[NI], cinAm[NI], Bm[NI], Sm[NI], Sg[NI];
+    double vm_own, keq;
+    NaKCell nkc;
+    CaCell cac;
+    bool ca_on;
+};
+
+template <int NI>
+__device__ __forceinline__ void cell_prologue(const KParams& P, CellSide<NI>& S, const double vm_own, const double cCa_fresh, unsigned int& flags)
 {
     constexpr int iNa = StdProf<NI>::iNa, iK = StdProf<NI>::iK, iCa = StdProf<NI>::iCa;
+    S.vm_own = vm_own;
+    MemSide ms;
+    mem_side(vm_own, P, ms);
+    S.keq = ms.keq;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        double Am;
+        ghk_pick(ms.t, StdProf<NI>::z(i), Am, S.Bm[i]);
+        S.cinAm[i] = __dmul_rn(S.cin[i], Am);
+        S.Sm[i] = 0.0; S.Sg[i] = 0.0;
+    }
+    nak_cell(S.cin[iNa], S.cin[iK], P, S.nkc);
+    S.cac.g1 = S.cac.g2 = 0.0;
+    S.ca_on = iCa >= 0 && P.alpha_Ca > 0.0;
+    if (S.ca_on) {
+        double cCai = cCa_fresh;                       // the fresh cell value (update_intra, sim.py:2310)
+        if (cCai != cCai) flags |= ST_NAN_CONC;
+        if (cCai < 0.0) cCai = 0.0;
+        ca_cell(cCai, ms.keq, P, S.cac);
+    }
+}
+
+template <int NI>
+__device__ __forceinline__ double membrane_fluxes(const KParams& P, CellSide<NI>& S, const double* __restrict__ co, const double* __restrict__ cnb,
+                                                  const double vnb, const double cao, const int nnp, const double* __restrict__ DmS,
+                                                  const double sa, double g, double* __restrict__ fl, unsigned int& flags)
+{
+    constexpr int iNa = StdProf<NI>::iNa, iK = StdProf<NI>::iK, iCa = StdProf<NI>::iCa;
+    // gap-junction side: vgj and its GHK table with p.T (sim.py:2166, 2197), gating sub-step g' = g*gc1 + gc2
+    const double vgj0 = vnb - S.vm_own;
+    const double ag1 = ((vgj0 + FLOAT_NONCE) * P.F) * P.inv_RT_p;
+    GhkAB tg;
+    ghk_table(ag1, tg);
+    double gc1, gc2;
+    gj_gate_map(vgj0, P, P.gj_block, gc1, gc2);
+    const double sa_g = (nnp < 0) ? 0.0 : sa;     // no gap-junction flux at boundary membranes (sim.py:2199-2201)
+    double fNa = 0.0, fK = 0.0;
+    if (P.alpha_NaK > 0.0) {
+        fNa = nak_flux(S.nkc, S.keq, co[iNa], co[iK], P.NaK_block, P);
+        fK = -(2.0 / 3.0) * fNa;
+        fNa = P.rho_pump * fNa;
+        fK = P.rho_pump * fK;
+    }
+    double fCa = 0.0;
+    if (S.ca_on) {
+        double cCao = cao;
+        if (cCao != cCao) flags |= ST_NAN_CONC;
+        if (cCao < 0.0) cCao = 0.0;
+        fCa = ca_flux(S.cac, cCao, P);
+        fCa = P.rho_pump * fCa;
+        fCa = P.rho_pump * fCa;                 // applied twice in the reference (sim.py:2141, 2155)
+    }
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        double Ag, Bg;
+        ghk_pick(tg, StdProf<NI>::z(i), Ag, Bg);
+        double fsa = ghk_mem_flux(DmS[i], S.cinAm[i], co[i], S.Bm[i]);
+        if (i == iNa) fsa = fma(fNa, sa, fsa);
+        if (i == iK) fsa = fma(fK, sa, fsa);
+        if (i == iCa) fsa = fma(fCa, sa, fsa);
+        g = fma(g, gc1, gc2);                                      // once per ion (sim.py:1272 -> 2180-2183)
+        const double fg = ghk_gj_flux(P.Dgj_len[i], __dmul_rn(g, sa_g), cnb[i], Ag, S.cin[i], Bg);
+        S.Sm[i] = __dadd_rn(S.Sm[i], fsa);
+        S.Sg[i] = __dadd_rn(S.Sg[i], fg);
+        fl[i * 32] = fsa;
+    }
+    return g;
+}
+
+// update_Co + update_all_concs, charge and Vmem of the cell (sim_toolbox.py:1177-1181; sim.py:2105-2111;
+// ion_current.py:19; sim.py:2027-2029)
+template <int NI>
+__device__ __forceinline__ void cell_epilogue(const KParams& P, const KArrays& A, const CellSide<NI>& S, const double* cc, const double vol,
+                                              const double dvt, const int c, const int nxt, unsigned int& flags)
+{
+    const int C = P.n_cells;
+    const double rvol = fast_rcp(vol);
+    double rho = 0.0;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        double cm_new, cn_new;
+        cell_conc_update(cc[i], S.Sm[i], S.Sg[i], rvol, P.dt, cm_new, cn_new);
+        if (cn_new != cn_new) flags |= ST_NAN_CONC;
+        if (cn_new < 0.0) { cn_new = 0.0; flags |= ST_NEG; }         // no_negs, sim.py:2111
+        A.cc_cells[(size_t)i * C + c] = cn_new;
+        A.cc_mid[nxt][(size_t)i * C + c] = cm_new;                   // the stale cc_at_mem (quirk list)
+        rho = fma(P.zF[i], cn_new, rho);
+    }
+    if (A.extra_rho_cells) rho += ldg(A.extra_rho_cells + c);
+    A.rho_cells[c] = rho;
+    const double vmn = P.inv_cm * (rho * dvt);
+    if (vmn != vmn) flags |= ST_NAN_VM;
+    A.vm_cell[nxt][c] = vmn;
+}
+
+// ---------------------------------------------------------------------------- register build
+// one block of 32 cells: lane = cell
+template <int NI>
+__device__ __forceinline__ void cell_task(const KParams& P, const KArrays& A, const int cur, const int task, const int lane, unsigned int& flags)
+{
+    constexpr int iCa = StdProf<NI>::iCa;
     constexpr int ROWB = KC_ROWB(NI);
     const int nxt = cur ^ 1;
     const int C = P.n_cells, E = P.ny * P.nx;
@@ -83,28 +190,26 @@ __device__ __forceinline__ void cell_task(const KParams& P, const KArrays& A, co
     const bool valid = c < P.n_cells_owned;
     int m_beg = 0, nm = 0;
     if (valid) { m_beg = ldgi(A.cell_mem_ptr + c); nm = ldgi(A.cell_mem_ptr + c + 1) - m_beg; }
-    // row k of the block: shared memory (staged) or the cell pack itself
-    const char* __restrict__ rows = STAGED ? stage : (A.cpack + (size_t)row0 * ROWB);
-    const double* __restrict__ gjs = STAGED ? reinterpret_cast<const double*>(stage + (size_t)P.kb_max * ROWB) + (m_beg - (h0.y & ~1))
-                                            : (A.gjopen + m_beg);
+    const char* __restrict__ rows = A.cpack + (size_t)row0 * ROWB;
+    const double* __restrict__ gjs = A.gjopen + m_beg;
     const double* __restrict__ cmid = A.cc_mid[cur];
     const double* __restrict__ vmc = A.vm_cell[cur];
     const double* __restrict__ cenv = A.cc_env[cur];
     const double* __restrict__ cenvCa = A.cc_env[nxt] + (size_t)(iCa >= 0 ? iCa : 0) * E;   // Ca after transport (sim.py:1282 after 2254)
 
-    // the block whose streams this task pulls into L2 (register build; issued after the first membrane, below)
+    // the block whose streams this task pulls into L2 (issued after the first membrane, below)
     const int up = task + P.pf_dist;
     int2 u0 = make_int2(0, 0), u1 = make_int2(0, 0);
-    if (!STAGED && P.pf_dist > 0 && up < P.n_blocks) {
+    if (P.pf_dist > 0 && up < P.n_blocks) {
         u0 = __ldg(reinterpret_cast<const int2*>(A.blk_row0) + up);
         u1 = __ldg(reinterpret_cast<const int2*>(A.blk_row0) + up + 1);
     }
 
-    // register build: the index pair of membrane k is loaded two membranes ahead (ia / ib), so that the gathers through
-    // them do not wait for a second round trip; staged build: they are in shared memory
+    // the index pair of membrane k is loaded two membranes ahead (ia / ib), so that the gathers through them do not
+    // wait for a second round trip
     int2 ia = make_int2(0, 0), ib = make_int2(0, 0);
     auto idx_load = [&](int2& x, const int k) {
-        if (!STAGED && k < nm) {
+        if (k < nm) {
             const char* r = rows + (size_t)k * ROWB;
             x.x = __ldcs(reinterpret_cast<const int*>(r + (NI + 1) * 256) + lane);
             x.y = __ldcs(reinterpret_cast<const int*>(r + (NI + 1) * 256 + 128) + lane);
@@ -112,24 +217,22 @@ __device__ __forceinline__ void cell_task(const KParams& P, const KArrays& A, co
     };
     auto gather = [&](MemIn<NI>& x, const int2& ix, const int k) {
         if (k < nm) {
-            const char* r = rows + (size_t)k * ROWB;
-            const int nnp = STAGED ? reinterpret_cast<const int*>(r + (NI + 1) * 256)[lane] : ix.x;
-            const unsigned q = (unsigned)(STAGED ? reinterpret_cast<const int*>(r + (NI + 1) * 256 + 128)[lane] : ix.y);
-            const unsigned cn = (unsigned)(nnp & 0x7fffffff);
+            const unsigned q = (unsigned)ix.y & KC_QMASK;
+            const unsigned cn = (unsigned)(ix.x & 0x7fffffff);
 #pragma unroll
             for (int i = 0; i < NI; ++i) x.co[i] = (cenv + (size_t)i * E)[q];
 #pragma unroll
             for (int i = 0; i < NI; ++i) x.cnb[i] = (cmid + (size_t)i * C)[cn];
             x.vnb = vmc[cn];
             x.cao = (iCa >= 0) ? cenvCa[q] : 0.0;
-            x.nnp = nnp;
+            x.nnp = ix.x;
         }
     };
 
-    // ---- this cell
-    double cc[NI], cin[NI], vm_own = 0.0, vol = 1.0, dvt = 0.0;
+    CellSide<NI> S;
+    double cc[NI], vm_own = 0.0, vol = 1.0, dvt = 0.0;
 #pragma unroll
-    for (int i = 0; i < NI; ++i) { cc[i] = 0.0; cin[i] = 0.0; }
+    for (int i = 0; i < NI; ++i) { cc[i] = 0.0; S.cin[i] = 0.0; }
     MemIn<NI> a, b;
     idx_load(ia, 0);
     idx_load(ib, 1);
@@ -137,86 +240,23 @@ __device__ __forceinline__ void cell_task(const KParams& P, const KArrays& A, co
     if (valid) {
         vm_own = vmc[c];
 #pragma unroll
-        for (int i = 0; i < NI; ++i) cin[i] = (cmid + (size_t)i * C)[c];
+        for (int i = 0; i < NI; ++i) S.cin[i] = (cmid + (size_t)i * C)[c];
 #pragma unroll
         for (int i = 0; i < NI; ++i) cc[i] = A.cc_cells[(size_t)i * C + c];
         vol = ldg(A.cell_vol + c);
         dvt = ldg(A.diviterm + c);
     }
-
-    // ---- per-cell part of the flux math (kmath.cuh)
-    MemSide ms;
-    mem_side(vm_own, P, ms);
-    double cinAm[NI], Bm[NI];
-#pragma unroll
-    for (int i = 0; i < NI; ++i) {
-        double Am;
-        ghk_pick(ms.t, StdProf<NI>::z(i), Am, Bm[i]);
-        cinAm[i] = __dmul_rn(cin[i], Am);
-    }
-    NaKCell nkc;
-    nak_cell(cin[iNa], cin[iK], P, nkc);
-    CaCell cac;
-    cac.g1 = cac.g2 = 0.0;
-    const bool ca_on = iCa >= 0 && P.alpha_Ca > 0.0;
-    if (ca_on) {
-        double cCai = cc[iCa >= 0 ? iCa : 0];          // the fresh cell value (update_intra, sim.py:2310)
-        if (cCai != cCai) flags |= ST_NAN_CONC;
-        if (cCai < 0.0) cCai = 0.0;
-        ca_cell(cCai, ms.keq, P, cac);
-    }
-    double Sm[NI], Sg[NI];
-#pragma unroll
-    for (int i = 0; i < NI; ++i) { Sm[i] = 0.0; Sg[i] = 0.0; }
+    cell_prologue<NI>(P, S, vm_own, cc[iCa >= 0 ? iCa : 0], flags);
 
     auto compute = [&](const MemIn<NI>& x, const int k) {
         if (k < nm) {
             const double* __restrict__ r = reinterpret_cast<const double*>(rows + (size_t)k * ROWB) + lane;
             double DmS[NI];
 #pragma unroll
-            for (int i = 0; i < NI; ++i) DmS[i] = STAGED ? r[i * 32] : __ldcs(r + i * 32);
-            const double sa = STAGED ? r[NI * 32] : __ldcs(r + NI * 32);
-            double g = gjs[k];
-            // gap-junction side: vgj and its GHK table with p.T (sim.py:2166, 2197), gating sub-step g' = g*gc1 + gc2
-            const double vgj0 = x.vnb - vm_own;
-            const double ag1 = ((vgj0 + FLOAT_NONCE) * P.F) * P.inv_RT_p;
-            GhkAB tg;
-            ghk_table(ag1, tg);
-            double gc1, gc2;
-            gj_gate_map(vgj0, P, P.gj_block, gc1, gc2);
-            const double sa_g = (x.nnp < 0) ? 0.0 : sa;     // no gap-junction flux at boundary membranes (sim.py:2199-2201)
-            double fNa = 0.0, fK = 0.0;
-            if (P.alpha_NaK > 0.0) {
-                fNa = nak_flux(nkc, ms.keq, x.co[iNa], x.co[iK], P.NaK_block, P);
-                fK = -(2.0 / 3.0) * fNa;
-                fNa = P.rho_pump * fNa;
-                fK = P.rho_pump * fK;
-            }
-            double fCa = 0.0;
-            if (ca_on) {
-                double cCao = x.cao;
-                if (cCao != cCao) flags |= ST_NAN_CONC;
-                if (cCao < 0.0) cCao = 0.0;
-                fCa = ca_flux(cac, cCao, P);
-                fCa = P.rho_pump * fCa;
-                fCa = P.rho_pump * fCa;                 // applied twice in the reference (sim.py:2141, 2155)
-            }
+            for (int i = 0; i < NI; ++i) DmS[i] = __ldcs(r + i * 32);
+            const double sa = __ldcs(r + NI * 32);
             double* __restrict__ fl = A.flux_ell + ((size_t)(row0 + k) * NI) * 32 + lane;
-#pragma unroll
-            for (int i = 0; i < NI; ++i) {
-                double Ag, Bg;
-                ghk_pick(tg, StdProf<NI>::z(i), Ag, Bg);
-                double fsa = ghk_mem_flux(DmS[i], cinAm[i], x.co[i], Bm[i]);
-                if (i == iNa) fsa = fma(fNa, sa, fsa);
-                if (i == iK) fsa = fma(fK, sa, fsa);
-                if (i == iCa) fsa = fma(fCa, sa, fsa);
-                g = fma(g, gc1, gc2);                                      // once per ion (sim.py:1272 -> 2180-2183)
-                const double fg = ghk_gj_flux(P.Dgj_len[i], __dmul_rn(g, sa_g), x.cnb[i], Ag, cin[i], Bg);
-                Sm[i] = __dadd_rn(Sm[i], fsa);
-                Sg[i] = __dadd_rn(Sg[i], fg);
-                fl[i * 32] = fsa;
-            }
-            A.gjopen[m_beg + k] = g;
+            A.gjopen[m_beg + k] = membrane_fluxes<NI>(P, S, x.co, x.cnb, x.vnb, x.cao, x.nnp, DmS, sa, gjs[k], fl, flags);
         }
     };
 
@@ -226,7 +266,7 @@ __device__ __forceinline__ void cell_task(const KParams& P, const KArrays& A, co
         gather(b, ib, k + 1);
         idx_load(ia, k + 2);
         compute(a, k);
-        if (!STAGED && k == 0 && u1.x > u0.x) {
+        if (k == 0 && u1.x > u0.x) {
             // streams of block `up`, one bulk prefetch per array and lane: its rows, gjopen, the cells' own state
             const int cu = up * 32;
             const int ncu = min(32, P.n_cells_owned - cu);
@@ -245,185 +285,215 @@ __device__ __forceinline__ void cell_task(const KParams& P, const KArrays& A, co
             compute(b, k + 1);
         }
     }
-
-    // ---- update_Co + update_all_concs, charge and Vmem of the cell (sim_toolbox.py:1177-1181; sim.py:2105-2111;
-    //      ion_current.py:19; sim.py:2027-2029)
-    if (valid) {
-        const double rvol = fast_rcp(vol);
-        double rho = 0.0;
-#pragma unroll
-        for (int i = 0; i < NI; ++i) {
-            double cm_new, cn_new;
-            cell_conc_update(cc[i], Sm[i], Sg[i], rvol, P.dt, cm_new, cn_new);
-            if (cn_new != cn_new) flags |= ST_NAN_CONC;
-            if (cn_new < 0.0) { cn_new = 0.0; flags |= ST_NEG; }         // no_negs, sim.py:2111
-            A.cc_cells[(size_t)i * C + c] = cn_new;
-            A.cc_mid[nxt][(size_t)i * C + c] = cm_new;                   // the stale cc_at_mem (quirk list)
-            rho = fma(P.zF[i], cn_new, rho);
-        }
-        if (A.extra_rho_cells) rho += ldg(A.extra_rho_cells + c);
-        A.rho_cells[c] = rho;
-        const double vmn = P.inv_cm * (rho * dvt);
-        if (vmn != vmn) flags |= ST_NAN_VM;
-        A.vm_cell[nxt][c] = vmn;
-    }
-    if (FUSE) {
-        // publish: the fluxes of this block are visible before its group's counter moves.  A RELEASE on the counter,
-        // not __threadfence(): a gpu-scope acq_rel fence makes ptxas invalidate the SM's whole L1 (CCTL.IVALL), which the
-        // other warps' gathers live on
-        __syncwarp();
-        if (lane == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(A.cell_done + task / KC_GRP) : "memory");
-    }
+    if (valid) cell_epilogue<NI>(P, A, S, cc, vol, dvt, c, nxt, flags);
 }
 
-// ---- fused env task: membrane -> env exchange of KC_ENV_CHUNK squares (the body of k_envacc_ell), run inside the
-//      membrane kernel once every cell block that feeds these squares has published its fluxes
+// Persistent: every warp draws tickets (ticket t = block t of the cell pack, so the blocks finish as a wavefront through
+// the tissue); kc_persist = 0: one block per warp.  After a block, its group's completion counter moves (release): the
+// env accumulation kernel running NEXT TO this one (k_envacc_ell, `deps`) consumes a block's fluxes out of L2 as soon as
+// every block that feeds its env squares has finished.
 template <int NI>
-__device__ __forceinline__ void env_task(const KParams& P, const KArrays& A, const int nxt, const int v, const int lane)
+__device__ __forceinline__ void k_cell_body(const KParams& P, const KArrays& A, const int cur)
 {
-    const int2 dep = __ldg(reinterpret_cast<const int2*>(A.env_dep) + v);       // groups [x, y] of cell tasks that feed the chunk
-    const int E = P.nx * P.ny;
-    const int base = v * KC_ENV_CHUNK;
-    constexpr int J = KC_ENV_CHUNK / 32;
-    // everything that does not depend on the fluxes first: slot ranges and the transported concentrations
-    int s0[J], s1[J];
-    double cenv[J][NI];
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-        const int k = base + j * 32 + lane;
-        s0[j] = s1[j] = 0;
-        if (k < E) {
-            s0[j] = ldgi(A.slot_ptr + k); s1[j] = ldgi(A.slot_ptr + k + 1);
-#pragma unroll
-            for (int i = 0; i < NI; ++i) cenv[j][i] = A.cc_env[nxt][(size_t)i * E + k];
-        }
-    }
-    if (lane == 0) {
-        for (int g = dep.x; g <= dep.y; ++g) {
-            const int want = min(KC_GRP, P.n_blocks - g * KC_GRP);
-            const volatile int* ctr = A.cell_done + g;
-            while (*ctr < want) __nanosleep(100);
-        }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-        const int k = base + j * 32 + lane;
-        if (k >= E) continue;
-        double acc[NI];
-#pragma unroll
-        for (int i = 0; i < NI; ++i) acc[i] = 0.0;
-        for (int jj = s0[j]; jj < s1[j]; ++jj) {
-            const int off = ldgi(A.slot_off + jj);
-            // L2 loads (ld.cg): the producers' stores are in L2, this SM's L1 may hold an older line
-            if (off >= 0) {
-#pragma unroll
-                for (int i = 0; i < NI; ++i) acc[i] += __ldcg(A.flux_ell + (size_t)off + i * 32);
-            } else {
-                const double* __restrict__ f = A.flux_slots + (size_t)(-(off + 1));
-#pragma unroll
-                for (int i = 0; i < NI; ++i) acc[i] += __ldcg(f + i);
-            }
-        }
-        double rho = 0.0;
-#pragma unroll
-        for (int i = 0; i < NI; ++i) {
-            const double delta_env = (-acc[i]) / P.env_vol_div;                     // sim_toolbox.py:1229
-            const double c = cenv[j][i] + delta_env * P.dt;
-            A.cc_env[nxt][(size_t)i * E + k] = c;
-            rho = fma(P.zF[i], c, rho);
-        }
-        if (A.extra_rho_env) rho += ldg(A.extra_rho_env + k);
-        A.rho_env[k] = rho;
-        A.v_raw[k] = (s1[j] > s0[j]) ? ((rho * P.env_vol_div) / P.memsa_mean) / P.ko_eo_er : 0.0;   // ion_current.py:93-97
-    }
-}
-
-// Persistent: every warp draws tickets; ticket t is block t of the cell pack, or (FUSE) entry t of the host-built
-// schedule, which interleaves the env tasks a fixed lag behind the cell blocks that feed them.  A waiting env task only
-// waits for cell tasks with SMALLER tickets; each of those is running, or is the next ticket of a warp whose current
-// ticket is smaller still — by induction over the ticket order somebody always makes progress.
-template <int NI, int MINB, bool STAGED, bool FUSE>
-__global__ void __launch_bounds__(KC_WARPS * 32, MINB)
-k_cell(const __grid_constant__ KParams P, const KArrays A, const int cur)
-{
-    extern __shared__ __align__(128) char kc_sm[];
-    constexpr int ROWB = KC_ROWB(NI);
     const int lane = threadIdx.x & 31;
     unsigned int flags = 0;
-    const int n_tickets = FUSE ? P.n_sched : P.n_blocks;
-    auto claim = [&]() {
+    for (;;) {
         int t = 0;
-        if (lane == 0) t = atomicAdd(A.ticket, 1);
-        return __shfl_sync(0xffffffffu, t, 0);
-    };
-    if (!STAGED) {
-        for (;;) {
-            const int t = P.kc_persist ? claim() : (int)(blockIdx.x * KC_WARPS + (threadIdx.x >> 5));
-            if (t >= n_tickets) break;
-            if (FUSE) {
-                const int code = ldgi(A.sched + t);
-                if (code < 0) env_task<NI>(P, A, cur ^ 1, code & 0x7fffffff, lane);
-                else cell_task<NI, false, FUSE>(P, A, cur, code, lane, nullptr, flags);
-            } else cell_task<NI, false, false>(P, A, cur, t, lane, nullptr, flags);
-            if (!P.kc_persist) break;
+        if (P.kc_persist) {
+            if (lane == 0) t = atomicAdd(A.ticket, 1);
+            t = __shfl_sync(0xffffffffu, t, 0);
+        } else t = (int)(blockIdx.x * KC_WARPS + (threadIdx.x >> 5));
+        if (t >= P.n_blocks) break;
+        cell_task<NI>(P, A, cur, t, lane, flags);
+        if (A.cell_done) {
+            // a RELEASE on the counter, not __threadfence(): a gpu-scope acq_rel fence makes ptxas invalidate the SM's
+            // whole L1 (CCTL.IVALL), which the other warps' gathers live on
+            __syncwarp();
+            if (lane == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(A.cell_done + t / KC_GRP) : "memory");
         }
-    } else {
-        // per warp: two mbarriers, two stages of [kb_max rows | gap-junction states of the block]
-        const size_t sst = (((size_t)P.kb_max * ROWB + ((size_t)P.kb_max * 32 + 2) * 8) + 127) & ~(size_t)127;
-        char* base = kc_sm + (size_t)(threadIdx.x >> 5) * (128 + 2 * sst);
-        const uint32_t bar = kc_smem_u32(base);
-        if (lane == 0) {
-            kc_mbar_init(bar, 1);
-            kc_mbar_init(bar + 8, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        }
-        __syncwarp();
-        // one TMA bulk copy brings a block's rows, a second its gap-junction states (from an even membrane index: 16-byte
-        // alignment); ticket -> block through the schedule when fused (env tasks need no stage)
-        auto task_of = [&](const int t) { return FUSE ? ldgi(A.sched + t) : t; };
-        auto issue = [&](const int code, const int s) {
-            if (code < 0) return;
-            const int2 h0 = __ldg(reinterpret_cast<const int2*>(A.blk_row0) + code);
-            const int2 h1 = __ldg(reinterpret_cast<const int2*>(A.blk_row0) + code + 1);
-            if (lane == 0) {
-                const unsigned rb = (unsigned)(h1.x - h0.x) * ROWB;
-                const int ma = h0.y & ~1;
-                const unsigned gb = (unsigned)(((h1.y - ma) * 8 + 15) & ~15);
-                char* st = base + 128 + (size_t)s * sst;
-                kc_mbar_expect_tx(bar + 8 * s, rb + gb);
-                kc_bulk_g2s(kc_smem_u32(st), A.cpack + (size_t)h0.x * ROWB, rb, bar + 8 * s);
-                kc_bulk_g2s(kc_smem_u32(st + (size_t)P.kb_max * ROWB), A.gjopen + ma, gb, bar + 8 * s);
-            }
-        };
-        // cell blocks alternate between the two stages; at most two are in flight (the current and the next ticket)
-        int t_cur = claim();
-        if (t_cur < n_tickets) {
-            int c_cur = task_of(t_cur);
-            unsigned ph = 0;                               // phase parity of the two barriers, bit s
-            int fill = 0, s_cur = 0;
-            if (c_cur >= 0) { issue(c_cur, fill); s_cur = fill; fill ^= 1; }
-            for (;;) {
-                const int t_next = claim();
-                const int c_next = t_next < n_tickets ? task_of(t_next) : -1;
-                int s_next = 0;
-                // the next block goes into the other stage (its last reader finished: __syncwarp below)
-                if (t_next < n_tickets && c_next >= 0) { issue(c_next, fill); s_next = fill; fill ^= 1; }
-                if (c_cur < 0) env_task<NI>(P, A, cur ^ 1, c_cur & 0x7fffffff, lane);
-                else {
-                    kc_mbar_wait(bar + 8 * s_cur, (ph >> s_cur) & 1u);
-                    ph ^= 1u << s_cur;
-                    cell_task<NI, true, FUSE>(P, A, cur, c_cur, lane, base + 128 + (size_t)s_cur * sst, flags);
-                    __syncwarp();
-                }
-                if (t_next >= n_tickets) break;
-                c_cur = c_next;
-                s_cur = s_next;
-            }
-        }
+        if (!P.kc_persist) break;
     }
     if (flags) atomicOr(A.status, flags);
+}
+
+// REGS = 0: all 255 registers (two CTAs fill the register file); REGS = 1: capped at 208, which leaves 12288 registers per
+// SM — one 256-thread CTA of the env kernels (k_ion, k_envacc_ell: <= 48 registers) runs next to the two k_cell CTAs
+template <int NI, int MINB>
+__global__ void __launch_bounds__(KC_WARPS * 32, MINB)
+k_cell(const __grid_constant__ KParams P, const KArrays A, const int cur) { k_cell_body<NI>(P, A, cur); }
+
+template <int NI>
+__global__ void __maxnreg__(208)
+k_cell_share(const __grid_constant__ KParams P, const KArrays A, const int cur) { k_cell_body<NI>(P, A, cur); }
+
+// ---------------------------------------------------------------------------- pipelined build
+template <int NI>
+struct KcPipe {
+    static constexpr int IDX_SLOTS = 8, BULK_SLOTS = 3, CELL_SLOTS = 2, MB_SLOTS = 4;
+    static constexpr int BULK_D = 3 * NI + 4;                 // co[NI], cnb[NI], DmS[NI], vnb, cao, sa, gj: doubles per lane
+    static constexpr int CELL_D = 2 * NI + 3;                 // cin[NI], cc[NI], vm, vol, diviterm
+    static constexpr int O_IDX = 0;
+    static constexpr int O_MB = O_IDX + IDX_SLOTS * 256;      // first membrane of the lane's cell, per block in flight
+    static constexpr int O_BULK = O_MB + MB_SLOTS * 128;
+    static constexpr int O_CELL = O_BULK + BULK_SLOTS * BULK_D * 256;
+    static constexpr int WARP_B = O_CELL + CELL_SLOTS * CELL_D * 256;
+    static constexpr int CTA_B = KC_WARPS * WARP_B;
+};
+
+template <int NI>
+__global__ void __launch_bounds__(KC_WARPS * 32, 2)
+k_cell_pipe(const __grid_constant__ KParams P, const KArrays A, const int cur)
+{
+    using L = KcPipe<NI>;
+    extern __shared__ __align__(128) char kc_sm[];
+    constexpr int iCa = StdProf<NI>::iCa;
+    constexpr int ROWB = KC_ROWB(NI);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nxt = cur ^ 1;
+    const int C = P.n_cells, E = P.ny * P.nx;
+    // this warp's blocks [b0, b1) = rows [r0, r1) of the pack
+    const long long gw = (long long)blockIdx.x * KC_WARPS + warp, W = (long long)gridDim.x * KC_WARPS;
+    const int b0 = (int)(gw * P.n_blocks / W), b1 = (int)((gw + 1) * P.n_blocks / W);
+    if (b0 >= b1) return;
+    const int r0 = ldgi(A.blk_row0 + 2 * b0), r1 = ldgi(A.blk_row0 + 2 * b1);
+    char* const base = kc_sm + (size_t)warp * L::WARP_B;
+    const uint32_t sb = kc_smem_u32(base);
+    const double* __restrict__ cmid = A.cc_mid[cur];
+    const double* __restrict__ vmc = A.vm_cell[cur];
+    const double* __restrict__ cenv = A.cc_env[cur];
+    const double* __restrict__ cenvCa = A.cc_env[nxt] + (size_t)(iCa >= 0 ? iCa : 0) * E;   // Ca after transport (sim.py:1282 after 2254)
+
+    // ---- stage 1: index pair of row r (and, with the first row of a block, the first membrane of the lane's cell)
+    int bp1 = b0 - 1, next1 = r0;                    // block of the stage-1 cursor, first row of the block after it
+    auto stage1 = [&](const int r) {
+        if (r < r1) {
+            if (r == next1) {
+                ++bp1;
+                next1 = ldgi(A.blk_row0 + 2 * (bp1 + 1));
+                const int c = bp1 * 32 + lane;
+                if (c < P.n_cells_owned) kc_cp4(sb + L::O_MB + (bp1 & (L::MB_SLOTS - 1)) * 128 + lane * 4, A.cell_mem_ptr + c);
+            }
+            const char* row = A.cpack + (size_t)r * ROWB + (NI + 1) * 256;
+            const uint32_t d = sb + L::O_IDX + (r & (L::IDX_SLOTS - 1)) * 256 + lane * 4;
+            kc_cp4(d, reinterpret_cast<const int*>(row) + lane);
+            kc_cp4(d + 128, reinterpret_cast<const int*>(row + 128) + lane);
+        }
+        kc_commit();
+    };
+    // ---- stage 2: everything of row r that is addressed through its index pair, the row's constants, the gap-junction
+    //      state; with the first row of a block the per-cell state of the block
+    int bp2 = b0 - 1, k2 = 0, mb2 = 0;
+    auto stage2 = [&](const int r) {
+        if (r < r1) {
+            const int* ix = reinterpret_cast<const int*>(base + L::O_IDX + (r & (L::IDX_SLOTS - 1)) * 256);
+            const int nnp = ix[lane];
+            const unsigned ew = (unsigned)ix[32 + lane];
+            if (ew & KC_FIRST) {
+                ++bp2; k2 = 0;
+                const int c = bp2 * 32 + lane;
+                mb2 = reinterpret_cast<const int*>(base + L::O_MB + (bp2 & (L::MB_SLOTS - 1)) * 128)[lane];
+                if (c < P.n_cells_owned) {
+                    const uint32_t d = sb + L::O_CELL + (bp2 & 1) * (L::CELL_D * 256) + lane * 8;
+#pragma unroll
+                    for (int i = 0; i < NI; ++i) kc_cp8(d + i * 256, cmid + (size_t)i * C + c);
+#pragma unroll
+                    for (int i = 0; i < NI; ++i) kc_cp8(d + (NI + i) * 256, A.cc_cells + (size_t)i * C + c);
+                    kc_cp8(d + (2 * NI) * 256, vmc + c);
+                    kc_cp8(d + (2 * NI + 1) * 256, A.cell_vol + c);
+                    kc_cp8(d + (2 * NI + 2) * 256, A.diviterm + c);
+                }
+            }
+            if (!(ew & KC_INV)) {
+                const unsigned q = ew & KC_QMASK;
+                const unsigned cn = (unsigned)nnp & 0x7fffffffu;
+                const uint32_t d = sb + L::O_BULK + (r % L::BULK_SLOTS) * (L::BULK_D * 256) + lane * 8;
+                const double* row = reinterpret_cast<const double*>(A.cpack + (size_t)r * ROWB) + lane;
+#pragma unroll
+                for (int i = 0; i < NI; ++i) kc_cp8(d + i * 256, cenv + (size_t)i * E + q);
+#pragma unroll
+                for (int i = 0; i < NI; ++i) kc_cp8(d + (NI + i) * 256, cmid + (size_t)i * C + cn);
+#pragma unroll
+                for (int i = 0; i < NI; ++i) kc_cp8(d + (2 * NI + i) * 256, row + i * 32);
+                kc_cp8(d + (3 * NI) * 256, vmc + cn);
+                if (iCa >= 0) kc_cp8(d + (3 * NI + 1) * 256, cenvCa + q);
+                kc_cp8(d + (3 * NI + 2) * 256, row + NI * 32);
+                kc_cp8(d + (3 * NI + 3) * 256, A.gjopen + mb2 + k2);
+            }
+            ++k2;
+        }
+        kc_commit();
+    };
+
+    // ---- fill the pipeline: index pairs of rows r0..r0+3, then rows r0 and r0+1 (commit groups arranged like the steady
+    //      state's: stage 1, stage 2, stage 1, stage 2)
+    stage1(r0); stage1(r0 + 1); stage1(r0 + 2); stage1(r0 + 3);
+    kc_wait<0>();
+    kc_commit();
+    stage2(r0);
+    kc_commit();
+    stage2(r0 + 1);
+
+    unsigned int flags = 0;
+    CellSide<NI> S;
+    double vol = 1.0, dvt = 0.0;
+    int bc = b0 - 1, kc = 0, mbc = 0;
+    bool valid = false;
+#pragma unroll 1
+    for (int r = r0; r < r1; ++r) {
+        stage1(r + 4);
+        kc_wait<4>();                       // index pair of row r+2 has landed
+        stage2(r + 2);
+        kc_wait<4>();                       // row r has landed
+        const int* ix = reinterpret_cast<const int*>(base + L::O_IDX + (r & (L::IDX_SLOTS - 1)) * 256);
+        const int nnp = ix[lane];
+        const unsigned ew = (unsigned)ix[32 + lane];
+        if (ew & KC_FIRST) {
+            ++bc; kc = 0;
+            const int c = bc * 32 + lane;
+            valid = c < P.n_cells_owned;
+            mbc = reinterpret_cast<const int*>(base + L::O_MB + (bc & (L::MB_SLOTS - 1)) * 128)[lane];
+            const double* cs = reinterpret_cast<const double*>(base + L::O_CELL + (bc & 1) * (L::CELL_D * 256)) + lane;
+            double vm_own = 0.0, cCa = 0.0;
+#pragma unroll
+            for (int i = 0; i < NI; ++i) S.cin[i] = valid ? cs[i * 32] : 0.0;
+            if (valid) {
+                vm_own = cs[(2 * NI) * 32];
+                vol = cs[(2 * NI + 1) * 32];
+                dvt = cs[(2 * NI + 2) * 32];
+                cCa = cs[(NI + (iCa >= 0 ? iCa : 0)) * 32];
+            }
+            cell_prologue<NI>(P, S, vm_own, cCa, flags);
+        }
+        if (!(ew & KC_INV)) {
+            const double* bs = reinterpret_cast<const double*>(base + L::O_BULK + (r % L::BULK_SLOTS) * (L::BULK_D * 256)) + lane;
+            double co[NI], cnb[NI], DmS[NI];
+#pragma unroll
+            for (int i = 0; i < NI; ++i) { co[i] = bs[i * 32]; cnb[i] = bs[(NI + i) * 32]; DmS[i] = bs[(2 * NI + i) * 32]; }
+            const double vnb = bs[(3 * NI) * 32];
+            const double cao = (iCa >= 0) ? bs[(3 * NI + 1) * 32] : 0.0;
+            const double sa = bs[(3 * NI + 2) * 32];
+            const double g = bs[(3 * NI + 3) * 32];
+            double* __restrict__ fl = A.flux_ell + ((size_t)r * NI) * 32 + lane;
+            A.gjopen[mbc + kc] = membrane_fluxes<NI>(P, S, co, cnb, vnb, cao, nnp, DmS, sa, g, fl, flags);
+        }
+        ++kc;
+        if ((ew & KC_LAST) && valid) {
+            const int c = bc * 32 + lane;
+            const double* cs = reinterpret_cast<const double*>(base + L::O_CELL + (bc & 1) * (L::CELL_D * 256)) + lane;
+            double cc[NI];
+#pragma unroll
+            for (int i = 0; i < NI; ++i) cc[i] = cs[(NI + i) * 32];
+            cell_epilogue<NI>(P, A, S, cc, vol, dvt, c, nxt, flags);
+        }
+    }
+    kc_wait<0>();
+    if (flags) atomicOr(A.status, flags);
+}
+
+static int kc_env_int(const char* name, int dflt)
+{
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
 }
 
 // ---------------------------------------------------------------------------- cell pack
@@ -443,15 +513,18 @@ __global__ void k_pack_cell_const(const __grid_constant__ KParams P, const KArra
     for (int k = 0; k < Kb; ++k) {
         char* r = pack + (size_t)(row0 + k) * rowb;
         double sa = 0.0;
-        int nnp = (int)0x80000000, esq = 0;
+        int nnp = (int)0x80000000;
+        unsigned esq = KC_INV;
         if (k < nm) {
             const int m = m_beg + k;
-            sa = A.mem_sa[m]; nnp = A.nn_cell_flag[m]; esq = A.map_mem2ecm[m];
+            sa = A.mem_sa[m]; nnp = A.nn_cell_flag[m]; esq = (unsigned)A.map_mem2ecm[m];
             mem_ell[m] = (int)(((size_t)(row0 + k) * ni) * 32 + lane);
         }
+        if (k == 0) esq |= KC_FIRST;            // block boundaries travel with the rows (k_cell_pipe)
+        if (k == Kb - 1) esq |= KC_LAST;
         reinterpret_cast<double*>(r + (size_t)ni * 256)[lane] = sa;
         reinterpret_cast<int*>(r + (size_t)(ni + 1) * 256)[lane] = nnp;
-        reinterpret_cast<int*>(r + (size_t)(ni + 1) * 256 + 128)[lane] = esq;
+        reinterpret_cast<int*>(r + (size_t)(ni + 1) * 256 + 128)[lane] = (int)esq;
     }
 }
 
@@ -528,22 +601,47 @@ size_t cell_pack_row_bytes(int ni) { return (size_t)(ni + 2) * 256; }
 // ---------------------------------------------------------------------------- membrane -> env exchange (ELL fluxes)
 // update_Co env branch + div_env (sim_toolbox.py:1189-1234), env charge, raw env voltage (ion_current.py:75-97):
 // kernels.cu:k_envacc with the fluxes read where k_cell left them.  Same summation order (global membrane index).
-template <int NI>
-__global__ void __launch_bounds__(256)
+// DEPS: the kernel runs NEXT TO k_cell (second stream): CTA b first waits until every group of cell blocks that feeds its
+// squares has finished (env_dep[b] = {first, last} group; CTAs are dispatched in order and the cell blocks finish in order,
+// so a CTA hardly waits and the fluxes it reads were written microseconds ago — they come out of L2, not DRAM).
+template <int NI, bool DEPS>
+__global__ void __launch_bounds__(256, DEPS ? 5 : 4)
 k_envacc_ell(const __grid_constant__ KParams P, const KArrays A, const int nxt)
 {
     const int k = P.ya0 * P.nx + blockIdx.x * blockDim.x + threadIdx.x;
     const int E = P.nx * P.ny;
-    if (k >= P.ya1 * P.nx) return;
-    const int s0 = ldgi(A.slot_ptr + k), s1 = ldgi(A.slot_ptr + k + 1);
+    const bool in = k < P.ya1 * P.nx;
+    // everything that does not depend on the fluxes first
+    int s0 = 0, s1 = 0;
     double acc[NI], cv[NI];
 #pragma unroll
-    for (int i = 0; i < NI; ++i) { acc[i] = 0.0; cv[i] = A.cc_env[nxt][(size_t)i * E + k]; }
+    for (int i = 0; i < NI; ++i) { acc[i] = 0.0; cv[i] = 0.0; }
+    if (in) {
+        s0 = ldgi(A.slot_ptr + k); s1 = ldgi(A.slot_ptr + k + 1);
+#pragma unroll
+        for (int i = 0; i < NI; ++i) cv[i] = A.cc_env[nxt][(size_t)i * E + k];
+    }
+    if (DEPS) {
+        if (threadIdx.x == 0) {
+            const int2 dep = __ldg(reinterpret_cast<const int2*>(A.env_dep) + blockIdx.x);
+            for (int g = dep.x; g <= dep.y; ++g) {
+                const int want = min(KC_GRP, P.n_blocks - g * KC_GRP);
+                int got;
+                do {
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(got) : "l"(A.cell_done + g) : "memory");
+                    if (got < want) __nanosleep(200);
+                } while (got < want);
+            }
+        }
+        __syncthreads();
+    }
+    if (!in) return;
     for (int j = s0; j < s1; ++j) {
         const int off = ldgi(A.slot_off + j);
         if (off >= 0) {
+            // DEPS: L2 loads (ld.cg) — the producers' stores are in L2, this SM's L1 may hold an older line
 #pragma unroll
-            for (int i = 0; i < NI; ++i) acc[i] += A.flux_ell[(size_t)off + i * 32];
+            for (int i = 0; i < NI; ++i) acc[i] += DEPS ? __ldcg(A.flux_ell + (size_t)off + i * 32) : A.flux_ell[(size_t)off + i * 32];
         } else {
             const double* __restrict__ f = A.flux_slots + (size_t)(-(off + 1));
 #pragma unroll
@@ -563,26 +661,32 @@ k_envacc_ell(const __grid_constant__ KParams P, const KArrays A, const int nxt)
     A.v_raw[k] = (s1 > s0) ? ((rho * P.env_vol_div) / P.memsa_mean) / P.ko_eo_er : 0.0;   // ion_current.py:93-97
 }
 
-void launch_envacc_ell(int ni, const KParams& P, const KArrays& A, int nxt, cudaStream_t st)
+// deps: run next to k_cell (the caller launches it on a second stream and has built env_dep for CTAs of 256 squares)
+void launch_envacc_ell(int ni, const KParams& P, const KArrays& A, int nxt, int deps, cudaStream_t st)
 {
     const int n = (P.ya1 - P.ya0) * P.nx;
     if (n <= 0) return;
     const int g = (n + 255) / 256;
+    if (deps) {
+        // KC_DEPS_SMEM of (unused) dynamic shared memory: at most ONE of these CTAs is resident per SM, so that its waiting
+        // CTAs can never keep k_cell — which they wait for — off the SMs
+        switch (ni) {
+            case 4: k_envacc_ell<4, true><<<g, 256, KC_DEPS_SMEM, st>>>(P, A, nxt); break;
+            case 5: k_envacc_ell<5, true><<<g, 256, KC_DEPS_SMEM, st>>>(P, A, nxt); break;
+            case 6: k_envacc_ell<6, true><<<g, 256, KC_DEPS_SMEM, st>>>(P, A, nxt); break;
+            default: k_envacc_ell<7, true><<<g, 256, KC_DEPS_SMEM, st>>>(P, A, nxt); break;
+        }
+        return;
+    }
     switch (ni) {
-        case 4: k_envacc_ell<4><<<g, 256, 0, st>>>(P, A, nxt); break;
-        case 5: k_envacc_ell<5><<<g, 256, 0, st>>>(P, A, nxt); break;
-        case 6: k_envacc_ell<6><<<g, 256, 0, st>>>(P, A, nxt); break;
-        default: k_envacc_ell<7><<<g, 256, 0, st>>>(P, A, nxt); break;
+        case 4: k_envacc_ell<4, false><<<g, 256, 0, st>>>(P, A, nxt); break;
+        case 5: k_envacc_ell<5, false><<<g, 256, 0, st>>>(P, A, nxt); break;
+        case 6: k_envacc_ell<6, false><<<g, 256, 0, st>>>(P, A, nxt); break;
+        default: k_envacc_ell<7, false><<<g, 256, 0, st>>>(P, A, nxt); break;
     }
 }
 
 // ---------------------------------------------------------------------------- launch
-static int kc_env_int(const char* name, int dflt)
-{
-    const char* e = getenv(name);
-    return e ? atoi(e) : dflt;
-}
-
 bool kcell_enabled()
 {
     static int v = -1;
@@ -594,76 +698,76 @@ static int g_kc_sms = 148;
 
 void kcell_set_sms(int n) { if (n > 0) g_kc_sms = n; }
 
-// dynamic shared memory of the staged build: per warp two barriers (128 bytes) + two stages
-static size_t kc_stage_smem(int ni, int kb_max)
-{
-    const size_t sst = (((size_t)kb_max * cell_pack_row_bytes(ni) + ((size_t)kb_max * 32 + 2) * 8) + 127) & ~(size_t)127;
-    return KC_WARPS * (128 + 2 * sst);
-}
-
-// the staged build needs two CTAs (8 warps) per SM in 227 KB of shared memory, each CTA also costs 1 KB of system use
-bool kcell_staged_fits(int ni, int kb_max)
+// the pipelined build needs two CTAs (8 warps) per SM in 227 KB of shared memory (each CTA also costs 1 KB of system
+// use) and blocks of at least two rows (its per-cell stage is double buffered: the fetch runs two rows ahead)
+template <int NI>
+static bool pipe_fits(int kb_min)
 {
     static int v = -1;
-    if (v < 0) v = kc_env_int("BETSE_KCELL_STAGED", 1) ? 1 : 0;
-    return v == 1 && kb_max > 0 && 2 * (kc_stage_smem(ni, kb_max) + 1024) <= (size_t)227 * 1024;
+    if (v < 0) v = kc_env_int("BETSE_KCELL_PIPE", 0) ? 1 : 0;    // measured slower than the register build (profiles/r02e_*): opt-in
+    return v == 1 && kb_min >= 2 && 2 * ((size_t)KcPipe<NI>::CTA_B + 1024) <= (size_t)227 * 1024;
+}
+
+bool kcell_pipe_fits(int ni, int kb_min)
+{
+    switch (ni) {
+        case 4: return pipe_fits<4>(kb_min);
+        case 5: return pipe_fits<5>(kb_min);
+        case 6: return pipe_fits<6>(kb_min);
+        case 7: return pipe_fits<7>(kb_min);
+        default: return false;
+    }
 }
 
 template <int NI>
-static cudaError_t prep_cell_t(int kb_max)
+static cudaError_t prep_cell_t(int kb_min)
 {
-    if (!kcell_staged_fits(NI, kb_max)) return cudaSuccess;
-    const int smem = (int)kc_stage_smem(NI, kb_max);
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(k_cell<NI, 2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
-    if ((e = cudaFuncSetAttribute(k_cell<NI, 2, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100))) return e;
-    if ((e = cudaFuncSetAttribute(k_cell<NI, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
-    return cudaFuncSetAttribute(k_cell<NI, 2, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if ((e = cudaFuncSetAttribute(k_envacc_ell<NI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, KC_DEPS_SMEM))) return e;
+    if (!pipe_fits<NI>(kb_min)) return cudaSuccess;
+    if ((e = cudaFuncSetAttribute(k_cell_pipe<NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, KcPipe<NI>::CTA_B))) return e;
+    return cudaFuncSetAttribute(k_cell_pipe<NI>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
 }
 
 // not capturable: once per context
-cudaError_t prepare_cell(int ni, int kb_max)
+cudaError_t prepare_cell(int ni, int kb_min)
 {
     switch (ni) {
-        case 4: return prep_cell_t<4>(kb_max);
-        case 5: return prep_cell_t<5>(kb_max);
-        case 6: return prep_cell_t<6>(kb_max);
-        case 7: return prep_cell_t<7>(kb_max);
+        case 4: return prep_cell_t<4>(kb_min);
+        case 5: return prep_cell_t<5>(kb_min);
+        case 6: return prep_cell_t<6>(kb_min);
+        case 7: return prep_cell_t<7>(kb_min);
         default: return cudaSuccess;
     }
 }
 
-template <int NI, bool FUSE>
-static void launch_cell_f(const KParams& P, const KArrays& A, int cur, cudaStream_t st)
+template <int NI>
+static void launch_cell_t(const KParams& P, const KArrays& A, int cur, cudaStream_t st)
 {
     static int minb = -1;
     if (minb < 0) minb = kc_env_int("BETSE_KCELL_MINB", 2);      // register build: resident CTAs (of 4 warps) per SM, 2 = 255 registers, 3 = 168
-    const int need = ((FUSE ? P.n_sched : P.n_blocks) + KC_WARPS - 1) / KC_WARPS;
-    if (kcell_staged_fits(NI, P.kb_max)) {
+    const int need = (P.n_blocks + KC_WARPS - 1) / KC_WARPS;
+    if (pipe_fits<NI>(P.kb_min)) {
         const int grid = need < g_kc_sms * 2 ? need : g_kc_sms * 2;
-        k_cell<NI, 2, true, FUSE><<<grid, KC_WARPS * 32, kc_stage_smem(NI, P.kb_max), st>>>(P, A, cur);
+        k_cell_pipe<NI><<<grid, KC_WARPS * 32, KcPipe<NI>::CTA_B, st>>>(P, A, cur);
         return;
     }
+    static int share = -1;
+    if (share < 0) share = kc_env_int("BETSE_KCELL_SHARE", 0);   // 208-register build: the env kernels run next to it (measured: no gain, profiles/r02f_*)
     const int mb = minb <= 2 ? 2 : 3;
     const int grid = (!P.kc_persist || need < g_kc_sms * mb) ? need : g_kc_sms * mb;
-    if (mb == 2) k_cell<NI, 2, false, FUSE><<<grid, KC_WARPS * 32, 0, st>>>(P, A, cur);
-    else k_cell<NI, 3, false, FUSE><<<grid, KC_WARPS * 32, 0, st>>>(P, A, cur);
+    if (mb == 2 && share) k_cell_share<NI><<<grid, KC_WARPS * 32, 0, st>>>(P, A, cur);
+    else if (mb == 2) k_cell<NI, 2><<<grid, KC_WARPS * 32, 0, st>>>(P, A, cur);
+    else k_cell<NI, 3><<<grid, KC_WARPS * 32, 0, st>>>(P, A, cur);
 }
 
-template <int NI>
-static void launch_cell_t(const KParams& P, const KArrays& A, int cur, int fuse, cudaStream_t st)
-{
-    if (fuse) launch_cell_f<NI, true>(P, A, cur, st);
-    else launch_cell_f<NI, false>(P, A, cur, st);
-}
-
-// the caller zeroes A.ticket (and, fused, A.cell_done) on the same stream before every launch
-void launch_cell(int ni, const KParams& P, const KArrays& A, int cur, int fuse, cudaStream_t st)
+// register build: the caller zeroes A.ticket on the same stream before every launch
+void launch_cell(int ni, const KParams& P, const KArrays& A, int cur, cudaStream_t st)
 {
     switch (ni) {
-        case 4: launch_cell_t<4>(P, A, cur, fuse, st); break;
-        case 5: launch_cell_t<5>(P, A, cur, fuse, st); break;
-        case 6: launch_cell_t<6>(P, A, cur, fuse, st); break;
-        default: launch_cell_t<7>(P, A, cur, fuse, st); break;
+        case 4: launch_cell_t<4>(P, A, cur, st); break;
+        case 5: launch_cell_t<5>(P, A, cur, st); break;
+        case 6: launch_cell_t<6>(P, A, cur, st); break;
+        default: launch_cell_t<7>(P, A, cur, st); break;
     }
 }

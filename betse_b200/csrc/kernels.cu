@@ -758,7 +758,7 @@ void launch_mem_pipe(int ni, const KParams& P, const KArrays& A, int n_sms, int 
 // kcell.cu: the lane-per-cell build of the specialised kernel (fluxes in flux_ell)
 bool kcell_enabled();
 void kcell_set_sms(int n);
-void launch_cell(int ni, const KParams& P, const KArrays& A, int cur, int fuse, cudaStream_t st);
+void launch_cell(int ni, const KParams& P, const KArrays& A, int cur, cudaStream_t st);
 
 // the specialised builds apply to the shipped ion profiles with the default feature switches
 template <int NI>
@@ -787,9 +787,9 @@ int mem_kernel_kind(int ni, const KParams& P, const KArrays& A, int diag)
     return kmem_pipe_enabled() ? 1 : 0;
 }
 
-// returns bit 0: the fluxes went to flux_ell (k_cell), bit 1: the env accumulation ran inside the kernel (fused)
+// returns 1 when the membrane -> env fluxes went to flux_ell (k_cell)
 template <int NI>
-static int launch_mem_t(const KParams& P, const KArrays& A, int n_ctas, int cur, int diag, int fuse, cudaStream_t st)
+static int launch_mem_t(const KParams& P, const KArrays& A, int n_ctas, int cur, int diag, cudaStream_t st)
 {
     const size_t smem = (size_t)KM_SMEM_DOUBLES(NI) * sizeof(double);
     const int grid = (P.n_tiles + (BT_TPB / 32) - 1) / (BT_TPB / 32);
@@ -797,7 +797,7 @@ static int launch_mem_t(const KParams& P, const KArrays& A, int n_ctas, int cur,
     const int kind = mem_kernel_kind(NI, P, A, diag);
     const bool std_prof = NI <= 7 && std_profile<(NI <= 7 ? NI : 7)>(P, A, diag);
     if (P.has_phi || P.polar) k_mem<NI, true, 2, 0><<<grid, BT_TPB, smem, st>>>(P, A, cur, diag);
-    else if (kind == 2) { const int f = fuse && P.n_sched > 0; launch_cell(NI, P, A, cur, f, st); return f ? 3 : 1; }
+    else if (kind == 2) { launch_cell(NI, P, A, cur, st); return 1; }
     else if (kind == 1) launch_mem_pipe(NI, P, A, g_n_sms, cur, st);
     else if (std_prof && minb2) k_mem<NI, false, 2, 1><<<grid, BT_TPB, smem, st>>>(P, A, cur, diag);
     else if (std_prof && kmem_minb() == 4) k_mem<NI, false, 4, 1><<<grid, BT_TPB, smem, st>>>(P, A, cur, diag);
@@ -843,14 +843,14 @@ cudaError_t prepare_kernels(int ni)
     }
 }
 
-int launch_mem(int ni, const KParams& P, const KArrays& A, int n_ctas, int cur, int diag, int fuse, cudaStream_t st)
+int launch_mem(int ni, const KParams& P, const KArrays& A, int n_ctas, int cur, int diag, cudaStream_t st)
 {
     switch (ni) {
-        case 4: return launch_mem_t<4>(P, A, n_ctas, cur, diag, fuse, st);
-        case 5: return launch_mem_t<5>(P, A, n_ctas, cur, diag, fuse, st);
-        case 6: return launch_mem_t<6>(P, A, n_ctas, cur, diag, fuse, st);
-        case 7: return launch_mem_t<7>(P, A, n_ctas, cur, diag, fuse, st);
-        default: return launch_mem_t<8>(P, A, n_ctas, cur, diag, fuse, st);
+        case 4: return launch_mem_t<4>(P, A, n_ctas, cur, diag, st);
+        case 5: return launch_mem_t<5>(P, A, n_ctas, cur, diag, st);
+        case 6: return launch_mem_t<6>(P, A, n_ctas, cur, diag, st);
+        case 7: return launch_mem_t<7>(P, A, n_ctas, cur, diag, st);
+        default: return launch_mem_t<8>(P, A, n_ctas, cur, diag, st);
     }
 }
 

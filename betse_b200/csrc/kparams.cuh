@@ -6,8 +6,8 @@
 #define BT_TPB 256          // threads per CTA of the membrane kernel == max membranes per CTA
 #define BT_MAX_CTA_CELLS 96 // max cells packed into one membrane-kernel CTA
 #define BT_TILE_MAXC 8      // max cells of one warp tile (<= 32 membranes)
-#define KC_GRP 16           // k_cell: cell blocks per completion counter (fused env tasks wait on whole groups)
-#define KC_ENV_CHUNK 128    // k_cell: env squares per fused env task (4 per lane)
+
+#define KC_GRP 16           // k_cell: cell blocks per completion counter (the env accumulation next to it waits on whole groups)
 
 // Scalars (passed BY VALUE as a __grid_constant__ kernel argument: lives in the constant bank).  Derived products are formed on
 // the host in the same operand order as the reference's NumPy expressions.
@@ -43,9 +43,8 @@ struct KParams {
     int ny, nx, y0, ny_global, y_own0, y_own1;
     int n_cells, n_cells_owned, n_mems_owned, n_ctas, n_tiles;
     int pf_tiles;                           // k_mem: L2 prefetch distance in tiles (0 = off)
-    int n_blocks, ell_rows, kb_max;         // k_cell: blocks of 32 cells, rows of the cell pack, rows of its widest block
-    int pf_dist;                            // k_cell: a block pulls the streams of block + pf_dist into L2 (0 = off)
-    int n_sched;                            // k_cell, fused: tickets of the schedule (cell blocks + env tasks)
+    int n_blocks, ell_rows, kb_max, kb_min; // k_cell: blocks of 32 cells, rows of the cell pack, rows of its widest / narrowest block
+    int pf_dist;                            // k_cell, register build: a block pulls the streams of block + pf_dist into L2 (0 = off)
     int kc_persist;                         // k_cell, register build: persistent warps drawing tickets (1) or one block per warp (0)
     int defer;                              // k_mem stores its membrane->cell sums instead of applying them (channels)
     int chan_charge;                        // p.substances_affect_charge: Jmem takes the channels' extra_J_mem
@@ -70,12 +69,11 @@ struct KArrays {
     const int *slot_ptr, *slot_idx;
     // cell pack of k_cell (SELL-32: block b = cells 32b..32b+31; row blk_row0[b] + k holds membrane k of each cell)
     const int *blk_row0;         // [n_blocks + 1] int2 {first row, first membrane} of every block
-    int *ticket;                 // k_cell: next ticket (zeroed before every launch)
-    int *cell_done;              // k_cell, fused: finished cell blocks per group of KC_GRP (zeroed before every launch)
-    const int *sched;            // k_cell, fused: ticket -> cell block (>= 0) or env task | 0x80000000
-    const int *env_dep;          // k_cell, fused: int2 {first, last} group of cell blocks that feed each env task
+    int *ticket;                 // k_cell, register build: next ticket (zeroed before every launch)
+    int *cell_done;              // k_cell: finished cell blocks per group of KC_GRP (zeroed before every launch; null = not published)
+    const int *env_dep;          // k_envacc_ell next to k_cell: int2 {first, last} group of cell blocks that feed each CTA's 256 squares
     const char *cpack;           // [rows] x {DmS[I][32] doubles = (Dm*(-rho_channel/tm))*mem_sa, mem_sa[32] doubles,
-                                 //            partner cell | boundary bit [32] ints, env square [32] ints}
+                                 //            partner cell | boundary bit [32] ints, env square | KC_FIRST/LAST/INV bits [32] ints}
     double *flux_ell;            // [rows][I][32] membrane -> env exchange, written by k_cell
     const int *slot_off;         // [slots] position of every env-square slot in flux_ell (>= 0) or in flux_slots (-(s*I)-1)
     const double *mem_sa, *mem_nx, *mem_ny, *cell_vol, *cell_sa, *diviterm, *num_mems;
