@@ -7,6 +7,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <thread>
 #include <vector>
@@ -210,8 +211,10 @@ static int xfer(betse_ctx* ctx, void* dst, const void* src, size_t bytes, cudaMe
 {
     cudaStream_t st = ctx->stream;
     const bool down = kind == cudaMemcpyDeviceToHost;
-    // uploads: the driver's own pageable path measured faster than a single-threaded host-side bounce (source pages are
-    // resident); BETSE_H2D_BOUNCE=1 stages them through the page-locked pair with the multi-threaded copy
+    // uploads: the driver's own pageable path (~6 GB/s on the B200 box) measured faster than a host-side bounce through
+    // the page-locked pair (BETSE_H2D_BOUNCE=1), single- or multi-threaded, and than slices issued from several threads
+    // on streams of their own (the driver serialises them: 1 thread 62-82 ms, 4 threads 115-124 ms for the index arrays
+    // of a 1 M-cell tissue, profiles/r02g_e2e_fixed_cost.txt)
     static const bool h2d_bounce = [] { const char* e = getenv("BETSE_H2D_BOUNCE"); return e && atoi(e) != 0; }();
     if ((!down && !h2d_bounce) || bytes < ((size_t)1 << 20) || host_is_pinned(down ? dst : src)) {
         CK(cudaMemcpyAsync(dst, src, bytes, kind, st));
@@ -377,8 +380,21 @@ extern "C" void betse_destroy(betse_ctx* ctx)
     delete ctx;
 }
 
+// BETSE_TIMING=1: wall-clock marks of the set-up phases on stderr (tools/e2e_cprofile.py)
+struct PhaseTimer {
+    bool on; std::chrono::steady_clock::time_point t0; const char* what;
+    explicit PhaseTimer(const char* w) : on(getenv("BETSE_TIMING") != nullptr), t0(std::chrono::steady_clock::now()), what(w) {}
+    void mark(const char* name) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[betse timing] %s: %-28s %7.2f ms\n", what, name, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_params* hp)
 {
+    PhaseTimer T("create");
     if (hp->abi_version != BETSE_ABI_VERSION) return fail(ctx, "betse_params.abi_version mismatch");
     if (hp->n_ions < 4 || hp->n_ions > BETSE_MAX_IONS) return fail(ctx, "n_ions must be in [4,8]");
     if (hp->cell_polarizability != 0.0) {
@@ -426,83 +442,82 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
         return fail(ctx, "I*max(C,M,E) must stay below 2^31 (32-bit device indices)");
     fill_kparams(ctx, hp);
 
-    // ---- index arrays
+    // ---- host-side index work on helper threads, next to the uploads of the raw arrays (the driver stages pageable
+    //      memory on the calling thread; both are memory-bound loops over 1e6..1e7 entries)
     int r;
+    std::vector<int> nnc(Mo);
+    std::string err_nnc, err_pack;
+    const bool par = [] { const char* e = getenv("BETSE_CREATE_THREADS"); return !(e && e[0] == '0'); }();
+    auto job_nnc = [&] {
+        for (int m = 0; m < Mo; ++m) {
+            int nn = mesh->nn_i[m];
+            int cn;
+            if (nn >= 0 && nn < Mo) cn = mesh->mem_to_cells[nn];
+            else if (nn <= -2) cn = -(nn + 2);      // multi-GPU: partner lives on a ghost cell: nn = -(ghost_cell+2)
+            else { err_nnc = "nn_i out of range"; return; }
+            if (cn < 0 || cn >= C) { err_nnc = "partner cell out of range"; return; }
+            if (mesh->map_mem2ecm[m] < 0 || mesh->map_mem2ecm[m] >= E) { err_nnc = "map_mem2ecm out of range"; return; }
+            if (mesh->mem_to_cells[m] < 0 || mesh->mem_to_cells[m] >= Co) { err_nnc = "mem_to_cells out of range"; return; }
+            nnc[m] = cn | (mesh->bflags_mems[m] ? (int)0x80000000 : 0);
+        }
+    };
+    // CTA packing (k_diag): contiguous runs of whole cells with <= BT_TPB membranes; warp packing (k_mem): contiguous runs
+    // of whole cells with <= 32 membranes, <= BT_TILE_MAXC cells
+    std::vector<int> cta_start, tile_start, tdesc;
+    auto job_pack = [&] {
+        cta_start.push_back(0);
+        for (int c = 0; c < Co;) {
+            int mstart = mesh->cell_mem_ptr[c];
+            int cc = c;
+            while (cc < Co && (mesh->cell_mem_ptr[cc + 1] - mstart) <= BT_TPB && (cc - c) < BT_MAX_CTA_CELLS) ++cc;
+            if (cc == c) { err_pack = "a cell has more than 256 membranes"; return; }
+            cta_start.push_back(cc);
+            c = cc;
+        }
+        tile_start.push_back(0);
+        for (int c = 0; c < Co;) {
+            int mstart = mesh->cell_mem_ptr[c];
+            int cc = c;
+            while (cc < Co && (mesh->cell_mem_ptr[cc + 1] - mstart) <= 32 && (cc - c) < BT_TILE_MAXC) ++cc;
+            if (cc == c) { err_pack = "a cell has more than 32 membranes (unsupported by the warp-tile kernel)"; return; }
+            tile_start.push_back(cc);
+            c = cc;
+        }
+        const int nt = (int)tile_start.size() - 1;
+        tdesc.resize((size_t)nt * 4);
+        for (int t = 0; t < nt; ++t) {
+            const int a = tile_start[t], b = tile_start[t + 1];
+            tdesc[4 * t] = a; tdesc[4 * t + 1] = b - a;
+            tdesc[4 * t + 2] = mesh->cell_mem_ptr[a]; tdesc[4 * t + 3] = mesh->cell_mem_ptr[b] - mesh->cell_mem_ptr[a];
+        }
+    };
+    // env point -> flux slot CSR (map_ecm2mem, cells.py:1793-1796), slots in membrane order
+    const bool own_csr = !(mesh->ecm_slot_ptr && mesh->ecm_slot_idx);
+    std::vector<int> csr_ptr, csr_idx;
+    auto job_csr = [&] {
+        if (!own_csr) return;
+        csr_ptr.assign((size_t)E + 1, 0); csr_idx.resize(Mo);
+        for (int m = 0; m < Mo; ++m) {
+            const int k = mesh->map_mem2ecm[m];
+            if (k >= 0 && k < E) csr_ptr[k + 1]++;
+        }
+        for (int k = 0; k < E; ++k) csr_ptr[k + 1] += csr_ptr[k];
+        std::vector<int> fillp(csr_ptr.begin(), csr_ptr.end() - 1);
+        for (int m = 0; m < Mo; ++m) {
+            const int k = mesh->map_mem2ecm[m];
+            if (k >= 0 && k < E) csr_idx[fillp[k]++] = m;
+        }
+    };
+    std::thread th_nnc, th_pack, th_csr;
+    if (par) { th_nnc = std::thread(job_nnc); th_pack = std::thread(job_pack); th_csr = std::thread(job_csr); }
+    else { job_nnc(); job_pack(); job_csr(); }
+    struct Joiner { std::thread &a, &b, &c; ~Joiner() { if (a.joinable()) a.join(); if (b.joinable()) b.join(); if (c.joinable()) c.join(); } } joiner{th_nnc, th_pack, th_csr};
+    T.mark("streams, params");
+    // ---- index arrays and geometry: raw uploads
     if ((r = dev_upload(ctx, (int**)&A.mem_to_cells, mesh->mem_to_cells, Mo))) return r;
     if ((r = dev_upload(ctx, (int**)&A.cell_mem_ptr, mesh->cell_mem_ptr, Co + 1))) return r;
     if ((r = dev_upload(ctx, (int**)&A.nn_i, mesh->nn_i, Mo))) return r;
     if ((r = dev_upload(ctx, (int**)&A.map_mem2ecm, mesh->map_mem2ecm, Mo))) return r;
-    std::vector<int> nnc(Mo);
-    for (int m = 0; m < Mo; ++m) {
-        int nn = mesh->nn_i[m];
-        int cn;
-        if (nn >= 0 && nn < Mo) cn = mesh->mem_to_cells[nn];
-        else if (nn <= -2) cn = -(nn + 2);      // multi-GPU: partner lives on a ghost cell: nn = -(ghost_cell+2)
-        else return fail(ctx, "nn_i out of range");
-        if (cn < 0 || cn >= C) return fail(ctx, "partner cell out of range");
-        if (mesh->map_mem2ecm[m] < 0 || mesh->map_mem2ecm[m] >= E) return fail(ctx, "map_mem2ecm out of range");
-        if (mesh->mem_to_cells[m] < 0 || mesh->mem_to_cells[m] >= Co) return fail(ctx, "mem_to_cells out of range");
-        nnc[m] = cn | (mesh->bflags_mems[m] ? (int)0x80000000 : 0);
-    }
-    if ((r = dev_upload(ctx, (int**)&A.nn_cell_flag, nnc.data(), Mo))) return r;
-
-    // ---- CTA packing: contiguous runs of whole cells with <= BT_TPB membranes
-    std::vector<int> cta_start;
-    cta_start.push_back(0);
-    {
-        int c = 0;
-        while (c < Co) {
-            int mstart = mesh->cell_mem_ptr[c];
-            int cc = c;
-            while (cc < Co && (mesh->cell_mem_ptr[cc + 1] - mstart) <= BT_TPB && (cc - c) < BT_MAX_CTA_CELLS) ++cc;
-            if (cc == c) return fail(ctx, "a cell has more than 256 membranes");
-            cta_start.push_back(cc);
-            c = cc;
-        }
-    }
-    ctx->n_ctas = (int)cta_start.size() - 1;
-    P.n_ctas = ctx->n_ctas;
-    if ((r = dev_upload(ctx, (int**)&A.cta_cell_start, cta_start.data(), cta_start.size()))) return r;
-    // ---- warp packing (k_mem): contiguous runs of whole cells with <= 32 membranes, <= BT_TILE_MAXC cells
-    std::vector<int> tile_start;
-    tile_start.push_back(0);
-    {
-        int c = 0;
-        while (c < Co) {
-            int mstart = mesh->cell_mem_ptr[c];
-            int cc = c;
-            while (cc < Co && (mesh->cell_mem_ptr[cc + 1] - mstart) <= 32 && (cc - c) < BT_TILE_MAXC) ++cc;
-            if (cc == c) return fail(ctx, "a cell has more than 32 membranes (unsupported by the warp-tile kernel)");
-            tile_start.push_back(cc);
-            c = cc;
-        }
-    }
-    ctx->n_tiles = (int)tile_start.size() - 1;
-    P.n_tiles = ctx->n_tiles;
-    { const char* e = getenv("BETSE_PF_TILES"); P.pf_tiles = e ? atoi(e) : 4096; }
-    std::vector<int> tdesc((size_t)ctx->n_tiles * 4);
-    for (int t = 0; t < ctx->n_tiles; ++t) {
-        const int a = tile_start[t], b = tile_start[t + 1];
-        tdesc[4 * t] = a; tdesc[4 * t + 1] = b - a;
-        tdesc[4 * t + 2] = mesh->cell_mem_ptr[a]; tdesc[4 * t + 3] = mesh->cell_mem_ptr[b] - mesh->cell_mem_ptr[a];
-    }
-    if ((r = dev_upload(ctx, (int**)&A.tile_desc, tdesc.data(), tdesc.size()))) return r;
-    // ---- env point -> flux slot CSR (map_ecm2mem, cells.py:1793-1796), slots in membrane order
-    ctx->n_slots = mesh->n_flux_slots > Mo ? mesh->n_flux_slots : Mo;
-    if (mesh->ecm_slot_ptr && mesh->ecm_slot_idx) {
-        if ((r = dev_upload(ctx, (int**)&A.slot_ptr, mesh->ecm_slot_ptr, E + 1))) return r;
-        if ((r = dev_upload(ctx, (int**)&A.slot_idx, mesh->ecm_slot_idx, mesh->ecm_slot_ptr[E]))) return r;
-    } else {
-        std::vector<int> ptr(E + 1, 0), idx(Mo);
-        for (int m = 0; m < Mo; ++m) ptr[mesh->map_mem2ecm[m] + 1]++;
-        for (int k = 0; k < E; ++k) ptr[k + 1] += ptr[k];
-        std::vector<int> fillp(ptr.begin(), ptr.end() - 1);
-        for (int m = 0; m < Mo; ++m) idx[fillp[mesh->map_mem2ecm[m]]++] = m;
-        if ((r = dev_upload(ctx, (int**)&A.slot_ptr, ptr.data(), E + 1))) return r;
-        if ((r = dev_upload(ctx, (int**)&A.slot_idx, idx.data(), Mo))) return r;
-    }
-
-    // ---- geometry
     if ((r = dev_upload(ctx, (double**)&A.mem_sa, mesh->mem_sa, Mo))) return r;
     if ((r = dev_upload(ctx, (double**)&A.mem_nx, mesh->mem_nx, Mo))) return r;
     if ((r = dev_upload(ctx, (double**)&A.mem_ny, mesh->mem_ny, Mo))) return r;
@@ -512,18 +527,34 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
     if ((r = dev_upload(ctx, (double**)&A.num_mems, mesh->num_mems, Co))) return r;
     if (mesh->memSa_per_envSquare) { if ((r = dev_upload(ctx, (double**)&A.memsa_env, mesh->memSa_per_envSquare, E))) return r; }
     else if (hp->fast_update_ecm) return fail(ctx, "fast_update_ecm needs memSa_per_envSquare");
-    if (mesh->gj_default_weights) { if ((r = dev_upload(ctx, (double**)&A.gj_w, mesh->gj_default_weights, Mo))) return r; }
+    // cells.gj_default_weights is read by the static gap-junction mode only (sim.py:2175-2177)
+    if (mesh->gj_default_weights && !hp->v_sensitive_gj) { if ((r = dev_upload(ctx, (double**)&A.gj_w, mesh->gj_default_weights, Mo))) return r; }
     else if (!hp->v_sensitive_gj) return fail(ctx, "static gap junctions need gj_default_weights");
-
-    // ---- tile pack (k_mem_pipe): every tile's constant inputs as one fixed-size block, built on the device; the DmS
-    //      rows are (re)built whenever Dm_cells or the schedule scalars are uploaded (launch_pack_dm)
-    if (hp->n_ions <= 7) {
-        const size_t bytes = (size_t)ctx->n_tiles * tile_pack_size(hp->n_ions);
-        if ((r = dev_alloc(ctx, (char**)&A.tile_pack, bytes))) return r;
-        launch_pack_const(ctx->P, A, ctx->stream);
-        CK(cudaGetLastError());
+    T.mark("raw uploads");
+    if (th_nnc.joinable()) th_nnc.join();
+    if (!err_nnc.empty()) return fail(ctx, err_nnc);
+    if ((r = dev_upload(ctx, (int**)&A.nn_cell_flag, nnc.data(), Mo))) return r;
+    if (th_pack.joinable()) th_pack.join();
+    if (!err_pack.empty()) return fail(ctx, err_pack);
+    ctx->n_ctas = (int)cta_start.size() - 1;
+    P.n_ctas = ctx->n_ctas;
+    if ((r = dev_upload(ctx, (int**)&A.cta_cell_start, cta_start.data(), cta_start.size()))) return r;
+    ctx->n_tiles = (int)tile_start.size() - 1;
+    P.n_tiles = ctx->n_tiles;
+    { const char* e = getenv("BETSE_PF_TILES"); P.pf_tiles = e ? atoi(e) : 4096; }
+    if ((r = dev_upload(ctx, (int**)&A.tile_desc, tdesc.data(), tdesc.size()))) return r;
+    if (th_csr.joinable()) th_csr.join();
+    ctx->n_slots = mesh->n_flux_slots > Mo ? mesh->n_flux_slots : Mo;
+    if (!own_csr) {
+        if ((r = dev_upload(ctx, (int**)&A.slot_ptr, mesh->ecm_slot_ptr, E + 1))) return r;
+        if ((r = dev_upload(ctx, (int**)&A.slot_idx, mesh->ecm_slot_idx, mesh->ecm_slot_ptr[E]))) return r;
+    } else {
+        if ((r = dev_upload(ctx, (int**)&A.slot_ptr, csr_ptr.data(), E + 1))) return r;
+        if ((r = dev_upload(ctx, (int**)&A.slot_idx, csr_idx.data(), Mo))) return r;
     }
-
+    CK(cudaStreamSynchronize(ctx->stream));       // the host vectors above die with this scope
+    T.mark("env slot CSR");
+    T.mark("derived index arrays");
     // ---- cell pack (k_cell): SELL-32 rows of the per-membrane constants, built on the device like the tile pack
     if (hp->n_ions <= 7 && hp->is_ecm) {
         const int nb = (Co + 31) / 32;
@@ -584,6 +615,18 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
         }
     }
 
+    T.mark("cell pack");
+    // ---- tile pack (k_mem_pipe): every tile's constant inputs as one fixed-size block, built on the device; the DmS
+    //      rows are (re)built whenever Dm_cells or the schedule scalars are uploaded (launch_pack_dm)
+    //      — only when k_cell (which supersedes k_mem_pipe) has no cell pack to run on
+    if (hp->n_ions <= 7 && !(A.cpack && kcell_enabled())) {
+        const size_t bytes = (size_t)ctx->n_tiles * tile_pack_size(hp->n_ions);
+        if ((r = dev_alloc(ctx, (char**)&A.tile_pack, bytes))) return r;
+        launch_pack_const(ctx->P, A, ctx->stream);
+        CK(cudaGetLastError());
+    }
+
+    T.mark("tile pack");
     // ---- state
     const size_t IC = (size_t)I * C, IE = (size_t)I * E, IM = (size_t)I * Mo;
     if ((r = dev_alloc(ctx, &A.cc_cells, IC))) return r;
@@ -641,9 +684,12 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
         for (int i = 0; i < 8; ++i) cu[i] = cu[8 + i] = hp->cenv_uniform[i];
         CK(cudaMemcpyAsync(A.cenv_u, cu, sizeof cu, cudaMemcpyHostToDevice, ctx->stream));
     }
+    T.mark("state allocations");
     CK(prepare_kernels(I));
     CK(prepare_cell(I, ctx->P.kb_min));
+    T.mark("prepare kernels");
     CK(cudaStreamSynchronize(ctx->stream));
+    T.mark("stream sync");
     return 0;
 }
 

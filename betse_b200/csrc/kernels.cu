@@ -784,7 +784,7 @@ int mem_kernel_kind(int ni, const KParams& P, const KArrays& A, int diag)
     }
     if (!sp) return 0;
     if (kcell_enabled() && A.cpack) return 2;
-    return kmem_pipe_enabled() ? 1 : 0;
+    return (kmem_pipe_enabled() && A.tile_pack) ? 1 : 0;
 }
 
 // returns 1 when the membrane -> env fluxes went to flux_ell (k_cell)

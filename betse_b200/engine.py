@@ -150,14 +150,28 @@ class TissueEngine:
         m.n_cells, m.n_mems, m.ny, m.nx = self.C, self.M, self.ny, self.nx
         m.mem_to_cells = i32(self.mem_to_cells)
         m.cell_mem_ptr = i32(self.cell_mem_ptr)
-        m.nn_i = i32(mesh["nn_i"])
-        m.map_mem2ecm = i32(mesh["map_mem2ecm"])
-        bf = np.zeros(self.M, dtype=np.uint8)
-        bfl = np.asarray(mesh["bflags_mems"])
-        if bfl.dtype == np.bool_ and bfl.size == self.M:
-            bf[:] = bfl
-        else:
-            bf[bfl.astype(np.int64)] = 1       # the reference stores a list of membrane indices
+        # the reference's index arrays are int64: narrowing them (and the mean below) are memory-bound passes over M
+        # entries, run side by side (NumPy releases the GIL inside them)
+        from concurrent.futures import ThreadPoolExecutor
+
+        def memsa_mean():
+            if "memsa_mean" in mesh or "memSa_per_envSquare" not in mesh:
+                return None
+            msa = np.asarray(mesh["memSa_per_envSquare"], dtype=np.float64)
+            return float(msa[np.asarray(mesh["map_mem2ecm"])].mean())
+        with ThreadPoolExecutor(3) as pool:
+            f_nn = pool.submit(capi.as_i32, mesh["nn_i"])
+            f_m2e = pool.submit(capi.as_i32, mesh["map_mem2ecm"])
+            f_mean = pool.submit(memsa_mean)
+            bf = np.zeros(self.M, dtype=np.uint8)
+            bfl = np.asarray(mesh["bflags_mems"])
+            if bfl.dtype == np.bool_ and bfl.size == self.M:
+                bf[:] = bfl
+            else:
+                bf[bfl.astype(np.int64)] = 1       # the reference stores a list of membrane indices
+            m.nn_i = i32(f_nn.result())
+            m.map_mem2ecm = i32(f_m2e.result())
+            mean = f_mean.result()
         k.append(bf)
         m.bflags_mems = bf.ctypes.data_as(C.POINTER(C.c_uint8))
         m.mem_sa, m.mem_nx, m.mem_ny = f64("mem_sa"), f64("mem_nx"), f64("mem_ny")
@@ -173,9 +187,8 @@ class TissueEngine:
         m.ecm_vol = float(mesh["ecm_vol"]) if "ecm_vol" in mesh else float(p["cell_height"]) * m.delta ** 2
         if "memsa_mean" in mesh:          # a strip of a decomposed tissue carries the global mean
             m.memsa_mean = float(mesh["memsa_mean"])
-        elif "memSa_per_envSquare" in mesh:
-            msa = np.asarray(mesh["memSa_per_envSquare"], dtype=np.float64)
-            m.memsa_mean = float(msa[np.asarray(mesh["map_mem2ecm"]).astype(np.int64)].mean())
+        elif mean is not None:
+            m.memsa_mean = mean
         else:
             m.memsa_mean = 1.0
         part = partition or {}
@@ -463,7 +476,9 @@ class TissueEngine:
                 continue
             if f not in _DOWN_SHAPES:
                 raise KeyError(f)
-            buf = self._pinned_buffer(f, shapes[_DOWN_SHAPES[f]]) if pinned else np.empty(shapes[_DOWN_SHAPES[f]])
+            # page-locking costs ~0.5 s/GB: it only pays for staging that many samples reuse (pin_staging, set by the loop)
+            buf = self._pinned_buffer(f, shapes[_DOWN_SHAPES[f]]) if (pinned and getattr(self, "pin_staging", True)) \
+                else np.empty(shapes[_DOWN_SHAPES[f]])
             setattr(sh, f, capi.ptr_f64(buf))
             out[f] = buf
         self._check(self.lib.betse_download_sample(self.ctx, C.byref(sh)), "betse_download_sample")

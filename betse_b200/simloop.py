@@ -312,6 +312,7 @@ def _copy_back(sim, eng, diag, sample_only=False):
     return 0
 
 
+PIN_MIN_SAMPLES = 8
 _closing = []        # engines being torn down on helper threads
 
 
@@ -375,8 +376,11 @@ def run_sim_core_loop(sim, phase, time_steps, time_steps_sampled, anim_cells=Non
     sampled = set(time_steps_sampled)
     if engine is None:
         _join_closing()                  # the previous phase's engine has released its device memory
+        # page-locked staging for the sampled-step downloads costs ~0.2 s per 435 MB to set up and saves ~40 ms per
+        # sample: worth it from PIN_MIN_SAMPLES samples on (measured, profiles/r02g_e2e_fixed_cost.txt)
+        pin = len(sampled) >= PIN_MIN_SAMPLES
         pf = _prefetch_staging(cells, p, device) if (
-            anim_cells is None and len(sampled) > 1 and hasattr(TissueEngine, "adopt_pinned")
+            anim_cells is None and pin and hasattr(TissueEngine, "adopt_pinned")
             and os.environ.get("BETSE_PIN_PREFETCH", "1") != "0") else None
         try:
             eng = engine_from_sim(sim, cells, p, device=device, phase_init=not is_sim)
@@ -386,6 +390,7 @@ def run_sim_core_loop(sim, phase, time_steps, time_steps_sampled, anim_cells=Non
             raise
         if pf is not None:
             eng.adopt_pinned(pf)
+        eng.pin_staging = pin
     else:
         eng = engine
     tm["engine"] = time.time() - t0
