@@ -276,7 +276,16 @@ def main():
     ds = None
     if strips:
         # one tissue cut into `world` strips (strong scaling): halo exchange over NVLink peer stores
-        from betse_b200.strips import DistributedStrips
+        from betse_b200.strips import DistributedStrips, verify_strips
+        # parity first: a small tissue cut into the same number of strips must equal the undivided one bit for bit
+        strips_parity = verify_strips(dist, local_rank, cells=60_000, steps=12)
+        verdict = [strips_parity["ok"] if rank == 0 else None]
+        dist.broadcast_object_list(verdict, src=0)
+        if not verdict[0]:
+            if rank == 0:
+                print(json.dumps({"error": "decomposed tissue differs from the undivided one", "strips_parity": strips_parity}))
+            dist.destroy_process_group()
+            sys.exit(1)
         ds = DistributedStrips(mesh, p, state, local_rank, dist)
         eng = ds.engine
         ds.update_V()
@@ -456,6 +465,7 @@ def main():
             "dtype": "f64", "data": "synthetic", "config": config, "clocks": sampler.summary(),
             "gpu_launches": int((len(kms) + (1 if "k_xchg" in kms else 0)) * args.steps * world * B),
             "status_word": status, "finite": finite,
+            **({"strips_parity": strips_parity} if strips else {}),
             **({"ensemble": {"members": B, "solo_ms_per_step": solo_ms, "speedup_vs_solo_per_gpu": B * solo_ms / ms_per_step,
                              "what": "B independent tissues, one CUDA graph of B streams x 10 timesteps per launch (betse_ensemble_step); "
                                      "kernel_ms are of one member stepped alone"}} if B > 1 else {}),

@@ -50,6 +50,9 @@ bool kcell_pipe_fits(int ni, int kb_min);
 void launch_slot_off(const int* slot_idx, const int* mem_ell, int* slot_off, int n, int Mo, int ni, cudaStream_t st);
 void launch_gather_int(int* dst, const int* src, const int* idx, int n, cudaStream_t st);
 void launch_envacc_ell(int ni, const KParams& P, const KArrays& A, int nxt, int deps, cudaStream_t st);
+void launch_envacc_ell_x(int ni, const KParams& P, const KArrays& A, const XPlan& X, int nxt, cudaStream_t st);
+void envacc_end_ctas(const KParams& P, int lo, int hi, int* n_lower, int* n_upper);
+void launch_cell_x(int ni, const KParams& P, const KArrays& A, const XPlan& X, int cur, cudaStream_t st);
 void launch_chan(const KParams& P, const KArrays& A, const KChan& ch, const KNet& N, int cur, cudaStream_t st);
 void launch_net(const KParams& P, const KArrays& A, const KNet& N, const double* h_Dgj, const double* h_Dm,
                 const unsigned char* h_env_on, const betse_substance_pump* pumps, int n_pumps, double dG_RT,
@@ -93,6 +96,14 @@ struct betse_ctx {
     char* win = nullptr;
     betse_window_info winfo;
     XPlan X;
+    // exchange points fused into k_cell / k_envacc_ell: host copies of the plans, tables built by prepare_xfuse
+    std::vector<int> h_cmp;                  // cell_mem_ptr
+    std::vector<int> xh_cells[2], xh_flux[2];
+    bool xfuse_dirty = true;
+    bool last_step_fused = false;
+    int xfuse_now = 0;                       // this step's k_cell / k_envacc_ell push to the neighbours themselves
+    int xwait_now = 0;                       // this step's env accumulation / field kernels wait for the neighbours themselves
+    bool xwait = false;                      // the consumers of an exchange wait inside their kernels (neighbours in other processes)
     std::vector<void*> ipc_opened;
     std::vector<KChan> chans;                // voltage-gated channels, applied in order
     HHBuf hh;                                // Helmholtz-Hodge diagnostics (sampled steps, undivided ECM tissues)
@@ -415,6 +426,7 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
     if (ctx->M != Mo) return fail(ctx, "ghost membranes are not supported: pass owned membranes only");
     if (mesh->cell_mem_ptr[Co] != Mo) return fail(ctx, "cell_mem_ptr[n_cells_owned] != n_mems_owned");
 
+    ctx->h_cmp.assign(mesh->cell_mem_ptr, mesh->cell_mem_ptr + Co + 1);
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
@@ -655,10 +667,25 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
         A.flux_slots = (double*)(ctx->win + W.off_flux);
         A.v_raw = (double*)(ctx->win + W.off_v_raw);
         memset(&ctx->X, 0, sizeof(XPlan));
+        ctx->X.side_k[0] = ctx->X.side_k[1] = -1;
         ctx->X.my_flags = (unsigned long long*)(ctx->win + W.off_flags);
         ctx->X.epoch = ctx->X.my_flags + 4;
         ctx->X.done_ctr = (unsigned int*)(ctx->X.my_flags + 6);
         { const char* e = getenv("BETSE_XCHG_TIMEOUT_MS"); ctx->X.timeout_ns = (unsigned long long)(e ? atoll(e) : 10000) * 1000000ull; }
+        A.xflags = ctx->X.my_flags; A.xepoch = ctx->X.epoch;
+        P.x_timeout_ns = ctx->X.timeout_ns;
+        // env squares that take flux slots a neighbour fills (slot >= Mo): local rows below xw_lo / from xw_hi on
+        P.xw_lo = P.y_own0 + 1; P.xw_hi = P.y_own1 - 1;
+        if (mesh->ecm_slot_ptr && mesh->ecm_slot_idx) {
+            const int mid = (P.y_own0 + P.y_own1) / 2;
+            for (int k = 0; k < E; ++k) {
+                bool remote = false;
+                for (int j = mesh->ecm_slot_ptr[k]; j < mesh->ecm_slot_ptr[k + 1] && !remote; ++j) remote = mesh->ecm_slot_idx[j] >= Mo;
+                if (!remote) continue;
+                const int y = k / ctx->nx;
+                if (y < mid) P.xw_lo = std::max(P.xw_lo, y + 1); else P.xw_hi = std::min(P.xw_hi, y);
+            }
+        }
     }
     if ((r = dev_alloc(ctx, &A.gjopen, Mo))) return r;
     if ((r = dev_alloc(ctx, (double**)&A.Dm, IM))) return r;
@@ -938,6 +965,70 @@ extern "C" int betse_set_schedule(betse_ctx* ctx, const betse_params* hp)
 // One timestep.  Order: env transport of every ion (reads last step's E field and
 // cc_env[cur], writes cc_env[nxt]) -> membranes+cells (reads cc_env[cur] for GHK/NaK, cc_env[nxt]
 // for the Ca pump) -> env accumulation + charge -> env field for the next step.
+// Tables of the fused exchange points (k_cell pushes X1, k_envacc_ell pushes X2; xchg.cuh): which blocks of the cell pack hold
+// cells that are ghosts on a neighbour or membranes whose env square a neighbour owns, their slots there, the ticket order
+// (those blocks first), and how many CTAs at each end of the accumulation rows push.  Not capturable: betse_step calls it.
+static int prepare_xfuse(betse_ctx* ctx)
+{
+    if (!ctx->xfuse_dirty || ctx->X.n_nbr == 0 || !ctx->A.cpack) return 0;
+    KArrays& A = ctx->A;
+    const int nb = ctx->P.n_blocks;
+    std::vector<int> h_row0(2 * ((size_t)nb + 1));
+    CK(cudaMemcpy(h_row0.data(), A.blk_row0, h_row0.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<char> has_g(nb, 0), has_r(nb, 0);
+    for (int k = 0; k < ctx->X.n_nbr; ++k) {
+        for (int c : ctx->xh_cells[k]) has_g[c / 32] = 1;
+        for (int m : ctx->xh_flux[k]) {
+            const int c = (int)(std::upper_bound(ctx->h_cmp.begin(), ctx->h_cmp.end(), m) - ctx->h_cmp.begin()) - 1;
+            has_r[c / 32] = 1;
+        }
+    }
+    std::vector<int> blk_x(2 * (size_t)nb, -1), ghost, rslot, sched;
+    int nbb = 0;
+    for (int b = 0; b < nb; ++b) {
+        if (has_g[b]) { blk_x[2 * b] = (int)ghost.size() / 2; ghost.resize(ghost.size() + 64, -1); }
+        if (has_r[b]) { blk_x[2 * b + 1] = (int)rslot.size(); rslot.resize(rslot.size() + (size_t)(h_row0[2 * (b + 1)] - h_row0[2 * b]) * 32, -1); }
+        if (has_g[b] || has_r[b]) { sched.push_back(b); ++nbb; }
+    }
+    for (int b = 0; b < nb; ++b) if (!(has_g[b] || has_r[b])) sched.push_back(b);
+    for (int k = 0; k < ctx->X.n_nbr; ++k) {
+        const XNbr& x = ctx->X.nb[k];
+        for (size_t j = 0; j < ctx->xh_cells[k].size(); ++j) {
+            const int c = ctx->xh_cells[k][j];
+            ghost[2 * ((size_t)blk_x[2 * (c / 32)] + (c & 31)) + x.side] = x.recv_cell0 + (int)j;
+        }
+        for (size_t j = 0; j < ctx->xh_flux[k].size(); ++j) {
+            const int m = ctx->xh_flux[k][j];
+            const int c = (int)(std::upper_bound(ctx->h_cmp.begin(), ctx->h_cmp.end(), m) - ctx->h_cmp.begin()) - 1;
+            const int kk = m - ctx->h_cmp[c];
+            int& slot = rslot[(size_t)blk_x[2 * (c / 32) + 1] + (size_t)kk * 32 + (c & 31)];
+            if (slot >= 0) return fail(ctx, "a membrane's env square cannot belong to two neighbours");
+            slot = (x.side << 30) | (x.recv_slot0 + (int)j);
+        }
+    }
+    if (ghost.empty()) ghost.resize(2, -1);
+    if (rslot.empty()) rslot.resize(1, -1);
+    int r;
+    if ((r = dev_upload(ctx, (int**)&A.sched, sched.data(), sched.size()))) return r;
+    if ((r = dev_upload(ctx, (int**)&A.blk_x, blk_x.data(), blk_x.size()))) return r;
+    if ((r = dev_upload(ctx, (int**)&A.ghost_tab, ghost.data(), ghost.size()))) return r;
+    if ((r = dev_upload(ctx, (int**)&A.rslot_tab, rslot.data(), rslot.size()))) return r;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->X.n_bblocks = nbb;
+    ctx->X.env_n0 = ctx->X.env_n1 = 0;
+    for (int k = 0; k < ctx->X.n_nbr; ++k) {
+        int lo = 0, up = 0;
+        envacc_end_ctas(ctx->P, ctx->X.nb[k].push_lo, ctx->X.nb[k].push_hi, &lo, &up);
+        ctx->X.env_n0 = std::max(ctx->X.env_n0, lo); ctx->X.env_n1 = std::max(ctx->X.env_n1, up);
+    }
+    const int g = ((ctx->P.ya1 - ctx->P.ya0) * ctx->P.nx + 255) / 256;
+    if (ctx->X.env_n0 + ctx->X.env_n1 > g) ctx->X.env_n1 = g - ctx->X.env_n0;      // the two ends overlap on a very thin strip
+    ctx->X.n_push_ctas = ctx->X.env_n0 + ctx->X.env_n1;
+    ctx->xfuse_dirty = false;
+    destroy_graphs(ctx);
+    return 0;
+}
+
 static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
 {
     const int I = ctx->I, cur = ctx->cur, nxt = cur ^ 1;
@@ -960,10 +1051,15 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
             if (iCa >= 0) launch_ion(ctx->P, A, ctx->nx, cur, diag, iCa, 1, st);
             cudaEventRecord(ctx->ev_fork, st);
             cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0);
+            // fused exchange: the halo rows of the other ions are written by the neighbours' env accumulation (X2) only —
+            // their flag-ordered stores must not race with a redundant transport of the same rows running next to k_cell
+            // (only the Ca row is read there before the exchange, and it is transported ahead of k_cell)
+            KParams Pi = ctx->P;
+            if (ctx->xfuse_now) { Pi.yi0 = std::max(Pi.yi0, Pi.y_own0); Pi.yi1 = std::min(Pi.yi1, Pi.y_own1); }
             if (iCa >= 0) {
-                launch_ion(ctx->P, A, ctx->nx, cur, diag, 0, iCa, ctx->stream2);
-                launch_ion(ctx->P, A, ctx->nx, cur, diag, iCa + 1, I - iCa - 1, ctx->stream2);
-            } else launch_ion(ctx->P, A, ctx->nx, cur, diag, 0, I, ctx->stream2);
+                launch_ion(Pi, A, ctx->nx, cur, diag, 0, iCa, ctx->stream2);
+                launch_ion(Pi, A, ctx->nx, cur, diag, iCa + 1, I - iCa - 1, ctx->stream2);
+            } else launch_ion(Pi, A, ctx->nx, cur, diag, 0, I, ctx->stream2);
             cudaEventRecord(ctx->ev_join, ctx->stream2);
         } else if (ecm) {
             launch_ion(ctx->P, A, ctx->nx, cur, diag, 0, I, st);
@@ -975,7 +1071,8 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
             }
         } else if (evs) cudaEventRecord(evs[1], st);
         if (evs) cudaEventRecord(evs[2], st);
-        ctx->flux_is_ell = launch_mem(I, ctx->P, A, ctx->n_ctas, cur, diag, st);
+        if (ctx->xfuse_now) { launch_cell_x(I, ctx->P, A, ctx->X, cur, st); ctx->flux_is_ell = 1; }
+        else ctx->flux_is_ell = launch_mem(I, ctx->P, A, ctx->n_ctas, cur, diag, st);
         if (consumer) {
             launch_envacc_ell(I, ctx->P, A, nxt, 1, ctx->stream2);
             cudaEventRecord(ctx->ev_join, ctx->stream2);
@@ -1043,12 +1140,21 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
         if (evs) cudaEventRecord(evs[3], st);
     } else if (phase == 1) {
         if (ecm && ctx->env_by_consumer) { /* launched next to k_cell */ }
-        else if (ecm && ctx->flux_is_ell) launch_envacc_ell(I, ctx->P, A, nxt, 0, st);
+        else if (ecm && ctx->flux_is_ell) {
+            KParams Pw = ctx->P;
+            Pw.xwait = ctx->xwait_now;
+            if (ctx->xfuse_now) launch_envacc_ell_x(I, Pw, A, ctx->X, nxt, st);
+            else launch_envacc_ell(I, Pw, A, nxt, 0, st);
+        }
         else if (ecm) launch_envacc(I, ctx->P, A, ctx->E, nxt, 1, st);
         else launch_envmix(I, ctx->P, A, cur, st);
         if (evs) cudaEventRecord(evs[4], st);
     } else {
-        if (ecm) launch_field(ctx->P, A, ctx->ny, ctx->nx, st);
+        if (ecm) {
+            KParams Pw = ctx->P;
+            Pw.xwait = ctx->xwait_now;
+            launch_field(Pw, A, ctx->ny, ctx->nx, st);
+        }
         if (evs) cudaEventRecord(evs[5], st);
         if (diag) launch_diag(I, ctx->P, A, ctx->n_ctas, nxt, st);
         if (diag && ctx->want_hh && ecm && ctx->hh_on && ctx->X.n_nbr == 0) {
@@ -1075,13 +1181,27 @@ static void enqueue_step(betse_ctx* ctx, int diag, cudaEvent_t* evs)
     if (evs) cudaEventRecord(evs[0], ctx->stream);
     const bool nbr = ctx->X.n_nbr > 0;
     const int nxt = ctx->cur ^ 1;
+    // exchange points of a decomposed tissue whose neighbours live in other processes: the wait sits inside the consuming
+    // kernels' edge CTAs (k_envacc_ell for X1, k_field for X2; everything later in the step is ordered behind them by the
+    // stream), and — fused — the push inside the producing kernels (k_cell: X1, k_envacc_ell: X2), no exchange kernel at
+    // all.  Sampled steps (k_mem + k_envacc) and strips that share this process keep the stand-alone k_xchg.
+    static const int fuse_ok = [] { const char* e = getenv("BETSE_XFUSE"); return (e && e[0] == '0') ? 0 : 1; }();
+    const bool inwait = nbr && ctx->xwait && !diag && !ctx->P.has_phi && !ctx->P.polar &&
+                        mem_kernel_kind(ctx->I, ctx->P, ctx->A, diag) == 2 && ctx->hp.is_ecm;
+    const bool fused = inwait && fuse_ok && !ctx->xfuse_dirty && ctx->A.ticket && ctx->P.kc_persist;
+    const int xmode = inwait ? BETSE_XCHG_PUSH : (BETSE_XCHG_PUSH | BETSE_XCHG_WAIT);
+    ctx->xwait_now = inwait ? 1 : 0;
+    ctx->xfuse_now = fused ? 1 : 0;
     enqueue_phase(ctx, 0, diag, evs);
-    if (nbr) launch_xchg(ctx->P, ctx->A, ctx->X, BETSE_XCHG_X1, nxt, BETSE_XCHG_PUSH | BETSE_XCHG_WAIT, ctx->flux_is_ell, ctx->stream);
+    if (nbr && !fused) launch_xchg(ctx->P, ctx->A, ctx->X, BETSE_XCHG_X1, nxt, xmode, ctx->flux_is_ell, ctx->stream);
     if (evs) cudaEventRecord(evs[7], ctx->stream);
     enqueue_phase(ctx, 1, diag, evs);
-    if (nbr) launch_xchg(ctx->P, ctx->A, ctx->X, BETSE_XCHG_X2, nxt, BETSE_XCHG_PUSH | BETSE_XCHG_WAIT, ctx->flux_is_ell, ctx->stream);
+    if (nbr && !fused) launch_xchg(ctx->P, ctx->A, ctx->X, BETSE_XCHG_X2, nxt, xmode, ctx->flux_is_ell, ctx->stream);
     if (evs) cudaEventRecord(evs[8], ctx->stream);
     enqueue_phase(ctx, 2, diag, evs);
+    ctx->xwait_now = 0;
+    ctx->xfuse_now = 0;
+    ctx->last_step_fused = fused;
 }
 
 static int build_graphs(betse_ctx* ctx)
@@ -1117,6 +1237,7 @@ extern "C" int betse_step(betse_ctx* ctx, int nsteps, int flags, uint32_t* statu
     CK(cudaSetDevice(ctx->device));
     const bool want_diag = (flags & BETSE_STEP_DIAG) != 0;
     if (want_diag || ctx->P.polar) { int r = ensure_diag_buffers(ctx); if (r) return r; }
+    if (ctx->xwait) { int r = prepare_xfuse(ctx); if (r) return r; }
     const int asked = nsteps;
     if (ctx->phi_lag && nsteps > 0) {
         // first step after a change of sim.bound_V: starts from the old potential, closes with the new one
@@ -1294,6 +1415,7 @@ extern "C" int betse_step_profile(betse_ctx* ctx, int nsteps, float* total_ms,
     if (!ctx || nsteps <= 0) return 2;
     CK(cudaSetDevice(ctx->device));
     if (ctx->P.polar) { int r = ensure_diag_buffers(ctx); if (r) return r; }
+    if (ctx->xwait) { int r = prepare_xfuse(ctx); if (r) return r; }
     if (!ctx->ev_init) {
         for (auto& e : ctx->ev) CK(cudaEventCreate(&e));
         ctx->ev_init = true;
@@ -1337,7 +1459,7 @@ extern "C" int betse_step_profile(betse_ctx* ctx, int nsteps, float* total_ms,
         }
         for (int k = 0; k < BETSE_NKERNELS; ++k) {
             kernel_ms[k] = cnt[k] ? (float)(acc[k] / cnt[k]) : 0.f;
-            if (kernel_launches) kernel_launches[k] = cnt[k] ? (k == K_XCHG ? 2 : 1) : 0;   // launches per step
+            if (kernel_launches) kernel_launches[k] = cnt[k] ? (k == K_XCHG ? (ctx->last_step_fused ? 0 : 2) : 1) : 0;   // launches per step
         }
     }
     ctx->diag_valid = false;
@@ -1905,6 +2027,7 @@ extern "C" int betse_set_row_ranges(betse_ctx* ctx, int yi0, int yi1, int ya0, i
         return fail(ctx, "row range outside the local grid");
     KParams& P = ctx->P;
     P.yi0 = yi0; P.yi1 = yi1; P.ya0 = ya0; P.ya1 = ya1; P.yf0 = yf0; P.yf1 = yf1;
+    ctx->xfuse_dirty = true;
     destroy_graphs(ctx);
     return 0;
 }
@@ -1973,7 +2096,18 @@ extern "C" int betse_attach_neighbor(betse_ctx* ctx, const betse_neighbor* nb)
         launch_gather_int(const_cast<int*>(x.send_flux_ell), ctx->mem_ell, x.send_flux, nb->n_send_flux, ctx->stream);
     }
     CK(cudaStreamSynchronize(ctx->stream));
+    x.push_lo = std::min(nb->cc_rows > 0 ? nb->cc_src_row0 : INT_MAX, nb->v_rows > 0 ? nb->v_src_row0 : INT_MAX);
+    x.push_hi = std::max(nb->cc_rows > 0 ? nb->cc_src_row0 + nb->cc_rows : -1, nb->v_rows > 0 ? nb->v_src_row0 + nb->v_rows : -1);
+    ctx->xh_cells[ctx->X.n_nbr].assign(nb->send_cells, nb->send_cells + nb->n_send_cells);
+    ctx->xh_flux[ctx->X.n_nbr].assign(nb->send_flux, nb->send_flux + nb->n_send_flux);
+    ctx->X.side_k[nb->side] = ctx->X.n_nbr;
+    ctx->xfuse_dirty = true;
     ctx->X.n_nbr++;
+    ctx->P.xsides |= 1 << nb->side;
+    // neighbours in other processes run on GPUs of their own: the consumers of an exchange may spin inside their kernels.
+    // Strips that share this process's device are stepped by one host thread — a spinning kernel could keep the kernel it
+    // waits for off the SMs — and keep the stand-alone wait.
+    { const char* e = getenv("BETSE_XWAIT"); ctx->xwait = !nb->same_process && !(e && e[0] == '0'); }
     destroy_graphs(ctx);
     return 0;
 }

@@ -28,8 +28,10 @@
 // Reference lines as in k_mem: sim.py:1193-1283, 2086-2111, 2162-2206; sim_toolbox.py:18-182, 1155-1207;
 // channels/gap_junction.py:53-77; ion_current.py:19; sim.py:2027-2029.
 #include <stdlib.h>
+#include <algorithm>
 #include <stdint.h>
 #include "kmath.cuh"
+#include "xchg.cuh"
 
 #define KC_WARPS 4
 #define KC_ROWB(NI) (((NI) + 2) * 256)          // bytes of one row of the cell pack
@@ -104,7 +106,8 @@ __device__ __forceinline__ void cell_prologue(const KParams& P, CellSide<NI>& S,
 template <int NI>
 __device__ __forceinline__ double membrane_fluxes(const KParams& P, CellSide<NI>& S, const double* __restrict__ co, const double* __restrict__ cnb,
                                                   const double vnb, const double cao, const int nnp, const double* __restrict__ DmS,
-                                                  const double sa, double g, double* __restrict__ fl, unsigned int& flags)
+                                                  const double sa, double g, double* __restrict__ fl, unsigned int& flags,
+                                                  double* __restrict__ frem = nullptr)
 {
     constexpr int iNa = StdProf<NI>::iNa, iK = StdProf<NI>::iK, iCa = StdProf<NI>::iCa;
     // gap-junction side: vgj and its GHK table with p.T (sim.py:2166, 2197), gating sub-step g' = g*gc1 + gc2
@@ -144,6 +147,7 @@ __device__ __forceinline__ double membrane_fluxes(const KParams& P, CellSide<NI>
         S.Sm[i] = __dadd_rn(S.Sm[i], fsa);
         S.Sg[i] = __dadd_rn(S.Sg[i], fg);
         fl[i * 32] = fsa;
+        if (frem) frem[i] = fsa;          // the membrane's env square belongs to a neighbouring strip: its slot there, [slot][ion]
     }
     return g;
 }
@@ -152,7 +156,8 @@ __device__ __forceinline__ double membrane_fluxes(const KParams& P, CellSide<NI>
 // ion_current.py:19; sim.py:2027-2029)
 template <int NI>
 __device__ __forceinline__ void cell_epilogue(const KParams& P, const KArrays& A, const CellSide<NI>& S, const double* cc, const double vol,
-                                              const double dvt, const int c, const int nxt, unsigned int& flags)
+                                              const double dvt, const int c, const int nxt, unsigned int& flags,
+                                              const XPlan* X = nullptr, const int2 gs = make_int2(-1, -1))
 {
     const int C = P.n_cells;
     const double rvol = fast_rcp(vol);
@@ -165,6 +170,11 @@ __device__ __forceinline__ void cell_epilogue(const KParams& P, const KArrays& A
         if (cn_new < 0.0) { cn_new = 0.0; flags |= ST_NEG; }         // no_negs, sim.py:2111
         A.cc_cells[(size_t)i * C + c] = cn_new;
         A.cc_mid[nxt][(size_t)i * C + c] = cm_new;                   // the stale cc_at_mem (quirk list)
+        if (X) {
+            // this cell is a ghost on a neighbouring strip: exchange point X1, stored straight into its window
+            if (gs.x >= 0) { const XNbr& nb = X->nb[X->side_k[0]]; nb.cc_mid[nxt][(size_t)i * nb.Cn + gs.x] = cm_new; }
+            if (gs.y >= 0) { const XNbr& nb = X->nb[X->side_k[1]]; nb.cc_mid[nxt][(size_t)i * nb.Cn + gs.y] = cm_new; }
+        }
         rho = fma(P.zF[i], cn_new, rho);
     }
     if (A.extra_rho_cells) rho += ldg(A.extra_rho_cells + c);
@@ -172,12 +182,17 @@ __device__ __forceinline__ void cell_epilogue(const KParams& P, const KArrays& A
     const double vmn = P.inv_cm * (rho * dvt);
     if (vmn != vmn) flags |= ST_NAN_VM;
     A.vm_cell[nxt][c] = vmn;
+    if (X) {
+        if (gs.x >= 0) X->nb[X->side_k[0]].vm_cell[nxt][gs.x] = vmn;
+        if (gs.y >= 0) X->nb[X->side_k[1]].vm_cell[nxt][gs.y] = vmn;
+    }
 }
 
 // ---------------------------------------------------------------------------- register build
 // one block of 32 cells: lane = cell
 template <int NI>
-__device__ __forceinline__ void cell_task(const KParams& P, const KArrays& A, const int cur, const int task, const int lane, unsigned int& flags)
+__device__ __forceinline__ void cell_task(const KParams& P, const KArrays& A, const int cur, const int task, const int lane, unsigned int& flags,
+                                          const XPlan* X = nullptr)
 {
     constexpr int iCa = StdProf<NI>::iCa;
     constexpr int ROWB = KC_ROWB(NI);
@@ -197,6 +212,12 @@ __device__ __forceinline__ void cell_task(const KParams& P, const KArrays& A, co
     const double* __restrict__ cenv = A.cc_env[cur];
     const double* __restrict__ cenvCa = A.cc_env[nxt] + (size_t)(iCa >= 0 ? iCa : 0) * E;   // Ca after transport (sim.py:1282 after 2254)
 
+    // strips with fused pushes: does this block hold cells that are ghosts on a neighbour / membranes of its env squares?
+    int2 bx = make_int2(-1, -1), gs = make_int2(-1, -1);
+    if (X) {
+        bx = __ldg(reinterpret_cast<const int2*>(A.blk_x) + task);
+        if (bx.x >= 0) gs = __ldg(reinterpret_cast<const int2*>(A.ghost_tab) + bx.x + lane);
+    }
     // the block whose streams this task pulls into L2 (issued after the first membrane, below)
     const int up = task + P.pf_dist;
     int2 u0 = make_int2(0, 0), u1 = make_int2(0, 0);
@@ -256,7 +277,12 @@ __device__ __forceinline__ void cell_task(const KParams& P, const KArrays& A, co
             for (int i = 0; i < NI; ++i) DmS[i] = __ldcs(r + i * 32);
             const double sa = __ldcs(r + NI * 32);
             double* __restrict__ fl = A.flux_ell + ((size_t)(row0 + k) * NI) * 32 + lane;
-            A.gjopen[m_beg + k] = membrane_fluxes<NI>(P, S, x.co, x.cnb, x.vnb, x.cao, x.nnp, DmS, sa, gjs[k], fl, flags);
+            double* frem = nullptr;
+            if (bx.y >= 0) {
+                const int rs = ldgi(A.rslot_tab + bx.y + k * 32 + lane);
+                if (rs >= 0) frem = X->nb[X->side_k[rs >> 30]].flux + (size_t)(rs & 0x3fffffff) * NI;
+            }
+            A.gjopen[m_beg + k] = membrane_fluxes<NI>(P, S, x.co, x.cnb, x.vnb, x.cao, x.nnp, DmS, sa, gjs[k], fl, flags, frem);
         }
     };
 
@@ -285,7 +311,12 @@ __device__ __forceinline__ void cell_task(const KParams& P, const KArrays& A, co
             compute(b, k + 1);
         }
     }
-    if (valid) cell_epilogue<NI>(P, A, S, cc, vol, dvt, c, nxt, flags);
+    if (valid) cell_epilogue<NI>(P, A, S, cc, vol, dvt, c, nxt, flags, (bx.x >= 0) ? X : nullptr, gs);
+    if (X && (bx.x >= 0 || bx.y >= 0)) {
+        // this block pushed: the last of the boundary blocks raises this rank's X1 flag on the neighbours
+        __syncwarp();
+        if (lane == 0) xchg_publish(*X, 0, X->n_bblocks);
+    }
 }
 
 // Persistent: every warp draws tickets (ticket t = block t of the cell pack, so the blocks finish as a wavefront through
@@ -293,7 +324,7 @@ __device__ __forceinline__ void cell_task(const KParams& P, const KArrays& A, co
 // env accumulation kernel running NEXT TO this one (k_envacc_ell, `deps`) consumes a block's fluxes out of L2 as soon as
 // every block that feeds its env squares has finished.
 template <int NI>
-__device__ __forceinline__ void k_cell_body(const KParams& P, const KArrays& A, const int cur)
+__device__ __forceinline__ void k_cell_body(const KParams& P, const KArrays& A, const int cur, const XPlan* X)
 {
     const int lane = threadIdx.x & 31;
     unsigned int flags = 0;
@@ -304,7 +335,9 @@ __device__ __forceinline__ void k_cell_body(const KParams& P, const KArrays& A, 
             t = __shfl_sync(0xffffffffu, t, 0);
         } else t = (int)(blockIdx.x * KC_WARPS + (threadIdx.x >> 5));
         if (t >= P.n_blocks) break;
-        cell_task<NI>(P, A, cur, t, lane, flags);
+        // strips: the blocks at the strip edges first, so that the neighbours have their values long before they need them
+        if (X) t = ldgi(A.sched + t);
+        cell_task<NI>(P, A, cur, t, lane, flags, X);
         if (A.cell_done) {
             // a RELEASE on the counter, not __threadfence(): a gpu-scope acq_rel fence makes ptxas invalidate the SM's
             // whole L1 (CCTL.IVALL), which the other warps' gathers live on
@@ -320,11 +353,16 @@ __device__ __forceinline__ void k_cell_body(const KParams& P, const KArrays& A, 
 // SM — one 256-thread CTA of the env kernels (k_ion, k_envacc_ell: <= 48 registers) runs next to the two k_cell CTAs
 template <int NI, int MINB>
 __global__ void __launch_bounds__(KC_WARPS * 32, MINB)
-k_cell(const __grid_constant__ KParams P, const KArrays A, const int cur) { k_cell_body<NI>(P, A, cur); }
+k_cell(const __grid_constant__ KParams P, const KArrays A, const int cur) { k_cell_body<NI>(P, A, cur, nullptr); }
+
+// decomposed tissue: the same kernel with exchange point X1 inside it (xchg.cuh)
+template <int NI>
+__global__ void __launch_bounds__(KC_WARPS * 32, 2)
+k_cell_x(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ XPlan X, const int cur) { k_cell_body<NI>(P, A, cur, &X); }
 
 template <int NI>
 __global__ void __maxnreg__(208)
-k_cell_share(const __grid_constant__ KParams P, const KArrays A, const int cur) { k_cell_body<NI>(P, A, cur); }
+k_cell_share(const __grid_constant__ KParams P, const KArrays A, const int cur) { k_cell_body<NI>(P, A, cur, nullptr); }
 
 // ---------------------------------------------------------------------------- pipelined build
 template <int NI>
@@ -604,11 +642,19 @@ size_t cell_pack_row_bytes(int ni) { return (size_t)(ni + 2) * 256; }
 // DEPS: the kernel runs NEXT TO k_cell (second stream): CTA b first waits until every group of cell blocks that feeds its
 // squares has finished (env_dep[b] = {first, last} group; CTAs are dispatched in order and the cell blocks finish in order,
 // so a CTA hardly waits and the fluxes it reads were written microseconds ago — they come out of L2, not DRAM).
-template <int NI, bool DEPS>
-__global__ void __launch_bounds__(256, DEPS ? 5 : 4)
-k_envacc_ell(const __grid_constant__ KParams P, const KArrays A, const int nxt)
+// XP (decomposed tissue, xchg.cuh): exchange point X2 inside the kernel — the CTAs at the two ends of the owned rows run
+// first (blockIdx is permuted), store their rows of cc_env and of the raw env voltage straight into the neighbours' halo
+// rows as well, and the last of them raises this rank's X2 flag there.
+template <int NI, bool DEPS, bool XP>
+__device__ __forceinline__ void envacc_ell_body(const KParams& P, const KArrays& A, const int nxt, const XPlan* X)
 {
-    const int k = P.ya0 * P.nx + blockIdx.x * blockDim.x + threadIdx.x;
+    int b = blockIdx.x;
+    if (XP) {
+        // [lower end | upper end | interior]
+        const int g = gridDim.x, n0 = X->env_n0, n1 = X->env_n1;
+        if (b >= n0) b = (b < n0 + n1) ? g - n1 + (b - n0) : n0 + (b - n0 - n1);
+    }
+    const int k = P.ya0 * P.nx + b * blockDim.x + threadIdx.x;
     const int E = P.nx * P.ny;
     const bool in = k < P.ya1 * P.nx;
     // everything that does not depend on the fluxes first
@@ -620,6 +666,16 @@ k_envacc_ell(const __grid_constant__ KParams P, const KArrays A, const int nxt)
         s0 = ldgi(A.slot_ptr + k); s1 = ldgi(A.slot_ptr + k + 1);
 #pragma unroll
         for (int i = 0; i < NI; ++i) cv[i] = A.cc_env[nxt][(size_t)i * E + k];
+    }
+    if (XP) {
+        // every CTA that pushes waits for the neighbours' X1 first: it tells that they are past the kernels that still read
+        // (field of the last step) or write (their own redundant transport of the halo rows) what this CTA is about to
+        // store into their windows; the CTAs whose squares take remote flux slots are among them
+        if (blockIdx.x < X->env_n0 + X->env_n1) xchg_wait_cta(P, A, 0);
+    } else if (!DEPS && P.xwait) {
+        // decomposed tissue: squares near the strip edges take fluxes the neighbours pushed (exchange point X1)
+        const int k0 = P.ya0 * P.nx + b * blockDim.x;
+        if (k0 / P.nx < P.xw_lo || (k0 + (int)blockDim.x - 1) / P.nx >= P.xw_hi) xchg_wait_cta(P, A, 0);
     }
     if (DEPS) {
         if (threadIdx.x == 0) {
@@ -635,30 +691,89 @@ k_envacc_ell(const __grid_constant__ KParams P, const KArrays A, const int nxt)
         }
         __syncthreads();
     }
-    if (!in) return;
-    for (int j = s0; j < s1; ++j) {
-        const int off = ldgi(A.slot_off + j);
-        if (off >= 0) {
-            // DEPS: L2 loads (ld.cg) — the producers' stores are in L2, this SM's L1 may hold an older line
+    if (in) {
+        for (int j = s0; j < s1; ++j) {
+            const int off = ldgi(A.slot_off + j);
+            if (off >= 0) {
+                // DEPS: L2 loads (ld.cg) — the producers' stores are in L2, this SM's L1 may hold an older line
 #pragma unroll
-            for (int i = 0; i < NI; ++i) acc[i] += DEPS ? __ldcg(A.flux_ell + (size_t)off + i * 32) : A.flux_ell[(size_t)off + i * 32];
-        } else {
-            const double* __restrict__ f = A.flux_slots + (size_t)(-(off + 1));
+                for (int i = 0; i < NI; ++i) acc[i] += DEPS ? __ldcg(A.flux_ell + (size_t)off + i * 32) : A.flux_ell[(size_t)off + i * 32];
+            } else {
+                const double* __restrict__ f = A.flux_slots + (size_t)(-(off + 1));
 #pragma unroll
-            for (int i = 0; i < NI; ++i) acc[i] += f[i];
+                for (int i = 0; i < NI; ++i) acc[i] += f[i];
+            }
+        }
+        const int y = k / P.nx, x = k - y * P.nx;
+        double rho = 0.0;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const double delta_env = (-acc[i]) / P.env_vol_div;                     // sim_toolbox.py:1229
+            const double c = cv[i] + delta_env * P.dt;
+            A.cc_env[nxt][(size_t)i * E + k] = c;
+            if (XP) {
+                for (int q = 0; q < X->n_nbr; ++q) {
+                    const XNbr& nb = X->nb[q];
+                    if (y >= nb.cc_src_row0 && y < nb.cc_src_row0 + nb.cc_rows)
+                        nb.cc_env[nxt][(size_t)i * nb.En + (size_t)(nb.cc_dst_row0 + (y - nb.cc_src_row0)) * P.nx + x] = c;
+                }
+            }
+            rho = fma(P.zF[i], c, rho);
+        }
+        if (A.extra_rho_env) rho += ldg(A.extra_rho_env + k);
+        A.rho_env[k] = rho;
+        const double vr = (s1 > s0) ? ((rho * P.env_vol_div) / P.memsa_mean) / P.ko_eo_er : 0.0;   // ion_current.py:93-97
+        A.v_raw[k] = vr;
+        if (XP) {
+            for (int q = 0; q < X->n_nbr; ++q) {
+                const XNbr& nb = X->nb[q];
+                if (y >= nb.v_src_row0 && y < nb.v_src_row0 + nb.v_rows)
+                    nb.v_raw[(size_t)(nb.v_dst_row0 + (y - nb.v_src_row0)) * P.nx + x] = vr;
+            }
         }
     }
-    double rho = 0.0;
-#pragma unroll
-    for (int i = 0; i < NI; ++i) {
-        const double delta_env = (-acc[i]) / P.env_vol_div;                     // sim_toolbox.py:1229
-        const double c = cv[i] + delta_env * P.dt;
-        A.cc_env[nxt][(size_t)i * E + k] = c;
-        rho = fma(P.zF[i], c, rho);
+    if (XP) {
+        // a CTA of the two end groups pushed (or could have): the last of them publishes
+        if (blockIdx.x < X->env_n0 + X->env_n1) {
+            __syncthreads();
+            if (threadIdx.x == 0) xchg_publish(*X, 1, X->n_push_ctas);
+        }
     }
-    if (A.extra_rho_env) rho += ldg(A.extra_rho_env + k);
-    A.rho_env[k] = rho;
-    A.v_raw[k] = (s1 > s0) ? ((rho * P.env_vol_div) / P.memsa_mean) / P.ko_eo_er : 0.0;   // ion_current.py:93-97
+}
+
+template <int NI, bool DEPS>
+__global__ void __launch_bounds__(256, DEPS ? 5 : 4)
+k_envacc_ell(const __grid_constant__ KParams P, const KArrays A, const int nxt) { envacc_ell_body<NI, DEPS, false>(P, A, nxt, nullptr); }
+
+template <int NI>
+__global__ void __launch_bounds__(256, 4)
+k_envacc_ell_x(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ XPlan X, const int nxt) { envacc_ell_body<NI, false, true>(P, A, nxt, &X); }
+
+// decomposed tissue, exchange point X2 inside the kernel
+void launch_envacc_ell_x(int ni, const KParams& P, const KArrays& A, const XPlan& X, int nxt, cudaStream_t st)
+{
+    const int n = (P.ya1 - P.ya0) * P.nx;
+    if (n <= 0) return;
+    const int g = (n + 255) / 256;
+    switch (ni) {
+        case 4: k_envacc_ell_x<4><<<g, 256, 0, st>>>(P, A, X, nxt); break;
+        case 5: k_envacc_ell_x<5><<<g, 256, 0, st>>>(P, A, X, nxt); break;
+        case 6: k_envacc_ell_x<6><<<g, 256, 0, st>>>(P, A, X, nxt); break;
+        default: k_envacc_ell_x<7><<<g, 256, 0, st>>>(P, A, X, nxt); break;
+    }
+}
+
+// number of 256-square CTAs of k_envacc_ell at the lower / upper end of the accumulation rows that cover rows [lo, hi)
+void envacc_end_ctas(const KParams& P, int lo, int hi, int* n_lower, int* n_upper)
+{
+    const int n = (P.ya1 - P.ya0) * P.nx, g = (n + 255) / 256;
+    const int mid = (P.ya0 + P.ya1) / 2;
+    *n_lower = *n_upper = 0;
+    if (hi <= lo || g <= 0) return;
+    const long long k_lo = (long long)(lo - P.ya0) * P.nx, k_hi = (long long)(hi - P.ya0) * P.nx;     // squares [k_lo, k_hi)
+    const int b_lo = (int)std::max(0LL, k_lo / 256), b_hi = (int)std::min((long long)g - 1, (k_hi - 1) / 256);
+    if (lo < mid) *n_lower = b_hi + 1;            // from CTA 0 up to the last one touching the range
+    else *n_upper = g - b_lo;                     // from the first one touching the range to the last CTA
 }
 
 // deps: run next to k_cell (the caller launches it on a second stream and has built env_dep for CTAs of 256 squares)
@@ -759,6 +874,19 @@ static void launch_cell_t(const KParams& P, const KArrays& A, int cur, cudaStrea
     if (mb == 2 && share) k_cell_share<NI><<<grid, KC_WARPS * 32, 0, st>>>(P, A, cur);
     else if (mb == 2) k_cell<NI, 2><<<grid, KC_WARPS * 32, 0, st>>>(P, A, cur);
     else k_cell<NI, 3><<<grid, KC_WARPS * 32, 0, st>>>(P, A, cur);
+}
+
+// decomposed tissue, exchange point X1 inside the kernel (register build, persistent)
+void launch_cell_x(int ni, const KParams& P, const KArrays& A, const XPlan& X, int cur, cudaStream_t st)
+{
+    const int need = (P.n_blocks + KC_WARPS - 1) / KC_WARPS;
+    const int grid = (!P.kc_persist || need < g_kc_sms * 2) ? need : g_kc_sms * 2;
+    switch (ni) {
+        case 4: k_cell_x<4><<<grid, KC_WARPS * 32, 0, st>>>(P, A, X, cur); break;
+        case 5: k_cell_x<5><<<grid, KC_WARPS * 32, 0, st>>>(P, A, X, cur); break;
+        case 6: k_cell_x<6><<<grid, KC_WARPS * 32, 0, st>>>(P, A, X, cur); break;
+        default: k_cell_x<7><<<grid, KC_WARPS * 32, 0, st>>>(P, A, X, cur); break;
+    }
 }
 
 // register build: the caller zeroes A.ticket on the same stream before every launch

@@ -18,6 +18,7 @@
 #include "kparams.cuh"
 
 #include "kmath.cuh"
+#include "xchg.cuh"
 
 static int g_n_sms = 148;
 
@@ -502,6 +503,8 @@ k_field(const __grid_constant__ KParams P, const KArrays A)
     const int x0 = blockIdx.x * FT, y0 = P.yf0 + blockIdx.y * FT;
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     const int gny = P.ny_global;
+    // decomposed tissue: tiles that reach into the halo rows read what the neighbours pushed (exchange point X2)
+    if (P.xwait && (y0 - FH < P.y_own0 || y0 + FT + FH > P.y_own1)) xchg_wait_cta(P, A, 1);
     for (int t = tid; t < (FT + 2 * FH) * (FT + 2 * FH); t += 256) {
         const int ly = t / (FT + 2 * FH), lx = t % (FT + 2 * FH);
         const int y = y0 + ly - FH, x = x0 + lx - FH;

@@ -51,6 +51,11 @@ struct KParams {
     // kernel row ranges in local rows (single GPU: all [0, ny)): ion transport, membrane->env
     // accumulation, env field (E rows; v_env is written on the accumulation rows)
     int yi0, yi1, ya0, ya1, yf0, yf1;
+    // halo exchange of a decomposed tissue (xchg.cuh): xwait = the consumers wait inside the kernel; xsides bit s = a neighbour on
+    // side s (0 below, 1 above); env squares in local rows < xw_lo or >= xw_hi take remote flux slots
+    int xwait, xsides, xw_lo, xw_hi;
+    int xpush;                              // the producers push their boundary values to the neighbours themselves (k_cell, k_envacc_ell)
+    unsigned long long x_timeout_ns;
     // reciprocals of constants (formed once on the host; x*inv differs from x/c by <= 1 ulp)
     double inv_RT_sim, inv_RT_p, inv_tm, inv_gjl, inv_kbT_sim, inv_delta, inv_2delta;
     double inv_KmNK_Na, inv_KmNK_K, inv_KmCa_Ca, tNK, tCa;   // tNK = cATP/KmNK_ATP, tCa = cATP/KmCa_ATP
@@ -71,6 +76,10 @@ struct KArrays {
     const int *blk_row0;         // [n_blocks + 1] int2 {first row, first membrane} of every block
     int *ticket;                 // k_cell, register build: next ticket (zeroed before every launch)
     int *cell_done;              // k_cell: finished cell blocks per group of KC_GRP (zeroed before every launch; null = not published)
+    const int *sched;            // k_cell: ticket -> block (boundary blocks of a strip first), null = identity
+    const int *blk_x;            // k_cell, strips: int2 per block {row of ghost_tab or -1, offset into rslot_tab or -1}
+    const int *ghost_tab;        //   int2 per (flagged block, lane): ghost index of the cell on the neighbour of side 0 / 1, or -1
+    const int *rslot_tab;        //   int per (flagged block, row, lane): side << 30 | remote flux slot on that neighbour, or -1
     const int *env_dep;          // k_envacc_ell next to k_cell: int2 {first, last} group of cell blocks that feed each CTA's 256 squares
     const char *cpack;           // [rows] x {DmS[I][32] doubles = (Dm*(-rho_channel/tm))*mem_sa, mem_sa[32] doubles,
                                  //            partner cell | boundary bit [32] ints, env square | KC_FIRST/LAST/INV bits [32] ints}
@@ -96,6 +105,7 @@ struct KArrays {
     double *cenv_u;          // [2][8] no-ECM bath concentrations (device-resident, double buffered)
     double *cenv_part;       // [n_tiles, 8] per-tile partial sums
     unsigned int *status;
+    const unsigned long long *xflags, *xepoch;   // this rank's exchange flags [2 points][2 sides] and epochs [2 points] (xchg.cuh)
     // diagnostics
     double *fl_mem, *fl_gj, *fl_env_x, *fl_env_y, *rate_NaK;
     double *Jmem, *Jgj, *Jn, *I_mem, *Jc, *Emc, *dvm, *vm_mem, *vm_ave;

@@ -13,25 +13,6 @@
 
 #define XCHG_PUSH 1
 #define XCHG_WAIT 2
-#define ST_XCHG_TIMEOUT 8u
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
-{
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
-{
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long globaltimer_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-
 __global__ void __launch_bounds__(256)
 k_xchg(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ XPlan X,
        const int which, const int buf, const int mode, const int flux_ell)

@@ -129,3 +129,39 @@ class DistributedStrips:
     def close(self):
         self.dist.barrier()
         self.engine.close()
+
+
+def verify_strips(dist, device, cells=60_000, steps=12, fields=("cc_cells", "cc_env", "vm", "gjopen", "E_env_x", "v_env")):
+    """Multi-process parity check, run by every rank of an initialised process group: one synthetic tissue stepped as
+    ``world`` strips (halo exchange over CUDA-IPC peer stores) must equal the same tissue stepped undivided on rank 0's
+    GPU, BIT FOR BIT.  Returns the verdict dict on rank 0 (None elsewhere).  bench.py runs it before timing a decomposed
+    tissue; tools/check_multigpu.py is the stand-alone form."""
+    from . import synth
+    from .partition import gather, partition
+    mesh, p, st = synth.make_tissue(cells)
+    ds = DistributedStrips(mesh, p, st, device, dist)
+    ds.update_V()
+    status = ds.step(steps)
+    mine = ds.download_local(list(fields))
+    allf = [None] * dist.get_world_size()
+    dist.all_gather_object(allf, mine)
+    ds.close()
+    out = None
+    if dist.get_rank() == 0:
+        parts = partition(mesh, p, st, dist.get_world_size())
+        got = gather(parts, allf)
+        eng = TissueEngine(mesh, p, st, device=device)
+        eng.update_V()
+        s0 = eng.step(steps)
+        ref = eng.download(list(fields))
+        eng.close()
+        worst, ok = {}, True
+        for f in fields:
+            a, b = got[f].reshape(ref[f].shape), ref[f]
+            same = bool(np.array_equal(a, b))
+            worst[f] = 0.0 if same else float(np.max(np.abs(a - b)))
+            ok &= same
+        out = {"check": "strips == single domain (bit-exact)", "ok": ok, "world": dist.get_world_size(),
+               "cells": len(mesh["cell_vol"]), "steps": steps, "status": [int(status), int(s0)], "max_abs_diff": worst}
+    dist.barrier()
+    return out

@@ -29,37 +29,12 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from betse_b200 import synth
-    from betse_b200.engine import TissueEngine
-    from betse_b200.partition import gather, partition
-    from betse_b200.strips import DistributedStrips
-    fields = ["cc_cells", "cc_env", "vm", "gjopen", "E_env_x", "v_env"]
-    mesh, p, st = synth.make_tissue(args.cells)
-    ds = DistributedStrips(mesh, p, st, local_rank, dist)
-    ds.update_V()
-    status = ds.step(args.steps)
-    mine = ds.download_local(fields)
-    allf = [None] * dist.get_world_size()
-    dist.all_gather_object(allf, mine)
-    ds.close()
+    from betse_b200.strips import verify_strips
+    out = verify_strips(dist, local_rank, cells=args.cells, steps=args.steps)
     ok = True
     if rank == 0:
-        parts = partition(mesh, p, st, dist.get_world_size())
-        got = gather(parts, allf)
-        eng = TissueEngine(mesh, p, st, device=local_rank)
-        eng.update_V()
-        s0 = eng.step(args.steps)
-        ref = eng.download(fields)
-        eng.close()
-        worst = {}
-        for f in fields:
-            a, b = got[f].reshape(ref[f].shape), ref[f]
-            same = bool(np.array_equal(a, b))
-            worst[f] = 0.0 if same else float(np.max(np.abs(a - b)))
-            ok &= same
-        print(json.dumps({"check": "strips == single domain (bit-exact)", "ok": ok, "world": dist.get_world_size(),
-                          "cells": len(mesh["cell_vol"]), "steps": args.steps, "status": [int(status), int(s0)],
-                          "max_abs_diff": worst}))
+        ok = out["ok"]
+        print(json.dumps(out))
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
