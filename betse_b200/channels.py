@@ -24,7 +24,15 @@ type  value                                    reference form
       W = -U
 7     1 where U >= p2, else                    exponential tau overwritten with 1 above a voltage
       p0 + p1*exp(-U/p3)                       (vg_ca.py Cav3p1: ``_mTau[V >= -10e-3] = 1.0``)
+8     p0/cosh((U - p1)/p2)                     Morris-Lecar time constants, Kir_ML steady state
+9     p0 + p1*tanh((U - p2)/p3)                Morris-Lecar steady states 0.5*(1 + tanh(...))
 ====  =======================================  ==============================================
+
+The Morris-Lecar family (``vg_morrislecar.py``, selected with ``channel class: ML``, networks.py:6611-6613) has one gate and
+its own update (``ChannelsABC.update_ml``, channelsabc.py:60-71): ``m = (m + dt*Phi*mInf/mTau)/(1 + dt*Phi/mTau)`` for a
+kinetic gate, ``m = mInf`` otherwise; P = m.  A model carries ``ml = {"phi": Phi, "kinetic": bool}``; the device
+runs it through the Hodgkin-Huxley update with the effective time constant ``mTau/Phi`` (the same quotient, multiplied
+through by mTau/Phi) or 0 (``device_quantities``).
 
 ``tests/test_channels_table.py`` holds every entry to the reference's own class over a voltage
 sweep (build container only: needs /root/reference).  The NumPy evaluator below is set-up / test
@@ -32,7 +40,7 @@ code (initial gate values of synthetic tissues); the per-timestep evaluation is 
 """
 import numpy as np
 
-CONST, SIG, LIN, EXP, GAUSS, LINOID, LINOID_NEG, EXP_CUT = range(8)
+CONST, SIG, LIN, EXP, GAUSS, LINOID, LINOID_NEG, EXP_CUT, SECH, TANH = range(10)
 KIND = {"T": 0, "R": 1, "S": 2}
 
 
@@ -90,6 +98,26 @@ def _multi(model, ions, rel_perm, module, init_shift=None):
 def _hcn(v0, s, tau, shift, pm_na=0.2, init_shift=None):
     m = _hh("Na", 1, 0, _T(_sig(v0, s)), _T(_c(tau)), _T(_c(1.0)), _T(_c(1.0)), shift=shift)
     return _multi(m, ["Na", "K", "Ca"], [pm_na, 1.0, 0.05], "vg_funny", init_shift)
+
+
+def _ml(ions, rel_perm, mInf, mTau, phi, kinetic):
+    """One Morris-Lecar model (vg_morrislecar.py): V = 1000*vm, P = m."""
+    one = _T(_c(1.0))
+    m = dict(ion=ions[0], time_unit=1.0e3, mpow=1, hpow=0, shift=0.0, q=[_T(mInf), _T(mTau), one, one],
+             ml={"phi": float(phi), "kinetic": bool(kinetic)}, module="vg_morrislecar")
+    if len(ions) > 1:
+        m.update(ions=list(ions), rel_perm=[float(x) for x in rel_perm])
+    return m
+
+
+def _mlk(v0, s, phi=0.066):
+    """Kinetic K+ channel: mInf = 0.5*(1 + tanh((V - v0)/s)), mTau = 1/cosh((V - v0)/(2 s))."""
+    return _ml(["K"], [1], (TANH, 0.5, 0.5, float(v0), float(s)), (SECH, 1.0, float(v0), 2.0 * s, 0.0), phi, True)
+
+
+def _mls(ions, rel_perm, v0, s):
+    """Instantaneous gate: m = mInf = 0.5*(1 + tanh((V - v0)/s))."""
+    return _ml(ions, rel_perm, (TANH, 0.5, 0.5, float(v0), float(s)), _c(1.0), 1.0, False)
 
 
 def _na_m(v0):          # the Hammil-type activation shared by Nav1p2/1p3/Rat1/Rat3 (vg_na.py:169-186 ...)
@@ -182,8 +210,22 @@ MODELS = {
     # ---- cation.py: non-selective leaks (ions, rel_perm: :64-65)
     "CatLeak": _multi(_leak("Na"), ["Na", "K", "Ca"], [1.0, 1.0, 0.0], "cation"),             # :113-159
     "CatLeak2": _multi(_leak("Na"), ["Na", "K", "Ca"], [1.0, 1.0, 1.0], "cation"),            # :162-208
+    # ---- vg_morrislecar.py (channel class "ML")
+    "Kv_ML1": _mlk(12.0, 17.0),                                                               # :119-154
+    "Kv2p1_ML": _mlk(14.0, 30.0),                                                             # :156-192
+    "Kv1p3_ML": _mlk(-14.0, 20.0),                                                            # :194-230
+    "Kv1p5_ML": _mlk(-6.0, 15.0),                                                             # :232-268
+    "Kv1p5S_ML": _mlk(-6.0, 15.0, phi=0.00066 * 2),                                           # :270-307
+    "Nav_ML": _mls(["Na"], [1], -17.0, 18.0),                                                 # :309-344
+    "Cav_L_ML": _mls(["Ca"], [1], -20.0, 24.0),                                               # :346-381
+    "Cav_L_ML2": _mls(["Ca"], [1], -20.0, 12.0),                                              # :383-418
+    "Cav_N_ML": _mls(["Ca"], [1], -1.0, 18.0),                                                # :420-455
+    "Cav_T_ML": _mls(["Ca"], [1], -43.0, 24.0),                                               # :457-492
+    "Kir_ML": _ml(["K"], [1], (SECH, 1.0, -135.0, 37.0, 0.0), _c(1.0), 1.0, False),           # :494-529
+    "HCN2_ML": _mls(["K", "Na"], [1, 0.2], -99.0, 12.4),                                      # :532-567
+    "HCN4_ML": _mls(["K", "Na"], [1, 0.2], -99.0, 19.2),                                      # :569-604
 }
-# Not tabulated (refused at set-up): Morris-Lecar (no YAML channel class selects it), wound.
+# Not tabulated (refused at set-up): the wound channel (channels/wound_channel.py).
 
 CLASS_OF_ION = {"Na": "vg_na", "K": "vg_k", "Ca": "vg_ca", "Cl": "vg_cl"}
 
@@ -207,6 +249,10 @@ def term(t, U):
         return p0 * (W - p1) / (1 - np.exp(-(W - p1) / p2))
     if ty == EXP_CUT:
         return np.where(U >= p2, 1.0, p0 + p1 * np.exp(-U / p3))
+    if ty == SECH:
+        return p0 / np.cosh((U - p1) / p2)
+    if ty == TANH:
+        return p0 + p1 * np.tanh((U - p2) / p3)
     raise ValueError(ty)
 
 
@@ -222,6 +268,33 @@ def gates(model, vm):
     M = MODELS[model]
     U = np.asarray(vm, dtype=float) * 1000 + M["shift"]
     return tuple(quantity(q, U) for q in M["q"])
+
+
+def device_quantities(model):
+    """The four quantities as the device kernel takes them: a Morris-Lecar gate becomes a Hodgkin-Huxley gate with the
+    time constant mTau/Phi (kinetic) or 0 (instantaneous: (0*m + dt*mInf)/(0 + dt))."""
+    M = MODELS[model]
+    q = list(M["q"])
+    if "ml" in M:
+        if M["ml"]["kinetic"]:
+            ty, p0, p1, p2, p3 = q[1][1]
+            q[1] = _T((ty, p0 / M["ml"]["phi"], p1, p2, p3))
+        else:
+            q[1] = _T(_c(0.0))
+    return q
+
+
+def advance_gates(model, m, h, vm, dt):
+    """One time step of the gates (channelsabc.py:40-71) at membrane voltages ``vm`` [V]; dt = p.dt (NumPy; oracle/tests)."""
+    M = MODELS[model]
+    mInf, mTau, hInf, hTau = gates(model, vm)
+    dtu = dt * M["time_unit"]
+    if "ml" in M:
+        if M["ml"]["kinetic"]:                     # update_ml, channelsabc.py:70-71
+            phi = M["ml"]["phi"]
+            return (m + (dtu * phi * mInf / mTau)) / (1 + ((dtu * phi) / mTau)), h
+        return mInf * np.ones_like(np.asarray(m, dtype=float)), h      # vg_morrislecar.py:92
+    return (mTau * m + dtu * mInf) / (mTau + dtu), (hTau * h + dtu * hInf) / (hTau + dtu)
 
 
 def initial_state(model, vm):

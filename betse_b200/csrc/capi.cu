@@ -983,14 +983,16 @@ static int prepare_xfuse(betse_ctx* ctx)
             has_r[c / 32] = 1;
         }
     }
-    std::vector<int> blk_x(2 * (size_t)nb, -1), ghost, rslot, sched;
-    int nbb = 0;
+    std::vector<int> blk_x(2 * (size_t)nb, -1), ghost, rslot;
+    int nbb = 0, n0 = 0, n1 = 0;
     for (int b = 0; b < nb; ++b) {
         if (has_g[b]) { blk_x[2 * b] = (int)ghost.size() / 2; ghost.resize(ghost.size() + 64, -1); }
         if (has_r[b]) { blk_x[2 * b + 1] = (int)rslot.size(); rslot.resize(rslot.size() + (size_t)(h_row0[2 * (b + 1)] - h_row0[2 * b]) * 32, -1); }
-        if (has_g[b] || has_r[b]) { sched.push_back(b); ++nbb; }
+        if (has_g[b] || has_r[b]) {
+            ++nbb;
+            if (b < nb / 2) n0 = std::max(n0, b + 1); else n1 = std::max(n1, nb - b);
+        }
     }
-    for (int b = 0; b < nb; ++b) if (!(has_g[b] || has_r[b])) sched.push_back(b);
     for (int k = 0; k < ctx->X.n_nbr; ++k) {
         const XNbr& x = ctx->X.nb[k];
         for (size_t j = 0; j < ctx->xh_cells[k].size(); ++j) {
@@ -1009,12 +1011,12 @@ static int prepare_xfuse(betse_ctx* ctx)
     if (ghost.empty()) ghost.resize(2, -1);
     if (rslot.empty()) rslot.resize(1, -1);
     int r;
-    if ((r = dev_upload(ctx, (int**)&A.sched, sched.data(), sched.size()))) return r;
     if ((r = dev_upload(ctx, (int**)&A.blk_x, blk_x.data(), blk_x.size()))) return r;
     if ((r = dev_upload(ctx, (int**)&A.ghost_tab, ghost.data(), ghost.size()))) return r;
     if ((r = dev_upload(ctx, (int**)&A.rslot_tab, rslot.data(), rslot.size()))) return r;
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->X.n_bblocks = nbb;
+    ctx->X.blk_n0 = n0; ctx->X.blk_n1 = n1;
     ctx->X.env_n0 = ctx->X.env_n1 = 0;
     for (int k = 0; k < ctx->X.n_nbr; ++k) {
         int lo = 0, up = 0;

@@ -42,6 +42,8 @@ __device__ __forceinline__ double gate_term(const KTerm& t, double U)
         case 4: { const double x = (U + t.p[2]) / t.p[3]; return t.p[0] + t.p[1] * exp(-(x * x)); }
         case 5: { const double x = U - t.p[1]; return t.p[0] * x / (1.0 - exp(-x / t.p[2])); }
         case 7: return (U >= t.p[2]) ? 1.0 : t.p[0] + t.p[1] * exp(-U / t.p[3]);   // vg_ca.py Cav3p1: tau overwritten with 1 above the cut
+        case 8: return t.p[0] / cosh((U - t.p[1]) / t.p[2]);                      // vg_morrislecar.py: 1/cosh time constants, Kir_ML
+        case 9: return t.p[0] + t.p[1] * tanh((U - t.p[2]) / t.p[3]);             // vg_morrislecar.py: 0.5*(1 + tanh(...))
         default: { const double x = -U - t.p[1]; return t.p[0] * x / (1.0 - exp(-x / t.p[2])); }
     }
 }

@@ -214,10 +214,7 @@ __device__ __forceinline__ void cell_task(const KParams& P, const KArrays& A, co
 
     // strips with fused pushes: does this block hold cells that are ghosts on a neighbour / membranes of its env squares?
     int2 bx = make_int2(-1, -1), gs = make_int2(-1, -1);
-    if (X) {
-        bx = __ldg(reinterpret_cast<const int2*>(A.blk_x) + task);
-        if (bx.x >= 0) gs = __ldg(reinterpret_cast<const int2*>(A.ghost_tab) + bx.x + lane);
-    }
+    if (X) bx = __ldg(reinterpret_cast<const int2*>(A.blk_x) + task);
     // the block whose streams this task pulls into L2 (issued after the first membrane, below)
     const int up = task + P.pf_dist;
     int2 u0 = make_int2(0, 0), u1 = make_int2(0, 0);
@@ -268,6 +265,7 @@ __device__ __forceinline__ void cell_task(const KParams& P, const KArrays& A, co
         dvt = ldg(A.diviterm + c);
     }
     cell_prologue<NI>(P, S, vm_own, cc[iCa >= 0 ? iCa : 0], flags);
+    if (bx.x >= 0) gs = __ldg(reinterpret_cast<const int2*>(A.ghost_tab) + bx.x + lane);
 
     auto compute = [&](const MemIn<NI>& x, const int k) {
         if (k < nm) {
@@ -335,8 +333,12 @@ __device__ __forceinline__ void k_cell_body(const KParams& P, const KArrays& A, 
             t = __shfl_sync(0xffffffffu, t, 0);
         } else t = (int)(blockIdx.x * KC_WARPS + (threadIdx.x >> 5));
         if (t >= P.n_blocks) break;
-        // strips: the blocks at the strip edges first, so that the neighbours have their values long before they need them
-        if (X) t = ldgi(A.sched + t);
+        // strips: the blocks at the two ends of the strip first (cells are numbered row by row, the strip's edge cells sit
+        // in its first and last blocks), so that the neighbours have their values long before they need them
+        if (X) {
+            const int n0 = X->blk_n0, n1 = X->blk_n1;
+            if (t >= n0) t = (t < n0 + n1) ? P.n_blocks - n1 + (t - n0) : n0 + (t - n0 - n1);
+        }
         cell_task<NI>(P, A, cur, t, lane, flags, X);
         if (A.cell_done) {
             // a RELEASE on the counter, not __threadfence(): a gpu-scope acq_rel fence makes ptxas invalidate the SM's

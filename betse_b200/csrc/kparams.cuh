@@ -76,7 +76,6 @@ struct KArrays {
     const int *blk_row0;         // [n_blocks + 1] int2 {first row, first membrane} of every block
     int *ticket;                 // k_cell, register build: next ticket (zeroed before every launch)
     int *cell_done;              // k_cell: finished cell blocks per group of KC_GRP (zeroed before every launch; null = not published)
-    const int *sched;            // k_cell: ticket -> block (boundary blocks of a strip first), null = identity
     const int *blk_x;            // k_cell, strips: int2 per block {row of ghost_tab or -1, offset into rslot_tab or -1}
     const int *ghost_tab;        //   int2 per (flagged block, lane): ghost index of the cell on the neighbour of side 0 / 1, or -1
     const int *rslot_tab;        //   int per (flagged block, row, lane): side << 30 | remote flux slot on that neighbour, or -1

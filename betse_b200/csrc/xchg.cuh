@@ -28,6 +28,7 @@ struct XPlan {
     // pushes fused into the producing kernels (k_cell: X1, k_envacc_ell: X2)
     int side_k[2];                  // index into nb[] of the neighbour on side 0 / 1, or -1
     int n_bblocks;                  // k_cell blocks that hold ghost-send cells or remote-flux membranes
+    int blk_n0, blk_n1;             // they lie within the first blk_n0 / last blk_n1 blocks, which k_cell runs first
     int env_n0, env_n1, n_push_ctas;   // k_envacc_ell CTAs (256 squares) at the lower / upper end of the owned rows that push
 };
 

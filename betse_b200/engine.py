@@ -526,7 +526,7 @@ class TissueEngine:
             if j > 0:
                 continue
             d.mpower, d.hpower = int(mdl["mpow"]), int(mdl["hpow"])
-            for q, spec in enumerate(mdl["q"]):
+            for q, spec in enumerate(chlib.device_quantities(c["model"])):
                 d.kind[q] = chlib.KIND[spec[0]]
                 terms = [spec[1], spec[2] if len(spec) > 2 else (0, 0.0, 0.0, 0.0, 0.0)]
                 for dst, t in zip((d.a[q], d.b[q]), terms):

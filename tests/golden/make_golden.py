@@ -86,7 +86,7 @@ def chan_extra(sim, phase):
         out["chan%d.init_active" % k] = np.asarray(int(bool(c.init_active)))
         out["chan%d.targets" % k] = np.asarray(cc.targets, dtype=np.int64)
         out["chan%d.m" % k] = np.asarray(cc.m, dtype=float) * np.ones(len(cc.targets))
-        out["chan%d.h" % k] = np.asarray(cc.h, dtype=float) * np.ones(len(cc.targets))
+        out["chan%d.h" % k] = np.asarray(getattr(cc, "h", 1.0), dtype=float) * np.ones(len(cc.targets))   # Morris-Lecar: no h gate
         if hasattr(cc, "P"):
             out["chan%d.P" % k] = np.asarray(cc.P, dtype=float)
         if getattr(cc, "chan_flux", None) is not None:
@@ -117,6 +117,20 @@ CHANNELS_MULTI = [
 SCENARIOS["mammal_ecm_chan_multi"] = dict(
     mods=_m(SMALL, {"cutting event": {"event happens": False}, "general options": {"ion profile": "mammal"},
                     "general network": {"implement network": True, "biomolecules": [], "channels": CHANNELS_MULTI}}),
+    snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=chan_extra)
+
+
+# Morris-Lecar family (vg_morrislecar.py, `channel class: ML`, networks.py:6611-6613): a kinetic K channel (update_ml), an
+# instantaneous Na gate (m = mInf) and the two-ion HCN2_ML, next to a Hodgkin-Huxley Ca channel
+CHANNELS_ML = [
+    {"name": "KvML", "channel class": "ML", "channel type": "Kv1p5_ML", "max Dm": 1.0e-17, "apply to": "all", "init active": True},
+    {"name": "NavML", "channel class": "ML", "channel type": "Nav_ML", "max Dm": 2.0e-17, "apply to": "all", "init active": False},
+    {"name": "FunnyML", "channel class": "ML", "channel type": "HCN2_ML", "max Dm": 5.0e-18, "apply to": ["Spot"], "init active": True},
+    {"name": "Cav", "channel class": "Ca", "channel type": "Cav1p2", "max Dm": 1.0e-15, "apply to": "all", "init active": False},
+]
+SCENARIOS["mammal_ecm_chan_ml"] = dict(
+    mods=_m(SMALL, {"cutting event": {"event happens": False}, "general options": {"ion profile": "mammal"},
+                    "general network": {"implement network": True, "biomolecules": [], "channels": CHANNELS_ML}}),
     snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=chan_extra)
 
 

@@ -25,6 +25,33 @@ def test_table_matches_reference_class(model):
     obj = _ref_class(model)()
     import types
     obj.init(vm.copy(), types.SimpleNamespace(mem_i=np.arange(len(vm))), None, targets=None)   # cation.py:47 reads cells.mem_i
+    M = ch.MODELS[model]
+    if "ml" in M:
+        # Morris-Lecar (vg_morrislecar.py): one gate, V = 1000*vm, P = m, its own update (update_ml)
+        m0 = np.array(obj.m, dtype=float) * np.ones_like(vm)
+        obj._calculate_state(vm * 1000)
+        got = ch.gates(model, vm)
+        for name, a, b in zip(("mInf", "mTau"), got, (obj._mInf, obj._mTau)):
+            b = np.asarray(b, dtype=float) * np.ones_like(vm)
+            assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)) < 5e-13, (model, name)
+        assert np.max(np.abs(ch.initial_state(model, vm)[0] - m0)) < 1e-13
+        assert obj.Phi == M["ml"]["phi"] and bool(obj.kinetic_gate) == M["ml"]["kinetic"]
+        ions, perms = ch.ions_of(model)
+        assert obj.time_unit == M["time_unit"] and list(obj.ions) == ions and [float(x) for x in obj.rel_perm] == perms
+        assert M["mpow"] == 1 and M["hpow"] == 0
+        # one time step of the class itself (run -> update_ml / m = mInf) against the table's update, and against the
+        # Hodgkin-Huxley form the device runs it through (device_quantities)
+        vm2 = vm[::-1].copy()
+        obj.run(vm2, types.SimpleNamespace(dt=1.0e-4))
+        m1, _ = ch.advance_gates(model, m0, np.ones_like(vm), vm2, 1.0e-4)
+        assert np.max(np.abs(m1 - np.asarray(obj.m, dtype=float))) < 1e-15
+        assert np.max(np.abs(np.asarray(obj.P, dtype=float) - m1)) < 1e-15
+        U = vm2 * 1000
+        q = ch.device_quantities(model)
+        mInf, tau = ch.quantity(q[0], U), ch.quantity(q[1], U)
+        dtu = 1.0e-4 * M["time_unit"]
+        assert np.max(np.abs((tau * m0 + dtu * mInf) / (tau + dtu) - m1)) < 1e-14
+        return
     V = vm * 1000 + obj.v_corr
     m0, h0 = np.array(obj.m, dtype=float) * np.ones_like(vm), np.array(obj.h, dtype=float) * np.ones_like(vm)
     obj._calculate_state(V)

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("kind", ["init", "sim"])
-@pytest.mark.parametrize("fixture", ["mammal_ecm_chan", "mammal_ecm_chan_multi"])   # _multi: vg_funny HCN2 + cation leak (Na/K/Ca each)
+@pytest.mark.parametrize("fixture", ["mammal_ecm_chan", "mammal_ecm_chan_multi", "mammal_ecm_chan_ml"])   # _multi: vg_funny HCN2 + cation leak (Na/K/Ca each); _ml: Morris-Lecar family
 def test_channels_match_reference(fixture, kind):
     from betse_b200.engine import TissueEngine
     cap = util.load_golden(fixture)
