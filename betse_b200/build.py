@@ -7,8 +7,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbetse_b200.so")
-SOURCES = ["capi.cu", "kernels.cu", "kmem_pipe.cu", "kcell.cu", "xchg.cu", "channels.cu", "network.cu", "hh.cu"]
-HEADERS = ["kparams.cuh", "kmath.cuh", "xchg.cuh", "channels.cuh", "network.cuh", "hh.cuh", os.path.join("..", "..", "include", "betse_b200.h")]
+SOURCES = ["capi.cu", "kernels.cu", "kmem_pipe.cu", "kcell.cu", "xchg.cu", "channels.cu", "network.cu", "hh.cu", "fast.cu"]
+HEADERS = ["kparams.cuh", "kmath.cuh", "xchg.cuh", "channels.cuh", "network.cuh", "hh.cuh", "fast.cuh", os.path.join("..", "..", "include", "betse_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

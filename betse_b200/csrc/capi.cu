@@ -15,6 +15,7 @@
 #include "../../include/betse_b200.h"
 #include "kparams.cuh"
 #include "xchg.cuh"
+#include "fast.cuh"
 #include <climits>
 #include "channels.cuh"
 #include "network.cuh"
@@ -68,6 +69,8 @@ void launch_transporter(const KParams& P, const KArrays& A, const KNet& N, const
 void launch_tw_gather(const KParams& P, const KArrays& A, double* row, const double* src, cudaStream_t st);
 void launch_net_mod(const KParams& P, const KArrays& A, const KNet& N, int prog, double max_val, double* dst, int cur, cudaStream_t st);
 void launch_cell_update(const KParams& P, const KArrays& A, int cur, cudaStream_t st);
+void launch_fast(const KParams& P, const KArrays& A, const KFast& Fz, int cur, cudaStream_t st);
+void launch_fast_diag(const KParams& P, const KArrays& A, const KFast& Fz, cudaStream_t st);
 void launch_xchg(const KParams& P, const KArrays& A, const XPlan& X, int which, int buf, int mode, int flux_ell, cudaStream_t st);
 
 enum { K_ION = 0, K_MEM, K_ENVACC, K_FIELD, K_ENVMIX, K_SMOOTH, K_DIAG, K_XCHG };
@@ -138,6 +141,12 @@ struct betse_ctx {
     double* lig_tmp[2] = {nullptr, nullptr};       // [n_gates][M] openings formed before the substances advance
     std::string err;
     std::vector<void*> allocs;
+    // fast (equivalent-circuit) solver (csrc/fast.cu)
+    KFast fast;
+    bool fast_on = false;
+    int fast_cur = 0;
+    cudaGraphExec_t fast_graph = nullptr;    // two steps (buffer parity returns)
+    int fast_graph_cur = 0;
     // CUDA graphs of one plain step, for cur = 0 and cur = 1
     cudaGraphExec_t gexec[2] = {nullptr, nullptr};
     bool graphs_built = false;
@@ -368,6 +377,7 @@ static void destroy_graphs(betse_ctx* ctx)
     for (int i = 0; i < 2; ++i)
         if (ctx->gexec[i]) { cudaGraphExecDestroy(ctx->gexec[i]); ctx->gexec[i] = nullptr; }
     ctx->graphs_built = false;
+    if (ctx->fast_graph) { cudaGraphExecDestroy(ctx->fast_graph); ctx->fast_graph = nullptr; }
     ctx->graph_epoch++;
     for (auto& g : ctx->ens) if (g.exec) cudaGraphExecDestroy(g.exec);
     ctx->ens.clear();
@@ -1354,6 +1364,108 @@ extern "C" int betse_ensemble_step(betse_ctx** ctxs, int n, int nsteps, int laun
         all |= st;
     }
     (void)all;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------- fast (equivalent-circuit) solver
+extern "C" int betse_fast_setup(betse_ctx* ctx, const betse_fast_host* s)
+{
+    if (!ctx || !s) return 2;
+    if (!s->vm_ave || !s->gjopen || !s->G_Leak || !s->E_Leak || !s->G_gj || !s->sigma_cell)
+        return fail(ctx, "betse_fast_setup: vm_ave, gjopen, G_Leak, E_Leak, G_gj and sigma_cell are required");
+    if (ctx->X.n_nbr > 0) return fail(ctx, "the fast solver on a domain-decomposed tissue is not implemented");
+    if (!ctx->chans.empty() || ctx->net_on[0] || ctx->net_on[1]) return fail(ctx, "the fast solver with networks is not implemented");
+    if (!ctx->hp.v_sensitive_gj && !ctx->A.gj_w) return fail(ctx, "static gap junctions need gj_default_weights");
+    CK(cudaSetDevice(ctx->device));
+    const int C = ctx->C, Mo = ctx->Mo;
+    KFast& Fz = ctx->fast;
+    int r;
+    if (!ctx->fast_on) {
+        memset(&Fz, 0, sizeof Fz);
+        for (int b = 0; b < 2; ++b) if ((r = dev_alloc(ctx, &Fz.vm_ave[b], (size_t)C))) return r;
+        if ((r = dev_alloc(ctx, (double**)&Fz.G_Leak, (size_t)C))) return r;
+        if ((r = dev_alloc(ctx, (double**)&Fz.E_Leak, (size_t)C))) return r;
+        if ((r = dev_alloc(ctx, (double**)&Fz.G_gj, (size_t)C))) return r;
+        if ((r = dev_alloc(ctx, (double**)&Fz.sigma_cell, (size_t)C))) return r;
+        if ((r = dev_alloc(ctx, &Fz.vgj, (size_t)Mo))) return r;
+        if ((r = dev_alloc(ctx, &Fz.Jn, (size_t)Mo))) return r;
+        if ((r = dev_alloc(ctx, &Fz.Emx, (size_t)Mo))) return r;
+        if ((r = dev_alloc(ctx, &Fz.Emy, (size_t)Mo))) return r;
+        if ((r = dev_alloc(ctx, &Fz.J_cell_x, (size_t)C))) return r;
+        if ((r = dev_alloc(ctx, &Fz.J_cell_y, (size_t)C))) return r;
+        if ((r = dev_alloc(ctx, &Fz.E_cell_x, (size_t)C))) return r;
+        if ((r = dev_alloc(ctx, &Fz.E_cell_y, (size_t)C))) return r;
+        ctx->fast_on = true;
+    }
+    destroy_graphs(ctx);
+    ctx->fast_cur = 0;
+#define UPF(dst, src, n) { int xr_ = xfer(ctx, (void*)(dst), (src), (size_t)(n) * sizeof(double), cudaMemcpyHostToDevice); if (xr_) return xr_; }
+    UPF(Fz.vm_ave[0], s->vm_ave, C);
+    UPF(ctx->A.gjopen, s->gjopen, Mo);
+    UPF(Fz.G_Leak, s->G_Leak, C);
+    UPF(Fz.E_Leak, s->E_Leak, C);
+    UPF(Fz.G_gj, s->G_gj, C);
+    UPF(Fz.sigma_cell, s->sigma_cell, C);
+    if ((r = opt_array(ctx, &Fz.extra_J, s->extra_J_mem, (size_t)Mo))) return r;
+#undef UPF
+    double mean = 0.0;                                    // sim.sigma_cell.mean(): NumPy's pairwise sum is within an ulp
+    for (int c = 0; c < C; ++c) mean += s->sigma_cell[c];
+    mean /= (double)C;
+    Fz.sm = 0.1 * mean;
+    Fz.dt_cm = ctx->hp.dt * (1.0 / ctx->hp.cm);            // p.dt*(1/p.cm), sim.py:1561
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int betse_fast_step(betse_ctx* ctx, int nsteps, int flags, uint32_t* status_out)
+{
+    if (!ctx || nsteps < 0) return 2;
+    if (!ctx->fast_on) return fail(ctx, "betse_fast_step before betse_fast_setup");
+    CK(cudaSetDevice(ctx->device));
+    int n = nsteps;
+    if (n >= 8 && ctx->use_graphs) {
+        if (!ctx->fast_graph) {
+            launch_fast(ctx->P, ctx->A, ctx->fast, ctx->fast_cur, ctx->stream);      // loads the kernel outside the capture
+            ctx->fast_cur ^= 1; --n;
+            cudaGraph_t g;
+            const int c0 = ctx->fast_cur;
+            CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+            launch_fast(ctx->P, ctx->A, ctx->fast, c0, ctx->stream);
+            launch_fast(ctx->P, ctx->A, ctx->fast, c0 ^ 1, ctx->stream);
+            CK(cudaStreamEndCapture(ctx->stream, &g));
+            CK(cudaGraphInstantiate(&ctx->fast_graph, g, 0));
+            CK(cudaGraphDestroy(g));
+            ctx->fast_graph_cur = c0;
+        }
+        if (ctx->fast_cur != ctx->fast_graph_cur && n > 0) { launch_fast(ctx->P, ctx->A, ctx->fast, ctx->fast_cur, ctx->stream); ctx->fast_cur ^= 1; --n; }
+        for (; n >= 2; n -= 2) CK(cudaGraphLaunch(ctx->fast_graph, ctx->stream));
+    }
+    for (; n > 0; --n) { launch_fast(ctx->P, ctx->A, ctx->fast, ctx->fast_cur, ctx->stream); ctx->fast_cur ^= 1; }
+    if (flags & BETSE_STEP_DIAG) launch_fast_diag(ctx->P, ctx->A, ctx->fast, ctx->stream);     // (nsteps == 0: of the last step run)
+    CK(cudaGetLastError());
+    return read_status(ctx, status_out);
+}
+
+extern "C" int betse_fast_download(betse_ctx* ctx, betse_fast_host* out)
+{
+    if (!ctx || !out) return 2;
+    if (!ctx->fast_on) return fail(ctx, "betse_fast_download before betse_fast_setup");
+    CK(cudaSetDevice(ctx->device));
+    const int C = ctx->C, Mo = ctx->Mo;
+    const KFast& Fz = ctx->fast;
+#define DNF(dst, src, n) if (dst) { int xr_ = xfer(ctx, (void*)(dst), (src), (size_t)(n) * sizeof(double), cudaMemcpyDeviceToHost); if (xr_) return xr_; }
+    DNF(out->vm_ave, Fz.vm_ave[ctx->fast_cur], C);
+    DNF(out->gjopen, ctx->A.gjopen, Mo);
+    DNF(out->vgj, Fz.vgj, Mo);
+    DNF(out->Jn, Fz.Jn, Mo);
+    DNF(out->Emx, Fz.Emx, Mo);
+    DNF(out->Emy, Fz.Emy, Mo);
+    DNF(out->J_cell_x, Fz.J_cell_x, C);
+    DNF(out->J_cell_y, Fz.J_cell_y, C);
+    DNF(out->E_cell_x, Fz.E_cell_x, C);
+    DNF(out->E_cell_y, Fz.E_cell_y, C);
+#undef DNF
+    CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 

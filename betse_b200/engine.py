@@ -492,6 +492,54 @@ class TissueEngine:
             out["cc_env"] = np.repeat(cenv[:, None], M, axis=1)   # the reference keeps [I,M] (sim.py:487-490)
         return out
 
+    # ------------------------------------------------------------------ fast (equivalent-circuit) solver
+    FAST_FIELDS = {"vm_ave": "C", "gjopen": "M", "vgj": "M", "Jn": "M", "Emx": "M", "Emy": "M",
+                   "J_cell_x": "C", "J_cell_y": "C", "E_cell_x": "C", "E_cell_y": "C"}
+
+    def fast_setup(self, state):
+        """The constants Simulator.fast_sim_init left on the Simulator (sim.py:1393-1452: G_Leak, E_Leak, G_gj) and the
+        state the fast loop advances (vm_ave, gjopen); optional ``extra_J_mem``."""
+        sh = capi.FastHost()
+        keep = []
+        n_of = {"vm_ave": self.C, "gjopen": self.M, "G_Leak": self.C, "E_Leak": self.C, "G_gj": self.C,
+                "sigma_cell": self.C, "extra_J_mem": self.M}
+        for name, n in n_of.items():
+            if name not in state or state[name] is None:
+                if name == "extra_J_mem":
+                    continue
+                raise BetseB200Error("fast solver: sim.%s is missing (Simulator.fast_sim_init has not run?)" % name)
+            a = capi.as_f64(np.broadcast_to(np.asarray(state[name], dtype=float), (n,)) if np.ndim(state[name]) == 0
+                            else state[name]).reshape(-1)
+            if a.size != n:
+                raise BetseB200Error("fast solver: %s has %d values, expected %d" % (name, a.size, n))
+            if name == "extra_J_mem" and not np.any(a):
+                continue
+            keep.append(a)
+            self.h2d_bytes += a.nbytes
+            setattr(sh, name, capi.ptr_f64(a))
+        self._check(self.lib.betse_fast_setup(self.ctx, C.byref(sh)), "betse_fast_setup")
+
+    def fast_step(self, n=1, diag=False):
+        """n iterations of Simulator._run_fast_sim_core_loop's body (sim.py:1547-1592); ``diag``: the currents and fields
+        of the last one are formed as well (sampled steps)."""
+        st = C.c_uint32(0)
+        self._check(self.lib.betse_fast_step(self.ctx, int(n), capi.STEP_DIAG if diag else 0, C.byref(st)), "betse_fast_step")
+        self.steps_done += n
+        return int(st.value)
+
+    def fast_download(self, fields=("vm_ave", "gjopen")):
+        sh = capi.FastHost()
+        out = {}
+        for f in fields:
+            n = self.C if self.FAST_FIELDS[f] == "C" else self.M
+            out[f] = np.empty(n)
+            setattr(sh, f, capi.ptr_f64(out[f]))
+        self._check(self.lib.betse_fast_download(self.ctx, C.byref(sh)), "betse_fast_download")
+        self.d2h_bytes += sum(a.nbytes for a in out.values())
+        if "vm_ave" in out:
+            out["vm"] = out["vm_ave"][self.mem_to_cells]          # sim.py:1563
+        return out
+
     # ------------------------------------------------------------------ voltage-gated channels
     def set_channels(self, specs, phase_init=False, affect_charge=None):
         """``specs``: channel dicts (betse_b200.channels.make_channel / the reference's

@@ -484,24 +484,109 @@ def run_sim_core_loop(sim, phase, time_steps, time_steps_sampled, anim_cells=Non
                           "seconds": {k: round(v, 4) for k, v in tm.items()}})
 
 
+def run_fast_sim_core_loop(sim, phase, time_steps, time_steps_sampled, anim_cells=None, *, engine=None, device=0, stats=None):
+    """Same signature and contract as Simulator._run_fast_sim_core_loop (sim.py:1454-1640), the equivalent-circuit
+    solver selected by ``solver options: type: fast``: the loop body runs on the device (csrc/fast.cu), scheduled events
+    stay the reference's own host code, and the sampled steps append to the Simulator's time series exactly what the
+    reference's loop appends (sim.py:1597-1628).  Networks under the fast solver are refused."""
+    p, cells = phase.p, phase.cells
+    if bool(getattr(p, "molecules_enabled", False)) or bool(getattr(p, "grn_enabled", False)):
+        raise BetseB200Error("betse_b200: networks under the fast solver (run_fast_loop_channels, networks.py:3217-3280) "
+                             "are not implemented")
+    kind = getattr(getattr(phase, "kind", None), "name", str(getattr(phase, "kind", "")))
+    fire = getattr(getattr(phase, "dyna", None), "fire_events", None) if kind.upper() == "SIM" else None
+    own = engine is None
+    t0 = time.time()
+    if own:
+        _join_closing()
+        eng = TissueEngine(mesh_from_cells(cells), params_from_p(p), state_from_sim(sim), device=device)
+    else:
+        eng = engine
+    eng.fast_setup({f: getattr(sim, f, None) for f in ("vm_ave", "gjopen", "G_Leak", "E_Leak", "G_gj", "sigma_cell", "extra_J_mem")})
+    Unstable = _unstable_exception()
+    sampled = set(time_steps_sampled)
+    gjb = np.array(getattr(sim, "gj_block", 1.0), dtype=float, copy=True)
+    n, n_total = 0, len(time_steps)
+    m2c = np.asarray(cells.mem_to_cells)
+
+    def copy_back(diag):
+        got = eng.fast_download(list(TissueEngine.FAST_FIELDS) if diag else ["vm_ave", "gjopen", "vgj"])
+        for f, a in got.items():
+            setattr(sim, f, a)
+        if diag:
+            sim.Jn = got["Jn"]
+    try:
+        while n < n_total:
+            if fire is not None:
+                fire(phase=phase, t=time_steps[n])
+                new = np.asarray(getattr(sim, "gj_block", 1.0), dtype=float)
+                if new.shape != gjb.shape or not np.array_equal(new, gjb):
+                    eng.set_field("gj_block", new)                 # the only scheduled quantity this solver reads
+                    gjb = np.array(new, copy=True)
+                run = 1
+            else:
+                run = 1
+                while n + run < n_total and time_steps[n + run - 1] not in sampled:
+                    run += 1
+            last_t = time_steps[n + run - 1]
+            is_sampled = last_t in sampled
+            status = eng.fast_step(run, diag=is_sampled)
+            n += run
+            if status & capi.STATUS_NAN_VM:
+                copy_back(False)
+                raise Unstable("Your simulation has become unstable. Please try a smaller time step,"
+                               "reduce gap junction radius, and/or reduce pump rate coefficients.")
+            if is_sampled:
+                copy_back(True)
+                phase.callbacks.progressed_next()
+                # sim.py:1603-1628
+                sim.vm_time.append(sim.vm * 1)
+                sim.dd_time.append(np.copy(sim.Dm_cells))
+                sim.I_cell_x_time.append(sim.J_cell_x * 1)
+                sim.I_cell_y_time.append(sim.J_cell_y * 1)
+                sim.efield_gj_x_time.append(sim.E_cell_x[m2c] * 1)
+                sim.efield_gj_y_time.append(sim.E_cell_y[m2c] * 1)
+                sim.gjopen_time.append(sim.gjopen * 1)
+                sim.time.append(last_t * 1)
+                sim.vm_ave_time.append(sim.vm_ave * 1)
+                if anim_cells is not None:
+                    anim_cells.plot_frame(time_step=-1)
+        if n_total and time_steps[n_total - 1] not in sampled:
+            # the reference forms the currents and fields on every step: leave the Simulator the last step's
+            eng.fast_step(0, diag=True)
+            copy_back(True)
+    finally:
+        if own:
+            _close_async(eng)
+        if stats is not None:
+            stats.update({"wall_s": time.time() - t0, "steps": n, "h2d_bytes": eng.h2d_bytes, "d2h_bytes": eng.d2h_bytes})
+
+
 _installed = None
+_installed_fast = None
 
 
 def install(device=0):
-    """Rebind the reference's full solver to the B200 loop (sim.py:1064-1075 seam)."""
-    global _installed
+    """Rebind the reference's solvers to the B200 loops (sim.py:1064-1075 seam): the full solver and the fast one."""
+    global _installed, _installed_fast
     from betse.science.sim import Simulator
     if _installed is None:
         _installed = Simulator._run_sim_core_loop
+        _installed_fast = Simulator._run_fast_sim_core_loop
 
     def _loop(self, phase, time_steps, time_steps_sampled, anim_cells):
         return run_sim_core_loop(self, phase, time_steps, time_steps_sampled, anim_cells, device=device)
+
+    def _fast(self, phase, time_steps, time_steps_sampled, anim_cells):
+        return run_fast_sim_core_loop(self, phase, time_steps, time_steps_sampled, anim_cells, device=device)
     Simulator._run_sim_core_loop = _loop
+    Simulator._run_fast_sim_core_loop = _fast
 
 
 def uninstall():
-    global _installed
+    global _installed, _installed_fast
     if _installed is not None:
         from betse.science.sim import Simulator
         Simulator._run_sim_core_loop = _installed
-        _installed = None
+        Simulator._run_fast_sim_core_loop = _installed_fast
+        _installed = _installed_fast = None

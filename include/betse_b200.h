@@ -188,6 +188,30 @@ int  betse_step(betse_ctx *ctx, int nsteps, int flags, uint32_t *status_out);
  * (nullable) receives one status word per member, device_ms (nullable) the device time of the launches. */
 int  betse_ensemble_step(betse_ctx **ctxs, int n, int nsteps, int launches, uint32_t *status_out, float *device_ms);
 
+/* ---------------------------------------------------------------------------------------------
+ * The FAST (equivalent-circuit) solver: Simulator._run_fast_sim_core_loop (betse/science/sim.py:1454-1640), selected by
+ * `solver options: type: fast` (sim.py:1068-1070), without networks.  The constants come from Simulator.fast_sim_init
+ * (sim.py:1393-1452), which the reference runs on the host before the loop.  A ctx steps EITHER solver. */
+typedef struct betse_fast_host {
+    /* betse_fast_setup reads, betse_fast_download fills (NULL members are skipped) */
+    double *vm_ave;          /* [C] sim.vm_ave                                                         */
+    double *gjopen;          /* [M] sim.gjopen                                                         */
+    /* betse_fast_setup only */
+    const double *G_Leak;    /* [C] sim.G_Leak       sim.py:1441                                       */
+    const double *E_Leak;    /* [C] sim.E_Leak = sim.vm_GHK, sim.py:1434                               */
+    const double *G_gj;      /* [C] sim.G_gj         sim.py:1445                                       */
+    const double *sigma_cell;/* [C] sim.sigma_cell (constant in this solver)                           */
+    const double *extra_J_mem; /* [M] sim.extra_J_mem, NULL = 0                                        */
+    /* betse_fast_download only */
+    double *vgj;             /* [M] sim.vgj of the last step, sim.py:1547                              */
+    double *Jn, *Emx, *Emy;  /* [M] sim.py:1566-1573; valid after a step with BETSE_STEP_DIAG          */
+    double *J_cell_x, *J_cell_y, *E_cell_x, *E_cell_y;   /* [C] sim.py:1579-1584; same                 */
+} betse_fast_host;
+int  betse_fast_setup(betse_ctx *ctx, const betse_fast_host *state);
+/* Replaces `nsteps` iterations of the fast loop body (sim.py:1547-1592). */
+int  betse_fast_step(betse_ctx *ctx, int nsteps, int flags, uint32_t *status_out);
+int  betse_fast_download(betse_ctx *ctx, betse_fast_host *out);
+
 /* Same as betse_step but timed with CUDA events on the ctx's stream; per-kernel mean
  * durations (ms per launch) and launch counts are returned for the roofline in bench.py. */
 int  betse_step_profile(betse_ctx *ctx, int nsteps, float *total_ms,

@@ -38,6 +38,8 @@ STATE_FIELDS = [
     "rho_cells", "vm_ave", "Jn", "envV",
     "E_cell_x", "E_cell_y",        # read by Molecule.update_intra of charged substances in the first step
 ]
+# The fast (equivalent-circuit) solver's own state and constants (Simulator.fast_sim_init, sim.py:1393-1452; loop sim.py:1454-1640)
+FAST_FIELDS = ["G_Leak", "E_Leak", "G_gj", "vm_GHK", "Emx", "Emy", "sigma_cell", "J_cell_x", "J_cell_y"]
 # Additional per-step outputs (diagnostics recomputed from scratch every step).
 DIAG_FIELDS = [
     "fluxes_mem", "fluxes_gj", "fluxes_env_x", "fluxes_env_y", "rate_NaKATP", "rate_CaATP",
@@ -155,7 +157,8 @@ class LoopRecorder:
     """Wraps the reference's Simulator._run_sim_core_loop to record entry state and the
     state after chosen step counts, without altering what the reference computes."""
 
-    def __init__(self, snap_steps, max_steps=None, extra=None, trace=(), precut=False):
+    def __init__(self, snap_steps, max_steps=None, extra=None, trace=(), precut=False, method="_run_sim_core_loop"):
+        self.method = method        # "_run_fast_sim_core_loop": the equivalent-circuit solver (sim.py:1454-1640)
         self.snap_steps = {k: sorted(set(v)) for k, v in snap_steps.items()}
         self.max_steps = max_steps or {}
         self.capture = {}
@@ -166,8 +169,9 @@ class LoopRecorder:
     def install(self):
         from betse.science.sim import Simulator
         rec = self
-        orig = Simulator._run_sim_core_loop
+        orig = getattr(Simulator, self.method)
         self._orig = orig
+        more = FAST_FIELDS if self.method == "_run_fast_sim_core_loop" else []
 
         def wrapped(sim, phase, time_steps, time_steps_sampled, anim_cells):
             kind = phase.kind.name.lower()
@@ -188,7 +192,7 @@ class LoopRecorder:
                     cap["cells." + k] = v
             for k, v in snapshot_p(phase.p).items():
                 cap["%s.p.%s" % (kind, k)] = v
-            for k, v in snapshot(sim, STATE_FIELDS).items():
+            for k, v in snapshot(sim, STATE_FIELDS + more).items():
                 cap["%s.s0.%s" % (kind, k)] = v
             if rec.extra:
                 for k, v in rec.extra(sim, phase).items():
@@ -221,7 +225,7 @@ class LoopRecorder:
                     for f in rec.trace:
                         tr[f].append(np.array(getattr(sim, f), dtype=float, copy=True))
                 if (n + 1) in snaps:
-                    for k, v in snapshot(sim, STATE_FIELDS + DIAG_FIELDS).items():
+                    for k, v in snapshot(sim, STATE_FIELDS + DIAG_FIELDS + more).items():
                         cap["%s.k%d.%s" % (kind, n + 1, k)] = v
                     if rec.extra:
                         for k, v in rec.extra(sim, phase).items():
@@ -232,16 +236,16 @@ class LoopRecorder:
                 for f in rec.trace:
                     cap["%s.trace.%s" % (kind, f)] = np.array(tr[f])
 
-        Simulator._run_sim_core_loop = wrapped
+        setattr(Simulator, self.method, wrapped)
         return self
 
     def uninstall(self):
         from betse.science.sim import Simulator
-        Simulator._run_sim_core_loop = self._orig
+        setattr(Simulator, self.method, self._orig)
 
 
 def run_reference(mods, seed=12345, snap_steps=None, max_steps=None, phases=("init", "sim"),
-                  extra=None, workdir=None, keep=False, tweak_p=None, trace=(), precut=False):
+                  extra=None, workdir=None, keep=False, tweak_p=None, trace=(), precut=False, method="_run_sim_core_loop"):
     """Run the real reference on the shipped default config + ``mods``.
 
     Returns the capture dict.  ``np.random.seed(seed)`` is set once before ``seed`` (the
@@ -263,7 +267,7 @@ def run_reference(mods, seed=12345, snap_steps=None, max_steps=None, phases=("in
         p.plot.is_after_sim = False
         if tweak_p:
             tweak_p(p)
-        rec = LoopRecorder(snap_steps, max_steps=max_steps, extra=extra, trace=trace, precut=precut).install()
+        rec = LoopRecorder(snap_steps, max_steps=max_steps, extra=extra, trace=trace, precut=precut, method=method).install()
         try:
             runner = SimRunner(p=p, callbacks=phasecallbacks.SimCallbacksNoop())
             runner.seed()

@@ -134,6 +134,25 @@ SCENARIOS["mammal_ecm_chan_ml"] = dict(
     snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=chan_extra)
 
 
+# the FAST (equivalent-circuit) solver, Simulator._run_fast_sim_core_loop (sim.py:1454-1640): no networks — gap-junction
+# coupled leak circuit with voltage-sensitive gap junctions; with and without extracellular spaces (fast_sim_init reads
+# the env concentrations either way)
+def _leaky_spot(p):
+    """A K-leaky tissue profile: its cells rest at another potential (vm_GHK -> E_Leak), so that current flows through
+    the gap junctions and their voltage gating moves."""
+    for t in p.tissue_profiles:
+        if t.name == "Spot":
+            t.Dm_K = 3.0e-17
+
+
+SCENARIOS["fast_basic"] = dict(
+    mods=_m(NO_NET, SMALL, {"solver options": {"type": "fast"}}), tweak_p=_leaky_spot,
+    snaps={"init": [1, 2, 5, 20], "sim": [1, 2, 5, 20]}, method="_run_fast_sim_core_loop")
+SCENARIOS["fast_mammal_noecm"] = dict(
+    mods=_m(NO_NET, SMALL, {"solver options": {"type": "fast"}, "general options": {"ion profile": "mammal", "simulate extracellular spaces": False}}),
+    tweak_p=_leaky_spot, snaps={"init": [1, 2, 5, 20], "sim": [1, 2, 5, 20]}, method="_run_fast_sim_core_loop")
+
+
 def _substance(name, prod, acts=None, inh=None, Dgj=1e-15, gj_imp=True, cell=0.1, z=0, apply_to="all"):
     gd = {"production rate": prod, "decay rate": 1.0, "apply to": apply_to, "modulator function": "None"}
     if acts:
@@ -414,7 +433,8 @@ def main(argv):
         cap = refrun.run_reference(sc["mods"], seed=12345, snap_steps=sc["snaps"],
                                    max_steps={"sim": max(max(sc["snaps"]["sim"]), 12)},
                                    extra=sc.get("extra"), tweak_p=sc.get("tweak_p"),
-                                   trace=sc.get("trace", ()), precut=sc.get("precut", False))
+                                   trace=sc.get("trace", ()), precut=sc.get("precut", False),
+                                   method=sc.get("method", "_run_sim_core_loop"))
         cap["meta.numpy"] = np.array(np.__version__)
         cap["meta.scipy"] = np.array(scipy.__version__)
         cap["meta.seed"] = np.array(12345)

@@ -7,7 +7,7 @@ oracle (tests/test_simloop_reference.py), and the device is held to the oracle /
 box (tests/test_gpu_*.py).  Never imported by the product."""
 import numpy as np
 
-from oracle.betse_oracle import OracleNetwork, OracleSim, SimUnstable
+from oracle.betse_oracle import OracleFastSim, OracleNetwork, OracleSim, SimUnstable
 
 
 class OracleEngine:
@@ -57,6 +57,9 @@ class OracleEngine:
 
     def set_field(self, name, value):
         self.sets.append(name)
+        if getattr(self, "_f", None) is not None and name == "gj_block":
+            self._f.gj_block = np.array(value, dtype=float)
+            return
         o = self._sim()
         if name == "bound_V":
             o.bound_V = dict(zip("TBLR", value))
@@ -124,6 +127,28 @@ class OracleEngine:
     def network_env_state(self, handler=0):
         net = self._sim().networks[sorted(self._descs).index(int(handler))]
         return np.stack([net.c_env.get(n, np.zeros(self.ny * self.nx)) for n in net.species])
+
+    # ---- fast (equivalent-circuit) solver
+    FAST_FIELDS = {"vm_ave": "C", "gjopen": "M", "vgj": "M", "Jn": "M", "Emx": "M", "Emy": "M",
+                   "J_cell_x": "C", "J_cell_y": "C", "E_cell_x": "C", "E_cell_y": "C"}
+
+    def fast_setup(self, state):
+        mesh, params, st = self._args
+        self._f = OracleFastSim(mesh, params, dict(st, **{k: v for k, v in state.items() if v is not None}))
+
+    def fast_step(self, n=1, diag=False):
+        for _ in range(n):
+            try:
+                self._f.step()
+            except FloatingPointError:
+                return 1
+        return 0
+
+    def fast_download(self, fields=("vm_ave", "gjopen")):
+        out = {f: np.array(getattr(self._f, f), dtype=float, copy=True) for f in fields}
+        if "vm_ave" in out:
+            out["vm"] = out["vm_ave"][np.asarray(self.mem_to_cells).astype(np.int64)]
+        return out
 
     def close(self):
         pass

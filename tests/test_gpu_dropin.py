@@ -15,7 +15,7 @@ def _have_reference():
     return refshim.reference_available()
 
 
-def _run(tmp_path, use_dropin, mods=None):
+def _run(tmp_path, use_dropin, mods=None, tweak_p=None):
     from oracle import refrun, refshim
     refshim.bypass_science_init()
     from betse.science.parameters import Parameters
@@ -29,6 +29,8 @@ def _run(tmp_path, use_dropin, mods=None):
         np.random.seed(12345)
         p = Parameters.make(fn)
         p.anim.is_while_sim = p.anim.is_after_sim = p.plot.is_after_sim = False
+        if tweak_p:
+            tweak_p(p)
         runner = SimRunner(p=p, callbacks=phasecallbacks.SimCallbacksNoop())
         runner.seed()
         runner.init()
@@ -68,3 +70,25 @@ def test_betse_try_reference_loop_vs_cuda_dropin(variant, tmp_path):
         x_new = new_sim.molecules.core.molecules["X"].c_cells
         x_ref = ref_sim.molecules.core.molecules["X"].c_cells
         assert np.max(np.abs(x_new - x_ref)) <= 1e-8 * np.max(np.abs(x_ref))
+
+
+def test_fast_solver_reference_loop_vs_cuda_dropin(tmp_path):
+    """`solver options: type: fast`: Simulator._run_fast_sim_core_loop of the unmodified reference against the drop-in
+    that install() binds in its place (csrc/fast.cu), both phases, a K-leaky tissue profile driving gap-junction currents."""
+    if not _have_reference():
+        pytest.skip("reference tree absent: neither /root/reference nor baseline/_ref (run tools/install_reference.py)")
+    from tests.golden import make_golden as mg
+    sc = mg.SCENARIOS["fast_basic"]
+    (tmp_path / "ref").mkdir()
+    (tmp_path / "new").mkdir()
+    ref_sim, _ = _run(tmp_path / "ref", False, sc["mods"], sc["tweak_p"])
+    new_sim, _ = _run(tmp_path / "new", True, sc["mods"], sc["tweak_p"])
+    for name in ("vm_time", "vm_ave_time", "gjopen_time", "I_cell_x_time", "I_cell_y_time", "efield_gj_x_time", "time"):
+        got, want = getattr(new_sim, name), getattr(ref_sim, name)
+        assert len(got) == len(want) >= 10, name
+        scale = max(float(np.max(np.abs(np.asarray(w, dtype=float)))) for w in want)
+        if name.startswith(("I_cell", "efield")):
+            # sums over a closed polygon: judged against the summands (the membrane currents), like tests/test_gpu_fast.py
+            scale = max(scale, float(np.max(np.abs(ref_sim.Jn))) / (0.1 * float(np.min(ref_sim.sigma_cell)) if name.startswith("efield") else 1.0))
+        for a, r in zip(got, want):
+            assert np.max(np.abs(np.asarray(a, dtype=float) - np.asarray(r, dtype=float))) <= 1e-9 * max(scale, 1e-300), name

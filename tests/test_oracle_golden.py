@@ -67,3 +67,22 @@ def test_oracle_reproduces_reference(name, kind):
                     assert util.rel_err(c["DChan"], ref[key]) < 1e-12, (name, kind, K, key)
                     checked += 1
     assert checked > 20
+
+
+@pytest.mark.parametrize("kind", ["init", "sim"])
+@pytest.mark.parametrize("fixture", ["fast_basic", "fast_mammal_noecm"])
+def test_fast_solver_oracle_matches_reference(fixture, kind):
+    """The equivalent-circuit solver (sim.py:1454-1640) restated in oracle.OracleFastSim against the real reference."""
+    from oracle.betse_oracle import OracleFastSim
+    cap = util.load_golden(fixture)
+    o = OracleFastSim(util.mesh_of(cap, kind), util.group(cap, kind + ".p."), util.group(cap, kind + ".s0."))
+    n = 0
+    for K in util.snap_steps(cap, kind):
+        while n < K:
+            o.step()
+            n += 1
+        ref = util.group(cap, "%s.k%d." % (kind, K))
+        for f in ("vm_ave", "vm", "gjopen", "vgj", "Jn", "J_cell_x", "J_cell_y", "E_cell_x", "E_cell_y", "Emx", "Emy"):
+            if f in ref:
+                a, r = getattr(o, f), ref[f]
+                assert np.max(np.abs(a - r)) <= 1e-12 * max(np.max(np.abs(r)), 1e-300), (kind, K, f)

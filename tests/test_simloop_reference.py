@@ -137,7 +137,7 @@ def test_unsupported_network_is_refused(monkeypatch, tmp_path):
     assert "update intracellular" in str(e.value)
 
 
-def _run_try(tmp_path, use_dropin, monkeypatch=None, mods=None):
+def _run_try(tmp_path, use_dropin, monkeypatch=None, mods=None, tweak_p=None):
     """`betse try` (seed + init + sim of the SHIPPED default config, cutting event included) -> the Simulator
     after the SIM phase.  ``use_dropin``: through betse_b200.simloop with the device replaced by the CPU oracle."""
     from oracle import refrun, refshim
@@ -177,6 +177,8 @@ def _run_try(tmp_path, use_dropin, monkeypatch=None, mods=None):
         np.random.seed(12345)
         p = Parameters.make(fn)
         p.anim.is_while_sim = p.anim.is_after_sim = p.plot.is_after_sim = False
+        if tweak_p:
+            tweak_p(p)
         runner = SimRunner(p=p, callbacks=phasecallbacks.SimCallbacksNoop())
         runner.seed()
         runner.init()
@@ -413,3 +415,26 @@ def test_bath_events_without_ecm_fail_like_the_reference(monkeypatch, tmp_path):
     (tmp_path / "new").mkdir()
     with pytest.raises(AttributeError, match="conc_env_k"):
         _run_try(tmp_path / "new", True, monkeypatch, mods=mods)
+
+
+def test_fast_solver_through_the_dropin_matches_the_reference(monkeypatch, tmp_path):
+    """`solver options: type: fast` (sim.py:1068-1070): install() rebinds Simulator._run_fast_sim_core_loop as well; both
+    phases of the reference's own run against the drop-in's host logic (events, sampling, the time series the fast loop
+    appends itself, sim.py:1597-1628) over the oracle."""
+    from tests.golden import make_golden as mg
+    sc = mg.SCENARIOS["fast_basic"]
+    ref_sim, _, _ = _run_try(tmp_path / "ref", False, mods=sc["mods"], tweak_p=sc["tweak_p"])
+    (tmp_path / "new").mkdir()
+    new_sim, _, engines = _run_try(tmp_path / "new", True, monkeypatch, mods=sc["mods"], tweak_p=sc["tweak_p"])
+    assert len(engines) == 2
+    for name in ("vm_time", "vm_ave_time", "gjopen_time", "I_cell_x_time", "I_cell_y_time", "efield_gj_x_time",
+                 "efield_gj_y_time", "time"):
+        got, want = getattr(new_sim, name), getattr(ref_sim, name)
+        assert len(got) == len(want) >= 10, name
+        for a, r in zip(got, want):
+            a, r = np.asarray(a, dtype=float), np.asarray(r, dtype=float)
+            assert a.shape == r.shape, name
+            assert np.max(np.abs(a - r)) <= 1e-9 * max(np.max(np.abs(r)), 1e-300), name
+    for f in ("vm", "vm_ave", "gjopen", "Emx", "Emy", "Jn"):
+        a, r = np.asarray(getattr(new_sim, f)), np.asarray(getattr(ref_sim, f))
+        assert np.max(np.abs(a - r)) <= 1e-9 * max(np.max(np.abs(r)), 1e-300), f

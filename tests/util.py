@@ -6,8 +6,10 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-GOLDEN = sorted(os.path.splitext(os.path.basename(f))[0]
-                for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+_ALL = sorted(os.path.splitext(os.path.basename(f))[0]
+              for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+GOLDEN = [n for n in _ALL if not n.startswith("fast_")]           # recordings of the full solver's loop
+GOLDEN_FAST = [n for n in _ALL if n.startswith("fast_")]         # ... of the fast (equivalent-circuit) solver's
 
 # Persistent state: the parity bar of BASELINE.json (1e-10 relative per step).
 STATE = ["cc_cells", "cc_at_mem", "cc_env", "vm", "gjopen", "rho_cells", "vm_ave"]
