@@ -1703,7 +1703,7 @@ extern "C" int betse_set_channels(betse_ctx* ctx, int n, const betse_channel* ch
         for (int q = 0; q < 4; ++q) {
             if (c.kind[q] < 0 || c.kind[q] > 2) return fail(ctx, "channel quantity kind must be 0, 1 or 2");
             d.kind[q] = c.kind[q];
-            if (c.a[q].type < 0 || c.a[q].type > 7 || c.b[q].type < 0 || c.b[q].type > 7) return fail(ctx, "unknown gate term type");
+            if (c.a[q].type < 0 || c.a[q].type > 9 || c.b[q].type < 0 || c.b[q].type > 9) return fail(ctx, "unknown gate term type");
             d.a[q].type = c.a[q].type; d.b[q].type = c.b[q].type;
             for (int j = 0; j < 4; ++j) { d.a[q].p[j] = c.a[q].p[j]; d.b[q].p[j] = c.b[q].p[j]; }
         }
