@@ -351,6 +351,9 @@ __device__ __forceinline__ void k_cell_body(const KParams& P, const KArrays& A, 
     if (flags) atomicOr(A.status, flags);
 }
 
+// (more resident warps at fewer registers were measured and lost: 255 registers / 8 warps per SM 0.258 ms, 200 / 10 warps
+// 0.278 ms, 184 / 11 warps 0.305 ms, 168 / 12 warps 0.31 ms — the spills cost more than the occupancy buys;
+// profiles/r02j_sweep_kcell_regs.txt)
 // REGS = 0: all 255 registers (two CTAs fill the register file); REGS = 1: capped at 208, which leaves 12288 registers per
 // SM — one 256-thread CTA of the env kernels (k_ion, k_envacc_ell: <= 48 registers) runs next to the two k_cell CTAs
 template <int NI, int MINB>
