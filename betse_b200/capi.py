@@ -204,7 +204,7 @@ def load(build_if_missing=True):
             raise BetseB200Error("libbetse_b200.so not built; run `python -m betse_b200.build`")
         from . import build as _build
         _build.build()
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(os.environ.get("BETSE_B200_LIB") or LIB_PATH)      # (the override is for A/B timing of two builds on one box)
     vp = C.c_void_p
     lib.betse_abi_version.restype = C.c_int
     lib.betse_device_count.restype = C.c_int

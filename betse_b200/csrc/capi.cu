@@ -43,14 +43,14 @@ void launch_pack_const(const KParams& P, const KArrays& A, cudaStream_t st);
 void launch_pack_dm(const KParams& P, const KArrays& A, cudaStream_t st);
 // kcell.cu: the lane-per-cell membrane kernel, its cell pack and the env accumulation that reads its fluxes
 bool kcell_enabled();
-void launch_pack_cell_const(const KParams& P, const KArrays& A, int* mem_ell, cudaStream_t st);
+void launch_pack_cell_const(const KParams& P, const KArrays& A, int* mem_ell, const int* mem_bidx, cudaStream_t st);
+bool kcell_patch_fits(int ni, int kb_max);
 void launch_pack_cell_dm(const KParams& P, const KArrays& A, cudaStream_t st);
 size_t cell_pack_row_bytes(int ni);
-cudaError_t prepare_cell(int ni, int kb_min);
-bool kcell_pipe_fits(int ni, int kb_min);
+cudaError_t prepare_cell(int ni, int kb_max, int ptab_max);
 void launch_slot_off(const int* slot_idx, const int* mem_ell, int* slot_off, int n, int Mo, int ni, cudaStream_t st);
 void launch_gather_int(int* dst, const int* src, const int* idx, int n, cudaStream_t st);
-void launch_envacc_ell(int ni, const KParams& P, const KArrays& A, int nxt, int deps, cudaStream_t st);
+void launch_envacc_ell(int ni, const KParams& P, const KArrays& A, int nxt, cudaStream_t st);
 void launch_envacc_ell_x(int ni, const KParams& P, const KArrays& A, const XPlan& X, int nxt, cudaStream_t st);
 void envacc_end_ctas(const KParams& P, int lo, int hi, int* n_lower, int* n_upper);
 void launch_cell_x(int ni, const KParams& P, const KArrays& A, const XPlan& X, int cur, cudaStream_t st);
@@ -90,10 +90,7 @@ struct betse_ctx {
     int C = 0, Co = 0, M = 0, Mo = 0, E = 0, ny = 0, nx = 0, I = 0, n_ctas = 0, n_tiles = 0, n_slots = 0;
     bool diag_valid = false;
     int* mem_ell = nullptr;                  // [Mo] position of every membrane's fluxes in flux_ell (cell pack of k_cell)
-    int* kc_sync = nullptr;                  // k_cell, register build: [ticket | completion counters per group of blocks], zeroed before every launch
-    int kc_sync_n = 0;
-    bool env_deps = false;                   // env_dep is built: k_envacc_ell may run next to k_cell (undivided tissues)
-    int env_by_consumer = 0;                 // this step's env accumulation was launched next to k_cell (phase 1 skips it)
+    int* kc_sync = nullptr;                  // k_cell: the ticket counter, zeroed before every launch
     int flux_is_ell = 0;                     // layout the last membrane kernel wrote its membrane -> env fluxes in
     // exchange window (every buffer a neighbouring rank writes) and the halo-exchange plan
     char* win = nullptr;
@@ -530,9 +527,109 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
             if (k >= 0 && k < E) csr_idx[fillp[k]++] = m;
         }
     };
+    // ---- patches of k_cell_patch (kcell.cu): undivided tissues with extracellular spaces.  Cells sorted into stripes of
+    //      PATCH_TY env rows and along x inside a stripe, cut into chunks of 128 = compact rectangles of cells whatever
+    //      the cell numbering; an env square all of whose membranes lie in one patch is OWNED by it and finished there
+    struct PatchPlan {
+        bool on = false;
+        int n_patches = 0, kb_max = 0, kb_min = INT_MAX, tab_max = 0;
+        std::vector<int> pcell, row0, ptab_ptr, ptab, slot_ptrp, out_sq;
+        std::vector<int> bidx;                 // compact border slot per membrane, -1 = its env square is owned by a patch
+        int n_border = 0;
+        std::string err;
+    } pp;
+    const bool want_patches = own_csr && hp->is_ecm && hp->n_ions <= 7 && Co == C && E < (1 << 28) && kcell_enabled();
+    auto job_patch = [&] {
+        if (!want_patches) return;
+        const int* cmp = mesh->cell_mem_ptr;
+        const int nx = ctx->nx, ny = ctx->ny;
+        int nm_max = 0;
+        for (int c = 0; c < Co; ++c) nm_max = std::max(nm_max, cmp[c + 1] - cmp[c]);
+        if (!kcell_patch_fits(I, nm_max)) return;
+        constexpr int PATCH_TY = 8;
+        const int n_str = (ny + PATCH_TY - 1) / PATCH_TY;
+        // counting sort of the cells by (stripe, x) of the env square of their first membrane
+        std::vector<int> cq(Co), cnt((size_t)n_str * nx + 1, 0), order(Co);
+        for (int c = 0; c < Co; ++c) {
+            const int q = (cmp[c + 1] > cmp[c]) ? mesh->map_mem2ecm[cmp[c]] : 0;
+            if (q < 0 || q >= E) { pp.err = "map_mem2ecm out of range"; return; }
+            cq[c] = q;
+            cnt[(size_t)((q / nx) / PATCH_TY) * nx + (q % nx) + 1]++;
+        }
+        for (size_t b = 1; b < cnt.size(); ++b) cnt[b] += cnt[b - 1];
+        for (int c = 0; c < Co; ++c) { const int q = cq[c]; order[cnt[(size_t)((q / nx) / PATCH_TY) * nx + (q % nx)]++] = c; }
+        const int np = (Co + 127) / 128;
+        pp.n_patches = np;
+        pp.pcell.assign((size_t)np * 128, -1);
+        std::vector<int> patch_of(Co), pos_of(Co);
+        for (int p = 0; p < np; ++p) {
+            const int a = p * 128, b = std::min(Co, a + 128);
+            // inside a patch: row by row, so that the lanes of a warp are neighbours along x (coalesced cell state)
+            std::sort(order.begin() + a, order.begin() + b, [&](int u, int v) { return cq[u] != cq[v] ? cq[u] < cq[v] : u < v; });
+            for (int j = a; j < b; ++j) { pp.pcell[j] = order[j]; patch_of[order[j]] = p; pos_of[order[j]] = j - a; }
+        }
+        const int nb = np * 4;
+        pp.row0.assign(2 * ((size_t)nb + 1), 0);
+        for (int b = 0; b < nb; ++b) {
+            int kb = 0;
+            for (int l = 0; l < 32; ++l) { const int c = pp.pcell[(size_t)b * 32 + l]; if (c >= 0) kb = std::max(kb, cmp[c + 1] - cmp[c]); }
+            pp.row0[2 * (b + 1)] = pp.row0[2 * b] + kb;
+            pp.kb_max = std::max(pp.kb_max, kb);
+            if (kb > 0) pp.kb_min = std::min(pp.kb_min, kb);
+        }
+        // owner of every env square: the patch that holds ALL its membranes, or -1
+        std::vector<int> owner(E, -1), n_own(np + 1, 0);
+        for (int q = 0; q < E; ++q) {
+            const int s0 = csr_ptr[q], s1 = csr_ptr[q + 1];
+            if (s1 == s0) continue;
+            const int p0 = patch_of[mesh->mem_to_cells[csr_idx[s0]]];
+            bool same = true;
+            for (int j = s0 + 1; j < s1 && same; ++j) same = patch_of[mesh->mem_to_cells[csr_idx[j]]] == p0;
+            if (same) { owner[q] = p0; n_own[p0 + 1]++; }
+        }
+        // border slots in pack order (patch, cell, membrane): a warp's border stores stay close together
+        pp.bidx.assign(Mo, -1);
+        for (size_t j = 0; j < pp.pcell.size(); ++j) {
+            const int c = pp.pcell[j];
+            if (c < 0) continue;
+            for (int m = cmp[c]; m < cmp[c + 1]; ++m) if (owner[mesh->map_mem2ecm[m]] < 0) pp.bidx[m] = pp.n_border++;
+        }
+        pp.slot_ptrp.assign(csr_ptr.begin(), csr_ptr.end());
+        for (int q = 0; q < E; ++q) if (owner[q] < 0) pp.out_sq.push_back(q);
+        for (int q = 0; q < E; ++q) if (owner[q] >= 0) pp.slot_ptrp[q] = (int)((unsigned)pp.slot_ptrp[q] | 0x80000000u);
+        for (int p = 0; p < np; ++p) n_own[p + 1] += n_own[p];
+        std::vector<int> own_sq(n_own[np]), fill(n_own.begin(), n_own.end() - 1);
+        for (int q = 0; q < E; ++q) if (owner[q] >= 0) own_sq[fill[owner[q]]++] = q;
+        // tables: [n, q[n], (first slot | count << 16)[n], slots as u16 ...] per patch
+        pp.ptab_ptr.assign((size_t)np + 1, 0);
+        pp.ptab.reserve((size_t)n_own[np] * 2 + (size_t)Mo / 2 + np * 2);
+        std::vector<unsigned short> sl;
+        for (int p = 0; p < np; ++p) {
+            pp.ptab_ptr[p] = (int)pp.ptab.size();
+            const int n = n_own[p + 1] - n_own[p];
+            pp.ptab.push_back(n);
+            for (int t = 0; t < n; ++t) pp.ptab.push_back(own_sq[n_own[p] + t]);
+            sl.clear();
+            for (int t = 0; t < n; ++t) {
+                const int q = own_sq[n_own[p] + t];
+                const int s0 = csr_ptr[q], s1 = csr_ptr[q + 1];
+                if (sl.size() > 65535 || s1 - s0 > 65535) { pp.err = "patch table overflow"; return; }
+                pp.ptab.push_back((int)((unsigned)sl.size() | ((unsigned)(s1 - s0) << 16)));
+                for (int j = s0; j < s1; ++j) {
+                    const int m = csr_idx[j], c = mesh->mem_to_cells[m], pos = pos_of[c];
+                    sl.push_back((unsigned short)((((pos >> 5) * pp.kb_max + (m - cmp[c])) * I) * 32 + (pos & 31)));
+                }
+            }
+            if (sl.size() & 1) sl.push_back(0);
+            for (size_t j = 0; j < sl.size(); j += 2) pp.ptab.push_back((int)((unsigned)sl[j] | ((unsigned)sl[j + 1] << 16)));
+        }
+        pp.ptab_ptr[np] = (int)pp.ptab.size();
+        for (int p = 0; p < np; ++p) pp.tab_max = std::max(pp.tab_max, pp.ptab_ptr[p + 1] - pp.ptab_ptr[p]);
+        pp.on = pp.tab_max <= 2048;
+    };
     std::thread th_nnc, th_pack, th_csr;
-    if (par) { th_nnc = std::thread(job_nnc); th_pack = std::thread(job_pack); th_csr = std::thread(job_csr); }
-    else { job_nnc(); job_pack(); job_csr(); }
+    if (par) { th_nnc = std::thread(job_nnc); th_pack = std::thread(job_pack); th_csr = std::thread([&] { job_csr(); job_patch(); }); }
+    else { job_nnc(); job_pack(); job_csr(); job_patch(); }
     struct Joiner { std::thread &a, &b, &c; ~Joiner() { if (a.joinable()) a.join(); if (b.joinable()) b.join(); if (c.joinable()) c.join(); } } joiner{th_nnc, th_pack, th_csr};
     T.mark("streams, params");
     // ---- index arrays and geometry: raw uploads
@@ -578,25 +675,30 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
     T.mark("env slot CSR");
     T.mark("derived index arrays");
     // ---- cell pack (k_cell): SELL-32 rows of the per-membrane constants, built on the device like the tile pack
+    if (th_csr.joinable()) th_csr.join();
+    if (!pp.err.empty()) return fail(ctx, pp.err);
     if (hp->n_ions <= 7 && hp->is_ecm) {
-        const int nb = (Co + 31) / 32;
-        std::vector<int> row0(2 * (nb + 1), 0);          // int2 {first row, first membrane} per block
-        for (int b = 0; b < nb; ++b) {
-            int kb = 0;
-            const int c1 = std::min(Co, (b + 1) * 32);
-            for (int c = b * 32; c < c1; ++c) kb = std::max(kb, mesh->cell_mem_ptr[c + 1] - mesh->cell_mem_ptr[c]);
-            row0[2 * (b + 1)] = row0[2 * b] + kb;
-            row0[2 * b + 1] = mesh->cell_mem_ptr[b * 32];
+        std::vector<int> row0;                           // int2 {first row, first membrane} per block
+        int nb, kb_max = 0, kb_min = INT_MAX;
+        if (pp.on) {
+            // blocks composed from the patches' spatial order (their "first membrane" is not used)
+            nb = pp.n_patches * 4; row0.swap(pp.row0); kb_max = pp.kb_max; kb_min = pp.kb_min;
+        } else {
+            nb = (Co + 31) / 32;
+            row0.assign(2 * ((size_t)nb + 1), 0);
+            for (int b = 0; b < nb; ++b) {
+                int kb = 0;
+                const int c1 = std::min(Co, (b + 1) * 32);
+                for (int c = b * 32; c < c1; ++c) kb = std::max(kb, mesh->cell_mem_ptr[c + 1] - mesh->cell_mem_ptr[c]);
+                row0[2 * (b + 1)] = row0[2 * b] + kb;
+                row0[2 * b + 1] = mesh->cell_mem_ptr[b * 32];
+                kb_max = std::max(kb_max, kb); kb_min = std::min(kb_min, kb);
+            }
+            row0[2 * nb + 1] = Mo;
         }
-        row0[2 * nb + 1] = Mo;
         const long long R32 = (long long)row0[2 * nb] * 32;
-        int kb_max = 0, kb_min = INT_MAX;
-        for (int b = 0; b < nb; ++b) {
-            kb_max = std::max(kb_max, row0[2 * (b + 1)] - row0[2 * b]);
-            kb_min = std::min(kb_min, row0[2 * (b + 1)] - row0[2 * b]);
-        }
-        // 32-bit flux positions and 29-bit env squares (the rows' flag bits); otherwise k_mem stays in charge
-        if (R32 * hp->n_ions < (1LL << 31) - 64 && E < (1 << 29) && nb > 0) {
+        // 32-bit flux positions and 28-bit env squares (the rows' flag bits); otherwise k_mem stays in charge
+        if (R32 * hp->n_ions < (1LL << 31) - 64 && E < (1 << 28) && nb > 0) {
             P.n_blocks = nb; P.ell_rows = row0[2 * nb]; P.kb_max = kb_max; P.kb_min = kb_min;
             { const char* e = getenv("BETSE_KCELL_PF"); P.pf_dist = e ? atoi(e) : 1024; }
             { const char* e = getenv("BETSE_KCELL_PERSIST"); P.kc_persist = e ? atoi(e) : 1; }
@@ -606,37 +708,27 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
             if ((r = dev_alloc(ctx, &ctx->mem_ell, (size_t)Mo))) return r;
             const int n_sl = mesh->ecm_slot_ptr ? mesh->ecm_slot_ptr[E] : Mo;
             if ((r = dev_alloc(ctx, (int**)&A.slot_off, (size_t)n_sl))) return r;
-            if (!kcell_pipe_fits(I, kb_min)) {
-                const int n_grp = (nb + KC_GRP - 1) / KC_GRP;
-                if ((r = dev_alloc(ctx, &ctx->kc_sync, (size_t)n_grp + 1))) return r;
-                A.ticket = ctx->kc_sync;
-                ctx->kc_sync_n = 1;
-                // env accumulation next to k_cell (undivided tissues): CTA v of k_envacc_ell = squares [256 v, 256 v + 256)
-                // waits for the groups of cell blocks [first, last] that feed them
-                const char* ed = getenv("BETSE_ENVDEPS");
-                // (measured, profiles/r02f_sweep.txt: 0.49 ms/step against 0.42 — with one 256-thread CTA per SM next to k_cell
-                //  the accumulation is latency-bound and becomes the critical path; opt-in with BETSE_ENVDEPS=1)
-                if (ctx->Co == ctx->C && !mesh->ecm_slot_ptr && ed && ed[0] == '1') {
-                    const int nv = (E + 255) / 256;
-                    std::vector<int> dep(2 * (size_t)nv);
-                    for (int v = 0; v < nv; ++v) { dep[2 * v] = INT_MAX; dep[2 * v + 1] = -1; }
-                    for (int m = 0; m < Mo; ++m) {
-                        const int v = mesh->map_mem2ecm[m] / 256, g = mesh->mem_to_cells[m] / 32 / KC_GRP;
-                        dep[2 * v] = std::min(dep[2 * v], g); dep[2 * v + 1] = std::max(dep[2 * v + 1], g);
-                    }
-                    for (int v = 0; v < nv; ++v) if (dep[2 * v + 1] < 0) { dep[2 * v] = 1; dep[2 * v + 1] = 0; }   // nothing to wait for
-                    if ((r = dev_upload(ctx, (int**)&A.env_dep, dep.data(), dep.size()))) return r;
-                    A.cell_done = ctx->kc_sync + 1;
-                    ctx->kc_sync_n = n_grp + 1;
-                    ctx->env_deps = true;
-                }
+            if ((r = dev_alloc(ctx, &ctx->kc_sync, (size_t)1))) return r;
+            A.ticket = ctx->kc_sync;
+            int* d_bidx = nullptr;
+            if (pp.on) {
+                P.n_patches = pp.n_patches; P.n_out_sq = (int)pp.out_sq.size(); P.ptab_max = pp.tab_max;
+                { std::vector<int> lst(pp.out_sq); if (lst.empty()) lst.push_back(0); if ((r = dev_upload(ctx, (int**)&A.out_sq, lst.data(), lst.size()))) return r; }
+                if ((r = dev_upload(ctx, (int**)&A.pcell, pp.pcell.data(), pp.pcell.size()))) return r;
+                if ((r = dev_upload(ctx, (int**)&A.ptab_ptr, pp.ptab_ptr.data(), pp.ptab_ptr.size()))) return r;
+                if ((r = dev_upload(ctx, (int**)&A.ptab, pp.ptab.data(), pp.ptab.size()))) return r;
+                if ((r = dev_upload(ctx, (int**)&A.slot_ptrp, pp.slot_ptrp.data(), pp.slot_ptrp.size()))) return r;
+                if ((r = dev_alloc(ctx, &A.sq_sum, (size_t)I * E))) return r;
+                if ((r = dev_upload(ctx, &d_bidx, pp.bidx.data(), pp.bidx.size()))) return r;
+                if ((r = dev_alloc(ctx, (int**)&A.bslot, (size_t)R32))) return r;
+                if ((size_t)pp.n_border * 8 > (size_t)ctx->n_slots * I) return fail(ctx, "internal: border slots exceed the exchange-slot buffer");
             }
-            launch_pack_cell_const(ctx->P, A, ctx->mem_ell, ctx->stream);
+            launch_pack_cell_const(ctx->P, A, ctx->mem_ell, d_bidx, ctx->stream);
             launch_slot_off(A.slot_idx, ctx->mem_ell, const_cast<int*>(A.slot_off), n_sl, Mo, I, ctx->stream);
             CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(ctx->stream));           // the plan's host vectors die with this scope
         }
     }
-
     T.mark("cell pack");
     // ---- tile pack (k_mem_pipe): every tile's constant inputs as one fixed-size block, built on the device; the DmS
     //      rows are (re)built whenever Dm_cells or the schedule scalars are uploaded (launch_pack_dm)
@@ -723,7 +815,7 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
     }
     T.mark("state allocations");
     CK(prepare_kernels(I));
-    CK(prepare_cell(I, ctx->P.kb_min));
+    CK(prepare_cell(I, ctx->P.kb_max, ctx->P.ptab_max));
     T.mark("prepare kernels");
     CK(cudaStreamSynchronize(ctx->stream));
     T.mark("stream sync");
@@ -1053,11 +1145,7 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
         // stream NEXT TO the membrane kernel (which is latency-bound and leaves issue slots free).
         const bool chans = !ctx->chans.empty() || ctx->net_on[0] || ctx->net_on[1] || ctx->noise_on;   // deferred-update mode
         const bool overlap = ecm && ctx->overlap && !evs && ctx->hp.sharpness >= 1.0 && !chans;
-        // the env accumulation runs NEXT TO k_cell (second stream, behind the other ions' transport) and consumes the fluxes
-        // of a cell block as soon as its neighbours have finished too
-        const bool consumer = overlap && ctx->env_deps && ctx->X.n_nbr == 0 && mem_kernel_kind(I, ctx->P, A, diag) == 2;
-        ctx->env_by_consumer = consumer ? 1 : 0;
-        if (ctx->kc_sync && mem_kernel_kind(I, ctx->P, A, diag) == 2) cudaMemsetAsync(ctx->kc_sync, 0, (size_t)ctx->kc_sync_n * sizeof(int), st);
+        if (ctx->kc_sync && mem_kernel_kind(I, ctx->P, A, diag) == 2) cudaMemsetAsync(ctx->kc_sync, 0, sizeof(int), st);
         if (ecm && overlap) {
             const int iCa = ctx->hp.iCa;
             if (iCa >= 0) launch_ion(ctx->P, A, ctx->nx, cur, diag, iCa, 1, st);
@@ -1085,10 +1173,6 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
         if (evs) cudaEventRecord(evs[2], st);
         if (ctx->xfuse_now) { launch_cell_x(I, ctx->P, A, ctx->X, cur, st); ctx->flux_is_ell = 1; }
         else ctx->flux_is_ell = launch_mem(I, ctx->P, A, ctx->n_ctas, cur, diag, st);
-        if (consumer) {
-            launch_envacc_ell(I, ctx->P, A, nxt, 1, ctx->stream2);
-            cudaEventRecord(ctx->ev_join, ctx->stream2);
-        }
         if (overlap) cudaStreamWaitEvent(st, ctx->ev_join, 0);
         if (chans) {
             // between the ion loop's fluxes and update_all_concs (sim.py:1290-1357), per handler: run_loop_channels
@@ -1151,12 +1235,11 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
         }
         if (evs) cudaEventRecord(evs[3], st);
     } else if (phase == 1) {
-        if (ecm && ctx->env_by_consumer) { /* launched next to k_cell */ }
-        else if (ecm && ctx->flux_is_ell) {
+        if (ecm && ctx->flux_is_ell) {
             KParams Pw = ctx->P;
             Pw.xwait = ctx->xwait_now;
             if (ctx->xfuse_now) launch_envacc_ell_x(I, Pw, A, ctx->X, nxt, st);
-            else launch_envacc_ell(I, Pw, A, nxt, 0, st);
+            else launch_envacc_ell(I, Pw, A, nxt, st);
         }
         else if (ecm) launch_envacc(I, ctx->P, A, ctx->E, nxt, 1, st);
         else launch_envmix(I, ctx->P, A, cur, st);

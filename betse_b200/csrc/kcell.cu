@@ -7,26 +7,31 @@
 //     equilibrium constant and every pump factor that depends on the cell's concentrations are formed ONCE per cell;
 //   * a lane walks its cell's membranes k = 0..nm-1, so the membranes->cell sums (update_Co, sim_toolbox.py:1177)
 //     are plain register accumulations in membrane order — no shared memory staging of fluxes, no shuffles;
-//   * per-membrane constants live in a sliced-ELL "cell pack" (SELL-32: block b = cells 32b..32b+31, row k of the
-//     block holds membrane k of each of its cells; a row is DmS[I][32], mem_sa[32], partner[32], env square[32]), so
-//     lane = cell reads them coalesced, and because neighbouring cells have neighbouring partners and env squares,
-//     the gathers of one row touch two or three lines instead of 32.
+//   * per-membrane constants live in a sliced-ELL "cell pack" (SELL-32: a block is 32 cells, row k of the block holds
+//     membrane k of each of its cells; a row is DmS[I][32], mem_sa[32], partner[32], env square[32]), so lane = cell
+//     reads them coalesced, and because neighbouring cells have neighbouring partners and env squares, the gathers of
+//     one row touch two or three lines instead of 32;
+//   * persistent warps draw blocks in order; the gathers of membrane k+1 load into a second register buffer while
+//     membrane k is computed, and a block pulls the streams of the block pf_dist tickets ahead into L2 with bulk prefetches.
 //
-// Two builds:
-//   * k_cell_pipe (default): the rows of the pack are ONE stream; every warp owns a contiguous range of blocks, i.e. a
-//     contiguous range of rows, and runs a three-stage software pipeline over it with cp.async (LDGSTS) into per-warp
-//     shared-memory rings — the row's index pair four rows ahead, everything addressed through it (env concentrations
-//     at the membrane's square, the partner cell's concentrations and Vmem, the transported Ca) together with the
-//     row's DmS / area / gap-junction state two rows ahead, the next block's per-cell state with its first row.  Every
-//     lane copies only what it consumes itself, so cp.async.wait_group is the only synchronisation.  (The register
-//     build below spent 46 % of its stall samples on the first use of a gathered value and on the dependent loads of a
-//     block's prologue, with two warps per scheduler to hide them: profiles/r02a_*.)  Block boundaries travel with the
-//     data: bits 29/30 of a row's env-square word mark the last / first row of a block, bit 31 a lane without membrane.
-//   * k_cell (register build; meshes with a one-membrane block, ion profiles whose rings do not fit): persistent warps
-//     draw blocks in order, the gathers of membrane k+1 load into a second register buffer while membrane k is computed.
+// Three kernels over the same block routine (cell_task):
+//   * k_cell        undivided tissue, blocks = 32 consecutive cells; every membrane's membrane->env fluxes go to flux_ell
+//                   and k_envacc_ell sums them per env square afterwards;
+//   * k_cell_x      strip of a decomposed tissue: the same, with exchange point X1 inside it (xchg.cuh);
+//   * k_cell_patch  undivided tissue, the membrane->env exchange done ON CHIP: a CTA owns a PATCH of 128 cells that are
+//                   neighbours in space (KArrays.pcell: the blocks are composed from a spatial sort of the cells, not
+//                   from their numbering); its warps leave the fluxes of their membranes in shared memory, and after one
+//                   barrier the CTA's threads sum them — in the order of the global membrane index, exactly like
+//                   k_envacc_ell — for every env square ALL of whose membranes belong to the patch, into sq_sum [I][E].
+//                   Only membranes of squares that several patches share write their fluxes to flux_ell as well (bit
+//                   KC_BORDER of the row's env-square word).  k_envacc_ell then takes an owned square's sums with one
+//                   load per ion instead of walking its slots (bit 31 of slot_ptrp marks them).  The env accumulation
+//                   stays a kernel of its own because the transport of the non-Ca ions (k_ion) runs NEXT TO the membrane
+//                   kernel and must have finished before its result is advanced.  The 576 MB round trip of the exchange
+//                   slots (1/3 of the step's DRAM traffic) shrinks to the border share + 64 MB of sums.
 //
-// Reference lines as in k_mem: sim.py:1193-1283, 2086-2111, 2162-2206; sim_toolbox.py:18-182, 1155-1207;
-// channels/gap_junction.py:53-77; ion_current.py:19; sim.py:2027-2029.
+// Reference lines as in k_mem: sim.py:1193-1283, 2086-2111, 2162-2206; sim_toolbox.py:18-182, 1155-1234;
+// channels/gap_junction.py:53-77; ion_current.py:19, 75-97; sim.py:2027-2029.
 #include <stdlib.h>
 #include <algorithm>
 #include <stdint.h>
@@ -35,27 +40,13 @@
 
 #define KC_WARPS 4
 #define KC_ROWB(NI) (((NI) + 2) * 256)          // bytes of one row of the cell pack
-#define KC_INV   0x80000000u                     // env-square word: the lane has no membrane in this row
-#define KC_FIRST 0x40000000u                     //                  first row of its block
-#define KC_LAST  0x20000000u                     //                  last row of its block
-#define KC_QMASK 0x1fffffffu
-#define KC_DEPS_SMEM (116 * 1024)
+#define KC_INV    0x80000000u                    // env-square word: the lane has no membrane in this row
+#define KC_BORDER 0x10000000u                    //                  the membrane's env square is shared between patches
+#define KC_QMASK  0x0fffffffu
 
 template <int NI>
-struct MemIn { double co[NI], cnb[NI], vnb, cao; int nnp; };
+struct MemIn { double co[NI], cnb[NI], vnb, cao; int nnp, bs; };     // bs: compact border slot of the membrane (patch build), or -1
 
-__device__ __forceinline__ uint32_t kc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void kc_cp8(uint32_t dst, const void* src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void kc_cp4(uint32_t dst, const void* src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void kc_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void kc_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 // hint: pull [p, p + bytes) into L2 (one bulk prefetch, no registers held)
 __device__ __forceinline__ void l2_prefetch(const void* p, unsigned bytes)
 {
@@ -147,7 +138,7 @@ __device__ __forceinline__ double membrane_fluxes(const KParams& P, CellSide<NI>
         S.Sm[i] = __dadd_rn(S.Sm[i], fsa);
         S.Sg[i] = __dadd_rn(S.Sg[i], fg);
         fl[i * 32] = fsa;
-        if (frem) frem[i] = fsa;          // the membrane's env square belongs to a neighbouring strip: its slot there, [slot][ion]
+        if (frem) frem[i] = fsa;          // the env square belongs to a neighbouring strip / is shared between patches: [slot][ion]
     }
     return g;
 }
@@ -188,11 +179,11 @@ __device__ __forceinline__ void cell_epilogue(const KParams& P, const KArrays& A
     }
 }
 
-// ---------------------------------------------------------------------------- register build
-// one block of 32 cells: lane = cell
-template <int NI>
+// ---------------------------------------------------------------------------- one block of 32 cells: lane = cell
+// fsm: the block's part of the CTA's flux buffer in shared memory (k_cell_patch), [row][ion][32]; null: fluxes to flux_ell
+template <int NI, bool PATCH = false>
 __device__ __forceinline__ void cell_task(const KParams& P, const KArrays& A, const int cur, const int task, const int lane, unsigned int& flags,
-                                          const XPlan* X = nullptr)
+                                          const XPlan* X = nullptr, double* __restrict__ fsm = nullptr, const int pf_up = -1, const int c_next = -1)
 {
     constexpr int iCa = StdProf<NI>::iCa;
     constexpr int ROWB = KC_ROWB(NI);
@@ -201,8 +192,8 @@ __device__ __forceinline__ void cell_task(const KParams& P, const KArrays& A, co
     const int2 h0 = __ldg(reinterpret_cast<const int2*>(A.blk_row0) + task);          // {first row, first membrane}
     const int2 h1 = __ldg(reinterpret_cast<const int2*>(A.blk_row0) + task + 1);
     const int row0 = h0.x, Kb = h1.x - h0.x;
-    const int c = task * 32 + lane;
-    const bool valid = c < P.n_cells_owned;
+    const int c = PATCH ? ldgi(A.pcell + task * 32 + lane) : task * 32 + lane;        // patches: blocks are spatial neighbours
+    const bool valid = (!PATCH || c >= 0) && c < P.n_cells_owned;
     int m_beg = 0, nm = 0;
     if (valid) { m_beg = ldgi(A.cell_mem_ptr + c); nm = ldgi(A.cell_mem_ptr + c + 1) - m_beg; }
     const char* __restrict__ rows = A.cpack + (size_t)row0 * ROWB;
@@ -214,15 +205,18 @@ __device__ __forceinline__ void cell_task(const KParams& P, const KArrays& A, co
 
     // strips with fused pushes: does this block hold cells that are ghosts on a neighbour / membranes of its env squares?
     int2 bx = make_int2(-1, -1), gs = make_int2(-1, -1);
-    if (X) bx = __ldg(reinterpret_cast<const int2*>(A.blk_x) + task);
+    if (!PATCH && X) bx = __ldg(reinterpret_cast<const int2*>(A.blk_x) + task);
     // the block whose streams this task pulls into L2 (issued after the first membrane, below)
-    const int up = task + P.pf_dist;
+    const int up = PATCH ? pf_up : task + P.pf_dist;
     int2 u0 = make_int2(0, 0), u1 = make_int2(0, 0);
     if (P.pf_dist > 0 && up < P.n_blocks) {
         u0 = __ldg(reinterpret_cast<const int2*>(A.blk_row0) + up);
         u1 = __ldg(reinterpret_cast<const int2*>(A.blk_row0) + up + 1);
     }
 
+    // patch build: first membrane of the cell this lane takes in the CTA's next patch (for the prefetch of its gap junctions)
+    int mb_next = 0;
+    if (PATCH && c_next >= 0) mb_next = ldgi(A.cell_mem_ptr + c_next);
     // the index pair of membrane k is loaded two membranes ahead (ia / ib), so that the gathers through them do not
     // wait for a second round trip
     int2 ia = make_int2(0, 0), ib = make_int2(0, 0);
@@ -244,6 +238,8 @@ __device__ __forceinline__ void cell_task(const KParams& P, const KArrays& A, co
             x.vnb = vmc[cn];
             x.cao = (iCa >= 0) ? cenvCa[q] : 0.0;
             x.nnp = ix.x;
+            // patch build: the env square is shared between patches — the membrane's compact border slot, fetched with the gathers
+            if (PATCH) x.bs = ((unsigned)ix.y & KC_BORDER) ? ldgi(A.bslot + (size_t)(row0 + k) * 32 + lane) : -1;
         }
     };
 
@@ -265,7 +261,7 @@ __device__ __forceinline__ void cell_task(const KParams& P, const KArrays& A, co
         dvt = ldg(A.diviterm + c);
     }
     cell_prologue<NI>(P, S, vm_own, cc[iCa >= 0 ? iCa : 0], flags);
-    if (bx.x >= 0) gs = __ldg(reinterpret_cast<const int2*>(A.ghost_tab) + bx.x + lane);
+    if (!PATCH && bx.x >= 0) gs = __ldg(reinterpret_cast<const int2*>(A.ghost_tab) + bx.x + lane);
 
     auto compute = [&](const MemIn<NI>& x, const int k) {
         if (k < nm) {
@@ -274,9 +270,13 @@ __device__ __forceinline__ void cell_task(const KParams& P, const KArrays& A, co
 #pragma unroll
             for (int i = 0; i < NI; ++i) DmS[i] = __ldcs(r + i * 32);
             const double sa = __ldcs(r + NI * 32);
-            double* __restrict__ fl = A.flux_ell + ((size_t)(row0 + k) * NI) * 32 + lane;
+            double* __restrict__ fg = A.flux_ell + ((size_t)(row0 + k) * NI) * 32 + lane;
+            double* __restrict__ fl = PATCH ? fsm + (k * NI) * 32 + lane : fg;
             double* frem = nullptr;
-            if (bx.y >= 0) {
+            // patch build, shared env square: the fluxes also go to the membrane's compact border slot (8 doubles, [slot][ion]
+            // like a remote slot), from where k_envacc_patch sums them
+            if (PATCH && x.bs >= 0) frem = A.flux_slots + (size_t)x.bs * 8;
+            if (!PATCH && bx.y >= 0) {
                 const int rs = ldgi(A.rslot_tab + bx.y + k * 32 + lane);
                 if (rs >= 0) frem = X->nb[X->side_k[rs >> 30]].flux + (size_t)(rs & 0x3fffffff) * NI;
             }
@@ -291,10 +291,12 @@ __device__ __forceinline__ void cell_task(const KParams& P, const KArrays& A, co
         idx_load(ia, k + 2);
         compute(a, k);
         if (k == 0 && u1.x > u0.x) {
-            // streams of block `up`, one bulk prefetch per array and lane: its rows, gjopen, the cells' own state
+            // streams of block `up`, one bulk prefetch per array and lane: its rows; with blocks of consecutive cells also
+            // gjopen and the cells' own state
             const int cu = up * 32;
             const int ncu = min(32, P.n_cells_owned - cu);
             if (lane == 0) l2_prefetch(A.cpack + (size_t)u0.x * ROWB, (unsigned)(u1.x - u0.x) * ROWB);
+            else if (PATCH) { /* the cells of a patch are not consecutive: every lane pulls its next cell's state, below */ }
             else if (lane == 1) l2_prefetch(A.gjopen + u0.y, (unsigned)(u1.y - u0.y) * 8u);
             else if (lane < NI + 2) l2_prefetch(A.cc_cells + (size_t)(lane - 2) * C + cu, ncu * 8u);
             else if (lane < 2 * NI + 2) l2_prefetch(cmid + (size_t)(lane - NI - 2) * C + cu, ncu * 8u);
@@ -303,14 +305,26 @@ __device__ __forceinline__ void cell_task(const KParams& P, const KArrays& A, co
             else if (lane == 2 * NI + 4) l2_prefetch(A.diviterm + cu, ncu * 8u);
             else if (lane == 2 * NI + 5) l2_prefetch(A.cell_mem_ptr + cu, (ncu + 1) * 4u);
         }
+        if (PATCH && k == 0 && c_next >= 0) {
+            // patch build: the state of the cell this lane takes in the CTA's next patch, one line each
+#pragma unroll
+            for (int i = 0; i < NI; ++i) prefetch_l2(A.cc_cells + (size_t)i * C + c_next);
+#pragma unroll
+            for (int i = 0; i < NI; ++i) prefetch_l2(cmid + (size_t)i * C + c_next);
+            prefetch_l2(vmc + c_next);
+            prefetch_l2(A.cell_vol + c_next);
+            prefetch_l2(A.diviterm + c_next);
+            prefetch_l2(A.gjopen + mb_next);
+            prefetch_l2(A.gjopen + mb_next + 4);
+        }
         if (k + 1 < Kb) {
             gather(a, ia, k + 2);
             idx_load(ib, k + 3);
             compute(b, k + 1);
         }
     }
-    if (valid) cell_epilogue<NI>(P, A, S, cc, vol, dvt, c, nxt, flags, (bx.x >= 0) ? X : nullptr, gs);
-    if (X && (bx.x >= 0 || bx.y >= 0)) {
+    if (valid) cell_epilogue<NI>(P, A, S, cc, vol, dvt, c, nxt, flags, (!PATCH && bx.x >= 0) ? X : nullptr, gs);
+    if (!PATCH && X && (bx.x >= 0 || bx.y >= 0)) {
         // this block pushed: the last of the boundary blocks raises this rank's X1 flag on the neighbours
         __syncwarp();
         if (lane == 0) xchg_publish(*X, 0, X->n_bblocks);
@@ -318,9 +332,7 @@ __device__ __forceinline__ void cell_task(const KParams& P, const KArrays& A, co
 }
 
 // Persistent: every warp draws tickets (ticket t = block t of the cell pack, so the blocks finish as a wavefront through
-// the tissue); kc_persist = 0: one block per warp.  After a block, its group's completion counter moves (release): the
-// env accumulation kernel running NEXT TO this one (k_envacc_ell, `deps`) consumes a block's fluxes out of L2 as soon as
-// every block that feeds its env squares has finished.
+// the tissue); kc_persist = 0: one block per warp.
 template <int NI>
 __device__ __forceinline__ void k_cell_body(const KParams& P, const KArrays& A, const int cur, const XPlan* X)
 {
@@ -340,22 +352,21 @@ __device__ __forceinline__ void k_cell_body(const KParams& P, const KArrays& A, 
             if (t >= n0) t = (t < n0 + n1) ? P.n_blocks - n1 + (t - n0) : n0 + (t - n0 - n1);
         }
         cell_task<NI>(P, A, cur, t, lane, flags, X);
-        if (A.cell_done) {
-            // a RELEASE on the counter, not __threadfence(): a gpu-scope acq_rel fence makes ptxas invalidate the SM's
-            // whole L1 (CCTL.IVALL), which the other warps' gathers live on
-            __syncwarp();
-            if (lane == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(A.cell_done + t / KC_GRP) : "memory");
-        }
+        // a compiler-only fence that keeps the block index live to the end of the iteration: without it ptxas moves the next
+        // ticket's atomic and header loads up into this block's epilogue and the kernel loses 6 % (0.258 -> 0.275 ms at 1 M
+        // cells, same SASS instruction mix; A/B on one box, profiles/r02l_sweep_patch.txt)
+        __syncwarp();
+        asm volatile("" ::"r"(t) : "memory");
         if (!P.kc_persist) break;
     }
     if (flags) atomicOr(A.status, flags);
 }
 
-// (more resident warps at fewer registers were measured and lost: 255 registers / 8 warps per SM 0.258 ms, 200 / 10 warps
-// 0.278 ms, 184 / 11 warps 0.305 ms, 168 / 12 warps 0.31 ms — the spills cost more than the occupancy buys;
-// profiles/r02j_sweep_kcell_regs.txt)
-// REGS = 0: all 255 registers (two CTAs fill the register file); REGS = 1: capped at 208, which leaves 12288 registers per
-// SM — one 256-thread CTA of the env kernels (k_ion, k_envacc_ell: <= 48 registers) runs next to the two k_cell CTAs
+// (measured and lost, profiles/r02e_*, r02f_*, r02j_*: a cp.async ring pipeline over the rows of the pack — 0.378 ms against 0.269;
+// more resident warps at fewer registers — 255 registers / 8 warps per SM 0.258 ms, 200 / 10 warps 0.278, 184 / 11 warps
+// 0.305, 168 / 12 warps 0.31: the spills cost more than the occupancy buys; a 208-register build that leaves room for the
+// env kernels next to it, with the env accumulation consuming the fluxes out of L2 behind a completion counter — 0.49 ms
+// per step against 0.42: one 256-thread CTA per SM is latency-bound and becomes the critical path)
 template <int NI, int MINB>
 __global__ void __launch_bounds__(KC_WARPS * 32, MINB)
 k_cell(const __grid_constant__ KParams P, const KArrays A, const int cur) { k_cell_body<NI>(P, A, cur, nullptr); }
@@ -365,171 +376,96 @@ template <int NI>
 __global__ void __launch_bounds__(KC_WARPS * 32, 2)
 k_cell_x(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ XPlan X, const int cur) { k_cell_body<NI>(P, A, cur, &X); }
 
+// ---------------------------------------------------------------------------- membrane -> env exchange of one env square
+// update_Co env branch + div_env (sim_toolbox.py:1189-1234), env charge, raw env voltage (ion_current.py:75-97) from the
+// square's summed fluxes: shared by k_envacc_ell, k_envacc_list and the patch build, so that all three give the same bits
 template <int NI>
-__global__ void __maxnreg__(208)
-k_cell_share(const __grid_constant__ KParams P, const KArrays A, const int cur) { k_cell_body<NI>(P, A, cur, nullptr); }
+__device__ __forceinline__ double env_square_finish(const KParams& P, const KArrays& A, const int nxt, const int k, const double* cv,
+                                                    const double* acc, const bool has_mems, double* c_out)
+{
+    const int E = P.nx * P.ny;
+    double rho = 0.0;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        const double delta_env = (-acc[i]) / P.env_vol_div;                     // sim_toolbox.py:1229
+        const double c = cv[i] + delta_env * P.dt;
+        A.cc_env[nxt][(size_t)i * E + k] = c;
+        c_out[i] = c;
+        rho = fma(P.zF[i], c, rho);
+    }
+    if (A.extra_rho_env) rho += ldg(A.extra_rho_env + k);
+    A.rho_env[k] = rho;
+    const double vr = has_mems ? ((rho * P.env_vol_div) / P.memsa_mean) / P.ko_eo_er : 0.0;   // ion_current.py:93-97
+    A.v_raw[k] = vr;
+    return vr;
+}
 
-// ---------------------------------------------------------------------------- pipelined build
+// ---------------------------------------------------------------------------- patch build
+// the env squares a patch owns: its table (A.ptab at A.ptab_ptr[patch], copied to shared memory while the blocks run) =
+// [n, q[n], (first slot | count << 16)[n], slots as u16...]; a slot = position of a membrane's fluxes in the CTA's buffer
+// ((warp*kb_max + row)*NI*32 + lane), in global membrane order
 template <int NI>
-struct KcPipe {
-    static constexpr int IDX_SLOTS = 8, BULK_SLOTS = 3, CELL_SLOTS = 2, MB_SLOTS = 4;
-    static constexpr int BULK_D = 3 * NI + 4;                 // co[NI], cnb[NI], DmS[NI], vnb, cao, sa, gj: doubles per lane
-    static constexpr int CELL_D = 2 * NI + 3;                 // cin[NI], cc[NI], vm, vol, diviterm
-    static constexpr int O_IDX = 0;
-    static constexpr int O_MB = O_IDX + IDX_SLOTS * 256;      // first membrane of the lane's cell, per block in flight
-    static constexpr int O_BULK = O_MB + MB_SLOTS * 128;
-    static constexpr int O_CELL = O_BULK + BULK_SLOTS * BULK_D * 256;
-    static constexpr int WARP_B = O_CELL + CELL_SLOTS * CELL_D * 256;
-    static constexpr int CTA_B = KC_WARPS * WARP_B;
-};
+__device__ __forceinline__ void patch_env(const KParams& P, const KArrays& A, const int* __restrict__ tab, const double* __restrict__ fsm)
+{
+    const int E = P.nx * P.ny;
+    const int n_owned = tab[0];
+    const int* __restrict__ qs = tab + 1;
+    const int* __restrict__ sc = qs + n_owned;
+    const unsigned short* __restrict__ slots = reinterpret_cast<const unsigned short*>(sc + n_owned);
+    for (int t = threadIdx.x; t < n_owned; t += blockDim.x) {
+        const int q = qs[t];
+        const unsigned w = (unsigned)sc[t];
+        const int s0 = (int)(w & 0xffffu), cnt = (int)(w >> 16);
+        double acc[NI];
+#pragma unroll
+        for (int i = 0; i < NI; ++i) acc[i] = 0.0;
+        for (int j = 0; j < cnt; ++j) {
+            const int pos = slots[s0 + j];
+#pragma unroll
+            for (int i = 0; i < NI; ++i) acc[i] += fsm[pos + i * 32];
+        }
+#pragma unroll
+        for (int i = 0; i < NI; ++i) A.sq_sum[(size_t)i * E + q] = acc[i];
+    }
+}
 
+// Static schedule: CTA b takes patches b, b + grid, ... — the next patch is known, so its table is fetched and the state of
+// its cells pulled into L2 while the current one is computed.  Shared memory: two flux buffers and two table buffers; ONE
+// barrier per patch (the fluxes of all four blocks and the table are in place; the other buffers are free again because
+// every thread came through this barrier after its env phase of the patch before).
 template <int NI>
 __global__ void __launch_bounds__(KC_WARPS * 32, 2)
-k_cell_pipe(const __grid_constant__ KParams P, const KArrays A, const int cur)
+k_cell_patch(const __grid_constant__ KParams P, const KArrays A, const int cur)
 {
-    using L = KcPipe<NI>;
-    extern __shared__ __align__(128) char kc_sm[];
-    constexpr int iCa = StdProf<NI>::iCa;
-    constexpr int ROWB = KC_ROWB(NI);
+    extern __shared__ __align__(16) double kc_fsm[];          // [2][KC_WARPS][kb_max][NI][32] fluxes | [2][ptab_max] table ints
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nxt = cur ^ 1;
-    const int C = P.n_cells, E = P.ny * P.nx;
-    // this warp's blocks [b0, b1) = rows [r0, r1) of the pack
-    const long long gw = (long long)blockIdx.x * KC_WARPS + warp, W = (long long)gridDim.x * KC_WARPS;
-    const int b0 = (int)(gw * P.n_blocks / W), b1 = (int)((gw + 1) * P.n_blocks / W);
-    if (b0 >= b1) return;
-    const int r0 = ldgi(A.blk_row0 + 2 * b0), r1 = ldgi(A.blk_row0 + 2 * b1);
-    char* const base = kc_sm + (size_t)warp * L::WARP_B;
-    const uint32_t sb = kc_smem_u32(base);
-    const double* __restrict__ cmid = A.cc_mid[cur];
-    const double* __restrict__ vmc = A.vm_cell[cur];
-    const double* __restrict__ cenv = A.cc_env[cur];
-    const double* __restrict__ cenvCa = A.cc_env[nxt] + (size_t)(iCa >= 0 ? iCa : 0) * E;   // Ca after transport (sim.py:1282 after 2254)
-
-    // ---- stage 1: index pair of row r (and, with the first row of a block, the first membrane of the lane's cell)
-    int bp1 = b0 - 1, next1 = r0;                    // block of the stage-1 cursor, first row of the block after it
-    auto stage1 = [&](const int r) {
-        if (r < r1) {
-            if (r == next1) {
-                ++bp1;
-                next1 = ldgi(A.blk_row0 + 2 * (bp1 + 1));
-                const int c = bp1 * 32 + lane;
-                if (c < P.n_cells_owned) kc_cp4(sb + L::O_MB + (bp1 & (L::MB_SLOTS - 1)) * 128 + lane * 4, A.cell_mem_ptr + c);
-            }
-            const char* row = A.cpack + (size_t)r * ROWB + (NI + 1) * 256;
-            const uint32_t d = sb + L::O_IDX + (r & (L::IDX_SLOTS - 1)) * 256 + lane * 4;
-            kc_cp4(d, reinterpret_cast<const int*>(row) + lane);
-            kc_cp4(d + 128, reinterpret_cast<const int*>(row + 128) + lane);
-        }
-        kc_commit();
-    };
-    // ---- stage 2: everything of row r that is addressed through its index pair, the row's constants, the gap-junction
-    //      state; with the first row of a block the per-cell state of the block
-    int bp2 = b0 - 1, k2 = 0, mb2 = 0;
-    auto stage2 = [&](const int r) {
-        if (r < r1) {
-            const int* ix = reinterpret_cast<const int*>(base + L::O_IDX + (r & (L::IDX_SLOTS - 1)) * 256);
-            const int nnp = ix[lane];
-            const unsigned ew = (unsigned)ix[32 + lane];
-            if (ew & KC_FIRST) {
-                ++bp2; k2 = 0;
-                const int c = bp2 * 32 + lane;
-                mb2 = reinterpret_cast<const int*>(base + L::O_MB + (bp2 & (L::MB_SLOTS - 1)) * 128)[lane];
-                if (c < P.n_cells_owned) {
-                    const uint32_t d = sb + L::O_CELL + (bp2 & 1) * (L::CELL_D * 256) + lane * 8;
-#pragma unroll
-                    for (int i = 0; i < NI; ++i) kc_cp8(d + i * 256, cmid + (size_t)i * C + c);
-#pragma unroll
-                    for (int i = 0; i < NI; ++i) kc_cp8(d + (NI + i) * 256, A.cc_cells + (size_t)i * C + c);
-                    kc_cp8(d + (2 * NI) * 256, vmc + c);
-                    kc_cp8(d + (2 * NI + 1) * 256, A.cell_vol + c);
-                    kc_cp8(d + (2 * NI + 2) * 256, A.diviterm + c);
-                }
-            }
-            if (!(ew & KC_INV)) {
-                const unsigned q = ew & KC_QMASK;
-                const unsigned cn = (unsigned)nnp & 0x7fffffffu;
-                const uint32_t d = sb + L::O_BULK + (r % L::BULK_SLOTS) * (L::BULK_D * 256) + lane * 8;
-                const double* row = reinterpret_cast<const double*>(A.cpack + (size_t)r * ROWB) + lane;
-#pragma unroll
-                for (int i = 0; i < NI; ++i) kc_cp8(d + i * 256, cenv + (size_t)i * E + q);
-#pragma unroll
-                for (int i = 0; i < NI; ++i) kc_cp8(d + (NI + i) * 256, cmid + (size_t)i * C + cn);
-#pragma unroll
-                for (int i = 0; i < NI; ++i) kc_cp8(d + (2 * NI + i) * 256, row + i * 32);
-                kc_cp8(d + (3 * NI) * 256, vmc + cn);
-                if (iCa >= 0) kc_cp8(d + (3 * NI + 1) * 256, cenvCa + q);
-                kc_cp8(d + (3 * NI + 2) * 256, row + NI * 32);
-                kc_cp8(d + (3 * NI + 3) * 256, A.gjopen + mb2 + k2);
-            }
-            ++k2;
-        }
-        kc_commit();
-    };
-
-    // ---- fill the pipeline: index pairs of rows r0..r0+3, then rows r0 and r0+1 (commit groups arranged like the steady
-    //      state's: stage 1, stage 2, stage 1, stage 2)
-    stage1(r0); stage1(r0 + 1); stage1(r0 + 2); stage1(r0 + 3);
-    kc_wait<0>();
-    kc_commit();
-    stage2(r0);
-    kc_commit();
-    stage2(r0 + 1);
-
+    const int per_warp = P.kb_max * NI * 32, per_buf = KC_WARPS * per_warp;
+    int* const tab_sm = reinterpret_cast<int*>(kc_fsm + 2 * per_buf);
     unsigned int flags = 0;
-    CellSide<NI> S;
-    double vol = 1.0, dvt = 0.0;
-    int bc = b0 - 1, kc = 0, mbc = 0;
-    bool valid = false;
-#pragma unroll 1
-    for (int r = r0; r < r1; ++r) {
-        stage1(r + 4);
-        kc_wait<4>();                       // index pair of row r+2 has landed
-        stage2(r + 2);
-        kc_wait<4>();                       // row r has landed
-        const int* ix = reinterpret_cast<const int*>(base + L::O_IDX + (r & (L::IDX_SLOTS - 1)) * 256);
-        const int nnp = ix[lane];
-        const unsigned ew = (unsigned)ix[32 + lane];
-        if (ew & KC_FIRST) {
-            ++bc; kc = 0;
-            const int c = bc * 32 + lane;
-            valid = c < P.n_cells_owned;
-            mbc = reinterpret_cast<const int*>(base + L::O_MB + (bc & (L::MB_SLOTS - 1)) * 128)[lane];
-            const double* cs = reinterpret_cast<const double*>(base + L::O_CELL + (bc & 1) * (L::CELL_D * 256)) + lane;
-            double vm_own = 0.0, cCa = 0.0;
-#pragma unroll
-            for (int i = 0; i < NI; ++i) S.cin[i] = valid ? cs[i * 32] : 0.0;
-            if (valid) {
-                vm_own = cs[(2 * NI) * 32];
-                vol = cs[(2 * NI + 1) * 32];
-                dvt = cs[(2 * NI + 2) * 32];
-                cCa = cs[(NI + (iCa >= 0 ? iCa : 0)) * 32];
-            }
-            cell_prologue<NI>(P, S, vm_own, cCa, flags);
+    int buf = 0;
+    int patch = blockIdx.x;
+    int off = 0, end = 0;
+    if (patch < P.n_patches) { off = ldgi(A.ptab_ptr + patch); end = ldgi(A.ptab_ptr + patch + 1); }
+    for (; patch < P.n_patches; patch += gridDim.x, buf ^= 1) {
+        const int next = patch + gridDim.x;
+        double* fsm = kc_fsm + buf * per_buf;
+        int* tab = tab_sm + buf * P.ptab_max;
+        for (int j = threadIdx.x; j < end - off; j += blockDim.x) {
+            const uint32_t d = (uint32_t)__cvta_generic_to_shared(tab + j);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(A.ptab + off + j) : "memory");
         }
-        if (!(ew & KC_INV)) {
-            const double* bs = reinterpret_cast<const double*>(base + L::O_BULK + (r % L::BULK_SLOTS) * (L::BULK_D * 256)) + lane;
-            double co[NI], cnb[NI], DmS[NI];
-#pragma unroll
-            for (int i = 0; i < NI; ++i) { co[i] = bs[i * 32]; cnb[i] = bs[(NI + i) * 32]; DmS[i] = bs[(2 * NI + i) * 32]; }
-            const double vnb = bs[(3 * NI) * 32];
-            const double cao = (iCa >= 0) ? bs[(3 * NI + 1) * 32] : 0.0;
-            const double sa = bs[(3 * NI + 2) * 32];
-            const double g = bs[(3 * NI + 3) * 32];
-            double* __restrict__ fl = A.flux_ell + ((size_t)r * NI) * 32 + lane;
-            A.gjopen[mbc + kc] = membrane_fluxes<NI>(P, S, co, cnb, vnb, cao, nnp, DmS, sa, g, fl, flags);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        int c_next = -1;
+        if (next < P.n_patches) {
+            c_next = ldgi(A.pcell + (size_t)next * (KC_WARPS * 32) + threadIdx.x);
+            off = ldgi(A.ptab_ptr + next); end = ldgi(A.ptab_ptr + next + 1);
         }
-        ++kc;
-        if ((ew & KC_LAST) && valid) {
-            const int c = bc * 32 + lane;
-            const double* cs = reinterpret_cast<const double*>(base + L::O_CELL + (bc & 1) * (L::CELL_D * 256)) + lane;
-            double cc[NI];
-#pragma unroll
-            for (int i = 0; i < NI; ++i) cc[i] = cs[(NI + i) * 32];
-            cell_epilogue<NI>(P, A, S, cc, vol, dvt, c, nxt, flags);
-        }
+        cell_task<NI, true>(P, A, cur, patch * KC_WARPS + warp, lane, flags, nullptr, fsm + warp * per_warp,
+                      next < P.n_patches ? next * KC_WARPS + warp : P.n_blocks, c_next);
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();
+        patch_env<NI>(P, A, tab, fsm);
     }
-    kc_wait<0>();
     if (flags) atomicOr(A.status, flags);
 }
 
@@ -540,16 +476,17 @@ static int kc_env_int(const char* name, int dflt)
 }
 
 // ---------------------------------------------------------------------------- cell pack
-// constant part: membrane areas and index rows in SELL-32 order, and the flux position of every membrane
-__global__ void k_pack_cell_const(const __grid_constant__ KParams P, const KArrays A, int* __restrict__ mem_ell)
+// constant part: membrane areas and index rows in SELL-32 order, and the flux position of every membrane.
+// mem_bidx (patch build, else null): compact border slot of the membranes whose env square several patches share, else -1
+__global__ void k_pack_cell_const(const __grid_constant__ KParams P, const KArrays A, int* mem_ell, const int* __restrict__ mem_bidx)
 {
     const int task = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (task >= P.n_blocks) return;
     const int row0 = A.blk_row0[2 * task], Kb = A.blk_row0[2 * task + 2] - row0;
-    const int c = task * 32 + lane;
+    const int c = A.pcell ? A.pcell[task * 32 + lane] : task * 32 + lane;
     int m_beg = 0, nm = 0;
-    if (c < P.n_cells_owned) { m_beg = A.cell_mem_ptr[c]; nm = A.cell_mem_ptr[c + 1] - m_beg; }
+    if (c >= 0 && c < P.n_cells_owned) { m_beg = A.cell_mem_ptr[c]; nm = A.cell_mem_ptr[c + 1] - m_beg; }
     const int ni = P.n_ions;
     const size_t rowb = (size_t)(ni + 2) * 256;
     char* pack = const_cast<char*>(A.cpack);
@@ -561,10 +498,12 @@ __global__ void k_pack_cell_const(const __grid_constant__ KParams P, const KArra
         if (k < nm) {
             const int m = m_beg + k;
             sa = A.mem_sa[m]; nnp = A.nn_cell_flag[m]; esq = (unsigned)A.map_mem2ecm[m];
-            mem_ell[m] = (int)(((size_t)(row0 + k) * ni) * 32 + lane);
+            int bi = -1;
+            if (mem_bidx) bi = mem_bidx[m];
+            if (bi >= 0) { esq |= KC_BORDER; const_cast<int*>(A.bslot)[(size_t)(row0 + k) * 32 + lane] = bi; }
+            // where k_envacc_* finds the membrane's fluxes: in flux_ell (stride 32 between ions), or in its compact border slot
+            mem_ell[m] = (bi >= 0) ? -(bi * 8) - 1 : (int)(((size_t)(row0 + k) * ni) * 32 + lane);
         }
-        if (k == 0) esq |= KC_FIRST;            // block boundaries travel with the rows (k_cell_pipe)
-        if (k == Kb - 1) esq |= KC_LAST;
         reinterpret_cast<double*>(r + (size_t)ni * 256)[lane] = sa;
         reinterpret_cast<int*>(r + (size_t)(ni + 1) * 256)[lane] = nnp;
         reinterpret_cast<int*>(r + (size_t)(ni + 1) * 256 + 128)[lane] = (int)esq;
@@ -579,9 +518,9 @@ __global__ void k_pack_cell_dm(const __grid_constant__ KParams P, const KArrays 
     const int lane = threadIdx.x & 31;
     if (task >= P.n_blocks) return;
     const int row0 = A.blk_row0[2 * task], Kb = A.blk_row0[2 * task + 2] - row0;
-    const int c = task * 32 + lane;
+    const int c = A.pcell ? A.pcell[task * 32 + lane] : task * 32 + lane;
     int m_beg = 0, nm = 0;
-    if (c < P.n_cells_owned) { m_beg = A.cell_mem_ptr[c]; nm = A.cell_mem_ptr[c + 1] - m_beg; }
+    if (c >= 0 && c < P.n_cells_owned) { m_beg = A.cell_mem_ptr[c]; nm = A.cell_mem_ptr[c + 1] - m_beg; }
     const int ni = P.n_ions;
     const size_t rowb = (size_t)(ni + 2) * 256;
     char* pack = const_cast<char*>(A.cpack);
@@ -621,10 +560,10 @@ void launch_gather_int(int* dst, const int* src, const int* idx, int n, cudaStre
     if (n > 0) k_gather_int<<<(n + 255) / 256, 256, 0, st>>>(dst, src, idx, n);
 }
 
-void launch_pack_cell_const(const KParams& P, const KArrays& A, int* mem_ell, cudaStream_t st)
+void launch_pack_cell_const(const KParams& P, const KArrays& A, int* mem_ell, const int* mem_bidx, cudaStream_t st)
 {
     if (!A.cpack || P.n_blocks <= 0) return;
-    k_pack_cell_const<<<(P.n_blocks + 7) / 8, 256, 0, st>>>(P, A, mem_ell);
+    k_pack_cell_const<<<(P.n_blocks + 7) / 8, 256, 0, st>>>(P, A, mem_ell, mem_bidx);
 }
 
 void launch_pack_cell_dm(const KParams& P, const KArrays& A, cudaStream_t st)
@@ -641,16 +580,17 @@ void launch_slot_off(const int* slot_idx, const int* mem_ell, int* slot_off, int
 
 size_t cell_pack_row_bytes(int ni) { return (size_t)(ni + 2) * 256; }
 
+
 // ---------------------------------------------------------------------------- membrane -> env exchange (ELL fluxes)
 // update_Co env branch + div_env (sim_toolbox.py:1189-1234), env charge, raw env voltage (ion_current.py:75-97):
 // kernels.cu:k_envacc with the fluxes read where k_cell left them.  Same summation order (global membrane index).
-// DEPS: the kernel runs NEXT TO k_cell (second stream): CTA b first waits until every group of cell blocks that feeds its
-// squares has finished (env_dep[b] = {first, last} group; CTAs are dispatched in order and the cell blocks finish in order,
-// so a CTA hardly waits and the fluxes it reads were written microseconds ago — they come out of L2, not DRAM).
 // XP (decomposed tissue, xchg.cuh): exchange point X2 inside the kernel — the CTAs at the two ends of the owned rows run
 // first (blockIdx is permuted), store their rows of cc_env and of the raw env voltage straight into the neighbours' halo
 // rows as well, and the last of them raises this rank's X2 flag there.
-template <int NI, bool DEPS, bool XP>
+// PATCH (after k_cell_patch): CTAs [0, n_dense) take the squares a patch owns (bit 31 of slot_ptrp[k]; their fluxes are
+// already summed in sq_sum: one load per ion), the CTAs behind them the squares of A.out_sq — those several patches share
+// and those without membranes — as a dense list, so that no warp mixes the one-load path with the slot walk.
+template <int NI, bool XP, bool PATCH>
 __device__ __forceinline__ void envacc_ell_body(const KParams& P, const KArrays& A, const int nxt, const XPlan* X)
 {
     int b = blockIdx.x;
@@ -659,16 +599,33 @@ __device__ __forceinline__ void envacc_ell_body(const KParams& P, const KArrays&
         const int g = gridDim.x, n0 = X->env_n0, n1 = X->env_n1;
         if (b >= n0) b = (b < n0 + n1) ? g - n1 + (b - n0) : n0 + (b - n0 - n1);
     }
-    const int k = P.ya0 * P.nx + b * blockDim.x + threadIdx.x;
+    int k = P.ya0 * P.nx + b * blockDim.x + threadIdx.x;
+    bool in = k < P.ya1 * P.nx;
     const int E = P.nx * P.ny;
-    const bool in = k < P.ya1 * P.nx;
+    bool listed = false;
+    if (PATCH) {
+        const int n_dense = ((P.ya1 - P.ya0) * P.nx + (int)blockDim.x - 1) / (int)blockDim.x;
+        if (b >= n_dense) {
+            const int t = (b - n_dense) * blockDim.x + threadIdx.x;
+            listed = true;
+            in = t < P.n_out_sq;
+            k = in ? ldgi(A.out_sq + t) : 0;
+        }
+    }
     // everything that does not depend on the fluxes first
     int s0 = 0, s1 = 0;
     double acc[NI], cv[NI];
 #pragma unroll
     for (int i = 0; i < NI; ++i) { acc[i] = 0.0; cv[i] = 0.0; }
+    bool summed = false;
     if (in) {
-        s0 = ldgi(A.slot_ptr + k); s1 = ldgi(A.slot_ptr + k + 1);
+        if (PATCH && !listed) {
+            summed = ((unsigned)ldgi(A.slot_ptrp + k) >> 31) != 0;
+            in = summed;                                  // the dense CTAs leave the other squares to the list
+            s0 = 0; s1 = 1;
+        } else { s0 = ldgi(A.slot_ptr + k); s1 = ldgi(A.slot_ptr + k + 1); }
+    }
+    if (in) {
 #pragma unroll
         for (int i = 0; i < NI; ++i) cv[i] = A.cc_env[nxt][(size_t)i * E + k];
     }
@@ -677,61 +634,38 @@ __device__ __forceinline__ void envacc_ell_body(const KParams& P, const KArrays&
         // (field of the last step) or write (their own redundant transport of the halo rows) what this CTA is about to
         // store into their windows; the CTAs whose squares take remote flux slots are among them
         if (blockIdx.x < X->env_n0 + X->env_n1) xchg_wait_cta(P, A, 0);
-    } else if (!DEPS && P.xwait) {
+    } else if (!PATCH && P.xwait) {
         // decomposed tissue: squares near the strip edges take fluxes the neighbours pushed (exchange point X1)
         const int k0 = P.ya0 * P.nx + b * blockDim.x;
         if (k0 / P.nx < P.xw_lo || (k0 + (int)blockDim.x - 1) / P.nx >= P.xw_hi) xchg_wait_cta(P, A, 0);
     }
-    if (DEPS) {
-        if (threadIdx.x == 0) {
-            const int2 dep = __ldg(reinterpret_cast<const int2*>(A.env_dep) + blockIdx.x);
-            for (int g = dep.x; g <= dep.y; ++g) {
-                const int want = min(KC_GRP, P.n_blocks - g * KC_GRP);
-                int got;
-                do {
-                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(got) : "l"(A.cell_done + g) : "memory");
-                    if (got < want) __nanosleep(200);
-                } while (got < want);
-            }
-        }
-        __syncthreads();
-    }
     if (in) {
+        if (PATCH && summed) {
+#pragma unroll
+            for (int i = 0; i < NI; ++i) acc[i] = A.sq_sum[(size_t)i * E + k];
+        } else
         for (int j = s0; j < s1; ++j) {
             const int off = ldgi(A.slot_off + j);
             if (off >= 0) {
-                // DEPS: L2 loads (ld.cg) — the producers' stores are in L2, this SM's L1 may hold an older line
 #pragma unroll
-                for (int i = 0; i < NI; ++i) acc[i] += DEPS ? __ldcg(A.flux_ell + (size_t)off + i * 32) : A.flux_ell[(size_t)off + i * 32];
+                for (int i = 0; i < NI; ++i) acc[i] += A.flux_ell[(size_t)off + i * 32];
             } else {
                 const double* __restrict__ f = A.flux_slots + (size_t)(-(off + 1));
 #pragma unroll
                 for (int i = 0; i < NI; ++i) acc[i] += f[i];
             }
         }
-        const int y = k / P.nx, x = k - y * P.nx;
-        double rho = 0.0;
-#pragma unroll
-        for (int i = 0; i < NI; ++i) {
-            const double delta_env = (-acc[i]) / P.env_vol_div;                     // sim_toolbox.py:1229
-            const double c = cv[i] + delta_env * P.dt;
-            A.cc_env[nxt][(size_t)i * E + k] = c;
-            if (XP) {
-                for (int q = 0; q < X->n_nbr; ++q) {
-                    const XNbr& nb = X->nb[q];
-                    if (y >= nb.cc_src_row0 && y < nb.cc_src_row0 + nb.cc_rows)
-                        nb.cc_env[nxt][(size_t)i * nb.En + (size_t)(nb.cc_dst_row0 + (y - nb.cc_src_row0)) * P.nx + x] = c;
-                }
-            }
-            rho = fma(P.zF[i], c, rho);
-        }
-        if (A.extra_rho_env) rho += ldg(A.extra_rho_env + k);
-        A.rho_env[k] = rho;
-        const double vr = (s1 > s0) ? ((rho * P.env_vol_div) / P.memsa_mean) / P.ko_eo_er : 0.0;   // ion_current.py:93-97
-        A.v_raw[k] = vr;
+        double c[NI];
+        const double vr = env_square_finish<NI>(P, A, nxt, k, cv, acc, s1 > s0, c);
         if (XP) {
+            const int y = k / P.nx, x = k - y * P.nx;
             for (int q = 0; q < X->n_nbr; ++q) {
                 const XNbr& nb = X->nb[q];
+                if (y >= nb.cc_src_row0 && y < nb.cc_src_row0 + nb.cc_rows) {
+#pragma unroll
+                    for (int i = 0; i < NI; ++i)
+                        nb.cc_env[nxt][(size_t)i * nb.En + (size_t)(nb.cc_dst_row0 + (y - nb.cc_src_row0)) * P.nx + x] = c[i];
+                }
                 if (y >= nb.v_src_row0 && y < nb.v_src_row0 + nb.v_rows)
                     nb.v_raw[(size_t)(nb.v_dst_row0 + (y - nb.v_src_row0)) * P.nx + x] = vr;
             }
@@ -746,13 +680,25 @@ __device__ __forceinline__ void envacc_ell_body(const KParams& P, const KArrays&
     }
 }
 
-template <int NI, bool DEPS>
-__global__ void __launch_bounds__(256, DEPS ? 5 : 4)
-k_envacc_ell(const __grid_constant__ KParams P, const KArrays A, const int nxt) { envacc_ell_body<NI, DEPS, false>(P, A, nxt, nullptr); }
+template <int NI>
+__global__ void __launch_bounds__(256, 4)
+k_envacc_ell(const __grid_constant__ KParams P, const KArrays A, const int nxt) { envacc_ell_body<NI, false, false>(P, A, nxt, nullptr); }
 
 template <int NI>
 __global__ void __launch_bounds__(256, 4)
-k_envacc_ell_x(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ XPlan X, const int nxt) { envacc_ell_body<NI, false, true>(P, A, nxt, &X); }
+k_envacc_patch(const __grid_constant__ KParams P, const KArrays A, const int nxt) { envacc_ell_body<NI, false, true>(P, A, nxt, nullptr); }
+
+template <int NI>
+__global__ void __launch_bounds__(256, 4)
+k_envacc_ell_x(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ XPlan X, const int nxt) { envacc_ell_body<NI, true, false>(P, A, nxt, &X); }
+
+#define KC_DISPATCH_NI(ni, CALL)                  \
+    switch (ni) {                                 \
+        case 4: { constexpr int NI = 4; CALL; } break; \
+        case 5: { constexpr int NI = 5; CALL; } break; \
+        case 6: { constexpr int NI = 6; CALL; } break; \
+        default: { constexpr int NI = 7; CALL; } break; \
+    }
 
 // decomposed tissue, exchange point X2 inside the kernel
 void launch_envacc_ell_x(int ni, const KParams& P, const KArrays& A, const XPlan& X, int nxt, cudaStream_t st)
@@ -760,12 +706,7 @@ void launch_envacc_ell_x(int ni, const KParams& P, const KArrays& A, const XPlan
     const int n = (P.ya1 - P.ya0) * P.nx;
     if (n <= 0) return;
     const int g = (n + 255) / 256;
-    switch (ni) {
-        case 4: k_envacc_ell_x<4><<<g, 256, 0, st>>>(P, A, X, nxt); break;
-        case 5: k_envacc_ell_x<5><<<g, 256, 0, st>>>(P, A, X, nxt); break;
-        case 6: k_envacc_ell_x<6><<<g, 256, 0, st>>>(P, A, X, nxt); break;
-        default: k_envacc_ell_x<7><<<g, 256, 0, st>>>(P, A, X, nxt); break;
-    }
+    KC_DISPATCH_NI(ni, (k_envacc_ell_x<NI><<<g, 256, 0, st>>>(P, A, X, nxt)));
 }
 
 // number of 256-square CTAs of k_envacc_ell at the lower / upper end of the accumulation rows that cover rows [lo, hi)
@@ -781,29 +722,13 @@ void envacc_end_ctas(const KParams& P, int lo, int hi, int* n_lower, int* n_uppe
     else *n_upper = g - b_lo;                     // from the first one touching the range to the last CTA
 }
 
-// deps: run next to k_cell (the caller launches it on a second stream and has built env_dep for CTAs of 256 squares)
-void launch_envacc_ell(int ni, const KParams& P, const KArrays& A, int nxt, int deps, cudaStream_t st)
+void launch_envacc_ell(int ni, const KParams& P, const KArrays& A, int nxt, cudaStream_t st)
 {
     const int n = (P.ya1 - P.ya0) * P.nx;
     if (n <= 0) return;
     const int g = (n + 255) / 256;
-    if (deps) {
-        // KC_DEPS_SMEM of (unused) dynamic shared memory: at most ONE of these CTAs is resident per SM, so that its waiting
-        // CTAs can never keep k_cell — which they wait for — off the SMs
-        switch (ni) {
-            case 4: k_envacc_ell<4, true><<<g, 256, KC_DEPS_SMEM, st>>>(P, A, nxt); break;
-            case 5: k_envacc_ell<5, true><<<g, 256, KC_DEPS_SMEM, st>>>(P, A, nxt); break;
-            case 6: k_envacc_ell<6, true><<<g, 256, KC_DEPS_SMEM, st>>>(P, A, nxt); break;
-            default: k_envacc_ell<7, true><<<g, 256, KC_DEPS_SMEM, st>>>(P, A, nxt); break;
-        }
-        return;
-    }
-    switch (ni) {
-        case 4: k_envacc_ell<4, false><<<g, 256, 0, st>>>(P, A, nxt); break;
-        case 5: k_envacc_ell<5, false><<<g, 256, 0, st>>>(P, A, nxt); break;
-        case 6: k_envacc_ell<6, false><<<g, 256, 0, st>>>(P, A, nxt); break;
-        default: k_envacc_ell<7, false><<<g, 256, 0, st>>>(P, A, nxt); break;
-    }
+    if (P.n_patches > 0) { const int gp = g + (P.n_out_sq + 255) / 256; KC_DISPATCH_NI(ni, (k_envacc_patch<NI><<<gp, 256, 0, st>>>(P, A, nxt))); }
+    else { KC_DISPATCH_NI(ni, (k_envacc_ell<NI><<<g, 256, 0, st>>>(P, A, nxt))); }
 }
 
 // ---------------------------------------------------------------------------- launch
@@ -818,89 +743,56 @@ static int g_kc_sms = 148;
 
 void kcell_set_sms(int n) { if (n > 0) g_kc_sms = n; }
 
-// the pipelined build needs two CTAs (8 warps) per SM in 227 KB of shared memory (each CTA also costs 1 KB of system
-// use) and blocks of at least two rows (its per-cell stage is double buffered: the fetch runs two rows ahead)
-template <int NI>
-static bool pipe_fits(int kb_min)
+// dynamic shared memory of the patch build: two flux buffers of [KC_WARPS][kb_max][ni][32] doubles; two CTAs per SM
+size_t kcell_patch_smem(int ni, int kb_max, int ptab_max) { return (size_t)2 * KC_WARPS * kb_max * ni * 32 * sizeof(double) + (size_t)2 * ptab_max * sizeof(int); }
+
+bool kcell_patch_fits(int ni, int kb_max)
 {
     static int v = -1;
-    if (v < 0) v = kc_env_int("BETSE_KCELL_PIPE", 0) ? 1 : 0;    // measured slower than the register build (profiles/r02e_*): opt-in
-    return v == 1 && kb_min >= 2 && 2 * ((size_t)KcPipe<NI>::CTA_B + 1024) <= (size_t)227 * 1024;
-}
-
-bool kcell_pipe_fits(int ni, int kb_min)
-{
-    switch (ni) {
-        case 4: return pipe_fits<4>(kb_min);
-        case 5: return pipe_fits<5>(kb_min);
-        case 6: return pipe_fits<6>(kb_min);
-        case 7: return pipe_fits<7>(kb_min);
-        default: return false;
-    }
-}
-
-template <int NI>
-static cudaError_t prep_cell_t(int kb_min)
-{
-    cudaError_t e;
-    if ((e = cudaFuncSetAttribute(k_envacc_ell<NI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, KC_DEPS_SMEM))) return e;
-    if (!pipe_fits<NI>(kb_min)) return cudaSuccess;
-    if ((e = cudaFuncSetAttribute(k_cell_pipe<NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, KcPipe<NI>::CTA_B))) return e;
-    return cudaFuncSetAttribute(k_cell_pipe<NI>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    // measured (profiles/r02l_*): the on-chip exchange halves the DRAM traffic of the env accumulation (415 -> 278 MB) and cuts
+    // the membrane kernel's writes by 40 %, but the kernel is latency-bound, not bandwidth-bound: with the cells of a warp
+    // in two rows instead of one and a barrier per patch it takes 0.387 ms against 0.259 — opt-in with BETSE_PATCH=1
+    if (v < 0) v = kc_env_int("BETSE_PATCH", 0) ? 1 : 0;
+    // (a patch's table: 1 + 2 squares + slots / 2 ints, at most ~128 cells x kb_max membranes: 8 KB is ample)
+    return v == 1 && ni >= 4 && ni <= 7 && kb_max > 0 && 2 * (kcell_patch_smem(ni, kb_max, 2048) + 1024) <= (size_t)227 * 1024 &&
+           (size_t)KC_WARPS * kb_max * ni * 32 <= 65535;
 }
 
 // not capturable: once per context
-cudaError_t prepare_cell(int ni, int kb_min)
+cudaError_t prepare_cell(int ni, int kb_max, int ptab_max)
 {
-    switch (ni) {
-        case 4: return prep_cell_t<4>(kb_min);
-        case 5: return prep_cell_t<5>(kb_min);
-        case 6: return prep_cell_t<6>(kb_min);
-        case 7: return prep_cell_t<7>(kb_min);
-        default: return cudaSuccess;
-    }
+    if (ptab_max <= 0 || !kcell_patch_fits(ni, kb_max)) return cudaSuccess;
+    const int smem = (int)kcell_patch_smem(ni, kb_max, ptab_max);
+    cudaError_t e = cudaSuccess;
+    KC_DISPATCH_NI(ni, (e = cudaFuncSetAttribute(k_cell_patch<NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)));
+    if (e) return e;
+    // two CTAs' worth of shared memory and no more: the gathers live on what is left for L1
+    const int pct = (int)((2 * ((size_t)smem + 1024) * 100 + (size_t)228 * 1024 - 1) / ((size_t)228 * 1024));
+    KC_DISPATCH_NI(ni, (e = cudaFuncSetAttribute(k_cell_patch<NI>, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct)));
+    return e;
 }
 
-template <int NI>
-static void launch_cell_t(const KParams& P, const KArrays& A, int cur, cudaStream_t st)
-{
-    static int minb = -1;
-    if (minb < 0) minb = kc_env_int("BETSE_KCELL_MINB", 2);      // register build: resident CTAs (of 4 warps) per SM, 2 = 255 registers, 3 = 168
-    const int need = (P.n_blocks + KC_WARPS - 1) / KC_WARPS;
-    if (pipe_fits<NI>(P.kb_min)) {
-        const int grid = need < g_kc_sms * 2 ? need : g_kc_sms * 2;
-        k_cell_pipe<NI><<<grid, KC_WARPS * 32, KcPipe<NI>::CTA_B, st>>>(P, A, cur);
-        return;
-    }
-    static int share = -1;
-    if (share < 0) share = kc_env_int("BETSE_KCELL_SHARE", 0);   // 208-register build: the env kernels run next to it (measured: no gain, profiles/r02f_*)
-    const int mb = minb <= 2 ? 2 : 3;
-    const int grid = (!P.kc_persist || need < g_kc_sms * mb) ? need : g_kc_sms * mb;
-    if (mb == 2 && share) k_cell_share<NI><<<grid, KC_WARPS * 32, 0, st>>>(P, A, cur);
-    else if (mb == 2) k_cell<NI, 2><<<grid, KC_WARPS * 32, 0, st>>>(P, A, cur);
-    else k_cell<NI, 3><<<grid, KC_WARPS * 32, 0, st>>>(P, A, cur);
-}
-
-// decomposed tissue, exchange point X1 inside the kernel (register build, persistent)
+// decomposed tissue, exchange point X1 inside the kernel (persistent)
 void launch_cell_x(int ni, const KParams& P, const KArrays& A, const XPlan& X, int cur, cudaStream_t st)
 {
     const int need = (P.n_blocks + KC_WARPS - 1) / KC_WARPS;
     const int grid = (!P.kc_persist || need < g_kc_sms * 2) ? need : g_kc_sms * 2;
-    switch (ni) {
-        case 4: k_cell_x<4><<<grid, KC_WARPS * 32, 0, st>>>(P, A, X, cur); break;
-        case 5: k_cell_x<5><<<grid, KC_WARPS * 32, 0, st>>>(P, A, X, cur); break;
-        case 6: k_cell_x<6><<<grid, KC_WARPS * 32, 0, st>>>(P, A, X, cur); break;
-        default: k_cell_x<7><<<grid, KC_WARPS * 32, 0, st>>>(P, A, X, cur); break;
-    }
+    KC_DISPATCH_NI(ni, (k_cell_x<NI><<<grid, KC_WARPS * 32, 0, st>>>(P, A, X, cur)));
 }
 
-// register build: the caller zeroes A.ticket on the same stream before every launch
+// the caller zeroes A.ticket on the same stream before every launch
 void launch_cell(int ni, const KParams& P, const KArrays& A, int cur, cudaStream_t st)
 {
-    switch (ni) {
-        case 4: launch_cell_t<4>(P, A, cur, st); break;
-        case 5: launch_cell_t<5>(P, A, cur, st); break;
-        case 6: launch_cell_t<6>(P, A, cur, st); break;
-        default: launch_cell_t<7>(P, A, cur, st); break;
+    if (P.n_patches > 0) {
+        const int grid = P.n_patches < g_kc_sms * 2 ? P.n_patches : g_kc_sms * 2;
+        const size_t smem = kcell_patch_smem(ni, P.kb_max, P.ptab_max);
+        KC_DISPATCH_NI(ni, (k_cell_patch<NI><<<grid, KC_WARPS * 32, smem, st>>>(P, A, cur)));
+        return;
     }
+    static int minb = -1;
+    if (minb < 0) minb = kc_env_int("BETSE_KCELL_MINB", 2);      // resident CTAs (of 4 warps) per SM, 2 = 255 registers, 3 = 168
+    const int need = (P.n_blocks + KC_WARPS - 1) / KC_WARPS;
+    const int grid = (!P.kc_persist || need < g_kc_sms * minb) ? need : g_kc_sms * (minb <= 2 ? 2 : 3);
+    if (minb <= 2) { KC_DISPATCH_NI(ni, (k_cell<NI, 2><<<grid, KC_WARPS * 32, 0, st>>>(P, A, cur))); }
+    else { KC_DISPATCH_NI(ni, (k_cell<NI, 3><<<grid, KC_WARPS * 32, 0, st>>>(P, A, cur))); }
 }

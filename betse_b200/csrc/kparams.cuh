@@ -7,8 +7,6 @@
 #define BT_MAX_CTA_CELLS 96 // max cells packed into one membrane-kernel CTA
 #define BT_TILE_MAXC 8      // max cells of one warp tile (<= 32 membranes)
 
-#define KC_GRP 16           // k_cell: cell blocks per completion counter (the env accumulation next to it waits on whole groups)
-
 // Scalars (passed BY VALUE as a __grid_constant__ kernel argument: lives in the constant bank).  Derived products are formed on
 // the host in the same operand order as the reference's NumPy expressions.
 struct KParams {
@@ -44,6 +42,7 @@ struct KParams {
     int n_cells, n_cells_owned, n_mems_owned, n_ctas, n_tiles;
     int pf_tiles;                           // k_mem: L2 prefetch distance in tiles (0 = off)
     int n_blocks, ell_rows, kb_max, kb_min; // k_cell: blocks of 32 cells, rows of the cell pack, rows of its widest / narrowest block
+    int n_patches, n_out_sq, ptab_max;      // k_cell_patch: patches of 4 blocks (0 = off); env squares no patch owns; ints of the longest patch table
     int pf_dist;                            // k_cell, register build: a block pulls the streams of block + pf_dist into L2 (0 = off)
     int kc_persist;                         // k_cell, register build: persistent warps drawing tickets (1) or one block per warp (0)
     int defer;                              // k_mem stores its membrane->cell sums instead of applying them (channels)
@@ -74,12 +73,16 @@ struct KArrays {
     const int *slot_ptr, *slot_idx;
     // cell pack of k_cell (SELL-32: block b = cells 32b..32b+31; row blk_row0[b] + k holds membrane k of each cell)
     const int *blk_row0;         // [n_blocks + 1] int2 {first row, first membrane} of every block
-    int *ticket;                 // k_cell, register build: next ticket (zeroed before every launch)
-    int *cell_done;              // k_cell: finished cell blocks per group of KC_GRP (zeroed before every launch; null = not published)
+    int *ticket;                 // k_cell: next ticket (zeroed before every launch)
+    const int *pcell;            // k_cell_patch: cell of every (block, lane), -1 = none; null = block b is cells 32b..32b+31
+    const int *ptab_ptr, *ptab;  //   per patch: the env squares it owns and where their membranes' fluxes sit in shared memory (kcell.cu)
+    const int *slot_ptrp;        //   slot_ptr with bit 31 set on the env squares a patch owns: their fluxes are summed in sq_sum
+    double *sq_sum;              //   [I][E] summed membrane -> env fluxes of the owned squares
+    const int *out_sq;           //   the other squares (shared between patches, or without membranes), as a list
+    const int *bslot;            //   [rows][32] compact border slot (8 doubles each in flux_slots) of the membranes of shared squares
     const int *blk_x;            // k_cell, strips: int2 per block {row of ghost_tab or -1, offset into rslot_tab or -1}
     const int *ghost_tab;        //   int2 per (flagged block, lane): ghost index of the cell on the neighbour of side 0 / 1, or -1
     const int *rslot_tab;        //   int per (flagged block, row, lane): side << 30 | remote flux slot on that neighbour, or -1
-    const int *env_dep;          // k_envacc_ell next to k_cell: int2 {first, last} group of cell blocks that feed each CTA's 256 squares
     const char *cpack;           // [rows] x {DmS[I][32] doubles = (Dm*(-rho_channel/tm))*mem_sa, mem_sa[32] doubles,
                                  //            partner cell | boundary bit [32] ints, env square | KC_FIRST/LAST/INV bits [32] ints}
     double *flux_ell;            // [rows][I][32] membrane -> env exchange, written by k_cell
