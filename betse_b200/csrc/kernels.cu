@@ -352,8 +352,28 @@ __device__ __forceinline__ void ion_tile(const KParams& P, const KArrays& A, con
         }
         sC[ly][lx] = v;
     }
+    // interior tiles: the diffusion constant and the field at this thread's flux points are requested BEFORE the barrier, so
+    // that one memory round trip serves both phases (the kernel is latency-bound: profiles/r02k_*: 11 long-scoreboard stalls
+    // per issue)
+    constexpr int NFP = ((IT_Y + 2) * (IT_X + 2) + 255) / 256;
+    double pD[NFP], pEx[NFP], pEy[NFP];
+    if (INTERIOR) {
+#pragma unroll
+        for (int j = 0; j < NFP; ++j) {
+            const int t = tid + j * 256;
+            pD[j] = pEx[j] = pEy[j] = 0.0;
+            if (t < (IT_Y + 2) * (IT_X + 2)) {
+                const int ly = t / (IT_X + 2), lx = t - ly * (IT_X + 2);
+                const int k = (ty0 + ly - 1) * nx + (tx0 + lx - 1);
+                pD[j] = D[k]; pEx[j] = A.E_x[k]; pEy[j] = A.E_y[k];
+            }
+        }
+    }
     __syncthreads();
-    for (int t = tid; t < (IT_Y + 2) * (IT_X + 2); t += 256) {
+#pragma unroll
+    for (int j = 0; j < NFP; ++j) {
+        const int t = tid + j * 256;
+        if (t >= (IT_Y + 2) * (IT_X + 2)) break;
         const int ly = t / (IT_X + 2), lx = t - ly * (IT_X + 2);
         const int y = ty0 + ly - 1, x = tx0 + lx - 1;
         double fx = 0.0, fy = 0.0;
@@ -368,10 +388,11 @@ __device__ __forceinline__ void ion_tile(const KParams& P, const KArrays& A, con
             if (!INTERIOR && g == 0) gcy = (sC[ly + 2][lx + 1] - cc) * inv_d;
             else if (!INTERIOR && g == gny - 1) gcy = (cc - sC[ly][lx + 1]) * inv_d;
             else gcy = -(sC[ly][lx + 1] - sC[ly + 2][lx + 1]) * inv_2d;
-            const double Dk = D[k];
+            const double Dk = INTERIOR ? pD[j] : D[k];
+            const double Exk = INTERIOR ? pEx[j] : A.E_x[k], Eyk = INTERIOR ? pEy[j] : A.E_y[k];
             const double al = (Dk * zq) * P.inv_kbT_sim;       // nernst_planck_flux, sim_toolbox.py:409-411
-            fx = -Dk * gcx - (al * (-A.E_x[k])) * cc;
-            fy = -Dk * gcy - (al * (-A.E_y[k])) * cc;
+            fx = -Dk * gcx - (al * (-Exk)) * cc;
+            fy = -Dk * gcy - (al * (-Eyk)) * cc;
             if (diag && ly >= 1 && ly <= IT_Y && lx >= 1 && lx <= IT_X && y < P.yi1) {
                 A.fl_env_x[(size_t)i * E + k] = fx;
                 A.fl_env_y[(size_t)i * E + k] = fy;
@@ -382,7 +403,7 @@ __device__ __forceinline__ void ion_tile(const KParams& P, const KArrays& A, con
     __syncthreads();
     // fd.divergence(-fx, -fy) with fd.diff's edge rows (finitediff.py:1268-1311)
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < IT_Y / 8; ++h) {
         const int oy = (tid >> 5) + 8 * h, ox = tid & 31;
         const int y = ty0 + oy, x = tx0 + ox;
         if (INTERIOR || (x < nx && y < P.yi1)) {
