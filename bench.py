@@ -117,7 +117,7 @@ def namespaces(mesh, p, state, kind="INIT"):
 
 
 # ---------------------------------------------------------------------------- workloads
-def build_workload(cfg, cells=None, profile="mammal", ecm=True):
+def build_workload(cfg, cells=None, profile="mammal", ecm=True, ragged=0.0):
     """-> dict(mesh, p, state, kind of extras).  Channel gate states / network tables are attached by `attach`."""
     from betse_b200 import synth
     w = {"config": cfg, "channels": False, "network": None}
@@ -128,8 +128,9 @@ def build_workload(cfg, cells=None, profile="mammal", ecm=True):
         w["what"] = "the reference's own %d-cell cluster (Cells.make_world, seed 12345; tests/golden/mammal_noecm.npz)" % len(w["mesh"]["cell_vol"])
         return w
     n = {"c2": 10_000, "c3": 100_000, "c4": 50_000, "c5": 1_000_000}[cfg] if cells is None else int(cells)
-    mesh, p, state = synth.make_tissue(n, profile=profile, ecm=ecm, dt=1.0e-4)
+    mesh, p, state = synth.make_tissue(n, profile=profile, ecm=ecm, dt=1.0e-4, ragged=ragged)
     w["mesh"], w["p"], w["state"] = mesh, p, state
+    w["ragged"] = ragged
     if cfg == "c3":
         p["substances_affect_charge"] = 1
         w["channels"] = True
@@ -203,6 +204,7 @@ def main():
     ap.add_argument("--config", default="c5", choices=sorted(BASELINE_CONFIG))
     ap.add_argument("--cells", type=int, default=None, help="override the synthetic tissue size of c2..c5")
     ap.add_argument("--ensemble", type=int, default=0, help="replicas of a small tissue advanced by one engine (c1/c2)")
+    ap.add_argument("--ragged", type=float, default=0.0, help="fraction of gap-junction membrane pairs removed from the synthetic sheet (cells with 3-6 membranes)")
     ap.add_argument("--profile", default="mammal")
     ap.add_argument("--no-ecm", action="store_true")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -218,7 +220,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     cfg = args.config
-    w = build_workload(cfg, args.cells, args.profile, not args.no_ecm)
+    w = build_workload(cfg, args.cells, args.profile, not args.no_ecm, args.ragged)
     mesh, p, state = w["mesh"], w["p"], w["state"]
     ecm = bool(p["is_ecm"])
     I = len(p["ions"])
@@ -233,12 +235,14 @@ def main():
         "extracellular grid %dx%d" % (gny, gnx) if ecm else "no extracellular spaces",
         ", %d voltage-gated channels on every membrane (Nav1p3, Kv1p5, KLeak, Cav1p2)" % n_chan if n_chan else "",
         ", gene regulatory network of %d substances (grn_basic.yaml)" % n_subst if n_subst else "")
+    if w.get("ragged"):
+        workload += ", ragged: %.0f %% of the gap-junction membrane pairs removed (3-6 membranes per cell)" % (100 * w["ragged"])
     if B > 1:
         workload += " x %d independent replicas in one engine" % B
     b_step, b_mem, b_env = algorithmic_bytes(I, C * B, M * B, E * B, ecm, n_chan, n_subst)
     config = {"decomposition": ("%d strips of env-grid rows, halo exchange by CUDA-IPC peer stores over NVLink (no NCCL on the data path)" % world)
               if (world > 1 and cfg == "c5") else ("one replica per GPU" if world > 1 else "single domain"),
-              "workload": workload, "baseline_config": BASELINE_CONFIG[cfg] if args.cells is None else "custom",
+              "workload": workload, "baseline_config": BASELINE_CONFIG[cfg] if (args.cells is None and not args.ragged) else "custom",
               "cells": C * B, "membranes": M * B, "env_points": E * B if ecm else 0, "ions": I, "dt": float(p["dt"]),
               "l2_policy": ("state per step (~%.2f GB) is larger than the 126 MB L2" % (b_step / 1e9)) if b_step > 2.5e8 else
                            ("state per step is %.1f MB: L2-resident — a write of a 256 MB scratch buffer flushes the L2 between timed batches" % (b_step / 1e6)),

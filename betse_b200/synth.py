@@ -139,6 +139,54 @@ def make_mesh(ncx, ncy, p, disorder=0.4, seed=20241017, grid_size=None, margin_c
     }
 
 
+def drop_membrane_pairs(mesh, frac, seed=7):
+    """A RAGGED variant of the hex sheet: a random fraction of the gap-junction membrane pairs is removed, so that cells
+    keep between 3 and 6 membranes (the reference's Voronoi meshes have 3-7) — the SELL-32 cell pack then holds blocks of
+    different heights with padded lanes.  Geometry per cell (surface, volume, diviterm) follows the membranes that remain."""
+    rng = np.random.RandomState(seed)
+    M = len(mesh["mem_sa"])
+    C = len(mesh["cell_vol"])
+    m2c = np.asarray(mesh["mem_to_cells"])
+    nn = np.asarray(mesh["nn_i"])
+    me = np.arange(M)
+    rep = (nn > me)                                       # one representative per interior pair
+    drop = rep & (rng.rand(M) < frac)
+    for _ in range(2):                                    # a cell may lose at most 3 of its 6 membranes
+        both = drop | np.zeros(M, dtype=bool)
+        both[nn[drop]] = True
+        lost = np.bincount(m2c[both], minlength=C)
+        bad = lost > 3
+        drop &= ~(bad[m2c] | bad[m2c[nn]])
+    gone = drop.copy()
+    gone[nn[drop]] = True
+    keep = ~gone
+    new_index = np.cumsum(keep) - 1
+    out = dict(mesh)
+    for k in ("mem_to_cells", "map_mem2ecm", "mem_sa", "mem_nx", "mem_ny", "R_rads", "mem_vol", "gj_default_weights"):
+        out[k] = np.asarray(mesh[k])[keep]
+    out["mem_mids_flat"] = np.asarray(mesh["mem_mids_flat"])[keep]
+    out["nn_i"] = new_index[nn[keep]]
+    cnt = np.bincount(out["mem_to_cells"], minlength=C)
+    out["cell_mem_ptr"] = np.concatenate(([0], np.cumsum(cnt)))
+    out["num_mems"] = cnt.astype(float)
+    out["cell_sa"] = np.bincount(out["mem_to_cells"], weights=out["mem_sa"], minlength=C)
+    out["cell_vol"] = np.bincount(out["mem_to_cells"], weights=out["mem_vol"], minlength=C)
+    out["diviterm"] = out["cell_vol"] / out["cell_sa"]
+    Mn = len(out["mem_sa"])
+    bnd = out["nn_i"] == np.arange(Mn)
+    out["bflags_mems"] = np.nonzero(bnd)[0]
+    out["bflags_cells"] = np.unique(out["mem_to_cells"][bnd])
+    E = int(np.prod(mesh["grid_shape"]))
+    out["memSa_per_envSquare"] = np.bincount(out["map_mem2ecm"], weights=out["mem_sa"], minlength=E)
+    out["envInds_inClust"] = np.nonzero(np.bincount(out["map_mem2ecm"], minlength=E))[0]
+    starts = out["cell_mem_ptr"][:-1]
+    bc = out["bflags_cells"]
+    sel = np.concatenate([np.arange(out["cell_mem_ptr"][c], out["cell_mem_ptr"][c + 1]) for c in bc]) if len(bc) < 200000 else \
+        np.nonzero(np.isin(out["mem_to_cells"], bc))[0]
+    out["all_bound_mem_inds"] = out["map_mem2ecm"][sel]
+    return out
+
+
 def make_state(mesh, p, prof):
     """Simulator attributes after init_core + init_dynamics for a fresh INIT phase
     (sim.py:452-755, 758-1012), before the first update_V."""
@@ -195,7 +243,7 @@ def make_state(mesh, p, prof):
 
 
 def make_tissue(n_cells, profile="mammal", ecm=True, dt=1.0e-4, seed=20241017, disorder=0.4,
-                overrides=None):
+                overrides=None, ragged=0.0):
     """(mesh, params, state) for a ~n_cells-cell sheet.  ``params`` are the shipped defaults of
     the reference (betse_b200/data/profiles.json) with ``dt`` and ``is_ecm`` set."""
     prof = load_profile(profile)
@@ -208,6 +256,8 @@ def make_tissue(n_cells, profile="mammal", ecm=True, dt=1.0e-4, seed=20241017, d
     ncx = max(2, ncx)
     ncy = max(2, int(round(n_cells / ncx)))
     mesh = make_mesh(ncx, ncy, p, disorder=disorder, seed=seed)
+    if ragged > 0.0:
+        mesh = drop_membrane_pairs(mesh, ragged)
     # p.vol_env (no-ECM bath volume) follows the world size in the reference; keep the default
     state = make_state(mesh, p, prof)
     return mesh, p, state

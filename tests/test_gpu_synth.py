@@ -8,11 +8,11 @@ from tests import util
 pytestmark = pytest.mark.gpu
 
 
-def _pair(n_cells, profile="mammal", ecm=True, **over):
+def _pair(n_cells, profile="mammal", ecm=True, ragged=0.0, **over):
     from betse_b200 import synth
     from betse_b200.engine import TissueEngine
     from oracle.betse_oracle import OracleSim
-    mesh, p, st = synth.make_tissue(n_cells, profile=profile, ecm=ecm, overrides=over or None)
+    mesh, p, st = synth.make_tissue(n_cells, profile=profile, ecm=ecm, overrides=over or None, ragged=ragged)
     eng = TissueEngine(mesh, p, st)
     eng.update_V()
     ora = OracleSim(mesh, p, st)
@@ -54,6 +54,18 @@ def test_gpu_vs_oracle(n_cells, profile, ecm, steps):
         ora.step()
         assert not (st & 3)
     _compare(eng, ora, mesh, p, ecm, "step%d" % steps)
+    eng.close()
+
+
+@pytest.mark.parametrize("n_cells,steps", [(10_000, 10), (100_000, 3)])
+def test_ragged_sheet_vs_oracle(n_cells, steps):
+    """3-6 membranes per cell (synth.drop_membrane_pairs): blocks of the cell pack with different heights and padded lanes."""
+    mesh, p, eng, ora = _pair(n_cells, ragged=0.2)
+    assert sorted(set(np.diff(mesh["cell_mem_ptr"]).tolist())) == [3, 4, 5, 6]
+    for n in range(steps):
+        assert not (eng.step(1) & 3)
+        ora.step()
+    _compare(eng, ora, mesh, p, True, "ragged step%d" % steps)
     eng.close()
 
 
@@ -276,3 +288,35 @@ np.savez(sys.argv[1], **{k + "." + f: a for k, d in out.items() for f, a in d.it
     assert res["cell"].keys() == res["generic"].keys() and len(res["cell"]) == 12
     for k in res["cell"]:
         assert np.array_equal(res["cell"][k], res["generic"][k]), k
+
+
+def test_patch_kernel_equals_plain_cell_kernel_bitwise():
+    """k_cell_patch (BETSE_PATCH=1: blocks composed from a spatial sort, membrane -> env exchange on chip for the env squares
+    a patch owns) sums every env square in the order of the global membrane index like k_envacc_ell: the states must be
+    bit-identical to the plain k_cell path, on the uniform sheet and on a ragged one."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+from betse_b200 import synth
+from betse_b200.engine import TissueEngine
+out = {}
+for tag, kw in (("sheet", {}), ("ragged", {"ragged": 0.2})):
+    mesh, p, st = synth.make_tissue(30000, **kw)
+    eng = TissueEngine(mesh, p, st); eng.update_V(); eng.step(9)
+    out[tag] = eng.download(["cc_cells", "cc_at_mem", "cc_env", "vm", "gjopen", "E_env_x", "v_env"]); eng.close()
+np.savez(sys.argv[1], **{k + "." + f: a for k, d in out.items() for f, a in d.items()})
+''' % util.ROOT
+    res = {}
+    with tempfile.TemporaryDirectory() as d:
+        for tag, env in (("patch", {"BETSE_PATCH": "1"}), ("plain", {"BETSE_PATCH": "0"})):
+            fn = os.path.join(d, tag + ".npz")
+            subprocess.run([sys.executable, "-c", code, fn], check=True, env=dict(os.environ, **env))
+            with np.load(fn) as z:
+                res[tag] = {k: z[k] for k in z.files}
+    assert res["patch"].keys() == res["plain"].keys() and len(res["patch"]) == 14
+    for k in res["patch"]:
+        assert np.array_equal(res["patch"][k], res["plain"][k]), k
