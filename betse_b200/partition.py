@@ -249,6 +249,38 @@ def partition(mesh, params, state, R, bounds=None, only=None):
     return parts
 
 
+def ownership(mesh, R, bounds=None):
+    """Who owns what, for every rank, without building any rank's mesh or state (cheap: O(C + M) integer work): a list of
+    light RankPart with ``own_cells``, ``own_mems`` (global indices, ascending), the owned rows ``[a, b)`` and the window
+    ``[row_lo, row_hi)`` a rank's env downloads cover.  What a rank needs to assemble global arrays from every rank's strip
+    (simloop's N-GPU loop); consistent with :func:`partition` by construction (same rules)."""
+    ny, nx = (int(x) for x in mesh["grid_shape"])
+    ptr = np.asarray(mesh["cell_mem_ptr"], dtype=np.int64)
+    m2c = np.asarray(mesh["mem_to_cells"], dtype=np.int64)
+    m2e = np.asarray(mesh["map_mem2ecm"], dtype=np.int64)
+    crow = (np.asarray(mesh["map_cell2ecm"]).astype(np.int64) // nx) if "map_cell2ecm" in mesh else (m2e // nx)[ptr[:-1]]
+    mrow = m2e // nx
+    bounds = strip_bounds(mesh, R) if bounds is None else np.asarray(bounds, dtype=np.int64)
+    owner_c = np.searchsorted(bounds[1:], crow, side="right")
+    owner_m = owner_c[m2c]
+    env_m = np.searchsorted(bounds[1:], mrow, side="right")
+    out_m = np.nonzero(env_m != owner_m)[0]
+    a_m, b_m = bounds[owner_m[out_m]], bounds[owner_m[out_m] + 1]
+    G = int(max(0, np.max(np.maximum(a_m - mrow[out_m], mrow[out_m] - (b_m - 1))))) if len(out_m) else 0
+    H = G + V_HALO
+    counts = np.diff(ptr)
+    out = []
+    for r in range(R):
+        oc = np.nonzero(owner_c == r)[0]
+        cnt = counts[oc]
+        lp = np.concatenate(([0], np.cumsum(cnt)))
+        om = np.repeat(ptr[oc] - lp[:-1], cnt) + np.arange(lp[-1])
+        a, b = int(bounds[r]), int(bounds[r + 1])
+        out.append(RankPart(rank=r, R=R, own_cells=oc, own_mems=om, Co=len(oc), Mo=len(om), a=a, b=b,
+                            row_lo=max(0, a - H), row_hi=min(ny, b + H), nx=nx, ny=ny, cells_local=oc))
+    return out
+
+
 def gather(parts, fields_per_rank):
     """Assemble global arrays from per-rank downloads ({name: array} per rank): cell fields take
     the owned cells, membrane fields the owned membranes, env fields the owned rows."""
@@ -261,7 +293,15 @@ def gather(parts, fields_per_rank):
         a0 = np.asarray(fields_per_rank[0][name])
         lead = a0.shape[:-1]
         n_last = a0.shape[-1]
-        if n_last == P0.Mo and name not in ("cc_cells", "rho_cells", "vm_ave"):
+        from .engine import _DOWN_SHAPES          # name -> IC / IM / IE / C / M / E: sizes can coincide, names cannot
+        key = {"cc_at_mem": "IM"}.get(name, _DOWN_SHAPES.get(name, ""))[-1:]
+        if key == "M":
+            kind, n = "M", M
+        elif key == "C":
+            kind, n = "C", C
+        elif key == "E":
+            kind, n = "E", ny * nx
+        elif n_last == P0.Mo and name not in ("cc_cells", "rho_cells", "vm_ave"):
             kind, n = "M", M
         elif n_last in (P0.Co, len(P0.cells_local)):
             kind, n = "C", C

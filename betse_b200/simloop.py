@@ -354,10 +354,120 @@ def _detach(sim, eng, own_engine=False):
     eng.__dict__["_lent"] = {}
 
 
+def _dist_world():
+    """torch.distributed, if this process is one rank of an initialised multi-rank group (torchrun), else None."""
+    if os.environ.get("BETSE_STRIPS", "1") == "0":
+        return None
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist
+    except Exception:
+        pass
+    return None
+
+
+def _run_strips(sim, phase, time_steps, time_steps_sampled, anim_cells, dist, stats):
+    """The loop over N GPUs: every rank of the process group runs the reference's host code on the WHOLE
+    Simulator (events, sampling, storage — a few scalars per step) and steps ONE strip of the tissue on its GPU
+    (strips.DistributedStrips: halo exchange inside the kernels, no collective on the data path).  At a sampled step every
+    rank downloads its strip and the strips are all-gathered (plumbing: torch.distributed objects), so that every rank's
+    Simulator holds the whole sampled state and `write2storage` stores the same series everywhere.  The ion path only:
+    channels, networks, a boundary-voltage potential, polarizability, dynamic noise and the Helmholtz-Hodge diagnostics are
+    refused on a decomposed tissue (`J_env_x/y`, `B_field`, `Jtx/y` keep their loop-entry values)."""
+    from .partition import gather, ownership
+    from .strips import DistributedStrips
+    p, cells = phase.p, phase.cells
+    check_supported(sim, p)
+    if _handlers(sim, p):
+        raise BetseB200Error("betse_b200: networks / channels on a domain-decomposed tissue are not implemented")
+    if not bool(p.is_ecm):
+        raise BetseB200Error("betse_b200: domain decomposition needs extracellular spaces (run one replica per GPU instead)")
+    if anim_cells is not None:
+        raise BetseB200Error("betse_b200: mid-simulation animations are not available on a domain-decomposed tissue")
+    kind = getattr(getattr(phase, "kind", None), "name", str(getattr(phase, "kind", "")))
+    is_sim = kind.upper() == "SIM"
+    fire = getattr(getattr(phase, "dyna", None), "fire_events", None) if is_sim else None
+    if is_sim and getattr(p, "dynamic_noise", False) == 1:
+        raise BetseB200Error("betse_b200: dynamic noise on a domain-decomposed tissue is not implemented")
+    t0 = time.time()
+    _join_closing()
+    mesh, params, state = mesh_from_cells(cells), params_from_p(p), state_from_sim(sim)
+    R, rank = dist.get_world_size(), dist.get_rank()
+    ds = DistributedStrips(mesh, params, state, int(os.environ.get("LOCAL_RANK", rank)), dist)
+    own = ownership(mesh, R)
+    Unstable = _unstable_exception()
+    sampled = set(time_steps_sampled)
+    cache = {f: np.array(getattr(sim, f), copy=True) for f in _SCHEDULED if hasattr(sim, f)
+             and getattr(sim, f) is not None} if fire else {}
+    hh = ("J_env_x", "J_env_y", "B_field", "Jtx", "Jty")
+
+    def copy_back(diag):
+        fields = [f for f in (_sample_fields(True, diag) if diag else list(_SAMPLED_STATE) + _SAMPLED_ENV) if f not in hh]
+        mine = ds.download_local(fields)
+        allf = [None] * R
+        dist.all_gather_object(allf, mine)
+        got = gather(own, allf)
+        shp = (int(mesh["grid_shape"][0]), int(mesh["grid_shape"][1]))
+        for f, a in got.items():
+            if f in ("E_env_x", "E_env_y"):
+                a = a.reshape(shp)
+            setattr(sim, f, a)
+        return sum(x.nbytes for x in mine.values())
+    n, n_total, d2h = 0, len(time_steps), 0
+    try:
+        while n < n_total:
+            if fire is not None:
+                fire(phase=phase, t=time_steps[n])
+                for f in list(cache):
+                    new = np.asarray(getattr(sim, f))
+                    if new.shape != cache[f].shape or not np.array_equal(new, cache[f]):
+                        ds.set_field(f, new)
+                        cache[f] = np.array(new, copy=True)
+                run = 1
+            else:
+                run = 1
+                while n + run < n_total and time_steps[n + run - 1] not in sampled:
+                    run += 1
+            last_t = time_steps[n + run - 1]
+            is_sampled = last_t in sampled
+            status = ds.step(run, diag=is_sampled)
+            n += run
+            # an instability anywhere stops every rank (the status word is local to a strip)
+            flags = [None] * R
+            dist.all_gather_object(flags, int(status))
+            status = 0
+            for x in flags:
+                status |= x
+            if status & (capi.STATUS_NAN_VM | capi.STATUS_NAN_CONC):
+                d2h += copy_back(False)
+                raise Unstable("Your simulation has become unstable. Please try a smaller time step,"
+                               "reduce gap junction radius, and/or reduce pump rate coefficients.")
+            if is_sampled:
+                d2h += copy_back(True)
+                phase.callbacks.progressed_next()
+                sim.write2storage(last_t, cells, p)
+        if n_total and time_steps[n_total - 1] not in sampled:
+            d2h += copy_back(False)
+    finally:
+        if stats is not None:
+            stats.update({"h2d_bytes": ds.engine.h2d_bytes, "d2h_bytes": d2h, "wall_s": time.time() - t0, "steps": n,
+                          "n_gpus": R})
+        ds.close()
+
+
 def run_sim_core_loop(sim, phase, time_steps, time_steps_sampled, anim_cells=None, *,
                       engine=None, device=0, stats=None):
-    """Same signature and contract as Simulator._run_sim_core_loop (sim.py:1132-1138)."""
+    """Same signature and contract as Simulator._run_sim_core_loop (sim.py:1132-1138).  Under torchrun (an initialised
+    torch.distributed group of N > 1 ranks) the tissue is stepped as N strips, one per GPU: see _run_strips."""
     p, cells = phase.p, phase.cells
+    dist = _dist_world() if engine is None else None
+    if dist is not None:
+        ev_cut = getattr(getattr(phase, "dyna", None), "event_cut", None)
+        kind0 = getattr(getattr(phase, "kind", None), "name", str(getattr(phase, "kind", "")))
+        if kind0.upper() == "SIM" and ev_cut is not None and not ev_cut.is_fired and len(time_steps):
+            phase.dyna.fire_events(phase=phase, t=time_steps[0])       # the cutting event, as below
+        return _run_strips(sim, phase, time_steps, time_steps_sampled, anim_cells, dist, stats)
     own_engine = engine is None
     kind = getattr(getattr(phase, "kind", None), "name", str(getattr(phase, "kind", "")))
     is_sim = kind.upper() == "SIM"

@@ -112,11 +112,22 @@ class DistributedStrips:
     def update_V(self):
         self.engine.update_V()
 
-    def step(self, n=1):
-        st = self.engine.step(n)
+    def step(self, n=1, diag=False):
+        st = self.engine.step(n, diag=diag)
         if st & capi.STATUS_XCHG_TIMEOUT:
             raise BetseB200Error("halo exchange timed out waiting for a neighbouring rank")
         return st
+
+    def set_field(self, name, value):
+        """A scheduled quantity of the GLOBAL tissue (what TissueHandler.fire_events rewrote): scalars and per-ion vectors
+        go to the rank as they are, per-membrane / per-env-square arrays are cut to this rank's strip first."""
+        v = np.asarray(value)
+        P = self.part
+        if v.ndim >= 1 and v.shape[-1] == P.g2l_m.shape[0]:                     # [.., M]
+            v = v[..., P.own_mems]
+        elif v.ndim >= 1 and v.shape[-1] == P.ny * P.nx:                         # [.., E]
+            v = v[..., P.row_lo * P.nx:P.row_hi * P.nx]
+        self.engine.set_field(name, v)
 
     def profile(self, n):
         return self.engine.profile(n)

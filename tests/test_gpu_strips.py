@@ -78,3 +78,25 @@ def test_multiprocess_strips_over_ipc():
                          capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert '"ok": true' in res.stdout
+
+
+def test_dropin_loop_over_two_gpus_matches_reference():
+    """run_sim_core_loop inside a torchrun process group: the unmodified reference's seed/init/sim with the tissue stepped
+    as strips, one per GPU, against the reference's own loop (tools/check_dropin_multigpu.py); needs >= 2 GPUs and the
+    reference tree (baseline/_ref)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    from oracle import refshim
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    if not refshim.reference_available():
+        pytest.skip("reference tree absent: neither /root/reference nor baseline/_ref (run tools/install_reference.py)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29544",
+                          os.path.join(root, "tools", "check_dropin_multigpu.py")],
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
+    assert '"ok": true' in res.stdout
