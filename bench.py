@@ -111,8 +111,11 @@ def namespaces(mesh, p, state, kind="INIT"):
     sim.write2storage = lambda t, cells, p: setattr(sim, "sampled", sim.sampled + 1)
     phase = NS(p=pp, cells=cells, sim=sim, kind=NS(name=kind), callbacks=NS(progressed_next=lambda: None))
     if kind == "SIM":
-        # a SIM phase calls TissueHandler.fire_events every step (sim.py:1187-1188): here one that schedules nothing
+        # a SIM phase calls TissueHandler.fire_events every step (sim.py:1187-1188): here one that schedules nothing, under
+        # a configuration without scheduled interventions (every entry of p.global_options / p.scheduled_options off)
         phase.dyna = NS(fire_events=lambda phase, t: None, event_cut=None)
+        pp.global_options = {k: 0 for k in ("K_env", "Cl_env", "Na_env", "T_change", "gj_block", "NaKATP_block")}
+        pp.scheduled_options = {k: 0 for k in ("Na_mem", "K_mem", "Cl_mem", "Ca_mem", "pressure", "ecmJ", "cuts")}
     return sim, phase
 
 

@@ -46,6 +46,39 @@ _STATE_FIELDS = [
 # what fire_events / makeAllChanges may rewrite between steps (tishandler.py:728-917, 1321-1332)
 _SCHEDULED = ["Dm_cells", "D_env", "TJ_modulator", "gj_block", "NaKATP_block", "c_env_bound", "T"]
 
+
+
+def _live_scheduled(p):
+    """The scheduled quantities this phase's events CAN move (tishandler.py:744-876 tests the same option entries before
+    it touches anything): comparing the others after every fire_events call would cost a pass over arrays of 10^7 entries
+    per time step for nothing (makeAllChanges rebinds sim.Dm_cells to an equal array each step, tishandler.py:1327-1330).
+    Unknown parameter objects: everything is live."""
+    go, so = getattr(p, "global_options", None), getattr(p, "scheduled_options", None)
+    if not isinstance(go, dict) or not isinstance(so, dict):
+        return list(_SCHEDULED)
+
+    def on(d, *keys):
+        for k in keys:
+            v = d.get(k, 0)
+            if not (np.ndim(v) == 0 and v == 0):
+                return True
+        return False
+    live = []
+    if on(so, "Na_mem", "K_mem", "Cl_mem", "Ca_mem"):
+        live.append("Dm_cells")
+    if on(so, "ecmJ"):
+        live.append("D_env")
+    if on(go, "gj_block"):
+        live.append("gj_block")
+    if on(go, "NaKATP_block"):
+        live.append("NaKATP_block")
+    if on(go, "K_env", "Cl_env", "Na_env"):
+        live.append("c_env_bound")
+    if on(go, "T_change"):
+        live.append("T")
+    return live
+
+
 # attributes refreshed at sampled steps (read by write2storage and the exporters)
 _SAMPLED_STATE = ["cc_cells", "cc_at_mem", "cc_env", "vm", "vm_ave", "gjopen", "rho_cells", "Phi_b"]
 _SAMPLED_ENV = ["E_env_x", "E_env_y", "v_env", "rho_env"]
@@ -398,7 +431,7 @@ def _run_strips(sim, phase, time_steps, time_steps_sampled, anim_cells, dist, st
     own = ownership(mesh, R)
     Unstable = _unstable_exception()
     sampled = set(time_steps_sampled)
-    cache = {f: np.array(getattr(sim, f), copy=True) for f in _SCHEDULED if hasattr(sim, f)
+    cache = {f: np.array(getattr(sim, f), copy=True) for f in _live_scheduled(p) if hasattr(sim, f)
              and getattr(sim, f) is not None} if fire else {}
     hh = ("J_env_x", "J_env_y", "B_field", "Jtx", "Jty")
 
@@ -508,7 +541,7 @@ def run_sim_core_loop(sim, phase, time_steps, time_steps_sampled, anim_cells=Non
     Unstable = _unstable_exception()
     h2d = d2h = 0
     h2d0, d2h0 = eng.h2d_bytes, eng.d2h_bytes
-    cache = {f: np.array(getattr(sim, f), copy=True) for f in _SCHEDULED if hasattr(sim, f)
+    cache = {f: np.array(getattr(sim, f), copy=True) for f in _live_scheduled(p) if hasattr(sim, f)
              and getattr(sim, f) is not None} if fire else {}
     bv_cache = dict(getattr(sim, "bound_V", {})) if fire else {}
     bath_events = _bath_event_ions(sim, p) if (fire and not eng.is_ecm) else []
