@@ -1133,8 +1133,16 @@ static int prepare_xfuse(betse_ctx* ctx)
     return 0;
 }
 
+// ligand-gated channels add their flux to the membrane -> env slots of the ion loop (k_net_lig, networks.py:5847-5916): the
+// slots must then be the [slot][ion] array of k_mem, not the ELL rows of k_cell
+static void refresh_defer_slots(betse_ctx* ctx)
+{
+    ctx->P.defer_slots = (!ctx->net_gates[0].empty() || !ctx->net_gates[1].empty()) ? 1 : 0;
+}
+
 static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
 {
+    if (phase == 0) refresh_defer_slots(ctx);
     const int I = ctx->I, cur = ctx->cur, nxt = cur ^ 1;
     cudaStream_t st = ctx->stream;
     const KArrays& A = ctx->A;

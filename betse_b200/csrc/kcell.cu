@@ -145,12 +145,18 @@ __device__ __forceinline__ double membrane_fluxes(const KParams& P, CellSide<NI>
 
 // update_Co + update_all_concs, charge and Vmem of the cell (sim_toolbox.py:1177-1181; sim.py:2105-2111;
 // ion_current.py:19; sim.py:2027-2029)
-template <int NI>
+template <int NI, bool DEFER = false>
 __device__ __forceinline__ void cell_epilogue(const KParams& P, const KArrays& A, const CellSide<NI>& S, const double* cc, const double vol,
                                               const double dvt, const int c, const int nxt, unsigned int& flags,
                                               const XPlan* X = nullptr, const int2 gs = make_int2(-1, -1))
 {
     const int C = P.n_cells;
+    if (DEFER) {
+        // channels / networks act between the ion loop and update_all_concs (sim.py:1290-1357): the sums go to k_cell_update
+#pragma unroll
+        for (int i = 0; i < NI; ++i) { A.dsum_m[(size_t)i * C + c] = S.Sm[i]; A.dsum_g[(size_t)i * C + c] = S.Sg[i]; }
+        return;
+    }
     const double rvol = fast_rcp(vol);
     double rho = 0.0;
 #pragma unroll
@@ -181,7 +187,7 @@ __device__ __forceinline__ void cell_epilogue(const KParams& P, const KArrays& A
 
 // ---------------------------------------------------------------------------- one block of 32 cells: lane = cell
 // fsm: the block's part of the CTA's flux buffer in shared memory (k_cell_patch), [row][ion][32]; null: fluxes to flux_ell
-template <int NI, bool PATCH = false>
+template <int NI, bool PATCH = false, bool DEFER = false>
 __device__ __forceinline__ void cell_task(const KParams& P, const KArrays& A, const int cur, const int task, const int lane, unsigned int& flags,
                                           const XPlan* X = nullptr, double* __restrict__ fsm = nullptr, const int pf_up = -1, const int c_next = -1)
 {
@@ -323,7 +329,7 @@ __device__ __forceinline__ void cell_task(const KParams& P, const KArrays& A, co
             compute(b, k + 1);
         }
     }
-    if (valid) cell_epilogue<NI>(P, A, S, cc, vol, dvt, c, nxt, flags, (!PATCH && bx.x >= 0) ? X : nullptr, gs);
+    if (valid) cell_epilogue<NI, DEFER>(P, A, S, cc, vol, dvt, c, nxt, flags, (!PATCH && bx.x >= 0) ? X : nullptr, gs);
     if (!PATCH && X && (bx.x >= 0 || bx.y >= 0)) {
         // this block pushed: the last of the boundary blocks raises this rank's X1 flag on the neighbours
         __syncwarp();
@@ -333,7 +339,7 @@ __device__ __forceinline__ void cell_task(const KParams& P, const KArrays& A, co
 
 // Persistent: every warp draws tickets (ticket t = block t of the cell pack, so the blocks finish as a wavefront through
 // the tissue); kc_persist = 0: one block per warp.
-template <int NI>
+template <int NI, bool DEFER = false>
 __device__ __forceinline__ void k_cell_body(const KParams& P, const KArrays& A, const int cur, const XPlan* X)
 {
     const int lane = threadIdx.x & 31;
@@ -351,7 +357,7 @@ __device__ __forceinline__ void k_cell_body(const KParams& P, const KArrays& A, 
             const int n0 = X->blk_n0, n1 = X->blk_n1;
             if (t >= n0) t = (t < n0 + n1) ? P.n_blocks - n1 + (t - n0) : n0 + (t - n0 - n1);
         }
-        cell_task<NI>(P, A, cur, t, lane, flags, X);
+        cell_task<NI, false, DEFER>(P, A, cur, t, lane, flags, X);
         // a compiler-only fence that keeps the block index live to the end of the iteration: without it ptxas moves the next
         // ticket's atomic and header loads up into this block's epilogue and the kernel loses 6 % (0.258 -> 0.275 ms at 1 M
         // cells, same SASS instruction mix; A/B on one box, profiles/r02l_sweep_patch.txt)
@@ -370,6 +376,11 @@ __device__ __forceinline__ void k_cell_body(const KParams& P, const KArrays& A, 
 template <int NI, int MINB>
 __global__ void __launch_bounds__(KC_WARPS * 32, MINB)
 k_cell(const __grid_constant__ KParams P, const KArrays A, const int cur) { k_cell_body<NI>(P, A, cur, nullptr); }
+
+// deferred-update mode (channels / networks): the membranes -> cell sums go to dsum_m / dsum_g for k_cell_update
+template <int NI>
+__global__ void __launch_bounds__(KC_WARPS * 32, 2)
+k_cell_defer(const __grid_constant__ KParams P, const KArrays A, const int cur) { k_cell_body<NI, true>(P, A, cur, nullptr); }
 
 // decomposed tissue: the same kernel with exchange point X1 inside it (xchg.cuh)
 template <int NI>
@@ -793,6 +804,7 @@ void launch_cell(int ni, const KParams& P, const KArrays& A, int cur, cudaStream
     if (minb < 0) minb = kc_env_int("BETSE_KCELL_MINB", 2);      // resident CTAs (of 4 warps) per SM, 2 = 255 registers, 3 = 168
     const int need = (P.n_blocks + KC_WARPS - 1) / KC_WARPS;
     const int grid = (!P.kc_persist || need < g_kc_sms * minb) ? need : g_kc_sms * (minb <= 2 ? 2 : 3);
-    if (minb <= 2) { KC_DISPATCH_NI(ni, (k_cell<NI, 2><<<grid, KC_WARPS * 32, 0, st>>>(P, A, cur))); }
+    if (P.defer) { KC_DISPATCH_NI(ni, (k_cell_defer<NI><<<grid, KC_WARPS * 32, 0, st>>>(P, A, cur))); }
+    else if (minb <= 2) { KC_DISPATCH_NI(ni, (k_cell<NI, 2><<<grid, KC_WARPS * 32, 0, st>>>(P, A, cur))); }
     else { KC_DISPATCH_NI(ni, (k_cell<NI, 3><<<grid, KC_WARPS * 32, 0, st>>>(P, A, cur))); }
 }

@@ -786,11 +786,11 @@ void launch_cell(int ni, const KParams& P, const KArrays& A, int cur, cudaStream
 
 // the specialised builds apply to the shipped ion profiles with the default feature switches
 template <int NI>
-static bool std_profile(const KParams& P, const KArrays& A, int diag)
+static bool std_profile(const KParams& P, const KArrays& A, int diag, bool allow_defer = false)
 {
     bool ok = NI <= 7 && P.is_ecm && P.v_sensitive_gj && P.cluster_open && !P.fast_update_ecm && !diag &&
               !A.gj_block && !A.NaK_block && P.iNa == StdProf<NI>::iNa && P.iK == StdProf<NI>::iK &&
-              P.iCa == StdProf<NI>::iCa && !kmem_generic() && !P.defer && !P.has_phi && !P.polar;
+              P.iCa == StdProf<NI>::iCa && !kmem_generic() && (allow_defer || !P.defer) && !P.has_phi && !P.polar;
     for (int i = 0; i < NI && ok; ++i) ok = (P.zi[i] == StdProf<NI>::z(i)) && P.zi[i] != 0;
     return ok;
 }
@@ -798,16 +798,20 @@ static bool std_profile(const KParams& P, const KArrays& A, int diag)
 // 0: k_mem (run-time configured), 1: k_mem_pipe, 2: k_cell
 int mem_kernel_kind(int ni, const KParams& P, const KArrays& A, int diag)
 {
+    // k_cell also runs the deferred-update mode of channels / networks (it leaves the membranes -> cell sums in dsum_m / dsum_g
+    // for k_cell_update); k_mem_pipe does not
+    const bool kc = kcell_enabled() && A.cpack && !(P.defer && (!A.dsum_m || P.n_patches > 0 || P.defer_slots));
     bool sp;
     switch (ni) {
-        case 4: sp = std_profile<4>(P, A, diag); break;
-        case 5: sp = std_profile<5>(P, A, diag); break;
-        case 6: sp = std_profile<6>(P, A, diag); break;
-        case 7: sp = std_profile<7>(P, A, diag); break;
+        case 4: sp = std_profile<4>(P, A, diag, kc); break;
+        case 5: sp = std_profile<5>(P, A, diag, kc); break;
+        case 6: sp = std_profile<6>(P, A, diag, kc); break;
+        case 7: sp = std_profile<7>(P, A, diag, kc); break;
         default: sp = false;
     }
     if (!sp) return 0;
-    if (kcell_enabled() && A.cpack) return 2;
+    if (kc) return 2;
+    if (P.defer) return 0;
     return (kmem_pipe_enabled() && A.tile_pack) ? 1 : 0;
 }
 

@@ -45,7 +45,8 @@ struct KParams {
     int n_patches, n_out_sq, ptab_max;      // k_cell_patch: patches of 4 blocks (0 = off); env squares no patch owns; ints of the longest patch table
     int pf_dist;                            // k_cell, register build: a block pulls the streams of block + pf_dist into L2 (0 = off)
     int kc_persist;                         // k_cell, register build: persistent warps drawing tickets (1) or one block per warp (0)
-    int defer;                              // k_mem stores its membrane->cell sums instead of applying them (channels)
+    int defer;                              // the membrane kernel stores its membrane->cell sums instead of applying them (channels, networks)
+    int defer_slots;                        // ... and a later kernel adds to its membrane->env fluxes in flux_slots: k_mem only
     int chan_charge;                        // p.substances_affect_charge: Jmem takes the channels' extra_J_mem
     // kernel row ranges in local rows (single GPU: all [0, ny)): ion transport, membrane->env
     // accumulation, env field (E rows; v_env is written on the accumulation rows)
