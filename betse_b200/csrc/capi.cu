@@ -55,6 +55,8 @@ void launch_envacc_ell_x(int ni, const KParams& P, const KArrays& A, const XPlan
 void envacc_end_ctas(const KParams& P, int lo, int hi, int* n_lower, int* n_upper);
 void launch_cell_x(int ni, const KParams& P, const KArrays& A, const XPlan& X, int cur, cudaStream_t st);
 void launch_chan(const KParams& P, const KArrays& A, const KChan& ch, const KNet& N, int cur, cudaStream_t st);
+void launch_chan_cell(const KParams& P, const KArrays& A, const KChan* chs, int n, double* ell, int cur, int diag, cudaStream_t st);
+void launch_chan_expand(const KChan& ch, const int* mem_to_cells, const int* mem_ell, int Mo, int ni, cudaStream_t st);
 void launch_net(const KParams& P, const KArrays& A, const KNet& N, const double* h_Dgj, const double* h_Dm,
                 const unsigned char* h_env_on, const betse_substance_pump* pumps, int n_pumps, double dG_RT,
                 const unsigned char* h_intra, int n_ions, int cur, cudaStream_t st);
@@ -106,6 +108,8 @@ struct betse_ctx {
     bool xwait = false;                      // the consumers of an exchange wait inside their kernels (neighbours in other processes)
     std::vector<void*> ipc_opened;
     std::vector<KChan> chans;                // voltage-gated channels, applied in order
+    bool chan_cell_mode = false;             // the channels run on the per-cell path (channels.cu:k_chan_cell): gate state in mc/hc/Pc/Dc
+    double* chan_ell = nullptr;              // [rows][I][32] f*sa of the channels of a pass, in the order of the cell pack
     HHBuf hh;                                // Helmholtz-Hodge diagnostics (sampled steps, undivided ECM tissues)
     bool hh_on = false;
     bool want_hh = true;
@@ -847,6 +851,8 @@ extern "C" int betse_create(betse_ctx** out, const betse_mesh* mesh, const betse
 static int ensure_phi(betse_ctx* ctx);
 static double nan_value() { return nan(""); }
 static void publish_affect(betse_ctx* ctx);
+static bool chan_cell_possible(betse_ctx* ctx);
+static void chan_layout_sync(betse_ctx* ctx);
 
 // sine matrices, eigenvalues and work buffers of the Dirichlet Poisson solve on the env grid (csrc/hh.cu)
 static int ensure_poisson(betse_ctx* ctx)
@@ -1207,12 +1213,29 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
                         launch_transporter(ctx->P, A, ctx->nets[h], ctx->net_trans[h][j], ctx->net_trans_cm[h][j],
                                            ctx->net_trans_em[h][j], ctx->net_trans_mm[h][j], cur, st);
                 }
-                for (const KChan& ch : ctx->chans) if (ch.handler == h) {
-                    launch_chan(ctx->P, A, ch, ctx->nets[h], cur, st);
-                    // the channel's update_Co renews sim.cc_at_mem[ion] (sim_toolbox.py:1182): a transporter's nudge of it ends here
-                    if (ctx->net_on[h] && ctx->nets[h].tw && ctx->nets[h].tw_i[ch.ion] >= 0)
-                        launch_tw_gather(ctx->P, A, ctx->nets[h].tw + (size_t)ctx->nets[h].tw_i[ch.ion] * ctx->Mo,
-                                         A.cc_cells + (size_t)ch.ion * ctx->C, st);
+                // per-cell path (channels.cu:k_chan_cell): consecutive channels that conduct different ions go as ONE pass —
+                // none of them sees another's update_Co.  Otherwise one kernel pair per channel.
+                const bool tw = ctx->net_on[h] && ctx->nets[h].tw;
+                const size_t nch = ctx->chans.size();
+                for (size_t k0 = 0; k0 < nch;) {
+                    if (ctx->chans[k0].handler != h) { ++k0; continue; }
+                    size_t k1 = k0 + 1;
+                    if (ctx->chan_cell_mode) {
+                        const size_t cap = (size_t)std::min(KCH_PACK, I);
+                        unsigned ions = 1u << ctx->chans[k0].ion;
+                        while (k1 < nch && k1 - k0 < cap && ctx->chans[k1].handler == h && !(ions & (1u << ctx->chans[k1].ion))) {
+                            ions |= 1u << ctx->chans[k1].ion; ++k1;
+                        }
+                        launch_chan_cell(ctx->P, A, &ctx->chans[k0], (int)(k1 - k0), ctx->chan_ell, cur, diag, st);
+                    } else {
+                        const KChan& ch = ctx->chans[k0];
+                        launch_chan(ctx->P, A, ch, ctx->nets[h], cur, st);
+                        // the channel's update_Co renews sim.cc_at_mem[ion] (sim_toolbox.py:1182): a transporter's nudge of it ends here
+                        if (tw && ctx->nets[h].tw_i[ch.ion] >= 0)
+                            launch_tw_gather(ctx->P, A, ctx->nets[h].tw + (size_t)ctx->nets[h].tw_i[ch.ion] * ctx->Mo,
+                                             A.cc_cells + (size_t)ch.ion * ctx->C, st);
+                    }
+                    k0 = k1;
                 }
                 if (ctx->net_on[h])
                     for (const betse_modulator& md : ctx->net_mods[h])
@@ -1341,6 +1364,7 @@ extern "C" int betse_step(betse_ctx* ctx, int nsteps, int flags, uint32_t* statu
     const bool want_diag = (flags & BETSE_STEP_DIAG) != 0;
     if (want_diag || ctx->P.polar) { int r = ensure_diag_buffers(ctx); if (r) return r; }
     if (ctx->xwait) { int r = prepare_xfuse(ctx); if (r) return r; }
+    chan_layout_sync(ctx);
     const int asked = nsteps;
     if (ctx->phi_lag && nsteps > 0) {
         // first step after a change of sim.bound_V: starts from the old potential, closes with the new one
@@ -1385,6 +1409,7 @@ extern "C" int betse_ensemble_step(betse_ctx** ctxs, int n, int nsteps, int laun
         betse_ctx* c = ctxs[j];
         if (!c) return fail(ctx, "betse_ensemble_step: null member");
         if (c->device != ctx->device) return fail(ctx, "betse_ensemble_step: members must live on one device");
+        chan_layout_sync(c);
         if (c->cur != ctx->cur) return fail(ctx, "betse_ensemble_step: members are not in lockstep (step them only through the ensemble)");
         if (c->X.n_nbr > 0) return fail(ctx, "betse_ensemble_step: a member is part of a decomposed tissue");
         if (c->phi_lag || c->noise_on || c->P.polar || c->need_emc)
@@ -1594,6 +1619,7 @@ extern "C" int betse_step_phase(betse_ctx* ctx, int phase, int flags)
     CK(cudaSetDevice(ctx->device));
     const int diag = (flags & BETSE_STEP_DIAG) ? 1 : 0;
     if (diag || ctx->P.polar) { int r = ensure_diag_buffers(ctx); if (r) return r; }
+    if (phase == 0) chan_layout_sync(ctx);
     enqueue_phase(ctx, phase, diag, nullptr);
     CK(cudaGetLastError());
     if (phase == 2) ctx->diag_valid = diag != 0;
@@ -1621,6 +1647,7 @@ extern "C" int betse_step_profile(betse_ctx* ctx, int nsteps, float* total_ms,
     CK(cudaSetDevice(ctx->device));
     if (ctx->P.polar) { int r = ensure_diag_buffers(ctx); if (r) return r; }
     if (ctx->xwait) { int r = prepare_xfuse(ctx); if (r) return r; }
+    chan_layout_sync(ctx);
     if (!ctx->ev_init) {
         for (auto& e : ctx->ev) CK(cudaEventCreate(&e));
         ctx->ev_init = true;
@@ -1775,6 +1802,21 @@ extern "C" int betse_set_channels(betse_ctx* ctx, int n, const betse_channel* ch
     if ((r = dev_alloc(ctx, &A.chan_part, (size_t)ctx->n_tiles))) return r;
         if ((r = dev_alloc(ctx, &A.chanJ, (size_t)Mo))) return r;
     }
+    // per-cell path (channels.cu:k_chan_cell): every channel on every membrane, unmodulated, its initial gates uniform
+    // within every cell (what the reference's initial conditions give: V is the cell's Vmem, vg_na.py:75-88)
+    bool cellp = chan_cell_possible(ctx);
+    { const char* e = getenv("BETSE_CHAN_CELL"); if (e && e[0] == '0') cellp = false; }      // A/B: one kernel pair per channel
+    for (int k = 0; k < n && cellp; ++k) {
+        const betse_channel& c = chs[k];
+        if (c.same_gates) continue;
+        cellp = !c.target_mask && c.mod_prog < 0 && c.m0 && c.h0;
+        for (int cc = 0; cc < ctx->Co && cellp; ++cc)
+            for (int m = ctx->h_cmp[cc] + 1; m < ctx->h_cmp[cc + 1]; ++m)
+                if (c.m0[m] != c.m0[ctx->h_cmp[cc]] || c.h0[m] != c.h0[ctx->h_cmp[cc]]) { cellp = false; break; }
+    }
+    ctx->chan_cell_mode = cellp && n > 0;
+    if (ctx->chan_cell_mode && !ctx->chan_ell)
+        if ((r = dev_alloc(ctx, &ctx->chan_ell, (size_t)ctx->P.ell_rows * 32 * ctx->I))) return r;
     for (int k = 0; k < n; ++k) {
         const betse_channel& c = chs[k];
         if (c.ion < 0 || c.ion >= ctx->I) return fail(ctx, "channel ion index out of range");
@@ -1811,11 +1853,51 @@ extern "C" int betse_set_channels(betse_ctx* ctx, int n, const betse_channel* ch
         if ((r = dev_alloc(ctx, &d.P, Mo))) return r;
         if ((r = dev_alloc(ctx, &d.flux, Mo))) return r;
         if ((r = dev_alloc(ctx, &d.D, Mo))) return r;
+        if (ctx->chan_cell_mode) {
+            std::vector<double> mc((size_t)ctx->C, 0.0), hc((size_t)ctx->C, 0.0);
+            for (int cc = 0; cc < ctx->Co; ++cc)
+                if (ctx->h_cmp[cc + 1] > ctx->h_cmp[cc]) { mc[cc] = c.m0[ctx->h_cmp[cc]]; hc[cc] = c.h0[ctx->h_cmp[cc]]; }
+            if ((r = dev_upload(ctx, &d.mc, mc.data(), (size_t)ctx->C))) return r;
+            if ((r = dev_upload(ctx, &d.hc, hc.data(), (size_t)ctx->C))) return r;
+            if ((r = dev_alloc(ctx, &d.Pc, (size_t)ctx->C))) return r;
+            if ((r = dev_alloc(ctx, &d.Dc, (size_t)ctx->C))) return r;
+            if ((r = dev_alloc(ctx, &d.fell, (size_t)ctx->P.ell_rows * 32))) return r;
+        }
         ctx->chans.push_back(d);
     }
     CK(cudaStreamSynchronize(ctx->stream));
     publish_affect(ctx);
     return 0;
+}
+
+// What the per-cell channel path needs from the tissue (the channels' own conditions are checked in betse_set_channels):
+// Vmem per cell (no polarizability, no boundary potential), extracellular spaces, the cell pack over consecutive cells, no
+// transporter-nudged membrane values (their refresh follows every single channel).
+static bool chan_cell_possible(betse_ctx* ctx)
+{
+    const KArrays& A = ctx->A;
+    if (!ctx->hp.is_ecm || ctx->P.polar || ctx->P.has_phi || ctx->phi_lag || !A.cpack || A.pcell || !A.slot_off || !ctx->mem_ell) return false;
+    if (ctx->X.n_nbr > 0 || ctx->P.n_blocks <= 0) return false;
+    for (int h = 0; h < 2; ++h) if (ctx->net_on[h] && ctx->nets[h].tw) return false;
+    return true;
+}
+
+// gate state of every channel back into the per-membrane arrays (betse_channel_state; leaving the per-cell path)
+static void chan_expand_all(betse_ctx* ctx)
+{
+    for (const KChan& ch : ctx->chans)
+        launch_chan_expand(ch, ctx->A.mem_to_cells, ctx->mem_ell, ctx->Mo, ctx->I, ctx->stream);
+}
+
+// Before anything is enqueued: the tissue may have left the conditions of the per-cell path since betse_set_channels (a
+// boundary potential switched on, a network with transporters set afterwards) — the state moves to the per-membrane arrays
+// and k_chan takes over, for good.
+static void chan_layout_sync(betse_ctx* ctx)
+{
+    if (!ctx->chan_cell_mode || chan_cell_possible(ctx)) return;
+    chan_expand_all(ctx);
+    ctx->chan_cell_mode = false;
+    destroy_graphs(ctx);
 }
 
 extern "C" int betse_channel_state(betse_ctx* ctx, int k, double* m, double* h, double* P, double* flux, double* DChan)
@@ -1825,6 +1907,7 @@ extern "C" int betse_channel_state(betse_ctx* ctx, int k, double* m, double* h, 
     if (k < 0 || k >= (int)ctx->chans.size()) return fail(ctx, "channel index out of range");
     const KChan& d = ctx->chans[k];
     const size_t nb = (size_t)ctx->Mo * sizeof(double);
+    if (ctx->chan_cell_mode) launch_chan_expand(d, ctx->A.mem_to_cells, ctx->mem_ell, ctx->Mo, ctx->I, ctx->stream);
     if (m) { int xr = xfer(ctx, m, d.m, nb, cudaMemcpyDeviceToHost); if (xr) return xr; }
     if (h) { int xr = xfer(ctx, h, d.h, nb, cudaMemcpyDeviceToHost); if (xr) return xr; }
     if (P) { int xr = xfer(ctx, P, d.P, nb, cudaMemcpyDeviceToHost); if (xr) return xr; }

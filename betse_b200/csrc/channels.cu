@@ -65,16 +65,10 @@ __device__ __forceinline__ double ipow(double x, int n)
 
 // One warp per tile of whole cells (the packing of k_mem): lanes = membranes for gates and flux,
 // then lanes = cells for the immediate concentration update of the conducted ion.
-__global__ void __launch_bounds__(BT_TPB)
-k_chan(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ KChan ch, const __grid_constant__ KNet N,
-       const int cur)
+// `slots`: where the channel leaves f*sa of every membrane for the env side of its update_Co.
+__device__ __forceinline__ void chan_apply(const KParams& P, const KArrays& A, const KChan& ch, const KNet& N, const int cur,
+                                           double* __restrict__ slots, double* s_f, const int lane, const int tile, const int4 td)
 {
-    __shared__ double s_all[(BT_TPB / 32) * 32];
-    const int lane = threadIdx.x & 31;
-    const int tile = blockIdx.x * (BT_TPB / 32) + (threadIdx.x >> 5);
-    if (tile >= P.n_tiles) return;
-    double* s_f = s_all + (threadIdx.x >> 5) * 32;
-    const int4 td = __ldg(reinterpret_cast<const int4*>(A.tile_desc) + tile);
     const int c0 = td.x, nc = td.y, m0 = td.z, nm = td.w;
     const int C = P.n_cells, E = P.ny * P.nx;
     const int ion = ch.ion;
@@ -112,7 +106,7 @@ k_chan(const __grid_constant__ KParams P, const KArrays A, const __grid_constant
         const double cB = ccell[c], cA = P.is_ecm ? cenv[e] : A.cenv_u[cur * 8 + ion];
         const double f = -((DChan * alpha) / P.tm) * ((cB - cA * ex) / deno) * P.rho_channel;
         fsa = f * __ldg(A.mem_sa + m);
-        if (P.is_ecm) A.chan_slots[m] = fsa;
+        if (P.is_ecm) slots[m] = fsa;
         if (ch.flux) ch.flux[m] = f;
         if (A.chanJ) A.chanJ[m] += (-f * P.F) * P.z[ion];         // extra_J_mem += -f_ED*p.F*zzz, networks.py:3199
     }
@@ -131,6 +125,132 @@ k_chan(const __grid_constant__ KParams P, const KArrays A, const __grid_constant
         const double cn = ccell[c] + (S / __ldg(A.cell_vol + c)) * P.dt;
         ccell[c] = cn;
     }
+}
+
+__global__ void __launch_bounds__(BT_TPB)
+k_chan(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ KChan ch, const __grid_constant__ KNet N,
+       const int cur)
+{
+    __shared__ double s_all[(BT_TPB / 32) * 32];
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * (BT_TPB / 32) + (threadIdx.x >> 5);
+    if (tile >= P.n_tiles) return;
+    const int4 td = __ldg(reinterpret_cast<const int4*>(A.tile_desc) + tile);
+    chan_apply(P, A, ch, N, cur, A.chan_slots, s_all + (threadIdx.x >> 5) * 32, lane, tile, td);
+}
+
+// ---------------------------------------------------------------------------- channels with ONE LANE PER CELL
+// In the default mode Vmem is a per-cell quantity (sim.py:2029), so the gates of a channel that sits on every membrane —
+// m, h, the open probability, DChan, and the exp / expm1 pair of its GHK flux — have ONE value per cell: k_chan evaluates
+// them once per membrane (six times per cell, ~10 exp and ~10 divisions each; the kernel is bound by fp64 issue, not by
+// memory: profiles/r02r_launches_c3.csv).  k_chan_cell walks the cell pack of k_cell (kcell.cu: SELL-32, lane = cell)
+// instead: gates once per cell, then the cell's membranes in order — env concentration gathered through the row's env
+// square, flux, f*sa into the pass's ELL exchange array, the membranes->cell sum as a register accumulation in membrane
+// order (the order of k_chan's sum).  Same expressions as chan_apply, evaluated once instead of six times.
+// A PASS = consecutive channels of the reference's application order that conduct DIFFERENT ions: none of them reads
+// what another's update_Co moves (each reads its own ion and Vmem, which no channel moves), so they run back to back
+// inside one kernel and one env kernel closes the update_Co of every ion of the pass.
+// Gate state lives per cell (KChan.mc/hc/Pc/Dc) while this path is in use; betse_channel_state expands it (k_chan_expand).
+// Eligibility (capi.cu:chan_cell_eligible): extracellular spaces, cell pack of consecutive cells, no polarizability, no
+// boundary potential, no target mask, no network modulation, initial gates uniform within every cell.
+#define KC_QMASK 0x0fffffffu                     // kcell.cu: env-square word of a pack row
+struct KChanPack { int n; KChan ch[KCH_PACK]; };
+
+__global__ void __launch_bounds__(128)
+k_chan_cell(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ KChanPack pk, double* __restrict__ ell,
+            const int cur, const int diag)
+{
+    const int lane = threadIdx.x & 31;
+    const int task = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (task >= P.n_blocks) return;
+    const int c = task * 32 + lane;
+    if (c >= P.n_cells_owned) return;
+    const int ni = P.n_ions;
+    const size_t rowb = (size_t)(ni + 2) * 256;
+    const int row0 = __ldg(A.blk_row0 + 2 * task);
+    const int m_beg = __ldg(A.cell_mem_ptr + c), nm = __ldg(A.cell_mem_ptr + c + 1) - m_beg;
+    const int C = P.n_cells, E = P.ny * P.nx;
+    const double vm = A.vm_cell[cur][c];
+    const double vol = __ldg(A.cell_vol + c);
+    const char* __restrict__ rows = A.cpack + (size_t)row0 * rowb;
+    for (int j = 0; j < pk.n; ++j) {
+        const KChan& ch = pk.ch[j];
+        const int ion = ch.ion;
+        double* __restrict__ ccell = A.cc_cells + (size_t)ion * C;
+        const double* __restrict__ cenv = A.cc_env[cur ^ 1] + (size_t)ion * E;
+        double Pm;
+        if (ch.frozen) Pm = ch.Pc[c];
+        else {
+            const double U = vm * 1000.0 + ch.shift;
+            const double mInf = gate_quantity(ch, 0, U), mTau = gate_quantity(ch, 1, U);
+            const double hInf = gate_quantity(ch, 2, U), hTau = gate_quantity(ch, 3, U);
+            const double dt = ch.dt_tu;
+            const double mm = (mTau * ch.mc[c] + dt * mInf) / (mTau + dt);
+            const double hh = (hTau * ch.hc[c] + dt * hInf) / (hTau + dt);
+            ch.mc[c] = mm; ch.hc[c] = hh;
+            Pm = ipow(mm, ch.mpow) * ipow(hh, ch.hpow);
+            ch.Pc[c] = Pm;
+        }
+        const double DChan = ((Pm * ch.rel_perm) * ch.maxDm) * 1.0;
+        ch.Dc[c] = DChan;
+        const double alpha = ((P.z[ion] + FLOAT_NONCE) * (vm + FLOAT_NONCE) * P.F) / P.RT_sim;
+        const double ex = exp(-alpha), deno = -expm1(-alpha);
+        const double cB = ccell[c];
+        const double coef = -((DChan * alpha) / P.tm);
+        const double zF = P.z[ion];
+        double S = 0.0;
+        for (int k = 0; k < nm; ++k) {
+            const char* r = rows + (size_t)k * rowb;
+            const double sa = __ldg(reinterpret_cast<const double*>(r + (size_t)ni * 256) + lane);
+            const unsigned q = (unsigned)__ldg(reinterpret_cast<const int*>(r + (size_t)(ni + 1) * 256 + 128) + lane) & KC_QMASK;
+            const double cA = cenv[q];
+            const double f = coef * ((cB - cA * ex) / deno) * P.rho_channel;
+            const double fsa = f * sa;
+            ell[((size_t)(row0 + k) * ni + j) * 32 + lane] = fsa;
+            ch.fell[(size_t)(row0 + k) * 32 + lane] = f;
+            if (diag && A.chanJ) A.chanJ[m_beg + k] += (-f * P.F) * zF;
+            S += fsa;
+        }
+        ccell[c] = cB + (S / vol) * P.dt;
+    }
+}
+
+// update_Co env branch of every channel of a pass (k_chan_env per conducted ion), fluxes read where k_chan_cell left them
+struct KPassIons { int n; int ion[KCH_PACK]; };
+
+__global__ void __launch_bounds__(256)
+k_chan_env_cell(const __grid_constant__ KParams P, const KArrays A, const KPassIons pi, const double* __restrict__ ell, const int nxt)
+{
+    const int k = P.ya0 * P.nx + blockIdx.x * blockDim.x + threadIdx.x;
+    const int E = P.nx * P.ny;
+    if (k >= P.ya1 * P.nx) return;
+    const int s0 = __ldg(A.slot_ptr + k), s1 = __ldg(A.slot_ptr + k + 1);
+    if (s1 == s0) return;
+    double acc[KCH_PACK];
+#pragma unroll
+    for (int q = 0; q < KCH_PACK; ++q) acc[q] = 0.0;
+    for (int j = s0; j < s1; ++j) {
+        const int off = __ldg(A.slot_off + j);
+#pragma unroll
+        for (int q = 0; q < KCH_PACK; ++q) if (q < pi.n) acc[q] += ell[(size_t)off + q * 32];
+    }
+#pragma unroll
+    for (int q = 0; q < KCH_PACK; ++q) if (q < pi.n) {
+        double* c = A.cc_env[nxt] + (size_t)pi.ion[q] * E + k;
+        *c = *c + ((-acc[q]) / P.env_vol_div) * P.dt;
+    }
+}
+
+// per-cell gate state -> the per-membrane arrays of the C ABI (betse_channel_state; leaving the per-cell path)
+__global__ void __launch_bounds__(256)
+k_chan_expand(const __grid_constant__ KChan ch, const int* __restrict__ mem_to_cells, const int* __restrict__ mem_ell, const int Mo, const int ni)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= Mo) return;
+    const int c = __ldg(mem_to_cells + m);
+    ch.m[m] = ch.mc[c]; ch.h[m] = ch.hc[c]; ch.P[m] = ch.Pc[c]; ch.D[m] = ch.Dc[c];
+    const int pos = __ldg(mem_ell + m);
+    ch.flux[m] = ch.fell[(size_t)(pos / (ni * 32)) * 32 + (pos & 31)];
 }
 
 // update_Co env branch for one channel: cc_env[ion] += div_env(-f)*dt (sim_toolbox.py:1189-1195, 1209-1234)
@@ -196,6 +316,24 @@ k_cell_update(const __grid_constant__ KParams P, const KArrays A, const int cur)
     if (vmn != vmn) flags |= ST_NAN_VM;
     A.vm_cell[nxt][c] = vmn;
     if (flags) atomicOr(A.status, flags);
+}
+
+// channels [0, n) of `chs` as one pass on the per-cell path (n <= min(KCH_PACK, n_ions), distinct ions); ell: [rows][I][32]
+void launch_chan_cell(const KParams& P, const KArrays& A, const KChan* chs, int n, double* ell, int cur, int diag, cudaStream_t st)
+{
+    KChanPack pk;
+    KPassIons pi;
+    pk.n = pi.n = n;
+    for (int j = 0; j < n; ++j) { pk.ch[j] = chs[j]; pi.ion[j] = chs[j].ion; }
+    for (int j = n; j < KCH_PACK; ++j) { pk.ch[j] = chs[0]; pi.ion[j] = 0; }
+    k_chan_cell<<<(P.n_blocks + 3) / 4, 128, 0, st>>>(P, A, pk, ell, cur, diag);
+    const int ne = (P.ya1 - P.ya0) * P.nx;
+    if (ne > 0) k_chan_env_cell<<<(ne + 255) / 256, 256, 0, st>>>(P, A, pi, ell, cur ^ 1);
+}
+
+void launch_chan_expand(const KChan& ch, const int* mem_to_cells, const int* mem_ell, int Mo, int ni, cudaStream_t st)
+{
+    if (Mo > 0) k_chan_expand<<<(Mo + 255) / 256, 256, 0, st>>>(ch, mem_to_cells, mem_ell, Mo, ni);
 }
 
 void launch_chan(const KParams& P, const KArrays& A, const KChan& ch, const KNet& N, int cur, cudaStream_t st)

@@ -60,7 +60,7 @@ def _live_scheduled(p):
     def on(d, *keys):
         for k in keys:
             v = d.get(k, 0)
-            if not (np.ndim(v) == 0 and v == 0):
+            if isinstance(v, (list, tuple, dict, np.ndarray)) or v is None or v != 0:      # the reference stores 0 for "off"
                 return True
         return False
     live = []

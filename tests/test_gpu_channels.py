@@ -138,3 +138,33 @@ def test_every_tabulated_model_on_the_device():
     finally:
         for name in added:
             del chlib.MODELS[name]
+
+
+def test_channel_cell_path_equals_one_pair_per_channel(monkeypatch):
+    """k_chan_cell (one lane per cell, consecutive channels of different ions in one pass, channels.cu) is the same arithmetic in the
+    same order as one k_chan / k_chan_env pair per channel: bit-identical state after 12 steps (BETSE_CHAN_CELL=0: pairs)."""
+    from betse_b200 import channels as chlib
+    from betse_b200 import synth
+    from betse_b200.engine import TissueEngine
+    mesh, p, st = synth.make_tissue(20_000)
+    p["substances_affect_charge"] = 1
+    out = []
+    for mode in ("1", "0"):
+        monkeypatch.setenv("BETSE_CHAN_CELL", mode)
+        eng = TissueEngine(mesh, p, st)
+        eng.update_V()
+        vm0 = eng.download(["vm"])["vm"]
+        specs = []
+        for name, model, dm in (("Nav", "Nav1p3", 2.0e-14), ("Kv", "Kv1p5", 1.0e-15), ("K_Leak", "KLeak", 0.6e-17),
+                                ("Cav", "Cav1p2", 1.0e-15), ("HCN", "HCN2", 1.0e-16)):
+            m0, h0 = chlib.initial_state(model, vm0)
+            specs.append(chlib.make_channel(name, model, dm, m=m0, h=h0))
+        eng.set_channels(specs)
+        assert not (eng.step(12) & 3)
+        got = eng.download(["cc_cells", "cc_env", "vm"])
+        for k in range(len(specs)):
+            got.update({"%s%d" % (f, k): a for f, a in eng.channel_state(k).items() if a is not None})
+        out.append(got)
+        eng.close()
+    for f in out[0]:
+        assert np.array_equal(out[0][f], out[1][f]), f

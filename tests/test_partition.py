@@ -187,3 +187,32 @@ def test_exchange_over_gloo_world_size_2():
     for pr in procs:
         pr.join(60)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def test_ownership_matches_partition():
+    """partition.ownership (what the N-GPU drop-in uses to assemble global arrays) agrees with the full partition."""
+    from betse_b200 import synth
+    from betse_b200.partition import ownership, partition
+    mesh, p, st = synth.make_tissue(6000)
+    parts = partition(mesh, p, st, 3)
+    own = ownership(mesh, 3)
+    for a, b in zip(parts, own):
+        assert np.array_equal(a.own_cells, b.own_cells) and np.array_equal(a.own_mems, b.own_mems)
+        assert (a.a, a.b, a.row_lo, a.row_hi, a.Co, a.Mo) == (b.a, b.b, b.row_lo, b.row_hi, b.Co, b.Mo)
+
+
+def test_live_scheduled_follows_the_event_options():
+    """simloop._live_scheduled: only what the phase's events can move (tishandler.py:744-876) is compared per step."""
+    import types
+    from betse_b200 import simloop
+    off = {k: 0 for k in ("K_env", "Cl_env", "Na_env", "T_change", "gj_block", "NaKATP_block")}
+    soff = {k: 0 for k in ("Na_mem", "K_mem", "Cl_mem", "Ca_mem", "pressure", "ecmJ", "cuts")}
+    p = types.SimpleNamespace(global_options=dict(off), scheduled_options=dict(soff))
+    assert simloop._live_scheduled(p) == []
+    p.global_options["gj_block"] = [1.0, 2.0, 0.5]
+    p.scheduled_options["K_mem"] = [1.0, 2.0, 0.5, 10.0, ["Spot"]]
+    assert simloop._live_scheduled(p) == ["Dm_cells", "gj_block"]
+    p.global_options.update(K_env=[1, 2, 3, 4], T_change=[1, 2, 3, 4], NaKATP_block=[1, 2, 3])
+    p.scheduled_options["ecmJ"] = [1, 2, 3, ["Spot"], 1.0]
+    assert simloop._live_scheduled(p) == ["Dm_cells", "D_env", "gj_block", "NaKATP_block", "c_env_bound", "T"]
+    assert simloop._live_scheduled(types.SimpleNamespace()) == list(simloop._SCHEDULED)      # unknown parameter object: all
