@@ -63,6 +63,24 @@ __device__ __forceinline__ double ipow(double x, int n)
     return r;
 }
 
+// ChannelsABC.update_mh (channelsabc.py:40-60): implicit step of both gates at the membrane voltage vm.  The roundings are
+// spelled out (fma / single operations) because k_chan and k_chan_cell must agree bit for bit.
+__device__ __forceinline__ void gate_advance(const KChan& ch, const double vm, double& m, double& h)
+{
+    const double U = fma(vm, 1000.0, ch.shift);                    // V = vm[targets]*1000 + v_corr (vg_na.py:91)
+    const double mInf = gate_quantity(ch, 0, U), mTau = gate_quantity(ch, 1, U);
+    const double hInf = gate_quantity(ch, 2, U), hTau = gate_quantity(ch, 3, U);
+    const double dt = ch.dt_tu;                                    // p.dt*time_unit (channelsabc.py:56)
+    m = fma(mTau, m, __dmul_rn(dt, mInf)) / __dadd_rn(mTau, dt);
+    h = fma(hTau, h, __dmul_rn(dt, hInf)) / __dadd_rn(hTau, dt);
+}
+
+// stb.electroflux with the cell-side factors formed by the caller (sim_toolbox.py:18-69): coef = -(DChan*alpha/tm)
+__device__ __forceinline__ double chan_flux(const double coef, const double cB, const double cA, const double ex, const double deno, const double rho)
+{
+    return __dmul_rn(__dmul_rn(coef, fma(-cA, ex, cB) / deno), rho);
+}
+
 // One warp per tile of whole cells (the packing of k_mem): lanes = membranes for gates and flux,
 // then lanes = cells for the immediate concentration update of the conducted ion.
 // `slots`: where the channel leaves f*sa of every membrane for the env side of its update_Co.
@@ -86,12 +104,8 @@ __device__ __forceinline__ void chan_apply(const KParams& P, const KArrays& A, c
         double Pm = 0.0;
         if (ch.frozen) Pm = ch.P[m];
         else if (!ch.mask || ch.mask[m]) {
-            const double U = vm * 1000.0 + ch.shift;              // V = vm[targets]*1000 + v_corr (vg_na.py:91)
-            const double mInf = gate_quantity(ch, 0, U), mTau = gate_quantity(ch, 1, U);
-            const double hInf = gate_quantity(ch, 2, U), hTau = gate_quantity(ch, 3, U);
-            const double dt = ch.dt_tu;                            // p.dt*time_unit (channelsabc.py:56)
-            const double mm = (mTau * ch.m[m] + dt * mInf) / (mTau + dt);
-            const double hh = (hTau * ch.h[m] + dt * hInf) / (hTau + dt);
+            double mm = ch.m[m], hh = ch.h[m];
+            gate_advance(ch, vm, mm, hh);
             ch.m[m] = mm; ch.h[m] = hh;
             Pm = ipow(mm, ch.mpow) * ipow(hh, ch.hpow);            // vg_na.py:104
         }
@@ -104,8 +118,8 @@ __device__ __forceinline__ void chan_apply(const KParams& P, const KArrays& A, c
         const double alpha = ((P.z[ion] + FLOAT_NONCE) * (vm + FLOAT_NONCE) * P.F) / P.RT_sim;
         const double ex = exp(-alpha), deno = -expm1(-alpha);
         const double cB = ccell[c], cA = P.is_ecm ? cenv[e] : A.cenv_u[cur * 8 + ion];
-        const double f = -((DChan * alpha) / P.tm) * ((cB - cA * ex) / deno) * P.rho_channel;
-        fsa = f * __ldg(A.mem_sa + m);
+        const double f = chan_flux(-((DChan * alpha) / P.tm), cB, cA, ex, deno, P.rho_channel);
+        fsa = __dmul_rn(f, __ldg(A.mem_sa + m));
         if (P.is_ecm) slots[m] = fsa;
         if (ch.flux) ch.flux[m] = f;
         if (A.chanJ) A.chanJ[m] += (-f * P.F) * P.z[ion];         // extra_J_mem += -f_ED*p.F*zzz, networks.py:3199
@@ -122,8 +136,7 @@ __device__ __forceinline__ void chan_apply(const KParams& P, const KArrays& A, c
         const int jb = __ldg(A.cell_mem_ptr + c) - m0, je = __ldg(A.cell_mem_ptr + c + 1) - m0;
         double S = 0.0;
         for (int j = jb; j < je; ++j) S += s_f[j];
-        const double cn = ccell[c] + (S / __ldg(A.cell_vol + c)) * P.dt;
-        ccell[c] = cn;
+        ccell[c] = fma(S / __ldg(A.cell_vol + c), P.dt, ccell[c]);
     }
 }
 
@@ -154,14 +167,16 @@ k_chan(const __grid_constant__ KParams P, const KArrays A, const __grid_constant
 // Eligibility (capi.cu:chan_cell_eligible): extracellular spaces, cell pack of consecutive cells, no polarizability, no
 // boundary potential, no target mask, no network modulation, initial gates uniform within every cell.
 #define KC_QMASK 0x0fffffffu                     // kcell.cu: env-square word of a pack row
+#define KCH_TPB 64                               // threads per CTA of k_chan_cell
+#define KCH_KREG 6                               // membranes of a cell whose row constants stay in registers
 struct KChanPack { int n; KChan ch[KCH_PACK]; };
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(KCH_TPB, 11)              // <= 93 registers: 100 k cells are resident in one wave
 k_chan_cell(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ KChanPack pk, double* __restrict__ ell,
             const int cur, const int diag)
 {
     const int lane = threadIdx.x & 31;
-    const int task = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int task = blockIdx.x * (KCH_TPB / 32) + (threadIdx.x >> 5);
     if (task >= P.n_blocks) return;
     const int c = task * 32 + lane;
     if (c >= P.n_cells_owned) return;
@@ -173,20 +188,34 @@ k_chan_cell(const __grid_constant__ KParams P, const KArrays A, const __grid_con
     const double vm = A.vm_cell[cur][c];
     const double vol = __ldg(A.cell_vol + c);
     const char* __restrict__ rows = A.cpack + (size_t)row0 * rowb;
+    // the rows' areas and env squares of the first KCH_KREG membranes stay in registers for the whole pass, and every
+    // channel requests its env concentrations BEFORE its gate arithmetic: with ~20 warps per SM nothing else hides the
+    // dependent gather (index -> concentration) of each membrane
+    double sa[KCH_KREG];
+    unsigned q[KCH_KREG];
+#pragma unroll
+    for (int k = 0; k < KCH_KREG; ++k) {
+        sa[k] = 0.0; q[k] = 0;
+        if (k < nm) {
+            const char* r = rows + (size_t)k * rowb;
+            sa[k] = __ldg(reinterpret_cast<const double*>(r + (size_t)ni * 256) + lane);
+            q[k] = (unsigned)__ldg(reinterpret_cast<const int*>(r + (size_t)(ni + 1) * 256 + 128) + lane) & KC_QMASK;
+        }
+    }
     for (int j = 0; j < pk.n; ++j) {
         const KChan& ch = pk.ch[j];
         const int ion = ch.ion;
         double* __restrict__ ccell = A.cc_cells + (size_t)ion * C;
         const double* __restrict__ cenv = A.cc_env[cur ^ 1] + (size_t)ion * E;
+        double cAk[KCH_KREG];
+#pragma unroll
+        for (int k = 0; k < KCH_KREG; ++k) cAk[k] = (k < nm) ? cenv[q[k]] : 0.0;
+        const double cB = ccell[c];
         double Pm;
         if (ch.frozen) Pm = ch.Pc[c];
         else {
-            const double U = vm * 1000.0 + ch.shift;
-            const double mInf = gate_quantity(ch, 0, U), mTau = gate_quantity(ch, 1, U);
-            const double hInf = gate_quantity(ch, 2, U), hTau = gate_quantity(ch, 3, U);
-            const double dt = ch.dt_tu;
-            const double mm = (mTau * ch.mc[c] + dt * mInf) / (mTau + dt);
-            const double hh = (hTau * ch.hc[c] + dt * hInf) / (hTau + dt);
+            double mm = ch.mc[c], hh = ch.hc[c];
+            gate_advance(ch, vm, mm, hh);
             ch.mc[c] = mm; ch.hc[c] = hh;
             Pm = ipow(mm, ch.mpow) * ipow(hh, ch.hpow);
             ch.Pc[c] = Pm;
@@ -195,23 +224,30 @@ k_chan_cell(const __grid_constant__ KParams P, const KArrays A, const __grid_con
         ch.Dc[c] = DChan;
         const double alpha = ((P.z[ion] + FLOAT_NONCE) * (vm + FLOAT_NONCE) * P.F) / P.RT_sim;
         const double ex = exp(-alpha), deno = -expm1(-alpha);
-        const double cB = ccell[c];
         const double coef = -((DChan * alpha) / P.tm);
         const double zF = P.z[ion];
         double S = 0.0;
-        for (int k = 0; k < nm; ++k) {
-            const char* r = rows + (size_t)k * rowb;
-            const double sa = __ldg(reinterpret_cast<const double*>(r + (size_t)ni * 256) + lane);
-            const unsigned q = (unsigned)__ldg(reinterpret_cast<const int*>(r + (size_t)(ni + 1) * 256 + 128) + lane) & KC_QMASK;
-            const double cA = cenv[q];
-            const double f = coef * ((cB - cA * ex) / deno) * P.rho_channel;
-            const double fsa = f * sa;
+#pragma unroll
+        for (int k = 0; k < KCH_KREG; ++k) if (k < nm) {
+            const double f = chan_flux(coef, cB, cAk[k], ex, deno, P.rho_channel);
+            const double fsa = __dmul_rn(f, sa[k]);
             ell[((size_t)(row0 + k) * ni + j) * 32 + lane] = fsa;
             ch.fell[(size_t)(row0 + k) * 32 + lane] = f;
             if (diag && A.chanJ) A.chanJ[m_beg + k] += (-f * P.F) * zF;
-            S += fsa;
+            S = __dadd_rn(S, fsa);
         }
-        ccell[c] = cB + (S / vol) * P.dt;
+        for (int k = KCH_KREG; k < nm; ++k) {
+            const char* r = rows + (size_t)k * rowb;
+            const double sak = __ldg(reinterpret_cast<const double*>(r + (size_t)ni * 256) + lane);
+            const unsigned qk = (unsigned)__ldg(reinterpret_cast<const int*>(r + (size_t)(ni + 1) * 256 + 128) + lane) & KC_QMASK;
+            const double f = chan_flux(coef, cB, cenv[qk], ex, deno, P.rho_channel);
+            const double fsa = __dmul_rn(f, sak);
+            ell[((size_t)(row0 + k) * ni + j) * 32 + lane] = fsa;
+            ch.fell[(size_t)(row0 + k) * 32 + lane] = f;
+            if (diag && A.chanJ) A.chanJ[m_beg + k] += (-f * P.F) * zF;
+            S = __dadd_rn(S, fsa);
+        }
+        ccell[c] = fma(S / vol, P.dt, cB);
     }
 }
 
@@ -326,7 +362,7 @@ void launch_chan_cell(const KParams& P, const KArrays& A, const KChan* chs, int 
     pk.n = pi.n = n;
     for (int j = 0; j < n; ++j) { pk.ch[j] = chs[j]; pi.ion[j] = chs[j].ion; }
     for (int j = n; j < KCH_PACK; ++j) { pk.ch[j] = chs[0]; pi.ion[j] = 0; }
-    k_chan_cell<<<(P.n_blocks + 3) / 4, 128, 0, st>>>(P, A, pk, ell, cur, diag);
+    k_chan_cell<<<(P.n_blocks + KCH_TPB / 32 - 1) / (KCH_TPB / 32), KCH_TPB, 0, st>>>(P, A, pk, ell, cur, diag);
     const int ne = (P.ya1 - P.ya0) * P.nx;
     if (ne > 0) k_chan_env_cell<<<(ne + 255) / 256, 256, 0, st>>>(P, A, pi, ell, cur ^ 1);
 }

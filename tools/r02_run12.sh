@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests/test_gpu_channels.py -m gpu -q -x --timeout 900 2>&1 | tail -5
+timeout 600 python bench.py --config c3 --steps 200 --warmup 20 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('c3', round(d['ms_per_step'],4), '%.3e'%d['value'], 'e2e %.3e'%d['e2e']['value'], {k:round(x,4) for k,x in d['roofline']['kernel_ms'].items()})"
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02s_launches_c3.csv python bench.py --config c3 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r02s_ncu_c3.log 2>&1
