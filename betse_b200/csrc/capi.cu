@@ -1158,7 +1158,9 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
         // sim.py:1282 after 2254): the Ca row is transported first, the other ions run on a second
         // stream NEXT TO the membrane kernel (which is latency-bound and leaves issue slots free).
         const bool chans = !ctx->chans.empty() || ctx->net_on[0] || ctx->net_on[1] || ctx->noise_on;   // deferred-update mode
-        const bool overlap = ecm && ctx->overlap && !evs && ctx->hp.sharpness >= 1.0 && !chans;
+        // (also in the deferred-update mode: the channels and networks read the transported cc_env, but they are enqueued
+        // behind the join below)
+        const bool overlap = ecm && ctx->overlap && !evs && ctx->hp.sharpness >= 1.0;
         if (ctx->kc_sync && mem_kernel_kind(I, ctx->P, A, diag) == 2) cudaMemsetAsync(ctx->kc_sync, 0, sizeof(int), st);
         if (ecm && overlap) {
             const int iCa = ctx->hp.iCa;

@@ -32,20 +32,27 @@ __device__ __forceinline__ double fast_rcp(double x)
     return r;
 }
 
+// One copy of the term evaluator in the kernel (not inlined): eight inlined copies of ten exp / division variants made
+// k_chan_cell 9 k instructions long and its warps stalled on instruction fetch (profiles/r02s_ncu_chan_summary.csv).
+__device__ __noinline__ double gate_term_eval(const int type, const double p0, const double p1, const double p2, const double p3, const double U)
+{
+    switch (type) {
+        case 0: return p0;
+        case 1: return p0 + p1 / (1.0 + exp((U - p2) / p3));
+        case 2: return p0 * U + p1;
+        case 3: return p0 + p1 * exp((p2 - U) / p3);
+        case 4: { const double x = (U + p2) / p3; return p0 + p1 * exp(-(x * x)); }
+        case 5: { const double x = U - p1; return p0 * x / (1.0 - exp(-x / p2)); }
+        case 7: return (U >= p2) ? 1.0 : p0 + p1 * exp(-U / p3);   // vg_ca.py Cav3p1: tau overwritten with 1 above the cut
+        case 8: return p0 / cosh((U - p1) / p2);                      // vg_morrislecar.py: 1/cosh time constants, Kir_ML
+        case 9: return p0 + p1 * tanh((U - p2) / p3);             // vg_morrislecar.py: 0.5*(1 + tanh(...))
+        default: { const double x = -U - p1; return p0 * x / (1.0 - exp(-x / p2)); }
+    }
+}
+
 __device__ __forceinline__ double gate_term(const KTerm& t, double U)
 {
-    switch (t.type) {
-        case 0: return t.p[0];
-        case 1: return t.p[0] + t.p[1] / (1.0 + exp((U - t.p[2]) / t.p[3]));
-        case 2: return t.p[0] * U + t.p[1];
-        case 3: return t.p[0] + t.p[1] * exp((t.p[2] - U) / t.p[3]);
-        case 4: { const double x = (U + t.p[2]) / t.p[3]; return t.p[0] + t.p[1] * exp(-(x * x)); }
-        case 5: { const double x = U - t.p[1]; return t.p[0] * x / (1.0 - exp(-x / t.p[2])); }
-        case 7: return (U >= t.p[2]) ? 1.0 : t.p[0] + t.p[1] * exp(-U / t.p[3]);   // vg_ca.py Cav3p1: tau overwritten with 1 above the cut
-        case 8: return t.p[0] / cosh((U - t.p[1]) / t.p[2]);                      // vg_morrislecar.py: 1/cosh time constants, Kir_ML
-        case 9: return t.p[0] + t.p[1] * tanh((U - t.p[2]) / t.p[3]);             // vg_morrislecar.py: 0.5*(1 + tanh(...))
-        default: { const double x = -U - t.p[1]; return t.p[0] * x / (1.0 - exp(-x / t.p[2])); }
-    }
+    return gate_term_eval(t.type, t.p[0], t.p[1], t.p[2], t.p[3], U);
 }
 
 __device__ __forceinline__ double gate_quantity(const KChan& ch, int q, double U)
@@ -262,19 +269,27 @@ k_chan_env_cell(const __grid_constant__ KParams P, const KArrays A, const KPassI
     if (k >= P.ya1 * P.nx) return;
     const int s0 = __ldg(A.slot_ptr + k), s1 = __ldg(A.slot_ptr + k + 1);
     if (s1 == s0) return;
-    double acc[KCH_PACK];
+    double acc[KCH_PACK], cv[KCH_PACK];
 #pragma unroll
-    for (int q = 0; q < KCH_PACK; ++q) acc[q] = 0.0;
-    for (int j = s0; j < s1; ++j) {
-        const int off = __ldg(A.slot_off + j);
+    for (int q = 0; q < KCH_PACK; ++q) { acc[q] = 0.0; cv[q] = (q < pi.n) ? A.cc_env[nxt][(size_t)pi.ion[q] * E + k] : 0.0; }
+    // the square's slots eight at a time: all positions first, then all fluxes, then the sums in slot order — one memory
+    // round trip per stage instead of two per slot
+    for (int j0 = s0; j0 < s1; j0 += 8) {
+        int off[8];
+        double v[8][KCH_PACK];
 #pragma unroll
-        for (int q = 0; q < KCH_PACK; ++q) if (q < pi.n) acc[q] += ell[(size_t)off + q * 32];
+        for (int u = 0; u < 8; ++u) off[u] = (j0 + u < s1) ? __ldg(A.slot_off + j0 + u) : -1;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int q = 0; q < KCH_PACK; ++q) v[u][q] = (off[u] >= 0 && q < pi.n) ? ell[(size_t)off[u] + q * 32] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int q = 0; q < KCH_PACK; ++q) if (j0 + u < s1) acc[q] += v[u][q];
     }
 #pragma unroll
-    for (int q = 0; q < KCH_PACK; ++q) if (q < pi.n) {
-        double* c = A.cc_env[nxt] + (size_t)pi.ion[q] * E + k;
-        *c = *c + ((-acc[q]) / P.env_vol_div) * P.dt;
-    }
+    for (int q = 0; q < KCH_PACK; ++q) if (q < pi.n) A.cc_env[nxt][(size_t)pi.ion[q] * E + k] = cv[q] + ((-acc[q]) / P.env_vol_div) * P.dt;
 }
 
 // per-cell gate state -> the per-membrane arrays of the C ABI (betse_channel_state; leaving the per-cell path)
@@ -335,20 +350,28 @@ k_cell_update(const __grid_constant__ KParams P, const KArrays A, const int cur)
     unsigned int flags = 0;
     const double rvol = fast_rcp(__ldg(A.cell_vol + c));
     double rho = 0.0;
-    for (int i = 0; i < P.n_ions; ++i) {
-        const double cc = A.cc_cells[i * C + c];
-        const double Sm = A.dsum_m[i * C + c], Sg = A.dsum_g[i * C + c];
-        const double cm_new = cc + (Sm * rvol) * P.dt;
-        double cn_new = cm_new + P.dt * ((-Sg) * rvol);
+    // every input first (the stores below would otherwise fence the next ion's loads: one memory round trip per ion)
+    double cc[BT_MAX_IONS], Sm[BT_MAX_IONS], Sg[BT_MAX_IONS];
+#pragma unroll
+    for (int i = 0; i < BT_MAX_IONS; ++i) {
+        cc[i] = Sm[i] = Sg[i] = 0.0;
+        if (i < P.n_ions) { cc[i] = A.cc_cells[i * C + c]; Sm[i] = A.dsum_m[i * C + c]; Sg[i] = A.dsum_g[i * C + c]; }
+    }
+    const double xr = A.extra_rho_cells ? __ldg(A.extra_rho_cells + c) : 0.0;
+    const double dvt = __ldg(A.diviterm + c);
+#pragma unroll
+    for (int i = 0; i < BT_MAX_IONS; ++i) if (i < P.n_ions) {
+        const double cm_new = cc[i] + (Sm[i] * rvol) * P.dt;
+        double cn_new = cm_new + P.dt * ((-Sg[i]) * rvol);
         if (cn_new != cn_new) flags |= ST_NAN_CONC;
         if (cn_new < 0.0) { cn_new = 0.0; flags |= ST_NEG; }
         A.cc_cells[i * C + c] = cn_new;
         A.cc_mid[nxt][i * C + c] = cm_new;
         rho = fma(P.zF[i], cn_new, rho);
     }
-    if (A.extra_rho_cells) rho += __ldg(A.extra_rho_cells + c);
+    if (A.extra_rho_cells) rho += xr;
     A.rho_cells[c] = rho;
-    const double vmn = P.inv_cm * (rho * __ldg(A.diviterm + c));
+    const double vmn = P.inv_cm * (rho * dvt);
     if (vmn != vmn) flags |= ST_NAN_VM;
     A.vm_cell[nxt][c] = vmn;
     if (flags) atomicOr(A.status, flags);

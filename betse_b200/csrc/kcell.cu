@@ -655,16 +655,27 @@ __device__ __forceinline__ void envacc_ell_body(const KParams& P, const KArrays&
 #pragma unroll
             for (int i = 0; i < NI; ++i) acc[i] = A.sq_sum[(size_t)i * E + k];
         } else
-        for (int j = s0; j < s1; ++j) {
-            const int off = ldgi(A.slot_off + j);
-            if (off >= 0) {
+        // the square's slots four at a time: all positions first, then all fluxes, then the sums in slot order — small
+        // tissues and thin strips are bound by the dependent round trips of this walk, not by bandwidth
+        for (int j0 = s0; j0 < s1; j0 += 4) {
+            int off[4];
+            double v[4][NI];
 #pragma unroll
-                for (int i = 0; i < NI; ++i) acc[i] += A.flux_ell[(size_t)off + i * 32];
-            } else {
-                const double* __restrict__ f = A.flux_slots + (size_t)(-(off + 1));
+            for (int u = 0; u < 4; ++u) off[u] = (j0 + u < s1) ? ldgi(A.slot_off + j0 + u) : 0;
 #pragma unroll
-                for (int i = 0; i < NI; ++i) acc[i] += f[i];
+            for (int u = 0; u < 4; ++u) {
+                // local membrane: flux_ell, stride 32 between ions; remote slot: the window's [slot][ion] array
+                const double* __restrict__ f = (off[u] >= 0) ? A.flux_ell + (size_t)off[u] : A.flux_slots + (size_t)(-(off[u] + 1));
+                const int st = (off[u] >= 0) ? 32 : 1;
+#pragma unroll
+                for (int i = 0; i < NI; ++i) v[u][i] = (j0 + u < s1) ? f[i * st] : 0.0;
             }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (j0 + u < s1) {
+#pragma unroll
+                    for (int i = 0; i < NI; ++i) acc[i] += v[u][i];
+                }
         }
         double c[NI];
         const double vr = env_square_finish<NI>(P, A, nxt, k, cv, acc, s1 > s0, c);

@@ -512,10 +512,12 @@ k_envacc(const __grid_constant__ KParams P, const KArrays A, const int nxt, cons
 // v_env = gaussian_filter(v_raw, sigma=1, mode='constant') + Phi_b ; E = -grad(screen*v_env)
 // Shared-memory tile: 32x32 outputs, halo 5 (4 Gaussian + 1 gradient); zero fill outside the
 // world reproduces scipy's mode='constant', cval=0 in both separable passes.
-#define FT 32
 #define FH 5
+// FT: 32 for large grids; 16 when 32x32 tiles would leave most SMs without a CTA (small tissues, thin strips of a
+// decomposed tissue: the kernel is then a chain of four barrier-separated phases, and its length is what counts)
+template <int FT>
 __global__ void __launch_bounds__(256)
-k_field(const __grid_constant__ KParams P, const KArrays A)
+k_field_t(const __grid_constant__ KParams P, const KArrays A)
 {
     __shared__ double sA[FT + 2 * FH][FT + 2 * FH + 1];   // raw
     __shared__ double sB[FT + 2][FT + 2 * FH + 1];        // after the axis-0 (y) pass
@@ -932,8 +934,11 @@ void launch_field(const KParams& P, const KArrays& A, int ny, int nx, cudaStream
 {
     const int rows = P.yf1 - P.yf0;
     if (rows <= 0) return;
-    dim3 b(32, 8), g((nx + FT - 1) / FT, (rows + FT - 1) / FT);
-    k_field<<<g, b, 0, st>>>(P, A);
+    static const int small_ok = [] { const char* e = getenv("BETSE_FIELD16"); return (e && e[0] == '0') ? 0 : 1; }();
+    const int n32 = ((nx + 31) / 32) * ((rows + 31) / 32);
+    dim3 b(32, 8);
+    if (small_ok && n32 < 2 * 148) k_field_t<16><<<dim3((nx + 15) / 16, (rows + 15) / 16), b, 0, st>>>(P, A);
+    else k_field_t<32><<<dim3((nx + 31) / 32, (rows + 31) / 32), b, 0, st>>>(P, A);
 }
 
 void launch_envmix(int ni, const KParams& P, const KArrays& A, int cur, cudaStream_t st)

@@ -11,7 +11,7 @@ for r in rows[1:]:
     v *= {'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(u, 1.0)
     d[r[ix['Metric Name']]] = v
 ids = list(per)
-ends = [i for i, k in enumerate(ids) if per[k]['name'].startswith('k_field')]
+ends = [i for i, k in enumerate(ids) if 'k_field' in per[k]['name']]
 a, b = (ends[-2] + 1, ends[-1] + 1) if len(ends) > 1 else (0, len(ids))
 tot = 0.0
 for k in ids[a:b]:
