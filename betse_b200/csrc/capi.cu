@@ -867,8 +867,8 @@ static int ensure_poisson(betse_ctx* ctx)
     if ((r = dev_alloc(ctx, &H.ly, my))) return r;
     if ((r = dev_alloc(ctx, &H.lx, mx))) return r;
     if ((r = dev_alloc(ctx, &H.bB, (size_t)ctx->E))) return r;
-    if ((r = dev_alloc(ctx, &H.R, my * mx))) return r;
-    if ((r = dev_alloc(ctx, &H.T1, my * mx))) return r;
+    if ((r = dev_alloc(ctx, &H.R, 2 * my * mx))) return r;          // two solves at once (hh.cu:poisson)
+    if ((r = dev_alloc(ctx, &H.T1, 2 * my * mx))) return r;
     launch_hh_setup(H, ctx->ny, ctx->nx, ctx->stream);
     CK(cudaGetLastError());
     ctx->poisson_on = true;

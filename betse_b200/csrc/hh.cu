@@ -98,48 +98,109 @@ __global__ void k_hh_lift(const __grid_constant__ KParams P, const double* b, do
     R[(size_t)(y - 1) * (nx - 2) + (x - 1)] = r;
 }
 
-// C[M][N] = A[M][K] . B[K][N] (row major), 64x64 tile per CTA, 4x4 per thread
-__global__ void __launch_bounds__(256)
-k_hh_gemm(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C, int M, int N, int K)
+// C[M][N] = A[M][K] . B[K][N] (row major), batched over blockIdx.z (operand strides sA / sB / sC elements, 0 = shared).
+// The Poisson solves are four such products each (2 GFLOP at a 1000^2 grid): bound by the fp64 pipe (36.7 TFLOP/s measured,
+// tools/micro/fp64_peak.cu).  A warp issues a DFMA every other cycle at best, so the pipe wants >= 4 warps per scheduler:
+// 128x64 tile per CTA of 256 threads, 8x4 accumulators per thread (~110 registers, two CTAs per SM), the k-tile of 16
+// double-buffered in shared memory and filled with cp.async (no staging registers; out-of-range elements are zero-filled
+// by the copy).  A thread owns rows {32g + 2ty + r} and columns {32h + 2tx + c} (g < 4, h < 2; r, c < 2): its 16-byte
+// shared loads are conflict-free across tx and broadcast across ty.  (An 8x8 tile at 255 registers ran the pipe at 48 %:
+// profiles/r02u_ncu_gemm_summary.csv.)
+#define GM 128
+#define GN 64
+#define GK 16
+#define GEMM_SMEM ((2 * GK * (GM + 2) + 2 * GK * GN) * 8)
+__device__ __forceinline__ void cp_async8(double* dst, const double* src, const bool ok)
 {
-    __shared__ double sA[16][64 + 1], sB[16][64 + 1];
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
-    double acc[4][4] = {};
-    for (int k0 = 0; k0 < K; k0 += 16) {
-        for (int t = threadIdx.x; t < 64 * 16; t += 256) {
-            const int rr = t >> 4, kk = t & 15;                       // A tile: rows r0.., cols k0..
-            sA[kk][rr] = (r0 + rr < M && k0 + kk < K) ? A[(size_t)(r0 + rr) * K + k0 + kk] : 0.0;
-            const int kb = t >> 6, cc = t & 63;                       // B tile: rows k0.., cols c0..
-            sB[kb][cc] = (k0 + kb < K && c0 + cc < N) ? B[(size_t)(k0 + kb) * N + c0 + cc] : 0.0;
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    const int n = ok ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 2)
+k_hh_gemm(const double* __restrict__ Ab, const double* __restrict__ Bb, double* __restrict__ Cb, const int M, const int N, const int K,
+          const size_t sA, const size_t sB, const size_t sC)
+{
+    extern __shared__ __align__(16) double sh_gemm[];                  // GEMM_SMEM bytes (opt-in size: launch_hh_setup)
+    double (*shA)[GK][GM + 2] = reinterpret_cast<double (*)[GK][GM + 2]>(sh_gemm);      // + 2: the transposing copies hit 2 banks, not 16
+    double (*shB)[GK][GN] = reinterpret_cast<double (*)[GK][GN]>(sh_gemm + 2 * GK * (GM + 2));
+    const double* __restrict__ A = Ab + (size_t)blockIdx.z * sA;
+    const double* __restrict__ B = Bb + (size_t)blockIdx.z * sB;
+    double* __restrict__ C = Cb + (size_t)blockIdx.z * sC;
+    const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+    const int r0 = blockIdx.y * GM, c0 = blockIdx.x * GN;
+    // global -> shared, coalesced: A as 8 copies of (16 rows x 16 k) — a warp covers two rows of 128 bytes per copy;
+    // B row k0 + t/16, 4 consecutive columns from c0 + 4 (t % 16)
+    const int ak = t & 15, ar = t >> 4;
+    const int bk = t >> 4, bc = (t & 15) * 4;
+    auto fill = [&](const int buf, const int k0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int row = r0 + q * 16 + ar;
+            const bool ok = row < M && k0 + ak < K;
+            cp_async8(&shA[buf][ak][q * 16 + ar], ok ? A + (size_t)row * K + k0 + ak : A, ok);
         }
-        __syncthreads();
 #pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
-            double a[4], b[4];
+        for (int q = 0; q < 4; ++q) {
+            const bool ok = k0 + bk < K && c0 + bc + q < N;
+            cp_async8(&shB[buf][bk][bc + q], ok ? B + (size_t)(k0 + bk) * N + c0 + bc + q : B, ok);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    double acc[8][4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { a[i] = sA[kk][ty * 4 + i]; b[i] = sB[kk][tx * 4 + i]; }
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    fill(0, 0);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = 0; k0 < K; k0 += GK) {
+        const bool more = k0 + GK < K;
+        if (more) fill(buf ^ 1, k0 + GK);
+#pragma unroll
+        for (int kk = 0; kk < GK; ++kk) {
+            double a[8], b[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const double2 va = *reinterpret_cast<const double2*>(&shA[buf][kk][32 * g + 2 * ty]);
+                a[2 * g] = va.x; a[2 * g + 1] = va.y;
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const double2 vb = *reinterpret_cast<const double2*>(&shB[buf][kk][32 * h + 2 * tx]);
+                b[2 * h] = vb.x; b[2 * h + 1] = vb.y;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
         }
-        __syncthreads();
+        if (more) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+            buf ^= 1;
+        }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i) {
+        const int r = r0 + 32 * (i >> 1) + 2 * ty + (i & 1);
+        if (r >= M) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int r = r0 + ty * 4 + i, c = c0 + tx * 4 + j;
-            if (r < M && c < N) C[(size_t)r * N + c] = acc[i][j];
+            const int c = c0 + 32 * (j >> 1) + 2 * tx + (j & 1);
+            if (c < N) C[(size_t)r * N + c] = acc[i][j];
         }
+    }
 }
 
 // spectral division (the two dstn factors of 2 folded in) / back-transform normalisation + scatter into u
-__global__ void k_hh_scale(double* T, const double* ly, const double* lx, int my, int mx)
+__global__ void k_hh_scale(double* Tb, const double* ly, const double* lx, int my, int mx)
 {
     const int l = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
     if (l >= mx) return;
+    double* T = Tb + (size_t)blockIdx.z * my * mx;
     T[(size_t)k * mx + l] = (4.0 * T[(size_t)k * mx + l]) / (ly[k] + lx[l]);
 }
 __global__ void k_hh_scatter(const double* T, double* u, int my, int mx)
@@ -176,30 +237,37 @@ __global__ void k_hh_out(const __grid_constant__ KParams P, HHBuf H)
     H.Jtx[k] = Fx + gBx; H.Jty[k] = Fy + gBy;         // ion_current.py:67-68
 }
 
-static void gemm(const double* A, const double* B, double* C, int M, int N, int K, cudaStream_t st)
+static void gemm(const double* A, const double* B, double* C, int M, int N, int K, int batch, size_t sA, size_t sB, size_t sC, cudaStream_t st)
 {
-    dim3 g((N + 63) / 64, (M + 63) / 64);
-    k_hh_gemm<<<g, 256, 0, st>>>(A, B, C, M, N, K);
+    dim3 g((N + GN - 1) / GN, (M + GM - 1) / GM, batch);
+    k_hh_gemm<<<g, 256, GEMM_SMEM, st>>>(A, B, C, M, N, K, sA, sB, sC);
 }
 
 void launch_hh_setup(const HHBuf& H, int ny, int nx, cudaStream_t st)
 {
     const int my = ny - 2, mx = nx - 2;
+    cudaFuncSetAttribute(k_hh_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
     k_hh_sine<<<dim3((my + 127) / 128, my), 128, 0, st>>>(H.Sy, H.ly, my);
     k_hh_sine<<<dim3((mx + 127) / 128, mx), 128, 0, st>>>(H.Sx, H.lx, mx);
 }
 
-static void poisson(const KParams& P, const HHBuf& H, const double* b, double* u, cudaStream_t st)
+// one Dirichlet solve (b -> u), or two that share the sine matrices (b2 -> u2 as well) as batched products: H.R / H.T1
+// hold two [my][mx] work arrays
+static void poisson(const KParams& P, const HHBuf& H, const double* b, double* u, cudaStream_t st, const double* b2 = nullptr, double* u2 = nullptr)
 {
     const int ny = P.ny, nx = P.nx, my = ny - 2, mx = nx - 2;
-    dim3 gE((nx + 127) / 128, ny), gI((mx + 127) / 128, my);
+    const int nb = b2 ? 2 : 1;
+    const size_t w = (size_t)my * mx;
+    dim3 gE((nx + 127) / 128, ny), gI((mx + 127) / 128, my), gIb((mx + 127) / 128, my, nb);
     k_hh_lift<<<gE, 128, 0, st>>>(P, b, u, H.R);
-    gemm(H.Sy, H.R, H.T1, my, mx, my, st);           // Sy . R
-    gemm(H.T1, H.Sx, H.R, my, mx, mx, st);           // . Sx
-    k_hh_scale<<<gI, 128, 0, st>>>(H.R, H.ly, H.lx, my, mx);
-    gemm(H.Sy, H.R, H.T1, my, mx, my, st);
-    gemm(H.T1, H.Sx, H.R, my, mx, mx, st);
+    if (b2) k_hh_lift<<<gE, 128, 0, st>>>(P, b2, u2, H.R + w);
+    gemm(H.Sy, H.R, H.T1, my, mx, my, nb, 0, w, w, st);           // Sy . R
+    gemm(H.T1, H.Sx, H.R, my, mx, mx, nb, w, 0, w, st);           // . Sx
+    k_hh_scale<<<gIb, 128, 0, st>>>(H.R, H.ly, H.lx, my, mx);
+    gemm(H.Sy, H.R, H.T1, my, mx, my, nb, 0, w, w, st);
+    gemm(H.T1, H.Sx, H.R, my, mx, mx, nb, w, 0, w, st);
     k_hh_scatter<<<gI, 128, 0, st>>>(H.R, u, my, mx);
+    if (b2) k_hh_scatter<<<gI, 128, 0, st>>>(H.R + w, u2, my, mx);
 }
 
 // -div_Jb of the boundary-voltage problem (ion_current.py:84-90 / 160-168): zero inside, +bound_V/d^2 on the border;
@@ -309,8 +377,7 @@ static void hh_core(const KParams& P, const HHBuf& H, cudaStream_t st)
 {
     dim3 gE((P.nx + 127) / 128, P.ny);
     k_hh_rhs<<<gE, 128, 0, st>>>(P, H);
-    poisson(P, H, H.bA, H.uA, st);
-    poisson(P, H, H.bB, H.uB, st);
+    poisson(P, H, H.bA, H.uA, st, H.bB, H.uB);
     k_hh_out<<<gE, 128, 0, st>>>(P, H);
 }
 
@@ -335,7 +402,6 @@ void launch_hh(const KParams& P, const KArrays& A, const HHBuf& H, cudaStream_t 
     dim3 gE((P.nx + 127) / 128, P.ny);
     k_hh_J<<<(E + 255) / 256, 256, 0, st>>>(P, A, H);
     k_hh_rhs<<<gE, 128, 0, st>>>(P, H);
-    poisson(P, H, H.bA, H.uA, st);
-    poisson(P, H, H.bB, H.uB, st);
+    poisson(P, H, H.bA, H.uA, st, H.bB, H.uB);
     k_hh_out<<<gE, 128, 0, st>>>(P, H);
 }

@@ -7,7 +7,7 @@ struct HHBuf {
     double *Jx, *Jy;          // [E] total current density of the ions
     double *bA, *bB;          // [E] right-hand sides of the two Poisson problems
     double *uA, *uB;          // [E] potentials AA, BB
-    double *R, *T1;           // [my][mx] work
+    double *R, *T1;           // [2][my][mx] work (two Poisson solves at once)
     double *J_env_x, *J_env_y, *B_field, *Jtx, *Jty;   // outputs [E]
     double mu, bound[4];      // p.mu; sim.bound_V T, B, L, R
 };
