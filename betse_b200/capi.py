@@ -183,7 +183,7 @@ class Neighbor(C.Structure):
 SYMBOLS = [
     "betse_abi_version", "betse_device_count", "betse_create", "betse_destroy", "betse_last_error",
     "betse_create_error", "betse_upload_state", "betse_set_schedule", "betse_step",
-    "betse_step_profile", "betse_ensemble_step", "betse_fast_setup", "betse_fast_step", "betse_fast_download", "betse_kernel_name", "betse_download_sample",
+    "betse_step_profile", "betse_ensemble_step", "betse_fast_setup", "betse_fast_step", "betse_fast_download", "betse_fast_set_channels", "betse_kernel_name", "betse_download_sample",
     "betse_step_phase", "betse_stream", "betse_sync", "betse_update_v", "betse_update_v_phase",
     "betse_set_row_ranges", "betse_window", "betse_attach_neighbor", "betse_exchange",
     "betse_set_channels", "betse_channel_state", "betse_set_network", "betse_network_state",
@@ -222,6 +222,7 @@ def load(build_if_missing=True):
     lib.betse_fast_setup.argtypes = [vp, C.POINTER(FastHost)]
     lib.betse_fast_step.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_uint32)]
     lib.betse_fast_download.argtypes = [vp, C.POINTER(FastHost)]
+    lib.betse_fast_set_channels.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.betse_kernel_name.argtypes = [C.c_int]
     lib.betse_kernel_name.restype = C.c_char_p
     lib.betse_download_sample.argtypes = [vp, C.POINTER(StateHost)]

@@ -57,6 +57,8 @@ void launch_cell_x(int ni, const KParams& P, const KArrays& A, const XPlan& X, i
 void launch_chan(const KParams& P, const KArrays& A, const KChan& ch, const KNet& N, int cur, cudaStream_t st);
 void launch_chan_cell(const KParams& P, const KArrays& A, const KChan* chs, int n, double* ell, int cur, int diag, cudaStream_t st);
 void launch_chan_expand(const KChan& ch, const int* mem_to_cells, const int* mem_ell, int Mo, int ni, cudaStream_t st);
+void launch_fast_chan(const KParams& P, const KArrays& A, const KChan* chs, int n, const double* coef, const double* rev_E,
+                      const double* vm_ave, double* extra_J, cudaStream_t st);
 void launch_net(const KParams& P, const KArrays& A, const KNet& N, const double* h_Dgj, const double* h_Dm,
                 const unsigned char* h_env_on, const betse_substance_pump* pumps, int n_pumps, double dG_RT,
                 const unsigned char* h_intra, int n_ions, int cur, cudaStream_t st);
@@ -146,6 +148,9 @@ struct betse_ctx {
     KFast fast;
     bool fast_on = false;
     int fast_cur = 0;
+    bool fast_chan_on = false;               // channels under the fast solver (betse_fast_set_channels)
+    double fast_coef[BT_MAX_IONS] = {0}, fast_revE[BT_MAX_IONS] = {0};
+    double* fast_extraJ = nullptr;           // [M] extra_J_mem the channels form each step
     cudaGraphExec_t fast_graph = nullptr;    // two steps (buffer parity returns)
     int fast_graph_cur = 0;
     // CUDA graphs of one plain step, for cur = 0 and cur = 1
@@ -853,6 +858,7 @@ static double nan_value() { return nan(""); }
 static void publish_affect(betse_ctx* ctx);
 static bool chan_cell_possible(betse_ctx* ctx);
 static void chan_layout_sync(betse_ctx* ctx);
+static void chan_expand_all(betse_ctx* ctx);
 
 // sine matrices, eigenvalues and work buffers of the Dirichlet Poisson solve on the env grid (csrc/hh.cu)
 static int ensure_poisson(betse_ctx* ctx)
@@ -1492,7 +1498,9 @@ extern "C" int betse_fast_setup(betse_ctx* ctx, const betse_fast_host* s)
     if (!s->vm_ave || !s->gjopen || !s->G_Leak || !s->E_Leak || !s->G_gj || !s->sigma_cell)
         return fail(ctx, "betse_fast_setup: vm_ave, gjopen, G_Leak, E_Leak, G_gj and sigma_cell are required");
     if (ctx->X.n_nbr > 0) return fail(ctx, "the fast solver on a domain-decomposed tissue is not implemented");
-    if (!ctx->chans.empty() || ctx->net_on[0] || ctx->net_on[1]) return fail(ctx, "the fast solver with networks is not implemented");
+    if (ctx->net_on[0] || ctx->net_on[1]) return fail(ctx, "the fast solver with network substances is not implemented");
+    if (!ctx->chans.empty() && !ctx->fast_chan_on)
+        return fail(ctx, "the fast solver with channels needs betse_fast_set_channels (conductance factors, reversal potentials)");
     if (!ctx->hp.v_sensitive_gj && !ctx->A.gj_w) return fail(ctx, "static gap junctions need gj_default_weights");
     CK(cudaSetDevice(ctx->device));
     const int C = ctx->C, Mo = ctx->Mo;
@@ -1525,6 +1533,11 @@ extern "C" int betse_fast_setup(betse_ctx* ctx, const betse_fast_host* s)
     UPF(Fz.G_gj, s->G_gj, C);
     UPF(Fz.sigma_cell, s->sigma_cell, C);
     if ((r = opt_array(ctx, &Fz.extra_J, s->extra_J_mem, (size_t)Mo))) return r;
+    if (ctx->fast_chan_on && !ctx->chans.empty()) {
+        // clear_run_loop zeroes extra_J_mem every step and the channels rebuild it (sim.py:1505-1512, networks.py:3272)
+        if (!ctx->fast_extraJ && (r = dev_alloc(ctx, &ctx->fast_extraJ, (size_t)Mo))) return r;
+        Fz.extra_J = ctx->fast_extraJ;
+    }
 #undef UPF
     double mean = 0.0;                                    // sim.sigma_cell.mean(): NumPy's pairwise sum is within an ulp
     for (int c = 0; c < C; ++c) mean += s->sigma_cell[c];
@@ -1532,6 +1545,28 @@ extern "C" int betse_fast_setup(betse_ctx* ctx, const betse_fast_host* s)
     Fz.sm = 0.1 * mean;
     Fz.dt_cm = ctx->hp.dt * (1.0 / ctx->hp.cm);            // p.dt*(1/p.cm), sim.py:1561
     CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// one iteration of the fast loop body: the channels' currents from the potentials the step starts with, then the circuit
+static void enqueue_fast(betse_ctx* ctx, int cur)
+{
+    if (ctx->fast_chan_on && !ctx->chans.empty())
+        launch_fast_chan(ctx->P, ctx->A, ctx->chans.data(), (int)ctx->chans.size(), ctx->fast_coef, ctx->fast_revE,
+                         ctx->fast.vm_ave[cur], ctx->fast_extraJ, ctx->stream);
+    launch_fast(ctx->P, ctx->A, ctx->fast, cur, ctx->stream);
+}
+
+extern "C" int betse_fast_set_channels(betse_ctx* ctx, const double* cond_coef, const double* rev_E)
+{
+    if (!ctx || !cond_coef || !rev_E) return 2;
+    CK(cudaSetDevice(ctx->device));
+    for (const KChan& ch : ctx->chans)
+        if (ch.mod_prog >= 0) return fail(ctx, "the fast solver with network-modulated channels is not implemented");
+    if (ctx->chan_cell_mode) { chan_expand_all(ctx); ctx->chan_cell_mode = false; }     // this solver keeps the gates per membrane
+    for (int i = 0; i < ctx->I; ++i) { ctx->fast_coef[i] = cond_coef[i]; ctx->fast_revE[i] = rev_E[i]; }
+    ctx->fast_chan_on = true;
+    if (ctx->fast_graph) { cudaGraphExecDestroy(ctx->fast_graph); ctx->fast_graph = nullptr; }
     return 0;
 }
 
@@ -1543,22 +1578,22 @@ extern "C" int betse_fast_step(betse_ctx* ctx, int nsteps, int flags, uint32_t* 
     int n = nsteps;
     if (n >= 8 && ctx->use_graphs) {
         if (!ctx->fast_graph) {
-            launch_fast(ctx->P, ctx->A, ctx->fast, ctx->fast_cur, ctx->stream);      // loads the kernel outside the capture
+            enqueue_fast(ctx, ctx->fast_cur);      // loads the kernel outside the capture
             ctx->fast_cur ^= 1; --n;
             cudaGraph_t g;
             const int c0 = ctx->fast_cur;
             CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-            launch_fast(ctx->P, ctx->A, ctx->fast, c0, ctx->stream);
-            launch_fast(ctx->P, ctx->A, ctx->fast, c0 ^ 1, ctx->stream);
+            enqueue_fast(ctx, c0);
+            enqueue_fast(ctx, c0 ^ 1);
             CK(cudaStreamEndCapture(ctx->stream, &g));
             CK(cudaGraphInstantiate(&ctx->fast_graph, g, 0));
             CK(cudaGraphDestroy(g));
             ctx->fast_graph_cur = c0;
         }
-        if (ctx->fast_cur != ctx->fast_graph_cur && n > 0) { launch_fast(ctx->P, ctx->A, ctx->fast, ctx->fast_cur, ctx->stream); ctx->fast_cur ^= 1; --n; }
+        if (ctx->fast_cur != ctx->fast_graph_cur && n > 0) { enqueue_fast(ctx, ctx->fast_cur); ctx->fast_cur ^= 1; --n; }
         for (; n >= 2; n -= 2) CK(cudaGraphLaunch(ctx->fast_graph, ctx->stream));
     }
-    for (; n > 0; --n) { launch_fast(ctx->P, ctx->A, ctx->fast, ctx->fast_cur, ctx->stream); ctx->fast_cur ^= 1; }
+    for (; n > 0; --n) { enqueue_fast(ctx, ctx->fast_cur); ctx->fast_cur ^= 1; }
     if (flags & BETSE_STEP_DIAG) launch_fast_diag(ctx->P, ctx->A, ctx->fast, ctx->stream);     // (nsteps == 0: of the last step run)
     CK(cudaGetLastError());
     return read_status(ctx, status_out);

@@ -292,6 +292,57 @@ k_chan_env_cell(const __grid_constant__ KParams P, const KArrays A, const KPassI
     for (int q = 0; q < KCH_PACK; ++q) if (q < pi.n) A.cc_env[nxt][(size_t)pi.ion[q] * E + k] = cv[q] + ((-acc[q]) / P.env_vol_div) * P.dt;
 }
 
+// ---------------------------------------------------------------------------- channels under the FAST solver
+// MasterOfNetworks.run_fast_loop_channels (networks.py:3217-3280): the gates advance at the membrane's potential (the cell
+// average of the equivalent-circuit solver), the open probability becomes a conductance
+//   G = stb.get_conductivity(DChan, z, cbar, tm, p) * geo_conv = DChan * (q z^2 F cbar / (tm kb T)) * geo_conv
+// (sim_toolbox.py:1363-1372; the bracket per ion comes from the host as `coef`), and the current against the FIXED
+// reversal potential of Simulator.fast_sim_init (sim.py:1393-1452) joins extra_J_mem: J = G (vm - E_rev).  No
+// concentration moves.  One thread per membrane, the channels of a pack back to back; `first` = this launch starts the sum.
+struct KFastChan { double coef[BT_MAX_IONS], rev_E[BT_MAX_IONS]; };
+
+__global__ void __launch_bounds__(256)
+k_fast_chan(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ KChanPack pk, const __grid_constant__ KFastChan fc,
+            const double* __restrict__ vm_ave, double* __restrict__ extra_J, const int first)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= P.n_mems_owned) return;
+    const double vm = vm_ave[__ldg(A.mem_to_cells + m)];
+    double acc = first ? 0.0 : extra_J[m];
+    for (int j = 0; j < pk.n; ++j) {
+        const KChan& ch = pk.ch[j];
+        double Pm = 0.0;
+        if (ch.frozen) Pm = ch.P[m];
+        else if (!ch.mask || ch.mask[m]) {
+            double mm = ch.m[m], hh = ch.h[m];
+            gate_advance(ch, vm, mm, hh);
+            ch.m[m] = mm; ch.h[m] = hh;
+            Pm = ipow(mm, ch.mpow) * ipow(hh, ch.hpow);
+        }
+        if (!ch.frozen) ch.P[m] = Pm;
+        const double DChan = ((Pm * ch.rel_perm) * ch.maxDm) * 1.0;
+        if (ch.D) ch.D[m] = DChan;
+        const double J = (DChan * fc.coef[ch.ion]) * (vm - fc.rev_E[ch.ion]);
+        acc += J;
+        if (ch.flux) ch.flux[m] = J / (P.z[ch.ion] * P.F);                 // chan_flux = J_ED/(zzz*p.F), networks.py:3280
+    }
+    extra_J[m] = acc;
+}
+
+// all channels of the ctx, KCH_PACK per launch (coef / rev_E: [n_ions])
+void launch_fast_chan(const KParams& P, const KArrays& A, const KChan* chs, int n, const double* coef, const double* rev_E,
+                      const double* vm_ave, double* extra_J, cudaStream_t st)
+{
+    KFastChan fc;
+    for (int i = 0; i < BT_MAX_IONS; ++i) { fc.coef[i] = i < P.n_ions ? coef[i] : 0.0; fc.rev_E[i] = i < P.n_ions ? rev_E[i] : 0.0; }
+    for (int k0 = 0; k0 < n; k0 += KCH_PACK) {
+        KChanPack pk;
+        pk.n = n - k0 < KCH_PACK ? n - k0 : KCH_PACK;
+        for (int j = 0; j < KCH_PACK; ++j) pk.ch[j] = chs[k0 + (j < pk.n ? j : 0)];
+        k_fast_chan<<<(P.n_mems_owned + 255) / 256, 256, 0, st>>>(P, A, pk, fc, vm_ave, extra_J, k0 == 0 ? 1 : 0);
+    }
+}
+
 // per-cell gate state -> the per-membrane arrays of the C ABI (betse_channel_state; leaving the per-cell path)
 __global__ void __launch_bounds__(256)
 k_chan_expand(const __grid_constant__ KChan ch, const int* __restrict__ mem_to_cells, const int* __restrict__ mem_ell, const int Mo, const int ni)

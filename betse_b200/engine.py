@@ -519,6 +519,19 @@ class TissueEngine:
             setattr(sh, name, capi.ptr_f64(a))
         self._check(self.lib.betse_fast_setup(self.ctx, C.byref(sh)), "betse_fast_setup")
 
+    def fast_set_channels(self, cbar, rev_E, geo_conv=1.0):
+        """Channels (set_channels) under the fast solver, run_fast_loop_channels (networks.py:3217-3280): ``cbar`` / ``rev_E``
+        [n_ions] = sim.cbar_dic / sim.rev_E_dic of Simulator.fast_sim_init in ion-index order.  Before fast_setup."""
+        P = self.p
+        z = np.array([float(self._hp.z[i]) for i in range(self.I)])
+        # stb.get_conductivity(D, z, c, d, p) = (D*q*z^2*F*c)/(d*kb*T) without D, times sim.geo_conv (networks.py:3267)
+        coef = capi.as_f64((float(P["q"]) * (z ** 2) * float(P["F"]) * np.asarray(cbar, dtype=float)) /
+                           (float(P["tm"]) * float(P["kb"]) * float(P["T"])) * float(geo_conv))
+        rev = capi.as_f64(np.asarray(rev_E, dtype=float))
+        if coef.size != self.I or rev.size != self.I:
+            raise BetseB200Error("fast solver channels: cbar / rev_E need one value per ion")
+        self._check(self.lib.betse_fast_set_channels(self.ctx, capi.ptr_f64(coef), capi.ptr_f64(rev)), "betse_fast_set_channels")
+
     def fast_step(self, n=1, diag=False):
         """n iterations of Simulator._run_fast_sim_core_loop's body (sim.py:1547-1592); ``diag``: the currents and fields
         of the last one are formed as well (sampled steps)."""

@@ -631,12 +631,21 @@ def run_fast_sim_core_loop(sim, phase, time_steps, time_steps_sampled, anim_cell
     """Same signature and contract as Simulator._run_fast_sim_core_loop (sim.py:1454-1640), the equivalent-circuit
     solver selected by ``solver options: type: fast``: the loop body runs on the device (csrc/fast.cu), scheduled events
     stay the reference's own host code, and the sampled steps append to the Simulator's time series exactly what the
-    reference's loop appends (sim.py:1597-1628).  Networks under the fast solver are refused."""
+    reference's loop appends (sim.py:1597-1628).  Networks under the fast solver: voltage-gated channels
+    (run_fast_loop_channels, networks.py:3217-3280) of handlers WITHOUT substances, transporters or modulators; the rest
+    (their run_loop moves concentrations the equivalent circuit never reads back) is refused."""
     p, cells = phase.p, phase.cells
-    if bool(getattr(p, "molecules_enabled", False)) or bool(getattr(p, "grn_enabled", False)):
-        raise BetseB200Error("betse_b200: networks under the fast solver (run_fast_loop_channels, networks.py:3217-3280) "
-                             "are not implemented")
     kind = getattr(getattr(phase, "kind", None), "name", str(getattr(phase, "kind", "")))
+    handlers = _handlers(sim, p)
+    for h, core in handlers:
+        if len(getattr(core, "molecules", None) or {}) or len(getattr(core, "transporters", None) or {}) or \
+                len(getattr(core, "modulators", None) or {}) or len(getattr(core, "reactions", None) or {}):
+            raise BetseB200Error("betse_b200: network substances / transporters / modulators under the fast solver "
+                                 "(networks.py:2805-2982 inside sim.py:1505-1545) are not implemented")
+    specs = channels_from_sim(sim, p) if handlers else []
+    for c in specs:
+        if c["_obj"].alpha_eval_string.replace(" ", "") not in ("((np.ones(sim.mdl))*(np.ones(sim.mdl)))",):
+            raise BetseB200Error("betse_b200: channel %r is modulated: not implemented under the fast solver" % c["name"])
     fire = getattr(getattr(phase, "dyna", None), "fire_events", None) if kind.upper() == "SIM" else None
     own = engine is None
     t0 = time.time()
@@ -645,6 +654,17 @@ def run_fast_sim_core_loop(sim, phase, time_steps, time_steps_sampled, anim_cell
         eng = TissueEngine(mesh_from_cells(cells), params_from_p(p), state_from_sim(sim), device=device)
     else:
         eng = engine
+    eng.chan_specs = []
+    if specs:
+        phase_init = kind.upper() == "INIT"
+        eng.set_channels(specs, phase_init=phase_init, affect_charge=False)
+        eng.chan_specs = [c for c in specs if not (phase_init and not c["init_active"])]
+        I = len(sim.zs)
+        cbar, rev = np.zeros(I), np.zeros(I)
+        for ion in sim.rev_E_dic:                       # Simulator.fast_sim_init, sim.py:1393-1452
+            cbar[sim.get_ion(ion)] = float(np.mean(sim.cbar_dic[ion]))
+            rev[sim.get_ion(ion)] = float(np.mean(sim.rev_E_dic[ion]))
+        eng.fast_set_channels(cbar, rev, float(getattr(sim, "geo_conv", 1.0)))
     eng.fast_setup({f: getattr(sim, f, None) for f in ("vm_ave", "gjopen", "G_Leak", "E_Leak", "G_gj", "sigma_cell", "extra_J_mem")})
     Unstable = _unstable_exception()
     sampled = set(time_steps_sampled)
@@ -658,6 +678,12 @@ def run_fast_sim_core_loop(sim, phase, time_steps, time_steps_sampled, anim_cell
             setattr(sim, f, a)
         if diag:
             sim.Jn = got["Jn"]
+        # channel objects keep their gate state / open probability / flux (networks.py:3256-3280; read by the exporters)
+        for k, c in enumerate(getattr(eng, "chan_specs", [])):
+            cc = c["_obj"].channel_core
+            stt = eng.channel_state(k)
+            tg = slice(None) if cc.targets is None else np.asarray(cc.targets)
+            cc.m, cc.h, cc.P, cc.chan_flux = stt["m"][tg], stt["h"][tg], stt["P"], stt["flux"]
     try:
         while n < n_total:
             if fire is not None:
@@ -691,6 +717,10 @@ def run_fast_sim_core_loop(sim, phase, time_steps, time_steps_sampled, anim_cell
                 sim.efield_gj_y_time.append(sim.E_cell_y[m2c] * 1)
                 sim.gjopen_time.append(sim.gjopen * 1)
                 sim.time.append(last_t * 1)
+                for _, core in handlers:                 # sim.py:1616-1622; chi: energy_charge at the tail of run_loop
+                    core.chi = np.zeros(eng.Co)
+                    core.write_data(sim, cells, p)
+                    core.report(sim, p)
                 sim.vm_ave_time.append(sim.vm_ave * 1)
                 if anim_cells is not None:
                     anim_cells.plot_frame(time_step=-1)
@@ -698,6 +728,8 @@ def run_fast_sim_core_loop(sim, phase, time_steps, time_steps_sampled, anim_cell
             # the reference forms the currents and fields on every step: leave the Simulator the last step's
             eng.fast_step(0, diag=True)
             copy_back(True)
+        for _, core in handlers:
+            core.chi = np.zeros(eng.Co)
     finally:
         if own:
             _close_async(eng)

@@ -211,6 +211,13 @@ int  betse_fast_setup(betse_ctx *ctx, const betse_fast_host *state);
 /* Replaces `nsteps` iterations of the fast loop body (sim.py:1547-1592). */
 int  betse_fast_step(betse_ctx *ctx, int nsteps, int flags, uint32_t *status_out);
 int  betse_fast_download(betse_ctx *ctx, betse_fast_host *out);
+/* Voltage-gated channels under the fast solver: MasterOfNetworks.run_fast_loop_channels (networks.py:3217-3280).  The
+ * channels are those of betse_set_channels (unmodulated ones); every step their gates advance at the cell's potential and
+ * J_ED = G (vm - E_rev) joins extra_J_mem, G = DChan * cond_coef[ion]:
+ *   cond_coef[ion] = q z^2 F cbar_dic[ion] / (tm kb p.T) * geo_conv     stb.get_conductivity, sim_toolbox.py:1363-1372
+ *   rev_E[ion]     = sim.rev_E_dic[ion]                                 fast_sim_init, sim.py:1393-1452
+ * Both [n_ions], in ion-index order.  Call after betse_set_channels and before betse_fast_setup. */
+int  betse_fast_set_channels(betse_ctx *ctx, const double *cond_coef, const double *rev_E);
 
 /* Same as betse_step but timed with CUDA events on the ctx's stream; per-kernel mean
  * durations (ms per launch) and launch counts are returned for the roofline in bench.py. */

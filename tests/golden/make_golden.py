@@ -91,6 +91,14 @@ def chan_extra(sim, phase):
             out["chan%d.P" % k] = np.asarray(cc.P, dtype=float)
         if getattr(cc, "chan_flux", None) is not None:
             out["chan%d.flux" % k] = np.asarray(cc.chan_flux, dtype=float)
+    if getattr(sim, "rev_E_dic", None):
+        # constants of Simulator.fast_sim_init (sim.py:1393-1452) the fast solver's channels read, in ion-index order
+        I = len(sim.zs)
+        rev, cbar = np.zeros(I), np.zeros(I)
+        for ion in sim.rev_E_dic:
+            rev[sim.get_ion(ion)] = float(np.mean(sim.rev_E_dic[ion]))
+            cbar[sim.get_ion(ion)] = float(np.mean(sim.cbar_dic[ion]))
+        out["fast.rev_E"], out["fast.cbar"], out["fast.geo_conv"] = rev, cbar, np.asarray(float(sim.geo_conv))
     return out
 
 
@@ -151,6 +159,15 @@ SCENARIOS["fast_basic"] = dict(
 SCENARIOS["fast_mammal_noecm"] = dict(
     mods=_m(NO_NET, SMALL, {"solver options": {"type": "fast"}, "general options": {"ion profile": "mammal", "simulate extracellular spaces": False}}),
     tweak_p=_leaky_spot, snaps={"init": [1, 2, 5, 20], "sim": [1, 2, 5, 20]}, method="_run_fast_sim_core_loop")
+
+
+# the fast solver with voltage-gated channels (run_fast_loop_channels, networks.py:3217-3280): conductances from the open
+# probabilities, currents against the fixed reversal potentials of fast_sim_init, joined into extra_J_mem
+SCENARIOS["fast_chan"] = dict(
+    mods=_m(SMALL, {"cutting event": {"event happens": False}, "solver options": {"type": "fast"},
+                    "general options": {"ion profile": "mammal"},
+                    "general network": {"implement network": True, "biomolecules": [], "channels": CHANNELS}}),
+    tweak_p=_leaky_spot, snaps={"init": [1, 2, 5, 20], "sim": [1, 2, 5, 20]}, method="_run_fast_sim_core_loop", extra=chan_extra)
 
 
 def _substance(name, prod, acts=None, inh=None, Dgj=1e-15, gj_imp=True, cell=0.1, z=0, apply_to="all"):

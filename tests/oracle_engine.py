@@ -132,9 +132,16 @@ class OracleEngine:
     FAST_FIELDS = {"vm_ave": "C", "gjopen": "M", "vgj": "M", "Jn": "M", "Emx": "M", "Emy": "M",
                    "J_cell_x": "C", "J_cell_y": "C", "E_cell_x": "C", "E_cell_y": "C"}
 
+    def fast_set_channels(self, cbar, rev_E, geo_conv=1.0):
+        self._fast_consts = {"cbar": np.asarray(cbar, dtype=float), "rev_E": np.asarray(rev_E, dtype=float),
+                             "geo_conv": float(geo_conv), "zs": np.asarray(self._args[2]["zs"], dtype=float)}
+
     def fast_setup(self, state):
         mesh, params, st = self._args
-        self._f = OracleFastSim(mesh, params, dict(st, **{k: v for k, v in state.items() if v is not None}))
+        specs = [dict(c, targets=np.arange(self.M) if c.get("targets") is None else c["targets"]) for c in self._specs]
+        self._f = OracleFastSim(mesh, params, dict(st, **{k: v for k, v in state.items() if v is not None}),
+                                channels=specs, phase_init=self._phase_init, fast_consts=getattr(self, "_fast_consts", None))
+        self._active = [c for c in self._f.channels if not (self._phase_init and not c["init_active"])]
 
     def fast_step(self, n=1, diag=False):
         for _ in range(n):

@@ -72,13 +72,14 @@ def test_betse_try_reference_loop_vs_cuda_dropin(variant, tmp_path):
         assert np.max(np.abs(x_new - x_ref)) <= 1e-8 * np.max(np.abs(x_ref))
 
 
-def test_fast_solver_reference_loop_vs_cuda_dropin(tmp_path):
+@pytest.mark.parametrize("scenario", ["fast_basic", "fast_chan"])       # fast_chan: run_fast_loop_channels (networks.py:3217-3280)
+def test_fast_solver_reference_loop_vs_cuda_dropin(tmp_path, scenario):
     """`solver options: type: fast`: Simulator._run_fast_sim_core_loop of the unmodified reference against the drop-in
     that install() binds in its place (csrc/fast.cu), both phases, a K-leaky tissue profile driving gap-junction currents."""
     if not _have_reference():
         pytest.skip("reference tree absent: neither /root/reference nor baseline/_ref (run tools/install_reference.py)")
     from tests.golden import make_golden as mg
-    sc = mg.SCENARIOS["fast_basic"]
+    sc = mg.SCENARIOS[scenario]
     (tmp_path / "ref").mkdir()
     (tmp_path / "new").mkdir()
     ref_sim, _ = _run(tmp_path / "ref", False, sc["mods"], sc["tweak_p"])

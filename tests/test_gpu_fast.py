@@ -23,6 +23,12 @@ def test_fast_solver_matches_reference(fixture, kind):
     cap = util.load_golden(fixture)
     s0 = util.group(cap, kind + ".s0.")
     eng = TissueEngine(util.mesh_of(cap, kind), util.group(cap, kind + ".p."), s0)
+    specs = util.channels_of(cap, kind)                 # fast_chan: run_fast_loop_channels (networks.py:3217-3280)
+    active = [c for c in specs if not (kind == "init" and not c["init_active"])]
+    if specs:
+        fc = util.fast_consts_of(cap, kind)
+        eng.set_channels(specs, phase_init=(kind == "init"))
+        eng.fast_set_channels(fc["cbar"], fc["rev_E"], fc["geo_conv"])
     eng.fast_setup(s0)
     n = 0
     for K in util.snap_steps(cap, kind):
@@ -42,6 +48,14 @@ def test_fast_solver_matches_reference(fixture, kind):
             elif f.startswith("E_cell"):
                 scale = jscale / (0.1 * float(np.min(s0["sigma_cell"])))
             assert _close(got[f], ref[f], scale), (kind, K, f, float(np.max(np.abs(got[f] - ref[f]))))
+        for k, c in enumerate(active):
+            j = [s["name"] for s in specs].index(c["name"])
+            stt = eng.channel_state(k)
+            for f in ("m", "h", "P", "flux"):
+                r = ref.get("chan%d.%s" % (j, f))
+                if r is not None:
+                    a = stt[f][c["targets"]] if f in ("m", "h") else stt[f]
+                    assert _close(a, r), (kind, K, c["name"], f)
     eng.close()
 
 

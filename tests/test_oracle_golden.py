@@ -70,19 +70,30 @@ def test_oracle_reproduces_reference(name, kind):
 
 
 @pytest.mark.parametrize("kind", ["init", "sim"])
-@pytest.mark.parametrize("fixture", ["fast_basic", "fast_mammal_noecm"])
+@pytest.mark.parametrize("fixture", ["fast_basic", "fast_mammal_noecm", "fast_chan"])
 def test_fast_solver_oracle_matches_reference(fixture, kind):
-    """The equivalent-circuit solver (sim.py:1454-1640) restated in oracle.OracleFastSim against the real reference."""
+    """The equivalent-circuit solver (sim.py:1454-1640) restated in oracle.OracleFastSim against the real reference;
+    fast_chan: with the voltage-gated channels of run_fast_loop_channels (networks.py:3217-3280)."""
     from oracle.betse_oracle import OracleFastSim
     cap = util.load_golden(fixture)
-    o = OracleFastSim(util.mesh_of(cap, kind), util.group(cap, kind + ".p."), util.group(cap, kind + ".s0."))
+    s0 = util.group(cap, kind + ".s0.")
+    o = OracleFastSim(util.mesh_of(cap, kind), util.group(cap, kind + ".p."), s0, channels=util.channels_of(cap, kind),
+                      phase_init=(kind == "init"), fast_consts=util.fast_consts_of(cap, kind))
     n = 0
     for K in util.snap_steps(cap, kind):
         while n < K:
             o.step()
             n += 1
         ref = util.group(cap, "%s.k%d." % (kind, K))
-        for f in ("vm_ave", "vm", "gjopen", "vgj", "Jn", "J_cell_x", "J_cell_y", "E_cell_x", "E_cell_y", "Emx", "Emy"):
+        for f in ("vm_ave", "vm", "gjopen", "vgj", "Jn", "J_cell_x", "J_cell_y", "E_cell_x", "E_cell_y", "Emx", "Emy") + \
+                (("extra_J_mem",) if o.channels else ()):
             if f in ref:
                 a, r = getattr(o, f), ref[f]
                 assert np.max(np.abs(a - r)) <= 1e-12 * max(np.max(np.abs(r)), 1e-300), (kind, K, f)
+        for k, c in enumerate(o.channels):
+            if kind == "init" and not c["init_active"]:
+                continue
+            for f in ("m", "h", "P", "flux"):
+                r = ref.get("chan%d.%s" % (k, f))
+                if r is not None and f in c:
+                    assert np.max(np.abs(c[f] - r)) <= 1e-12 * max(np.max(np.abs(r)), 1e-300), (kind, K, k, f)

@@ -417,12 +417,13 @@ def test_bath_events_without_ecm_fail_like_the_reference(monkeypatch, tmp_path):
         _run_try(tmp_path / "new", True, monkeypatch, mods=mods)
 
 
-def test_fast_solver_through_the_dropin_matches_the_reference(monkeypatch, tmp_path):
+@pytest.mark.parametrize("scenario", ["fast_basic", "fast_chan"])       # fast_chan: run_fast_loop_channels (networks.py:3217-3280)
+def test_fast_solver_through_the_dropin_matches_the_reference(monkeypatch, tmp_path, scenario):
     """`solver options: type: fast` (sim.py:1068-1070): install() rebinds Simulator._run_fast_sim_core_loop as well; both
     phases of the reference's own run against the drop-in's host logic (events, sampling, the time series the fast loop
     appends itself, sim.py:1597-1628) over the oracle."""
     from tests.golden import make_golden as mg
-    sc = mg.SCENARIOS["fast_basic"]
+    sc = mg.SCENARIOS[scenario]
     ref_sim, _, _ = _run_try(tmp_path / "ref", False, mods=sc["mods"], tweak_p=sc["tweak_p"])
     (tmp_path / "new").mkdir()
     new_sim, _, engines = _run_try(tmp_path / "new", True, monkeypatch, mods=sc["mods"], tweak_p=sc["tweak_p"])
@@ -438,3 +439,11 @@ def test_fast_solver_through_the_dropin_matches_the_reference(monkeypatch, tmp_p
     for f in ("vm", "vm_ave", "gjopen", "Emx", "Emy", "Jn"):
         a, r = np.asarray(getattr(new_sim, f)), np.asarray(getattr(ref_sim, f))
         assert np.max(np.abs(a - r)) <= 1e-9 * max(np.max(np.abs(r)), 1e-300), f
+    if scenario == "fast_chan":
+        # what MasterOfNetworks.write_data stored for the channels at the sampled steps (networks.py:4244-4250)
+        for name, ch in ref_sim.molecules.core.channels.items():
+            got, want = new_sim.molecules.core.channels[name].flux_time, ch.flux_time
+            assert len(got) == len(want) >= 10, name
+            scale = max(float(np.max(np.abs(w))) for w in want)
+            for a, r in zip(got, want):
+                assert np.max(np.abs(np.asarray(a) - np.asarray(r))) <= 1e-9 * max(scale, 1e-300), name

@@ -195,6 +195,14 @@ def channels_of(cap, kind, where="s0"):
     return out
 
 
+def fast_consts_of(cap, kind, where="s0"):
+    """Constants of Simulator.fast_sim_init the fast solver's channels read (make_golden.py:chan_extra), or None."""
+    g = group(cap, "%s.%s." % (kind, where))
+    if "fast.rev_E" not in g:
+        return None
+    return {"rev_E": g["fast.rev_E"], "cbar": g["fast.cbar"], "geo_conv": float(g["fast.geo_conv"]), "zs": g["zs"]}
+
+
 def network_handlers(cap, kind, where="s0"):
     """Handler ids of the recorded networks: 0 = general network (sim.molecules.core), 1 = gene regulatory network."""
     return [h for h in range(2) if "%s.%s.net%d.species" % (kind, where, h) in cap]
