@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-T=r02p
+T=r02z
 timeout 1500 python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/${T}_pytest.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/${T}_pytest.log
 tail -6 gpurun_out/${T}_pytest.log
@@ -17,7 +17,7 @@ timeout 600 python bench.py --config c1 --ensemble 128 --steps 200 --warmup 20 -
 timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/${T}_bench_reference_arm.json 2>/dev/null; echo "ref rc=$?"
 python - <<'PY'
 import json,glob
-for f in sorted(glob.glob('gpurun_out/r02p_bench_*.json')):
+for f in sorted(glob.glob('gpurun_out/r02z_bench_*.json')):
     try:
         d=json.loads(open(f).read().strip().splitlines()[-1])
         print(f.split('/')[-1], 'ms/step %.4f value %.3e e2e %.3e' % (d['ms_per_step'], d['value'], d.get('e2e',{}).get('value',0)), 'roof %.3f step %.3f' % (d.get('roofline',{}).get('frac',0), d.get('roofline',{}).get('step',{}).get('frac',0)), {k: round(x,4) for k,x in d.get('roofline',{}).get('kernel_ms',{}).items()}, 'cpu', d.get('cpu_baseline',{}).get('value'), d.get('ensemble',{}).get('speedup_vs_solo_per_gpu'))
