@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <chrono>
 #include <string>
+#include <atomic>
 #include <thread>
 #include <vector>
 
@@ -928,6 +929,43 @@ static int opt_array(betse_ctx* ctx, const T** slot, const T* host, size_t n)
     return 0;
 }
 
+// every row of a[rows][n] one repeated value?  (the values go to vals)  Threads split each row; the first difference
+// found anywhere stops all of them.
+static bool rows_uniform(const double* a, int rows, size_t n, double* vals)
+{
+    if (n == 0) return false;
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int T = (n * (size_t)rows < ((size_t)1 << 20)) ? 1 : (hw >= 16 ? 8 : hw >= 8 ? 4 : 2);
+    std::atomic<bool> differs(false);
+    for (int r = 0; r < rows; ++r) vals[r] = a[(size_t)r * n];
+    auto scan = [&](int t) {
+        const size_t lo = n * (size_t)t / T, hi = n * (size_t)(t + 1) / T;
+        for (int r = 0; r < rows && !differs.load(std::memory_order_relaxed); ++r) {
+            const double* p = a + (size_t)r * n;
+            const double v = vals[r];
+            for (size_t j0 = lo; j0 < hi; j0 += 4096) {
+                const size_t j1 = j0 + 4096 < hi ? j0 + 4096 : hi;
+                bool d = false;
+                for (size_t j = j0; j < j1; ++j) d |= (p[j] != v);
+                if (d) { differs.store(true, std::memory_order_relaxed); return; }
+                if (differs.load(std::memory_order_relaxed)) return;
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; ++t) th.emplace_back(scan, t);
+    scan(0);
+    for (auto& x : th) x.join();
+    return !differs.load();
+}
+
+struct KRowVals { double v[BT_MAX_IONS]; };
+static __global__ void k_fill_rows(double* __restrict__ dst, const KRowVals rv, const int n)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) dst[(size_t)blockIdx.y * n + j] = rv.v[blockIdx.y];
+}
+
 extern "C" int betse_upload_state(betse_ctx* ctx, const betse_state_host* s)
 {
     if (!ctx || !s) return 2;
@@ -947,8 +985,18 @@ extern "C" int betse_upload_state(betse_ctx* ctx, const betse_state_host* s)
         UP(A.E_y, s->E_env_y, E);
     }
     UP(A.gjopen, s->gjopen, Mo);
-    UP(A.Dm, s->Dm_cells, IM);
-    if (s->Dm_cells) { launch_pack_dm(ctx->P, A, st); launch_pack_cell_dm(ctx->P, A, st); }
+    if (s->Dm_cells) {
+        // sim.Dm_cells is one value per ion on every membrane unless tissue profiles or scheduled interventions differ
+        // (sim.py:676-690, tishandler.py:1321-1332): I scalars and a device fill instead of I*M doubles over PCIe
+        // (288 MB = ~48 ms of the pageable path at 1 M cells); the scan stops at the first membrane that differs
+        double vals[BT_MAX_IONS];
+        if (rows_uniform(s->Dm_cells, I, (size_t)Mo, vals)) {
+            KRowVals rv;
+            for (int i = 0; i < BT_MAX_IONS; ++i) rv.v[i] = i < I ? vals[i] : 0.0;
+            k_fill_rows<<<dim3((unsigned)((Mo + 255) / 256), (unsigned)I), 256, 0, st>>>(const_cast<double*>(A.Dm), rv, Mo);
+        } else { UP(A.Dm, s->Dm_cells, IM); }
+        launch_pack_dm(ctx->P, A, st); launch_pack_cell_dm(ctx->P, A, st);
+    }
     if (ctx->P.polar && s->vm)
         CK(cudaMemcpyAsync(A.vm_pol[cur], s->vm, (size_t)Mo * sizeof(double), cudaMemcpyHostToDevice, st));
     if (s->vm_cell) {
