@@ -56,7 +56,7 @@ void launch_envacc_ell_x(int ni, const KParams& P, const KArrays& A, const XPlan
 void envacc_end_ctas(const KParams& P, int lo, int hi, int* n_lower, int* n_upper);
 void launch_cell_x(int ni, const KParams& P, const KArrays& A, const XPlan& X, int cur, cudaStream_t st);
 void launch_chan(const KParams& P, const KArrays& A, const KChan& ch, const KNet& N, int cur, cudaStream_t st);
-void launch_chan_cell(const KParams& P, const KArrays& A, const KChan* chs, int n, double* ell, int cur, int diag, cudaStream_t st);
+void launch_chan_cell(const KParams& P, const KArrays& A, const KChan* chs, int n, double* ell, int cur, int diag, int fuse_update, cudaStream_t st);
 void launch_chan_expand(const KChan& ch, const int* mem_to_cells, const int* mem_ell, int Mo, int ni, cudaStream_t st);
 void launch_fast_chan(const KParams& P, const KArrays& A, const KChan* chs, int n, const double* coef, const double* rev_E,
                       const double* vm_ave, double* extra_J, cudaStream_t st);
@@ -1247,6 +1247,12 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
         if (chans) {
             // between the ion loop's fluxes and update_all_concs (sim.py:1290-1357), per handler: run_loop_channels
             // (networks.py:3115-3213), then run_loop (networks.py:2805-2982)
+            // per-cell channel passes with nothing behind them (no network, no noise): the last pass closes the step itself
+            // (update_all_concs, charge, Vmem of its cells: k_cell_update's arithmetic) and k_cell_update is not launched
+            const bool fuse_tail = ctx->chan_cell_mode && !ctx->chans.empty() && !ctx->net_on[0] && !ctx->net_on[1] && !ctx->noise_pending;
+            bool tail_done = false;
+            int hmax = 0;
+            for (const KChan& ch : ctx->chans) hmax = std::max(hmax, ch.handler);
             for (int h = 0; h < 2; ++h) {
                 // every MasterOfNetworks keeps its OWN extra_J_mem / extra_Jenv (clear_run_loop, networks.py:2790-2801) and
                 // publishes them at the end of its run_loop (networks.py:2971-2977): with both handlers enabled the LAST one
@@ -1282,7 +1288,10 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
                         while (k1 < nch && k1 - k0 < cap && ctx->chans[k1].handler == h && !(ions & (1u << ctx->chans[k1].ion))) {
                             ions |= 1u << ctx->chans[k1].ion; ++k1;
                         }
-                        launch_chan_cell(ctx->P, A, &ctx->chans[k0], (int)(k1 - k0), ctx->chan_ell, cur, diag, st);
+                        bool last = fuse_tail && h == hmax;                 // the last pass of the last handler that has channels
+                        for (size_t k = k1; k < nch && last; ++k) if (ctx->chans[k].handler == h) last = false;
+                        launch_chan_cell(ctx->P, A, &ctx->chans[k0], (int)(k1 - k0), ctx->chan_ell, cur, diag, last ? 1 : 0, st);
+                        tail_done = tail_done || last;
                     } else {
                         const KChan& ch = ctx->chans[k0];
                         launch_chan(ctx->P, A, ch, ctx->nets[h], cur, st);
@@ -1318,7 +1327,7 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
                 launch_chan_env(ctx->P, A, ctx->noise_ion, cur, st);
                 ctx->noise_pending = false;
             }
-            launch_cell_update(ctx->P, A, cur, st);
+            if (!tail_done) launch_cell_update(ctx->P, A, cur, st);
         }
         if (evs) cudaEventRecord(evs[3], st);
     } else if (phase == 1) {

@@ -159,6 +159,51 @@ k_chan(const __grid_constant__ KParams P, const KArrays A, const __grid_constant
     chan_apply(P, A, ch, N, cur, A.chan_slots, s_all + (threadIdx.x >> 5) * 32, lane, tile, td);
 }
 
+// The deferred tail of k_mem (update_all_concs, sim.py:2086-2111; charge and Vmem, ion_current.py:19,
+// sim.py:2027-2029), applied to the concentrations the channels left behind: one cell.  Shared by k_cell_update and by the
+// last channel pass of a step (k_chan_cell with `fuse_update`: nothing else runs between the two, and a cell's update
+// reads and writes that cell only).
+__device__ __forceinline__ void cell_update_one(const KParams& P, const KArrays& A, const int c, const int cur, unsigned int& flags)
+{
+    const int C = P.n_cells, nxt = cur ^ 1;
+    const double rvol = fast_rcp(__ldg(A.cell_vol + c));
+    double rho = 0.0;
+    // every input first (the stores below would otherwise fence the next ion's loads: one memory round trip per ion)
+    double cc[BT_MAX_IONS], Sm[BT_MAX_IONS], Sg[BT_MAX_IONS];
+#pragma unroll
+    for (int i = 0; i < BT_MAX_IONS; ++i) {
+        cc[i] = Sm[i] = Sg[i] = 0.0;
+        if (i < P.n_ions) { cc[i] = A.cc_cells[i * C + c]; Sm[i] = A.dsum_m[i * C + c]; Sg[i] = A.dsum_g[i * C + c]; }
+    }
+    const double xr = A.extra_rho_cells ? __ldg(A.extra_rho_cells + c) : 0.0;
+    const double dvt = __ldg(A.diviterm + c);
+#pragma unroll
+    for (int i = 0; i < BT_MAX_IONS; ++i) if (i < P.n_ions) {
+        const double cm_new = cc[i] + (Sm[i] * rvol) * P.dt;
+        double cn_new = cm_new + P.dt * ((-Sg[i]) * rvol);
+        if (cn_new != cn_new) flags |= ST_NAN_CONC;
+        if (cn_new < 0.0) { cn_new = 0.0; flags |= ST_NEG; }
+        A.cc_cells[i * C + c] = cn_new;
+        A.cc_mid[nxt][i * C + c] = cm_new;
+        rho = fma(P.zF[i], cn_new, rho);
+    }
+    if (A.extra_rho_cells) rho += xr;
+    A.rho_cells[c] = rho;
+    const double vmn = P.inv_cm * (rho * dvt);
+    if (vmn != vmn) flags |= ST_NAN_VM;
+    A.vm_cell[nxt][c] = vmn;
+}
+
+__global__ void __launch_bounds__(256)
+k_cell_update(const __grid_constant__ KParams P, const KArrays A, const int cur)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.n_cells_owned) return;
+    unsigned int flags = 0;
+    cell_update_one(P, A, c, cur, flags);
+    if (flags) atomicOr(A.status, flags);
+}
+
 // ---------------------------------------------------------------------------- channels with ONE LANE PER CELL
 // In the default mode Vmem is a per-cell quantity (sim.py:2029), so the gates of a channel that sits on every membrane —
 // m, h, the open probability, DChan, and the exp / expm1 pair of its GHK flux — have ONE value per cell: k_chan evaluates
@@ -180,7 +225,7 @@ struct KChanPack { int n; KChan ch[KCH_PACK]; };
 
 __global__ void __launch_bounds__(KCH_TPB, 11)              // <= 93 registers: 100 k cells are resident in one wave
 k_chan_cell(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ KChanPack pk, double* __restrict__ ell,
-            const int cur, const int diag)
+            const int cur, const int diag, const int fuse_update)
 {
     const int lane = threadIdx.x & 31;
     const int task = blockIdx.x * (KCH_TPB / 32) + (threadIdx.x >> 5);
@@ -212,7 +257,7 @@ k_chan_cell(const __grid_constant__ KParams P, const KArrays A, const __grid_con
     for (int j = 0; j < pk.n; ++j) {
         const KChan& ch = pk.ch[j];
         const int ion = ch.ion;
-        double* __restrict__ ccell = A.cc_cells + (size_t)ion * C;
+        double* ccell = A.cc_cells + (size_t)ion * C;             // (read again by the fused cell update below: not restrict)
         const double* __restrict__ cenv = A.cc_env[cur ^ 1] + (size_t)ion * E;
         double cAk[KCH_KREG];
 #pragma unroll
@@ -255,6 +300,12 @@ k_chan_cell(const __grid_constant__ KParams P, const KArrays A, const __grid_con
             S = __dadd_rn(S, fsa);
         }
         ccell[c] = fma(S / vol, P.dt, cB);
+    }
+    if (fuse_update) {
+        // the step's last channel pass: update_all_concs, charge and Vmem of this cell right away (k_cell_update's arithmetic)
+        unsigned int flags = 0;
+        cell_update_one(P, A, c, cur, flags);
+        if (flags) atomicOr(A.status, flags);
     }
 }
 
@@ -390,53 +441,15 @@ k_chan_mix(const __grid_constant__ KParams P, const KArrays A, const int ion, co
     }
 }
 
-// The deferred tail of k_mem (update_all_concs, sim.py:2086-2111; charge and Vmem, ion_current.py:19,
-// sim.py:2027-2029), applied to the concentrations the channels left behind.
-__global__ void __launch_bounds__(256)
-k_cell_update(const __grid_constant__ KParams P, const KArrays A, const int cur)
-{
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= P.n_cells_owned) return;
-    const int C = P.n_cells, nxt = cur ^ 1;
-    unsigned int flags = 0;
-    const double rvol = fast_rcp(__ldg(A.cell_vol + c));
-    double rho = 0.0;
-    // every input first (the stores below would otherwise fence the next ion's loads: one memory round trip per ion)
-    double cc[BT_MAX_IONS], Sm[BT_MAX_IONS], Sg[BT_MAX_IONS];
-#pragma unroll
-    for (int i = 0; i < BT_MAX_IONS; ++i) {
-        cc[i] = Sm[i] = Sg[i] = 0.0;
-        if (i < P.n_ions) { cc[i] = A.cc_cells[i * C + c]; Sm[i] = A.dsum_m[i * C + c]; Sg[i] = A.dsum_g[i * C + c]; }
-    }
-    const double xr = A.extra_rho_cells ? __ldg(A.extra_rho_cells + c) : 0.0;
-    const double dvt = __ldg(A.diviterm + c);
-#pragma unroll
-    for (int i = 0; i < BT_MAX_IONS; ++i) if (i < P.n_ions) {
-        const double cm_new = cc[i] + (Sm[i] * rvol) * P.dt;
-        double cn_new = cm_new + P.dt * ((-Sg[i]) * rvol);
-        if (cn_new != cn_new) flags |= ST_NAN_CONC;
-        if (cn_new < 0.0) { cn_new = 0.0; flags |= ST_NEG; }
-        A.cc_cells[i * C + c] = cn_new;
-        A.cc_mid[nxt][i * C + c] = cm_new;
-        rho = fma(P.zF[i], cn_new, rho);
-    }
-    if (A.extra_rho_cells) rho += xr;
-    A.rho_cells[c] = rho;
-    const double vmn = P.inv_cm * (rho * dvt);
-    if (vmn != vmn) flags |= ST_NAN_VM;
-    A.vm_cell[nxt][c] = vmn;
-    if (flags) atomicOr(A.status, flags);
-}
-
 // channels [0, n) of `chs` as one pass on the per-cell path (n <= min(KCH_PACK, n_ions), distinct ions); ell: [rows][I][32]
-void launch_chan_cell(const KParams& P, const KArrays& A, const KChan* chs, int n, double* ell, int cur, int diag, cudaStream_t st)
+void launch_chan_cell(const KParams& P, const KArrays& A, const KChan* chs, int n, double* ell, int cur, int diag, int fuse_update, cudaStream_t st)
 {
     KChanPack pk;
     KPassIons pi;
     pk.n = pi.n = n;
     for (int j = 0; j < n; ++j) { pk.ch[j] = chs[j]; pi.ion[j] = chs[j].ion; }
     for (int j = n; j < KCH_PACK; ++j) { pk.ch[j] = chs[0]; pi.ion[j] = 0; }
-    k_chan_cell<<<(P.n_blocks + KCH_TPB / 32 - 1) / (KCH_TPB / 32), KCH_TPB, 0, st>>>(P, A, pk, ell, cur, diag);
+    k_chan_cell<<<(P.n_blocks + KCH_TPB / 32 - 1) / (KCH_TPB / 32), KCH_TPB, 0, st>>>(P, A, pk, ell, cur, diag, fuse_update);
     const int ne = (P.ya1 - P.ya0) * P.nx;
     if (ne > 0) k_chan_env_cell<<<(ne + 255) / 256, 256, 0, st>>>(P, A, pi, ell, cur ^ 1);
 }
