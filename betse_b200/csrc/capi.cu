@@ -990,7 +990,8 @@ extern "C" int betse_upload_state(betse_ctx* ctx, const betse_state_host* s)
         // (sim.py:676-690, tishandler.py:1321-1332): I scalars and a device fill instead of I*M doubles over PCIe
         // (288 MB = ~48 ms of the pageable path at 1 M cells); the scan stops at the first membrane that differs
         double vals[BT_MAX_IONS];
-        if (rows_uniform(s->Dm_cells, I, (size_t)Mo, vals)) {
+        const char* eu = getenv("BETSE_DM_UNIFORM");                  // 0: always the full upload (A/B test)
+        if (!(eu && eu[0] == '0') && rows_uniform(s->Dm_cells, I, (size_t)Mo, vals)) {
             KRowVals rv;
             for (int i = 0; i < BT_MAX_IONS; ++i) rv.v[i] = i < I ? vals[i] : 0.0;
             k_fill_rows<<<dim3((unsigned)((Mo + 255) / 256), (unsigned)I), 256, 0, st>>>(const_cast<double*>(A.Dm), rv, Mo);

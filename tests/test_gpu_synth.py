@@ -320,3 +320,32 @@ np.savez(sys.argv[1], **{k + "." + f: a for k, d in out.items() for f, a in d.it
     assert res["patch"].keys() == res["plain"].keys() and len(res["patch"]) == 14
     for k in res["patch"]:
         assert np.array_equal(res["patch"][k], res["plain"][k]), k
+
+
+def test_uniform_permeability_upload_equals_full_upload(monkeypatch):
+    """betse_upload_state sends sim.Dm_cells as I scalars + a device fill when every row is one repeated value (capi.cu:
+    rows_uniform): same device state as the full I*M upload (BETSE_DM_UNIFORM=0), bit for bit; a tissue with ONE membrane
+    of different permeability takes the full path and differs from the uniform one."""
+    from betse_b200 import synth
+    from betse_b200.engine import TissueEngine
+    mesh, p, st = synth.make_tissue(20_000)
+    out = []
+    for mode in ("1", "0"):
+        monkeypatch.setenv("BETSE_DM_UNIFORM", mode)
+        eng = TissueEngine(mesh, p, st)
+        eng.update_V()
+        assert not (eng.step(12) & 3)
+        out.append(eng.download(["cc_cells", "cc_env", "vm"]))
+        eng.close()
+    for f in out[0]:
+        assert np.array_equal(out[0][f], out[1][f]), f
+    monkeypatch.setenv("BETSE_DM_UNIFORM", "1")
+    st2 = dict(st)
+    st2["Dm_cells"] = np.array(st["Dm_cells"], copy=True)
+    st2["Dm_cells"][1, -1] *= 50.0                       # the LAST membrane of the K row: found by the last scanning thread
+    eng = TissueEngine(mesh, p, st2)
+    eng.update_V()
+    assert not (eng.step(12) & 3)
+    got = eng.download(["cc_cells"])
+    eng.close()
+    assert not np.array_equal(got["cc_cells"], out[0]["cc_cells"])
