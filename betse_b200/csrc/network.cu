@@ -563,25 +563,35 @@ k_sub_div(const __grid_constant__ KParams P, const KArrays A, const __grid_const
 // Molecule.update_intra with intracellular transport (networks.py:5727-5795; transmem False, no motor transport): the
 // membrane value relaxes implicitly towards the cell value the step started with; charged substances also drift in the
 // cell's field normal to the membrane (sim.Emc of the previous step's update_V)
+// (one thread per membrane walks ALL substances with intracellular transport: the membrane's geometry, cell and field are
+// loaded once, and a network with three such substances is one launch of ~9 us instead of three)
+#define NET_INTRA_MAX 32
+struct KIntraList { int n; int k[NET_INTRA_MAX]; };
+
 __global__ void __launch_bounds__(256)
-k_net_intra(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ KNet N, const int k)
+k_net_intra(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ KNet N, const __grid_constant__ KIntraList L)
 {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= P.n_mems_owned) return;
     const double g = __ldg(N.sa_over_vol + m) / 0.75;                        // gamma = mem_sa/((3/4)*mem_vol)
-    const double Do = __ldg(N.Do + k), dt = P.dt * __ldg(N.tdf + k), Rr = __ldg(N.R_rads + m);
-    const double cav = N.c[(size_t)k * P.n_cells + __ldg(A.mem_to_cells + m)];
-    double* cm = N.cmem + (size_t)k * P.n_mems_owned + m;
-    const double z = __ldg(N.z + k), mu = N.mu_mem ? __ldg(N.mu_mem + k) : 0.0;
-    double alpha_tot = 0.0;
-    if (z != 0.0 || mu != 0.0) {
-        const double En = A.Emc[m];
-        alpha_tot = ((0.0 + (((Do * P.q) * z) / P.kbT_sim) * En) + mu * En) + 0.0;
+    const double Rr = __ldg(N.R_rads + m);
+    const int c = __ldg(A.mem_to_cells + m);
+    const double En = A.Emc ? A.Emc[m] : 0.0;
+    bool neg = false;
+    for (int j = 0; j < L.n; ++j) {
+        const int k = L.k[j];
+        const double Do = __ldg(N.Do + k), dt = P.dt * __ldg(N.tdf + k);
+        const double cav = N.c[(size_t)k * P.n_cells + c];
+        double* cm = N.cmem + (size_t)k * P.n_mems_owned + m;
+        const double z = __ldg(N.z + k), mu = N.mu_mem ? __ldg(N.mu_mem + k) : 0.0;
+        double alpha_tot = 0.0;
+        if (z != 0.0 || mu != 0.0) alpha_tot = ((0.0 + (((Do * P.q) * z) / P.kbT_sim) * En) + mu * En) + 0.0;
+        const double v = (((((g * Do) * dt) * cav) / Rr) + ((((g * alpha_tot) * cav) * dt) / 2.0) + *cm) /
+                         ((1.0 + (((g * Do) * dt) / Rr)) - (((g * alpha_tot) * dt) / 2.0));
+        neg = neg || v < 0.0;                                                // networks.py:5798-5804
+        *cm = v;
     }
-    const double v = (((((g * Do) * dt) * cav) / Rr) + ((((g * alpha_tot) * cav) * dt) / 2.0) + *cm) /
-                     ((1.0 + (((g * Do) * dt) / Rr)) - (((g * alpha_tot) * dt) / 2.0));
-    if (v < 0.0) atomicOr(A.status, ST_NEG_NET);                             // networks.py:5798-5804
-    *cm = v;
+    if (neg) atomicOr(A.status, ST_NEG_NET);
 }
 
 // the membrane values of an 'update intracellular' substance after its gap-junction flux (sim_toolbox.py:1001-1005),
@@ -606,9 +616,17 @@ void launch_net(const KParams& P, const KArrays& A, const KNet& N, const double*
     const int tgrid = (P.n_tiles + (BT_TPB / 32) - 1) / (BT_TPB / 32);
     const int E = P.nx * P.ny;
     auto pump_of = [&](int k) { for (int j = 0; j < n_pumps; ++j) if (pumps[j].species == k) return j; return -1; };
-    if (N.cmem)
-        for (int k = 0; k < N.K; ++k)
-            if (h_intra && h_intra[k]) k_net_intra<<<(P.n_mems_owned + 255) / 256, 256, 0, st>>>(P, A, N, k);
+    if (N.cmem && h_intra) {
+        KIntraList L;
+        L.n = 0;
+        for (int k = 0; k <= N.K; ++k) {
+            if (k < N.K && h_intra[k]) L.k[L.n++] = k;
+            if (L.n == NET_INTRA_MAX || (k == N.K && L.n > 0)) {
+                k_net_intra<<<(P.n_mems_owned + 255) / 256, 256, 0, st>>>(P, A, N, L);
+                L.n = 0;
+            }
+        }
+    }
     if (N.c_env)
         for (int k = 0; k < N.K; ++k) {
             if (!h_env_on[k] || h_Dm[k] == 0.0 || pump_of(k) >= 0) continue;
