@@ -17,19 +17,29 @@
 #define FLOAT_NONCE 1.0e-25
 #define ST_NEG_NET 16u
 
+// (two kernels: one thread per (rate law, cell) — a 50 k-cell tissue has too few cells to hide the interpreter's latency
+// with one thread per cell walking all ~20 programs —, then one thread per cell for np.dot(reaction_matrix, all_rates) and
+// the update, in the order of the single loop this replaces)
+__global__ void __launch_bounds__(128)
+k_net_rates(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ KNet N, const int cur)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (c >= P.n_cells_owned) return;
+    const int C = P.n_cells, M = P.n_mems_owned;
+    double v = rl_eval(N, j, c, -1, A, C, M, cur, 0.0);
+    if (j < N.K && N.gmask && !N.gmask[(size_t)j * C + c]) v = 0.0;         // mat[trgs] = rts[trgs], networks.py:2844-2846
+    N.rates[(size_t)j * C + c] = v;
+}
+
 __global__ void __launch_bounds__(128)
 k_net(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ KNet N, const int cur)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= P.n_cells_owned) return;
-    const int C = P.n_cells, M = P.n_mems_owned;
+    const int C = P.n_cells;
     double r[NET_MAX_RATES];
-    for (int j = 0; j < N.n_rates; ++j) {
-        double v = rl_eval(N, j, c, -1, A, C, M, cur, 0.0);
-        if (j < N.K && N.gmask && !N.gmask[(size_t)j * C + c]) v = 0.0;     // mat[trgs] = rts[trgs], networks.py:2844-2846
-        r[j] = v;
-        N.rates[(size_t)j * C + c] = v;
-    }
+    for (int j = 0; j < N.n_rates; ++j) r[j] = N.rates[(size_t)j * C + c];
     unsigned int flags = 0;
     for (int k = 0; k < N.K; ++k) {
         double d = 0.0;
@@ -639,6 +649,7 @@ void launch_net(const KParams& P, const KArrays& A, const KNet& N, const double*
         if (h_Dm[pumps[j].species] != 0.0)
             cudaMemcpyAsync(N.c_save + (size_t)j * P.n_cells, N.c + (size_t)pumps[j].species * P.n_cells,
                             (size_t)P.n_cells * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    if (N.n_rates > 0) k_net_rates<<<dim3((unsigned)((P.n_cells_owned + 127) / 128), (unsigned)N.n_rates), 128, 0, st>>>(P, A, N, cur);
     k_net<<<(P.n_cells_owned + 127) / 128, 128, 0, st>>>(P, A, N, cur);
     for (int j = 0; j < n_pumps; ++j) {
         const betse_substance_pump& q = pumps[j];
