@@ -24,7 +24,7 @@ def _is_none(v):
 
 
 # run_loop_modulators targets implemented on the device (networks.py:3296-3299); 'TJ' works in the env zone
-MOD_TARGETS = {"GJ": 0, "Na/K-ATPase": 1}
+MOD_TARGETS = {"GJ": 0, "Na/K-ATPase": 1, "TJ": 2}       # TJ: an extracellular-zone rate law rewrites sim.TJ_modulator (networks.py:3301-3317)
 
 
 def unsupported_reasons(core, p):
@@ -34,7 +34,9 @@ def unsupported_reasons(core, p):
         bad.append("mitochondria")
     for name, mod in (getattr(core, "modulators", None) or {}).items():
         if str(mod.target_label) not in MOD_TARGETS:
-            bad.append("modulator %r of %s (extracellular zone)" % (name, mod.target_label))
+            bad.append("modulator %r of %s" % (name, mod.target_label))
+        if str(mod.target_label) == "TJ" and not bool(getattr(p, "is_ecm", False)):
+            bad.append("tight-junction modulator %r without extracellular spaces" % name)
     for name, t in (getattr(core, "transporters", None) or {}).items():
         if str(getattr(t, "reaction_zone", "cell")) != "cell":
             bad.append("transporter %r outside the cell zone" % name)
@@ -160,6 +162,13 @@ def describe_core(core, sim, p, cells, record_static=True):
         "modulator_strings": [m.alpha_eval_string for m in (getattr(core, "modulators", None) or {}).values()],
         "modulator_targets": [str(m.target_label) for m in (getattr(core, "modulators", None) or {}).values()],
         "modulator_max": np.array([float(m.max_val) for m in (getattr(core, "modulators", None) or {}).values()]),
+        # tight-junction modulators: the ion they act on (Modulator.init_modulator, networks.py:6684-6692; -1 = all ions) and
+        # the env squares of the barrier (sim.TJ_targets, sim.py:2394-2395)
+        "modulator_ions": np.array([-1 if getattr(m, "ion_i", None) is None else int(m.ion_i)
+                                    for m in (getattr(core, "modulators", None) or {}).values()], dtype=np.int64),
+        "tj_targets": np.asarray(getattr(sim, "TJ_targets", np.zeros(0)), dtype=np.int64)
+        if any(str(m.target_label) == "TJ" for m in (getattr(core, "modulators", None) or {}).values()) else np.zeros(0, dtype=np.int64),
+        "n_env": int(len(cells.xypts)) if getattr(cells, "xypts", None) is not None else 0,
         "static": {},
     }
     # Molecule.transport -> stb.molecule_mover (networks.py:5670-5700, sim_toolbox.py:909-1153): membrane and
@@ -258,12 +267,14 @@ def compile_network(desc, n_cells, n_mems, resolver=None):
         resolver = ratelaw.table_resolver(desc["static"])
     species = list(desc["species"])
     K = len(species)
-    tabs = ratelaw.Tables(species, list(desc["ions"]), n_cells, n_mems)
+    tabs = ratelaw.Tables(species, list(desc["ions"]), n_cells, n_mems, int(desc.get("n_env", 0)))
+    mtargets = list(desc.get("modulator_targets", []))
     try:
         rates = [ratelaw.compile_expr(s, tabs, resolver, "cell") for s in desc["gad_strings"]]
         rates += [ratelaw.compile_expr(s, tabs, resolver, "cell") for s in desc["reaction_strings"]]
         mods = [ratelaw.compile_expr(s, tabs, resolver, "mem") for s in desc["chan_mod_strings"]]
-        modulators = [ratelaw.compile_expr(s, tabs, resolver, "mem") for s in desc.get("modulator_strings", [])]
+        modulators = [ratelaw.compile_expr(s, tabs, resolver, "env" if t == "TJ" else "mem")
+                      for s, t in zip(desc.get("modulator_strings", []), mtargets)]
     except ratelaw.RateLawError as e:
         raise BetseB200Error("network rate law not supported on the device: %s" % e)
     stoich = np.asarray(desc["stoich"], dtype=float).reshape(K, -1)
@@ -342,8 +353,10 @@ def compile_network(desc, n_cells, n_mems, resolver=None):
     return {"species": species, "tables": tabs, "rate_programs": rates, "mod_programs": mod_programs,
             "mod_index": mod_index, "ligand_gates": gates, "pumps": list(desc.get("pumps", [])), "transporters": transporters,
             "events": list(desc.get("events", [])),
-            "modulators": [(MOD_TARGETS[t], i, float(mx)) for t, i, mx in
-                           zip(desc.get("modulator_targets", []), modulator_index, desc.get("modulator_max", []))], "c_cells": np.asarray(desc["c_cells"], dtype=float), "stoich": stoich,
+            "modulators": [(MOD_TARGETS[t], i, float(mx), int(ion)) for t, i, mx, ion in
+                           zip(mtargets, modulator_index, desc.get("modulator_max", []),
+                               desc.get("modulator_ions", [-1] * len(mtargets)))],
+            "tj_targets": np.asarray(desc.get("tj_targets", np.zeros(0)), dtype=np.int64), "c_cells": np.asarray(desc["c_cells"], dtype=float), "stoich": stoich,
             "growth_mask": None if mask.all() else mask, "Dgj": np.asarray(desc["Dgj"], dtype=float),
             "z": np.asarray(desc["z"], dtype=float), "time_factor": np.asarray(desc["time_factor"], dtype=float),
             "chan_names": list(desc["chan_names"]),
@@ -382,7 +395,10 @@ def flatten(desc, prefix):
         out.update({prefix + "modulator_names": np.array(desc["modulator_names"], dtype=str),
                     prefix + "modulator_strings": np.array(desc["modulator_strings"], dtype=str),
                     prefix + "modulator_targets": np.array(desc["modulator_targets"], dtype=str),
-                    prefix + "modulator_max": np.asarray(desc["modulator_max"], dtype=float)})
+                    prefix + "modulator_max": np.asarray(desc["modulator_max"], dtype=float),
+                    prefix + "modulator_ions": np.asarray(desc.get("modulator_ions", -np.ones(len(desc["modulator_names"]))), dtype=np.int64),
+                    prefix + "tj_targets": np.asarray(desc.get("tj_targets", np.zeros(0)), dtype=np.int64),
+                    prefix + "n_env": np.asarray(int(desc.get("n_env", 0)))})
     for k in ("env_on", "Dm", "c_bound", "c_env", "D_env", "scale_factor", "intra_on", "Do", "mu_mem", "c_mems"):
         if k in desc:
             out[prefix + k] = np.asarray(desc[k])
@@ -430,6 +446,9 @@ def unflatten(cap, prefix):
     if prefix + "modulator_names" in cap:
         mods = {**mods, **{"modulator_names": [str(x) for x in g("modulator_names")], "modulator_strings": [str(x) for x in g("modulator_strings")],
                 "modulator_targets": [str(x) for x in g("modulator_targets")], "modulator_max": np.asarray(g("modulator_max"))}}
+        if prefix + "modulator_ions" in cap:
+            mods.update({"modulator_ions": np.asarray(g("modulator_ions")), "tj_targets": np.asarray(g("tj_targets")),
+                         "n_env": int(g("n_env"))})
     return {**mods, **{k: np.asarray(cap[prefix + k]) for k in ("env_on", "Dm", "c_bound", "c_env", "D_env", "scale_factor", "intra_on", "Do", "mu_mem", "c_mems") if prefix + k in cap},
             "species": species, "ions": [str(x) for x in g("ions")], "c_cells": np.asarray(g("c_cells")),
             "gad_strings": [str(x) for x in g("gad_strings")],

@@ -67,10 +67,10 @@ class Program:
 
 
 class Tables:
-    def __init__(self, species, ions, n_cells, n_mems):
+    def __init__(self, species, ions, n_cells, n_mems, n_env=0):
         self.species = list(species)
         self.ions = list(ions)
-        self.n_cells, self.n_mems = int(n_cells), int(n_mems)
+        self.n_cells, self.n_mems, self.n_env = int(n_cells), int(n_mems), int(n_env)
         self.consts = []
         self.cell_arrays = []
         self.mem_arrays = []
@@ -85,6 +85,8 @@ class Tables:
         return len(self.consts) - 1
 
     def array(self, a, zone):
+        if zone == "env":
+            raise RateLawError("a non-uniform static array in the extracellular zone is not implemented")
         tab = self.cell_arrays if zone == "cell" else self.mem_arrays
         for k, b in enumerate(tab):
             if np.array_equal(a, b):
@@ -122,6 +124,15 @@ def _dynamic(node, tables, zone):
     if isinstance(node, ast.Subscript) and isinstance(node.value, ast.Attribute) \
             and isinstance(node.value.value, ast.Name) and node.value.value.id == "self":
         dic, key = node.value.attr, _subscript_key(node)
+        if dic == "env_concs" and zone == "env" and key is not None:
+            # extracellular zone (tight-junction modulators, get_influencers with reaction_zone 'env', networks.py:5270-5281):
+            # the whole env array, evaluated square by square
+            if key in tables.species:
+                tables.env_species.add(tables.species.index(key))
+                return (PUSHE, tables.species.index(key))
+            if key in tables.ions:
+                return (PUSHJ, tables.ions.index(key))
+            raise RateLawError("unknown substance %r" % key)
         if dic in ("cell_concs", "mem_concs") and key is not None:
             if (dic == "cell_concs") != (zone == "cell"):
                 raise RateLawError("%s[%r] used in the %s zone" % (dic, key, zone))
@@ -171,7 +182,7 @@ def compile_expr(src, tables, resolver, zone="cell"):
     (an attribute chain such as ``self.molecules['X'].r_production`` or a call such as
     ``np.ones(sim.cdl)``) and returns a float or an array of the zone's length."""
     tree = ast.parse(src.strip(), mode="eval").body
-    n_zone = tables.n_cells if zone == "cell" else tables.n_mems
+    n_zone = tables.n_cells if zone == "cell" else (tables.n_env if zone == "env" else tables.n_mems)
 
     def static_value(v, what):
         if isinstance(v, (bool, np.bool_)):
@@ -276,6 +287,7 @@ def run_numpy(prog, tables, species, ions=None, ions_mid=None, vm=None, mem_to_c
     gather cell quantities through ``mem_to_cells``."""
     st = []
     g = (lambda a: a[mem_to_cells]) if prog.zone == "mem" else (lambda a: a)
+    env_ix = slice(None) if prog.zone == "env" else (map_mem2ecm if prog.zone == "mem" else map_cell2ecm)
     for op, arg in prog.code:
         if op == PUSHC:
             st.append(tables.consts[arg])
@@ -290,9 +302,9 @@ def run_numpy(prog, tables, species, ions=None, ions_mid=None, vm=None, mem_to_c
         elif op == PUSHV:
             st.append(vm)
         elif op == PUSHE:
-            st.append(species_env[arg][map_mem2ecm if prog.zone == "mem" else map_cell2ecm])
+            st.append(species_env[arg][env_ix])
         elif op == PUSHJ:
-            st.append(ions_env[arg][map_mem2ecm if prog.zone == "mem" else map_cell2ecm])
+            st.append(ions_env[arg][env_ix])
         elif op == NEG:
             st.append(-st.pop())
         elif op == EXP:
@@ -304,5 +316,5 @@ def run_numpy(prog, tables, species, ions=None, ions_mid=None, vm=None, mem_to_c
                 st.append({ADD: operator.add, SUB: operator.sub, MUL: operator.mul, DIV: operator.truediv,
                            POW: np.power}[op](a, b))
     assert len(st) == 1
-    n = tables.n_cells if prog.zone == "cell" else tables.n_mems
+    n = tables.n_cells if prog.zone == "cell" else (tables.n_env if prog.zone == "env" else tables.n_mems)
     return st[0] * np.ones(n)

@@ -276,6 +276,24 @@ SCENARIOS["mammal_ecm_net_mod"] = dict(
     snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=net_extra)
 
 
+# tight-junction modulators (run_loop_modulators, target 'TJ', networks.py:3301-3317): an extracellular-zone rate law
+# (get_influencers with reaction_zone 'env', networks.py:5270-5281) rewrites sim.TJ_modulator on the tight-junction squares
+# every step — S1 in the bath opens the barrier for all ions, S3 closes it for Na only
+_TJ_MODS = [{"name": "tj_all", "target": "TJ", "max effect": 3.0, "activators": ["S1"], "activator Km": [0.3], "activator n": [2.0],
+             "activator zone": ["env"]},
+            {"name": "tj_na", "target": "TJ", "target ion": "Na", "max effect": 0.5, "inhibitors": ["S3"], "inhibitor Km": [0.2],
+             "inhibitor n": [1.0], "inhibitor zone": ["env"]}]
+SCENARIOS["mammal_ecm_net_tj"] = dict(
+    mods=_m(SMALL, {"cutting event": {"event happens": False}, "general options": {"ion profile": "mammal"},
+                    "internal parameters": {"substances affect Vmem": False},
+                    "general network": {"implement network": True, "biomolecules": _ENV_BIO, "reactions": [], "channels": [],
+                                        "modulators": _TJ_MODS}}),
+    snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=net_extra,
+    # the recorder files every change of sim.TJ_modulator between two steps under the scheduled interventions; here the
+    # network itself rewrites it inside the loop body — not an input of the step
+    drop_sched=("TJ_modulator",))
+
+
 # ligand-gated channels (Molecule.gating, networks.py:5847-5916): L1 opens a Na/K channel from inside the cell, L2 a Ca
 # channel from the extracellular side (it lives in the bath and crosses the membrane slowly)
 def _ligand(sub, ions, K, peak, extracell):
@@ -452,6 +470,9 @@ def main(argv):
                                    extra=sc.get("extra"), tweak_p=sc.get("tweak_p"),
                                    trace=sc.get("trace", ()), precut=sc.get("precut", False),
                                    method=sc.get("method", "_run_sim_core_loop"))
+        for f in sc.get("drop_sched", ()):
+            for k in [k for k in cap if ".sched." in k and k.endswith("." + f)]:
+                cap.pop(k)
         cap["meta.numpy"] = np.array(np.__version__)
         cap["meta.scipy"] = np.array(scipy.__version__)
         cap["meta.seed"] = np.array(12345)

@@ -44,6 +44,10 @@ def test_oracle_reproduces_reference(name, kind):
                 if key in ref and not (kind == "init" and not c["init_active"]):
                     assert util.rel_err(c[f], ref[key]) < 1e-12, (name, kind, K, key)
                     checked += 1
+        if name == "mammal_ecm_net_tj" and "TJ_modulator" in ref:                 # what the tight-junction modulators left (networks.py:3301-3317)
+            assert util.rel_err(o.TJ_modulator, ref["TJ_modulator"]) < 1e-12, (name, kind, K)
+            assert float(np.ptp(ref["TJ_modulator"])) > 0.5
+            checked += 1
         for h, net in zip(util.network_handlers(cap, kind), o.networks):        # network substances, rates, channel DChan (networks.py:2805-2982, 3164)
             want = ref["net%d.c_cells" % h]
             for k, nme in enumerate(net.species):
