@@ -116,7 +116,7 @@ class Channel(C.Structure):
 
 
 class Modulator(C.Structure):
-    _fields_ = [("target", C.c_int32), ("prog", C.c_int32), ("max_val", C.c_double)]
+    _fields_ = [("target", C.c_int32), ("prog", C.c_int32), ("max_val", C.c_double), ("ion", C.c_int32), ("pad", C.c_int32)]
 
 
 class LigandGate(C.Structure):
@@ -157,6 +157,7 @@ class Network(C.Structure):
         ("mem_sa_over_vol", _dp),
         ("intra_on", _bp), ("Do", _dp), ("c_mems", _dp), ("R_rads", _dp), ("map_cell2ecm", _ip),
         ("mu_mem", _dp), ("Emc", _dp),
+        ("tj_targets", _ip), ("n_tj", C.c_int32), ("reserved2", C.c_int32), ("D_env_raw", _dp), ("TJ_modulator", _dp),
     ]
 
 
@@ -187,7 +188,7 @@ SYMBOLS = [
     "betse_step_phase", "betse_stream", "betse_sync", "betse_update_v", "betse_update_v_phase",
     "betse_set_row_ranges", "betse_window", "betse_attach_neighbor", "betse_exchange",
     "betse_set_channels", "betse_channel_state", "betse_set_network", "betse_network_state",
-    "betse_network_env_state", "betse_network_mem_state", "betse_network_set_events", "betse_set_noise_flux",
+    "betse_network_env_state", "betse_network_mem_state", "betse_network_tj_modulator", "betse_network_set_events", "betse_set_noise_flux",
     "betse_host_alloc", "betse_host_alloc_on", "betse_host_copy", "betse_host_expand", "betse_host_free",
 ]
 
@@ -237,6 +238,7 @@ def load(build_if_missing=True):
     lib.betse_network_state.argtypes = [vp, C.c_int, _dp, _dp]
     lib.betse_network_env_state.argtypes = [vp, C.c_int, _dp]
     lib.betse_network_mem_state.argtypes = [vp, C.c_int, _dp]
+    lib.betse_network_tj_modulator.argtypes = [vp, _dp]
     lib.betse_network_set_events.argtypes = [vp, C.c_int, _dp, _dp]
     lib.betse_set_noise_flux.argtypes = [vp, C.c_int, _dp]
     lib.betse_step_phase.argtypes = [vp, C.c_int, C.c_int]

@@ -73,6 +73,8 @@ void launch_transporter(const KParams& P, const KArrays& A, const KNet& N, const
                         int cur, cudaStream_t st);
 void launch_tw_gather(const KParams& P, const KArrays& A, double* row, const double* src, cudaStream_t st);
 void launch_net_mod(const KParams& P, const KArrays& A, const KNet& N, int prog, double max_val, double* dst, int cur, cudaStream_t st);
+void launch_net_mod_tj(const KParams& P, const KArrays& A, const KNet& N, int prog, double max_val, int ion, const int* tj, int n_tj,
+                       const double* denv_raw, double* tj_mod, int cur, cudaStream_t st);
 void launch_cell_update(const KParams& P, const KArrays& A, int cur, cudaStream_t st);
 void launch_fast(const KParams& P, const KArrays& A, const KFast& Fz, int cur, cudaStream_t st);
 void launch_fast_diag(const KParams& P, const KArrays& A, const KFast& Fz, cudaStream_t st);
@@ -131,6 +133,10 @@ struct betse_ctx {
     std::vector<unsigned char> net_env_on[2];
     bool net_affect[2] = {false, false};
     std::vector<betse_modulator> net_mods[2];   // sim modulators of each handler (run_loop_modulators)
+    int* net_tj[2] = {nullptr, nullptr};         // tight-junction modulators: env squares of the barrier (sim.TJ_targets)
+    int net_ntj[2] = {0, 0};
+    double* denv_raw = nullptr;                  // [I][E] sim.D_env without TJ_modulator
+    double* tj_mod = nullptr;                    // [I][E] sim.TJ_modulator as the modulators leave it
     std::vector<betse_ligand_gate> net_gates[2];   // ligand-gated channels (Molecule.gating)
     std::vector<betse_substance_pump> net_pumps[2]; // the substances' own pumps / transporters (Molecule.pump)
     std::vector<betse_transporter> net_trans[2];    // transporters (run_loop_transporters); masks below are device copies
@@ -1305,8 +1311,12 @@ static void enqueue_phase(betse_ctx* ctx, int phase, int diag, cudaEvent_t* evs)
                 }
                 if (ctx->net_on[h])
                     for (const betse_modulator& md : ctx->net_mods[h])
-                        launch_net_mod(ctx->P, A, ctx->nets[h], md.prog, md.max_val,
-                                       const_cast<double*>(md.target == 0 ? A.gj_block : A.NaK_block), cur, st);
+                        if (md.target == 2)
+                            launch_net_mod_tj(ctx->P, A, ctx->nets[h], md.prog, md.max_val, md.ion, ctx->net_tj[h], ctx->net_ntj[h],
+                                              ctx->denv_raw, ctx->tj_mod, cur, st);
+                        else
+                            launch_net_mod(ctx->P, A, ctx->nets[h], md.prog, md.max_val,
+                                           const_cast<double*>(md.target == 0 ? A.gj_block : A.NaK_block), cur, st);
                 if (ctx->net_on[h]) {
                     const std::vector<betse_ligand_gate>& gs = ctx->net_gates[h];
                     for (size_t j = 0; j < gs.size(); ++j)
@@ -2225,8 +2235,31 @@ extern "C" int betse_set_network(betse_ctx* ctx, int handler, const betse_networ
     ctx->net_mods[handler].clear();
     for (int j = 0; j < net->n_modulators; ++j) {
         const betse_modulator& md = net->modulators[j];
-        if (md.target < 0 || md.target > 1) return fail(ctx, "network: modulator target must be 0 (gap junctions) or 1 (Na/K-ATPase)");
+        if (md.target < 0 || md.target > 2) return fail(ctx, "network: modulator target must be 0 (gap junctions), 1 (Na/K-ATPase) or 2 (tight junctions)");
         if (md.prog < R || md.prog >= net->n_programs) return fail(ctx, "network: modulator program is not a membrane-zone program");
+        if (md.target == 2) {
+            // tight junctions: an extracellular-zone program over the squares of the barrier
+            if (!ctx->hp.is_ecm || !net->tj_targets || net->n_tj <= 0 || !net->D_env_raw)
+                return fail(ctx, "network: a tight-junction modulator needs extracellular spaces, tj_targets and D_env_raw");
+            if (md.ion >= ctx->I) return fail(ctx, "network: tight-junction modulator ion out of range");
+            if (ctx->X.n_nbr > 0) return fail(ctx, "network: tight-junction modulators on a domain-decomposed tissue are not implemented");
+            for (int q = 0; q < net->n_tj; ++q)
+                if (net->tj_targets[q] < 0 || net->tj_targets[q] >= ctx->E) return fail(ctx, "network: tj_targets out of range");
+            if (!ctx->net_tj[handler]) {
+                if ((r = dev_upload(ctx, &ctx->net_tj[handler], (const int*)net->tj_targets, (size_t)net->n_tj))) return r;
+                ctx->net_ntj[handler] = net->n_tj;
+            }
+            if (!ctx->denv_raw) { if ((r = dev_upload(ctx, &ctx->denv_raw, net->D_env_raw, (size_t)ctx->I * ctx->E))) return r; }
+            if (!ctx->tj_mod) {
+                std::vector<double> ones;
+                if (!net->TJ_modulator) ones.assign((size_t)ctx->I * ctx->E, 1.0);
+                if ((r = dev_upload(ctx, &ctx->tj_mod, net->TJ_modulator ? net->TJ_modulator : (const double*)ones.data(), (size_t)ctx->I * ctx->E))) return r;
+                CK(cudaStreamSynchronize(ctx->stream));
+            }
+            CK(cudaStreamSynchronize(ctx->stream));
+            ctx->net_mods[handler].push_back(md);
+            continue;
+        }
         // the block becomes a per-membrane array (it starts from the value in force now)
         const double** slot = md.target == 0 ? &ctx->A.gj_block : &ctx->A.NaK_block;
         if (!*slot) {
@@ -2275,6 +2308,17 @@ extern "C" int betse_network_state(betse_ctx* ctx, int handler, double* c_cells,
     const KNet& N = ctx->nets[handler];
     if (c_cells) { int xr = xfer(ctx, c_cells, N.c, (size_t)N.K * ctx->C * sizeof(double), cudaMemcpyDeviceToHost); if (xr) return xr; }
     if (rates) { int xr = xfer(ctx, rates, N.rates, (size_t)N.n_rates * ctx->C * sizeof(double), cudaMemcpyDeviceToHost); if (xr) return xr; }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int betse_network_tj_modulator(betse_ctx* ctx, double* tj_modulator)
+{
+    if (!ctx || !tj_modulator) return 2;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->tj_mod) return fail(ctx, "no tight-junction modulator is configured");
+    int xr = xfer(ctx, tj_modulator, ctx->tj_mod, (size_t)ctx->I * ctx->E * sizeof(double), cudaMemcpyDeviceToHost);
+    if (xr) return xr;
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }

@@ -248,6 +248,32 @@ k_net_mod(const __grid_constant__ KParams P, const KArrays A, const __grid_const
     dst[m] = max_val * rl_eval(N, prog, c, m, A, P.n_cells, P.n_mems_owned, cur, vm);
 }
 
+// Tight-junction modulator (run_loop_modulators, target 'TJ', networks.py:3301-3317): modulator = max_val * eval(extracellular-
+// zone rate law) on the env squares of the barrier (sim.TJ_targets) becomes sim.TJ_modulator there — for one ion or for all —,
+// i.e. the effective diffusion constant the next step's transport reads is D_env * modulator (sim.py:2231-2233).
+__global__ void __launch_bounds__(256)
+k_net_mod_tj(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ KNet N, const int prog, const double max_val,
+             const int ion, const int* __restrict__ tj, const int n_tj, const double* __restrict__ denv_raw, double* __restrict__ tj_mod,
+             const int cur)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tj) return;
+    const int k = __ldg(tj + t);
+    const int E = P.nx * P.ny;
+    const double v = max_val * rl_eval(N, prog, 0, -2 - k, A, P.n_cells, P.n_mems_owned, cur, 0.0);
+    double* Denv = const_cast<double*>(A.Denv);
+    for (int i = (ion >= 0 ? ion : 0); i < (ion >= 0 ? ion + 1 : P.n_ions); ++i) {
+        tj_mod[(size_t)i * E + k] = v;                                          // sim.TJ_modulator itself (what the host reads back)
+        Denv[(size_t)i * E + k] = __ldg(denv_raw + (size_t)i * E + k) * v;
+    }
+}
+
+void launch_net_mod_tj(const KParams& P, const KArrays& A, const KNet& N, int prog, double max_val, int ion, const int* tj, int n_tj,
+                       const double* denv_raw, double* tj_mod, int cur, cudaStream_t st)
+{
+    if (n_tj > 0) k_net_mod_tj<<<(n_tj + 255) / 256, 256, 0, st>>>(P, A, N, prog, max_val, ion, tj, n_tj, denv_raw, tj_mod, cur);
+}
+
 void launch_net_mod(const KParams& P, const KArrays& A, const KNet& N, int prog, double max_val, double* dst, int cur, cudaStream_t st)
 {
     k_net_mod<<<(P.n_mems_owned + 255) / 256, 256, 0, st>>>(P, A, N, prog, max_val, dst, cur);

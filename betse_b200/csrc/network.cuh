@@ -78,8 +78,9 @@ __device__ __forceinline__ double rl_eval(const KNet& N, const int prog, const i
                 // outside the cells: substance / ion at the membrane's env square (membrane zone) or at the env square of
                 // the cell centre (cell zone, cells.map_cell2ecm); the ions' env
                 // field is the one this step's transport left (cc_env[cur ^ 1]), what sim.cc_env holds during the network block
-                case RL_PUSHE: v = N.c_env[(size_t)arg * N.E + (m >= 0 ? __ldg(A.map_mem2ecm + m) : __ldg(N.cell2ecm + c))]; break;
-                case RL_PUSHJ: v = A.cc_env[cur ^ 1][(size_t)arg * N.E + (m >= 0 ? __ldg(A.map_mem2ecm + m) : __ldg(N.cell2ecm + c))]; break;
+                // (m < -1: an extracellular-zone program — tight-junction modulators — evaluated at env square -2 - m)
+                case RL_PUSHE: v = N.c_env[(size_t)arg * N.E + (m >= 0 ? __ldg(A.map_mem2ecm + m) : (m < -1 ? -2 - m : __ldg(N.cell2ecm + c)))]; break;
+                case RL_PUSHJ: v = A.cc_env[cur ^ 1][(size_t)arg * N.E + (m >= 0 ? __ldg(A.map_mem2ecm + m) : (m < -1 ? -2 - m : __ldg(N.cell2ecm + c)))]; break;
                 case RL_PUSHC: v = __ldg(N.consts + arg); break;
                 case RL_PUSHS: v = (m >= 0 && N.tw && N.tw_s[arg] >= 0) ? N.tw[(size_t)N.tw_s[arg] * M + m] : N.c[(size_t)arg * C + c];
                                break;

@@ -22,7 +22,7 @@ _DOWN_SHAPES = {
     "dvm": "M", "J_cell_x": "C", "J_cell_y": "C", "E_cell_x": "C", "E_cell_y": "C",
     "sigma_cell": "C", "E_gj_x": "M", "E_gj_y": "M",
     "J_env_x": "E", "J_env_y": "E", "B_field": "E", "Jtx": "E", "Jty": "E", "Phi_b": "E",
-    "extra_rho_cells": "C", "extra_rho_env": "E", "extra_J_mem": "M",
+    "extra_rho_cells": "C", "extra_rho_env": "E", "extra_J_mem": "M", "D_env_eff": "IE",
 }
 # what get_current leaves on the env grid of a tissue WITHOUT extracellular spaces (ion_current.py:116-158)
 _NOECM_FIELD = ("v_env", "E_env_x", "E_env_y", "J_env_x", "J_env_y", "B_field", "Jtx", "Jty")
@@ -628,6 +628,16 @@ class TissueEngine:
                     "betse_channel_state")
         return out
 
+    def tj_modulator(self):
+        """sim.TJ_modulator [I][E] as the tight-junction modulators of a network left it (networks.py:3301-3317); None
+        without such modulators."""
+        if getattr(self, "_tj_targets", None) is None:
+            return None
+        out = np.empty((self.I, self.E))
+        self._check(self.lib.betse_network_tj_modulator(self.ctx, capi.ptr_f64(out)), "betse_network_tj_modulator")
+        self.d2h_bytes += out.nbytes
+        return out
+
     # ------------------------------------------------------------------ general / gene network
     def set_network(self, net, handler=0):
         """``net``: a compiled network (betse_b200.network.compile_network): substances, rate
@@ -676,8 +686,23 @@ class TissueEngine:
         mods = list(net.get("modulators") or [])
         if mods:
             marr = (capi.Modulator * len(mods))()
-            for j, (target, prog, mx) in enumerate(mods):
+            for j, md in enumerate(mods):
+                target, prog, mx = md[:3]
                 marr[j].target, marr[j].prog, marr[j].max_val = int(target), int(prog), float(mx)
+                marr[j].ion = int(md[3]) if len(md) > 3 else -1
+            if any(int(md[0]) == 2 for md in mods):
+                # tight-junction modulators (networks.py:3301-3317): the squares of the barrier and sim.D_env itself (the
+                # device otherwise holds only D_env * TJ_modulator)
+                if not self.is_ecm or getattr(self, "_denv", None) is None:
+                    raise BetseB200Error("tight-junction modulators need extracellular spaces and sim.D_env")
+                tj = capi.as_i32(np.asarray(net["tj_targets"]).reshape(-1))
+                keep.append(tj)
+                n.tj_targets, n.n_tj = tj.ctypes.data_as(C.POINTER(C.c_int32)), int(tj.size)
+                n.D_env_raw = f64(np.asarray(self._denv, dtype=float).reshape(self.I, self.E))
+                n.TJ_modulator = f64(np.array(np.broadcast_to(np.asarray(getattr(self, "_tj", 1.0), dtype=float).reshape(-1, self.E)
+                                                              if np.ndim(getattr(self, "_tj", 1.0)) else np.asarray(getattr(self, "_tj", 1.0), dtype=float),
+                                                              (self.I, self.E)), dtype=float, copy=True))
+                self._tj_targets = np.asarray(tj, dtype=np.int64)
             keep.append(marr)
             n.n_modulators, n.modulators = len(mods), marr
         gates = list(net.get("ligand_gates") or [])

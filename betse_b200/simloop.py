@@ -305,6 +305,10 @@ def _copy_back(sim, eng, diag, sample_only=False):
         elif sample_only:
             eng.__dict__.setdefault("_lent", {})[f] = a          # a view of engine-owned staging, see _detach
         setattr(sim, f, a)
+    if not sample_only and callable(getattr(eng, "tj_modulator", None)):
+        tjm = eng.tj_modulator()                    # tight-junction modulators rewrite it inside the loop (networks.py:3301-3317)
+        if tjm is not None:
+            sim.TJ_modulator = tjm.reshape(np.shape(sim.TJ_modulator)) if hasattr(sim, "TJ_modulator") else tjm
     # channel objects keep their gate state / open probability / flux (read by the exporters and by
     # the next phase through the pickled Simulator)
     for k, c in enumerate(getattr(eng, "chan_specs", [])):

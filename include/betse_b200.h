@@ -295,8 +295,11 @@ void betse_host_free(void *p);
 #define BETSE_STATUS_NEG_NET 16u  /* a network substance went negative (sim_toolbox.py:1124-1150 raises) */
 
 /* One sim modulator (Modulator, networks.py:6655-6700; run_loop_modulators, networks.py:3282-3325):
- * target = max_val * program(membrane), written over sim.gj_block (target 0) or sim.NaKATP_block (target 1). */
-typedef struct betse_modulator { int32_t target; int32_t prog; double max_val; } betse_modulator;
+ * target = max_val * program(membrane), written over sim.gj_block (target 0) or sim.NaKATP_block (target 1);
+ * target 2 = tight junctions (networks.py:3301-3317): max_val * program(env square) — an EXTRACELLULAR-zone program —
+ * written over sim.TJ_modulator on the squares betse_network.tj_targets, for ion `ion` or for all ions (ion < 0); the
+ * transport of the NEXT step then sees D_env_raw * TJ_modulator there (sim.py:2231-2233). */
+typedef struct betse_modulator { int32_t target; int32_t prog; double max_val; int32_t ion; int32_t pad; } betse_modulator;
 
 /* One ligand-gated channel (Molecule.gating, networks.py:5847-5916): substance `species` opens a channel for ion `ion`,
  * Dchan = rho_channel * Dm_mod * mod, Dm_mod = rho_channel*max*hill(c at the membrane) (intracellular ligand) or
@@ -392,6 +395,12 @@ typedef struct betse_network {
      * read and move the membrane values (sim_toolbox.py:962-1005, 1183-1185). */
     const double  *mu_mem;               /* [K] Molecule.Mu_mem (NULL: zeros)                            */
     const double  *Emc;                  /* [M] sim.Emc at loop entry (NULL: zeros)                      */
+    /* tight-junction modulators (betse_modulator.target == 2) */
+    const int32_t *tj_targets;           /* [n_tj] sim.TJ_targets: env squares of the barrier (sim.py:2394-2395) */
+    int32_t n_tj;
+    int32_t reserved2;
+    const double  *D_env_raw;            /* [I][E] sim.D_env WITHOUT sim.TJ_modulator (betse_state_host.D_env_eff is their product) */
+    const double  *TJ_modulator;         /* [I][E] sim.TJ_modulator at loop entry (NULL: ones)            */
 } betse_network;
 
 /* handler 0 = sim.molecules.core, 1 = sim.grn.core (run in that order, sim.py:1290-1318).  net == NULL
@@ -401,6 +410,8 @@ int  betse_set_network(betse_ctx *ctx, int handler, const betse_network *net);
 int  betse_network_state(betse_ctx *ctx, int handler, double *c_cells, double *rates);
 /* Env concentrations [K][E] of the substances (rows with env_on == 0 come back as zeros). */
 int  betse_network_env_state(betse_ctx *ctx, int handler, double *c_env);
+/* sim.TJ_modulator [I][E] as the tight-junction modulators left it (networks.py:3301-3317); an error without such modulators. */
+int  betse_network_tj_modulator(betse_ctx *ctx, double *tj_modulator);
 /* Membrane values [K][M] (Molecule.cc_at_mem): the cell value gathered, or the transported value with intra_on. */
 int  betse_network_mem_state(betse_ctx *ctx, int handler, double *c_mems);
 /* The substances' own timed events, evaluated by the host for the step about to run (scalar schedule logic like

@@ -31,7 +31,8 @@ def _attach(eng, desc, specs, phase_init):
                                      "mammal_ecm_polar_net",                         # per-membrane Vmem (polarizability) under all of it
                                      "mammal_ecm_net_envzone",                       # cell-zone rate laws regulated from outside the cells
                                      "mammal_ecm_net_events",                        # boundary ramp and cell clamp of substances
-                                     "mammal_ecm_net_intra"])                        # 'update intracellular': transported membrane values
+                                     "mammal_ecm_net_intra",                         # 'update intracellular': transported membrane values
+                                     "mammal_ecm_net_tj"])                           # tight-junction modulators (extracellular-zone rate laws)
 def test_network_matches_reference(fixture, kind):
     from betse_b200.engine import TissueEngine
     cap = util.load_golden(fixture)
@@ -74,6 +75,9 @@ def test_network_matches_reference(fixture, kind):
             cm = eng.network_mem_state(0)
             for k, nme in enumerate(desc["species"]):
                 assert util.rel_err(cm[k], ref["net0.c_mems"][k]) <= 1e-10, (kind, K, nme, "mems", util.rel_err(cm[k], ref["net0.c_mems"][k]))
+        if fixture == "mammal_ecm_net_tj" and "TJ_modulator" in ref:
+            tjm = eng.tj_modulator()
+            assert util.rel_err(tjm, ref["TJ_modulator"].reshape(tjm.shape)) <= 1e-10, (kind, K, "TJ_modulator")
         for k, ch in enumerate(active):
             j = [s["name"] for s in specs].index(ch["name"])
             stt = eng.channel_state(k)

@@ -45,7 +45,7 @@ def apply_schedule(obj, cap, kind, n):
     """Apply what fire_events rewrote for (1-based) step n (oracle/refrun.py)."""
     # sim modulators rewrite these inside the loop (run_loop_modulators, networks.py:3296-3299): not a schedule
     targets = [str(t) for h in range(2) for t in cap.get("%s.s0.net%d.modulator_targets" % (kind, h), [])]
-    skip = {"GJ": "gj_block", "Na/K-ATPase": "NaKATP_block"}
+    skip = {"GJ": "gj_block", "Na/K-ATPase": "NaKATP_block", "TJ": "TJ_modulator"}
     skip = {skip[t] for t in targets if t in skip}
     key = "%s.noise.k%d" % (kind, n)
     if key in cap:          # dynamic noise: the reference's own draw of this step (oracle/refrun.py)
