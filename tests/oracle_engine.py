@@ -120,6 +120,11 @@ class OracleEngine:
         net = self._sim().networks[sorted(self._descs).index(int(handler))]
         net.forced_events = (np.array(c_bound, dtype=float), np.array(clamp, dtype=float))
 
+    def tj_modulator(self):
+        if not any(len(np.asarray(d.get("tj_targets", []))) for d in self._descs.values()):
+            return None
+        return np.array(self._sim().TJ_modulator, dtype=float, copy=True)
+
     def network_mem_state(self, handler=0):
         net = self._sim().networks[sorted(self._descs).index(int(handler))]
         return np.stack([net.cmem[n] for n in net.species])

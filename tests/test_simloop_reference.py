@@ -261,6 +261,27 @@ def test_env_substances_through_the_dropin_match_the_reference(monkeypatch, tmp_
         assert np.max(np.abs(a - r)) <= 1e-9 * np.max(np.abs(r))
 
 
+def test_tight_junction_modulators_through_the_dropin_match_the_reference(monkeypatch, tmp_path):
+    """run_loop_modulators with target 'TJ' (networks.py:3301-3317): the shim hands over sim.TJ_targets, sim.D_env and the
+    modulators' ion; the ion concentrations outside the cells (which the modulated barrier shapes), the substances and the
+    sim.TJ_modulator the phase ends with — what the NEXT phase starts from — against the reference's own run."""
+    from tests.golden import make_golden as mg
+    mods = mg.SCENARIOS["mammal_ecm_net_tj"]["mods"]
+    ref_sim, _, _ = _run_try(tmp_path / "ref", False, mods=mods)
+    (tmp_path / "new").mkdir()
+    new_sim, _, engines = _run_try(tmp_path / "new", True, monkeypatch, mods=mods)
+    for name in ("S1", "S2", "S3"):
+        a, r = new_sim.molecules.core.molecules[name], ref_sim.molecules.core.molecules[name]
+        assert len(a.c_env_time) == len(r.c_env_time) >= 30
+        for x, y in zip(a.c_env_time, r.c_env_time):
+            assert np.max(np.abs(np.asarray(x) - np.asarray(y))) <= 1e-9 * max(np.max(np.abs(np.asarray(y))), 1e-300), name
+    for a, r in zip(new_sim.cc_env_time, ref_sim.cc_env_time):
+        assert np.max(np.abs(np.asarray(a) - np.asarray(r))) <= 1e-9 * np.max(np.abs(np.asarray(r)))
+    tj_new, tj_ref = np.asarray(new_sim.TJ_modulator), np.asarray(ref_sim.TJ_modulator)
+    assert float(np.ptp(tj_ref)) > 0.5
+    assert np.max(np.abs(tj_new - tj_ref)) <= 1e-9 * np.max(np.abs(tj_ref))
+
+
 def test_gene_network_through_the_dropin_matches_the_reference(monkeypatch, tmp_path):
     """BASELINE configs[3]: the shipped gene regulatory network (extra_configs/grn_basic.yaml) is the SECOND handler
     (sim.grn.core); the shim compiles it from the live MasterOfGenes and writes the genes back for write_data."""
