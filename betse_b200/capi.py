@@ -158,6 +158,7 @@ class Network(C.Structure):
         ("intra_on", _bp), ("Do", _dp), ("c_mems", _dp), ("R_rads", _dp), ("map_cell2ecm", _ip),
         ("mu_mem", _dp), ("Emc", _dp),
         ("tj_targets", _ip), ("n_tj", C.c_int32), ("reserved2", C.c_int32), ("D_env_raw", _dp), ("TJ_modulator", _dp),
+        ("env_rx_prog", _ip), ("n_env_rx", C.c_int32), ("reserved3", C.c_int32), ("stoich_env", _dp),
     ]
 
 

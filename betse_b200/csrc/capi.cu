@@ -2137,7 +2137,23 @@ extern "C" int betse_set_network(betse_ctx* ctx, int handler, const betse_networ
             if ((r = dev_upload(ctx, (double**)&N.D_env, net->D_env, (size_t)K * E))) return r;
             ctx->net_Dm[handler].assign(net->Dm, net->Dm + K);
             ctx->net_env_on[handler].assign(net->env_on, net->env_on + K);
+            if ((r = dev_upload(ctx, (unsigned char**)&N.env_on_d, (const unsigned char*)net->env_on, (size_t)K))) return r;
         }
+    }
+    N.n_env_rx = 0;
+    if (net->n_env_rx > 0) {
+        // reactions outside the cells (networks.py:2872-2889)
+        if (!N.c_env) return fail(ctx, "network: extracellular reactions need substances with env_on");
+        if (net->n_env_rx > 16 || !net->env_rx_prog || !net->stoich_env) return fail(ctx, "network: at most 16 extracellular reactions, with programs and stoich_env");
+        for (int j = 0; j < net->n_env_rx; ++j)
+            if (net->env_rx_prog[j] < R || net->env_rx_prog[j] >= net->n_programs) return fail(ctx, "network: extracellular reaction program out of range");
+        for (int k = 0; k < K; ++k)
+            for (int j = 0; j < net->n_env_rx; ++j)
+                if (net->stoich_env[(size_t)k * net->n_env_rx + j] != 0.0 && !net->env_on[k])
+                    return fail(ctx, "network: an extracellular reaction moves a substance without env_on");
+        if ((r = dev_upload(ctx, (int**)&N.env_rx_prog, (const int*)net->env_rx_prog, (size_t)net->n_env_rx))) return r;
+        if ((r = dev_upload(ctx, (double**)&N.stoich_env, net->stoich_env, (size_t)K * net->n_env_rx))) return r;
+        N.n_env_rx = net->n_env_rx;
     }
     if ((r = ensure_defer_buffers(ctx))) return r;
     {

@@ -54,6 +54,26 @@ k_net(const __grid_constant__ KParams P, const KArrays A, const __grid_constant_
     if (flags) atomicOr(A.status, flags);
 }
 
+// Reactions outside the cells (write_reactions_env, networks.py:1830-2088): one thread per env square evaluates the
+// extracellular-zone rate laws from the env concentrations the step found and applies reaction_matrix_env . rates * dt to
+// the substances that live there — the top of run_loop (networks.py:2872-2889), before any transport of the step.
+#define NET_MAX_ENV_RX 16
+__global__ void __launch_bounds__(128)
+k_net_env_rx(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ KNet N, const int cur)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N.E) return;
+    double r[NET_MAX_ENV_RX];
+    for (int j = 0; j < N.n_env_rx; ++j) r[j] = rl_eval(N, __ldg(N.env_rx_prog + j), 0, -2 - e, A, P.n_cells, P.n_mems_owned, cur, 0.0);
+    for (int k = 0; k < N.K; ++k) {
+        if (!N.env_on_d[k]) continue;
+        double d = 0.0;
+        for (int j = 0; j < N.n_env_rx; ++j) d += __ldg(N.stoich_env + k * N.n_env_rx + j) * r[j];      // np.dot(reaction_matrix_env, rates)
+        double* c = N.c_env + (size_t)k * N.E + e;
+        *c = *c + d * P.dt;
+    }
+}
+
 // gap-junction transport of substance k: per-cell sum of -f_gj*mem_sa (one warp per tile, the packing of k_mem)
 __global__ void __launch_bounds__(BT_TPB)
 k_net_gj(const __grid_constant__ KParams P, const KArrays A, const __grid_constant__ KNet N, const int k, const int cur,
@@ -652,6 +672,7 @@ void launch_net(const KParams& P, const KArrays& A, const KNet& N, const double*
     const int tgrid = (P.n_tiles + (BT_TPB / 32) - 1) / (BT_TPB / 32);
     const int E = P.nx * P.ny;
     auto pump_of = [&](int k) { for (int j = 0; j < n_pumps; ++j) if (pumps[j].species == k) return j; return -1; };
+    if (N.n_env_rx > 0 && N.c_env) k_net_env_rx<<<(E + 127) / 128, 128, 0, st>>>(P, A, N, cur);
     if (N.cmem && h_intra) {
         KIntraList L;
         L.n = 0;

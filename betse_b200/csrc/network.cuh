@@ -35,6 +35,10 @@ struct KNet {
     const double* Dm;           // [K]
     const double* c_bound;      // [K]
     const double* D_env;        // [K][E]
+    const int* env_rx_prog;     // [n_env_rx] extracellular reactions: program indices
+    int n_env_rx;
+    const double* stoich_env;   // [K][n_env_rx] substance rows of reaction_matrix_env
+    const unsigned char* env_on_d; // [K] the substance exists outside the cells
     // Membrane values (mem_concs[X] = Molecule.cc_at_mem / sim.cc_at_mem[ion]) of everything a transporter moves in the
     // cells: the reference updates the cell value AND nudges the membrane value (networks.py:3016-3022), two separate
     // arrays until the next update_intra / update_Co — so later membrane-zone rate laws of the step read these rows

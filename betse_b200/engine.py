@@ -683,6 +683,14 @@ class TissueEngine:
             n.Dm, n.c_bound = f64(np.asarray(net["Dm"], dtype=float).reshape(K)), f64(np.asarray(net["c_bound"], dtype=float).reshape(K))
             n.c_env = f64(np.asarray(net["c_env"], dtype=float).reshape(K, self.E))
             n.D_env = f64(np.asarray(net["D_env"], dtype=float).reshape(K, self.E))
+        erx = list(net.get("env_rx_index") or [])
+        if erx:
+            if not self.is_ecm or env_on is None or not np.any(env_on):
+                raise BetseB200Error("extracellular reactions need extracellular spaces and substances that live there")
+            ei = capi.as_i32(np.asarray(erx))
+            keep.append(ei)
+            n.env_rx_prog, n.n_env_rx = ei.ctypes.data_as(C.POINTER(C.c_int32)), len(erx)
+            n.stoich_env = f64(np.asarray(net["stoich_env"], dtype=float).reshape(K, len(erx)))
         mods = list(net.get("modulators") or [])
         if mods:
             marr = (capi.Modulator * len(mods))()

@@ -42,9 +42,11 @@ def unsupported_reasons(core, p):
             bad.append("transporter %r outside the cell zone" % name)
         if not bool(getattr(p, "is_ecm", False)):
             bad.append("transporter %r without extracellular spaces" % name)
-    for attr, what in (("reactions_env", "extracellular reactions"), ("reactions_mit", "mitochondrial reactions")):
+    for attr, what in (("reactions_mit", "mitochondrial reactions"),):
         if len(getattr(core, attr, None) or {}):
             bad.append(what)
+    if len(getattr(core, "reactions_env", None) or {}) and not bool(getattr(p, "is_ecm", False)):
+        bad.append("extracellular reactions without extracellular spaces")
     for name, m in (getattr(core, "molecules", None) or {}).items():
         why = []
         if bool(getattr(m, "update_intra_conc", False)):
@@ -150,6 +152,10 @@ def describe_core(core, sim, p, cells, record_static=True):
         "reaction_names": list(core.reactions),
         "reaction_strings": [core.reactions[r].reaction_eval_string for r in core.reactions],
         "stoich": rmat[rows] if rmat.size else np.zeros((K, K)),
+        # reactions outside the cells (write_reactions_env, networks.py:1830-2088; applied at the top of run_loop,
+        # networks.py:2872-2889): extracellular-zone rate laws, env_concs += reaction_matrix_env . rates * dt
+        "reaction_env_names": list(getattr(core, "reactions_env", None) or {}),
+        "reaction_env_strings": [r.reaction_eval_string for r in (getattr(core, "reactions_env", None) or {}).values()],
         "growth_targets": [np.asarray(core.molecules[s].growth_targets_cell, dtype=np.int64) for s in species],
         "Dgj": np.array([-1.0 if core.molecules[s].ignoreGJ else float(core.molecules[s].Dgj) for s in species]),
         "z": np.array([float(core.molecules[s].z) for s in species]),
@@ -171,6 +177,14 @@ def describe_core(core, sim, p, cells, record_static=True):
         "n_env": int(len(cells.xypts)) if getattr(cells, "xypts", None) is not None else 0,
         "static": {},
     }
+    if desc["reaction_env_names"]:
+        names_e = list(core.env_concs.keys())                     # rows of reaction_matrix_env (create_reaction_matrix_env, networks.py:2758-2790)
+        rme = np.asarray(core.reaction_matrix_env, dtype=float)
+        rows_e = [names_e.index(s) for s in species]
+        other_e = [i for i in range(len(names_e)) if i not in rows_e]
+        if np.any(rme[other_e] != 0.0):
+            raise BetseB200Error("extracellular reactions that produce or consume simulation ions are not implemented")
+        desc["stoich_env"] = rme[rows_e]
     # Molecule.transport -> stb.molecule_mover (networks.py:5670-5700, sim_toolbox.py:909-1153): membrane and
     # extracellular legs of the substances that have them
     events = []
@@ -275,6 +289,7 @@ def compile_network(desc, n_cells, n_mems, resolver=None):
         mods = [ratelaw.compile_expr(s, tabs, resolver, "mem") for s in desc["chan_mod_strings"]]
         modulators = [ratelaw.compile_expr(s, tabs, resolver, "env" if t == "TJ" else "mem")
                       for s, t in zip(desc.get("modulator_strings", []), mtargets)]
+        env_rx = [ratelaw.compile_expr(s, tabs, resolver, "env") for s in desc.get("reaction_env_strings", [])]
     except ratelaw.RateLawError as e:
         raise BetseB200Error("network rate law not supported on the device: %s" % e)
     stoich = np.asarray(desc["stoich"], dtype=float).reshape(K, -1)
@@ -299,6 +314,27 @@ def compile_network(desc, n_cells, n_mems, resolver=None):
     for t in desc.get("modulator_targets", []):
         if t not in MOD_TARGETS:
             raise BetseB200Error("modulator target %r is not implemented" % t)
+    # extracellular reactions: their programs follow the modulators'
+    env_rx_index = []
+    for pr in env_rx:
+        env_rx_index.append(len(rates) + len(mod_programs))
+        mod_programs.append(pr)
+    stoich_env = np.asarray(desc.get("stoich_env", np.zeros((K, 0))), dtype=float).reshape(K, -1)
+    if stoich_env.shape[1] != len(env_rx):
+        raise BetseB200Error("reaction_matrix_env has %d columns for %d extracellular reactions" % (stoich_env.shape[1], len(env_rx)))
+    if env_rx:
+        # run_loop applies them before anything else of the step reads the env concentrations (networks.py:2872-2889);
+        # the device evaluates the other zones' rate laws later in the step: a substance they move must not be read there
+        moved = {k for k in range(K) if np.any(stoich_env[k] != 0.0)}
+        eo_ = np.asarray(desc.get("env_on", np.zeros(K)), dtype=bool)
+        for k in moved:
+            if not eo_[k]:
+                raise BetseB200Error("an extracellular reaction moves %r, which does not exist outside the cells" % species[k])
+        for pr in rates:            # (channel and modulator programs run before run_loop, like the reference's)
+            for op, arg in pr.code:
+                if op == ratelaw.PUSHE and arg in moved:
+                    raise BetseB200Error("a cell-zone rate law reads %r outside the cells while an extracellular reaction "
+                                         "moves it: not implemented" % species[arg])
     # transporters: one membrane-zone program each, after the modulators' programs
     transporters = []
     ions = list(desc["ions"])
@@ -356,7 +392,8 @@ def compile_network(desc, n_cells, n_mems, resolver=None):
             "modulators": [(MOD_TARGETS[t], i, float(mx), int(ion)) for t, i, mx, ion in
                            zip(mtargets, modulator_index, desc.get("modulator_max", []),
                                desc.get("modulator_ions", [-1] * len(mtargets)))],
-            "tj_targets": np.asarray(desc.get("tj_targets", np.zeros(0)), dtype=np.int64), "c_cells": np.asarray(desc["c_cells"], dtype=float), "stoich": stoich,
+            "tj_targets": np.asarray(desc.get("tj_targets", np.zeros(0)), dtype=np.int64),
+            "env_rx_index": env_rx_index, "stoich_env": stoich_env, "c_cells": np.asarray(desc["c_cells"], dtype=float), "stoich": stoich,
             "growth_mask": None if mask.all() else mask, "Dgj": np.asarray(desc["Dgj"], dtype=float),
             "z": np.asarray(desc["z"], dtype=float), "time_factor": np.asarray(desc["time_factor"], dtype=float),
             "chan_names": list(desc["chan_names"]),
@@ -373,6 +410,11 @@ def flatten(desc, prefix):
            prefix + "time_factor": desc["time_factor"], prefix + "chan_names": np.array(desc["chan_names"], dtype=str),
            prefix + "chan_mod_strings": np.array(desc["chan_mod_strings"], dtype=str),
            prefix + "static_keys": np.array(list(desc["static"].keys()), dtype=str)}
+    if desc.get("reaction_env_names"):
+        out.update({prefix + "reaction_env_names": np.array(desc["reaction_env_names"], dtype=str),
+                    prefix + "reaction_env_strings": np.array(desc["reaction_env_strings"], dtype=str),
+                    prefix + "stoich_env": np.asarray(desc["stoich_env"], dtype=float),
+                    prefix + "n_env": np.asarray(int(desc.get("n_env", 0)))})
     for j, g in enumerate(desc.get("ligand_gates", [])):
         out["%slig%d" % (prefix, j)] = np.array([g["species"], g["ion"], g["K"], g["n"], g["max"], float(g["extracell"])])
         out["%slig%d.mod_string" % (prefix, j)] = np.array(g["mod_string"])
@@ -443,6 +485,10 @@ def unflatten(cap, prefix):
         mods.setdefault("pumps", []).append({"species": int(v[0]), "into_cell": bool(v[1]), "max": float(v[2]), "Km": float(v[3]),
                                              "uses_ATP": bool(v[4])})
         j += 1
+    if prefix + "reaction_env_names" in cap:
+        mods = {**mods, **{"reaction_env_names": [str(x) for x in g("reaction_env_names")],
+                           "reaction_env_strings": [str(x) for x in g("reaction_env_strings")],
+                           "stoich_env": np.asarray(g("stoich_env")), "n_env": int(g("n_env"))}}
     if prefix + "modulator_names" in cap:
         mods = {**mods, **{"modulator_names": [str(x) for x in g("modulator_names")], "modulator_strings": [str(x) for x in g("modulator_strings")],
                 "modulator_targets": [str(x) for x in g("modulator_targets")], "modulator_max": np.asarray(g("modulator_max"))}}

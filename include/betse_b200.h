@@ -401,6 +401,12 @@ typedef struct betse_network {
     int32_t reserved2;
     const double  *D_env_raw;            /* [I][E] sim.D_env WITHOUT sim.TJ_modulator (betse_state_host.D_env_eff is their product) */
     const double  *TJ_modulator;         /* [I][E] sim.TJ_modulator at loop entry (NULL: ones)            */
+    /* reactions OUTSIDE the cells (write_reactions_env, networks.py:1830-2088; the top of run_loop, networks.py:2872-2889):
+     * extracellular-zone programs, c_env += stoich_env . rates * dt before anything else of the handler's run_loop */
+    const int32_t *env_rx_prog;          /* [n_env_rx] program indices                                    */
+    int32_t n_env_rx;
+    int32_t reserved3;
+    const double  *stoich_env;           /* [K][n_env_rx] substance rows of reaction_matrix_env            */
 } betse_network;
 
 /* handler 0 = sim.molecules.core, 1 = sim.grn.core (run in that order, sim.py:1290-1318).  net == NULL

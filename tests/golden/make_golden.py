@@ -294,6 +294,18 @@ SCENARIOS["mammal_ecm_net_tj"] = dict(
     drop_sched=("TJ_modulator",))
 
 
+# a reaction OUTSIDE the cells (write_reactions_env, networks.py:1830-2088; applied at the top of run_loop,
+# networks.py:2872-2889): S1 turns into S2 in the bath, inhibited by S3 there
+_ENV_RX = [{"name": "S1_to_S2", "reaction zone": "env", "reactants": ["S1"], "reactant multipliers": [1], "Km reactants": [0.2],
+            "products": ["S2"], "product multipliers": [1], "Km products": [0.5], "max rate": 5.0e-2, "standard free energy": "None",
+            "reaction inhibitors": ["S3"], "inhibitor Km": [0.4], "inhibitor n": [1.0], "inhibitor zone": ["env"]}]
+SCENARIOS["mammal_ecm_net_envrx"] = dict(
+    mods=_m(SMALL, {"cutting event": {"event happens": False}, "general options": {"ion profile": "mammal"},
+                    "internal parameters": {"substances affect Vmem": False},
+                    "general network": {"implement network": True, "biomolecules": _ENV_BIO[:3], "reactions": _ENV_RX, "channels": []}}),
+    snaps={"init": [1, 2], "sim": [1, 2, 5, 20]}, extra=net_extra)
+
+
 # ligand-gated channels (Molecule.gating, networks.py:5847-5916): L1 opens a Na/K channel from inside the cell, L2 a Ca
 # channel from the extracellular side (it lives in the bath and crosses the membrane slowly)
 def _ligand(sub, ions, K, peak, extracell):

@@ -32,7 +32,8 @@ def _attach(eng, desc, specs, phase_init):
                                      "mammal_ecm_net_envzone",                       # cell-zone rate laws regulated from outside the cells
                                      "mammal_ecm_net_events",                        # boundary ramp and cell clamp of substances
                                      "mammal_ecm_net_intra",                         # 'update intracellular': transported membrane values
-                                     "mammal_ecm_net_tj"])                           # tight-junction modulators (extracellular-zone rate laws)
+                                     "mammal_ecm_net_tj",                            # tight-junction modulators (extracellular-zone rate laws)
+                                     "mammal_ecm_net_envrx"])                        # a reaction outside the cells (write_reactions_env)
 def test_network_matches_reference(fixture, kind):
     from betse_b200.engine import TissueEngine
     cap = util.load_golden(fixture)

@@ -282,6 +282,24 @@ def test_tight_junction_modulators_through_the_dropin_match_the_reference(monkey
     assert np.max(np.abs(tj_new - tj_ref)) <= 1e-9 * np.max(np.abs(tj_ref))
 
 
+def test_extracellular_reaction_through_the_dropin_matches_the_reference(monkeypatch, tmp_path):
+    """A reaction outside the cells (write_reactions_env, networks.py:1830-2088; applied at the top of run_loop,
+    networks.py:2872-2889): the shim compiles reaction_eval_string as an extracellular-zone rate law and hands over the
+    substance rows of reaction_matrix_env; the env concentrations of reactant and product against the reference's own run."""
+    from tests.golden import make_golden as mg
+    mods = mg.SCENARIOS["mammal_ecm_net_envrx"]["mods"]
+    ref_sim, _, _ = _run_try(tmp_path / "ref", False, mods=mods)
+    (tmp_path / "new").mkdir()
+    new_sim, _, engines = _run_try(tmp_path / "new", True, monkeypatch, mods=mods)
+    for name in ("S1", "S2", "S3"):
+        a, r = new_sim.molecules.core.molecules[name], ref_sim.molecules.core.molecules[name]
+        assert len(a.c_env_time) == len(r.c_env_time) >= 30
+        for x, y in zip(a.c_env_time + a.c_cells_time, r.c_env_time + r.c_cells_time):
+            assert np.max(np.abs(np.asarray(x) - np.asarray(y))) <= 1e-9 * max(np.max(np.abs(np.asarray(y))), 1e-300), name
+    s2 = ref_sim.molecules.core.molecules["S2"].c_env_time
+    assert float(np.max(s2[-1]) - np.max(s2[0])) > 1e-4            # the reaction did produce S2 out there
+
+
 def test_gene_network_through_the_dropin_matches_the_reference(monkeypatch, tmp_path):
     """BASELINE configs[3]: the shipped gene regulatory network (extra_configs/grn_basic.yaml) is the SECOND handler
     (sim.grn.core); the shim compiles it from the live MasterOfGenes and writes the genes back for write_data."""
