@@ -93,3 +93,31 @@ def test_fast_solver_reference_loop_vs_cuda_dropin(tmp_path, scenario):
             scale = max(scale, float(np.max(np.abs(ref_sim.Jn))) / (0.1 * float(np.min(ref_sim.sigma_cell)) if name.startswith("efield") else 1.0))
         for a, r in zip(got, want):
             assert np.max(np.abs(np.asarray(a, dtype=float) - np.asarray(r, dtype=float))) <= 1e-9 * max(scale, 1e-300), name
+
+
+def test_env_zone_network_reference_loop_vs_cuda_dropin(tmp_path):
+    """The extracellular zone of the networks on the GPU through the real drop-in: two tight-junction modulators
+    (run_loop_modulators, target 'TJ', networks.py:3301-3317) and a reaction outside the cells (write_reactions_env,
+    networks.py:1830-2088) in one general network — the env concentrations of ions and substances, Vmem and the
+    sim.TJ_modulator the run ends with, against the unmodified reference's own loop."""
+    if not _have_reference():
+        pytest.skip("reference tree absent: neither /root/reference nor baseline/_ref (run tools/install_reference.py)")
+    import copy
+    from tests.golden import make_golden as mg
+    mods = copy.deepcopy(mg.SCENARIOS["mammal_ecm_net_tj"]["mods"])
+    mods["general network"]["reactions"] = copy.deepcopy(mg._ENV_RX)
+    (tmp_path / "ref").mkdir()
+    (tmp_path / "new").mkdir()
+    ref_sim, _ = _run(tmp_path / "ref", False, mods)
+    new_sim, _ = _run(tmp_path / "new", True, mods)
+    assert len(new_sim.time) == len(ref_sim.time) and len(ref_sim.vm_time) >= 30
+    for a, r in zip(new_sim.vm_time, ref_sim.vm_time):
+        assert np.max(np.abs(a - r)) <= 1e-6
+    for a, r in zip(new_sim.cc_env_time, ref_sim.cc_env_time):
+        assert np.max(np.abs(np.asarray(a) - np.asarray(r))) <= 1e-8 * np.max(np.abs(np.asarray(r)))
+    for name in ("S1", "S2", "S3"):
+        a, r = new_sim.molecules.core.molecules[name], ref_sim.molecules.core.molecules[name]
+        for x, y in zip(a.c_env_time, r.c_env_time):
+            assert np.max(np.abs(np.asarray(x) - np.asarray(y))) <= 1e-8 * max(np.max(np.abs(np.asarray(y))), 1e-300), name
+    tj_new, tj_ref = np.asarray(new_sim.TJ_modulator), np.asarray(ref_sim.TJ_modulator)
+    assert float(np.ptp(tj_ref)) > 0.5 and np.max(np.abs(tj_new - tj_ref)) <= 1e-8 * np.max(np.abs(tj_ref))
