@@ -882,6 +882,14 @@ static int ensure_poisson(betse_ctx* ctx)
     if ((r = dev_alloc(ctx, &H.bB, (size_t)ctx->E))) return r;
     if ((r = dev_alloc(ctx, &H.R, 2 * my * mx))) return r;          // two solves at once (hh.cu:poisson)
     if ((r = dev_alloc(ctx, &H.T1, 2 * my * mx))) return r;
+    {   // the folded (even / odd) sine transform: packed matrices and work
+        const size_t hy = (my + 1) / 2, hx = (mx + 1) / 2;
+        if ((r = dev_alloc(ctx, &H.PLy, hy * my))) return r;
+        if ((r = dev_alloc(ctx, &H.PRy, my * hy))) return r;
+        if ((r = dev_alloc(ctx, &H.PLx, hx * mx))) return r;
+        if ((r = dev_alloc(ctx, &H.PRx, mx * hx))) return r;
+        if ((r = dev_alloc(ctx, &H.EO, 4 * std::max(hy * mx, my * hx)))) return r;
+    }
     launch_hh_setup(H, ctx->ny, ctx->nx, ctx->stream);
     CK(cudaGetLastError());
     ctx->poisson_on = true;

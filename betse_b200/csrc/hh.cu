@@ -14,6 +14,7 @@
 // every ~10th step a transform as two dense products with the sine matrices is plenty
 // (u = Sy (Sy R Sx / lambda) Sx / ((my+1)(mx+1)), 4 x ~1e9 FMA at a 1000^2 grid).
 #include <math.h>
+#include <stdlib.h>
 #include "kparams.cuh"
 
 #include "hh.cuh"
@@ -117,16 +118,20 @@ __device__ __forceinline__ void cp_async8(double* dst, const double* src, const 
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
 }
 
+// one product per blockIdx.z: operands, inner dimension; element (row, k) of A at A[row*lda + k*ask], (k, col) of B at
+// B[k*ldb + col], C[row*ldc + col] — the strides let a product read every other row / column of a matrix in place
+struct GemmArgs { const double* A[4]; const double* B[4]; double* C[4]; int K[4]; };
+
 __global__ void __launch_bounds__(256, 2)
-k_hh_gemm(const double* __restrict__ Ab, const double* __restrict__ Bb, double* __restrict__ Cb, const int M, const int N, const int K,
-          const size_t sA, const size_t sB, const size_t sC)
+k_hh_gemm(const __grid_constant__ GemmArgs g, const int M, const int N, const int lda, const int ask, const int ldb, const int ldc)
 {
     extern __shared__ __align__(16) double sh_gemm[];                  // GEMM_SMEM bytes (opt-in size: launch_hh_setup)
     double (*shA)[GK][GM + 2] = reinterpret_cast<double (*)[GK][GM + 2]>(sh_gemm);      // + 2: the transposing copies hit 2 banks, not 16
     double (*shB)[GK][GN] = reinterpret_cast<double (*)[GK][GN]>(sh_gemm + 2 * GK * (GM + 2));
-    const double* __restrict__ A = Ab + (size_t)blockIdx.z * sA;
-    const double* __restrict__ B = Bb + (size_t)blockIdx.z * sB;
-    double* __restrict__ C = Cb + (size_t)blockIdx.z * sC;
+    const double* __restrict__ A = g.A[blockIdx.z];
+    const double* __restrict__ B = g.B[blockIdx.z];
+    double* __restrict__ C = g.C[blockIdx.z];
+    const int K = g.K[blockIdx.z];
     const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
     const int r0 = blockIdx.y * GM, c0 = blockIdx.x * GN;
     // global -> shared, coalesced: A as 8 copies of (16 rows x 16 k) — a warp covers two rows of 128 bytes per copy;
@@ -138,12 +143,12 @@ k_hh_gemm(const double* __restrict__ Ab, const double* __restrict__ Bb, double* 
         for (int q = 0; q < 8; ++q) {
             const int row = r0 + q * 16 + ar;
             const bool ok = row < M && k0 + ak < K;
-            cp_async8(&shA[buf][ak][q * 16 + ar], ok ? A + (size_t)row * K + k0 + ak : A, ok);
+            cp_async8(&shA[buf][ak][q * 16 + ar], ok ? A + (size_t)row * lda + (size_t)(k0 + ak) * ask : A, ok);
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const bool ok = k0 + bk < K && c0 + bc + q < N;
-            cp_async8(&shB[buf][bk][bc + q], ok ? B + (size_t)(k0 + bk) * N + c0 + bc + q : B, ok);
+            cp_async8(&shB[buf][bk][bc + q], ok ? B + (size_t)(k0 + bk) * ldb + c0 + bc + q : B, ok);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -190,7 +195,7 @@ k_hh_gemm(const double* __restrict__ Ab, const double* __restrict__ Bb, double* 
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int c = c0 + 32 * (j >> 1) + 2 * tx + (j & 1);
-            if (c < N) C[(size_t)r * N + c] = acc[i][j];
+            if (c < N) C[(size_t)r * ldc + c] = acc[i][j];
         }
     }
 }
@@ -239,8 +244,86 @@ __global__ void k_hh_out(const __grid_constant__ KParams P, HHBuf H)
 
 static void gemm(const double* A, const double* B, double* C, int M, int N, int K, int batch, size_t sA, size_t sB, size_t sC, cudaStream_t st)
 {
+    GemmArgs a;
+    for (int z = 0; z < 4; ++z) { const int q = z < batch ? z : 0; a.A[z] = A + q * sA; a.B[z] = B + q * sB; a.C[z] = C + q * sC; a.K[z] = K; }
     dim3 g((N + GN - 1) / GN, (M + GM - 1) / GM, batch);
-    k_hh_gemm<<<g, 256, GEMM_SMEM, st>>>(A, B, C, M, N, K, sA, sB, sC);
+    k_hh_gemm<<<g, 256, GEMM_SMEM, st>>>(a, M, N, K, 1, N, N);
+}
+
+// ---- the sine transform at half the arithmetic.  S[n-1-j][k] = (-1)^k S[j][k], so with the even and the odd rows of X
+// transformed separately — E = Se . X[0::2], O = So . X[1::2], Se[j][k'] = S[j][2k'], So[j][k'] = S[j][2k'+1], j < h =
+// ceil(n/2) — the transform is Y[j] = E[j] + O[j], Y[n-1-j] = E[j] - O[j]: two products of (h x h x N) instead of one of
+// (n x n x N).  The same on the right (columns).  Packed matrices: PL [h][n] = [Se | So] for S . X, PR [n][h] = its
+// transpose layout (rows 0..h-1: S[2k'][l'], rows h..n-1: S[2k'+1][l']) for X . S.
+__global__ void k_hh_sine_packed(double* __restrict__ PL, double* __restrict__ PR, const int n)
+{
+    const int h = (n + 1) / 2;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;       // j < h: the row of PL / column of PR
+    if (q >= n) return;
+    const int k = q < h ? 2 * q : 2 * (q - h) + 1;                             // the column of S behind packed column q
+    const long long prod = (long long)(j + 1) * (k + 1) % (2LL * (n + 1));     // exact argument reduction
+    const double v = sinpi((double)prod / (double)(n + 1));
+    PL[(size_t)j * n + q] = v;
+    PR[(size_t)q * h + j] = v;                                                  // S is symmetric
+}
+
+// Y[j] = E[j] + O[j], Y[n-1-j] = E[j] - O[j] (rows: left transform of an [n][N] array; E, O: [h][N])
+__global__ void k_hh_fold_rows(const double* __restrict__ Eb, const double* __restrict__ Ob, double* __restrict__ Yb, const int n, const int N,
+                               const size_t sEO, const size_t sY)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (c >= N) return;
+    const double* E = Eb + blockIdx.z * sEO; const double* O = Ob + blockIdx.z * sEO; double* Y = Yb + blockIdx.z * sY;
+    const double e = E[(size_t)j * N + c], o = O[(size_t)j * N + c];
+    Y[(size_t)j * N + c] = e + o;
+    if (n - 1 - j != j) Y[(size_t)(n - 1 - j) * N + c] = e - o;
+}
+// Z[r][l] = E[r][l] + O[r][l], Z[r][n-1-l] = E[r][l] - O[r][l] (columns: right transform of an [M][n] array; E, O: [M][h])
+__global__ void k_hh_fold_cols(const double* __restrict__ Eb, const double* __restrict__ Ob, double* __restrict__ Zb, const int M, const int n,
+                               const size_t sEO, const size_t sZ)
+{
+    const int h = (n + 1) / 2;
+    const int l = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (l >= h) return;
+    const double* E = Eb + blockIdx.z * sEO; const double* O = Ob + blockIdx.z * sEO; double* Z = Zb + blockIdx.z * sZ;
+    const double e = E[(size_t)r * h + l], o = O[(size_t)r * h + l];
+    Z[(size_t)r * n + l] = e + o;
+    if (n - 1 - l != l) Z[(size_t)r * n + (n - 1 - l)] = e - o;
+}
+
+// Y = S . X for nb arrays X [n][N] (stride sX) -> Y (stride sY); EO: work, 2 * nb * h * N doubles
+static void dst_left(const HHBuf& H, const double* X, double* Y, int n, int N, int nb, size_t sX, size_t sY, cudaStream_t st)
+{
+    const int h = (n + 1) / 2, l = n / 2;
+    const size_t w = (size_t)h * N;
+    GemmArgs a;
+    for (int z = 0; z < 4; ++z) {
+        const int sv = (z < 2 * nb ? z : 0) >> 1, par = z & 1;
+        a.A[z] = H.PLy + (par ? h : 0);                       // [Se | So]
+        a.B[z] = X + sv * sX + (par ? N : 0);                 // even / odd rows of X
+        a.C[z] = H.EO + (size_t)(2 * sv + par) * w;
+        a.K[z] = par ? l : h;
+    }
+    dim3 g((N + GN - 1) / GN, (h + GM - 1) / GM, 2 * nb);
+    k_hh_gemm<<<g, 256, GEMM_SMEM, st>>>(a, h, N, n, 1, 2 * N, N);
+    k_hh_fold_rows<<<dim3((N + 127) / 128, h, nb), 128, 0, st>>>(H.EO, H.EO + w, Y, n, N, 2 * w, sY);
+}
+// Z = X . S for nb arrays X [M][n]
+static void dst_right(const HHBuf& H, const double* X, double* Z, int M, int n, int nb, size_t sX, size_t sZ, cudaStream_t st)
+{
+    const int h = (n + 1) / 2, l = n / 2;
+    const size_t w = (size_t)M * h;
+    GemmArgs a;
+    for (int z = 0; z < 4; ++z) {
+        const int sv = (z < 2 * nb ? z : 0) >> 1, par = z & 1;
+        a.A[z] = X + sv * sX + (par ? 1 : 0);                 // even / odd columns of X
+        a.B[z] = H.PRx + (par ? (size_t)h * h : 0);           // rows S[2k'][.] / S[2k'+1][.]
+        a.C[z] = H.EO + (size_t)(2 * sv + par) * w;
+        a.K[z] = par ? l : h;
+    }
+    dim3 g((h + GN - 1) / GN, (M + GM - 1) / GM, 2 * nb);
+    k_hh_gemm<<<g, 256, GEMM_SMEM, st>>>(a, M, h, n, 2, h, h);
+    k_hh_fold_cols<<<dim3((h + 127) / 128, M, nb), 128, 0, st>>>(H.EO, H.EO + w, Z, M, n, 2 * w, sZ);
 }
 
 void launch_hh_setup(const HHBuf& H, int ny, int nx, cudaStream_t st)
@@ -249,6 +332,10 @@ void launch_hh_setup(const HHBuf& H, int ny, int nx, cudaStream_t st)
     cudaFuncSetAttribute(k_hh_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
     k_hh_sine<<<dim3((my + 127) / 128, my), 128, 0, st>>>(H.Sy, H.ly, my);
     k_hh_sine<<<dim3((mx + 127) / 128, mx), 128, 0, st>>>(H.Sx, H.lx, mx);
+    if (H.PLy) {
+        k_hh_sine_packed<<<dim3((my + 127) / 128, (my + 1) / 2), 128, 0, st>>>(H.PLy, H.PRy, my);
+        k_hh_sine_packed<<<dim3((mx + 127) / 128, (mx + 1) / 2), 128, 0, st>>>(H.PLx, H.PRx, mx);
+    }
 }
 
 // one Dirichlet solve (b -> u), or two that share the sine matrices (b2 -> u2 as well) as batched products: H.R / H.T1
@@ -261,11 +348,20 @@ static void poisson(const KParams& P, const HHBuf& H, const double* b, double* u
     dim3 gE((nx + 127) / 128, ny), gI((mx + 127) / 128, my), gIb((mx + 127) / 128, my, nb);
     k_hh_lift<<<gE, 128, 0, st>>>(P, b, u, H.R);
     if (b2) k_hh_lift<<<gE, 128, 0, st>>>(P, b2, u2, H.R + w);
-    gemm(H.Sy, H.R, H.T1, my, mx, my, nb, 0, w, w, st);           // Sy . R
-    gemm(H.T1, H.Sx, H.R, my, mx, mx, nb, w, 0, w, st);           // . Sx
-    k_hh_scale<<<gIb, 128, 0, st>>>(H.R, H.ly, H.lx, my, mx);
-    gemm(H.Sy, H.R, H.T1, my, mx, my, nb, 0, w, w, st);
-    gemm(H.T1, H.Sx, H.R, my, mx, mx, nb, w, 0, w, st);
+    static const int sym = [] { const char* e = getenv("BETSE_HH_SYM"); return (e && e[0] == '0') ? 0 : 1; }();
+    if (sym && H.PLy) {
+        dst_left(H, H.R, H.T1, my, mx, nb, w, w, st);             // Sy . R at half the arithmetic (even / odd split)
+        dst_right(H, H.T1, H.R, my, mx, nb, w, w, st);            // . Sx
+        k_hh_scale<<<gIb, 128, 0, st>>>(H.R, H.ly, H.lx, my, mx);
+        dst_left(H, H.R, H.T1, my, mx, nb, w, w, st);
+        dst_right(H, H.T1, H.R, my, mx, nb, w, w, st);
+    } else {
+        gemm(H.Sy, H.R, H.T1, my, mx, my, nb, 0, w, w, st);           // Sy . R
+        gemm(H.T1, H.Sx, H.R, my, mx, mx, nb, w, 0, w, st);           // . Sx
+        k_hh_scale<<<gIb, 128, 0, st>>>(H.R, H.ly, H.lx, my, mx);
+        gemm(H.Sy, H.R, H.T1, my, mx, my, nb, 0, w, w, st);
+        gemm(H.T1, H.Sx, H.R, my, mx, mx, nb, w, 0, w, st);
+    }
     k_hh_scatter<<<gI, 128, 0, st>>>(H.R, u, my, mx);
     if (b2) k_hh_scatter<<<gI, 128, 0, st>>>(H.R + w, u2, my, mx);
 }
