@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libbetse_b200.so")
 
 MAX_IONS = 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 NKERNELS = 8
 
 STATUS_NAN_VM = 1

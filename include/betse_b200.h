@@ -26,7 +26,7 @@ extern "C" {
 #endif
 
 #define BETSE_MAX_IONS 8
-#define BETSE_ABI_VERSION 2
+#define BETSE_ABI_VERSION 3
 
 typedef struct betse_ctx betse_ctx;
 
