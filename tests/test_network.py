@@ -111,3 +111,49 @@ def test_transporter_programs_equal_python_eval():
         scale = float(np.max(np.abs(want)))
         print(t["name"], float(np.max(np.abs(got - want))) / scale)
         assert np.max(np.abs(got - want)) <= 1e-12 * scale, t["name"]
+
+
+@pytest.mark.parametrize("fixture", ["mammal_ecm_net_tj", "mammal_ecm_net_envrx"])
+def test_extracellular_zone_programs_equal_python_eval(fixture):
+    """Rate laws of the extracellular zone (get_influencers / write_reactions_env with reaction_zone 'env',
+    networks.py:1830-2088, 5270-5281): tight-junction modulators and reactions in the bath read ``self.env_concs['X']`` over
+    the whole grid — bytecode on the host interpreter == eval of the reference's string, on random env concentrations."""
+    cap = util.load_golden(fixture)
+    kind = "sim"
+    descs = util.networks_of(cap, kind)
+    o = OracleSim(util.mesh_of(cap, kind), util.group(cap, kind + ".p."), util.group(cap, kind + ".s0."), networks=descs)
+    d, net = descs[0], o.networks[0]
+    comp = netlib.compile_network(d, o.cdl, o.mdl)
+    progs = comp["rate_programs"] + comp["mod_programs"]
+    strings = [(s, progs[i]) for s, (t, i, _, _) in zip(d.get("modulator_strings", []), comp["modulators"]) if t == 2]
+    strings += [(s, progs[i]) for s, i in zip(d.get("reaction_env_strings", []), comp["env_rx_index"])]
+    assert strings and all(pr.zone == "env" for _, pr in strings)
+    rng = np.random.default_rng(5)
+    for trial in range(3):
+        for n in net.species:
+            if n in net.c_env:
+                net.c_env[n] = rng.uniform(0.0, 2.0, o.n_env)
+        spec = np.stack([net.c[n] for n in net.species])
+        spec_env = np.stack([net.c_env.get(n, np.zeros(o.n_env)) for n in net.species])
+        for s, pr in strings:
+            want = net.eval_string(s) * np.ones(o.n_env)
+            got = ratelaw.run_numpy(pr, comp["tables"], spec, ions=o.cc_cells, species_env=spec_env, ions_env=o.cc_env)
+            assert got.shape == (o.n_env,)
+            assert np.max(np.abs(got - want)) <= 1e-14 * max(float(np.max(np.abs(want))), 1e-300), s
+    if fixture == "mammal_ecm_net_tj":
+        assert [(t, ion) for t, _, _, ion in comp["modulators"]] == [(2, -1), (2, 0)]      # all ions; Na only
+        assert comp["tj_targets"].size and comp["tj_targets"].max() < o.n_env
+    else:
+        assert comp["stoich_env"].tolist() == [[-1.0], [1.0], [0.0]]                       # S1 -> S2 out there
+
+
+def test_cell_zone_law_reading_a_substance_an_env_reaction_moves_is_refused():
+    """The device evaluates the cell-zone rate laws after the extracellular reactions of the step, the reference before
+    (networks.py:2826-2889): a network that couples the two through a substance in the bath is refused, not approximated."""
+    import copy
+    cap = util.load_golden("mammal_ecm_net_envrx")
+    d = copy.deepcopy(util.networks_of(cap, "sim")[0])
+    C, M = len(cap["cells.cell_vol"]), len(cap["cells.mem_sa"])
+    d["gad_strings"][2] = d["gad_strings"][2] + "*(self.env_concs['S2'][cells.map_cell2ecm]/(1 + self.env_concs['S2'][cells.map_cell2ecm]))"
+    with pytest.raises(netlib.BetseB200Error, match="extracellular reaction"):
+        netlib.compile_network(d, C, M)
