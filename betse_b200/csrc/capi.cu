@@ -885,8 +885,6 @@ static int ensure_poisson(betse_ctx* ctx)
     {   // the folded (even / odd) sine transform: packed matrices and work
         const size_t hy = (my + 1) / 2, hx = (mx + 1) / 2;
         if ((r = dev_alloc(ctx, &H.PLy, hy * my))) return r;
-        if ((r = dev_alloc(ctx, &H.PRy, my * hy))) return r;
-        if ((r = dev_alloc(ctx, &H.PLx, hx * mx))) return r;
         if ((r = dev_alloc(ctx, &H.PRx, mx * hx))) return r;
         if ((r = dev_alloc(ctx, &H.EO, 4 * std::max(hy * mx, my * hx)))) return r;
     }

@@ -255,7 +255,7 @@ static void gemm(const double* A, const double* B, double* C, int M, int N, int 
 // ceil(n/2) — the transform is Y[j] = E[j] + O[j], Y[n-1-j] = E[j] - O[j]: two products of (h x h x N) instead of one of
 // (n x n x N).  The same on the right (columns).  Packed matrices: PL [h][n] = [Se | So] for S . X, PR [n][h] = its
 // transpose layout (rows 0..h-1: S[2k'][l'], rows h..n-1: S[2k'+1][l']) for X . S.
-__global__ void k_hh_sine_packed(double* __restrict__ PL, double* __restrict__ PR, const int n)
+__global__ void k_hh_sine_packed(double* __restrict__ PL, double* __restrict__ PR, const int n)       // either may be null
 {
     const int h = (n + 1) / 2;
     const int q = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;       // j < h: the row of PL / column of PR
@@ -263,8 +263,8 @@ __global__ void k_hh_sine_packed(double* __restrict__ PL, double* __restrict__ P
     const int k = q < h ? 2 * q : 2 * (q - h) + 1;                             // the column of S behind packed column q
     const long long prod = (long long)(j + 1) * (k + 1) % (2LL * (n + 1));     // exact argument reduction
     const double v = sinpi((double)prod / (double)(n + 1));
-    PL[(size_t)j * n + q] = v;
-    PR[(size_t)q * h + j] = v;                                                  // S is symmetric
+    if (PL) PL[(size_t)j * n + q] = v;
+    if (PR) PR[(size_t)q * h + j] = v;                                          // S is symmetric
 }
 
 // Y[j] = E[j] + O[j], Y[n-1-j] = E[j] - O[j] (rows: left transform of an [n][N] array; E, O: [h][N])
@@ -333,8 +333,8 @@ void launch_hh_setup(const HHBuf& H, int ny, int nx, cudaStream_t st)
     k_hh_sine<<<dim3((my + 127) / 128, my), 128, 0, st>>>(H.Sy, H.ly, my);
     k_hh_sine<<<dim3((mx + 127) / 128, mx), 128, 0, st>>>(H.Sx, H.lx, mx);
     if (H.PLy) {
-        k_hh_sine_packed<<<dim3((my + 127) / 128, (my + 1) / 2), 128, 0, st>>>(H.PLy, H.PRy, my);
-        k_hh_sine_packed<<<dim3((mx + 127) / 128, (mx + 1) / 2), 128, 0, st>>>(H.PLx, H.PRx, mx);
+        k_hh_sine_packed<<<dim3((my + 127) / 128, (my + 1) / 2), 128, 0, st>>>(H.PLy, nullptr, my);      // Sy . X: left
+        k_hh_sine_packed<<<dim3((mx + 127) / 128, (mx + 1) / 2), 128, 0, st>>>(nullptr, H.PRx, mx);      // X . Sx: right
     }
 }
 

@@ -8,7 +8,7 @@ struct HHBuf {
     double *bA, *bB;          // [E] right-hand sides of the two Poisson problems
     double *uA, *uB;          // [E] potentials AA, BB
     double *R, *T1;           // [2][my][mx] work (two Poisson solves at once)
-    double *PLy, *PRy, *PLx, *PRx;   // packed even / odd sine matrices (hh.cu: dst_left / dst_right): PL [h][n], PR [n][h]
+    double *PLy, *PRx;        // packed even / odd sine matrices (hh.cu: dst_left / dst_right): PLy [hy][my] = [Se | So], PRx [mx][hx]
     double *EO;               // [2 solves][even, odd][max(hy*mx, my*hx)] work of the folded transforms
     double *J_env_x, *J_env_y, *B_field, *Jtx, *Jty;   // outputs [E]
     double mu, bound[4];      // p.mu; sim.bound_V T, B, L, R
