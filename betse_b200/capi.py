@@ -168,6 +168,7 @@ class WindowInfo(C.Structure):
         ("off_cc_mid", C.c_uint64 * 2), ("off_vm_cell", C.c_uint64 * 2), ("off_flux", C.c_uint64),
         ("off_cc_env", C.c_uint64 * 2), ("off_v_raw", C.c_uint64), ("off_flags", C.c_uint64),
         ("n_cells", C.c_int32), ("n_env", C.c_int32), ("nx", C.c_int32), ("n_ions", C.c_int32),
+        ("n_flux_slots", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

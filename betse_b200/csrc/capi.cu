@@ -777,6 +777,7 @@ static int create_impl(betse_ctx* ctx, const betse_mesh* mesh, const betse_param
         if ((r = dev_alloc(ctx, &ctx->win, off))) return r;
         W.base = ctx->win;
         W.n_cells = C; W.n_env = E; W.nx = ctx->nx; W.n_ions = I;
+        W.n_flux_slots = hp->is_ecm ? ctx->n_slots : 0;
         for (int b = 0; b < 2; ++b) {
             A.cc_mid[b] = (double*)(ctx->win + W.off_cc_mid[b]);
             A.vm_cell[b] = (double*)(ctx->win + W.off_vm_cell[b]);
@@ -2502,6 +2503,8 @@ extern "C" int betse_attach_neighbor(betse_ctx* ctx, const betse_neighbor* nb)
     if (!ctx->hp.is_ecm) return fail(ctx, "domain decomposition needs extracellular spaces (no-ECM tissues run as replicas)");
     if (ctx->P.has_phi) return fail(ctx, "domain decomposition does not support a boundary-voltage potential (Phi_b)");
     if (!ctx->chans.empty()) return fail(ctx, "channels on a domain-decomposed tissue are not implemented");
+    if (ctx->net_on[0] || ctx->net_on[1]) return fail(ctx, "networks on a domain-decomposed tissue are not implemented");
+    if (ctx->noise_on) return fail(ctx, "dynamic noise on a domain-decomposed tissue is not implemented");
     const betse_window_info& W = nb->info;
     if (W.n_ions != ctx->I || W.nx != ctx->nx) return fail(ctx, "neighbour window has different n_ions / nx");
     char* base = (char*)W.base;
@@ -2515,6 +2518,8 @@ extern "C" int betse_attach_neighbor(betse_ctx* ctx, const betse_neighbor* nb)
     }
     if (!base) return fail(ctx, "neighbour window pointer is null");
     if (nb->recv_cell0 < 0 || nb->recv_cell0 + nb->n_send_cells > W.n_cells) return fail(ctx, "ghost-cell range outside the neighbour");
+    if (nb->n_send_flux < 0 || (nb->n_send_flux > 0 && (nb->recv_slot0 < 0 || nb->recv_slot0 + nb->n_send_flux > W.n_flux_slots)))
+        return fail(ctx, "remote flux-slot range outside the neighbour's exchange slots");
     if (nb->cc_rows < 0 || nb->v_rows < 0 || (nb->cc_dst_row0 + nb->cc_rows) * W.nx > W.n_env ||
         (nb->v_dst_row0 + nb->v_rows) * W.nx > W.n_env || (nb->cc_src_row0 + nb->cc_rows) > ctx->ny ||
         (nb->v_src_row0 + nb->v_rows) > ctx->ny) return fail(ctx, "row block outside the grid");

@@ -460,6 +460,7 @@ typedef struct betse_window_info {
     uint64_t off_v_raw;        /* [E]                                                            */
     uint64_t off_flags;        /* uint64 [2 exchange points][2 sides]                            */
     int32_t  n_cells, n_env, nx, n_ions;   /* leading dimensions of the arrays above             */
+    int32_t  n_flux_slots, reserved;       /* rows of the flux array: betse_attach_neighbor checks recv_slot0 + n_send_flux against it */
 } betse_window_info;
 
 /* One neighbouring strip.  side 0 = the strip below (smaller y), 1 = above. */
