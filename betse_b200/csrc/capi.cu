@@ -2256,6 +2256,7 @@ extern "C" int betse_set_network(betse_ctx* ctx, int handler, const betse_networ
         if ((r = dev_alloc(ctx, &ctx->lig_tmp[handler], (size_t)net->n_ligand_gates * Mo))) return r;
     }
     ctx->net_mods[handler].clear();
+    bool tj_fresh = false;
     for (int j = 0; j < net->n_modulators; ++j) {
         const betse_modulator& md = net->modulators[j];
         if (md.target < 0 || md.target > 2) return fail(ctx, "network: modulator target must be 0 (gap junctions), 1 (Na/K-ATPase) or 2 (tight junctions)");
@@ -2268,9 +2269,11 @@ extern "C" int betse_set_network(betse_ctx* ctx, int handler, const betse_networ
             if (ctx->X.n_nbr > 0) return fail(ctx, "network: tight-junction modulators on a domain-decomposed tissue are not implemented");
             for (int q = 0; q < net->n_tj; ++q)
                 if (net->tj_targets[q] < 0 || net->tj_targets[q] >= ctx->E) return fail(ctx, "network: tj_targets out of range");
-            if (!ctx->net_tj[handler]) {
+            if (!tj_fresh) {              // (a repeated betse_set_network replaces the list; the old one goes with the ctx)
+                ctx->net_tj[handler] = nullptr;
                 if ((r = dev_upload(ctx, &ctx->net_tj[handler], (const int*)net->tj_targets, (size_t)net->n_tj))) return r;
                 ctx->net_ntj[handler] = net->n_tj;
+                tj_fresh = true;
             }
             if (!ctx->denv_raw) { if ((r = dev_upload(ctx, &ctx->denv_raw, net->D_env_raw, (size_t)ctx->I * ctx->E))) return r; }
             if (!ctx->tj_mod) {
