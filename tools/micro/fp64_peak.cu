@@ -1,4 +1,5 @@
-// fp64 peak of this GPU: vector DFMA and tensor DMMA (mma.sync.m8n8k4.f64).  nvcc -arch=sm_100a -O3 -o fp64_peak fp64_peak.cu
+// fp64 peak of this GPU: vector DFMA and tensor DMMA (mma.sync.m8n8k4.f64).
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o fp64_peak fp64_peak.cu  (the binary is git-ignored; results: profiles/r02u_fp64_peak.txt)
 #include <cstdio>
 #include <cuda_runtime.h>
 __global__ void k_dfma(double* out, int iters, double x)
